@@ -1,0 +1,333 @@
+/* ospcuda.h — the thin C-ABI between the host-side `cuda` OSPRay device (C++) and the
+ * hand-written sm_100a kernels (libospcuda.so).
+ *
+ * Plain C: pointers, sizes and POD structs only; no CUDA, torch or C++ types appear in
+ * any signature, so the host module never includes a CUDA header.
+ * Every entry point names the reference interface it stands in for (paths relative to
+ * the OSPRay v3.3.0 tree):
+ *
+ *   ospcuda_bvh_build_group / ospcuda_bvh_build_tlas
+ *        -> Embree rtcCommitScene as called from modules/cpu/common/Group.cpp:129-142
+ *           and modules/cpu/common/World.cpp:167-171
+ *   ospcuda_trace
+ *        -> rtcIntersectV / rtcOccludedV as called from modules/cpu/common/World.ih:29-52,
+ *           :311-335 (closest hit / occlusion for arbitrary ray batches; used by tests)
+ *   ospcuda_render_frame
+ *        -> devicert::Device::launchRendererKernel (ospray/common/DeviceRT.h:140-197) with
+ *           PathTracer_renderTask (modules/cpu/render/pathtracer/PathTracer.ispc:218-249),
+ *           SciVis_renderTask (render/scivis/SciVis.ispc:287-298) or AORenderer_renderTask
+ *           (render/ao/AORenderer.ispc:155-166), plus LocalFB_accumulateSample
+ *           (modules/cpu/fb/LocalFB.ispc:14-78) fused into the epilogue
+ *   ospcuda_fb_variance      -> Variance_kernel   (fb/frame_ops/Variance.ispc:11-59)
+ *   ospcuda_fb_tonemap       -> ToneMapper_kernel (fb/frame_ops/ToneMapper.ispc:12-41)
+ *   ospcuda_fb_color_convert -> ColorConversion_kernel (fb/frame_ops/ColorConversion.ispc:11-36)
+ *   ospcuda_fb_accumulate    -> LocalFB_accumulateSample for an externally produced sample
+ *                               image (used by tests and by the roofline bench leg)
+ *   ospcuda_fb_gather_tiles  -> LocalFrameBuffer::writeTiles (fb/LocalFB.cpp:286-353), the
+ *                               multi-device untile step after the NCCL gather
+ *   ospcuda_volume_macrocells-> Open VKL structuredRegular acceleration build done inside
+ *                               vklCommit (modules/cpu/volume/Volume.cpp:77-94)
+ *   ospcuda_malloc/free/memcpy/... -> devicert::Device::malloc/free/memcpy (DeviceRT.h:150-170)
+ *
+ * All functions return 0 on success, non-zero CUDA error code otherwise;
+ * ospcuda_last_error() returns the message. Nothing here falls back to the CPU.        */
+#ifndef OSPCUDA_H
+#define OSPCUDA_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSPCUDA_API __attribute__((visibility("default")))
+
+/* ---- POD views --------------------------------------------------------------------- */
+typedef struct { float x, y, z; } OcVec3f;
+typedef struct { float x, y, z, w; } OcVec4f;
+typedef struct { OcVec3f vx, vy, vz, p; } OcAffine3f; /* column-major 3x4 (OSP_AFFINE3F) */
+
+/* strided 1-D array living in device memory (reference: ispc::Data1D, common/Data.h:15-21) */
+typedef struct {
+  const uint8_t *addr;
+  int64_t byteStride;
+  uint32_t numItems;
+  uint32_t pad;
+} OcData1D;
+
+enum { OC_GEOM_TRIANGLES = 0, OC_GEOM_QUADS = 1, OC_GEOM_SPHERES = 2, OC_GEOM_BOXES = 3 };
+enum { OC_GEOMFLAG_NORMAL_FACEVARYING = 1, OC_GEOMFLAG_COLOR_FACEVARYING = 2,
+       OC_GEOMFLAG_TEXCOORD_FACEVARYING = 4, OC_GEOMFLAG_HAS_ALPHA = 8, OC_GEOMFLAG_COLOR_IS_VEC4 = 16 };
+
+/* geometry (reference: ispc::Mesh MeshShared.h:12-44, ispc::Spheres, ispc::Boxes) */
+typedef struct {
+  uint32_t type;
+  uint32_t numPrims;
+  uint32_t flags;
+  uint32_t pad;
+  OcData1D index;    /* vec3ui (triangles) or vec4ui (quads) */
+  OcData1D vertex;   /* vec3f */
+  OcData1D normal;   /* vec3f, optional */
+  OcData1D color;    /* vec3f or vec4f, optional */
+  OcData1D texcoord; /* vec2f, optional */
+  OcData1D sphere;   /* vec4f (x,y,z,r) interleaved at commit (Spheres.cpp:58-96) */
+  OcData1D box;      /* box3f (6 floats) */
+} OcGeometry;
+
+enum { OC_MAT_NONE = 0, OC_MAT_FROM_MODEL = 1, OC_MAT_FROM_RENDERER = 2 };
+
+/* geometric model (reference: ispc::GeometricModel, geometry/GeometricModel.ih:21-76) */
+typedef struct {
+  const OcGeometry *geom;
+  OcData1D color;           /* vec4f per-prim colour, optional */
+  OcData1D index;           /* uint8 indirection, optional */
+  const uint32_t *material; /* indices into OcWorld.materials (mode FROM_MODEL) or renderer ids */
+  uint32_t numMaterials;
+  uint32_t materialMode;
+  uint32_t invertedNormals;
+  uint32_t userID;          /* 0xFFFFFFFF = unset */
+} OcModel;
+
+enum { OC_MATERIAL_OBJ = 0, OC_MATERIAL_OTHER = 1 };
+/* material (reference: ispc::OBJ, render/materials/OBJShared.h; OBJ.cpp:30-66) */
+typedef struct {
+  uint32_t type;
+  float d;
+  OcVec3f Kd;
+  OcVec3f Ks;
+  float Ns;
+  OcVec3f Tf;
+  float pad[4];
+} OcMaterial;
+
+/* 4-wide BVH node, 128 B = one cache line, fetched as 8 x 128-bit loads */
+typedef struct {
+  float lox[4], hix[4], loy[4], hiy[4], loz[4], hiz[4];
+  uint32_t child[4]; /* 0xFFFFFFFF empty; bit31: leaf (bits 27..30 count, bits 0..26 first record) */
+  uint32_t pad[4];
+} OcNode4;
+
+enum { OC_PRIM_TRI = 0, OC_PRIM_TRI_QUAD2ND = 1, OC_PRIM_SPHERE = 2, OC_PRIM_BOX = 3, OC_PRIM_INSTANCE = 4 };
+
+typedef struct {
+  const OcNode4 *nodes;
+  const OcVec4f *prims; /* 3 x float4 per record, in leaf order */
+  uint32_t numNodes;
+  uint32_t numRecords;
+  float bounds[6];
+} OcBVH;
+
+/* linear transfer function (reference: LinearTransferFunction.ispc:11-43) */
+typedef struct {
+  const OcVec3f *color;
+  const float *opacity;
+  uint32_t numColors;
+  uint32_t numOpacities;
+  float valueLower, valueUpper;
+} OcTransferFunction;
+
+/* structuredRegular volume + its volumetric model
+ * (reference: volume/Volume.cpp:60-222 -> Open VKL; VolumetricModel.cpp:29-82) */
+typedef struct {
+  const float *voxels;       /* x fastest */
+  uint32_t dims[3];
+  uint32_t mcDims[3];        /* macrocell grid, 16^3 cells each (Open VKL GridAccelerator) */
+  const float *mcRange;      /* 2 floats (min,max) per macrocell */
+  OcVec3f gridOrigin, gridSpacing;
+  float bounds[6];
+  OcTransferFunction tf;
+  float densityScale, anisotropy, gradientShadingScale;
+  uint32_t userID;
+  uint32_t numRanges;        /* TF positive-opacity value ranges (VolumetricModel.cpp:46-62) */
+  float ranges[2 * 8];
+} OcVolume;
+
+typedef struct {
+  const OcModel *models;
+  uint32_t numModels;
+  uint32_t numVolumes;
+  const OcVolume *volumes;
+  OcBVH bvh;
+} OcGroup;
+
+/* instance (reference: ispc::Instance, common/InstanceShared.h; Instance.cpp:20-34) */
+typedef struct {
+  OcAffine3f xfm, rcp_xfm;
+  const OcGroup *group;
+  uint32_t userID;
+  uint32_t isIdentity;
+  float bounds[6]; /* world-space */
+} OcInstance;
+
+enum { OC_LIGHT_AMBIENT = 0, OC_LIGHT_DISTANT = 2, OC_LIGHT_QUAD = 5 };
+/* lights (reference: lights/LightShared.h:79-110, QuadLightShared.h, DirectionalLightShared.h,
+ * AmbientLightShared.h) */
+typedef struct {
+  uint32_t type;
+  uint32_t isVisible;
+  OcVec3f radiance;            /* ambient/quad: radiance; distant: irradiance */
+  OcVec3f position, edge1, edge2, nnormal; /* quad */
+  float ppdf;                  /* quad: 1/area */
+  OcVec3f fx, fy, fz;          /* distant: frame (vz = direction towards light) */
+  float cosAngle, pdf;         /* distant */
+} OcLight;
+
+typedef struct {
+  const OcInstance *instances;
+  uint32_t numInstances;
+  uint32_t hasVolumes;
+  OcBVH tlas;                  /* used when numInstances > OC_TLAS_THRESHOLD */
+  const OcMaterial *materials;
+  uint32_t numMaterials;
+  /* pathtracer light list (PathTracerData.cpp:32-82): geo lights first (none), world, instance */
+  uint32_t numLights;
+  const OcLight *lights;
+  const float *lightsCDF;
+  /* scivis light list (SciVisData.cpp:74-105): visible-only lights first, ambient folded */
+  const OcLight *scivisLights;
+  uint32_t numScivisLights;
+  uint32_t numScivisLightsVisibleOnly;
+  OcVec3f aoColorPi;
+  float bounds[6];
+} OcWorld;
+
+/* perspective camera (reference: PerspectiveCameraShared.h; PerspectiveCamera.cpp:26-117) */
+typedef struct {
+  OcVec3f org, dir_00, du_size, dv_up, direction;
+  float nearClip;
+  float subImage[4];           /* lower.x, lower.y, upper.x, upper.y */
+  float scaledAperture, aspect, imgPlaneSizeY;
+  uint32_t needLensSample, needTimeSample;
+} OcCamera;
+
+enum { OC_RENDERER_PATHTRACER = 0, OC_RENDERER_SCIVIS = 1, OC_RENDERER_AO = 2, OC_RENDERER_DEBUG_ID = 3 };
+enum { OC_PF_POINT = 0, OC_PF_BOX = 1, OC_PF_LUT = 2 };
+
+/* renderer (reference: Renderer.cpp:38-92, PathTracer.cpp:29-51, SciVis.cpp:27-36,
+ * AORenderer.cpp:26-35, pf/PixelFilter.cpp:23-69) */
+typedef struct {
+  uint32_t type;
+  int32_t spp;
+  uint32_t maxDepth;
+  float minContribution;
+  float bgColor[4];
+  /* pixel filter */
+  uint32_t pfType;
+  float pfWidth;
+  uint32_t pfLutW, pfLutH;
+  const float *pfCdfX;         /* pfLutW*pfLutH */
+  const float *pfCdfY;         /* pfLutH */
+  /* renderer material list (for OC_MAT_FROM_RENDERER) : indices into OcWorld.materials */
+  const uint32_t *materials;
+  uint32_t numMaterials;
+  /* pathtracer */
+  int32_t rouletteDepth;
+  int32_t maxScatteringEvents;
+  float maxRadiance;
+  int32_t numLightSamples;
+  uint32_t limitIndirectLightSamples;
+  uint32_t backgroundRefraction;
+  /* scivis / ao */
+  uint32_t shadowsEnabled;
+  uint32_t visibleLights;
+  int32_t aoSamples;
+  float aoRadius;
+  float aoIntensity;
+  float volumeSamplingRate;
+} OcRenderer;
+
+/* framebuffer (reference: LocalFBShared.h, FrameBufferShared.h; LocalFB.cpp:49-180) */
+typedef struct {
+  int32_t sizeX, sizeY;
+  int32_t frameID;             /* already incremented by beginFrame (FrameBuffer.cpp:115-118) */
+  uint32_t channels;
+  uint32_t accumulateVariance;
+  uint32_t projectedDepth;
+  int32_t targetFrames;
+  uint32_t colorFormat;        /* OSPFrameBufferFormat */
+  OcVec4f *color;
+  OcVec4f *variance;
+  float *depth;
+  OcVec3f *normal, *firstNormal, *albedo, *position;
+  uint32_t *primID, *objID, *instID;
+  /* image-tile partition across ranks (reference: MultiDevice.cpp:403-416: tile % N == rank) */
+  uint32_t numRanks, rank;
+  /* per-frame ray statistics: [0] primary, [1] continuation, [2] shadow/occlusion segments */
+  unsigned long long *rayCounters;
+} OcFrameBuffer;
+
+typedef struct {
+  float exposure, a, b, c, d;
+  uint32_t acesColor;
+} OcToneMapper;
+
+/* a ray / hit record for ospcuda_trace (reference: struct Ray, common/Ray.ih:15-42) */
+typedef struct {
+  float org[3], t0, dir[3], t;
+  float Ng[3], u, v;
+  uint32_t primID, geomID, instID;
+} OcRayHit;
+
+/* ---- runtime ----------------------------------------------------------------------- */
+OSPCUDA_API int ospcuda_init(int deviceOrdinal);
+OSPCUDA_API const char *ospcuda_last_error(void);
+OSPCUDA_API int ospcuda_device_count(void);
+OSPCUDA_API int ospcuda_malloc(void **ptr, size_t bytes);
+OSPCUDA_API int ospcuda_free(void *ptr);
+OSPCUDA_API int ospcuda_malloc_host(void **ptr, size_t bytes); /* pinned */
+OSPCUDA_API int ospcuda_free_host(void *ptr);
+OSPCUDA_API int ospcuda_memcpy_h2d(void *dst, const void *src, size_t bytes);
+OSPCUDA_API int ospcuda_memcpy_d2h(void *dst, const void *src, size_t bytes);
+OSPCUDA_API int ospcuda_memcpy_d2h_async(void *dst, const void *src, size_t bytes);
+OSPCUDA_API int ospcuda_memset(void *dst, int value, size_t bytes);
+OSPCUDA_API int ospcuda_synchronize(void);
+/* render-stream events: create, record (on the render stream), wait, query, elapsed ms */
+OSPCUDA_API int ospcuda_event_create(void **ev);
+OSPCUDA_API int ospcuda_event_destroy(void *ev);
+OSPCUDA_API int ospcuda_event_record(void *ev);
+OSPCUDA_API int ospcuda_event_synchronize(void *ev);
+OSPCUDA_API int ospcuda_event_query(void *ev); /* 1 done, 0 pending, <0 error */
+OSPCUDA_API int ospcuda_event_elapsed_ms(void *start, void *stop, float *ms);
+OSPCUDA_API void *ospcuda_stream(void); /* cudaStream_t of the render stream */
+OSPCUDA_API unsigned long long ospcuda_kernel_launch_count(void);
+
+/* ---- scene build ------------------------------------------------------------------- */
+/* Build the group BVH over every primitive of models[0..numModels) (device pointers).
+ * Allocates bvh->nodes / bvh->prims with ospcuda_malloc; free with ospcuda_bvh_free.  */
+OSPCUDA_API int ospcuda_bvh_build_group(const OcModel *d_models, uint32_t numModels,
+    const uint32_t *h_numPrims, const uint32_t *h_types, OcBVH *bvh, float *buildMs);
+/* Build the top-level BVH over instance world bounds (h_bounds: 6 floats per instance). */
+OSPCUDA_API int ospcuda_bvh_build_tlas(const float *h_bounds, uint32_t numInstances, OcBVH *bvh);
+OSPCUDA_API int ospcuda_bvh_free(OcBVH *bvh);
+/* macrocell (16^3 cells) value ranges of a structured volume; d_ranges: 2*mcx*mcy*mcz floats */
+OSPCUDA_API int ospcuda_volume_macrocells(const float *d_voxels, const uint32_t dims[3],
+    float *d_ranges, const uint32_t mcDims[3]);
+
+/* ---- traversal (batch API) --------------------------------------------------------- */
+OSPCUDA_API int ospcuda_trace(const OcWorld *d_world, OcRayHit *d_rays, uint32_t numRays, int occlusionOnly);
+
+/* ---- frame ------------------------------------------------------------------------- */
+OSPCUDA_API int ospcuda_render_frame(const OcWorld *d_world, const OcCamera *camera,
+    const OcRenderer *renderer, const OcFrameBuffer *fb);
+
+/* ---- framebuffer ops --------------------------------------------------------------- */
+OSPCUDA_API int ospcuda_fb_accumulate(const OcFrameBuffer *fb, const OcVec4f *d_sampleColor,
+    const float *d_sampleDepth);
+OSPCUDA_API int ospcuda_fb_variance(const OcVec4f *d_color, const OcVec4f *d_variance, int sizeX,
+    int sizeY, int taskSize, float *d_taskError);
+OSPCUDA_API int ospcuda_fb_tonemap(const OcVec4f *d_in, OcVec4f *d_out, uint32_t numPixels,
+    const OcToneMapper *tm);
+OSPCUDA_API int ospcuda_fb_color_convert(const OcVec4f *d_in, void *d_out, uint32_t numPixels,
+    uint32_t colorFormat);
+/* fused tonemap (optional, tm may be NULL) + colour conversion: one pass over the image */
+OSPCUDA_API int ospcuda_fb_postprocess(const OcVec4f *d_in, OcVec4f *d_ppOut, void *d_out,
+    uint32_t numPixels, uint32_t colorFormat, const OcToneMapper *tm);
+/* copy the 64x64 tiles owned by `srcRank` (tile % numRanks == srcRank) from a rank-local
+ * full-size image into dst (both device, row-major, bytesPerPixel each) */
+OSPCUDA_API int ospcuda_fb_gather_tiles(void *d_dst, const void *d_src, int sizeX, int sizeY,
+    uint32_t bytesPerPixel, uint32_t numRanks, uint32_t srcRank);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSPCUDA_H */

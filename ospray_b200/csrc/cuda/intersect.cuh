@@ -1,0 +1,356 @@
+// Ray / primitive intersection and two-level wide-BVH traversal.
+//
+// Stands in for Embree 4.3.3 rtcIntersectV / rtcOccludedV as called from
+// modules/cpu/common/World.ih:29-52, :311-335 (un-vendored dependency; algorithm restated
+// from Embree's published kernels: Moeller-Trumbore triangle test with edges e1=v0-v1,
+// e2=v2-v0 and Ng=cross(e2,e1); quads as (v0,v1,v3)+(v2,v3,v1) with (1-u,1-v) remap, the same
+// split the reference mirrors in geometry/Mesh.ispc:315-345; sphere test with projected
+// centre; OSPRay's own box slab test common/Intersect.ih:194-221 + FilterIntersect.ih:41-116).
+//
+// Arithmetic in the primitive tests is spelled with explicit fused ops so the CPU oracle
+// (oracle/oracle.cpp, fmaf) reproduces hit/miss decisions bit for bit.
+#pragma once
+#include "../../../include/ospcuda.h"
+#include "../common/osp_math.h"
+
+namespace oc {
+using namespace ospm;
+
+#define OC_INVALID_ID 0xFFFFFFFFu
+#define OC_TLAS_THRESHOLD 4u
+#define OC_STACK_SIZE 48
+
+struct Ray
+{
+  vec3f org; float t0;
+  vec3f dir; float t;
+  vec3f Ng;  float u, v;
+  uint32_t primID, geomID, instID;
+};
+
+__device__ __forceinline__ void setRay(Ray &r, vec3f org, vec3f dir, float t0, float t1)
+{
+  r.org = org; r.dir = dir; r.t0 = t0; r.t = t1;
+  r.primID = r.geomID = r.instID = OC_INVALID_ID;
+}
+__device__ __forceinline__ bool hadHit(const Ray &r) { return r.geomID != OC_INVALID_ID; }
+
+__device__ __forceinline__ vec3f toV(const OcVec3f &v) { return make_vec3f(v.x, v.y, v.z); }
+__device__ __forceinline__ affine3f toA(const OcAffine3f &a)
+{
+  affine3f r; r.l.vx = toV(a.vx); r.l.vy = toV(a.vy); r.l.vz = toV(a.vz); r.p = toV(a.p); return r;
+}
+
+// fused dot / cross (Embree AVX2 madd/msub pattern)
+__device__ __forceinline__ float dotF(vec3f a, vec3f b)
+{
+  return __fmaf_rn(a.x, b.x, __fmaf_rn(a.y, b.y, __fmul_rn(a.z, b.z)));
+}
+__device__ __forceinline__ vec3f crossF(vec3f a, vec3f b)
+{
+  return make_vec3f(__fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y)), __fmaf_rn(a.z, b.x, -__fmul_rn(a.x, b.z)),
+      __fmaf_rn(a.x, b.y, -__fmul_rn(a.y, b.x)));
+}
+
+// ---- triangle (v0, e1 = v0 - v1, e2 = v2 - v0) ---------------------------------------
+__device__ __forceinline__ bool intersectTriangle(const Ray &ray, vec3f v0, vec3f e1, vec3f e2,
+    float &t, float &u, float &v, vec3f &Ng)
+{
+  const vec3f triNg = crossF(e2, e1);
+  const vec3f C = make_vec3f(__fsub_rn(v0.x, ray.org.x), __fsub_rn(v0.y, ray.org.y), __fsub_rn(v0.z, ray.org.z));
+  const vec3f R = crossF(C, ray.dir);
+  const float den = dotF(triNg, ray.dir);
+  const float absDen = fabsf(den);
+  const uint32_t sgn = __float_as_uint(den) & 0x80000000u;
+  const float U = __uint_as_float(__float_as_uint(dotF(R, e2)) ^ sgn);
+  const float V = __uint_as_float(__float_as_uint(dotF(R, e1)) ^ sgn);
+  if (!(den != 0.f && U >= 0.f && V >= 0.f && __fadd_rn(U, V) <= absDen))
+    return false;
+  const float T = __uint_as_float(__float_as_uint(dotF(triNg, C)) ^ sgn);
+  if (!(__fmul_rn(absDen, ray.t0) < T && T <= __fmul_rn(absDen, ray.t)))
+    return false;
+  const float rcpAbsDen = __frcp_rn(absDen);
+  u = __fmul_rn(U, rcpAbsDen);
+  v = __fmul_rn(V, rcpAbsDen);
+  t = __fmul_rn(T, rcpAbsDen);
+  Ng = triNg;
+  return true;
+}
+
+// ---- sphere (centre c, radius r) ------------------------------------------------------
+__device__ __forceinline__ bool intersectSphere(const Ray &ray, vec3f c, float r, float &t, vec3f &Ng)
+{
+  const float rd2 = __frcp_rn(dotF(ray.dir, ray.dir));
+  const vec3f c0 = make_vec3f(__fsub_rn(c.x, ray.org.x), __fsub_rn(c.y, ray.org.y), __fsub_rn(c.z, ray.org.z));
+  const float projC0 = __fmul_rn(dotF(c0, ray.dir), rd2);
+  const vec3f perp = make_vec3f(__fmaf_rn(-projC0, ray.dir.x, c0.x), __fmaf_rn(-projC0, ray.dir.y, c0.y),
+      __fmaf_rn(-projC0, ray.dir.z, c0.z));
+  const float l2 = dotF(perp, perp);
+  const float r2 = __fmul_rn(r, r);
+  if (!(l2 <= r2))
+    return false;
+  const float td = __fsqrt_rn(__fmul_rn(__fsub_rn(r2, l2), rd2));
+  const float tFront = __fsub_rn(projC0, td);
+  const float tBack = __fadd_rn(projC0, td);
+  float tdSel;
+  if (ray.t0 <= tFront && tFront <= ray.t) { t = tFront; tdSel = -td; }
+  else if (ray.t0 <= tBack && tBack <= ray.t) { t = tBack; tdSel = td; }
+  else return false;
+  Ng = make_vec3f(__fmaf_rn(tdSel, ray.dir.x, -perp.x), __fmaf_rn(tdSel, ray.dir.y, -perp.y),
+      __fmaf_rn(tdSel, ray.dir.z, -perp.z));
+  return true;
+}
+
+// ---- box (OSPRay user geometry; common/Intersect.ih:194-221) ---------------------------
+__device__ __forceinline__ float rcp_safe(float f)
+{
+  // rkcommon rcp_safe: avoid division by ~0 (un-vendored; restated)
+  return __frcp_rn(fabsf(f) < 1e-8f ? (f < 0.f ? -1e-8f : 1e-8f) : f);
+}
+__device__ __forceinline__ bool intersectBox(const Ray &ray, vec3f lo, vec3f hi, float &t, vec3f &Ng)
+{
+  const vec3f rd = make_vec3f(rcp_safe(ray.dir.x), rcp_safe(ray.dir.y), rcp_safe(ray.dir.z));
+  const vec3f mins = make_vec3f(__fmul_rn(__fsub_rn(lo.x, ray.org.x), rd.x), __fmul_rn(__fsub_rn(lo.y, ray.org.y), rd.y),
+      __fmul_rn(__fsub_rn(lo.z, ray.org.z), rd.z));
+  const vec3f maxs = make_vec3f(__fmul_rn(__fsub_rn(hi.x, ray.org.x), rd.x), __fmul_rn(__fsub_rn(hi.y, ray.org.y), rd.y),
+      __fmul_rn(__fsub_rn(hi.z, ray.org.z), rd.z));
+  const vec3f nears = vmin(mins, maxs), fars = vmax(mins, maxs);
+  const float tEntry = reduce_max(nears), tExit = reduce_min(fars);
+  if (!(tEntry < tExit))
+    return false;
+  if (tEntry > ray.t0 && tEntry <= ray.t) {
+    t = tEntry;
+    if (tEntry == nears.x) Ng = make_vec3f(ray.dir.x > 0.f ? -1.f : 1.f, 0.f, 0.f);
+    else if (tEntry == nears.y) Ng = make_vec3f(0.f, ray.dir.y > 0.f ? -1.f : 1.f, 0.f);
+    else Ng = make_vec3f(0.f, 0.f, ray.dir.z > 0.f ? -1.f : 1.f);
+    return true;
+  }
+  if (tExit > ray.t0 && tExit <= ray.t) {
+    t = tExit;
+    if (tExit == fars.x) Ng = make_vec3f(ray.dir.x > 0.f ? 1.f : -1.f, 0.f, 0.f);
+    else if (tExit == fars.y) Ng = make_vec3f(0.f, ray.dir.y > 0.f ? 1.f : -1.f, 0.f);
+    else Ng = make_vec3f(0.f, 0.f, ray.dir.z > 0.f ? 1.f : -1.f);
+    return true;
+  }
+  return false;
+}
+
+// ---- leaf records -----------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg4(const OcVec4f *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+template <bool OCCLUSION>
+__device__ __forceinline__ bool intersectRecord(Ray &ray, const OcVec4f *rec, uint32_t instID)
+{
+  const float4 r0 = ldg4(rec), r1 = ldg4(rec + 1), r2 = ldg4(rec + 2);
+  const uint32_t kind = __float_as_uint(r2.w);
+  float t, u = 0.f, v = 0.f;
+  vec3f Ng;
+  bool hit;
+  if (kind <= OC_PRIM_TRI_QUAD2ND) {
+    hit = intersectTriangle(ray, make_vec3f(r0.x, r0.y, r0.z), make_vec3f(r1.x, r1.y, r1.z),
+        make_vec3f(r2.x, r2.y, r2.z), t, u, v, Ng);
+    if (hit && kind == OC_PRIM_TRI_QUAD2ND) { u = __fsub_rn(1.f, u); v = __fsub_rn(1.f, v); }
+  } else if (kind == OC_PRIM_SPHERE) {
+    hit = intersectSphere(ray, make_vec3f(r0.x, r0.y, r0.z), r1.x, t, Ng);
+  } else {
+    hit = intersectBox(ray, make_vec3f(r0.x, r0.y, r0.z), make_vec3f(r1.x, r1.y, r1.z), t, Ng);
+  }
+  if (!hit)
+    return false;
+  ray.t = t;
+  if (!OCCLUSION) {
+    ray.u = u; ray.v = v; ray.Ng = Ng;
+    ray.primID = __float_as_uint(r0.w);
+    ray.geomID = __float_as_uint(r1.w);
+    ray.instID = instID;
+  }
+  return true;
+}
+
+// ---- wide-BVH traversal -------------------------------------------------------------------
+struct NodeHit { float t[4]; };
+
+// slab test of one 128-byte node against the ray: 8 x LDG.128, conservative (far side padded
+// by 2 ulp) so that the BVH never culls a primitive the exact test would accept.
+__device__ __forceinline__ uint32_t nodeTest(const OcNode4 *node, vec3f org, vec3f rdir, float t0, float t1,
+    float (&tnear)[4], uint4 &child)
+{
+  const float4 *n = reinterpret_cast<const float4 *>(node);
+  const float4 lox = __ldg(n + 0), hix = __ldg(n + 1), loy = __ldg(n + 2), hiy = __ldg(n + 3),
+               loz = __ldg(n + 4), hiz = __ldg(n + 5);
+  child = __ldg(reinterpret_cast<const uint4 *>(n + 6));
+  uint32_t mask = 0;
+#define OC_SLAB(i, LX, HX, LY, HY, LZ, HZ, CH)                                                   \
+  {                                                                                              \
+    const float ax = (LX - org.x) * rdir.x, bx = (HX - org.x) * rdir.x;                          \
+    const float ay = (LY - org.y) * rdir.y, by = (HY - org.y) * rdir.y;                          \
+    const float az = (LZ - org.z) * rdir.z, bz = (HZ - org.z) * rdir.z;                          \
+    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), t0));       \
+    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), t1)) * 1.0000005f; \
+    tnear[i] = tn;                                                                               \
+    if (CH != OC_INVALID_ID && tn <= tf) mask |= 1u << i;                                        \
+  }
+  OC_SLAB(0, lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, child.x)
+  OC_SLAB(1, lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, child.y)
+  OC_SLAB(2, lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, child.z)
+  OC_SLAB(3, lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, child.w)
+#undef OC_SLAB
+  return mask;
+}
+
+__device__ __forceinline__ vec3f safeRcpDir(vec3f d)
+{
+  const float eps = 1e-30f;
+  return make_vec3f(1.f / (fabsf(d.x) < eps ? copysignf(eps, d.x) : d.x), 1.f / (fabsf(d.y) < eps ? copysignf(eps, d.y) : d.y),
+      1.f / (fabsf(d.z) < eps ? copysignf(eps, d.z) : d.z));
+}
+
+// Traverse one BVH (group BLAS). Leaves are primitive records. The traversal stack is a
+// per-thread array; callers place it in shared memory (short stack) or local memory.
+template <bool OCCLUSION>
+__device__ __forceinline__ bool traverseBLAS(const OcBVH &bvh, Ray &ray, uint32_t instID, uint32_t *stack)
+{
+  if (bvh.numNodes == 0)
+    return false;
+  const vec3f rdir = safeRcpDir(ray.dir);
+  int sp = 0;
+  uint32_t cur = 0; // root
+  bool any = false;
+  while (true) {
+    if (!(cur & 0x80000000u)) {
+      float tn[4];
+      uint4 ch;
+      uint32_t mask = nodeTest(bvh.nodes + cur, ray.org, rdir, ray.t0, ray.t, tn, ch);
+      if (mask == 0) {
+        if (sp == 0) break;
+        cur = stack[--sp];
+        continue;
+      }
+      const uint32_t chs[4] = {ch.x, ch.y, ch.z, ch.w};
+      // visit nearest first: pick nearest, push the rest (unsorted is fine for correctness)
+      int best = -1;
+      float bestT = INFINITY;
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if ((mask >> i) & 1u) {
+          if (tn[i] < bestT) { bestT = tn[i]; best = i; }
+        }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (((mask >> i) & 1u) && i != best && sp < OC_STACK_SIZE)
+          stack[sp++] = chs[i];
+      cur = chs[best];
+    } else {
+      const uint32_t first = cur & 0x07FFFFFFu;
+      const uint32_t count = (cur >> 27) & 0xFu;
+      for (uint32_t i = 0; i < count; i++) {
+        if (intersectRecord<OCCLUSION>(ray, bvh.prims + 3 * (size_t)(first + i), instID)) {
+          any = true;
+          if (OCCLUSION) return true;
+        }
+      }
+      if (sp == 0) break;
+      cur = stack[--sp];
+    }
+  }
+  return any;
+}
+
+__device__ __forceinline__ bool rayBoxOverlap(const float *b, vec3f org, vec3f rdir, float t0, float t1)
+{
+  const float ax = (b[0] - org.x) * rdir.x, bx = (b[3] - org.x) * rdir.x;
+  const float ay = (b[1] - org.y) * rdir.y, by = (b[4] - org.y) * rdir.y;
+  const float az = (b[2] - org.z) * rdir.z, bz = (b[5] - org.z) * rdir.z;
+  const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), t0));
+  const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), t1)) * 1.0000005f;
+  return tn <= tf;
+}
+
+template <bool OCCLUSION>
+__device__ __forceinline__ bool traceInstance(const OcInstance *inst, uint32_t instID, Ray &ray, uint32_t *stack)
+{
+  const OcGroup *g = inst->group;
+  if (g->bvh.numNodes == 0)
+    return false;
+  if (inst->isIdentity)
+    return traverseBLAS<OCCLUSION>(g->bvh, ray, instID, stack);
+  // Embree transforms the ray into instance space and keeps t (no renormalisation)
+  const affine3f rx = toA(inst->rcp_xfm);
+  Ray local = ray;
+  local.org = xfmPoint(rx, ray.org);
+  local.dir = xfmVector(rx, ray.dir);
+  const bool h = traverseBLAS<OCCLUSION>(g->bvh, local, instID, stack);
+  if (h) {
+    ray.t = local.t;
+    if (!OCCLUSION) {
+      ray.u = local.u; ray.v = local.v; ray.Ng = local.Ng; // Ng stays in instance space (World.ih:411-420)
+      ray.primID = local.primID; ray.geomID = local.geomID; ray.instID = local.instID;
+    }
+  }
+  return h;
+}
+
+// closest hit over the whole world (two-level). Equivalent of traceGeometryRay (World.ih:29-52).
+template <bool OCCLUSION>
+__device__ __forceinline__ bool traceWorld(const OcWorld *world, Ray &ray, uint32_t *stack)
+{
+  bool any = false;
+  const uint32_t n = world->numInstances;
+  if (n <= OC_TLAS_THRESHOLD) {
+    const vec3f rdir = safeRcpDir(ray.dir);
+    for (uint32_t i = 0; i < n; i++) {
+      const OcInstance *inst = world->instances + i;
+      if (!rayBoxOverlap(inst->bounds, ray.org, rdir, ray.t0, ray.t))
+        continue;
+      if (traceInstance<OCCLUSION>(inst, i, ray, stack)) {
+        any = true;
+        if (OCCLUSION) return true;
+      }
+    }
+    return any;
+  }
+  // TLAS: leaves hold instance indices in record[0].w; BLAS traversal uses the upper stack half
+  const OcBVH &tlas = world->tlas;
+  const vec3f rdir = safeRcpDir(ray.dir);
+  uint32_t tstack[24];
+  int sp = 0;
+  uint32_t cur = 0;
+  while (true) {
+    if (!(cur & 0x80000000u)) {
+      float tn[4];
+      uint4 ch;
+      const uint32_t mask = nodeTest(tlas.nodes + cur, ray.org, rdir, ray.t0, ray.t, tn, ch);
+      const uint32_t chs[4] = {ch.x, ch.y, ch.z, ch.w};
+      int best = -1;
+      float bestT = INFINITY;
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (((mask >> i) & 1u) && tn[i] < bestT) { bestT = tn[i]; best = i; }
+      if (best < 0) {
+        if (sp == 0) break;
+        cur = tstack[--sp];
+        continue;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (((mask >> i) & 1u) && i != best && sp < 24)
+          tstack[sp++] = chs[i];
+      cur = chs[best];
+    } else {
+      const uint32_t first = cur & 0x07FFFFFFu;
+      const uint32_t count = (cur >> 27) & 0xFu;
+      for (uint32_t i = 0; i < count; i++) {
+        const uint32_t instID = __float_as_uint(ldg4(tlas.prims + 3 * (size_t)(first + i)).w);
+        if (traceInstance<OCCLUSION>(world->instances + instID, instID, ray, stack)) {
+          any = true;
+          if (OCCLUSION) return true;
+        }
+      }
+      if (sp == 0) break;
+      cur = tstack[--sp];
+    }
+  }
+  return any;
+}
+
+} // namespace oc

@@ -1,0 +1,867 @@
+// Frame kernels: pathtracer, scivis and ao renderers with the framebuffer accumulation fused
+// into the epilogue. One thread per pixel, one 8x8 render task per CTA-half, tiles (64x64)
+// assigned to ranks round-robin like modules/multiDevice/MultiDevice.cpp:403-416.
+//
+// reference: render/pathtracer/PathTracer.ispc:75-249, PathSampler.ispc:109-415,
+// NextEventEstimation.ispc:25-160, TransparentShadow.ispc:18-85, VirtualLight.ispc:38-107,
+// PathTracerUtil.ih:30-46; render/RendererRenderTaskFn.inl:5-88; render/scivis/SciVis.ispc:24-281,
+// scivis/surfaces.ispc:17-128, scivis/surfaces.ih:49-92, scivis/lightAlpha.ispc:19-122,
+// scivis/volumes.ispc:302-439; render/ao/AORenderer.ispc:23-149, ao/surfaces.ispc:18-74,
+// ao/volumes.ispc, render/util.ispc:12-54; render/ScreenSample.ih:12-92; fb/LocalFB.ispc:14-78.
+#include "runtime.h"
+#include "volume.cuh"
+
+namespace oc {
+
+struct ScreenSample
+{
+  vec3f rgb; float alpha; float z;
+  vec3f position, firstNormal, normal, albedo;
+  uint32_t primID, geomID, instID;
+};
+__device__ __forceinline__ void ScreenSample_zero(ScreenSample &s)
+{
+  s.rgb = make_vec3f(0.f); s.alpha = 0.f; s.z = INFINITY;
+  s.position = s.firstNormal = s.normal = s.albedo = make_vec3f(0.f);
+  s.primID = s.geomID = s.instID = OC_INVALID_ID;
+}
+__device__ __forceinline__ void ScreenSample_accumulate(ScreenSample &a, const ScreenSample &s)
+{
+  a.rgb = a.rgb + s.rgb; a.alpha = a.alpha + s.alpha;
+  a.position = a.position + s.position; a.firstNormal = a.firstNormal + s.firstNormal;
+  a.normal = a.normal + s.normal; a.albedo = a.albedo + s.albedo;
+  if (fabsf(s.z) < fabsf(a.z)) { a.z = s.z; a.primID = s.primID; a.geomID = s.geomID; a.instID = s.instID; }
+}
+__device__ __forceinline__ void ScreenSample_normalize(ScreenSample &s, float rspp)
+{
+  s.rgb = s.rgb * rspp; s.alpha *= rspp; s.position = s.position * rspp;
+  s.firstNormal = s.firstNormal * rspp; s.normal = s.normal * rspp; s.albedo = s.albedo * rspp;
+}
+
+struct Counters { uint32_t primary, secondary, shadow; };
+
+struct Ctx
+{
+  const OcWorld *world;
+  const OcRenderer &ren;
+  const OcCamera &cam;
+  const OcFrameBuffer &fb;
+  uint32_t *stack;
+  Counters cnt;
+  __device__ Ctx(const OcWorld *w, const OcRenderer &r, const OcCamera &c, const OcFrameBuffer &f, uint32_t *s)
+      : world(w), ren(r), cam(c), fb(f), stack(s) { cnt.primary = cnt.secondary = cnt.shadow = 0; }
+};
+
+__device__ __forceinline__ vec4f getBackground(const OcRenderer &r)
+{
+  return make_vec4f(r.bgColor[0], r.bgColor[1], r.bgColor[2], r.bgColor[3]);
+}
+
+// ===================================== path tracer =========================================
+struct PathVertexLite { vec3f P, Ns; float pdf_w; uint32_t numLightSamples; };
+
+__device__ __forceinline__ float misHeuristic(float pdf1, float pdf2)
+{
+  const float p = sqr(pdf1) * (1.f / (sqr(pdf1) + sqr(pdf2)));
+  return pdf1 > 1e17f ? 1.0f : p;
+}
+
+__device__ vec3f transparentShadow(Ctx &c, vec3f lightContrib, Ray &shadowRay)
+{
+  uint32_t maxDepth = c.ren.maxDepth;
+  const float tOriginal = shadowRay.t;
+  while (1) {
+    c.cnt.shadow++;
+    traceWorld<false>(c.world, shadowRay, c.stack);
+    if (!hadHit(shadowRay))
+      return lightContrib;
+    DifferentialGeometry dg;
+    postIntersect(c.world, c.ren, dg, shadowRay, DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR);
+    lightContrib = lightContrib * materialTransparency(dg);
+    if (reduce_max(lightContrib) <= c.ren.minContribution || --maxDepth <= 0)
+      return make_vec3f(0.f);
+    setRay(shadowRay, shadowRay.org, shadowRay.dir, shadowRay.t + dg.epsilon, tOriginal);
+  }
+}
+
+__device__ vec3f evaluateVirtualLights(Ctx &c, bool straightPath, vec3f throughput, const PathVertexLite &last,
+    bool environment, const Ray &ray)
+{
+  vec3f L = make_vec3f(0.f);
+  const uint32_t numLights = c.world->numLights;
+  if (numLights == 0) return L;
+  const float lower = length(last.P - ray.org);
+  const float upper = environment ? INFINITY : length(last.P - (ray.org + ray.t * ray.dir));
+  const float selectionPDF = last.numLightSamples / (float)numLights;
+  for (uint32_t i = 0; i < numLights; i++) {
+    const OcLight &l = c.world->lights[i];
+    if (!straightPath || l.isVisible) {
+      const LightEval le = Light_eval(l, last.P, last.Ns, ray.dir, lower, upper);
+      if (reduce_max(le.radiance) > 0.0f) {
+        float misWeight = 1.0f;
+        if (selectionPDF) misWeight = misHeuristic(last.pdf_w, selectionPDF * le.pdf);
+        L = L + throughput * le.radiance * misWeight;
+      }
+    }
+  }
+  return L;
+}
+
+__device__ vec3f nextEventEstimation(Ctx &c, const LDSampler &ld, bool firstBounceLight, uint32_t nFirst, uint32_t nIndirect,
+    vec3f throughput, const DifferentialGeometry &dg, const ObjBSDF &bsdf, vec3f wo, uint32_t &numLightSamplesOut)
+{
+  vec3f L = make_vec3f(0.f);
+  const uint32_t numLightSamples = firstBounceLight ? nFirst : nIndirect;
+  numLightSamplesOut = numLightSamples;
+  const uint32_t numLights = c.world->numLights;
+  for (uint32_t i = 0; i < numLightSamples; i++) {
+    float ss;
+    const vec2f s = LDSampler_get3LightSamples(ld, i, numLightSamples > 1, ss);
+    const Sample1D sel = Distribution1D_sample((int)numLights, c.world->lightsCDF, 0, ss);
+    const float lightSelectionProb = sel.prob * numLightSamples;
+    LightSample ls = Light_sample(c.world->lights[sel.idx], dg, s);
+    ls.weight = ls.weight / lightSelectionProb;
+    ls.pdf *= lightSelectionProb;
+    if (reduce_max(ls.weight) <= 0.0f || ls.pdf <= 0.0f)
+      continue;
+    const EvalRes fe = OBJ_eval(bsdf, wo, ls.dir);
+    if (reduce_max(fe.value) <= 0.0f)
+      continue;
+    vec3f org = dg.P;
+    if (dot(dg.Ng, ls.dir) < 0.f)
+      org = org - (2.0f * dg.epsilon) * dg.Ng;
+    Ray shadowRay;
+    setRay(shadowRay, org, ls.dir, 0.f, ls.dist);
+    const vec3f unshadedLightContrib = throughput * fe.value * ls.weight;
+    const vec3f lightContrib = transparentShadow(c, unshadedLightContrib, shadowRay);
+    if (reduce_max(lightContrib) > 0)
+      L = L + lightContrib * misHeuristic(ls.pdf, fe.pdf);
+  }
+  return L;
+}
+
+__device__ void samplePath(Ctx &c, LDSampler &ld, uint32_t nFirst, uint32_t nIndirect, Ray &ray, ScreenSample &sample)
+{
+  PathVertexLite last;
+  last.P = ray.org; last.Ns = ray.dir; last.pdf_w = INFINITY; last.numLightSamples = 0;
+  bool straightPath = true, specularTransmissionPath = true, firstBounceLight = true;
+  uint32_t depth = 0, scatteringEvents = 0;
+  vec3f throughput = make_vec3f(1.f), contribution = make_vec3f(0.f);
+  sample.alpha = 1.0f;
+  const OcRenderer &ren = c.ren;
+
+  do {
+    if (depth == 0) c.cnt.primary++; else c.cnt.secondary++;
+    traceWorld<false>(c.world, ray, c.stack);
+    const bool surface = hadHit(ray);
+    const vec3f wo = neg(ray.dir);
+
+    if (depth == 0)
+      sample.z = c.fb.projectedDepth ? ray.t * dot(ray.dir, toV(c.cam.direction)) : ray.t;
+
+    if (!surface && (ren.backgroundRefraction ? specularTransmissionPath : straightPath)) {
+      const vec4f bg = getBackground(ren);
+      sample.alpha -= luminance(throughput) * (1.0f - bg.w);
+      contribution = contribution + throughput * make_vec3f(bg);
+    }
+
+    contribution = contribution + evaluateVirtualLights(c, straightPath, throughput, last, !surface, ray);
+
+    if (!surface)
+      break;
+    if (depth >= ren.maxDepth) // numGeoLights == 0
+      break;
+
+    DifferentialGeometry dg;
+    postIntersect(c.world, ren, dg, ray,
+        DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR | DG_TANGENTS | DG_MOTIONBLUR);
+
+    if (depth == 0) {
+      sample.position = dg.P; sample.firstNormal = dg.Ns;
+      sample.primID = dg.primID; sample.geomID = dg.objID; sample.instID = dg.instID;
+    }
+    if (depth >= ren.maxDepth || scatteringEvents >= (uint32_t)ren.maxScatteringEvents)
+      break;
+
+    ObjBSDF bsdf;
+    OBJ_getBSDF(bsdf, dg);
+    if (!bsdf.valid)
+      break;
+
+    LDSampler_nextGroup(ld);
+    uint32_t vertexLightSamples = 0;
+    if (bsdf.scatteringType & SC_SMOOTH) {
+      if (scatteringEvents == 0) {
+        sample.albedo = throughput * bsdf.albedo;
+        sample.normal = throughput * bsdf.frame.vz;
+      }
+      contribution = contribution
+          + nextEventEstimation(c, ld, firstBounceLight, nFirst, nIndirect, throughput, dg, bsdf, wo, vertexLightSamples);
+      firstBounceLight = false;
+    }
+
+    float ss;
+    uint32_t uu3;
+    const vec2f s = LDSampler_getNext4Samples(ld, ss, uu3);
+    SampleRes fs = OBJ_sample(bsdf, wo, s, ss);
+    {
+      const bool sameSide = dot(fs.wi, dg.Ng) >= 0.f;
+      const bool reflection = fs.type & SC_REFLECTION;
+      if (sameSide != reflection) fs.weight = make_vec3f(0.0f);
+    }
+    if (reduce_max(fs.weight) <= 0.0f || fs.pdf <= 0.0f)
+      break;
+    throughput = throughput * fs.weight;
+
+    if (depth >= (uint32_t)ren.rouletteDepth) {
+      const float rr = LDSampler_finalizeDim3(ld, uu3);
+      const float contProb = fminf(reduce_max(throughput), 0.95f);
+      if (rr > contProb)
+        break;
+      throughput = throughput * (1.f / contProb);
+    }
+
+    vec3f ray_org = dg.P;
+    if (fs.type & SC_TRANSMISSION)
+      ray_org = ray_org - (2.0f * dg.epsilon) * dg.Ng;
+
+    if ((fs.type & ~SC_SPECULAR_TRANSMISSION)) {
+      last.P = dg.P; last.Ns = dg.Ns; last.pdf_w = fs.pdf; last.numLightSamples = vertexLightSamples;
+    }
+    if (!eq3(ray.dir, fs.wi)) straightPath = false;
+    if (!(fs.type & SC_SPECULAR_TRANSMISSION)) specularTransmissionPath = false;
+
+    setRay(ray, ray_org, fs.wi, 0.f, INFINITY);
+    depth++;
+    if (fs.type & SC_SMOOTH) scatteringEvents++;
+  } while (reduce_max(throughput) > ren.minContribution);
+
+  sample.rgb = contribution;
+  if (isnan(contribution.x) || isnan(contribution.y) || isnan(contribution.z)) {
+    sample.rgb = make_vec3f(0.f);
+    sample.alpha = 1.0f;
+  }
+}
+
+__device__ void PathTracer_renderPixel(Ctx &c, uint32_t ix, uint32_t iy, ScreenSample &screenSample)
+{
+  const OcRenderer &ren = c.ren;
+  const OcFrameBuffer &fb = c.fb;
+  ScreenSample_zero(screenSample);
+  const uint32_t numLights = c.world->numLights;
+  const uint32_t nFirst = (ren.numLightSamples >= 0 && numLights > 0) ? (uint32_t)ren.numLightSamples : min(1024u, numLights);
+  const uint32_t nIndirect = (ren.limitIndirectLightSamples && nFirst >= 1) ? 1u : nFirst;
+  const int spp = ren.spp;
+  uint32_t sampleOffs, sampleOffsLight, sampleBits, sampleBitsLight;
+  uint32_t seed = 0x49c5f37eu;
+  if (fb.targetFrames) {
+    const uint32_t targetSpp = (uint32_t)fb.targetFrames * spp;
+    sampleOffs = OwenScramble4(interleaveZOrder16(ix, iy), seed) * targetSpp;
+    sampleOffsLight = sampleOffs * nFirst;
+    sampleBits = 16 + 32 - __clz(targetSpp - 1);
+    sampleBitsLight = 48 - __clz(targetSpp * nFirst - 1);
+  } else {
+    seed ^= (uint32_t)fb.sizeX * iy + ix;
+    sampleOffs = 0; sampleOffsLight = 0; sampleBits = 16; sampleBitsLight = 16;
+  }
+  const vec2f rcpSize = make_vec2f(1.f / (float)fb.sizeX, 1.f / (float)fb.sizeY);
+  for (int s = 0; s < spp; s++) {
+    const uint32_t sampleID = (uint32_t)fb.frameID * spp + s;
+    LDSampler ld;
+    LDSampler_init(ld, seed, sampleOffs + sampleID, sampleOffsLight + sampleID * nFirst, sampleBits, sampleBitsLight);
+    const vec2f pixel_center = make_vec2f(((float)ix + 0.5f) * rcpSize.x, ((float)iy + 0.5f) * rcpSize.y);
+    uint32_t ss234[3];
+    const vec2f pixelSample = LDSampler_getNext5Samples(ld, ss234);
+    const vec2f pfSample = pixelFilterSample(ren, pixelSample);
+    const vec2f screen = pixel_center + pfSample * rcpSize;
+    vec2f lens = make_vec2f(0.5f, 0.5f);
+    if (c.cam.needLensSample) lens = LDSampler_finalizeDim23(ld, ss234);
+    Ray ray;
+    cameraInitRay(c.cam, ray, screen, lens);
+    ScreenSample sample;
+    ScreenSample_zero(sample);
+    samplePath(c, ld, nFirst, nIndirect, ray, sample);
+    sample.rgb = vmin(sample.rgb, make_vec3f(ren.maxRadiance));
+    ScreenSample_accumulate(screenSample, sample);
+  }
+  ScreenSample_normalize(screenSample, 1.f / (float)spp);
+}
+
+// ============================== scivis / ao shared pieces ==================================
+struct SciVisBSDF { vec3f diffuse, specular, transmission, albedo; float shininess, opacity; };
+
+// scivis/surfaces.ih:49-92
+__device__ __forceinline__ SciVisBSDF evalMaterial(const DifferentialGeometry &dg)
+{
+  SciVisBSDF r;
+  r.diffuse = make_vec3f(dg.color);
+  r.specular = make_vec3f(0.f);
+  r.shininess = 10.f;
+  r.transmission = make_vec3f(1.f - dg.color.w);
+  r.opacity = dg.color.w;
+  const OcMaterial *m = dg.material;
+  if (m && m->type == OC_MATERIAL_OBJ) {
+    const float d = m->d * dg.color.w;
+    r.diffuse = r.diffuse * toV(m->Kd);
+    r.diffuse = r.diffuse * d;
+    r.specular = d * toV(m->Ks);
+    r.shininess = m->Ns;
+    r.transmission = toV(m->Tf) * d + make_vec3f(1.f - d);
+    r.opacity = d;
+  }
+  r.albedo = r.diffuse + r.specular;
+  r.shininess *= 4.0f;
+  r.diffuse = r.diffuse * OC_ONE_OVER_PI;
+  r.specular = r.specular * ((r.shininess + 2.f) * OC_ONE_OVER_FOUR_PI * (1.f / (2.f - expf(r.shininess * -OC_LNTWO_OVER_TWO))));
+  return r;
+}
+
+// single-volume marcher, AO flavour (ao/volumes.ispc:244-330): returns (rgb, alpha)
+__device__ vec4f integrateVolumeAO(Ctx &c, const VolumeHit &vh, const Ray &ray, RandomSampler &rs, float samplingRate)
+{
+  const OcVolume &v = *vh.vol;
+  vec3f org = ray.org, dir = ray.dir;
+  if (!vh.inst->isIdentity) {
+    const affine3f rx = toA(vh.inst->rcp_xfm);
+    org = xfmPoint(rx, ray.org); dir = xfmVector(rx, ray.dir);
+  }
+  vec3f color = make_vec3f(0.f);
+  float alpha = 0.f;
+  VolumeIterator it;
+  volumeIteratorInit(it, v, org, dir, vh.t0, vh.t1);
+  const float jitter = RandomSampler_getFloat(rs);
+  float distance = INFINITY, iuDistance = jitter, iuLength = 0.f;
+  float ivLower = 0.f, ivUpper = INFINITY, samplingStep = 0.f;
+  while (alpha < .99f) {
+    float emptySpace = 0.f;
+    while (iuDistance > iuLength) {
+      const float prevUpper = ivUpper;
+      if (volumeIteratorNext(it, v, ivLower, ivUpper)) {
+        emptySpace += fmaxf(ivLower - prevUpper, 0.f);
+        iuDistance -= iuLength;
+        samplingStep = it.nominalDeltaT / samplingRate;
+        iuLength = (ivUpper - ivLower) / samplingStep;
+        distance = (distance == INFINITY) ? ivLower : distance;
+      } else {
+        return make_vec4f(color, alpha);
+      }
+    }
+    const float newDistance = ivLower + iuDistance * samplingStep;
+    const vec3f p = org + newDistance * dir;
+    const float sampleVal = volumeSample(v, p);
+    if (!isnan(sampleVal)) {
+      vec4f sc = transferFunctionGet(v.tf, sampleVal);
+      const float dt = newDistance - distance - emptySpace;
+      sc.w = 1.f - expf(-sc.w * dt * v.densityScale);
+      color = color + ((1.f - alpha) * sc.w * make_vec3f(sc));
+      alpha = alpha + ((1.f - alpha) * sc.w);
+    }
+    iuDistance += 1.f;
+    distance = newDistance;
+  }
+  return make_vec4f(color, alpha);
+}
+
+struct SSI { vec3f shadedColor, transmission, albedo; float opacity; };
+__device__ SSI SciVis_computeShading(Ctx &c, const DifferentialGeometry &dg, RandomSampler &rs, vec3f inDir, uint32_t px,
+    uint32_t py, int sampleIDz);
+
+// lightAlpha (scivis/lightAlpha.ispc:19-122)
+__device__ vec3f lightAlpha(Ctx &c, Ray &ray, RandomSampler &rs, vec3f weight, float quality)
+{
+  vec3f alpha = make_vec3f(1.f);
+  const float org_t_max = ray.t;
+  while (true) {
+    c.cnt.shadow++;
+    traceWorld<false>(c.world, ray, c.stack);
+    if (c.world->hasVolumes) {
+      VolumeHit vh;
+      if (traceVolumeRay(c.world, ray, vh)) {
+        const vec4f vc = integrateVolumeAO(c, vh, ray, rs, c.ren.volumeSamplingRate * quality);
+        alpha = alpha * make_vec3f(1.f - vc.w);
+      }
+    }
+    if (hadHit(ray)) {
+      DifferentialGeometry dg;
+      postIntersect(c.world, c.ren, dg, ray, DG_COLOR | DG_TEXCOORD);
+      const SciVisBSDF bsdf = evalMaterial(dg);
+      alpha = alpha * bsdf.transmission;
+      setRay(ray, ray.org, ray.dir, ray.t + dg.epsilon, org_t_max);
+    } else
+      break;
+    if (luminance(alpha * weight) < c.ren.minContribution) {
+      alpha = make_vec3f(0.f);
+      break;
+    }
+  }
+  return alpha;
+}
+
+// SciVis_computeAO (scivis/SciVis.ispc:224-281)
+__device__ vec3f SciVis_computeAO(Ctx &c, RandomSampler &rs, const DifferentialGeometry &dg, int sampleCnt, float aoRadius,
+    uint32_t px, uint32_t py, int sampleIDz)
+{
+  const int accumID = sampleIDz * sampleCnt;
+  uint32_t v0 = px, v1 = py;
+  tea8(v0, v1);
+  const vec2f rot = make_vec2f(to_float_unorm(v0), to_float_unorm(v1));
+  vec3f hits = make_vec3f(0.f);
+  const linear3f localToWorld = frame(dg.Ns);
+  for (int i = 0; i < sampleCnt; i++) {
+    const vec2f halton = make_vec2f(PermHalton_sample5(accumID + i), PermHalton_sample7(accumID + i));
+    const vec2f r = make_vec2f(CranleyPattersonRotation(halton.x, rot.x), CranleyPattersonRotation(halton.y, rot.y));
+    const vec3f ao_dir = localToWorld * cosineSampleHemisphere(r);
+    if (dot(ao_dir, dg.Ns) < 0.01f) {
+      hits = hits + make_vec3f(1.f);
+      continue;
+    }
+    Ray ao_ray;
+    setRay(ao_ray, dg.P, ao_dir, dg.epsilon, aoRadius);
+    hits = hits + (make_vec3f(1.f) - lightAlpha(c, ao_ray, rs, make_vec3f(1.f), 0.1f));
+  }
+  return make_vec3f(1.0f) - (hits / (float)sampleCnt);
+}
+
+// scivis/surfaces.ispc:17-128
+__device__ SSI SciVis_computeShading(Ctx &c, const DifferentialGeometry &dg, RandomSampler &rs, vec3f inDir, uint32_t px,
+    uint32_t py, int sampleIDz)
+{
+  SSI ret;
+  const SciVisBSDF bsdf = evalMaterial(dg);
+  ret.albedo = bsdf.albedo;
+  vec3f color = make_vec3f(0.f);
+  const OcWorld *w = c.world;
+  for (uint32_t i = w->numScivisLightsVisibleOnly; i < w->numScivisLights; i++) {
+    const LightSample light = Light_sample(w->scivisLights[i], dg, make_vec2f(0.f, 0.f));
+    if (reduce_max(light.weight) > 0.f) {
+      const float cosNL = dot(light.dir, dg.Ns);
+      if (cosNL < 0.0f) continue;
+      const vec3f H = normalize(light.dir - inDir);
+      const float cosNH = dot(H, dg.Ns);
+      const vec3f specular = bsdf.specular * powf(cosNH, bsdf.shininess);
+      const vec3f diffuse = bsdf.diffuse * cosNL;
+      const vec3f light_contrib = (diffuse + specular) * light.weight;
+      if (c.ren.shadowsEnabled) {
+        if (luminance(light_contrib) > c.ren.minContribution) {
+          vec3f P = dg.P;
+          if (dot(dg.Ng, light.dir) < 0.0f) P = P - (2.f * dg.epsilon) * dg.Ng;
+          Ray shadowRay;
+          setRay(shadowRay, P, light.dir, 0.0f, light.dist);
+          const vec3f la = lightAlpha(c, shadowRay, rs, light_contrib, 0.25f);
+          color = color + la * light_contrib;
+        }
+      } else {
+        color = color + light_contrib;
+      }
+    }
+  }
+  vec3f ao = make_vec3f(1.f);
+  const vec3f aoColorPi = toV(w->aoColorPi);
+  if (c.ren.aoSamples > 0 && luminance(aoColorPi) > c.ren.minContribution)
+    ao = SciVis_computeAO(c, rs, dg, c.ren.aoSamples, c.ren.aoRadius, px, py, sampleIDz);
+  color = color + bsdf.diffuse * ao * aoColorPi;
+  ret.shadedColor = color;
+  ret.transmission = bsdf.transmission;
+  ret.opacity = bsdf.opacity;
+  return ret;
+}
+
+// single-volume marcher, SciVis flavour with gradient shading (scivis/volumes.ispc:302-439):
+// returns (rgb, transmission)
+// volT / volHit follow the reference CPU form (sampleAllVolumes, scivis/volumes.ispc:160-169): the
+// first sample in front of the surface hit that is not fully transparent defines depth and IDs.
+__device__ vec4f integrateVolumeSciVis(Ctx &c, const VolumeHit &vh, const Ray &ray, RandomSampler &rs, float samplingRate,
+    uint32_t px, uint32_t py, int sampleIDz, float &volT, bool &volHit)
+{
+  const OcVolume &v = *vh.vol;
+  vec3f org = ray.org, dir = ray.dir;
+  if (!vh.inst->isIdentity) {
+    const affine3f rx = toA(vh.inst->rcp_xfm);
+    org = xfmPoint(rx, ray.org); dir = xfmVector(rx, ray.dir);
+  }
+  vec3f color = make_vec3f(0.f);
+  float transmission = 1.f;
+  VolumeIterator it;
+  volumeIteratorInit(it, v, org, dir, vh.t0, vh.t1);
+  const float jitter = RandomSampler_getFloat(rs);
+  float distance = INFINITY, iuDistance = jitter, iuLength = 0.f;
+  float ivLower = 0.f, ivUpper = INFINITY, samplingStep = 0.f;
+  while (transmission > c.ren.minContribution) {
+    float emptySpace = 0.f;
+    while (iuDistance > iuLength) {
+      const float prevUpper = ivUpper;
+      if (volumeIteratorNext(it, v, ivLower, ivUpper)) {
+        emptySpace += fmaxf(ivLower - prevUpper, 0.f);
+        iuDistance -= iuLength;
+        samplingStep = it.nominalDeltaT / samplingRate;
+        iuLength = (ivUpper - ivLower) / samplingStep;
+        distance = (distance == INFINITY) ? ivLower : distance;
+      } else {
+        return make_vec4f(color, transmission);
+      }
+    }
+    const float newDistance = ivLower + iuDistance * samplingStep;
+    const vec3f p = org + newDistance * dir;
+    const float sampleVal = volumeSample(v, p);
+    if (!isnan(sampleVal)) {
+      vec4f sc = transferFunctionGet(v.tf, sampleVal);
+      const float dt = newDistance - distance - emptySpace;
+      if (v.gradientShadingScale > 0.f && sc.w > 0.0f) {
+        vec3f ns = volumeGradient(v, p);
+        if (dot(ns, ns) > 1e-6f) {
+          ns = neg(ns);
+          DifferentialGeometry dg;
+          dg.color = sc;
+          dg.material = nullptr;
+          dg.epsilon = dt / 2.f;
+          const vec3f nw = vh.inst->isIdentity ? ns : xfmVector(transposed(toA(vh.inst->rcp_xfm).l), ns);
+          dg.Ns = dg.Ng = normalize(nw);
+          dg.P = p;
+          dg.dPds = make_vec3f(1.f, 0.f, 0.f);
+          dg.primID = 0; dg.objID = dg.instID = OC_INVALID_ID;
+          const SSI shading = SciVis_computeShading(c, dg, rs, ray.dir, px, py, sampleIDz);
+          const vec4f shadedColor = make_vec4f(shading.shadedColor, 1.f - luminance(shading.transmission));
+          sc = lerp4(v.gradientShadingScale, sc, shadedColor);
+        }
+      }
+      sc.w = expf(-sc.w * dt * v.densityScale);
+      if (newDistance < volT && sc.w < 1.0f - c.ren.minContribution) { volT = newDistance; volHit = true; }
+      color = color + transmission * (1.f - sc.w) * make_vec3f(sc);
+      transmission *= sc.w;
+    }
+    iuDistance += 1.f;
+    distance = newDistance;
+  }
+  return make_vec4f(color, transmission);
+}
+
+// visible lights (scivis/surfaces.ispc:130-150)
+__device__ vec3f evaluateLightsSciVis(Ctx &c, const Ray &ray)
+{
+  vec3f color = make_vec3f(0.f);
+  const OcWorld *w = c.world;
+  for (uint32_t i = 0; i < w->numScivisLights; i++) {
+    const OcLight &l = w->scivisLights[i];
+    if (!l.isVisible) continue;
+    const LightEval le = Light_eval(l, ray.org, make_vec3f(0.f), ray.dir, ray.t0, ray.t);
+    color = color + le.radiance;
+  }
+  return color;
+}
+
+// SciVis_renderSample (scivis/SciVis.ispc:24-222)
+__device__ void SciVis_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint32_t px, uint32_t py, int sampleIDz)
+{
+  const OcRenderer &ren = c.ren;
+  RandomSampler rs;
+  RandomSampler_init(rs, px + (uint32_t)c.fb.sizeX * py, (uint32_t)sampleIDz);
+  bool firstHit = true, allHitsFullyTransmissive = true;
+  const float originalRayTFar = ray.t;
+  vec3f outColor = make_vec3f(0.f), outTransmission = make_vec3f(1.f);
+  bool primary = true;
+  while (true) {
+    if (primary) c.cnt.primary++; else c.cnt.secondary++;
+    primary = false;
+    traceWorld<false>(c.world, ray, c.stack);
+    float volumeT = ray.t;
+    if (c.world->hasVolumes) {
+      VolumeHit vh;
+      if (traceVolumeRay(c.world, ray, vh)) {
+        bool volHit = false;
+        const vec4f volumeColor = integrateVolumeSciVis(c, vh, ray, rs, ren.volumeSamplingRate, px, py, sampleIDz, volumeT, volHit);
+        outColor = outColor + outTransmission * make_vec3f(volumeColor);
+        outTransmission = outTransmission * volumeColor.w;
+        if (volHit && sample.geomID == OC_INVALID_ID) {
+          sample.primID = 0;
+          sample.instID = (vh.inst->userID == OC_INVALID_ID) ? vh.instID : vh.inst->userID;
+          sample.geomID = (vh.vol->userID == OC_INVALID_ID) ? vh.geomID : vh.vol->userID;
+        }
+      }
+    }
+    if (ren.visibleLights)
+      outColor = outColor + outTransmission * evaluateLightsSciVis(c, ray);
+    if (firstHit || allHitsFullyTransmissive) {
+      sample.z = fminf(ray.t, volumeT);
+      if (c.fb.projectedDepth) sample.z *= dot(ray.dir, toV(c.cam.direction));
+    }
+    if (hadHit(ray)) {
+      DifferentialGeometry dg;
+      postIntersect(c.world, ren, dg, ray, DG_NG | DG_NS | DG_NORMALIZE | DG_FACEFORWARD | DG_COLOR | DG_TANGENTS | DG_TEXCOORD);
+      const SSI sh = SciVis_computeShading(c, dg, rs, ray.dir, px, py, sampleIDz);
+      if (firstHit || allHitsFullyTransmissive) {
+        sample.position = dg.P; sample.firstNormal = dg.Ns; sample.normal = dg.Ns; sample.albedo = sh.albedo;
+        if (sample.geomID == OC_INVALID_ID) { sample.instID = dg.instID; sample.geomID = dg.objID; sample.primID = dg.primID; }
+        firstHit = false;
+      }
+      allHitsFullyTransmissive = allHitsFullyTransmissive && sh.opacity < ren.minContribution;
+      outColor = outColor + outTransmission * sh.shadedColor;
+      outTransmission = outTransmission * sh.transmission;
+      if (luminance(outTransmission) < ren.minContribution) {
+        outTransmission = make_vec3f(0.f);
+        break;
+      }
+      setRay(ray, ray.org, ray.dir, ray.t + dg.epsilon, originalRayTFar);
+    } else {
+      const vec4f bg = getBackground(ren);
+      outColor = outColor + outTransmission * make_vec3f(bg);
+      outTransmission = outTransmission * (1.f - bg.w);
+      break;
+    }
+  }
+  sample.rgb = outColor;
+  sample.alpha = 1.f - luminance(outTransmission);
+}
+
+// computeAO (render/util.ispc:12-54)
+__device__ float computeAO(Ctx &c, const DifferentialGeometry &dg, int sampleCnt, float aoRadius, uint32_t px, uint32_t py,
+    int sampleIDz)
+{
+  const int accumID = sampleIDz * sampleCnt;
+  uint32_t v0 = px, v1 = py;
+  tea8(v0, v1);
+  const vec2f rot = make_vec2f(to_float_unorm(v0), to_float_unorm(v1));
+  int hits = 0;
+  const linear3f localToWorld = frame(dg.Ns);
+  for (int i = 0; i < sampleCnt; i++) {
+    const vec2f halton = make_vec2f(PermHalton_sample5(accumID + i), PermHalton_sample7(accumID + i));
+    const vec2f r = make_vec2f(CranleyPattersonRotation(halton.x, rot.x), CranleyPattersonRotation(halton.y, rot.y));
+    const vec3f ao_dir = localToWorld * cosineSampleHemisphere(r);
+    if (dot(ao_dir, dg.Ns) < 0.01f) { hits++; continue; }
+    Ray ao_ray;
+    setRay(ao_ray, dg.P, ao_dir, dg.epsilon, aoRadius);
+    c.cnt.shadow++;
+    if (traceWorld<true>(c.world, ao_ray, c.stack)) hits++;
+  }
+  return 1.0f - (hits / (float)sampleCnt);
+}
+
+// AORenderer_renderSample (render/ao/AORenderer.ispc:23-149)
+__device__ void AO_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint32_t px, uint32_t py, int sampleIDz)
+{
+  const OcRenderer &ren = c.ren;
+  RandomSampler rs;
+  RandomSampler_init(rs, px + (uint32_t)c.fb.sizeX * py, (uint32_t)sampleIDz);
+  bool firstHit = true;
+  const float originalRayTFar = ray.t;
+  const vec3f primaryDir = ray.dir;
+  vec4f outputColor = make_vec4f(0.f, 0.f, 0.f, 0.f);
+  while (outputColor.w < 0.99f) {
+    if (firstHit) c.cnt.primary++; else c.cnt.secondary++;
+    traceWorld<false>(c.world, ray, c.stack);
+    if (c.world->hasVolumes) {
+      VolumeHit vh;
+      if (traceVolumeRay(c.world, ray, vh)) {
+        const vec4f vc = integrateVolumeAO(c, vh, ray, rs, ren.volumeSamplingRate);
+        outputColor = outputColor + (1.f - outputColor.w) * vc;
+      }
+    }
+    vec4f blendedColor;
+    const bool rayHadHit = hadHit(ray);
+    if (rayHadHit) {
+      DifferentialGeometry dg;
+      postIntersect(c.world, ren, dg, ray, DG_NG | DG_NS | DG_NORMALIZE | DG_FACEFORWARD | DG_COLOR | DG_TEXCOORD | DG_TANGENTS);
+      // getSurfaceColor (ao/surfaces.ispc:18-42)
+      vec3f surfaceColor = make_vec3f(1.f);
+      float opacity = 1.f;
+      if (dg.material && dg.material->type == OC_MATERIAL_OBJ) {
+        surfaceColor = toV(dg.material->Kd);
+        opacity *= dg.material->d;
+      }
+      const vec3f color = surfaceColor * make_vec3f(dg.color);
+      opacity = opacity * dg.color.w;
+      float intensity = fabsf(dot(dg.Ns, primaryDir)) * opacity;
+      if (ren.aoSamples > 0 && ren.aoIntensity > 0.01f) {
+        const float ao = computeAO(c, dg, ren.aoSamples, ren.aoRadius, px, py, sampleIDz);
+        intensity *= (1.0f - ren.aoIntensity) + (ao * ren.aoIntensity);
+      }
+      blendedColor = make_vec4f(color * intensity, opacity);
+      if (firstHit) {
+        sample.z = ray.t;
+        if (c.fb.projectedDepth) sample.z *= dot(ray.dir, toV(c.cam.direction));
+        sample.albedo = color; sample.position = dg.P; sample.firstNormal = dg.Ns; sample.normal = dg.Ns;
+        sample.instID = dg.instID; sample.geomID = dg.objID; sample.primID = dg.primID;
+      }
+      setRay(ray, ray.org, ray.dir, ray.t + dg.epsilon, originalRayTFar);
+    } else {
+      blendedColor = getBackground(ren);
+      if (firstHit) {
+        sample.z = ray.t;
+        sample.albedo = make_vec3f(blendedColor);
+        sample.normal = primaryDir;
+      }
+    }
+    outputColor = outputColor + (1.f - outputColor.w) * blendedColor;
+    firstHit = false;
+    if (!rayHadHit) break;
+  }
+  sample.rgb = make_vec3f(outputColor);
+  sample.alpha = outputColor.w;
+}
+
+// Renderer_default_renderTask pixel body (render/RendererRenderTaskFn.inl:30-86)
+template <int RENDERER>
+__device__ void defaultRenderPixel(Ctx &c, uint32_t x, uint32_t y, ScreenSample &screenSample)
+{
+  const OcRenderer &ren = c.ren;
+  const OcFrameBuffer &fb = c.fb;
+  const int spp = ren.spp;
+  const int startSampleID = fb.frameID * spp + 1;
+  ScreenSample_zero(screenSample);
+  const vec2f rcpSize = make_vec2f(1.f / (float)fb.sizeX, 1.f / (float)fb.sizeY);
+  for (int s = 0; s < spp; s++) {
+    const float pixel_du = Halton_sample2(startSampleID + s);
+    const float pixel_dv = CranleyPattersonRotation(Halton_sample3(startSampleID + s), 1.f / 6.f);
+    const vec2f pfSample = pixelFilterSample(ren, make_vec2f(pixel_du, pixel_dv));
+    const vec2f pixel_center = make_vec2f(((float)x + 0.5f) * rcpSize.x, ((float)y + 0.5f) * rcpSize.y);
+    const vec2f screen = pixel_center + pfSample * rcpSize;
+    Ray ray;
+    cameraInitRay(c.cam, ray, screen, make_vec2f(0.f, 0.f));
+    ScreenSample sample;
+    ScreenSample_zero(sample);
+    if (RENDERER == OC_RENDERER_SCIVIS) SciVis_renderSample(c, ray, sample, x, y, startSampleID + s);
+    else AO_renderSample(c, ray, sample, x, y, startSampleID + s);
+    ScreenSample_accumulate(screenSample, sample);
+  }
+  ScreenSample_normalize(screenSample, 1.f / (float)spp);
+}
+
+// ================================ framebuffer accumulation ==================================
+// LocalFB_accumulateSample (fb/LocalFB.ispc:14-78), FRAMEBUFFER_ACCUMULATE_VALUE (FrameBuffer.ih:17-22)
+__device__ __forceinline__ float accum1(float value, float nv, float f) { return (f > 0.8f) ? nv : lerpf(f, value, nv); }
+__device__ __forceinline__ void accum3(OcVec3f *buf, size_t i, vec3f nv, float f)
+{
+  if (f > 0.8f) { buf[i].x = nv.x; buf[i].y = nv.y; buf[i].z = nv.z; return; }
+  const OcVec3f o = buf[i];
+  buf[i].x = lerpf(f, o.x, nv.x); buf[i].y = lerpf(f, o.y, nv.y); buf[i].z = lerpf(f, o.z, nv.z);
+}
+__device__ __forceinline__ void accum4(OcVec4f *buf, size_t i, vec4f nv, float f)
+{
+  float4 *p = reinterpret_cast<float4 *>(buf) + i;
+  float4 o;
+  if (f > 0.8f) o = make_float4(nv.x, nv.y, nv.z, nv.w);
+  else {
+    o = *p;
+    o.x = lerpf(f, o.x, nv.x); o.y = lerpf(f, o.y, nv.y); o.z = lerpf(f, o.z, nv.z); o.w = lerpf(f, o.w, nv.w);
+  }
+  *p = o;
+}
+
+__device__ __forceinline__ void accumulateSample(const OcFrameBuffer &fb, uint32_t x, uint32_t y, const ScreenSample &s)
+{
+  const size_t pixelID = x + (size_t)fb.sizeX * y;
+  const int accumID = fb.frameID;
+  const float accScale = 1.f / (float)(accumID + 1);
+  const vec4f colorSample = make_vec4f(s.rgb, s.alpha);
+  if (fb.color) accum4(fb.color, pixelID, colorSample, accScale);
+  if (fb.accumulateVariance) accum4(fb.variance, pixelID, colorSample, 1.f / (float)(accumID / 2 + 1));
+  bool updateIDBufs = accumID == 0;
+  if (fb.depth) {
+    if (accumID > 0 && fabsf(s.z) < fabsf(fb.depth[pixelID])) updateIDBufs = true;
+    if (updateIDBufs) fb.depth[pixelID] = s.z;
+  }
+  if (updateIDBufs) {
+    if (fb.primID) fb.primID[pixelID] = s.primID;
+    if (fb.objID) fb.objID[pixelID] = s.geomID;
+    if (fb.instID) fb.instID[pixelID] = s.instID;
+  }
+  if (fb.normal) accum3(fb.normal, pixelID, s.normal, accScale);
+  if (fb.firstNormal) accum3(fb.firstNormal, pixelID, s.firstNormal, accScale);
+  if (fb.albedo) accum3(fb.albedo, pixelID, s.albedo, accScale);
+  if (fb.position) accum3(fb.position, pixelID, s.position, accScale);
+}
+
+// ======================================= kernels ===========================================
+struct FrameArgs
+{
+  const OcWorld *world;
+  OcCamera cam;
+  OcRenderer ren;
+  OcFrameBuffer fb;
+  uint32_t tilesX, tilesY;
+};
+
+template <int RENDERER>
+__global__ void __launch_bounds__(64) renderFrameKernel(const __grid_constant__ FrameArgs a)
+{
+  // block -> (owned tile, 8x8 task inside the 64x64 tile); thread -> pixel inside the task
+  const uint32_t ownedTile = blockIdx.x >> 6, taskInTile = blockIdx.x & 63u;
+  const uint32_t tileID = a.fb.rank + ownedTile * a.fb.numRanks;
+  const uint32_t tx = tileID % a.tilesX, ty = tileID / a.tilesX;
+  const uint32_t x = tx * 64 + (taskInTile & 7u) * 8 + (threadIdx.x & 7u);
+  const uint32_t y = ty * 64 + (taskInTile >> 3) * 8 + (threadIdx.x >> 3);
+  uint32_t stack[OC_STACK_SIZE];
+  Ctx c(a.world, a.ren, a.cam, a.fb, stack);
+  if (x < (uint32_t)a.fb.sizeX && y < (uint32_t)a.fb.sizeY) {
+    ScreenSample ss;
+    if (RENDERER == OC_RENDERER_PATHTRACER) PathTracer_renderPixel(c, x, y, ss);
+    else defaultRenderPixel<RENDERER>(c, x, y, ss);
+    accumulateSample(a.fb, x, y, ss);
+  }
+  if (a.fb.rayCounters) {
+    uint32_t p = c.cnt.primary, s = c.cnt.secondary, h = c.cnt.shadow;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      p += __shfl_xor_sync(0xffffffffu, p, o);
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      h += __shfl_xor_sync(0xffffffffu, h, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(a.fb.rayCounters + 0, (unsigned long long)p);
+      atomicAdd(a.fb.rayCounters + 1, (unsigned long long)s);
+      atomicAdd(a.fb.rayCounters + 2, (unsigned long long)h);
+    }
+  }
+}
+
+// batch traversal for tests / ospPick-like queries
+__global__ void traceKernel(const OcWorld *world, OcRayHit *rays, uint32_t n, int occlusion)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t stack[OC_STACK_SIZE];
+  OcRayHit rh = rays[i];
+  Ray r;
+  setRay(r, make_vec3f(rh.org[0], rh.org[1], rh.org[2]), make_vec3f(rh.dir[0], rh.dir[1], rh.dir[2]), rh.t0, rh.t);
+  r.u = r.v = 0.f; r.Ng = make_vec3f(0.f);
+  if (occlusion) {
+    if (traceWorld<true>(world, r, stack)) r.t = -INFINITY;
+  } else
+    traceWorld<false>(world, r, stack);
+  rh.t = r.t; rh.u = r.u; rh.v = r.v; rh.Ng[0] = r.Ng.x; rh.Ng[1] = r.Ng.y; rh.Ng[2] = r.Ng.z;
+  rh.primID = r.primID; rh.geomID = r.geomID; rh.instID = r.instID;
+  rays[i] = rh;
+}
+
+} // namespace oc
+
+using namespace oc;
+
+extern "C" int ospcuda_render_frame(const OcWorld *d_world, const OcCamera *camera, const OcRenderer *renderer,
+    const OcFrameBuffer *fb)
+{
+  FrameArgs a;
+  a.world = d_world; a.cam = *camera; a.ren = *renderer; a.fb = *fb;
+  if (a.fb.numRanks == 0) { a.fb.numRanks = 1; a.fb.rank = 0; }
+  a.tilesX = (fb->sizeX + 63) / 64; a.tilesY = (fb->sizeY + 63) / 64;
+  const uint32_t totalTiles = a.tilesX * a.tilesY;
+  const uint32_t owned = a.fb.rank < totalTiles ? (totalTiles - a.fb.rank + a.fb.numRanks - 1) / a.fb.numRanks : 0;
+  if (owned == 0) return 0;
+  const dim3 grid(owned * 64), block(64);
+  cudaStream_t st = (cudaStream_t)ospcuda_stream();
+  switch (renderer->type) {
+  case OC_RENDERER_PATHTRACER: renderFrameKernel<OC_RENDERER_PATHTRACER><<<grid, block, 0, st>>>(a); break;
+  case OC_RENDERER_SCIVIS: renderFrameKernel<OC_RENDERER_SCIVIS><<<grid, block, 0, st>>>(a); break;
+  case OC_RENDERER_AO: renderFrameKernel<OC_RENDERER_AO><<<grid, block, 0, st>>>(a); break;
+  default: return oc_set_error(cudaErrorInvalidValue, "ospcuda_render_frame: unknown renderer type");
+  }
+  oc_count_launch();
+  return oc_check(cudaGetLastError(), "ospcuda_render_frame");
+}
+
+extern "C" int ospcuda_trace(const OcWorld *d_world, OcRayHit *d_rays, uint32_t numRays, int occlusionOnly)
+{
+  if (numRays == 0) return 0;
+  traceKernel<<<(numRays + 127) / 128, 128, 0, (cudaStream_t)ospcuda_stream()>>>(d_world, d_rays, numRays, occlusionOnly);
+  oc_count_launch();
+  return oc_check(cudaGetLastError(), "ospcuda_trace");
+}

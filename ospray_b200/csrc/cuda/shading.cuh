@@ -1,0 +1,654 @@
+// Hit -> DifferentialGeometry, OBJ material (3-lobe MultiBSDF evaluated in registers), lights.
+// reference: common/World.ih:389-465 (postIntersect), common/Instance.ih:44-105,
+// geometry/GeometricModel.ih:21-76, geometry/Mesh.ispc:65-268, Spheres.ispc:24-42,
+// Boxes.ispc:65-71, common/DifferentialGeometry.ih:46-58, render/Material.ih:25-37,
+// render/materials/OBJ.ispc:29-144, render/bsdfs/{Lambert,Specular,Transmission,MultiBSDF}.ih,
+// lights/QuadLight.ispc:15-215, lights/SphericalQuadSampling.ih:10-204,
+// lights/AmbientLight.ispc:17-57, lights/DirectionalLight.ispc:14-80, math/sampling.ih.
+#pragma once
+#include "intersect.cuh"
+#include "samplers.cuh"
+
+namespace oc {
+
+#define OC_PI 3.14159265358979323846f
+#define OC_TWO_PI 6.28318530717958647692f
+#define OC_ONE_OVER_PI 0.31830988618379067154f
+#define OC_ONE_OVER_TWO_PI 0.15915494309189533577f
+#define OC_ONE_OVER_FOUR_PI 0.079577471545947667884f
+#define OC_FOUR_PI 12.566370614359172954f
+#define OC_LNTWO_OVER_TWO 0.34657359027997265471f
+#define OC_ULP_EPSILON 0x1.0fp-21f
+
+enum {
+  DG_FACEFORWARD = 1 << 0, DG_NORMALIZE = 1 << 1, DG_NG = 1 << 2, DG_NS = 1 << 3,
+  DG_COLOR = 1 << 4, DG_TEXCOORD = 1 << 5, DG_TANGENTS = 1 << 6, DG_MOTIONBLUR = 1 << 7
+};
+
+struct DifferentialGeometry
+{
+  vec3f P, Ng, Ns, dPds;
+  vec4f color;
+  float epsilon;
+  uint32_t primID, objID, instID;
+  const OcMaterial *material;
+};
+
+__device__ __forceinline__ float calcEpsilon(vec3f P, float t)
+{
+  return fmaxf(fmaxf(fabsf(P.x), fabsf(P.y)), fmaxf(fabsf(P.z), t)) * OC_ULP_EPSILON;
+}
+__device__ __forceinline__ float calcEpsilon(vec3f P, vec3f dir, float t)
+{
+  return calcEpsilon(P, reduce_max(vabs(dir)) * t);
+}
+
+// strided fetches (reference: common/Data.ih get_* accessors)
+__device__ __forceinline__ vec3f get3f(const OcData1D &d, uint32_t i)
+{
+  const float *p = reinterpret_cast<const float *>(d.addr + (int64_t)i * d.byteStride);
+  return make_vec3f(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+}
+__device__ __forceinline__ vec4f get4f(const OcData1D &d, uint32_t i)
+{
+  const float *p = reinterpret_cast<const float *>(d.addr + (int64_t)i * d.byteStride);
+  return make_vec4f(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+}
+__device__ __forceinline__ uint32_t get1ui(const OcData1D &d, uint32_t i, int c)
+{
+  return __ldg(reinterpret_cast<const uint32_t *>(d.addr + (int64_t)i * d.byteStride) + c);
+}
+__device__ __forceinline__ vec4f getColor(const OcGeometry *g, uint32_t i)
+{
+  if (g->flags & OC_GEOMFLAG_COLOR_IS_VEC4) return get4f(g->color, i);
+  return make_vec4f(get3f(g->color, i), 1.f);
+}
+
+__device__ __forceinline__ const OcMaterial *getMaterial(const OcWorld *world, const OcRenderer &ren,
+    const OcModel *m, uint32_t primID)
+{
+  if (m->materialMode == OC_MAT_NONE || m->numMaterials == 0)
+    return nullptr;
+  uint32_t idx = primID;
+  if (m->index.addr)
+    idx = __ldg(m->index.addr + (int64_t)min(idx, m->index.numItems - 1) * m->index.byteStride);
+  uint32_t matIdx = __ldg(m->material + min(idx, m->numMaterials - 1));
+  if (m->materialMode == OC_MAT_FROM_RENDERER) {
+    if (!ren.materials || ren.numMaterials == 0) return nullptr;
+    matIdx = __ldg(ren.materials + min(matIdx, ren.numMaterials - 1));
+  }
+  return world->materials + matIdx;
+}
+
+__device__ __forceinline__ void geometryPostIntersect(const OcGeometry *g, DifferentialGeometry &dg,
+    const Ray &ray, uint32_t flags)
+{
+  dg.Ng = dg.Ns = ray.Ng;
+  if (g->type == OC_GEOM_QUADS) {
+    const uint32_t i0 = get1ui(g->index, ray.primID, 0), i1 = get1ui(g->index, ray.primID, 1),
+                   i2 = get1ui(g->index, ray.primID, 2), i3 = get1ui(g->index, ray.primID, 3);
+    const uint32_t fo = ray.primID * 4;
+    const float u = ray.u, v = ray.v;
+    vec4f uv;
+    if (i2 == i3) uv = make_vec4f(1.f - u - v, u, v, 0.f);
+    else uv = make_vec4f((1 - v) * (1 - u), (1 - v) * u, v * u, v * (1 - u));
+    if ((flags & DG_NS) && g->normal.addr) {
+      const bool fv = g->flags & OC_GEOMFLAG_NORMAL_FACEVARYING;
+      const vec3f a = get3f(g->normal, fv ? fo : i0), b = get3f(g->normal, fv ? fo + 1 : i1),
+                  c = get3f(g->normal, fv ? fo + 2 : i2), d = get3f(g->normal, fv ? fo + 3 : i3);
+      dg.Ns = uv.x * a + uv.y * b + uv.z * c + uv.w * d;
+    }
+    if ((flags & DG_COLOR) && g->color.addr) {
+      const bool fv = g->flags & OC_GEOMFLAG_COLOR_FACEVARYING;
+      const vec4f a = getColor(g, fv ? fo : i0), b = getColor(g, fv ? fo + 1 : i1),
+                  c = getColor(g, fv ? fo + 2 : i2), d = getColor(g, fv ? fo + 3 : i3);
+      dg.color = uv.x * a + uv.y * b + uv.z * c + uv.w * d;
+      if (!(g->flags & OC_GEOMFLAG_HAS_ALPHA)) dg.color.w = 1.f;
+    }
+    const vec3f va = get3f(g->vertex, i0), vb = get3f(g->vertex, i1), vc = get3f(g->vertex, i2),
+                vd = get3f(g->vertex, i3);
+    dg.epsilon = reduce_max(vmax(vmax(vabs(va), vabs(vb)), vmax(vabs(vc), vabs(vd)))) * OC_ULP_EPSILON;
+    if (flags & DG_TANGENTS) dg.dPds = vb - va; // no texcoords: (Mesh.ispc:170-173)
+  } else if (g->type == OC_GEOM_TRIANGLES) {
+    const uint32_t i0 = get1ui(g->index, ray.primID, 0), i1 = get1ui(g->index, ray.primID, 1),
+                   i2 = get1ui(g->index, ray.primID, 2);
+    const uint32_t fo = ray.primID * 3;
+    const vec3f uv = make_vec3f(1.0f - ray.u - ray.v, ray.u, ray.v);
+    if ((flags & DG_NS) && g->normal.addr) {
+      const bool fv = g->flags & OC_GEOMFLAG_NORMAL_FACEVARYING;
+      const vec3f a = get3f(g->normal, fv ? fo : i0), b = get3f(g->normal, fv ? fo + 1 : i1),
+                  c = get3f(g->normal, fv ? fo + 2 : i2);
+      dg.Ns = uv.x * a + uv.y * b + uv.z * c;
+    }
+    if ((flags & DG_COLOR) && g->color.addr) {
+      const bool fv = g->flags & OC_GEOMFLAG_COLOR_FACEVARYING;
+      const vec4f a = getColor(g, fv ? fo : i0), b = getColor(g, fv ? fo + 1 : i1), c = getColor(g, fv ? fo + 2 : i2);
+      dg.color = uv.x * a + uv.y * b + uv.z * c;
+      if (!(g->flags & OC_GEOMFLAG_HAS_ALPHA)) dg.color.w = 1.f;
+    }
+    const vec3f va = get3f(g->vertex, i0), vb = get3f(g->vertex, i1), vc = get3f(g->vertex, i2);
+    dg.epsilon = reduce_max(vmax(vmax(vabs(va), vabs(vb)), vabs(vc))) * OC_ULP_EPSILON;
+    if (flags & DG_TANGENTS) dg.dPds = vb - va;
+  } else if (g->type == OC_GEOM_SPHERES) {
+    dg.epsilon = get4f(g->sphere, ray.primID).w * OC_ULP_EPSILON;
+  }
+  // boxes: nothing else (Boxes.ispc:65-71)
+}
+
+// World.ih:389-465
+__device__ __forceinline__ void postIntersect(const OcWorld *world, const OcRenderer &ren,
+    DifferentialGeometry &dg, const Ray &ray, uint32_t flags)
+{
+  dg.primID = ray.primID;
+  dg.material = nullptr;
+  if (flags & DG_COLOR) dg.color = make_vec4f(1.f, 1.f, 1.f, 1.f);
+  if (flags & DG_TANGENTS) dg.dPds = make_vec3f(1.f, 0.f, 0.f);
+  dg.P = ray.org + ray.t * ray.dir;
+  dg.epsilon = 0.f;
+
+  if (ray.instID != OC_INVALID_ID) {
+    const OcInstance *inst = world->instances + ray.instID;
+    const OcModel *m = inst->group->models + ray.geomID;
+    geometryPostIntersect(m->geom, dg, ray, flags);
+    dg.objID = (m->userID == OC_INVALID_ID) ? ray.geomID : m->userID;
+    if ((flags & DG_COLOR) && m->color.addr) {
+      uint32_t idx = ray.primID;
+      if (m->index.addr)
+        idx = __ldg(m->index.addr + (int64_t)min(idx, m->index.numItems - 1) * m->index.byteStride);
+      dg.color = get4f(m->color, min(idx, m->color.numItems - 1));
+    }
+    dg.material = getMaterial(world, ren, m, ray.primID);
+    if ((flags & DG_NS) && m->invertedNormals) dg.Ns = neg(dg.Ns);
+    dg.instID = (inst->userID == OC_INVALID_ID) ? ray.instID : inst->userID;
+    if (!inst->isIdentity) {
+      const affine3f xfm = toA(inst->xfm), rxfm = toA(inst->rcp_xfm);
+      const linear3f rt = transposed(rxfm.l);
+      dg.Ns = xfmVector(rt, dg.Ns);
+      dg.Ng = xfmVector(rt, dg.Ng);
+      dg.epsilon *= fmaxf(fabsf(xfm.l.vx.x), fmaxf(fabsf(xfm.l.vy.y), fabsf(xfm.l.vz.z)));
+      if (flags & DG_TANGENTS) dg.dPds = xfmVector(xfm, dg.dPds);
+    }
+  } else {
+    dg.Ns = dg.Ng = ray.Ng;
+    dg.objID = OC_INVALID_ID; dg.instID = OC_INVALID_ID;
+  }
+
+  dg.epsilon = fmaxf(dg.epsilon, calcEpsilon(dg.P, ray.dir, ray.t));
+
+  vec3f ffnng = normalize(dg.Ng);
+  if ((flags & (DG_NG | DG_NORMALIZE)) == (DG_NG | DG_NORMALIZE)) dg.Ng = ffnng;
+  if ((flags & (DG_NS | DG_NORMALIZE)) == (DG_NS | DG_NORMALIZE)) dg.Ns = normalize(dg.Ns);
+  const bool flip = dot(ray.dir, dg.Ng) >= 0.f;
+  if (flip) ffnng = neg(ffnng);
+  if ((flags & (DG_NG | DG_FACEFORWARD)) == (DG_NG | DG_FACEFORWARD) && flip) dg.Ng = neg(dg.Ng);
+  if ((flags & (DG_NS | DG_FACEFORWARD)) == (DG_NS | DG_FACEFORWARD)) {
+    if (dot(dg.Ng, dg.Ns) < 0.f) dg.Ns = neg(dg.Ns);
+  }
+  dg.P = dg.P + dg.epsilon * ffnng;
+}
+
+// ---- sampling helpers (math/sampling.ih) ---------------------------------------------------
+__device__ __forceinline__ vec3f cartesian(float phi, float sinTheta, float cosTheta)
+{
+  float s, c;
+  sincosf(phi, &s, &c);
+  return make_vec3f(c * sinTheta, s * sinTheta, cosTheta);
+}
+__device__ __forceinline__ float cos2sin(float c) { return sqrtf(fmaxf(0.f, 1.f - c * c)); }
+__device__ __forceinline__ vec3f cosineSampleHemisphere(vec2f s)
+{
+  return cartesian(OC_TWO_PI * s.x, sqrtf(1.0f - s.y), sqrtf(s.y));
+}
+__device__ __forceinline__ vec3f powerCosineSampleHemisphere(float n, vec2f s)
+{
+  const float cosTheta = powf(s.y, 1.0f / (n + 1.0f));
+  return cartesian(OC_TWO_PI * s.x, cos2sin(cosTheta), cosTheta);
+}
+__device__ __forceinline__ float powerCosineSampleHemispherePDF(float cosTheta, float n)
+{
+  return (n + 1.0f) * OC_ONE_OVER_TWO_PI * powf(cosTheta, n);
+}
+__device__ __forceinline__ vec3f uniformSampleCone(float cosAngle, vec2f s)
+{
+  const float cosTheta = 1.0f - s.y * (1.0f - cosAngle);
+  return cartesian(OC_TWO_PI * s.x, cos2sin(cosTheta), cosTheta);
+}
+__device__ __forceinline__ vec3f uniformSampleSphere(float radius, vec2f s)
+{
+  return cartesian(OC_TWO_PI * s.x, 2.f * radius * sqrtf(s.y * (1.f - s.y)), radius * (1.f - 2.f * s.y));
+}
+
+// ---- OBJ material: Lambert + Transmission + Specular MultiBSDF, in registers ----------------
+enum {
+  SC_SPECULAR_REFLECTION = 1 << 0, SC_GLOSSY_REFLECTION = 1 << 1, SC_DIFFUSE_REFLECTION = 1 << 2,
+  SC_SPECULAR_TRANSMISSION = 1 << 3, SC_GLOSSY_TRANSMISSION = 1 << 4, SC_DIFFUSE_TRANSMISSION = 1 << 5,
+  SC_DIFFUSE = SC_DIFFUSE_REFLECTION | SC_DIFFUSE_TRANSMISSION,
+  SC_GLOSSY = SC_GLOSSY_REFLECTION | SC_GLOSSY_TRANSMISSION,
+  SC_SPECULAR = SC_SPECULAR_REFLECTION | SC_SPECULAR_TRANSMISSION,
+  SC_REFLECTION = SC_DIFFUSE_REFLECTION | SC_GLOSSY_REFLECTION | SC_SPECULAR_REFLECTION,
+  SC_TRANSMISSION = SC_DIFFUSE_TRANSMISSION | SC_GLOSSY_TRANSMISSION | SC_SPECULAR_TRANSMISSION,
+  SC_SMOOTH = SC_DIFFUSE | SC_GLOSSY
+};
+
+struct EvalRes { vec3f value; float pdf; };
+struct SampleRes { vec3f weight; vec3f wi; float pdf; uint32_t type; };
+
+struct ObjBSDF
+{
+  linear3f frame;          // shading frame (vz = N)
+  vec3f Kd, T, ks, specWeight;
+  float ns;                // Blinn exponent
+  float impL, impT, impS, importanceSum;
+  vec3f albedo;
+  uint32_t scatteringType;
+  bool valid;
+};
+
+// render/Material.ih:25-37
+__device__ __forceinline__ linear3f makeShadingFrame(const DifferentialGeometry &dg)
+{
+  const vec3f N = dg.Ns;
+  vec3f U = normalize(dg.dPds);
+  vec3f V = cross(N, U);
+  if (dot(V, V) > 0.f) {
+    V = normalize(V);
+    U = cross(V, N);
+    linear3f f; f.vx = U; f.vy = V; f.vz = N; return f;
+  }
+  return frame(N);
+}
+
+// materials/OBJ.ispc:29-91. A NULL / non-OBJ material yields no BSDF (path terminates).
+__device__ __forceinline__ void OBJ_getBSDF(ObjBSDF &b, const DifferentialGeometry &dg)
+{
+  const OcMaterial *m = dg.material;
+  b.valid = false;
+  if (!m || m->type != OC_MATERIAL_OBJ)
+    return;
+  b.valid = true;
+  b.frame = makeShadingFrame(dg);
+  b.albedo = make_vec3f(0.f);
+  b.scatteringType = 0;
+  b.importanceSum = 0.f;
+  b.impL = b.impT = b.impS = 0.f;
+  const float d = m->d * dg.color.w;
+  const vec3f Kd = toV(m->Kd) * d * make_vec3f(dg.color);
+  b.Kd = Kd;
+  if (reduce_max(Kd) > 0.0f) {
+    b.albedo = b.albedo + Kd;
+    b.scatteringType |= SC_DIFFUSE_REFLECTION;
+    b.impL = luminance(Kd);
+    b.importanceSum += b.impL;
+  }
+  const vec3f T = toV(m->Tf) * d + make_vec3f(1.f - d);
+  b.T = T;
+  if (reduce_max(T) > 0.0f) {
+    b.albedo = b.albedo + T;
+    b.scatteringType |= SC_SPECULAR_TRANSMISSION;
+    b.impT = luminance(T);
+    b.importanceSum += b.impT;
+  }
+  const vec3f Ks = d * toV(m->Ks);
+  if (reduce_max(Ks) > 0.0f) {
+    b.albedo = b.albedo + Ks;
+    b.scatteringType |= SC_GLOSSY_REFLECTION;
+    b.impS = luminance(Ks);
+    b.importanceSum += b.impS;
+    b.ns = m->Ns * 4.f; // Phong -> Blinn (Specular.ih:71-79)
+    const float tmp = (b.ns + 2.f) * (1.f / (2.f - expf(b.ns * -OC_LNTWO_OVER_TWO)));
+    b.ks = Ks * (OC_ONE_OVER_FOUR_PI * tmp);
+    b.specWeight = Ks * (2.f * tmp * (1.f / (b.ns + 1.f)));
+  }
+}
+
+__device__ __forceinline__ EvalRes Lambert_eval(const ObjBSDF &b, vec3f wi)
+{
+  EvalRes r;
+  const float cosThetaI = fmaxf(dot(wi, b.frame.vz), 0.f);
+  r.pdf = cosThetaI * OC_ONE_OVER_PI;
+  r.value = b.Kd * OC_ONE_OVER_PI * cosThetaI;
+  return r;
+}
+__device__ __forceinline__ EvalRes Specular_eval(const ObjBSDF &b, vec3f wo, vec3f wi)
+{
+  EvalRes r; r.value = make_vec3f(0.f); r.pdf = 0.f;
+  const vec3f N = b.frame.vz;
+  const float cosThetaO = dot(wo, N), cosThetaI = dot(wi, N);
+  if (cosThetaO <= 0.0f || cosThetaI <= 0.0f) return r;
+  const vec3f wh = normalize(wo + wi);
+  const float cosThetaH = dot(wh, N);
+  r.pdf = powerCosineSampleHemispherePDF(cosThetaH, b.ns) * (1.f / (4.0f * dot(wo, wh)));
+  r.value = b.ks * powf(cosThetaH, b.ns);
+  return r;
+}
+// MULTIBSDF_EVAL_* (bsdfs/MultiBSDF.ih:70-90); `skip` = lobe already sampled (-1: none)
+__device__ __forceinline__ void OBJ_evalChildren(const ObjBSDF &b, vec3f wo, vec3f wi, int skip, EvalRes &e)
+{
+  if (b.impL > 0.f && skip != 0) {
+    const EvalRes c = Lambert_eval(b, wi);
+    e.value = e.value + c.value;
+    e.pdf += c.pdf * b.impL;
+  }
+  if (b.impS > 0.f && skip != 2) {
+    const EvalRes c = Specular_eval(b, wo, wi);
+    e.value = e.value + c.value;
+    e.pdf += c.pdf * b.impS;
+  }
+}
+__device__ __forceinline__ EvalRes OBJ_eval(const ObjBSDF &b, vec3f wo, vec3f wi)
+{
+  EvalRes e; e.value = make_vec3f(0.f); e.pdf = 0.f;
+  OBJ_evalChildren(b, wo, wi, -1, e);
+  e.pdf *= 1.f / b.importanceSum;
+  return e;
+}
+// MULTIBSDF_SAMPLE_* (bsdfs/MultiBSDF.ih:93-128)
+__device__ __forceinline__ SampleRes OBJ_sample(const ObjBSDF &b, vec3f wo, vec2f s, float ss)
+{
+  SampleRes res; res.weight = make_vec3f(0.f); res.wi = make_vec3f(0.f); res.pdf = 0.f; res.type = 0;
+  if (b.importanceSum == 0.f) return res;
+  const float x = ss * b.importanceSum;
+  int choice = 0;
+  float prefix = 0.f;
+  float choiceImp = 0.f;
+  if (x < (prefix += b.impL)) {
+    choice = 0; choiceImp = b.impL;
+    const vec3f localDir = cosineSampleHemisphere(s);
+    res.wi = b.frame * localDir;
+    res.pdf = localDir.z * OC_ONE_OVER_PI;
+    res.type = SC_DIFFUSE_REFLECTION;
+    res.weight = b.Kd;
+  } else if (x < (prefix += b.impT)) {
+    choice = 1; choiceImp = b.impT;
+    res.wi = neg(wo);
+    res.pdf = INFINITY;
+    res.type = SC_SPECULAR_TRANSMISSION;
+    res.weight = b.T;
+  } else if (x < (prefix += b.impS)) {
+    choice = 2; choiceImp = b.impS;
+    const vec3f whl = powerCosineSampleHemisphere(b.ns, s);
+    const vec3f wh = b.frame * whl;
+    const float cosThetaOH = dot(wo, wh);
+    res.wi = 2.f * cosThetaOH * wh - wo; // reflect(wo, wh, cosThetaOH)
+    const float cosThetaI = dot(res.wi, b.frame.vz);
+    if (cosThetaI <= 0.0f) {
+      res.weight = make_vec3f(0.f); // below surface; pdf/type left as in the reference's zero result
+    } else {
+      res.pdf = powerCosineSampleHemispherePDF(whl.z, b.ns) * (1.f / (4.0f * cosThetaOH));
+      res.type = SC_GLOSSY_REFLECTION;
+      res.weight = b.specWeight * cosThetaOH;
+    }
+  }
+  if ((res.weight.x == 0.f && res.weight.y == 0.f && res.weight.z == 0.f) || res.pdf == 0.0f) {
+    res.weight = make_vec3f(0.f);
+    return res;
+  }
+  if (res.type & SC_SPECULAR) {
+    res.weight = res.weight * (b.importanceSum * (1.f / choiceImp));
+    return res;
+  }
+  EvalRes e;
+  e.value = res.weight * res.pdf;
+  res.pdf *= choiceImp;
+  e.pdf = res.pdf;
+  OBJ_evalChildren(b, wo, res.wi, choice, e);
+  res.pdf = e.pdf * (1.f / b.importanceSum);
+  res.weight = e.value * (1.f / res.pdf);
+  return res;
+}
+// materials/OBJ.ispc:93-111
+__device__ __forceinline__ vec3f materialTransparency(const DifferentialGeometry &dg)
+{
+  const OcMaterial *m = dg.material;
+  if (!m || m->type != OC_MATERIAL_OBJ) return make_vec3f(0.f);
+  const float d = m->d * dg.color.w;
+  return toV(m->Tf) * d + make_vec3f(1.f - d);
+}
+
+// ---- lights -------------------------------------------------------------------------------
+struct LightSample { vec3f weight, dir; float dist, pdf; };
+struct LightEval { vec3f radiance; float pdf; };
+
+struct SphericalQuad
+{
+  vec3f e0, e1, z;
+  float S, k, n0z, n0z2, n2z, x0, x1, y0, y1, z0;
+};
+__device__ __forceinline__ SphericalQuad SphericalQuad_create(vec3f q0, vec3f e0, vec3f e1, vec3f n, vec3f P)
+{
+  SphericalQuad q;
+  const float e0l = length(e0), e1l = length(e1);
+  q.e0 = e0 / e0l; q.e1 = e1 / e1l; q.z = n;
+  const vec3f d = q0 - P;
+  q.z0 = dot(d, q.z);
+  q.z = q.z0 > 0.f ? neg(q.z) : q.z;
+  q.z0 = -fabsf(q.z0);
+  q.x0 = dot(d, q.e0); q.y0 = dot(d, q.e1);
+  q.x1 = q.x0 + e0l; q.y1 = q.y0 + e1l;
+  const vec3f v00 = make_vec3f(q.x0, q.y0, q.z0), v01 = make_vec3f(q.x0, q.y1, q.z0),
+              v10 = make_vec3f(q.x1, q.y0, q.z0), v11 = make_vec3f(q.x1, q.y1, q.z0);
+  const vec3f n0 = normalize(cross(v00, v10));
+  q.n0z = n0.z; q.n0z2 = n0.z * n0.z;
+  const vec3f n1 = normalize(cross(v10, v11)), n2 = normalize(cross(v11, v01)), n3 = normalize(cross(v01, v00));
+  q.n2z = n2.z;
+  const float g0 = acosf(clampf(-dot(n0, n1), -1.f, 1.f)), g1 = acosf(clampf(-dot(n1, n2), -1.f, 1.f)),
+              g2 = acosf(clampf(-dot(n2, n3), -1.f, 1.f)), g3 = acosf(clampf(-dot(n3, n0), -1.f, 1.f));
+  q.k = OC_TWO_PI - g2 - g3;
+  q.S = fmaxf(0.f, g0 + g1 - q.k);
+  return q;
+}
+__device__ __forceinline__ float signf(float x) { return (float)(0.f < x) - (float)(x < 0.f); }
+__device__ __forceinline__ vec3f sampleSphericalQuad(const SphericalQuad &q, vec2f s)
+{
+  const float au = s.x * q.S + q.k;
+  float sinau, cosau;
+  sincosf(au, &sinau, &cosau);
+  const float fu = (cosau * q.n0z - q.n2z) * (1.f / sinau);
+  const float cu = clampf(rsqrtf(fu * fu + sqr(q.n0z)) * signf(fu), -1.f, 1.f);
+  const float x0 = -(cu * q.z0) * rsqrtf(1.f - cu * cu);
+  const float xu = clampf(x0, q.x0, q.x1);
+  const float ds = sqrtf(sqr(xu) + sqr(q.z0));
+  const float ds2 = sqr(ds);
+  const float h0 = q.y0 * rsqrtf(ds2 + sqr(q.y0));
+  const float h1 = q.y1 * rsqrtf(ds2 + sqr(q.y1));
+  const float hv = s.y * (h1 - h0) + h0;
+  const float hv2 = sqr(hv);
+  const float yv = (hv2 < 1.f - 1e-4f) ? (hv * ds) * rsqrtf(1.f - hv2) : q.y1;
+  return xu * q.e0 + yv * q.e1 + q.z0 * q.z;
+}
+__device__ __forceinline__ float solve_quadratic(float A, float B, float C)
+{
+  if (A == 0.f) return -C / B;
+  float rad = B * B - 4.f * A * C;
+  if (rad < 0.f) return 0.f;
+  rad = sqrtf(rad);
+  float root;
+  if (B >= 0.f) {
+    root = (-B - rad) / (2.f * A);
+    if (root < 0.f || root > 1.f) root = 2.f * C / (-B - rad);
+  } else {
+    root = 2.f * C / (-B + rad);
+    if (root < 0.f || root > 1.f) root = (-B + rad) / (2.f * A);
+  }
+  return root;
+}
+__device__ __forceinline__ vec3f computeCosineWeightedRNG(vec3f q0, vec3f e0, vec3f e1, vec3f P, vec3f Ng, vec2f s)
+{
+  vec3f wp[4];
+  float prob[4];
+  wp[0] = q0; wp[1] = q0 + e0; wp[2] = q0 + e1; wp[3] = wp[1] + e1;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+    prob[i] = fmaxf(0.f, dot(normalize(wp[i] - P), Ng));
+  if ((prob[0] + prob[2]) == 0.f)
+    return make_vec3f(s.x, s.y, 1.f);
+  const float totProb = prob[0] + prob[2] + prob[1] + prob[3];
+  const float W00 = prob[0], W01 = prob[2], W10 = prob[1], W11 = prob[3];
+  float u;
+  {
+    const float A = W10 + W11 - W01 - W00, B = 2.f * (W01 + W00);
+    if (A + B == 0.f) u = s.x;
+    else u = solve_quadratic(A, B, -(W00 + W01 + W10 + W11) * s.x);
+  }
+  float v;
+  {
+    const float A = (1.f - u) * W01 + u * W11 - (1.f - u) * W00 - u * W10;
+    const float B = 2.f * (1.f - u) * W00 + 2.f * u * W10;
+    if (A + B == 0.f) v = s.y;
+    else v = solve_quadratic(A, B, -((1.f - u) * W01 + u * W11 + (1.f - u) * W00 + u * W10) * s.y);
+  }
+  const float pdf = 4.f * ((1.f - u) * (1.f - v) * prob[0] + u * (1.f - v) * prob[1] + u * v * prob[3] + (1.f - u) * v * prob[2])
+      / totProb;
+  return make_vec3f(u, v, pdf);
+}
+
+__device__ __forceinline__ LightSample QuadLight_sampleArea(const OcLight &l, vec3f P, vec2f s)
+{
+  LightSample r;
+  const vec3f p = toV(l.position) + toV(l.edge1) * s.x + toV(l.edge2) * s.y;
+  const vec3f dir = p - P;
+  const float dist = length(dir);
+  r.dir = dir / dist;
+  r.dist = dist;
+  const float cosd = dot(toV(l.nnormal), r.dir);
+  r.pdf = l.ppdf * sqr(dist) / fabsf(cosd);
+  const float weight = cosd > 0.f ? 1.f / r.pdf : 0.f;
+  r.weight = toV(l.radiance) * weight;
+  return r;
+}
+__device__ __forceinline__ LightSample QuadLight_sample(const OcLight &l, const DifferentialGeometry &dg, vec2f s)
+{
+  if (s.x == 0.0f && s.y == 0.0f)
+    return QuadLight_sampleArea(l, dg.P, make_vec2f(0.5f, 0.5f));
+  LightSample r;
+  const vec3f pos = toV(l.position), e1 = toV(l.edge1), e2 = toV(l.edge2), nn = toV(l.nnormal);
+  const SphericalQuad quad = SphericalQuad_create(pos, e1, e2, neg(nn), dg.P);
+  const vec3f cosW = computeCosineWeightedRNG(pos, e1, e2, dg.P, dg.Ng, s);
+  const vec3f dir = sampleSphericalQuad(quad, make_vec2f(cosW.x, cosW.y));
+  const float dist = length(dir);
+  r.dir = dir / dist;
+  r.dist = dist;
+  const float cosd = dot(nn, r.dir);
+  r.pdf = quad.S == 0.f ? 0.f : cosW.z / quad.S;
+  r.weight = (cosd > 0.f) && (r.pdf != 0.f) ? toV(l.radiance) * (1.f / r.pdf) : make_vec3f(0.f);
+  return r;
+}
+__device__ __forceinline__ LightEval QuadLight_eval(const OcLight &l, vec3f P, vec3f dir, float minDist, float maxDist)
+{
+  LightEval r; r.radiance = make_vec3f(0.f); r.pdf = 0.f;
+  const vec3f nn = toV(l.nnormal), pos = toV(l.position), e1 = toV(l.edge1), e2 = toV(l.edge2);
+  const float cosd = dot(nn, dir);
+  if (cosd <= 0.f) return r;
+  const vec3f c = pos - P;
+  const vec3f rr = cross(c, dir);
+  const float rcosd = 1.f / cosd;
+  const float u = dot(rr, e1) * rcosd;
+  const float v = -dot(rr, e2) * rcosd;
+  if (fminf(u, v) < 0.f || fmaxf(u, v) * l.ppdf > 1.0f) return r;
+  const float dist = dot(nn, c) * rcosd;
+  if (dist <= minDist || dist > maxDist) return r;
+  const SphericalQuad quad = SphericalQuad_create(pos, e1, e2, neg(nn), P);
+  if (quad.S > 0.f) {
+    r.radiance = toV(l.radiance);
+    r.pdf = 1.f / quad.S;
+  }
+  return r;
+}
+
+__device__ __forceinline__ LightSample Light_sample(const OcLight &l, const DifferentialGeometry &dg, vec2f s)
+{
+  LightSample r;
+  if (l.type == OC_LIGHT_QUAD)
+    return QuadLight_sample(l, dg, s);
+  if (l.type == OC_LIGHT_AMBIENT) {
+    if (reduce_max(vabs(dg.Ns)) > 0) {
+      const vec3f localDir = cosineSampleHemisphere(s);
+      r.dir = frame(dg.Ns) * localDir;
+      r.pdf = localDir.z * OC_ONE_OVER_PI;
+    } else {
+      r.dir = uniformSampleSphere(1.f, s);
+      r.pdf = 1.f / OC_FOUR_PI;
+    }
+    r.dist = INFINITY;
+    r.weight = toV(l.radiance) * (1.f / r.pdf);
+    return r;
+  }
+  // distant
+  r.dir = toV(l.fz);
+  r.dist = INFINITY;
+  r.pdf = l.pdf;
+  if (l.cosAngle < 0.99999988f) {
+    linear3f f; f.vx = toV(l.fx); f.vy = toV(l.fy); f.vz = toV(l.fz);
+    r.dir = f * uniformSampleCone(l.cosAngle, s);
+  }
+  r.weight = toV(l.radiance);
+  return r;
+}
+__device__ __forceinline__ LightEval Light_eval(const OcLight &l, vec3f P, vec3f Ns, vec3f dir, float minDist, float maxDist)
+{
+  LightEval r; r.radiance = make_vec3f(0.f); r.pdf = 0.f;
+  if (l.type == OC_LIGHT_QUAD)
+    return QuadLight_eval(l, P, dir, minDist, maxDist);
+  if (l.type == OC_LIGHT_AMBIENT) {
+    r.radiance = INFINITY <= maxDist ? toV(l.radiance) : make_vec3f(0.f);
+    if (reduce_max(vabs(Ns)) > 0) r.pdf = fmaxf(dot(Ns, dir), 0.f) * OC_ONE_OVER_PI;
+    else r.pdf = 1.f / OC_FOUR_PI;
+    return r;
+  }
+  if (INFINITY <= maxDist && l.cosAngle < 0.99999988f && dot(toV(l.fz), dir) > l.cosAngle) {
+    r.radiance = toV(l.radiance) * l.pdf;
+    r.pdf = l.pdf;
+  }
+  return r;
+}
+
+// Distribution1D_sample (math/Distribution1D.ih:26-57)
+struct Sample1D { int idx; float frac, pdf, prob; };
+__device__ __forceinline__ Sample1D Distribution1D_sample(int size, const float *cdf, int start, float s)
+{
+  int first = start, len = size;
+  while (len > 0) {
+    const int half = len >> 1, mid = first + half;
+    if (s < __ldg(cdf + mid)) len = half;
+    else { first = mid + 1; len -= half + 1; }
+  }
+  Sample1D r;
+  r.idx = first - start;
+  const float bef = first == start ? 0.0f : __ldg(cdf + first - 1);
+  const float dpdf = __ldg(cdf + first) - bef;
+  r.prob = dpdf;
+  r.pdf = dpdf * size;
+  r.frac = (s - bef) * (1.f / dpdf);
+  return r;
+}
+
+// pixel filter (pf/PixelFilter.ih:20-28, pf/LUTPixelFilter.ispc:9-15, Distribution2D.ispc:9-25)
+__device__ __forceinline__ vec2f pixelFilterSample(const OcRenderer &r, vec2f s)
+{
+  if (r.pfType == OC_PF_POINT) return make_vec2f(0.f, 0.f);
+  if (r.pfType == OC_PF_BOX) return (s + make_vec2f(-0.5f, -0.5f)) * r.pfWidth;
+  const Sample1D sy = Distribution1D_sample((int)r.pfLutH, r.pfCdfY, 0, s.y);
+  const int x0 = sy.idx * (int)r.pfLutW;
+  const Sample1D sx = Distribution1D_sample((int)r.pfLutW, r.pfCdfX, x0, s.x);
+  const vec2f uv = make_vec2f((sx.idx + sx.frac) * (1.f / (float)r.pfLutW), (sy.idx + sy.frac) * (1.f / (float)r.pfLutH));
+  return (uv + make_vec2f(-0.5f, -0.5f)) * r.pfWidth;
+}
+
+// PerspectiveCamera_initRay (camera/PerspectiveCamera.ispc:16-64); no stereo / motion blur
+__device__ __forceinline__ void cameraInitRay(const OcCamera &cam, Ray &ray, vec2f screen, vec2f lens)
+{
+  screen = make_vec2f(lerpf(screen.x, cam.subImage[0], cam.subImage[2]), lerpf(screen.y, cam.subImage[1], cam.subImage[3]));
+  vec3f org = toV(cam.org);
+  vec3f dir = toV(cam.dir_00) + screen.x * toV(cam.du_size) + screen.y * toV(cam.dv_up);
+  if (cam.scaledAperture > 0.f) {
+    const float r = sqrtf(lens.x) * cam.scaledAperture;
+    float sp, cp;
+    sincosf(OC_TWO_PI * lens.y, &sp, &cp);
+    const vec3f lp = ((r * cp) * toV(cam.du_size)) + (((r * sp) * cam.aspect) * toV(cam.dv_up));
+    org = org + lp;
+    dir = dir - lp;
+  }
+  setRay(ray, org, normalize(dir), cam.nearClip, INFINITY);
+}
+
+} // namespace oc

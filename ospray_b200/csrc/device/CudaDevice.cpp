@@ -1,0 +1,220 @@
+// CudaDevice implementation + module entry point. See CudaDevice.h for the reference map.
+#include "CudaDevice.h"
+#include <cstdlib>
+#include "ospray_cuda_ext.h"
+
+namespace ospray {
+namespace cuda {
+
+CudaDevice::~CudaDevice() {}
+
+void CudaDevice::commit()
+{
+  api::Device::commit();
+  // which GPU: device param "cudaDevice" <- env OSPRAY_CUDA_DEVICE <- LOCAL_RANK (torchrun)
+  int ord = getParam<int>("cudaDevice", -1);
+  if (const char *e = getenv("OSPRAY_CUDA_DEVICE")) ord = atoi(e);
+  if (ord < 0) {
+    const char *lr = getenv("LOCAL_RANK");
+    ord = lr ? atoi(lr) : 0;
+    const int n = ospcuda_device_count();
+    if (n > 0) ord %= n;
+  }
+  // image-tile partition, the multidevice analogue (MultiDevice.cpp:32-57: numSubdevices)
+  int nr = getParam<int>("numSubdevices", getParam<int>("numRanks", 1));
+  int rk = getParam<int>("subdeviceRank", getParam<int>("rank", 0));
+  if (const char *e = getenv("OSPRAY_NUM_SUBDEVICES")) nr = atoi(e);
+  if (const char *e = getenv("OSPRAY_SUBDEVICE_RANK")) rk = atoi(e);
+  numRanks = (uint32_t)std::max(1, nr);
+  rank = (uint32_t)std::max(0, rk) % numRanks;
+  cudaOrdinal = ord;
+  checkCuda(ospcuda_init(ord), "CUDA initialisation (the cuda device has no CPU fallback)");
+  initialized = true;
+  postStatusMsg(OSP_LOG_INFO, "cuda device: using CUDA device " + std::to_string(ord) + ", tile partition " + std::to_string(rank) + "/"
+          + std::to_string(numRanks));
+}
+
+int CudaDevice::loadModule(const char *name) { return loadLocalModule(name); }
+
+OSPData CudaDevice::newSharedData(const void *sharedData, OSPDataType t, const vec3ul &n, const vec3l &s, OSPDeleterCallback cb,
+    const void *up)
+{
+  return (OSPData) new Data(sharedData, t, n, s, cb, up);
+}
+OSPData CudaDevice::newData(OSPDataType t, const vec3ul &n) { return (OSPData) new Data(t, n); }
+void CudaDevice::copyData(const OSPData source, OSPData destination, const vec3ul &di)
+{
+  Data *dst = (Data *)destination;
+  Data *src = (Data *)source;
+  dst->copy(*src, di);
+}
+
+OSPLight CudaDevice::newLight(const char *type)
+{
+  const std::string t(type);
+  if (t != "ambient" && t != "distant" && t != "quad") return nullptr;
+  return (OSPLight) new Light(t);
+}
+OSPCamera CudaDevice::newCamera(const char *type)
+{
+  if (std::string(type) != "perspective") return nullptr;
+  return (OSPCamera) new Camera(type);
+}
+OSPGeometry CudaDevice::newGeometry(const char *type)
+{
+  const std::string t(type);
+  if (t != "mesh" && t != "sphere" && t != "box") return nullptr;
+  return (OSPGeometry) new Geometry(t);
+}
+OSPVolume CudaDevice::newVolume(const char *type)
+{
+  const std::string t(type);
+  if (t != "structuredRegular" && t != "structured_regular") return nullptr;
+  return (OSPVolume) new Volume(t);
+}
+OSPGeometricModel CudaDevice::newGeometricModel(OSPGeometry g) { return (OSPGeometricModel) new GeometricModel((Geometry *)g); }
+OSPVolumetricModel CudaDevice::newVolumetricModel(OSPVolume v) { return (OSPVolumetricModel) new VolumetricModel((Volume *)v); }
+OSPMaterial CudaDevice::newMaterial(const char *type) { return (OSPMaterial) new Material(*this, type); }
+OSPTransferFunction CudaDevice::newTransferFunction(const char *type)
+{
+  if (std::string(type) != "piecewiseLinear") return nullptr;
+  return (OSPTransferFunction) new TransferFunction;
+}
+OSPTexture CudaDevice::newTexture(const char *) { return nullptr; } // textures: out of scope
+OSPGroup CudaDevice::newGroup() { return (OSPGroup) new Group; }
+OSPInstance CudaDevice::newInstance(OSPGroup g) { return (OSPInstance) new Instance((Group *)g); }
+OSPWorld CudaDevice::newWorld() { return (OSPWorld) new World(*this); }
+
+box3f CudaDevice::getBounds(OSPObject o)
+{
+  const box3f b = ((ManagedObject *)o)->getBounds();
+  if (box_is_empty(b)) {
+    // rkcommon's empty box: lower = +inf, upper = -inf
+    return b;
+  }
+  return b;
+}
+
+void CudaDevice::setObjectParam(OSPObject object, const char *name, OSPDataType type, const void *mem)
+{
+  if (type == OSP_UNKNOWN) throw std::runtime_error("cannot set OSP_UNKNOWN parameter type");
+  ((ManagedObject *)object)->setParam(name, type, mem);
+}
+void CudaDevice::removeObjectParam(OSPObject object, const char *name) { ((ManagedObject *)object)->removeParam(name); }
+void CudaDevice::commit(OSPObject object)
+{
+  ManagedObject *o = (ManagedObject *)object;
+  o->commit();
+  o->checkUnused();
+  o->resetAllParamQueryStatus();
+}
+void CudaDevice::release(OSPObject o) { ((ManagedObject *)o)->refDec(); }
+void CudaDevice::retain(OSPObject o) { ((ManagedObject *)o)->refInc(); }
+
+OSPFrameBuffer CudaDevice::frameBufferCreate(const vec2i &size, const OSPFrameBufferFormat mode, const uint32_t channels)
+{
+  return (OSPFrameBuffer) new FrameBuffer(*this, size, mode, channels);
+}
+OSPImageOperation CudaDevice::newImageOp(const char *type)
+{
+  if (std::string(type) != "tonemapper") return nullptr; // blur / debug / denoiser: out of scope
+  return (OSPImageOperation) new ImageOp(type);
+}
+const void *CudaDevice::frameBufferMap(OSPFrameBuffer fb, const OSPFrameBufferChannel ch) { return ((FrameBuffer *)fb)->map(ch); }
+void CudaDevice::frameBufferUnmap(const void *mapped, OSPFrameBuffer fb) { ((FrameBuffer *)fb)->unmap(mapped); }
+float CudaDevice::getVariance(OSPFrameBuffer fb) { return ((FrameBuffer *)fb)->getVariance(); }
+void CudaDevice::resetAccumulation(OSPFrameBuffer fb) { ((FrameBuffer *)fb)->clear(); }
+
+OSPRenderer CudaDevice::newRenderer(const char *type)
+{
+  const std::string t(type);
+  if (t != "pathtracer" && t != "scivis" && t != "ao") return nullptr;
+  return (OSPRenderer) new Renderer(*this, t);
+}
+
+// ISPCDevice.cpp:568-600 + LoadBalancer.cpp:13-32, enqueued on the render stream
+OSPFuture CudaDevice::renderFrame(OSPFrameBuffer _fb, OSPRenderer _r, OSPCamera _c, OSPWorld _w)
+{
+  FrameBuffer *fb = (FrameBuffer *)_fb;
+  Renderer *r = (Renderer *)_r;
+  Camera *c = (Camera *)_c;
+  World *w = (World *)_w;
+  Future *f = new Future(fb, r, c, w);
+  try {
+    fb->beginFrame();
+    fb->errorThreshold = r->errorThreshold;
+    const OcWorld *dw = w->prepareFrame();
+    checkCuda(ospcuda_event_record(f->evStart), "event record");
+    const bool finished = fb->sh.targetFrames && fb->doAccum && fb->sh.frameID >= fb->sh.targetFrames; // accumulationFinished()
+    if (!finished) checkCuda(ospcuda_render_frame(dw, &c->sh, &r->sh, &fb->sh), "render kernel");
+    checkCuda(ospcuda_event_record(f->evRendered), "event record");
+    fb->postProcess();
+    checkCuda(ospcuda_event_record(f->evFinished), "event record");
+  } catch (...) {
+    f->refDec();
+    throw;
+  }
+  return (OSPFuture)f;
+}
+
+int CudaDevice::isReady(OSPFuture f, OSPSyncEvent e) { return ((Future *)f)->isFinished(e); }
+void CudaDevice::wait(OSPFuture f, OSPSyncEvent e) { ((Future *)f)->wait(e); }
+void CudaDevice::cancel(OSPFuture) {} // a frame is a single kernel; nothing to cancel mid-flight
+float CudaDevice::getProgress(OSPFuture f) { return ((Future *)f)->isFinished(OSP_TASK_FINISHED) ? 1.f : 0.f; }
+float CudaDevice::getTaskDuration(OSPFuture f) { return ((Future *)f)->duration(); }
+
+uint32_t CudaDevice::allocMaterialSlot()
+{
+  uint32_t s;
+  if (!freeSlots.empty()) { s = freeSlots.back(); freeSlots.pop_back(); }
+  else { s = (uint32_t)materials.size(); materials.push_back(OcMaterial{}); }
+  materials[s] = OcMaterial{};
+  materials[s].type = OC_MATERIAL_OTHER;
+  materialsDirty = true;
+  return s;
+}
+void CudaDevice::freeMaterialSlot(uint32_t slot) { freeSlots.push_back(slot); }
+void CudaDevice::setMaterial(uint32_t slot, const OcMaterial &m)
+{
+  materials[slot] = m;
+  materialsDirty = true;
+}
+const OcMaterial *CudaDevice::materialTable()
+{
+  if (materialsDirty && !materials.empty()) {
+    materialsDev.upload(materials.data(), materials.size() * sizeof(OcMaterial));
+    materialsDirty = false;
+  }
+  return materialsDev.as<OcMaterial>();
+}
+
+} // namespace cuda
+} // namespace ospray
+
+using namespace ospray;
+
+// modules/cpu/ModuleInit.cpp:24-54
+extern "C" __attribute__((visibility("default"))) OSPError ospray_module_init_cuda(int16_t versionMajor, int16_t versionMinor,
+    int16_t /*versionPatch*/)
+{
+  const OSPError status = moduleVersionCheck(versionMajor, versionMinor);
+  if (status == OSP_NO_ERROR) api::Device::registerType<cuda::CudaDevice>("cuda");
+  return status;
+}
+
+extern "C" {
+void *ospcudaFrameBufferDevicePointer(OSPFrameBuffer fb, OSPFrameBufferChannel ch, uint64_t *bpp)
+{
+  cuda::FrameBuffer *f = (cuda::FrameBuffer *)fb;
+  if (bpp) *bpp = f->bytesPerPixel(ch);
+  return f->devicePointer(ch);
+}
+void ospcudaGetRayCounts(OSPFrameBuffer fb, uint64_t counts[3])
+{
+  cuda::FrameBuffer *f = (cuda::FrameBuffer *)fb;
+  for (int i = 0; i < 3; i++) counts[i] = f->rayCounts[i];
+}
+float ospcudaGetGroupBuildTime(OSPGroup g) { return ((cuda::Group *)g)->lastBuildMs; }
+uint64_t ospcudaKernelLaunchCount(void) { return ospcuda_kernel_launch_count(); }
+void *ospcudaRenderStream(void) { return ospcuda_stream(); }
+}

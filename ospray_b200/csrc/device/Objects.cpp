@@ -1,0 +1,888 @@
+// Object graph implementation (scene side). See Objects.h for the reference map.
+#include "Objects.h"
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include "CudaDevice.h"
+
+namespace ospray {
+namespace cuda {
+
+void checkCuda(int rc, const char *what)
+{
+  if (rc != 0) throw std::runtime_error(std::string("cuda device: ") + what + " failed: " + ospcuda_last_error());
+}
+
+// ---- DevMem ---------------------------------------------------------------------------------
+void DevMem::release()
+{
+  if (p) ospcuda_free(p);
+  p = nullptr;
+  bytes = 0;
+}
+void DevMem::reserve(size_t n)
+{
+  if (n <= bytes && p) return;
+  release();
+  if (n == 0) return;
+  checkCuda(ospcuda_malloc(&p, n), "device allocation");
+  bytes = n;
+}
+void DevMem::upload(const void *src, size_t n)
+{
+  reserve(n);
+  if (n) checkCuda(ospcuda_memcpy_h2d(p, src, n), "host-to-device copy");
+}
+
+// ---- Data (modules/cpu/common/Data.cpp:12-201) -------------------------------------------------
+Data::Data(const void *sharedData, OSPDataType t, const vec3ul &n, const vec3l &s, OSPDeleterCallback cb, const void *up)
+    : addr((char *)sharedData), shared(true), type(t), numItems(n), byteStride(s), freeFunction(cb), userData(up)
+{
+  if (sharedData == nullptr) throw std::runtime_error("OSPData: shared buffer is NULL");
+  init();
+  if (isObjectType(type))
+    for (size_t z = 0; z < numItems.z; z++)
+      for (size_t y = 0; y < numItems.y; y++)
+        for (size_t x = 0; x < numItems.x; x++) {
+          ManagedObject *c = *(ManagedObject **)data(vec3ul{x, y, z});
+          if (c) c->refInc();
+        }
+}
+
+Data::Data(OSPDataType t, const vec3ul &n) : shared(false), type(t), numItems(n), byteStride{0, 0, 0}
+{
+  owned.resize(size() * sizeOf(type) + 16, 0);
+  addr = owned.data();
+  init();
+}
+
+Data::~Data()
+{
+  if (isObjectType(type))
+    for (size_t z = 0; z < numItems.z; z++)
+      for (size_t y = 0; y < numItems.y; y++)
+        for (size_t x = 0; x < numItems.x; x++) {
+          ManagedObject *c = *(ManagedObject **)data(vec3ul{x, y, z});
+          if (c) c->refDec();
+        }
+  if (freeFunction) freeFunction(userData, addr);
+}
+
+void Data::init()
+{
+  managedObjectType = OSP_DATA;
+  if (std::min(numItems.x, std::min(numItems.y, numItems.z)) == 0)
+    throw std::out_of_range("OSPData: all numItems must be positive");
+  dimensions = std::max(1, (int)(numItems.x > 1) + (int)(numItems.y > 1) + (int)(numItems.z > 1));
+  if (byteStride.x == 0) byteStride.x = (int64_t)sizeOf(type);
+  if (byteStride.y == 0) byteStride.y = (int64_t)numItems.x * byteStride.x;
+  if (byteStride.z == 0) byteStride.z = (int64_t)numItems.y * byteStride.y;
+  // dominant axis of 1-D arrays (Data.cpp:139-155)
+  stride1D = byteStride.x;
+  numItems1D = numItems.x;
+  if (numItems.y > 1) { stride1D = byteStride.y; numItems1D = numItems.y; }
+  else if (numItems.z > 1) { stride1D = byteStride.z; numItems1D = numItems.z; }
+  if (dimensions != 1) { stride1D = byteStride.x; numItems1D = size(); }
+}
+
+bool Data::compact() const
+{
+  return data(vec3ul{0, 0, 0}) + sizeOf(type) * (size() - 1) == data(vec3ul{numItems.x - 1, numItems.y - 1, numItems.z - 1});
+}
+
+void Data::copy(const Data &source, const vec3ul &di)
+{
+  if (type != source.type && !(type == OSP_OBJECT && isObjectType(source.type)))
+    throw std::runtime_error(toString() + "::copy: types must match (cannot copy '" + stringFor(source.type) + "' into '"
+        + stringFor(type) + "')");
+  if (shared && !source.shared) throw std::runtime_error("OSPData::copy: cannot copy opaque (non-shared) data into shared data");
+  if (numItems.x < di.x + source.numItems.x || numItems.y < di.y + source.numItems.y || numItems.z < di.z + source.numItems.z)
+    throw std::out_of_range("OSPData::copy: source does not fit into destination");
+  const size_t es = sizeOf(type);
+  for (size_t z = 0; z < source.numItems.z; z++)
+    for (size_t y = 0; y < source.numItems.y; y++)
+      for (size_t x = 0; x < source.numItems.x; x++) {
+        char *dst = data(vec3ul{x + di.x, y + di.y, z + di.z});
+        const char *src = source.data(vec3ul{x, y, z});
+        if (dst == src) continue;
+        if (isObjectType(type)) {
+          ManagedObject *s = *(ManagedObject *const *)src;
+          if (s) s->refInc();
+          ManagedObject **d = (ManagedObject **)dst;
+          if (*d) (*d)->refDec();
+          *d = s;
+        } else
+          std::memcpy(dst, src, es);
+      }
+  deviceDirty = true;
+}
+
+OcData1D Data::deviceView1D()
+{
+  OcData1D v{};
+  const size_t es = sizeOf(type);
+  if (deviceDirty || !dev.p || devIsCompact) {
+    if (stride1D >= (int64_t)es) {
+      // upload the strided span as is
+      dev.upload(addr, (size_t)stride1D * (numItems1D - 1) + es);
+      devIsCompact = false;
+    } else {
+      // negative / overlapping strides: compact on the host
+      std::vector<char> tmp(numItems1D * es);
+      for (size_t i = 0; i < numItems1D; i++) std::memcpy(tmp.data() + i * es, data(i), es);
+      dev.upload(tmp.data(), tmp.size());
+      devIsCompact = true;
+    }
+    deviceDirty = false;
+  }
+  v.addr = dev.as<uint8_t>();
+  v.byteStride = devIsCompact ? (int64_t)es : stride1D;
+  v.numItems = (uint32_t)numItems1D;
+  return v;
+}
+
+const void *Data::deviceCompact()
+{
+  const size_t es = sizeOf(type);
+  if (deviceDirty || !dev.p || !devIsCompact) {
+    if (compact()) {
+      dev.upload(addr, size() * es);
+    } else {
+      std::vector<char> tmp(size() * es);
+      size_t o = 0;
+      for (size_t z = 0; z < numItems.z; z++)
+        for (size_t y = 0; y < numItems.y; y++)
+          for (size_t x = 0; x < numItems.x; x++, o += es) std::memcpy(tmp.data() + o, data(vec3ul{x, y, z}), es);
+      dev.upload(tmp.data(), tmp.size());
+    }
+    devIsCompact = true;
+    deviceDirty = false;
+  }
+  return dev.p;
+}
+
+Data *getParamData(ManagedObject &o, const std::string &name, OSPDataType elemType, bool required, bool promoteScalar,
+    Ref<Data> *promoted)
+{
+  auto it = o.params.find(name);
+  if (it != o.params.end()) {
+    Param &p = it->second;
+    if (isObjectType(p.type) && p.obj) {
+      Data *d = dynamic_cast<Data *>(p.obj);
+      if (d && (d->type == elemType || (isObjectType(elemType) && isObjectType(d->type) && (elemType == OSP_OBJECT || d->type == OSP_OBJECT)))
+          && d->dimensions == 1) {
+        p.queried = true;
+        return d;
+      }
+      // single object promoted to an array of one (GeometricModel.cpp:27)
+      if (!d && promoteScalar && promoted && isObjectType(elemType) && (p.type == elemType || p.type == OSP_OBJECT || elemType == OSP_OBJECT)) {
+        p.queried = true;
+        Data *nd = new Data(elemType, vec3ul{1, 1, 1});
+        *(ManagedObject **)nd->addr = p.obj;
+        p.obj->refInc();
+        *promoted = nd;
+        nd->refDec();
+        return promoted->get();
+      }
+    } else if (promoteScalar && promoted && p.type == elemType && !isObjectType(elemType)) {
+      p.queried = true;
+      Data *nd = new Data(elemType, vec3ul{1, 1, 1});
+      std::memcpy(nd->addr, p.bytes, sizeOf(elemType));
+      *promoted = nd;
+      nd->refDec();
+      return promoted->get();
+    }
+  }
+  if (required)
+    throw std::runtime_error(o.toString() + " must have '" + name + "' array with element type " + stringFor(elemType));
+  return nullptr;
+}
+
+// ---- Camera (camera/Camera.cpp:33-126, PerspectiveCamera.cpp:26-117) ------------------------------
+Camera::Camera(const std::string &) { managedObjectType = OSP_CAMERA; }
+
+void Camera::commit()
+{
+  vec3f pos = getParam<vec3f>("position", make_vec3f(0.f));
+  vec3f dir = getParam<vec3f>("direction", make_vec3f(0.f, 0.f, 1.f));
+  vec3f up = getParam<vec3f>("up", make_vec3f(0.f, 1.f, 0.f));
+  const float nearClip = std::max(getParam<float>("nearClip", 1e-6f), 0.f);
+  const vec2f imageStart = getParam<vec2f>("imageStart", make_vec2f(0.f, 0.f));
+  const vec2f imageEnd = getParam<vec2f>("imageEnd", make_vec2f(1.f, 1.f));
+  getParam<box1f>("shutter", box1f{0.5f, 0.5f});
+  getParam<uint32_t>("shutterType", 0);
+  getParam<float>("rollingShutterDuration", 0.f);
+  const affine3f xfm = getParam<affine3f>("transform", getParam<affine3f>("xfm", affine_identity()));
+  pos = xfmPoint(xfm, pos);
+  dir = normalize(xfmVector(xfm, dir));
+  up = normalize(xfmVector(xfm, up));
+
+  const float fovy = getParam<float>("fovy", 60.f);
+  float aspect = getParam<float>("aspect", 1.f);
+  const float apertureRadius = getParam<float>("apertureRadius", 0.f);
+  const float focusDistance = getParam<float>("focusDistance", 1.f);
+  const bool architectural = getParam<bool>("architectural", false);
+  const uint32_t stereoMode = getParam<uint32_t>("stereoMode", OSP_STEREO_NONE);
+  getParam<float>("interpupillaryDistance", 0.0635f);
+  if (stereoMode != OSP_STEREO_NONE)
+    postStatusMsg(OSP_LOG_WARNING, "cuda device: stereo cameras are not supported, rendering mono");
+
+  const float imgPlaneY = 2.f * tanf((0.5f * fovy) * (float)(M_PI / 180.0));
+  const float imgPlaneX = imgPlaneY * aspect;
+  const float scaledAperture = apertureRadius ? apertureRadius / (imgPlaneX * focusDistance) : 0.0f;
+  vec3f dir_00 = normalize(dir);
+  vec3f du = normalize(cross(dir_00, up));
+  vec3f dv = architectural ? normalize(up) : cross(du, dir_00);
+  du = du * imgPlaneX;
+  dv = dv * imgPlaneY;
+  dir_00 = dir_00 - 0.5f * du - 0.5f * dv;
+  if (scaledAperture > 0.f) {
+    du = du * focusDistance;
+    dv = dv * focusDistance;
+    dir_00 = dir_00 * focusDistance;
+  }
+  sh.org = toOc(pos);
+  sh.dir_00 = toOc(dir_00);
+  sh.du_size = toOc(du);
+  sh.dv_up = toOc(dv);
+  sh.direction = toOc(dir);
+  sh.nearClip = nearClip;
+  sh.subImage[0] = imageStart.x; sh.subImage[1] = imageStart.y; sh.subImage[2] = imageEnd.x; sh.subImage[3] = imageEnd.y;
+  sh.scaledAperture = scaledAperture;
+  sh.aspect = aspect;
+  sh.imgPlaneSizeY = imgPlaneY;
+  sh.needLensSample = scaledAperture > 0.f;
+  sh.needTimeSample = 0;
+}
+
+// ---- Geometry (geometry/Mesh.cpp:37-204, Spheres.cpp:46-106, Boxes.cpp:33-42) ----------------------
+Geometry::Geometry(const std::string &t) : type(t) { managedObjectType = OSP_GEOMETRY; }
+
+void Geometry::commit()
+{
+  sh = OcGeometry{};
+  if (type == "mesh") {
+    vertexData = getParamData(*this, "vertex.position", OSP_VEC3F, true);
+    bool normalFV = true, colorFV = true, texFV = true;
+    normalData = getParamData(*this, "normal", OSP_VEC3F);
+    if (!normalData) { normalData = getParamData(*this, "vertex.normal", OSP_VEC3F); normalFV = false; }
+    Data *col = getParamObject<Data>("color");
+    if (!col) { col = getParamObject<Data>("vertex.color"); colorFV = false; }
+    if (col && col->type != OSP_VEC3F && col->type != OSP_VEC4F) throw std::runtime_error("mesh colour must be vec3f or vec4f");
+    colorData = col;
+    texcoordData = getParamData(*this, "texcoord", OSP_VEC2F);
+    if (!texcoordData) { texcoordData = getParamData(*this, "vertex.texcoord", OSP_VEC2F); texFV = false; }
+    indexData = getParamData(*this, "index", OSP_VEC3UI);
+    if (!indexData) indexData = getParamData(*this, "index", OSP_VEC4UI);
+    if (!indexData) {
+      const bool quadSoup = getParam<bool>("quadSoup", false);
+      const int elements = quadSoup ? 4 : 3;
+      Data *gen = new Data(quadSoup ? OSP_VEC4UI : OSP_VEC3UI, vec3ul{vertexData->size() / elements, 1, 1});
+      uint32_t *b = (uint32_t *)gen->addr;
+      std::iota(b, b + gen->size() * elements, 0u);
+      indexData = gen;
+      gen->refDec();
+    }
+    const bool isTri = indexData->type == OSP_VEC3UI;
+    sh.type = isTri ? OC_GEOM_TRIANGLES : OC_GEOM_QUADS;
+    sh.numPrims = (uint32_t)indexData->size();
+    sh.index = indexData->deviceView1D();
+    sh.vertex = vertexData->deviceView1D();
+    if (normalData) sh.normal = normalData->deviceView1D();
+    if (colorData) sh.color = colorData->deviceView1D();
+    if (texcoordData) sh.texcoord = texcoordData->deviceView1D();
+    sh.flags = (normalFV ? OC_GEOMFLAG_NORMAL_FACEVARYING : 0) | (colorFV ? OC_GEOMFLAG_COLOR_FACEVARYING : 0)
+        | (texFV ? OC_GEOMFLAG_TEXCOORD_FACEVARYING : 0)
+        | ((colorData && colorData->type == OSP_VEC4F) ? (OC_GEOMFLAG_HAS_ALPHA | OC_GEOMFLAG_COLOR_IS_VEC4) : 0);
+  } else if (type == "sphere") {
+    const uint32_t sphereType = getParam<uint32_t>("type", OSP_SPHERE);
+    if (sphereType != OSP_SPHERE) throw std::runtime_error("cuda device: only OSP_SPHERE sphere geometry is supported");
+    const float radius = getParam<float>("radius", 0.01f);
+    vertexData = getParamData(*this, "sphere.position", OSP_VEC3F, true);
+    radiusData = getParamData(*this, "sphere.radius", OSP_FLOAT);
+    texcoordData = getParamData(*this, "sphere.texcoord", OSP_VEC2F);
+    const size_t n = vertexData->size();
+    std::vector<vec4f> inter(n);
+    for (size_t i = 0; i < n; i++) {
+      const vec3f p = vertexData->at<vec3f>(i);
+      inter[i] = make_vec4f(p, radiusData ? radiusData->at<float>(i) : radius);
+    }
+    generated.upload(inter.data(), n * sizeof(vec4f));
+    sh.type = OC_GEOM_SPHERES;
+    sh.numPrims = (uint32_t)n;
+    sh.sphere.addr = generated.as<uint8_t>();
+    sh.sphere.byteStride = sizeof(vec4f);
+    sh.sphere.numItems = (uint32_t)n;
+    if (texcoordData) sh.texcoord = texcoordData->deviceView1D();
+  } else if (type == "box") {
+    boxData = getParamData(*this, "box", OSP_BOX3F, true);
+    sh.type = OC_GEOM_BOXES;
+    sh.numPrims = (uint32_t)boxData->size();
+    sh.box = boxData->deviceView1D();
+  } else
+    throw std::runtime_error("cuda device: geometry type '" + type + "' is not supported");
+  dev.upload(&sh, sizeof(sh));
+}
+
+// ---- Material (render/materials/OBJ.cpp:30-66) ---------------------------------------------------
+Material::Material(CudaDevice &d, const std::string &t) : device(d), type(t), slot(d.allocMaterialSlot())
+{
+  managedObjectType = OSP_MATERIAL;
+}
+Material::~Material() { device.freeMaterialSlot(slot); }
+
+void Material::commit()
+{
+  OcMaterial m{};
+  if (type == "obj") {
+    m.type = OC_MATERIAL_OBJ;
+    float d = getParam<float>("d", 1.f);
+    vec3f Kd = getParam<vec3f>("kd", make_vec3f(0.8f));
+    vec3f Ks = getParam<vec3f>("ks", make_vec3f(0.f));
+    const float Ns = getParam<float>("ns", 10.f);
+    vec3f Tf = getParam<vec3f>("tf", make_vec3f(0.f));
+    const float total = reduce_max(Kd + Ks + Tf);
+    if (total > 1.f) { Kd = Kd / total; Ks = Ks / total; Tf = Tf / total; }
+    for (const char *tex : {"map_d", "map_kd", "map_ks", "map_ns", "map_bump"})
+      if (getParamObjectRaw(tex))
+        postStatusMsg(OSP_LOG_WARNING, std::string("cuda device: texture '") + tex + "' ignored (textures are out of scope)");
+    m.d = d; m.Kd = toOc(Kd); m.Ks = toOc(Ks); m.Ns = Ns; m.Tf = toOc(Tf);
+  } else {
+    m.type = OC_MATERIAL_OTHER;
+    for (auto &p : params) p.second.queried = true;
+    postStatusMsg(OSP_LOG_INFO, "cuda device: material '" + type + "' is not implemented; surfaces using it terminate paths");
+  }
+  device.setMaterial(slot, m);
+}
+
+// ---- GeometricModel (geometry/GeometricModel.cpp:21-87) -------------------------------------------
+GeometricModel::GeometricModel(Geometry *g) : geomAPI(g) { managedObjectType = OSP_GEOMETRIC_MODEL; }
+
+void GeometricModel::commit()
+{
+  geom = getParamObject<Geometry>("geometry", geomAPI.get());
+  if (!geom) throw std::runtime_error(toString() + " received NULL 'geometry'");
+  sh = OcModel{};
+  sh.geom = geom->devicePtr();
+  materialData = getParamData(*this, "material", OSP_MATERIAL, false, true, &promotedMat);
+  sh.materialMode = OC_MAT_NONE;
+  if (materialData) {
+    std::vector<uint32_t> slots(materialData->size());
+    for (size_t i = 0; i < slots.size(); i++) {
+      Material *m = dynamic_cast<Material *>(materialData->objectAt(i));
+      if (!m) throw std::runtime_error(toString() + ": 'material' array holds a non-material object");
+      slots[i] = m->slot;
+    }
+    matList.upload(slots.data(), slots.size() * sizeof(uint32_t));
+    sh.material = matList.as<uint32_t>();
+    sh.numMaterials = (uint32_t)slots.size();
+    sh.materialMode = OC_MAT_FROM_MODEL;
+  } else {
+    materialData = getParamData(*this, "material", OSP_UINT, false, true, &promotedMat);
+    if (materialData) {
+      std::vector<uint32_t> ids(materialData->size());
+      for (size_t i = 0; i < ids.size(); i++) ids[i] = materialData->at<uint32_t>(i);
+      matList.upload(ids.data(), ids.size() * sizeof(uint32_t));
+      sh.material = matList.as<uint32_t>();
+      sh.numMaterials = (uint32_t)ids.size();
+      sh.materialMode = OC_MAT_FROM_RENDERER;
+    }
+  }
+  colorData = getParamData(*this, "color", OSP_VEC4F, false, true, &promotedColor);
+  if (colorData) sh.color = colorData->deviceView1D();
+  indexData = getParamData(*this, "index", OSP_UCHAR);
+  if (indexData) sh.index = indexData->deviceView1D();
+  sh.invertedNormals = getParam<bool>("invertNormals", false);
+  sh.userID = getParam<uint32_t>("id", 0xFFFFFFFFu);
+}
+
+// ---- TransferFunction (LinearTransferFunction.cpp:22-155) -------------------------------------------
+void TransferFunction::commit()
+{
+  managedObjectType = OSP_TRANSFER_FUNCTION;
+  valueRange = getParam<box1f>("value", box1f{0.f, 1.f});
+  colorData = getParamData(*this, "color", OSP_VEC3F, true, true, &promC);
+  opacityData = getParamData(*this, "opacity", OSP_FLOAT, true, true, &promO);
+  sh.color = (const OcVec3f *)colorData->deviceCompact();
+  sh.opacity = (const float *)opacityData->deviceCompact();
+  sh.numColors = (uint32_t)colorData->size();
+  sh.numOpacities = (uint32_t)opacityData->size();
+  sh.valueLower = valueRange.lower;
+  sh.valueUpper = valueRange.upper;
+  opacities.resize(opacityData->size());
+  for (size_t i = 0; i < opacities.size(); i++) opacities[i] = opacityData->at<float>(i);
+}
+
+std::vector<box1f> TransferFunction::positiveOpacityValueRanges() const
+{
+  // index ranges with positive opacity, widened by one entry on each side (linear interpolation)
+  std::vector<std::pair<int, int>> idx;
+  bool active = false;
+  int lo = 0;
+  const int n = (int)opacities.size();
+  for (int i = 0; i < n; i++) {
+    if (opacities[i] > 0.f && !active) { active = true; lo = i; }
+    else if (opacities[i] <= 0.f && active) { active = false; idx.emplace_back(lo, i); }
+  }
+  if (n && opacities[n - 1] > 0.f && active) idx.emplace_back(lo, n);
+  std::vector<box1f> out;
+  const float size = valueRange.upper - valueRange.lower;
+  for (auto &r : idx) {
+    box1f v{-INFINITY, INFINITY};
+    const int minIdx = r.first - 1, maxIdx = r.second;
+    if (minIdx >= 0) v.lower = valueRange.lower + minIdx * size / (n - 1.f);
+    if (maxIdx < n) v.upper = valueRange.lower + maxIdx * size / (n - 1.f);
+    out.push_back(v);
+  }
+  return out;
+}
+
+// ---- Volume (volume/Volume.cpp:60-222 -> Open VKL structuredRegular) ------------------------------
+Volume::Volume(const std::string &t) : type(t) { managedObjectType = OSP_VOLUME; }
+
+void Volume::commit()
+{
+  if (type != "structuredRegular" && type != "structured_regular")
+    throw std::runtime_error("cuda device: volume type '" + type + "' is not supported (structuredRegular only)");
+  gridOrigin = getParam<vec3f>("gridOrigin", make_vec3f(0.f));
+  gridSpacing = getParam<vec3f>("gridSpacing", make_vec3f(1.f));
+  getParam<bool>("cellCentered", false);
+  getParam<uint32_t>("filter", OSP_VOLUME_FILTER_LINEAR);
+  getParam<uint32_t>("gradientFilter", OSP_VOLUME_FILTER_LINEAR);
+  getParam<float>("background", NAN);
+  Data *d = getParamObject<Data>("data");
+  if (!d) throw std::runtime_error("structuredRegular volume needs a 3-D 'data' array");
+  data = d;
+  dims[0] = (uint32_t)d->numItems.x; dims[1] = (uint32_t)d->numItems.y; dims[2] = (uint32_t)d->numItems.z;
+  const size_t n = d->size();
+  if (d->type == OSP_FLOAT && d->compact()) {
+    voxels.upload(d->addr, n * sizeof(float));
+  } else {
+    std::vector<float> tmp(n);
+    size_t o = 0;
+    for (size_t z = 0; z < d->numItems.z; z++)
+      for (size_t y = 0; y < d->numItems.y; y++)
+        for (size_t x = 0; x < d->numItems.x; x++, o++) {
+          const char *p = d->data(vec3ul{x, y, z});
+          switch (d->type) {
+          case OSP_UCHAR: tmp[o] = *(const uint8_t *)p; break;
+          case OSP_SHORT: tmp[o] = *(const int16_t *)p; break;
+          case OSP_USHORT: tmp[o] = *(const uint16_t *)p; break;
+          case OSP_FLOAT: tmp[o] = *(const float *)p; break;
+          case OSP_DOUBLE: tmp[o] = (float)*(const double *)p; break;
+          default: throw std::runtime_error("structuredRegular volume: unsupported voxel type");
+          }
+        }
+    voxels.upload(tmp.data(), n * sizeof(float));
+  }
+  for (int a = 0; a < 3; a++) mcDims[a] = std::max(1u, (dims[a] - 1 + 15) / 16);
+  mcRange.reserve(sizeof(float) * 2 * (size_t)mcDims[0] * mcDims[1] * mcDims[2]);
+  checkCuda(ospcuda_volume_macrocells(voxels.as<float>(), dims, mcRange.as<float>(), mcDims), "macrocell build");
+  bounds.lower = gridOrigin;
+  bounds.upper = gridOrigin + make_vec3f((dims[0] - 1) * gridSpacing.x, (dims[1] - 1) * gridSpacing.y, (dims[2] - 1) * gridSpacing.z);
+}
+
+VolumetricModel::VolumetricModel(Volume *v) : volumeAPI(v) { managedObjectType = OSP_VOLUMETRIC_MODEL; }
+
+void VolumetricModel::commit()
+{
+  volume = getParamObject<Volume>("volume", volumeAPI.get());
+  if (!volume) throw std::runtime_error(toString() + " received NULL 'volume'");
+  tf = getParamObject<TransferFunction>("transferFunction");
+  if (!tf) throw std::runtime_error(toString() + " received NULL 'transferFunction'");
+  sh = OcVolume{};
+  sh.voxels = volume->voxels.as<float>();
+  sh.mcRange = volume->mcRange.as<float>();
+  for (int a = 0; a < 3; a++) { sh.dims[a] = volume->dims[a]; sh.mcDims[a] = volume->mcDims[a]; }
+  sh.gridOrigin = toOc(volume->gridOrigin);
+  sh.gridSpacing = toOc(volume->gridSpacing);
+  const box3f b = volume->getBounds();
+  sh.bounds[0] = b.lower.x; sh.bounds[1] = b.lower.y; sh.bounds[2] = b.lower.z;
+  sh.bounds[3] = b.upper.x; sh.bounds[4] = b.upper.y; sh.bounds[5] = b.upper.z;
+  sh.tf = tf->sh;
+  sh.densityScale = getParam<float>("densityScale", 1.f);
+  sh.anisotropy = getParam<float>("anisotropy", 0.f);
+  sh.gradientShadingScale = getParam<float>("gradientShadingScale", 0.f);
+  sh.userID = getParam<uint32_t>("id", 0xFFFFFFFFu);
+  const std::vector<box1f> ranges = tf->positiveOpacityValueRanges();
+  sh.numRanges = (uint32_t)std::min<size_t>(ranges.size(), 8);
+  if (ranges.size() > 8) { // too many disjoint ranges: fall back to "everything"
+    sh.numRanges = 1; sh.ranges[0] = -INFINITY; sh.ranges[1] = INFINITY;
+  } else
+    for (uint32_t i = 0; i < sh.numRanges; i++) { sh.ranges[2 * i] = ranges[i].lower; sh.ranges[2 * i + 1] = ranges[i].upper; }
+}
+
+// ---- Light (lights/Light.cpp:20-25, AmbientLight.cpp, DirectionalLight.cpp, QuadLight.cpp:68-108) ---
+Light::Light(const std::string &t) : type(t) { managedObjectType = OSP_LIGHT; }
+
+void Light::commit()
+{
+  sh = OcLight{};
+  sh.isVisible = getParam<bool>("visible", true);
+  const vec3f coloredIntensity = getParam<vec3f>("color", make_vec3f(1.f)) * getParam<float>("intensity", 1.f);
+  ambientRadiance = make_vec3f(0.f);
+  if (type == "ambient") {
+    const uint32_t iq = getParam<uint32_t>("intensityQuantity", OSP_INTENSITY_QUANTITY_RADIANCE);
+    vec3f radiance = make_vec3f(0.f);
+    if (iq == OSP_INTENSITY_QUANTITY_IRRADIANCE) radiance = coloredIntensity / (float)M_PI;
+    else if (iq == OSP_INTENSITY_QUANTITY_RADIANCE) radiance = coloredIntensity;
+    else postStatusMsg(OSP_LOG_WARNING, toString() + " unsupported 'intensityQuantity' value");
+    sh.type = OC_LIGHT_AMBIENT;
+    sh.radiance = toOc(radiance);
+    ambientRadiance = radiance;
+  } else if (type == "distant") {
+    vec3f direction = getParam<vec3f>("direction", make_vec3f(0.f, 0.f, 1.f));
+    float angularDiameter = getParam<float>("angularDiameter", .0f);
+    direction = -normalize(direction);
+    angularDiameter = std::min(std::max(angularDiameter, 0.f), 180.f);
+    const float cosAngle = std::cos((0.5f * angularDiameter) * (float)(M_PI / 180.0));
+    const uint32_t iq = getParam<uint32_t>("intensityQuantity", OSP_INTENSITY_QUANTITY_IRRADIANCE);
+    vec3f irradiance = make_vec3f(0.f);
+    if (iq == OSP_INTENSITY_QUANTITY_RADIANCE) irradiance = (2.0f * (float)M_PI * (1.0f - cosAngle)) * coloredIntensity;
+    else if (iq == OSP_INTENSITY_QUANTITY_IRRADIANCE) irradiance = coloredIntensity;
+    else postStatusMsg(OSP_LOG_WARNING, toString() + " unsupported 'intensityQuantity' value");
+    const linear3f f = frame(direction);
+    sh.type = OC_LIGHT_DISTANT;
+    sh.radiance = toOc(irradiance);
+    sh.fx = toOc(f.vx); sh.fy = toOc(f.vy); sh.fz = toOc(f.vz);
+    sh.cosAngle = cosAngle;
+    sh.pdf = cosAngle < 0.99999988f ? 1.f / (2.f * (float)M_PI * (1.0f - cosAngle)) : INFINITY;
+  } else if (type == "quad") {
+    const vec3f position = getParam<vec3f>("position", make_vec3f(0.f));
+    const vec3f edge1 = getParam<vec3f>("edge1", make_vec3f(1.f, 0.f, 0.f));
+    const vec3f edge2 = getParam<vec3f>("edge2", make_vec3f(0.f, 1.f, 0.f));
+    const uint32_t iq = getParam<uint32_t>("intensityQuantity", OSP_INTENSITY_QUANTITY_RADIANCE);
+    const float quadArea = length(cross(edge1, edge2));
+    vec3f radiance = make_vec3f(0.f);
+    if (iq == OSP_INTENSITY_QUANTITY_INTENSITY) radiance = coloredIntensity / quadArea;
+    else if (iq == OSP_INTENSITY_QUANTITY_POWER) radiance = coloredIntensity / ((float)M_PI * quadArea);
+    else if (iq == OSP_INTENSITY_QUANTITY_RADIANCE) radiance = coloredIntensity;
+    else postStatusMsg(OSP_LOG_WARNING, toString() + " unsupported 'intensityQuantity' value");
+    const vec3f ndirection = cross(edge2, edge1);
+    const float ppdf = 1.f / length(ndirection);
+    sh.type = OC_LIGHT_QUAD;
+    sh.radiance = toOc(radiance);
+    sh.position = toOc(position); sh.edge1 = toOc(edge1); sh.edge2 = toOc(edge2);
+    sh.ppdf = ppdf;
+    sh.nnormal = toOc(ndirection * ppdf);
+  } else
+    throw std::runtime_error("cuda device: light type '" + type + "' is not supported (ambient, distant, quad)");
+}
+
+// ---- Group (common/Group.cpp:69-209) ------------------------------------------------------------------
+Group::~Group() { ospcuda_bvh_free(&sh.bvh); }
+
+void Group::commit()
+{
+  managedObjectType = OSP_GROUP;
+  geometricModels = getParamData(*this, "geometry", OSP_GEOMETRIC_MODEL);
+  volumetricModels = getParamData(*this, "volume", OSP_VOLUMETRIC_MODEL);
+  lights = getParamData(*this, "light", OSP_LIGHT);
+  if (getParamData(*this, "clippingGeometry", OSP_GEOMETRIC_MODEL))
+    postStatusMsg(OSP_LOG_WARNING, "cuda device: clipping geometry is not supported and is ignored");
+  getParam<bool>("dynamicScene", false);
+  getParam<bool>("compactMode", false);
+  getParam<bool>("robustMode", false);
+
+  ospcuda_bvh_free(&sh.bvh);
+  sh = OcGroup{};
+  bounds = box_empty();
+  lastBuildMs = 0.f;
+  if (geometricModels) {
+    const size_t n = geometricModels->size();
+    std::vector<OcModel> models(n);
+    std::vector<uint32_t> numPrims(n), types(n);
+    for (size_t i = 0; i < n; i++) {
+      GeometricModel *m = dynamic_cast<GeometricModel *>(geometricModels->objectAt(i));
+      if (!m || !m->geom) throw std::runtime_error("ospray::Group: 'geometry' holds an uncommitted or foreign object");
+      models[i] = m->sh;
+      numPrims[i] = m->geom->sh.numPrims;
+      types[i] = m->geom->sh.type;
+    }
+    modelsDev.upload(models.data(), n * sizeof(OcModel));
+    sh.models = modelsDev.as<OcModel>();
+    sh.numModels = (uint32_t)n;
+    checkCuda(ospcuda_bvh_build_group(sh.models, sh.numModels, numPrims.data(), types.data(), &sh.bvh, &lastBuildMs), "BVH build");
+    if (sh.bvh.numRecords) {
+      box3f b;
+      b.lower = make_vec3f(sh.bvh.bounds[0], sh.bvh.bounds[1], sh.bvh.bounds[2]);
+      b.upper = make_vec3f(sh.bvh.bounds[3], sh.bvh.bounds[4], sh.bvh.bounds[5]);
+      box_extend(bounds, b);
+    }
+  }
+  if (volumetricModels) {
+    const size_t n = volumetricModels->size();
+    std::vector<OcVolume> vols(n);
+    for (size_t i = 0; i < n; i++) {
+      VolumetricModel *m = dynamic_cast<VolumetricModel *>(volumetricModels->objectAt(i));
+      if (!m || !m->volume) throw std::runtime_error("ospray::Group: 'volume' holds an uncommitted or foreign object");
+      vols[i] = m->sh;
+      box_extend(bounds, m->getBounds());
+    }
+    volumesDev.upload(vols.data(), n * sizeof(OcVolume));
+    sh.volumes = volumesDev.as<OcVolume>();
+    sh.numVolumes = (uint32_t)n;
+  }
+  dev.upload(&sh, sizeof(sh));
+}
+
+// ---- Instance (common/Instance.cpp:20-52) ----------------------------------------------------------------
+Instance::Instance(Group *g) : groupAPI(g) { managedObjectType = OSP_INSTANCE; }
+
+void Instance::commit()
+{
+  group = getParamObject<Group>("group", groupAPI.get());
+  if (!group) throw std::runtime_error(toString() + " received NULL 'group'");
+  xfm = getParam<affine3f>("transform", getParam<affine3f>("xfm", affine_identity()));
+  if (getParamObjectRaw("motion.transform"))
+    postStatusMsg(OSP_LOG_WARNING, "cuda device: motion blur transforms are not supported");
+  rcp_xfm = rcp(xfm);
+  userID = getParam<uint32_t>("id", 0xFFFFFFFFu);
+  const affine3f I = affine_identity();
+  identity = std::memcmp(&xfm, &I, sizeof(affine3f)) == 0;
+}
+
+box3f Instance::getBounds() const
+{
+  if (!group) return box_empty();
+  const box3f g = group->getBounds();
+  if (box_is_empty(g)) return g;
+  return xfmBounds(xfm, g);
+}
+
+// ---- World (common/World.cpp:70-209; PathTracerData.cpp:32-82; SciVisData.cpp:74-105) -----------------------
+World::~World() { ospcuda_bvh_free(&sh.tlas); }
+
+static float distribution1D_create(std::vector<float> &cdf) // math/Distribution1D.ispc:14-41
+{
+  float sum = cdf[0];
+  for (size_t i = 1; i < cdf.size(); i++) cdf[i] = sum += cdf[i];
+  const float rcpSum = 1.0f / sum;
+  for (float &c : cdf) c = c >= sum ? 0x1.000002p+0f : c * rcpSum;
+  return sum;
+}
+
+void World::commit()
+{
+  instances = getParamData(*this, "instance", OSP_INSTANCE);
+  lights = getParamData(*this, "light", OSP_LIGHT);
+  getParam<bool>("dynamicScene", false);
+  getParam<bool>("compactMode", false);
+  getParam<bool>("robustMode", false);
+
+  ospcuda_bvh_free(&sh.tlas);
+  sh = OcWorld{};
+  bounds = box_empty();
+  std::vector<OcInstance> inst;
+  std::vector<float> instBounds;
+  if (instances) {
+    inst.resize(instances->size());
+    for (size_t i = 0; i < inst.size(); i++) {
+      Instance *in = dynamic_cast<Instance *>(instances->objectAt(i));
+      if (!in || !in->group) throw std::runtime_error("ospray::World: 'instance' holds an uncommitted or foreign object");
+      OcInstance &o = inst[i];
+      o = OcInstance{};
+      o.xfm = toOc(in->xfm);
+      o.rcp_xfm = toOc(in->rcp_xfm);
+      o.group = in->group->devicePtr();
+      o.userID = in->userID;
+      o.isIdentity = in->identity;
+      const box3f b = in->getBounds();
+      o.bounds[0] = b.lower.x; o.bounds[1] = b.lower.y; o.bounds[2] = b.lower.z;
+      o.bounds[3] = b.upper.x; o.bounds[4] = b.upper.y; o.bounds[5] = b.upper.z;
+      instBounds.insert(instBounds.end(), o.bounds, o.bounds + 6);
+      if (!box_is_empty(b)) box_extend(bounds, b);
+      if (in->group->hasVolumes()) sh.hasVolumes = 1;
+    }
+    instDev.upload(inst.data(), inst.size() * sizeof(OcInstance));
+    sh.instances = instDev.as<OcInstance>();
+    sh.numInstances = (uint32_t)inst.size();
+    if (inst.size() > 4) checkCuda(ospcuda_bvh_build_tlas(instBounds.data(), (uint32_t)inst.size(), &sh.tlas), "TLAS build");
+  }
+  // light lists: world lights, then instance (group) lights -- the latter are not transformed yet
+  std::vector<Light *> all;
+  if (lights)
+    for (size_t i = 0; i < lights->size(); i++) all.push_back(dynamic_cast<Light *>(lights->objectAt(i)));
+  if (instances)
+    for (size_t i = 0; i < instances->size(); i++) {
+      Instance *in = dynamic_cast<Instance *>(instances->objectAt(i));
+      if (in && in->group && in->group->lights)
+        for (size_t k = 0; k < in->group->lights->size(); k++) {
+          if (!in->identity) postStatusMsg(OSP_LOG_WARNING, "cuda device: lights in transformed instances are used untransformed");
+          all.push_back(dynamic_cast<Light *>(in->group->lights->objectAt(k)));
+        }
+    }
+  std::vector<OcLight> pt, sv;
+  uint32_t visibleOnly = 0;
+  vec3f aoColor = make_vec3f(0.f);
+  for (Light *l : all) {
+    if (!l) continue;
+    pt.push_back(l->sh);
+    if (l->sh.type == OC_LIGHT_AMBIENT) {
+      // SciVisData.cpp:17-30: ambient lights go to the visible-only front partition
+      if (visibleOnly == sv.size()) sv.push_back(l->sh);
+      else { sv.push_back(sv[visibleOnly]); sv[visibleOnly] = l->sh; }
+      visibleOnly++;
+      aoColor = aoColor + l->ambientRadiance;
+    } else
+      sv.push_back(l->sh);
+  }
+  if (!pt.empty()) {
+    std::vector<float> cdf(pt.size(), 1.f);
+    distribution1D_create(cdf);
+    lightsDev.upload(pt.data(), pt.size() * sizeof(OcLight));
+    cdfDev.upload(cdf.data(), cdf.size() * sizeof(float));
+    scivisLightsDev.upload(sv.data(), sv.size() * sizeof(OcLight));
+    sh.lights = lightsDev.as<OcLight>();
+    sh.lightsCDF = cdfDev.as<float>();
+    sh.scivisLights = scivisLightsDev.as<OcLight>();
+  }
+  sh.numLights = (uint32_t)pt.size();
+  sh.numScivisLights = (uint32_t)sv.size();
+  sh.numScivisLightsVisibleOnly = visibleOnly;
+  sh.aoColorPi = toOc(aoColor * (float)M_PI);
+  sh.bounds[0] = bounds.lower.x; sh.bounds[1] = bounds.lower.y; sh.bounds[2] = bounds.lower.z;
+  sh.bounds[3] = bounds.upper.x; sh.bounds[4] = bounds.upper.y; sh.bounds[5] = bounds.upper.z;
+  dirty = true;
+}
+
+const OcWorld *World::prepareFrame()
+{
+  const OcMaterial *mt = device.materialTable();
+  if (dirty || mt != uploadedMaterials) {
+    sh.materials = mt;
+    dev.upload(&sh, sizeof(sh));
+    uploadedMaterials = mt;
+    dirty = false;
+  }
+  return dev.as<OcWorld>();
+}
+
+// ---- ImageOp (fb/frame_ops/ToneMapper.cpp:14-51) ------------------------------------------------------------
+void ImageOp::commit()
+{
+  if (type != "tonemapper") return;
+  tm.exposure = getParam<float>("exposure", 1.f);
+  const float a = std::max(getParam<float>("contrast", 1.6773f), 0.0001f);
+  const float d = std::min(std::max(getParam<float>("shoulder", 0.9714f), 0.0001f), 1.f);
+  const float m = std::min(std::max(getParam<float>("midIn", 0.18f), 0.0001f), 1.f);
+  const float n = std::min(std::max(getParam<float>("midOut", 0.18f), 0.0001f), 1.f);
+  const float w = std::max(getParam<float>("hdrMax", 11.0785f), 1.f);
+  tm.acesColor = getParam<bool>("acesColor", true);
+  tm.a = a;
+  tm.d = d;
+  tm.b = -((powf(m, -a * d) * (-powf(m, a) + (n * (powf(m, a * d) * n * powf(w, a) - powf(m, a) * powf(w, a * d))) / (powf(m, a * d) * n - n * powf(w, a * d)))) / n);
+  tm.c = std::max((powf(m, a * d) * n * powf(w, a) - powf(m, a) * powf(w, a * d)) / (powf(m, a * d) * n - n * powf(w, a * d)), 0.f);
+}
+
+// ---- Renderer (render/Renderer.cpp:38-92,146-178; PathTracer.cpp:29-51; SciVis.cpp:27-36; AORenderer.cpp:26-35)
+Renderer::Renderer(CudaDevice &d, const std::string &t) : device(d), type(t) { managedObjectType = OSP_RENDERER; }
+
+static float filterEval(uint32_t pf, float width, float x, float y) // pf/LUTPixelFilter.ispc:17-66
+{
+  if (pf == OSP_PIXELFILTER_GAUSS) {
+    const float sigma = (0.5f * width) / 3.0f;
+    return std::exp(-0.5f * ((x * x + y * y) / (sigma * sigma)));
+  }
+  if (pf == OSP_PIXELFILTER_MITCHELL) {
+    const float B = 1.0f / 3.0f, C = 1.0f / 3.0f, oneOverSix = 1.0f / 6.0f;
+    const float tx = (x / width) * 4.0f, ty = (y / width) * 4.0f;
+    const float fx = std::sqrt(tx * tx + ty * ty), fx2 = fx * fx, fx3 = fx2 * fx;
+    if (fx < 1.0f) return oneOverSix * ((12.0f - 9.0f * B - 6.0f * C) * fx3 + (-18.0f + 12.0f * B + 6.0f * C) * fx2 + (6.0f - 2.0f * B));
+    if (fx < 2.0f) return oneOverSix * ((-B - 6.0f * C) * fx3 + (6.0f * B + 30.0f * C) * fx2 + (-12.0f * B - 48.0f * C) * fx + (8.0f * B + 24.0f * C));
+    return 0.f;
+  }
+  // Blackman-Harris
+  const float a0 = 0.35875f, a1 = 0.48829f, a2 = 0.14128f, a3 = 0.01168f;
+  const float fx = std::sqrt(x * x + y * y) + width / 2.0f;
+  const float ow = 1.0f / width;
+  return a0 - a1 * std::cos((2.0f * (float)M_PI * fx) * ow) + a2 * std::cos((4.0f * (float)M_PI * fx) * ow)
+      - a3 * std::cos((6.0f * (float)M_PI * fx) * ow);
+}
+
+void Renderer::commit()
+{
+  sh = OcRenderer{};
+  if (type == "pathtracer") sh.type = OC_RENDERER_PATHTRACER;
+  else if (type == "scivis") sh.type = OC_RENDERER_SCIVIS;
+  else if (type == "ao") sh.type = OC_RENDERER_AO;
+  sh.spp = std::max(1, getParam<int>("pixelSamples", 1));
+  getParam<float>("mipMapBias", 0.f);
+  sh.maxDepth = (uint32_t)std::max(0, getParam<int>("maxPathLength", 20));
+  sh.minContribution = getParam<float>("minContribution", 0.001f);
+  errorThreshold = getParam<float>("varianceThreshold", 0.f);
+  if (getParamObjectRaw("map_maxDepth") || getParamObjectRaw("map_backplate"))
+    postStatusMsg(OSP_LOG_WARNING, "cuda device: renderer textures (map_maxDepth, map_backplate) are not supported");
+  const vec3f bg3 = getParam<vec3f>("backgroundColor", make_vec3f(getParam<float>("backgroundColor", 0.f)));
+  const vec4f bg = getParam<vec4f>("backgroundColor", make_vec4f(bg3, 0.f));
+  sh.bgColor[0] = bg.x; sh.bgColor[1] = bg.y; sh.bgColor[2] = bg.z; sh.bgColor[3] = bg.w;
+
+  materialData = getParamData(*this, "material", OSP_MATERIAL);
+  if (materialData) {
+    std::vector<uint32_t> slots(materialData->size());
+    for (size_t i = 0; i < slots.size(); i++) {
+      Material *m = dynamic_cast<Material *>(materialData->objectAt(i));
+      if (!m) throw std::runtime_error("renderer 'material' array holds a non-material object");
+      slots[i] = m->slot;
+    }
+    matList.upload(slots.data(), slots.size() * sizeof(uint32_t));
+    sh.materials = matList.as<uint32_t>();
+    sh.numMaterials = (uint32_t)slots.size();
+  }
+
+  // pixel filter (Renderer.cpp:146-178, pf/PixelFilter.cpp:23-69, LUTPixelFilter.ispc:68-142)
+  const uint32_t pf = getParam<uint32_t>("pixelFilter", OSP_PIXELFILTER_GAUSS);
+  if (pf == OSP_PIXELFILTER_POINT) { sh.pfType = OC_PF_POINT; sh.pfWidth = 0.f; }
+  else if (pf == OSP_PIXELFILTER_BOX) { sh.pfType = OC_PF_BOX; sh.pfWidth = 1.f; }
+  else {
+    const float width = pf == OSP_PIXELFILTER_MITCHELL ? 4.f : 3.f;
+    const int lut = (int)std::ceil(width) * 5; // LUTPIXELFILTER_PER_PIXEL_BINS
+    std::vector<float> cdfx((size_t)lut * lut), cdfy(lut);
+    for (int y = 0; y < lut; y++) {
+      const float fy = (y + 0.5f) * (1.0f / (float)lut);
+      std::vector<float> row(lut);
+      for (int x = 0; x < lut; x++) {
+        const float fx = (x + 0.5f) * (1.0f / (float)lut);
+        row[x] = std::max(0.0f, filterEval(pf == OSP_PIXELFILTER_MITCHELL || pf == OSP_PIXELFILTER_BLACKMAN_HARRIS ? pf : OSP_PIXELFILTER_GAUSS,
+                                    width, (fx - 0.5f) * width, (fy - 0.5f) * width));
+      }
+      cdfy[y] = distribution1D_create(row);
+      std::copy(row.begin(), row.end(), cdfx.begin() + (size_t)y * lut);
+    }
+    distribution1D_create(cdfy);
+    pfCdfX.upload(cdfx.data(), cdfx.size() * sizeof(float));
+    pfCdfY.upload(cdfy.data(), cdfy.size() * sizeof(float));
+    sh.pfType = OC_PF_LUT;
+    sh.pfWidth = width;
+    sh.pfLutW = sh.pfLutH = (uint32_t)lut;
+    sh.pfCdfX = pfCdfX.as<float>();
+    sh.pfCdfY = pfCdfY.as<float>();
+  }
+
+  if (sh.type == OC_RENDERER_PATHTRACER) {
+    sh.rouletteDepth = getParam<int>("roulettePathLength", 5);
+    sh.maxScatteringEvents = getParam<int>("maxScatteringEvents", 20);
+    sh.maxRadiance = getParam<float>("maxContribution", INFINITY);
+    sh.numLightSamples = getParam<int>("lightSamples", -1);
+    sh.limitIndirectLightSamples = getParam<bool>("limitIndirectLightSamples", true);
+    const vec4f scp = getParam<vec4f>("shadowCatcherPlane", make_vec4f(0.f, 0.f, 0.f, 0.f));
+    if (scp.x != 0.f || scp.y != 0.f || scp.z != 0.f)
+      postStatusMsg(OSP_LOG_WARNING, "cuda device: the shadow catcher plane is not supported");
+    getParam<bool>("geometryLights", true);
+    sh.backgroundRefraction = getParam<bool>("backgroundRefraction", false);
+  } else if (sh.type == OC_RENDERER_SCIVIS) {
+    sh.shadowsEnabled = getParam<bool>("shadows", false);
+    sh.visibleLights = getParam<bool>("visibleLights", false);
+    sh.aoSamples = getParam<int>("aoSamples", 0);
+    sh.aoRadius = getParam<float>("aoDistance", 1e20f);
+    sh.volumeSamplingRate = getParam<float>("volumeSamplingRate", 1.f);
+  } else {
+    sh.aoSamples = getParam<int>("aoSamples", 1);
+    sh.aoRadius = getParam<float>("aoDistance", getParam<float>("aoRadius", 1e20f));
+    sh.aoIntensity = getParam<float>("aoIntensity", 1.f);
+    sh.volumeSamplingRate = getParam<float>("volumeSamplingRate", 1.f);
+  }
+}
+
+} // namespace cuda
+} // namespace ospray

@@ -199,9 +199,16 @@ const char *ospDeviceGetLastErrorMsg(OSPDevice _d)
 }
 void ospDeviceCommit(OSPDevice _d)
 {
-  OSP_TRY
-  ((Device *)_d)->commit();
-  OSP_CATCH()
+  Device *d = (Device *)_d;
+  try {
+    d->commit();
+  } catch (const std::exception &e) {
+    // the device being committed is usually not current yet: record the failure on it directly
+    d->lastErrorCode = OSP_UNKNOWN_ERROR;
+    d->lastErrorMsg = std::string("#ospray: ") + e.what();
+    d->error_fcn(d->errorUserData, OSP_UNKNOWN_ERROR, e.what());
+    if (!api::deviceIsSet() || Device::current.get() != d) handleError(OSP_UNKNOWN_ERROR, e.what());
+  }
 }
 void ospDeviceRelease(OSPDevice _d)
 {

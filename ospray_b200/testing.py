@@ -1,0 +1,398 @@
+"""Procedural scenes of the reference's ospray_testing library, restated as neutral SceneSpec
+objects plus adapters: `to_ospray()` replays a spec through the unchanged OSPRay C API (the same
+call sequence the C++ builders issue), and tests feed the very same spec to the CPU oracle.
+
+reference: apps/common/ospray_testing/builders/Builder.cpp:12-93 (world, transfer function),
+CornellBox.cpp:26-251, GravitySpheresVolume.cpp:68-134,180-253, Boxes.cpp:40-105,
+RandomSpheres.cpp:42-111; apps/common/arcball_camera/ArcballCamera.cpp:6-24,53-85;
+apps/ospBenchmark/BaseFixture.cpp:18-50 (camera / framebuffer setup).
+rkcommon's utility::uniform_real_distribution (un-vendored) is restated as
+(g() - g.min()) * ((hi - lo) / float(g.max() - g.min())) + lo in float32."""
+from dataclasses import dataclass, field
+from typing import List, Optional
+import numpy as np
+
+from . import capi as osp
+
+
+# ---- spec ---------------------------------------------------------------------------------------
+@dataclass
+class MaterialSpec:
+    type: str = "obj"
+    kd: tuple = (0.8, 0.8, 0.8)
+    ks: tuple = (0.0, 0.0, 0.0)
+    ns: float = 10.0
+    d: float = 1.0
+    tf: tuple = (0.0, 0.0, 0.0)
+
+
+@dataclass
+class GeometrySpec:
+    type: str                                  # mesh | sphere | box
+    vertex: Optional[np.ndarray] = None        # (N,3) f32
+    index: Optional[np.ndarray] = None         # (M,3|4) u32; None = soup
+    quad_soup: bool = False
+    vertex_color: Optional[np.ndarray] = None  # (N,4) f32
+    vertex_normal: Optional[np.ndarray] = None
+    sphere_position: Optional[np.ndarray] = None
+    sphere_radius: Optional[np.ndarray] = None
+    radius: float = 0.01
+    boxes: Optional[np.ndarray] = None         # (N,6) f32
+
+
+@dataclass
+class ModelSpec:
+    geometry: GeometrySpec
+    material: Optional[MaterialSpec] = None
+    color: Optional[np.ndarray] = None         # (P,4) per-primitive colour
+    id: Optional[int] = None
+
+
+@dataclass
+class VolumeSpec:
+    voxels: np.ndarray                         # (z,y,x) f32
+    grid_origin: tuple = (0, 0, 0)
+    grid_spacing: tuple = (1, 1, 1)
+    tf_colors: Optional[np.ndarray] = None
+    tf_opacities: Optional[np.ndarray] = None
+    value_range: tuple = (0.0, 1.0)
+    density_scale: float = 1.0
+    gradient_shading_scale: float = 0.0
+
+
+@dataclass
+class GroupSpec:
+    models: List[ModelSpec] = field(default_factory=list)
+    volumes: List[VolumeSpec] = field(default_factory=list)
+
+
+@dataclass
+class InstanceSpec:
+    group: GroupSpec
+    xfm: Optional[np.ndarray] = None           # 12 floats column-major (vx, vy, vz, p)
+    id: Optional[int] = None
+
+
+@dataclass
+class LightSpec:
+    type: str
+    params: dict = field(default_factory=dict)
+
+
+@dataclass
+class SceneSpec:
+    instances: List[InstanceSpec] = field(default_factory=list)
+    lights: List[LightSpec] = field(default_factory=list)
+
+
+# ---- deterministic RNG ----------------------------------------------------------------------------
+class Mt19937:
+    """std::mt19937 stream (init_genrand seeding)"""
+
+    def __init__(self, seed):
+        self.bg = np.random.MT19937()
+        self.bg._legacy_seeding(int(seed))
+
+    def raw(self, n):
+        return self.bg.random_raw(n).astype(np.uint64)
+
+    def uniform(self, lo, hi, n):
+        lo, hi = np.float32(lo), np.float32(hi)
+        scale = np.float32(hi - lo) / np.float32(4294967295.0)
+        return (self.raw(n).astype(np.float32) * scale + lo).astype(np.float32)
+
+
+# ---- builders ---------------------------------------------------------------------------------------
+def _default_lights():
+    # Builder::buildWorld: one invisible ambient light (Builder.cpp:43-47)
+    return [LightSpec("ambient", {"visible": False})]
+
+
+_CORNELL_QUADS = [
+    # Floor, Ceiling, Backwall, RightWall, LeftWall
+    [(1, -1, -1), (-1, -1, -1), (-1, -1, 1), (1, -1, 1)],
+    [(1, 1, -1), (1, 1, 1), (-1, 1, 1), (-1, 1, -1)],
+    [(1, -1, 1), (-1, -1, 1), (-1, 1, 1), (1, 1, 1)],
+    [(-1, -1, 1), (-1, -1, -1), (-1, 1, -1), (-1, 1, 1)],
+    [(1, -1, -1), (1, -1, 1), (1, 1, 1), (1, 1, -1)],
+    # ShortBox: top, left, front, right, back, bottom
+    [(-0.53, -0.40, -0.75), (-0.70, -0.40, -0.17), (-0.13, -0.40, -0.00), (0.05, -0.40, -0.57)],
+    [(0.05, -1.00, -0.57), (0.05, -0.40, -0.57), (-0.13, -0.40, -0.00), (-0.13, -1.00, -0.00)],
+    [(-0.53, -1.00, -0.75), (-0.53, -0.40, -0.75), (0.05, -0.40, -0.57), (0.05, -1.00, -0.57)],
+    [(-0.70, -1.00, -0.17), (-0.70, -0.40, -0.17), (-0.53, -0.40, -0.75), (-0.53, -1.00, -0.75)],
+    [(-0.13, -1.00, -0.00), (-0.13, -0.40, -0.00), (-0.70, -0.40, -0.17), (-0.70, -1.00, -0.17)],
+    [(-0.53, -1.00, -0.75), (-0.70, -1.00, -0.17), (-0.13, -1.00, -0.00), (0.05, -1.00, -0.57)],
+    # TallBox: top, left, front, right, back, bottom
+    [(0.53, 0.20, -0.09), (-0.04, 0.20, 0.09), (0.14, 0.20, 0.67), (0.71, 0.20, 0.49)],
+    [(0.53, -1.00, -0.09), (0.53, 0.20, -0.09), (0.71, 0.20, 0.49), (0.71, -1.00, 0.49)],
+    [(0.71, -1.00, 0.49), (0.71, 0.20, 0.49), (0.14, 0.20, 0.67), (0.14, -1.00, 0.67)],
+    [(0.14, -1.00, 0.67), (0.14, 0.20, 0.67), (-0.04, 0.20, 0.09), (-0.04, -1.00, 0.09)],
+    [(-0.04, -1.00, 0.09), (-0.04, 0.20, 0.09), (0.53, 0.20, -0.09), (0.53, -1.00, -0.09)],
+    [(0.53, -1.00, -0.09), (-0.04, -1.00, 0.09), (0.14, -1.00, 0.67), (0.71, -1.00, 0.49)],
+]
+_CORNELL_WHITE, _CORNELL_GREEN, _CORNELL_RED = (0.725, 0.710, 0.68, 1.0), (0.140, 0.450, 0.091, 1.0), (0.630, 0.065, 0.05, 1.0)
+
+
+def cornell_box():
+    """CornellBox.cpp:26-251: 17 quads as a quad soup with per-vertex colours, default obj material,
+    one quad light that replaces the builder's ambient light."""
+    verts = np.array([v for q in _CORNELL_QUADS for v in q], dtype=np.float32)
+    cols = []
+    for qi in range(len(_CORNELL_QUADS)):
+        c = _CORNELL_GREEN if qi == 3 else _CORNELL_RED if qi == 4 else _CORNELL_WHITE
+        cols += [c] * 4
+    geom = GeometrySpec("mesh", vertex=verts, quad_soup=True, vertex_color=np.array(cols, dtype=np.float32))
+    group = GroupSpec(models=[ModelSpec(geom, MaterialSpec())])
+    light = LightSpec("quad", {"color": (0.78, 0.551, 0.183), "intensity": 47.0, "position": (-0.23, 0.98, -0.16),
+                               "edge1": (0.47, 0.0, 0.0), "edge2": (0.0, 0.0, 0.38)})
+    return SceneSpec(instances=[InstanceSpec(group)], lights=[light])
+
+
+def boxes(dimensions=(4, 4, 4), lit=False):
+    """Boxes.cpp:40-105: a lattice of box primitives with per-primitive colours."""
+    dim = max(dimensions)
+    bl, cl = [], []
+    # index_sequence_3D iterates x fastest
+    for k in range(dimensions[2]):
+        for j in range(dimensions[1]):
+            for i in range(dimensions[0]):
+                f = np.array([i, j, k], dtype=np.float32)
+                lower = f * np.float32(5.0)
+                upper = lower + np.float32(0.75 * 5.0)
+                bl.append(np.concatenate([lower, upper]))
+                c = (np.float32(0.8) * f / np.float32(dim)) + np.float32(0.2)
+                cl.append([c[0], c[1], c[2], 1.0])
+    geom = GeometrySpec("box", boxes=np.array(bl, dtype=np.float32))
+    model = ModelSpec(geom, MaterialSpec(ks=(0.3, 0.3, 0.3), ns=10.0), color=np.array(cl, dtype=np.float32))
+    lights = _default_lights()
+    if lit:
+        lights = [LightSpec("distant", {"color": (0.78, 0.551, 0.483), "intensity": 3.14, "direction": (-0.8, -0.6, 0.3)}),
+                  LightSpec("ambient", {"intensity": 0.35, "visible": False})]
+    return SceneSpec(instances=[InstanceSpec(GroupSpec(models=[model]))], lights=lights)
+
+
+def _ground_plane(bounds_lower, bounds_upper):
+    """Builder::makeGroundPlane (Builder.cpp:95-200): a quad plus 2x10 stripes at y = -1."""
+    lo, hi = np.asarray(bounds_lower, np.float32), np.asarray(bounds_upper, np.float32)
+    center = 0.5 * (lo + hi)
+    extent = np.float32(0.8) * np.float32(np.linalg.norm(center - lo))
+    pos, col, idx = [], [], []
+    plane_color, stripe_color = (0.9, 0.9, 0.9, 1.0), (1.0, 0.1, 0.1, 1.0)
+
+    def quad(p0, p1, p2, p3, c):
+        s = len(pos)
+        pos.extend([p0, p1, p2, p3])
+        col.extend([c] * 4)
+        idx.append([s, s + 1, s + 2, s + 3])
+    quad((-extent, -1, -extent), (extent, -1, -extent), (extent, -1, extent), (-extent, -1, extent), plane_color)
+    sw = np.float32(0.025)
+    padded = extent + sw
+    y = np.float32(-1.0 + 1e-3)
+    for i in range(10):
+        coord = -extent + np.float32(i) / np.float32(9) * np.float32(2.0) * extent
+        quad((coord - sw, y, -padded), (coord + sw, y, -padded), (coord + sw, y, padded), (coord - sw, y, padded), stripe_color)
+        quad((-padded, y, coord - sw), (padded, y, coord - sw), (padded, y, coord + sw), (-padded, y, coord + sw), stripe_color)
+    n = len(pos)
+    geom = GeometrySpec("mesh", vertex=np.array(pos, np.float32), index=np.array(idx, np.uint32),
+                        vertex_color=np.array(col, np.float32), vertex_normal=np.tile(np.array([[0, 1, 0]], np.float32), (n, 1)))
+    return InstanceSpec(GroupSpec(models=[ModelSpec(geom, MaterialSpec())]))
+
+
+def random_spheres(num_spheres=100, seed=0, add_plane=True):
+    """RandomSpheres.cpp:42-111 (scivis / ao flavour: default obj material, per-sphere colours)."""
+    gen = Mt19937(seed)
+    centers = gen.uniform(-1, 1, 3 * num_spheres).reshape(num_spheres, 3)
+    radii = gen.uniform(0.05, 0.15, num_spheres)
+    colors = gen.uniform(0.5, 1.0, 4 * num_spheres).reshape(num_spheres, 4)
+    geom = GeometrySpec("sphere", sphere_position=centers, sphere_radius=radii)
+    group = GroupSpec(models=[ModelSpec(geom, MaterialSpec(), color=colors)])
+    inst = [InstanceSpec(group)]
+    if add_plane:
+        lo = (centers - radii[:, None]).min(axis=0)
+        hi = (centers + radii[:, None]).max(axis=0)
+        inst.append(_ground_plane(lo, hi))
+    return SceneSpec(instances=inst, lights=_default_lights())
+
+
+def jet_transfer_function():
+    colors = np.array([(0, 0, 0.562493), (0, 0, 1), (0, 1, 1), (0.500008, 1, 0.500008), (1, 1, 0), (1, 0, 0),
+                       (0.500008, 0, 0)], dtype=np.float32)
+    opacities = np.array([0.0, 1.0], dtype=np.float32)
+    return colors, opacities
+
+
+def gravity_spheres_voxels(dim=128, num_points=10, seed=0):
+    """GravitySpheresVolume.cpp:180-232"""
+    gen = Mt19937(seed)
+    pts = np.zeros((num_points, 4), dtype=np.float32)
+    for p in range(num_points):  # interleaved draws: x, y, z (centre dist) then weight
+        pts[p, 0:3] = gen.uniform(-1, 1, 3)
+        pts[p, 3] = gen.uniform(0.1, 0.3, 1)[0]
+    ax = (np.float32(-1.0) + np.arange(dim, dtype=np.float32) / np.float32(dim - 1) * np.float32(2.0)).astype(np.float32)
+    z, y, x = np.meshgrid(ax, ax, ax, indexing="ij")
+    vox = np.zeros((dim, dim, dim), dtype=np.float32)
+    for p in range(num_points):
+        dx, dy, dz = x - pts[p, 0], y - pts[p, 1], z - pts[p, 2]
+        d2 = (dx * dx + dy * dy + dz * dz).astype(np.float32)
+        dist = np.sqrt(d2).astype(np.float32)
+        with np.errstate(divide="ignore"):
+            vox += (pts[p, 3] / (dist * dist)).astype(np.float32)
+    return vox
+
+
+def gravity_spheres_volume(dim=128, seed=0):
+    """GravitySpheresVolume.cpp:68-134,234-253: one structuredRegular volume, jet/linear TF over [0,10]."""
+    vox = gravity_spheres_voxels(dim, 10, seed)
+    colors, opac = jet_transfer_function()
+    s = np.float32(2.0) / np.float32(dim)
+    vol = VolumeSpec(vox, grid_origin=(-1.0, -1.0, -1.0), grid_spacing=(float(s),) * 3, tf_colors=colors, tf_opacities=opac,
+                     value_range=(0.0, 10.0))
+    return SceneSpec(instances=[InstanceSpec(GroupSpec(volumes=[vol]))], lights=_default_lights())
+
+
+def box_mesh(n_boxes_per_axis, seed=0, jitter=0.25):
+    """synthetic stress mesh: K^3 jittered boxes, 12 triangles each, one indexed mesh."""
+    K = int(n_boxes_per_axis)
+    gen = Mt19937(seed)
+    nb = K * K * K
+    ii, jj, kk = np.meshgrid(np.arange(K), np.arange(K), np.arange(K), indexing="ij")
+    base = np.stack([ii.ravel(), jj.ravel(), kk.ravel()], axis=1).astype(np.float32)
+    off = gen.uniform(-jitter, jitter, 3 * nb).reshape(nb, 3)
+    size = gen.uniform(0.25, 0.45, nb).astype(np.float32)
+    c = (base + off + 0.5) / np.float32(K) * 2.0 - 1.0
+    h = (size / np.float32(K))[:, None]
+    corners = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], np.float32)
+    verts = (c[:, None, :] + corners[None, :, :] * h[:, None, :]).reshape(-1, 3).astype(np.float32)
+    tri = np.array([[0, 2, 1], [0, 3, 2], [4, 5, 6], [4, 6, 7], [0, 1, 5], [0, 5, 4], [2, 3, 7], [2, 7, 6], [1, 2, 6], [1, 6, 5],
+                    [0, 4, 7], [0, 7, 3]], np.uint32)
+    index = (tri[None, :, :] + (np.arange(nb, dtype=np.uint32) * 8)[:, None, None]).reshape(-1, 3).astype(np.uint32)
+    colors = np.concatenate([0.3 + 0.7 * (c * 0.5 + 0.5), np.ones((nb, 1), np.float32)], axis=1).astype(np.float32)
+    vcol = np.repeat(colors, 8, axis=0)
+    geom = GeometrySpec("mesh", vertex=verts, index=index, vertex_color=vcol)
+    return SceneSpec(instances=[InstanceSpec(GroupSpec(models=[ModelSpec(geom, MaterialSpec())]))], lights=_default_lights())
+
+
+BUILDERS = {"cornell_box": cornell_box, "boxes": boxes, "random_spheres": random_spheres,
+            "gravity_spheres_volume": gravity_spheres_volume, "box_mesh": box_mesh}
+
+
+# ---- arcball camera ------------------------------------------------------------------------------------
+def arcball_camera(bounds_lower, bounds_upper):
+    """ArcballCamera ctor + eyePos/lookDir/upDir for the un-rotated camera (ArcballCamera.cpp:6-24,53-71)"""
+    lo, hi = np.asarray(bounds_lower, np.float32), np.asarray(bounds_upper, np.float32)
+    diag = (hi - lo).astype(np.float32)
+    diag = np.maximum(diag, np.float32(0.3) * np.float32(np.linalg.norm(diag))).astype(np.float32)
+    center = (np.float32(0.5) * (lo + hi)).astype(np.float32)
+    dist = np.float32(np.linalg.norm(diag))
+    eye = center + np.array([0, 0, np.float32(1.0) - dist], dtype=np.float32)
+    return {"position": tuple(float(v) for v in eye), "direction": (0.0, 0.0, 1.0), "up": (0.0, 1.0, 0.0)}
+
+
+# ---- replay a spec through the OSPRay API -----------------------------------------------------------------
+def _geometry(g: GeometrySpec):
+    geo = osp.Geometry(g.type)
+    if g.type == "mesh":
+        geo.set("vertex.position", g.vertex)
+        if g.vertex_color is not None:
+            geo.set("vertex.color", g.vertex_color)
+        if g.vertex_normal is not None:
+            geo.set("vertex.normal", g.vertex_normal)
+        if g.index is not None:
+            geo.set("index", g.index)
+        elif g.quad_soup:
+            geo.set("quadSoup", True)
+    elif g.type == "sphere":
+        geo.set("sphere.position", g.sphere_position)
+        if g.sphere_radius is not None:
+            geo.set("sphere.radius", g.sphere_radius)
+        else:
+            geo.set("radius", float(g.radius))
+    elif g.type == "box":
+        geo.set("box", g.boxes)
+    return geo.commit()
+
+
+def _material(m: MaterialSpec):
+    mat = osp.Material(m.type)
+    d = MaterialSpec()
+    if m.kd != d.kd: mat.set("kd", tuple(float(x) for x in m.kd))
+    if m.ks != d.ks: mat.set("ks", tuple(float(x) for x in m.ks))
+    if m.ns != d.ns or m.ks != d.ks: mat.set("ns", float(m.ns))
+    if m.d != d.d: mat.set("d", float(m.d))
+    if m.tf != d.tf: mat.set("tf", tuple(float(x) for x in m.tf))
+    return mat.commit()
+
+
+def to_ospray(scene: SceneSpec):
+    """returns (world, keepalive list)"""
+    keep = []
+    instances = []
+    for inst in scene.instances:
+        models, vmodels = [], []
+        for ms in inst.group.models:
+            geo = _geometry(ms.geometry)
+            model = osp.GeometricModel(geo)
+            if ms.material is not None:
+                model.set("material", _material(ms.material))
+            if ms.color is not None:
+                model.set("color", ms.color)
+            if ms.id is not None:
+                model.set("id", osp.Typed(osp.OSP_UINT, ms.id))
+            models.append(model.commit())
+        for vs in inst.group.volumes:
+            vol = osp.Volume("structuredRegular")
+            vol.set("gridOrigin", tuple(float(x) for x in vs.grid_origin))
+            vol.set("gridSpacing", tuple(float(x) for x in vs.grid_spacing))
+            vol.set("data", vs.voxels)
+            vol.commit()
+            tf = osp.TransferFunction("piecewiseLinear")
+            tf.set("color", vs.tf_colors).set("opacity", vs.tf_opacities)
+            tf.set("value", osp.Typed(osp.OSP_BOX1F, vs.value_range)).commit()
+            vm = osp.VolumetricModel(vol)
+            vm.set("transferFunction", tf)
+            if vs.density_scale != 1.0: vm.set("densityScale", float(vs.density_scale))
+            if vs.gradient_shading_scale != 0.0: vm.set("gradientShadingScale", float(vs.gradient_shading_scale))
+            vmodels.append(vm.commit())
+            keep += [vol, tf]
+        group = osp.Group()
+        if models: group.set("geometry", models)
+        if vmodels: group.set("volume", vmodels)
+        group.commit()
+        oi = osp.Instance(group)
+        if inst.xfm is not None:
+            oi.set("transform", osp.Typed(osp.OSP_AFFINE3F, np.asarray(inst.xfm, np.float32)))
+        if inst.id is not None:
+            oi.set("id", osp.Typed(osp.OSP_UINT, inst.id))
+        instances.append(oi.commit())
+        keep += models + vmodels + [group]
+    world = osp.World()
+    if instances:
+        world.set("instance", instances)
+    lights = []
+    for ls in scene.lights:
+        l = osp.Light(ls.type)
+        for k, v in ls.params.items():
+            l.set(k, v)
+        lights.append(l.commit())
+    if lights:
+        world.set("light", lights)
+    world.commit()
+    keep += instances + lights
+    return world, keep
+
+
+def make_camera(world, width, height):
+    """BaseFixture::Init camera (BaseFixture.cpp:36-47)"""
+    lo, hi = world.bounds()
+    p = arcball_camera(lo, hi)
+    cam = osp.Camera("perspective")
+    cam.set("aspect", float(np.float32(width) / np.float32(height)))
+    cam.set("position", p["position"]).set("direction", p["direction"]).set("up", p["up"])
+    return cam.commit(), p
+
+
+def make_renderer(kind, **params):
+    r = osp.Renderer(kind)
+    for k, v in params.items():
+        r.set(k, v)
+    return r.commit()

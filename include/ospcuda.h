@@ -289,6 +289,8 @@ OSPCUDA_API int ospcuda_event_synchronize(void *ev);
 OSPCUDA_API int ospcuda_event_query(void *ev); /* 1 done, 0 pending, <0 error */
 OSPCUDA_API int ospcuda_event_elapsed_ms(void *start, void *stop, float *ms);
 OSPCUDA_API void *ospcuda_stream(void); /* cudaStream_t of the render stream */
+/* render on an externally owned cudaStream_t (NULL: back to the library's own stream); drains the old one */
+OSPCUDA_API int ospcuda_set_stream(void *stream);
 OSPCUDA_API unsigned long long ospcuda_kernel_launch_count(void);
 
 /* ---- scene build ------------------------------------------------------------------- */
@@ -325,6 +327,15 @@ OSPCUDA_API int ospcuda_fb_postprocess(const OcVec4f *d_in, OcVec4f *d_ppOut, vo
 /* copy the 64x64 tiles owned by `srcRank` (tile % numRanks == srcRank) from a rank-local
  * full-size image into dst (both device, row-major, bytesPerPixel each) */
 OSPCUDA_API int ospcuda_fb_gather_tiles(void *d_dst, const void *d_src, int sizeX, int sizeY,
+    uint32_t bytesPerPixel, uint32_t numRanks, uint32_t srcRank);
+
+/* NCCL tile gather staging (the multi-device path, modules/multiDevice/MultiDeviceLoadBalancer.cpp:41-47 +
+ * fb/LocalFB.cpp:286-353 writeTiles): pack copies the 64x64 tiles owned by `rank` (tile % numRanks == rank)
+ * from a row-major image into a tile-major buffer (owned tile k at k*64*64*bytesPerPixel, border tiles
+ * padded); unpack scatters a received shard of `srcRank` into the row-major image on GPU 0. */
+OSPCUDA_API int ospcuda_fb_pack_tiles(void *d_packed, const void *d_image, int sizeX, int sizeY,
+    uint32_t bytesPerPixel, uint32_t numRanks, uint32_t rank);
+OSPCUDA_API int ospcuda_fb_unpack_tiles(void *d_image, const void *d_packed, int sizeX, int sizeY,
     uint32_t bytesPerPixel, uint32_t numRanks, uint32_t srcRank);
 
 #ifdef __cplusplus

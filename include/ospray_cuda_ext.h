@@ -20,6 +20,15 @@ OSPRAY_INTERFACE float ospcudaGetGroupBuildTime(OSPGroup);
 OSPRAY_INTERFACE uint64_t ospcudaKernelLaunchCount(void);
 /* cudaStream_t the device renders on (so that external consumers can order after a frame) */
 OSPRAY_INTERFACE void *ospcudaRenderStream(void);
+/* device time of a finished frame in ms: [0] the renderer kernel (incl. fused accumulation), [1] post-processing
+ * (variance / tone mapping / colour conversion); CUDA events on the render stream */
+OSPRAY_INTERFACE void ospcudaGetFrameStageTimes(OSPFuture, float ms[2]);
+/* render on an external cudaStream_t (e.g. torch's current stream, so NCCL and event timing order with the
+ * frame); NULL returns to the device's own stream */
+OSPRAY_INTERFACE void ospcudaSetRenderStream(void *stream);
+/* device pointer of the committed world's OcWorld (include/ospcuda.h), valid until the next commit;
+ * lets a consumer call the batch traversal entry point ospcuda_trace directly */
+OSPRAY_INTERFACE const void *ospcudaWorldDevicePointer(OSPWorld);
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,528 @@
+"""Python front end of the CPU oracle (liboracle.so).  TEST INFRASTRUCTURE ONLY -- see oracle.cpp.
+
+Builds the host-pointer scene description (the POD structs of include/ospcuda.h, mirrored here with
+ctypes) from an `ospray_b200.testing.SceneSpec`, following the reference's commit() functions:
+  geometry/Mesh.cpp:37-204 (soup index = iota), Spheres.cpp:46-106 (interleave xyz+r),
+  geometry/GeometricModel.cpp:21-87, render/materials/OBJ.cpp:30-66 (energy normalisation),
+  volume/Volume.cpp:60-222 + VolumetricModel.cpp:29-82, common/World.cpp:70-188,
+  render/pathtracer/PathTracerData.cpp:32-82 (uniform light CDF), render/scivis/SciVisData.cpp:17-105,
+  render/Renderer.cpp:38-92, PathTracer.cpp:29-51, SciVis.cpp:27-36, AORenderer.cpp:26-35.
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may import this."""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+INVALID_ID = 0xFFFFFFFF
+OC_GEOM_TRIANGLES, OC_GEOM_QUADS, OC_GEOM_SPHERES, OC_GEOM_BOXES = 0, 1, 2, 3
+OC_GEOMFLAG_NORMAL_FV, OC_GEOMFLAG_COLOR_FV, OC_GEOMFLAG_TEX_FV, OC_GEOMFLAG_HAS_ALPHA, OC_GEOMFLAG_COLOR_VEC4 = 1, 2, 4, 8, 16
+OC_MAT_NONE, OC_MAT_FROM_MODEL, OC_MAT_FROM_RENDERER = 0, 1, 2
+OC_LIGHT_AMBIENT, OC_LIGHT_DISTANT, OC_LIGHT_QUAD = 0, 2, 5
+OC_RENDERER = {"pathtracer": 0, "scivis": 1, "ao": 2}
+OC_PF_POINT, OC_PF_BOX, OC_PF_LUT = 0, 1, 2
+
+
+class Vec3(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
+
+
+class Vec4(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float), ("w", C.c_float)]
+
+
+class Affine(C.Structure):
+    _fields_ = [("vx", Vec3), ("vy", Vec3), ("vz", Vec3), ("p", Vec3)]
+
+
+class Data1D(C.Structure):
+    _fields_ = [("addr", C.c_void_p), ("byteStride", C.c_int64), ("numItems", C.c_uint32), ("pad", C.c_uint32)]
+
+
+class Geometry(C.Structure):
+    _fields_ = [("type", C.c_uint32), ("numPrims", C.c_uint32), ("flags", C.c_uint32), ("pad", C.c_uint32),
+                ("index", Data1D), ("vertex", Data1D), ("normal", Data1D), ("color", Data1D), ("texcoord", Data1D),
+                ("sphere", Data1D), ("box", Data1D)]
+
+
+class Model(C.Structure):
+    _fields_ = [("geom", C.POINTER(Geometry)), ("color", Data1D), ("index", Data1D), ("material", C.POINTER(C.c_uint32)),
+                ("numMaterials", C.c_uint32), ("materialMode", C.c_uint32), ("invertedNormals", C.c_uint32), ("userID", C.c_uint32)]
+
+
+class Material(C.Structure):
+    _fields_ = [("type", C.c_uint32), ("d", C.c_float), ("Kd", Vec3), ("Ks", Vec3), ("Ns", C.c_float), ("Tf", Vec3),
+                ("pad", C.c_float * 4)]
+
+
+class BVH(C.Structure):
+    _fields_ = [("nodes", C.c_void_p), ("prims", C.c_void_p), ("numNodes", C.c_uint32), ("numRecords", C.c_uint32),
+                ("bounds", C.c_float * 6)]
+
+
+class TransferFunction(C.Structure):
+    _fields_ = [("color", C.c_void_p), ("opacity", C.c_void_p), ("numColors", C.c_uint32), ("numOpacities", C.c_uint32),
+                ("valueLower", C.c_float), ("valueUpper", C.c_float)]
+
+
+class Volume(C.Structure):
+    _fields_ = [("voxels", C.c_void_p), ("dims", C.c_uint32 * 3), ("mcDims", C.c_uint32 * 3), ("mcRange", C.c_void_p),
+                ("gridOrigin", Vec3), ("gridSpacing", Vec3), ("bounds", C.c_float * 6), ("tf", TransferFunction),
+                ("densityScale", C.c_float), ("anisotropy", C.c_float), ("gradientShadingScale", C.c_float),
+                ("userID", C.c_uint32), ("numRanges", C.c_uint32), ("ranges", C.c_float * 16)]
+
+
+class Group(C.Structure):
+    _fields_ = [("models", C.POINTER(Model)), ("numModels", C.c_uint32), ("numVolumes", C.c_uint32),
+                ("volumes", C.POINTER(Volume)), ("bvh", BVH)]
+
+
+class Instance(C.Structure):
+    _fields_ = [("xfm", Affine), ("rcp_xfm", Affine), ("group", C.POINTER(Group)), ("userID", C.c_uint32),
+                ("isIdentity", C.c_uint32), ("bounds", C.c_float * 6)]
+
+
+class Light(C.Structure):
+    _fields_ = [("type", C.c_uint32), ("isVisible", C.c_uint32), ("radiance", Vec3), ("position", Vec3), ("edge1", Vec3),
+                ("edge2", Vec3), ("nnormal", Vec3), ("ppdf", C.c_float), ("fx", Vec3), ("fy", Vec3), ("fz", Vec3),
+                ("cosAngle", C.c_float), ("pdf", C.c_float)]
+
+
+class World(C.Structure):
+    _fields_ = [("instances", C.POINTER(Instance)), ("numInstances", C.c_uint32), ("hasVolumes", C.c_uint32), ("tlas", BVH),
+                ("materials", C.POINTER(Material)), ("numMaterials", C.c_uint32), ("numLights", C.c_uint32),
+                ("lights", C.POINTER(Light)), ("lightsCDF", C.POINTER(C.c_float)), ("scivisLights", C.POINTER(Light)),
+                ("numScivisLights", C.c_uint32), ("numScivisLightsVisibleOnly", C.c_uint32), ("aoColorPi", Vec3),
+                ("bounds", C.c_float * 6)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("org", Vec3), ("dir_00", Vec3), ("du_size", Vec3), ("dv_up", Vec3), ("direction", Vec3),
+                ("nearClip", C.c_float), ("subImage", C.c_float * 4), ("scaledAperture", C.c_float), ("aspect", C.c_float),
+                ("imgPlaneSizeY", C.c_float), ("needLensSample", C.c_uint32), ("needTimeSample", C.c_uint32)]
+
+
+class Renderer(C.Structure):
+    _fields_ = [("type", C.c_uint32), ("spp", C.c_int32), ("maxDepth", C.c_uint32), ("minContribution", C.c_float),
+                ("bgColor", C.c_float * 4), ("pfType", C.c_uint32), ("pfWidth", C.c_float), ("pfLutW", C.c_uint32),
+                ("pfLutH", C.c_uint32), ("pfCdfX", C.POINTER(C.c_float)), ("pfCdfY", C.POINTER(C.c_float)),
+                ("materials", C.POINTER(C.c_uint32)), ("numMaterials", C.c_uint32), ("rouletteDepth", C.c_int32),
+                ("maxScatteringEvents", C.c_int32), ("maxRadiance", C.c_float), ("numLightSamples", C.c_int32),
+                ("limitIndirectLightSamples", C.c_uint32), ("backgroundRefraction", C.c_uint32),
+                ("shadowsEnabled", C.c_uint32), ("visibleLights", C.c_uint32), ("aoSamples", C.c_int32),
+                ("aoRadius", C.c_float), ("aoIntensity", C.c_float), ("volumeSamplingRate", C.c_float)]
+
+
+class FrameBuffer(C.Structure):
+    _fields_ = [("sizeX", C.c_int32), ("sizeY", C.c_int32), ("frameID", C.c_int32), ("channels", C.c_uint32),
+                ("accumulateVariance", C.c_uint32), ("projectedDepth", C.c_uint32), ("targetFrames", C.c_int32),
+                ("colorFormat", C.c_uint32), ("color", C.c_void_p), ("variance", C.c_void_p), ("depth", C.c_void_p),
+                ("normal", C.c_void_p), ("firstNormal", C.c_void_p), ("albedo", C.c_void_p), ("position", C.c_void_p),
+                ("primID", C.c_void_p), ("objID", C.c_void_p), ("instID", C.c_void_p), ("numRanks", C.c_uint32),
+                ("rank", C.c_uint32), ("rayCounters", C.c_void_p)]
+
+
+class ToneMapper(C.Structure):
+    _fields_ = [("exposure", C.c_float), ("a", C.c_float), ("b", C.c_float), ("c", C.c_float), ("d", C.c_float),
+                ("acesColor", C.c_uint32)]
+
+
+class RayHit(C.Structure):
+    _fields_ = [("org", C.c_float * 3), ("t0", C.c_float), ("dir", C.c_float * 3), ("t", C.c_float), ("Ng", C.c_float * 3),
+                ("u", C.c_float), ("v", C.c_float), ("primID", C.c_uint32), ("geomID", C.c_uint32), ("instID", C.c_uint32)]
+
+
+RAYHIT_DTYPE = np.dtype([("org", "<f4", 3), ("t0", "<f4"), ("dir", "<f4", 3), ("t", "<f4"), ("Ng", "<f4", 3), ("u", "<f4"),
+                         ("v", "<f4"), ("primID", "<u4"), ("geomID", "<u4"), ("instID", "<u4")])
+assert RAYHIT_DTYPE.itemsize == C.sizeof(RayHit) == 64
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        p = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(p):
+            raise RuntimeError(f"{p} missing: run `make -C oracle` (or __graft_entry__.build())")
+        L = C.CDLL(p)
+        L.oracle_render_frame.argtypes = [C.POINTER(World), C.POINTER(Camera), C.POINTER(Renderer), C.POINTER(FrameBuffer), C.c_int]
+        L.oracle_trace.argtypes = [C.POINTER(World), C.c_void_p, C.c_uint32, C.c_int]
+        L.oracle_camera_rays.argtypes = [C.POINTER(Camera), C.POINTER(Renderer), C.POINTER(FrameBuffer), C.c_void_p, C.c_void_p,
+                                         C.c_uint32, C.c_int, C.c_void_p]
+        L.oracle_sampler_kat.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.oracle_gauss_pixelfilter_lut.argtypes = [C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+        F3 = C.c_float * 3
+        L.oracle_commit_camera.argtypes = [F3, F3, F3, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(Camera)]
+        L.oracle_commit_light.argtypes = [C.c_int, F3, C.c_float, C.c_int, F3, F3, F3, F3, C.c_float, C.POINTER(Light)]
+        L.oracle_fb_accumulate.argtypes = [C.POINTER(FrameBuffer), C.c_void_p, C.c_void_p]
+        L.oracle_fb_variance.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.oracle_fb_tonemap.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(ToneMapper)]
+        L.oracle_fb_color_convert.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.oracle_fb_gather_tiles.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.oracle_hardware_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+def _data1d(arr, keep):
+    a = np.ascontiguousarray(arr)
+    keep.append(a)
+    stride = a.strides[0] if a.ndim > 0 else a.itemsize
+    return Data1D(a.ctypes.data, stride, a.shape[0], 0)
+
+
+def _affine(m):
+    m = np.asarray(m, np.float32).reshape(4, 3)
+    return Affine(*[Vec3(*[float(x) for x in m[i]]) for i in range(4)])
+
+
+def _rcp_affine(m):
+    """rkcommon rcp(AffineSpace3f): adjoint/determinant in float32"""
+    m = np.asarray(m, np.float32).reshape(4, 3)
+    vx, vy, vz, p = m
+    c0, c1, c2 = np.cross(vy, vz), np.cross(vz, vx), np.cross(vx, vy)
+    det = np.float32(np.dot(vx, c0))
+    r = np.float32(1.0) / det
+    l = (np.stack([c0, c1, c2], axis=1) * r).astype(np.float32)  # columns of the inverse
+    lx, ly, lz = l[0], l[1], l[2]
+    np_ = -(p[0] * lx + p[1] * ly + p[2] * lz).astype(np.float32)
+    return np.stack([lx, ly, lz, np_]).astype(np.float32)
+
+
+def _xfm_bounds(m, lo, hi):
+    m = np.asarray(m, np.float32).reshape(4, 3)
+    pts = []
+    for i in range(8):
+        c = np.array([hi[0] if i & 1 else lo[0], hi[1] if i & 2 else lo[1], hi[2] if i & 4 else lo[2]], np.float32)
+        pts.append(c[0] * m[0] + c[1] * m[1] + c[2] * m[2] + m[3])
+    pts = np.array(pts, np.float32)
+    return pts.min(axis=0), pts.max(axis=0)
+
+
+class Scene:
+    """host-pointer OcWorld built from a SceneSpec; keeps every numpy / ctypes buffer alive"""
+
+    def __init__(self, spec):
+        self.keep = []
+        self.materials = []
+        L = lib()
+        insts = []
+        wlo, whi = np.full(3, np.inf, np.float32), np.full(3, -np.inf, np.float32)
+        has_volumes = 0
+        for ispec in spec.instances:
+            models = []
+            glo, ghi = np.full(3, np.inf, np.float32), np.full(3, -np.inf, np.float32)
+            for ms in ispec.group.models:
+                g, lo, hi = self._geometry(ms.geometry)
+                glo, ghi = np.minimum(glo, lo), np.maximum(ghi, hi)
+                m = Model()
+                m.geom = C.pointer(g)
+                self.keep.append(g)
+                m.materialMode = OC_MAT_NONE
+                if ms.material is not None:
+                    slot = self._material(ms.material)
+                    arr = (C.c_uint32 * 1)(slot)
+                    self.keep.append(arr)
+                    m.material = C.cast(arr, C.POINTER(C.c_uint32))
+                    m.numMaterials = 1
+                    m.materialMode = OC_MAT_FROM_MODEL
+                if ms.color is not None:
+                    m.color = _data1d(np.asarray(ms.color, np.float32), self.keep)
+                m.userID = INVALID_ID if ms.id is None else ms.id
+                models.append(m)
+            vols = []
+            for vs in ispec.group.volumes:
+                v, lo, hi = self._volume(vs)
+                glo, ghi = np.minimum(glo, lo), np.maximum(ghi, hi)
+                vols.append(v)
+                has_volumes = 1
+            grp = Group()
+            if models:
+                marr = (Model * len(models))(*models)
+                self.keep.append(marr)
+                grp.models = C.cast(marr, C.POINTER(Model))
+                grp.numModels = len(models)
+            if vols:
+                varr = (Volume * len(vols))(*vols)
+                self.keep.append(varr)
+                grp.volumes = C.cast(varr, C.POINTER(Volume))
+                grp.numVolumes = len(vols)
+            self.keep.append(grp)
+            inst = Instance()
+            ident = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], np.float32)
+            xfm = ident if ispec.xfm is None else np.asarray(ispec.xfm, np.float32).ravel()
+            inst.xfm = _affine(xfm)
+            inst.rcp_xfm = _affine(_rcp_affine(xfm))
+            inst.group = C.pointer(grp)
+            inst.userID = INVALID_ID if ispec.id is None else ispec.id
+            inst.isIdentity = int(np.array_equal(xfm, ident))
+            lo, hi = (glo, ghi) if inst.isIdentity else _xfm_bounds(xfm, glo, ghi)
+            for k in range(3):
+                inst.bounds[k], inst.bounds[3 + k] = float(lo[k]), float(hi[k])
+            wlo, whi = np.minimum(wlo, lo), np.maximum(whi, hi)
+            insts.append(inst)
+        w = World()
+        if insts:
+            iarr = (Instance * len(insts))(*insts)
+            self.keep.append(iarr)
+            w.instances = C.cast(iarr, C.POINTER(Instance))
+            w.numInstances = len(insts)
+        w.hasVolumes = has_volumes
+        if self.materials:
+            marr = (Material * len(self.materials))(*self.materials)
+            self.keep.append(marr)
+            w.materials = C.cast(marr, C.POINTER(Material))
+            w.numMaterials = len(self.materials)
+        # lights: PathTracerData (world lights in order, uniform CDF) and SciVisData (ambient first)
+        pt, sv, visible_only = [], [], 0
+        ao = np.zeros(3, np.float32)
+        for ls in spec.lights:
+            l = Light()
+            p = ls.params
+            t = {"ambient": OC_LIGHT_AMBIENT, "distant": OC_LIGHT_DISTANT, "quad": OC_LIGHT_QUAD}[ls.type]
+            L.oracle_commit_light(t, _f3(p.get("color", (1, 1, 1))), float(p.get("intensity", 1.0)), int(p.get("visible", True)),
+                                  _f3(p.get("position", (0, 0, 0))), _f3(p.get("edge1", (1, 0, 0))), _f3(p.get("edge2", (0, 1, 0))),
+                                  _f3(p.get("direction", (0, 0, 1))), float(p.get("angularDiameter", 0.0)), C.byref(l))
+            pt.append(l)
+            if t == OC_LIGHT_AMBIENT:
+                if visible_only == len(sv):
+                    sv.append(l)
+                else:
+                    sv.append(sv[visible_only])
+                    sv[visible_only] = l
+                visible_only += 1
+                ao += np.array([l.radiance.x, l.radiance.y, l.radiance.z], np.float32)
+            else:
+                sv.append(l)
+        if pt:
+            parr, sarr = (Light * len(pt))(*pt), (Light * len(sv))(*sv)
+            n = len(pt)
+            cdf = np.cumsum(np.ones(n, np.float32), dtype=np.float32)
+            total = cdf[-1]
+            cdf = np.where(cdf >= total, np.float32(1.0000001192092896), cdf * (np.float32(1.0) / total)).astype(np.float32)
+            self.keep += [parr, sarr, cdf]
+            w.lights = C.cast(parr, C.POINTER(Light))
+            w.scivisLights = C.cast(sarr, C.POINTER(Light))
+            w.lightsCDF = cdf.ctypes.data_as(C.POINTER(C.c_float))
+        w.numLights = len(pt)
+        w.numScivisLights = len(sv)
+        w.numScivisLightsVisibleOnly = visible_only
+        aopi = (ao * np.float32(np.pi)).astype(np.float32)
+        w.aoColorPi = Vec3(float(aopi[0]), float(aopi[1]), float(aopi[2]))
+        for k in range(3):
+            w.bounds[k], w.bounds[3 + k] = float(wlo[k]), float(whi[k])
+        self.world = w
+        self.bounds = (wlo, whi)
+
+    def _material(self, ms):
+        m = Material()
+        if ms.type == "obj":
+            kd, ks, tf = (np.asarray(x, np.float32) for x in (ms.kd, ms.ks, ms.tf))
+            total = np.float32(np.max(kd + ks + tf))
+            if total > 1.0:
+                kd, ks, tf = kd / total, ks / total, tf / total
+            m.type, m.d, m.Ns = 0, float(ms.d), float(ms.ns)
+            m.Kd, m.Ks, m.Tf = Vec3(*map(float, kd)), Vec3(*map(float, ks)), Vec3(*map(float, tf))
+        else:
+            m.type = 1
+        self.materials.append(m)
+        return len(self.materials) - 1
+
+    def _geometry(self, gs):
+        g = Geometry()
+        if gs.type == "mesh":
+            v = np.asarray(gs.vertex, np.float32)
+            if gs.index is not None:
+                idx = np.asarray(gs.index, np.uint32)
+            else:
+                e = 4 if gs.quad_soup else 3
+                idx = np.arange((len(v) // e) * e, dtype=np.uint32).reshape(-1, e)
+            g.type = OC_GEOM_TRIANGLES if idx.shape[1] == 3 else OC_GEOM_QUADS
+            g.numPrims = len(idx)
+            g.index, g.vertex = _data1d(idx, self.keep), _data1d(v, self.keep)
+            flags = OC_GEOMFLAG_TEX_FV  # texcoord absent: the device flags it face-varying by default
+            if gs.vertex_normal is not None:
+                g.normal = _data1d(np.asarray(gs.vertex_normal, np.float32), self.keep)
+            else:
+                flags |= OC_GEOMFLAG_NORMAL_FV
+            if gs.vertex_color is not None:
+                c = np.asarray(gs.vertex_color, np.float32)
+                g.color = _data1d(c, self.keep)
+                if c.shape[1] == 4:
+                    flags |= OC_GEOMFLAG_HAS_ALPHA | OC_GEOMFLAG_COLOR_VEC4
+            else:
+                flags |= OC_GEOMFLAG_COLOR_FV
+            g.flags = flags
+            used = v[idx.ravel()]
+            return g, used.min(axis=0), used.max(axis=0)
+        if gs.type == "sphere":
+            pos = np.asarray(gs.sphere_position, np.float32)
+            rad = np.asarray(gs.sphere_radius, np.float32) if gs.sphere_radius is not None else np.full(len(pos), gs.radius, np.float32)
+            inter = np.concatenate([pos, rad[:, None]], axis=1).astype(np.float32)
+            g.type, g.numPrims = OC_GEOM_SPHERES, len(pos)
+            g.sphere = _data1d(inter, self.keep)
+            return g, (pos - rad[:, None]).min(axis=0), (pos + rad[:, None]).max(axis=0)
+        b = np.asarray(gs.boxes, np.float32)
+        g.type, g.numPrims = OC_GEOM_BOXES, len(b)
+        g.box = _data1d(b, self.keep)
+        return g, b[:, :3].min(axis=0), b[:, 3:].max(axis=0)
+
+    def _volume(self, vs):
+        v = Volume()
+        vox = np.ascontiguousarray(vs.voxels, np.float32)
+        self.keep.append(vox)
+        v.voxels = vox.ctypes.data
+        dz, dy, dx = vox.shape
+        v.dims[0], v.dims[1], v.dims[2] = dx, dy, dz
+        go, gs_ = np.asarray(vs.grid_origin, np.float32), np.asarray(vs.grid_spacing, np.float32)
+        v.gridOrigin, v.gridSpacing = Vec3(*map(float, go)), Vec3(*map(float, gs_))
+        hi = (go + np.array([dx - 1, dy - 1, dz - 1], np.float32) * gs_).astype(np.float32)
+        for k in range(3):
+            v.bounds[k], v.bounds[3 + k] = float(go[k]), float(hi[k])
+        col, opa = np.ascontiguousarray(vs.tf_colors, np.float32), np.ascontiguousarray(vs.tf_opacities, np.float32)
+        self.keep += [col, opa]
+        v.tf = TransferFunction(col.ctypes.data, opa.ctypes.data, len(col), len(opa), float(vs.value_range[0]), float(vs.value_range[1]))
+        v.densityScale, v.anisotropy, v.gradientShadingScale = float(vs.density_scale), 0.0, float(vs.gradient_shading_scale)
+        v.userID = INVALID_ID
+        v.numRanges = 1
+        v.ranges[0], v.ranges[1] = -np.inf, np.inf
+        return v, go, hi
+
+
+def make_camera(position, direction=(0, 0, 1), up=(0, 1, 0), fovy=60.0, aspect=1.0, aperture_radius=0.0, focus_distance=1.0):
+    cam = Camera()
+    lib().oracle_commit_camera(_f3(position), _f3(direction), _f3(up), fovy, float(np.float32(aspect)), aperture_radius, focus_distance, C.byref(cam))
+    return cam
+
+
+class RendererParams:
+    """OcRenderer with the reference defaults (Renderer.cpp:38-92 etc.); keeps the pixel-filter LUT alive"""
+
+    def __init__(self, kind, pixelSamples=1, pixelFilter="gauss", maxPathLength=20, minContribution=0.001, backgroundColor=(0, 0, 0, 0),
+                 roulettePathLength=5, maxScatteringEvents=20, maxContribution=np.inf, lightSamples=-1, limitIndirectLightSamples=True,
+                 backgroundRefraction=False, shadows=False, visibleLights=False, aoSamples=None, aoDistance=1e20, aoIntensity=1.0,
+                 volumeSamplingRate=1.0):
+        r = Renderer()
+        r.type, r.spp, r.maxDepth, r.minContribution = OC_RENDERER[kind], max(1, pixelSamples), maxPathLength, minContribution
+        bg = list(backgroundColor) + [0.0] * (4 - len(backgroundColor))
+        for k in range(4):
+            r.bgColor[k] = float(bg[k])
+        if pixelFilter == "point":
+            r.pfType, r.pfWidth = OC_PF_POINT, 0.0
+        elif pixelFilter == "box":
+            r.pfType, r.pfWidth = OC_PF_BOX, 1.0
+        else:
+            lut = 15
+            self.cdfx, self.cdfy = np.zeros(lut * lut, np.float32), np.zeros(lut, np.float32)
+            lib().oracle_gauss_pixelfilter_lut(3.0, lut, self.cdfx.ctypes.data, self.cdfy.ctypes.data)
+            r.pfType, r.pfWidth, r.pfLutW, r.pfLutH = OC_PF_LUT, 3.0, lut, lut
+            r.pfCdfX = self.cdfx.ctypes.data_as(C.POINTER(C.c_float))
+            r.pfCdfY = self.cdfy.ctypes.data_as(C.POINTER(C.c_float))
+        r.rouletteDepth, r.maxScatteringEvents, r.maxRadiance = roulettePathLength, maxScatteringEvents, maxContribution
+        r.numLightSamples, r.limitIndirectLightSamples, r.backgroundRefraction = lightSamples, int(limitIndirectLightSamples), int(backgroundRefraction)
+        r.shadowsEnabled, r.visibleLights = int(shadows), int(visibleLights)
+        r.aoSamples = (1 if kind == "ao" else 0) if aoSamples is None else aoSamples
+        r.aoRadius, r.aoIntensity, r.volumeSamplingRate = aoDistance, aoIntensity, volumeSamplingRate
+        self.sh = r
+
+
+class HostFrameBuffer:
+    """numpy-backed OcFrameBuffer (fb/LocalFB.cpp:49-180: buffers per requested channel)"""
+
+    def __init__(self, width, height, channels=("color", "depth"), accumulate=True, variance=False, num_ranks=1, rank=0):
+        self.w, self.h = width, height
+        n = width * height
+        fb = FrameBuffer()
+        fb.sizeX, fb.sizeY, fb.frameID = width, height, -1
+        fb.targetFrames = 0 if accumulate else 1
+        self.accumulate = accumulate
+        self.buf = {}
+        spec = {"color": ("color", np.float32, 4), "variance": ("variance", np.float32, 4), "depth": ("depth", np.float32, 1),
+                "normal": ("normal", np.float32, 3), "firstNormal": ("firstNormal", np.float32, 3), "albedo": ("albedo", np.float32, 3),
+                "position": ("position", np.float32, 3), "primID": ("primID", np.uint32, 1), "objID": ("objID", np.uint32, 1),
+                "instID": ("instID", np.uint32, 1)}
+        chans = list(channels) + (["variance"] if variance else [])
+        for cname in chans:
+            field, dt, comps = spec[cname]
+            a = np.zeros((height, width, comps) if comps > 1 else (height, width), dt)
+            if cname == "depth":
+                a[:] = np.inf
+            self.buf[cname] = a
+            setattr(fb, field, a.ctypes.data)
+        fb.accumulateVariance = 0
+        self.variance = variance
+        fb.numRanks, fb.rank = num_ranks, rank
+        self.counters = np.zeros(3, np.uint64)
+        fb.rayCounters = self.counters.ctypes.data
+        self.sh = fb
+
+    def begin_frame(self):
+        """FrameBuffer::beginFrame (fb/FrameBuffer.cpp:115-137); variance accumulates on odd frames"""
+        self.sh.frameID = self.sh.frameID + 1 if self.accumulate else 0
+        self.sh.accumulateVariance = int(self.variance and (self.sh.frameID & 1) == 1)
+        self.counters[:] = 0
+
+
+def render_frame(scene, camera, renderer, fb, threads=0):
+    fb.begin_frame()
+    lib().oracle_render_frame(C.byref(scene.world), C.byref(camera), C.byref(renderer.sh), C.byref(fb.sh), threads)
+    return fb
+
+
+def trace(scene, rays, occlusion=False):
+    """rays: numpy structured array of RAYHIT_DTYPE (modified in place)"""
+    assert rays.dtype == RAYHIT_DTYPE and rays.flags.c_contiguous
+    lib().oracle_trace(C.byref(scene.world), rays.ctypes.data, len(rays), int(occlusion))
+    return rays
+
+
+def camera_rays(camera, renderer, fb, px, py, sample_index=0):
+    px, py = np.ascontiguousarray(px, np.uint32), np.ascontiguousarray(py, np.uint32)
+    out = np.zeros(len(px), RAYHIT_DTYPE)
+    lib().oracle_camera_rays(C.byref(camera), C.byref(renderer.sh), C.byref(fb.sh), px.ctypes.data, py.ctypes.data, len(px), sample_index,
+                             out.ctypes.data)
+    return out
+
+
+def sampler_kat(kind, seed, first, count):
+    width = {0: 12, 1: 4, 2: 4, 3: 2, 4: 1}[kind]
+    out = np.zeros((count, width), np.float32)
+    lib().oracle_sampler_kat(kind, seed, first, count, out.ctypes.data)
+    return out.view(np.uint32) if kind == 4 else out
+
+
+def color_convert(img_f32, fmt):
+    a = np.ascontiguousarray(img_f32, np.float32).reshape(-1, 4)
+    out = np.zeros((len(a), 4), np.float32) if fmt == 3 else np.zeros(len(a), np.uint32)
+    lib().oracle_fb_color_convert(a.ctypes.data, out.ctypes.data, len(a), fmt)
+    return out
+
+
+def tonemap(img_f32, tm):
+    a = np.ascontiguousarray(img_f32, np.float32).reshape(-1, 4)
+    out = np.zeros_like(a)
+    lib().oracle_fb_tonemap(a.ctypes.data, out.ctypes.data, len(a), C.byref(tm))
+    return out
+
+
+def variance(color, var, task=8):
+    h, w = color.shape[:2]
+    tx, ty = (w + task - 1) // task, (h + task - 1) // task
+    out = np.zeros(tx * ty, np.float32)
+    c, v = np.ascontiguousarray(color, np.float32), np.ascontiguousarray(var, np.float32)
+    lib().oracle_fb_variance(c.ctypes.data, v.ctypes.data, w, h, task, out.ctypes.data)
+    return out
+
+
+def default_tonemapper(exposure=1.0, contrast=1.6773, shoulder=0.9714, midIn=0.18, midOut=0.18, hdrMax=11.0785, acesColor=True):
+    """ToneMapper::commit coefficients (fb/frame_ops/ToneMapper.cpp:14-51) in float32"""
+    f = np.float32
+    a, d, m, n, w = f(max(contrast, 0.0001)), f(min(max(shoulder, 0.0001), 1)), f(min(max(midIn, 0.0001), 1)), f(min(max(midOut, 0.0001), 1)), f(max(hdrMax, 1))
+    p = lambda x, y: f(np.power(f(x), f(y)))
+    b = -((p(m, -a * d) * (-p(m, a) + (n * (p(m, a * d) * n * p(w, a) - p(m, a) * p(w, a * d))) / (p(m, a * d) * n - n * p(w, a * d)))) / n)
+    c = max((p(m, a * d) * n * p(w, a) - p(m, a) * p(w, a * d)) / (p(m, a * d) * n - n * p(w, a * d)), f(0))
+    return ToneMapper(float(exposure), float(a), float(b), float(c), float(d), int(acesColor))

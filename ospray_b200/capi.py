@@ -94,6 +94,12 @@ def ext():
         E.ospcudaGetGroupBuildTime.argtypes = [C.c_void_p]
         E.ospcudaKernelLaunchCount.restype = C.c_uint64
         E.ospcudaRenderStream.restype = C.c_void_p
+        E.ospcudaWorldDevicePointer.restype = C.c_void_p
+        E.ospcudaGetFrameStageTimes.restype = None
+        E.ospcudaGetFrameStageTimes.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        E.ospcudaSetRenderStream.restype = None
+        E.ospcudaSetRenderStream.argtypes = [C.c_void_p]
+        E.ospcudaWorldDevicePointer.argtypes = [C.c_void_p]
         _ext = E
     return _ext
 
@@ -147,6 +153,34 @@ def init(device="cuda", module="cuda", warn_as_error=True, **device_params):
     _device = d
     check_errors()
     return d
+
+
+def new_device(device="cuda", warn_as_error=True, **device_params):
+    """an additional device object (e.g. one per tile-partition rank); make it current with set_current()"""
+    L = lib()
+    d = L.ospNewDevice(device.encode())
+    if not d:
+        raise OSPRayError(f"ospNewDevice({device}) failed")
+    L.ospDeviceSetErrorCallback(d, _on_error, None)
+    if warn_as_error:
+        b = C.c_bool(True)
+        L.ospDeviceSetParam(d, b"warnAsError", OSP_BOOL, C.byref(b))
+    for k, v in device_params.items():
+        iv = C.c_int(int(v))
+        L.ospDeviceSetParam(d, k.encode(), OSP_INT, C.byref(iv))
+    L.ospDeviceCommit(d)
+    if L.ospDeviceGetLastErrorCode(d) != OSP_NO_ERROR:
+        msg = L.ospDeviceGetLastErrorMsg(d)
+        L.ospDeviceRelease(d)
+        _errors.clear()
+        raise OSPRayError(f"device commit failed: {(msg or b'').decode()}")
+    return d
+
+
+def set_current(device):
+    global _device
+    lib().ospSetCurrentDevice(device)
+    _device = device
 
 
 def shutdown():
@@ -350,6 +384,10 @@ class World(Object):
     def __init__(self):
         super().__init__(lib().ospNewWorld())
 
+    def device_pointer(self):
+        """const OcWorld* in device memory (for ospcuda_trace)"""
+        return ext().ospcudaWorldDevicePointer(self.h)
+
 
 class Future(Object):
     kind = OSP_FUTURE
@@ -363,6 +401,12 @@ class Future(Object):
 
     def duration(self):
         return float(lib().ospGetTaskDuration(self.h))
+
+    def stage_ms(self):
+        """(renderer kernel ms, post-process ms) of the finished frame"""
+        ms = (C.c_float * 2)()
+        ext().ospcudaGetFrameStageTimes(self.h, ms)
+        return float(ms[0]), float(ms[1])
 
 
 _CHANNEL_DTYPE = {
@@ -420,6 +464,11 @@ class FrameBuffer(Object):
         c = (C.c_uint64 * 3)()
         ext().ospcudaGetRayCounts(self.h, c)
         return int(c[0]), int(c[1]), int(c[2])
+
+
+def set_render_stream(stream_handle):
+    """render on an external cudaStream_t (torch.cuda.Stream().cuda_stream); None restores the own stream"""
+    ext().ospcudaSetRenderStream(stream_handle)
 
 
 def kernel_launch_count():

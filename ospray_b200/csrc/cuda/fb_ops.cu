@@ -149,6 +149,39 @@ __global__ void __launch_bounds__(256) gatherTilesKernel(uint8_t *__restrict__ d
   }
 }
 
+// tile-major staging for the NCCL gather: owned tile k of `rank` <-> packed + k * 64*64*bpp (tiles on the
+// right / top image border are stored padded to 64x64 so that every rank's shard has a fixed pitch).
+// PACK: image -> staging (before ncclSend); !PACK: staging -> image on GPU 0 (after ncclRecv), the device
+// analogue of LocalFrameBuffer::writeTiles (fb/LocalFB.cpp:286-353). 16-byte lanes, one CTA per tile.
+template <bool PACK>
+__global__ void __launch_bounds__(256) packTilesKernel(uint8_t *__restrict__ packed, uint8_t *__restrict__ image, int sizeX, int sizeY,
+    uint32_t bpp, uint32_t numRanks, uint32_t rank, uint32_t tilesX, uint32_t ownedTiles)
+{
+  const uint32_t ownedTile = blockIdx.x;
+  if (ownedTile >= ownedTiles) return;
+  const uint32_t tileID = rank + ownedTile * numRanks;
+  const uint32_t tx = tileID % tilesX, ty = tileID / tilesX;
+  const int x0 = tx * 64, y0 = ty * 64;
+  const int w = min(64, sizeX - x0), h = min(64, sizeY - y0);
+  const uint32_t rowBytes = (uint32_t)w * bpp, tilePitch = 64u * bpp;
+  uint8_t *tile = packed + (size_t)ownedTile * 64u * tilePitch;
+  for (int r = threadIdx.x >> 4; r < h; r += blockDim.x >> 4) { // 16 threads per row
+    const size_t off = ((size_t)(y0 + r) * sizeX + x0) * bpp;
+    uint8_t *a = tile + (size_t)r * tilePitch, *b = image + off;
+    if (((off | rowBytes) & 15u) == 0) {
+      for (uint32_t k = (threadIdx.x & 15) * 16; k < rowBytes; k += 256) {
+        if (PACK) *reinterpret_cast<uint4 *>(a + k) = *reinterpret_cast<const uint4 *>(b + k);
+        else *reinterpret_cast<uint4 *>(b + k) = *reinterpret_cast<const uint4 *>(a + k);
+      }
+    } else {
+      for (uint32_t k = (threadIdx.x & 15) * 4; k < rowBytes; k += 64) {
+        if (PACK) *reinterpret_cast<uint32_t *>(a + k) = *reinterpret_cast<const uint32_t *>(b + k);
+        else *reinterpret_cast<uint32_t *>(b + k) = *reinterpret_cast<const uint32_t *>(a + k);
+      }
+    }
+  }
+}
+
 static int numSMs()
 {
   static int n = 0;
@@ -237,4 +270,27 @@ extern "C" int ospcuda_fb_gather_tiles(void *d_dst, const void *d_src, int sizeX
       bytesPerPixel, numRanks, srcRank, tilesX, owned);
   oc_count_launch();
   return oc_check(cudaGetLastError(), "ospcuda_fb_gather_tiles");
+}
+
+static int packTiles(bool pack, void *d_packed, void *d_image, int sizeX, int sizeY, uint32_t bpp, uint32_t numRanks, uint32_t rank)
+{
+  if (bpp % 4 != 0 || numRanks == 0) return oc_set_error(cudaErrorInvalidValue, "ospcuda_fb_pack_tiles: bytesPerPixel must be a multiple of 4");
+  const uint32_t tilesX = (sizeX + 63) / 64, tilesY = (sizeY + 63) / 64, total = tilesX * tilesY;
+  if (rank >= total) return 0;
+  const uint32_t owned = (total - rank + numRanks - 1) / numRanks;
+  cudaStream_t st = (cudaStream_t)ospcuda_stream();
+  if (pack) packTilesKernel<true><<<owned, 256, 0, st>>>((uint8_t *)d_packed, (uint8_t *)d_image, sizeX, sizeY, bpp, numRanks, rank, tilesX, owned);
+  else packTilesKernel<false><<<owned, 256, 0, st>>>((uint8_t *)d_packed, (uint8_t *)d_image, sizeX, sizeY, bpp, numRanks, rank, tilesX, owned);
+  oc_count_launch();
+  return oc_check(cudaGetLastError(), "ospcuda_fb_pack_tiles");
+}
+extern "C" int ospcuda_fb_pack_tiles(void *d_packed, const void *d_image, int sizeX, int sizeY, uint32_t bytesPerPixel, uint32_t numRanks,
+    uint32_t rank)
+{
+  return packTiles(true, d_packed, (void *)d_image, sizeX, sizeY, bytesPerPixel, numRanks, rank);
+}
+extern "C" int ospcuda_fb_unpack_tiles(void *d_image, const void *d_packed, int sizeX, int sizeY, uint32_t bytesPerPixel, uint32_t numRanks,
+    uint32_t srcRank)
+{
+  return packTiles(false, (void *)d_packed, d_image, sizeX, sizeY, bytesPerPixel, numRanks, srcRank);
 }

@@ -707,6 +707,10 @@ __device__ void defaultRenderPixel(Ctx &c, uint32_t x, uint32_t y, ScreenSample 
   const int spp = ren.spp;
   const int startSampleID = fb.frameID * spp + 1;
   ScreenSample_zero(screenSample);
+  // the reference declares `sample` outside the spp loop and never re-zeroes it
+  // (RendererRenderTaskFn.inl:32-33): AOVs / IDs of an earlier sample persist through a miss
+  ScreenSample sample;
+  ScreenSample_zero(sample);
   const vec2f rcpSize = make_vec2f(1.f / (float)fb.sizeX, 1.f / (float)fb.sizeY);
   for (int s = 0; s < spp; s++) {
     const float pixel_du = Halton_sample2(startSampleID + s);
@@ -716,8 +720,6 @@ __device__ void defaultRenderPixel(Ctx &c, uint32_t x, uint32_t y, ScreenSample 
     const vec2f screen = pixel_center + pfSample * rcpSize;
     Ray ray;
     cameraInitRay(c.cam, ray, screen, make_vec2f(0.f, 0.f));
-    ScreenSample sample;
-    ScreenSample_zero(sample);
     if (RENDERER == OC_RENDERER_SCIVIS) SciVis_renderSample(c, ray, sample, x, y, startSampleID + s);
     else AO_renderSample(c, ray, sample, x, y, startSampleID + s);
     ScreenSample_accumulate(screenSample, sample);

@@ -61,6 +61,17 @@ int ospcuda_init(int deviceOrdinal)
 }
 
 void *ospcuda_stream(void) { return (void *)g_stream; }
+
+static cudaStream_t g_ownStream = nullptr;
+int ospcuda_set_stream(void *stream)
+{
+  // adopt an external stream (e.g. torch's current stream so that NCCL work and CUDA-event timing order
+  // naturally with the frame); NULL restores the library's own stream
+  if (!g_ownStream) g_ownStream = g_stream;
+  if (g_stream) OC_TRY(cudaStreamSynchronize(g_stream));
+  g_stream = stream ? (cudaStream_t)stream : g_ownStream;
+  return 0;
+}
 unsigned long long ospcuda_kernel_launch_count(void) { return g_launches.load(); }
 
 int ospcuda_malloc(void **ptr, size_t bytes)

@@ -217,4 +217,14 @@ void ospcudaGetRayCounts(OSPFrameBuffer fb, uint64_t counts[3])
 float ospcudaGetGroupBuildTime(OSPGroup g) { return ((cuda::Group *)g)->lastBuildMs; }
 uint64_t ospcudaKernelLaunchCount(void) { return ospcuda_kernel_launch_count(); }
 void *ospcudaRenderStream(void) { return ospcuda_stream(); }
+void ospcudaGetFrameStageTimes(OSPFuture f, float ms[2])
+{
+  cuda::Future *fu = (cuda::Future *)f;
+  fu->wait(OSP_TASK_FINISHED);
+  ms[0] = ms[1] = 0.f;
+  ospcuda_event_elapsed_ms(fu->evStart, fu->evRendered, &ms[0]);
+  ospcuda_event_elapsed_ms(fu->evRendered, fu->evFinished, &ms[1]);
+}
+void ospcudaSetRenderStream(void *stream) { ospray::cuda::checkCuda(ospcuda_set_stream(stream), "set stream"); }
+const void *ospcudaWorldDevicePointer(OSPWorld w) { return ((cuda::World *)w)->prepareFrame(); }
 }

@@ -52,7 +52,8 @@ FrameBuffer::FrameBuffer(CudaDevice &d, const vec2i &sz, OSPFrameBufferFormat fo
 
 FrameBuffer::~FrameBuffer()
 {
-  for (auto &m : mapped) ospcuda_free_host(m.second);
+  for (auto &s : staging) ospcuda_free_host(s.second.host);
+  for (void *m : extraMapped) ospcuda_free_host(m);
 }
 
 void FrameBuffer::commit()
@@ -157,10 +158,18 @@ const void *FrameBuffer::map(OSPFrameBufferChannel channel)
   void *src = devicePointer(channel);
   if (!src) return nullptr;
   const size_t bytes = (size_t)size.x * size.y * bytesPerPixel(channel);
+  // pinned staging is cached per channel: cudaMallocHost costs more than the copy itself
   void *host = nullptr;
-  checkCuda(ospcuda_malloc_host(&host, bytes), "pinned allocation");
+  auto st = staging.find((int)channel);
+  if (st != staging.end() && !st->second.inUse) {
+    host = st->second.host;
+    st->second.inUse = true;
+  } else {
+    checkCuda(ospcuda_malloc_host(&host, bytes), "pinned allocation");
+    if (st == staging.end()) staging[(int)channel] = Staging{host, true};
+    else extraMapped.insert(host); // the channel is already mapped: one-off buffer
+  }
   checkCuda(ospcuda_memcpy_d2h(host, src, bytes), "framebuffer read-back"); // orders after the frame on the render stream
-  mapped[host] = host;
   this->refInc();
   return host;
 }
@@ -168,10 +177,13 @@ const void *FrameBuffer::map(OSPFrameBufferChannel channel)
 void FrameBuffer::unmap(const void *m)
 {
   if (!m) return;
-  auto it = mapped.find(m);
-  if (it != mapped.end()) {
-    ospcuda_free_host(it->second);
-    mapped.erase(it);
+  auto ex = extraMapped.find((void *)m);
+  if (ex != extraMapped.end()) {
+    ospcuda_free_host(*ex);
+    extraMapped.erase(ex);
+  } else {
+    for (auto &s : staging)
+      if (s.second.host == m) s.second.inUse = false;
   }
   this->refDec();
 }

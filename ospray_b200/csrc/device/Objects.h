@@ -10,6 +10,8 @@
 #pragma once
 #include <memory>
 #include <random>
+#include <set>
+#include <map>
 #include "../common/Managed.h"
 #include "ospcuda.h"
 
@@ -283,7 +285,9 @@ struct FrameBuffer : public ManagedObject
          *ppBuf = nullptr, *taskErrBuf = nullptr, *counterBuf = nullptr;
   Ref<Data> imageOpData;
   std::vector<Ref<ImageOp>> toneMappers;
-  std::map<const void *, void *> mapped; // host pinned staging per mapped pointer
+  struct Staging { void *host; bool inUse; };
+  std::map<int, Staging> staging;  // pinned read-back buffer per channel, reused across maps
+  std::set<void *> extraMapped;    // one-off buffers when a channel is mapped twice
   std::vector<float> taskErrors;
   bool taskErrorsValid = false, taskErrorsPending = false;
   float frameVariance = INFINITY;

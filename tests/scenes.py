@@ -1,0 +1,108 @@
+"""Shared test cases: (scene spec, renderer params, framebuffer setup) rendered both by the oracle and by the
+cuda device through the OSPRay C API. Small enough for the scalar oracle to finish in seconds."""
+import numpy as np
+
+from ospray_b200 import testing as T
+
+
+def instanced_boxes_and_spheres():
+    """two groups instanced with non-trivial transforms + ids (exercises Instance.ih:44-105, userIDs)"""
+    spheres = T.random_spheres(24, seed=3, add_plane=False).instances[0].group
+    boxes = T.boxes((2, 2, 2)).instances[0].group
+    boxes.models[0].id = 7
+    s = np.float32(0.1)
+    rot = np.array([[0.8, 0.6, 0.0], [-0.6, 0.8, 0.0], [0.0, 0.0, 1.0]], np.float32)
+    xf_boxes = np.concatenate([(rot * s).ravel(), np.array([-0.6, -0.5, 0.2], np.float32)])
+    xf_sph = np.array([1.2, 0, 0, 0, 0.9, 0, 0, 0, 1.0, 0.3, 0.1, 0.0], np.float32)
+    inst = [T.InstanceSpec(spheres, xfm=xf_sph, id=11), T.InstanceSpec(boxes, xfm=xf_boxes), T.InstanceSpec(spheres)]
+    lights = [T.LightSpec("distant", {"color": (1.0, 0.9, 0.8), "intensity": 2.5, "direction": (-0.4, -0.7, 0.6)}),
+              T.LightSpec("ambient", {"intensity": 0.4})]
+    return T.SceneSpec(instances=inst, lights=lights)
+
+
+def translucent_cornell():
+    """cornell box with a semi-transparent specular material: transparent shadows, Specular + Transmission lobes"""
+    s = T.cornell_box()
+    s.instances[0].group.models[0].material = T.MaterialSpec(kd=(0.6, 0.6, 0.6), ks=(0.2, 0.2, 0.2), ns=20.0, d=0.7, tf=(0.1, 0.1, 0.1))
+    s.lights.append(T.LightSpec("ambient", {"intensity": 0.2, "color": (0.6, 0.7, 1.0)}))
+    return s
+
+
+def shaded_volume():
+    s = T.gravity_spheres_volume(24)
+    s.instances[0].group.volumes[0].gradient_shading_scale = 0.6
+    s.lights = [T.LightSpec("distant", {"direction": (0.3, -0.5, 0.8), "intensity": 2.0}), T.LightSpec("ambient", {"intensity": 0.3})]
+    return s
+
+
+def volume_with_geometry():
+    s = T.gravity_spheres_volume(20)
+    sp = T.random_spheres(12, seed=5, add_plane=False).instances[0]
+    s.instances.append(sp)
+    s.lights = [T.LightSpec("distant", {"direction": (0.0, -0.5, 0.8), "intensity": 2.0}), T.LightSpec("ambient", {"intensity": 0.5})]
+    return s
+
+
+# name -> (spec builder, renderer kind, renderer params, frames)
+CASES = {
+    "cornell_pt": (T.cornell_box, "pathtracer", {"pixelSamples": 2}, 2),
+    "cornell_pt_lights4": (T.cornell_box, "pathtracer", {"pixelSamples": 1, "lightSamples": 4, "limitIndirectLightSamples": False}, 1),
+    "cornell_scivis": (T.cornell_box, "scivis", {"pixelSamples": 2, "shadows": True, "aoSamples": 2, "visibleLights": True}, 2),
+    "cornell_ao": (T.cornell_box, "ao", {"pixelSamples": 2, "aoSamples": 4}, 1),
+    "translucent_pt": (translucent_cornell, "pathtracer", {"pixelSamples": 2, "backgroundColor": (0.1, 0.2, 0.3, 0.5)}, 1),
+    "translucent_scivis": (translucent_cornell, "scivis", {"shadows": True, "aoSamples": 1}, 1),
+    "boxes_scivis": (lambda: T.boxes(lit=True), "scivis", {"shadows": True, "aoSamples": 1}, 1),
+    "boxes_pt": (lambda: T.boxes(lit=True), "pathtracer", {"pixelSamples": 2}, 1),
+    "spheres_ao": (T.random_spheres, "ao", {"pixelSamples": 2}, 1),
+    "spheres_pt": (T.random_spheres, "pathtracer", {"pixelSamples": 1, "backgroundColor": (1.0, 1.0, 1.0, 1.0)}, 2),
+    "instanced_scivis": (instanced_boxes_and_spheres, "scivis", {"shadows": True}, 1),
+    "instanced_pt": (instanced_boxes_and_spheres, "pathtracer", {"pixelSamples": 1}, 1),
+    "mesh_ao": (lambda: T.box_mesh(5), "ao", {"aoSamples": 2}, 1),
+    "gravity_scivis": (lambda: T.gravity_spheres_volume(24), "scivis", {"pixelSamples": 2}, 1),
+    "gravity_ao": (lambda: T.gravity_spheres_volume(24), "ao", {}, 1),
+    "gravity_shaded": (shaded_volume, "scivis", {"shadows": True}, 1),
+    "volume_geometry": (volume_with_geometry, "scivis", {"shadows": True, "aoSamples": 1}, 1),
+}
+
+W, H = 48, 40  # not a multiple of 8 or 64: exercises clipped render tasks and border tiles
+
+
+def oracle_render(name, width=W, height=H, pixel_filter=None, threads=0, num_ranks=1, rank=0, channels=None):
+    from oracle import pyoracle as O
+    build, kind, params, frames = CASES[name]
+    spec = build()
+    scene = O.Scene(spec)
+    pose = T.arcball_camera(*scene.bounds)
+    cam = O.make_camera(pose["position"], pose["direction"], pose["up"], aspect=np.float32(width) / np.float32(height))
+    p = dict(params)
+    if pixel_filter:
+        p["pixelFilter"] = pixel_filter
+    ren = O.RendererParams(kind, **p)
+    fb = O.HostFrameBuffer(width, height, channels or ("color", "depth", "primID", "objID", "instID", "normal", "albedo"),
+                           num_ranks=num_ranks, rank=rank)
+    for _ in range(frames):
+        O.render_frame(scene, cam, ren, fb, threads)
+    return fb
+
+
+_PF = {"point": 0, "box": 1, "gauss": 2}
+
+
+def device_render(osp, name, width=W, height=H, pixel_filter=None, channels=None, fmt=None):
+    """the same case through the unchanged OSPRay C API on the cuda device"""
+    build, kind, params, frames = CASES[name]
+    spec = build()
+    world, keep = T.to_ospray(spec)
+    cam, _ = T.make_camera(world, width, height)
+    p = {}
+    for k, v in params.items():
+        p[k] = tuple(float(x) for x in v) if isinstance(v, tuple) else v
+    if pixel_filter:
+        p["pixelFilter"] = osp.Typed(osp.OSP_UINT, _PF[pixel_filter])
+    ren = T.make_renderer(kind, **p)
+    ch = channels if channels is not None else (osp.OSP_FB_COLOR | osp.OSP_FB_ACCUM | osp.OSP_FB_DEPTH | osp.OSP_FB_ID_PRIMITIVE
+                                                | osp.OSP_FB_ID_OBJECT | osp.OSP_FB_ID_INSTANCE | osp.OSP_FB_NORMAL | osp.OSP_FB_ALBEDO)
+    fb = osp.FrameBuffer(width, height, osp.OSP_FB_RGBA32F if fmt is None else fmt, ch)
+    for _ in range(frames):
+        fb.render_frame(ren, cam, world).wait()
+    return fb, (world, keep, cam, ren)

@@ -30,10 +30,10 @@ $(LIB)/libospcuda.so: $(CU_OBJS)
 
 $(LIB)/libospray.so: $(API_SRCS) $(HOST_HDRS)
 	@mkdir -p $(LIB)
-	$(CXX) $(CXXFLAGS) -shared $(API_SRCS) -ldl -o $@
+	$(CXX) $(CXXFLAGS) -shared $(API_SRCS) -ldl -Wl,--exclude-libs,ALL -o $@
 
 $(LIB)/libospray_module_cuda.so: $(DEV_SRCS) $(HOST_HDRS) $(LIB)/libospray.so $(LIB)/libospcuda.so
-	$(CXX) $(CXXFLAGS) -shared $(DEV_SRCS) -L$(LIB) -lospray -lospcuda -lpthread -Wl,-rpath,'$$ORIGIN' -o $@
+	$(CXX) $(CXXFLAGS) -shared $(DEV_SRCS) -L$(LIB) -lospray -lospcuda -lpthread -Wl,--exclude-libs,ALL -Wl,-rpath,'$$ORIGIN' -o $@
 
 oracle:
 	$(MAKE) -C oracle

@@ -68,7 +68,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -221,6 +221,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
         clocks = ClockSampler(local) if rank == 0 else None
+        time.sleep(0.3 if rank == 0 else 0.0)  # let nvidia-smi start sampling
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         rays = np.zeros(3, np.int64)
         kernel_ms, post_ms = 0.0, 0.0

@@ -181,16 +181,23 @@ def _affine(m):
 
 
 def _rcp_affine(m):
-    """rkcommon rcp(AffineSpace3f): adjoint/determinant in float32"""
+    """rkcommon rcp(AffineSpace3f): adjoint / determinant, every op rounded to float32 in source order"""
+    f = np.float32
     m = np.asarray(m, np.float32).reshape(4, 3)
     vx, vy, vz, p = m
-    c0, c1, c2 = np.cross(vy, vz), np.cross(vz, vx), np.cross(vx, vy)
-    det = np.float32(np.dot(vx, c0))
-    r = np.float32(1.0) / det
-    l = (np.stack([c0, c1, c2], axis=1) * r).astype(np.float32)  # columns of the inverse
-    lx, ly, lz = l[0], l[1], l[2]
-    np_ = -(p[0] * lx + p[1] * ly + p[2] * lz).astype(np.float32)
-    return np.stack([lx, ly, lz, np_]).astype(np.float32)
+
+    def cross(a, b):
+        return np.array([f(f(a[1] * b[2]) - f(a[2] * b[1])), f(f(a[2] * b[0]) - f(a[0] * b[2])), f(f(a[0] * b[1]) - f(a[1] * b[0]))], f)
+    c0, c1, c2 = cross(vy, vz), cross(vz, vx), cross(vx, vy)
+    det = f(f(f(vx[0] * c0[0]) + f(vx[1] * c0[1])) + f(vx[2] * c0[2]))
+    r = f(f(1.0) / det)
+    lx = np.array([c0[0], c1[0], c2[0]], f) * r
+    ly = np.array([c0[1], c1[1], c2[1]], f) * r
+    lz = np.array([c0[2], c1[2], c2[2]], f) * r
+    t = (f(p[0]) * lx).astype(f)
+    t = (t + (f(p[1]) * ly).astype(f)).astype(f)
+    t = (t + (f(p[2]) * lz).astype(f)).astype(f)
+    return np.stack([lx, ly, lz, -t]).astype(f)
 
 
 def _xfm_bounds(m, lo, hi):

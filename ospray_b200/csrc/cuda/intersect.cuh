@@ -19,6 +19,7 @@ using namespace ospm;
 #define OC_INVALID_ID 0xFFFFFFFFu
 #define OC_TLAS_THRESHOLD 4u
 #define OC_STACK_SIZE 48
+#define OC_MAX_BLOCK 128 // largest CTA of a kernel that traverses (shared stack = OC_STACK_SIZE * blockDim.x words)
 
 struct Ray
 {
@@ -50,6 +51,20 @@ __device__ __forceinline__ vec3f crossF(vec3f a, vec3f b)
 {
   return make_vec3f(__fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y)), __fmaf_rn(a.z, b.x, -__fmul_rn(a.x, b.z)),
       __fmaf_rn(a.x, b.y, -__fmul_rn(a.y, b.x)));
+}
+
+// ray -> instance space with every product and sum rounded separately (no fma contraction), so that the
+// local ray -- and with it every hit decision inside the instance -- is bit-identical to the oracle's
+__device__ __forceinline__ vec3f xfmVectorExact(const linear3f &l, vec3f v)
+{
+  return make_vec3f(__fadd_rn(__fadd_rn(__fmul_rn(v.x, l.vx.x), __fmul_rn(v.y, l.vy.x)), __fmul_rn(v.z, l.vz.x)),
+      __fadd_rn(__fadd_rn(__fmul_rn(v.x, l.vx.y), __fmul_rn(v.y, l.vy.y)), __fmul_rn(v.z, l.vz.y)),
+      __fadd_rn(__fadd_rn(__fmul_rn(v.x, l.vx.z), __fmul_rn(v.y, l.vy.z)), __fmul_rn(v.z, l.vz.z)));
+}
+__device__ __forceinline__ vec3f xfmPointExact(const affine3f &a, vec3f v)
+{
+  const vec3f r = xfmVectorExact(a.l, v);
+  return make_vec3f(__fadd_rn(r.x, a.p.x), __fadd_rn(r.y, a.p.y), __fadd_rn(r.z, a.p.z));
 }
 
 // ---- triangle (v0, e1 = v0 - v1, e2 = v2 - v0) ---------------------------------------
@@ -205,55 +220,61 @@ __device__ __forceinline__ vec3f safeRcpDir(vec3f d)
       1.f / (fabsf(d.z) < eps ? copysignf(eps, d.z) : d.z));
 }
 
-// Traverse one BVH (group BLAS). Leaves are primitive records. The traversal stack is a
-// per-thread array; callers place it in shared memory (short stack) or local memory.
-template <bool OCCLUSION>
-__device__ __forceinline__ bool traverseBLAS(const OcBVH &bvh, Ray &ray, uint32_t instID, uint32_t *stack)
+// Per-thread traversal stack in SHARED memory, laid out [depth][thread] so that the 32 lanes of a warp hit 32
+// different banks whatever their individual depths are (a local-memory stack puts lanes at different depths
+// into different 32-byte sectors). Kernels declare `__shared__ uint32_t s[OC_STACK_SIZE * blockDim.x]`.
+struct Stack
 {
-  if (bvh.numNodes == 0)
-    return false;
+  uint32_t *base;   // s + threadIdx.x
+  uint32_t stride;  // blockDim.x
+  __device__ __forceinline__ uint32_t &at(int d) const { return base[(uint32_t)d * stride]; }
+};
+
+// Traverse one BVH (group BLAS), "while-while": descend inner nodes until a leaf is reached, then test its
+// records. Not inlined on purpose: the frame kernels call it from many places and an inlined copy per call
+// site made them instruction-fetch bound (ncu: stall_no_instruction 7.3 per issue, profiles/r1_*).
+template <bool OCCLUSION>
+__device__ __noinline__ bool traverseBLAS(const OcNode4 *__restrict__ nodes, const OcVec4f *__restrict__ prims, Ray &ray,
+    uint32_t instID, Stack st, int sp0)
+{
   const vec3f rdir = safeRcpDir(ray.dir);
-  int sp = 0;
+  int sp = sp0;
   uint32_t cur = 0; // root
   bool any = false;
   while (true) {
-    if (!(cur & 0x80000000u)) {
+    // ---- inner nodes ----
+    while (!(cur & 0x80000000u)) {
       float tn[4];
       uint4 ch;
-      uint32_t mask = nodeTest(bvh.nodes + cur, ray.org, rdir, ray.t0, ray.t, tn, ch);
+      const uint32_t mask = nodeTest(nodes + cur, ray.org, rdir, ray.t0, ray.t, tn, ch);
       if (mask == 0) {
-        if (sp == 0) break;
-        cur = stack[--sp];
+        if (sp == sp0) return any;
+        cur = st.at(--sp);
         continue;
       }
       const uint32_t chs[4] = {ch.x, ch.y, ch.z, ch.w};
-      // visit nearest first: pick nearest, push the rest (unsorted is fine for correctness)
-      int best = -1;
+      int best = 0;
       float bestT = INFINITY;
 #pragma unroll
       for (int i = 0; i < 4; i++)
-        if ((mask >> i) & 1u) {
-          if (tn[i] < bestT) { bestT = tn[i]; best = i; }
-        }
+        if (((mask >> i) & 1u) && tn[i] < bestT) { bestT = tn[i]; best = i; }
 #pragma unroll
       for (int i = 0; i < 4; i++)
-        if (((mask >> i) & 1u) && i != best && sp < OC_STACK_SIZE)
-          stack[sp++] = chs[i];
+        if (((mask >> i) & 1u) && i != best && sp < OC_STACK_SIZE) st.at(sp++) = chs[i];
       cur = chs[best];
-    } else {
-      const uint32_t first = cur & 0x07FFFFFFu;
-      const uint32_t count = (cur >> 27) & 0xFu;
-      for (uint32_t i = 0; i < count; i++) {
-        if (intersectRecord<OCCLUSION>(ray, bvh.prims + 3 * (size_t)(first + i), instID)) {
-          any = true;
-          if (OCCLUSION) return true;
-        }
-      }
-      if (sp == 0) break;
-      cur = stack[--sp];
     }
+    // ---- leaf ----
+    const uint32_t first = cur & 0x07FFFFFFu;
+    const uint32_t count = (cur >> 27) & 0xFu;
+    for (uint32_t i = 0; i < count; i++) {
+      if (intersectRecord<OCCLUSION>(ray, prims + 3 * (size_t)(first + i), instID)) {
+        any = true;
+        if (OCCLUSION) return true;
+      }
+    }
+    if (sp == sp0) return any;
+    cur = st.at(--sp);
   }
-  return any;
 }
 
 __device__ __forceinline__ bool rayBoxOverlap(const float *b, vec3f org, vec3f rdir, float t0, float t1)
@@ -266,20 +287,21 @@ __device__ __forceinline__ bool rayBoxOverlap(const float *b, vec3f org, vec3f r
   return tn <= tf;
 }
 
+// one instance: ray -> instance space (Embree keeps t, no renormalisation), one BLAS traversal, hit back
 template <bool OCCLUSION>
-__device__ __forceinline__ bool traceInstance(const OcInstance *inst, uint32_t instID, Ray &ray, uint32_t *stack)
+__device__ __forceinline__ bool traceInstance(const OcInstance *__restrict__ inst, uint32_t instID, Ray &ray, Stack st, int sp0)
 {
   const OcGroup *g = inst->group;
-  if (g->bvh.numNodes == 0)
+  const uint32_t numNodes = g->bvh.numNodes;
+  if (numNodes == 0)
     return false;
-  if (inst->isIdentity)
-    return traverseBLAS<OCCLUSION>(g->bvh, ray, instID, stack);
-  // Embree transforms the ray into instance space and keeps t (no renormalisation)
-  const affine3f rx = toA(inst->rcp_xfm);
   Ray local = ray;
-  local.org = xfmPoint(rx, ray.org);
-  local.dir = xfmVector(rx, ray.dir);
-  const bool h = traverseBLAS<OCCLUSION>(g->bvh, local, instID, stack);
+  if (!inst->isIdentity) {
+    const affine3f rx = toA(inst->rcp_xfm);
+    local.org = xfmPointExact(rx, ray.org);
+    local.dir = xfmVectorExact(rx.l, ray.dir);
+  }
+  const bool h = traverseBLAS<OCCLUSION>(g->bvh.nodes, g->bvh.prims, local, instID, st, sp0);
   if (h) {
     ray.t = local.t;
     if (!OCCLUSION) {
@@ -290,67 +312,63 @@ __device__ __forceinline__ bool traceInstance(const OcInstance *inst, uint32_t i
   return h;
 }
 
-// closest hit over the whole world (two-level). Equivalent of traceGeometryRay (World.ih:29-52).
+// closest hit / occlusion over the whole world (two-level). Equivalent of traceGeometryRay /
+// isOccludedNoClipping (World.ih:29-52, 311-335).
 template <bool OCCLUSION>
-__device__ __forceinline__ bool traceWorld(const OcWorld *world, Ray &ray, uint32_t *stack)
+__device__ __noinline__ bool traceWorld(const OcWorld *__restrict__ world, Ray &ray, Stack st)
 {
   bool any = false;
   const uint32_t n = world->numInstances;
+  const vec3f rdir = safeRcpDir(ray.dir);
   if (n <= OC_TLAS_THRESHOLD) {
-    const vec3f rdir = safeRcpDir(ray.dir);
     for (uint32_t i = 0; i < n; i++) {
       const OcInstance *inst = world->instances + i;
       if (!rayBoxOverlap(inst->bounds, ray.org, rdir, ray.t0, ray.t))
         continue;
-      if (traceInstance<OCCLUSION>(inst, i, ray, stack)) {
+      if (traceInstance<OCCLUSION>(inst, i, ray, st, 0)) {
         any = true;
         if (OCCLUSION) return true;
       }
     }
     return any;
   }
-  // TLAS: leaves hold instance indices in record[0].w; BLAS traversal uses the upper stack half
+  // TLAS: leaves hold instance indices in record[0].w; the BLAS traversal continues on the same stack above sp
   const OcBVH &tlas = world->tlas;
-  const vec3f rdir = safeRcpDir(ray.dir);
-  uint32_t tstack[24];
   int sp = 0;
   uint32_t cur = 0;
   while (true) {
-    if (!(cur & 0x80000000u)) {
+    while (!(cur & 0x80000000u)) {
       float tn[4];
       uint4 ch;
       const uint32_t mask = nodeTest(tlas.nodes + cur, ray.org, rdir, ray.t0, ray.t, tn, ch);
+      if (mask == 0) {
+        if (sp == 0) return any;
+        cur = st.at(--sp);
+        continue;
+      }
       const uint32_t chs[4] = {ch.x, ch.y, ch.z, ch.w};
-      int best = -1;
+      int best = 0;
       float bestT = INFINITY;
 #pragma unroll
       for (int i = 0; i < 4; i++)
         if (((mask >> i) & 1u) && tn[i] < bestT) { bestT = tn[i]; best = i; }
-      if (best < 0) {
-        if (sp == 0) break;
-        cur = tstack[--sp];
-        continue;
-      }
 #pragma unroll
       for (int i = 0; i < 4; i++)
-        if (((mask >> i) & 1u) && i != best && sp < 24)
-          tstack[sp++] = chs[i];
+        if (((mask >> i) & 1u) && i != best && sp < OC_STACK_SIZE / 2) st.at(sp++) = chs[i];
       cur = chs[best];
-    } else {
-      const uint32_t first = cur & 0x07FFFFFFu;
-      const uint32_t count = (cur >> 27) & 0xFu;
-      for (uint32_t i = 0; i < count; i++) {
-        const uint32_t instID = __float_as_uint(ldg4(tlas.prims + 3 * (size_t)(first + i)).w);
-        if (traceInstance<OCCLUSION>(world->instances + instID, instID, ray, stack)) {
-          any = true;
-          if (OCCLUSION) return true;
-        }
-      }
-      if (sp == 0) break;
-      cur = tstack[--sp];
     }
+    const uint32_t first = cur & 0x07FFFFFFu;
+    const uint32_t count = (cur >> 27) & 0xFu;
+    for (uint32_t i = 0; i < count; i++) {
+      const uint32_t instID = __float_as_uint(ldg4(tlas.prims + 3 * (size_t)(first + i)).w);
+      if (traceInstance<OCCLUSION>(world->instances + instID, instID, ray, st, sp)) {
+        any = true;
+        if (OCCLUSION) return true;
+      }
+    }
+    if (sp == 0) return any;
+    cur = st.at(--sp);
   }
-  return any;
 }
 
 } // namespace oc

@@ -46,9 +46,9 @@ struct Ctx
   const OcRenderer &ren;
   const OcCamera &cam;
   const OcFrameBuffer &fb;
-  uint32_t *stack;
+  Stack stack;
   Counters cnt;
-  __device__ Ctx(const OcWorld *w, const OcRenderer &r, const OcCamera &c, const OcFrameBuffer &f, uint32_t *s)
+  __device__ Ctx(const OcWorld *w, const OcRenderer &r, const OcCamera &c, const OcFrameBuffer &f, Stack s)
       : world(w), ren(r), cam(c), fb(f), stack(s) { cnt.primary = cnt.secondary = cnt.shadow = 0; }
 };
 
@@ -66,7 +66,7 @@ __device__ __forceinline__ float misHeuristic(float pdf1, float pdf2)
   return pdf1 > 1e17f ? 1.0f : p;
 }
 
-__device__ vec3f transparentShadow(Ctx &c, vec3f lightContrib, Ray &shadowRay)
+__device__ __noinline__ vec3f transparentShadow(Ctx &c, vec3f lightContrib, Ray &shadowRay)
 {
   uint32_t maxDepth = c.ren.maxDepth;
   const float tOriginal = shadowRay.t;
@@ -84,7 +84,7 @@ __device__ vec3f transparentShadow(Ctx &c, vec3f lightContrib, Ray &shadowRay)
   }
 }
 
-__device__ vec3f evaluateVirtualLights(Ctx &c, bool straightPath, vec3f throughput, const PathVertexLite &last,
+__device__ __noinline__ vec3f evaluateVirtualLights(Ctx &c, bool straightPath, vec3f throughput, const PathVertexLite &last,
     bool environment, const Ray &ray)
 {
   vec3f L = make_vec3f(0.f);
@@ -107,7 +107,7 @@ __device__ vec3f evaluateVirtualLights(Ctx &c, bool straightPath, vec3f throughp
   return L;
 }
 
-__device__ vec3f nextEventEstimation(Ctx &c, const LDSampler &ld, bool firstBounceLight, uint32_t nFirst, uint32_t nIndirect,
+__device__ __noinline__ vec3f nextEventEstimation(Ctx &c, const LDSampler &ld, bool firstBounceLight, uint32_t nFirst, uint32_t nIndirect,
     vec3f throughput, const DifferentialGeometry &dg, const ObjBSDF &bsdf, vec3f wo, uint32_t &numLightSamplesOut)
 {
   vec3f L = make_vec3f(0.f);
@@ -317,7 +317,7 @@ __device__ __forceinline__ SciVisBSDF evalMaterial(const DifferentialGeometry &d
 }
 
 // single-volume marcher, AO flavour (ao/volumes.ispc:244-330): returns (rgb, alpha)
-__device__ vec4f integrateVolumeAO(Ctx &c, const VolumeHit &vh, const Ray &ray, RandomSampler &rs, float samplingRate)
+__device__ __noinline__ vec4f integrateVolumeAO(Ctx &c, const VolumeHit &vh, const Ray &ray, RandomSampler &rs, float samplingRate)
 {
   const OcVolume &v = *vh.vol;
   vec3f org = ray.org, dir = ray.dir;
@@ -367,7 +367,7 @@ __device__ SSI SciVis_computeShading(Ctx &c, const DifferentialGeometry &dg, Ran
     uint32_t py, int sampleIDz);
 
 // lightAlpha (scivis/lightAlpha.ispc:19-122)
-__device__ vec3f lightAlpha(Ctx &c, Ray &ray, RandomSampler &rs, vec3f weight, float quality)
+__device__ __noinline__ vec3f lightAlpha(Ctx &c, Ray &ray, RandomSampler &rs, vec3f weight, float quality)
 {
   vec3f alpha = make_vec3f(1.f);
   const float org_t_max = ray.t;
@@ -398,7 +398,7 @@ __device__ vec3f lightAlpha(Ctx &c, Ray &ray, RandomSampler &rs, vec3f weight, f
 }
 
 // SciVis_computeAO (scivis/SciVis.ispc:224-281)
-__device__ vec3f SciVis_computeAO(Ctx &c, RandomSampler &rs, const DifferentialGeometry &dg, int sampleCnt, float aoRadius,
+__device__ __noinline__ vec3f SciVis_computeAO(Ctx &c, RandomSampler &rs, const DifferentialGeometry &dg, int sampleCnt, float aoRadius,
     uint32_t px, uint32_t py, int sampleIDz)
 {
   const int accumID = sampleIDz * sampleCnt;
@@ -423,7 +423,7 @@ __device__ vec3f SciVis_computeAO(Ctx &c, RandomSampler &rs, const DifferentialG
 }
 
 // scivis/surfaces.ispc:17-128
-__device__ SSI SciVis_computeShading(Ctx &c, const DifferentialGeometry &dg, RandomSampler &rs, vec3f inDir, uint32_t px,
+__device__ __noinline__ SSI SciVis_computeShading(Ctx &c, const DifferentialGeometry &dg, RandomSampler &rs, vec3f inDir, uint32_t px,
     uint32_t py, int sampleIDz)
 {
   SSI ret;
@@ -470,7 +470,7 @@ __device__ SSI SciVis_computeShading(Ctx &c, const DifferentialGeometry &dg, Ran
 // returns (rgb, transmission)
 // volT / volHit follow the reference CPU form (sampleAllVolumes, scivis/volumes.ispc:160-169): the
 // first sample in front of the surface hit that is not fully transparent defines depth and IDs.
-__device__ vec4f integrateVolumeSciVis(Ctx &c, const VolumeHit &vh, const Ray &ray, RandomSampler &rs, float samplingRate,
+__device__ __noinline__ vec4f integrateVolumeSciVis(Ctx &c, const VolumeHit &vh, const Ray &ray, RandomSampler &rs, float samplingRate,
     uint32_t px, uint32_t py, int sampleIDz, float &volT, bool &volHit)
 {
   const OcVolume &v = *vh.vol;
@@ -613,7 +613,7 @@ __device__ void SciVis_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint
 }
 
 // computeAO (render/util.ispc:12-54)
-__device__ float computeAO(Ctx &c, const DifferentialGeometry &dg, int sampleCnt, float aoRadius, uint32_t px, uint32_t py,
+__device__ __noinline__ float computeAO(Ctx &c, const DifferentialGeometry &dg, int sampleCnt, float aoRadius, uint32_t px, uint32_t py,
     int sampleIDz)
 {
   const int accumID = sampleIDz * sampleCnt;
@@ -791,7 +791,10 @@ __global__ void __launch_bounds__(64) renderFrameKernel(const __grid_constant__ 
   const uint32_t tx = tileID % a.tilesX, ty = tileID / a.tilesX;
   const uint32_t x = tx * 64 + (taskInTile & 7u) * 8 + (threadIdx.x & 7u);
   const uint32_t y = ty * 64 + (taskInTile >> 3) * 8 + (threadIdx.x >> 3);
-  uint32_t stack[OC_STACK_SIZE];
+  __shared__ uint32_t s_stack[OC_STACK_SIZE * 64];
+  Stack stack;
+  stack.base = s_stack + threadIdx.x;
+  stack.stride = 64;
   Ctx c(a.world, a.ren, a.cam, a.fb, stack);
   if (x < (uint32_t)a.fb.sizeX && y < (uint32_t)a.fb.sizeY) {
     ScreenSample ss;
@@ -819,8 +822,11 @@ __global__ void __launch_bounds__(64) renderFrameKernel(const __grid_constant__ 
 __global__ void traceKernel(const OcWorld *world, OcRayHit *rays, uint32_t n, int occlusion)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ uint32_t s_stack[OC_STACK_SIZE * OC_MAX_BLOCK];
   if (i >= n) return;
-  uint32_t stack[OC_STACK_SIZE];
+  Stack stack;
+  stack.base = s_stack + threadIdx.x;
+  stack.stride = blockDim.x;
   OcRayHit rh = rays[i];
   Ray r;
   setRay(r, make_vec3f(rh.org[0], rh.org[1], rh.org[2]), make_vec3f(rh.dir[0], rh.dir[1], rh.dir[2]), rh.t0, rh.t);

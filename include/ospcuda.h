@@ -234,6 +234,9 @@ typedef struct {
   float aoRadius;
   float aoIntensity;
   float volumeSamplingRate;
+  /* host-side copy of OcWorld.numLights of the world this frame renders (set per ospRenderFrame by the
+   * device; PathTracerData is per world, PathTracerData.cpp:32-82): sizes the pathtracer's light-sample loop */
+  uint32_t worldNumLights;
 } OcRenderer;
 
 /* framebuffer (reference: LocalFBShared.h, FrameBufferShared.h; LocalFB.cpp:49-180) */

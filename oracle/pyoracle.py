@@ -111,7 +111,8 @@ class Renderer(C.Structure):
                 ("maxScatteringEvents", C.c_int32), ("maxRadiance", C.c_float), ("numLightSamples", C.c_int32),
                 ("limitIndirectLightSamples", C.c_uint32), ("backgroundRefraction", C.c_uint32),
                 ("shadowsEnabled", C.c_uint32), ("visibleLights", C.c_uint32), ("aoSamples", C.c_int32),
-                ("aoRadius", C.c_float), ("aoIntensity", C.c_float), ("volumeSamplingRate", C.c_float)]
+                ("aoRadius", C.c_float), ("aoIntensity", C.c_float), ("volumeSamplingRate", C.c_float),
+                ("worldNumLights", C.c_uint32)]
 
 
 class FrameBuffer(C.Structure):

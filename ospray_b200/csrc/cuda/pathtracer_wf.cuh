@@ -1,0 +1,440 @@
+// Wavefront path tracer: the pathtracer renderer as TRACE / SHADE kernel pairs over compacted path queues.
+//
+// Same algorithm, same sampler call order and the same per-path arithmetic as the megakernel in render.cu
+// (reference: render/pathtracer/PathTracer.ispc:75-249, PathSampler.ispc:109-415, NextEventEstimation.ispc:25-160,
+// TransparentShadow.ispc:18-85, VirtualLight.ispc:38-107); only the schedule differs:
+//
+//   TRACE<first>(d=0)   one thread per pixel sample: sampler init, pixel filter, camera ray, closest hit
+//   SHADE(d)            everything between two traces of samplePath(): background, virtual lights, postIntersect,
+//                       BSDF, NEE light sampling (shadow rays are EMITTED, not traced), BSDF sampling, roulette
+//   TRACE(d+1)          the shadow rays emitted at vertex d (transparent-shadow loop) and the continuation ray
+//   ...                 until maxPathLength; finished paths accumulate into the framebuffer where they end
+//
+// Why: the megakernel ran with 11.6 of 32 lanes active per instruction and stalled 7.3 issue slots per
+// instruction on instruction fetch (289 KB of SASS, profiles/r1_pt_megakernel_ncu.txt). Here every kernel is a
+// persistent grid-stride loop over a queue of live paths, appended with warp-aggregated atomics, so warps stay
+// full as paths die, and each kernel's code fits the instruction cache. Path state lives in HBM as float4
+// SoA arrays (128-bit coalesced accesses, ~180 B read + written per path and bounce).
+#pragma once
+
+#include <cooperative_groups.h>
+
+namespace oc {
+namespace cg = cooperative_groups;
+
+enum : uint32_t {
+  PT_DEPTH_MASK = 0xffu, PT_SCAT_SHIFT = 8, PT_SCAT_MASK = 0xff00u,
+  PT_STRAIGHT = 1u << 16, PT_SPECTRANS = 1u << 17, PT_FIRSTBOUNCE = 1u << 18, PT_DONE = 1u << 19, PT_HAS_SHADOW = 1u << 20
+};
+
+struct PtScratch
+{
+  float4 *rayO;   // org.xyz, t (far)
+  float4 *rayD;   // dir.xyz, t0
+  float4 *hit0;   // t, u, v, primID
+  float4 *hit1;   // Ng.xyz, geomID
+  uint32_t *hitInst;
+  float4 *thr;    // throughput.xyz, sample alpha
+  float4 *con;    // contribution.xyz, lastVertex.pdf_w
+  float4 *lastP;  // lastVertex.P.xyz, lastVertex.numLightSamples
+  float4 *lastN;  // lastVertex.Ns.xyz
+  uint2 *smp;     // LDSampler revIndex, scramble
+  uint32_t *flags;
+  float4 *sZ;     // this sample: z, primID, geomID, instID
+  float4 *sPos, *sFN, *sNrm, *sAlb; // this sample's AOVs (only when the framebuffer has the channel)
+  float4 *shA, *shB, *shC;          // shadow entries [slot * nls + i]: org.xyz,tmax | dir.xyz,mis | contrib.xyz,valid
+  float4 *accC, *accZ, *accPos, *accFN, *accNrm, *accAlb; // ScreenSample sums across the spp passes (spp > 1)
+  uint32_t *queue[2];
+  uint32_t *counters;
+  uint32_t nls;
+};
+
+struct PtArgs
+{
+  FrameArgs a;
+  PtScratch s;
+  uint32_t numPaths;   // slots in this batch
+  uint32_t firstTile;  // first owned tile of the batch
+  uint32_t nFirst, nIndirect;
+  int pass;            // sample index within the pixel (0 .. spp-1)
+  uint32_t depth;
+  const uint32_t *qIn;
+  uint32_t *qOut;
+  const uint32_t *cntIn;
+  uint32_t *cntOut;
+};
+
+__device__ __forceinline__ void ptAppend(uint32_t *q, uint32_t *cnt, uint32_t p)
+{
+  cg::coalesced_group g = cg::coalesced_threads();
+  uint32_t base = 0;
+  if (g.thread_rank() == 0) base = atomicAdd(cnt, g.size());
+  base = g.shfl(base, 0);
+  q[base + g.thread_rank()] = p;
+}
+
+__device__ __forceinline__ void ptSlotToPixel(const PtArgs &k, uint32_t slot, uint32_t &x, uint32_t &y)
+{
+  const uint32_t ownedTile = k.firstTile + (slot >> 12), taskInTile = (slot >> 6) & 63u, pin = slot & 63u;
+  const uint32_t tileID = k.a.fb.rank + ownedTile * k.a.fb.numRanks;
+  const uint32_t tx = tileID % k.a.tilesX, ty = tileID / k.a.tilesX;
+  x = tx * 64 + (taskInTile & 7u) * 8 + (pin & 7u);
+  y = ty * 64 + (taskInTile >> 3) * 8 + (pin >> 3);
+}
+
+__device__ __forceinline__ void ptSamplerParams(const PtArgs &k, uint32_t ix, uint32_t iy, uint32_t &seed, uint32_t &sampleOffs,
+    uint32_t &sampleOffsLight, uint32_t &bits, uint32_t &bitsLight)
+{
+  // PathTracer.ispc:126-147
+  const OcFrameBuffer &fb = k.a.fb;
+  seed = 0x49c5f37eu;
+  if (fb.targetFrames) {
+    const uint32_t targetSpp = (uint32_t)fb.targetFrames * k.a.ren.spp;
+    sampleOffs = OwenScramble4(interleaveZOrder16(ix, iy), seed) * targetSpp;
+    sampleOffsLight = sampleOffs * k.nFirst;
+    bits = 16 + 32 - __clz(targetSpp - 1);
+    bitsLight = 48 - __clz(targetSpp * k.nFirst - 1);
+  } else {
+    seed ^= (uint32_t)fb.sizeX * iy + ix;
+    sampleOffs = 0; sampleOffsLight = 0; bits = 16; bitsLight = 16;
+  }
+}
+
+// a path ended: clamp, fold into the pixel's ScreenSample (spp > 1) and accumulate into the framebuffer
+__device__ __forceinline__ void ptFinishPath(const PtArgs &k, uint32_t p, vec3f contribution, float alpha)
+{
+  const PtScratch &s = k.s;
+  const OcFrameBuffer &fb = k.a.fb;
+  uint32_t x, y;
+  ptSlotToPixel(k, p, x, y);
+  ScreenSample sm;
+  sm.rgb = contribution;
+  sm.alpha = alpha;
+  if (isnan(contribution.x) || isnan(contribution.y) || isnan(contribution.z)) { sm.rgb = make_vec3f(0.f); sm.alpha = 1.0f; }
+  sm.rgb = vmin(sm.rgb, make_vec3f(k.a.ren.maxRadiance));
+  const float4 z = s.sZ[p];
+  sm.z = z.x; sm.primID = __float_as_uint(z.y); sm.geomID = __float_as_uint(z.z); sm.instID = __float_as_uint(z.w);
+  sm.position = sm.firstNormal = sm.normal = sm.albedo = make_vec3f(0.f);
+  if (fb.position) { const float4 v = s.sPos[p]; sm.position = make_vec3f(v.x, v.y, v.z); }
+  if (fb.firstNormal) { const float4 v = s.sFN[p]; sm.firstNormal = make_vec3f(v.x, v.y, v.z); }
+  if (fb.normal) { const float4 v = s.sNrm[p]; sm.normal = make_vec3f(v.x, v.y, v.z); }
+  if (fb.albedo) { const float4 v = s.sAlb[p]; sm.albedo = make_vec3f(v.x, v.y, v.z); }
+  const int spp = k.a.ren.spp;
+  if (spp > 1) {
+    ScreenSample acc;
+    if (k.pass == 0) ScreenSample_zero(acc);
+    else {
+      const float4 c = s.accC[p], az = s.accZ[p];
+      acc.rgb = make_vec3f(c.x, c.y, c.z); acc.alpha = c.w;
+      acc.z = az.x; acc.primID = __float_as_uint(az.y); acc.geomID = __float_as_uint(az.z); acc.instID = __float_as_uint(az.w);
+      acc.position = acc.firstNormal = acc.normal = acc.albedo = make_vec3f(0.f);
+      if (fb.position) { const float4 v = s.accPos[p]; acc.position = make_vec3f(v.x, v.y, v.z); }
+      if (fb.firstNormal) { const float4 v = s.accFN[p]; acc.firstNormal = make_vec3f(v.x, v.y, v.z); }
+      if (fb.normal) { const float4 v = s.accNrm[p]; acc.normal = make_vec3f(v.x, v.y, v.z); }
+      if (fb.albedo) { const float4 v = s.accAlb[p]; acc.albedo = make_vec3f(v.x, v.y, v.z); }
+    }
+    ScreenSample_accumulate(acc, sm);
+    if (k.pass < spp - 1) {
+      s.accC[p] = make_float4(acc.rgb.x, acc.rgb.y, acc.rgb.z, acc.alpha);
+      s.accZ[p] = make_float4(acc.z, __uint_as_float(acc.primID), __uint_as_float(acc.geomID), __uint_as_float(acc.instID));
+      if (fb.position) s.accPos[p] = make_float4(acc.position.x, acc.position.y, acc.position.z, 0.f);
+      if (fb.firstNormal) s.accFN[p] = make_float4(acc.firstNormal.x, acc.firstNormal.y, acc.firstNormal.z, 0.f);
+      if (fb.normal) s.accNrm[p] = make_float4(acc.normal.x, acc.normal.y, acc.normal.z, 0.f);
+      if (fb.albedo) s.accAlb[p] = make_float4(acc.albedo.x, acc.albedo.y, acc.albedo.z, 0.f);
+      return;
+    }
+    sm = acc;
+    ScreenSample_normalize(sm, 1.f / (float)spp);
+  }
+  accumulateSample(fb, x, y, sm);
+}
+
+__device__ __forceinline__ void ptCountRays(const OcFrameBuffer &fb, uint32_t a, uint32_t b, uint32_t c)
+{
+  if (!fb.rayCounters) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (a) atomicAdd(fb.rayCounters + 0, (unsigned long long)a);
+    if (b) atomicAdd(fb.rayCounters + 1, (unsigned long long)b);
+    if (c) atomicAdd(fb.rayCounters + 2, (unsigned long long)c);
+  }
+}
+
+#define PT_TRACE_BLOCK 128
+
+// ---- TRACE --------------------------------------------------------------------------------------------------
+template <bool FIRST>
+__global__ void __launch_bounds__(PT_TRACE_BLOCK) ptTraceKernel(const __grid_constant__ PtArgs k)
+{
+  __shared__ uint32_t s_stack[OC_STACK_SIZE * PT_TRACE_BLOCK];
+  Stack stack;
+  stack.base = s_stack + threadIdx.x;
+  stack.stride = PT_TRACE_BLOCK;
+  const PtScratch &s = k.s;
+  const OcRenderer &ren = k.a.ren;
+  const OcFrameBuffer &fb = k.a.fb;
+  uint32_t nPrimary = 0, nSecondary = 0, nShadow = 0;
+  const uint32_t n = FIRST ? k.numPaths : *k.cntIn;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t p = FIRST ? i : k.qIn[i];
+    Ray ray;
+    if (FIRST) {
+      uint32_t ix, iy;
+      ptSlotToPixel(k, p, ix, iy);
+      if (ix >= (uint32_t)fb.sizeX || iy >= (uint32_t)fb.sizeY) continue;
+      // PathTracer_renderPixel, one sample (PathTracer.ispc:149-193)
+      uint32_t seed, sampleOffs, sampleOffsLight, bits, bitsLight;
+      ptSamplerParams(k, ix, iy, seed, sampleOffs, sampleOffsLight, bits, bitsLight);
+      const uint32_t sampleID = (uint32_t)fb.frameID * ren.spp + k.pass;
+      LDSampler ld;
+      LDSampler_init(ld, seed, sampleOffs + sampleID, sampleOffsLight + sampleID * k.nFirst, bits, bitsLight);
+      const vec2f rcpSize = make_vec2f(1.f / (float)fb.sizeX, 1.f / (float)fb.sizeY);
+      const vec2f pixel_center = make_vec2f(((float)ix + 0.5f) * rcpSize.x, ((float)iy + 0.5f) * rcpSize.y);
+      uint32_t ss234[3];
+      const vec2f pixelSample = LDSampler_getNext5Samples(ld, ss234);
+      const vec2f pfSample = pixelFilterSample(ren, pixelSample);
+      const vec2f screen = pixel_center + pfSample * rcpSize;
+      vec2f lens = make_vec2f(0.5f, 0.5f);
+      if (k.a.cam.needLensSample) lens = LDSampler_finalizeDim23(ld, ss234);
+      cameraInitRay(k.a.cam, ray, screen, lens);
+      // samplePath() prologue (PathSampler.ispc:116-133)
+      s.smp[p] = make_uint2(ld.revIndex, ld.scramble);
+      s.flags[p] = PT_STRAIGHT | PT_SPECTRANS | PT_FIRSTBOUNCE;
+      s.thr[p] = make_float4(1.f, 1.f, 1.f, 1.f);
+      s.con[p] = make_float4(0.f, 0.f, 0.f, INFINITY);
+      s.lastP[p] = make_float4(ray.org.x, ray.org.y, ray.org.z, __uint_as_float(0u));
+      s.lastN[p] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, 0.f);
+      s.sZ[p] = make_float4(INFINITY, __uint_as_float(OC_INVALID_ID), __uint_as_float(OC_INVALID_ID), __uint_as_float(OC_INVALID_ID));
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (fb.position) s.sPos[p] = zero;
+      if (fb.firstNormal) s.sFN[p] = zero;
+      if (fb.normal) s.sNrm[p] = zero;
+      if (fb.albedo) s.sAlb[p] = zero;
+      s.rayO[p] = make_float4(ray.org.x, ray.org.y, ray.org.z, ray.t);
+      s.rayD[p] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, ray.t0);
+      nPrimary++;
+    } else {
+      const uint32_t flags = s.flags[p];
+      if (flags & PT_HAS_SHADOW) {
+        // shadow rays of the previous vertex: transparentShadow (TransparentShadow.ispc:18-85) per light sample,
+        // summed in sample order like nextEventEstimation's L (NextEventEstimation.ispc:140-156)
+        vec3f L = make_vec3f(0.f);
+        for (uint32_t j = 0; j < s.nls; j++) {
+          const size_t e = (size_t)p * s.nls + j;
+          const float4 c = s.shC[e];
+          if (c.w == 0.f) continue;
+          const float4 a = s.shA[e], b = s.shB[e];
+          Ray sr;
+          setRay(sr, make_vec3f(a.x, a.y, a.z), make_vec3f(b.x, b.y, b.z), 0.f, a.w);
+          vec3f lightContrib = make_vec3f(c.x, c.y, c.z);
+          uint32_t maxDepth = ren.maxDepth;
+          const float tOriginal = sr.t;
+          while (1) {
+            nShadow++;
+            traceWorld<false>(k.a.world, sr, stack);
+            if (!hadHit(sr)) break;
+            DifferentialGeometry dg;
+            postIntersect(k.a.world, ren, dg, sr, DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR);
+            lightContrib = lightContrib * materialTransparency(dg);
+            if (reduce_max(lightContrib) <= ren.minContribution || --maxDepth <= 0) { lightContrib = make_vec3f(0.f); break; }
+            setRay(sr, sr.org, sr.dir, sr.t + dg.epsilon, tOriginal);
+          }
+          if (reduce_max(lightContrib) > 0) L = L + lightContrib * b.w;
+        }
+        float4 con = s.con[p];
+        con.x += L.x; con.y += L.y; con.z += L.z;
+        if (flags & PT_DONE) {
+          ptFinishPath(k, p, make_vec3f(con.x, con.y, con.z), s.thr[p].w);
+          continue;
+        }
+        s.con[p] = con;
+      }
+      const float4 o = s.rayO[p], d = s.rayD[p];
+      setRay(ray, make_vec3f(o.x, o.y, o.z), make_vec3f(d.x, d.y, d.z), d.w, o.w);
+      nSecondary++;
+    }
+    ray.u = ray.v = 0.f;
+    ray.Ng = make_vec3f(0.f);
+    traceWorld<false>(k.a.world, ray, stack);
+    s.hit0[p] = make_float4(ray.t, ray.u, ray.v, __uint_as_float(ray.primID));
+    s.hit1[p] = make_float4(ray.Ng.x, ray.Ng.y, ray.Ng.z, __uint_as_float(ray.geomID));
+    s.hitInst[p] = ray.instID;
+    ptAppend(k.qOut, k.cntOut, p);
+  }
+  ptCountRays(fb, nPrimary, nSecondary, nShadow);
+}
+
+// ---- SHADE --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ptShadeKernel(const __grid_constant__ PtArgs k)
+{
+  const PtScratch &s = k.s;
+  const OcRenderer &ren = k.a.ren;
+  const OcFrameBuffer &fb = k.a.fb;
+  Stack dummy;
+  dummy.base = nullptr; dummy.stride = 0;
+  Ctx c(k.a.world, k.a.ren, k.a.cam, k.a.fb, dummy);
+  const uint32_t n = *k.cntIn;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t p = k.qIn[i];
+    uint32_t flags = s.flags[p] & ~(PT_HAS_SHADOW | PT_DONE);
+    const uint32_t depth = flags & PT_DEPTH_MASK;
+    uint32_t scatteringEvents = (flags & PT_SCAT_MASK) >> PT_SCAT_SHIFT;
+    bool straightPath = flags & PT_STRAIGHT, specularTransmissionPath = flags & PT_SPECTRANS, firstBounceLight = flags & PT_FIRSTBOUNCE;
+    Ray ray;
+    {
+      const float4 o = s.rayO[p], d = s.rayD[p], h0 = s.hit0[p], h1 = s.hit1[p];
+      ray.org = make_vec3f(o.x, o.y, o.z); ray.dir = make_vec3f(d.x, d.y, d.z); ray.t0 = d.w;
+      ray.t = h0.x; ray.u = h0.y; ray.v = h0.z; ray.primID = __float_as_uint(h0.w);
+      ray.Ng = make_vec3f(h1.x, h1.y, h1.z); ray.geomID = __float_as_uint(h1.w);
+      ray.instID = s.hitInst[p];
+    }
+    float4 thr4 = s.thr[p], con4 = s.con[p];
+    vec3f throughput = make_vec3f(thr4.x, thr4.y, thr4.z), contribution = make_vec3f(con4.x, con4.y, con4.z);
+    float alpha = thr4.w;
+    PathVertexLite last;
+    {
+      const float4 lp = s.lastP[p], ln = s.lastN[p];
+      last.P = make_vec3f(lp.x, lp.y, lp.z); last.Ns = make_vec3f(ln.x, ln.y, ln.z);
+      last.pdf_w = con4.w; last.numLightSamples = __float_as_uint(lp.w);
+    }
+    LDSampler ld;
+    {
+      uint32_t ix, iy, seed, so, sol, bits, bitsLight;
+      ptSlotToPixel(k, p, ix, iy);
+      ptSamplerParams(k, ix, iy, seed, so, sol, bits, bitsLight);
+      const uint32_t sampleID = (uint32_t)fb.frameID * ren.spp + k.pass;
+      LDSampler_init(ld, seed, so + sampleID, sol + sampleID * k.nFirst, bits, bitsLight);
+      const uint2 sm = s.smp[p];
+      ld.revIndex = sm.x; ld.scramble = sm.y;
+    }
+
+    // ---- one iteration of samplePath()'s loop, after the trace (PathSampler.ispc:196-412) ----
+    bool alive = false, hasShadow = false;
+    do {
+      const bool surface = hadHit(ray);
+      const vec3f wo = neg(ray.dir);
+      if (depth == 0) {
+        float4 z = s.sZ[p];
+        z.x = fb.projectedDepth ? ray.t * dot(ray.dir, toV(k.a.cam.direction)) : ray.t;
+        s.sZ[p] = z;
+      }
+      if (!surface && (ren.backgroundRefraction ? specularTransmissionPath : straightPath)) {
+        const vec4f bg = getBackground(ren);
+        alpha -= luminance(throughput) * (1.0f - bg.w);
+        contribution = contribution + throughput * make_vec3f(bg);
+      }
+      contribution = contribution + evaluateVirtualLights(c, straightPath, throughput, last, !surface, ray);
+      if (!surface) break;
+      if (depth >= ren.maxDepth) break; // numGeoLights == 0
+
+      DifferentialGeometry dg;
+      postIntersect(k.a.world, ren, dg, ray,
+          DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR | DG_TANGENTS | DG_MOTIONBLUR);
+      if (depth == 0) {
+        float4 z = s.sZ[p];
+        z.y = __uint_as_float(dg.primID); z.z = __uint_as_float(dg.objID); z.w = __uint_as_float(dg.instID);
+        s.sZ[p] = z;
+        if (fb.position) s.sPos[p] = make_float4(dg.P.x, dg.P.y, dg.P.z, 0.f);
+        if (fb.firstNormal) s.sFN[p] = make_float4(dg.Ns.x, dg.Ns.y, dg.Ns.z, 0.f);
+      }
+      if (depth >= ren.maxDepth || scatteringEvents >= (uint32_t)ren.maxScatteringEvents) break;
+
+      ObjBSDF bsdf;
+      OBJ_getBSDF(bsdf, dg);
+      if (!bsdf.valid) break;
+
+      LDSampler_nextGroup(ld);
+      uint32_t vertexLightSamples = 0;
+      if (bsdf.scatteringType & SC_SMOOTH) {
+        if (scatteringEvents == 0) {
+          if (fb.albedo) { const vec3f v = throughput * bsdf.albedo; s.sAlb[p] = make_float4(v.x, v.y, v.z, 0.f); }
+          if (fb.normal) { const vec3f v = throughput * bsdf.frame.vz; s.sNrm[p] = make_float4(v.x, v.y, v.z, 0.f); }
+        }
+        // nextEventEstimation up to the shadow ray (NextEventEstimation.ispc:36-118): emit, TRACE(d+1) resolves
+        const uint32_t numLightSamples = firstBounceLight ? k.nFirst : k.nIndirect;
+        vertexLightSamples = numLightSamples;
+        const uint32_t numLights = k.a.world->numLights;
+        for (uint32_t j = 0; j < s.nls; j++) {
+          const size_t e = (size_t)p * s.nls + j;
+          bool valid = false;
+          if (j < numLightSamples) {
+            float ss;
+            const vec2f sl = LDSampler_get3LightSamples(ld, j, numLightSamples > 1, ss);
+            const Sample1D sel = Distribution1D_sample((int)numLights, k.a.world->lightsCDF, 0, ss);
+            const float lightSelectionProb = sel.prob * numLightSamples;
+            LightSample ls = Light_sample(k.a.world->lights[sel.idx], dg, sl);
+            ls.weight = ls.weight / lightSelectionProb;
+            ls.pdf *= lightSelectionProb;
+            if (!(reduce_max(ls.weight) <= 0.0f || ls.pdf <= 0.0f)) {
+              const EvalRes fe = OBJ_eval(bsdf, wo, ls.dir);
+              if (!(reduce_max(fe.value) <= 0.0f)) {
+                vec3f org = dg.P;
+                if (dot(dg.Ng, ls.dir) < 0.f) org = org - (2.0f * dg.epsilon) * dg.Ng;
+                const vec3f unshaded = throughput * fe.value * ls.weight;
+                s.shA[e] = make_float4(org.x, org.y, org.z, ls.dist);
+                s.shB[e] = make_float4(ls.dir.x, ls.dir.y, ls.dir.z, misHeuristic(ls.pdf, fe.pdf));
+                s.shC[e] = make_float4(unshaded.x, unshaded.y, unshaded.z, 1.f);
+                valid = true;
+                hasShadow = true;
+              }
+            }
+          }
+          if (!valid) s.shC[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        firstBounceLight = false;
+      }
+
+      float ss;
+      uint32_t uu3;
+      const vec2f sb = LDSampler_getNext4Samples(ld, ss, uu3);
+      SampleRes fs = OBJ_sample(bsdf, wo, sb, ss);
+      {
+        const bool sameSide = dot(fs.wi, dg.Ng) >= 0.f;
+        const bool reflection = fs.type & SC_REFLECTION;
+        if (sameSide != reflection) fs.weight = make_vec3f(0.0f);
+      }
+      if (reduce_max(fs.weight) <= 0.0f || fs.pdf <= 0.0f) break;
+      throughput = throughput * fs.weight;
+      if (depth >= (uint32_t)ren.rouletteDepth) {
+        const float rr = LDSampler_finalizeDim3(ld, uu3);
+        const float contProb = fminf(reduce_max(throughput), 0.95f);
+        if (rr > contProb) break;
+        throughput = throughput * (1.f / contProb);
+      }
+      vec3f ray_org = dg.P;
+      if (fs.type & SC_TRANSMISSION) ray_org = ray_org - (2.0f * dg.epsilon) * dg.Ng;
+      if ((fs.type & ~SC_SPECULAR_TRANSMISSION)) {
+        last.P = dg.P; last.Ns = dg.Ns; last.pdf_w = fs.pdf; last.numLightSamples = vertexLightSamples;
+      }
+      if (!eq3(ray.dir, fs.wi)) straightPath = false;
+      if (!(fs.type & SC_SPECULAR_TRANSMISSION)) specularTransmissionPath = false;
+      s.rayO[p] = make_float4(ray_org.x, ray_org.y, ray_org.z, INFINITY);
+      s.rayD[p] = make_float4(fs.wi.x, fs.wi.y, fs.wi.z, 0.f);
+      if (fs.type & SC_SMOOTH) scatteringEvents++;
+      alive = reduce_max(throughput) > ren.minContribution;
+    } while (false);
+
+    if (!alive && !hasShadow) {
+      ptFinishPath(k, p, contribution, alpha);
+      continue;
+    }
+    s.thr[p] = make_float4(throughput.x, throughput.y, throughput.z, alpha);
+    s.con[p] = make_float4(contribution.x, contribution.y, contribution.z, last.pdf_w);
+    if (alive) {
+      s.lastP[p] = make_float4(last.P.x, last.P.y, last.P.z, __uint_as_float(last.numLightSamples));
+      s.lastN[p] = make_float4(last.Ns.x, last.Ns.y, last.Ns.z, 0.f);
+      s.smp[p] = make_uint2(ld.revIndex, ld.scramble);
+    }
+    s.flags[p] = ((depth + 1) & PT_DEPTH_MASK) | (scatteringEvents << PT_SCAT_SHIFT) | (straightPath ? PT_STRAIGHT : 0u)
+        | (specularTransmissionPath ? PT_SPECTRANS : 0u) | (firstBounceLight ? PT_FIRSTBOUNCE : 0u) | (hasShadow ? PT_HAS_SHADOW : 0u)
+        | (alive ? 0u : PT_DONE);
+    ptAppend(k.qOut, k.cntOut, p);
+  }
+}
+
+} // namespace oc

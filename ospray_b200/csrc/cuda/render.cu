@@ -8,6 +8,7 @@
 // scivis/surfaces.ispc:17-128, scivis/surfaces.ih:49-92, scivis/lightAlpha.ispc:19-122,
 // scivis/volumes.ispc:302-439; render/ao/AORenderer.ispc:23-149, ao/surfaces.ispc:18-74,
 // ao/volumes.ispc, render/util.ispc:12-54; render/ScreenSample.ih:12-92; fb/LocalFB.ispc:14-78.
+#include <algorithm>
 #include "runtime.h"
 #include "volume.cuh"
 
@@ -780,7 +781,12 @@ struct FrameArgs
   OcRenderer ren;
   OcFrameBuffer fb;
   uint32_t tilesX, tilesY;
+  uint32_t ptFirstBounceLightSamples, ptIndirectLightSamples; // wavefront pathtracer (PathTracer.ispc:96-104)
 };
+
+} // namespace oc
+#include "pathtracer_wf.cuh"
+namespace oc {
 
 template <int RENDERER>
 __global__ void __launch_bounds__(64) renderFrameKernel(const __grid_constant__ FrameArgs a)
@@ -844,6 +850,117 @@ __global__ void traceKernel(const OcWorld *world, OcRayHit *rays, uint32_t n, in
 
 using namespace oc;
 
+// ---- wavefront path tracer: scratch + launch sequence ----------------------------------------------------------
+namespace {
+struct PtHost
+{
+  void *block = nullptr;
+  size_t blockBytes = 0;
+  int device = -1;
+  int traceBlocks = 0, shadeBlocks = 0; // persistent grids (resident CTAs per SM x SM count)
+} g_pt;
+
+size_t alignUp(size_t v) { return (v + 255) & ~size_t(255); }
+
+// carve the SoA arrays for `paths` slots out of one allocation (grown on demand, kept across frames)
+int ptCarve(oc::PtScratch &s, uint32_t paths, uint32_t nls, bool needAcc, uint32_t numCounters)
+{
+  const size_t P = paths;
+  size_t bytes = 0;
+  auto take = [&](size_t n) { const size_t o = bytes; bytes += alignUp(n); return o; };
+  size_t off[32];
+  int k = 0;
+  for (int i = 0; i < 8; i++) off[k++] = take(P * 16);       // rayO rayD hit0 hit1 thr con lastP lastN
+  off[k++] = take(P * 4);                                    // hitInst
+  off[k++] = take(P * 8);                                    // smp
+  off[k++] = take(P * 4);                                    // flags
+  for (int i = 0; i < 5; i++) off[k++] = take(P * 16);       // sZ sPos sFN sNrm sAlb
+  for (int i = 0; i < 3; i++) off[k++] = take(P * 16 * nls); // shA shB shC
+  for (int i = 0; i < 6; i++) off[k++] = take(needAcc ? P * 16 : 0);
+  off[k++] = take(P * 4); off[k++] = take(P * 4);            // queues
+  off[k++] = take(numCounters * 4);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (bytes > g_pt.blockBytes || dev != g_pt.device) {
+    if (g_pt.block) cudaFree(g_pt.block);
+    g_pt.block = nullptr; g_pt.blockBytes = 0;
+    OC_TRY(cudaMalloc(&g_pt.block, bytes));
+    g_pt.blockBytes = bytes; g_pt.device = dev;
+    g_pt.traceBlocks = g_pt.shadeBlocks = 0;
+  }
+  char *b = (char *)g_pt.block;
+  k = 0;
+  s.rayO = (float4 *)(b + off[k++]); s.rayD = (float4 *)(b + off[k++]); s.hit0 = (float4 *)(b + off[k++]); s.hit1 = (float4 *)(b + off[k++]);
+  s.thr = (float4 *)(b + off[k++]); s.con = (float4 *)(b + off[k++]); s.lastP = (float4 *)(b + off[k++]); s.lastN = (float4 *)(b + off[k++]);
+  s.hitInst = (uint32_t *)(b + off[k++]); s.smp = (uint2 *)(b + off[k++]); s.flags = (uint32_t *)(b + off[k++]);
+  s.sZ = (float4 *)(b + off[k++]); s.sPos = (float4 *)(b + off[k++]); s.sFN = (float4 *)(b + off[k++]); s.sNrm = (float4 *)(b + off[k++]);
+  s.sAlb = (float4 *)(b + off[k++]);
+  s.shA = (float4 *)(b + off[k++]); s.shB = (float4 *)(b + off[k++]); s.shC = (float4 *)(b + off[k++]);
+  s.accC = (float4 *)(b + off[k++]); s.accZ = (float4 *)(b + off[k++]); s.accPos = (float4 *)(b + off[k++]); s.accFN = (float4 *)(b + off[k++]);
+  s.accNrm = (float4 *)(b + off[k++]); s.accAlb = (float4 *)(b + off[k++]);
+  s.queue[0] = (uint32_t *)(b + off[k++]); s.queue[1] = (uint32_t *)(b + off[k++]);
+  s.counters = (uint32_t *)(b + off[k++]);
+  s.nls = nls;
+  return 0;
+}
+
+size_t ptBytesPerPath(uint32_t nls, bool needAcc) { return 8 * 16 + 16 + 5 * 16 + 48 * (size_t)nls + (needAcc ? 96 : 0) + 8; }
+
+int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
+{
+  using namespace oc;
+  cudaStream_t st = (cudaStream_t)ospcuda_stream();
+  PtArgs k;
+  k.a = fa;
+  // light sample counts (PathTracer.ispc:96-104); world->numLights lives in device memory: mirror it via the args
+  k.nFirst = fa.ptFirstBounceLightSamples;
+  k.nIndirect = fa.ptIndirectLightSamples;
+  const uint32_t maxDepth = fa.ren.maxDepth < 250u ? fa.ren.maxDepth : 250u;
+  k.a.ren.maxDepth = maxDepth;
+  const uint32_t nls = k.nFirst > 0 ? k.nFirst : 1;
+  const bool needAcc = fa.ren.spp > 1;
+  const uint32_t numCounters = 2 * (maxDepth + 2);
+  // batch the owned tiles so that the path state stays under ~1.5 GB (many light samples / 4K frames)
+  const size_t budget = size_t(1536) << 20;
+  uint32_t tilesPerBatch = (uint32_t)std::max<size_t>(1, budget / (ptBytesPerPath(nls, needAcc) * 4096));
+  if (tilesPerBatch > ownedTiles) tilesPerBatch = ownedTiles;
+  if (int rc = ptCarve(k.s, tilesPerBatch * 4096u, nls, needAcc, numCounters)) return rc;
+  if (!g_pt.traceBlocks) {
+    int dev = 0, sms = 148, a = 1, b = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, ptTraceKernel<false>, PT_TRACE_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ptShadeKernel, 128, 0);
+    g_pt.traceBlocks = sms * (a > 0 ? a : 1);
+    g_pt.shadeBlocks = sms * (b > 0 ? b : 1);
+  }
+  for (uint32_t tile0 = 0; tile0 < ownedTiles; tile0 += tilesPerBatch) {
+    const uint32_t nt = std::min(tilesPerBatch, ownedTiles - tile0);
+    k.firstTile = tile0;
+    k.numPaths = nt * 4096u;
+    for (int pass = 0; pass < fa.ren.spp; pass++) {
+      k.pass = pass;
+      OC_TRY(cudaMemsetAsync(k.s.counters, 0, numCounters * sizeof(uint32_t), st));
+      k.depth = 0; k.qIn = nullptr; k.cntIn = nullptr; k.qOut = k.s.queue[0]; k.cntOut = k.s.counters + 0;
+      ptTraceKernel<true><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+      oc_count_launch();
+      for (uint32_t d = 0; d <= maxDepth; d++) {
+        k.depth = d;
+        if (d > 0) {
+          k.qIn = k.s.queue[1]; k.cntIn = k.s.counters + (2 * d - 1); k.qOut = k.s.queue[0]; k.cntOut = k.s.counters + 2 * d;
+          ptTraceKernel<false><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+          oc_count_launch();
+        }
+        k.qIn = k.s.queue[0]; k.cntIn = k.s.counters + 2 * d; k.qOut = k.s.queue[1]; k.cntOut = k.s.counters + (2 * d + 1);
+        ptShadeKernel<<<g_pt.shadeBlocks, 128, 0, st>>>(k);
+        oc_count_launch();
+      }
+    }
+  }
+  return oc_check(cudaGetLastError(), "wavefront pathtracer");
+}
+} // namespace
+
 extern "C" int ospcuda_render_frame(const OcWorld *d_world, const OcCamera *camera, const OcRenderer *renderer,
     const OcFrameBuffer *fb)
 {
@@ -857,7 +974,13 @@ extern "C" int ospcuda_render_frame(const OcWorld *d_world, const OcCamera *came
   const dim3 grid(owned * 64), block(64);
   cudaStream_t st = (cudaStream_t)ospcuda_stream();
   switch (renderer->type) {
-  case OC_RENDERER_PATHTRACER: renderFrameKernel<OC_RENDERER_PATHTRACER><<<grid, block, 0, st>>>(a); break;
+  case OC_RENDERER_PATHTRACER: {
+    const uint32_t numLights = renderer->worldNumLights;
+    a.ptFirstBounceLightSamples = (renderer->numLightSamples >= 0 && numLights > 0) ? (uint32_t)renderer->numLightSamples
+                                                                                     : std::min(1024u, numLights);
+    a.ptIndirectLightSamples = (renderer->limitIndirectLightSamples && a.ptFirstBounceLightSamples >= 1) ? 1u : a.ptFirstBounceLightSamples;
+    return renderPathTracerWavefront(a, owned);
+  }
   case OC_RENDERER_SCIVIS: renderFrameKernel<OC_RENDERER_SCIVIS><<<grid, block, 0, st>>>(a); break;
   case OC_RENDERER_AO: renderFrameKernel<OC_RENDERER_AO><<<grid, block, 0, st>>>(a); break;
   default: return oc_set_error(cudaErrorInvalidValue, "ospcuda_render_frame: unknown renderer type");

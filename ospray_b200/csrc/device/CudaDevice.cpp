@@ -146,7 +146,9 @@ OSPFuture CudaDevice::renderFrame(OSPFrameBuffer _fb, OSPRenderer _r, OSPCamera 
     const OcWorld *dw = w->prepareFrame();
     checkCuda(ospcuda_event_record(f->evStart), "event record");
     const bool finished = fb->sh.targetFrames && fb->doAccum && fb->sh.frameID >= fb->sh.targetFrames; // accumulationFinished()
-    if (!finished) checkCuda(ospcuda_render_frame(dw, &c->sh, &r->sh, &fb->sh), "render kernel");
+    OcRenderer rsh = r->sh;
+    rsh.worldNumLights = w->sh.numLights;
+    if (!finished) checkCuda(ospcuda_render_frame(dw, &c->sh, &rsh, &fb->sh), "render kernel");
     checkCuda(ospcuda_event_record(f->evRendered), "event record");
     fb->postProcess();
     checkCuda(ospcuda_event_record(f->evFinished), "event record");

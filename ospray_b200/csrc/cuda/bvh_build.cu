@@ -14,6 +14,7 @@
 //      opened first; subtrees of <= 4 records become leaves (records are contiguous after the sort)
 //   6. gather records into leaf order
 #include <cub/device/device_radix_sort.cuh>
+#include <cstdlib>
 #include <vector>
 #include "runtime.h"
 #include "shading.cuh"
@@ -449,7 +450,24 @@ extern "C" int ospcuda_bvh_build_group(const OcModel *d_models, uint32_t numMode
   initBoundsKernel<<<1, 32, 0, st>>>(d_bounds.p);
   emitRecordsKernel<<<(n + 255) / 256, 256, 0, st>>>(d_models, numModels, d_off.p, n, records.p, boxes.p, d_bounds.p);
   oc_count_launch();
-  const int rc = buildFromBoxes(boxes.p, records.p, n, d_bounds.p, bvh);
+  int rc = 0;
+  static const uint32_t linearMax = getenv("OSPCUDA_LINEAR_MAX") ? (uint32_t)atoi(getenv("OSPCUDA_LINEAR_MAX")) : OC_LINEAR_MAX;
+  if (n <= linearMax) {
+    // tiny group: a hierarchy costs more than it saves. Keep the records in (model, primitive) order and let
+    // traversal scan them linearly (uniform trip count and broadcast loads across the warp: no divergence).
+    float4 *recOut = nullptr;
+    OC_TRY(cudaMalloc((void **)&recOut, sizeof(float4) * 3 * (size_t)n));
+    OC_TRY(cudaMemcpyAsync(recOut, records.p, sizeof(float4) * 3 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    uint32_t h_enc[6];
+    OC_TRY(cudaMemcpyAsync(h_enc, d_bounds.p, sizeof(h_enc), cudaMemcpyDeviceToHost, st));
+    OC_TRY(cudaStreamSynchronize(st));
+    bvh->nodes = nullptr;
+    bvh->prims = reinterpret_cast<const OcVec4f *>(recOut);
+    bvh->numNodes = 0;
+    bvh->numRecords = n;
+    for (int k = 0; k < 6; k++) bvh->bounds[k] = decF(h_enc[k]);
+  } else
+    rc = buildFromBoxes(boxes.p, records.p, n, d_bounds.p, bvh);
   OC_TRY(cudaEventRecord(e1, st));
   OC_TRY(cudaEventSynchronize(e1));
   float ms = 0.f;

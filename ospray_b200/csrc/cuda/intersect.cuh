@@ -19,6 +19,7 @@ using namespace ospm;
 #define OC_INVALID_ID 0xFFFFFFFFu
 #define OC_TLAS_THRESHOLD 4u
 #define OC_STACK_SIZE 48
+#define OC_LINEAR_MAX 8u // groups with at most this many leaf records are scanned linearly (no hierarchy)
 #define OC_MAX_BLOCK 128 // largest CTA of a kernel that traverses (shared stack = OC_STACK_SIZE * blockDim.x words)
 
 struct Ray
@@ -77,9 +78,13 @@ __device__ __forceinline__ bool intersectTriangle(const Ray &ray, vec3f v0, vec3
   const float den = dotF(triNg, ray.dir);
   const float absDen = fabsf(den);
   const uint32_t sgn = __float_as_uint(den) & 0x80000000u;
+  // staged rejection (identical decisions: V >= 0 and fl(U+V) <= absDen imply U <= absDen); with coherent
+  // rays most warps leave at the first test and never issue the V / T arithmetic
   const float U = __uint_as_float(__float_as_uint(dotF(R, e2)) ^ sgn);
+  if (!(den != 0.f && U >= 0.f && U <= absDen))
+    return false;
   const float V = __uint_as_float(__float_as_uint(dotF(R, e1)) ^ sgn);
-  if (!(den != 0.f && U >= 0.f && V >= 0.f && __fadd_rn(U, V) <= absDen))
+  if (!(V >= 0.f && __fadd_rn(U, V) <= absDen))
     return false;
   const float T = __uint_as_float(__float_as_uint(dotF(triNg, C)) ^ sgn);
   if (!(__fmul_rn(absDen, ray.t0) < T && T <= __fmul_rn(absDen, ray.t)))
@@ -173,12 +178,10 @@ __device__ __forceinline__ bool intersectRecord(Ray &ray, const OcVec4f *rec, ui
   if (!hit)
     return false;
   ray.t = t;
-  if (!OCCLUSION) {
-    ray.u = u; ray.v = v; ray.Ng = Ng;
-    ray.primID = __float_as_uint(r0.w);
-    ray.geomID = __float_as_uint(r1.w);
-    ray.instID = instID;
-  }
+  ray.primID = __float_as_uint(r0.w);
+  ray.geomID = __float_as_uint(r1.w);
+  ray.instID = instID;
+  if (!OCCLUSION) { ray.u = u; ray.v = v; ray.Ng = Ng; }
   return true;
 }
 
@@ -231,16 +234,26 @@ struct Stack
 };
 
 // Traverse one BVH (group BLAS), "while-while": descend inner nodes until a leaf is reached, then test its
-// records. Not inlined on purpose: the frame kernels call it from many places and an inlined copy per call
-// site made them instruction-fetch bound (ncu: stall_no_instruction 7.3 per issue, profiles/r1_*).
+// records. Inlined: a by-reference Ray handed to a non-inlined function lives in local memory (309 LDL / 198 STL
+// in the first wavefront TRACE kernel). Kernels with many trace call sites (the scivis / ao megakernels) go
+// through the non-inlined wrapper traceWorldNI below instead, which bounds their code size.
 template <bool OCCLUSION>
-__device__ __noinline__ bool traverseBLAS(const OcNode4 *__restrict__ nodes, const OcVec4f *__restrict__ prims, Ray &ray,
-    uint32_t instID, Stack st, int sp0)
+__device__ __forceinline__ bool traverseBLAS(const OcNode4 *__restrict__ nodes, const OcVec4f *__restrict__ prims, uint32_t numRecords,
+    Ray &ray, uint32_t instID, Stack st, int sp0)
 {
+  bool any = false;
+  if (nodes == nullptr) { // linear group (<= OC_LINEAR_MAX records): uniform loop, warp-broadcast loads
+    const uint32_t n = numRecords;
+    for (uint32_t i = 0; i < n; i++)
+      if (intersectRecord<OCCLUSION>(ray, prims + 3 * (size_t)i, instID)) {
+        any = true;
+        if (OCCLUSION) return true;
+      }
+    return any;
+  }
   const vec3f rdir = safeRcpDir(ray.dir);
   int sp = sp0;
   uint32_t cur = 0; // root
-  bool any = false;
   while (true) {
     // ---- inner nodes ----
     while (!(cur & 0x80000000u)) {
@@ -292,8 +305,8 @@ template <bool OCCLUSION>
 __device__ __forceinline__ bool traceInstance(const OcInstance *__restrict__ inst, uint32_t instID, Ray &ray, Stack st, int sp0)
 {
   const OcGroup *g = inst->group;
-  const uint32_t numNodes = g->bvh.numNodes;
-  if (numNodes == 0)
+  const uint32_t numRecords = g->bvh.numRecords;
+  if (numRecords == 0)
     return false;
   Ray local = ray;
   if (!inst->isIdentity) {
@@ -301,13 +314,11 @@ __device__ __forceinline__ bool traceInstance(const OcInstance *__restrict__ ins
     local.org = xfmPointExact(rx, ray.org);
     local.dir = xfmVectorExact(rx.l, ray.dir);
   }
-  const bool h = traverseBLAS<OCCLUSION>(g->bvh.nodes, g->bvh.prims, local, instID, st, sp0);
+  const bool h = traverseBLAS<OCCLUSION>(g->bvh.nodes, g->bvh.prims, numRecords, local, instID, st, sp0);
   if (h) {
     ray.t = local.t;
-    if (!OCCLUSION) {
-      ray.u = local.u; ray.v = local.v; ray.Ng = local.Ng; // Ng stays in instance space (World.ih:411-420)
-      ray.primID = local.primID; ray.geomID = local.geomID; ray.instID = local.instID;
-    }
+    ray.primID = local.primID; ray.geomID = local.geomID; ray.instID = local.instID;
+    if (!OCCLUSION) { ray.u = local.u; ray.v = local.v; ray.Ng = local.Ng; } // Ng stays in instance space (World.ih:411-420)
   }
   return h;
 }
@@ -315,7 +326,7 @@ __device__ __forceinline__ bool traceInstance(const OcInstance *__restrict__ ins
 // closest hit / occlusion over the whole world (two-level). Equivalent of traceGeometryRay /
 // isOccludedNoClipping (World.ih:29-52, 311-335).
 template <bool OCCLUSION>
-__device__ __noinline__ bool traceWorld(const OcWorld *__restrict__ world, Ray &ray, Stack st)
+__device__ __forceinline__ bool traceWorld(const OcWorld *__restrict__ world, Ray &ray, Stack st)
 {
   bool any = false;
   const uint32_t n = world->numInstances;
@@ -369,6 +380,13 @@ __device__ __noinline__ bool traceWorld(const OcWorld *__restrict__ world, Ray &
     if (sp == 0) return any;
     cur = st.at(--sp);
   }
+}
+
+// one shared, non-inlined copy per kernel for code with many call sites
+template <bool OCCLUSION>
+__device__ __noinline__ bool traceWorldNI(const OcWorld *__restrict__ world, Ray &ray, Stack st)
+{
+  return traceWorld<OCCLUSION>(world, ray, st);
 }
 
 } // namespace oc

@@ -62,6 +62,7 @@ struct PtArgs
   uint32_t *qOut;
   const uint32_t *cntIn;
   uint32_t *cntOut;
+  uint32_t *tailFlag, *tailArrive;
 };
 
 __device__ __forceinline__ void ptAppend(uint32_t *q, uint32_t *cnt, uint32_t p)
@@ -166,76 +167,97 @@ __device__ __forceinline__ void ptCountRays(const OcFrameBuffer &fb, uint32_t a,
 }
 
 #define PT_TRACE_BLOCK 128
+#define PT_TAIL_THRESHOLD 16384u // at most this many live paths: finish them inside one kernel (see ptTraceKernel)
 
-// ---- TRACE --------------------------------------------------------------------------------------------------
-template <bool FIRST>
-__global__ void __launch_bounds__(PT_TRACE_BLOCK) ptTraceKernel(const __grid_constant__ PtArgs k)
+// Is the surface hit by `ray` certainly opaque for shadow rays, i.e. OBJ_getTransparency == 0 exactly
+// (OBJ.ispc:93-111: T = Tf*d + (1-d), d = material.d * dg.color.w)? Conservative: anything that could carry
+// alpha (per-primitive model colours, vec4 vertex colours) answers "no" and takes the general path.
+__device__ __forceinline__ bool ptOccluderIsOpaque(const OcWorld *world, const OcRenderer &ren, const Ray &ray)
 {
-  __shared__ uint32_t s_stack[OC_STACK_SIZE * PT_TRACE_BLOCK];
-  Stack stack;
-  stack.base = s_stack + threadIdx.x;
-  stack.stride = PT_TRACE_BLOCK;
+  const OcInstance *inst = world->instances + ray.instID;
+  const OcModel *m = inst->group->models + ray.geomID;
+  if (m->color.addr || (m->geom->flags & OC_GEOMFLAG_HAS_ALPHA)) return false;
+  const OcMaterial *mat = getMaterial(world, ren, m, ray.primID);
+  if (!mat || mat->type != OC_MATERIAL_OBJ) return true; // no / foreign material: transparency 0 (shading.cuh)
+  return mat->d == 1.f && mat->Tf.x == 0.f && mat->Tf.y == 0.f && mat->Tf.z == 0.f;
+}
+
+struct PtCounts { uint32_t primary, secondary, shadow; };
+
+// TRACE step of one path: resolve the shadow rays emitted at the previous vertex, then (unless the path is
+// done) trace the continuation ray. Returns false when the path finished here.
+template <bool FIRST>
+__device__ __forceinline__ bool ptTraceStep(const PtArgs &k, uint32_t p, Stack stack, PtCounts &cnt)
+{
   const PtScratch &s = k.s;
   const OcRenderer &ren = k.a.ren;
   const OcFrameBuffer &fb = k.a.fb;
-  uint32_t nPrimary = 0, nSecondary = 0, nShadow = 0;
-  const uint32_t n = FIRST ? k.numPaths : *k.cntIn;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t p = FIRST ? i : k.qIn[i];
-    Ray ray;
-    if (FIRST) {
-      uint32_t ix, iy;
-      ptSlotToPixel(k, p, ix, iy);
-      if (ix >= (uint32_t)fb.sizeX || iy >= (uint32_t)fb.sizeY) continue;
-      // PathTracer_renderPixel, one sample (PathTracer.ispc:149-193)
-      uint32_t seed, sampleOffs, sampleOffsLight, bits, bitsLight;
-      ptSamplerParams(k, ix, iy, seed, sampleOffs, sampleOffsLight, bits, bitsLight);
-      const uint32_t sampleID = (uint32_t)fb.frameID * ren.spp + k.pass;
-      LDSampler ld;
-      LDSampler_init(ld, seed, sampleOffs + sampleID, sampleOffsLight + sampleID * k.nFirst, bits, bitsLight);
-      const vec2f rcpSize = make_vec2f(1.f / (float)fb.sizeX, 1.f / (float)fb.sizeY);
-      const vec2f pixel_center = make_vec2f(((float)ix + 0.5f) * rcpSize.x, ((float)iy + 0.5f) * rcpSize.y);
-      uint32_t ss234[3];
-      const vec2f pixelSample = LDSampler_getNext5Samples(ld, ss234);
-      const vec2f pfSample = pixelFilterSample(ren, pixelSample);
-      const vec2f screen = pixel_center + pfSample * rcpSize;
-      vec2f lens = make_vec2f(0.5f, 0.5f);
-      if (k.a.cam.needLensSample) lens = LDSampler_finalizeDim23(ld, ss234);
-      cameraInitRay(k.a.cam, ray, screen, lens);
-      // samplePath() prologue (PathSampler.ispc:116-133)
-      s.smp[p] = make_uint2(ld.revIndex, ld.scramble);
-      s.flags[p] = PT_STRAIGHT | PT_SPECTRANS | PT_FIRSTBOUNCE;
-      s.thr[p] = make_float4(1.f, 1.f, 1.f, 1.f);
-      s.con[p] = make_float4(0.f, 0.f, 0.f, INFINITY);
-      s.lastP[p] = make_float4(ray.org.x, ray.org.y, ray.org.z, __uint_as_float(0u));
-      s.lastN[p] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, 0.f);
-      s.sZ[p] = make_float4(INFINITY, __uint_as_float(OC_INVALID_ID), __uint_as_float(OC_INVALID_ID), __uint_as_float(OC_INVALID_ID));
-      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (fb.position) s.sPos[p] = zero;
-      if (fb.firstNormal) s.sFN[p] = zero;
-      if (fb.normal) s.sNrm[p] = zero;
-      if (fb.albedo) s.sAlb[p] = zero;
-      s.rayO[p] = make_float4(ray.org.x, ray.org.y, ray.org.z, ray.t);
-      s.rayD[p] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, ray.t0);
-      nPrimary++;
-    } else {
-      const uint32_t flags = s.flags[p];
-      if (flags & PT_HAS_SHADOW) {
-        // shadow rays of the previous vertex: transparentShadow (TransparentShadow.ispc:18-85) per light sample,
-        // summed in sample order like nextEventEstimation's L (NextEventEstimation.ispc:140-156)
-        vec3f L = make_vec3f(0.f);
-        for (uint32_t j = 0; j < s.nls; j++) {
-          const size_t e = (size_t)p * s.nls + j;
-          const float4 c = s.shC[e];
-          if (c.w == 0.f) continue;
-          const float4 a = s.shA[e], b = s.shB[e];
-          Ray sr;
-          setRay(sr, make_vec3f(a.x, a.y, a.z), make_vec3f(b.x, b.y, b.z), 0.f, a.w);
-          vec3f lightContrib = make_vec3f(c.x, c.y, c.z);
+  Ray ray;
+  if (FIRST) {
+    uint32_t ix, iy;
+    ptSlotToPixel(k, p, ix, iy);
+    if (ix >= (uint32_t)fb.sizeX || iy >= (uint32_t)fb.sizeY) return false;
+    // PathTracer_renderPixel, one sample (PathTracer.ispc:149-193)
+    uint32_t seed, sampleOffs, sampleOffsLight, bits, bitsLight;
+    ptSamplerParams(k, ix, iy, seed, sampleOffs, sampleOffsLight, bits, bitsLight);
+    const uint32_t sampleID = (uint32_t)fb.frameID * ren.spp + k.pass;
+    LDSampler ld;
+    LDSampler_init(ld, seed, sampleOffs + sampleID, sampleOffsLight + sampleID * k.nFirst, bits, bitsLight);
+    const vec2f rcpSize = make_vec2f(1.f / (float)fb.sizeX, 1.f / (float)fb.sizeY);
+    const vec2f pixel_center = make_vec2f(((float)ix + 0.5f) * rcpSize.x, ((float)iy + 0.5f) * rcpSize.y);
+    uint32_t ss234[3];
+    const vec2f pixelSample = LDSampler_getNext5Samples(ld, ss234);
+    const vec2f pfSample = pixelFilterSample(ren, pixelSample);
+    const vec2f screen = pixel_center + pfSample * rcpSize;
+    vec2f lens = make_vec2f(0.5f, 0.5f);
+    if (k.a.cam.needLensSample) lens = LDSampler_finalizeDim23(ld, ss234);
+    cameraInitRay(k.a.cam, ray, screen, lens);
+    // samplePath() prologue (PathSampler.ispc:116-133)
+    s.smp[p] = make_uint2(ld.revIndex, ld.scramble);
+    s.flags[p] = PT_STRAIGHT | PT_SPECTRANS | PT_FIRSTBOUNCE;
+    s.thr[p] = make_float4(1.f, 1.f, 1.f, 1.f);
+    s.con[p] = make_float4(0.f, 0.f, 0.f, INFINITY);
+    s.lastP[p] = make_float4(ray.org.x, ray.org.y, ray.org.z, __uint_as_float(0u));
+    s.lastN[p] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, 0.f);
+    s.sZ[p] = make_float4(INFINITY, __uint_as_float(OC_INVALID_ID), __uint_as_float(OC_INVALID_ID), __uint_as_float(OC_INVALID_ID));
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (fb.position) s.sPos[p] = zero;
+    if (fb.firstNormal) s.sFN[p] = zero;
+    if (fb.normal) s.sNrm[p] = zero;
+    if (fb.albedo) s.sAlb[p] = zero;
+    s.rayO[p] = make_float4(ray.org.x, ray.org.y, ray.org.z, ray.t);
+    s.rayD[p] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, ray.t0);
+    cnt.primary++;
+  } else {
+    const uint32_t flags = s.flags[p];
+    if (flags & PT_HAS_SHADOW) {
+      // shadow rays of the previous vertex: transparentShadow (TransparentShadow.ispc:18-85) per light sample,
+      // summed in sample order like nextEventEstimation's L (NextEventEstimation.ispc:140-156)
+      vec3f L = make_vec3f(0.f);
+      for (uint32_t j = 0; j < s.nls; j++) {
+        const size_t e = (size_t)p * s.nls + j;
+        const float4 c = s.shC[e];
+        if (c.w == 0.f) continue;
+        const float4 a = s.shA[e], b = s.shB[e];
+        Ray sr;
+        setRay(sr, make_vec3f(a.x, a.y, a.z), make_vec3f(b.x, b.y, b.z), 0.f, a.w);
+        vec3f lightContrib = make_vec3f(c.x, c.y, c.z);
+        // fast path: ANY opaque occluder makes the product of transparencies exactly 0, whatever lies in front
+        // of it -> one any-hit query; only a non-opaque first find falls back to the reference's closest-hit loop
+        bool resolved = false;
+        if (isfinite(lightContrib.x) && isfinite(lightContrib.y) && isfinite(lightContrib.z)) {
+          Ray occ = sr;
+          cnt.shadow++;
+          if (!traceWorld<true>(k.a.world, occ, stack)) resolved = true; // unoccluded: lightContrib unchanged
+          else if (ptOccluderIsOpaque(k.a.world, ren, occ)) { lightContrib = make_vec3f(0.f); resolved = true; }
+        }
+        if (!resolved) {
           uint32_t maxDepth = ren.maxDepth;
           const float tOriginal = sr.t;
+          bool counted = isfinite(lightContrib.x) && isfinite(lightContrib.y) && isfinite(lightContrib.z); // the any-hit query was this segment
           while (1) {
-            nShadow++;
+            if (!counted) cnt.shadow++;
+            counted = false;
             traceWorld<false>(k.a.world, sr, stack);
             if (!hadHit(sr)) break;
             DifferentialGeometry dg;
@@ -244,33 +266,83 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK) ptTraceKernel(const __grid_con
             if (reduce_max(lightContrib) <= ren.minContribution || --maxDepth <= 0) { lightContrib = make_vec3f(0.f); break; }
             setRay(sr, sr.org, sr.dir, sr.t + dg.epsilon, tOriginal);
           }
-          if (reduce_max(lightContrib) > 0) L = L + lightContrib * b.w;
         }
-        float4 con = s.con[p];
-        con.x += L.x; con.y += L.y; con.z += L.z;
-        if (flags & PT_DONE) {
-          ptFinishPath(k, p, make_vec3f(con.x, con.y, con.z), s.thr[p].w);
-          continue;
-        }
-        s.con[p] = con;
+        if (reduce_max(lightContrib) > 0) L = L + lightContrib * b.w;
       }
-      const float4 o = s.rayO[p], d = s.rayD[p];
-      setRay(ray, make_vec3f(o.x, o.y, o.z), make_vec3f(d.x, d.y, d.z), d.w, o.w);
-      nSecondary++;
+      float4 con = s.con[p];
+      con.x += L.x; con.y += L.y; con.z += L.z;
+      if (flags & PT_DONE) {
+        ptFinishPath(k, p, make_vec3f(con.x, con.y, con.z), s.thr[p].w);
+        return false;
+      }
+      s.con[p] = con;
     }
-    ray.u = ray.v = 0.f;
-    ray.Ng = make_vec3f(0.f);
-    traceWorld<false>(k.a.world, ray, stack);
-    s.hit0[p] = make_float4(ray.t, ray.u, ray.v, __uint_as_float(ray.primID));
-    s.hit1[p] = make_float4(ray.Ng.x, ray.Ng.y, ray.Ng.z, __uint_as_float(ray.geomID));
-    s.hitInst[p] = ray.instID;
-    ptAppend(k.qOut, k.cntOut, p);
+    const float4 o = s.rayO[p], d = s.rayD[p];
+    setRay(ray, make_vec3f(o.x, o.y, o.z), make_vec3f(d.x, d.y, d.z), d.w, o.w);
+    cnt.secondary++;
   }
-  ptCountRays(fb, nPrimary, nSecondary, nShadow);
+  ray.u = ray.v = 0.f;
+  ray.Ng = make_vec3f(0.f);
+  traceWorld<false>(k.a.world, ray, stack);
+  s.hit0[p] = make_float4(ray.t, ray.u, ray.v, __uint_as_float(ray.primID));
+  s.hit1[p] = make_float4(ray.Ng.x, ray.Ng.y, ray.Ng.z, __uint_as_float(ray.geomID));
+  s.hitInst[p] = ray.instID;
+  return true;
 }
 
-// ---- SHADE --------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) ptShadeKernel(const __grid_constant__ PtArgs k)
+__device__ bool ptShadeStep(const PtArgs &k, uint32_t p);
+
+// ---- TRACE --------------------------------------------------------------------------------------------------
+// Persistent grid-stride loop over the live-path queue. When few paths are left (RR has culled the frame down to
+// a long thin tail), every further TRACE/SHADE launch would cost a launch + drain latency for almost no work
+// (profiles/r1_pt_wavefront_launches.txt: 30 launches x ~35 us): instead each thread then carries its path to
+// the end right here (TAIL mode); the queue it leaves behind is empty and the remaining launches exit at once.
+template <bool FIRST>
+__global__ void __launch_bounds__(PT_TRACE_BLOCK) ptTraceKernel(const __grid_constant__ PtArgs k)
+{
+  __shared__ uint32_t s_stack[OC_STACK_SIZE * PT_TRACE_BLOCK];
+  if (!FIRST && *k.tailFlag) return; // the tail kernel already finished every path of this queue
+  Stack stack;
+  stack.base = s_stack + threadIdx.x;
+  stack.stride = PT_TRACE_BLOCK;
+  PtCounts cnt = {0, 0, 0};
+  const uint32_t n = FIRST ? k.numPaths : *k.cntIn;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t p = FIRST ? i : k.qIn[i];
+    if (ptTraceStep<FIRST>(k, p, stack, cnt)) ptAppend(k.qOut, k.cntOut, p);
+  }
+  ptCountRays(k.a.fb, cnt.primary, cnt.secondary, cnt.shadow);
+}
+
+// TAIL: launched after SHADE(d). When at most PT_TAIL_THRESHOLD paths are left, each thread carries its path to
+// the end (trace, shade, trace, ...) and raises tailFlag so that the TRACE launch that follows skips the queue.
+__global__ void __launch_bounds__(PT_TRACE_BLOCK) ptTailKernel(const __grid_constant__ PtArgs k)
+{
+  __shared__ uint32_t s_stack[OC_STACK_SIZE * PT_TRACE_BLOCK];
+  const uint32_t n = *k.cntIn;
+  if (n == 0 || n > PT_TAIL_THRESHOLD || *k.tailFlag) return;
+  Stack stack;
+  stack.base = s_stack + threadIdx.x;
+  stack.stride = PT_TRACE_BLOCK;
+  PtCounts cnt = {0, 0, 0};
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t p = k.qIn[i];
+    while (ptTraceStep<false>(k, p, stack, cnt) && ptShadeStep(k, p)) {}
+  }
+  ptCountRays(k.a.fb, cnt.primary, cnt.secondary, cnt.shadow);
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(k.tailArrive, 1u);
+}
+
+// runs after the tail kernel (stream order): publish the flag only once every tail CTA is done
+__global__ void ptTailFlagKernel(uint32_t *tailArrive, uint32_t *tailFlag)
+{
+  if (*tailArrive) *tailFlag = 1u;
+}
+
+// SHADE step of one path; returns true when the path goes on to the next TRACE step (alive, or done with
+// shadow rays pending), false when it finished here.
+__device__ bool ptShadeStep(const PtArgs &k, uint32_t p)
 {
   const PtScratch &s = k.s;
   const OcRenderer &ren = k.a.ren;
@@ -278,9 +350,7 @@ __global__ void __launch_bounds__(128) ptShadeKernel(const __grid_constant__ PtA
   Stack dummy;
   dummy.base = nullptr; dummy.stride = 0;
   Ctx c(k.a.world, k.a.ren, k.a.cam, k.a.fb, dummy);
-  const uint32_t n = *k.cntIn;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t p = k.qIn[i];
+  {
     uint32_t flags = s.flags[p] & ~(PT_HAS_SHADOW | PT_DONE);
     const uint32_t depth = flags & PT_DEPTH_MASK;
     uint32_t scatteringEvents = (flags & PT_SCAT_MASK) >> PT_SCAT_SHIFT;
@@ -421,7 +491,7 @@ __global__ void __launch_bounds__(128) ptShadeKernel(const __grid_constant__ PtA
 
     if (!alive && !hasShadow) {
       ptFinishPath(k, p, contribution, alpha);
-      continue;
+      return false;
     }
     s.thr[p] = make_float4(throughput.x, throughput.y, throughput.z, alpha);
     s.con[p] = make_float4(contribution.x, contribution.y, contribution.z, last.pdf_w);
@@ -433,7 +503,16 @@ __global__ void __launch_bounds__(128) ptShadeKernel(const __grid_constant__ PtA
     s.flags[p] = ((depth + 1) & PT_DEPTH_MASK) | (scatteringEvents << PT_SCAT_SHIFT) | (straightPath ? PT_STRAIGHT : 0u)
         | (specularTransmissionPath ? PT_SPECTRANS : 0u) | (firstBounceLight ? PT_FIRSTBOUNCE : 0u) | (hasShadow ? PT_HAS_SHADOW : 0u)
         | (alive ? 0u : PT_DONE);
-    ptAppend(k.qOut, k.cntOut, p);
+    return true;
+  }
+}
+
+__global__ void __launch_bounds__(128, 4) ptShadeKernel(const __grid_constant__ PtArgs k)
+{
+  const uint32_t n = *k.cntIn;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t p = k.qIn[i];
+    if (ptShadeStep(k, p)) ptAppend(k.qOut, k.cntOut, p);
   }
 }
 

@@ -67,25 +67,7 @@ __device__ __forceinline__ float misHeuristic(float pdf1, float pdf2)
   return pdf1 > 1e17f ? 1.0f : p;
 }
 
-__device__ __noinline__ vec3f transparentShadow(Ctx &c, vec3f lightContrib, Ray &shadowRay)
-{
-  uint32_t maxDepth = c.ren.maxDepth;
-  const float tOriginal = shadowRay.t;
-  while (1) {
-    c.cnt.shadow++;
-    traceWorld<false>(c.world, shadowRay, c.stack);
-    if (!hadHit(shadowRay))
-      return lightContrib;
-    DifferentialGeometry dg;
-    postIntersect(c.world, c.ren, dg, shadowRay, DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR);
-    lightContrib = lightContrib * materialTransparency(dg);
-    if (reduce_max(lightContrib) <= c.ren.minContribution || --maxDepth <= 0)
-      return make_vec3f(0.f);
-    setRay(shadowRay, shadowRay.org, shadowRay.dir, shadowRay.t + dg.epsilon, tOriginal);
-  }
-}
-
-__device__ __noinline__ vec3f evaluateVirtualLights(Ctx &c, bool straightPath, vec3f throughput, const PathVertexLite &last,
+__device__ __forceinline__ vec3f evaluateVirtualLights(Ctx &c, bool straightPath, vec3f throughput, const PathVertexLite &last,
     bool environment, const Ray &ray)
 {
   vec3f L = make_vec3f(0.f);
@@ -106,186 +88,6 @@ __device__ __noinline__ vec3f evaluateVirtualLights(Ctx &c, bool straightPath, v
     }
   }
   return L;
-}
-
-__device__ __noinline__ vec3f nextEventEstimation(Ctx &c, const LDSampler &ld, bool firstBounceLight, uint32_t nFirst, uint32_t nIndirect,
-    vec3f throughput, const DifferentialGeometry &dg, const ObjBSDF &bsdf, vec3f wo, uint32_t &numLightSamplesOut)
-{
-  vec3f L = make_vec3f(0.f);
-  const uint32_t numLightSamples = firstBounceLight ? nFirst : nIndirect;
-  numLightSamplesOut = numLightSamples;
-  const uint32_t numLights = c.world->numLights;
-  for (uint32_t i = 0; i < numLightSamples; i++) {
-    float ss;
-    const vec2f s = LDSampler_get3LightSamples(ld, i, numLightSamples > 1, ss);
-    const Sample1D sel = Distribution1D_sample((int)numLights, c.world->lightsCDF, 0, ss);
-    const float lightSelectionProb = sel.prob * numLightSamples;
-    LightSample ls = Light_sample(c.world->lights[sel.idx], dg, s);
-    ls.weight = ls.weight / lightSelectionProb;
-    ls.pdf *= lightSelectionProb;
-    if (reduce_max(ls.weight) <= 0.0f || ls.pdf <= 0.0f)
-      continue;
-    const EvalRes fe = OBJ_eval(bsdf, wo, ls.dir);
-    if (reduce_max(fe.value) <= 0.0f)
-      continue;
-    vec3f org = dg.P;
-    if (dot(dg.Ng, ls.dir) < 0.f)
-      org = org - (2.0f * dg.epsilon) * dg.Ng;
-    Ray shadowRay;
-    setRay(shadowRay, org, ls.dir, 0.f, ls.dist);
-    const vec3f unshadedLightContrib = throughput * fe.value * ls.weight;
-    const vec3f lightContrib = transparentShadow(c, unshadedLightContrib, shadowRay);
-    if (reduce_max(lightContrib) > 0)
-      L = L + lightContrib * misHeuristic(ls.pdf, fe.pdf);
-  }
-  return L;
-}
-
-__device__ void samplePath(Ctx &c, LDSampler &ld, uint32_t nFirst, uint32_t nIndirect, Ray &ray, ScreenSample &sample)
-{
-  PathVertexLite last;
-  last.P = ray.org; last.Ns = ray.dir; last.pdf_w = INFINITY; last.numLightSamples = 0;
-  bool straightPath = true, specularTransmissionPath = true, firstBounceLight = true;
-  uint32_t depth = 0, scatteringEvents = 0;
-  vec3f throughput = make_vec3f(1.f), contribution = make_vec3f(0.f);
-  sample.alpha = 1.0f;
-  const OcRenderer &ren = c.ren;
-
-  do {
-    if (depth == 0) c.cnt.primary++; else c.cnt.secondary++;
-    traceWorld<false>(c.world, ray, c.stack);
-    const bool surface = hadHit(ray);
-    const vec3f wo = neg(ray.dir);
-
-    if (depth == 0)
-      sample.z = c.fb.projectedDepth ? ray.t * dot(ray.dir, toV(c.cam.direction)) : ray.t;
-
-    if (!surface && (ren.backgroundRefraction ? specularTransmissionPath : straightPath)) {
-      const vec4f bg = getBackground(ren);
-      sample.alpha -= luminance(throughput) * (1.0f - bg.w);
-      contribution = contribution + throughput * make_vec3f(bg);
-    }
-
-    contribution = contribution + evaluateVirtualLights(c, straightPath, throughput, last, !surface, ray);
-
-    if (!surface)
-      break;
-    if (depth >= ren.maxDepth) // numGeoLights == 0
-      break;
-
-    DifferentialGeometry dg;
-    postIntersect(c.world, ren, dg, ray,
-        DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR | DG_TANGENTS | DG_MOTIONBLUR);
-
-    if (depth == 0) {
-      sample.position = dg.P; sample.firstNormal = dg.Ns;
-      sample.primID = dg.primID; sample.geomID = dg.objID; sample.instID = dg.instID;
-    }
-    if (depth >= ren.maxDepth || scatteringEvents >= (uint32_t)ren.maxScatteringEvents)
-      break;
-
-    ObjBSDF bsdf;
-    OBJ_getBSDF(bsdf, dg);
-    if (!bsdf.valid)
-      break;
-
-    LDSampler_nextGroup(ld);
-    uint32_t vertexLightSamples = 0;
-    if (bsdf.scatteringType & SC_SMOOTH) {
-      if (scatteringEvents == 0) {
-        sample.albedo = throughput * bsdf.albedo;
-        sample.normal = throughput * bsdf.frame.vz;
-      }
-      contribution = contribution
-          + nextEventEstimation(c, ld, firstBounceLight, nFirst, nIndirect, throughput, dg, bsdf, wo, vertexLightSamples);
-      firstBounceLight = false;
-    }
-
-    float ss;
-    uint32_t uu3;
-    const vec2f s = LDSampler_getNext4Samples(ld, ss, uu3);
-    SampleRes fs = OBJ_sample(bsdf, wo, s, ss);
-    {
-      const bool sameSide = dot(fs.wi, dg.Ng) >= 0.f;
-      const bool reflection = fs.type & SC_REFLECTION;
-      if (sameSide != reflection) fs.weight = make_vec3f(0.0f);
-    }
-    if (reduce_max(fs.weight) <= 0.0f || fs.pdf <= 0.0f)
-      break;
-    throughput = throughput * fs.weight;
-
-    if (depth >= (uint32_t)ren.rouletteDepth) {
-      const float rr = LDSampler_finalizeDim3(ld, uu3);
-      const float contProb = fminf(reduce_max(throughput), 0.95f);
-      if (rr > contProb)
-        break;
-      throughput = throughput * (1.f / contProb);
-    }
-
-    vec3f ray_org = dg.P;
-    if (fs.type & SC_TRANSMISSION)
-      ray_org = ray_org - (2.0f * dg.epsilon) * dg.Ng;
-
-    if ((fs.type & ~SC_SPECULAR_TRANSMISSION)) {
-      last.P = dg.P; last.Ns = dg.Ns; last.pdf_w = fs.pdf; last.numLightSamples = vertexLightSamples;
-    }
-    if (!eq3(ray.dir, fs.wi)) straightPath = false;
-    if (!(fs.type & SC_SPECULAR_TRANSMISSION)) specularTransmissionPath = false;
-
-    setRay(ray, ray_org, fs.wi, 0.f, INFINITY);
-    depth++;
-    if (fs.type & SC_SMOOTH) scatteringEvents++;
-  } while (reduce_max(throughput) > ren.minContribution);
-
-  sample.rgb = contribution;
-  if (isnan(contribution.x) || isnan(contribution.y) || isnan(contribution.z)) {
-    sample.rgb = make_vec3f(0.f);
-    sample.alpha = 1.0f;
-  }
-}
-
-__device__ void PathTracer_renderPixel(Ctx &c, uint32_t ix, uint32_t iy, ScreenSample &screenSample)
-{
-  const OcRenderer &ren = c.ren;
-  const OcFrameBuffer &fb = c.fb;
-  ScreenSample_zero(screenSample);
-  const uint32_t numLights = c.world->numLights;
-  const uint32_t nFirst = (ren.numLightSamples >= 0 && numLights > 0) ? (uint32_t)ren.numLightSamples : min(1024u, numLights);
-  const uint32_t nIndirect = (ren.limitIndirectLightSamples && nFirst >= 1) ? 1u : nFirst;
-  const int spp = ren.spp;
-  uint32_t sampleOffs, sampleOffsLight, sampleBits, sampleBitsLight;
-  uint32_t seed = 0x49c5f37eu;
-  if (fb.targetFrames) {
-    const uint32_t targetSpp = (uint32_t)fb.targetFrames * spp;
-    sampleOffs = OwenScramble4(interleaveZOrder16(ix, iy), seed) * targetSpp;
-    sampleOffsLight = sampleOffs * nFirst;
-    sampleBits = 16 + 32 - __clz(targetSpp - 1);
-    sampleBitsLight = 48 - __clz(targetSpp * nFirst - 1);
-  } else {
-    seed ^= (uint32_t)fb.sizeX * iy + ix;
-    sampleOffs = 0; sampleOffsLight = 0; sampleBits = 16; sampleBitsLight = 16;
-  }
-  const vec2f rcpSize = make_vec2f(1.f / (float)fb.sizeX, 1.f / (float)fb.sizeY);
-  for (int s = 0; s < spp; s++) {
-    const uint32_t sampleID = (uint32_t)fb.frameID * spp + s;
-    LDSampler ld;
-    LDSampler_init(ld, seed, sampleOffs + sampleID, sampleOffsLight + sampleID * nFirst, sampleBits, sampleBitsLight);
-    const vec2f pixel_center = make_vec2f(((float)ix + 0.5f) * rcpSize.x, ((float)iy + 0.5f) * rcpSize.y);
-    uint32_t ss234[3];
-    const vec2f pixelSample = LDSampler_getNext5Samples(ld, ss234);
-    const vec2f pfSample = pixelFilterSample(ren, pixelSample);
-    const vec2f screen = pixel_center + pfSample * rcpSize;
-    vec2f lens = make_vec2f(0.5f, 0.5f);
-    if (c.cam.needLensSample) lens = LDSampler_finalizeDim23(ld, ss234);
-    Ray ray;
-    cameraInitRay(c.cam, ray, screen, lens);
-    ScreenSample sample;
-    ScreenSample_zero(sample);
-    samplePath(c, ld, nFirst, nIndirect, ray, sample);
-    sample.rgb = vmin(sample.rgb, make_vec3f(ren.maxRadiance));
-    ScreenSample_accumulate(screenSample, sample);
-  }
-  ScreenSample_normalize(screenSample, 1.f / (float)spp);
 }
 
 // ============================== scivis / ao shared pieces ==================================
@@ -374,7 +176,7 @@ __device__ __noinline__ vec3f lightAlpha(Ctx &c, Ray &ray, RandomSampler &rs, ve
   const float org_t_max = ray.t;
   while (true) {
     c.cnt.shadow++;
-    traceWorld<false>(c.world, ray, c.stack);
+    traceWorldNI<false>(c.world, ray, c.stack);
     if (c.world->hasVolumes) {
       VolumeHit vh;
       if (traceVolumeRay(c.world, ray, vh)) {
@@ -384,7 +186,7 @@ __device__ __noinline__ vec3f lightAlpha(Ctx &c, Ray &ray, RandomSampler &rs, ve
     }
     if (hadHit(ray)) {
       DifferentialGeometry dg;
-      postIntersect(c.world, c.ren, dg, ray, DG_COLOR | DG_TEXCOORD);
+      postIntersectNI(c.world, c.ren, dg, ray, DG_COLOR | DG_TEXCOORD);
       const SciVisBSDF bsdf = evalMaterial(dg);
       alpha = alpha * bsdf.transmission;
       setRay(ray, ray.org, ray.dir, ray.t + dg.epsilon, org_t_max);
@@ -563,7 +365,7 @@ __device__ void SciVis_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint
   while (true) {
     if (primary) c.cnt.primary++; else c.cnt.secondary++;
     primary = false;
-    traceWorld<false>(c.world, ray, c.stack);
+    traceWorldNI<false>(c.world, ray, c.stack);
     float volumeT = ray.t;
     if (c.world->hasVolumes) {
       VolumeHit vh;
@@ -587,7 +389,7 @@ __device__ void SciVis_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint
     }
     if (hadHit(ray)) {
       DifferentialGeometry dg;
-      postIntersect(c.world, ren, dg, ray, DG_NG | DG_NS | DG_NORMALIZE | DG_FACEFORWARD | DG_COLOR | DG_TANGENTS | DG_TEXCOORD);
+      postIntersectNI(c.world, ren, dg, ray, DG_NG | DG_NS | DG_NORMALIZE | DG_FACEFORWARD | DG_COLOR | DG_TANGENTS | DG_TEXCOORD);
       const SSI sh = SciVis_computeShading(c, dg, rs, ray.dir, px, py, sampleIDz);
       if (firstHit || allHitsFullyTransmissive) {
         sample.position = dg.P; sample.firstNormal = dg.Ns; sample.normal = dg.Ns; sample.albedo = sh.albedo;
@@ -631,7 +433,7 @@ __device__ __noinline__ float computeAO(Ctx &c, const DifferentialGeometry &dg, 
     Ray ao_ray;
     setRay(ao_ray, dg.P, ao_dir, dg.epsilon, aoRadius);
     c.cnt.shadow++;
-    if (traceWorld<true>(c.world, ao_ray, c.stack)) hits++;
+    if (traceWorldNI<true>(c.world, ao_ray, c.stack)) hits++;
   }
   return 1.0f - (hits / (float)sampleCnt);
 }
@@ -648,7 +450,7 @@ __device__ void AO_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint32_t
   vec4f outputColor = make_vec4f(0.f, 0.f, 0.f, 0.f);
   while (outputColor.w < 0.99f) {
     if (firstHit) c.cnt.primary++; else c.cnt.secondary++;
-    traceWorld<false>(c.world, ray, c.stack);
+    traceWorldNI<false>(c.world, ray, c.stack);
     if (c.world->hasVolumes) {
       VolumeHit vh;
       if (traceVolumeRay(c.world, ray, vh)) {
@@ -660,7 +462,7 @@ __device__ void AO_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint32_t
     const bool rayHadHit = hadHit(ray);
     if (rayHadHit) {
       DifferentialGeometry dg;
-      postIntersect(c.world, ren, dg, ray, DG_NG | DG_NS | DG_NORMALIZE | DG_FACEFORWARD | DG_COLOR | DG_TEXCOORD | DG_TANGENTS);
+      postIntersectNI(c.world, ren, dg, ray, DG_NG | DG_NS | DG_NORMALIZE | DG_FACEFORWARD | DG_COLOR | DG_TEXCOORD | DG_TANGENTS);
       // getSurfaceColor (ao/surfaces.ispc:18-42)
       vec3f surfaceColor = make_vec3f(1.f);
       float opacity = 1.f;
@@ -804,8 +606,7 @@ __global__ void __launch_bounds__(64) renderFrameKernel(const __grid_constant__ 
   Ctx c(a.world, a.ren, a.cam, a.fb, stack);
   if (x < (uint32_t)a.fb.sizeX && y < (uint32_t)a.fb.sizeY) {
     ScreenSample ss;
-    if (RENDERER == OC_RENDERER_PATHTRACER) PathTracer_renderPixel(c, x, y, ss);
-    else defaultRenderPixel<RENDERER>(c, x, y, ss);
+    defaultRenderPixel<RENDERER>(c, x, y, ss);
     accumulateSample(a.fb, x, y, ss);
   }
   if (a.fb.rayCounters) {
@@ -919,7 +720,7 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
   k.a.ren.maxDepth = maxDepth;
   const uint32_t nls = k.nFirst > 0 ? k.nFirst : 1;
   const bool needAcc = fa.ren.spp > 1;
-  const uint32_t numCounters = 2 * (maxDepth + 2);
+  const uint32_t numCounters = 2 * (maxDepth + 2) + 2; // queue counts + tail flag + tail arrival count
   // batch the owned tiles so that the path state stays under ~1.5 GB (many light samples / 4K frames)
   const size_t budget = size_t(1536) << 20;
   uint32_t tilesPerBatch = (uint32_t)std::max<size_t>(1, budget / (ptBytesPerPath(nls, needAcc) * 4096));
@@ -941,6 +742,7 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
     for (int pass = 0; pass < fa.ren.spp; pass++) {
       k.pass = pass;
       OC_TRY(cudaMemsetAsync(k.s.counters, 0, numCounters * sizeof(uint32_t), st));
+      k.tailFlag = k.s.counters + numCounters - 2; k.tailArrive = k.s.counters + numCounters - 1;
       k.depth = 0; k.qIn = nullptr; k.cntIn = nullptr; k.qOut = k.s.queue[0]; k.cntOut = k.s.counters + 0;
       ptTraceKernel<true><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
       oc_count_launch();
@@ -954,6 +756,13 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
         k.qIn = k.s.queue[0]; k.cntIn = k.s.counters + 2 * d; k.qOut = k.s.queue[1]; k.cntOut = k.s.counters + (2 * d + 1);
         ptShadeKernel<<<g_pt.shadeBlocks, 128, 0, st>>>(k);
         oc_count_launch();
+        if (d >= 2 && d < maxDepth) {
+          // few paths left? finish them in one kernel instead of 2 launches per remaining bounce
+          k.qIn = k.s.queue[1]; k.cntIn = k.s.counters + (2 * d + 1);
+          ptTailKernel<<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+          ptTailFlagKernel<<<1, 1, 0, st>>>(k.tailArrive, k.tailFlag);
+          oc_count_launch();
+        }
       }
     }
   }

@@ -136,7 +136,7 @@ __device__ __forceinline__ void geometryPostIntersect(const OcGeometry *g, Diffe
 }
 
 // World.ih:389-465
-static __device__ __noinline__ void postIntersect(const OcWorld *world, const OcRenderer &ren,
+__device__ __forceinline__ void postIntersect(const OcWorld *world, const OcRenderer &ren,
     DifferentialGeometry &dg, const Ray &ray, uint32_t flags)
 {
   dg.primID = ray.primID;
@@ -185,6 +185,11 @@ static __device__ __noinline__ void postIntersect(const OcWorld *world, const Oc
     if (dot(dg.Ng, dg.Ns) < 0.f) dg.Ns = neg(dg.Ns);
   }
   dg.P = dg.P + dg.epsilon * ffnng;
+}
+static __device__ __noinline__ void postIntersectNI(const OcWorld *world, const OcRenderer &ren, DifferentialGeometry &dg,
+    const Ray &ray, uint32_t flags)
+{
+  postIntersect(world, ren, dg, ray, flags);
 }
 
 // ---- sampling helpers (math/sampling.ih) ---------------------------------------------------
@@ -516,7 +521,7 @@ __device__ __forceinline__ LightSample QuadLight_sampleArea(const OcLight &l, ve
   r.weight = toV(l.radiance) * weight;
   return r;
 }
-static __device__ __noinline__ LightSample QuadLight_sample(const OcLight &l, const DifferentialGeometry &dg, vec2f s)
+__device__ __forceinline__ LightSample QuadLight_sample(const OcLight &l, const DifferentialGeometry &dg, vec2f s)
 {
   if (s.x == 0.0f && s.y == 0.0f)
     return QuadLight_sampleArea(l, dg.P, make_vec2f(0.5f, 0.5f));
@@ -533,7 +538,7 @@ static __device__ __noinline__ LightSample QuadLight_sample(const OcLight &l, co
   r.weight = (cosd > 0.f) && (r.pdf != 0.f) ? toV(l.radiance) * (1.f / r.pdf) : make_vec3f(0.f);
   return r;
 }
-static __device__ __noinline__ LightEval QuadLight_eval(const OcLight &l, vec3f P, vec3f dir, float minDist, float maxDist)
+__device__ __forceinline__ LightEval QuadLight_eval(const OcLight &l, vec3f P, vec3f dir, float minDist, float maxDist)
 {
   LightEval r; r.radiance = make_vec3f(0.f); r.pdf = 0.f;
   const vec3f nn = toV(l.nnormal), pos = toV(l.position), e1 = toV(l.edge1), e2 = toV(l.edge2);

@@ -218,9 +218,10 @@ __device__ __forceinline__ uint32_t nodeTest(const OcNode4 *node, vec3f org, vec
 
 __device__ __forceinline__ vec3f safeRcpDir(vec3f d)
 {
+  // __frcp_rn is the correctly rounded reciprocal == 1.f / x, without the full division sequence
   const float eps = 1e-30f;
-  return make_vec3f(1.f / (fabsf(d.x) < eps ? copysignf(eps, d.x) : d.x), 1.f / (fabsf(d.y) < eps ? copysignf(eps, d.y) : d.y),
-      1.f / (fabsf(d.z) < eps ? copysignf(eps, d.z) : d.z));
+  return make_vec3f(__frcp_rn(fabsf(d.x) < eps ? copysignf(eps, d.x) : d.x), __frcp_rn(fabsf(d.y) < eps ? copysignf(eps, d.y) : d.y),
+      __frcp_rn(fabsf(d.z) < eps ? copysignf(eps, d.z) : d.z));
 }
 
 // Per-thread traversal stack in SHARED memory, laid out [depth][thread] so that the 32 lanes of a warp hit 32

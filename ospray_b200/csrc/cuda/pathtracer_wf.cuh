@@ -62,7 +62,6 @@ struct PtArgs
   uint32_t *qOut;
   const uint32_t *cntIn;
   uint32_t *cntOut;
-  uint32_t *tailFlag, *tailArrive;
 };
 
 __device__ __forceinline__ void ptAppend(uint32_t *q, uint32_t *cnt, uint32_t p)
@@ -301,7 +300,6 @@ template <bool FIRST>
 __global__ void __launch_bounds__(PT_TRACE_BLOCK) ptTraceKernel(const __grid_constant__ PtArgs k)
 {
   __shared__ uint32_t s_stack[OC_STACK_SIZE * PT_TRACE_BLOCK];
-  if (!FIRST && *k.tailFlag) return; // the tail kernel already finished every path of this queue
   Stack stack;
   stack.base = s_stack + threadIdx.x;
   stack.stride = PT_TRACE_BLOCK;
@@ -314,30 +312,33 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK) ptTraceKernel(const __grid_con
   ptCountRays(k.a.fb, cnt.primary, cnt.secondary, cnt.shadow);
 }
 
-// TAIL: launched after SHADE(d). When at most PT_TAIL_THRESHOLD paths are left, each thread carries its path to
-// the end (trace, shade, trace, ...) and raises tailFlag so that the TRACE launch that follows skips the queue.
-__global__ void __launch_bounds__(PT_TRACE_BLOCK) ptTailKernel(const __grid_constant__ PtArgs k)
+// FUSED(d), used from depth PT_FUSED_FROM_ROULETTE past the roulette depth on, where Russian roulette has thinned
+// the frame out: one launch per bounce doing TRACE and SHADE back to back for each path (no cross-path
+// dependency between the two), with the usual compaction into the next queue. When at most PT_TAIL_THRESHOLD
+// paths are left, every thread instead carries its path to the end (TAIL mode): the queue it leaves behind is
+// empty and the remaining launches return at once. Without this the long thin tail cost ~30 launch+drain
+// latencies for ~1 % of the paths (profiles/r1_pt_wavefront_launches.txt).
+__global__ void __launch_bounds__(PT_TRACE_BLOCK) ptFusedKernel(const __grid_constant__ PtArgs k)
 {
   __shared__ uint32_t s_stack[OC_STACK_SIZE * PT_TRACE_BLOCK];
   const uint32_t n = *k.cntIn;
-  if (n == 0 || n > PT_TAIL_THRESHOLD || *k.tailFlag) return;
+  if (n == 0) return;
+  const bool tail = n <= PT_TAIL_THRESHOLD;
   Stack stack;
   stack.base = s_stack + threadIdx.x;
   stack.stride = PT_TRACE_BLOCK;
   PtCounts cnt = {0, 0, 0};
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t p = k.qIn[i];
+    if (!ptTraceStep<false>(k, p, stack, cnt)) continue;
+    if (!ptShadeStep(k, p)) continue;
+    if (!tail) {
+      ptAppend(k.qOut, k.cntOut, p);
+      continue;
+    }
     while (ptTraceStep<false>(k, p, stack, cnt) && ptShadeStep(k, p)) {}
   }
   ptCountRays(k.a.fb, cnt.primary, cnt.secondary, cnt.shadow);
-  __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(k.tailArrive, 1u);
-}
-
-// runs after the tail kernel (stream order): publish the flag only once every tail CTA is done
-__global__ void ptTailFlagKernel(uint32_t *tailArrive, uint32_t *tailFlag)
-{
-  if (*tailArrive) *tailFlag = 1u;
 }
 
 // SHADE step of one path; returns true when the path goes on to the next TRACE step (alive, or done with

@@ -720,7 +720,7 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
   k.a.ren.maxDepth = maxDepth;
   const uint32_t nls = k.nFirst > 0 ? k.nFirst : 1;
   const bool needAcc = fa.ren.spp > 1;
-  const uint32_t numCounters = 2 * (maxDepth + 2) + 2; // queue counts + tail flag + tail arrival count
+  const uint32_t numCounters = 2 * (maxDepth + 2);
   // batch the owned tiles so that the path state stays under ~1.5 GB (many light samples / 4K frames)
   const size_t budget = size_t(1536) << 20;
   uint32_t tilesPerBatch = (uint32_t)std::max<size_t>(1, budget / (ptBytesPerPath(nls, needAcc) * 4096));
@@ -742,27 +742,31 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
     for (int pass = 0; pass < fa.ren.spp; pass++) {
       k.pass = pass;
       OC_TRY(cudaMemsetAsync(k.s.counters, 0, numCounters * sizeof(uint32_t), st));
-      k.tailFlag = k.s.counters + numCounters - 2; k.tailArrive = k.s.counters + numCounters - 1;
-      k.depth = 0; k.qIn = nullptr; k.cntIn = nullptr; k.qOut = k.s.queue[0]; k.cntOut = k.s.counters + 0;
+      // queue / counter ping-pong: every launch reads (queue[q], counters[c]) and appends to (queue[q^1], counters[c+1])
+      uint32_t q = 0, c = 0;
+      k.depth = 0; k.qIn = nullptr; k.cntIn = nullptr; k.qOut = k.s.queue[q]; k.cntOut = k.s.counters + c;
       ptTraceKernel<true><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
       oc_count_launch();
+      auto next = [&]() { k.qIn = k.s.queue[q]; k.cntIn = k.s.counters + c; q ^= 1u; c++; k.qOut = k.s.queue[q]; k.cntOut = k.s.counters + c; };
+      // separate TRACE / SHADE launches while the frame is densely populated, fused one-launch-per-bounce kernels
+      // (with the finish-in-place tail mode) once Russian roulette has started to cull
+      const uint32_t fusedFrom = std::min<uint32_t>(maxDepth, (uint32_t)std::max(1, fa.ren.rouletteDepth + 1));
       for (uint32_t d = 0; d <= maxDepth; d++) {
         k.depth = d;
+        if (d > 0 && d >= fusedFrom) {
+          next();
+          ptFusedKernel<<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+          oc_count_launch();
+          continue;
+        }
         if (d > 0) {
-          k.qIn = k.s.queue[1]; k.cntIn = k.s.counters + (2 * d - 1); k.qOut = k.s.queue[0]; k.cntOut = k.s.counters + 2 * d;
+          next();
           ptTraceKernel<false><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
           oc_count_launch();
         }
-        k.qIn = k.s.queue[0]; k.cntIn = k.s.counters + 2 * d; k.qOut = k.s.queue[1]; k.cntOut = k.s.counters + (2 * d + 1);
+        next();
         ptShadeKernel<<<g_pt.shadeBlocks, 128, 0, st>>>(k);
         oc_count_launch();
-        if (d >= 2 && d < maxDepth) {
-          // few paths left? finish them in one kernel instead of 2 launches per remaining bounce
-          k.qIn = k.s.queue[1]; k.cntIn = k.s.counters + (2 * d + 1);
-          ptTailKernel<<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
-          ptTailFlagKernel<<<1, 1, 0, st>>>(k.tailArrive, k.tailFlag);
-          oc_count_launch();
-        }
       }
     }
   }

@@ -115,13 +115,16 @@ __device__ __forceinline__ uint32_t interleaveZOrder16(uint32_t x, uint32_t y)
 template <int DIMS>
 __device__ __forceinline__ void Sobol_revSample(uint32_t revIndex, uint32_t (&r)[4])
 {
+  // same XOR of matrix columns as the reference's bit-serial loop, visiting set bits only (clz)
   r[0] = r[1] = r[2] = r[3] = 0;
-  for (uint32_t i = 0; revIndex; revIndex <<= 1, i += 4) {
-    if (revIndex & 0x80000000u) {
-#pragma unroll
-      for (int d = 0; d < DIMS; d++)
-        r[d] ^= kSobolRev[i + d];
-    }
+  while (revIndex) {
+    const uint32_t b = __clz(revIndex); // column index = position from the MSB
+    revIndex &= ~(0x80000000u >> b);
+    const uint4 col = __ldg(reinterpret_cast<const uint4 *>(kSobolRev) + b);
+    r[0] ^= col.x;
+    if (DIMS > 1) r[1] ^= col.y;
+    if (DIMS > 2) r[2] ^= col.z;
+    if (DIMS > 3) r[3] ^= col.w;
   }
 }
 

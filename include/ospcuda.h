@@ -315,6 +315,12 @@ OSPCUDA_API int ospcuda_trace(const OcWorld *d_world, OcRayHit *d_rays, uint32_t
 OSPCUDA_API int ospcuda_render_frame(const OcWorld *d_world, const OcCamera *camera,
     const OcRenderer *renderer, const OcFrameBuffer *fb);
 
+/* per-launch-class device timing of the wavefront pathtracer (bench.py roofline leg): while enabled every
+ * launch is bracketed by CUDA events on the render stream; read returns and clears the summed milliseconds and
+ * launch counts of class 0 = TRACE (traversal), 1 = SHADE, 2 = FUSED trace+shade (tail). */
+OSPCUDA_API int ospcuda_profile_enable(int on);
+OSPCUDA_API int ospcuda_profile_read(float ms[3], uint32_t launches[3]);
+
 /* ---- framebuffer ops --------------------------------------------------------------- */
 OSPCUDA_API int ospcuda_fb_accumulate(const OcFrameBuffer *fb, const OcVec4f *d_sampleColor,
     const float *d_sampleDepth);

@@ -297,7 +297,7 @@ __device__ bool ptShadeStep(const PtArgs &k, uint32_t p);
 // (profiles/r1_pt_wavefront_launches.txt: 30 launches x ~35 us): instead each thread then carries its path to
 // the end right here (TAIL mode); the queue it leaves behind is empty and the remaining launches exit at once.
 template <bool FIRST>
-__global__ void __launch_bounds__(PT_TRACE_BLOCK) ptTraceKernel(const __grid_constant__ PtArgs k)
+__global__ void __launch_bounds__(PT_TRACE_BLOCK, 5) ptTraceKernel(const __grid_constant__ PtArgs k)
 {
   __shared__ uint32_t s_stack[OC_STACK_SIZE * PT_TRACE_BLOCK];
   Stack stack;
@@ -508,7 +508,7 @@ __device__ bool ptShadeStep(const PtArgs &k, uint32_t p)
   }
 }
 
-__global__ void __launch_bounds__(128, 4) ptShadeKernel(const __grid_constant__ PtArgs k)
+__global__ void __launch_bounds__(128, 5) ptShadeKernel(const __grid_constant__ PtArgs k)
 {
   const uint32_t n = *k.cntIn;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {

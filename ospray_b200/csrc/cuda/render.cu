@@ -9,6 +9,8 @@
 // scivis/volumes.ispc:302-439; render/ao/AORenderer.ispc:23-149, ao/surfaces.ispc:18-74,
 // ao/volumes.ispc, render/util.ispc:12-54; render/ScreenSample.ih:12-92; fb/LocalFB.ispc:14-78.
 #include <algorithm>
+#include <utility>
+#include <vector>
 #include "runtime.h"
 #include "volume.cuh"
 
@@ -653,6 +655,27 @@ using namespace oc;
 
 // ---- wavefront path tracer: scratch + launch sequence ----------------------------------------------------------
 namespace {
+// optional per-launch-class timing (ospcuda_profile_enable): CUDA event pairs around every wavefront launch
+struct PtProfile
+{
+  bool enabled = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3]; // 0 TRACE, 1 SHADE, 2 FUSED
+  std::vector<cudaEvent_t> pool;
+  size_t poolNext = 0;
+  cudaEvent_t get()
+  {
+    if (poolNext == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    return pool[poolNext++];
+  }
+} g_prof;
+
+struct ProfScope
+{
+  int cls; cudaEvent_t a = nullptr, b = nullptr; cudaStream_t st;
+  ProfScope(int c, cudaStream_t s) : cls(c), st(s) { if (g_prof.enabled) { a = g_prof.get(); b = g_prof.get(); cudaEventRecord(a, st); } }
+  ~ProfScope() { if (a) { cudaEventRecord(b, st); g_prof.ev[cls].emplace_back(a, b); } }
+};
+
 struct PtHost
 {
   void *block = nullptr;
@@ -745,7 +768,7 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
       // queue / counter ping-pong: every launch reads (queue[q], counters[c]) and appends to (queue[q^1], counters[c+1])
       uint32_t q = 0, c = 0;
       k.depth = 0; k.qIn = nullptr; k.cntIn = nullptr; k.qOut = k.s.queue[q]; k.cntOut = k.s.counters + c;
-      ptTraceKernel<true><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+      { ProfScope ps(0, st); ptTraceKernel<true><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k); }
       oc_count_launch();
       auto next = [&]() { k.qIn = k.s.queue[q]; k.cntIn = k.s.counters + c; q ^= 1u; c++; k.qOut = k.s.queue[q]; k.cntOut = k.s.counters + c; };
       // separate TRACE / SHADE launches while the frame is densely populated, fused one-launch-per-bounce kernels
@@ -755,17 +778,17 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
         k.depth = d;
         if (d > 0 && d >= fusedFrom) {
           next();
-          ptFusedKernel<<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+          { ProfScope ps(2, st); ptFusedKernel<<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k); }
           oc_count_launch();
           continue;
         }
         if (d > 0) {
           next();
-          ptTraceKernel<false><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+          { ProfScope ps(0, st); ptTraceKernel<false><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k); }
           oc_count_launch();
         }
         next();
-        ptShadeKernel<<<g_pt.shadeBlocks, 128, 0, st>>>(k);
+        { ProfScope ps(1, st); ptShadeKernel<<<g_pt.shadeBlocks, 128, 0, st>>>(k); }
         oc_count_launch();
       }
     }
@@ -773,6 +796,31 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
   return oc_check(cudaGetLastError(), "wavefront pathtracer");
 }
 } // namespace
+
+extern "C" int ospcuda_profile_enable(int on)
+{
+  g_prof.enabled = on != 0;
+  for (auto &v : g_prof.ev) v.clear();
+  g_prof.poolNext = 0;
+  return 0;
+}
+
+extern "C" int ospcuda_profile_read(float ms[3], uint32_t launches[3])
+{
+  OC_TRY(cudaStreamSynchronize((cudaStream_t)ospcuda_stream()));
+  for (int c = 0; c < 3; c++) {
+    ms[c] = 0.f;
+    launches[c] = (uint32_t)g_prof.ev[c].size();
+    for (auto &e : g_prof.ev[c]) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, e.first, e.second);
+      ms[c] += t;
+    }
+    g_prof.ev[c].clear();
+  }
+  g_prof.poolNext = 0;
+  return 0;
+}
 
 extern "C" int ospcuda_render_frame(const OcWorld *d_world, const OcCamera *camera, const OcRenderer *renderer,
     const OcFrameBuffer *fb)

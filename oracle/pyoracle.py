@@ -165,6 +165,30 @@ def lib():
     return _lib
 
 
+_ref = None
+
+
+def ref_available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libospref.so"))
+
+
+def ref_lib():
+    """oracle/_ref/libospref.so: the REFERENCE's own kernels (modules/cpu/**/*.ispc compiled in their scalar C++ mode by
+    oracle/build_ref.py) behind the same entry-point signatures as liboracle.so, prefix ospref_."""
+    global _ref
+    if _ref is None:
+        p = os.path.join(_HERE, "_ref", "libospref.so")
+        if not os.path.exists(p):
+            raise RuntimeError(f"{p} missing: run `python oracle/build_ref.py` where /root/reference is present")
+        L = C.CDLL(p)
+        L.ospref_render_frame.argtypes = [C.POINTER(World), C.POINTER(Camera), C.POINTER(Renderer), C.POINTER(FrameBuffer), C.c_int]
+        L.ospref_sampler_kat.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.ospref_gauss_pixelfilter_lut.argtypes = [C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+        L.ospref_hardware_threads.restype = C.c_int
+        _ref = L
+    return _ref
+
+
 def _f3(v):
     return (C.c_float * 3)(*[float(x) for x in v])
 
@@ -475,9 +499,15 @@ class HostFrameBuffer:
         self.counters[:] = 0
 
 
-def render_frame(scene, camera, renderer, fb, threads=0):
+def render_frame(scene, camera, renderer, fb, threads=0, backend="oracle"):
+    """backend "oracle": the restatement (liboracle.so); "ref": the reference's own kernels (oracle/_ref/libospref.so)"""
     fb.begin_frame()
-    lib().oracle_render_frame(C.byref(scene.world), C.byref(camera), C.byref(renderer.sh), C.byref(fb.sh), threads)
+    if backend == "ref":
+        rc = ref_lib().ospref_render_frame(C.byref(scene.world), C.byref(camera), C.byref(renderer.sh), C.byref(fb.sh), threads)
+        if rc != 0:
+            raise RuntimeError("ospref_render_frame: image size must be a multiple of the 8x8 render task")
+    else:
+        lib().oracle_render_frame(C.byref(scene.world), C.byref(camera), C.byref(renderer.sh), C.byref(fb.sh), threads)
     return fb
 
 
@@ -496,10 +526,10 @@ def camera_rays(camera, renderer, fb, px, py, sample_index=0):
     return out
 
 
-def sampler_kat(kind, seed, first, count):
+def sampler_kat(kind, seed, first, count, backend="oracle"):
     width = {0: 12, 1: 4, 2: 4, 3: 2, 4: 1}[kind]
     out = np.zeros((count, width), np.float32)
-    lib().oracle_sampler_kat(kind, seed, first, count, out.ctypes.data)
+    (ref_lib().ospref_sampler_kat if backend == "ref" else lib().oracle_sampler_kat)(kind, seed, first, count, out.ctypes.data)
     return out.view(np.uint32) if kind == 4 else out
 
 

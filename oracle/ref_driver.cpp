@@ -1,0 +1,431 @@
+// ref_driver.cpp -- runs the REFERENCE's own render kernels (compiled from /root/reference/modules/cpu/**/*.ispc in
+// the scalar C++ mode its `ospray_module_gpu_kernels` target uses, see oracle/build_ref.py) on the scene PODs of
+// include/ospcuda.h.  TEST INFRASTRUCTURE ONLY: oracle/_ref/libospref.so is loaded by tests/, smoke() and
+// bench.py's reference arm, never by the product.
+//
+// What this file does is the reference's HOST side for this path, restated: it fills the reference's shared
+// structs (ispc::World, Instance, Group, GeometricModel, Mesh/Spheres/Boxes, OBJ, QuadLight/DirectionalLight/
+// AmbientLight, PathTracerData/SciVisData, PathTracer/SciVis/AORenderer, PerspectiveCamera, LocalFB) from the
+// already-committed Oc* values the way ISPCDevice's commit code does (file:line beside each block), then calls
+// the reference's own launchers (PathTracer_renderTaskLauncher etc., DEFINE_RENDERER_KERNEL_LAUNCHER,
+// common/DeviceRT.ih:60-94).  No reference source is copied: the kernels are compiled where they lie.
+// std headers first: common/OSPCommon.ih defines the macro `in` for its scalar foreach_unique emulation
+#include <algorithm>
+#include <deque>
+#include <iostream>
+#include <memory>
+#include <thread>
+#include <vector>
+#include "ref_embree_stub.h"
+#include "ospray/OSPEnums.h"
+#include "common/OSPCommon.ih"
+#include "common/Data.ih"
+#include "common/World.ih"
+#include "common/GroupShared.h"
+#include "geometry/GeometricModelShared.h"
+#include "geometry/MeshShared.h"
+#include "geometry/SpheresShared.h"
+#include "geometry/BoxesShared.h"
+#include "render/MaterialShared.h"
+#include "render/materials/OBJShared.h"
+#include "lights/QuadLightShared.h"
+#include "lights/DirectionalLightShared.h"
+#include "lights/AmbientLightShared.h"
+#include "render/pathtracer/PathTracerShared.h"
+#include "render/scivis/SciVisShared.h"
+#include "render/ao/AORendererShared.h"
+#include "pf/LUTPixelFilterShared.h"
+#include "camera/PerspectiveCameraShared.h"
+#include "fb/LocalFBShared.h"
+#include "fb/FrameBufferView.ih"
+#include "math/random.ih"
+#include "math/halton.ih"
+#include "render/util.ih"
+#ifdef OSPRAY_ENABLE_VOLUMES
+#include "volume/VolumeShared.h"
+#include "volume/VolumetricModelShared.h"
+#include "volume/transferFunction/LinearTransferFunctionShared.h"
+#include "ref_vkl_stub.h"
+#endif
+
+#define REF_API extern "C" __attribute__((visibility("default")))
+
+using namespace ispc;
+
+// the reference's launchers (extern "C", defined by DEFINE_*_KERNEL_LAUNCHER in the kernel TUs)
+extern "C" {
+void PathTracer_renderTaskLauncher(void *, void *, const vec3ui &, Renderer *, FrameBuffer *, Camera *, World *, const uint32_t *, const ospray::FeatureFlags &);
+void SciVis_renderTaskLauncher(void *, void *, const vec3ui &, Renderer *, FrameBuffer *, Camera *, World *, const uint32_t *, const ospray::FeatureFlags &);
+void AORenderer_renderTaskLauncher(void *, void *, const vec3ui &, Renderer *, FrameBuffer *, Camera *, World *, const uint32_t *, const ospray::FeatureFlags &);
+void ColorConversion_kernelLauncher(void *, void *, const vec2ui &, const FrameBufferView *);
+void ToneMapper_kernelLauncher(void *, void *, const vec2ui &, const FrameBufferView *);
+void Variance_kernelLauncher(void *, void *, const vec2ui &, const FrameBufferView *);
+void ospref_ray_counters(uint64_t out[2], int reset);
+}
+namespace ispc {
+void LUTPixelFilter_buildLUT(void *self);
+float Distribution1D_create(const int size, float *cdf);
+}
+
+namespace {
+
+inline vec3f v3(const OcVec3f &o) { return make_vec3f(o.x, o.y, o.z); }
+inline Data1D d1(const OcData1D &d)
+{
+  Data1D r; r.addr = (uint8 *)d.addr; r.byteStride = d.byteStride; r.numItems = d.numItems; r.huge = false;
+  if (!d.addr) { r.byteStride = 0; r.numItems = 0; }
+  return r;
+}
+inline affine3f a3(const OcAffine3f &a) { return affine3f(linear3f(v3(a.vx), v3(a.vy), v3(a.vz)), v3(a.p)); }
+
+ospray::FeatureFlags allFeatures()
+{
+  ospray::FeatureFlags ff;
+  ff.geometry = ospray::FFG_ALL;
+#ifdef OSPRAY_ENABLE_VOLUMES
+  ff.volume = VKL_FEATURE_FLAGS_DEFAULT;
+#endif
+  ff.other = ospray::FFO_ALL;
+  return ff;
+}
+
+// Everything one frame needs, with stable addresses (deques never move their elements)
+struct Scene
+{
+  std::deque<Mesh> meshes; std::deque<Spheres> spheres; std::deque<Boxes> boxes;
+  std::deque<GeometricModel> models; std::deque<Group> groups; std::deque<Instance> instances;
+  std::deque<std::vector<GeometricModel *>> modelPtrs;
+  std::deque<std::vector<Material *>> materialPtrs;
+  std::deque<OBJ> objs; std::vector<Material *> allMaterials;
+  std::vector<Instance *> instancePtrs;
+  std::deque<QuadLight> quads; std::deque<DirectionalLight> dirs; std::deque<AmbientLight> ambients;
+  std::vector<Light *> ptLights, svLights;
+  Instance identityInstance; // stands in for the NULL instance of world lights: the scalar light dispatch reads
+                             // self->instance->motionBlur unconditionally (lights/LightDispatch.ispc:36-60)
+  PathTracerData ptData; SciVisData svData;
+  World world;
+  RTCSceneTy geomScene, volScene;
+#ifdef OSPRAY_ENABLE_VOLUMES
+  std::deque<Volume> volumes; std::deque<VolumetricModel> vmodels; std::deque<LinearTransferFunction> tfs;
+  std::deque<std::vector<VolumetricModel *>> vmodelPtrs;
+  std::deque<RefVklVolume> vklVolumes; std::deque<RefVklSampler> vklSamplers; std::deque<RefVklIntervalContext> vklContexts;
+#endif
+};
+
+Geometry *makeGeometry(Scene &s, const OcGeometry *g)
+{
+  if (g->type == OC_GEOM_TRIANGLES || g->type == OC_GEOM_QUADS) {
+    // geometry/Mesh.cpp:137-196
+    s.meshes.emplace_back();
+    Mesh &m = s.meshes.back();
+    const bool isTri = g->type == OC_GEOM_TRIANGLES;
+    m.super.type = isTri ? GEOMETRY_TYPE_TRIANGLE_MESH : GEOMETRY_TYPE_QUAD_MESH;
+    m.super.numPrimitives = g->numPrims;
+    m.index = d1(g->index); m.vertex = d1(g->vertex); m.normal = d1(g->normal); m.color = d1(g->color); m.texcoord = d1(g->texcoord);
+    m.has_alpha = (g->flags & OC_GEOMFLAG_COLOR_IS_VEC4) != 0 && g->color.addr;
+    m.is_triangleMesh = isTri;
+    m.isColorFaceVarying = (g->flags & OC_GEOMFLAG_COLOR_FACEVARYING) != 0;
+    m.isTexcoordFaceVarying = (g->flags & OC_GEOMFLAG_TEXCOORD_FACEVARYING) != 0;
+    m.isNormalFaceVarying = (g->flags & OC_GEOMFLAG_NORMAL_FACEVARYING) != 0;
+    m.flagMask = -1;
+    if (!g->normal.addr) m.flagMask &= int64(~DG_NS);
+    if (!g->color.addr) m.flagMask &= int64(~DG_COLOR);
+    if (!g->texcoord.addr) m.flagMask &= int64(~DG_TEXCOORD);
+    return &m.super;
+  }
+  if (g->type == OC_GEOM_SPHERES) {
+    // geometry/Spheres.cpp:46-106 (the interleaved vec4f array is the committed state)
+    s.spheres.emplace_back();
+    Spheres &sp = s.spheres.back();
+    sp.super.numPrimitives = g->numPrims;
+    sp.sphere = d1(g->sphere); sp.texcoord = d1(g->texcoord);
+    Data1D_Constructor(&sp.normalData);
+    sp.sphereType = OSP_SPHERE;
+    return &sp.super;
+  }
+  // geometry/Boxes.cpp:33-42
+  s.boxes.emplace_back();
+  Boxes &b = s.boxes.back();
+  b.super.numPrimitives = g->numPrims;
+  b.boxes = d1(g->box);
+  return &b.super;
+}
+
+void buildScene(Scene &s, const OcWorld *w, const OcRenderer *ren)
+{
+  // materials: render/materials/OBJ.cpp:30-66 (values arrive already normalised by the commit)
+  for (uint32_t i = 0; i < w->numMaterials; i++) {
+    const OcMaterial &m = w->materials[i];
+    s.objs.emplace_back();
+    OBJ &o = s.objs.back();
+    o.d = m.d; o.Kd = v3(m.Kd); o.Ks = v3(m.Ks); o.Ns = m.Ns; o.Tf = v3(m.Tf);
+    s.allMaterials.push_back(&o.super);
+  }
+  bool anyGeometry = false, anyVolume = false;
+  s.geomScene.world = w; s.volScene.world = w; s.volScene.volumes = true;
+  s.geomScene.userPtr.resize(w->numInstances); s.volScene.userPtr.resize(w->numInstances);
+  for (uint32_t i = 0; i < w->numInstances; i++) {
+    const OcInstance &oi = w->instances[i];
+    const OcGroup *og = oi.group;
+    // common/Group.cpp:69-209
+    s.groups.emplace_back();
+    Group &grp = s.groups.back();
+    s.modelPtrs.emplace_back();
+    for (uint32_t m = 0; m < og->numModels; m++) {
+      const OcModel &om = og->models[m];
+      // geometry/GeometricModel.cpp:20-88
+      s.models.emplace_back();
+      GeometricModel &gm = s.models.back();
+      gm.geom = makeGeometry(s, om.geom);
+      gm.color = d1(om.color); gm.index = d1(om.index);
+      gm.numMaterials = om.numMaterials;
+      if (om.materialMode == OC_MAT_FROM_MODEL && om.numMaterials) {
+        s.materialPtrs.emplace_back();
+        for (uint32_t k = 0; k < om.numMaterials; k++) s.materialPtrs.back().push_back(s.allMaterials[om.material[k]]);
+        gm.material = s.materialPtrs.back().data();
+      } else if (om.materialMode == OC_MAT_FROM_RENDERER && om.numMaterials) {
+        gm.materialID = (uint32 *)om.material;
+      } else
+        gm.numMaterials = 0;
+      gm.invertedNormals = om.invertedNormals != 0;
+      gm.userID = om.userID;
+      s.modelPtrs.back().push_back(&gm);
+      s.geomScene.userPtr[i].push_back(gm.geom);
+      anyGeometry = true;
+    }
+    grp.geometricModels = s.modelPtrs.back().empty() ? nullptr : s.modelPtrs.back().data();
+    grp.numGeometricModels = og->numModels;
+#ifdef OSPRAY_ENABLE_VOLUMES
+    s.vmodelPtrs.emplace_back();
+    for (uint32_t v = 0; v < og->numVolumes; v++) {
+      VolumetricModel *vm = refMakeVolumetricModel(s.volumes, s.vmodels, s.tfs, s.vklVolumes, s.vklSamplers, s.vklContexts, og->volumes[v]);
+      s.vmodelPtrs.back().push_back(vm);
+      s.volScene.userPtr[i].push_back(vm->volume);
+      anyVolume = true;
+    }
+    grp.volumetricModels = s.vmodelPtrs.back().empty() ? nullptr : s.vmodelPtrs.back().data();
+    grp.numVolumetricModels = og->numVolumes;
+#endif
+    // common/Instance.cpp:20-34
+    s.instances.emplace_back();
+    Instance &inst = s.instances.back();
+    inst.group = &grp; inst.scene = &s.geomScene; inst.geomID = i;
+    inst.xfm = a3(oi.xfm); inst.rcp_xfm = a3(oi.rcp_xfm);
+    inst.userID = oi.userID;
+  }
+  for (auto &inst : s.instances) s.instancePtrs.push_back(&inst);
+
+  // lights: lights/QuadLight.cpp:17-59, DirectionalLight.cpp, AmbientLight.cpp (committed values)
+  auto makeLight = [&](const OcLight &l) -> Light * {
+    if (l.type == OC_LIGHT_QUAD) {
+      s.quads.emplace_back();
+      QuadLight &q = s.quads.back();
+      q.super.isVisible = l.isVisible != 0; q.super.instance = &s.identityInstance;
+      q.radiance = v3(l.radiance);
+      q.pre.position = v3(l.position); q.pre.edge1 = v3(l.edge1); q.pre.edge2 = v3(l.edge2);
+      q.pre.nnormal = v3(l.nnormal); q.pre.ppdf = l.ppdf;
+      q.pre.c90 = normalize(cross(q.pre.nnormal, q.pre.edge2));
+      q.pre.c0 = cross(q.pre.c90, q.pre.nnormal);
+      return &q.super;
+    }
+    if (l.type == OC_LIGHT_DISTANT) {
+      s.dirs.emplace_back();
+      DirectionalLight &d = s.dirs.back();
+      d.super.isVisible = l.isVisible != 0; d.super.instance = &s.identityInstance;
+      d.frame = linear3f(v3(l.fx), v3(l.fy), v3(l.fz));
+      d.irradiance = v3(l.radiance); d.cosAngle = l.cosAngle; d.pdf = l.pdf;
+      return &d.super;
+    }
+    s.ambients.emplace_back();
+    AmbientLight &a = s.ambients.back();
+    a.super.isVisible = l.isVisible != 0; a.super.instance = &s.identityInstance;
+    a.radiance = v3(l.radiance);
+    return &a.super;
+  };
+  // render/pathtracer/PathTracerData.cpp:32-82
+  for (uint32_t i = 0; i < w->numLights; i++) s.ptLights.push_back(makeLight(w->lights[i]));
+  s.ptData.lights = s.ptLights.empty() ? nullptr : s.ptLights.data();
+  s.ptData.numLights = w->numLights; s.ptData.numGeoLights = 0; s.ptData.lightsCDF = (float *)w->lightsCDF;
+  // render/scivis/SciVisData.cpp:17-105
+  for (uint32_t i = 0; i < w->numScivisLights; i++) s.svLights.push_back(makeLight(w->scivisLights[i]));
+  s.svData.lights = s.svLights.empty() ? nullptr : s.svLights.data();
+  s.svData.numLights = w->numScivisLights; s.svData.numLightsVisibleOnly = w->numScivisLightsVisibleOnly;
+  s.svData.aoColorPi = v3(w->aoColorPi);
+
+  // common/World.cpp:70-188
+  s.world.instances = s.instancePtrs.empty() ? nullptr : s.instancePtrs.data();
+  s.world.embreeSceneHandleGeometries = anyGeometry ? &s.geomScene : nullptr;
+#ifdef OSPRAY_ENABLE_VOLUMES
+  s.world.embreeSceneHandleVolumes = anyVolume ? &s.volScene : nullptr;
+#endif
+  s.world.scivisData = &s.svData; s.world.pathtracerData = &s.ptData;
+  (void)ren; (void)anyVolume;
+}
+
+struct RendererSet
+{
+  PathTracer pt; SciVis sv; AORenderer ao;
+  PixelFilter pf; LUTPixelFilter lut; Distribution2D dist;
+  std::vector<Material *> materials;
+};
+
+Renderer *buildRenderer(RendererSet &r, Scene &s, const OcRenderer *o)
+{
+  Renderer *base = o->type == OC_RENDERER_PATHTRACER ? &r.pt.super : (o->type == OC_RENDERER_SCIVIS ? &r.sv.super : &r.ao.super);
+  // render/Renderer.cpp:38-92
+  base->spp = o->spp; base->bgColor = make_vec4f(o->bgColor[0], o->bgColor[1], o->bgColor[2], o->bgColor[3]);
+  base->maxDepth = o->maxDepth; base->minContribution = o->minContribution;
+  for (uint32_t i = 0; i < o->numMaterials; i++) r.materials.push_back(s.allMaterials[o->materials[i]]);
+  base->numMaterials = o->numMaterials; base->material = r.materials.empty() ? nullptr : r.materials.data();
+  // render/Renderer.cpp:146-178 + pf/PixelFilter.cpp:23-69
+  if (o->pfType == OC_PF_LUT) {
+    r.dist.size = make_vec2i(o->pfLutW, o->pfLutH); r.dist.rcpSize = make_vec2f(1.f / o->pfLutW, 1.f / o->pfLutH);
+    r.dist.cdf_x = (float *)o->pfCdfX; r.dist.cdf_y = (float *)o->pfCdfY;
+    r.lut.super.width = o->pfWidth; r.lut.distribution = &r.dist;
+    base->pixelFilter = &r.lut.super;
+  } else {
+    r.pf.type = o->pfType == OC_PF_POINT ? PIXEL_FILTER_TYPE_POINT : PIXEL_FILTER_TYPE_BOX;
+    r.pf.width = o->pfWidth;
+    base->pixelFilter = &r.pf;
+  }
+  base->mipBiasFactor = 1.f;
+  if (o->type == OC_RENDERER_PATHTRACER) { // render/pathtracer/PathTracer.cpp:29-51
+    r.pt.rouletteDepth = o->rouletteDepth; r.pt.maxScatteringEvents = o->maxScatteringEvents; r.pt.maxRadiance = o->maxRadiance;
+    r.pt.numLightSamples = o->numLightSamples; r.pt.limitIndirectLightSamples = o->limitIndirectLightSamples != 0;
+    r.pt.backgroundRefraction = o->backgroundRefraction != 0;
+  } else if (o->type == OC_RENDERER_SCIVIS) { // render/scivis/SciVis.cpp:27-36
+    r.sv.shadowsEnabled = o->shadowsEnabled != 0; r.sv.visibleLights = o->visibleLights != 0; r.sv.aoSamples = o->aoSamples;
+    r.sv.aoRadius = o->aoRadius; r.sv.volumeSamplingRate = o->volumeSamplingRate;
+  } else { // render/ao/AORenderer.cpp:26-35
+    r.ao.aoSamples = o->aoSamples; r.ao.aoRadius = o->aoRadius; r.ao.aoIntensity = o->aoIntensity;
+    r.ao.volumeSamplingRate = o->volumeSamplingRate;
+  }
+  return base;
+}
+
+} // namespace
+
+// Same contract as oracle_render_frame (oracle.cpp): renders one frame of `fb` (frameID already advanced) into the
+// HOST buffers of `fb`.  Returns 0, or -1 when the image size is not a multiple of the 8x8 render task (the scalar
+// render task of the reference does not clip partial tasks, PathTracer.ispc:232-236).
+REF_API int ospref_render_frame(const OcWorld *w, const OcCamera *cam, const OcRenderer *ren, const OcFrameBuffer *fb, int numThreads)
+{
+  if (fb->sizeX % 8 || fb->sizeY % 8) return -1;
+  auto s = std::make_unique<Scene>();
+  buildScene(*s, w, ren);
+  auto rs = std::make_unique<RendererSet>();
+  Renderer *renderer = buildRenderer(*rs, *s, ren);
+
+  // camera/PerspectiveCamera.cpp:26-117 (committed values)
+  PerspectiveCamera pc;
+  pc.super.direction = v3(cam->direction); pc.super.nearClip = cam->nearClip;
+  pc.super.subImage = box2f(make_vec2f(cam->subImage[0], cam->subImage[1]), make_vec2f(cam->subImage[2], cam->subImage[3]));
+  pc.super.shutter = box1f(0.5f, 0.5f);
+  pc.super.needLensSample = cam->needLensSample != 0; pc.super.needTimeSample = cam->needTimeSample != 0;
+  pc.org = v3(cam->org); pc.dir_00 = v3(cam->dir_00); pc.du_size = v3(cam->du_size); pc.dv_up = v3(cam->dv_up);
+  pc.imgPlaneSize = make_vec2f(cam->imgPlaneSizeY * cam->aspect, cam->imgPlaneSizeY);
+  pc.scaledAperture = cam->scaledAperture; pc.aspect = cam->aspect;
+
+  // fb/LocalFB.cpp:49-180, fb/FrameBuffer.cpp:31-137
+  LocalFB lfb;
+  lfb.super.size = make_vec2i(fb->sizeX, fb->sizeY);
+  lfb.super.rcpSize = make_vec2f(1.f / fb->sizeX, 1.f / fb->sizeY);
+  lfb.super.renderTaskSize = make_vec2i(8, 8);
+  lfb.super.frameID = fb->frameID; lfb.super.targetFrames = fb->targetFrames; lfb.super.channels = fb->channels;
+  lfb.super.projectedDepth = fb->projectedDepth != 0; lfb.super.accumulateVariance = fb->accumulateVariance != 0;
+  lfb.colorBuffer = (vec4f *)fb->color; lfb.varianceBuffer = (vec4f *)fb->variance; lfb.depthBuffer = fb->depth;
+  lfb.normalBuffer = (vec3f *)fb->normal; lfb.firstNormalBuffer = (vec3f *)fb->firstNormal;
+  lfb.positionBuffer = (vec3f *)fb->position; lfb.albedoBuffer = (vec3f *)fb->albedo;
+  lfb.numRenderTasks = make_vec2i(fb->sizeX / 8, fb->sizeY / 8);
+  lfb.primitiveIDBuffer = fb->primID; lfb.objectIDBuffer = fb->objID; lfb.instanceIDBuffer = fb->instID;
+
+  // task list: every 8x8 task inside a 64x64 tile this rank owns (modules/multiDevice/MultiDevice.cpp:403-416)
+  std::vector<uint32_t> taskIDs;
+  const int tilesX = (fb->sizeX + 63) / 64;
+  const uint32_t numRanks = fb->numRanks ? fb->numRanks : 1;
+  for (int ty = 0; ty < lfb.numRenderTasks.y; ty++)
+    for (int tx = 0; tx < lfb.numRenderTasks.x; tx++) {
+      const uint32_t tile = (uint32_t)((ty / 8) * tilesX + tx / 8);
+      if (tile % numRanks == fb->rank) taskIDs.push_back((uint32_t)(ty * lfb.numRenderTasks.x + tx));
+    }
+
+  sycl::queue q; q.numThreads = numThreads > 0 ? numThreads : (int)std::max(1u, std::thread::hardware_concurrency());
+  sycl::event ev;
+  const ospray::FeatureFlags ff = allFeatures();
+  const vec3ui dims = make_vec3ui(8, 8, (uint32_t)taskIDs.size());
+  uint64_t before[2]; ospref_ray_counters(before, 0);
+  if (ren->type == OC_RENDERER_PATHTRACER)
+    PathTracer_renderTaskLauncher(&q, &ev, dims, renderer, &lfb.super, &pc.super, &s->world, taskIDs.data(), ff);
+  else if (ren->type == OC_RENDERER_SCIVIS)
+    SciVis_renderTaskLauncher(&q, &ev, dims, renderer, &lfb.super, &pc.super, &s->world, taskIDs.data(), ff);
+  else
+    AORenderer_renderTaskLauncher(&q, &ev, dims, renderer, &lfb.super, &pc.super, &s->world, taskIDs.data(), ff);
+  if (fb->rayCounters) {
+    uint64_t after[2]; ospref_ray_counters(after, 0);
+    fb->rayCounters[0] += (unsigned long long)taskIDs.size() * 64ull * (unsigned long long)ren->spp;
+    const unsigned long long total = (after[0] - before[0]) + (after[1] - before[1]);
+    fb->rayCounters[1] += (after[0] - before[0]) - std::min<unsigned long long>(after[0] - before[0], taskIDs.size() * 64ull * ren->spp);
+    fb->rayCounters[2] += after[1] - before[1];
+    (void)total;
+  }
+  return 0;
+}
+
+// ---- known-answer vectors straight from the reference's sampler sources (math/random.ih, sobol.ih, halton.ih,
+// render/util.ih); same layout as oracle_sampler_kat ---------------------------------------------------------
+REF_API void ospref_sampler_kat(int kind, uint32_t seed, uint32_t first, uint32_t count, float *out)
+{
+  for (uint32_t k = 0; k < count; k++) {
+    const uint32_t i = first + k;
+    if (kind == 0) {
+      float *o = out + 12 * (size_t)k;
+      LDSampler ld;
+      LDSampler_init(ld, seed, i, i, 16, 16);
+      vec3ui ss;
+      const vec2f p = LDSampler_getNext5Samples(ld, ss);
+      const vec2f l = LDSampler_finalizeDim23(ld, ss);
+      o[0] = p.x; o[1] = p.y; o[2] = l.x; o[3] = l.y; o[4] = LDSampler_finalizeDim4(ld, ss);
+      LDSampler_nextGroup(ld);
+      float s1;
+      const vec2f ls = LDSampler_get3LightSamples(ld, 0, false, s1);
+      o[5] = ls.x; o[6] = ls.y; o[7] = s1;
+      float s2; uint32 u3;
+      const vec2f b = LDSampler_getNext4Samples(ld, s2, u3);
+      o[8] = b.x; o[9] = b.y; o[10] = s2; o[11] = LDSampler_finalizeDim3(ld, u3);
+    } else if (kind == 1) {
+      float *o = out + 4 * (size_t)k;
+      o[0] = Halton_sample2(i); o[1] = CranleyPattersonRotation(Halton_sample3(i), 1.f / 6.f);
+      o[2] = PermHalton_sample5(i); o[3] = PermHalton_sample7(i);
+    } else if (kind == 2) {
+      float *o = out + 4 * (size_t)k;
+      RandomSampler rs;
+      RandomSampler_init(&rs, seed, i);
+      for (int j = 0; j < 4; j++) o[j] = RandomSampler_getFloat(&rs);
+    } else if (kind == 3) {
+      uint32 v0 = seed, v1 = i;
+      tea8(v0, v1);
+      out[2 * (size_t)k] = to_float_unorm(v0); out[2 * (size_t)k + 1] = to_float_unorm(v1);
+    } else {
+      const uint32 v = OwenScramble4(interleaveZOrder16(i, seed), 0x49c5f37eu);
+      memcpy(out + k, &v, 4);
+    }
+  }
+}
+
+// default (Gaussian) pixel filter LUT built by the reference's LUTPixelFilter_buildLUT (pf/LUTPixelFilter.ispc:120-142)
+// + Distribution2D create (math/Distribution2D.cpp restated: per-row Distribution1D_create, then the marginal)
+REF_API void ospref_gauss_pixelfilter_lut(float width, int lut, float *cdfX, float *cdfY)
+{
+  LUTPixelFilter f; Distribution2D d;
+  d.size = make_vec2i(lut, lut); d.rcpSize = make_vec2f(1.f / lut, 1.f / lut); d.cdf_x = cdfX; d.cdf_y = cdfY;
+  f.super.width = width; f.distribution = &d; f.lutFilterType = LUT_PIXEL_FILTER_TYPE_GAUSSIAN;
+  LUTPixelFilter_buildLUT(&f);
+  for (int y = 0; y < lut; y++) cdfY[y] = Distribution1D_create(lut, cdfX + (size_t)y * lut);
+  Distribution1D_create(lut, cdfY);
+}
+
+// frame ops through the reference's own kernels (fb/frame_ops/*.ispc)
+REF_API void ospref_fb_color_convert(const OcVec4f *src, void *out, uint32_t n, uint32_t format);
+REF_API void ospref_fb_tonemap(const OcVec4f *src, OcVec4f *out, uint32_t n, const OcToneMapper *tm);
+REF_API void ospref_fb_variance(const OcVec4f *color, const OcVec4f *variance, int sizeX, int sizeY, int taskSize, float *taskError);
+REF_API int ospref_hardware_threads(void) { return (int)std::max(1u, std::thread::hardware_concurrency()); }

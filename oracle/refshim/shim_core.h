@@ -15,6 +15,10 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <cassert>
+#ifndef SYCL_EXTERNAL
+#define SYCL_EXTERNAL
+#endif
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
@@ -33,35 +37,30 @@ using int8 = int8_t;
 using uint = unsigned int;
 
 // ---- constants (rkcommon/math/math.ih) -------------------------------------------------------------------
-#define inf ((float)INFINITY)
-#define neg_inf (-(float)INFINITY)
-#define pos_inf ((float)INFINITY)
-#define nan ((float)NAN)
-#define flt_min 1.17549435e-38f
-#define flt_max 3.40282347e+38f
-#define ulp 5.9604644775390625e-8f
-#define one_over_255 (1.f / 255.f)
-#define pi 3.14159265358979323846
-#define two_pi 6.283185307179586232
-#define four_pi 12.566370614359172464
-#define half_pi 1.57079632679489661923
-#define one_over_pi 0.31830988618379069122
-#define one_over_two_pi 0.15915494309189534561
-#define one_over_four_pi 0.079577471545947672804
-#define one_over_two_pi_sqr 0.050660591821168885722
-#define lntwo_over_two 0.346573590279972654709
-#define two_over_pi 0.636619772367581343076
-#define sqrt_two 1.41421356237309504880
+static const float inf = INFINITY, neg_inf = -INFINITY, pos_inf = INFINITY, nan = NAN;
+static const float flt_min = 1.17549435e-38f, flt_max = 3.40282347e+38f, ulp = 5.9604644775390625e-8f, one_over_255 = 1.f / 255.f;
+static const double pi = 3.14159265358979323846, two_pi = 6.283185307179586232, four_pi = 12.566370614359172464,
+                    half_pi = 1.57079632679489661923, one_over_pi = 0.31830988618379069122,
+                    one_over_two_pi = 0.15915494309189534561, one_over_four_pi = 0.079577471545947672804,
+                    one_over_two_pi_sqr = 0.050660591821168885722, lntwo_over_two = 0.346573590279972654709,
+                    two_over_pi = 0.636619772367581343076, sqrt_two = 1.41421356237309504880;
+struct OneTy {}; struct ZeroTy {}; struct EmptyTy {};
+static const OneTy one{}; static const ZeroTy zero{}; static const EmptyTy empty{};
 
 // ---- ISPC stdlib scalars ---------------------------------------------------------------------------------
 inline float abs(float x) { return fabsf(x); }
 inline int abs(int x) { return x < 0 ? -x : x; }
+inline float absf(float x) { return fabsf(x); }
 inline float sqrt(float x) { return sqrtf(x); }
 inline float rcp(float x) { return 1.0f / x; }
 inline float rcpf(float x) { return 1.0f / x; }
 inline float rsqrt(float x) { return 1.0f / sqrtf(x); }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 inline float rcp_safe(float f) { return rcp((fabsf(f) < flt_min) ? (f >= 0.f ? flt_min : -flt_min) : f); }
+inline float sqrt_safe(float x) { return sqrtf(x > 0.f ? x : 0.f); }
+inline int exclusive_scan_add(int) { return 0; }
+inline float expf(float x) { return ::expf(x); }
+inline float logf(float x) { return ::logf(x); }
 inline float sqr(float x) { return x * x; }
 inline float sin(float x) { return sinf(x); }
 inline float cos(float x) { return cosf(x); }
@@ -127,14 +126,15 @@ inline float sin2cos(float f) { return cos2sin(f); }
 inline float roundToPow2(float x) { return x; }
 inline bool similar(float a, float b) { return fabsf(a - b) <= 1e-5f * max(fabsf(a), fabsf(b)); }
 inline float divide_safe(float f) { return 1.f / ((fabsf(f) < flt_min) ? (f >= 0.f ? flt_min : -flt_min) : f); }
+inline uint32 signbits(float x) { return intbits(x) & 0x80000000u; }
 inline float nextafter(float a, float b) { return ::nextafterf(a, b); }
 // rkcommon/math/math.ih: u32 -> [0,1]: one int->float conversion then an exact power-of-two scale
 inline float to_float_unorm(uint32 a) { return (float)a * 0x1.0p-32f; }
 
 // ---- short vectors ---------------------------------------------------------------------------------------
-template <typename T> struct V2 { T x, y; };
-template <typename T> struct V3 { T x, y, z; };
-template <typename T> struct V4 { T x, y, z, w; };
+template <typename T> struct V2 { T x, y; V2() = default; V2(T x_, T y_) : x(x_), y(y_) {} V2(T s) : x(s), y(s) {} };
+template <typename T> struct V3 { T x, y, z; V3() = default; V3(T x_, T y_, T z_) : x(x_), y(y_), z(z_) {} V3(T s) : x(s), y(s), z(s) {} };
+template <typename T> struct V4 { T x, y, z, w; V4() = default; V4(T x_, T y_, T z_, T w_) : x(x_), y(y_), z(z_), w(w_) {} V4(T s) : x(s), y(s), z(s), w(s) {} };
 using vec2f = V2<float>; using vec3f = V3<float>; using vec4f = V4<float>;
 using vec2i = V2<int32>; using vec3i = V3<int32>; using vec4i = V4<int32>;
 using vec2ui = V2<uint32>; using vec3ui = V3<uint32>; using vec4ui = V4<uint32>;
@@ -210,6 +210,8 @@ inline vec3f operator-(double a, const vec3f &b) { return (float)a - b; }
 inline vec2f operator-(const vec2f &a, double b) { return a - (float)b; }
 inline vec2f operator+(const vec2f &a, double b) { return a + (float)b; }
 inline vec2f operator/(const vec2f &a, double b) { return a / (float)b; }
+inline vec2ui operator-(const vec2ui &a, int b) { return {a.x - (uint32)b, a.y - (uint32)b}; }
+inline vec2ui operator+(const vec2ui &a, int b) { return {a.x + (uint32)b, a.y + (uint32)b}; }
 inline vec2i operator*(const vec2i &a, uint32 b) { return {(int)(a.x * b), (int)(a.y * b)}; }
 
 template <typename T> inline V2<T> operator-(const V2<T> &a) { return {(T)-a.x, (T)-a.y}; }
@@ -247,13 +249,14 @@ inline vec3b lt(const vec3f &a, float b) { return {a.x < b, a.y < b, a.z < b}; }
 inline vec3b gt(const vec3f &a, float b) { return {a.x > b, a.y > b, a.z > b}; }
 inline bool any(const vec3b &b) { return b.x || b.y || b.z; }
 inline bool all(const vec3b &b) { return b.x && b.y && b.z; }
+inline vec3ui intbits(const vec3f &v) { return {intbits(v.x), intbits(v.y), intbits(v.z)}; }
 inline bool isnan(const vec3f &v) { return isnan(v.x + v.y + v.z); }
 
 #define SHIM_UNARY(fn)                                                                                       \
   inline vec2f fn(const vec2f &a) { return {fn(a.x), fn(a.y)}; }                                             \
   inline vec3f fn(const vec3f &a) { return {fn(a.x), fn(a.y), fn(a.z)}; }                                    \
   inline vec4f fn(const vec4f &a) { return {fn(a.x), fn(a.y), fn(a.z), fn(a.w)}; }
-SHIM_UNARY(abs) SHIM_UNARY(sqrt) SHIM_UNARY(rcp) SHIM_UNARY(rcp_safe) SHIM_UNARY(exp) SHIM_UNARY(log) SHIM_UNARY(floor)
+SHIM_UNARY(expf) SHIM_UNARY(logf) SHIM_UNARY(sqrt_safe) SHIM_UNARY(abs) SHIM_UNARY(absf) SHIM_UNARY(sqrt) SHIM_UNARY(rcp) SHIM_UNARY(rcp_safe) SHIM_UNARY(exp) SHIM_UNARY(log) SHIM_UNARY(floor)
 SHIM_UNARY(ceil) SHIM_UNARY(frac) SHIM_UNARY(sqr) SHIM_UNARY(rsqrt) SHIM_UNARY(sin) SHIM_UNARY(cos) SHIM_UNARY(divide_safe)
 #undef SHIM_UNARY
 inline vec3f rcpf(const vec3f &a) { return rcp(a); }
@@ -306,6 +309,7 @@ inline float luminance(const vec3f &c) { return 0.212671f * c.x + 0.715160f * c.
 inline vec2f lerp(float f, const vec2f &a, const vec2f &b) { return (1.f - f) * a + f * b; }
 inline vec3f lerp(float f, const vec3f &a, const vec3f &b) { return (1.f - f) * a + f * b; }
 inline vec4f lerp(float f, const vec4f &a, const vec4f &b) { return (1.f - f) * a + f * b; }
+inline vec2f lerp(const vec2f &f, const vec2f &a, const vec2f &b) { return (make_vec2f(1.f) - f) * a + f * b; }
 inline vec3f lerp(const vec3f &f, const vec3f &a, const vec3f &b) { return (make_vec3f(1.f) - f) * a + f * b; }
 inline vec3f interpolate(const vec3f &f, const vec3f &a, const vec3f &b, const vec3f &c) { return f.x * a + f.y * b + f.z * c; }
 inline vec4f interpolate(const vec3f &f, const vec4f &a, const vec4f &b, const vec4f &c) { return f.x * a + f.y * b + f.z * c; }
@@ -319,23 +323,21 @@ inline vec3f select(bool c, const vec3f &a, const vec3f &b) { return c ? a : b; 
 inline vec3f madd(const vec3f &a, const vec3f &b, const vec3f &c) { return a * b + c; }
 inline vec3f madd(float a, const vec3f &b, const vec3f &c) { return a * b + c; }
 // orthonormal frame (rkcommon/math/LinearSpace.ih frame()): restated, see oracle.cpp frame()
-inline vec3f cartesian(float phi, float sinTheta, float cosTheta)
+inline vec3f rotate(const vec3f &v, const vec3f &axis, float theta) // Rodrigues (rkcommon/math/vec.ih, restated)
 {
-  float sinPhi, cosPhi; sincos(phi, &sinPhi, &cosPhi);
-  return make_vec3f(cosPhi * sinTheta, sinPhi * sinTheta, cosTheta);
+  return v * cos(theta) + cross(axis, v) * sin(theta) + axis * dot(axis, v) * (1.f - cos(theta));
 }
-inline vec3f cartesian(float phi, float cosTheta) { return cartesian(phi, cos2sin(cosTheta), cosTheta); }
 inline int maxDim(const vec3f &v) { return v.x > v.y ? (v.x > v.z ? 0 : 2) : (v.y > v.z ? 1 : 2); }
 inline float component(const vec3f &v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
 
 // ---- linear / affine space, boxes ------------------------------------------------------------------------
-struct linear3f { vec3f vx, vy, vz; };
+struct linear3f { vec3f vx, vy, vz; linear3f() = default; linear3f(const vec3f &x, const vec3f &y, const vec3f &z) : vx(x), vy(y), vz(z) {} linear3f(OneTy) : vx(1, 0, 0), vy(0, 1, 0), vz(0, 0, 1) {} };
 using LinearSpace3f = linear3f;
-struct LinearSpace2f { vec2f vx, vy; };
+struct LinearSpace2f { vec2f vx, vy; LinearSpace2f() = default; LinearSpace2f(const vec2f &x, const vec2f &y) : vx(x), vy(y) {} LinearSpace2f(OneTy) : vx(1, 0), vy(0, 1) {} };
 using linear2f = LinearSpace2f;
-struct affine3f { linear3f l; vec3f p; };
+struct affine3f { linear3f l; vec3f p; affine3f() = default; affine3f(const linear3f &l_, const vec3f &p_) : l(l_), p(p_) {} affine3f(OneTy) : l(one), p(0, 0, 0) {} };
 using AffineSpace3f = affine3f;
-struct AffineSpace2f { LinearSpace2f l; vec2f p; };
+struct AffineSpace2f { LinearSpace2f l; vec2f p; AffineSpace2f() = default; AffineSpace2f(const LinearSpace2f &l_, const vec2f &p_) : l(l_), p(p_) {} AffineSpace2f(OneTy) : l(one), p(0, 0) {} };
 using affine2f = AffineSpace2f;
 inline linear3f make_LinearSpace3f(const vec3f &x, const vec3f &y, const vec3f &z) { return {x, y, z}; }
 inline linear3f make_LinearSpace3f_identity() { return {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}; }
@@ -364,17 +366,19 @@ inline linear3f frame(const vec3f &N)
   const vec3f dy = cross(N, dx);
   return make_LinearSpace3f(dx, dy, N);
 }
+inline vec2f xfmPoint(const AffineSpace2f &a, const vec2f &v) { return a.p + v.x * a.l.vx + v.y * a.l.vy; }
+inline vec2f xfmVector(const AffineSpace2f &a, const vec2f &v) { return v.x * a.l.vx + v.y * a.l.vy; }
 inline vec2f operator*(const LinearSpace2f &l, const vec2f &v) { return v.x * l.vx + v.y * l.vy; }
 inline vec2f operator*(const AffineSpace2f &a, const vec2f &v) { return a.p + v.x * a.l.vx + v.y * a.l.vy; }
 
-struct box1f { float lower, upper; };
+struct box1f { float lower, upper; box1f() = default; box1f(float l, float u) : lower(l), upper(u) {} explicit box1f(float v) : lower(v), upper(v) {} box1f(EmptyTy) : lower(INFINITY), upper(-INFINITY) {} };
 using range1f = box1f;
-struct box2f { vec2f lower, upper; };
-struct box2i { vec2i lower, upper; };
+struct box2f { vec2f lower, upper; box2f() = default; box2f(const vec2f &l, const vec2f &u) : lower(l), upper(u) {} explicit box2f(float v) : lower(v), upper(v) {} box2f(EmptyTy) : lower(INFINITY), upper(-INFINITY) {} };
+struct box2i { vec2i lower, upper; box2i() = default; box2i(const vec2i &l, const vec2i &u) : lower(l), upper(u) {} box2i(EmptyTy) : lower(INT32_MAX), upper(INT32_MIN) {} };
 using range2i = box2i;
-struct box3f { vec3f lower, upper; };
+struct box3f { vec3f lower, upper; box3f() = default; box3f(const vec3f &l, const vec3f &u) : lower(l), upper(u) {} explicit box3f(float v) : lower(v), upper(v) {} box3f(EmptyTy) : lower(INFINITY), upper(-INFINITY) {} };
 using box3fa = box3f;
-struct box3i { vec3i lower, upper; };
+struct box3i { vec3i lower, upper; box3i() = default; box3i(const vec3i &l, const vec3i &u) : lower(l), upper(u) {} box3i(EmptyTy) : lower(INT32_MAX), upper(INT32_MIN) {} };
 struct box4f { vec4f lower, upper; };
 inline box1f make_box1f(float lo, float hi) { return {lo, hi}; }
 inline box1f make_box1f(const vec2f &v) { return {v.x, v.y}; }
@@ -383,12 +387,14 @@ inline box2i make_box2i(const vec2i &lo, const vec2i &hi) { return {lo, hi}; }
 inline box3f make_box3f(const vec3f &lo, const vec3f &hi) { return {lo, hi}; }
 inline box3f make_box3fa(const vec3f &lo, const vec3f &hi) { return {lo, hi}; }
 inline box3i make_box3i(const vec3i &lo, const vec3i &hi) { return {lo, hi}; }
+inline box3f make_box3fa(const box3f &b) { return b; }
 inline box3f make_box3f_empty() { return {make_vec3f(inf), make_vec3f(neg_inf)}; }
 inline box3f make_box3fa_empty() { return make_box3f_empty(); }
 inline box1f make_box1f_empty() { return {inf, neg_inf}; }
 inline bool isEmpty(const box1f &b) { return b.upper <= b.lower; }
 inline bool isEmpty(const box2i &b) { return b.upper.x <= b.lower.x || b.upper.y <= b.lower.y; }
 inline bool isEmpty(const box3f &b) { return anyLessThan(b.upper, b.lower); }
+inline vec2f box_size(const box2f &b) { return b.upper - b.lower; }
 inline vec3f box_size(const box3f &b) { return b.upper - b.lower; }
 inline vec2i box_size(const box2i &b) { return b.upper - b.lower; }
 inline float box_size(const box1f &b) { return b.upper - b.lower; }
@@ -416,6 +422,16 @@ inline uint32 cvt_uint32(float f) { return (uint32)round(255.f * clamp(f, 0.f, 1
 inline uint32 cvt_uint32(const vec4f &v) { return (cvt_uint32(v.x) << 0) | (cvt_uint32(v.y) << 8) | (cvt_uint32(v.z) << 16) | (cvt_uint32(v.w) << 24); }
 inline uint32 cvt_uint32(const vec3f &v) { return (cvt_uint32(v.x) << 0) | (cvt_uint32(v.y) << 8) | (cvt_uint32(v.z) << 16); }
 inline uint32 linear_to_srgba8(const vec4f &c) { return cvt_uint32(linear_to_srgba(c)); }
+inline float srgb_to_linear_(float x) { return x <= 0.04045f ? x * (1.f / 12.92f) : powf((x + 0.055f) * (1.f / 1.055f), 2.4f); }
+inline vec4f srgba_to_linear(const vec4f &c) { return {srgb_to_linear_(c.x), srgb_to_linear_(c.y), srgb_to_linear_(c.z), c.w}; }
+inline vec3f srgb_to_linear(const vec3f &c) { return {srgb_to_linear_(c.x), srgb_to_linear_(c.y), srgb_to_linear_(c.z)}; }
+// rkcommon/utility/random.ih makeRandomColor (debug renderer only; restated)
+inline vec3f makeRandomColor(uint32 i)
+{
+  const uint32 mx = 13 * 17 * 43, my = 11 * 29, mz = 7 * 23 * 63, g = (i * (3 * 5 * 127) + 12312314);
+  if (i == (uint32)-1) return make_vec3f(0.f);
+  return make_vec3f((g % mx) * (1.f / (mx - 1)), (g % my) * (1.f / (my - 1)), (g % mz) * (1.f / (mz - 1)));
+}
 inline float srgb_to_linear(float x) { return x <= 0.04045f ? x * (1.f / 12.92f) : pow((x + 0.055f) * (1.f / 1.055f), 2.4f); }
 
 } // namespace ispc

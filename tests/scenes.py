@@ -67,7 +67,7 @@ CASES = {
 W, H = 48, 40  # not a multiple of 8 or 64: exercises clipped render tasks and border tiles
 
 
-def oracle_render(name, width=W, height=H, pixel_filter=None, threads=0, num_ranks=1, rank=0, channels=None):
+def oracle_render(name, width=W, height=H, pixel_filter=None, threads=0, num_ranks=1, rank=0, channels=None, backend="oracle"):
     from oracle import pyoracle as O
     build, kind, params, frames = CASES[name]
     spec = build()
@@ -81,7 +81,7 @@ def oracle_render(name, width=W, height=H, pixel_filter=None, threads=0, num_ran
     fb = O.HostFrameBuffer(width, height, channels or ("color", "depth", "primID", "objID", "instID", "normal", "albedo"),
                            num_ranks=num_ranks, rank=rank)
     for _ in range(frames):
-        O.render_frame(scene, cam, ren, fb, threads)
+        O.render_frame(scene, cam, ren, fb, threads, backend=backend)
     return fb
 
 

@@ -17,8 +17,10 @@ them to GPU 0 -- total work is fixed, so this is STRONG scaling.
             (the step's host-side inputs; they reach the device as the kernel parameter block), ospRenderFrame,
             ospWait, ospMapFrameBuffer(OSP_FB_COLOR) = D2H of the finished sRGBA8 image into pinned memory.
 `roofline`  dominant kernel = the renderer megakernel; algorithmic bytes per DESIGN.md section 4.
-`cpu_baseline` / `--impl reference`: the scalar oracle port (oracle/oracle.cpp; the reference CPU device cannot
-            be built here: no ISPC / Embree / Open VKL / rkcommon) on all host threads."""
+`cpu_baseline` / `--impl reference`: the reference's own PathTracer kernels, compiled from /root/reference in their scalar
+            C++ mode into oracle/_ref/libospref.so (oracle/build_ref.py; kind "reference"), on all host threads; falls
+            back to the scalar oracle port (oracle/oracle.cpp, kind "port") when that library did not travel. The
+            reference's ISPC/Embree CPU device itself cannot be built here (no ISPC / Embree / Open VKL / rkcommon)."""
 import argparse
 import json
 import os
@@ -114,26 +116,38 @@ def oracle_setup(width, height):
     return O, scene, cam, ren
 
 
-def oracle_frames(width, height, frames, warm, stride=1):
-    """time `frames` oracle frames on all host threads; stride k renders the tiles with tileID % k == 0 only
+def cpu_backend():
+    """("ref", "reference") when oracle/_ref/libospref.so (the reference's own kernels, oracle/build_ref.py) travelled
+    with the snapshot and the frame is a multiple of its 8x8 render task, else ("oracle", "port")"""
+    from oracle import pyoracle as O
+    return ("ref", "reference") if O.ref_available() else ("oracle", "port")
+
+
+CPU_NOTE = {"reference": "the reference's own PathTracer kernels (modules/cpu/**/*.ispc compiled in their scalar C++ mode, oracle/build_ref.py; "
+                         "brute-force scene queries stand in for Embree), one pixel per work item on all host threads",
+            "port": "scalar CPU port of the reference algorithm (oracle/oracle.cpp, brute-force intersection)"}
+
+
+def oracle_frames(width, height, frames, warm, stride=1, backend="oracle"):
+    """time `frames` CPU frames on all host threads; stride k renders the tiles with tileID % k == 0 only
     (a bounded sample of the same workload). Returns (rays, seconds, threads)."""
     O, scene, cam, ren = oracle_setup(width, height)
     fb = O.HostFrameBuffer(width, height, ("color", "depth"), num_ranks=stride, rank=0)
     threads = O.lib().oracle_hardware_threads()
     for _ in range(warm):
-        O.render_frame(scene, cam, ren, fb, threads)
+        O.render_frame(scene, cam, ren, fb, threads, backend=backend)
     rays, secs = 0, 0.0
     for _ in range(frames):
         t0 = time.perf_counter()
-        O.render_frame(scene, cam, ren, fb, threads)
+        O.render_frame(scene, cam, ren, fb, threads, backend=backend)
         secs += time.perf_counter() - t0
         rays += int(fb.counters.sum())
     return rays, secs, threads
 
 
-def calibrate_stride(width, height, budget_s):
-    """pick the tile stride so that one oracle step stays under budget_s on this host"""
-    rays, secs, _ = oracle_frames(width, height, 1, 0, stride=16)
+def calibrate_stride(width, height, budget_s, backend="oracle"):
+    """pick the tile stride so that one CPU step stays under budget_s on this host"""
+    rays, secs, _ = oracle_frames(width, height, 1, 0, stride=16, backend=backend)
     full = secs * 16
     stride = 1
     while full / stride > budget_s and stride < 64:
@@ -146,16 +160,19 @@ def run_reference(args):
     if rank != 0:
         return
     w, h = args.width, args.height
-    stride = calibrate_stride(w, h, 4.0)
+    backend, kind = cpu_backend()
+    if w % 8 or h % 8:
+        backend, kind = "oracle", "port"
+    stride = calibrate_stride(w, h, 4.0, backend)
     _, _, threads = oracle_frames(w, h, 0, 0)
     O, scene, cam, ren = oracle_setup(w, h)
     fb = O.HostFrameBuffer(w, h, ("color", "depth"), num_ranks=stride, rank=0)
     for _ in range(args.warmup):
-        O.render_frame(scene, cam, ren, fb, threads)
+        O.render_frame(scene, cam, ren, fb, threads, backend=backend)
     rays, secs = 0, 0.0
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        O.render_frame(scene, cam, ren, fb, threads)
+        O.render_frame(scene, cam, ren, fb, threads, backend=backend)
         secs += time.perf_counter() - t0
         rays += int(fb.counters.sum())
     v = rays / secs / 1e6
@@ -164,9 +181,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "Mrays/s", "value": round(v, 3), "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_full, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "scalar CPU port of the reference algorithm (oracle/oracle.cpp, brute-force "
-                       "intersection); the reference CPU device itself is unbuildable here; ms_per_step is scaled to the full frame"},
-            "cpu_baseline": {"value": round(v, 3), "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": WORKLOAD, "note": CPU_NOTE[kind] + "; the reference's ISPC/Embree CPU device itself is unbuildable "
+                       "here; ms_per_step is scaled to the full frame"},
+            "cpu_baseline": {"value": round(v, 3), "unit": "Mrays/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": round(v, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -316,10 +333,11 @@ def run_ours(args):
                                      "(DESIGN.md 4); ncu issue/divergence figures in profiles/"}}
         if world == 1 and not args.no_cpu_baseline:
             try:
-                stride = calibrate_stride(w, h, 6.0)
-                r, s, threads = oracle_frames(w, h, 2, 1, stride)
-                line["cpu_baseline"] = {"value": round(r / s / 1e6, 3), "unit": "Mrays/s", "cores": threads, "kind": "port",
-                                        "sample": f"2 frames, tiles with tileID % {stride} == 0 of the {w}x{h} frame, scalar oracle port on all host threads",
+                backend, kind = cpu_backend() if (w % 8 == 0 and h % 8 == 0) else ("oracle", "port")
+                stride = calibrate_stride(w, h, 6.0, backend)
+                r, s, threads = oracle_frames(w, h, 2, 1, stride, backend)
+                line["cpu_baseline"] = {"value": round(r / s / 1e6, 3), "unit": "Mrays/s", "cores": threads, "kind": kind,
+                                        "sample": f"2 frames, tiles with tileID % {stride} == 0 of the {w}x{h} frame; " + CPU_NOTE[kind],
                                         "frame_ms_full": round(s / 2 * stride * 1e3, 1)}
             except Exception as e:  # the baseline must never take the bench line down
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}

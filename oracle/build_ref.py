@@ -50,9 +50,9 @@ render/materials/Metal.ispc render/materials/Alloy.ispc render/materials/ThinGla
 render/materials/MetallicPaint.ispc render/materials/Plastic.ispc render/materials/Luminous.ispc render/materials/Mix.ispc
 texture/TextureDispatch.ispc texture/Texture2DFormats.ispc texture/Texture2D.ispc texture/TextureParam.ispc
 """.split()
-# modules/cpu/CMakeLists.txt:228-247 (OSPRAY_ENABLE_VOLUMES additions)
+# modules/cpu/CMakeLists.txt:229-241 (OSPRAY_ENABLE_VOLUMES additions)
 VOLUME_SOURCES = """
-geometry/Isosurfaces.ispc volume/Volume.ispc volume/VolumetricModel.ispc volume/transferFunction/LinearTransferFunction.ispc
+geometry/Isosurfaces.ispc volume/Volume.ispc volume/transferFunction/LinearTransferFunction.ispc
 volume/transferFunction/TransferFunctionDispatch.ispc render/ao/volumes.ispc render/scivis/volumes.ispc
 render/pathtracer/volumes/VolumeSampler.ispc texture/TextureVolume.ispc
 """.split()
@@ -87,13 +87,14 @@ def main():
     ap.add_argument("--jobs", type=int, default=os.cpu_count() or 4)
     ap.add_argument("--no-volumes", action="store_true")
     ap.add_argument("--cxx", default=os.environ.get("CXX", "g++"))
+    ap.add_argument("--debug", action="store_true", help="-g for addr2line on a crash backtrace")
     a = ap.parse_args()
     cpu = os.path.join(a.reference, "modules", "cpu")
     if not os.path.isdir(cpu):
         print(f"build_ref: {cpu} not present; keeping any prebuilt oracle/_ref/libospref.so", file=sys.stderr)
         return 0
     volumes = not a.no_volumes
-    fl = flags(a.reference, volumes)
+    fl = flags(a.reference, volumes) + (["-g"] if a.debug else [])
     out_dir = os.path.join(HERE, "_ref")
     os.makedirs(out_dir, exist_ok=True)
     tmp = tempfile.mkdtemp(prefix="ospref_build_")

@@ -4,10 +4,14 @@
 // load liboracle.so, and only as the checker or the timed CPU baseline; nothing under
 // ospray_b200/ links or imports it. The product path is libospcuda.so (sm_100a kernels).
 //
-// PARITY UNPINNED: the reference holds no numeric golden vectors for this path (its tests are
-// image regressions whose baseline PNGs are not vendored) and its CPU device
-// cannot be compiled here (needs ISPC, Embree 4.3.3, Open VKL 2.0.1, rkcommon 1.14.2). This file
-// restates, function by function, the in-tree sources listed beside each routine
+// PARITY STATUS: pinned against the reference's own kernels for everything that lives in /root/reference. The
+// reference's modules/cpu/**/*.ispc compile as scalar C++ (the mode its SYCL target uses); oracle/build_ref.py builds
+// them where they lie into oracle/_ref/libospref.so, and tests/test_oracle_vs_reference.py checks this file against
+// that build bit for bit (sampler streams, pixel-filter LUT, frame ops, accumulation) and pixel for pixel (PT / SciVis /
+// AO renders of every tests/scenes.py case), live and through the committed vectors tests/golden/ref_*.npz.
+// UNPINNED remains only the arithmetic of dependencies that are not vendored (needs ISPC, Embree 4.3.3, Open VKL 2.0.1,
+// rkcommon 1.14.2 to build the real CPU device): both this file and the _ref build use the same restatement of those
+// pieces, listed below. This file restates, function by function, the in-tree sources listed beside each routine
 // (paths relative to /root/reference/modules/cpu); the arithmetic that lives in the absent
 // dependencies is restated from their published algorithms and named where used:
 //   Embree 4.3.3  triangle (Moeller-Trumbore, e1=v0-v1, e2=v2-v0, Ng=cross(e2,e1)), quad split

@@ -185,6 +185,11 @@ def ref_lib():
         L.ospref_sampler_kat.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         L.ospref_gauss_pixelfilter_lut.argtypes = [C.c_float, C.c_int, C.c_void_p, C.c_void_p]
         L.ospref_hardware_threads.restype = C.c_int
+        L.ospref_fb_accumulate.argtypes = [C.POINTER(FrameBuffer), C.c_void_p, C.c_void_p]
+        L.ospref_fb_variance.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.ospref_fb_tonemap.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(ToneMapper)]
+        L.ospref_fb_color_convert.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.ospref_ray_counters.argtypes = [C.c_void_p, C.c_int]
         _ref = L
     return _ref
 
@@ -533,27 +538,43 @@ def sampler_kat(kind, seed, first, count, backend="oracle"):
     return out.view(np.uint32) if kind == 4 else out
 
 
-def color_convert(img_f32, fmt):
+def color_convert(img_f32, fmt, backend="oracle"):
     a = np.ascontiguousarray(img_f32, np.float32).reshape(-1, 4)
     out = np.zeros((len(a), 4), np.float32) if fmt == 3 else np.zeros(len(a), np.uint32)
-    lib().oracle_fb_color_convert(a.ctypes.data, out.ctypes.data, len(a), fmt)
+    (ref_lib().ospref_fb_color_convert if backend == "ref" else lib().oracle_fb_color_convert)(a.ctypes.data, out.ctypes.data, len(a), fmt)
     return out
 
 
-def tonemap(img_f32, tm):
+def tonemap(img_f32, tm, backend="oracle"):
     a = np.ascontiguousarray(img_f32, np.float32).reshape(-1, 4)
     out = np.zeros_like(a)
-    lib().oracle_fb_tonemap(a.ctypes.data, out.ctypes.data, len(a), C.byref(tm))
+    (ref_lib().ospref_fb_tonemap if backend == "ref" else lib().oracle_fb_tonemap)(a.ctypes.data, out.ctypes.data, len(a), C.byref(tm))
     return out
 
 
-def variance(color, var, task=8):
+def variance(color, var, task=8, backend="oracle"):
     h, w = color.shape[:2]
     tx, ty = (w + task - 1) // task, (h + task - 1) // task
     out = np.zeros(tx * ty, np.float32)
     c, v = np.ascontiguousarray(color, np.float32), np.ascontiguousarray(var, np.float32)
-    lib().oracle_fb_variance(c.ctypes.data, v.ctypes.data, w, h, task, out.ctypes.data)
+    (ref_lib().ospref_fb_variance if backend == "ref" else lib().oracle_fb_variance)(c.ctypes.data, v.ctypes.data, w, h, task, out.ctypes.data)
     return out
+
+
+def accumulate(fb, sample_color, sample_depth=None, backend="oracle"):
+    """one LocalFB_accumulateSample pass of an externally produced sample image into fb (frameID advanced first)"""
+    fb.begin_frame()
+    sc = np.ascontiguousarray(sample_color, np.float32)
+    sz = None if sample_depth is None else np.ascontiguousarray(sample_depth, np.float32)
+    fn = ref_lib().ospref_fb_accumulate if backend == "ref" else lib().oracle_fb_accumulate
+    fn(C.byref(fb.sh), sc.ctypes.data, None if sz is None else sz.ctypes.data)
+    return fb
+
+
+def gauss_pixelfilter_lut(width=3.0, lut=15, backend="oracle"):
+    cx, cy = np.zeros(lut * lut, np.float32), np.zeros(lut, np.float32)
+    (ref_lib().ospref_gauss_pixelfilter_lut if backend == "ref" else lib().oracle_gauss_pixelfilter_lut)(width, lut, cx.ctypes.data, cy.ctypes.data)
+    return cx, cy
 
 
 def default_tonemapper(exposure=1.0, contrast=1.6773, shoulder=0.9714, midIn=0.18, midOut=0.18, hdrMax=11.0785, acesColor=True):

@@ -38,6 +38,11 @@
 #include "camera/PerspectiveCameraShared.h"
 #include "fb/LocalFBShared.h"
 #include "fb/FrameBufferView.ih"
+#include "fb/RenderTaskDesc.ih"
+#include "fb/frame_ops/ColorConversionShared.h"
+#include "fb/frame_ops/ToneMapperShared.h"
+#include "fb/frame_ops/VarianceShared.h"
+#include "render/ScreenSample.ih"
 #include "math/random.ih"
 #include "math/halton.ih"
 #include "render/util.ih"
@@ -63,6 +68,7 @@ void Variance_kernelLauncher(void *, void *, const vec2ui &, const FrameBufferVi
 void ospref_ray_counters(uint64_t out[2], int reset);
 }
 namespace ispc {
+void LocalFB_accumulateSample(FrameBuffer *fb, const ScreenSample &screenSample, RenderTaskDesc &);
 void LUTPixelFilter_buildLUT(void *self);
 float Distribution1D_create(const int size, float *cdf);
 }
@@ -88,6 +94,33 @@ ospray::FeatureFlags allFeatures()
   ff.other = ospray::FFO_ALL;
   return ff;
 }
+
+#ifdef OSPRAY_ENABLE_VOLUMES
+// volume/Volume.cpp:60-222 (structuredRegular -> VKL handles), volume/VolumetricModel.cpp:29-82,
+// volume/transferFunction/LinearTransferFunction.cpp:22-33 (maxOpacityInRange is only read by the path tracer's delta
+// tracking, which is outside this path, and stays zero)
+VolumetricModel *refMakeVolumetricModel(std::deque<Volume> &vols, std::deque<VolumetricModel> &vms, std::deque<LinearTransferFunction> &tfs,
+    std::deque<RefVklVolume> &vklVols, std::deque<RefVklSampler> &, std::deque<RefVklIntervalContext> &, const OcVolume &ov)
+{
+  vklVols.push_back(RefVklVolume{&ov});
+  vols.emplace_back();
+  Volume &vol = vols.back();
+  vol.vklVolume.host = &vklVols.back(); vol.vklSampler.host = &vklVols.back();
+  vol.boundingBox = box3f(make_vec3f(ov.bounds[0], ov.bounds[1], ov.bounds[2]), make_vec3f(ov.bounds[3], ov.bounds[4], ov.bounds[5]));
+  tfs.emplace_back();
+  LinearTransferFunction &tf = tfs.back();
+  memset(tf.maxOpacityInRange, 0, sizeof(tf.maxOpacityInRange));
+  tf.super.valueRange = box1f(ov.tf.valueLower, ov.tf.valueUpper);
+  tf.color.addr = (uint8 *)ov.tf.color; tf.color.byteStride = 12; tf.color.numItems = ov.tf.numColors; tf.color.huge = false;
+  tf.opacity.addr = (uint8 *)ov.tf.opacity; tf.opacity.byteStride = 4; tf.opacity.numItems = ov.tf.numOpacities; tf.opacity.huge = false;
+  vms.emplace_back();
+  VolumetricModel &vm = vms.back();
+  vm.volume = &vol; vm.transferFunction = &tf.super; vm.vklIntervalContext.host = &vklVols.back();
+  vm.boundingBox = vol.boundingBox; vm.densityScale = ov.densityScale; vm.anisotropy = ov.anisotropy;
+  vm.gradientShadingScale = ov.gradientShadingScale; vm.userID = ov.userID;
+  return &vm;
+}
+#endif
 
 // Everything one frame needs, with stable addresses (deques never move their elements)
 struct Scene
@@ -413,19 +446,58 @@ REF_API void ospref_sampler_kat(int kind, uint32_t seed, uint32_t first, uint32_
 }
 
 // default (Gaussian) pixel filter LUT built by the reference's LUTPixelFilter_buildLUT (pf/LUTPixelFilter.ispc:120-142)
-// + Distribution2D create (math/Distribution2D.cpp restated: per-row Distribution1D_create, then the marginal)
+// (which also runs Distribution1D_create per row and Distribution2D_init, math/Distribution2D.ispc)
 REF_API void ospref_gauss_pixelfilter_lut(float width, int lut, float *cdfX, float *cdfY)
 {
   LUTPixelFilter f; Distribution2D d;
   d.size = make_vec2i(lut, lut); d.rcpSize = make_vec2f(1.f / lut, 1.f / lut); d.cdf_x = cdfX; d.cdf_y = cdfY;
   f.super.width = width; f.distribution = &d; f.lutFilterType = LUT_PIXEL_FILTER_TYPE_GAUSSIAN;
-  LUTPixelFilter_buildLUT(&f);
-  for (int y = 0; y < lut; y++) cdfY[y] = Distribution1D_create(lut, cdfX + (size_t)y * lut);
-  Distribution1D_create(lut, cdfY);
+  LUTPixelFilter_buildLUT(&f); // rows via Distribution1D_create, then Distribution2D_init builds the marginal
 }
 
-// frame ops through the reference's own kernels (fb/frame_ops/*.ispc)
-REF_API void ospref_fb_color_convert(const OcVec4f *src, void *out, uint32_t n, uint32_t format);
-REF_API void ospref_fb_tonemap(const OcVec4f *src, OcVec4f *out, uint32_t n, const OcToneMapper *tm);
-REF_API void ospref_fb_variance(const OcVec4f *color, const OcVec4f *variance, int sizeX, int sizeY, int taskSize, float *taskError);
+// frame ops through the reference's own kernels and launchers (fb/frame_ops/*.ispc, DEFINE_FRAMEOP_KERNEL_LAUNCHER)
+REF_API void ospref_fb_color_convert(const OcVec4f *src, void *out, uint32_t n, uint32_t format)
+{
+  LiveColorConversion l;
+  l.super = FrameBufferView(make_vec2ui(n, 1), (const vec4f *)src);
+  l.targetColorFormat = (OSPFrameBufferFormat)format; l.convBuffer = out;
+  sycl::queue q; sycl::event ev;
+  ColorConversion_kernelLauncher(&q, &ev, make_vec2ui(n, 1), &l.super);
+}
+REF_API void ospref_fb_tonemap(const OcVec4f *src, OcVec4f *out, uint32_t n, const OcToneMapper *tm)
+{
+  LiveToneMapper l;
+  l.super = FrameBufferView(make_vec2ui(n, 1), (const vec4f *)src);
+  l.super.colorBufferOutput = (vec4f *)out;
+  l.exposure = tm->exposure; l.a = tm->a; l.b = tm->b; l.c = tm->c; l.d = tm->d; l.acesColor = tm->acesColor != 0;
+  sycl::queue q; sycl::event ev;
+  ToneMapper_kernelLauncher(&q, &ev, make_vec2ui(n, 1), &l.super);
+}
+REF_API void ospref_fb_variance(const OcVec4f *color, const OcVec4f *variance, int sizeX, int sizeY, int taskSize, float *taskError)
+{
+  const vec2ui tasks = make_vec2ui((sizeX + taskSize - 1) / taskSize, (sizeY + taskSize - 1) / taskSize);
+  LiveVariance l;
+  l.super = FrameBufferView(make_vec2ui(sizeX, sizeY), (const vec4f *)color);
+  l.super.viewDims = tasks; // fb/frame_ops/Variance.cpp: the view is the render-task grid
+  l.rtSize = make_vec2ui(taskSize, taskSize); l.varianceBuffer = (const vec4f *)variance; l.taskVarianceBuffer = taskError;
+  sycl::queue q; sycl::event ev;
+  Variance_kernelLauncher(&q, &ev, tasks, &l.super);
+}
+// LocalFB_accumulateSample (fb/LocalFB.ispc:14-78) applied to an externally produced sample image
+REF_API void ospref_fb_accumulate(const OcFrameBuffer *fb, const OcVec4f *sc, const float *sz)
+{
+  LocalFB lfb;
+  lfb.super.size = make_vec2i(fb->sizeX, fb->sizeY); lfb.super.frameID = fb->frameID;
+  lfb.super.accumulateVariance = fb->accumulateVariance != 0 && fb->variance;
+  lfb.colorBuffer = (vec4f *)fb->color; lfb.varianceBuffer = (vec4f *)fb->variance; lfb.depthBuffer = sz ? fb->depth : nullptr;
+  RenderTaskDesc desc;
+  for (int y = 0; y < fb->sizeY; y++)
+    for (int x = 0; x < fb->sizeX; x++) {
+      const size_t i = (size_t)y * fb->sizeX + x;
+      ScreenSample s = make_ScreenSample_zero();
+      s.sampleID.x = x; s.sampleID.y = y;
+      s.rgb = make_vec3f(sc[i].x, sc[i].y, sc[i].z); s.alpha = sc[i].w; s.z = sz ? sz[i] : inf;
+      LocalFB_accumulateSample(&lfb.super, s, desc);
+    }
+}
 REF_API int ospref_hardware_threads(void) { return (int)std::max(1u, std::thread::hardware_concurrency()); }

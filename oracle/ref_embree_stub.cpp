@@ -197,7 +197,7 @@ ThreadCounters *myCounters()
 
 extern "C" void rtcIntersect1(RTCScene scene, RTCRayHit *rayhit, RTCIntersectArguments *args)
 {
-  myCounters()->intersect.fetch_add(1, std::memory_order_relaxed);
+  if (!scene->volumes) myCounters()->intersect.fetch_add(1, std::memory_order_relaxed); // volume-box queries are not BVH rays
   RTCRayQueryContext dummy; rtcInitRayQueryContext(&dummy);
   Callbacks cb{args ? args->intersect : nullptr, nullptr, (args && args->context) ? args->context : &dummy};
   traceScene(scene, *rayhit, cb, false);
@@ -205,7 +205,7 @@ extern "C" void rtcIntersect1(RTCScene scene, RTCRayHit *rayhit, RTCIntersectArg
 
 extern "C" void rtcOccluded1(RTCScene scene, RTCRay *ray, RTCOccludedArguments *args)
 {
-  myCounters()->occluded.fetch_add(1, std::memory_order_relaxed);
+  if (!scene->volumes) myCounters()->occluded.fetch_add(1, std::memory_order_relaxed);
   RTCRayQueryContext dummy; rtcInitRayQueryContext(&dummy);
   Callbacks cb{nullptr, args ? args->occluded : nullptr, (args && args->context) ? args->context : &dummy};
   RTCRayHit rh; rh.ray = *ray; memset(&rh.hit, 0, sizeof(rh.hit));

@@ -56,7 +56,7 @@ inline float rcp(float x) { return 1.0f / x; }
 inline float rcpf(float x) { return 1.0f / x; }
 inline float rsqrt(float x) { return 1.0f / sqrtf(x); }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
-inline float rcp_safe(float f) { return rcp((fabsf(f) < flt_min) ? (f >= 0.f ? flt_min : -flt_min) : f); }
+inline float rcp_safe(float f) { return 1.f / (fabsf(f) < 1e-8f ? (f < 0.f ? -1e-8f : 1e-8f) : f); }
 inline float sqrt_safe(float x) { return sqrtf(x > 0.f ? x : 0.f); }
 inline int exclusive_scan_add(int) { return 0; }
 inline float expf(float x) { return ::expf(x); }
@@ -415,10 +415,11 @@ inline box3f xfmBox(const affine3f &m, const box3f &b)
 inline box3f intersectionOf(const box3f &a, const box3f &b) { return {max(a.lower, b.lower), min(a.upper, b.upper)}; }
 inline box2f intersect(const box2f &a, const box2f &b) { return {max(a.lower, b.lower), min(a.upper, b.upper)}; }
 
-// rkcommon colour helpers used by the frame ops (restated)
-inline float linear_to_srgb(float x) { return x <= 0.0031308f ? 12.92f * x : (1 + 0.055f) * pow(x, 1.f / 2.4f) - 0.055f; }
-inline vec4f linear_to_srgba(const vec4f &c) { return {linear_to_srgb(max(c.x, 0.f)), linear_to_srgb(max(c.y, 0.f)), linear_to_srgb(max(c.z, 0.f)), max(c.w, 0.f)}; }
-inline uint32 cvt_uint32(float f) { return (uint32)round(255.f * clamp(f, 0.f, 1.f)); }
+// rkcommon colour helpers used by the frame ops (restated exactly as in oracle.cpp: IEC 61966-2-1 transfer, ISPC round =
+// round-half-even)
+inline float linear_to_srgb(float f) { const float c = max(f, 0.f); return c <= 0.0031308f ? 12.92f * c : powf(c, 1.f / 2.4f) * 1.055f - 0.055f; }
+inline vec4f linear_to_srgba(const vec4f &c) { return {linear_to_srgb(c.x), linear_to_srgb(c.y), linear_to_srgb(c.z), max(c.w, 0.f)}; }
+inline uint32 cvt_uint32(float f) { return (uint32)rintf(255.f * min(max(f, 0.f), 1.f)); }
 inline uint32 cvt_uint32(const vec4f &v) { return (cvt_uint32(v.x) << 0) | (cvt_uint32(v.y) << 8) | (cvt_uint32(v.z) << 16) | (cvt_uint32(v.w) << 24); }
 inline uint32 cvt_uint32(const vec3f &v) { return (cvt_uint32(v.x) << 0) | (cvt_uint32(v.y) << 8) | (cvt_uint32(v.z) << 16); }
 inline uint32 linear_to_srgba8(const vec4f &c) { return cvt_uint32(linear_to_srgba(c)); }

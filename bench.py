@@ -234,11 +234,11 @@ def run_ours(args):
         for _ in range(W):
             step().wait()
             flush.zero_()
+        clocks = ClockSampler(local) if rank == 0 else None
+        time.sleep(0.3 if rank == 0 else 0.0)  # let nvidia-smi start sampling (before the barrier: ranks start the timed steps together)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        clocks = ClockSampler(local) if rank == 0 else None
-        time.sleep(0.3 if rank == 0 else 0.0)  # let nvidia-smi start sampling
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         rays = np.zeros(3, np.int64)
         kernel_ms, post_ms = 0.0, 0.0

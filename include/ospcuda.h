@@ -88,8 +88,10 @@ typedef struct {
   uint32_t userID;          /* 0xFFFFFFFF = unset */
 } OcModel;
 
-enum { OC_MATERIAL_OBJ = 0, OC_MATERIAL_OTHER = 1 };
-/* material (reference: ispc::OBJ, render/materials/OBJShared.h; OBJ.cpp:30-66) */
+enum { OC_MATERIAL_OBJ = 0, OC_MATERIAL_OTHER = 1, OC_MATERIAL_THINGLASS = 2 };
+/* material (reference: ispc::OBJ, render/materials/OBJShared.h, OBJ.cpp:30-66; ispc::ThinGlass,
+ * render/materials/ThinGlassShared.h, ThinGlass.cpp:33-48: eta = 1/ior, attenuationScale = thickness /
+ * max(attenuationDistance, EPS), attenuation = log(attenuationColor) * attenuationScale) */
 typedef struct {
   uint32_t type;
   float d;
@@ -97,7 +99,10 @@ typedef struct {
   OcVec3f Ks;
   float Ns;
   OcVec3f Tf;
-  float pad[4];
+  float eta;
+  OcVec3f attenuation;
+  float attenuationScale;
+  float pad[3];
 } OcMaterial;
 
 /* 4-wide BVH node, 128 B = one cache line, fetched as 8 x 128-bit loads */

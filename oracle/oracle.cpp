@@ -591,7 +591,47 @@ struct SampleRes { V3 weight, wi; float pdf; uint32_t type; };
 struct ObjBSDF
 {
   L3 frame; V3 Kd, T, ks, specWeight, albedo; float ns; float imp[3], importanceSum; uint32_t scatteringType; bool valid;
+  bool thinGlass; // RobustThinDielectric (materials/ThinGlass.ispc): eta in `ns`, attenuation in `Kd`
 };
+// ---- thin glass: bsdfs/Fresnel.ih:19-47, Optics.ih:13-28, RobustThinDielectric.ih, materials/ThinGlass.ispc ----
+inline float sqrCosT(float cosI, float eta) { return 1.0f - sqr(eta) * (1.0f - sqr(cosI)); }
+inline float fresnelDielectric3(float cosI, float cosT, float eta)
+{
+  const float Rper = (eta * cosI - cosT) * (1.f / (eta * cosI + cosT));
+  const float Rpar = (cosI - eta * cosT) * (1.f / (cosI + eta * cosT));
+  return 0.5f * (sqr(Rpar) + sqr(Rper));
+}
+inline float fresnelDielectric(float cosI, float eta)
+{
+  const float sqrcost = sqrCosT(cosI, eta);
+  if (sqrcost < 0.0f) return 1.0f;
+  return fresnelDielectric3(cosI, sqrtf(sqrcost), eta);
+}
+inline float fresnelDielectricEx(float cosI, float &cosT, float eta)
+{
+  const float sqrcost = sqrCosT(cosI, eta);
+  if (sqrcost < 0.0f) { cosT = 0.0f; return 1.0f; }
+  cosT = sqrtf(sqrcost);
+  return fresnelDielectric3(cosI, cosT, eta);
+}
+inline V3 expf3(V3 v) { return {expf(v.x), expf(v.y), expf(v.z)}; }
+inline V3 logf3(V3 v) { return {logf(v.x), logf(v.y), logf(v.z)}; }
+inline V3 rcp3(V3 v) { return {1.f / v.x, 1.f / v.y, 1.f / v.z}; }
+inline V3 operator+(float a, V3 b) { return {a + b.x, a + b.y, a + b.z}; }
+inline V3 operator-(float a, V3 b) { return {a - b.x, a - b.y, a - b.z}; }
+inline V3 ThinGlass_getAttenuation(const OcMaterial *m, const DG &dg) // ThinGlass.ispc:17-30
+{
+  return v3(m->attenuation) + logf3(v3(dg.color)) * m->attenuationScale;
+}
+inline V3 RobustThinDielectric_getTransparency(float cosThetaO, float eta, V3 attenuation) // RobustThinDielectric.ih:99-117
+{
+  float cosThetaT;
+  const float Fo = fresnelDielectricEx(cosThetaO, cosThetaT, eta);
+  const float Ft = fresnelDielectric(cosThetaT, 1.f / eta);
+  const float length = 1.f / cosThetaT;
+  const V3 A = expf3(attenuation * length);
+  return (1.f - Fo) * A * (1.f - Ft) * (1.f + (Ft * A) * (Ft * A) * rcp3(1.f - (Ft * A) * (Ft * A)));
+}
 inline L3 makeShadingFrame(const DG &dg) // render/Material.ih:25-37
 {
   const V3 N = dg.Ns;
@@ -604,6 +644,17 @@ void OBJ_getBSDF(ObjBSDF &b, const DG &dg)
 {
   const OcMaterial *m = dg.material;
   b.valid = false;
+  b.thinGlass = false;
+  if (m && m->type == OC_MATERIAL_THINGLASS) { // ThinGlass_getBSDF (ThinGlass.ispc:32-50)
+    b.valid = b.thinGlass = true;
+    b.frame = frame(dg.Ns);
+    b.Kd = ThinGlass_getAttenuation(m, dg);
+    b.ns = m->eta;
+    b.albedo = expf3(b.Kd);
+    b.scatteringType = SC_SPECULAR;
+    b.importanceSum = 1.f; b.imp[0] = b.imp[1] = b.imp[2] = 0.f;
+    return;
+  }
   if (!m || m->type != OC_MATERIAL_OBJ) return;
   b.valid = true;
   b.frame = makeShadingFrame(dg);
@@ -649,12 +700,34 @@ inline void evalChildren(const ObjBSDF &b, V3 wo, V3 wi, int choice, EvalRes &e)
 inline EvalRes OBJ_eval(const ObjBSDF &b, V3 wo, V3 wi)
 {
   EvalRes e = {v3(0.f), 0.f};
+  if (b.thinGlass) return e; // purely specular
   evalChildren(b, wo, wi, -1, e);
   e.pdf *= 1.f / b.importanceSum;
   return e;
 }
+SampleRes RobustThinDielectric_sample(const ObjBSDF &b, V3 wo, float ss) // RobustThinDielectric.ih:17-62
+{
+  SampleRes res;
+  const V3 N = b.frame.vz;
+  const float eta = b.ns;
+  const float cosThetaO = fmaxf(dot(wo, N), 0.f);
+  float cosThetaT;
+  const float Fo = fresnelDielectricEx(cosThetaO, cosThetaT, eta);
+  const float Ft = fresnelDielectric(cosThetaT, 1.f / eta);
+  const float length = 1.f / cosThetaT;
+  const V3 A = expf3(b.Kd * length);
+  const V3 R = Fo + (1.f - Fo) * (1.f - Ft) * (Ft * (A * A)) * rcp3(1.f - (Ft * A) * (Ft * A));
+  const V3 T = (1.f - Fo) * A * (1.f - Ft) * (1.f + (Ft * A) * (Ft * A) * rcp3(1.f - (Ft * A) * (Ft * A)));
+  const float pR = luminance(R), pT = luminance(T);
+  const float p = fmaxf(0.25f, fminf(pR * (1.f / (pR + pT)), 0.75f));
+  if (ss <= p) { res.wi = (2.0f * cosThetaO) * N - wo; res.type = SC_SPECULAR_REFLECTION; res.weight = R * (1.f / p); }
+  else { res.wi = -wo; res.type = SC_SPECULAR_TRANSMISSION; res.weight = T * (1.f / (1.f - p)); }
+  res.pdf = INF;
+  return res;
+}
 SampleRes OBJ_sample(const ObjBSDF &b, V3 wo, V2 s, float ss) // MultiBSDF.ih:83-128
 {
+  if (b.thinGlass) return RobustThinDielectric_sample(b, wo, ss);
   SampleRes res = {v3(0.f), v3(0.f), 0.f, 0};
   if (b.importanceSum == 0.f) return res;
   const float x = ss * b.importanceSum;
@@ -692,9 +765,11 @@ SampleRes OBJ_sample(const ObjBSDF &b, V3 wo, V2 s, float ss) // MultiBSDF.ih:83
   res.weight = e.value * (1.f / res.pdf);
   return res;
 }
-inline V3 OBJ_getTransparency(const DG &dg) // OBJ.ispc:93-111; NULL material: transparency undefined -> 0
+inline V3 OBJ_getTransparency(const DG &dg, V3 rayDir) // OBJ.ispc:93-111, ThinGlass.ispc:52-64; NULL material -> 0
 {
   const OcMaterial *m = dg.material;
+  if (m && m->type == OC_MATERIAL_THINGLASS)
+    return RobustThinDielectric_getTransparency(fmaxf(-dot(rayDir, dg.Ns), 0.0f), m->eta, ThinGlass_getAttenuation(m, dg));
   if (!m || m->type != OC_MATERIAL_OBJ) return v3(0.f);
   const float d = m->d * dg.color.w;
   return v3(m->Tf) * d + v3(1.f - d);
@@ -933,7 +1008,7 @@ V3 transparentShadow(Ctx &c, V3 lightContrib, Ray &shadowRay) // pathtracer/Tran
     if (!hadHit(shadowRay)) return lightContrib;
     DG dg;
     postIntersect(c.w, c.ren, dg, shadowRay, DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR | DG_MOTIONBLUR);
-    lightContrib = lightContrib * OBJ_getTransparency(dg);
+    lightContrib = lightContrib * OBJ_getTransparency(dg, shadowRay.dir);
     if (rmax(lightContrib) <= c.ren.minContribution || --maxDepth <= 0) return v3(0.f);
     setRayInterval(shadowRay, shadowRay.t + dg.epsilon, tOriginal);
   }

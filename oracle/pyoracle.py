@@ -53,7 +53,7 @@ class Model(C.Structure):
 
 class Material(C.Structure):
     _fields_ = [("type", C.c_uint32), ("d", C.c_float), ("Kd", Vec3), ("Ks", Vec3), ("Ns", C.c_float), ("Tf", Vec3),
-                ("pad", C.c_float * 4)]
+                ("eta", C.c_float), ("attenuation", Vec3), ("attenuationScale", C.c_float), ("pad", C.c_float * 3)]
 
 
 class BVH(C.Structure):
@@ -364,6 +364,15 @@ class Scene:
                 kd, ks, tf = kd / total, ks / total, tf / total
             m.type, m.d, m.Ns = 0, float(ms.d), float(ms.ns)
             m.Kd, m.Ks, m.Tf = Vec3(*map(float, kd)), Vec3(*map(float, ks)), Vec3(*map(float, tf))
+        elif ms.type == "thinGlass":
+            # render/materials/ThinGlass.cpp:33-48 in float32 (std::log of a float is the float overload)
+            f = np.float32
+            m.type = 2
+            m.eta = float(f(1.0) / f(ms.eta))
+            scale = f(ms.thickness) * (f(1.0) / max(f(ms.attenuation_distance), f(1e-5)))
+            m.attenuationScale = float(scale)
+            att = np.log(np.asarray(ms.attenuation_color, np.float32)).astype(np.float32) * scale
+            m.attenuation = Vec3(*map(float, att))
         else:
             m.type = 1
         self.materials.append(m)

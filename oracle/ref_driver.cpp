@@ -28,6 +28,7 @@
 #include "geometry/BoxesShared.h"
 #include "render/MaterialShared.h"
 #include "render/materials/OBJShared.h"
+#include "render/materials/ThinGlassShared.h"
 #include "lights/QuadLightShared.h"
 #include "lights/DirectionalLightShared.h"
 #include "lights/AmbientLightShared.h"
@@ -129,7 +130,7 @@ struct Scene
   std::deque<GeometricModel> models; std::deque<Group> groups; std::deque<Instance> instances;
   std::deque<std::vector<GeometricModel *>> modelPtrs;
   std::deque<std::vector<Material *>> materialPtrs;
-  std::deque<OBJ> objs; std::vector<Material *> allMaterials;
+  std::deque<OBJ> objs; std::deque<ThinGlass> glasses; std::vector<Material *> allMaterials;
   std::vector<Instance *> instancePtrs;
   std::deque<QuadLight> quads; std::deque<DirectionalLight> dirs; std::deque<AmbientLight> ambients;
   std::vector<Light *> ptLights, svLights;
@@ -189,6 +190,13 @@ void buildScene(Scene &s, const OcWorld *w, const OcRenderer *ren)
   // materials: render/materials/OBJ.cpp:30-66 (values arrive already normalised by the commit)
   for (uint32_t i = 0; i < w->numMaterials; i++) {
     const OcMaterial &m = w->materials[i];
+    if (m.type == OC_MATERIAL_THINGLASS) { // render/materials/ThinGlass.cpp:33-48 (committed values)
+      s.glasses.emplace_back();
+      ThinGlass &g = s.glasses.back();
+      g.eta = m.eta; g.attenuation = v3(m.attenuation); g.attenuationScale = m.attenuationScale;
+      s.allMaterials.push_back(&g.super);
+      continue;
+    }
     s.objs.emplace_back();
     OBJ &o = s.objs.back();
     o.d = m.d; o.Kd = v3(m.Kd); o.Ks = v3(m.Ks); o.Ns = m.Ns; o.Tf = v3(m.Tf);

@@ -177,6 +177,7 @@ __device__ __forceinline__ bool ptOccluderIsOpaque(const OcWorld *world, const O
   const OcModel *m = inst->group->models + ray.geomID;
   if (m->color.addr || (m->geom->flags & OC_GEOMFLAG_HAS_ALPHA)) return false;
   const OcMaterial *mat = getMaterial(world, ren, m, ray.primID);
+  if (mat && mat->type == OC_MATERIAL_THINGLASS) return false;
   if (!mat || mat->type != OC_MATERIAL_OBJ) return true; // no / foreign material: transparency 0 (shading.cuh)
   return mat->d == 1.f && mat->Tf.x == 0.f && mat->Tf.y == 0.f && mat->Tf.z == 0.f;
 }
@@ -261,7 +262,7 @@ __device__ __forceinline__ bool ptTraceStep(const PtArgs &k, uint32_t p, Stack s
             if (!hadHit(sr)) break;
             DifferentialGeometry dg;
             postIntersect(k.a.world, ren, dg, sr, DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR);
-            lightContrib = lightContrib * materialTransparency(dg);
+            lightContrib = lightContrib * materialTransparency(dg, sr.dir);
             if (reduce_max(lightContrib) <= ren.minContribution || --maxDepth <= 0) { lightContrib = make_vec3f(0.f); break; }
             setRay(sr, sr.org, sr.dir, sr.t + dg.epsilon, tOriginal);
           }

@@ -247,6 +247,7 @@ struct ObjBSDF
   vec3f albedo;
   uint32_t scatteringType;
   bool valid;
+  bool thinGlass;          // RobustThinDielectric (materials/ThinGlass.ispc): eta in `ns`, attenuation in `Kd`
 };
 
 // render/Material.ih:25-37
@@ -263,11 +264,66 @@ __device__ __forceinline__ linear3f makeShadingFrame(const DifferentialGeometry 
   return frame(N);
 }
 
-// materials/OBJ.ispc:29-91. A NULL / non-OBJ material yields no BSDF (path terminates).
+// ---- thin glass: bsdfs/Fresnel.ih:19-47, Optics.ih:13-28, RobustThinDielectric.ih, materials/ThinGlass.ispc ----
+__device__ __forceinline__ float sqrCosT(float cosI, float eta) { return 1.0f - (eta * eta) * (1.0f - cosI * cosI); }
+__device__ __forceinline__ float fresnelDielectric3(float cosI, float cosT, float eta)
+{
+  const float Rper = (eta * cosI - cosT) * (1.f / (eta * cosI + cosT));
+  const float Rpar = (cosI - eta * cosT) * (1.f / (cosI + eta * cosT));
+  return 0.5f * (Rpar * Rpar + Rper * Rper);
+}
+__device__ __forceinline__ float fresnelDielectric(float cosI, float eta)
+{
+  const float sqrcost = sqrCosT(cosI, eta);
+  if (sqrcost < 0.0f) return 1.0f;
+  return fresnelDielectric3(cosI, sqrtf(sqrcost), eta);
+}
+__device__ __forceinline__ float fresnelDielectricEx(float cosI, float &cosT, float eta)
+{
+  const float sqrcost = sqrCosT(cosI, eta);
+  if (sqrcost < 0.0f) { cosT = 0.0f; return 1.0f; }
+  cosT = sqrtf(sqrcost);
+  return fresnelDielectric3(cosI, cosT, eta);
+}
+__device__ __forceinline__ vec3f expf3(vec3f v) { return make_vec3f(expf(v.x), expf(v.y), expf(v.z)); }
+__device__ __forceinline__ vec3f logf3(vec3f v) { return make_vec3f(logf(v.x), logf(v.y), logf(v.z)); }
+__device__ __forceinline__ vec3f sqr3(vec3f v) { return v * v; }
+__device__ __forceinline__ vec3f rcp3(vec3f v) { return make_vec3f(1.f / v.x, 1.f / v.y, 1.f / v.z); }
+// ThinGlass.ispc:17-30 (no attenuationColor texture)
+__device__ __forceinline__ vec3f ThinGlass_getAttenuation(const OcMaterial *m, const DifferentialGeometry &dg)
+{
+  return toV(m->attenuation) + logf3(make_vec3f(dg.color)) * m->attenuationScale;
+}
+// RobustThinDielectric.ih:99-117
+__device__ __forceinline__ vec3f RobustThinDielectric_getTransparency(float cosThetaO, float eta, vec3f attenuation)
+{
+  float cosThetaT;
+  const float Fo = fresnelDielectricEx(cosThetaO, cosThetaT, eta);
+  const float Ft = fresnelDielectric(cosThetaT, 1.f / eta);
+  const float length = 1.f / cosThetaT;
+  const vec3f A = expf3(attenuation * length);
+  return (1.f - Fo) * A * (1.f - Ft) * (make_vec3f(1.f) + sqr3(Ft * A) * rcp3(make_vec3f(1.f) - sqr3(Ft * A)));
+}
+
+// materials/OBJ.ispc:29-91, materials/ThinGlass.ispc:32-50. A NULL / unsupported material yields no BSDF (path
+// terminates).
 __device__ __forceinline__ void OBJ_getBSDF(ObjBSDF &b, const DifferentialGeometry &dg)
 {
   const OcMaterial *m = dg.material;
   b.valid = false;
+  b.thinGlass = false;
+  if (m && m->type == OC_MATERIAL_THINGLASS) {
+    b.valid = true;
+    b.thinGlass = true;
+    b.frame = frame(dg.Ns);
+    b.Kd = ThinGlass_getAttenuation(m, dg);
+    b.ns = m->eta;
+    b.albedo = expf3(b.Kd);
+    b.scatteringType = SC_SPECULAR;
+    b.importanceSum = 1.f;
+    b.impL = b.impT = b.impS = 0.f;
+    return;
+  }
   if (!m || m->type != OC_MATERIAL_OBJ)
     return;
   b.valid = true;
@@ -343,13 +399,44 @@ __device__ __forceinline__ void OBJ_evalChildren(const ObjBSDF &b, vec3f wo, vec
 __device__ __forceinline__ EvalRes OBJ_eval(const ObjBSDF &b, vec3f wo, vec3f wi)
 {
   EvalRes e; e.value = make_vec3f(0.f); e.pdf = 0.f;
+  if (b.thinGlass) return e; // purely specular
   OBJ_evalChildren(b, wo, wi, -1, e);
   e.pdf *= 1.f / b.importanceSum;
   return e;
 }
 // MULTIBSDF_SAMPLE_* (bsdfs/MultiBSDF.ih:93-128)
+// RobustThinDielectric_sample (bsdfs/RobustThinDielectric.ih:17-62)
+__device__ __forceinline__ SampleRes RobustThinDielectric_sample(const ObjBSDF &b, vec3f wo, float ss)
+{
+  SampleRes res;
+  const vec3f N = b.frame.vz;
+  const float eta = b.ns;
+  const float cosThetaO = fmaxf(dot(wo, N), 0.f);
+  float cosThetaT;
+  const float Fo = fresnelDielectricEx(cosThetaO, cosThetaT, eta);
+  const float Ft = fresnelDielectric(cosThetaT, 1.f / eta);
+  const float length = 1.f / cosThetaT;
+  const vec3f A = expf3(b.Kd * length);
+  const vec3f one = make_vec3f(1.f);
+  const vec3f R = make_vec3f(Fo) + (1.f - Fo) * (1.f - Ft) * (Ft * sqr3(A)) * rcp3(one - sqr3(Ft * A));
+  const vec3f T = (1.f - Fo) * A * (1.f - Ft) * (one + sqr3(Ft * A) * rcp3(one - sqr3(Ft * A)));
+  const float pR = luminance(R), pT = luminance(T);
+  const float p = fmaxf(0.25f, fminf(pR * (1.f / (pR + pT)), 0.75f));
+  if (ss <= p) {
+    res.wi = (2.0f * cosThetaO) * N - wo;
+    res.type = SC_SPECULAR_REFLECTION;
+    res.weight = R * (1.f / p);
+  } else {
+    res.wi = neg(wo);
+    res.type = SC_SPECULAR_TRANSMISSION;
+    res.weight = T * (1.f / (1.f - p));
+  }
+  res.pdf = INFINITY;
+  return res;
+}
 __device__ __forceinline__ SampleRes OBJ_sample(const ObjBSDF &b, vec3f wo, vec2f s, float ss)
 {
+  if (b.thinGlass) return RobustThinDielectric_sample(b, wo, ss);
   SampleRes res; res.weight = make_vec3f(0.f); res.wi = make_vec3f(0.f); res.pdf = 0.f; res.type = 0;
   if (b.importanceSum == 0.f) return res;
   const float x = ss * b.importanceSum;
@@ -401,10 +488,14 @@ __device__ __forceinline__ SampleRes OBJ_sample(const ObjBSDF &b, vec3f wo, vec2
   res.weight = e.value * (1.f / res.pdf);
   return res;
 }
-// materials/OBJ.ispc:93-111
-__device__ __forceinline__ vec3f materialTransparency(const DifferentialGeometry &dg)
+// materials/OBJ.ispc:93-111, materials/ThinGlass.ispc:52-64
+__device__ __forceinline__ vec3f materialTransparency(const DifferentialGeometry &dg, vec3f rayDir)
 {
   const OcMaterial *m = dg.material;
+  if (m && m->type == OC_MATERIAL_THINGLASS) {
+    const float cosThetaO = fmaxf(-dot(rayDir, dg.Ns), 0.0f);
+    return RobustThinDielectric_getTransparency(cosThetaO, m->eta, ThinGlass_getAttenuation(m, dg));
+  }
   if (!m || m->type != OC_MATERIAL_OBJ) return make_vec3f(0.f);
   const float d = m->d * dg.color.w;
   return toV(m->Tf) * d + make_vec3f(1.f - d);

@@ -347,6 +347,18 @@ void Material::commit()
       if (getParamObjectRaw(tex))
         postStatusMsg(OSP_LOG_WARNING, std::string("cuda device: texture '") + tex + "' ignored (textures are out of scope)");
     m.d = d; m.Kd = toOc(Kd); m.Ks = toOc(Ks); m.Ns = Ns; m.Tf = toOc(Tf);
+  } else if (type == "thinGlass") {
+    // render/materials/ThinGlass.cpp:33-48
+    m.type = OC_MATERIAL_THINGLASS;
+    const float eta = getParam<float>("eta", 1.5f);
+    const vec3f acf = getParam<vec3f>("attenuationColor", make_vec3f(1.f));
+    const float attenuationDistance = getParam<float>("attenuationDistance", 1.f);
+    const float thickness = getParam<float>("thickness", 1.f);
+    if (getParamObjectRaw("map_attenuationColor"))
+      postStatusMsg(OSP_LOG_WARNING, "cuda device: texture 'map_attenuationColor' ignored (textures are out of scope)");
+    m.eta = 1.f / eta;
+    m.attenuationScale = thickness * (1.f / std::max(attenuationDistance, 1e-5f));
+    m.attenuation = toOc(make_vec3f(std::log(acf.x), std::log(acf.y), std::log(acf.z)) * m.attenuationScale);
   } else {
     m.type = OC_MATERIAL_OTHER;
     for (auto &p : params) p.second.queried = true;

@@ -24,6 +24,10 @@ class MaterialSpec:
     ns: float = 10.0
     d: float = 1.0
     tf: tuple = (0.0, 0.0, 0.0)
+    eta: float = 1.5                           # thinGlass (render/materials/ThinGlass.cpp:33-48)
+    attenuation_color: tuple = (1.0, 1.0, 1.0)
+    attenuation_distance: float = 1.0
+    thickness: float = 1.0
 
 
 @dataclass
@@ -198,14 +202,16 @@ def _ground_plane(bounds_lower, bounds_upper):
     return InstanceSpec(GroupSpec(models=[ModelSpec(geom, MaterialSpec())]))
 
 
-def random_spheres(num_spheres=100, seed=0, add_plane=True):
-    """RandomSpheres.cpp:42-111 (scivis / ao flavour: default obj material, per-sphere colours)."""
+def random_spheres(num_spheres=100, seed=0, add_plane=True, renderer_type="scivis"):
+    """RandomSpheres.cpp:42-111: per-sphere colours; default obj material, or thinGlass with attenuationDistance 0.2 when
+    built for the pathtracer (:89-99)."""
     gen = Mt19937(seed)
     centers = gen.uniform(-1, 1, 3 * num_spheres).reshape(num_spheres, 3)
     radii = gen.uniform(0.05, 0.15, num_spheres)
     colors = gen.uniform(0.5, 1.0, 4 * num_spheres).reshape(num_spheres, 4)
     geom = GeometrySpec("sphere", sphere_position=centers, sphere_radius=radii)
-    group = GroupSpec(models=[ModelSpec(geom, MaterialSpec(), color=colors)])
+    mat = MaterialSpec(type="thinGlass", attenuation_distance=0.2) if renderer_type == "pathtracer" else MaterialSpec()
+    group = GroupSpec(models=[ModelSpec(geom, mat, color=colors)])
     inst = [InstanceSpec(group)]
     if add_plane:
         lo = (centers - radii[:, None]).min(axis=0)
@@ -315,6 +321,12 @@ def _geometry(g: GeometrySpec):
 def _material(m: MaterialSpec):
     mat = osp.Material(m.type)
     d = MaterialSpec()
+    if m.type == "thinGlass":
+        if m.eta != d.eta: mat.set("eta", float(m.eta))
+        if m.attenuation_color != d.attenuation_color: mat.set("attenuationColor", tuple(float(x) for x in m.attenuation_color))
+        if m.attenuation_distance != d.attenuation_distance: mat.set("attenuationDistance", float(m.attenuation_distance))
+        if m.thickness != d.thickness: mat.set("thickness", float(m.thickness))
+        return mat.commit()
     if m.kd != d.kd: mat.set("kd", tuple(float(x) for x in m.kd))
     if m.ks != d.ks: mat.set("ks", tuple(float(x) for x in m.ks))
     if m.ns != d.ns or m.ks != d.ks: mat.set("ns", float(m.ns))

@@ -51,6 +51,22 @@ def volume_with_opaque_geometry():
     return s
 
 
+def glass_spheres():
+    """random_spheres as the reference builds it for the pathtracer: thinGlass, attenuationDistance 0.2
+    (RandomSpheres.cpp:89-99), over the striped ground plane"""
+    return T.random_spheres(40, seed=1, renderer_type="pathtracer")
+
+
+def tinted_glass_cornell():
+    """cornell box whose quads are tinted thin glass (eta 1.3, attenuationColor): specular reflection + transmission chains,
+    transparent shadows through RobustThinDielectric_getTransparency"""
+    s = T.cornell_box()
+    s.instances[0].group.models[0].material = T.MaterialSpec(type="thinGlass", eta=1.3, attenuation_color=(0.9, 0.7, 0.5),
+                                                             attenuation_distance=0.7, thickness=0.5)
+    s.lights.append(T.LightSpec("ambient", {"intensity": 0.5, "color": (0.8, 0.9, 1.0)}))
+    return s
+
+
 # name -> (spec builder, renderer kind, renderer params, frames)
 CASES = {
     "cornell_pt": (T.cornell_box, "pathtracer", {"pixelSamples": 2}, 2),
@@ -63,6 +79,8 @@ CASES = {
     "boxes_pt": (lambda: T.boxes(lit=True), "pathtracer", {"pixelSamples": 2}, 1),
     "spheres_ao": (T.random_spheres, "ao", {"pixelSamples": 2}, 1),
     "spheres_pt": (T.random_spheres, "pathtracer", {"pixelSamples": 1, "backgroundColor": (1.0, 1.0, 1.0, 1.0)}, 2),
+    "glass_spheres_pt": (glass_spheres, "pathtracer", {"pixelSamples": 2, "backgroundColor": (0.2, 0.3, 0.4, 1.0)}, 2),
+    "glass_cornell_pt": (tinted_glass_cornell, "pathtracer", {"pixelSamples": 2, "maxPathLength": 12}, 1),
     "instanced_scivis": (instanced_boxes_and_spheres, "scivis", {"shadows": True}, 1),
     "instanced_pt": (instanced_boxes_and_spheres, "pathtracer", {"pixelSamples": 1}, 1),
     "mesh_ao": (lambda: T.box_mesh(5), "ao", {"aoSamples": 2}, 1),

@@ -57,7 +57,8 @@ typedef struct {
 
 enum { OC_GEOM_TRIANGLES = 0, OC_GEOM_QUADS = 1, OC_GEOM_SPHERES = 2, OC_GEOM_BOXES = 3 };
 enum { OC_GEOMFLAG_NORMAL_FACEVARYING = 1, OC_GEOMFLAG_COLOR_FACEVARYING = 2,
-       OC_GEOMFLAG_TEXCOORD_FACEVARYING = 4, OC_GEOMFLAG_HAS_ALPHA = 8, OC_GEOMFLAG_COLOR_IS_VEC4 = 16 };
+       OC_GEOMFLAG_TEXCOORD_FACEVARYING = 4, OC_GEOMFLAG_HAS_ALPHA = 8, OC_GEOMFLAG_COLOR_IS_VEC4 = 16,
+       OC_GEOMFLAG_ALPHA_ALL_ONE = 32 /* every vec4f vertex colour has w == 1.0f (checked on the host at commit) */ };
 
 /* geometry (reference: ispc::Mesh MeshShared.h:12-44, ispc::Spheres, ispc::Boxes) */
 typedef struct {

@@ -8,7 +8,7 @@ ospTestSuite image metric (imgdiff) and the one-process-per-GPU tile gather (mul
 import os
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
+LIB_DIR = os.environ.get("OSPRAY_B200_LIB_DIR") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
 
 
 def lib_path(name):

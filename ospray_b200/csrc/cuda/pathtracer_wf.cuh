@@ -62,6 +62,7 @@ struct PtArgs
   uint32_t *qOut;
   const uint32_t *cntIn;
   uint32_t *cntOut;
+  uint32_t tailThreshold; // at most this many live paths: the fused kernel finishes them in place (PT_TAIL_THRESHOLD)
 };
 
 __device__ __forceinline__ void ptAppend(uint32_t *q, uint32_t *cnt, uint32_t p)
@@ -168,14 +169,24 @@ __device__ __forceinline__ void ptCountRays(const OcFrameBuffer &fb, uint32_t a,
 #define PT_TRACE_BLOCK 128
 #define PT_TAIL_THRESHOLD 16384u // at most this many live paths: finish them inside one kernel (see ptTraceKernel)
 
-// Is the surface hit by `ray` certainly opaque for shadow rays, i.e. OBJ_getTransparency == 0 exactly
-// (OBJ.ispc:93-111: T = Tf*d + (1-d), d = material.d * dg.color.w)? Conservative: anything that could carry
-// alpha (per-primitive model colours, vec4 vertex colours) answers "no" and takes the general path.
-__device__ __forceinline__ bool ptOccluderIsOpaque(const OcWorld *world, const OcRenderer &ren, const Ray &ray)
+// Does the surface hit by the any-hit query `ray` certainly take the shadow-ray contribution to exactly 0, as the
+// reference's closest-hit loop would (TransparentShadow.ispc:18-85: lightContrib *= transparency per hit, result 0 as
+// soon as reduce_max(lightContrib) <= minContribution)?  OBJ_getTransparency (OBJ.ispc:93-111) is T = Tf*d + (1-d) with
+// d = material.d * dg.color.w.
+//  * no colour alpha, d == 1, Tf == 0: T == 0 exactly.
+//  * vec4 vertex colours whose alphas are ALL 1.0f (cornell_box): the interpolated alpha is 1 up to a few ulp
+//    (barycentric / bilinear weights sum to 1 +- 4 ulp), so |T| <= 1e-6 and the product is <= maxContrib * 1e-6, which the
+//    reference zeroes whenever that is <= minContribution. Checked here with the actual contribution.
+// Anything else (per-primitive model colours, real alpha, thin glass, ...) answers "no" and takes the reference loop.
+__device__ __forceinline__ bool ptOccluderIsOpaque(const OcWorld *world, const OcRenderer &ren, const Ray &ray, float maxContrib)
 {
   const OcInstance *inst = world->instances + ray.instID;
   const OcModel *m = inst->group->models + ray.geomID;
-  if (m->color.addr || (m->geom->flags & OC_GEOMFLAG_HAS_ALPHA)) return false;
+  if (m->color.addr) return false;
+  const uint32_t gf = m->geom->flags;
+  if (gf & OC_GEOMFLAG_HAS_ALPHA) {
+    if (!(gf & OC_GEOMFLAG_ALPHA_ALL_ONE) || !(maxContrib * 1e-6f <= ren.minContribution)) return false;
+  }
   const OcMaterial *mat = getMaterial(world, ren, m, ray.primID);
   if (mat && mat->type == OC_MATERIAL_THINGLASS) return false;
   if (!mat || mat->type != OC_MATERIAL_OBJ) return true; // no / foreign material: transparency 0 (shading.cuh)
@@ -183,6 +194,39 @@ __device__ __forceinline__ bool ptOccluderIsOpaque(const OcWorld *world, const O
 }
 
 struct PtCounts { uint32_t primary, secondary, shadow; };
+
+// The reference's closest-hit transparent-shadow loop (TransparentShadow.ispc:18-85), taken only when the any-hit
+// query of ptTraceStep found a non-opaque occluder (or the contribution is not finite). Kept out of line: inlined,
+// postIntersect + the material transparencies (OBJ, thin glass) doubled the spill traffic of the TRACE kernels for a
+// path that opaque scenes never take.
+// Returns the attenuated contribution in xyz and the number of additional shadow segments traced in w (by value: a
+// by-reference counter would pin the caller's ray counters into local memory).
+static __device__ __noinline__ float4 ptTransparentShadowSlow(const PtArgs &k, size_t e, float cx, float cy, float cz, uint32_t *stackBase)
+{
+  uint32_t shadowCount = 0;
+  Stack stack;
+  stack.base = stackBase; stack.stride = PT_TRACE_BLOCK;
+  vec3f lightContrib = make_vec3f(cx, cy, cz);
+  const float4 a = k.s.shA[e], b = k.s.shB[e];
+  Ray sr;
+  setRay(sr, make_vec3f(a.x, a.y, a.z), make_vec3f(b.x, b.y, b.z), 0.f, a.w);
+  const OcRenderer &ren = k.a.ren;
+  uint32_t maxDepth = ren.maxDepth;
+  const float tOriginal = sr.t;
+  bool counted = isfinite(lightContrib.x) && isfinite(lightContrib.y) && isfinite(lightContrib.z); // the any-hit query was this segment
+  while (1) {
+    if (!counted) shadowCount++;
+    counted = false;
+    traceWorld<false>(k.a.world, sr, stack);
+    if (!hadHit(sr)) break;
+    DifferentialGeometry dg;
+    postIntersect(k.a.world, ren, dg, sr, DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR);
+    lightContrib = lightContrib * materialTransparency(dg, sr.dir);
+    if (reduce_max(lightContrib) <= ren.minContribution || --maxDepth <= 0) { lightContrib = make_vec3f(0.f); break; }
+    setRay(sr, sr.org, sr.dir, sr.t + dg.epsilon, tOriginal);
+  }
+  return make_float4(lightContrib.x, lightContrib.y, lightContrib.z, __uint_as_float(shadowCount));
+}
 
 // TRACE step of one path: resolve the shadow rays emitted at the previous vertex, then (unless the path is
 // done) trace the continuation ray. Returns false when the path finished here.
@@ -249,23 +293,12 @@ __device__ __forceinline__ bool ptTraceStep(const PtArgs &k, uint32_t p, Stack s
           Ray occ = sr;
           cnt.shadow++;
           if (!traceWorld<true>(k.a.world, occ, stack)) resolved = true; // unoccluded: lightContrib unchanged
-          else if (ptOccluderIsOpaque(k.a.world, ren, occ)) { lightContrib = make_vec3f(0.f); resolved = true; }
+          else if (ptOccluderIsOpaque(k.a.world, ren, occ, reduce_max(lightContrib))) { lightContrib = make_vec3f(0.f); resolved = true; }
         }
         if (!resolved) {
-          uint32_t maxDepth = ren.maxDepth;
-          const float tOriginal = sr.t;
-          bool counted = isfinite(lightContrib.x) && isfinite(lightContrib.y) && isfinite(lightContrib.z); // the any-hit query was this segment
-          while (1) {
-            if (!counted) cnt.shadow++;
-            counted = false;
-            traceWorld<false>(k.a.world, sr, stack);
-            if (!hadHit(sr)) break;
-            DifferentialGeometry dg;
-            postIntersect(k.a.world, ren, dg, sr, DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR);
-            lightContrib = lightContrib * materialTransparency(dg, sr.dir);
-            if (reduce_max(lightContrib) <= ren.minContribution || --maxDepth <= 0) { lightContrib = make_vec3f(0.f); break; }
-            setRay(sr, sr.org, sr.dir, sr.t + dg.epsilon, tOriginal);
-          }
+          const float4 r = ptTransparentShadowSlow(k, e, lightContrib.x, lightContrib.y, lightContrib.z, stack.base);
+          lightContrib = make_vec3f(r.x, r.y, r.z);
+          cnt.shadow += __float_as_uint(r.w);
         }
         if (reduce_max(lightContrib) > 0) L = L + lightContrib * b.w;
       }
@@ -324,7 +357,7 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK) ptFusedKernel(const __grid_con
   __shared__ uint32_t s_stack[OC_STACK_SIZE * PT_TRACE_BLOCK];
   const uint32_t n = *k.cntIn;
   if (n == 0) return;
-  const bool tail = n <= PT_TAIL_THRESHOLD;
+  const bool tail = n <= k.tailThreshold;
   Stack stack;
   stack.base = s_stack + threadIdx.x;
   stack.stride = PT_TRACE_BLOCK;

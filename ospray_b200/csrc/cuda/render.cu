@@ -592,8 +592,11 @@ struct FrameArgs
 #include "pathtracer_wf.cuh"
 namespace oc {
 
+#ifndef OC_RENDER_MIN_BLOCKS
+#define OC_RENDER_MIN_BLOCKS 1
+#endif
 template <int RENDERER>
-__global__ void __launch_bounds__(64) renderFrameKernel(const __grid_constant__ FrameArgs a)
+__global__ void __launch_bounds__(64, OC_RENDER_MIN_BLOCKS) renderFrameKernel(const __grid_constant__ FrameArgs a)
 {
   // block -> (owned tile, 8x8 task inside the 64x64 tile); thread -> pixel inside the task
   const uint32_t ownedTile = blockIdx.x >> 6, taskInTile = blockIdx.x & 63u;
@@ -741,6 +744,8 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
   k.nIndirect = fa.ptIndirectLightSamples;
   const uint32_t maxDepth = fa.ren.maxDepth < 250u ? fa.ren.maxDepth : 250u;
   k.a.ren.maxDepth = maxDepth;
+  static const uint32_t tailThreshold = getenv("OSPCUDA_PT_TAIL") ? (uint32_t)atoi(getenv("OSPCUDA_PT_TAIL")) : PT_TAIL_THRESHOLD;
+  k.tailThreshold = tailThreshold;
   const uint32_t nls = k.nFirst > 0 ? k.nFirst : 1;
   const bool needAcc = fa.ren.spp > 1;
   const uint32_t numCounters = 2 * (maxDepth + 2);

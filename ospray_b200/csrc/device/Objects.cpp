@@ -294,6 +294,12 @@ void Geometry::commit()
     sh.flags = (normalFV ? OC_GEOMFLAG_NORMAL_FACEVARYING : 0) | (colorFV ? OC_GEOMFLAG_COLOR_FACEVARYING : 0)
         | (texFV ? OC_GEOMFLAG_TEXCOORD_FACEVARYING : 0)
         | ((colorData && colorData->type == OSP_VEC4F) ? (OC_GEOMFLAG_HAS_ALPHA | OC_GEOMFLAG_COLOR_IS_VEC4) : 0);
+    if (colorData && colorData->type == OSP_VEC4F) {
+      // lets shadow rays treat such a mesh like one without alpha (pathtracer_wf.cuh ptOccluderIsOpaque)
+      bool allOne = true;
+      for (size_t i = 0; i < colorData->size() && allOne; i++) allOne = colorData->at<vec4f>(i).w == 1.0f;
+      if (allOne) sh.flags |= OC_GEOMFLAG_ALPHA_ALL_ONE;
+    }
   } else if (type == "sphere") {
     const uint32_t sphereType = getParam<uint32_t>("type", OSP_SPHERE);
     if (sphereType != OSP_SPHERE) throw std::runtime_error("cuda device: only OSP_SPHERE sphere geometry is supported");

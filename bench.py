@@ -288,7 +288,8 @@ def run_ours(args):
                 gather.gather(conv_ptr)
             f.wait()
             if rank == 0:
-                img = fb.map(osp.OSP_FB_COLOR)                     # D2H of the finished frame (pinned staging)
+                with fb.mapped(osp.OSP_FB_COLOR) as img:           # ospMapFrameBuffer: D2H of the finished frame into pinned
+                    e2e_probe = int(img[h // 2, w // 2, 0])        # host memory, read in place like a C application would
             e2e_rays += np.array(fb.ray_counts(), np.int64)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0

@@ -455,6 +455,32 @@ class FrameBuffer(Object):
         L.ospUnmapFrameBuffer(p, self.h)
         return out
 
+    def mapped(self, channel=OSP_FB_COLOR):
+        """context manager: zero-copy numpy view of ospMapFrameBuffer's pointer, valid until the block ends
+        (ospUnmapFrameBuffer) - what a C application does; map() additionally copies into a fresh array"""
+        fbo = self
+
+        class _Mapped:
+            def __enter__(self_m):
+                L = lib()
+                self_m.p = L.ospMapFrameBuffer(fbo.h, channel)
+                check_errors()
+                if not self_m.p:
+                    raise OSPRayError(f"channel {channel} not available")
+                if channel == OSP_FB_COLOR:
+                    ct, shape = (C.c_float, (fbo.height, fbo.width, 4)) if fbo.format == OSP_FB_RGBA32F else (C.c_uint8, (fbo.height, fbo.width, 4))
+                else:
+                    dt, comps = _CHANNEL_DTYPE[channel]
+                    ct = C.c_float if dt == np.float32 else C.c_uint32
+                    shape = (fbo.height, fbo.width) if comps == 1 else (fbo.height, fbo.width, comps)
+                return np.ctypeslib.as_array(C.cast(self_m.p, C.POINTER(ct)), shape)
+
+            def __exit__(self_m, *exc):
+                lib().ospUnmapFrameBuffer(self_m.p, fbo.h)
+                return False
+
+        return _Mapped()
+
     def device_pointer(self, channel=OSP_FB_COLOR):
         bpp = C.c_uint64(0)
         p = ext().ospcudaFrameBufferDevicePointer(self.h, channel, C.byref(bpp))

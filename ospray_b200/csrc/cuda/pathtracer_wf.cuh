@@ -62,7 +62,7 @@ struct PtArgs
   uint32_t *qOut;
   const uint32_t *cntIn;
   uint32_t *cntOut;
-  uint32_t tailThreshold; // at most this many live paths: the fused kernel finishes them in place (PT_TAIL_THRESHOLD)
+  uint32_t *fetchCursor;  // ptFusedKernel's work-fetch cursor into qIn (zeroed with the counters every pass)
 };
 
 __device__ __forceinline__ void ptAppend(uint32_t *q, uint32_t *cnt, uint32_t p)
@@ -167,7 +167,6 @@ __device__ __forceinline__ void ptCountRays(const OcFrameBuffer &fb, uint32_t a,
 }
 
 #define PT_TRACE_BLOCK 128
-#define PT_TAIL_THRESHOLD 16384u // at most this many live paths: finish them inside one kernel (see ptTraceKernel)
 
 // Does the surface hit by the any-hit query `ray` certainly take the shadow-ray contribution to exactly 0, as the
 // reference's closest-hit loop would (TransparentShadow.ispc:18-85: lightContrib *= transparency per hit, result 0 as
@@ -346,31 +345,38 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, 5) ptTraceKernel(const __grid_
   ptCountRays(k.a.fb, cnt.primary, cnt.secondary, cnt.shadow);
 }
 
-// FUSED(d), used from depth PT_FUSED_FROM_ROULETTE past the roulette depth on, where Russian roulette has thinned
-// the frame out: one launch per bounce doing TRACE and SHADE back to back for each path (no cross-path
-// dependency between the two), with the usual compaction into the next queue. When at most PT_TAIL_THRESHOLD
-// paths are left, every thread instead carries its path to the end (TAIL mode): the queue it leaves behind is
-// empty and the remaining launches return at once. Without this the long thin tail cost ~30 launch+drain
-// latencies for ~1 % of the paths (profiles/r1_pt_wavefront_launches.txt).
+// FUSED, launched ONCE at the depth where Russian roulette starts to cull (PathTracer.cpp:33 rouletteDepth): every
+// remaining path is carried to its end here. Paths are independent, so instead of one launch + queue compaction per
+// bounce (15 launches for ~20 % of the frame's rays, each paying a launch + drain latency for an ever thinner queue:
+// profiles/r1_launches_bench_c1_wavefront.csv), each lane runs TRACE and SHADE back to back for its path and, when
+// the path dies, immediately fetches the next live path from the input queue (warp-aggregated atomic on a fetch
+// cursor). All lanes of a warp are at the same phase (trace, then shade) of *some* path until the queue runs dry.
 __global__ void __launch_bounds__(PT_TRACE_BLOCK) ptFusedKernel(const __grid_constant__ PtArgs k)
 {
   __shared__ uint32_t s_stack[OC_STACK_SIZE * PT_TRACE_BLOCK];
   const uint32_t n = *k.cntIn;
   if (n == 0) return;
-  const bool tail = n <= k.tailThreshold;
   Stack stack;
   stack.base = s_stack + threadIdx.x;
   stack.stride = PT_TRACE_BLOCK;
   PtCounts cnt = {0, 0, 0};
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t p = k.qIn[i];
-    if (!ptTraceStep<false>(k, p, stack, cnt)) continue;
-    if (!ptShadeStep(k, p)) continue;
-    if (!tail) {
-      ptAppend(k.qOut, k.cntOut, p);
-      continue;
+  const uint32_t lane = threadIdx.x & 31u;
+  bool alive = false;
+  uint32_t p = 0;
+  while (true) {
+    __syncwarp();
+    const uint32_t need = __ballot_sync(0xffffffffu, !alive);
+    if (need) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(k.fetchCursor, (uint32_t)__popc(need));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (!alive) {
+        const uint32_t i = base + __popc(need & ((1u << lane) - 1u));
+        if (i < n) { p = k.qIn[i]; alive = true; }
+      }
+      if (__ballot_sync(0xffffffffu, alive) == 0) break; // queue exhausted and every lane's path finished
     }
-    while (ptTraceStep<false>(k, p, stack, cnt) && ptShadeStep(k, p)) {}
+    if (alive) alive = ptTraceStep<false>(k, p, stack, cnt) && ptShadeStep(k, p);
   }
   ptCountRays(k.a.fb, cnt.primary, cnt.secondary, cnt.shadow);
 }

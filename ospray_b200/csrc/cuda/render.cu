@@ -684,7 +684,7 @@ struct PtHost
   void *block = nullptr;
   size_t blockBytes = 0;
   int device = -1;
-  int traceBlocks = 0, shadeBlocks = 0; // persistent grids (resident CTAs per SM x SM count)
+  int traceBlocks = 0, shadeBlocks = 0, fusedBlocks = 0; // persistent grids (resident CTAs per SM x SM count)
 } g_pt;
 
 size_t alignUp(size_t v) { return (v + 255) & ~size_t(255); }
@@ -713,7 +713,7 @@ int ptCarve(oc::PtScratch &s, uint32_t paths, uint32_t nls, bool needAcc, uint32
     g_pt.block = nullptr; g_pt.blockBytes = 0;
     OC_TRY(cudaMalloc(&g_pt.block, bytes));
     g_pt.blockBytes = bytes; g_pt.device = dev;
-    g_pt.traceBlocks = g_pt.shadeBlocks = 0;
+    g_pt.traceBlocks = g_pt.shadeBlocks = g_pt.fusedBlocks = 0;
   }
   char *b = (char *)g_pt.block;
   k = 0;
@@ -744,24 +744,24 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
   k.nIndirect = fa.ptIndirectLightSamples;
   const uint32_t maxDepth = fa.ren.maxDepth < 250u ? fa.ren.maxDepth : 250u;
   k.a.ren.maxDepth = maxDepth;
-  static const uint32_t tailThreshold = getenv("OSPCUDA_PT_TAIL") ? (uint32_t)atoi(getenv("OSPCUDA_PT_TAIL")) : PT_TAIL_THRESHOLD;
-  k.tailThreshold = tailThreshold;
   const uint32_t nls = k.nFirst > 0 ? k.nFirst : 1;
   const bool needAcc = fa.ren.spp > 1;
-  const uint32_t numCounters = 2 * (maxDepth + 2);
+  const uint32_t numCounters = 2 * (maxDepth + 2) + 1; // queue counters of every launch + the fused kernel's fetch cursor
   // batch the owned tiles so that the path state stays under ~1.5 GB (many light samples / 4K frames)
   const size_t budget = size_t(1536) << 20;
   uint32_t tilesPerBatch = (uint32_t)std::max<size_t>(1, budget / (ptBytesPerPath(nls, needAcc) * 4096));
   if (tilesPerBatch > ownedTiles) tilesPerBatch = ownedTiles;
   if (int rc = ptCarve(k.s, tilesPerBatch * 4096u, nls, needAcc, numCounters)) return rc;
   if (!g_pt.traceBlocks) {
-    int dev = 0, sms = 148, a = 1, b = 1;
+    int dev = 0, sms = 148, a = 1, b = 1, f = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, ptTraceKernel<false>, PT_TRACE_BLOCK, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ptShadeKernel, 128, 0);
     g_pt.traceBlocks = sms * (a > 0 ? a : 1);
     g_pt.shadeBlocks = sms * (b > 0 ? b : 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f, ptFusedKernel, PT_TRACE_BLOCK, 0);
+    g_pt.fusedBlocks = sms * (f > 0 ? f : 1);
   }
   for (uint32_t tile0 = 0; tile0 < ownedTiles; tile0 += tilesPerBatch) {
     const uint32_t nt = std::min(tilesPerBatch, ownedTiles - tile0);
@@ -781,11 +781,12 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
       const uint32_t fusedFrom = std::min<uint32_t>(maxDepth, (uint32_t)std::max(1, fa.ren.rouletteDepth + 1));
       for (uint32_t d = 0; d <= maxDepth; d++) {
         k.depth = d;
-        if (d > 0 && d >= fusedFrom) {
+        if (d > 0 && d >= fusedFrom) { // one launch carries every remaining path to its end
           next();
-          { ProfScope ps(2, st); ptFusedKernel<<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k); }
+          k.fetchCursor = k.s.counters + (numCounters - 1);
+          { ProfScope ps(2, st); ptFusedKernel<<<g_pt.fusedBlocks, PT_TRACE_BLOCK, 0, st>>>(k); }
           oc_count_launch();
-          continue;
+          break;
         }
         if (d > 0) {
           next();

@@ -593,7 +593,7 @@ struct FrameArgs
 namespace oc {
 
 #ifndef OC_RENDER_MIN_BLOCKS
-#define OC_RENDER_MIN_BLOCKS 1
+#define OC_RENDER_MIN_BLOCKS 10 // 96 registers: C2 7.9 -> 7.5 ms, C3 143 -> 137 ms vs the unconstrained 128 (tools/ab_workloads.sh)
 #endif
 template <int RENDERER>
 __global__ void __launch_bounds__(64, OC_RENDER_MIN_BLOCKS) renderFrameKernel(const __grid_constant__ FrameArgs a)
@@ -778,7 +778,9 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
       auto next = [&]() { k.qIn = k.s.queue[q]; k.cntIn = k.s.counters + c; q ^= 1u; c++; k.qOut = k.s.queue[q]; k.cntOut = k.s.counters + c; };
       // separate TRACE / SHADE launches while the frame is densely populated, fused one-launch-per-bounce kernels
       // (with the finish-in-place tail mode) once Russian roulette has started to cull
-      const uint32_t fusedFrom = std::min<uint32_t>(maxDepth, (uint32_t)std::max(1, fa.ren.rouletteDepth + 1));
+      static const int fusedFromEnv = getenv("OSPCUDA_PT_FUSED_FROM") ? atoi(getenv("OSPCUDA_PT_FUSED_FROM")) : -1;
+      const uint32_t fusedFrom = fusedFromEnv > 0 ? std::min<uint32_t>(maxDepth, (uint32_t)fusedFromEnv)
+                                                  : std::min<uint32_t>(maxDepth, (uint32_t)std::max(1, fa.ren.rouletteDepth + 1));
       for (uint32_t d = 0; d <= maxDepth; d++) {
         k.depth = d;
         if (d > 0 && d >= fusedFrom) { // one launch carries every remaining path to its end

@@ -11,9 +11,10 @@
 //   3. cub::DeviceRadixSort on (key, record index)
 //   4. Karras hierarchy, bottom-up refit with arrival counters
 //   5. level-synchronous collapse binary -> BVH4: children with the largest surface area are
-//      opened first; subtrees of <= 4 records become leaves (records are contiguous after the sort)
+//      opened first; subtrees of <= OC_LEAF_MAX (2) records become leaves (records are contiguous after the sort)
 //   6. gather records into leaf order
 #include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 #include "runtime.h"
@@ -21,7 +22,7 @@
 
 namespace oc {
 
-#define OC_LEAF_MAX 4u
+#define OC_LEAF_MAX 2u // records per leaf: 2 beats 4 on every workload (C3 136 -> 106 ms, cornell 2.62 -> 2.41 ms; tools/sweep_leaf_max.sh)
 
 struct Aabb { float lo[3], hi[3]; };
 
@@ -251,14 +252,14 @@ __device__ __forceinline__ uint32_t subtreeFirst(const BinNode *nodes, int n, ui
 struct WorkItem { uint32_t bin, wide; };
 
 __global__ void collapseKernel(const BinNode *nodes, const Aabb *nodeBoxes, int n, const WorkItem *inQ, uint32_t inCount,
-    WorkItem *outQ, uint32_t *outCount, uint32_t *wideCount, OcNode4 *wide)
+    WorkItem *outQ, uint32_t *outCount, uint32_t *wideCount, OcNode4 *wide, uint32_t leafMax)
 {
   const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= inCount) return;
   const WorkItem item = inQ[w];
   uint32_t slot[4];
   int cnt = 0;
-  if (subtreeSize(nodes, n, item.bin) <= OC_LEAF_MAX) {
+  if (subtreeSize(nodes, n, item.bin) <= leafMax) {
     slot[cnt++] = item.bin; // tiny tree: root holds one leaf
   } else {
     slot[cnt++] = nodes[item.bin].left;
@@ -267,7 +268,7 @@ __global__ void collapseKernel(const BinNode *nodes, const Aabb *nodeBoxes, int 
       int best = -1;
       float bestA = -1.f;
       for (int k = 0; k < cnt; k++) {
-        if (subtreeSize(nodes, n, slot[k]) <= OC_LEAF_MAX) continue;
+        if (subtreeSize(nodes, n, slot[k]) <= leafMax) continue;
         const float a = halfArea(nodeBoxes[slot[k]]);
         if (a > bestA) { bestA = a; best = k; }
       }
@@ -285,7 +286,7 @@ __global__ void collapseKernel(const BinNode *nodes, const Aabb *nodeBoxes, int 
       out.lox[k] = b.lo[0]; out.loy[k] = b.lo[1]; out.loz[k] = b.lo[2];
       out.hix[k] = b.hi[0]; out.hiy[k] = b.hi[1]; out.hiz[k] = b.hi[2];
       const uint32_t sz = subtreeSize(nodes, n, slot[k]);
-      if (sz <= OC_LEAF_MAX) {
+      if (sz <= leafMax) {
         out.child[k] = 0x80000000u | (sz << 27) | subtreeFirst(nodes, n, slot[k]);
       } else {
         const uint32_t wi = atomicAdd(wideCount, 1u);
@@ -367,9 +368,10 @@ static int buildFromBoxes(Aabb *d_boxes, float4 *d_records, uint32_t n, const ui
   OC_TRY(cudaMemcpyAsync(q0.p, &root, sizeof(root), cudaMemcpyHostToDevice, st));
   uint32_t inCount = 1;
   WorkItem *inQ = q0.p, *outQ = q1.p;
+  static const uint32_t leafMax = getenv("OSPCUDA_LEAF_MAX") ? std::min(15u, std::max(1u, (uint32_t)atoi(getenv("OSPCUDA_LEAF_MAX")))) : OC_LEAF_MAX;
   while (inCount) {
     collapseKernel<<<(inCount + 127) / 128, 128, 0, st>>>(bin.p, nodeBoxes.p, (int)n, inQ, inCount, outQ, counters.p, counters.p + 1,
-        wideTmp.p);
+        wideTmp.p, leafMax);
     oc_count_launch();
     OC_TRY(cudaMemcpyAsync(h_counts, counters.p, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
     OC_TRY(cudaStreamSynchronize(st));

@@ -197,13 +197,17 @@ typedef struct {
   float bounds[6];
 } OcWorld;
 
-/* perspective camera (reference: PerspectiveCameraShared.h; PerspectiveCamera.cpp:26-117) */
+enum { OC_CAMERA_PERSPECTIVE = 0, OC_CAMERA_ORTHOGRAPHIC = 1 };
+/* camera (reference: PerspectiveCameraShared.h, PerspectiveCamera.cpp:26-117; OrthographicCameraShared.h,
+ * OrthographicCamera.cpp:25-49: for the orthographic type dir_00 is the (normalised) view direction, org the lower
+ * left corner of the image plane, du_size / dv_up its extents, imgPlaneSizeY the `height` parameter) */
 typedef struct {
   OcVec3f org, dir_00, du_size, dv_up, direction;
   float nearClip;
   float subImage[4];           /* lower.x, lower.y, upper.x, upper.y */
   float scaledAperture, aspect, imgPlaneSizeY;
   uint32_t needLensSample, needTimeSample;
+  uint32_t type;
 } OcCamera;
 
 enum { OC_RENDERER_PATHTRACER = 0, OC_RENDERER_SCIVIS = 1, OC_RENDERER_AO = 2, OC_RENDERER_DEBUG_ID = 3 };

@@ -958,6 +958,10 @@ V2 pixelFilterSample(const OcRenderer &r, V2 s)
 void cameraInitRay(const OcCamera &cam, Ray &ray, V2 screen, V2 lens)
 {
   screen = {lerp(screen.x, cam.subImage[0], cam.subImage[2]), lerp(screen.y, cam.subImage[1], cam.subImage[3])};
+  if (cam.type == OC_CAMERA_ORTHOGRAPHIC) { // OrthographicCamera_initRay (camera/OrthographicCamera.ispc:12-50)
+    setRay(ray, v3(cam.org) + screen.x * v3(cam.du_size) + screen.y * v3(cam.dv_up), v3(cam.dir_00), cam.nearClip, INF);
+    return;
+  }
   V3 org = v3(cam.org);
   V3 dir = v3(cam.dir_00) + screen.x * v3(cam.du_size) + screen.y * v3(cam.dv_up);
   if (cam.scaledAperture > 0.f) { // uniformSampleDisk(radius, s)
@@ -1741,6 +1745,23 @@ ORACLE_API void oracle_sampler_kat(int kind, uint32_t seed, uint32_t first, uint
       memcpy(out + k, &v, 4);
     }
   }
+}
+
+// camera/Camera.cpp:33-126 + OrthographicCamera.cpp:25-49 (no transform / motion blur)
+ORACLE_API void oracle_commit_ortho_camera(const float pos[3], const float dir[3], const float up[3], float height, float aspect, OcCamera *out)
+{
+  const V3 d = normalize(v3(dir[0], dir[1], dir[2])), u = normalize(v3(up[0], up[1], up[2]));
+  const V3 dn = normalize(d);
+  V3 du = normalize(cross(dn, u));
+  const V3 dv = cross(du, dn) * height;
+  du = du * (height * aspect);
+  const V3 org = v3(pos[0], pos[1], pos[2]) - 0.5f * du - 0.5f * dv;
+  memset(out, 0, sizeof(*out));
+  out->type = OC_CAMERA_ORTHOGRAPHIC;
+  out->org = {org.x, org.y, org.z}; out->dir_00 = {dn.x, dn.y, dn.z}; out->du_size = {du.x, du.y, du.z};
+  out->dv_up = {dv.x, dv.y, dv.z}; out->direction = {d.x, d.y, d.z};
+  out->nearClip = 1e-6f; out->subImage[2] = 1.f; out->subImage[3] = 1.f;
+  out->aspect = aspect; out->imgPlaneSizeY = height;
 }
 
 // ---- host-side commit restatements ---------------------------------------------------------------------

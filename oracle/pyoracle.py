@@ -100,7 +100,7 @@ class World(C.Structure):
 class Camera(C.Structure):
     _fields_ = [("org", Vec3), ("dir_00", Vec3), ("du_size", Vec3), ("dv_up", Vec3), ("direction", Vec3),
                 ("nearClip", C.c_float), ("subImage", C.c_float * 4), ("scaledAperture", C.c_float), ("aspect", C.c_float),
-                ("imgPlaneSizeY", C.c_float), ("needLensSample", C.c_uint32), ("needTimeSample", C.c_uint32)]
+                ("imgPlaneSizeY", C.c_float), ("needLensSample", C.c_uint32), ("needTimeSample", C.c_uint32), ("type", C.c_uint32)]
 
 
 class Renderer(C.Structure):
@@ -154,6 +154,7 @@ def lib():
         L.oracle_gauss_pixelfilter_lut.argtypes = [C.c_float, C.c_int, C.c_void_p, C.c_void_p]
         F3 = C.c_float * 3
         L.oracle_commit_camera.argtypes = [F3, F3, F3, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(Camera)]
+        L.oracle_commit_ortho_camera.argtypes = [F3, F3, F3, C.c_float, C.c_float, C.POINTER(Camera)]
         L.oracle_commit_light.argtypes = [C.c_int, F3, C.c_float, C.c_int, F3, F3, F3, F3, C.c_float, C.POINTER(Light)]
         L.oracle_fb_accumulate.argtypes = [C.POINTER(FrameBuffer), C.c_void_p, C.c_void_p]
         L.oracle_fb_variance.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -439,8 +440,12 @@ class Scene:
         return v, go, hi
 
 
-def make_camera(position, direction=(0, 0, 1), up=(0, 1, 0), fovy=60.0, aspect=1.0, aperture_radius=0.0, focus_distance=1.0):
+def make_camera(position, direction=(0, 0, 1), up=(0, 1, 0), fovy=60.0, aspect=1.0, aperture_radius=0.0, focus_distance=1.0,
+                kind="perspective", height=1.0):
     cam = Camera()
+    if kind == "orthographic":
+        lib().oracle_commit_ortho_camera(_f3(position), _f3(direction), _f3(up), float(height), float(np.float32(aspect)), C.byref(cam))
+        return cam
     lib().oracle_commit_camera(_f3(position), _f3(direction), _f3(up), fovy, float(np.float32(aspect)), aperture_radius, focus_distance, C.byref(cam))
     return cam
 

@@ -37,6 +37,7 @@
 #include "render/ao/AORendererShared.h"
 #include "pf/LUTPixelFilterShared.h"
 #include "camera/PerspectiveCameraShared.h"
+#include "camera/OrthographicCameraShared.h"
 #include "fb/LocalFBShared.h"
 #include "fb/FrameBufferView.ih"
 #include "fb/RenderTaskDesc.ih"
@@ -357,6 +358,12 @@ REF_API int ospref_render_frame(const OcWorld *w, const OcCamera *cam, const OcR
   auto rs = std::make_unique<RendererSet>();
   Renderer *renderer = buildRenderer(*rs, *s, ren);
 
+  // camera/OrthographicCamera.cpp:25-49 (committed values)
+  OrthographicCamera oc;
+  oc.super.direction = v3(cam->direction); oc.super.nearClip = cam->nearClip;
+  oc.super.subImage = box2f(make_vec2f(cam->subImage[0], cam->subImage[1]), make_vec2f(cam->subImage[2], cam->subImage[3]));
+  oc.super.shutter = box1f(0.5f, 0.5f);
+  oc.dir = v3(cam->dir_00); oc.org = v3(cam->org); oc.du_size = v3(cam->du_size); oc.dv_up = v3(cam->dv_up); oc.height = cam->imgPlaneSizeY;
   // camera/PerspectiveCamera.cpp:26-117 (committed values)
   PerspectiveCamera pc;
   pc.super.direction = v3(cam->direction); pc.super.nearClip = cam->nearClip;
@@ -394,13 +401,14 @@ REF_API int ospref_render_frame(const OcWorld *w, const OcCamera *cam, const OcR
   sycl::event ev;
   const ospray::FeatureFlags ff = allFeatures();
   const vec3ui dims = make_vec3ui(8, 8, (uint32_t)taskIDs.size());
+  Camera *camera = cam->type == OC_CAMERA_ORTHOGRAPHIC ? &oc.super : &pc.super;
   uint64_t before[2]; ospref_ray_counters(before, 0);
   if (ren->type == OC_RENDERER_PATHTRACER)
-    PathTracer_renderTaskLauncher(&q, &ev, dims, renderer, &lfb.super, &pc.super, &s->world, taskIDs.data(), ff);
+    PathTracer_renderTaskLauncher(&q, &ev, dims, renderer, &lfb.super, camera, &s->world, taskIDs.data(), ff);
   else if (ren->type == OC_RENDERER_SCIVIS)
-    SciVis_renderTaskLauncher(&q, &ev, dims, renderer, &lfb.super, &pc.super, &s->world, taskIDs.data(), ff);
+    SciVis_renderTaskLauncher(&q, &ev, dims, renderer, &lfb.super, camera, &s->world, taskIDs.data(), ff);
   else
-    AORenderer_renderTaskLauncher(&q, &ev, dims, renderer, &lfb.super, &pc.super, &s->world, taskIDs.data(), ff);
+    AORenderer_renderTaskLauncher(&q, &ev, dims, renderer, &lfb.super, camera, &s->world, taskIDs.data(), ff);
   if (fb->rayCounters) {
     uint64_t after[2]; ospref_ray_counters(after, 0);
     fb->rayCounters[0] += (unsigned long long)taskIDs.size() * 64ull * (unsigned long long)ren->spp;

@@ -730,10 +730,15 @@ __device__ __forceinline__ vec2f pixelFilterSample(const OcRenderer &r, vec2f s)
   return (uv + make_vec2f(-0.5f, -0.5f)) * r.pfWidth;
 }
 
-// PerspectiveCamera_initRay (camera/PerspectiveCamera.ispc:16-64); no stereo / motion blur
+// PerspectiveCamera_initRay (camera/PerspectiveCamera.ispc:16-64), OrthographicCamera_initRay
+// (camera/OrthographicCamera.ispc:12-50); no stereo / motion blur
 __device__ __forceinline__ void cameraInitRay(const OcCamera &cam, Ray &ray, vec2f screen, vec2f lens)
 {
   screen = make_vec2f(lerpf(screen.x, cam.subImage[0], cam.subImage[2]), lerpf(screen.y, cam.subImage[1], cam.subImage[3]));
+  if (cam.type == OC_CAMERA_ORTHOGRAPHIC) {
+    setRay(ray, toV(cam.org) + screen.x * toV(cam.du_size) + screen.y * toV(cam.dv_up), toV(cam.dir_00), cam.nearClip, INFINITY);
+    return;
+  }
   vec3f org = toV(cam.org);
   vec3f dir = toV(cam.dir_00) + screen.x * toV(cam.du_size) + screen.y * toV(cam.dv_up);
   if (cam.scaledAperture > 0.f) {

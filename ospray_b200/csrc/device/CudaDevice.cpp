@@ -57,7 +57,7 @@ OSPLight CudaDevice::newLight(const char *type)
 }
 OSPCamera CudaDevice::newCamera(const char *type)
 {
-  if (std::string(type) != "perspective") return nullptr;
+  if (std::string(type) != "perspective" && std::string(type) != "orthographic") return nullptr;
   return (OSPCamera) new Camera(type);
 }
 OSPGeometry CudaDevice::newGeometry(const char *type)

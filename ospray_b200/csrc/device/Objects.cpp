@@ -199,7 +199,7 @@ Data *getParamData(ManagedObject &o, const std::string &name, OSPDataType elemTy
 }
 
 // ---- Camera (camera/Camera.cpp:33-126, PerspectiveCamera.cpp:26-117) ------------------------------
-Camera::Camera(const std::string &) { managedObjectType = OSP_CAMERA; }
+Camera::Camera(const std::string &t) : type(t) { managedObjectType = OSP_CAMERA; }
 
 void Camera::commit()
 {
@@ -217,6 +217,22 @@ void Camera::commit()
   dir = normalize(xfmVector(xfm, dir));
   up = normalize(xfmVector(xfm, up));
 
+  if (type == "orthographic") { // camera/OrthographicCamera.cpp:25-49
+    const float height = getParam<float>("height", 1.f);
+    const float oaspect = getParam<float>("aspect", 1.f);
+    const vec3f dn = normalize(dir);
+    vec3f du = normalize(cross(dn, up));
+    const vec3f dv = cross(du, dn) * height;
+    du = du * (height * oaspect);
+    sh = OcCamera{};
+    sh.type = OC_CAMERA_ORTHOGRAPHIC;
+    sh.org = toOc(pos - 0.5f * du - 0.5f * dv);
+    sh.dir_00 = toOc(dn); sh.du_size = toOc(du); sh.dv_up = toOc(dv); sh.direction = toOc(dir);
+    sh.nearClip = nearClip;
+    sh.subImage[0] = imageStart.x; sh.subImage[1] = imageStart.y; sh.subImage[2] = imageEnd.x; sh.subImage[3] = imageEnd.y;
+    sh.aspect = oaspect; sh.imgPlaneSizeY = height;
+    return;
+  }
   const float fovy = getParam<float>("fovy", 60.f);
   float aspect = getParam<float>("aspect", 1.f);
   const float apertureRadius = getParam<float>("apertureRadius", 0.f);
@@ -253,6 +269,7 @@ void Camera::commit()
   sh.imgPlaneSizeY = imgPlaneY;
   sh.needLensSample = scaledAperture > 0.f;
   sh.needTimeSample = 0;
+  sh.type = OC_CAMERA_PERSPECTIVE;
 }
 
 // ---- Geometry (geometry/Mesh.cpp:37-204, Spheres.cpp:46-106, Boxes.cpp:33-42) ----------------------

@@ -393,11 +393,13 @@ def to_ospray(scene: SceneSpec):
     return world, keep
 
 
-def make_camera(world, width, height):
+def make_camera(world, width, height, kind="perspective", ortho_height=1.0):
     """BaseFixture::Init camera (BaseFixture.cpp:36-47)"""
     lo, hi = world.bounds()
     p = arcball_camera(lo, hi)
-    cam = osp.Camera("perspective")
+    cam = osp.Camera(kind)
+    if kind == "orthographic":
+        cam.set("height", float(ortho_height))
     cam.set("aspect", float(np.float32(width) / np.float32(height)))
     cam.set("position", p["position"]).set("direction", p["direction"]).set("up", p["up"])
     return cam.commit(), p

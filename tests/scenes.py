@@ -67,7 +67,7 @@ def tinted_glass_cornell():
     return s
 
 
-# name -> (spec builder, renderer kind, renderer params, frames)
+# name -> (spec builder, renderer kind, renderer params, frames[, {camera: kind, height: h}])
 CASES = {
     "cornell_pt": (T.cornell_box, "pathtracer", {"pixelSamples": 2}, 2),
     "cornell_pt_lights4": (T.cornell_box, "pathtracer", {"pixelSamples": 1, "lightSamples": 4, "limitIndirectLightSamples": False}, 1),
@@ -81,6 +81,8 @@ CASES = {
     "spheres_pt": (T.random_spheres, "pathtracer", {"pixelSamples": 1, "backgroundColor": (1.0, 1.0, 1.0, 1.0)}, 2),
     "glass_spheres_pt": (glass_spheres, "pathtracer", {"pixelSamples": 2, "backgroundColor": (0.2, 0.3, 0.4, 1.0)}, 2),
     "glass_cornell_pt": (tinted_glass_cornell, "pathtracer", {"pixelSamples": 2, "maxPathLength": 12}, 1),
+    "cornell_ortho_pt": (T.cornell_box, "pathtracer", {"pixelSamples": 2}, 1, {"camera": "orthographic", "height": 2.2}),
+    "spheres_ortho_scivis": (T.random_spheres, "scivis", {"shadows": True, "aoSamples": 1}, 1, {"camera": "orthographic", "height": 2.6}),
     "instanced_scivis": (instanced_boxes_and_spheres, "scivis", {"shadows": True}, 1),
     "instanced_pt": (instanced_boxes_and_spheres, "pathtracer", {"pixelSamples": 1}, 1),
     "mesh_ao": (lambda: T.box_mesh(5), "ao", {"aoSamples": 2}, 1),
@@ -101,11 +103,13 @@ W, H = 48, 40  # not a multiple of 8 or 64: exercises clipped render tasks and b
 
 def oracle_render(name, width=W, height=H, pixel_filter=None, threads=0, num_ranks=1, rank=0, channels=None, backend="oracle"):
     from oracle import pyoracle as O
-    build, kind, params, frames = CASES[name]
+    build, kind, params, frames = CASES[name][:4]
+    extra = CASES[name][4] if len(CASES[name]) > 4 else {}
     spec = build()
     scene = O.Scene(spec)
     pose = T.arcball_camera(*scene.bounds)
-    cam = O.make_camera(pose["position"], pose["direction"], pose["up"], aspect=np.float32(width) / np.float32(height))
+    cam = O.make_camera(pose["position"], pose["direction"], pose["up"], aspect=np.float32(width) / np.float32(height),
+                        kind=extra.get("camera", "perspective"), height=extra.get("height", 1.0))
     p = dict(params)
     if pixel_filter:
         p["pixelFilter"] = pixel_filter
@@ -122,10 +126,11 @@ _PF = {"point": 0, "box": 1, "gauss": 2}
 
 def device_render(osp, name, width=W, height=H, pixel_filter=None, channels=None, fmt=None):
     """the same case through the unchanged OSPRay C API on the cuda device"""
-    build, kind, params, frames = CASES[name]
+    build, kind, params, frames = CASES[name][:4]
+    extra = CASES[name][4] if len(CASES[name]) > 4 else {}
     spec = build()
     world, keep = T.to_ospray(spec)
-    cam, _ = T.make_camera(world, width, height)
+    cam, _ = T.make_camera(world, width, height, kind=extra.get("camera", "perspective"), ortho_height=extra.get("height", 1.0))
     p = {}
     for k, v in params.items():
         p[k] = tuple(float(x) for x in v) if isinstance(v, tuple) else v

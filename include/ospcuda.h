@@ -165,7 +165,7 @@ typedef struct {
   float bounds[6]; /* world-space */
 } OcInstance;
 
-enum { OC_LIGHT_AMBIENT = 0, OC_LIGHT_DISTANT = 2, OC_LIGHT_QUAD = 5 };
+enum { OC_LIGHT_AMBIENT = 0, OC_LIGHT_DISTANT = 2, OC_LIGHT_SPHERE = 4, OC_LIGHT_QUAD = 5 }; /* values of ispc::LightType */
 /* lights (reference: lights/LightShared.h:79-110, QuadLightShared.h, DirectionalLightShared.h,
  * AmbientLightShared.h) */
 typedef struct {
@@ -176,6 +176,8 @@ typedef struct {
   float ppdf;                  /* quad: 1/area */
   OcVec3f fx, fy, fz;          /* distant: frame (vz = direction towards light) */
   float cosAngle, pdf;         /* distant */
+  OcVec3f intensity;           /* sphere ("sphere" = ispc::PointLight, lights/PointLightShared.h): radiant intensity (r = 0 path) */
+  float radius;                /* sphere: radius; `radiance` is its surface radiance, `position` its centre */
 } OcLight;
 
 typedef struct {

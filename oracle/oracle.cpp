@@ -858,9 +858,60 @@ LightSample QuadLight_sampleArea(const OcLight &l, V3 P, V2 s) // lights/QuadLig
   r.weight = v3(l.radiance) * (cosd > 0.f ? 1.f / r.pdf : 0.f);
   return r;
 }
+// PointLight ("sphere" light): lights/PointLight.ispc:38-92 (Sample), :131-160 (Eval); no intensity distribution
+LightSample PointLight_sample(const OcLight &l, const DG &dg, V2 s)
+{
+  LightSample res;
+  const V3 dir = v3(l.position) - dg.P;
+  const float dist2 = dot(dir, dir);
+  const float invdist = 1.f / sqrtf(dist2);
+  res.dir = dir * invdist;
+  res.dist = dist2 * invdist;
+  res.pdf = INF;
+  const float sinTheta = l.radius * invdist;
+  if ((l.radius > 0.f) & (sinTheta > 0.005f)) {
+    if (sinTheta < 1.f) {
+      const float cosTheta = sqrtf(1.f - sinTheta * sinTheta);
+      const V3 localDir = uniformSampleCone(cosTheta, s);
+      res.dir = xfmVector(frame(res.dir), localDir);
+      res.pdf = 1.f / (TWO_PI * (1.0f - cosTheta));
+      const float c = localDir.z;
+      const float disc = sqr(l.radius) - (1.f - c * c) * dist2;
+      res.dist = c * res.dist - sqrtf(disc > 0.f ? disc : 0.f);
+      res.weight = v3(l.radiance) / res.pdf;
+    } else
+      res.weight = v3(0.f);
+  } else
+    res.weight = v3(l.intensity) * sqr(invdist);
+  return res;
+}
+LightEval PointLight_eval(const OcLight &l, V3 P, V3 dir, float minDist, float maxDist)
+{
+  LightEval res = {v3(0.f), 0.f};
+  const V3 A = v3(l.position) - P;
+  const float centerDist2 = dot(A, A);
+  const float sinTheta2 = sqr(l.radius) * (1.f / centerDist2);
+  if (l.radius > 0.f && sqrtf(sinTheta2) > 0.005f) {
+    // intersectSphere (common/Intersect.ih:29-78), entry hit only
+    const float rd2 = 1.0f / dot(dir, dir);
+    const float projCO = dot(A, dir) * rd2;
+    const V3 perp = A - projCO * dir;
+    const float l2 = dot(perp, perp), r2 = sqr(l.radius);
+    if (!(l2 > r2)) {
+      const float t = projCO - sqrtf((r2 - l2) * rd2);
+      if (t > minDist && t < maxDist) {
+        const float cosTheta = sqrtf(1.f - sinTheta2);
+        res.pdf = 1.f / (TWO_PI * (1.0f - cosTheta));
+        res.radiance = v3(l.radiance);
+      }
+    }
+  }
+  return res;
+}
 LightSample Light_sample(const OcLight &l, const DG &dg, V2 s)
 {
   LightSample r;
+  if (l.type == OC_LIGHT_SPHERE) return PointLight_sample(l, dg, s);
   if (l.type == OC_LIGHT_QUAD) { // QuadLight.ispc:82-135
     if (s.x == 0.0f && s.y == 0.0f) return QuadLight_sampleArea(l, dg.P, {0.5f, 0.5f});
     const V3 pos = v3(l.position), e1 = v3(l.edge1), e2 = v3(l.edge2), nn = v3(l.nnormal);
@@ -893,6 +944,7 @@ LightSample Light_sample(const OcLight &l, const DG &dg, V2 s)
 LightEval Light_eval(const OcLight &l, V3 P, V3 Ns, V3 dir, float minDist, float maxDist)
 {
   LightEval r = {v3(0.f), 0.f};
+  if (l.type == OC_LIGHT_SPHERE) return PointLight_eval(l, P, dir, minDist, maxDist);
   if (l.type == OC_LIGHT_QUAD) { // QuadLight.ispc:169-215
     const V3 nn = v3(l.nnormal), pos = v3(l.position), e1 = v3(l.edge1), e2 = v3(l.edge2);
     const float cosd = dot(nn, dir);
@@ -1826,6 +1878,23 @@ ORACLE_API void oracle_commit_light(int type, const float color[3], float intens
     out->fx = {f.vx.x, f.vx.y, f.vx.z}; out->fy = {f.vy.x, f.vy.y, f.vy.z}; out->fz = {f.vz.x, f.vz.y, f.vz.z};
     out->cosAngle = cosAngle;
     out->pdf = cosAngle < 0.99999988f ? 1.f / (TWO_PI * (1.0f - cosAngle)) : INF;
+  }
+}
+
+// lights/PointLight.cpp:77-124 ("sphere" light, default intensityQuantity INTENSITY, no intensity distribution)
+ORACLE_API void oracle_commit_sphere_light(const float color[3], float intensity, int visible, const float position[3], float radius, OcLight *out)
+{
+  memset(out, 0, sizeof(*out));
+  const V3 ci = v3(color[0], color[1], color[2]) * intensity;
+  out->type = OC_LIGHT_SPHERE;
+  out->isVisible = visible;
+  out->position = {position[0], position[1], position[2]};
+  out->radius = radius;
+  out->intensity = {ci.x, ci.y, ci.z};
+  if (radius > 0.0f) {
+    const float sphereArea = 4.0f * M_PI * radius * radius; // double product, rounded once (as written in the reference)
+    const V3 rad = ci / (sphereArea / 4.0f);
+    out->radiance = {rad.x, rad.y, rad.z};
   }
 }
 

@@ -30,6 +30,7 @@
 #include "render/materials/OBJShared.h"
 #include "render/materials/ThinGlassShared.h"
 #include "lights/QuadLightShared.h"
+#include "lights/PointLightShared.h"
 #include "lights/DirectionalLightShared.h"
 #include "lights/AmbientLightShared.h"
 #include "render/pathtracer/PathTracerShared.h"
@@ -133,7 +134,7 @@ struct Scene
   std::deque<std::vector<Material *>> materialPtrs;
   std::deque<OBJ> objs; std::deque<ThinGlass> glasses; std::vector<Material *> allMaterials;
   std::vector<Instance *> instancePtrs;
-  std::deque<QuadLight> quads; std::deque<DirectionalLight> dirs; std::deque<AmbientLight> ambients;
+  std::deque<QuadLight> quads; std::deque<PointLight> points; std::deque<DirectionalLight> dirs; std::deque<AmbientLight> ambients;
   std::vector<Light *> ptLights, svLights;
   Instance identityInstance; // stands in for the NULL instance of world lights: the scalar light dispatch reads
                              // self->instance->motionBlur unconditionally (lights/LightDispatch.ispc:36-60)
@@ -269,6 +270,14 @@ void buildScene(Scene &s, const OcWorld *w, const OcRenderer *ren)
       q.pre.c90 = normalize(cross(q.pre.nnormal, q.pre.edge2));
       q.pre.c0 = cross(q.pre.c90, q.pre.nnormal);
       return &q.super;
+    }
+    if (l.type == OC_LIGHT_SPHERE) { // lights/PointLight.cpp:22-62
+      s.points.emplace_back();
+      PointLight &pl = s.points.back();
+      pl.super.isVisible = l.isVisible != 0; pl.super.instance = &s.identityInstance;
+      pl.radiance = v3(l.radiance); pl.intensity = v3(l.intensity); pl.radius = l.radius;
+      pl.pre.position = v3(l.position);
+      return &pl.super;
     }
     if (l.type == OC_LIGHT_DISTANT) {
       s.dirs.emplace_back();

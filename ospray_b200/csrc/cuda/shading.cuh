@@ -651,11 +651,64 @@ __device__ __forceinline__ LightEval QuadLight_eval(const OcLight &l, vec3f P, v
   return r;
 }
 
+// PointLight ("sphere" light): lights/PointLight.ispc:38-92 (sample), :131-160 (eval); no intensity distribution
+__device__ __forceinline__ LightSample PointLight_sample(const OcLight &l, const DifferentialGeometry &dg, vec2f s)
+{
+  LightSample res;
+  const vec3f dir = toV(l.position) - dg.P;
+  const float dist2 = dot(dir, dir);
+  const float invdist = 1.f / sqrtf(dist2);
+  res.dir = dir * invdist;
+  res.dist = dist2 * invdist;
+  res.pdf = INFINITY;
+  const float sinTheta = l.radius * invdist;
+  if ((l.radius > 0.f) & (sinTheta > 0.005f)) {
+    if (sinTheta < 1.f) {
+      const float cosTheta = sqrtf(1.f - sinTheta * sinTheta);
+      const vec3f localDir = uniformSampleCone(cosTheta, s);
+      res.dir = frame(res.dir) * localDir;
+      res.pdf = 1.f / (OC_TWO_PI * (1.0f - cosTheta));
+      const float c = localDir.z;
+      const float disc = l.radius * l.radius - (1.f - c * c) * dist2;
+      res.dist = c * res.dist - sqrtf(disc > 0.f ? disc : 0.f);
+      res.weight = toV(l.radiance) / res.pdf;
+    } else
+      res.weight = make_vec3f(0.f);
+  } else
+    res.weight = toV(l.intensity) * (invdist * invdist);
+  return res;
+}
+__device__ __forceinline__ LightEval PointLight_eval(const OcLight &l, vec3f P, vec3f dir, float minDist, float maxDist)
+{
+  LightEval res; res.radiance = make_vec3f(0.f); res.pdf = 0.f;
+  const vec3f A = toV(l.position) - P;
+  const float centerDist2 = dot(A, A);
+  const float sinTheta2 = (l.radius * l.radius) * (1.f / centerDist2);
+  if (l.radius > 0.f && sqrtf(sinTheta2) > 0.005f) {
+    // intersectSphere (common/Intersect.ih:29-78), entry hit only
+    const float rd2 = 1.0f / dot(dir, dir);
+    const float projCO = dot(A, dir) * rd2;
+    const vec3f perp = A - projCO * dir;
+    const float l2 = dot(perp, perp), r2 = l.radius * l.radius;
+    if (!(l2 > r2)) {
+      const float t = projCO - sqrtf((r2 - l2) * rd2);
+      if (t > minDist && t < maxDist) {
+        const float cosTheta = sqrtf(1.f - sinTheta2);
+        res.pdf = 1.f / (OC_TWO_PI * (1.0f - cosTheta));
+        res.radiance = toV(l.radiance);
+      }
+    }
+  }
+  return res;
+}
+
 __device__ __forceinline__ LightSample Light_sample(const OcLight &l, const DifferentialGeometry &dg, vec2f s)
 {
   LightSample r;
   if (l.type == OC_LIGHT_QUAD)
     return QuadLight_sample(l, dg, s);
+  if (l.type == OC_LIGHT_SPHERE)
+    return PointLight_sample(l, dg, s);
   if (l.type == OC_LIGHT_AMBIENT) {
     if (reduce_max(vabs(dg.Ns)) > 0) {
       const vec3f localDir = cosineSampleHemisphere(s);
@@ -685,6 +738,8 @@ __device__ __forceinline__ LightEval Light_eval(const OcLight &l, vec3f P, vec3f
   LightEval r; r.radiance = make_vec3f(0.f); r.pdf = 0.f;
   if (l.type == OC_LIGHT_QUAD)
     return QuadLight_eval(l, P, dir, minDist, maxDist);
+  if (l.type == OC_LIGHT_SPHERE)
+    return PointLight_eval(l, P, dir, minDist, maxDist);
   if (l.type == OC_LIGHT_AMBIENT) {
     r.radiance = INFINITY <= maxDist ? toV(l.radiance) : make_vec3f(0.f);
     if (reduce_max(vabs(Ns)) > 0) r.pdf = fmaxf(dot(Ns, dir), 0.f) * OC_ONE_OVER_PI;

@@ -600,8 +600,30 @@ void Light::commit()
     sh.position = toOc(position); sh.edge1 = toOc(edge1); sh.edge2 = toOc(edge2);
     sh.ppdf = ppdf;
     sh.nnormal = toOc(ndirection * ppdf);
+  } else if (type == "sphere") { // lights/PointLight.cpp:77-124 (no intensity distribution)
+    const vec3f position = getParam<vec3f>("position", make_vec3f(0.f));
+    const float radius = getParam<float>("radius", 0.f);
+    getParam<vec3f>("direction", make_vec3f(0.f, 0.f, 1.f));
+    const uint32_t iq = getParam<uint32_t>("intensityQuantity", OSP_INTENSITY_QUANTITY_INTENSITY);
+    const float sphereArea = 4.0f * M_PI * radius * radius;
+    vec3f radIntensity = make_vec3f(0.f), radiance = make_vec3f(0.f);
+    if (iq == OSP_INTENSITY_QUANTITY_INTENSITY) {
+      radIntensity = coloredIntensity;
+      if (radius > 0.0f) radiance = coloredIntensity / (sphereArea / 4.0f);
+    } else if (iq == OSP_INTENSITY_QUANTITY_POWER) {
+      radIntensity = coloredIntensity / (float)(4.0f * M_PI);
+      if (radius > 0.0f) radiance = coloredIntensity / (float)(M_PI * sphereArea);
+    } else if (iq == OSP_INTENSITY_QUANTITY_RADIANCE) {
+      if (radius > 0.0f) radiance = coloredIntensity;
+    } else
+      postStatusMsg(OSP_LOG_WARNING, toString() + " unsupported 'intensityQuantity' value");
+    sh.type = OC_LIGHT_SPHERE;
+    sh.position = toOc(position);
+    sh.radius = radius;
+    sh.intensity = toOc(radIntensity);
+    sh.radiance = toOc(radiance);
   } else
-    throw std::runtime_error("cuda device: light type '" + type + "' is not supported (ambient, distant, quad)");
+    throw std::runtime_error("cuda device: light type '" + type + "' is not supported (ambient, distant, quad, sphere)");
 }
 
 // ---- Group (common/Group.cpp:69-209) ------------------------------------------------------------------

@@ -67,6 +67,16 @@ def tinted_glass_cornell():
     return s
 
 
+def sphere_lit_boxes():
+    """boxes under two "sphere" lights (ispc::PointLight): one with a radius (cone sampling, visible emitter), one a true
+    point (inverse-square intensity)"""
+    s = T.boxes(lit=True)
+    s.lights = [T.LightSpec("sphere", {"position": (0.4, 1.4, -0.8), "radius": 0.25, "intensity": 6.0, "color": (1.0, 0.8, 0.6)}),
+                T.LightSpec("sphere", {"position": (-1.2, 0.6, -1.5), "intensity": 3.0}),
+                T.LightSpec("ambient", {"intensity": 0.1})]
+    return s
+
+
 # name -> (spec builder, renderer kind, renderer params, frames[, {camera: kind, height: h}])
 CASES = {
     "cornell_pt": (T.cornell_box, "pathtracer", {"pixelSamples": 2}, 2),
@@ -83,6 +93,8 @@ CASES = {
     "glass_cornell_pt": (tinted_glass_cornell, "pathtracer", {"pixelSamples": 2, "maxPathLength": 12}, 1),
     "cornell_ortho_pt": (T.cornell_box, "pathtracer", {"pixelSamples": 2}, 1, {"camera": "orthographic", "height": 2.2}),
     "spheres_ortho_scivis": (T.random_spheres, "scivis", {"shadows": True, "aoSamples": 1}, 1, {"camera": "orthographic", "height": 2.6}),
+    "sphere_lights_pt": (sphere_lit_boxes, "pathtracer", {"pixelSamples": 2}, 2),
+    "sphere_lights_scivis": (sphere_lit_boxes, "scivis", {"shadows": True, "visibleLights": True}, 1),
     "instanced_scivis": (instanced_boxes_and_spheres, "scivis", {"shadows": True}, 1),
     "instanced_pt": (instanced_boxes_and_spheres, "pathtracer", {"pixelSamples": 1}, 1),
     "mesh_ao": (lambda: T.box_mesh(5), "ao", {"aoSamples": 2}, 1),

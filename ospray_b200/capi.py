@@ -389,6 +389,24 @@ class World(Object):
         return ext().ospcudaWorldDevicePointer(self.h)
 
 
+class PickResult(C.Structure):
+    _fields_ = [("hasHit", C.c_int), ("worldPosition", C.c_float * 3), ("instance", C.c_void_p), ("model", C.c_void_p), ("primID", C.c_uint32)]
+
+
+def pick(fb, renderer, camera, world, x, y):
+    """ospPick at normalised screen position (x, y); returns (hasHit, worldPosition, instance handle, model handle, primID).
+    The returned handles are retained by the device (Renderer.cpp:128-129) and released here after reading their values."""
+    L = lib()
+    r = PickResult()
+    L.ospPick(C.byref(r), fb.h, renderer.h, camera.h, world.h, float(x), float(y))
+    check_errors()
+    out = (bool(r.hasHit), np.array(list(r.worldPosition), np.float32), r.instance, r.model, int(r.primID))
+    if r.hasHit:
+        L.ospRelease(r.instance)
+        L.ospRelease(r.model)
+    return out
+
+
 class Future(Object):
     kind = OSP_FUTURE
 

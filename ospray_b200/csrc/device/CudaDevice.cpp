@@ -159,6 +159,45 @@ OSPFuture CudaDevice::renderFrame(OSPFrameBuffer _fb, OSPRenderer _r, OSPCamera 
   return (OSPFuture)f;
 }
 
+// ospPick: Renderer::pick (render/Renderer.cpp:94-137) + Renderer_pick (render/Renderer.ispc:43-84): the camera ray
+// through screenPos (centre of the lens, no pixel filter), closest hit, retained instance / model handles
+OSPPickResult CudaDevice::pick(OSPFrameBuffer, OSPRenderer, OSPCamera _c, OSPWorld _w, const vec2f &screenPos)
+{
+  Camera *c = (Camera *)_c;
+  World *w = (World *)_w;
+  OSPPickResult res{};
+  res.instance = nullptr; res.model = nullptr; res.primID = 0xFFFFFFFFu; res.hasHit = 0;
+  const OcCamera &cam = c->sh;
+  const auto lerpf = [](float f, float a, float b) { return (1.f - f) * a + f * b; };
+  const float sx = lerpf(screenPos.x, cam.subImage[0], cam.subImage[2]), sy = lerpf(screenPos.y, cam.subImage[1], cam.subImage[3]);
+  const vec3f du = make_vec3f(cam.du_size.x, cam.du_size.y, cam.du_size.z), dv = make_vec3f(cam.dv_up.x, cam.dv_up.y, cam.dv_up.z);
+  vec3f org = make_vec3f(cam.org.x, cam.org.y, cam.org.z), dir = make_vec3f(cam.dir_00.x, cam.dir_00.y, cam.dir_00.z);
+  if (cam.type == OC_CAMERA_ORTHOGRAPHIC) org = org + sx * du + sy * dv;
+  else dir = normalize(dir + sx * du + sy * dv);
+  OcRayHit rh{};
+  rh.org[0] = org.x; rh.org[1] = org.y; rh.org[2] = org.z; rh.t0 = cam.nearClip;
+  rh.dir[0] = dir.x; rh.dir[1] = dir.y; rh.dir[2] = dir.z; rh.t = INFINITY;
+  rh.primID = rh.geomID = rh.instID = 0xFFFFFFFFu;
+  const OcWorld *dw = w->prepareFrame();
+  DevMem ray;
+  ray.upload(&rh, sizeof(rh));
+  checkCuda(ospcuda_trace(dw, ray.as<OcRayHit>(), 1, 0), "pick trace");
+  checkCuda(ospcuda_memcpy_d2h(&rh, ray.p, sizeof(rh)), "pick read-back");
+  if (rh.geomID == 0xFFFFFFFFu || !w->instances) return res;
+  Instance *instance = dynamic_cast<Instance *>(w->instances->objectAt(rh.instID));
+  Group *group = instance ? instance->group.ptr : nullptr;
+  if (!group || !group->geometricModels) return res;
+  ManagedObject *model = group->geometricModels->objectAt(rh.geomID);
+  instance->refInc();
+  model->refInc();
+  res.hasHit = 1;
+  res.worldPosition[0] = org.x + dir.x * rh.t; res.worldPosition[1] = org.y + dir.y * rh.t; res.worldPosition[2] = org.z + dir.z * rh.t;
+  res.instance = (OSPInstance)instance;
+  res.model = (OSPGeometricModel)model;
+  res.primID = rh.primID;
+  return res;
+}
+
 int CudaDevice::isReady(OSPFuture f, OSPSyncEvent e) { return ((Future *)f)->isFinished(e); }
 void CudaDevice::wait(OSPFuture f, OSPSyncEvent e) { ((Future *)f)->wait(e); }
 void CudaDevice::cancel(OSPFuture) {} // a frame is a single kernel; nothing to cancel mid-flight

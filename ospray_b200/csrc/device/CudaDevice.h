@@ -43,6 +43,7 @@ struct CudaDevice : public api::Device
   const void *frameBufferMap(OSPFrameBuffer fb, const OSPFrameBufferChannel) override;
   void frameBufferUnmap(const void *mapped, OSPFrameBuffer fb) override;
   float getVariance(OSPFrameBuffer) override;
+  OSPPickResult pick(OSPFrameBuffer, OSPRenderer, OSPCamera, OSPWorld, const vec2f &screenPos) override;
   void resetAccumulation(OSPFrameBuffer fb) override;
   OSPRenderer newRenderer(const char *type) override;
   OSPFuture renderFrame(OSPFrameBuffer, OSPRenderer, OSPCamera, OSPWorld) override;

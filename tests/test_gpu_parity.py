@@ -229,3 +229,35 @@ def test_big_mesh_traversal_vs_bruteforce(osp, abi):
     d = np.abs(got["t"].view(np.int32).astype(np.int64) - want["t"].view(np.int32).astype(np.int64))
     assert d.max() <= 2 and (d > 0).mean() < 0.01
     assert ((got["primID"] != want["primID"]).mean()) < 0.01
+
+
+def test_pick_matches_oracle_primary_hit(osp):
+    """ospPick (Renderer.cpp:94-137, Renderer.ispc:43-84): camera ray through the screen position, centre of the lens, no
+    pixel filter; the hit primitive, model and instance equal the oracle's primary hit for the same ray and the world
+    position is org + t * dir."""
+    from oracle import pyoracle as O
+    spec = scenes.instanced_boxes_and_spheres()
+    world, keep = T.to_ospray(spec)
+    w, h = 64, 48
+    cam, pose = T.make_camera(world, w, h)
+    ren = T.make_renderer("scivis")
+    fb = osp.FrameBuffer(w, h, osp.OSP_FB_RGBA32F, osp.OSP_FB_COLOR)
+    sc = O.Scene(spec)
+    ocam = O.make_camera(pose["position"], pose["direction"], pose["up"], aspect=np.float32(w) / np.float32(h))
+    oren = O.RendererParams("scivis", pixelFilter="point")
+    ofb = O.HostFrameBuffer(w, h, ("color",))
+    px, py = np.meshgrid(np.arange(4, w, 8), np.arange(4, h, 8))
+    px, py = px.ravel().astype(np.uint32), py.ravel().astype(np.uint32)
+    rays = O.camera_rays(ocam, oren, ofb, px, py)  # point filter: rays through the pixel centres
+    want = O.trace(sc, rays.copy())
+    hits = 0
+    for i in range(len(px)):
+        has, pos, inst, model, prim = osp.pick(fb, ren, cam, world, (px[i] + 0.5) / w, (py[i] + 0.5) / h)
+        hit = want["geomID"][i] != O.INVALID_ID
+        assert has == hit, (i, has, hit)
+        if hit:
+            hits += 1
+            assert prim == want["primID"][i]
+            np.testing.assert_allclose(pos, want["org"][i] + want["dir"][i] * want["t"][i], rtol=1e-5, atol=1e-5)
+            assert inst and model
+    assert 3 < hits < len(px)

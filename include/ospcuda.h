@@ -165,7 +165,7 @@ typedef struct {
   float bounds[6]; /* world-space */
 } OcInstance;
 
-enum { OC_LIGHT_AMBIENT = 0, OC_LIGHT_DISTANT = 2, OC_LIGHT_SPHERE = 4, OC_LIGHT_QUAD = 5 }; /* values of ispc::LightType */
+enum { OC_LIGHT_AMBIENT = 0, OC_LIGHT_DISTANT = 2, OC_LIGHT_SPHERE = 4, OC_LIGHT_QUAD = 5, OC_LIGHT_SPOT = 6 }; /* values of ispc::LightType */
 /* lights (reference: lights/LightShared.h:79-110, QuadLightShared.h, DirectionalLightShared.h,
  * AmbientLightShared.h) */
 typedef struct {
@@ -178,6 +178,9 @@ typedef struct {
   float cosAngle, pdf;         /* distant */
   OcVec3f intensity;           /* sphere ("sphere" = ispc::PointLight, lights/PointLightShared.h): radiant intensity (r = 0 path) */
   float radius;                /* sphere: radius; `radiance` is its surface radiance, `position` its centre */
+  /* spot (ispc::SpotLight, lights/SpotLightShared.h): position, fx/fy/fz = c0/c90/direction, radiance, intensity,
+   * cosAngle = cosAngleMax, ppdf = areaPdf (ring), radius, plus: */
+  float cosAngleScale, innerRadius;
 } OcLight;
 
 typedef struct {

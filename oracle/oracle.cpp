@@ -908,10 +908,61 @@ LightEval PointLight_eval(const OcLight &l, V3 P, V3 dir, float minDist, float m
   }
   return res;
 }
+// SpotLight: lights/SpotLight.ispc:26-86 (AngularAttenuation, Sample), :124-164 (Eval); no intensity distribution
+inline float SpotLight_attenuation(const OcLight &l, float cosAngle) { return fmaxf(0.f, fminf((cosAngle - l.cosAngle) * l.cosAngleScale, 1.f)); }
+LightSample SpotLight_sample(const OcLight &l, const DG &dg, V2 s)
+{
+  LightSample res;
+  const V3 direction = v3(l.fz);
+  res.dir = v3(l.position) - dg.P;
+  if (l.radius > 0.0f) {
+    const float r = sqrtf(lerp(s.x, sqr(l.innerRadius), sqr(l.radius))); // uniformSampleRing (math/sampling.ih:114-122)
+    const float phi = TWO_PI * s.y;
+    res.dir = xfmVector(L3{v3(l.fx), v3(l.fy), direction}, v3(r * cosf(phi), r * sinf(phi), 0.f)) + res.dir;
+  }
+  const float dist2 = dot(res.dir, res.dir);
+  const float invdist = 1.f / sqrtf(dist2);
+  res.dir = res.dir * invdist;
+  res.dist = dist2 * invdist;
+  const float cosAngle = -dot(direction, res.dir);
+  float weight = SpotLight_attenuation(l, cosAngle);
+  if (l.radius > 0.0f) {
+    res.pdf = l.ppdf * (dist2 / fabsf(cosAngle));
+    weight /= res.pdf;
+    res.weight = v3(l.radiance) * weight;
+  } else {
+    res.pdf = INF;
+    weight *= fabsf(cosAngle);
+    res.weight = v3(l.intensity) * (sqr(invdist) * weight);
+  }
+  return res;
+}
+LightEval SpotLight_eval(const OcLight &l, V3 P, V3 dir, float minDist, float maxDist)
+{
+  LightEval res = {v3(0.f), 0.f};
+  if (l.radius > 0.f) {
+    const V3 direction = v3(l.fz);
+    const float cosAngle = -dot(direction, dir);
+    if (cosAngle > l.cosAngle) {
+      const V3 vp = P - v3(l.position);
+      const float t = dot(vp, direction) * (1.f / cosAngle);
+      if ((t > minDist) & (t <= maxDist)) {
+        const V3 vd = vp + t * dir;
+        const float d2 = dot(vd, vd);
+        if (d2 < sqr(l.radius) && d2 > sqr(l.innerRadius)) {
+          res.radiance = v3(l.radiance) * SpotLight_attenuation(l, cosAngle);
+          res.pdf = l.ppdf * (sqr(t) / fabsf(cosAngle));
+        }
+      }
+    }
+  }
+  return res;
+}
 LightSample Light_sample(const OcLight &l, const DG &dg, V2 s)
 {
   LightSample r;
   if (l.type == OC_LIGHT_SPHERE) return PointLight_sample(l, dg, s);
+  if (l.type == OC_LIGHT_SPOT) return SpotLight_sample(l, dg, s);
   if (l.type == OC_LIGHT_QUAD) { // QuadLight.ispc:82-135
     if (s.x == 0.0f && s.y == 0.0f) return QuadLight_sampleArea(l, dg.P, {0.5f, 0.5f});
     const V3 pos = v3(l.position), e1 = v3(l.edge1), e2 = v3(l.edge2), nn = v3(l.nnormal);
@@ -945,6 +996,7 @@ LightEval Light_eval(const OcLight &l, V3 P, V3 Ns, V3 dir, float minDist, float
 {
   LightEval r = {v3(0.f), 0.f};
   if (l.type == OC_LIGHT_SPHERE) return PointLight_eval(l, P, dir, minDist, maxDist);
+  if (l.type == OC_LIGHT_SPOT) return SpotLight_eval(l, P, dir, minDist, maxDist);
   if (l.type == OC_LIGHT_QUAD) { // QuadLight.ispc:169-215
     const V3 nn = v3(l.nnormal), pos = v3(l.position), e1 = v3(l.edge1), e2 = v3(l.edge2);
     const float cosd = dot(nn, dir);
@@ -1894,6 +1946,39 @@ ORACLE_API void oracle_commit_sphere_light(const float color[3], float intensity
   if (radius > 0.0f) {
     const float sphereArea = 4.0f * M_PI * radius * radius; // double product, rounded once (as written in the reference)
     const V3 rad = ci / (sphereArea / 4.0f);
+    out->radiance = {rad.x, rad.y, rad.z};
+  }
+}
+
+// lights/SpotLight.cpp:22-128 (default intensityQuantity INTENSITY, no intensity distribution, no instance transform)
+ORACLE_API void oracle_commit_spot_light(const float color[3], float intensity, int visible, const float position[3], const float direction[3],
+    float openingAngle, float penumbraAngle, float radius, float innerRadius, OcLight *out)
+{
+  memset(out, 0, sizeof(*out));
+  const V3 ci = v3(color[0], color[1], color[2]) * intensity;
+  out->type = OC_LIGHT_SPOT;
+  out->isVisible = visible;
+  out->position = {position[0], position[1], position[2]};
+  radius = fmaxf(0.0f, radius);
+  innerRadius = fminf(fmaxf(innerRadius, 0.0f), 0.999f * radius);
+  const V3 dp = v3(direction[0], direction[1], direction[2]);
+  const V3 c0i = fabsf(dp.x) < fabsf(dp.y) ? v3(0.0f, dp.z, dp.y) : v3(dp.z, 0.0f, dp.x);
+  const V3 d = normalize(dp);
+  const V3 c90 = normalize(cross(c0i, d));
+  const V3 c0 = cross(d, c90);
+  out->fx = {c0.x, c0.y, c0.z}; out->fy = {c90.x, c90.y, c90.z}; out->fz = {d.x, d.y, d.z};
+  openingAngle = fminf(fmaxf(openingAngle, 0.f), 360.f);
+  penumbraAngle = fminf(fmaxf(penumbraAngle, 0.f), 0.5f * openingAngle);
+  const float deg = 1.74532925199432957692e-2f; // rkcommon deg2rad
+  out->cosAngle = cosf((0.5f * openingAngle) * deg);
+  const float cosAngleMin = cosf((0.5f * openingAngle - penumbraAngle) * deg);
+  out->cosAngleScale = 1.0f / (cosAngleMin - out->cosAngle);
+  out->radius = radius; out->innerRadius = innerRadius;
+  out->ppdf = 1.f / (PI * (sqr(radius) - sqr(innerRadius))); // uniformSampleRingPDF
+  out->intensity = {ci.x, ci.y, ci.z};
+  if (radius > 0.0f) {
+    const float ringDiskArea = M_PI * (sqr(radius) - sqr(innerRadius));
+    const V3 rad = ci / ringDiskArea;
     out->radiance = {rad.x, rad.y, rad.z};
   }
 }

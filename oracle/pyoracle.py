@@ -86,7 +86,8 @@ class Instance(C.Structure):
 class Light(C.Structure):
     _fields_ = [("type", C.c_uint32), ("isVisible", C.c_uint32), ("radiance", Vec3), ("position", Vec3), ("edge1", Vec3),
                 ("edge2", Vec3), ("nnormal", Vec3), ("ppdf", C.c_float), ("fx", Vec3), ("fy", Vec3), ("fz", Vec3),
-                ("cosAngle", C.c_float), ("pdf", C.c_float), ("intensity", Vec3), ("radius", C.c_float)]
+                ("cosAngle", C.c_float), ("pdf", C.c_float), ("intensity", Vec3), ("radius", C.c_float),
+                ("cosAngleScale", C.c_float), ("innerRadius", C.c_float)]
 
 
 class World(C.Structure):
@@ -155,6 +156,7 @@ def lib():
         F3 = C.c_float * 3
         L.oracle_commit_camera.argtypes = [F3, F3, F3, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(Camera)]
         L.oracle_commit_ortho_camera.argtypes = [F3, F3, F3, C.c_float, C.c_float, C.POINTER(Camera)]
+        L.oracle_commit_spot_light.argtypes = [F3, C.c_float, C.c_int, F3, F3, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(Light)]
         L.oracle_commit_sphere_light.argtypes = [F3, C.c_float, C.c_int, F3, C.c_float, C.POINTER(Light)]
         L.oracle_commit_light.argtypes = [C.c_int, F3, C.c_float, C.c_int, F3, F3, F3, F3, C.c_float, C.POINTER(Light)]
         L.oracle_fb_accumulate.argtypes = [C.POINTER(FrameBuffer), C.c_void_p, C.c_void_p]
@@ -322,8 +324,13 @@ class Scene:
         for ls in spec.lights:
             l = Light()
             p = ls.params
-            t = {"ambient": OC_LIGHT_AMBIENT, "distant": OC_LIGHT_DISTANT, "quad": OC_LIGHT_QUAD, "sphere": 4}[ls.type]
-            if ls.type == "sphere":
+            t = {"ambient": OC_LIGHT_AMBIENT, "distant": OC_LIGHT_DISTANT, "quad": OC_LIGHT_QUAD, "sphere": 4, "spot": 6}[ls.type]
+            if ls.type == "spot":
+                L.oracle_commit_spot_light(_f3(p.get("color", (1, 1, 1))), float(p.get("intensity", 1.0)), int(p.get("visible", True)),
+                                           _f3(p.get("position", (0, 0, 0))), _f3(p.get("direction", (0, 0, 1))),
+                                           float(p.get("openingAngle", 180.0)), float(p.get("penumbraAngle", 5.0)),
+                                           float(p.get("radius", 0.0)), float(p.get("innerRadius", 0.0)), C.byref(l))
+            elif ls.type == "sphere":
                 L.oracle_commit_sphere_light(_f3(p.get("color", (1, 1, 1))), float(p.get("intensity", 1.0)), int(p.get("visible", True)),
                                              _f3(p.get("position", (0, 0, 0))), float(p.get("radius", 0.0)), C.byref(l))
             else:

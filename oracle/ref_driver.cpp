@@ -31,6 +31,7 @@
 #include "render/materials/ThinGlassShared.h"
 #include "lights/QuadLightShared.h"
 #include "lights/PointLightShared.h"
+#include "lights/SpotLightShared.h"
 #include "lights/DirectionalLightShared.h"
 #include "lights/AmbientLightShared.h"
 #include "render/pathtracer/PathTracerShared.h"
@@ -134,7 +135,7 @@ struct Scene
   std::deque<std::vector<Material *>> materialPtrs;
   std::deque<OBJ> objs; std::deque<ThinGlass> glasses; std::vector<Material *> allMaterials;
   std::vector<Instance *> instancePtrs;
-  std::deque<QuadLight> quads; std::deque<PointLight> points; std::deque<DirectionalLight> dirs; std::deque<AmbientLight> ambients;
+  std::deque<QuadLight> quads; std::deque<PointLight> points; std::deque<SpotLight> spots; std::deque<DirectionalLight> dirs; std::deque<AmbientLight> ambients;
   std::vector<Light *> ptLights, svLights;
   Instance identityInstance; // stands in for the NULL instance of world lights: the scalar light dispatch reads
                              // self->instance->motionBlur unconditionally (lights/LightDispatch.ispc:36-60)
@@ -278,6 +279,16 @@ void buildScene(Scene &s, const OcWorld *w, const OcRenderer *ren)
       pl.radiance = v3(l.radiance); pl.intensity = v3(l.intensity); pl.radius = l.radius;
       pl.pre.position = v3(l.position);
       return &pl.super;
+    }
+    if (l.type == OC_LIGHT_SPOT) { // lights/SpotLight.cpp:22-62
+      s.spots.emplace_back();
+      SpotLight &sl = s.spots.back();
+      sl.super.isVisible = l.isVisible != 0; sl.super.instance = &s.identityInstance;
+      sl.pre.position = v3(l.position); sl.pre.c0 = v3(l.fx); sl.pre.c90 = v3(l.fy); sl.pre.direction = v3(l.fz);
+      sl.radiance = v3(l.radiance); sl.intensity = v3(l.intensity);
+      sl.cosAngleMax = l.cosAngle; sl.cosAngleScale = l.cosAngleScale;
+      sl.radius = l.radius; sl.innerRadius = l.innerRadius; sl.areaPdf = l.ppdf;
+      return &sl.super;
     }
     if (l.type == OC_LIGHT_DISTANT) {
       s.dirs.emplace_back();

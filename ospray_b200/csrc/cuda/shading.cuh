@@ -702,11 +702,69 @@ __device__ __forceinline__ LightEval PointLight_eval(const OcLight &l, vec3f P, 
   return res;
 }
 
+// SpotLight: lights/SpotLight.ispc:26-86 (AngularAttenuation, Sample), :124-164 (Eval); no intensity distribution
+__device__ __forceinline__ float SpotLight_attenuation(const OcLight &l, float cosAngle)
+{
+  return fmaxf(0.f, fminf((cosAngle - l.cosAngle) * l.cosAngleScale, 1.f));
+}
+__device__ __forceinline__ LightSample SpotLight_sample(const OcLight &l, const DifferentialGeometry &dg, vec2f s)
+{
+  LightSample res;
+  const vec3f direction = toV(l.fz);
+  res.dir = toV(l.position) - dg.P;
+  if (l.radius > 0.0f) {
+    linear3f l2w; l2w.vx = toV(l.fx); l2w.vy = toV(l.fy); l2w.vz = direction;
+    const float r = sqrtf(lerpf(s.x, l.innerRadius * l.innerRadius, l.radius * l.radius)); // uniformSampleRing
+    float sinPhi, cosPhi;
+    sincosf(OC_TWO_PI * s.y, &sinPhi, &cosPhi);
+    res.dir = l2w * make_vec3f(r * cosPhi, r * sinPhi, 0.f) + res.dir;
+  }
+  const float dist2 = dot(res.dir, res.dir);
+  const float invdist = 1.f / sqrtf(dist2);
+  res.dir = res.dir * invdist;
+  res.dist = dist2 * invdist;
+  const float cosAngle = -dot(direction, res.dir);
+  float weight = SpotLight_attenuation(l, cosAngle);
+  if (l.radius > 0.0f) {
+    res.pdf = l.ppdf * (dist2 / fabsf(cosAngle));
+    weight /= res.pdf;
+    res.weight = toV(l.radiance) * weight;
+  } else {
+    res.pdf = INFINITY;
+    weight *= fabsf(cosAngle);
+    res.weight = toV(l.intensity) * ((invdist * invdist) * weight);
+  }
+  return res;
+}
+__device__ __forceinline__ LightEval SpotLight_eval(const OcLight &l, vec3f P, vec3f dir, float minDist, float maxDist)
+{
+  LightEval res; res.radiance = make_vec3f(0.f); res.pdf = 0.f;
+  if (l.radius > 0.f) {
+    const vec3f direction = toV(l.fz);
+    const float cosAngle = -dot(direction, dir);
+    if (cosAngle > l.cosAngle) {
+      const vec3f vp = P - toV(l.position);
+      const float t = dot(vp, direction) * (1.f / cosAngle);
+      if ((t > minDist) & (t <= maxDist)) {
+        const vec3f vd = vp + t * dir;
+        const float d2 = dot(vd, vd);
+        if (d2 < l.radius * l.radius && d2 > l.innerRadius * l.innerRadius) {
+          res.radiance = toV(l.radiance) * SpotLight_attenuation(l, cosAngle);
+          res.pdf = l.ppdf * ((t * t) / fabsf(cosAngle));
+        }
+      }
+    }
+  }
+  return res;
+}
+
 __device__ __forceinline__ LightSample Light_sample(const OcLight &l, const DifferentialGeometry &dg, vec2f s)
 {
   LightSample r;
   if (l.type == OC_LIGHT_QUAD)
     return QuadLight_sample(l, dg, s);
+  if (l.type == OC_LIGHT_SPOT)
+    return SpotLight_sample(l, dg, s);
   if (l.type == OC_LIGHT_SPHERE)
     return PointLight_sample(l, dg, s);
   if (l.type == OC_LIGHT_AMBIENT) {
@@ -740,6 +798,8 @@ __device__ __forceinline__ LightEval Light_eval(const OcLight &l, vec3f P, vec3f
     return QuadLight_eval(l, P, dir, minDist, maxDist);
   if (l.type == OC_LIGHT_SPHERE)
     return PointLight_eval(l, P, dir, minDist, maxDist);
+  if (l.type == OC_LIGHT_SPOT)
+    return SpotLight_eval(l, P, dir, minDist, maxDist);
   if (l.type == OC_LIGHT_AMBIENT) {
     r.radiance = INFINITY <= maxDist ? toV(l.radiance) : make_vec3f(0.f);
     if (reduce_max(vabs(Ns)) > 0) r.pdf = fmaxf(dot(Ns, dir), 0.f) * OC_ONE_OVER_PI;

@@ -622,8 +622,50 @@ void Light::commit()
     sh.radius = radius;
     sh.intensity = toOc(radIntensity);
     sh.radiance = toOc(radiance);
+  } else if (type == "spot") { // lights/SpotLight.cpp:22-128 (no intensity distribution)
+    const vec3f position = getParam<vec3f>("position", make_vec3f(0.f));
+    const vec3f direction = getParam<vec3f>("direction", make_vec3f(0.f, 0.f, 1.f));
+    float openingAngle = getParam<float>("openingAngle", 180.f);
+    float penumbraAngle = getParam<float>("penumbraAngle", 5.f);
+    const float radius = std::max(0.0f, getParam<float>("radius", 0.f));
+    const float innerRadius = std::min(std::max(getParam<float>("innerRadius", 0.f), 0.0f), 0.999f * radius);
+    const vec3f c0i = std::abs(direction.x) < std::abs(direction.y) ? make_vec3f(0.0f, direction.z, direction.y)
+                                                                    : make_vec3f(direction.z, 0.0f, direction.x);
+    const vec3f d = normalize(direction);
+    const vec3f c90 = normalize(cross(c0i, d));
+    const vec3f c0 = cross(d, c90);
+    openingAngle = std::min(std::max(openingAngle, 0.f), 360.f);
+    penumbraAngle = std::min(std::max(penumbraAngle, 0.f), 0.5f * openingAngle);
+    const float deg = 1.74532925199432957692e-2f;
+    const float cosAngleMax = std::cos((0.5f * openingAngle) * deg);
+    const float cosAngleMin = std::cos((0.5f * openingAngle - penumbraAngle) * deg);
+    const uint32_t iq = getParam<uint32_t>("intensityQuantity", OSP_INTENSITY_QUANTITY_INTENSITY);
+    const float halfOpeningAngleRad = M_PI * (openingAngle * 0.5f) / 180.0f;
+    const float cosHalfOpeningAngle = cos(halfOpeningAngleRad);
+    const float ringDiskArea = M_PI * (radius * radius - innerRadius * innerRadius);
+    const float sphericalCapCosInt = M_PI * (1.0f - cosHalfOpeningAngle * cosHalfOpeningAngle);
+    vec3f radIntensity = make_vec3f(0.f), radiance = make_vec3f(0.f);
+    if (iq == OSP_INTENSITY_QUANTITY_INTENSITY) {
+      radIntensity = coloredIntensity;
+      if (radius > 0.0f) radiance = radIntensity / ringDiskArea;
+    } else if (iq == OSP_INTENSITY_QUANTITY_POWER) {
+      radIntensity = coloredIntensity / sphericalCapCosInt;
+      if (radius > 0.0f) radiance = coloredIntensity / (sphericalCapCosInt * ringDiskArea);
+    } else if (iq == OSP_INTENSITY_QUANTITY_RADIANCE) {
+      if (radius > 0.0f) radiance = coloredIntensity;
+    } else
+      postStatusMsg(OSP_LOG_WARNING, toString() + " unsupported 'intensityQuantity' value");
+    sh.type = OC_LIGHT_SPOT;
+    sh.position = toOc(position);
+    sh.fx = toOc(c0); sh.fy = toOc(c90); sh.fz = toOc(d);
+    sh.cosAngle = cosAngleMax;
+    sh.cosAngleScale = 1.0f / (cosAngleMin - cosAngleMax);
+    sh.radius = radius; sh.innerRadius = innerRadius;
+    sh.ppdf = 1.f / ((float)M_PI * (radius * radius - innerRadius * innerRadius));
+    sh.intensity = toOc(radIntensity);
+    sh.radiance = toOc(radiance);
   } else
-    throw std::runtime_error("cuda device: light type '" + type + "' is not supported (ambient, distant, quad, sphere)");
+    throw std::runtime_error("cuda device: light type '" + type + "' is not supported (ambient, distant, quad, sphere, spot)");
 }
 
 // ---- Group (common/Group.cpp:69-209) ------------------------------------------------------------------

@@ -77,6 +77,16 @@ def sphere_lit_boxes():
     return s
 
 
+def spot_lit_cornell():
+    """cornell box lit by a ring-shaped spot (radius / innerRadius: area sampling, visible emitter) and a point spot with a
+    penumbra (ispc::SpotLight)"""
+    s = T.cornell_box()
+    s.lights = [T.LightSpec("spot", {"position": (0.0, 0.9, 0.0), "direction": (0.1, -1.0, 0.2), "openingAngle": 100.0, "penumbraAngle": 15.0,
+                                     "radius": 0.3, "innerRadius": 0.1, "intensity": 8.0, "color": (1.0, 0.9, 0.7)}),
+                T.LightSpec("spot", {"position": (-0.8, 0.2, -0.9), "direction": (1.0, -0.3, 0.8), "openingAngle": 60.0, "intensity": 3.0})]
+    return s
+
+
 # name -> (spec builder, renderer kind, renderer params, frames[, {camera: kind, height: h}])
 CASES = {
     "cornell_pt": (T.cornell_box, "pathtracer", {"pixelSamples": 2}, 2),
@@ -95,6 +105,8 @@ CASES = {
     "spheres_ortho_scivis": (T.random_spheres, "scivis", {"shadows": True, "aoSamples": 1}, 1, {"camera": "orthographic", "height": 2.6}),
     "sphere_lights_pt": (sphere_lit_boxes, "pathtracer", {"pixelSamples": 2}, 2),
     "sphere_lights_scivis": (sphere_lit_boxes, "scivis", {"shadows": True, "visibleLights": True}, 1),
+    "spot_lights_pt": (spot_lit_cornell, "pathtracer", {"pixelSamples": 2}, 2),
+    "spot_lights_scivis": (spot_lit_cornell, "scivis", {"shadows": True, "visibleLights": True}, 1),
     "instanced_scivis": (instanced_boxes_and_spheres, "scivis", {"shadows": True}, 1),
     "instanced_pt": (instanced_boxes_and_spheres, "pathtracer", {"pixelSamples": 1}, 1),
     "mesh_ao": (lambda: T.box_mesh(5), "ao", {"aoSamples": 2}, 1),

@@ -34,7 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = "C1: ospray_testing cornell_box, pathtracer, 1024x1024, 1 spp/frame, OSP_FB_SRGBA COLOR|ACCUM|DEPTH"
-BYTES_PER_RAY = 52 + 2 * 128 + 4 * 48   # ray in 32 + hit out 20 + D=2 wide nodes + one 4-record leaf
+BYTES_PER_RAY = 532  # 32 ray in + 20 hit out + D*128 nodes + L*48 records; cornell: 34 records, L = 2 per leaf, D = ceil(log4(17)) = 3
 BYTES_PER_PIXEL = 40 + 20               # accumulate colour+depth r/w (40) + colour conversion 16 r + 4 w (20)
 
 

@@ -260,11 +260,13 @@ def run_ours(args):
         LC = C.CDLL(lib_path("libospcuda.so"))
         LC.ospcuda_profile_enable(1)
         prof_rays = np.zeros(3, np.int64)
+        prof_fused_rays = 0
         PF = 3
         for i in range(PF):
             f = step()
             f.wait()
             prof_rays += np.array(fb.ray_counts(), np.int64)
+            prof_fused_rays += fb.fused_ray_count()
             flush.zero_()
         cls_ms, cls_n = (C.c_float * 3)(), (C.c_uint32 * 3)()
         LC.ospcuda_profile_read(cls_ms, cls_n)
@@ -305,10 +307,10 @@ def run_ours(args):
         value = tot[0] / (mx[0] * 1e-3) / 1e6
         e2e = tot[1] / mx[1] / 1e6
         # roofline of the dominant kernel class: TRACE (ptTraceKernel: BVH traversal + intersection of the shadow and
-        # continuation rays). Its launches of one frame trace every ray except those of the fused tail launches;
-        # algorithmic bytes = rays x BYTES_PER_RAY. The tail's share of rays is < 2 % and is left in.
+        # continuation rays). Its launches of one frame trace every ray except those of the fused tail launch (counted apart);
+        # algorithmic bytes = TRACE rays x BYTES_PER_RAY.
         trace_ms, shade_ms, fused_ms = cls_ms
-        rays_frame = prof_rays.sum() / PF
+        rays_frame = (prof_rays.sum() - prof_fused_rays) / PF  # rays traced by the TRACE launches (the fused tail kernel counts its own)
         achieved = rays_frame * BYTES_PER_RAY / (trace_ms * 1e-3) / 1e9
         line = {"metric": "Mrays/s", "value": round(float(value), 2), "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": round(float(mx[0] / K), 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -270,7 +270,8 @@ typedef struct {
   uint32_t *primID, *objID, *instID;
   /* image-tile partition across ranks (reference: MultiDevice.cpp:403-416: tile % N == rank) */
   uint32_t numRanks, rank;
-  /* per-frame ray statistics: [0] primary, [1] continuation, [2] shadow/occlusion segments */
+  /* per-frame ray statistics: [0] primary, [1] continuation, [2] shadow/occlusion segments; [3] = how many of those the
+   * pathtracer's fused tail kernel traced (bench.py: rays of the TRACE launches = total - [3]) */
   unsigned long long *rayCounters;
 } OcFrameBuffer;
 

@@ -14,6 +14,8 @@ OSPRAY_INTERFACE void *ospcudaFrameBufferDevicePointer(OSPFrameBuffer, OSPFrameB
 /* rays handed to traversal during the last finished frame: [0] primary, [1] continuation /
  * transparency, [2] shadow + occlusion segments */
 OSPRAY_INTERFACE void ospcudaGetRayCounts(OSPFrameBuffer, uint64_t counts[3]);
+/* of those, the rays the pathtracer's fused tail kernel traced in the last finished frame */
+OSPRAY_INTERFACE uint64_t ospcudaGetFusedRayCount(OSPFrameBuffer);
 /* milliseconds spent in the last BVH build of a group */
 OSPRAY_INTERFACE float ospcudaGetGroupBuildTime(OSPGroup);
 /* number of kernels launched so far by this process through libospcuda */

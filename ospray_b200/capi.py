@@ -88,6 +88,8 @@ def ext():
         E = C.CDLL(lib_path("libospray_module_cuda.so"), mode=C.RTLD_GLOBAL)
         E.ospcudaFrameBufferDevicePointer.restype = C.c_void_p
         E.ospcudaFrameBufferDevicePointer.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]
+        E.ospcudaGetFusedRayCount.restype = C.c_uint64
+        E.ospcudaGetFusedRayCount.argtypes = [C.c_void_p]
         E.ospcudaGetRayCounts.restype = None
         E.ospcudaGetRayCounts.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         E.ospcudaGetGroupBuildTime.restype = C.c_float
@@ -503,6 +505,10 @@ class FrameBuffer(Object):
         bpp = C.c_uint64(0)
         p = ext().ospcudaFrameBufferDevicePointer(self.h, channel, C.byref(bpp))
         return p, int(bpp.value)
+
+    def fused_ray_count(self):
+        """rays of the last frame traced inside the pathtracer's fused tail kernel (subset of ray_counts())"""
+        return int(ext().ospcudaGetFusedRayCount(self.h))
 
     def ray_counts(self):
         c = (C.c_uint64 * 3)()

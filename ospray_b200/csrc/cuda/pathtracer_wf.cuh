@@ -379,6 +379,12 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK) ptFusedKernel(const __grid_con
     if (alive) alive = ptTraceStep<false>(k, p, stack, cnt) && ptShadeStep(k, p);
   }
   ptCountRays(k.a.fb, cnt.primary, cnt.secondary, cnt.shadow);
+  if (k.a.fb.rayCounters) { // [3]: rays traced by this kernel
+    uint32_t t = cnt.primary + cnt.secondary + cnt.shadow;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0 && t) atomicAdd(k.a.fb.rayCounters + 3, (unsigned long long)t);
+  }
 }
 
 // SHADE step of one path; returns true when the path goes on to the next TRACE step (alive, or done with

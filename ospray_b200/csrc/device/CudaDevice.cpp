@@ -250,6 +250,7 @@ void *ospcudaFrameBufferDevicePointer(OSPFrameBuffer fb, OSPFrameBufferChannel c
   if (bpp) *bpp = f->bytesPerPixel(ch);
   return f->devicePointer(ch);
 }
+uint64_t ospcudaGetFusedRayCount(OSPFrameBuffer fb) { return ((ospray::cuda::FrameBuffer *)fb)->rayCounts[3]; }
 void ospcudaGetRayCounts(OSPFrameBuffer fb, uint64_t counts[3])
 {
   cuda::FrameBuffer *f = (cuda::FrameBuffer *)fb;

@@ -276,7 +276,7 @@ struct FrameBuffer : public ManagedObject
   uint32_t channels;
   bool doAccum, hasVariance;
   OcFrameBuffer sh{};
-  unsigned long long rayCounts[3] = {0, 0, 0}; // last finished frame (host)
+  unsigned long long rayCounts[4] = {0, 0, 0, 0}; // last finished frame (host); [3]: traced by the PT fused tail kernel
   float errorThreshold = 0.f;
 
  private:

@@ -270,6 +270,11 @@ typedef struct {
   uint32_t *primID, *objID, *instID;
   /* image-tile partition across ranks (reference: MultiDevice.cpp:403-416: tile % N == rank) */
   uint32_t numRanks, rank;
+  /* adaptive accumulation (reference: LocalFrameBuffer::getRenderTaskIDs, fb/LocalFB.cpp:238-261): when taskError is
+   * not NULL only the 8x8 render tasks with taskError[task] > errorThreshold are rendered this frame; task =
+   * (y/8) * ceil(sizeX/8) + x/8; the errors are those of the Variance frame op (ospcuda_fb_variance) */
+  const float *taskError;
+  float errorThreshold;
   /* per-frame ray statistics: [0] primary, [1] continuation, [2] shadow/occlusion segments; [3] = how many of those the
    * pathtracer's fused tail kernel traced (bench.py: rays of the TRACE launches = total - [3]) */
   unsigned long long *rayCounters;

@@ -1736,6 +1736,8 @@ void renderRows(const OcWorld *w, const OcCamera *cam, const OcRenderer *ren, co
       // image-tile partition of the multidevice path (MultiDevice.cpp:403-416: tile % N == rank)
       const uint32_t tileID = (uint32_t)(y / 64) * tilesX + (uint32_t)(x / 64);
       if (tileID % numRanks != rank) continue;
+      // adaptive accumulation: only render tasks above the error threshold (LocalFB.cpp:238-261)
+      if (fb->taskError && !(fb->taskError[(size_t)(y / 8) * ((fb->sizeX + 7) / 8) + (x / 8)] > fb->errorThreshold)) continue;
       const ScreenSample ss = ren->type == OC_RENDERER_PATHTRACER ? PathTracer_renderPixel(c, x, y) : defaultRenderPixel(c, x, y);
       accumulateSample(*fb, x, y, ss);
     }

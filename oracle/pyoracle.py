@@ -122,7 +122,8 @@ class FrameBuffer(C.Structure):
                 ("colorFormat", C.c_uint32), ("color", C.c_void_p), ("variance", C.c_void_p), ("depth", C.c_void_p),
                 ("normal", C.c_void_p), ("firstNormal", C.c_void_p), ("albedo", C.c_void_p), ("position", C.c_void_p),
                 ("primID", C.c_void_p), ("objID", C.c_void_p), ("instID", C.c_void_p), ("numRanks", C.c_uint32),
-                ("rank", C.c_uint32), ("rayCounters", C.c_void_p)]
+                ("rank", C.c_uint32), ("taskError", C.c_void_p), ("errorThreshold", C.c_float),
+                ("rayCounters", C.c_void_p)]
 
 
 class ToneMapper(C.Structure):
@@ -522,6 +523,13 @@ class HostFrameBuffer:
         self.counters = np.zeros(3, np.uint64)
         fb.rayCounters = self.counters.ctypes.data
         self.sh = fb
+
+    def set_adaptive(self, task_error, threshold):
+        """LocalFrameBuffer::getRenderTaskIDs (fb/LocalFB.cpp:238-261): render only the 8x8 tasks whose error is above the
+        threshold; task_error None switches it off"""
+        self.task_error = None if task_error is None else np.ascontiguousarray(task_error, np.float32)
+        self.sh.taskError = None if task_error is None else self.task_error.ctypes.data
+        self.sh.errorThreshold = float(threshold)
 
     def begin_frame(self):
         """FrameBuffer::beginFrame (fb/FrameBuffer.cpp:115-137); variance accumulates on odd frames"""

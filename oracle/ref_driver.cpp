@@ -414,7 +414,10 @@ REF_API int ospref_render_frame(const OcWorld *w, const OcCamera *cam, const OcR
   for (int ty = 0; ty < lfb.numRenderTasks.y; ty++)
     for (int tx = 0; tx < lfb.numRenderTasks.x; tx++) {
       const uint32_t tile = (uint32_t)((ty / 8) * tilesX + tx / 8);
-      if (tile % numRanks == fb->rank) taskIDs.push_back((uint32_t)(ty * lfb.numRenderTasks.x + tx));
+      const uint32_t task = (uint32_t)(ty * lfb.numRenderTasks.x + tx);
+      // LocalFrameBuffer::getRenderTaskIDs (fb/LocalFB.cpp:238-261): adaptive selection of the active tasks
+      if (fb->taskError && !(fb->taskError[task] > fb->errorThreshold)) continue;
+      if (tile % numRanks == fb->rank) taskIDs.push_back(task);
     }
 
   sycl::queue q; q.numThreads = numThreads > 0 ? numThreads : (int)std::max(1u, std::thread::hardware_concurrency());

@@ -240,6 +240,8 @@ __device__ __forceinline__ bool ptTraceStep(const PtArgs &k, uint32_t p, Stack s
     uint32_t ix, iy;
     ptSlotToPixel(k, p, ix, iy);
     if (ix >= (uint32_t)fb.sizeX || iy >= (uint32_t)fb.sizeY) return false;
+    // adaptive accumulation: pixels of a converged render task start no path (LocalFB.cpp:245-257)
+    if (fb.taskError && !(fb.taskError[(iy >> 3) * (((uint32_t)fb.sizeX + 7u) >> 3) + (ix >> 3)] > fb.errorThreshold)) return false;
     // PathTracer_renderPixel, one sample (PathTracer.ispc:149-193)
     uint32_t seed, sampleOffs, sampleOffsLight, bits, bitsLight;
     ptSamplerParams(k, ix, iy, seed, sampleOffs, sampleOffsLight, bits, bitsLight);

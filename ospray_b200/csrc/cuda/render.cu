@@ -609,7 +609,9 @@ __global__ void __launch_bounds__(64, OC_RENDER_MIN_BLOCKS) renderFrameKernel(co
   stack.base = s_stack + threadIdx.x;
   stack.stride = 64;
   Ctx c(a.world, a.ren, a.cam, a.fb, stack);
-  if (x < (uint32_t)a.fb.sizeX && y < (uint32_t)a.fb.sizeY) {
+  // adaptive accumulation: a converged render task is skipped as a whole (one CTA = one task; LocalFB.cpp:245-257)
+  const bool active = !a.fb.taskError || a.fb.taskError[(y >> 3) * (((uint32_t)a.fb.sizeX + 7u) >> 3) + (x >> 3)] > a.fb.errorThreshold;
+  if (active && x < (uint32_t)a.fb.sizeX && y < (uint32_t)a.fb.sizeY) {
     ScreenSample ss;
     defaultRenderPixel<RENDERER>(c, x, y, ss);
     accumulateSample(a.fb, x, y, ss);

@@ -1,4 +1,5 @@
 // CudaDevice implementation + module entry point. See CudaDevice.h for the reference map.
+#include <algorithm>
 #include "CudaDevice.h"
 #include <cstdlib>
 #include "ospray_cuda_ext.h"
@@ -143,6 +144,13 @@ OSPFuture CudaDevice::renderFrame(OSPFrameBuffer _fb, OSPRenderer _r, OSPCamera 
   try {
     fb->beginFrame();
     fb->errorThreshold = r->errorThreshold;
+    // LocalFrameBuffer::getRenderTaskIDs (fb/LocalFB.cpp:238-261): once minimumAdaptiveFrames (FrameBuffer.h:183-186) have
+    // been accumulated, only the render tasks whose variance estimate is above the renderer's varianceThreshold go on
+    fb->sh.taskError = nullptr;
+    fb->sh.errorThreshold = r->errorThreshold;
+    if (r->errorThreshold > 0.f && fb->hasVariance && fb->taskErrBuf
+        && fb->sh.frameID >= (int32_t)std::max(2u, 16u / (uint32_t)std::max(1, r->sh.spp)))
+      fb->sh.taskError = fb->taskErrBuf->as<float>();
     const OcWorld *dw = w->prepareFrame();
     checkCuda(ospcuda_event_record(f->evStart), "event record");
     const bool finished = fb->sh.targetFrames && fb->doAccum && fb->sh.frameID >= fb->sh.targetFrames; // accumulationFinished()

@@ -116,3 +116,31 @@ def test_converged_1024spp_pathtracer_rmse(osp):
     rmse = np.sqrt(((got - want) ** 2).mean())
     assert rmse <= 2e-3 * mean, (rmse, mean, backend)
     assert np.abs(got - want).max() <= 2e-2 * mean
+
+
+def test_adaptive_variance_termination(osp):
+    """renderer `varianceThreshold` + OSP_FB_VARIANCE: after minimumAdaptiveFrames (FrameBuffer.h:183-186: max(2, 16/spp))
+    only render tasks whose variance estimate is above the threshold are rendered (LocalFB.cpp:238-261). With an
+    unreachable threshold every task counts as converged: no ray is traced any more and the image stops changing; with
+    threshold 0 rendering goes on; ospGetVariance reports the estimate."""
+    w = h = 128
+    world, keep = T.to_ospray(T.cornell_box())
+    cam, _ = T.make_camera(world, w, h)
+    ch = osp.OSP_FB_COLOR | osp.OSP_FB_ACCUM | osp.OSP_FB_VARIANCE
+    for threshold, expect_stop in ((1e9, True), (0.0, False)):
+        ren = T.make_renderer("pathtracer", pixelSamples=8, varianceThreshold=float(threshold))
+        fb = osp.FrameBuffer(w, h, osp.OSP_FB_RGBA32F, ch)
+        for _ in range(2):                                   # frames 0 and 1: below minimumAdaptiveFrames(8) = 2
+            fb.render_frame(ren, cam, world).wait()
+            assert fb.ray_counts()[0] == w * h * 8
+        v = fb.variance()
+        assert np.isfinite(v) and v > 0
+        before = fb.map(osp.OSP_FB_COLOR)
+        fb.render_frame(ren, cam, world).wait()              # frame 2: adaptive selection is on
+        after = fb.map(osp.OSP_FB_COLOR)
+        if expect_stop:
+            assert sum(fb.ray_counts()) == 0
+            np.testing.assert_array_equal(before, after)
+        else:
+            assert fb.ray_counts()[0] == w * h * 8
+            assert (before != after).any()

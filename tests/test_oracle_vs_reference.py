@@ -95,3 +95,30 @@ def test_reference_tile_partition_is_exact():
         p = scenes.oracle_render("cornell_pt", 128, 64, num_ranks=2, rank=r, backend="ref")
         O.lib().oracle_fb_gather_tiles(comp.ctypes.data, p.buf["color"].ctypes.data, 128, 64, 16, 2, r)
     np.testing.assert_array_equal(comp, full.buf["color"])
+
+
+@needs_ref
+def test_adaptive_task_selection_matches_reference():
+    """LocalFrameBuffer::getRenderTaskIDs (fb/LocalFB.cpp:238-261): with a task-error map only the 8x8 render tasks above
+    the threshold are rendered; the skipped tasks keep their accumulated pixels. Oracle and reference kernels agree bit for
+    bit, and the inactive tasks are untouched by the second frame."""
+    def run(backend):
+        from ospray_b200 import testing as T
+        sc = O.Scene(T.cornell_box())
+        pose = T.arcball_camera(*sc.bounds)
+        cam = O.make_camera(pose["position"], pose["direction"], pose["up"], aspect=np.float32(64) / np.float32(48))
+        ren = O.RendererParams("pathtracer", pixelSamples=1)
+        fb = O.HostFrameBuffer(64, 48, ("color", "depth"))
+        O.render_frame(sc, cam, ren, fb, backend=backend)
+        first = fb.buf["color"].copy()
+        err = np.linspace(0.0, 1.0, 8 * 6, dtype=np.float32)  # task errors 0 .. 1 over the 8 x 6 tasks
+        fb.set_adaptive(err, 0.5)
+        O.render_frame(sc, cam, ren, fb, backend=backend)
+        return first, fb.buf["color"].copy(), err, int(fb.counters.sum())
+    f_o, s_o, err, rays_o = run("oracle")
+    f_r, s_r, _, rays_r = run("ref")
+    np.testing.assert_array_equal(s_o, s_r)
+    assert rays_o == rays_r
+    active = (err > 0.5).reshape(6, 8).repeat(8, axis=0).repeat(8, axis=1)
+    np.testing.assert_array_equal(s_o[~active], f_o[~active])          # converged tasks: untouched
+    assert (s_o[active] != f_o[active]).any(axis=-1).mean() > 0.5       # active tasks: accumulated a second sample

@@ -55,7 +55,10 @@ typedef struct {
   uint32_t pad;
 } OcData1D;
 
-enum { OC_GEOM_TRIANGLES = 0, OC_GEOM_QUADS = 1, OC_GEOM_SPHERES = 2, OC_GEOM_BOXES = 3 };
+enum { OC_GEOM_TRIANGLES = 0, OC_GEOM_QUADS = 1, OC_GEOM_SPHERES = 2, OC_GEOM_BOXES = 3, OC_GEOM_CURVES = 4 };
+/* round curves are tessellated into OC_CURVE_SUBDIV capsules per segment at BVH build */
+#define OC_CURVE_SUBDIV 8u
+enum { OC_CURVE_BASIS_LINEAR = 0, OC_CURVE_BASIS_BEZIER = 1, OC_CURVE_BASIS_BSPLINE = 2, OC_CURVE_BASIS_HERMITE = 3, OC_CURVE_BASIS_CATMULL_ROM = 4 }; /* = OSPCurveBasis */
 enum { OC_GEOMFLAG_NORMAL_FACEVARYING = 1, OC_GEOMFLAG_COLOR_FACEVARYING = 2,
        OC_GEOMFLAG_TEXCOORD_FACEVARYING = 4, OC_GEOMFLAG_HAS_ALPHA = 8, OC_GEOMFLAG_COLOR_IS_VEC4 = 16,
        OC_GEOMFLAG_ALPHA_ALL_ONE = 32 /* every vec4f vertex colour has w == 1.0f (checked on the host at commit) */ };
@@ -65,13 +68,13 @@ typedef struct {
   uint32_t type;
   uint32_t numPrims;
   uint32_t flags;
-  uint32_t pad;
-  OcData1D index;    /* vec3ui (triangles) or vec4ui (quads) */
+  uint32_t curveBasis; /* curves: OC_CURVE_BASIS_* (linear and Catmull-Rom are implemented) */
+  OcData1D index;    /* vec3ui (triangles), vec4ui (quads) or uint32 first control point per segment (curves) */
   OcData1D vertex;   /* vec3f */
   OcData1D normal;   /* vec3f, optional */
   OcData1D color;    /* vec3f or vec4f, optional */
   OcData1D texcoord; /* vec2f, optional */
-  OcData1D sphere;   /* vec4f (x,y,z,r) interleaved at commit (Spheres.cpp:58-96) */
+  OcData1D sphere;   /* vec4f (x,y,z,r) interleaved at commit (Spheres.cpp:58-96); curves: vertex.position_radius */
   OcData1D box;      /* box3f (6 floats) */
 } OcGeometry;
 
@@ -113,7 +116,8 @@ typedef struct {
   uint32_t pad[4];
 } OcNode4;
 
-enum { OC_PRIM_TRI = 0, OC_PRIM_TRI_QUAD2ND = 1, OC_PRIM_SPHERE = 2, OC_PRIM_BOX = 3, OC_PRIM_INSTANCE = 4 };
+enum { OC_PRIM_TRI = 0, OC_PRIM_TRI_QUAD2ND = 1, OC_PRIM_SPHERE = 2, OC_PRIM_BOX = 3, OC_PRIM_INSTANCE = 4,
+       OC_PRIM_CAPSULE = 5 /* one piece of a round curve: (p0|primID, p1|geomID, (radius, u0, du, kind)) */ };
 
 typedef struct {
   const OcNode4 *nodes;

@@ -1,0 +1,66 @@
+// curve_capsule.h -- the round-curve stand-in shared by oracle.cpp and ref_embree_stub.cpp.  TEST INFRASTRUCTURE ONLY.
+//
+// Embree's round-curve sweep intersector (kernels/geometry/curve_intersector_sweep.h) is not vendored. The restatement
+// used on every side (CUDA path, oracle, Embree stand-in of oracle/_ref) is a tessellation: each curve segment becomes
+// CURVE_SUBDIV capsules whose end points are the curve basis (geometry/Curves.ispc:40-75 polynomials) at k/8 and whose
+// radius is the mean of the two end radii; front hits only, u = (k + s)/8, Ng = P - axis(s). Plain C float operations,
+// compiled with -ffp-contract=off: the CUDA side spells the same operations with __f*_rn intrinsics.
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+namespace curvecap {
+const uint32_t CURVE_SUBDIV = 8;
+struct F3 { float x, y, z; };
+struct F4 { float x, y, z, w; };
+inline float dot3(F3 a, F3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+inline F3 sub3(F3 a, F3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline F3 madd3(F3 a, float s, F3 b) { return {a.x + s * b.x, a.y + s * b.y, a.z + s * b.z}; }
+
+// basis == 0: linear over (v0, v1); else Catmull-Rom over (v0..v3), the segment spanning v1 -> v2
+inline F4 curveEval(int basis, F4 v0, F4 v1, F4 v2, F4 v3, float t)
+{
+  const float s = 1.0f - t;
+  if (basis == 0) return {s * v0.x + t * v1.x, s * v0.y + t * v1.y, s * v0.z + t * v1.z, s * v0.w + t * v1.w};
+  const float s2 = s * s, t2 = t * t, s2t = s2 * t, t2s = t2 * s;
+  const float b0 = -s2t, b1 = 2.0f + t2 * (3.0f * t - 5.0f), b2 = 2.0f + s2 * (3.0f * s - 5.0f), b3 = -t2s;
+  auto comb = [&](float a, float b, float c, float d) { return 0.5f * (((b0 * a + b1 * b) + b2 * c) + b3 * d); };
+  return {comb(v0.x, v1.x, v2.x, v3.x), comb(v0.y, v1.y, v2.y, v3.y), comb(v0.z, v1.z, v2.z, v3.z), comb(v0.w, v1.w, v2.w, v3.w)};
+}
+
+inline bool intersectCapsule(F3 org, F3 d, float t0, float t1, F3 pa, F3 pb, float r, float &t, float &sOut, F3 &Ng)
+{
+  const F3 ba = sub3(pb, pa), oa = sub3(org, pa);
+  const float baba = dot3(ba, ba), bard = dot3(ba, d), baoa = dot3(ba, oa), rdoa = dot3(d, oa), oaoa = dot3(oa, oa), dd = dot3(d, d);
+  const float rr = r * r;
+  const float a = baba * dd - bard * bard;
+  float y;
+  if (a > 0.f) {
+    const float b = baba * rdoa - baoa * bard;
+    const float c = (baba * oaoa - baoa * baoa) - rr * baba;
+    const float h = b * b - a * c;
+    if (!(h >= 0.f)) return false;
+    const float tb = (-b - sqrtf(h)) / a;
+    y = baoa + tb * bard;
+    if (y > 0.f && y < baba) {
+      if (!(tb > t0 && tb <= t1)) return false;
+      const float s = y / baba;
+      t = tb; sOut = s;
+      Ng = madd3(madd3(oa, tb, d), -s, ba);
+      return true;
+    }
+  } else
+    y = bard > 0.f ? -1.f : baba + 1.f;
+  const bool first = y <= 0.f;
+  const F3 oc = first ? oa : sub3(org, pb);
+  const float b2 = dot3(d, oc);
+  const float c2 = dot3(oc, oc) - rr;
+  const float h2 = b2 * b2 - dd * c2;
+  if (!(h2 > 0.f)) return false;
+  const float tc = (-b2 - sqrtf(h2)) / dd;
+  if (!(tc > t0 && tc <= t1)) return false;
+  t = tc; sOut = first ? 0.f : 1.f;
+  Ng = madd3(oc, tc, d);
+  return true;
+}
+} // namespace curvecap

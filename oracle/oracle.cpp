@@ -38,6 +38,7 @@
 #include <vector>
 #include "../include/ospcuda.h"
 #include "tables.inc"
+#include "curve_capsule.h"
 
 #define ORACLE_API extern "C" __attribute__((visibility("default")))
 
@@ -401,6 +402,28 @@ bool traceGroup(const OcGroup *g, Ray &ray, uint32_t instID, bool occl)
           h = true; ray.t = t;
           if (!occl) { ray.u = ray.v = 0.f; ray.Ng = Ng; ray.primID = p; ray.geomID = m; ray.instID = instID; }
         }
+      } else if (geo->type == OC_GEOM_CURVES) { // round curve = 8 capsules per segment (curve_capsule.h)
+        const uint32_t first = get1ui(geo->index, p, 0);
+        curvecap::F4 cv[4];
+        for (int k = 0; k < 4; k++) {
+          const bool need = k < 2 || geo->curveBasis != OC_CURVE_BASIS_LINEAR;
+          const V4 c = need ? get4f(geo->sphere, first + k) : V4{0, 0, 0, 0};
+          cv[k] = {c.x, c.y, c.z, c.w};
+        }
+        const int basis = geo->curveBasis == OC_CURVE_BASIS_LINEAR ? 0 : 1;
+        for (uint32_t k = 0; k < curvecap::CURVE_SUBDIV; k++) {
+          const float u0 = (float)k * (1.f / curvecap::CURVE_SUBDIV), u1 = (float)(k + 1) * (1.f / curvecap::CURVE_SUBDIV);
+          const curvecap::F4 a4 = curvecap::curveEval(basis, cv[0], cv[1], cv[2], cv[3], u0), b4 = curvecap::curveEval(basis, cv[0], cv[1], cv[2], cv[3], u1);
+          const float rad = fmaxf(0.f, 0.5f * (a4.w + b4.w));
+          float t, sPar; curvecap::F3 N;
+          if (curvecap::intersectCapsule({ray.org.x, ray.org.y, ray.org.z}, {ray.dir.x, ray.dir.y, ray.dir.z}, ray.t0, ray.t, {a4.x, a4.y, a4.z},
+                  {b4.x, b4.y, b4.z}, rad, t, sPar, N)) {
+            h = true; ray.t = t;
+            if (occl) break;
+            ray.u = u0 + (1.f / curvecap::CURVE_SUBDIV) * sPar; ray.v = 0.f; ray.Ng = {N.x, N.y, N.z};
+            ray.primID = p; ray.geomID = m; ray.instID = instID;
+          }
+        }
       } else {
         const float *b = (const float *)(geo->box.addr + (int64_t)p * geo->box.byteStride);
         float t; V3 Ng;
@@ -494,6 +517,19 @@ void geometryPostIntersect(const OcGeometry *g, DG &dg, const Ray &ray, uint32_t
     if (flags & DG_TANGENTS) dg.dPds = vb - va;
   } else if (g->type == OC_GEOM_SPHERES) {
     dg.epsilon = get4f(g->sphere, ray.primID).w * ULP_EPS;
+  } else if (g->type == OC_GEOM_CURVES) { // Curves_postIntersect + interpolate<vec4f> (geometry/Curves.ispc:17-94)
+    if ((flags & DG_COLOR) && g->color.addr) {
+      const uint32_t index = get1ui(g->index, ray.primID, 0);
+      const float t = ray.u;
+      const V4 v0 = get4f(g->color, index + 0), v1 = get4f(g->color, index + 1);
+      if (g->curveBasis == OC_CURVE_BASIS_LINEAR) dg.color = lerp(t, v0, v1);
+      else {
+        const V4 v2 = get4f(g->color, index + 2), v3 = get4f(g->color, index + 3);
+        const float s = 1.0f - t, s2 = s * s, t2 = t * t, s2t = s2 * t, t2s = t2 * s;
+        const float b0 = -s2t, b1 = 2.0f + t2 * (3.0f * t - 5.0f), b2 = 2.0f + s2 * (3.0f * s - 5.0f), b3 = -t2s;
+        dg.color = 0.5f * (((b0 * v0 + b1 * v1) + b2 * v2) + b3 * v3);
+      }
+    }
   }
 }
 

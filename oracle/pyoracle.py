@@ -41,7 +41,7 @@ class Data1D(C.Structure):
 
 
 class Geometry(C.Structure):
-    _fields_ = [("type", C.c_uint32), ("numPrims", C.c_uint32), ("flags", C.c_uint32), ("pad", C.c_uint32),
+    _fields_ = [("type", C.c_uint32), ("numPrims", C.c_uint32), ("flags", C.c_uint32), ("curveBasis", C.c_uint32),
                 ("index", Data1D), ("vertex", Data1D), ("normal", Data1D), ("color", Data1D), ("texcoord", Data1D),
                 ("sphere", Data1D), ("box", Data1D)]
 
@@ -197,6 +197,32 @@ def ref_lib():
         L.ospref_ray_counters.argtypes = [C.c_void_p, C.c_int]
         _ref = L
     return _ref
+
+
+def curve_eval(basis, v, t):
+    """float32, operation by operation as oracle/curve_capsule.h curveEval: v = (4, n, 4) control points, t scalar"""
+    f = np.float32
+    t = f(t)
+    s = f(1.0) - t
+    if basis == 0:
+        return s * v[0] + t * v[1]
+    s2, t2 = s * s, t * t
+    s2t, t2s = s2 * t, t2 * s
+    b0, b1, b2, b3 = -s2t, f(2.0) + t2 * (f(3.0) * t - f(5.0)), f(2.0) + s2 * (f(3.0) * s - f(5.0)), -t2s
+    return f(0.5) * (((b0 * v[0] + b1 * v[1]) + b2 * v[2]) + b3 * v[3])
+
+
+def curve_bounds(pos_radius, index, basis, subdiv=8):
+    """bounds of the capsule tessellation (end points -+ mean end radius), as the BVH builder reports them"""
+    pr = np.asarray(pos_radius, np.float32)
+    v = np.stack([pr[index + k] for k in range(4 if basis != 0 else 2)] + ([pr[index]] * 2 if basis == 0 else []))
+    lo, hi = np.full(3, np.inf, np.float32), np.full(3, -np.inf, np.float32)
+    for k in range(subdiv):
+        a, b = curve_eval(basis, v, np.float32(k) * np.float32(1.0 / subdiv)), curve_eval(basis, v, np.float32(k + 1) * np.float32(1.0 / subdiv))
+        rad = np.maximum(np.float32(0), np.float32(0.5) * (a[:, 3] + b[:, 3]))[:, None]
+        lo = np.minimum(lo, (np.minimum(a[:, :3], b[:, :3]) - rad).min(axis=0))
+        hi = np.maximum(hi, (np.maximum(a[:, :3], b[:, :3]) + rad).max(axis=0))
+    return lo.astype(np.float32), hi.astype(np.float32)
 
 
 def _f3(v):
@@ -426,6 +452,16 @@ class Scene:
             g.type, g.numPrims = OC_GEOM_SPHERES, len(pos)
             g.sphere = _data1d(inter, self.keep)
             return g, (pos - rad[:, None]).min(axis=0), (pos + rad[:, None]).max(axis=0)
+        if gs.type == "curve":
+            pr = np.ascontiguousarray(gs.curve_vertex, np.float32)
+            idx = np.ascontiguousarray(gs.curve_index, np.uint32).reshape(-1, 1)
+            g.type, g.numPrims, g.curveBasis = 4, len(idx), {"linear": 0, "catmull-rom": 4}[gs.curve_basis]
+            g.sphere, g.index = _data1d(pr, self.keep), _data1d(idx, self.keep)
+            if gs.vertex_color is not None:
+                g.color = _data1d(np.asarray(gs.vertex_color, np.float32), self.keep)
+                g.flags = OC_GEOMFLAG_HAS_ALPHA | OC_GEOMFLAG_COLOR_VEC4
+            lo, hi = curve_bounds(pr, idx.ravel(), g.curveBasis)
+            return g, lo, hi
         b = np.asarray(gs.boxes, np.float32)
         g.type, g.numPrims = OC_GEOM_BOXES, len(b)
         g.box = _data1d(b, self.keep)

@@ -26,6 +26,7 @@
 #include "geometry/MeshShared.h"
 #include "geometry/SpheresShared.h"
 #include "geometry/BoxesShared.h"
+#include "geometry/CurvesShared.h"
 #include "render/MaterialShared.h"
 #include "render/materials/OBJShared.h"
 #include "render/materials/ThinGlassShared.h"
@@ -129,7 +130,7 @@ VolumetricModel *refMakeVolumetricModel(std::deque<Volume> &vols, std::deque<Vol
 // Everything one frame needs, with stable addresses (deques never move their elements)
 struct Scene
 {
-  std::deque<Mesh> meshes; std::deque<Spheres> spheres; std::deque<Boxes> boxes;
+  std::deque<Mesh> meshes; std::deque<Spheres> spheres; std::deque<Boxes> boxes; std::deque<Curves> curves;
   std::deque<GeometricModel> models; std::deque<Group> groups; std::deque<Instance> instances;
   std::deque<std::vector<GeometricModel *>> modelPtrs;
   std::deque<std::vector<Material *>> materialPtrs;
@@ -179,6 +180,18 @@ Geometry *makeGeometry(Scene &s, const OcGeometry *g)
     Data1D_Constructor(&sp.normalData);
     sp.sphereType = OSP_SPHERE;
     return &sp.super;
+  }
+  if (g->type == OC_GEOM_CURVES) {
+    // geometry/Curves.cpp:84-194 (round curves; the Embree geometry handle is not used by Curves_postIntersect)
+    s.curves.emplace_back();
+    Curves &c = s.curves.back();
+    c.super.numPrimitives = g->numPrims;
+    c.curveType = OSP_ROUND; c.curveBasis = (OSPCurveBasis)g->curveBasis;
+    c.index = d1(g->index); c.color = d1(g->color); c.texcoord = d1(g->texcoord);
+    c.flagMask = -1;
+    if (!g->color.addr) c.flagMask &= int64(~DG_COLOR);
+    if (!g->texcoord.addr) c.flagMask &= int64(~DG_TEXCOORD);
+    return &c.super;
   }
   // geometry/Boxes.cpp:33-42
   s.boxes.emplace_back();

@@ -17,6 +17,7 @@
 #include <mutex>
 #include <vector>
 #include "ref_embree_stub.h"
+#include "curve_capsule.h"
 
 namespace {
 
@@ -135,6 +136,27 @@ bool traceGroup(const RTCSceneTy *s, uint32_t instIdx, RTCRayHit &rh, const Call
           h = true; rh.ray.tfar = t;
           if (!occl) {
             rh.hit.u = rh.hit.v = 0.f; rh.hit.Ng_x = Ng.x; rh.hit.Ng_y = Ng.y; rh.hit.Ng_z = Ng.z;
+            rh.hit.primID = p; rh.hit.geomID = m; rh.hit.instID[0] = instIdx;
+          }
+        }
+      } else if (geo->type == OC_GEOM_CURVES) { // round curve = 8 capsules per segment (curve_capsule.h)
+        const uint32_t first = get1ui(geo->index, p, 0);
+        curvecap::F4 cv[4] = {};
+        for (int k = 0; k < (geo->curveBasis == OC_CURVE_BASIS_LINEAR ? 2 : 4); k++) {
+          const float *c = (const float *)(geo->sphere.addr + (int64_t)(first + k) * geo->sphere.byteStride);
+          cv[k] = {c[0], c[1], c[2], c[3]};
+        }
+        const int basis = geo->curveBasis == OC_CURVE_BASIS_LINEAR ? 0 : 1;
+        for (uint32_t k = 0; k < curvecap::CURVE_SUBDIV; k++) {
+          const float u0 = (float)k * (1.f / curvecap::CURVE_SUBDIV), u1 = (float)(k + 1) * (1.f / curvecap::CURVE_SUBDIV);
+          const curvecap::F4 a4 = curvecap::curveEval(basis, cv[0], cv[1], cv[2], cv[3], u0), b4 = curvecap::curveEval(basis, cv[0], cv[1], cv[2], cv[3], u1);
+          const float rad = fmaxf(0.f, 0.5f * (a4.w + b4.w));
+          float t, sPar; curvecap::F3 N;
+          if (curvecap::intersectCapsule({rh.ray.org_x, rh.ray.org_y, rh.ray.org_z}, {rh.ray.dir_x, rh.ray.dir_y, rh.ray.dir_z}, rh.ray.tnear,
+                  rh.ray.tfar, {a4.x, a4.y, a4.z}, {b4.x, b4.y, b4.z}, rad, t, sPar, N)) {
+            h = true; rh.ray.tfar = t;
+            if (occl) break;
+            rh.hit.u = u0 + (1.f / curvecap::CURVE_SUBDIV) * sPar; rh.hit.v = 0.f; rh.hit.Ng_x = N.x; rh.hit.Ng_y = N.y; rh.hit.Ng_z = N.z;
             rh.hit.primID = p; rh.hit.geomID = m; rh.hit.instID[0] = instIdx;
           }
         }

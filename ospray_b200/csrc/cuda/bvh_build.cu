@@ -41,6 +41,25 @@ __host__ __device__ __forceinline__ float decF(uint32_t e)
 #endif
 }
 
+// position + radius of a curve segment (control points first .. first+3 of vertex.position_radius) at parameter t, with
+// the basis polynomials of geometry/Curves.ispc:40-75 and every operation rounded separately (oracle: same expression)
+__device__ __forceinline__ vec4f curveEval(const OcGeometry *g, uint32_t first, float t)
+{
+  const vec4f v0 = get4f(g->sphere, first), v1 = get4f(g->sphere, first + 1);
+  const float s = __fsub_rn(1.0f, t);
+  if (g->curveBasis == OC_CURVE_BASIS_LINEAR)
+    return make_vec4f(__fadd_rn(__fmul_rn(s, v0.x), __fmul_rn(t, v1.x)), __fadd_rn(__fmul_rn(s, v0.y), __fmul_rn(t, v1.y)),
+        __fadd_rn(__fmul_rn(s, v0.z), __fmul_rn(t, v1.z)), __fadd_rn(__fmul_rn(s, v0.w), __fmul_rn(t, v1.w)));
+  const vec4f v2 = get4f(g->sphere, first + 2), v3 = get4f(g->sphere, first + 3);
+  const float s2 = __fmul_rn(s, s), t2 = __fmul_rn(t, t), s2t = __fmul_rn(s2, t), t2s = __fmul_rn(t2, s);
+  const float b0 = -s2t, b1 = __fadd_rn(2.0f, __fmul_rn(t2, __fsub_rn(__fmul_rn(3.0f, t), 5.0f))),
+              b2 = __fadd_rn(2.0f, __fmul_rn(s2, __fsub_rn(__fmul_rn(3.0f, s), 5.0f))), b3 = -t2s;
+  auto comb = [&](float a, float b, float c, float d) {
+    return __fmul_rn(0.5f, __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(b0, a), __fmul_rn(b1, b)), __fmul_rn(b2, c)), __fmul_rn(b3, d)));
+  };
+  return make_vec4f(comb(v0.x, v1.x, v2.x, v3.x), comb(v0.y, v1.y, v2.y, v3.y), comb(v0.z, v1.z, v2.z, v3.z), comb(v0.w, v1.w, v2.w, v3.w));
+}
+
 // ---- 1. records ---------------------------------------------------------------------------
 __global__ void emitRecordsKernel(const OcModel *models, uint32_t numModels, const uint32_t *recOffset /*numModels+1*/,
     uint32_t numRecords, float4 *records, Aabb *boxes, uint32_t *sceneBounds /*6 enc*/)
@@ -49,6 +68,7 @@ __global__ void emitRecordsKernel(const OcModel *models, uint32_t numModels, con
   Aabb b;
   b.lo[0] = b.lo[1] = b.lo[2] = INFINITY;
   b.hi[0] = b.hi[1] = b.hi[2] = -INFINITY;
+  float cullPad = 0.f;
   if (r < numRecords) {
     // model lookup: binary search in the prefix array
     uint32_t lo = 0, hi = numModels;
@@ -85,6 +105,22 @@ __global__ void emitRecordsKernel(const OcModel *models, uint32_t numModels, con
       r0 = make_float4(v0.x, v0.y, v0.z, __uint_as_float(primID));
       r1 = make_float4(e1.x, e1.y, e1.z, __uint_as_float(geomID));
       r2 = make_float4(e2.x, e2.y, e2.z, __uint_as_float(kind));
+    } else if (g->type == OC_GEOM_CURVES) {
+      // one capsule of the tessellated curve segment: end points = basis at k/8 and (k+1)/8, radius = mean end radius
+      const uint32_t primID = local / OC_CURVE_SUBDIV, k = local % OC_CURVE_SUBDIV;
+      const uint32_t first = get1ui(g->index, primID, 0);
+      const float u0 = (float)k * (1.f / OC_CURVE_SUBDIV), u1 = (float)(k + 1) * (1.f / OC_CURVE_SUBDIV);
+      const vec4f a4 = curveEval(g, first, u0), b4 = curveEval(g, first, u1);
+      const float rad = fmaxf(0.f, __fmul_rn(0.5f, __fadd_rn(a4.w, b4.w)));
+      const vec3f pa = make_vec3f(a4.x, a4.y, a4.z), pb = make_vec3f(b4.x, b4.y, b4.z);
+      // reported bounds: end points -+ radius, one rounding per operation (pyoracle reproduces them)
+      ext(make_vec3f(__fsub_rn(fminf(pa.x, pb.x), rad), __fsub_rn(fminf(pa.y, pb.y), rad), __fsub_rn(fminf(pa.z, pb.z), rad)));
+      ext(make_vec3f(__fadd_rn(fmaxf(pa.x, pb.x), rad), __fadd_rn(fmaxf(pa.y, pb.y), rad), __fadd_rn(fmaxf(pa.z, pb.z), rad)));
+      // culling box of the BVH: a few ulp wider (the capsule test rounds every operation)
+      cullPad = rad * 1e-4f + 4e-7f * fmaxf(fmaxf(reduce_max(vabs(pa)), reduce_max(vabs(pb))), rad);
+      r0 = make_float4(pa.x, pa.y, pa.z, __uint_as_float(primID));
+      r1 = make_float4(pb.x, pb.y, pb.z, __uint_as_float(geomID));
+      r2 = make_float4(rad, u0, 1.f / OC_CURVE_SUBDIV, __uint_as_float((uint32_t)OC_PRIM_CAPSULE));
     } else if (g->type == OC_GEOM_SPHERES) {
       const vec4f s = get4f(g->sphere, local);
       ext(make_vec3f(s.x - s.w, s.y - s.w, s.z - s.w));
@@ -101,7 +137,9 @@ __global__ void emitRecordsKernel(const OcModel *models, uint32_t numModels, con
       r2 = make_float4(0.f, 0.f, 0.f, __uint_as_float((uint32_t)OC_PRIM_BOX));
     }
     records[3 * (size_t)r + 0] = r0; records[3 * (size_t)r + 1] = r1; records[3 * (size_t)r + 2] = r2;
-    boxes[r] = b;
+    Aabb bp = b;
+    for (int a = 0; a < 3; a++) { bp.lo[a] -= cullPad; bp.hi[a] += cullPad; }
+    boxes[r] = bp;
   }
   // block-level bounds reduction, then 6 atomics per warp
 #pragma unroll
@@ -434,7 +472,7 @@ extern "C" int ospcuda_bvh_build_group(const OcModel *d_models, uint32_t numMode
   uint64_t total = 0;
   for (uint32_t i = 0; i < numModels; i++) {
     off[i] = (uint32_t)total;
-    total += (uint64_t)h_numPrims[i] * (h_types[i] == OC_GEOM_QUADS ? 2u : 1u);
+    total += (uint64_t)h_numPrims[i] * (h_types[i] == OC_GEOM_QUADS ? 2u : (h_types[i] == OC_GEOM_CURVES ? OC_CURVE_SUBDIV : 1u));
   }
   off[numModels] = (uint32_t)total;
   if (total == 0) return 0;

@@ -155,6 +155,56 @@ __device__ __forceinline__ bool intersectBox(const Ray &ray, vec3f lo, vec3f hi,
   return false;
 }
 
+// ---- capsule = one piece of a round curve -------------------------------------------------------------------------
+// Stands in for Embree's round-curve sweep intersector (kernels/geometry/curve_intersector_sweep.h, un-vendored):
+// every curve segment is tessellated at BVH build into OC_CURVE_SUBDIV capsules whose end points are the curve basis
+// evaluated at k/8 and whose radius is the mean of the two end radii (bvh_build.cu). Front hit only; u = u0 + du * s,
+// Ng = P - axis(s). Every operation is rounded separately so that the oracle (plain C, -ffp-contract=off) reproduces it.
+__device__ __forceinline__ float dotRN(vec3f a, vec3f b)
+{
+  return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+}
+__device__ __forceinline__ vec3f subRN(vec3f a, vec3f b) { return make_vec3f(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)); }
+__device__ __forceinline__ vec3f maddRN(vec3f a, float s, vec3f b) // a + s * b
+{
+  return make_vec3f(__fadd_rn(a.x, __fmul_rn(s, b.x)), __fadd_rn(a.y, __fmul_rn(s, b.y)), __fadd_rn(a.z, __fmul_rn(s, b.z)));
+}
+__device__ __forceinline__ bool intersectCapsule(const Ray &ray, vec3f pa, vec3f pb, float r, float &t, float &sOut, vec3f &Ng)
+{
+  const vec3f ba = subRN(pb, pa), oa = subRN(ray.org, pa), d = ray.dir;
+  const float baba = dotRN(ba, ba), bard = dotRN(ba, d), baoa = dotRN(ba, oa), rdoa = dotRN(d, oa), oaoa = dotRN(oa, oa), dd = dotRN(d, d);
+  const float rr = __fmul_rn(r, r);
+  const float a = __fsub_rn(__fmul_rn(baba, dd), __fmul_rn(bard, bard));
+  float y;
+  if (a > 0.f) {
+    const float b = __fsub_rn(__fmul_rn(baba, rdoa), __fmul_rn(baoa, bard));
+    const float c = __fsub_rn(__fsub_rn(__fmul_rn(baba, oaoa), __fmul_rn(baoa, baoa)), __fmul_rn(rr, baba));
+    const float h = __fsub_rn(__fmul_rn(b, b), __fmul_rn(a, c));
+    if (!(h >= 0.f)) return false; // misses the infinite cylinder, hence the capsule
+    const float tb = __fdiv_rn(__fsub_rn(-b, __fsqrt_rn(h)), a);
+    y = __fadd_rn(baoa, __fmul_rn(tb, bard));
+    if (y > 0.f && y < baba) {
+      if (!(tb > ray.t0 && tb <= ray.t)) return false;
+      const float s = __fdiv_rn(y, baba);
+      t = tb; sOut = s;
+      Ng = maddRN(maddRN(oa, tb, d), -s, ba);
+      return true;
+    }
+  } else
+    y = bard > 0.f ? -1.f : __fadd_rn(baba, 1.f); // ray parallel to the axis: it enters through the cap it faces
+  const bool first = y <= 0.f;
+  const vec3f oc = first ? oa : subRN(ray.org, pb);
+  const float b2 = dotRN(d, oc);
+  const float c2 = __fsub_rn(dotRN(oc, oc), rr);
+  const float h2 = __fsub_rn(__fmul_rn(b2, b2), __fmul_rn(dd, c2));
+  if (!(h2 > 0.f)) return false;
+  const float tc = __fdiv_rn(__fsub_rn(-b2, __fsqrt_rn(h2)), dd);
+  if (!(tc > ray.t0 && tc <= ray.t)) return false;
+  t = tc; sOut = first ? 0.f : 1.f;
+  Ng = maddRN(oc, tc, d);
+  return true;
+}
+
 // ---- leaf records -----------------------------------------------------------------------
 __device__ __forceinline__ float4 ldg4(const OcVec4f *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 
@@ -172,6 +222,10 @@ __device__ __forceinline__ bool intersectRecord(Ray &ray, const OcVec4f *rec, ui
     if (hit && kind == OC_PRIM_TRI_QUAD2ND) { u = __fsub_rn(1.f, u); v = __fsub_rn(1.f, v); }
   } else if (kind == OC_PRIM_SPHERE) {
     hit = intersectSphere(ray, make_vec3f(r0.x, r0.y, r0.z), r1.x, t, Ng);
+  } else if (kind == OC_PRIM_CAPSULE) {
+    float s;
+    hit = intersectCapsule(ray, make_vec3f(r0.x, r0.y, r0.z), make_vec3f(r1.x, r1.y, r1.z), r2.x, t, s, Ng);
+    if (hit) u = __fadd_rn(r2.y, __fmul_rn(r2.z, s)); // curve parameter of the segment (ray.u, Curves.ispc:21)
   } else {
     hit = intersectBox(ray, make_vec3f(r0.x, r0.y, r0.z), make_vec3f(r1.x, r1.y, r1.z), t, Ng);
   }

@@ -131,6 +131,21 @@ __device__ __forceinline__ void geometryPostIntersect(const OcGeometry *g, Diffe
     if (flags & DG_TANGENTS) dg.dPds = vb - va;
   } else if (g->type == OC_GEOM_SPHERES) {
     dg.epsilon = get4f(g->sphere, ray.primID).w * OC_ULP_EPSILON;
+  } else if (g->type == OC_GEOM_CURVES) {
+    // Curves_postIntersect + interpolate<vec4f> (geometry/Curves.ispc:17-94): vertex colours through the curve basis at ray.u
+    if ((flags & DG_COLOR) && g->color.addr) {
+      const uint32_t index = get1ui(g->index, ray.primID, 0);
+      const float t = ray.u;
+      const vec4f v0 = get4f(g->color, index + 0), v1 = get4f(g->color, index + 1);
+      if (g->curveBasis == OC_CURVE_BASIS_LINEAR)
+        dg.color = (1.f - t) * v0 + t * v1;
+      else {
+        const vec4f v2 = get4f(g->color, index + 2), v3 = get4f(g->color, index + 3);
+        const float s = 1.0f - t, s2 = s * s, t2 = t * t, s2t = s2 * t, t2s = t2 * s;
+        const float b0 = -s2t, b1 = 2.0f + t2 * (3.0f * t - 5.0f), b2 = 2.0f + s2 * (3.0f * s - 5.0f), b3 = -t2s;
+        dg.color = 0.5f * (b0 * v0 + b1 * v1 + b2 * v2 + b3 * v3);
+      }
+    }
   }
   // boxes: nothing else (Boxes.ispc:65-71)
 }

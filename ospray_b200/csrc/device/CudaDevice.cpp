@@ -64,7 +64,7 @@ OSPCamera CudaDevice::newCamera(const char *type)
 OSPGeometry CudaDevice::newGeometry(const char *type)
 {
   const std::string t(type);
-  if (t != "mesh" && t != "sphere" && t != "box") return nullptr;
+  if (t != "mesh" && t != "sphere" && t != "box" && t != "curve") return nullptr;
   return (OSPGeometry) new Geometry(t);
 }
 OSPVolume CudaDevice::newVolume(const char *type)

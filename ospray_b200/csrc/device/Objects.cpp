@@ -342,6 +342,29 @@ void Geometry::commit()
     sh.type = OC_GEOM_BOXES;
     sh.numPrims = (uint32_t)boxData->size();
     sh.box = boxData->deviceView1D();
+  } else if (type == "curve") {
+    // geometry/Curves.cpp:84-194: round curves only (type OSP_ROUND), linear and Catmull-Rom bases; the segments are
+    // tessellated into capsules by the BVH builder (include/ospcuda.h OC_CURVE_SUBDIV)
+    vertexData = getParamData(*this, "vertex.position_radius", OSP_VEC4F, true);
+    indexData = getParamData(*this, "index", OSP_UINT, true);
+    colorData = getParamData(*this, "vertex.color", OSP_VEC4F);
+    texcoordData = getParamData(*this, "vertex.texcoord", OSP_VEC2F);
+    const uint32_t curveType = getParam<uint32_t>("type", OSP_UNKNOWN_CURVE_TYPE);
+    const uint32_t basis = getParam<uint32_t>("basis", OSP_UNKNOWN_CURVE_BASIS);
+    if (curveType != OSP_ROUND) throw std::runtime_error("cuda device: only OSP_ROUND curves are supported");
+    if (basis != OSP_LINEAR && basis != OSP_CATMULL_ROM)
+      throw std::runtime_error("cuda device: curve basis must be OSP_LINEAR or OSP_CATMULL_ROM");
+    const uint32_t need = basis == OSP_LINEAR ? 2u : 4u;
+    for (size_t i = 0; i < indexData->size(); i++)
+      if ((size_t)indexData->at<uint32_t>(i) + need > vertexData->size())
+        throw std::runtime_error("cuda device: curve 'index' refers past the end of 'vertex.position_radius'");
+    sh.type = OC_GEOM_CURVES;
+    sh.numPrims = (uint32_t)indexData->size();
+    sh.curveBasis = basis;
+    sh.index = indexData->deviceView1D();
+    sh.sphere = vertexData->deviceView1D();
+    if (colorData) { sh.color = colorData->deviceView1D(); sh.flags = OC_GEOMFLAG_HAS_ALPHA | OC_GEOMFLAG_COLOR_IS_VEC4; }
+    if (texcoordData) sh.texcoord = texcoordData->deviceView1D();
   } else
     throw std::runtime_error("cuda device: geometry type '" + type + "' is not supported");
   dev.upload(&sh, sizeof(sh));

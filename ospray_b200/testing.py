@@ -42,6 +42,9 @@ class GeometrySpec:
     sphere_radius: Optional[np.ndarray] = None
     radius: float = 0.01
     boxes: Optional[np.ndarray] = None         # (N,6) f32
+    curve_vertex: Optional[np.ndarray] = None  # (N,4) f32 vertex.position_radius
+    curve_index: Optional[np.ndarray] = None   # (M,) u32 first control point of each segment
+    curve_basis: str = "catmull-rom"           # | "linear"
 
 
 @dataclass
@@ -220,6 +223,55 @@ def random_spheres(num_spheres=100, seed=0, add_plane=True, renderer_type="scivi
     return SceneSpec(instances=inst, lights=_default_lights())
 
 
+def streamlines(seed=0, num_lines=100):
+    """Streamlines.cpp:31-128: spirals of round Catmull-Rom curves with tapering radius, one colour per line, obj material.
+    The builder's arithmetic is replayed in its types (int degrees, double sin/cos arguments, float results)."""
+    f = np.float32
+    gen = Mt19937(seed)
+    # the reference draws every number from ONE generator, alternating between five distributions: one raw value per draw
+    def draw(lo, hi):
+        return gen.uniform(lo, hi, 1)[0]
+    points, indices, colors = [], [], []
+
+    def lerp(t, a, b):
+        return (f(1.0) - f(t)) * a + f(t) * b
+
+    for _ in range(num_lines):
+        d_start, d_end = int(draw(0, 360)), int(draw(360, 720))
+        radius, h, h_step, fr = draw(0.5, 1.5), f(0.0), draw(0.001, 0.1), draw(0.5, 1.5)
+        r = f(720 - d_end) / f(360.0)
+        c = np.array([r, f(1) - r, f(1) - r / f(2), f(1.0)], np.float32)
+        d = d_start
+        while d < d_start + d_end:
+            p = np.array([radius * np.sin(d * np.pi / f(180.0)), h - f(2), radius * np.cos(d * np.pi / f(180.0))]).astype(np.float32)
+            start_radius = f(f(0.015) * np.sin(np.float64(fr) * d * np.pi / 180) + f(0.02))
+            q = np.array([(radius - f(0.05)) * np.sin((d + 10) * np.pi / f(180.0)), h + h_step - f(2),
+                          (radius - f(0.05)) * np.cos((d + 10) * np.pi / f(180.0))]).astype(np.float32)
+            end_radius = f(f(0.015) * np.sin(np.float64(fr) * (d + 10) * np.pi / 180) + f(0.02))
+            if d == d_start:
+                rim = lerp(f(1.0) + end_radius / f(np.linalg.norm(q - p)), q, p)
+                cap = lerp(f(1.0) + start_radius / f(np.linalg.norm(rim - p)), p, rim)
+                points += [np.append(cap, f(0)), np.append(rim, f(0)), np.append(p, start_radius), np.append(q, end_radius)]
+                indices.append(len(points) - 4)
+                colors += [c, c]
+            elif d + 10 < d_start + d_end and d + 20 > d_start + d_end:
+                rim = lerp(f(1.0) + start_radius / f(np.linalg.norm(p - q)), p, q)
+                cap = lerp(f(1.0) + end_radius / f(np.linalg.norm(rim - q)), q, rim)
+                points += [np.append(p, start_radius), np.append(q, end_radius), np.append(rim, f(0)), np.append(cap, f(0))]
+                indices += [len(points) - 7, len(points) - 6, len(points) - 5, len(points) - 4]
+                colors += [c, c]
+            elif (d != d_start and d != d_start + 10) and d + 20 < d_start + d_end:
+                points.append(np.append(p, start_radius))
+                indices.append(len(points) - 4)
+            colors.append(c)
+            radius = radius - f(0.05)
+            d += 10
+            h = h + h_step
+    geom = GeometrySpec("curve", curve_vertex=np.array(points, np.float32), curve_index=np.array(indices, np.uint32),
+                        vertex_color=np.array(colors, np.float32)[:len(points)], curve_basis="catmull-rom")
+    return SceneSpec(instances=[InstanceSpec(GroupSpec(models=[ModelSpec(geom, MaterialSpec())]))], lights=_default_lights())
+
+
 def jet_transfer_function():
     colors = np.array([(0, 0, 0.562493), (0, 0, 1), (0, 1, 1), (0.500008, 1, 0.500008), (1, 1, 0), (1, 0, 0),
                        (0.500008, 0, 0)], dtype=np.float32)
@@ -315,6 +367,13 @@ def _geometry(g: GeometrySpec):
             geo.set("radius", float(g.radius))
     elif g.type == "box":
         geo.set("box", g.boxes)
+    elif g.type == "curve":
+        geo.set("vertex.position_radius", np.ascontiguousarray(g.curve_vertex, np.float32))
+        geo.set("index", np.ascontiguousarray(g.curve_index, np.uint32))
+        if g.vertex_color is not None:
+            geo.set("vertex.color", g.vertex_color)
+        geo.set("type", osp.Typed(osp.OSP_UINT, 0))                                               # OSP_ROUND
+        geo.set("basis", osp.Typed(osp.OSP_UINT, {"linear": 0, "catmull-rom": 4}[g.curve_basis]))  # OSPCurveBasis
     return geo.commit()
 
 

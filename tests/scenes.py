@@ -87,6 +87,32 @@ def spot_lit_cornell():
     return s
 
 
+def few_streamlines():
+    """ospray_testing `streamlines` (Streamlines.cpp:31-128) with 12 of its 100 lines: round Catmull-Rom curves with
+    per-vertex colours and tapering radius, lit by a distant + ambient light"""
+    s = T.streamlines(num_lines=12)
+    s.lights = [T.LightSpec("distant", {"direction": (0.3, -0.8, 0.5), "intensity": 2.5}), T.LightSpec("ambient", {"intensity": 0.4})]
+    return s
+
+
+def linear_curves():
+    """round LINEAR curves (two control points per segment), instanced with a non-trivial transform"""
+    rng = np.random.default_rng(11)
+    pts = []
+    for k in range(6):
+        a = rng.uniform(-1, 1, 3)
+        for j in range(6):
+            pts.append(np.append(a + 0.25 * j * np.array([np.cos(k), 0.4, np.sin(k)]) + 0.05 * rng.normal(size=3), 0.03 + 0.01 * j))
+    pts = np.array(pts, np.float32)
+    idx = np.array([k * 6 + j for k in range(6) for j in range(5)], np.uint32)
+    col = np.concatenate([rng.uniform(0.3, 1.0, (len(pts), 3)), np.ones((len(pts), 1))], axis=1).astype(np.float32)
+    geom = T.GeometrySpec("curve", curve_vertex=pts, curve_index=idx, vertex_color=col, curve_basis="linear")
+    grp = T.GroupSpec(models=[T.ModelSpec(geom, T.MaterialSpec(ks=(0.2, 0.2, 0.2), ns=30.0))])
+    xf = np.array([0.9, 0.1, 0, -0.1, 0.9, 0, 0, 0, 1.1, 0.2, -0.1, 0.3], np.float32)
+    return T.SceneSpec(instances=[T.InstanceSpec(grp, xfm=xf), T.InstanceSpec(grp)],
+                       lights=[T.LightSpec("distant", {"direction": (-0.2, -0.6, 0.7), "intensity": 2.0}), T.LightSpec("ambient", {"intensity": 0.5})])
+
+
 # name -> (spec builder, renderer kind, renderer params, frames[, {camera: kind, height: h}])
 CASES = {
     "cornell_pt": (T.cornell_box, "pathtracer", {"pixelSamples": 2}, 2),
@@ -107,6 +133,9 @@ CASES = {
     "sphere_lights_scivis": (sphere_lit_boxes, "scivis", {"shadows": True, "visibleLights": True}, 1),
     "spot_lights_pt": (spot_lit_cornell, "pathtracer", {"pixelSamples": 2}, 2),
     "spot_lights_scivis": (spot_lit_cornell, "scivis", {"shadows": True, "visibleLights": True}, 1),
+    "streamlines_pt": (few_streamlines, "pathtracer", {"pixelSamples": 2}, 1),
+    "streamlines_scivis": (few_streamlines, "scivis", {"shadows": True, "aoSamples": 1}, 1),
+    "linear_curves_ao": (linear_curves, "ao", {"aoSamples": 2}, 1),
     "instanced_scivis": (instanced_boxes_and_spheres, "scivis", {"shadows": True}, 1),
     "instanced_pt": (instanced_boxes_and_spheres, "pathtracer", {"pixelSamples": 1}, 1),
     "mesh_ao": (lambda: T.box_mesh(5), "ao", {"aoSamples": 2}, 1),

@@ -57,6 +57,7 @@ def _gpu_trace(abi, world, rays, occlusion):
 TRACE_SCENES = {
     "cornell_box": T.cornell_box, "random_spheres": T.random_spheres, "boxes": T.boxes, "box_mesh_8": lambda: T.box_mesh(8),
     "instanced": scenes.instanced_boxes_and_spheres, "many_instances": lambda: _many_instances(),
+    "streamlines": scenes.few_streamlines, "linear_curves": scenes.linear_curves,
 }
 
 
@@ -102,7 +103,7 @@ def test_traversal_matches_bruteforce(osp, abi, name):
 
 
 ID_CASES = ["cornell_pt", "cornell_scivis", "cornell_ao", "boxes_scivis", "spheres_ao", "instanced_scivis", "instanced_pt", "mesh_ao",
-            "translucent_scivis", "volume_geometry"]
+            "translucent_scivis", "volume_geometry", "streamlines_scivis", "linear_curves_ao"]
 
 
 @pytest.mark.parametrize("name", ID_CASES)

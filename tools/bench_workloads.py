@@ -4,6 +4,8 @@
   C1  cornell_box            pathtracer 1024x1024  1 spp
   C2  gravity_spheres_volume scivis     1920x1080  4 spp   (structured volume 128^3; --dim for 32/512)
   C3  ~10 M-triangle mesh    ao         3840x2160 16 spp   (94^3 boxes x 12 triangles; --boxes K for smaller)
+  C4  random_spheres (thinGlass) + streamlines (round Catmull-Rom curves), pathtracer 1920x1080, 1 spp/frame
+      accumulated progressively (--frames 64 gives the config's 64 spp)
   C5s cornell_box + mesh     pathtracer 3840x2160  1 spp/frame (the single-GPU leg of C5)
 
   python tools/bench_workloads.py C2 C3 [--frames 5] [--out gpurun_out/x/workloads.json]
@@ -52,6 +54,8 @@ def main():
                 spec, ren_kind, w, h, spp, rp = T.gravity_spheres_volume(args.dim), "scivis", 1920, 1080, 4, {}
             elif wl == "C3":
                 spec, ren_kind, w, h, spp, rp = T.box_mesh(args.boxes), "ao", 3840, 2160, 16, {}
+            elif wl == "C4":
+                spec, ren_kind, w, h, spp, rp = merged(T.random_spheres(renderer_type="pathtracer"), T.streamlines()), "pathtracer", 1920, 1080, 1, {}
             elif wl == "C5s":
                 spec, ren_kind, w, h, spp, rp = merged(T.cornell_box(), T.box_mesh(args.boxes)), "pathtracer", 3840, 2160, 1, {}
             else:

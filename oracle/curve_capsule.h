@@ -28,10 +28,17 @@ inline F4 curveEval(int basis, F4 v0, F4 v1, F4 v2, F4 v3, float t)
   return {comb(v0.x, v1.x, v2.x, v3.x), comb(v0.y, v1.y, v2.y, v3.y), comb(v0.z, v1.z, v2.z, v3.z), comb(v0.w, v1.w, v2.w, v3.w)};
 }
 
+// The ray origin is first moved along the ray to the point closest to pa (parameter tp): the quadratic's coefficients
+// then carry |org' - pa| ~ the capsule's own size instead of the camera distance, so the discriminant of a grazing ray
+// does not cancel catastrophically and the accepted rays stay within a few ulp of the exact capsule (the BVH culling
+// box of bvh_build.cu relies on that). Embree's sweep intersector re-centres the ray the same way.
 inline bool intersectCapsule(F3 org, F3 d, float t0, float t1, F3 pa, F3 pb, float r, float &t, float &sOut, F3 &Ng)
 {
-  const F3 ba = sub3(pb, pa), oa = sub3(org, pa);
-  const float baba = dot3(ba, ba), bard = dot3(ba, d), baoa = dot3(ba, oa), rdoa = dot3(d, oa), oaoa = dot3(oa, oa), dd = dot3(d, d);
+  const F3 ba = sub3(pb, pa), oa0 = sub3(org, pa);
+  const float dd = dot3(d, d);
+  const float tp = -(dot3(d, oa0) / dd);
+  const F3 oa = madd3(oa0, tp, d);
+  const float baba = dot3(ba, ba), bard = dot3(ba, d), baoa = dot3(ba, oa), rdoa = dot3(d, oa), oaoa = dot3(oa, oa);
   const float rr = r * r;
   const float a = baba * dd - bard * bard;
   float y;
@@ -43,23 +50,25 @@ inline bool intersectCapsule(F3 org, F3 d, float t0, float t1, F3 pa, F3 pb, flo
     const float tb = (-b - sqrtf(h)) / a;
     y = baoa + tb * bard;
     if (y > 0.f && y < baba) {
-      if (!(tb > t0 && tb <= t1)) return false;
+      const float tt = tp + tb;
+      if (!(tt > t0 && tt <= t1)) return false;
       const float s = y / baba;
-      t = tb; sOut = s;
+      t = tt; sOut = s;
       Ng = madd3(madd3(oa, tb, d), -s, ba);
       return true;
     }
   } else
     y = bard > 0.f ? -1.f : baba + 1.f;
   const bool first = y <= 0.f;
-  const F3 oc = first ? oa : sub3(org, pb);
+  const F3 oc = first ? oa : sub3(oa, ba);
   const float b2 = dot3(d, oc);
   const float c2 = dot3(oc, oc) - rr;
   const float h2 = b2 * b2 - dd * c2;
   if (!(h2 > 0.f)) return false;
   const float tc = (-b2 - sqrtf(h2)) / dd;
-  if (!(tc > t0 && tc <= t1)) return false;
-  t = tc; sOut = first ? 0.f : 1.f;
+  const float tt = tp + tc;
+  if (!(tt > t0 && tt <= t1)) return false;
+  t = tt; sOut = first ? 0.f : 1.f;
   Ng = madd3(oc, tc, d);
   return true;
 }

@@ -117,7 +117,7 @@ __global__ void emitRecordsKernel(const OcModel *models, uint32_t numModels, con
       ext(make_vec3f(__fsub_rn(fminf(pa.x, pb.x), rad), __fsub_rn(fminf(pa.y, pb.y), rad), __fsub_rn(fminf(pa.z, pb.z), rad)));
       ext(make_vec3f(__fadd_rn(fmaxf(pa.x, pb.x), rad), __fadd_rn(fmaxf(pa.y, pb.y), rad), __fadd_rn(fmaxf(pa.z, pb.z), rad)));
       // culling box of the BVH: a few ulp wider (the capsule test rounds every operation)
-      cullPad = rad * 1e-4f + 4e-7f * fmaxf(fmaxf(reduce_max(vabs(pa)), reduce_max(vabs(pb))), rad);
+      cullPad = rad * 1e-3f + 4e-6f * fmaxf(fmaxf(reduce_max(vabs(pa)), reduce_max(vabs(pb))), rad);
       r0 = make_float4(pa.x, pa.y, pa.z, __uint_as_float(primID));
       r1 = make_float4(pb.x, pb.y, pb.z, __uint_as_float(geomID));
       r2 = make_float4(rad, u0, 1.f / OC_CURVE_SUBDIV, __uint_as_float((uint32_t)OC_PRIM_CAPSULE));

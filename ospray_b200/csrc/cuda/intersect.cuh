@@ -169,10 +169,15 @@ __device__ __forceinline__ vec3f maddRN(vec3f a, float s, vec3f b) // a + s * b
 {
   return make_vec3f(__fadd_rn(a.x, __fmul_rn(s, b.x)), __fadd_rn(a.y, __fmul_rn(s, b.y)), __fadd_rn(a.z, __fmul_rn(s, b.z)));
 }
+// The ray origin is first moved along the ray to the point closest to pa (parameter tp) so that the discriminant of a
+// grazing ray seen from far away does not cancel catastrophically (see oracle/curve_capsule.h); t = tp + t'.
 __device__ __forceinline__ bool intersectCapsule(const Ray &ray, vec3f pa, vec3f pb, float r, float &t, float &sOut, vec3f &Ng)
 {
-  const vec3f ba = subRN(pb, pa), oa = subRN(ray.org, pa), d = ray.dir;
-  const float baba = dotRN(ba, ba), bard = dotRN(ba, d), baoa = dotRN(ba, oa), rdoa = dotRN(d, oa), oaoa = dotRN(oa, oa), dd = dotRN(d, d);
+  const vec3f ba = subRN(pb, pa), oa0 = subRN(ray.org, pa), d = ray.dir;
+  const float dd = dotRN(d, d);
+  const float tp = -__fdiv_rn(dotRN(d, oa0), dd);
+  const vec3f oa = maddRN(oa0, tp, d);
+  const float baba = dotRN(ba, ba), bard = dotRN(ba, d), baoa = dotRN(ba, oa), rdoa = dotRN(d, oa), oaoa = dotRN(oa, oa);
   const float rr = __fmul_rn(r, r);
   const float a = __fsub_rn(__fmul_rn(baba, dd), __fmul_rn(bard, bard));
   float y;
@@ -184,23 +189,25 @@ __device__ __forceinline__ bool intersectCapsule(const Ray &ray, vec3f pa, vec3f
     const float tb = __fdiv_rn(__fsub_rn(-b, __fsqrt_rn(h)), a);
     y = __fadd_rn(baoa, __fmul_rn(tb, bard));
     if (y > 0.f && y < baba) {
-      if (!(tb > ray.t0 && tb <= ray.t)) return false;
+      const float tt = __fadd_rn(tp, tb);
+      if (!(tt > ray.t0 && tt <= ray.t)) return false;
       const float s = __fdiv_rn(y, baba);
-      t = tb; sOut = s;
+      t = tt; sOut = s;
       Ng = maddRN(maddRN(oa, tb, d), -s, ba);
       return true;
     }
   } else
     y = bard > 0.f ? -1.f : __fadd_rn(baba, 1.f); // ray parallel to the axis: it enters through the cap it faces
   const bool first = y <= 0.f;
-  const vec3f oc = first ? oa : subRN(ray.org, pb);
+  const vec3f oc = first ? oa : subRN(oa, ba);
   const float b2 = dotRN(d, oc);
   const float c2 = __fsub_rn(dotRN(oc, oc), rr);
   const float h2 = __fsub_rn(__fmul_rn(b2, b2), __fmul_rn(dd, c2));
   if (!(h2 > 0.f)) return false;
   const float tc = __fdiv_rn(__fsub_rn(-b2, __fsqrt_rn(h2)), dd);
-  if (!(tc > ray.t0 && tc <= ray.t)) return false;
-  t = tc; sOut = first ? 0.f : 1.f;
+  const float tt = __fadd_rn(tp, tc);
+  if (!(tt > ray.t0 && tt <= ray.t)) return false;
+  t = tt; sOut = first ? 0.f : 1.f;
   Ng = maddRN(oc, tc, d);
   return true;
 }

@@ -1,4 +1,5 @@
-// GPU BVH builder: Morton-code LBVH (Karras 2012) collapsed into 4-wide, 128-byte nodes.
+// GPU BVH builder: Morton-code LBVH (Karras 2012) refined by SAH treelet restructuring (Karras & Aila 2013, treelet.h),
+// collapsed into 4-wide, 128-byte nodes.
 //
 // Stands in for Embree 4.3.3 rtcCommitScene (un-vendored) as called by
 // modules/cpu/common/Group.cpp:129-142 (one BVH per group over all primitives of all geometric
@@ -10,8 +11,11 @@
 //   2. scene bounds (ordered-uint atomics), 63-bit Morton keys of centroids
 //   3. cub::DeviceRadixSort on (key, record index)
 //   4. Karras hierarchy, bottom-up refit with arrival counters
+//   4b. OC_TREELET_PASSES bottom-up passes of 7-leaf treelet restructuring (optimal topology by dynamic programming
+//      over leaf subsets, surface-area cost)
 //   5. level-synchronous collapse binary -> BVH4: children with the largest surface area are
-//      opened first; subtrees of <= OC_LEAF_MAX (2) records become leaves (records are contiguous after the sort)
+//      opened first; subtrees of <= OC_LEAF_MAX (2) records become leaves; the pass hands every subtree its position
+//      in depth-first leaf order
 //   6. gather records into leaf order
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
@@ -19,12 +23,12 @@
 #include <vector>
 #include "runtime.h"
 #include "shading.cuh"
+#include "treelet.h"
 
 namespace oc {
 
+#define OC_TREELET_PASSES 2 // treelet restructuring passes over the LBVH (OSPCUDA_TREELET_PASSES overrides; 0 = plain LBVH)
 #define OC_LEAF_MAX 2u // records per leaf: 2 beats 4 on every workload (C3 136 -> 106 ms, cornell 2.62 -> 2.41 ms; tools/sweep_leaf_max.sh)
-
-struct Aabb { float lo[3], hi[3]; };
 
 __device__ __forceinline__ uint32_t encF(float f)
 {
@@ -205,43 +209,15 @@ __global__ void mortonKernel(const Aabb *boxes, uint32_t n, const uint32_t *scen
 }
 
 // ---- 4. Karras hierarchy ----------------------------------------------------------------------
-// node ids: internal i in [0, n-1), leaf j as (n-1)+j
-struct BinNode { uint32_t left, right, first, last; };
-
-__device__ __forceinline__ int deltaKey(const uint64_t *keys, int n, int i, int j)
-{
-  if (j < 0 || j >= n) return -1;
-  const uint64_t a = keys[i], b = keys[j];
-  if (a == b) return 64 + __clz((uint32_t)i ^ (uint32_t)j);
-  return __clzll((long long)(a ^ b));
-}
-
+// node ids: internal i in [0, n-1), leaf j as (n-1)+j (BinNode, karrasNode: treelet.h)
 __global__ void karrasKernel(const uint64_t *keys, int n, BinNode *nodes, uint32_t *parent)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
-  const int d = (deltaKey(keys, n, i, i + 1) - deltaKey(keys, n, i, i - 1)) >= 0 ? 1 : -1;
-  const int dmin = deltaKey(keys, n, i, i - d);
-  int lmax = 2;
-  while (deltaKey(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
-  int l = 0;
-  for (int t = lmax >> 1; t >= 1; t >>= 1)
-    if (deltaKey(keys, n, i, i + (l + t) * d) > dmin) l += t;
-  const int j = i + l * d;
-  const int dnode = deltaKey(keys, n, i, j);
-  int s = 0;
-  for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) {
-    if (deltaKey(keys, n, i, i + (s + t) * d) > dnode) s += t;
-    if (t == 1) break;
-  }
-  const int gamma = i + s * d + min(d, 0);
-  const int lo = min(i, j), hi = max(i, j);
-  const uint32_t left = (lo == gamma) ? (uint32_t)(n - 1 + gamma) : (uint32_t)gamma;
-  const uint32_t right = (hi == gamma + 1) ? (uint32_t)(n - 1 + gamma + 1) : (uint32_t)(gamma + 1);
-  BinNode b; b.left = left; b.right = right; b.first = lo; b.last = hi;
+  const BinNode b = karrasNode(keys, n, i);
   nodes[i] = b;
-  parent[left] = i;
-  parent[right] = i;
+  parent[b.left] = i;
+  parent[b.right] = i;
   if (i == 0) parent[0] = 0xFFFFFFFFu;
 }
 
@@ -272,36 +248,64 @@ __global__ void refitKernel(const uint32_t *sortedIds, const Aabb *primBoxes, in
   }
 }
 
-// ---- 5. collapse ---------------------------------------------------------------------------------
-__device__ __forceinline__ float halfArea(const Aabb &b)
+// ---- 4b. treelet restructuring (SAH refinement of the LBVH; treelet.h) ---------------------------------------------
+// One thread per leaf climbs the tree; the second thread to reach a node owns the finished subtree below it (same
+// arrival protocol as refitKernel) and restructures the 7-leaf treelet rooted there. Rewrites stay inside that subtree,
+// whose other threads have all retired; reads of nodes / boxes / parents written by them go through L2.
+__global__ void treeletKernel(int n, BinNode *nodes, uint32_t *parent, Aabb *nodeBoxes, uint32_t *flags, uint32_t *rewritten)
 {
-  const float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
-  return dx * dy + dy * dz + dz * dx;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  uint32_t p = __ldcg(parent + (n - 1 + j));
+  uint32_t count = 0;
+  while (p != 0xFFFFFFFFu) {
+    if (atomicAdd(flags + p, 1u) == 0) break;
+    __threadfence();
+    const BinNode b = ocLdNode(nodes + p);
+    if (b.last - b.first + 1u >= (uint32_t)OC_TREELET_LEAVES) {
+      count += optimizeTreelet(p, n, nodes, parent, nodeBoxes) ? 1u : 0u;
+      __threadfence();
+    }
+    p = __ldcg(parent + p);
+  }
+  if (count) atomicAdd(rewritten, count);
 }
+
+// surface-area cost of the binary tree (sum of internal-node half areas / root half area), OSPCUDA_BVH_STATS=1 only
+__global__ void sahCostKernel(const Aabb *nodeBoxes, uint32_t numBin, double *sum)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  double a = i < numBin ? (double)halfArea(nodeBoxes[i]) : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0 && a != 0.0) atomicAdd(sum, a);
+}
+
+// ---- 5. collapse ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t subtreeSize(const BinNode *nodes, int n, uint32_t id)
 {
   return id >= (uint32_t)(n - 1) ? 1u : nodes[id].last - nodes[id].first + 1u;
 }
-__device__ __forceinline__ uint32_t subtreeFirst(const BinNode *nodes, int n, uint32_t id)
-{
-  return id >= (uint32_t)(n - 1) ? id - (uint32_t)(n - 1) : nodes[id].first;
-}
-
-struct WorkItem { uint32_t bin, wide; };
+// `first`: position of the subtree's first record in leaf order = number of leaves to its left in a depth-first walk.
+// It is handed down here (the treelet pass reorders subtrees, so the sorted-key ranges of the Karras pass no longer
+// describe them); leaves write leafOrder[position] = record index, which gatherRecordsKernel then follows.
+struct WorkItem { uint32_t bin, wide, first; };
 
 __global__ void collapseKernel(const BinNode *nodes, const Aabb *nodeBoxes, int n, const WorkItem *inQ, uint32_t inCount,
-    WorkItem *outQ, uint32_t *outCount, uint32_t *wideCount, OcNode4 *wide, uint32_t leafMax)
+    WorkItem *outQ, uint32_t *outCount, uint32_t *wideCount, OcNode4 *wide, uint32_t leafMax, const uint32_t *sortedIds,
+    uint32_t *leafOrder)
 {
   const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= inCount) return;
   const WorkItem item = inQ[w];
-  uint32_t slot[4];
+  uint32_t slot[4], first[4];
   int cnt = 0;
   if (subtreeSize(nodes, n, item.bin) <= leafMax) {
-    slot[cnt++] = item.bin; // tiny tree: root holds one leaf
+    slot[0] = item.bin; first[0] = item.first; cnt = 1; // tiny tree: root holds one leaf
   } else {
-    slot[cnt++] = nodes[item.bin].left;
-    slot[cnt++] = nodes[item.bin].right;
+    slot[0] = nodes[item.bin].left; first[0] = item.first;
+    slot[1] = nodes[item.bin].right; first[1] = item.first + subtreeSize(nodes, n, slot[0]);
+    cnt = 2;
     while (cnt < 4) {
       int best = -1;
       float bestA = -1.f;
@@ -313,7 +317,9 @@ __global__ void collapseKernel(const BinNode *nodes, const Aabb *nodeBoxes, int 
       if (best < 0) break;
       const uint32_t open = slot[best];
       slot[best] = nodes[open].left;
-      slot[cnt++] = nodes[open].right;
+      slot[cnt] = nodes[open].right;
+      first[cnt] = first[best] + subtreeSize(nodes, n, slot[best]);
+      cnt++;
     }
   }
   OcNode4 out;
@@ -325,12 +331,20 @@ __global__ void collapseKernel(const BinNode *nodes, const Aabb *nodeBoxes, int 
       out.hix[k] = b.hi[0]; out.hiy[k] = b.hi[1]; out.hiz[k] = b.hi[2];
       const uint32_t sz = subtreeSize(nodes, n, slot[k]);
       if (sz <= leafMax) {
-        out.child[k] = 0x80000000u | (sz << 27) | subtreeFirst(nodes, n, slot[k]);
+        out.child[k] = 0x80000000u | (sz << 27) | first[k];
+        // records of the leaf in depth-first order (leafMax <= 15)
+        uint32_t stk[16], sp = 0, pos = first[k];
+        stk[sp++] = slot[k];
+        while (sp) {
+          const uint32_t id = stk[--sp];
+          if (id >= (uint32_t)(n - 1)) leafOrder[pos++] = sortedIds[id - (uint32_t)(n - 1)];
+          else { stk[sp++] = nodes[id].right; stk[sp++] = nodes[id].left; }
+        }
       } else {
         const uint32_t wi = atomicAdd(wideCount, 1u);
         out.child[k] = wi;
         const uint32_t qi = atomicAdd(outCount, 1u);
-        WorkItem ni; ni.bin = slot[k]; ni.wide = wi;
+        WorkItem ni; ni.bin = slot[k]; ni.wide = wi; ni.first = first[k];
         outQ[qi] = ni;
       }
     } else {
@@ -347,11 +361,11 @@ __global__ void collapseKernel(const BinNode *nodes, const Aabb *nodeBoxes, int 
   for (int k = 0; k < 8; k++) dst[k] = src[k];
 }
 
-__global__ void gatherRecordsKernel(const float4 *records, const uint32_t *sortedIds, uint32_t n, float4 *out)
+__global__ void gatherRecordsKernel(const float4 *records, const uint32_t *leafOrder, uint32_t n, float4 *out)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const size_t s = 3 * (size_t)sortedIds[i];
+  const size_t s = 3 * (size_t)leafOrder[i];
   out[3 * (size_t)i + 0] = records[s + 0];
   out[3 * (size_t)i + 1] = records[s + 1];
   out[3 * (size_t)i + 2] = records[s + 2];
@@ -371,7 +385,7 @@ static int buildFromBoxes(Aabb *d_boxes, float4 *d_records, uint32_t n, const ui
   cudaStream_t st = (cudaStream_t)ospcuda_stream();
   const uint32_t B = 256, G = (n + B - 1) / B;
   DevBuf<uint64_t> keys, keysSorted;
-  DevBuf<uint32_t> ids, idsSorted, parent, flags, counters;
+  DevBuf<uint32_t> ids, idsSorted, parent, flags, counters, leafOrder;
   DevBuf<BinNode> bin;
   DevBuf<Aabb> nodeBoxes;
   DevBuf<WorkItem> q0, q1;
@@ -396,20 +410,49 @@ static int buildFromBoxes(Aabb *d_boxes, float4 *d_records, uint32_t n, const ui
   }
   refitKernel<<<G, B, 0, st>>>(idsSorted.p, d_boxes, (int)n, bin.p, parent.p, nodeBoxes.p, flags.p);
   oc_count_launch();
+  // SAH refinement: treelet restructuring passes (each pass lowers the tree's surface-area cost; the third adds little)
+  static const int treeletPasses = getenv("OSPCUDA_TREELET_PASSES") ? std::max(0, atoi(getenv("OSPCUDA_TREELET_PASSES"))) : OC_TREELET_PASSES;
+  static const bool stats = getenv("OSPCUDA_BVH_STATS") && atoi(getenv("OSPCUDA_BVH_STATS")) > 0;
+  DevBuf<double> costSum;
+  auto reportCost = [&](const char *what) -> int {
+    if (!stats || !numBin) return 0;
+    if (!costSum.p) OC_TRY(costSum.alloc(1));
+    OC_TRY(cudaMemsetAsync(costSum.p, 0, sizeof(double), st));
+    sahCostKernel<<<(numBin + B - 1) / B, B, 0, st>>>(nodeBoxes.p, numBin, costSum.p);
+    double h_sum = 0.0; Aabb rootBox; uint32_t h_rew = 0;
+    OC_TRY(cudaMemcpyAsync(&h_sum, costSum.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    OC_TRY(cudaMemcpyAsync(&rootBox, nodeBoxes.p, sizeof(Aabb), cudaMemcpyDeviceToHost, st));
+    OC_TRY(cudaMemcpyAsync(&h_rew, counters.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    OC_TRY(cudaStreamSynchronize(st));
+    fprintf(stderr, "[ospcuda bvh] n=%u %s: SAH cost (internal area / root area) = %.3f, treelets rewritten so far = %u\n", n, what,
+        h_sum / (double)halfArea(rootBox), h_rew);
+    return 0;
+  };
+  OC_TRY(counters.alloc(4));
+  OC_TRY(cudaMemsetAsync(counters.p + 2, 0, sizeof(uint32_t), st));
+  if (n >= OC_TREELET_LEAVES && treeletPasses > 0) {
+    if (reportCost("LBVH")) return -1;
+    for (int pass = 0; pass < treeletPasses; pass++) {
+      OC_TRY(cudaMemsetAsync(flags.p, 0, sizeof(uint32_t) * numBin, st));
+      treeletKernel<<<G, B, 0, st>>>((int)n, bin.p, parent.p, nodeBoxes.p, flags.p, counters.p + 2);
+      oc_count_launch();
+      if (reportCost("after a treelet pass")) return -1;
+    }
+  }
 
   // collapse, level by level
   const uint32_t maxWide = numBin ? numBin : 1;
-  OC_TRY(wideTmp.alloc(maxWide)); OC_TRY(q0.alloc(maxWide)); OC_TRY(q1.alloc(maxWide)); OC_TRY(counters.alloc(2));
+  OC_TRY(wideTmp.alloc(maxWide)); OC_TRY(q0.alloc(maxWide)); OC_TRY(q1.alloc(maxWide)); OC_TRY(leafOrder.alloc(n));
   uint32_t h_counts[2] = {0, 1}; // [0] next-queue size, [1] wide nodes allocated
   OC_TRY(cudaMemcpyAsync(counters.p, h_counts, sizeof(h_counts), cudaMemcpyHostToDevice, st));
-  WorkItem root; root.bin = n > 1 ? 0u : 0u /* single leaf id = (n-1)+0 = 0 */; root.wide = 0;
+  WorkItem root; root.bin = 0u /* n == 1: the single leaf's id is (n-1)+0 = 0 too */; root.wide = 0; root.first = 0;
   OC_TRY(cudaMemcpyAsync(q0.p, &root, sizeof(root), cudaMemcpyHostToDevice, st));
   uint32_t inCount = 1;
   WorkItem *inQ = q0.p, *outQ = q1.p;
   static const uint32_t leafMax = getenv("OSPCUDA_LEAF_MAX") ? std::min(15u, std::max(1u, (uint32_t)atoi(getenv("OSPCUDA_LEAF_MAX")))) : OC_LEAF_MAX;
   while (inCount) {
     collapseKernel<<<(inCount + 127) / 128, 128, 0, st>>>(bin.p, nodeBoxes.p, (int)n, inQ, inCount, outQ, counters.p, counters.p + 1,
-        wideTmp.p, leafMax);
+        wideTmp.p, leafMax, idsSorted.p, leafOrder.p);
     oc_count_launch();
     OC_TRY(cudaMemcpyAsync(h_counts, counters.p, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
     OC_TRY(cudaStreamSynchronize(st));
@@ -425,7 +468,7 @@ static int buildFromBoxes(Aabb *d_boxes, float4 *d_records, uint32_t n, const ui
   OC_TRY(cudaMemcpyAsync(nodesOut, wideTmp.p, sizeof(OcNode4) * (size_t)numWide, cudaMemcpyDeviceToDevice, st));
   float4 *recOut = nullptr;
   OC_TRY(cudaMalloc((void **)&recOut, sizeof(float4) * 3 * (size_t)n));
-  gatherRecordsKernel<<<G, B, 0, st>>>(d_records, idsSorted.p, n, recOut);
+  gatherRecordsKernel<<<G, B, 0, st>>>(d_records, leafOrder.p, n, recOut);
   oc_count_launch();
   uint32_t h_enc[6];
   OC_TRY(cudaMemcpyAsync(h_enc, d_sceneBounds, sizeof(h_enc), cudaMemcpyDeviceToHost, st));

@@ -238,9 +238,20 @@ __device__ __forceinline__ bool intersectRecord(Ray &ray, const OcVec4f *rec, ui
   }
   if (!hit)
     return false;
+  const uint32_t primID = __float_as_uint(r0.w), geomID = __float_as_uint(r1.w);
+  if (!OCCLUSION && t == ray.t && ray.geomID != OC_INVALID_ID) {
+    // exact tie with the hit already held (coplanar faces, shared edges): the primitive tests accept t <= ray.t, so a
+    // scan in record order ends with the LAST of the tied primitives (what the oracle's and the Embree stand-in's loops
+    // do). Same rule here whatever order the BVH visits them in: the later (instance, geometry, primitive, quad half) wins.
+    const bool later = instID != ray.instID ? instID > ray.instID
+        : geomID != ray.geomID              ? geomID > ray.geomID
+        : primID != ray.primID              ? primID > ray.primID
+                                            : kind == OC_PRIM_TRI_QUAD2ND;
+    if (!later) return false;
+  }
   ray.t = t;
-  ray.primID = __float_as_uint(r0.w);
-  ray.geomID = __float_as_uint(r1.w);
+  ray.primID = primID;
+  ray.geomID = geomID;
   ray.instID = instID;
   if (!OCCLUSION) { ray.u = u; ray.v = v; ray.Ng = Ng; }
   return true;

@@ -11,7 +11,7 @@ NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -X
 CXXFLAGS  := -std=c++17 -O2 -fPIC -Iinclude -Wall -Wno-unused-function
 CUDA_LIBDIR ?= /usr/local/cuda/lib64
 
-CU_SRCS   := $(CSRC)/cuda/runtime.cu $(CSRC)/cuda/render.cu $(CSRC)/cuda/fb_ops.cu $(CSRC)/cuda/bvh_build.cu
+CU_SRCS   := $(CSRC)/cuda/runtime.cu $(CSRC)/cuda/render.cu $(CSRC)/cuda/fb_ops.cu $(CSRC)/cuda/bvh_build.cu $(CSRC)/cuda/peer_exchange.cu
 CU_OBJS   := $(CU_SRCS:$(CSRC)/cuda/%.cu=build/cuda/%.o)
 CU_HDRS   := $(wildcard $(CSRC)/cuda/*.cuh) $(wildcard $(CSRC)/cuda/*.h) $(CSRC)/cuda/tables.inc $(CSRC)/common/osp_math.h include/ospcuda.h
 API_SRCS  := $(CSRC)/common/Managed.cpp $(CSRC)/api/Device.cpp $(CSRC)/api/API.cpp

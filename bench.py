@@ -7,12 +7,13 @@ pathtracer cornell_box, 1 spp per frame, at 1/2/4/8 B200; CPU baseline beside it
 
 One step = one ospRenderFrame of workload C1 (progressive accumulation, frameID advances every step).
 N > 1: one process per GPU; the scene is replicated, image tiles are partitioned `tile % N == rank`
-(modules/multiDevice semantics), each rank converts its tiles to sRGBA8 and one NCCL gather per frame moves
-them to GPU 0 -- total work is fixed, so this is STRONG scaling.
+(modules/multiDevice semantics), each rank converts its tiles to sRGBA8 and stores them straight into GPU 0's image
+over NVLink peer memory (ospray_b200.multigpu.PeerTileExchange: one push kernel per rank and a flag handshake per
+frame; `--gather nccl` = pack + one NCCL gather + unpack instead) -- total work is fixed, so this is STRONG scaling.
 
 `value`     device-timed Mrays/s: every ray handed to traversal (primary + continuation + shadow segments) on
             all ranks / (max over ranks of the summed per-step CUDA-event time: renderer kernel + accumulation +
-            colour conversion [+ pack, NCCL gather, unpack]); scene and framebuffer resident in HBM.
+            colour conversion [+ the tile exchange]); scene and framebuffer resident in HBM.
 `e2e`       the same metric through the public API with host buffers, wall clock per step: ospCommit(camera)
             (the step's host-side inputs; they reach the device as the kernel parameter block), ospRenderFrame,
             ospWait, ospMapFrameBuffer(OSP_FB_COLOR) = D2H of the finished sRGBA8 image into pinned memory.
@@ -47,6 +48,9 @@ def parse():
     ap.add_argument("--width", type=int, default=1024)
     ap.add_argument("--height", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N>1: 'peer' = every rank stores its tiles into GPU 0's image over NVLink peer memory (CUDA IPC); "
+                         "'nccl' = pack + one NCCL gather + unpack")
     return ap.parse_args()
 
 
@@ -215,14 +219,21 @@ def run_ours(args):
         cam, pose = T.make_camera(world_obj, w, h)
         ren = T.make_renderer("pathtracer", pixelSamples=1)
         fb = osp.FrameBuffer(w, h, osp.OSP_FB_SRGBA, osp.OSP_FB_COLOR | osp.OSP_FB_ACCUM | osp.OSP_FB_DEPTH)
-        gather = multigpu.TileGather(w, h, 4, torch.device("cuda", local), ops=multigpu.CudaTileOps(shared_stream=True)) if world > 1 else None
         conv_ptr, bpp = fb.device_pointer(osp.OSP_FB_COLOR)
         assert bpp == 4
+        if world == 1:
+            gather = None
+        elif args.gather == "peer":   # tiles stored straight into GPU 0's image over NVLink peer memory (one kernel per rank)
+            gather = multigpu.PeerTileExchange(w, h, 4, conv_ptr)
+        else:                         # pack + one NCCL gather + unpack
+            gather = multigpu.TileGather(w, h, 4, torch.device("cuda", local), ops=multigpu.CudaTileOps(shared_stream=True))
+        begin = getattr(gather, "begin_frame", lambda: None)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
         def step(timed_events=None):
             if timed_events is not None:
                 timed_events[0].record(stream)
+            begin()
             f = fb.render_frame(ren, cam, world_obj)
             if gather is not None:
                 gather.gather(conv_ptr)
@@ -285,6 +296,7 @@ def run_ours(args):
         t0 = time.perf_counter()
         for i in range(K):
             cam.set("position", pose["position"]).commit()       # the step's host inputs
+            begin()
             f = fb.render_frame(ren, cam, world_obj)
             if gather is not None:
                 gather.gather(conv_ptr)
@@ -315,7 +327,8 @@ def run_ours(args):
         line = {"metric": "Mrays/s", "value": round(float(value), 2), "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": round(float(mx[0] / K), 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "partition": f"image tiles 64x64, tile % {world} == rank, NCCL gather of sRGBA8 to GPU 0" if world > 1 else "single device",
+                "config": {"workload": WORKLOAD, "partition": (f"image tiles 64x64, tile % {world} == rank, " + ("sRGBA8 tiles stored into GPU 0's image over NVLink peer memory (one push kernel per rank, flag handshake)"
+                                                                                              if args.gather == "peer" else "NCCL gather of sRGBA8 to GPU 0")) if world > 1 else "single device",
                            "l2": "256 MiB memset between timed steps (L2 flush)", "frame_ms": round(float(mx[0] / K), 4),
                            "rays_per_frame": int(tot[0] / K), "mpixel_samples_per_s": round(w * h * K / (mx[0] * 1e-3) / 1e6, 1),
                            "scene_setup_ms_incl_bvh": round(setup_ms, 2)},
@@ -346,6 +359,9 @@ def run_ours(args):
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
         print(json.dumps(line), flush=True)
     if world > 1:
+        if hasattr(gather, "check"):
+            gather.check()   # a device-side wait that timed out would have produced a wrong frame: fail loudly
+            gather.close()
         dist.barrier()
         dist.destroy_process_group()
 

@@ -372,6 +372,27 @@ OSPCUDA_API int ospcuda_fb_pack_tiles(void *d_packed, const void *d_image, int s
 OSPCUDA_API int ospcuda_fb_unpack_tiles(void *d_image, const void *d_packed, int sizeX, int sizeY,
     uint32_t bytesPerPixel, uint32_t numRanks, uint32_t srcRank);
 
+/* Peer-memory tile exchange (peer_exchange.cu): the same composition (MultiDeviceLoadBalancer.cpp:41-47 +
+ * LocalFB.cpp:286-353 writeTiles) without staging or a collective call, for one process per GPU on an NVLink/NVSwitch
+ * box. Rank 0 exports its display image and its synchronisation block with ospcuda_ipc_export; the other ranks map
+ * them (ospcuda_ipc_open) and push their owned tiles straight into rank 0's image. Per frame (epoch = 1, 2, ...):
+ * rank 0 calls post_ready at the start of the frame (the previous image has been consumed in stream order) and
+ * wait_arrive at its end; every other rank calls push_tiles after its colour conversion. All calls enqueue on the render
+ * stream and return at once; spins on the device are bounded and report through ospcuda_peer_error. */
+#define OSPCUDA_IPC_HANDLE_BYTES 64
+#define OSPCUDA_PEER_BLOCK_WORDS 64
+#define OSPCUDA_MAX_PEERS 16
+OSPCUDA_API int ospcuda_peer_block_alloc(uint32_t **d_block); /* zeroed; free with ospcuda_free */
+OSPCUDA_API int ospcuda_ipc_export(const void *d_ptr, unsigned char *handle /* OSPCUDA_IPC_HANDLE_BYTES */);
+OSPCUDA_API int ospcuda_ipc_open(const unsigned char *handle, void **d_ptr);
+OSPCUDA_API int ospcuda_ipc_close(void *d_ptr);
+OSPCUDA_API int ospcuda_peer_post_ready(uint32_t *const *peerBlocks /* host array [numRanks], entry 0 unused */,
+    uint32_t numRanks, uint32_t epoch);
+OSPCUDA_API int ospcuda_peer_wait_arrive(uint32_t *d_rootBlock, uint32_t numRanks, uint32_t epoch);
+OSPCUDA_API int ospcuda_peer_push_tiles(void *peerImage, const void *d_image, int sizeX, int sizeY, uint32_t bytesPerPixel,
+    uint32_t numRanks, uint32_t rank, uint32_t *d_localBlock, uint32_t *peerRootBlock, uint32_t epoch);
+OSPCUDA_API int ospcuda_peer_error(const uint32_t *d_block, uint32_t *timedOut); /* synchronous read of the block's error word */
+
 #ifdef __cplusplus
 }
 #endif

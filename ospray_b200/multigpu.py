@@ -1,4 +1,5 @@
-"""One-process-per-GPU tile partition and NCCL gather of the finished tiles to GPU 0.
+"""One-process-per-GPU tile partition and composition of the finished tiles on GPU 0: PeerTileExchange (stores over
+NVLink peer memory, the default on a CUDA box) or TileGather (pack + one NCCL gather + unpack).
 
 The rendering analogue of modules/multiDevice (MultiDevice.cpp:395-418: every sub-device owns the 64x64 tiles
 with `tileID % numSubdevices == rank`; MultiDeviceLoadBalancer.cpp:19-60: render everywhere, then
@@ -107,8 +108,157 @@ class TileGather:
                 self.ops.synchronize()
 
 
+class CudaPeerOps:
+    """the peer-exchange entry points of libospcuda.so (include/ospcuda.h, peer_exchange.cu)"""
+
+    def __init__(self):
+        L = C.CDLL(lib_path("libospcuda.so"), mode=C.RTLD_GLOBAL)
+        L.ospcuda_last_error.restype = C.c_char_p
+        L.ospcuda_peer_block_alloc.argtypes = [C.POINTER(C.c_void_p)]
+        L.ospcuda_ipc_export.argtypes = [C.c_void_p, C.c_char_p]
+        L.ospcuda_ipc_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.ospcuda_ipc_close.argtypes = [C.c_void_p]
+        L.ospcuda_free.argtypes = [C.c_void_p]
+        L.ospcuda_peer_post_ready.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32]
+        L.ospcuda_peer_wait_arrive.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        L.ospcuda_peer_push_tiles.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                              C.c_void_p, C.c_uint32]
+        L.ospcuda_peer_error.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+        self.L = L
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"libospcuda: {self.L.ospcuda_last_error().decode()}")
+
+    def alloc_block(self):
+        p = C.c_void_p()
+        self._check(self.L.ospcuda_peer_block_alloc(C.byref(p)))
+        return p.value
+
+    def free_block(self, ptr):
+        self._check(self.L.ospcuda_free(ptr))
+
+    def export(self, ptr):
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+        self._check(self.L.ospcuda_ipc_export(ptr, buf))
+        return buf.raw
+
+    def open(self, handle):
+        p = C.c_void_p()
+        self._check(self.L.ospcuda_ipc_open(handle, C.byref(p)))
+        return p.value
+
+    def close(self, ptr):
+        self._check(self.L.ospcuda_ipc_close(ptr))
+
+    def post_ready(self, blocks, epoch):
+        arr = (C.c_void_p * len(blocks))(*blocks)
+        self._check(self.L.ospcuda_peer_post_ready(arr, len(blocks), epoch))
+
+    def wait_arrive(self, root_block, world_size, epoch):
+        self._check(self.L.ospcuda_peer_wait_arrive(root_block, world_size, epoch))
+
+    def push(self, peer_image, image_ptr, width, height, bpp, world_size, rank, local_block, root_block, epoch):
+        self._check(self.L.ospcuda_peer_push_tiles(peer_image, image_ptr, width, height, bpp, world_size, rank, local_block, root_block, epoch))
+
+    def timed_out(self, block):
+        v = C.c_uint32(0)
+        self._check(self.L.ospcuda_peer_error(block, C.byref(v)))
+        return bool(v.value)
+
+
+IPC_HANDLE_BYTES = 64
+
+
+class PeerTileExchange:
+    """Composes the display channel on rank 0 by peer stores: every rank r != 0 writes the tiles it owns straight into
+    rank 0's row-major image (mapped through CUDA IPC) from one kernel; no staging buffer, no collective call per frame.
+    The process group is used once, to exchange the IPC handles. Per frame:
+
+        x.begin_frame()          # rank 0: tells the peers the previous image has been consumed (stream order)
+        ... render + colour conversion on the render stream ...
+        x.gather(image_ptr)      # rank r: push tiles + arrival flag;  rank 0: wait for the N-1 arrival flags
+
+    Everything is enqueued on the render stream; nothing blocks the host. `image_ptr` on rank 0 must be the pointer
+    handed to the constructor (the framebuffer's display buffer: the base of its own cudaMalloc allocation)."""
+
+    def __init__(self, width, height, bpp, image_ptr, ops=None, group=None):
+        self.width, self.height, self.bpp = width, height, bpp
+        self.group = group
+        self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.ops = ops if ops is not None else CudaPeerOps()
+        self.epoch = 0
+        self._open = False  # begin_frame() called, gather() not yet
+        self.image_ptr = image_ptr
+        self.bytes_gathered = 0
+        ws, rk = self.world_size, self.rank
+        if ws == 1:
+            return
+        tx, ty = tile_grid(width, height)
+        if ws > tx * ty or ws > 16:
+            raise ValueError("PeerTileExchange: more ranks than tiles (or than OSPCUDA_MAX_PEERS)")
+        self.block = self.ops.alloc_block()
+        mine = {"block": self.ops.export(self.block), "image": self.ops.export(image_ptr) if rk == 0 else None}
+        everyone = [None] * ws
+        dist.all_gather_object(everyone, mine, group=group)
+        if rk == 0:
+            self.peer_blocks = [self.block] + [self.ops.open(everyone[r]["block"]) for r in range(1, ws)]
+            self.root_image, self.root_block = image_ptr, self.block
+        else:
+            self.peer_blocks = None
+            self.root_image = self.ops.open(everyone[0]["image"])
+            self.root_block = self.ops.open(everyone[0]["block"])
+        self.shard_bytes = [len(owned_tiles(width, height, ws, r)) * TILE * TILE * bpp for r in range(ws)]
+        dist.barrier(group=group)  # every mapping exists before the first frame
+
+    def begin_frame(self):
+        if self.world_size == 1:
+            return
+        if self._open:
+            return
+        self.epoch += 1
+        self._open = True
+        if self.rank == 0:
+            self.ops.post_ready(self.peer_blocks, self.epoch)
+
+    def gather(self, image_ptr):
+        if self.world_size == 1:
+            return
+        self.begin_frame()  # no-op when the caller opened the frame before rendering (the overlapping form)
+        self._open = False
+        if self.rank == 0:
+            if image_ptr != self.image_ptr:
+                raise ValueError("PeerTileExchange.gather: rank 0 must pass the image it exported")
+            self.ops.wait_arrive(self.root_block, self.world_size, self.epoch)
+            self.bytes_gathered = sum(self.shard_bytes[1:])
+        else:
+            self.ops.push(self.root_image, image_ptr, self.width, self.height, self.bpp, self.world_size, self.rank, self.block,
+                          self.root_block, self.epoch)
+
+    def check(self):
+        """synchronous: raises if a device-side wait of this rank timed out (a peer never showed up)"""
+        if self.world_size > 1 and self.ops.timed_out(self.block):
+            raise RuntimeError(f"PeerTileExchange: rank {self.rank} timed out waiting for a peer")
+
+    def close(self):
+        if self.world_size == 1:
+            return
+        dist.barrier(group=self.group)  # nobody unmaps while a peer may still be writing
+        if self.rank == 0:
+            for p in self.peer_blocks[1:]:
+                self.ops.close(p)
+        else:
+            self.ops.close(self.root_image)
+            self.ops.close(self.root_block)
+        dist.barrier(group=self.group)
+        self.ops.free_block(self.block)
+        self.world_size = 1
+
+
 def init_process_group_from_env():
-    """torchrun environment -> (rank, world_size, local_rank); NCCL when CUDA is present, else gloo"""
+    """torchrun environment -> (rank, world_size, local_rank); NCCL when CUDA is present, else gloo
+    (OSPRAY_B200_DIST_BACKEND=gloo forces gloo: ranks that share one GPU, where NCCL refuses to run)"""
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1 and not dist.is_initialized():
@@ -116,7 +266,8 @@ def init_process_group_from_env():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
-        if torch.cuda.is_available():
+        backend = os.environ.get("OSPRAY_B200_DIST_BACKEND", "nccl" if torch.cuda.is_available() else "gloo")
+        if backend == "nccl":
             torch.cuda.set_device(local)
             dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
         else:

@@ -154,9 +154,10 @@ REF_UNSUPPORTED = {"volume_geometry"}
 W, H = 48, 40  # not a multiple of 8 or 64: exercises clipped render tasks and border tiles
 
 
-def oracle_render(name, width=W, height=H, pixel_filter=None, threads=0, num_ranks=1, rank=0, channels=None, backend="oracle"):
+def oracle_render(name, width=W, height=H, pixel_filter=None, threads=0, num_ranks=1, rank=0, channels=None, backend="oracle", frames=None):
     from oracle import pyoracle as O
-    build, kind, params, frames = CASES[name][:4]
+    build, kind, params, case_frames = CASES[name][:4]
+    frames = case_frames if frames is None else frames
     extra = CASES[name][4] if len(CASES[name]) > 4 else {}
     spec = build()
     scene = O.Scene(spec)

@@ -93,3 +93,128 @@ def test_cuda_tile_ops_refuse_cpu_tensors():
     ops = multigpu.CudaTileOps()
     with pytest.raises(RuntimeError, match="no CPU path"):
         ops.pack(torch.zeros(16, dtype=torch.uint8), 0, 64, 64, 4, 2, 1)
+
+
+# ---- PeerTileExchange: the handle exchange, epochs and the ready/arrive handshake, on CPU ------------------------------
+class ShmPeerOps:
+    """stands in for CudaPeerOps: "device memory" = POSIX shared memory, an IPC handle = the segment's name, the push
+    kernel = a numpy tile copy into the mapped image. Same call sequence and flag protocol as peer_exchange.cu."""
+    READY, ARRIVE = 0, 8
+
+    def __init__(self):
+        from multiprocessing import shared_memory
+        self.shm_mod, self.segs = shared_memory, {}
+
+    def _new(self, nbytes):
+        seg = self.shm_mod.SharedMemory(create=True, size=nbytes)
+        self.segs[seg.name] = seg
+        np.ndarray(nbytes, np.uint8, seg.buf)[:] = 0
+        return seg.name
+
+    def _arr(self, name, dtype):
+        seg = self.segs[name]
+        return np.ndarray(seg.size // np.dtype(dtype).itemsize, dtype, seg.buf)
+
+    def alloc_block(self): return self._new(256)
+    def alloc_image(self, nbytes): return self._new(nbytes)
+    def export(self, ptr): return ptr.encode()
+
+    def open(self, handle):
+        name = handle.decode()
+        if name not in self.segs:
+            self.segs[name] = self.shm_mod.SharedMemory(name=name)
+        return name
+
+    def close(self, ptr): pass
+
+    def free_block(self, ptr): pass
+
+    def _spin(self, get, epoch):
+        import time
+        t0 = time.time()
+        while get() < epoch:
+            time.sleep(0.001)
+            assert time.time() - t0 < 60, "peer never showed up"
+
+    def post_ready(self, blocks, epoch):
+        for b in blocks[1:]:
+            self._arr(b, np.uint32)[self.READY] = epoch
+
+    def wait_arrive(self, root_block, world_size, epoch):
+        a = self._arr(root_block, np.uint32)
+        for r in range(1, world_size):
+            self._spin(lambda: a[self.ARRIVE + r], epoch)
+
+    def push(self, peer_image, image, width, height, bpp, world_size, rank, local_block, root_block, epoch):
+        from ospray_b200 import multigpu
+        self._spin(lambda: self._arr(local_block, np.uint32)[self.READY], epoch)
+        dst = self._arr(peer_image, np.uint8)[: width * height * bpp].reshape(height, width, bpp)
+        tx, _ = multigpu.tile_grid(width, height)
+        for t in multigpu.owned_tiles(width, height, world_size, rank):
+            x0, y0 = (t % tx) * 64, (t // tx) * 64
+            dst[y0:y0 + 64, x0:x0 + 64] = image[y0:y0 + 64, x0:x0 + 64]
+        self._arr(root_block, np.uint32)[self.ARRIVE + rank] = epoch
+
+    def timed_out(self, block): return False
+
+    def unlink(self):
+        for seg in self.segs.values():
+            seg.close()
+
+
+def _peer_worker(rank, world, port, w, h, out_path):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import pyoracle as O
+    import scenes
+    from ospray_b200 import multigpu
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    multigpu.init_process_group_from_env()
+    ops = ShmPeerOps()
+    root_image = ops.alloc_image(w * h * 4) if rank == 0 else None
+    x = multigpu.PeerTileExchange(w, h, 4, root_image, ops=ops)
+    frames = []
+    for frame in range(2):  # two epochs: the second frame may only be pushed after rank 0 has consumed the first
+        x.begin_frame()
+        fb = scenes.oracle_render("cornell_pt", w, h, num_ranks=world, rank=rank, threads=1, frames=frame + 1)
+        srgb = O.color_convert(fb.buf["color"], 2).view(np.uint8).reshape(h, w, 4).copy()
+        if rank == 0:
+            img = ops._arr(root_image, np.uint8).reshape(h, w, 4)
+            tx, _ = multigpu.tile_grid(w, h)
+            for t in multigpu.owned_tiles(w, h, world, 0):
+                x0, y0 = (t % tx) * 64, (t // tx) * 64
+                img[y0:y0 + 64, x0:x0 + 64] = srgb[y0:y0 + 64, x0:x0 + 64]
+            x.gather(root_image)
+            frames.append(img.copy())  # "ospMapFrameBuffer": consumed before the next begin_frame
+        else:
+            x.gather(srgb)
+    assert x.epoch == 2
+    x.check()
+    if rank == 0:
+        np.savez(out_path, f0=frames[0], f1=frames[1], gathered=x.bytes_gathered)
+    x.close()
+    ops.unlink()
+    if rank == 0:
+        for name in (root_image,):
+            ops.segs[name].unlink()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_tile_exchange_protocol_gloo(tmp_path, world):
+    """PeerTileExchange with shared memory standing in for NVLink peer memory: IPC handle exchange through the process
+    group, per-frame epochs, ready/arrive flags; the composed frames equal the single-process frames bit for bit"""
+    import scenes
+    from oracle import pyoracle as O
+    from ospray_b200 import multigpu
+    w, h = 200, 136
+    out = str(tmp_path / "peer.npz")
+    mp.spawn(_peer_worker, args=(world, _free_port(), w, h, out), nprocs=world, join=True)
+    got = np.load(out)
+    for k, frames in (("f0", 1), ("f1", 2)):
+        full = scenes.oracle_render("cornell_pt", w, h, threads=1, frames=frames)
+        want = O.color_convert(full.buf["color"], 2).view(np.uint8).reshape(h, w, 4)
+        np.testing.assert_array_equal(got[k], want)
+    tiles = multigpu.tile_grid(w, h)[0] * multigpu.tile_grid(w, h)[1]
+    assert int(got["gathered"]) == (tiles - len(multigpu.owned_tiles(w, h, world, 0))) * 64 * 64 * 4

@@ -308,6 +308,10 @@ def run_ours(args):
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
 
+        # N > 1: the image composed on GPU 0 must hold, tile for tile, what every rank rendered (checksums of each rank's
+        # owned tiles, taken from its own display buffer, against the same tiles of GPU 0's image)
+        composed_ok = multigpu.verify_composition(fb.map(osp.OSP_FB_COLOR)) if world > 1 else None
+
         tot = torch.tensor([float(rays.sum()), float(e2e_rays.sum()), float(launches)], dtype=torch.float64, device="cuda")
         mx = torch.tensor([dev_ms, e2e_s, kernel_ms], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -329,7 +333,7 @@ def run_ours(args):
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "partition": (f"image tiles 64x64, tile % {world} == rank, " + ("sRGBA8 tiles stored into GPU 0's image over NVLink peer memory (one push kernel per rank, flag handshake)"
                                                                                               if args.gather == "peer" else "NCCL gather of sRGBA8 to GPU 0")) if world > 1 else "single device",
-                           "l2": "256 MiB memset between timed steps (L2 flush)", "frame_ms": round(float(mx[0] / K), 4),
+                           "l2": "256 MiB memset between timed steps (L2 flush)", **({"composition_check": "GPU 0's image == every rank's own tiles (checksums)"} if composed_ok else {}), "frame_ms": round(float(mx[0] / K), 4),
                            "rays_per_frame": int(tot[0] / K), "mpixel_samples_per_s": round(w * h * K / (mx[0] * 1e-3) / 1e6, 1),
                            "scene_setup_ms_incl_bvh": round(setup_ms, 2)},
                 "e2e": {"value": round(float(e2e), 2), "unit": "Mrays/s", "h2d_bytes_per_step": 472, "d2h_bytes_per_step": w * h * 4 + 24,

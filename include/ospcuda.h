@@ -358,6 +358,10 @@ OSPCUDA_API int ospcuda_fb_color_convert(const OcVec4f *d_in, void *d_out, uint3
 /* fused tonemap (optional, tm may be NULL) + colour conversion: one pass over the image */
 OSPCUDA_API int ospcuda_fb_postprocess(const OcVec4f *d_in, OcVec4f *d_ppOut, void *d_out,
     uint32_t numPixels, uint32_t colorFormat, const OcToneMapper *tm);
+/* the same pass restricted to the 64x64 tiles with tile % numRanks == rank (the sub-device's share of a multi-device
+ * frame, MultiDevice.cpp:403-416): the rest of d_out is left to the tile exchange */
+OSPCUDA_API int ospcuda_fb_postprocess_tiles(const OcVec4f *d_in, OcVec4f *d_ppOut, void *d_out, int sizeX, int sizeY,
+    uint32_t colorFormat, const OcToneMapper *tm, uint32_t numRanks, uint32_t rank);
 /* copy the 64x64 tiles owned by `srcRank` (tile % numRanks == srcRank) from a rank-local
  * full-size image into dst (both device, row-major, bytesPerPixel each) */
 OSPCUDA_API int ospcuda_fb_gather_tiles(void *d_dst, const void *d_src, int sizeX, int sizeY,

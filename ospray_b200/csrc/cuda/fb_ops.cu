@@ -42,11 +42,18 @@ __device__ __forceinline__ float4 toneMap(float4 col, const OcToneMapper &tm)
 }
 
 // one pass: optional tonemap -> optional float4 store (post-processed colour) -> format conversion
+// numRanks > 1: only the pixels of the 64x64 tiles this rank owns (tile % numRanks == rank) are converted; the other
+// pixels of the display buffer belong to the tile exchange (peers store their tiles there, possibly while this runs)
 template <int FORMAT, bool TONEMAP>
 __global__ void __launch_bounds__(256) postprocessKernel(const float4 *__restrict__ in, float4 *__restrict__ ppOut,
-    void *__restrict__ out, uint32_t n, OcToneMapper tm)
+    void *__restrict__ out, uint32_t n, OcToneMapper tm, uint32_t sizeX, uint32_t numRanks, uint32_t rank)
 {
+  const uint32_t tilesX = (sizeX + 63u) >> 6;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (numRanks > 1) {
+      const uint32_t y = i / sizeX, x = i - y * sizeX;
+      if (((y >> 6) * tilesX + (x >> 6)) % numRanks != rank) continue;
+    }
     float4 v = __ldcs(in + i);
     if (TONEMAP) {
       v = toneMap(v, tm);
@@ -204,10 +211,12 @@ static uint32_t streamGrid(uint32_t n, int perSM = 8)
 
 using namespace oc;
 
-extern "C" int ospcuda_fb_postprocess(const OcVec4f *d_in, OcVec4f *d_ppOut, void *d_out, uint32_t numPixels,
-    uint32_t colorFormat, const OcToneMapper *tm)
+extern "C" int ospcuda_fb_postprocess_tiles(const OcVec4f *d_in, OcVec4f *d_ppOut, void *d_out, int sizeX, int sizeY,
+    uint32_t colorFormat, const OcToneMapper *tm, uint32_t numRanks, uint32_t rank)
 {
+  const uint32_t numPixels = (uint32_t)sizeX * (uint32_t)sizeY;
   if (numPixels == 0) return 0;
+  if (numRanks == 0 || rank >= numRanks) return oc_set_error(cudaErrorInvalidValue, "ospcuda_fb_postprocess_tiles: bad rank");
   cudaStream_t st = (cudaStream_t)ospcuda_stream();
   const uint32_t grid = streamGrid(numPixels);
   const float4 *in = reinterpret_cast<const float4 *>(d_in);
@@ -215,8 +224,8 @@ extern "C" int ospcuda_fb_postprocess(const OcVec4f *d_in, OcVec4f *d_ppOut, voi
   OcToneMapper t{};
   if (tm) t = *tm;
 #define OC_PP(F)                                                                                   \
-  if (tm) postprocessKernel<F, true><<<grid, 256, 0, st>>>(in, pp, d_out, numPixels, t);          \
-  else postprocessKernel<F, false><<<grid, 256, 0, st>>>(in, pp, d_out, numPixels, t);
+  if (tm) postprocessKernel<F, true><<<grid, 256, 0, st>>>(in, pp, d_out, numPixels, t, (uint32_t)sizeX, numRanks, rank); \
+  else postprocessKernel<F, false><<<grid, 256, 0, st>>>(in, pp, d_out, numPixels, t, (uint32_t)sizeX, numRanks, rank);
   switch (colorFormat) {
   case 0: if (!tm) return 0; OC_PP(0) break;
   case 1: OC_PP(1) break;
@@ -227,6 +236,12 @@ extern "C" int ospcuda_fb_postprocess(const OcVec4f *d_in, OcVec4f *d_ppOut, voi
 #undef OC_PP
   oc_count_launch();
   return oc_check(cudaGetLastError(), "ospcuda_fb_postprocess");
+}
+
+extern "C" int ospcuda_fb_postprocess(const OcVec4f *d_in, OcVec4f *d_ppOut, void *d_out, uint32_t numPixels,
+    uint32_t colorFormat, const OcToneMapper *tm)
+{
+  return ospcuda_fb_postprocess_tiles(d_in, d_ppOut, d_out, (int)numPixels, 1, colorFormat, tm, 1, 0);
 }
 
 extern "C" int ospcuda_fb_color_convert(const OcVec4f *d_in, void *d_out, uint32_t numPixels, uint32_t colorFormat)

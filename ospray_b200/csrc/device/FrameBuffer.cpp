@@ -118,8 +118,8 @@ void FrameBuffer::postProcess()
   }
   const OcToneMapper *last = toneMappers.empty() ? nullptr : &toneMappers.back()->tm;
   if (convBuf || last)
-    checkCuda(ospcuda_fb_postprocess(in, last ? ppBuf->as<OcVec4f>() : nullptr, convBuf ? convBuf->p : nullptr, np,
-                  convBuf ? (uint32_t)colorFormat : 0u, last),
+    checkCuda(ospcuda_fb_postprocess_tiles(in, last ? ppBuf->as<OcVec4f>() : nullptr, convBuf ? convBuf->p : nullptr, size.x, size.y,
+                  convBuf ? (uint32_t)colorFormat : 0u, last, sh.numRanks ? sh.numRanks : 1u, sh.rank),
         "colour conversion");
 }
 

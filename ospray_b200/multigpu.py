@@ -256,6 +256,38 @@ class PeerTileExchange:
         self.world_size = 1
 
 
+def tile_checksums(img, world_size):
+    """per owner rank: (sum of all bytes, sum of bytes * position) over the pixels of the tiles that rank owns, of an
+    (H, W, C) uint8 image"""
+    import numpy as np
+    h, w = img.shape[:2]
+    tx, _ = tile_grid(w, h)
+    owner = ((np.arange(h)[:, None] // TILE) * tx + (np.arange(w)[None, :] // TILE)) % world_size
+    flat = img.reshape(h, w, -1).astype(np.uint64).sum(axis=2)
+    pos = (np.arange(h, dtype=np.uint64)[:, None] * np.uint64(w) + np.arange(w, dtype=np.uint64)[None, :]) % np.uint64(65521) + np.uint64(1)
+    return [(int(flat[owner == r].sum()), int((flat * pos)[owner == r].sum())) for r in range(world_size)]
+
+
+def verify_composition(local_img, group=None):
+    """Every rank passes its own mapped display image (rank 0: the composed one). Checks on rank 0 that the tiles of
+    every rank r in the composed image carry exactly what rank r rendered (checksums of r's owned tiles, compared
+    through the process group). Returns True on rank 0 when all match (raises otherwise), None elsewhere."""
+    ws = dist.get_world_size(group) if dist.is_initialized() else 1
+    rk = dist.get_rank(group) if dist.is_initialized() else 0
+    sums = tile_checksums(local_img, ws)
+    everyone = [None] * ws
+    if ws > 1:
+        dist.all_gather_object(everyone, sums[rk], group=group)
+    else:
+        everyone[0] = sums[0]
+    if rk != 0:
+        return None
+    bad = [r for r in range(ws) if tuple(everyone[r]) != tuple(sums[r])]
+    if bad:
+        raise RuntimeError(f"tile composition mismatch: GPU 0's image does not hold the tiles rendered by rank(s) {bad}")
+    return True
+
+
 def init_process_group_from_env():
     """torchrun environment -> (rank, world_size, local_rank); NCCL when CUDA is present, else gloo
     (OSPRAY_B200_DIST_BACKEND=gloo forces gloo: ranks that share one GPU, where NCCL refuses to run)"""

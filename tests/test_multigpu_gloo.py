@@ -190,6 +190,7 @@ def _peer_worker(rank, world, port, w, h, out_path):
             x.gather(srgb)
     assert x.epoch == 2
     x.check()
+    assert multigpu.verify_composition(frames[-1] if rank == 0 else srgb) is (True if rank == 0 else None)
     if rank == 0:
         np.savez(out_path, f0=frames[0], f1=frames[1], gathered=x.bytes_gathered)
     x.close()
@@ -218,3 +219,17 @@ def test_peer_tile_exchange_protocol_gloo(tmp_path, world):
         np.testing.assert_array_equal(got[k], want)
     tiles = multigpu.tile_grid(w, h)[0] * multigpu.tile_grid(w, h)[1]
     assert int(got["gathered"]) == (tiles - len(multigpu.owned_tiles(w, h, world, 0))) * 64 * 64 * 4
+
+
+def test_tile_checksums_see_a_missing_tile():
+    from ospray_b200 import multigpu
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (136, 200, 4), dtype=np.uint8)
+    a = multigpu.tile_checksums(img, 3)
+    broken = img.copy()
+    broken[64:128, 64:128] = 0          # tile 5 of a 4 x 3 grid: owned by rank 5 % 3 == 2
+    b = multigpu.tile_checksums(broken, 3)
+    assert a[0] == b[0] and a[1] == b[1] and a[2] != b[2]
+    swapped = img.copy()
+    swapped[0:64, 0:64], swapped[64:128, 128:192] = img[64:128, 128:192], img[0:64, 0:64]   # tiles 0 and 6, both rank 0
+    assert multigpu.tile_checksums(swapped, 3)[0] != a[0]                                   # position-weighted sum

@@ -9,6 +9,8 @@
   C5s cornell_box + mesh     pathtracer 3840x2160  1 spp/frame (the single-GPU leg of C5)
 
   python tools/bench_workloads.py C2 C3 [--frames 5] [--out gpurun_out/x/workloads.json]
+  torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/bench_workloads.py C5s ...   (N GPUs: config C5 --
+      replicated scene, tile % N == rank, tiles stored into GPU 0's image over NVLink peer memory; frame time = max over ranks)
 
 Prints one JSON object per workload: frame ms (CUDA events on the render stream around ospRenderFrame's kernels,
 L2 flushed between frames), rays per frame, Mrays/s, scene commit / BVH build ms. These are parity-test-sized
@@ -39,8 +41,11 @@ def main():
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     import torch
-    from ospray_b200 import capi as osp, testing as T
-    osp.init(cudaDevice=0)
+    import torch.distributed as dist
+    from ospray_b200 import capi as osp, multigpu, testing as T
+    rank, nranks, local = multigpu.init_process_group_from_env()
+    torch.cuda.set_device(local)
+    osp.init(cudaDevice=local, numSubdevices=nranks, subdeviceRank=rank)
     stream = torch.cuda.Stream()
     osp.set_render_stream(stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -69,15 +74,28 @@ def main():
             cam, pose = T.make_camera(world, w, h)
             ren = T.make_renderer(ren_kind, pixelSamples=spp, **rp)
             fb = osp.FrameBuffer(w, h, osp.OSP_FB_SRGBA, osp.OSP_FB_COLOR | osp.OSP_FB_ACCUM | osp.OSP_FB_DEPTH)
+            conv_ptr, bpp = fb.device_pointer(osp.OSP_FB_COLOR)
+            exch = multigpu.PeerTileExchange(w, h, bpp, conv_ptr) if nranks > 1 else None
+
+            def frame():
+                if exch:
+                    exch.begin_frame()
+                f = fb.render_frame(ren, cam, world)
+                if exch:
+                    exch.gather(conv_ptr)
+                return f
+
             for _ in range(args.warmup):
-                fb.render_frame(ren, cam, world).wait()
+                frame().wait()
                 flush.zero_()
             torch.cuda.synchronize()
+            if nranks > 1:
+                dist.barrier()
             ms, rays = [], np.zeros(3, np.int64)
             for _ in range(args.frames):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
-                f = fb.render_frame(ren, cam, world)
+                f = frame()
                 e1.record(stream)
                 f.wait()
                 torch.cuda.synchronize()
@@ -85,6 +103,17 @@ def main():
                 rays += np.array(fb.ray_counts(), np.int64)
                 flush.zero_()
             img = fb.map(osp.OSP_FB_COLOR)
+            if nranks > 1:
+                multigpu.verify_composition(img)  # GPU 0's image holds every rank's tiles (raises otherwise)
+            if nranks > 1:  # frame time = max over ranks per frame, rays = sum over ranks
+                t = torch.tensor(ms, dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = t.tolist()
+                rt = torch.tensor(rays, dtype=torch.float64, device="cuda")
+                dist.all_reduce(rt, op=dist.ReduceOp.SUM)
+                rays = rt.cpu().numpy().astype(np.int64)
+                exch.check()
+                exch.close()
             tot_ms = float(np.sum(ms))
             r = {"workload": wl, "renderer": ren_kind, "size": [w, h], "spp": spp, "frames": args.frames,
                  "frame_ms": round(tot_ms / args.frames, 4), "frame_ms_min": round(float(np.min(ms)), 4),
@@ -97,10 +126,17 @@ def main():
                 r["triangles"] = int(sum(m.geometry.index.shape[0] for i in spec.instances for m in i.group.models if m.geometry.index is not None))
             if wl == "C2":
                 r["volume_dim"] = args.dim
-            print(json.dumps(r), flush=True)
+            if nranks > 1:
+                r["n_gpus"] = nranks
+                r["partition"] = f"tile % {nranks} == rank, peer-memory tile exchange to GPU 0; frame_ms = max over ranks"
+            if rank == 0:
+                print(json.dumps(r), flush=True)
             results.append(r)
             del fb, ren, cam, world, keep
-    if args.out:
+    if nranks > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if args.out and rank == 0:
         os.makedirs(os.path.dirname(args.out), exist_ok=True)
         json.dump(results, open(args.out, "w"), indent=1)
 

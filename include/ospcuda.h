@@ -219,7 +219,11 @@ typedef struct {
   uint32_t type;
 } OcCamera;
 
-enum { OC_RENDERER_PATHTRACER = 0, OC_RENDERER_SCIVIS = 1, OC_RENDERER_AO = 2, OC_RENDERER_DEBUG_ID = 3 };
+enum { OC_RENDERER_PATHTRACER = 0, OC_RENDERER_SCIVIS = 1, OC_RENDERER_AO = 2, OC_RENDERER_DEBUG = 3 };
+/* debug renderer methods: ispc::DebugRendererType (render/debug/DebugRendererShared.h:12-30), same order */
+enum { OC_DEBUG_TEST_FRAME = 0, OC_DEBUG_RAY_DIR, OC_DEBUG_EYE_LIGHT, OC_DEBUG_NG, OC_DEBUG_NS, OC_DEBUG_COLOR, OC_DEBUG_TEX_COORD,
+       OC_DEBUG_DPDS, OC_DEBUG_DPDT, OC_DEBUG_PRIM_ID, OC_DEBUG_GEOM_ID, OC_DEBUG_INST_ID, OC_DEBUG_BACKFACING_NG,
+       OC_DEBUG_BACKFACING_NS, OC_DEBUG_VOLUME };
 enum { OC_PF_POINT = 0, OC_PF_BOX = 1, OC_PF_LUT = 2 };
 
 /* renderer (reference: Renderer.cpp:38-92, PathTracer.cpp:29-51, SciVis.cpp:27-36,
@@ -256,6 +260,8 @@ typedef struct {
   /* host-side copy of OcWorld.numLights of the world this frame renders (set per ospRenderFrame by the
    * device; PathTracerData is per world, PathTracerData.cpp:32-82): sizes the pathtracer's light-sample loop */
   uint32_t worldNumLights;
+  /* debug renderer (DebugRenderer.cpp:69-75): OC_DEBUG_* */
+  uint32_t debugMethod;
 } OcRenderer;
 
 /* framebuffer (reference: LocalFBShared.h, FrameBufferShared.h; LocalFB.cpp:49-180) */

@@ -1702,6 +1702,70 @@ void AO_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint32_t px, uint32
   sample.rgb = v3(outputColor);
   sample.alpha = outputColor.w;
 }
+// ---- debug renderer: render/debug/DebugRenderer.ispc:27-420 (texCoord, dPdt and volume methods are not restated) ----
+inline V3 makeRandomColor(uint32_t i) // rkcommon/utility/random.ih (un-vendored; restated)
+{
+  const uint32_t mx = 13 * 17 * 43, my = 11 * 29, mz = 7 * 23 * 63;
+  const uint32_t g = i * (3 * 5 * 127) + 12312314;
+  if (i == 0xFFFFFFFFu) return {0.f, 0.f, 0.f};
+  return {(g % mx) * (1.f / (mx - 1)), (g % my) * (1.f / (my - 1)), (g % mz) * (1.f / (mz - 1))};
+}
+inline float debugEyeLight(const Ray &ray) { return 0.2f + 0.8f * fabsf(dot(normalize(ray.Ng), ray.dir)); } // :39-42
+inline V3 debugTangentColor(V3 t) // :133-141
+{
+  V3 c = normalize(t);
+  if (c.x < 0.f) c.x = c.x * -0.3f;
+  if (c.y < 0.f) c.y = c.y * -0.3f;
+  if (c.z < 0.f) c.z = c.z * -0.3f;
+  return c;
+}
+void Debug_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint32_t px, uint32_t py, int sampleIDz)
+{
+  const OcRenderer &ren = c.ren;
+  const uint32_t method = ren.debugMethod;
+  if (method == OC_DEBUG_TEST_FRAME) { // :47-62
+    sample.rgb = {(px % 256) / 255.f, (py % 256) / 255.f, ((px + py + (uint32_t)sampleIDz) % 256) / 255.f};
+    sample.alpha = 1.f; sample.z = 1.f;
+  } else if (method == OC_DEBUG_RAY_DIR) { // :66-72
+    sample.rgb = vabs(ray.dir);
+    sample.alpha = 1.f; sample.z = 1.f;
+  } else {
+    c.cnt.primary++;
+    traceWorld(c.w, ray, false); // hitBackground :27-38
+    sample.z = ray.t;
+    sample.alpha = 1.f;
+    sample.rgb = v3(getBackground(ren));
+    if (hadHit(ray)) {
+      DG dg;
+      switch (method) {
+      case OC_DEBUG_EYE_LIGHT: sample.rgb = v3(debugEyeLight(ray)); break;
+      case OC_DEBUG_NG: postIntersect(c.w, ren, dg, ray, DG_NORMALIZE | DG_NG); sample.rgb = vabs(dg.Ng); break;
+      case OC_DEBUG_NS: postIntersect(c.w, ren, dg, ray, DG_NORMALIZE | DG_NS); sample.rgb = vabs(dg.Ns); break;
+      case OC_DEBUG_COLOR:
+        postIntersect(c.w, ren, dg, ray, DG_COLOR | DG_NS);
+        sample.rgb = v3(dg.color) * fabsf(dot(normalize(ray.dir), normalize(dg.Ns)));
+        break;
+      case OC_DEBUG_DPDS: postIntersect(c.w, ren, dg, ray, DG_TANGENTS); sample.rgb = debugTangentColor(dg.dPds); break;
+      case OC_DEBUG_PRIM_ID: sample.rgb = debugEyeLight(ray) * makeRandomColor(ray.primID); break;
+      case OC_DEBUG_GEOM_ID: sample.rgb = debugEyeLight(ray) * makeRandomColor(ray.geomID); break;
+      case OC_DEBUG_INST_ID: sample.rgb = debugEyeLight(ray) * makeRandomColor(ray.instID); break;
+      case OC_DEBUG_BACKFACING_NG:
+        sample.rgb = v3(debugEyeLight(ray));
+        if (dot(ray.Ng, ray.dir) > 0.f) sample.rgb.y = 0.f;
+        break;
+      case OC_DEBUG_BACKFACING_NS: {
+        postIntersect(c.w, ren, dg, ray, DG_NORMALIZE | DG_NS);
+        const float cs = dot(dg.Ns, ray.dir);
+        sample.rgb = v3(.2f + .8f * fabsf(cs));
+        if (cs > 0.f) sample.rgb.y = 0.f;
+        break;
+      }
+      default: break;
+      }
+    }
+  }
+  if (c.fb.projectedDepth) sample.z *= dot(ray.dir, v3(c.cam.direction)); // :397-398
+}
 // render/RendererRenderTaskFn.inl:30-86 -- NOTE `sample` lives outside the spp loop (not re-zeroed)
 ScreenSample defaultRenderPixel(Ctx &c, uint32_t x, uint32_t y)
 {
@@ -1721,6 +1785,7 @@ ScreenSample defaultRenderPixel(Ctx &c, uint32_t x, uint32_t y)
     Ray ray;
     cameraInitRay(c.cam, ray, screen, {0.f, 0.f});
     if (ren.type == OC_RENDERER_SCIVIS) SciVis_renderSample(c, ray, sample, x, y, startSampleID + s);
+    else if (ren.type == OC_RENDERER_DEBUG) Debug_renderSample(c, ray, sample, x, y, startSampleID + s);
     else AO_renderSample(c, ray, sample, x, y, startSampleID + s);
     ScreenSample_accumulate(screenSample, sample);
   }

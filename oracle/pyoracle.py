@@ -20,7 +20,9 @@ OC_GEOM_TRIANGLES, OC_GEOM_QUADS, OC_GEOM_SPHERES, OC_GEOM_BOXES = 0, 1, 2, 3
 OC_GEOMFLAG_NORMAL_FV, OC_GEOMFLAG_COLOR_FV, OC_GEOMFLAG_TEX_FV, OC_GEOMFLAG_HAS_ALPHA, OC_GEOMFLAG_COLOR_VEC4 = 1, 2, 4, 8, 16
 OC_MAT_NONE, OC_MAT_FROM_MODEL, OC_MAT_FROM_RENDERER = 0, 1, 2
 OC_LIGHT_AMBIENT, OC_LIGHT_DISTANT, OC_LIGHT_QUAD = 0, 2, 5
-OC_RENDERER = {"pathtracer": 0, "scivis": 1, "ao": 2}
+OC_RENDERER = {"pathtracer": 0, "scivis": 1, "ao": 2, "debug": 3}
+OC_DEBUG = {n: i for i, n in enumerate(["testFrame", "rayDir", "eyeLight", "Ng", "Ns", "color", "texCoord", "dPds", "dPdt", "primID", "geomID",
+                                        "instID", "backfacing_Ng", "backfacing_Ns", "volume"])}  # ispc::DebugRendererType order
 OC_PF_POINT, OC_PF_BOX, OC_PF_LUT = 0, 1, 2
 
 
@@ -113,7 +115,7 @@ class Renderer(C.Structure):
                 ("limitIndirectLightSamples", C.c_uint32), ("backgroundRefraction", C.c_uint32),
                 ("shadowsEnabled", C.c_uint32), ("visibleLights", C.c_uint32), ("aoSamples", C.c_int32),
                 ("aoRadius", C.c_float), ("aoIntensity", C.c_float), ("volumeSamplingRate", C.c_float),
-                ("worldNumLights", C.c_uint32)]
+                ("worldNumLights", C.c_uint32), ("debugMethod", C.c_uint32)]
 
 
 class FrameBuffer(C.Structure):
@@ -505,8 +507,9 @@ class RendererParams:
     def __init__(self, kind, pixelSamples=1, pixelFilter="gauss", maxPathLength=20, minContribution=0.001, backgroundColor=(0, 0, 0, 0),
                  roulettePathLength=5, maxScatteringEvents=20, maxContribution=np.inf, lightSamples=-1, limitIndirectLightSamples=True,
                  backgroundRefraction=False, shadows=False, visibleLights=False, aoSamples=None, aoDistance=1e20, aoIntensity=1.0,
-                 volumeSamplingRate=1.0):
+                 volumeSamplingRate=1.0, method="eyeLight"):
         r = Renderer()
+        r.debugMethod = OC_DEBUG.get(method, 0)  # DebugRenderer.cpp:18-52: unknown names fall back to the test frame
         r.type, r.spp, r.maxDepth, r.minContribution = OC_RENDERER[kind], max(1, pixelSamples), maxPathLength, minContribution
         bg = list(backgroundColor) + [0.0] * (4 - len(backgroundColor))
         for k in range(4):

@@ -38,6 +38,7 @@
 #include "render/pathtracer/PathTracerShared.h"
 #include "render/scivis/SciVisShared.h"
 #include "render/ao/AORendererShared.h"
+#include "render/debug/DebugRendererShared.h"
 #include "pf/LUTPixelFilterShared.h"
 #include "camera/PerspectiveCameraShared.h"
 #include "camera/OrthographicCameraShared.h"
@@ -67,6 +68,7 @@ extern "C" {
 void PathTracer_renderTaskLauncher(void *, void *, const vec3ui &, Renderer *, FrameBuffer *, Camera *, World *, const uint32_t *, const ospray::FeatureFlags &);
 void SciVis_renderTaskLauncher(void *, void *, const vec3ui &, Renderer *, FrameBuffer *, Camera *, World *, const uint32_t *, const ospray::FeatureFlags &);
 void AORenderer_renderTaskLauncher(void *, void *, const vec3ui &, Renderer *, FrameBuffer *, Camera *, World *, const uint32_t *, const ospray::FeatureFlags &);
+void DebugRenderer_renderTaskLauncher(void *, void *, const vec3ui &, Renderer *, FrameBuffer *, Camera *, World *, const uint32_t *, const ospray::FeatureFlags &);
 void ColorConversion_kernelLauncher(void *, void *, const vec2ui &, const FrameBufferView *);
 void ToneMapper_kernelLauncher(void *, void *, const vec2ui &, const FrameBufferView *);
 void Variance_kernelLauncher(void *, void *, const vec2ui &, const FrameBufferView *);
@@ -339,14 +341,17 @@ void buildScene(Scene &s, const OcWorld *w, const OcRenderer *ren)
 
 struct RendererSet
 {
-  PathTracer pt; SciVis sv; AORenderer ao;
+  PathTracer pt; SciVis sv; AORenderer ao; DebugRenderer dbg;
   PixelFilter pf; LUTPixelFilter lut; Distribution2D dist;
   std::vector<Material *> materials;
 };
 
 Renderer *buildRenderer(RendererSet &r, Scene &s, const OcRenderer *o)
 {
-  Renderer *base = o->type == OC_RENDERER_PATHTRACER ? &r.pt.super : (o->type == OC_RENDERER_SCIVIS ? &r.sv.super : &r.ao.super);
+  Renderer *base = o->type == OC_RENDERER_PATHTRACER ? &r.pt.super
+      : o->type == OC_RENDERER_SCIVIS ? &r.sv.super
+      : o->type == OC_RENDERER_DEBUG  ? &r.dbg.super
+                                      : &r.ao.super;
   // render/Renderer.cpp:38-92
   base->spp = o->spp; base->bgColor = make_vec4f(o->bgColor[0], o->bgColor[1], o->bgColor[2], o->bgColor[3]);
   base->maxDepth = o->maxDepth; base->minContribution = o->minContribution;
@@ -371,6 +376,8 @@ Renderer *buildRenderer(RendererSet &r, Scene &s, const OcRenderer *o)
   } else if (o->type == OC_RENDERER_SCIVIS) { // render/scivis/SciVis.cpp:27-36
     r.sv.shadowsEnabled = o->shadowsEnabled != 0; r.sv.visibleLights = o->visibleLights != 0; r.sv.aoSamples = o->aoSamples;
     r.sv.aoRadius = o->aoRadius; r.sv.volumeSamplingRate = o->volumeSamplingRate;
+  } else if (o->type == OC_RENDERER_DEBUG) { // render/debug/DebugRenderer.cpp:69-75 (OC_DEBUG_* == ispc::DebugRendererType)
+    r.dbg.type = (DebugRendererType)o->debugMethod;
   } else { // render/ao/AORenderer.cpp:26-35
     r.ao.aoSamples = o->aoSamples; r.ao.aoRadius = o->aoRadius; r.ao.aoIntensity = o->aoIntensity;
     r.ao.volumeSamplingRate = o->volumeSamplingRate;
@@ -443,11 +450,15 @@ REF_API int ospref_render_frame(const OcWorld *w, const OcCamera *cam, const OcR
     PathTracer_renderTaskLauncher(&q, &ev, dims, renderer, &lfb.super, camera, &s->world, taskIDs.data(), ff);
   else if (ren->type == OC_RENDERER_SCIVIS)
     SciVis_renderTaskLauncher(&q, &ev, dims, renderer, &lfb.super, camera, &s->world, taskIDs.data(), ff);
+  else if (ren->type == OC_RENDERER_DEBUG)
+    DebugRenderer_renderTaskLauncher(&q, &ev, dims, renderer, &lfb.super, camera, &s->world, taskIDs.data(), ff);
   else
     AORenderer_renderTaskLauncher(&q, &ev, dims, renderer, &lfb.super, camera, &s->world, taskIDs.data(), ff);
   if (fb->rayCounters) {
     uint64_t after[2]; ospref_ray_counters(after, 0);
-    fb->rayCounters[0] += (unsigned long long)taskIDs.size() * 64ull * (unsigned long long)ren->spp;
+    // (the two debug methods that trace nothing hand no primary ray to the scene)
+    const bool noRays = ren->type == OC_RENDERER_DEBUG && (ren->debugMethod == OC_DEBUG_TEST_FRAME || ren->debugMethod == OC_DEBUG_RAY_DIR);
+    fb->rayCounters[0] += noRays ? 0ull : (unsigned long long)taskIDs.size() * 64ull * (unsigned long long)ren->spp;
     const unsigned long long total = (after[0] - before[0]) + (after[1] - before[1]);
     fb->rayCounters[1] += (after[0] - before[0]) - std::min<unsigned long long>(after[0] - before[0], taskIDs.size() * 64ull * ren->spp);
     fb->rayCounters[2] += after[1] - before[1];

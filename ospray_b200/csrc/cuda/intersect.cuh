@@ -351,6 +351,17 @@ __device__ __forceinline__ bool traverseBLAS(const OcNode4 *__restrict__ nodes, 
         if (k3 < INFINITY && sp < OC_STACK_SIZE) st.at(sp++) = c3;
         if (k2 < INFINITY && sp < OC_STACK_SIZE) st.at(sp++) = c2;
         if (k1 < INFINITY && sp < OC_STACK_SIZE) st.at(sp++) = c1;
+#ifdef OC_PREFETCH_NEXT
+        // the entry just pushed last is what the next pop returns: start fetching its node / first record now
+        if (k1 < INFINITY) {
+          const void *nx = (c1 & 0x80000000u) ? (const void *)(prims + 3 * (size_t)(c1 & 0x07FFFFFFu)) : (const void *)(nodes + c1);
+          #ifdef OC_PREFETCH_L1
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+#else
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+#endif
+        }
+#endif
         cur = c0;
         continue;
       }

@@ -503,6 +503,86 @@ __device__ void AO_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint32_t
   sample.alpha = outputColor.w;
 }
 
+// ======================================= debug renderer ======================================
+// render/debug/DebugRenderer.ispc:27-420 (methods of DebugRendererShared.h:12-30; texCoord, dPdt and volume are refused at
+// commit: no texture coordinates / second tangent / debug volume marcher on this device)
+__device__ __forceinline__ vec3f makeRandomColor(uint32_t i) // rkcommon/utility/random.ih (un-vendored; restated)
+{
+  const uint32_t mx = 13 * 17 * 43, my = 11 * 29, mz = 7 * 23 * 63;
+  const uint32_t g = i * (3 * 5 * 127) + 12312314;
+  if (i == 0xFFFFFFFFu) return make_vec3f(0.f);
+  return make_vec3f((g % mx) * (1.f / (mx - 1)), (g % my) * (1.f / (my - 1)), (g % mz) * (1.f / (mz - 1)));
+}
+__device__ __forceinline__ float debugEyeLight(const Ray &ray) { return 0.2f + 0.8f * fabsf(dot(normalize(ray.Ng), ray.dir)); }
+__device__ __forceinline__ vec3f debugTangentColor(vec3f t)
+{
+  vec3f c = normalize(t);
+  if (c.x < 0.f) c.x = c.x * -0.3f;
+  if (c.y < 0.f) c.y = c.y * -0.3f;
+  if (c.z < 0.f) c.z = c.z * -0.3f;
+  return c;
+}
+
+__device__ void Debug_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint32_t px, uint32_t py, int sampleIDz)
+{
+  const OcRenderer &ren = c.ren;
+  const uint32_t method = ren.debugMethod;
+  if (method == OC_DEBUG_TEST_FRAME) { // no ray at all (DebugRenderer.ispc:50-62)
+    sample.rgb = make_vec3f((px % 256) / 255.f, (py % 256) / 255.f, ((px + py + (uint32_t)sampleIDz) % 256) / 255.f);
+    sample.alpha = 1.f;
+    sample.z = 1.f;
+  } else if (method == OC_DEBUG_RAY_DIR) {
+    sample.rgb = vabs(ray.dir);
+    sample.alpha = 1.f;
+    sample.z = 1.f;
+  } else {
+    // hitBackground (DebugRenderer.ispc:27-38)
+    c.cnt.primary++;
+    traceWorldNI<false>(c.world, ray, c.stack);
+    sample.z = ray.t;
+    sample.alpha = 1.f;
+    sample.rgb = make_vec3f(getBackground(ren));
+    if (hadHit(ray)) {
+      DifferentialGeometry dg;
+      switch (method) {
+      case OC_DEBUG_EYE_LIGHT: sample.rgb = make_vec3f(debugEyeLight(ray)); break;
+      case OC_DEBUG_NG:
+        postIntersect(c.world, ren, dg, ray, DG_NORMALIZE | DG_NG);
+        sample.rgb = vabs(dg.Ng);
+        break;
+      case OC_DEBUG_NS:
+        postIntersect(c.world, ren, dg, ray, DG_NORMALIZE | DG_NS);
+        sample.rgb = vabs(dg.Ns);
+        break;
+      case OC_DEBUG_COLOR:
+        postIntersect(c.world, ren, dg, ray, DG_COLOR | DG_NS);
+        sample.rgb = make_vec3f(dg.color) * fabsf(dot(normalize(ray.dir), normalize(dg.Ns)));
+        break;
+      case OC_DEBUG_DPDS:
+        postIntersect(c.world, ren, dg, ray, DG_TANGENTS);
+        sample.rgb = debugTangentColor(dg.dPds);
+        break;
+      case OC_DEBUG_PRIM_ID: sample.rgb = debugEyeLight(ray) * makeRandomColor(ray.primID); break;
+      case OC_DEBUG_GEOM_ID: sample.rgb = debugEyeLight(ray) * makeRandomColor(ray.geomID); break;
+      case OC_DEBUG_INST_ID: sample.rgb = debugEyeLight(ray) * makeRandomColor(ray.instID); break;
+      case OC_DEBUG_BACKFACING_NG:
+        sample.rgb = make_vec3f(debugEyeLight(ray));
+        if (dot(ray.Ng, ray.dir) > 0.f) sample.rgb.y = 0.f;
+        break;
+      case OC_DEBUG_BACKFACING_NS: {
+        postIntersect(c.world, ren, dg, ray, DG_NORMALIZE | DG_NS);
+        const float cs = dot(dg.Ns, ray.dir);
+        sample.rgb = make_vec3f(.2f + .8f * fabsf(cs));
+        if (cs > 0.f) sample.rgb.y = 0.f;
+        break;
+      }
+      default: break;
+      }
+    }
+  }
+  if (c.fb.projectedDepth) sample.z *= dot(ray.dir, toV(c.cam.direction));
+}
+
 // Renderer_default_renderTask pixel body (render/RendererRenderTaskFn.inl:30-86)
 template <int RENDERER>
 __device__ void defaultRenderPixel(Ctx &c, uint32_t x, uint32_t y, ScreenSample &screenSample)
@@ -526,6 +606,7 @@ __device__ void defaultRenderPixel(Ctx &c, uint32_t x, uint32_t y, ScreenSample 
     Ray ray;
     cameraInitRay(c.cam, ray, screen, make_vec2f(0.f, 0.f));
     if (RENDERER == OC_RENDERER_SCIVIS) SciVis_renderSample(c, ray, sample, x, y, startSampleID + s);
+    else if (RENDERER == OC_RENDERER_DEBUG) Debug_renderSample(c, ray, sample, x, y, startSampleID + s);
     else AO_renderSample(c, ray, sample, x, y, startSampleID + s);
     ScreenSample_accumulate(screenSample, sample);
   }
@@ -854,6 +935,7 @@ extern "C" int ospcuda_render_frame(const OcWorld *d_world, const OcCamera *came
   }
   case OC_RENDERER_SCIVIS: renderFrameKernel<OC_RENDERER_SCIVIS><<<grid, block, 0, st>>>(a); break;
   case OC_RENDERER_AO: renderFrameKernel<OC_RENDERER_AO><<<grid, block, 0, st>>>(a); break;
+  case OC_RENDERER_DEBUG: renderFrameKernel<OC_RENDERER_DEBUG><<<grid, block, 0, st>>>(a); break;
   default: return oc_set_error(cudaErrorInvalidValue, "ospcuda_render_frame: unknown renderer type");
   }
   oc_count_launch();

@@ -129,7 +129,7 @@ void CudaDevice::resetAccumulation(OSPFrameBuffer fb) { ((FrameBuffer *)fb)->cle
 OSPRenderer CudaDevice::newRenderer(const char *type)
 {
   const std::string t(type);
-  if (t != "pathtracer" && t != "scivis" && t != "ao") return nullptr;
+  if (t != "pathtracer" && t != "scivis" && t != "ao" && t != "debug") return nullptr;
   return (OSPRenderer) new Renderer(*this, t);
 }
 

@@ -928,6 +928,22 @@ void Renderer::commit()
   if (type == "pathtracer") sh.type = OC_RENDERER_PATHTRACER;
   else if (type == "scivis") sh.type = OC_RENDERER_SCIVIS;
   else if (type == "ao") sh.type = OC_RENDERER_AO;
+  else if (type == "debug") {
+    // DebugRenderer::commit (render/debug/DebugRenderer.cpp:18-75): "method", default eyeLight; unknown names -> testFrame
+    sh.type = OC_RENDERER_DEBUG;
+    static const struct { const char *name; uint32_t id; } methods[] = {{"rayDir", OC_DEBUG_RAY_DIR}, {"eyeLight", OC_DEBUG_EYE_LIGHT},
+        {"Ng", OC_DEBUG_NG}, {"Ns", OC_DEBUG_NS}, {"color", OC_DEBUG_COLOR}, {"texCoord", OC_DEBUG_TEX_COORD},
+        {"backfacing_Ng", OC_DEBUG_BACKFACING_NG}, {"backfacing_Ns", OC_DEBUG_BACKFACING_NS}, {"dPds", OC_DEBUG_DPDS},
+        {"dPdt", OC_DEBUG_DPDT}, {"primID", OC_DEBUG_PRIM_ID}, {"geomID", OC_DEBUG_GEOM_ID}, {"instID", OC_DEBUG_INST_ID},
+        {"volume", OC_DEBUG_VOLUME}};
+    const std::string method = getParamString("method", "eyeLight");
+    uint32_t id = OC_DEBUG_TEST_FRAME;
+    for (const auto &m : methods)
+      if (method == m.name) id = m.id;
+    if (id == OC_DEBUG_TEX_COORD || id == OC_DEBUG_DPDT || id == OC_DEBUG_VOLUME)
+      throw std::runtime_error("cuda device: debug renderer method '" + method + "' is not supported (texCoord, dPdt, volume)");
+    sh.debugMethod = id;
+  }
   sh.spp = std::max(1, getParam<int>("pixelSamples", 1));
   getParam<float>("mipMapBias", 0.f);
   sh.maxDepth = (uint32_t)std::max(0, getParam<int>("maxPathLength", 20));

@@ -144,6 +144,19 @@ CASES = {
     "gravity_shaded": (shaded_volume, "scivis", {"shadows": True}, 1),
     "volume_geometry": (volume_with_geometry, "scivis", {"shadows": True, "aoSamples": 1}, 1),
     "volume_opaque_geometry": (volume_with_opaque_geometry, "scivis", {"pixelSamples": 2}, 1),
+    # debug renderer (render/debug/DebugRenderer.ispc), every method the device accepts
+    "debug_testFrame": (T.cornell_box, "debug", {"method": "testFrame", "pixelSamples": 2}, 2),
+    "debug_rayDir": (T.cornell_box, "debug", {"method": "rayDir"}, 1),
+    "debug_eyeLight": (T.cornell_box, "debug", {"method": "eyeLight", "pixelSamples": 2, "backgroundColor": (0.1, 0.2, 0.3, 1.0)}, 1),
+    "debug_Ng": (instanced_boxes_and_spheres, "debug", {"method": "Ng"}, 1),
+    "debug_Ns": (few_streamlines, "debug", {"method": "Ns"}, 1),
+    "debug_color": (T.cornell_box, "debug", {"method": "color"}, 1),
+    "debug_dPds": (instanced_boxes_and_spheres, "debug", {"method": "dPds"}, 1),
+    "debug_primID": (T.cornell_box, "debug", {"method": "primID"}, 1),
+    "debug_geomID": (instanced_boxes_and_spheres, "debug", {"method": "geomID"}, 1),
+    "debug_instID": (instanced_boxes_and_spheres, "debug", {"method": "instID"}, 1),
+    "debug_backfacing_Ng": (lambda: T.boxes(lit=True), "debug", {"method": "backfacing_Ng"}, 1),
+    "debug_backfacing_Ns": (T.random_spheres, "debug", {"method": "backfacing_Ns"}, 1),
 }
 # Cases the reference's scalar-mode kernels (oracle/_ref) cannot run: SciVis_renderSample and lightAlpha keep ONE
 # VolumeInterval on the stack (render/scivis/SciVis.ispc:45-50, lightAlpha.ispc:36-41) but Volume_intersect_kernel bumps

@@ -265,3 +265,16 @@ def test_pick_matches_oracle_primary_hit(osp):
             np.testing.assert_allclose(pos, want["org"][i] + want["dir"][i] * want["t"][i], rtol=1e-5, atol=1e-5)
             assert inst and model
     assert 3 < hits < len(px)
+
+
+@pytest.mark.gpu
+def test_debug_renderer_refuses_unsupported_methods(osp):
+    """texCoord / dPdt / volume need data this device does not carry: the commit fails through the API's error convention
+    (API.cpp:45-66) instead of rendering something else; unknown names fall back to the test frame like the reference
+    (DebugRenderer.cpp:18-52)"""
+    for method in ("texCoord", "dPdt", "volume"):
+        r = osp.Renderer("debug")
+        r.set("method", method)
+        with pytest.raises(osp.OSPRayError, match="not supported"):
+            r.commit()
+    osp.Renderer("debug").set("method", "noSuchMethod").commit()

@@ -171,9 +171,17 @@ __device__ __forceinline__ vec3f maddRN(vec3f a, float s, vec3f b) // a + s * b
 }
 // The ray origin is first moved along the ray to the point closest to pa (parameter tp) so that the discriminant of a
 // grazing ray seen from far away does not cancel catastrophically (see oracle/curve_capsule.h); t = tp + t'.
-__device__ __forceinline__ bool intersectCapsule(const Ray &ray, vec3f pa, vec3f pb, float r, float &t, float &sOut, vec3f &Ng)
+// Out of line, hit returned by value: inlined into intersectRecord, the capsule's early-out control flow made the compiler
+// restructure the whole leaf loop and traversal ran with half the lanes per warp (C3: 95 -> 190 ms, tools/ab_commits.sh).
+struct CapsuleHit { float t, s; vec3f Ng; bool hit; };
+static __device__ __noinline__ CapsuleHit intersectCapsuleNI(vec3f org, vec3f d, float rayT0, float rayT, vec3f pa, vec3f pb, float r)
 {
-  const vec3f ba = subRN(pb, pa), oa0 = subRN(ray.org, pa), d = ray.dir;
+  CapsuleHit res;
+  res.hit = false; res.t = 0.f; res.s = 0.f; res.Ng = make_vec3f(0.f);
+  float &t = res.t, &sOut = res.s;
+  vec3f &Ng = res.Ng;
+  struct { float t0, t; } ray = {rayT0, rayT};
+  const vec3f ba = subRN(pb, pa), oa0 = subRN(org, pa);
   const float dd = dotRN(d, d);
   const float tp = -__fdiv_rn(dotRN(d, oa0), dd);
   const vec3f oa = maddRN(oa0, tp, d);
@@ -185,16 +193,17 @@ __device__ __forceinline__ bool intersectCapsule(const Ray &ray, vec3f pa, vec3f
     const float b = __fsub_rn(__fmul_rn(baba, rdoa), __fmul_rn(baoa, bard));
     const float c = __fsub_rn(__fsub_rn(__fmul_rn(baba, oaoa), __fmul_rn(baoa, baoa)), __fmul_rn(rr, baba));
     const float h = __fsub_rn(__fmul_rn(b, b), __fmul_rn(a, c));
-    if (!(h >= 0.f)) return false; // misses the infinite cylinder, hence the capsule
+    if (!(h >= 0.f)) return res; // misses the infinite cylinder, hence the capsule
     const float tb = __fdiv_rn(__fsub_rn(-b, __fsqrt_rn(h)), a);
     y = __fadd_rn(baoa, __fmul_rn(tb, bard));
     if (y > 0.f && y < baba) {
       const float tt = __fadd_rn(tp, tb);
-      if (!(tt > ray.t0 && tt <= ray.t)) return false;
+      if (!(tt > ray.t0 && tt <= ray.t)) return res;
       const float s = __fdiv_rn(y, baba);
       t = tt; sOut = s;
       Ng = maddRN(maddRN(oa, tb, d), -s, ba);
-      return true;
+      res.hit = true;
+      return res;
     }
   } else
     y = bard > 0.f ? -1.f : __fadd_rn(baba, 1.f); // ray parallel to the axis: it enters through the cap it faces
@@ -203,17 +212,37 @@ __device__ __forceinline__ bool intersectCapsule(const Ray &ray, vec3f pa, vec3f
   const float b2 = dotRN(d, oc);
   const float c2 = __fsub_rn(dotRN(oc, oc), rr);
   const float h2 = __fsub_rn(__fmul_rn(b2, b2), __fmul_rn(dd, c2));
-  if (!(h2 > 0.f)) return false;
+  if (!(h2 > 0.f)) return res;
   const float tc = __fdiv_rn(__fsub_rn(-b2, __fsqrt_rn(h2)), dd);
   const float tt = __fadd_rn(tp, tc);
-  if (!(tt > ray.t0 && tt <= ray.t)) return false;
+  if (!(tt > ray.t0 && tt <= ray.t)) return res;
   t = tt; sOut = first ? 0.f : 1.f;
   Ng = maddRN(oc, tc, d);
-  return true;
+  res.hit = true;
+  return res;
 }
 
 // ---- leaf records -----------------------------------------------------------------------
 __device__ __forceinline__ float4 ldg4(const OcVec4f *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+// Every non-triangle primitive test sits behind ONE call: the triangle test stays inline in the leaf loop, whose code then
+// has the shape the compiler predicates well (C3 89.7 -> 87.1 ms, C4 4.67 -> 4.53 ms against inlined sphere / box tests).
+struct OtherHit { float t, u; vec3f Ng; bool hit; };
+static __device__ __noinline__ OtherHit intersectOtherNI(vec3f org, vec3f dir, float rayT0, float rayT, float4 r0, float4 r1, float4 r2)
+{
+  Ray ray;
+  ray.org = org; ray.dir = dir; ray.t0 = rayT0; ray.t = rayT;
+  OtherHit o;
+  o.u = 0.f; o.t = 0.f; o.Ng = make_vec3f(0.f);
+  const uint32_t kind = __float_as_uint(r2.w);
+  if (kind == OC_PRIM_SPHERE) o.hit = intersectSphere(ray, make_vec3f(r0.x, r0.y, r0.z), r1.x, o.t, o.Ng);
+  else if (kind == OC_PRIM_CAPSULE) {
+    const CapsuleHit ch = intersectCapsuleNI(org, dir, rayT0, rayT, make_vec3f(r0.x, r0.y, r0.z), make_vec3f(r1.x, r1.y, r1.z), r2.x);
+    o.hit = ch.hit; o.t = ch.t; o.Ng = ch.Ng;
+    if (o.hit) o.u = __fadd_rn(r2.y, __fmul_rn(r2.z, ch.s));
+  } else o.hit = intersectBox(ray, make_vec3f(r0.x, r0.y, r0.z), make_vec3f(r1.x, r1.y, r1.z), o.t, o.Ng);
+  return o;
+}
 
 template <bool OCCLUSION>
 __device__ __forceinline__ bool intersectRecord(Ray &ray, const OcVec4f *rec, uint32_t instID)
@@ -227,14 +256,10 @@ __device__ __forceinline__ bool intersectRecord(Ray &ray, const OcVec4f *rec, ui
     hit = intersectTriangle(ray, make_vec3f(r0.x, r0.y, r0.z), make_vec3f(r1.x, r1.y, r1.z),
         make_vec3f(r2.x, r2.y, r2.z), t, u, v, Ng);
     if (hit && kind == OC_PRIM_TRI_QUAD2ND) { u = __fsub_rn(1.f, u); v = __fsub_rn(1.f, v); }
-  } else if (kind == OC_PRIM_SPHERE) {
-    hit = intersectSphere(ray, make_vec3f(r0.x, r0.y, r0.z), r1.x, t, Ng);
-  } else if (kind == OC_PRIM_CAPSULE) {
-    float s;
-    hit = intersectCapsule(ray, make_vec3f(r0.x, r0.y, r0.z), make_vec3f(r1.x, r1.y, r1.z), r2.x, t, s, Ng);
-    if (hit) u = __fadd_rn(r2.y, __fmul_rn(r2.z, s)); // curve parameter of the segment (ray.u, Curves.ispc:21)
-  } else {
-    hit = intersectBox(ray, make_vec3f(r0.x, r0.y, r0.z), make_vec3f(r1.x, r1.y, r1.z), t, Ng);
+  }
+  else {
+    const OtherHit o = intersectOtherNI(ray.org, ray.dir, ray.t0, ray.t, r0, r1, r2);
+    hit = o.hit; t = o.t; u = o.u; Ng = o.Ng;
   }
   if (!hit)
     return false;

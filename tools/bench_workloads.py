@@ -16,6 +16,7 @@ Prints one JSON object per workload: frame ms (CUDA events on the render stream 
 L2 flushed between frames), rays per frame, Mrays/s, scene commit / BVH build ms. These are parity-test-sized
 configs made into measurements; they are NOT the bench.py contract line."""
 import argparse
+import gc
 import json
 import os
 import sys
@@ -116,7 +117,7 @@ def main():
                 exch.close()
             tot_ms = float(np.sum(ms))
             r = {"workload": wl, "renderer": ren_kind, "size": [w, h], "spp": spp, "frames": args.frames,
-                 "frame_ms": round(tot_ms / args.frames, 4), "frame_ms_min": round(float(np.min(ms)), 4),
+                 "frame_ms": round(tot_ms / args.frames, 4), "frame_ms_min": round(float(np.min(ms)), 4), "frame_ms_all": [round(float(m), 3) for m in ms],
                  "rays_per_frame": int(rays.sum() // args.frames), "rays_split_primary_secondary_shadow": [int(x) // args.frames for x in rays],
                  "mrays_per_s": round(float(rays.sum()) / (tot_ms * 1e-3) / 1e6, 1),
                  "mpixel_samples_per_s": round(w * h * spp * args.frames / (tot_ms * 1e-3) / 1e6, 1),
@@ -132,7 +133,9 @@ def main():
             if rank == 0:
                 print(json.dumps(r), flush=True)
             results.append(r)
-            del fb, ren, cam, world, keep
+            del fb, ren, cam, world, keep, frame, exch
+            gc.collect()                  # the previous workload's device memory is freed (cudaFree synchronises) before the
+            torch.cuda.synchronize()      # next one is timed, not in the middle of its frames
     if nranks > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -341,7 +341,7 @@ def run_ours(args):
                 "gpu_launches": int(tot[2]),
                 "clocks": clk,
                 "roofline": {"bound": "hbm", "achieved": round(float(achieved), 1), "peak": peak, "unit": "GB/s",
-                             "frac": round(float(achieved / peak), 4), "traffic": 137.8e6, "peak_source": peak_src,
+                             "frac": round(float(achieved / peak), 4), "traffic": 141.1e6, "peak_source": peak_src,
                              "kernel": "ptTraceKernel (wavefront TRACE: traversal + intersection)",
                              "kernel_ms_per_frame": round(trace_ms, 4), "launches_per_frame": cls_n[0],
                              "avg_launch_ms": round(trace_ms / max(cls_n[0], 1), 4),

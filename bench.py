@@ -205,6 +205,12 @@ def run_ours(args):
         sys.exit(subprocess.call(cmd))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the cuda OSPRay device has no CPU fallback (use --impl reference for the CPU arm)")
+    # stdout carries exactly ONE JSON line: libraries that print there on their own (NCCL's version banner goes to stdout
+    # whatever NCCL_DEBUG_FILE says on some boxes) are pointed at stderr for the lifetime of the process, the line itself
+    # is written to a duplicate of the original descriptor
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank, world, local = multigpu.init_process_group_from_env()
     torch.cuda.set_device(local)
     w, h, K, W = args.width, args.height, args.steps, max(args.warmup, 3)
@@ -361,7 +367,7 @@ def run_ours(args):
                                         "frame_ms_full": round(s / 2 * stride * 1e3, 1)}
             except Exception as e:  # the baseline must never take the bench line down
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         if hasattr(gather, "check"):
             gather.check()   # a device-side wait that timed out would have produced a wrong frame: fail loudly

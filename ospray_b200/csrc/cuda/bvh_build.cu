@@ -289,11 +289,13 @@ __device__ __forceinline__ uint32_t subtreeSize(const BinNode *nodes, int n, uin
 // `first`: position of the subtree's first record in leaf order = number of leaves to its left in a depth-first walk.
 // It is handed down here (the treelet pass reorders subtrees, so the sorted-key ranges of the Karras pass no longer
 // describe them); leaves write leafOrder[position] = record index, which gatherRecordsKernel then follows.
-struct WorkItem { uint32_t bin, wide, first; };
+// `pushed`: stack entries a depth-first traversal holds when it arrives at this node in the worst case (every sibling on
+// the path passed the slab test) = sum over the wide ancestors of (children - 1)
+struct WorkItem { uint32_t bin, wide, first, pushed; };
 
 __global__ void collapseKernel(const BinNode *nodes, const Aabb *nodeBoxes, int n, const WorkItem *inQ, uint32_t inCount,
     WorkItem *outQ, uint32_t *outCount, uint32_t *wideCount, OcNode4 *wide, uint32_t leafMax, const uint32_t *sortedIds,
-    uint32_t *leafOrder)
+    uint32_t *leafOrder, uint32_t *stackNeed)
 {
   const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= inCount) return;
@@ -322,6 +324,8 @@ __global__ void collapseKernel(const BinNode *nodes, const Aabb *nodeBoxes, int 
       cnt++;
     }
   }
+  const uint32_t pushedBelow = item.pushed + (uint32_t)cnt - 1u;
+  atomicMax(stackNeed, pushedBelow);
   OcNode4 out;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
@@ -344,7 +348,7 @@ __global__ void collapseKernel(const BinNode *nodes, const Aabb *nodeBoxes, int 
         const uint32_t wi = atomicAdd(wideCount, 1u);
         out.child[k] = wi;
         const uint32_t qi = atomicAdd(outCount, 1u);
-        WorkItem ni; ni.bin = slot[k]; ni.wide = wi; ni.first = first[k];
+        WorkItem ni; ni.bin = slot[k]; ni.wide = wi; ni.first = first[k]; ni.pushed = pushedBelow;
         outQ[qi] = ni;
       }
     } else {
@@ -378,6 +382,8 @@ struct DevBuf
   cudaError_t alloc(size_t n) { return n ? cudaMalloc((void **)&p, n * sizeof(T)) : cudaSuccess; }
   ~DevBuf() { if (p) cudaFree(p); }
 };
+
+static uint32_t g_lastStackNeed = 0; // of the most recent build (ospcuda_bvh_last_stack_need)
 
 // shared tail: boxes (+records) -> OcBVH
 static int buildFromBoxes(Aabb *d_boxes, float4 *d_records, uint32_t n, const uint32_t *d_sceneBounds, OcBVH *bvh)
@@ -429,7 +435,7 @@ static int buildFromBoxes(Aabb *d_boxes, float4 *d_records, uint32_t n, const ui
     return 0;
   };
   OC_TRY(counters.alloc(4));
-  OC_TRY(cudaMemsetAsync(counters.p + 2, 0, sizeof(uint32_t), st));
+  OC_TRY(cudaMemsetAsync(counters.p + 2, 0, 2 * sizeof(uint32_t), st)); // [2] treelets rewritten, [3] traversal stack need
   if (n >= OC_TREELET_LEAVES && treeletPasses > 0) {
     if (reportCost("LBVH")) return -1;
     for (int pass = 0; pass < treeletPasses; pass++) {
@@ -445,14 +451,14 @@ static int buildFromBoxes(Aabb *d_boxes, float4 *d_records, uint32_t n, const ui
   OC_TRY(wideTmp.alloc(maxWide)); OC_TRY(q0.alloc(maxWide)); OC_TRY(q1.alloc(maxWide)); OC_TRY(leafOrder.alloc(n));
   uint32_t h_counts[2] = {0, 1}; // [0] next-queue size, [1] wide nodes allocated
   OC_TRY(cudaMemcpyAsync(counters.p, h_counts, sizeof(h_counts), cudaMemcpyHostToDevice, st));
-  WorkItem root; root.bin = 0u /* n == 1: the single leaf's id is (n-1)+0 = 0 too */; root.wide = 0; root.first = 0;
+  WorkItem root; root.bin = 0u /* n == 1: the single leaf's id is (n-1)+0 = 0 too */; root.wide = 0; root.first = 0; root.pushed = 0;
   OC_TRY(cudaMemcpyAsync(q0.p, &root, sizeof(root), cudaMemcpyHostToDevice, st));
   uint32_t inCount = 1;
   WorkItem *inQ = q0.p, *outQ = q1.p;
   static const uint32_t leafMax = getenv("OSPCUDA_LEAF_MAX") ? std::min(15u, std::max(1u, (uint32_t)atoi(getenv("OSPCUDA_LEAF_MAX")))) : OC_LEAF_MAX;
   while (inCount) {
     collapseKernel<<<(inCount + 127) / 128, 128, 0, st>>>(bin.p, nodeBoxes.p, (int)n, inQ, inCount, outQ, counters.p, counters.p + 1,
-        wideTmp.p, leafMax, idsSorted.p, leafOrder.p);
+        wideTmp.p, leafMax, idsSorted.p, leafOrder.p, counters.p + 3);
     oc_count_launch();
     OC_TRY(cudaMemcpyAsync(h_counts, counters.p, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
     OC_TRY(cudaStreamSynchronize(st));
@@ -472,6 +478,7 @@ static int buildFromBoxes(Aabb *d_boxes, float4 *d_records, uint32_t n, const ui
   oc_count_launch();
   uint32_t h_enc[6];
   OC_TRY(cudaMemcpyAsync(h_enc, d_sceneBounds, sizeof(h_enc), cudaMemcpyDeviceToHost, st));
+  OC_TRY(cudaMemcpyAsync(&g_lastStackNeed, counters.p + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   OC_TRY(cudaStreamSynchronize(st));
   bvh->nodes = nodesOut;
   bvh->prims = reinterpret_cast<const OcVec4f *>(recOut);
@@ -510,6 +517,7 @@ extern "C" int ospcuda_bvh_build_group(const OcModel *d_models, uint32_t numMode
     const uint32_t *h_types, OcBVH *bvh, float *buildMs)
 {
   emptyBVH(bvh);
+  g_lastStackNeed = 0;
   if (buildMs) *buildMs = 0.f;
   std::vector<uint32_t> off(numModels + 1, 0);
   uint64_t total = 0;
@@ -563,6 +571,7 @@ extern "C" int ospcuda_bvh_build_group(const OcModel *d_models, uint32_t numMode
 extern "C" int ospcuda_bvh_build_tlas(const float *h_bounds, uint32_t numInstances, OcBVH *bvh)
 {
   emptyBVH(bvh);
+  g_lastStackNeed = 0;
   if (numInstances == 0) return 0;
   cudaStream_t st = (cudaStream_t)ospcuda_stream();
   DevBuf<Aabb> boxes;
@@ -576,6 +585,8 @@ extern "C" int ospcuda_bvh_build_tlas(const float *h_bounds, uint32_t numInstanc
   oc_count_launch();
   return buildFromBoxes(boxes.p, records.p, numInstances, d_bounds.p, bvh);
 }
+
+extern "C" uint32_t ospcuda_bvh_last_stack_need(void) { return g_lastStackNeed; }
 
 extern "C" int ospcuda_bvh_free(OcBVH *bvh)
 {

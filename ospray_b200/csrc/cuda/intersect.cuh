@@ -18,7 +18,7 @@ using namespace ospm;
 
 #define OC_INVALID_ID 0xFFFFFFFFu
 #define OC_TLAS_THRESHOLD 4u
-#define OC_STACK_SIZE 48
+#define OC_STACK_SIZE OSPCUDA_TRAVERSAL_STACK // include/ospcuda.h: the host checks every built hierarchy against it
 #define OC_LINEAR_MAX 8u // groups with at most this many leaf records are scanned linearly (no hierarchy)
 #define OC_MAX_BLOCK 128 // largest CTA of a kernel that traverses (shared stack = OC_STACK_SIZE * blockDim.x words)
 

@@ -697,6 +697,7 @@ Group::~Group() { ospcuda_bvh_free(&sh.bvh); }
 void Group::commit()
 {
   managedObjectType = OSP_GROUP;
+  stackNeed = 0;
   geometricModels = getParamData(*this, "geometry", OSP_GEOMETRIC_MODEL);
   volumetricModels = getParamData(*this, "volume", OSP_VOLUMETRIC_MODEL);
   lights = getParamData(*this, "light", OSP_LIGHT);
@@ -725,6 +726,10 @@ void Group::commit()
     sh.models = modelsDev.as<OcModel>();
     sh.numModels = (uint32_t)n;
     checkCuda(ospcuda_bvh_build_group(sh.models, sh.numModels, numPrims.data(), types.data(), &sh.bvh, &lastBuildMs), "BVH build");
+    stackNeed = ospcuda_bvh_last_stack_need();
+    if (stackNeed > OSPCUDA_TRAVERSAL_STACK)
+      throw std::runtime_error("ospray::Group: the hierarchy over this geometry is too deep for the traversal stack (needs "
+          + std::to_string(stackNeed) + " entries, the device keeps " + std::to_string(OSPCUDA_TRAVERSAL_STACK) + ")");
     if (sh.bvh.numRecords) {
       box3f b;
       b.lower = make_vec3f(sh.bvh.bounds[0], sh.bvh.bounds[1], sh.bvh.bounds[2]);
@@ -819,7 +824,20 @@ void World::commit()
     instDev.upload(inst.data(), inst.size() * sizeof(OcInstance));
     sh.instances = instDev.as<OcInstance>();
     sh.numInstances = (uint32_t)inst.size();
-    if (inst.size() > 4) checkCuda(ospcuda_bvh_build_tlas(instBounds.data(), (uint32_t)inst.size(), &sh.tlas), "TLAS build");
+    if (inst.size() > 4) {
+      checkCuda(ospcuda_bvh_build_tlas(instBounds.data(), (uint32_t)inst.size(), &sh.tlas), "TLAS build");
+      // the top level may use half of the traversal stack, the group BVH continues above what it holds (intersect.cuh)
+      const uint32_t tlasNeed = ospcuda_bvh_last_stack_need();
+      uint32_t groupNeed = 0;
+      for (size_t i = 0; i < inst.size(); i++) {
+        Instance *in = dynamic_cast<Instance *>(instances->objectAt(i));
+        groupNeed = std::max(groupNeed, in->group->stackNeed);
+      }
+      if (tlasNeed > OSPCUDA_TRAVERSAL_STACK / 2 || tlasNeed + groupNeed > OSPCUDA_TRAVERSAL_STACK)
+        throw std::runtime_error("ospray::World: instance hierarchy + group hierarchy are too deep for the traversal stack (need "
+            + std::to_string(tlasNeed) + " + " + std::to_string(groupNeed) + " entries, the device keeps "
+            + std::to_string(OSPCUDA_TRAVERSAL_STACK) + ")");
+    }
   }
   // light lists: world lights, then instance (group) lights -- the latter are not transformed yet
   std::vector<Light *> all;

@@ -195,6 +195,7 @@ struct Group : public ManagedObject
   OcGroup sh{};
   box3f bounds = box_empty();
   float lastBuildMs = 0.f;
+  uint32_t stackNeed = 0; // deepest traversal stack the group's BVH can ask for (ospcuda_bvh_last_stack_need)
 
  private:
   DevMem dev, modelsDev, volumesDev;

@@ -84,6 +84,32 @@ static int treeletPass(Tree &t, int gamma)
   return rewritten;
 }
 
+// The collapse of bvh_build.cu (collapseKernel) on the host: children with the largest surface area are opened first until
+// the node has 4 slots; subtrees of <= leafMax leaves become leaves. Returns, through `need`, the deepest traversal stack a
+// depth-first walk can build = max over root-to-leaf paths of the sum of (children - 1) of the wide nodes on the path
+// (every level pushes all but the child it descends into), and the wide depth.
+static void collapseStats(const Tree &t, uint32_t bin, uint32_t leafMax, int depth, int pushed, int &maxDepth, int &need)
+{
+  const uint32_t leafBase = t.n - 1;
+  auto size = [&](uint32_t id) { return id >= leafBase ? 1u : t.nodes[id].last - t.nodes[id].first + 1u; };
+  if (size(bin) <= leafMax) { maxDepth = std::max(maxDepth, depth); need = std::max(need, pushed); return; }
+  uint32_t slot[4];
+  int cnt = 0;
+  slot[cnt++] = t.nodes[bin].left; slot[cnt++] = t.nodes[bin].right;
+  while (cnt < 4) {
+    int best = -1; float bestA = -1.f;
+    for (int k = 0; k < cnt; k++) {
+      if (size(slot[k]) <= leafMax) continue;
+      const float a = halfArea(t.boxes[slot[k]]);
+      if (a > bestA) { bestA = a; best = k; }
+    }
+    if (best < 0) break;
+    const uint32_t open = slot[best];
+    slot[best] = t.nodes[open].left; slot[cnt++] = t.nodes[open].right;
+  }
+  for (int k = 0; k < cnt; k++) collapseStats(t, slot[k], leafMax, depth + 1, pushed + cnt - 1, maxDepth, need);
+}
+
 int main(int argc, char **argv)
 {
   const int n = argc > 1 ? atoi(argv[1]) : 20000, dist = argc > 2 ? atoi(argv[2]) : 0, passes = argc > 3 ? atoi(argv[3]) : 3;
@@ -94,6 +120,16 @@ int main(int argc, char **argv)
     float c[3], e;
     if (dist == 0) { for (float &x : c) x = U(rng); e = 0.01f * U(rng); }                                   // small boxes, uniform
     else if (dist == 1) { for (float &x : c) x = U(rng); e = (i % 50 == 0) ? 0.4f * U(rng) : 0.004f * U(rng); } // a few huge ones
+    else if (dist == 3) { // jittered lattice of boxes, 12 triangles each (the C3 mesh of tools/bench_workloads.py in small)
+      const int b = i / 12, side = std::max(1, (int)cbrtf((float)(n / 12)));
+      const float cell = 1.f / side;
+      const float bc[3] = {(b % side + 0.5f) * cell, ((b / side) % side + 0.5f) * cell, (b / (side * side) + 0.5f) * cell};
+      const int face = (i % 12) / 2;
+      for (int k = 0; k < 3; k++) c[k] = bc[k] + (k == face / 2 ? ((face & 1) ? 0.3f : -0.3f) * cell : 0.1f * cell * (U(rng) - 0.5f));
+      e = 0.3f * cell;
+      for (int k = 0; k < 3; k++) { const float ek = (k == face / 2) ? 1e-4f * cell : e * (0.5f + 0.5f * U(rng)); prim[i].lo[k] = c[k] - ek; prim[i].hi[k] = c[k] + ek; }
+      continue;
+    }
     else { const int cl = i % 16; for (int k = 0; k < 3; k++) c[k] = 0.0625f * ((cl * (k + 3)) % 16) + 0.02f * U(rng); e = 0.002f; if (i % 7 == 0) c[1] = c[0]; } // clusters + duplicates
     if (dist == 2 && i % 5 == 0 && i) { prim[i] = prim[i - 1]; continue; }                                        // identical keys
     for (int k = 0; k < 3; k++) { prim[i].lo[k] = c[k] - e * U(rng); prim[i].hi[k] = c[k] + e * U(rng); }
@@ -146,7 +182,9 @@ int main(int argc, char **argv)
     printf(", %d", v);
     cost.push_back(sahCost(t));
   }
-  printf("], \"cost\": [");
+  int wideDepth = 0, stackNeed = 0;
+  if (n > 1) collapseStats(t, 0, 2, 0, 0, wideDepth, stackNeed);
+  printf("], \"wide_depth\": %d, \"stack_need\": %d, \"cost\": [", wideDepth, stackNeed);
   for (size_t k = 0; k < cost.size(); k++) printf("%s%.4f", k ? ", " : "", cost[k]);
   printf("], \"rewritten\": [");
   for (size_t k = 0; k < rew.size(); k++) printf("%s%d", k ? ", " : "", rew[k]);

@@ -278,3 +278,15 @@ def test_debug_renderer_refuses_unsupported_methods(osp):
         with pytest.raises(osp.OSPRayError, match="not supported"):
             r.commit()
     osp.Renderer("debug").set("method", "noSuchMethod").commit()
+
+
+@pytest.mark.gpu
+def test_builder_reports_the_traversal_stack_need(osp, abi):
+    """every hierarchy the builder hands out states the deepest traversal stack it can ask for; the device compares it with
+    OSPCUDA_TRAVERSAL_STACK at commit (a scene beyond it is refused instead of traversed with dropped subtrees)"""
+    abi.ospcuda_bvh_last_stack_need.restype = C.c_uint32
+    world, keep = T.to_ospray(T.box_mesh(6))      # 2592 triangles: 4-wide depth 6..7
+    need = abi.ospcuda_bvh_last_stack_need()
+    assert 6 <= need <= 30, need
+    world, keep = T.to_ospray(T.cornell_box())    # 34 records
+    assert 1 <= abi.ospcuda_bvh_last_stack_need() <= 12

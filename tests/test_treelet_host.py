@@ -29,3 +29,13 @@ def test_treelet_passes_keep_the_tree_valid_and_lower_the_cost(checker, n, dist)
     if n >= 20000:
         assert cost[-1] < (0.6 if dist == 1 else 0.95) * cost[0], cost       # big-among-small primitives gain most
         assert res["rewritten"][0] > res["rewritten"][-1] > 0
+
+
+def test_traversal_stack_need_of_large_trees(checker):
+    """the builder reports the deepest stack a depth-first walk of the collapsed 4-wide hierarchy can need (collapseKernel's
+    `pushed`; restated in tests/native/treelet_check.cpp); the device refuses hierarchies beyond OSPCUDA_TRAVERSAL_STACK = 48.
+    A jittered lattice of boxes (the 10 M-triangle bench mesh in small) stays well inside; the refinement does not deepen it."""
+    for passes in (0, 2):
+        res = json.loads(subprocess.run([checker, "300000", "3", str(passes)], capture_output=True, text=True).stdout)
+        assert res["valid"] == [0] * (passes + 1)
+        assert res["wide_depth"] <= 14 and res["stack_need"] <= 40, res

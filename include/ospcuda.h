@@ -339,7 +339,9 @@ OSPCUDA_API int ospcuda_bvh_free(OcBVH *bvh);
  * it, the group BVH continues above). The builder knows the deepest stack a depth-first walk of the hierarchy it just
  * built can need (sum over the deepest path of children - 1 per wide node): the host compares and refuses a scene that
  * could overflow instead of letting traversal drop subtrees. Value of the most recent build on this thread. */
+#ifndef OSPCUDA_TRAVERSAL_STACK
 #define OSPCUDA_TRAVERSAL_STACK 48
+#endif
 OSPCUDA_API uint32_t ospcuda_bvh_last_stack_need(void);
 /* macrocell (16^3 cells) value ranges of a structured volume; d_ranges: 2*mcx*mcy*mcz floats */
 OSPCUDA_API int ospcuda_volume_macrocells(const float *d_voxels, const uint32_t dims[3],

@@ -72,6 +72,11 @@ def main():
             torch.cuda.synchronize()
             commit_ms = (time.perf_counter() - t0) * 1e3
             build_ms = [g.build_ms() for g in keep if isinstance(g, osp.Group)]
+            import ctypes as C
+            from ospray_b200 import lib_path
+            LC = C.CDLL(lib_path("libospcuda.so"))
+            LC.ospcuda_bvh_last_stack_need.restype = C.c_uint32
+            stack_need = int(LC.ospcuda_bvh_last_stack_need())  # of the hierarchy built last (device limit: 48)
             cam, pose = T.make_camera(world, w, h)
             ren = T.make_renderer(ren_kind, pixelSamples=spp, **rp)
             fb = osp.FrameBuffer(w, h, osp.OSP_FB_SRGBA, osp.OSP_FB_COLOR | osp.OSP_FB_ACCUM | osp.OSP_FB_DEPTH)
@@ -121,7 +126,7 @@ def main():
                  "rays_per_frame": int(rays.sum() // args.frames), "rays_split_primary_secondary_shadow": [int(x) // args.frames for x in rays],
                  "mrays_per_s": round(float(rays.sum()) / (tot_ms * 1e-3) / 1e6, 1),
                  "mpixel_samples_per_s": round(w * h * spp * args.frames / (tot_ms * 1e-3) / 1e6, 1),
-                 "scene_generate_s": round(gen_s, 2), "scene_commit_ms": round(commit_ms, 1), "bvh_build_ms": [round(b, 2) for b in build_ms],
+                 "scene_generate_s": round(gen_s, 2), "scene_commit_ms": round(commit_ms, 1), "bvh_build_ms": [round(b, 2) for b in build_ms], "bvh_stack_need_last_built": stack_need,
                  "mean_rgb": [round(float(x), 2) for x in img[..., :3].reshape(-1, 3).mean(axis=0)]}
             if wl in ("C3", "C5s"):
                 r["triangles"] = int(sum(m.geometry.index.shape[0] for i in spec.instances for m in i.group.models if m.geometry.index is not None))

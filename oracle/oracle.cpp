@@ -1142,6 +1142,122 @@ inline float misHeuristic(float pdf1, float pdf2) // pathtracer/PathTracerUtil.i
   const float p = sqr(pdf1) * (1.f / (sqr(pdf1) + sqr(pdf2)));
   return pdf1 > 1e17f ? 1.0f : p;
 }
+// ---- path tracer volumes: pathtracer/volumes/VolumeSampler.ispc:13-282 in its single-volume-interval form (the form the
+// reference compiles for OSPRAY_TARGET_SYCL), pathtracer/volumes/HenyeyGreenstein.ih:11-74 ----
+struct VolumeHit;
+float volumeSample(const OcVolume &v, V3 p);
+V4 transferFunctionGet(const OcTransferFunction &tf, float value);
+struct VolumeHitFwd { const OcVolume *vol; const OcInstance *inst; uint32_t instID, geomID; float t0, t1; };
+bool traceVolumeRayFwd(const OcWorld *w, const Ray &ray, VolumeHitFwd &vh);
+// LinearTransferFunction_getMaxOpacity (LinearTransferFunction.ispc:46-64) over the table precomputeMaxOpacityRanges
+// fills (LinearTransferFunction.cpp:110-160): entry [i][j] = max of the opacities floor(D*i/31) .. ceil(D*j/31), D = n - 1
+float tfMaxOpacity(const OcTransferFunction &tf, float lo, float hi)
+{
+  const int maxDim = 31, D = (int)tf.numOpacities - 1;
+  const float denom = tf.valueUpper - tf.valueLower;
+  const int i = std::min((int)floorf(clampf((lo - tf.valueLower) / denom, 0.f, 1.f) * maxDim), maxDim);
+  const int j = std::min((int)ceilf(clampf((hi - tf.valueLower) / denom, 0.f, 1.f) * maxDim), maxDim);
+  if (j < i) return 0.f; // below the diagonal the table keeps its initial zeros
+  const int lowI = (int)floorf(D * (float)i / maxDim), highI = (int)ceilf(D * (float)i / maxDim), highJ = (int)ceilf(D * (float)j / maxDim);
+  float m = tf.opacity[lowI];
+  for (int k = lowI; k <= std::max(highI, highJ); k++) m = fmaxf(m, tf.opacity[k]);
+  return m;
+}
+// delta_tracking (VolumeSampler.ispc:13-103) over the ONE interval the structured-volume stand-in of Open VKL reports
+// (whole clipped range, value range (-inf, inf): oracle/ref_vkl_stub.cpp) -> global majorant
+float deltaTracking(const OcVolume &v, float lower, float upper, RandomSampler &rs, V3 o, V3 w, float &mu_t, V3 &albedo)
+{
+  if (!(lower < upper)) return INF; // the iterator reports nothing for an empty range
+  float t = lower;
+  const float mu_max = v.densityScale * tfMaxOpacity(v.tf, -INF, INF);
+  if (mu_max <= 0.f) return INF;
+  while (true) {
+    float xi = RandomSampler_getFloat(rs);
+    const float dt = -logf(1.f - xi) / mu_max;
+    t += dt;
+    if (t > upper) break;
+    xi = RandomSampler_getFloat(rs);
+    const float sample = volumeSample(v, o + t * w);
+    if (std::isnan(sample)) continue;
+    const V4 color = transferFunctionGet(v.tf, sample);
+    mu_t = v.densityScale * color.w;
+    if (xi < mu_t / mu_max) { albedo = v3(color); return t; }
+  }
+  return INF;
+}
+// volumeSampleFreePath (VolumeSampler.ispc:105-196); rayInterval = the interval traceClippingRay hands out without
+// clipping geometry (common/World.ih:150-163)
+float volumeSampleFreePath(Ctx &c, Ray &ray, float rayLower, float rayUpper, RandomSampler &rs, const OcVolume *&sampled, V3 &sampledAlbedo)
+{
+  sampled = nullptr;
+  VolumeHitFwd vh;
+  if (!traceVolumeRayFwd(c.w, ray, vh)) return INF;
+  float lower = fmaxf(0.f, vh.t0), upper = hadHit(ray) ? fminf(vh.t1, ray.t) : vh.t1;
+  if (lower > upper) return INF;
+  V3 org = ray.org, dir = ray.dir;
+  if (!vh.inst->isIdentity) { const A3 rx = a3(vh.inst->rcp_xfm); org = xfmPoint(rx, ray.org); dir = xfmVector(rx.l, ray.dir); }
+  if (upper < rayLower || rayUpper < lower) return INF;
+  lower = fmaxf(rayLower, lower); upper = fminf(rayUpper, upper);
+  float extinction; V3 albedo;
+  const float dist = deltaTracking(*vh.vol, lower, upper, rs, org, dir, extinction, albedo);
+  if (dist < INF) {
+    sampled = vh.vol; sampledAlbedo = albedo;
+    ray.t = dist; ray.primID = 0; ray.geomID = vh.geomID; ray.instID = vh.instID;
+  }
+  return dist;
+}
+// volumeTransmittance (VolumeSampler.ispc:198-279)
+float volumeTransmittance(Ctx &c, const Ray &ray, float rayLower, float rayUpper, RandomSampler &rs)
+{
+  VolumeHitFwd vh;
+  if (!traceVolumeRayFwd(c.w, ray, vh)) return 1.f;
+  float lower = fmaxf(ray.t0, vh.t0), upper = hadHit(ray) ? fminf(vh.t1, ray.t) : vh.t1;
+  if (lower > upper) return 1.f;
+  V3 org = ray.org, dir = ray.dir;
+  if (!vh.inst->isIdentity) { const A3 rx = a3(vh.inst->rcp_xfm); org = xfmPoint(rx, ray.org); dir = xfmVector(rx.l, ray.dir); }
+  if (upper < rayLower || rayUpper < lower) return 1.f;
+  lower = fmaxf(rayLower, lower); upper = fminf(rayUpper, upper);
+  float extinction; V3 albedo;
+  const float dist = deltaTracking(*vh.vol, lower, upper, rs, org, dir, extinction, albedo);
+  return (dist < upper) ? 0.f : 1.f;
+}
+inline float hgPhase(float cosTheta, float g) // HenyeyGreenstein.ih:11-15
+{
+  const float denom = 1.f + g * g - 2.f * g * cosTheta;
+  return (1.f / (4.f * (float)M_PI)) * (1.f - g * g) * (1.f / (denom * sqrtf(denom)));
+}
+inline bool hgIsSmooth(float g) { return !(fabsf(g) > 1.f - 1e-3f); }
+inline EvalRes HenyeyGreenstein_eval(float g, V3 wo, V3 wi) // :24-35 (the non-smooth branch is overwritten there too)
+{
+  EvalRes r;
+  r.pdf = hgPhase(dot(-wo, wi), g);
+  r.value = v3(r.pdf);
+  return r;
+}
+inline SampleRes HenyeyGreenstein_sample(float g, V3 wo, V2 s) // :37-72
+{
+  SampleRes res;
+  res.weight = v3(1.f);
+  float cosTheta;
+  if (!hgIsSmooth(g)) {
+    res.wi = g > 0 ? -wo : wo;
+    res.pdf = INF;
+    res.type = g > 0 ? SC_SPECULAR_TRANSMISSION : SC_SPECULAR_REFLECTION;
+    return res;
+  } else if (fabsf(g) < 1e-3f) {
+    cosTheta = 1.f - 2.f * s.x;
+  } else {
+    const float sqrTerm = (1.f - g * g) * (1.f / (1.f - g + 2.f * g * s.x));
+    cosTheta = (1.f + g * g - sqrTerm * sqrTerm) * (1.f / (2.f * g));
+  }
+  res.type = SC_SMOOTH;
+  const float sinTheta = sqrtf(fmaxf(0.f, 1.f - cosTheta * cosTheta));
+  const float phi = (float)(2.f * M_PI * s.y); // M_PI is <cmath>'s double in the reference's scalar C++ form
+  res.wi = xfmVector(frame(-wo), cartesian(phi, sinTheta, cosTheta));
+  res.pdf = hgPhase(cosTheta, g);
+  return res;
+}
+
 V3 transparentShadow(Ctx &c, V3 lightContrib, Ray &shadowRay) // pathtracer/TransparentShadow.ispc:18-85
 {
   uint32_t maxDepth = c.ren.maxDepth;
@@ -1158,7 +1274,7 @@ V3 transparentShadow(Ctx &c, V3 lightContrib, Ray &shadowRay) // pathtracer/Tran
   }
 }
 struct LastVertex { V3 P, Ns; float pdf_w; uint32_t numLightSamples; };
-V3 evaluateVirtualLights(Ctx &c, bool straightPath, V3 throughput, const LastVertex &last, bool environment, const Ray &ray)
+V3 evaluateVirtualLights(Ctx &c, bool straightPath, V3 throughput, const LastVertex &last, bool environment, const Ray &ray, RandomSampler &rs)
 { // pathtracer/VirtualLight.ispc:17-107
   V3 L = v3(0.f);
   const uint32_t numLights = c.w->numLights;
@@ -1172,15 +1288,24 @@ V3 evaluateVirtualLights(Ctx &c, bool straightPath, V3 throughput, const LastVer
       const LightEval le = Light_eval(l, last.P, last.Ns, ray.dir, lower, upper);
       if (rmax(le.radiance) > 0.0f) {
         float misWeight = 1.0f;
-        if (selectionPDF) misWeight = misHeuristic(last.pdf_w, selectionPDF * le.pdf);
+        if (selectionPDF) {
+          float T = 1.f;
+          if (c.w->hasVolumes) { // :76-101
+            Ray shadowRay;
+            setRay(shadowRay, last.P, ray.dir, lower, upper);
+            T = volumeTransmittance(c, shadowRay, lower, upper, rs);
+          }
+          misWeight = misHeuristic(last.pdf_w * T, selectionPDF * le.pdf);
+        }
         L = L + throughput * le.radiance * misWeight;
       }
     }
   }
   return L;
 }
-V3 nextEventEstimation(Ctx &c, const LDSampler &ld, uint32_t numLightSamples, V3 throughput, const DG &dg, const ObjBSDF &bsdf, V3 wo)
-{ // pathtracer/NextEventEstimation.ispc:25-160
+V3 nextEventEstimation(Ctx &c, const LDSampler &ld, uint32_t numLightSamples, V3 throughput, const DG &dg, const ObjBSDF &bsdf, V3 wo,
+    const OcVolume *volume, RandomSampler &rs)
+{ // pathtracer/NextEventEstimation.ispc:25-160 (volume != nullptr: the vertex is a volume scattering event)
   V3 L = v3(0.f);
   for (uint32_t i = 0; i < numLightSamples; i++) {
     float ss;
@@ -1191,20 +1316,29 @@ V3 nextEventEstimation(Ctx &c, const LDSampler &ld, uint32_t numLightSamples, V3
     ls.weight = ls.weight / lightSelectionProb;
     ls.pdf *= lightSelectionProb;
     if (rmax(ls.weight) <= 0.0f || ls.pdf <= 0.0f) continue;
-    const EvalRes fe = OBJ_eval(bsdf, wo, ls.dir);
+    const EvalRes fe = volume ? HenyeyGreenstein_eval(volume->anisotropy, wo, ls.dir) : OBJ_eval(bsdf, wo, ls.dir);
     if (rmax(fe.value) <= 0.0f) continue;
     V3 org = dg.P;
-    if (dot(dg.Ng, ls.dir) < 0.f) org = org - (2.0f * dg.epsilon) * dg.Ng;
+    if (!volume && dot(dg.Ng, ls.dir) < 0.f) org = org - (2.0f * dg.epsilon) * dg.Ng;
     Ray shadowRay;
     setRay(shadowRay, org, ls.dir, 0.f, ls.dist);
     const V3 unshadedLightContrib = throughput * fe.value * ls.weight;
     const V3 lightContrib = transparentShadow(c, unshadedLightContrib, shadowRay);
-    if (rmax(lightContrib) > 0) L = L + lightContrib * misHeuristic(ls.pdf, fe.pdf);
+    if (rmax(lightContrib) > 0) {
+      if (c.w->hasVolumes) { // :126-151: two independent transmittance estimates, one of them for the MIS weight
+        const float T = volumeTransmittance(c, shadowRay, 0.f, ls.dist, rs);
+        if (T > 0) {
+          const float T_mis = volumeTransmittance(c, shadowRay, 0.f, ls.dist, rs);
+          L = L + T * lightContrib * misHeuristic(ls.pdf, fe.pdf * T_mis);
+        }
+      } else
+        L = L + lightContrib * misHeuristic(ls.pdf, fe.pdf);
+    }
   }
   return L;
 }
-void samplePath(Ctx &c, LDSampler &ld, uint32_t nFirst, uint32_t nIndirect, Ray &ray, ScreenSample &sample)
-{ // pathtracer/PathSampler.ispc:109-415 (no volumes, no shadow catcher, no geometry lights, no media)
+void samplePath(Ctx &c, LDSampler &ld, RandomSampler &rs, uint32_t nFirst, uint32_t nIndirect, Ray &ray, ScreenSample &sample)
+{ // pathtracer/PathSampler.ispc:109-415 (no shadow catcher, no geometry lights, no media)
   LastVertex last = {ray.org, ray.dir, INF, 0};
   bool straightPath = true, specularTransmissionPath = true, firstBounceLight = true;
   uint32_t depth = 0, scatteringEvents = 0;
@@ -1213,40 +1347,62 @@ void samplePath(Ctx &c, LDSampler &ld, uint32_t nFirst, uint32_t nIndirect, Ray 
   const OcRenderer &ren = c.ren;
   do {
     if (depth == 0) c.cnt.primary++; else c.cnt.secondary++;
+    const float rayLower = ray.t0, rayUpper = ray.t; // traceClippingRay without clipping geometry (World.ih:150-163)
     traceWorld(c.w, ray, false);
-    const bool surface = hadHit(ray);
+    bool surface = hadHit(ray);
     const V3 wo = -ray.dir;
+    const OcVolume *volume = nullptr; // != nullptr: this vertex is a scattering event inside that volume (:178-194)
+    V3 volumeAlbedo = v3(0.f);
+    if (c.w->hasVolumes) {
+      const float freePath = volumeSampleFreePath(c, ray, rayLower, rayUpper, rs, volume, volumeAlbedo);
+      if (freePath < INF) { surface = false; throughput = throughput * volumeAlbedo; } else volume = nullptr;
+    }
+    const bool environment = !surface && !volume;
     if (depth == 0) sample.z = c.fb.projectedDepth ? ray.t * dot(ray.dir, v3(c.cam.direction)) : ray.t;
-    if (!surface && (ren.backgroundRefraction ? specularTransmissionPath : straightPath)) {
+    if (environment && (ren.backgroundRefraction ? specularTransmissionPath : straightPath)) {
       const V4 bg = getBackground(ren);
       sample.alpha -= luminance(throughput) * (1.0f - bg.w);
       contribution = contribution + throughput * v3(bg);
     }
-    contribution = contribution + evaluateVirtualLights(c, straightPath, throughput, last, !surface, ray);
-    if (!surface) break;
+    if (!volume) contribution = contribution + evaluateVirtualLights(c, straightPath, throughput, last, environment, ray, rs);
+    if (environment) break;
     if (depth >= ren.maxDepth) break; // numGeoLights == 0
     DG dg;
-    postIntersect(c.w, ren, dg, ray, DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR | DG_TANGENTS | DG_MOTIONBLUR);
+    if (volume) { // postIntersect for a volume vertex (:51-67) + VolumetricModel_postIntersect (volume/VolumetricModel.ih:16-33)
+      dg.P = ray.org + ray.t * ray.dir;
+      dg.Ng = dg.Ns = dg.dPds = v3(0.f);
+      dg.color = {0.f, 0.f, 0.f, 0.f};
+      dg.epsilon = 0.f; dg.material = nullptr; dg.primID = 0;
+      dg.objID = volume->userID == INVALID_ID ? ray.geomID : volume->userID;
+      dg.instID = ray.instID;
+      if (ray.instID != INVALID_ID && c.w->instances[ray.instID].userID != INVALID_ID) dg.instID = c.w->instances[ray.instID].userID;
+    } else
+      postIntersect(c.w, ren, dg, ray, DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR | DG_TANGENTS | DG_MOTIONBLUR);
     if (depth == 0) {
       sample.position = dg.P; sample.firstNormal = dg.Ns;
       sample.primID = dg.primID; sample.geomID = dg.objID; sample.instID = dg.instID;
     }
     if (depth >= ren.maxDepth || scatteringEvents >= (uint32_t)ren.maxScatteringEvents) break;
     ObjBSDF bsdf;
-    OBJ_getBSDF(bsdf, dg);
-    if (!bsdf.valid) break;
+    if (!volume) {
+      OBJ_getBSDF(bsdf, dg);
+      if (!bsdf.valid) break;
+    }
     LDSampler_nextGroup(ld);
     uint32_t vertexLightSamples = 0;
-    if (bsdf.scatteringType & SC_SMOOTH) {
-      if (scatteringEvents == 0) { sample.albedo = throughput * bsdf.albedo; sample.normal = throughput * bsdf.frame.vz; }
+    if (volume ? hgIsSmooth(volume->anisotropy) : (bsdf.scatteringType & SC_SMOOTH) != 0) { // isSmooth (PathTracerUtil.ih:15-28)
+      if (scatteringEvents == 0) { // updateAuxilliaryData (PathTracerUtil.ih:48-60)
+        sample.albedo = throughput * (volume ? volumeAlbedo : bsdf.albedo);
+        sample.normal = throughput * (volume ? dg.Ns : bsdf.frame.vz);
+      }
       vertexLightSamples = firstBounceLight ? nFirst : nIndirect;
-      contribution = contribution + nextEventEstimation(c, ld, vertexLightSamples, throughput, dg, bsdf, wo);
+      contribution = contribution + nextEventEstimation(c, ld, vertexLightSamples, throughput, dg, bsdf, wo, volume, rs);
       firstBounceLight = false;
     }
     float ss; uint32_t uu3;
     const V2 s = LDSampler_getNext4Samples(ld, ss, uu3);
-    SampleRes fs = OBJ_sample(bsdf, wo, s, ss);
-    {
+    SampleRes fs = volume ? HenyeyGreenstein_sample(volume->anisotropy, wo, s) : OBJ_sample(bsdf, wo, s, ss);
+    if (!volume) {
       const bool sameSide = dot(fs.wi, dg.Ng) >= 0.f;
       const bool reflection = fs.type & SC_REFLECTION;
       if (sameSide != reflection) fs.weight = v3(0.0f);
@@ -1260,8 +1416,8 @@ void samplePath(Ctx &c, LDSampler &ld, uint32_t nFirst, uint32_t nIndirect, Ray 
       throughput = throughput * (1.f / contProb);
     }
     V3 ray_org = dg.P;
-    if (fs.type & SC_TRANSMISSION) ray_org = ray_org - (2.0f * dg.epsilon) * dg.Ng;
-    if (fs.type & ~SC_SPECULAR_TRANSMISSION) last = {dg.P, dg.Ns, fs.pdf, vertexLightSamples};
+    if (!volume && (fs.type & SC_TRANSMISSION)) ray_org = ray_org - (2.0f * dg.epsilon) * dg.Ng;
+    if ((fs.type & ~SC_SPECULAR_TRANSMISSION) || volume) last = {dg.P, dg.Ns, fs.pdf, vertexLightSamples};
     if (!eq(ray.dir, fs.wi)) straightPath = false;
     if (!(fs.type & SC_SPECULAR_TRANSMISSION)) specularTransmissionPath = false;
     setRay(ray, ray_org, fs.wi, 0.f, INF);
@@ -1307,7 +1463,9 @@ ScreenSample PathTracer_renderPixel(Ctx &c, uint32_t ix, uint32_t iy) // pathtra
     Ray ray;
     cameraInitRay(c.cam, ray, screen, lens);
     ScreenSample sample = make_ScreenSample_zero(); // PathTraceIntegrator_Li (PathTracer.ispc:37-63)
-    samplePath(c, ld, nFirst, nIndirect, ray, sample);
+    RandomSampler rs;
+    RandomSampler_init(rs, seed, sampleOffs + sampleID); // pathState.randomSampler (PathTracer.ispc:157): volumes only
+    samplePath(c, ld, rs, nFirst, nIndirect, ray, sample);
     sample.rgb = vmin(sample.rgb, v3(ren.maxRadiance));
     ScreenSample_accumulate(screenSample, sample);
   }
@@ -1380,6 +1538,13 @@ bool traceVolumeRay(const OcWorld *w, const Ray &ray, VolumeHit &vh)
     }
   }
   return vh.vol != nullptr;
+}
+bool traceVolumeRayFwd(const OcWorld *w, const Ray &ray, VolumeHitFwd &vh)
+{
+  VolumeHit h;
+  const bool r = traceVolumeRay(w, ray, h);
+  vh = {h.vol, h.inst, h.instID, h.geomID, h.t0, h.t1};
+  return r;
 }
 inline float nominalDeltaT(const OcVolume &v, V3 dir)
 {

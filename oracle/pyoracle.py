@@ -484,7 +484,7 @@ class Scene:
         col, opa = np.ascontiguousarray(vs.tf_colors, np.float32), np.ascontiguousarray(vs.tf_opacities, np.float32)
         self.keep += [col, opa]
         v.tf = TransferFunction(col.ctypes.data, opa.ctypes.data, len(col), len(opa), float(vs.value_range[0]), float(vs.value_range[1]))
-        v.densityScale, v.anisotropy, v.gradientShadingScale = float(vs.density_scale), 0.0, float(vs.gradient_shading_scale)
+        v.densityScale, v.anisotropy, v.gradientShadingScale = float(vs.density_scale), float(getattr(vs, "anisotropy", 0.0)), float(vs.gradient_shading_scale)
         v.userID = INVALID_ID
         v.numRanges = 1
         v.ranges[0], v.ranges[1] = -np.inf, np.inf

@@ -104,8 +104,8 @@ ospray::FeatureFlags allFeatures()
 
 #ifdef OSPRAY_ENABLE_VOLUMES
 // volume/Volume.cpp:60-222 (structuredRegular -> VKL handles), volume/VolumetricModel.cpp:29-82,
-// volume/transferFunction/LinearTransferFunction.cpp:22-33 (maxOpacityInRange is only read by the path tracer's delta
-// tracking, which is outside this path, and stays zero)
+// volume/transferFunction/LinearTransferFunction.cpp:22-33 and :110-160 (precomputeMaxOpacityRanges: the table the path
+// tracer's delta tracking reads through LinearTransferFunction_getMaxOpacity)
 VolumetricModel *refMakeVolumetricModel(std::deque<Volume> &vols, std::deque<VolumetricModel> &vms, std::deque<LinearTransferFunction> &tfs,
     std::deque<RefVklVolume> &vklVols, std::deque<RefVklSampler> &, std::deque<RefVklIntervalContext> &, const OcVolume &ov)
 {
@@ -117,6 +117,23 @@ VolumetricModel *refMakeVolumetricModel(std::deque<Volume> &vols, std::deque<Vol
   tfs.emplace_back();
   LinearTransferFunction &tf = tfs.back();
   memset(tf.maxOpacityInRange, 0, sizeof(tf.maxOpacityInRange));
+  if (ov.tf.numOpacities) {
+    const float *opacities = ov.tf.opacity;
+    const int N = PRECOMPUTED_OPACITY_SUBRANGE_COUNT, maxOpacityDim = (int)ov.tf.numOpacities - 1, maxPrecomputedDim = N - 1;
+    for (int i = 0; i < N; i++) { // the diagonal
+      const int lo = (int)floorf(maxOpacityDim * (float)i / maxPrecomputedDim), hi = (int)ceilf(maxOpacityDim * (float)i / maxPrecomputedDim);
+      float m = opacities[lo];
+      for (int k = lo; k <= hi; k++) m = std::max(m, opacities[k]);
+      tf.maxOpacityInRange[i][i] = m;
+    }
+    for (int i = 0; i < N; i++) // each column from the diagonal up
+      for (int j = i + 1; j < N; j++) {
+        const int lo = (int)floorf(maxOpacityDim * (float)i / maxPrecomputedDim), hi = (int)ceilf(maxOpacityDim * (float)j / maxPrecomputedDim);
+        float m = tf.maxOpacityInRange[i][i];
+        for (int k = lo; k <= hi; k++) m = std::max(m, opacities[k]);
+        tf.maxOpacityInRange[i][j] = m;
+      }
+  }
   tf.super.valueRange = box1f(ov.tf.valueLower, ov.tf.valueUpper);
   tf.color.addr = (uint8 *)ov.tf.color; tf.color.byteStride = 12; tf.color.numItems = ov.tf.numColors; tf.color.huge = false;
   tf.opacity.addr = (uint8 *)ov.tf.opacity; tf.opacity.byteStride = 4; tf.opacity.numItems = ov.tf.numOpacities; tf.opacity.huge = false;

@@ -140,6 +140,10 @@ OSPFuture CudaDevice::renderFrame(OSPFrameBuffer _fb, OSPRenderer _r, OSPCamera 
   Renderer *r = (Renderer *)_r;
   Camera *c = (Camera *)_c;
   World *w = (World *)_w;
+  // volumes under the pathtracer (pathtracer/volumes/VolumeSampler.ispc) are restated and pinned in the checker but not on
+  // the device yet: refuse the frame instead of rendering the world without its volumes
+  if (r->sh.type == OC_RENDERER_PATHTRACER && w->sh.hasVolumes)
+    throw std::runtime_error("cuda device: the pathtracer does not render volumes yet (use the scivis or ao renderer)");
   Future *f = new Future(fb, r, c, w);
   try {
     fb->beginFrame();

@@ -65,6 +65,7 @@ class VolumeSpec:
     value_range: tuple = (0.0, 1.0)
     density_scale: float = 1.0
     gradient_shading_scale: float = 0.0
+    anisotropy: float = 0.0                    # VolumetricModel 'anisotropy' (Henyey-Greenstein g, pathtracer only)
 
 
 @dataclass
@@ -423,6 +424,7 @@ def to_ospray(scene: SceneSpec):
             vm.set("transferFunction", tf)
             if vs.density_scale != 1.0: vm.set("densityScale", float(vs.density_scale))
             if vs.gradient_shading_scale != 0.0: vm.set("gradientShadingScale", float(vs.gradient_shading_scale))
+            if vs.anisotropy != 0.0: vm.set("anisotropy", float(vs.anisotropy))
             vmodels.append(vm.commit())
             keep += [vol, tf]
         group = osp.Group()

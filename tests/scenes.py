@@ -51,6 +51,17 @@ def volume_with_opaque_geometry():
     return s
 
 
+def forward_scattering_volume():
+    """gravity_spheres_volume with a forward-scattering phase function (Henyey-Greenstein g = 0.6) and a denser medium:
+    the general branch of HenyeyGreenstein_sample and multiple scattering under the pathtracer"""
+    s = T.gravity_spheres_volume(24)
+    for inst in s.instances:
+        for v in inst.group.volumes:
+            v.anisotropy = 0.6
+            v.density_scale = 3.0
+    return s
+
+
 def glass_spheres():
     """random_spheres as the reference builds it for the pathtracer: thinGlass, attenuationDistance 0.2
     (RandomSpheres.cpp:89-99), over the striped ground plane"""
@@ -144,6 +155,11 @@ CASES = {
     "gravity_shaded": (shaded_volume, "scivis", {"shadows": True}, 1),
     "volume_geometry": (volume_with_geometry, "scivis", {"shadows": True, "aoSamples": 1}, 1),
     "volume_opaque_geometry": (volume_with_opaque_geometry, "scivis", {"pixelSamples": 2}, 1),
+    # volumes under the pathtracer (pathtracer/volumes/VolumeSampler.ispc delta tracking + Henyey-Greenstein): oracle and
+    # reference kernels only -- the cuda device refuses such a frame (DEVICE_UNSUPPORTED)
+    "gravity_pt": (lambda: T.gravity_spheres_volume(24), "pathtracer", {"pixelSamples": 2}, 2),
+    "gravity_aniso_pt": (forward_scattering_volume, "pathtracer", {"pixelSamples": 2, "maxPathLength": 8}, 1),
+    "volume_geometry_pt": (volume_with_opaque_geometry, "pathtracer", {"pixelSamples": 2}, 1),
     # debug renderer (render/debug/DebugRenderer.ispc), every method the device accepts
     "debug_testFrame": (T.cornell_box, "debug", {"method": "testFrame", "pixelSamples": 2}, 2),
     "debug_rayDir": (T.cornell_box, "debug", {"method": "rayDir"}, 1),
@@ -163,6 +179,8 @@ CASES = {
 # numVolumeIntervals on every pass of their transparency loops (volume/Volume.ispc:68-71), so the pass after a
 # transmissive geometry hit indexes past it (common/World.ih:121-128).  Undefined in the reference's scalar mode.
 REF_UNSUPPORTED = {"volume_geometry"}
+# Cases the cuda device does not render yet (volumes under the pathtracer): ospRenderFrame fails with an API error
+DEVICE_UNSUPPORTED = {"gravity_pt", "gravity_aniso_pt", "volume_geometry_pt"}
 
 W, H = 48, 40  # not a multiple of 8 or 64: exercises clipped render tasks and border tiles
 

@@ -24,6 +24,11 @@ REF_RENDERS = np.load(os.path.join(sys_path_golden, "ref_renders.npz"))
 REF_KATS = np.load(os.path.join(sys_path_golden, "ref_kats.npz"))
 REF_CASES = [n for n in scenes.CASES if n not in scenes.REF_UNSUPPORTED]
 VOLUME_CASES = {"gravity_scivis", "gravity_ao", "gravity_shaded", "volume_opaque_geometry"}
+# volumes under the pathtracer: ids / depth of volume vertices are part of the path state on both sides and compared in
+# full; delta tracking chains hundreds of logf / expf / lerp steps per path, so the 1-ulp libm differences between the two
+# translation units (see _check_render) grow to a few 1e-6 relative on < 1 % of the pixels
+PT_VOLUME_CASES = {"gravity_pt", "gravity_aniso_pt", "volume_geometry_pt"}
+NO_GEOMETRY_CASES = VOLUME_CASES | {"gravity_pt", "gravity_aniso_pt"}
 
 import importlib.util  # noqa: E402
 
@@ -37,8 +42,8 @@ needs_ref = pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref/libosp
 def _check_render(fb, ref, name):
     c, r = fb.buf["color"], ref("color")
     exact = (c == r).all(axis=-1)
-    assert exact.mean() >= 0.97, (name, exact.mean())
-    np.testing.assert_allclose(c, r, rtol=4e-7, atol=1e-7, err_msg=name)
+    assert exact.mean() >= (0.93 if name in PT_VOLUME_CASES else 0.97), (name, exact.mean())
+    np.testing.assert_allclose(c, r, rtol=2e-5 if name in PT_VOLUME_CASES else 4e-7, atol=1e-7, err_msg=name)
     # pixels whose ids/depth come from geometry on both sides: all of them without volumes; none behind/inside a volume
     geo = np.zeros(exact.shape, bool) if name in VOLUME_CASES and name != "gravity_ao" else np.ones(exact.shape, bool)
     for ch in ("primID", "objID", "instID"):
@@ -60,7 +65,7 @@ def test_oracle_render_matches_reference_live(name):
     pf = "point" if len(name) % 2 else None
     ref = scenes.oracle_render(name, 64, 56, pixel_filter=pf, backend="ref")
     _check_render(scenes.oracle_render(name, 64, 56, pixel_filter=pf), lambda ch: ref.buf[ch], name)
-    if name not in VOLUME_CASES:  # same number of rays handed to the scene (the reference skips the query without geometry)
+    if name not in NO_GEOMETRY_CASES:  # same number of rays handed to the scene (the reference skips the query without geometry)
         assert int(ref.counters.sum()) == int(scenes.oracle_render(name, 64, 56, pixel_filter=pf).counters.sum())
 
 

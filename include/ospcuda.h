@@ -262,6 +262,9 @@ typedef struct {
   uint32_t worldNumLights;
   /* debug renderer (DebugRenderer.cpp:69-75): OC_DEBUG_* */
   uint32_t debugMethod;
+  /* host-side copy of OcWorld.hasVolumes of the world this frame renders (set per ospRenderFrame like worldNumLights):
+   * the pathtracer then samples free paths / transmittance and carries a RandomSampler per path */
+  uint32_t worldHasVolumes;
 } OcRenderer;
 
 /* framebuffer (reference: LocalFBShared.h, FrameBufferShared.h; LocalFB.cpp:49-180) */

@@ -115,7 +115,7 @@ class Renderer(C.Structure):
                 ("limitIndirectLightSamples", C.c_uint32), ("backgroundRefraction", C.c_uint32),
                 ("shadowsEnabled", C.c_uint32), ("visibleLights", C.c_uint32), ("aoSamples", C.c_int32),
                 ("aoRadius", C.c_float), ("aoIntensity", C.c_float), ("volumeSamplingRate", C.c_float),
-                ("worldNumLights", C.c_uint32), ("debugMethod", C.c_uint32)]
+                ("worldNumLights", C.c_uint32), ("debugMethod", C.c_uint32), ("worldHasVolumes", C.c_uint32)]
 
 
 class FrameBuffer(C.Structure):

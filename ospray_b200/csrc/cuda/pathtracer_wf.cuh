@@ -24,7 +24,8 @@ namespace cg = cooperative_groups;
 
 enum : uint32_t {
   PT_DEPTH_MASK = 0xffu, PT_SCAT_SHIFT = 8, PT_SCAT_MASK = 0xff00u,
-  PT_STRAIGHT = 1u << 16, PT_SPECTRANS = 1u << 17, PT_FIRSTBOUNCE = 1u << 18, PT_DONE = 1u << 19, PT_HAS_SHADOW = 1u << 20
+  PT_STRAIGHT = 1u << 16, PT_SPECTRANS = 1u << 17, PT_FIRSTBOUNCE = 1u << 18, PT_DONE = 1u << 19, PT_HAS_SHADOW = 1u << 20,
+  PT_VOLUME = 1u << 21 // the vertex TRACE found is a scattering event inside a volume (hit1.xyz = its albedo)
 };
 
 struct PtScratch
@@ -44,6 +45,8 @@ struct PtScratch
   float4 *sPos, *sFN, *sNrm, *sAlb; // this sample's AOVs (only when the framebuffer has the channel)
   float4 *shA, *shB, *shC;          // shadow entries [slot * nls + i]: org.xyz,tmax | dir.xyz,mis | contrib.xyz,valid
   float4 *accC, *accZ, *accPos, *accFN, *accNrm, *accAlb; // ScreenSample sums across the spp passes (spp > 1)
+  uint4 *rnd;     // worlds with volumes: pathState.randomSampler (PCG32 state lo/hi, stream)
+  float *shT0;    // worlds with volumes: t0 of shadow entry [slot * nls + i] after the transparent-shadow loop
   uint32_t *queue[2];
   uint32_t *counters;
   uint32_t nls;
@@ -63,6 +66,7 @@ struct PtArgs
   const uint32_t *cntIn;
   uint32_t *cntOut;
   uint32_t *fetchCursor;  // ptFusedKernel's work-fetch cursor into qIn (zeroed with the counters every pass)
+  uint32_t vol;           // the world holds volumes (host copy of OcWorld.hasVolumes): free-path sampling + transmittance
 };
 
 __device__ __forceinline__ void ptAppend(uint32_t *q, uint32_t *cnt, uint32_t p)
@@ -168,6 +172,160 @@ __device__ __forceinline__ void ptCountRays(const OcFrameBuffer &fb, uint32_t a,
 
 #define PT_TRACE_BLOCK 128
 
+// ---- volumes under the pathtracer ------------------------------------------------------------------------------------
+// pathtracer/volumes/VolumeSampler.ispc:13-282 in its single-volume-interval form (what the reference compiles for its GPU
+// target) and pathtracer/volumes/HenyeyGreenstein.ih:11-74. The structured-volume stand-in of Open VKL reports ONE interval
+// with the value range (-inf, inf) to this renderer, i.e. delta tracking runs against the global majorant
+// densityScale * max opacity (oracle.cpp deltaTracking is the same statement). Everything volume-related sits behind
+// out-of-line functions that load and store the path's RandomSampler themselves: worlds without volumes (k.vol == 0)
+// never touch them and the register allocation of the TRACE / SHADE kernels is unchanged.
+__device__ __forceinline__ RandomSampler ptLoadRs(const PtScratch &s, uint32_t p)
+{
+  const uint4 v = s.rnd[p];
+  RandomSampler rs;
+  rs.state = ((uint64_t)v.y << 32) | v.x; rs.stream = v.z;
+  return rs;
+}
+__device__ __forceinline__ void ptStoreRs(const PtScratch &s, uint32_t p, const RandomSampler &rs)
+{
+  s.rnd[p] = make_uint4((uint32_t)rs.state, (uint32_t)(rs.state >> 32), rs.stream, 0u);
+}
+// LinearTransferFunction_getMaxOpacity over (-inf, inf) = table entry [0][31] of precomputeMaxOpacityRanges
+// (LinearTransferFunction.cpp:110-160) = the largest opacity
+__device__ __forceinline__ float ptTfMaxOpacityAll(const OcTransferFunction &tf)
+{
+  float m = __ldg(tf.opacity);
+  for (uint32_t i = 1; i < tf.numOpacities; i++) m = fmaxf(m, __ldg(tf.opacity + i));
+  return m;
+}
+// delta_tracking (VolumeSampler.ispc:13-103): returns (albedo.xyz, t) with t = INFINITY when the ray leaves unscattered
+__device__ __forceinline__ float4 ptDeltaTracking(const OcVolume &v, float lower, float upper, RandomSampler &rs, vec3f o, vec3f w)
+{
+  const float4 none = make_float4(0.f, 0.f, 0.f, INFINITY);
+  if (!(lower < upper)) return none;
+  float t = lower;
+  const float mu_max = v.densityScale * ptTfMaxOpacityAll(v.tf);
+  if (mu_max <= 0.f) return none;
+  while (true) {
+    float xi = RandomSampler_getFloat(rs);
+    const float dt = -logf(1.f - xi) / mu_max;
+    t += dt;
+    if (t > upper) break;
+    xi = RandomSampler_getFloat(rs);
+    const float sample = volumeSample(v, o + t * w);
+    if (isnan(sample)) continue;
+    const vec4f color = transferFunctionGet(v.tf, sample);
+    const float mu_t = v.densityScale * color.w;
+    if (xi < mu_t / mu_max) return make_float4(color.x, color.y, color.z, t);
+  }
+  return none;
+}
+// the clipped interval both volume queries track over (VolumeSampler.ispc:139-171 / :222-254); false: nothing to track
+__device__ __forceinline__ bool ptVolumeInterval(const OcWorld *world, const Ray &ray, float firstLower, float rayLower, float rayUpper,
+    VolumeHit &vh, vec3f &org, vec3f &dir, float &lower, float &upper)
+{
+  if (!traceVolumeRay(world, ray, vh)) return false;
+  lower = fmaxf(firstLower, vh.t0);
+  upper = hadHit(ray) ? fminf(vh.t1, ray.t) : vh.t1;
+  if (lower > upper) return false;
+  org = ray.org; dir = ray.dir;
+  if (!vh.inst->isIdentity) {
+    const affine3f rx = toA(vh.inst->rcp_xfm);
+    org = xfmPoint(rx, ray.org); dir = xfmVector(rx, ray.dir);
+  }
+  if (upper < rayLower || rayUpper < lower) return false;
+  lower = fmaxf(rayLower, lower); upper = fminf(rayUpper, upper);
+  return true;
+}
+struct PtFreePath { float4 albedoDist; uint32_t geomID, instID; };
+// volumeSampleFreePath (VolumeSampler.ispc:105-196) for the ray TRACE just resolved against the geometry
+static __device__ __noinline__ PtFreePath ptVolumeFreePath(const PtArgs &k, uint32_t p, vec3f rorg, vec3f rdir, float t0, float t,
+    uint32_t hitGeomID, float rayLower, float rayUpper)
+{
+  PtFreePath r;
+  r.albedoDist = make_float4(0.f, 0.f, 0.f, INFINITY); r.geomID = r.instID = OC_INVALID_ID;
+  Ray ray;
+  setRay(ray, rorg, rdir, t0, t);
+  ray.geomID = hitGeomID; // hadHit() of the geometry query
+  VolumeHit vh;
+  vec3f org, dir;
+  float lower, upper;
+  if (!ptVolumeInterval(k.a.world, ray, 0.f, rayLower, rayUpper, vh, org, dir, lower, upper)) return r;
+  RandomSampler rs = ptLoadRs(k.s, p);
+  r.albedoDist = ptDeltaTracking(*vh.vol, lower, upper, rs, org, dir);
+  ptStoreRs(k.s, p, rs);
+  r.geomID = vh.geomID; r.instID = vh.instID;
+  return r;
+}
+// volumeTransmittance (VolumeSampler.ispc:198-279) with the RandomSampler handed in
+__device__ __forceinline__ float ptVolumeTransmittance(const OcWorld *world, const Ray &ray, float rayLower, float rayUpper, RandomSampler &rs)
+{
+  VolumeHit vh;
+  vec3f org, dir;
+  float lower, upper;
+  if (!ptVolumeInterval(world, ray, ray.t0, rayLower, rayUpper, vh, org, dir, lower, upper)) return 1.f;
+  const float4 r = ptDeltaTracking(*vh.vol, lower, upper, rs, org, dir);
+  return (r.w < upper) ? 0.f : 1.f;
+}
+// nextEventEstimation's volume part for one unoccluded shadow ray (NextEventEstimation.ispc:126-151): T and an independent
+// T_mis; returns the factor that replaces the surface-only MIS weight, T * misHeuristic(ls.pdf, fe.pdf * T_mis)
+__device__ __forceinline__ float ptMis(float pdf1, float pdf2)
+{
+  const float q = sqr(pdf1) * (1.f / (sqr(pdf1) + sqr(pdf2)));
+  return pdf1 > 1e17f ? 1.0f : q;
+}
+static __device__ __noinline__ float ptVolumeShadowWeight(const PtArgs &k, uint32_t p, vec3f org, vec3f dir, float t0, float tmax,
+    float lsPdf, float fePdf)
+{
+  Ray sr;
+  setRay(sr, org, dir, t0, tmax); // no hit: the state transparentShadow leaves behind when the light is reached
+  RandomSampler rs = ptLoadRs(k.s, p);
+  float w = 0.f;
+  const float T = ptVolumeTransmittance(k.a.world, sr, 0.f, tmax, rs);
+  if (T > 0.f) {
+    const float T_mis = ptVolumeTransmittance(k.a.world, sr, 0.f, tmax, rs);
+    w = T * ptMis(lsPdf, fePdf * T_mis);
+  }
+  ptStoreRs(k.s, p, rs);
+  return w;
+}
+__device__ __forceinline__ float hgPhase(float cosTheta, float g) // HenyeyGreenstein.ih:11-15
+{
+  const float denom = 1.f + g * g - 2.f * g * cosTheta;
+  return (1.f / (4.f * (float)M_PI)) * (1.f - g * g) * (1.f / (denom * sqrtf(denom)));
+}
+__device__ __forceinline__ bool hgIsSmooth(float g) { return !(fabsf(g) > 1.f - 1e-3f); }
+__device__ __forceinline__ EvalRes HenyeyGreenstein_eval(float g, vec3f wo, vec3f wi) // :24-35
+{
+  EvalRes r;
+  r.pdf = hgPhase(dot(neg(wo), wi), g);
+  r.value = make_vec3f(r.pdf);
+  return r;
+}
+static __device__ __noinline__ SampleRes HenyeyGreenstein_sample(float g, vec3f wo, vec2f s) // :37-72
+{
+  SampleRes res;
+  res.weight = make_vec3f(1.f);
+  float cosTheta;
+  if (!hgIsSmooth(g)) {
+    res.wi = g > 0 ? neg(wo) : wo;
+    res.pdf = INFINITY;
+    res.type = g > 0 ? SC_SPECULAR_TRANSMISSION : SC_SPECULAR_REFLECTION;
+    return res;
+  } else if (fabsf(g) < 1e-3f) {
+    cosTheta = 1.f - 2.f * s.x;
+  } else {
+    const float sqrTerm = (1.f - g * g) * (1.f / (1.f - g + 2.f * g * s.x));
+    cosTheta = (1.f + g * g - sqrTerm * sqrTerm) * (1.f / (2.f * g));
+  }
+  res.type = SC_SMOOTH;
+  const float sinTheta = sqrtf(fmaxf(0.f, 1.f - cosTheta * cosTheta));
+  const float phi = (float)(2.0 * 3.14159265358979323846 * (double)s.y); // M_PI is a double in the reference's scalar form
+  res.wi = frame(neg(wo)) * cartesian(phi, sinTheta, cosTheta);
+  res.pdf = hgPhase(cosTheta, g);
+  return res;
+}
+
 // Does the surface hit by the any-hit query `ray` certainly take the shadow-ray contribution to exactly 0, as the
 // reference's closest-hit loop would (TransparentShadow.ispc:18-85: lightContrib *= transparency per hit, result 0 as
 // soon as reduce_max(lightContrib) <= minContribution)?  OBJ_getTransparency (OBJ.ispc:93-111) is T = Tf*d + (1-d) with
@@ -224,12 +382,15 @@ static __device__ __noinline__ float4 ptTransparentShadowSlow(const PtArgs &k, s
     if (reduce_max(lightContrib) <= ren.minContribution || --maxDepth <= 0) { lightContrib = make_vec3f(0.f); break; }
     setRay(sr, sr.org, sr.dir, sr.t + dg.epsilon, tOriginal);
   }
+  if (k.vol) k.s.shT0[e] = sr.t0; // where the ray stands after the transparent surfaces it crossed (volumeTransmittance starts there)
   return make_float4(lightContrib.x, lightContrib.y, lightContrib.z, __uint_as_float(shadowCount));
 }
 
 // TRACE step of one path: resolve the shadow rays emitted at the previous vertex, then (unless the path is
 // done) trace the continuation ray. Returns false when the path finished here.
-template <bool FIRST>
+// VOL: the world holds volumes. A template parameter, not a run-time flag: with the volume calls compiled into the one
+// instantiation every world used, SHADE ran 12 % slower on cornell_box (register allocation around the call sites).
+template <bool FIRST, bool VOL>
 __device__ __forceinline__ bool ptTraceStep(const PtArgs &k, uint32_t p, Stack stack, PtCounts &cnt)
 {
   const PtScratch &s = k.s;
@@ -259,6 +420,11 @@ __device__ __forceinline__ bool ptTraceStep(const PtArgs &k, uint32_t p, Stack s
     cameraInitRay(k.a.cam, ray, screen, lens);
     // samplePath() prologue (PathSampler.ispc:116-133)
     s.smp[p] = make_uint2(ld.revIndex, ld.scramble);
+    if (VOL) { // pathState.randomSampler (PathTracer.ispc:157)
+      RandomSampler rs;
+      RandomSampler_init(rs, seed, sampleOffs + sampleID);
+      ptStoreRs(s, p, rs);
+    }
     s.flags[p] = PT_STRAIGHT | PT_SPECTRANS | PT_FIRSTBOUNCE;
     s.thr[p] = make_float4(1.f, 1.f, 1.f, 1.f);
     s.con[p] = make_float4(0.f, 0.f, 0.f, INFINITY);
@@ -290,6 +456,7 @@ __device__ __forceinline__ bool ptTraceStep(const PtArgs &k, uint32_t p, Stack s
         // fast path: ANY opaque occluder makes the product of transparencies exactly 0, whatever lies in front
         // of it -> one any-hit query; only a non-opaque first find falls back to the reference's closest-hit loop
         bool resolved = false;
+        float shadowT0 = 0.f;
         if (isfinite(lightContrib.x) && isfinite(lightContrib.y) && isfinite(lightContrib.z)) {
           Ray occ = sr;
           cnt.shadow++;
@@ -300,8 +467,14 @@ __device__ __forceinline__ bool ptTraceStep(const PtArgs &k, uint32_t p, Stack s
           const float4 r = ptTransparentShadowSlow(k, e, lightContrib.x, lightContrib.y, lightContrib.z, stack.base);
           lightContrib = make_vec3f(r.x, r.y, r.z);
           cnt.shadow += __float_as_uint(r.w);
+          if (VOL) shadowT0 = s.shT0[e];
         }
-        if (reduce_max(lightContrib) > 0) L = L + lightContrib * b.w;
+        if (reduce_max(lightContrib) > 0) {
+          // worlds with volumes: b.w = ls.pdf, c.w = fe.pdf (SHADE); the weight carries the transmittance estimates
+          const float w = VOL ? ptVolumeShadowWeight(k, p, make_vec3f(a.x, a.y, a.z), make_vec3f(b.x, b.y, b.z), shadowT0, a.w, b.w, c.w == FLT_MIN ? 0.f : c.w)
+                                : b.w;
+          if (VOL) L = L + w * lightContrib; else L = L + lightContrib * w;
+        }
       }
       float4 con = s.con[p];
       con.x += L.x; con.y += L.y; con.z += L.z;
@@ -317,21 +490,66 @@ __device__ __forceinline__ bool ptTraceStep(const PtArgs &k, uint32_t p, Stack s
   }
   ray.u = ray.v = 0.f;
   ray.Ng = make_vec3f(0.f);
+  const float rayLower = ray.t0, rayUpper = ray.t; // traceClippingRay without clipping geometry (World.ih:150-163)
   traceWorld<false>(k.a.world, ray, stack);
+  if (VOL) { // volumeSampleFreePath (PathSampler.ispc:178-194): a scattering event before the surface replaces the hit
+    const PtFreePath fp = ptVolumeFreePath(k, p, ray.org, ray.dir, ray.t0, ray.t, ray.geomID, rayLower, rayUpper);
+    if (fp.albedoDist.w < INFINITY) {
+      s.hit0[p] = make_float4(fp.albedoDist.w, 0.f, 0.f, __uint_as_float(0u));
+      s.hit1[p] = make_float4(fp.albedoDist.x, fp.albedoDist.y, fp.albedoDist.z, __uint_as_float(fp.geomID));
+      s.hitInst[p] = fp.instID;
+      s.flags[p] |= PT_VOLUME;
+      return true;
+    }
+  }
   s.hit0[p] = make_float4(ray.t, ray.u, ray.v, __uint_as_float(ray.primID));
   s.hit1[p] = make_float4(ray.Ng.x, ray.Ng.y, ray.Ng.z, __uint_as_float(ray.geomID));
   s.hitInst[p] = ray.instID;
   return true;
 }
 
+template <bool VOL>
 __device__ bool ptShadeStep(const PtArgs &k, uint32_t p);
+
+// evaluateVirtualLights in a world with volumes (VirtualLight.ispc:76-101): the MIS weight of a light the path runs into
+// carries a transmittance estimate along the segment since the last vertex
+static __device__ __noinline__ vec3f ptVirtualLightsVol(const PtArgs &k, uint32_t p, bool straightPath, vec3f throughput, vec3f lastP,
+    vec3f lastNs, float lastPdf, uint32_t lastNumLightSamples, bool environment, vec3f rorg, vec3f rdir, float rt)
+{
+  const OcWorld *world = k.a.world;
+  vec3f L = make_vec3f(0.f);
+  const uint32_t numLights = world->numLights;
+  if (numLights == 0) return L;
+  const float lower = length(lastP - rorg);
+  const float upper = environment ? INFINITY : length(lastP - (rorg + rt * rdir));
+  const float selectionPDF = lastNumLightSamples / (float)numLights;
+  RandomSampler rs = ptLoadRs(k.s, p);
+  for (uint32_t i = 0; i < numLights; i++) {
+    const OcLight &l = world->lights[i];
+    if (!straightPath || l.isVisible) {
+      const LightEval le = Light_eval(l, lastP, lastNs, rdir, lower, upper);
+      if (reduce_max(le.radiance) > 0.0f) {
+        float misWeight = 1.0f;
+        if (selectionPDF) {
+          Ray shadowRay;
+          setRay(shadowRay, lastP, rdir, lower, upper);
+          const float T = ptVolumeTransmittance(world, shadowRay, lower, upper, rs);
+          misWeight = ptMis(lastPdf * T, selectionPDF * le.pdf);
+        }
+        L = L + throughput * le.radiance * misWeight;
+      }
+    }
+  }
+  ptStoreRs(k.s, p, rs);
+  return L;
+}
 
 // ---- TRACE --------------------------------------------------------------------------------------------------
 // Persistent grid-stride loop over the live-path queue. When few paths are left (RR has culled the frame down to
 // a long thin tail), every further TRACE/SHADE launch would cost a launch + drain latency for almost no work
 // (profiles/r1_pt_wavefront_launches.txt: 30 launches x ~35 us): instead each thread then carries its path to
 // the end right here (TAIL mode); the queue it leaves behind is empty and the remaining launches exit at once.
-template <bool FIRST>
+template <bool FIRST, bool VOL>
 __global__ void __launch_bounds__(PT_TRACE_BLOCK, 5) ptTraceKernel(const __grid_constant__ PtArgs k)
 {
   __shared__ uint32_t s_stack[OC_STACK_SIZE * PT_TRACE_BLOCK];
@@ -342,7 +560,7 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, 5) ptTraceKernel(const __grid_
   const uint32_t n = FIRST ? k.numPaths : *k.cntIn;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t p = FIRST ? i : k.qIn[i];
-    if (ptTraceStep<FIRST>(k, p, stack, cnt)) ptAppend(k.qOut, k.cntOut, p);
+    if (ptTraceStep<FIRST, VOL>(k, p, stack, cnt)) ptAppend(k.qOut, k.cntOut, p);
   }
   ptCountRays(k.a.fb, cnt.primary, cnt.secondary, cnt.shadow);
 }
@@ -353,6 +571,7 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, 5) ptTraceKernel(const __grid_
 // profiles/r1_launches_bench_c1_wavefront.csv), each lane runs TRACE and SHADE back to back for its path and, when
 // the path dies, immediately fetches the next live path from the input queue (warp-aggregated atomic on a fetch
 // cursor). All lanes of a warp are at the same phase (trace, then shade) of *some* path until the queue runs dry.
+template <bool VOL>
 __global__ void __launch_bounds__(PT_TRACE_BLOCK) ptFusedKernel(const __grid_constant__ PtArgs k)
 {
   __shared__ uint32_t s_stack[OC_STACK_SIZE * PT_TRACE_BLOCK];
@@ -378,7 +597,7 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK) ptFusedKernel(const __grid_con
       }
       if (__ballot_sync(0xffffffffu, alive) == 0) break; // queue exhausted and every lane's path finished
     }
-    if (alive) alive = ptTraceStep<false>(k, p, stack, cnt) && ptShadeStep(k, p);
+    if (alive) alive = ptTraceStep<false, VOL>(k, p, stack, cnt) && ptShadeStep<VOL>(k, p);
   }
   ptCountRays(k.a.fb, cnt.primary, cnt.secondary, cnt.shadow);
   if (k.a.fb.rayCounters) { // [3]: rays traced by this kernel
@@ -391,6 +610,7 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK) ptFusedKernel(const __grid_con
 
 // SHADE step of one path; returns true when the path goes on to the next TRACE step (alive, or done with
 // shadow rays pending), false when it finished here.
+template <bool VOL>
 __device__ bool ptShadeStep(const PtArgs &k, uint32_t p)
 {
   const PtScratch &s = k.s;
@@ -400,7 +620,8 @@ __device__ bool ptShadeStep(const PtArgs &k, uint32_t p)
   dummy.base = nullptr; dummy.stride = 0;
   Ctx c(k.a.world, k.a.ren, k.a.cam, k.a.fb, dummy);
   {
-    uint32_t flags = s.flags[p] & ~(PT_HAS_SHADOW | PT_DONE);
+    const bool volume = VOL && (s.flags[p] & PT_VOLUME) != 0; // scattering event inside a volume (ptVolumeFreePath)
+    uint32_t flags = s.flags[p] & ~(PT_HAS_SHADOW | PT_DONE | PT_VOLUME);
     const uint32_t depth = flags & PT_DEPTH_MASK;
     uint32_t scatteringEvents = (flags & PT_SCAT_MASK) >> PT_SCAT_SHIFT;
     bool straightPath = flags & PT_STRAIGHT, specularTransmissionPath = flags & PT_SPECTRANS, firstBounceLight = flags & PT_FIRSTBOUNCE;
@@ -435,25 +656,48 @@ __device__ bool ptShadeStep(const PtArgs &k, uint32_t p)
     // ---- one iteration of samplePath()'s loop, after the trace (PathSampler.ispc:196-412) ----
     bool alive = false, hasShadow = false;
     do {
-      const bool surface = hadHit(ray);
+      const bool surface = !volume && hadHit(ray);
+      const bool environment = !surface && !volume;
+      const vec3f volumeAlbedo = ray.Ng; // hit1.xyz of a volume vertex
+      const OcVolume *vmodel = nullptr;
+      if (volume) {
+        throughput = throughput * volumeAlbedo; // PathSampler.ispc:189-192
+        vmodel = k.a.world->instances[ray.instID].group->volumes + ray.geomID;
+      }
       const vec3f wo = neg(ray.dir);
       if (depth == 0) {
         float4 z = s.sZ[p];
         z.x = fb.projectedDepth ? ray.t * dot(ray.dir, toV(k.a.cam.direction)) : ray.t;
         s.sZ[p] = z;
       }
-      if (!surface && (ren.backgroundRefraction ? specularTransmissionPath : straightPath)) {
+      if (environment && (ren.backgroundRefraction ? specularTransmissionPath : straightPath)) {
         const vec4f bg = getBackground(ren);
         alpha -= luminance(throughput) * (1.0f - bg.w);
         contribution = contribution + throughput * make_vec3f(bg);
       }
-      contribution = contribution + evaluateVirtualLights(c, straightPath, throughput, last, !surface, ray);
-      if (!surface) break;
+      if (!volume) { // PathSampler.ispc:220-228
+        if (VOL)
+          contribution = contribution + ptVirtualLightsVol(k, p, straightPath, throughput, last.P, last.Ns, last.pdf_w, last.numLightSamples,
+                                            environment, ray.org, ray.dir, ray.t);
+        else
+          contribution = contribution + evaluateVirtualLights(c, straightPath, throughput, last, environment, ray);
+      }
+      if (environment) break;
       if (depth >= ren.maxDepth) break; // numGeoLights == 0
 
       DifferentialGeometry dg;
-      postIntersect(k.a.world, ren, dg, ray,
-          DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR | DG_TANGENTS | DG_MOTIONBLUR);
+      if (volume) { // postIntersect of a volume vertex (PathSampler.ispc:51-67) + VolumetricModel_postIntersect (VolumetricModel.ih:16-33)
+        dg.P = ray.org + ray.t * ray.dir;
+        dg.Ng = dg.Ns = dg.dPds = make_vec3f(0.f);
+        dg.color = make_vec4f(0.f, 0.f, 0.f, 0.f);
+        dg.epsilon = 0.f; dg.material = nullptr; dg.primID = 0;
+        dg.objID = vmodel->userID == OC_INVALID_ID ? ray.geomID : vmodel->userID;
+        dg.instID = ray.instID;
+        if (ray.instID != OC_INVALID_ID && k.a.world->instances[ray.instID].userID != OC_INVALID_ID)
+          dg.instID = k.a.world->instances[ray.instID].userID;
+      } else
+        postIntersect(k.a.world, ren, dg, ray,
+            DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR | DG_TANGENTS | DG_MOTIONBLUR);
       if (depth == 0) {
         float4 z = s.sZ[p];
         z.y = __uint_as_float(dg.primID); z.z = __uint_as_float(dg.objID); z.w = __uint_as_float(dg.instID);
@@ -464,15 +708,17 @@ __device__ bool ptShadeStep(const PtArgs &k, uint32_t p)
       if (depth >= ren.maxDepth || scatteringEvents >= (uint32_t)ren.maxScatteringEvents) break;
 
       ObjBSDF bsdf;
-      OBJ_getBSDF(bsdf, dg);
-      if (!bsdf.valid) break;
+      if (!volume) {
+        OBJ_getBSDF(bsdf, dg);
+        if (!bsdf.valid) break;
+      }
 
       LDSampler_nextGroup(ld);
       uint32_t vertexLightSamples = 0;
-      if (bsdf.scatteringType & SC_SMOOTH) {
-        if (scatteringEvents == 0) {
-          if (fb.albedo) { const vec3f v = throughput * bsdf.albedo; s.sAlb[p] = make_float4(v.x, v.y, v.z, 0.f); }
-          if (fb.normal) { const vec3f v = throughput * bsdf.frame.vz; s.sNrm[p] = make_float4(v.x, v.y, v.z, 0.f); }
+      if (volume ? hgIsSmooth(vmodel->anisotropy) : (bsdf.scatteringType & SC_SMOOTH) != 0) { // isSmooth (PathTracerUtil.ih:15-28)
+        if (scatteringEvents == 0) { // updateAuxilliaryData (PathTracerUtil.ih:48-60)
+          if (fb.albedo) { const vec3f v = throughput * (volume ? volumeAlbedo : bsdf.albedo); s.sAlb[p] = make_float4(v.x, v.y, v.z, 0.f); }
+          if (fb.normal) { const vec3f v = throughput * (volume ? dg.Ns : bsdf.frame.vz); s.sNrm[p] = make_float4(v.x, v.y, v.z, 0.f); }
         }
         // nextEventEstimation up to the shadow ray (NextEventEstimation.ispc:36-118): emit, TRACE(d+1) resolves
         const uint32_t numLightSamples = firstBounceLight ? k.nFirst : k.nIndirect;
@@ -490,14 +736,15 @@ __device__ bool ptShadeStep(const PtArgs &k, uint32_t p)
             ls.weight = ls.weight / lightSelectionProb;
             ls.pdf *= lightSelectionProb;
             if (!(reduce_max(ls.weight) <= 0.0f || ls.pdf <= 0.0f)) {
-              const EvalRes fe = OBJ_eval(bsdf, wo, ls.dir);
+              const EvalRes fe = volume ? HenyeyGreenstein_eval(vmodel->anisotropy, wo, ls.dir) : OBJ_eval(bsdf, wo, ls.dir);
               if (!(reduce_max(fe.value) <= 0.0f)) {
                 vec3f org = dg.P;
-                if (dot(dg.Ng, ls.dir) < 0.f) org = org - (2.0f * dg.epsilon) * dg.Ng;
+                if (!volume && dot(dg.Ng, ls.dir) < 0.f) org = org - (2.0f * dg.epsilon) * dg.Ng;
                 const vec3f unshaded = throughput * fe.value * ls.weight;
                 s.shA[e] = make_float4(org.x, org.y, org.z, ls.dist);
-                s.shB[e] = make_float4(ls.dir.x, ls.dir.y, ls.dir.z, misHeuristic(ls.pdf, fe.pdf));
-                s.shC[e] = make_float4(unshaded.x, unshaded.y, unshaded.z, 1.f);
+                // worlds with volumes: TRACE needs the two pdfs apart (the MIS weight carries a transmittance estimate)
+                s.shB[e] = make_float4(ls.dir.x, ls.dir.y, ls.dir.z, VOL ? ls.pdf : misHeuristic(ls.pdf, fe.pdf));
+                s.shC[e] = make_float4(unshaded.x, unshaded.y, unshaded.z, VOL ? (fe.pdf > 0.f ? fe.pdf : FLT_MIN) : 1.f);
                 valid = true;
                 hasShadow = true;
               }
@@ -511,8 +758,8 @@ __device__ bool ptShadeStep(const PtArgs &k, uint32_t p)
       float ss;
       uint32_t uu3;
       const vec2f sb = LDSampler_getNext4Samples(ld, ss, uu3);
-      SampleRes fs = OBJ_sample(bsdf, wo, sb, ss);
-      {
+      SampleRes fs = volume ? HenyeyGreenstein_sample(vmodel->anisotropy, wo, sb) : OBJ_sample(bsdf, wo, sb, ss);
+      if (!volume) {
         const bool sameSide = dot(fs.wi, dg.Ng) >= 0.f;
         const bool reflection = fs.type & SC_REFLECTION;
         if (sameSide != reflection) fs.weight = make_vec3f(0.0f);
@@ -526,8 +773,8 @@ __device__ bool ptShadeStep(const PtArgs &k, uint32_t p)
         throughput = throughput * (1.f / contProb);
       }
       vec3f ray_org = dg.P;
-      if (fs.type & SC_TRANSMISSION) ray_org = ray_org - (2.0f * dg.epsilon) * dg.Ng;
-      if ((fs.type & ~SC_SPECULAR_TRANSMISSION)) {
+      if (!volume && (fs.type & SC_TRANSMISSION)) ray_org = ray_org - (2.0f * dg.epsilon) * dg.Ng;
+      if ((fs.type & ~SC_SPECULAR_TRANSMISSION) || volume) {
         last.P = dg.P; last.Ns = dg.Ns; last.pdf_w = fs.pdf; last.numLightSamples = vertexLightSamples;
       }
       if (!eq3(ray.dir, fs.wi)) straightPath = false;
@@ -556,12 +803,13 @@ __device__ bool ptShadeStep(const PtArgs &k, uint32_t p)
   }
 }
 
+template <bool VOL>
 __global__ void __launch_bounds__(128, 5) ptShadeKernel(const __grid_constant__ PtArgs k)
 {
   const uint32_t n = *k.cntIn;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t p = k.qIn[i];
-    if (ptShadeStep(k, p)) ptAppend(k.qOut, k.cntOut, p);
+    if (ptShadeStep<VOL>(k, p)) ptAppend(k.qOut, k.cntOut, p);
   }
 }
 

@@ -12,6 +12,7 @@
 #include <utility>
 #include <vector>
 #include "runtime.h"
+#include <cfloat>
 #include "volume.cuh"
 
 namespace oc {
@@ -773,7 +774,7 @@ struct PtHost
 size_t alignUp(size_t v) { return (v + 255) & ~size_t(255); }
 
 // carve the SoA arrays for `paths` slots out of one allocation (grown on demand, kept across frames)
-int ptCarve(oc::PtScratch &s, uint32_t paths, uint32_t nls, bool needAcc, uint32_t numCounters)
+int ptCarve(oc::PtScratch &s, uint32_t paths, uint32_t nls, bool needAcc, uint32_t numCounters, bool hasVol)
 {
   const size_t P = paths;
   size_t bytes = 0;
@@ -787,6 +788,8 @@ int ptCarve(oc::PtScratch &s, uint32_t paths, uint32_t nls, bool needAcc, uint32
   for (int i = 0; i < 5; i++) off[k++] = take(P * 16);       // sZ sPos sFN sNrm sAlb
   for (int i = 0; i < 3; i++) off[k++] = take(P * 16 * nls); // shA shB shC
   for (int i = 0; i < 6; i++) off[k++] = take(needAcc ? P * 16 : 0);
+  off[k++] = take(hasVol ? P * 16 : 0);                      // rnd
+  off[k++] = take(hasVol ? P * 4 * nls : 0);                 // shT0
   off[k++] = take(P * 4); off[k++] = take(P * 4);            // queues
   off[k++] = take(numCounters * 4);
   int dev = 0;
@@ -808,13 +811,17 @@ int ptCarve(oc::PtScratch &s, uint32_t paths, uint32_t nls, bool needAcc, uint32
   s.shA = (float4 *)(b + off[k++]); s.shB = (float4 *)(b + off[k++]); s.shC = (float4 *)(b + off[k++]);
   s.accC = (float4 *)(b + off[k++]); s.accZ = (float4 *)(b + off[k++]); s.accPos = (float4 *)(b + off[k++]); s.accFN = (float4 *)(b + off[k++]);
   s.accNrm = (float4 *)(b + off[k++]); s.accAlb = (float4 *)(b + off[k++]);
+  s.rnd = (uint4 *)(b + off[k++]); s.shT0 = (float *)(b + off[k++]);
   s.queue[0] = (uint32_t *)(b + off[k++]); s.queue[1] = (uint32_t *)(b + off[k++]);
   s.counters = (uint32_t *)(b + off[k++]);
   s.nls = nls;
   return 0;
 }
 
-size_t ptBytesPerPath(uint32_t nls, bool needAcc) { return 8 * 16 + 16 + 5 * 16 + 48 * (size_t)nls + (needAcc ? 96 : 0) + 8; }
+size_t ptBytesPerPath(uint32_t nls, bool needAcc, bool hasVol)
+{
+  return 8 * 16 + 16 + 5 * 16 + 48 * (size_t)nls + (needAcc ? 96 : 0) + 8 + (hasVol ? 16 + 4 * (size_t)nls : 0);
+}
 
 int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
 {
@@ -832,18 +839,20 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
   const uint32_t numCounters = 2 * (maxDepth + 2) + 1; // queue counters of every launch + the fused kernel's fetch cursor
   // batch the owned tiles so that the path state stays under ~1.5 GB (many light samples / 4K frames)
   const size_t budget = size_t(1536) << 20;
-  uint32_t tilesPerBatch = (uint32_t)std::max<size_t>(1, budget / (ptBytesPerPath(nls, needAcc) * 4096));
+  const bool hasVol = fa.ren.worldHasVolumes != 0;
+  k.vol = hasVol ? 1u : 0u;
+  uint32_t tilesPerBatch = (uint32_t)std::max<size_t>(1, budget / (ptBytesPerPath(nls, needAcc, hasVol) * 4096));
   if (tilesPerBatch > ownedTiles) tilesPerBatch = ownedTiles;
-  if (int rc = ptCarve(k.s, tilesPerBatch * 4096u, nls, needAcc, numCounters)) return rc;
+  if (int rc = ptCarve(k.s, tilesPerBatch * 4096u, nls, needAcc, numCounters, hasVol)) return rc;
   if (!g_pt.traceBlocks) {
     int dev = 0, sms = 148, a = 1, b = 1, f = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, ptTraceKernel<false>, PT_TRACE_BLOCK, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ptShadeKernel, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, ptTraceKernel<false, false>, PT_TRACE_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ptShadeKernel<false>, 128, 0);
     g_pt.traceBlocks = sms * (a > 0 ? a : 1);
     g_pt.shadeBlocks = sms * (b > 0 ? b : 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f, ptFusedKernel, PT_TRACE_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f, ptFusedKernel<false>, PT_TRACE_BLOCK, 0);
     g_pt.fusedBlocks = sms * (f > 0 ? f : 1);
   }
   for (uint32_t tile0 = 0; tile0 < ownedTiles; tile0 += tilesPerBatch) {
@@ -856,7 +865,11 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
       // queue / counter ping-pong: every launch reads (queue[q], counters[c]) and appends to (queue[q^1], counters[c+1])
       uint32_t q = 0, c = 0;
       k.depth = 0; k.qIn = nullptr; k.cntIn = nullptr; k.qOut = k.s.queue[q]; k.cntOut = k.s.counters + c;
-      { ProfScope ps(0, st); ptTraceKernel<true><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k); }
+      {
+        ProfScope ps(0, st);
+        if (hasVol) ptTraceKernel<true, true><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+        else ptTraceKernel<true, false><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+      }
       oc_count_launch();
       auto next = [&]() { k.qIn = k.s.queue[q]; k.cntIn = k.s.counters + c; q ^= 1u; c++; k.qOut = k.s.queue[q]; k.cntOut = k.s.counters + c; };
       // separate TRACE / SHADE launches while the frame is densely populated, fused one-launch-per-bounce kernels
@@ -869,17 +882,29 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
         if (d > 0 && d >= fusedFrom) { // one launch carries every remaining path to its end
           next();
           k.fetchCursor = k.s.counters + (numCounters - 1);
-          { ProfScope ps(2, st); ptFusedKernel<<<g_pt.fusedBlocks, PT_TRACE_BLOCK, 0, st>>>(k); }
+          {
+            ProfScope ps(2, st);
+            if (hasVol) ptFusedKernel<true><<<g_pt.fusedBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+            else ptFusedKernel<false><<<g_pt.fusedBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+          }
           oc_count_launch();
           break;
         }
         if (d > 0) {
           next();
-          { ProfScope ps(0, st); ptTraceKernel<false><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k); }
+          {
+            ProfScope ps(0, st);
+            if (hasVol) ptTraceKernel<false, true><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+            else ptTraceKernel<false, false><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+          }
           oc_count_launch();
         }
         next();
-        { ProfScope ps(1, st); ptShadeKernel<<<g_pt.shadeBlocks, 128, 0, st>>>(k); }
+        {
+          ProfScope ps(1, st);
+          if (hasVol) ptShadeKernel<true><<<g_pt.shadeBlocks, 128, 0, st>>>(k);
+          else ptShadeKernel<false><<<g_pt.shadeBlocks, 128, 0, st>>>(k);
+        }
         oc_count_launch();
       }
     }

@@ -140,10 +140,6 @@ OSPFuture CudaDevice::renderFrame(OSPFrameBuffer _fb, OSPRenderer _r, OSPCamera 
   Renderer *r = (Renderer *)_r;
   Camera *c = (Camera *)_c;
   World *w = (World *)_w;
-  // volumes under the pathtracer (pathtracer/volumes/VolumeSampler.ispc) are restated and pinned in the checker but not on
-  // the device yet: refuse the frame instead of rendering the world without its volumes
-  if (r->sh.type == OC_RENDERER_PATHTRACER && w->sh.hasVolumes)
-    throw std::runtime_error("cuda device: the pathtracer does not render volumes yet (use the scivis or ao renderer)");
   Future *f = new Future(fb, r, c, w);
   try {
     fb->beginFrame();
@@ -160,6 +156,7 @@ OSPFuture CudaDevice::renderFrame(OSPFrameBuffer _fb, OSPRenderer _r, OSPCamera 
     const bool finished = fb->sh.targetFrames && fb->doAccum && fb->sh.frameID >= fb->sh.targetFrames; // accumulationFinished()
     OcRenderer rsh = r->sh;
     rsh.worldNumLights = w->sh.numLights;
+    rsh.worldHasVolumes = w->sh.hasVolumes;
     if (!finished) checkCuda(ospcuda_render_frame(dw, &c->sh, &rsh, &fb->sh), "render kernel");
     checkCuda(ospcuda_event_record(f->evRendered), "event record");
     fb->postProcess();

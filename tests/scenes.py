@@ -155,8 +155,7 @@ CASES = {
     "gravity_shaded": (shaded_volume, "scivis", {"shadows": True}, 1),
     "volume_geometry": (volume_with_geometry, "scivis", {"shadows": True, "aoSamples": 1}, 1),
     "volume_opaque_geometry": (volume_with_opaque_geometry, "scivis", {"pixelSamples": 2}, 1),
-    # volumes under the pathtracer (pathtracer/volumes/VolumeSampler.ispc delta tracking + Henyey-Greenstein): oracle and
-    # reference kernels only -- the cuda device refuses such a frame (DEVICE_UNSUPPORTED)
+    # volumes under the pathtracer (pathtracer/volumes/VolumeSampler.ispc delta tracking + Henyey-Greenstein)
     "gravity_pt": (lambda: T.gravity_spheres_volume(24), "pathtracer", {"pixelSamples": 2}, 2),
     "gravity_aniso_pt": (forward_scattering_volume, "pathtracer", {"pixelSamples": 2, "maxPathLength": 8}, 1),
     "volume_geometry_pt": (volume_with_opaque_geometry, "pathtracer", {"pixelSamples": 2}, 1),
@@ -179,8 +178,12 @@ CASES = {
 # numVolumeIntervals on every pass of their transparency loops (volume/Volume.ispc:68-71), so the pass after a
 # transmissive geometry hit indexes past it (common/World.ih:121-128).  Undefined in the reference's scalar mode.
 REF_UNSUPPORTED = {"volume_geometry"}
-# Cases the cuda device does not render yet (volumes under the pathtracer): ospRenderFrame fails with an API error
-DEVICE_UNSUPPORTED = {"gravity_pt", "gravity_aniso_pt", "volume_geometry_pt"}
+# Cases the cuda device does not render (none at present; the GPU parity tests skip what is listed here)
+DEVICE_UNSUPPORTED = set()
+# Volumes under the pathtracer: delta tracking takes hundreds of accept/reject decisions per path on logf / expf / lerp
+# results, so a last-bit libm difference (CUDA vs glibc) sends a few per cent of the paths down another random walk: the
+# device-vs-checker bars for these cases are statistical (tests/test_gpu_parity.py), the checker-vs-reference ones are not
+PT_VOLUME_CASES = {"gravity_pt", "gravity_aniso_pt", "volume_geometry_pt"}
 
 W, H = 48, 40  # not a multiple of 8 or 64: exercises clipped render tasks and border tiles
 

@@ -138,8 +138,9 @@ def test_images_match_reference_golden(osp, name):
     got = fb.map(osp.OSP_FB_COLOR)
     wc = REF_GOLD[name + "/color"]
     err = np.abs(got - wc).max(axis=-1)
-    assert (err > 1e-4 + 2e-3 * np.abs(wc).max(axis=-1)).mean() <= 0.02
-    np.testing.assert_allclose(got.reshape(-1, 4).mean(axis=0), wc.reshape(-1, 4).mean(axis=0), rtol=0.01, atol=1e-4)
+    ptvol = name in scenes.PT_VOLUME_CASES  # statistical bars, see scenes.PT_VOLUME_CASES
+    assert (err > 1e-4 + 2e-3 * np.abs(wc).max(axis=-1)).mean() <= (0.12 if ptvol else 0.02)
+    np.testing.assert_allclose(got.reshape(-1, 4).mean(axis=0), wc.reshape(-1, 4).mean(axis=0), rtol=0.03 if ptvol else 0.01, atol=1e-4)
     from oracle import pyoracle as O
     a = O.color_convert(np.ascontiguousarray(got), 2).view(np.uint8).reshape(got.shape)
     b = O.color_convert(wc, 2).view(np.uint8).reshape(got.shape)
@@ -165,8 +166,9 @@ def test_images_match_oracle(osp, name):
     err = np.abs(got - wc).max(axis=-1)
     tol = 1e-4 + 2e-3 * np.abs(wc).max(axis=-1)
     frac_bad = (err > tol).mean()
-    assert frac_bad <= 0.02, frac_bad
-    np.testing.assert_allclose(got.reshape(-1, 4).mean(axis=0), wc.reshape(-1, 4).mean(axis=0), rtol=0.01, atol=1e-4)
+    ptvol = name in scenes.PT_VOLUME_CASES  # statistical bars, see scenes.PT_VOLUME_CASES
+    assert frac_bad <= (0.12 if ptvol else 0.02), frac_bad
+    np.testing.assert_allclose(got.reshape(-1, 4).mean(axis=0), wc.reshape(-1, 4).mean(axis=0), rtol=0.03 if ptvol else 0.01, atol=1e-4)
     from oracle import pyoracle as O
     a = O.color_convert(np.ascontiguousarray(got), 2).view(np.uint8).reshape(got.shape)
     b = O.color_convert(wc, 2).view(np.uint8).reshape(got.shape)
@@ -174,9 +176,14 @@ def test_images_match_oracle(osp, name):
     assert res["ok"], res
     rc = fb.ray_counts()
     assert rc[0] == int(want.counters[0])
-    assert abs(sum(rc) - int(want.counters.sum())) <= 0.01 * int(want.counters.sum()) + 4
+    assert abs(sum(rc) - int(want.counters.sum())) <= (0.05 if ptvol else 0.01) * int(want.counters.sum()) + 4
     # the committed golden fixture (oracle output at generation time) tells the same story
-    np.testing.assert_allclose(got.reshape(-1, 4).mean(axis=0), GOLD[name + "/color"].reshape(-1, 4).mean(axis=0), rtol=0.01, atol=1e-4)
+    np.testing.assert_allclose(got.reshape(-1, 4).mean(axis=0), GOLD[name + "/color"].reshape(-1, 4).mean(axis=0), rtol=0.03 if ptvol else 0.01, atol=1e-4)
+    if ptvol:  # the first vertex is sampled before any rounding can tell the two sides apart: depth of most pixels is identical
+        d, dw = fb.map(osp.OSP_FB_DEPTH), want.buf["depth"]
+        assert (np.isinf(d) == np.isinf(dw)).mean() >= 0.97
+        both = np.isfinite(d) & np.isfinite(dw)
+        assert (np.abs(d[both] - dw[both]) <= 1e-4 * np.abs(dw[both])).mean() >= 0.9
 
 
 def test_aov_channels(osp):
@@ -290,15 +297,3 @@ def test_builder_reports_the_traversal_stack_need(osp, abi):
     assert 6 <= need <= 30, need
     world, keep = T.to_ospray(T.cornell_box())    # 34 records
     assert 1 <= abi.ospcuda_bvh_last_stack_need() <= 12
-
-
-@pytest.mark.gpu
-def test_pathtracer_refuses_worlds_with_volumes(osp):
-    """volumes under the pathtracer are pinned in the checker (oracle == reference kernels) but not on the device yet:
-    ospRenderFrame fails through the API's error convention instead of rendering the world without its volumes"""
-    world, keep = T.to_ospray(T.gravity_spheres_volume(16))
-    cam, _ = T.make_camera(world, 32, 32)
-    fb = osp.FrameBuffer(32, 32, osp.OSP_FB_RGBA32F, osp.OSP_FB_COLOR)
-    with pytest.raises(osp.OSPRayError, match="does not render volumes"):
-        fb.render_frame(T.make_renderer("pathtracer"), cam, world)
-    fb.render_frame(T.make_renderer("scivis"), cam, world).wait()   # the same world renders under scivis

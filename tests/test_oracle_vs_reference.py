@@ -27,7 +27,7 @@ VOLUME_CASES = {"gravity_scivis", "gravity_ao", "gravity_shaded", "volume_opaque
 # volumes under the pathtracer: ids / depth of volume vertices are part of the path state on both sides and compared in
 # full; delta tracking chains hundreds of logf / expf / lerp steps per path, so the 1-ulp libm differences between the two
 # translation units (see _check_render) grow to a few 1e-6 relative on < 1 % of the pixels
-PT_VOLUME_CASES = {"gravity_pt", "gravity_aniso_pt", "volume_geometry_pt"}
+PT_VOLUME_CASES = scenes.PT_VOLUME_CASES
 NO_GEOMETRY_CASES = VOLUME_CASES | {"gravity_pt", "gravity_aniso_pt"}
 
 import importlib.util  # noqa: E402

@@ -23,6 +23,13 @@ def _dev(a):
     return t
 
 
+def _zeros(*a, **kw):
+    """torch fills on ITS stream; libospcuda works on its own: the fill must have finished before the library writes"""
+    t = torch.zeros(*a, **kw)
+    torch.cuda.synchronize()
+    return t
+
+
 @pytest.mark.parametrize("shape", [(1, 1), (7, 3), (64, 64), (333, 517), (1024, 1024)])
 def test_accumulate_matches_oracle(L, shape):
     from oracle import pyoracle as O
@@ -30,8 +37,8 @@ def test_accumulate_matches_oracle(L, shape):
     rng = np.random.default_rng(w * 7 + h)
     host = O.HostFrameBuffer(w, h, ("color", "depth"), variance=True)
     color = torch.full((h * w * 4,), 99.0, dtype=torch.float32, device="cuda")
-    var = torch.zeros(h * w * 4, dtype=torch.float32, device="cuda")
-    depth = torch.zeros(h * w, dtype=torch.float32, device="cuda")
+    var = _zeros(h * w * 4, dtype=torch.float32, device="cuda")
+    depth = _zeros(h * w, dtype=torch.float32, device="cuda")
     dfb = O.FrameBuffer()
     dfb.sizeX, dfb.sizeY = w, h
     dfb.color, dfb.variance, dfb.depth = color.data_ptr(), var.data_ptr(), depth.data_ptr()
@@ -61,7 +68,7 @@ def test_color_convert_matches_oracle(L, n, fmt):
     x = rng.uniform(-0.2, 1.4, (n, 4)).astype(np.float32)
     x[: min(n, 8)] = [0, 0.0031308, 0.5, 1.0]
     dx = _dev(x)
-    out = torch.zeros(n * (16 if fmt == 3 else 4), dtype=torch.uint8, device="cuda")
+    out = _zeros(n * (16 if fmt == 3 else 4), dtype=torch.uint8, device="cuda")
     L.ospcuda_fb_color_convert.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     assert L.ospcuda_fb_color_convert(dx.data_ptr(), out.data_ptr(), n, fmt) == 0, L.ospcuda_last_error()
     assert L.ospcuda_synchronize() == 0
@@ -81,7 +88,7 @@ def test_tonemap_matches_oracle(L):
     x = np.random.default_rng(3).uniform(0, 6, (n, 4)).astype(np.float32)
     tm = O.default_tonemapper(exposure=1.3)
     dx = _dev(x)
-    out = torch.zeros(n * 4, dtype=torch.float32, device="cuda")
+    out = _zeros(n * 4, dtype=torch.float32, device="cuda")
     L.ospcuda_fb_tonemap.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(O.ToneMapper)]
     assert L.ospcuda_fb_tonemap(dx.data_ptr(), out.data_ptr(), n, C.byref(tm)) == 0, L.ospcuda_last_error()
     assert L.ospcuda_synchronize() == 0
@@ -97,7 +104,7 @@ def test_variance_matches_oracle(L, shape):
     v = (c + rng.normal(0, 0.05, (h, w, 4))).astype(np.float32)
     c[: h // 2, : w // 3] = [0, 0, 0, 1]  # den2 == 0 pixels are skipped
     tasks = ((w + 7) // 8) * ((h + 7) // 8)
-    out = torch.zeros(tasks, dtype=torch.float32, device="cuda")
+    out = _zeros(tasks, dtype=torch.float32, device="cuda")
     dc, dv = _dev(c), _dev(v)
     L.ospcuda_fb_variance.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     assert L.ospcuda_fb_variance(dc.data_ptr(), dv.data_ptr(), w, h, 8, out.data_ptr()) == 0, L.ospcuda_last_error()
@@ -118,11 +125,12 @@ def test_tile_pack_unpack_roundtrip(L, size, bpp):
     img = np.random.default_rng(1).integers(0, 255, (h, w, bpp), dtype=np.uint8)
     dimg = _dev(img)
     dst = torch.zeros_like(dimg)
+    torch.cuda.synchronize()
     for fn in (L.ospcuda_fb_pack_tiles, L.ospcuda_fb_unpack_tiles):
         fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
     for r in range(n):
         shard = multigpu.max_owned(w, h, n) * 64 * 64 * bpp
-        packed = torch.zeros(shard, dtype=torch.uint8, device="cuda")
+        packed = _zeros(shard, dtype=torch.uint8, device="cuda")
         torch.cuda.synchronize()
         assert L.ospcuda_fb_pack_tiles(packed.data_ptr(), dimg.data_ptr(), w, h, bpp, n, r) == 0
         assert L.ospcuda_synchronize() == 0

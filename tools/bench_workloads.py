@@ -3,6 +3,7 @@
 
   C1  cornell_box            pathtracer 1024x1024  1 spp
   C2  gravity_spheres_volume scivis     1920x1080  4 spp   (structured volume 128^3; --dim for 32/512)
+  C2pt gravity_spheres_volume pathtracer 1920x1080 1 spp/frame (ospBenchmark's gravity_spheres_volume/dim_*/pathtracer)
   C3  ~10 M-triangle mesh    ao         3840x2160 16 spp   (94^3 boxes x 12 triangles; --boxes K for smaller)
   C4  random_spheres (thinGlass) + streamlines (round Catmull-Rom curves), pathtracer 1920x1080, 1 spp/frame
       accumulated progressively (--frames 64 gives the config's 64 spp)
@@ -58,6 +59,8 @@ def main():
                 spec, ren_kind, w, h, spp, rp = T.cornell_box(), "pathtracer", 1024, 1024, 1, {}
             elif wl == "C2":
                 spec, ren_kind, w, h, spp, rp = T.gravity_spheres_volume(args.dim), "scivis", 1920, 1080, 4, {}
+            elif wl == "C2pt":  # the same volume under the pathtracer (delta tracking + Henyey-Greenstein), 1 spp/frame
+                spec, ren_kind, w, h, spp, rp = T.gravity_spheres_volume(args.dim), "pathtracer", 1920, 1080, 1, {}
             elif wl == "C3":
                 spec, ren_kind, w, h, spp, rp = T.box_mesh(args.boxes), "ao", 3840, 2160, 16, {}
             elif wl == "C4":

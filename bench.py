@@ -229,10 +229,15 @@ def run_ours(args):
         assert bpp == 4
         if world == 1:
             gather = None
-        elif args.gather == "peer":   # tiles stored straight into GPU 0's image over NVLink peer memory (one kernel per rank)
-            gather = multigpu.PeerTileExchange(w, h, 4, conv_ptr)
-        else:                         # pack + one NCCL gather + unpack
-            gather = multigpu.TileGather(w, h, 4, torch.device("cuda", local), ops=multigpu.CudaTileOps(shared_stream=True))
+        else:
+            gather, gather_note = None, None
+            if args.gather == "peer":  # tiles stored straight into GPU 0's image over NVLink peer memory (one kernel per rank)
+                try:
+                    gather = multigpu.PeerTileExchange(w, h, 4, conv_ptr)
+                except multigpu.PeerSetupError as e:  # raised on every rank together: all ranks take the NCCL gather
+                    gather_note = f"peer mapping unavailable ({e}); "
+            if gather is None:         # pack + one NCCL gather + unpack
+                gather = multigpu.TileGather(w, h, 4, torch.device("cuda", local), ops=multigpu.CudaTileOps(shared_stream=True))
         begin = getattr(gather, "begin_frame", lambda: None)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
@@ -338,7 +343,7 @@ def run_ours(args):
                 "ms_per_step": round(float(mx[0] / K), 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "partition": (f"image tiles 64x64, tile % {world} == rank, " + ("sRGBA8 tiles stored into GPU 0's image over NVLink peer memory (one push kernel per rank, flag handshake)"
-                                                                                              if args.gather == "peer" else "NCCL gather of sRGBA8 to GPU 0")) if world > 1 else "single device",
+                                                                                              if isinstance(gather, multigpu.PeerTileExchange) else (gather_note or "") + "NCCL gather of sRGBA8 to GPU 0")) if world > 1 else "single device",
                            "l2": "256 MiB memset between timed steps (L2 flush)", **({"composition_check": "GPU 0's image == every rank's own tiles (checksums)"} if composed_ok else {}), "frame_ms": round(float(mx[0] / K), 4),
                            "rays_per_frame": int(tot[0] / K), "mpixel_samples_per_s": round(w * h * K / (mx[0] * 1e-3) / 1e6, 1),
                            "scene_setup_ms_incl_bvh": round(setup_ms, 2)},

@@ -170,6 +170,10 @@ class CudaPeerOps:
 IPC_HANDLE_BYTES = 64
 
 
+class PeerSetupError(RuntimeError):
+    """raised on EVERY rank when any rank could not export or map the peer memory"""
+
+
 class PeerTileExchange:
     """Composes the display channel on rank 0 by peer stores: every rank r != 0 writes the tiles it owns straight into
     rank 0's row-major image (mapped through CUDA IPC) from one kernel; no staging buffer, no collective call per frame.
@@ -198,17 +202,51 @@ class PeerTileExchange:
         tx, ty = tile_grid(width, height)
         if ws > tx * ty or ws > 16:
             raise ValueError("PeerTileExchange: more ranks than tiles (or than OSPCUDA_MAX_PEERS)")
-        self.block = self.ops.alloc_block()
-        mine = {"block": self.ops.export(self.block), "image": self.ops.export(image_ptr) if rk == 0 else None}
+        # Set-up is collective and fails collectively: a rank that cannot export or map (no peer access between two GPUs,
+        # IPC not permitted in the container) must not leave the others waiting in a collective call, so every step is
+        # followed by an exchange of its outcome and all ranks raise PeerSetupError together (bench.py then takes the NCCL
+        # gather on every rank).
+        self.block, mine = None, {"block": None, "image": None, "error": None}
+        try:
+            self.block = self.ops.alloc_block()
+            mine["block"] = self.ops.export(self.block)
+            mine["image"] = self.ops.export(image_ptr) if rk == 0 else None
+        except Exception as e:  # noqa: BLE001 -- reported to every rank below
+            mine["error"] = f"rank {rk}: {e}"
         everyone = [None] * ws
         dist.all_gather_object(everyone, mine, group=group)
-        if rk == 0:
-            self.peer_blocks = [self.block] + [self.ops.open(everyone[r]["block"]) for r in range(1, ws)]
-            self.root_image, self.root_block = image_ptr, self.block
-        else:
-            self.peer_blocks = None
-            self.root_image = self.ops.open(everyone[0]["image"])
-            self.root_block = self.ops.open(everyone[0]["block"])
+        errors = [m["error"] for m in everyone if m["error"]]
+        opened = []
+        if not errors:
+            try:
+                if rk == 0:
+                    self.peer_blocks = [self.block]
+                    for r in range(1, ws):
+                        self.peer_blocks.append(self.ops.open(everyone[r]["block"]))
+                        opened.append(self.peer_blocks[-1])
+                    self.root_image, self.root_block = image_ptr, self.block
+                else:
+                    self.peer_blocks = None
+                    self.root_image = self.ops.open(everyone[0]["image"])
+                    opened.append(self.root_image)
+                    self.root_block = self.ops.open(everyone[0]["block"])
+                    opened.append(self.root_block)
+                mapped = None
+            except Exception as e:  # noqa: BLE001
+                mapped = f"rank {rk}: {e}"
+            outcomes = [None] * ws
+            dist.all_gather_object(outcomes, mapped, group=group)
+            errors = [o for o in outcomes if o]
+        if errors:
+            for ptr in opened:
+                try:
+                    self.ops.close(ptr)
+                except Exception:  # noqa: BLE001
+                    pass
+            if self.block is not None:
+                self.ops.free_block(self.block)
+            self.world_size = 1  # close() / gather() become no-ops
+            raise PeerSetupError("; ".join(errors))
         self.shard_bytes = [len(owned_tiles(width, height, ws, r)) * TILE * TILE * bpp for r in range(ws)]
         dist.barrier(group=group)  # every mapping exists before the first frame
 

@@ -233,3 +233,44 @@ def test_tile_checksums_see_a_missing_tile():
     swapped = img.copy()
     swapped[0:64, 0:64], swapped[64:128, 128:192] = img[64:128, 128:192], img[0:64, 0:64]   # tiles 0 and 6, both rank 0
     assert multigpu.tile_checksums(swapped, 3)[0] != a[0]                                   # position-weighted sum
+
+
+class _FailingOpenOps(ShmPeerOps):
+    """rank 1 cannot map rank 0's memory (no peer access / IPC not permitted)"""
+
+    def __init__(self, rank):
+        super().__init__()
+        self.rank = rank
+
+    def open(self, handle):
+        if self.rank == 1:
+            raise RuntimeError("peer access is not supported between these two devices")
+        return super().open(handle)
+
+
+def _peer_failure_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    from ospray_b200 import multigpu
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    multigpu.init_process_group_from_env()
+    ops = _FailingOpenOps(rank)
+    img = ops.alloc_image(128 * 128 * 4) if rank == 0 else None
+    msg = "no error"
+    try:
+        multigpu.PeerTileExchange(128, 128, 4, img, ops=ops)
+    except multigpu.PeerSetupError as e:
+        msg = str(e)
+    dist.barrier()  # every rank got here: nobody is stuck in a collective of the failed set-up
+    open(os.path.join(out_dir, f"rank{rank}.txt"), "w").write(msg)
+    ops.unlink()
+    if rank == 0:
+        ops.segs[img].unlink()
+    dist.destroy_process_group()
+
+
+def test_peer_setup_failure_is_raised_on_every_rank(tmp_path):
+    """one rank failing to map the peer memory makes ALL ranks raise PeerSetupError (so that all of them fall back to the NCCL
+    gather together) instead of leaving the others waiting in a collective call"""
+    mp.spawn(_peer_failure_worker, args=(3, _free_port(), str(tmp_path)), nprocs=3, join=True)
+    msgs = [open(tmp_path / f"rank{r}.txt").read() for r in range(3)]
+    assert all("rank 1: peer access is not supported" in m for m in msgs), msgs

@@ -159,6 +159,7 @@ CASES = {
     "gravity_pt": (lambda: T.gravity_spheres_volume(24), "pathtracer", {"pixelSamples": 2}, 2),
     "gravity_aniso_pt": (forward_scattering_volume, "pathtracer", {"pixelSamples": 2, "maxPathLength": 8}, 1),
     "volume_geometry_pt": (volume_with_opaque_geometry, "pathtracer", {"pixelSamples": 2}, 1),
+    "volume_glass_geometry_pt": (volume_with_geometry, "pathtracer", {"pixelSamples": 2}, 1),  # transparent shadows through the medium
     # debug renderer (render/debug/DebugRenderer.ispc), every method the device accepts
     "debug_testFrame": (T.cornell_box, "debug", {"method": "testFrame", "pixelSamples": 2}, 2),
     "debug_rayDir": (T.cornell_box, "debug", {"method": "rayDir"}, 1),
@@ -183,7 +184,7 @@ DEVICE_UNSUPPORTED = set()
 # Volumes under the pathtracer: delta tracking takes hundreds of accept/reject decisions per path on logf / expf / lerp
 # results, so a last-bit libm difference (CUDA vs glibc) sends a few per cent of the paths down another random walk: the
 # device-vs-checker bars for these cases are statistical (tests/test_gpu_parity.py), the checker-vs-reference ones are not
-PT_VOLUME_CASES = {"gravity_pt", "gravity_aniso_pt", "volume_geometry_pt"}
+PT_VOLUME_CASES = {"gravity_pt", "gravity_aniso_pt", "volume_geometry_pt", "volume_glass_geometry_pt"}
 
 W, H = 48, 40  # not a multiple of 8 or 64: exercises clipped render tasks and border tiles
 

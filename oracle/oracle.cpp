@@ -19,8 +19,11 @@
 //                 sphere with projected centre
 //   Open VKL 2.0.1 structuredRegular vertex-centred trilinear sample (NaN outside), forward
 //                 difference gradient, nominalDeltaT = min_i spacing_i/|dir_i|
+//                 round curves: Embree's sweep intersector is replaced by a stated tessellation into 8 capsules per segment
+//                 (curve_capsule.h); under the pathtracer the interval iterator hands delta tracking ONE interval with the
+//                 value range (-inf, inf) -> global majorant (real VKL: macrocell intervals with tighter ranges)
 //   rkcommon 1.14.2 to_float_unorm, frame(), lerp(f,a,b), luminance, rcp_safe, cvt_uint32,
-//                 linear_to_srgba8
+//                 linear_to_srgba8, makeRandomColor (debug renderer)
 // Intersection is brute force (no BVH): the oracle is independent of the GPU builder/traversal.
 // The volume interval iterator is restated as ONE interval over the clipped box (mathematically
 // equal to any macrocell subdivision: skipped cells have zero opacity and `emptySpace`

@@ -191,7 +191,7 @@ typedef struct {
   const OcInstance *instances;
   uint32_t numInstances;
   uint32_t hasVolumes;
-  OcBVH tlas;                  /* used when numInstances > OC_TLAS_THRESHOLD */
+  OcBVH tlas;                  /* top level over the instance bounds, one instance per leaf record (always built) */
   const OcMaterial *materials;
   uint32_t numMaterials;
   /* pathtracer light list (PathTracerData.cpp:32-82): geo lights first (none), world, instance */
@@ -338,14 +338,17 @@ OSPCUDA_API int ospcuda_bvh_build_group(const OcModel *d_models, uint32_t numMod
 /* Build the top-level BVH over instance world bounds (h_bounds: 6 floats per instance). */
 OSPCUDA_API int ospcuda_bvh_build_tlas(const float *h_bounds, uint32_t numInstances, OcBVH *bvh);
 OSPCUDA_API int ospcuda_bvh_free(OcBVH *bvh);
-/* Traversal keeps a per-thread stack of OSPCUDA_TRAVERSAL_STACK entries in shared memory (the top level may use half of
- * it, the group BVH continues above). The builder knows the deepest stack a depth-first walk of the hierarchy it just
+/* Traversal keeps a per-thread stack of OSPCUDA_TRAVERSAL_STACK entries (the first 32 in shared memory, the rest in a
+ * local-memory overflow array that costs nothing until a walk gets that deep); the top level and the group hierarchy it
+ * enters share it. The builder knows the deepest stack a depth-first walk of the hierarchy it just
  * built can need (sum over the deepest path of children - 1 per wide node): the host compares and refuses a scene that
  * could overflow instead of letting traversal drop subtrees. Value of the most recent build on this thread. */
 #ifndef OSPCUDA_TRAVERSAL_STACK
-#define OSPCUDA_TRAVERSAL_STACK 48
+#define OSPCUDA_TRAVERSAL_STACK 64
 #endif
 OSPCUDA_API uint32_t ospcuda_bvh_last_stack_need(void);
+/* largest value over the builds since the last call with reset != 0 (a world commit builds group and top-level hierarchies) */
+OSPCUDA_API uint32_t ospcuda_bvh_peak_stack_need(int reset);
 /* macrocell (16^3 cells) value ranges of a structured volume; d_ranges: 2*mcx*mcy*mcz floats */
 OSPCUDA_API int ospcuda_volume_macrocells(const float *d_voxels, const uint32_t dims[3],
     float *d_ranges, const uint32_t mcDims[3]);

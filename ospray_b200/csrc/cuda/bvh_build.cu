@@ -384,6 +384,7 @@ struct DevBuf
 };
 
 static uint32_t g_lastStackNeed = 0; // of the most recent build (ospcuda_bvh_last_stack_need)
+static uint32_t g_peakStackNeed = 0; // largest since the last reset (ospcuda_bvh_peak_stack_need)
 
 // shared tail: boxes (+records) -> OcBVH
 static int buildFromBoxes(Aabb *d_boxes, float4 *d_records, uint32_t n, const uint32_t *d_sceneBounds, OcBVH *bvh)
@@ -480,6 +481,7 @@ static int buildFromBoxes(Aabb *d_boxes, float4 *d_records, uint32_t n, const ui
   OC_TRY(cudaMemcpyAsync(h_enc, d_sceneBounds, sizeof(h_enc), cudaMemcpyDeviceToHost, st));
   OC_TRY(cudaMemcpyAsync(&g_lastStackNeed, counters.p + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   OC_TRY(cudaStreamSynchronize(st));
+  if (g_lastStackNeed > g_peakStackNeed) g_peakStackNeed = g_lastStackNeed;
   bvh->nodes = nodesOut;
   bvh->prims = reinterpret_cast<const OcVec4f *>(recOut);
   bvh->numNodes = numWide;
@@ -541,24 +543,9 @@ extern "C" int ospcuda_bvh_build_group(const OcModel *d_models, uint32_t numMode
   initBoundsKernel<<<1, 32, 0, st>>>(d_bounds.p);
   emitRecordsKernel<<<(n + 255) / 256, 256, 0, st>>>(d_models, numModels, d_off.p, n, records.p, boxes.p, d_bounds.p);
   oc_count_launch();
-  int rc = 0;
-  static const uint32_t linearMax = getenv("OSPCUDA_LINEAR_MAX") ? (uint32_t)atoi(getenv("OSPCUDA_LINEAR_MAX")) : OC_LINEAR_MAX;
-  if (n <= linearMax) {
-    // tiny group: a hierarchy costs more than it saves. Keep the records in (model, primitive) order and let
-    // traversal scan them linearly (uniform trip count and broadcast loads across the warp: no divergence).
-    float4 *recOut = nullptr;
-    OC_TRY(cudaMalloc((void **)&recOut, sizeof(float4) * 3 * (size_t)n));
-    OC_TRY(cudaMemcpyAsync(recOut, records.p, sizeof(float4) * 3 * (size_t)n, cudaMemcpyDeviceToDevice, st));
-    uint32_t h_enc[6];
-    OC_TRY(cudaMemcpyAsync(h_enc, d_bounds.p, sizeof(h_enc), cudaMemcpyDeviceToHost, st));
-    OC_TRY(cudaStreamSynchronize(st));
-    bvh->nodes = nullptr;
-    bvh->prims = reinterpret_cast<const OcVec4f *>(recOut);
-    bvh->numNodes = 0;
-    bvh->numRecords = n;
-    for (int k = 0; k < 6; k++) bvh->bounds[k] = decF(h_enc[k]);
-  } else
-    rc = buildFromBoxes(boxes.p, records.p, n, d_bounds.p, bvh);
+  // every group gets a hierarchy, however small (one record: a root node with one leaf): traversal is one state machine
+  // over nodes, without a second code path for record lists
+  const int rc = buildFromBoxes(boxes.p, records.p, n, d_bounds.p, bvh);
   OC_TRY(cudaEventRecord(e1, st));
   OC_TRY(cudaEventSynchronize(e1));
   float ms = 0.f;
@@ -587,6 +574,12 @@ extern "C" int ospcuda_bvh_build_tlas(const float *h_bounds, uint32_t numInstanc
 }
 
 extern "C" uint32_t ospcuda_bvh_last_stack_need(void) { return g_lastStackNeed; }
+extern "C" uint32_t ospcuda_bvh_peak_stack_need(int reset)
+{
+  const uint32_t v = g_peakStackNeed;
+  if (reset) g_peakStackNeed = 0;
+  return v;
+}
 
 extern "C" int ospcuda_bvh_free(OcBVH *bvh)
 {

@@ -17,10 +17,12 @@ namespace oc {
 using namespace ospm;
 
 #define OC_INVALID_ID 0xFFFFFFFFu
-#define OC_TLAS_THRESHOLD 4u
-#define OC_STACK_SIZE OSPCUDA_TRAVERSAL_STACK // include/ospcuda.h: the host checks every built hierarchy against it
-#define OC_LINEAR_MAX 8u // groups with at most this many leaf records are scanned linearly (no hierarchy)
-#define OC_MAX_BLOCK 128 // largest CTA of a kernel that traverses (shared stack = OC_STACK_SIZE * blockDim.x words)
+#define OC_STACK_TOTAL OSPCUDA_TRAVERSAL_STACK // include/ospcuda.h: the host checks every built hierarchy against it
+#ifndef OC_STACK_SHARED
+#define OC_STACK_SHARED 32 // entries per thread kept in shared memory; deeper ones go to the local overflow array (Stack)
+#endif
+#define OC_STACK_OVF (OC_STACK_TOTAL - OC_STACK_SHARED)
+#define OC_MAX_BLOCK 128 // largest CTA of a kernel that traverses (shared stack = OC_STACK_SHARED * blockDim.x words)
 
 struct Ray
 {
@@ -244,48 +246,76 @@ static __device__ __noinline__ OtherHit intersectOtherNI(vec3f org, vec3f dir, f
   return o;
 }
 
-template <bool OCCLUSION>
-__device__ __forceinline__ bool intersectRecord(Ray &ray, const OcVec4f *rec, uint32_t instID)
+// What traversal carries per ray: 5 registers. The geometric normal and the ids are NOT live during the walk; they are
+// recomputed from the leaf record the hit points at once the ray is done (resolveHit below). `rec` indexes the records of
+// the hit instance's group BVH; inst == OC_INVALID_ID: no hit.
+struct Hit { float t, u, v; uint32_t rec, inst; };
+
+// the triangle test without the normal output (traversal form of intersectTriangle: same arithmetic, same decisions)
+__device__ __forceinline__ bool intersectTriangleT(vec3f org, vec3f dir, float t0, float t1, vec3f v0, vec3f e1, vec3f e2,
+    float &t, float &u, float &v)
 {
+  const vec3f triNg = crossF(e2, e1);
+  const vec3f C = make_vec3f(__fsub_rn(v0.x, org.x), __fsub_rn(v0.y, org.y), __fsub_rn(v0.z, org.z));
+  const vec3f R = crossF(C, dir);
+  const float den = dotF(triNg, dir);
+  const float absDen = fabsf(den);
+  const uint32_t sgn = __float_as_uint(den) & 0x80000000u;
+  const float U = __uint_as_float(__float_as_uint(dotF(R, e2)) ^ sgn);
+  if (!(den != 0.f && U >= 0.f && U <= absDen))
+    return false;
+  const float V = __uint_as_float(__float_as_uint(dotF(R, e1)) ^ sgn);
+  if (!(V >= 0.f && __fadd_rn(U, V) <= absDen))
+    return false;
+  const float T = __uint_as_float(__float_as_uint(dotF(triNg, C)) ^ sgn);
+  if (!(__fmul_rn(absDen, t0) < T && T <= __fmul_rn(absDen, t1)))
+    return false;
+  const float rcpAbsDen = __frcp_rn(absDen);
+  u = __fmul_rn(U, rcpAbsDen);
+  v = __fmul_rn(V, rcpAbsDen);
+  t = __fmul_rn(T, rcpAbsDen);
+  return true;
+}
+
+// one leaf record against the ray in the current (instance) space. Exact-t ties with the hit already held (coplanar
+// faces, shared edges) are resolved by record identity -- the later (instance, geometry, primitive, quad half) wins, what
+// a scan in record order (the oracle's and the Embree stand-in's loops) ends with -- so the result does not depend on the
+// BVH topology or the visiting order. The ids of the held hit are read back from its record only in that rare case.
+__device__ __forceinline__ bool intersectRecordH(vec3f org, vec3f dir, float t0, Hit &h, const OcVec4f *__restrict__ prims,
+    uint32_t recIdx, uint32_t instID, bool occlusion)
+{
+  const OcVec4f *rec = prims + 3 * (size_t)recIdx;
   const float4 r0 = ldg4(rec), r1 = ldg4(rec + 1), r2 = ldg4(rec + 2);
   const uint32_t kind = __float_as_uint(r2.w);
   float t, u = 0.f, v = 0.f;
-  vec3f Ng;
   bool hit;
   if (kind <= OC_PRIM_TRI_QUAD2ND) {
-    hit = intersectTriangle(ray, make_vec3f(r0.x, r0.y, r0.z), make_vec3f(r1.x, r1.y, r1.z),
-        make_vec3f(r2.x, r2.y, r2.z), t, u, v, Ng);
+    hit = intersectTriangleT(org, dir, t0, h.t, make_vec3f(r0.x, r0.y, r0.z), make_vec3f(r1.x, r1.y, r1.z),
+        make_vec3f(r2.x, r2.y, r2.z), t, u, v);
     if (hit && kind == OC_PRIM_TRI_QUAD2ND) { u = __fsub_rn(1.f, u); v = __fsub_rn(1.f, v); }
-  }
-  else {
-    const OtherHit o = intersectOtherNI(ray.org, ray.dir, ray.t0, ray.t, r0, r1, r2);
-    hit = o.hit; t = o.t; u = o.u; Ng = o.Ng;
+  } else {
+    const OtherHit o = intersectOtherNI(org, dir, t0, h.t, r0, r1, r2);
+    hit = o.hit; t = o.t; u = o.u;
   }
   if (!hit)
     return false;
-  const uint32_t primID = __float_as_uint(r0.w), geomID = __float_as_uint(r1.w);
-  if (!OCCLUSION && t == ray.t && ray.geomID != OC_INVALID_ID) {
-    // exact tie with the hit already held (coplanar faces, shared edges): the primitive tests accept t <= ray.t, so a
-    // scan in record order ends with the LAST of the tied primitives (what the oracle's and the Embree stand-in's loops
-    // do). Same rule here whatever order the BVH visits them in: the later (instance, geometry, primitive, quad half) wins.
-    const bool later = instID != ray.instID ? instID > ray.instID
-        : geomID != ray.geomID              ? geomID > ray.geomID
-        : primID != ray.primID              ? primID > ray.primID
-                                            : kind == OC_PRIM_TRI_QUAD2ND;
+  if (!occlusion && t == h.t && h.inst != OC_INVALID_ID) {
+    bool later;
+    if (instID != h.inst) later = instID > h.inst;
+    else {
+      const OcVec4f *held = prims + 3 * (size_t)h.rec;
+      const uint32_t hPrim = __float_as_uint(ldg4(held).w), hGeom = __float_as_uint(ldg4(held + 1).w);
+      const uint32_t primID = __float_as_uint(r0.w), geomID = __float_as_uint(r1.w);
+      later = geomID != hGeom ? geomID > hGeom : primID != hPrim ? primID > hPrim : kind == OC_PRIM_TRI_QUAD2ND;
+    }
     if (!later) return false;
   }
-  ray.t = t;
-  ray.primID = primID;
-  ray.geomID = geomID;
-  ray.instID = instID;
-  if (!OCCLUSION) { ray.u = u; ray.v = v; ray.Ng = Ng; }
+  h.t = t; h.u = u; h.v = v; h.rec = recIdx; h.inst = instID;
   return true;
 }
 
 // ---- wide-BVH traversal -------------------------------------------------------------------
-struct NodeHit { float t[4]; };
-
-// slab test of one 128-byte node against the ray: 8 x LDG.128, conservative (far side padded
+// slab test of one 128-byte node against the ray: 7 x LDG.128, conservative (far side padded
 // by 2 ulp) so that the BVH never culls a primitive the exact test would accept.
 __device__ __forceinline__ uint32_t nodeTest(const OcNode4 *node, vec3f org, vec3f rdir, float t0, float t1,
     float (&tnear)[4], uint4 &child)
@@ -321,198 +351,232 @@ __device__ __forceinline__ vec3f safeRcpDir(vec3f d)
       __frcp_rn(fabsf(d.z) < eps ? copysignf(eps, d.z) : d.z));
 }
 
-// Per-thread traversal stack in SHARED memory, laid out [depth][thread] so that the 32 lanes of a warp hit 32
-// different banks whatever their individual depths are (a local-memory stack puts lanes at different depths
-// into different 32-byte sectors). Kernels declare `__shared__ uint32_t s[OC_STACK_SIZE * blockDim.x]`.
+// Per-thread traversal stack. The first OC_STACK_SHARED entries live in SHARED memory, laid out [depth][thread] so that
+// the 32 lanes of a warp hit 32 different banks whatever their individual depths are; deeper entries (up to
+// OSPCUDA_TRAVERSAL_STACK in total: the host checks every hierarchy it builds against that) spill into a per-thread
+// local-memory array that costs nothing until a walk actually gets that deep. Kernels declare
+// `__shared__ uint32_t s[OC_STACK_SHARED * blockDim.x]` and `uint32_t ovf[OC_STACK_OVF]`.
 struct Stack
 {
   uint32_t *base;   // s + threadIdx.x
   uint32_t stride;  // blockDim.x
-  __device__ __forceinline__ uint32_t &at(int d) const { return base[(uint32_t)d * stride]; }
+  uint32_t *ovf;    // local overflow
+  __device__ __forceinline__ void push(int &sp, uint32_t v) const
+  {
+    if (sp < OC_STACK_SHARED) { base[(uint32_t)sp * stride] = v; sp++; }
+    else if (sp < OC_STACK_TOTAL) { ovf[sp - OC_STACK_SHARED] = v; sp++; }
+  }
+  __device__ __forceinline__ uint32_t pop(int &sp) const
+  {
+    --sp;
+    return sp < OC_STACK_SHARED ? base[(uint32_t)sp * stride] : ovf[sp - OC_STACK_SHARED];
+  }
 };
 
-// Traverse one BVH (group BLAS), "while-while": descend inner nodes until a leaf is reached, then test its
-// records. Inlined: a by-reference Ray handed to a non-inlined function lives in local memory (309 LDL / 198 STL
-// in the first wavefront TRACE kernel). Kernels with many trace call sites (the scivis / ao megakernels) go
-// through the non-inlined wrapper traceWorldNI below instead, which bounds their code size.
-template <bool OCCLUSION>
-__device__ __forceinline__ bool traverseBLAS(const OcNode4 *__restrict__ nodes, const OcVec4f *__restrict__ prims, uint32_t numRecords,
-    Ray &ray, uint32_t instID, Stack st, int sp0)
+// where a walk re-reads its world-space ray from when it leaves an instance: values held in registers (megakernels,
+// single queries) or the ray arrays of a queue kernel (global memory: 6 registers less across the whole walk)
+struct RayRegs
 {
-  bool any = false;
-  if (nodes == nullptr) { // linear group (<= OC_LINEAR_MAX records): uniform loop, warp-broadcast loads
-    const uint32_t n = numRecords;
-    for (uint32_t i = 0; i < n; i++)
-      if (intersectRecord<OCCLUSION>(ray, prims + 3 * (size_t)i, instID)) {
-        any = true;
-        if (OCCLUSION) return true;
-      }
-    return any;
+  vec3f o, d;
+  __device__ __forceinline__ vec3f org() const { return o; }
+  __device__ __forceinline__ vec3f dir() const { return d; }
+};
+struct RayMem
+{
+  const float4 *po, *pd;
+  __device__ __forceinline__ vec3f org() const { const float4 v = *po; return make_vec3f(v.x, v.y, v.z); }
+  __device__ __forceinline__ vec3f dir() const { const float4 v = *pd; return make_vec3f(v.x, v.y, v.z); }
+};
+
+// Two-level traversal as ONE resumable state machine. The top level (World::commit builds it over the instance bounds,
+// one instance per leaf) and the group BVHs share the loop and the stack: a top-level leaf switches the walk into the
+// instance (ray -> instance space, Embree keeps t, no renormalisation; spBase marks where the group's entries start), an
+// empty group part of the stack switches it back. Equivalent of traceGeometryRay / isOccludedNoClipping (World.ih:29-52,
+// 311-335). The walk is cut into the two steps a warp wants to take together -- inner(): one node, leaf(): one leaf --
+// so that a kernel can line its lanes up between them (ptTraceKernel); traceHit() below is the plain loop.
+// The hit children of a node are ordered by entry distance (5 compare-exchanges), the nearest is visited next and the rest
+// pushed far-to-near (C3 106 -> 94 ms against an unordered push); any-hit rays take the same order.
+// MODE 0: closest hit, 1: occlusion, 2: decided per ray at run time (`occ`; queue kernels that mix both kinds).
+template <int MODE>
+struct Traversal
+{
+  vec3f org, dir, rdir;
+  float t0;
+  Hit h;
+  const OcNode4 *nodes;
+  const OcVec4f *prims;
+  uint32_t cur, curInst;
+  int sp, spBase;
+  bool occ, xformed; // xformed: org / dir are in the space of a non-identity instance
+
+  __device__ __forceinline__ bool occlusion() const { return MODE == 2 ? occ : MODE == 1; }
+  __device__ __forceinline__ bool atLeaf() const { return (cur & 0x80000000u) != 0u; }
+
+  __device__ __forceinline__ void enterInstance(const OcWorld *__restrict__ world, uint32_t instID, const OcGroup *__restrict__ g)
+  {
+    const OcInstance *__restrict__ inst = world->instances + instID;
+    xformed = !inst->isIdentity;
+    if (xformed) {
+      const affine3f rx = toA(inst->rcp_xfm);
+      const vec3f wo = org, wd = dir;
+      org = xfmPointExact(rx, wo);
+      dir = xfmVectorExact(rx.l, wd);
+      rdir = safeRcpDir(dir);
+    }
+    nodes = g->bvh.nodes; prims = g->bvh.prims;
+    curInst = instID; spBase = sp; cur = 0;
   }
-  const vec3f rdir = safeRcpDir(ray.dir);
-  int sp = sp0;
-  uint32_t cur = 0; // root
-  while (true) {
-    // ---- inner nodes ----
-    while (!(cur & 0x80000000u)) {
-      float tn[4];
-      uint4 ch;
-      const uint32_t mask = nodeTest(nodes + cur, ray.org, rdir, ray.t0, ray.t, tn, ch);
-      if (mask == 0) {
-        if (sp == sp0) return any;
-        cur = st.at(--sp);
-        continue;
-      }
-#ifndef OC_UNSORTED_PUSH // sorted: C3 106 -> 94 ms, C5s 51 -> 45 ms (tools/ab_all.sh)
-      if (!OCCLUSION) {
-        // closest hit: order the hit children by entry distance (5 compare-exchanges); the nearest is visited next, the
-        // others are pushed far-to-near so that pops come back nearest-first and ray.t culls the rest early
-        float k0 = (mask & 1u) ? tn[0] : INFINITY, k1 = (mask & 2u) ? tn[1] : INFINITY, k2 = (mask & 4u) ? tn[2] : INFINITY,
-              k3 = (mask & 8u) ? tn[3] : INFINITY;
-        uint32_t c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
+
+  // false: nothing to traverse (empty world)
+  __device__ __forceinline__ bool init(const OcWorld *__restrict__ world, vec3f rorg, vec3f rdirection, float rt0, float rt1, bool occlusionRay)
+  {
+    occ = occlusionRay; xformed = false;
+    h.t = rt1; h.u = h.v = 0.f; h.rec = 0; h.inst = OC_INVALID_ID;
+    t0 = rt0;
+    nodes = world->tlas.nodes;
+    prims = world->tlas.prims;
+    if (nodes == nullptr) return false;
+    org = rorg; dir = rdirection;
+    rdir = safeRcpDir(dir);
+    cur = 0; curInst = OC_INVALID_ID; sp = 0; spBase = 0;
+    if (world->numInstances == 1) { // the top level is one leaf: start inside the instance (its root node does the bounds test)
+      const OcGroup *__restrict__ g = world->instances[0].group;
+      if (g->bvh.numRecords == 0) return false;
+      enterInstance(world, 0u, g);
+    }
+    return true;
+  }
+
+  // the group part of the stack is empty: back to the top level; false when that is empty too (walk finished)
+  template <typename Src>
+  __device__ __forceinline__ bool popNext(const OcWorld *__restrict__ world, const Src &src, const Stack &st)
+  {
+    if (curInst != OC_INVALID_ID && sp == spBase) {
+      if (sp == 0) return false;
+      if (xformed) { org = src.org(); dir = src.dir(); rdir = safeRcpDir(dir); xformed = false; }
+      nodes = world->tlas.nodes; prims = world->tlas.prims;
+      curInst = OC_INVALID_ID;
+    }
+    if (sp == 0) return false;
+    cur = st.pop(sp);
+    return true;
+  }
+
+  // cur is an inner node: test it, descend into the nearest hit child (or pop). false: the walk is finished
+  template <typename Src>
+  __device__ __forceinline__ bool inner(const OcWorld *__restrict__ world, const Src &src, const Stack &st)
+  {
+    float tn[4];
+    uint4 ch;
+    const uint32_t mask = nodeTest(nodes + cur, org, rdir, t0, h.t, tn, ch);
+    if (mask == 0) return popNext(world, src, st);
+    float k0 = (mask & 1u) ? tn[0] : INFINITY, k1 = (mask & 2u) ? tn[1] : INFINITY, k2 = (mask & 4u) ? tn[2] : INFINITY,
+          k3 = (mask & 8u) ? tn[3] : INFINITY;
+    uint32_t c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
 #define OC_CSWAP(ka, ca, kb, cb) { const bool sw = kb < ka; const float tk = sw ? kb : ka; kb = sw ? ka : kb; ka = tk; const uint32_t tc = sw ? cb : ca; cb = sw ? ca : cb; ca = tc; }
-        OC_CSWAP(k0, c0, k1, c1) OC_CSWAP(k2, c2, k3, c3) OC_CSWAP(k0, c0, k2, c2) OC_CSWAP(k1, c1, k3, c3) OC_CSWAP(k1, c1, k2, c2)
+    OC_CSWAP(k0, c0, k1, c1) OC_CSWAP(k2, c2, k3, c3) OC_CSWAP(k0, c0, k2, c2) OC_CSWAP(k1, c1, k3, c3) OC_CSWAP(k1, c1, k2, c2)
 #undef OC_CSWAP
-        if (k3 < INFINITY && sp < OC_STACK_SIZE) st.at(sp++) = c3;
-        if (k2 < INFINITY && sp < OC_STACK_SIZE) st.at(sp++) = c2;
-        if (k1 < INFINITY && sp < OC_STACK_SIZE) st.at(sp++) = c1;
-#ifdef OC_PREFETCH_NEXT
-        // the entry just pushed last is what the next pop returns: start fetching its node / first record now
-        if (k1 < INFINITY) {
-          const void *nx = (c1 & 0x80000000u) ? (const void *)(prims + 3 * (size_t)(c1 & 0x07FFFFFFu)) : (const void *)(nodes + c1);
-          #ifdef OC_PREFETCH_L1
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
-#else
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
-#endif
-        }
-#endif
-        cur = c0;
-        continue;
-      }
-#endif
-      const uint32_t chs[4] = {ch.x, ch.y, ch.z, ch.w};
-      int best = 0;
-      float bestT = INFINITY;
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-        if (((mask >> i) & 1u) && tn[i] < bestT) { bestT = tn[i]; best = i; }
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-        if (((mask >> i) & 1u) && i != best && sp < OC_STACK_SIZE) st.at(sp++) = chs[i];
-      cur = chs[best];
-    }
-    // ---- leaf ----
+    if (k3 < INFINITY) st.push(sp, c3);
+    if (k2 < INFINITY) st.push(sp, c2);
+    if (k1 < INFINITY) st.push(sp, c1);
+    cur = c0;
+    return true;
+  }
+
+  // cur is a leaf. Top level: enter the instance of its first record (the rest of the leaf -- the builder makes
+  // one-instance leaves, this keeps any other count correct -- goes back on the stack). Group: test the records, pop.
+  // false: the walk is finished (stack empty, or an occlusion ray found its hit)
+  template <typename Src>
+  __device__ __forceinline__ bool leaf(const OcWorld *__restrict__ world, const Src &src, const Stack &st)
+  {
     const uint32_t first = cur & 0x07FFFFFFu;
     const uint32_t count = (cur >> 27) & 0xFu;
-    for (uint32_t i = 0; i < count; i++) {
-      if (intersectRecord<OCCLUSION>(ray, prims + 3 * (size_t)(first + i), instID)) {
-        any = true;
-        if (OCCLUSION) return true;
+    if (curInst == OC_INVALID_ID) {
+      if (count > 1) st.push(sp, 0x80000000u | ((count - 1u) << 27) | (first + 1u));
+      const uint32_t instID = __float_as_uint(ldg4(prims + 3 * (size_t)first).w);
+      const OcGroup *__restrict__ g = world->instances[instID].group;
+      if (g->bvh.numRecords != 0) {
+        enterInstance(world, instID, g);
+        return true;
       }
+    } else {
+      for (uint32_t i = 0; i < count; i++)
+        if (intersectRecordH(org, dir, t0, h, prims, first + i, curInst, occlusion()) && occlusion()) return false;
     }
-    if (sp == sp0) return any;
-    cur = st.at(--sp);
+    return popNext(world, src, st);
+  }
+};
+
+// a whole walk, for code that traces one ray at a time
+template <int MODE>
+__device__ __forceinline__ Hit traceHit(const OcWorld *__restrict__ world, vec3f org, vec3f dir, float t0, float t1, const Stack &st)
+{
+  RayRegs src; src.o = org; src.d = dir;
+  Traversal<MODE> tr;
+  if (tr.init(world, org, dir, t0, t1, MODE == 1)) {
+    bool go = true;
+    while (go) {
+      while (go && !tr.atLeaf()) go = tr.inner(world, src, st);
+      if (go) go = tr.leaf(world, src, st);
+    }
+  }
+  return tr.h;
+}
+
+// the hit's geometric normal (instance space, unnormalised: World.ih:411-420) and ids, recomputed from its leaf record.
+// Triangles: Ng = cross(e2, e1) of the record. Everything else re-runs the primitive test on the ray clipped to the hit
+// distance: the tests are deterministic in (org, dir, t0, record) and take ray.t only as an upper bound, so the same t and
+// normal come back.
+__device__ __forceinline__ void resolveHit(const OcWorld *__restrict__ world, const Hit &h, Ray &ray)
+{
+  ray.t = h.t; ray.u = h.u; ray.v = h.v;
+  ray.instID = h.inst;
+  if (h.inst == OC_INVALID_ID) { ray.primID = ray.geomID = OC_INVALID_ID; ray.Ng = make_vec3f(0.f); return; }
+  const OcInstance *__restrict__ inst = world->instances + h.inst;
+  const OcVec4f *rec = inst->group->bvh.prims + 3 * (size_t)h.rec;
+  const float4 r0 = ldg4(rec), r1 = ldg4(rec + 1), r2 = ldg4(rec + 2);
+  ray.primID = __float_as_uint(r0.w);
+  ray.geomID = __float_as_uint(r1.w);
+  const uint32_t kind = __float_as_uint(r2.w);
+  if (kind <= OC_PRIM_TRI_QUAD2ND)
+    ray.Ng = crossF(make_vec3f(r2.x, r2.y, r2.z), make_vec3f(r1.x, r1.y, r1.z));
+  else {
+    vec3f lo = ray.org, ld = ray.dir;
+    if (!inst->isIdentity) {
+      const affine3f rx = toA(inst->rcp_xfm);
+      lo = xfmPointExact(rx, ray.org);
+      ld = xfmVectorExact(rx.l, ray.dir);
+    }
+    ray.Ng = intersectOtherNI(lo, ld, ray.t0, h.t, r0, r1, r2).Ng;
   }
 }
-
-__device__ __forceinline__ bool rayBoxOverlap(const float *b, vec3f org, vec3f rdir, float t0, float t1)
+// ids only (occluder checks)
+__device__ __forceinline__ void resolveHitIds(const OcWorld *__restrict__ world, uint32_t rec, uint32_t instID, uint32_t &primID, uint32_t &geomID)
 {
-  const float ax = (b[0] - org.x) * rdir.x, bx = (b[3] - org.x) * rdir.x;
-  const float ay = (b[1] - org.y) * rdir.y, by = (b[4] - org.y) * rdir.y;
-  const float az = (b[2] - org.z) * rdir.z, bz = (b[5] - org.z) * rdir.z;
-  const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), t0));
-  const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), t1)) * 1.0000005f;
-  return tn <= tf;
+  const OcVec4f *r = world->instances[instID].group->bvh.prims + 3 * (size_t)rec;
+  primID = __float_as_uint(ldg4(r).w);
+  geomID = __float_as_uint(ldg4(r + 1).w);
 }
 
-// one instance: ray -> instance space (Embree keeps t, no renormalisation), one BLAS traversal, hit back
+// one shared, non-inlined copy per kernel for code with many call sites (the scivis / ao / debug megakernels). The hit
+// comes back by value and the Ray of the caller stays in registers.
+template <int MODE>
+static __device__ __noinline__ Hit traceHitNI(const OcWorld *__restrict__ world, vec3f org, vec3f dir, float t0, float t1, uint32_t *stackBase,
+    uint32_t stackStride)
+{
+  uint32_t ovf[OC_STACK_OVF];
+  Stack st;
+  st.base = stackBase; st.stride = stackStride; st.ovf = ovf;
+  return traceHit<MODE>(world, org, dir, t0, t1, st);
+}
+// Ray-in / Ray-out form of the above: closest hit fills t, u, v, Ng and the ids; occlusion returns whether anything was hit
 template <bool OCCLUSION>
-__device__ __forceinline__ bool traceInstance(const OcInstance *__restrict__ inst, uint32_t instID, Ray &ray, Stack st, int sp0)
+__device__ __forceinline__ bool traceWorldNI(const OcWorld *__restrict__ world, Ray &ray, const Stack &st)
 {
-  const OcGroup *g = inst->group;
-  const uint32_t numRecords = g->bvh.numRecords;
-  if (numRecords == 0)
-    return false;
-  Ray local = ray;
-  if (!inst->isIdentity) {
-    const affine3f rx = toA(inst->rcp_xfm);
-    local.org = xfmPointExact(rx, ray.org);
-    local.dir = xfmVectorExact(rx.l, ray.dir);
-  }
-  const bool h = traverseBLAS<OCCLUSION>(g->bvh.nodes, g->bvh.prims, numRecords, local, instID, st, sp0);
-  if (h) {
-    ray.t = local.t;
-    ray.primID = local.primID; ray.geomID = local.geomID; ray.instID = local.instID;
-    if (!OCCLUSION) { ray.u = local.u; ray.v = local.v; ray.Ng = local.Ng; } // Ng stays in instance space (World.ih:411-420)
-  }
-  return h;
-}
-
-// closest hit / occlusion over the whole world (two-level). Equivalent of traceGeometryRay /
-// isOccludedNoClipping (World.ih:29-52, 311-335).
-template <bool OCCLUSION>
-__device__ __forceinline__ bool traceWorld(const OcWorld *__restrict__ world, Ray &ray, Stack st)
-{
-  bool any = false;
-  const uint32_t n = world->numInstances;
-  const vec3f rdir = safeRcpDir(ray.dir);
-  if (n <= OC_TLAS_THRESHOLD) {
-    for (uint32_t i = 0; i < n; i++) {
-      const OcInstance *inst = world->instances + i;
-      if (!rayBoxOverlap(inst->bounds, ray.org, rdir, ray.t0, ray.t))
-        continue;
-      if (traceInstance<OCCLUSION>(inst, i, ray, st, 0)) {
-        any = true;
-        if (OCCLUSION) return true;
-      }
-    }
-    return any;
-  }
-  // TLAS: leaves hold instance indices in record[0].w; the BLAS traversal continues on the same stack above sp
-  const OcBVH &tlas = world->tlas;
-  int sp = 0;
-  uint32_t cur = 0;
-  while (true) {
-    while (!(cur & 0x80000000u)) {
-      float tn[4];
-      uint4 ch;
-      const uint32_t mask = nodeTest(tlas.nodes + cur, ray.org, rdir, ray.t0, ray.t, tn, ch);
-      if (mask == 0) {
-        if (sp == 0) return any;
-        cur = st.at(--sp);
-        continue;
-      }
-      const uint32_t chs[4] = {ch.x, ch.y, ch.z, ch.w};
-      int best = 0;
-      float bestT = INFINITY;
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-        if (((mask >> i) & 1u) && tn[i] < bestT) { bestT = tn[i]; best = i; }
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-        if (((mask >> i) & 1u) && i != best && sp < OC_STACK_SIZE / 2) st.at(sp++) = chs[i];
-      cur = chs[best];
-    }
-    const uint32_t first = cur & 0x07FFFFFFu;
-    const uint32_t count = (cur >> 27) & 0xFu;
-    for (uint32_t i = 0; i < count; i++) {
-      const uint32_t instID = __float_as_uint(ldg4(tlas.prims + 3 * (size_t)(first + i)).w);
-      if (traceInstance<OCCLUSION>(world->instances + instID, instID, ray, st, sp)) {
-        any = true;
-        if (OCCLUSION) return true;
-      }
-    }
-    if (sp == 0) return any;
-    cur = st.at(--sp);
-  }
-}
-
-// one shared, non-inlined copy per kernel for code with many call sites
-template <bool OCCLUSION>
-__device__ __noinline__ bool traceWorldNI(const OcWorld *__restrict__ world, Ray &ray, Stack st)
-{
-  return traceWorld<OCCLUSION>(world, ray, st);
+  const Hit h = traceHitNI<OCCLUSION ? 1 : 0>(world, ray.org, ray.dir, ray.t0, ray.t, st.base, st.stride);
+  if (OCCLUSION) return h.inst != OC_INVALID_ID;
+  resolveHit(world, h, ray);
+  return h.inst != OC_INVALID_ID;
 }
 
 } // namespace oc

@@ -1,20 +1,23 @@
-// Wavefront path tracer: the pathtracer renderer as TRACE / SHADE kernel pairs over compacted path queues.
+// Wavefront path tracer: the pathtracer renderer as GEN / TRACE / SHADE kernels over compacted path and ray queues.
 //
-// Same algorithm, same sampler call order and the same per-path arithmetic as the megakernel in render.cu
-// (reference: render/pathtracer/PathTracer.ispc:75-249, PathSampler.ispc:109-415, NextEventEstimation.ispc:25-160,
-// TransparentShadow.ispc:18-85, VirtualLight.ispc:38-107); only the schedule differs:
+// Same algorithm, same sampler call order and the same per-path arithmetic as the reference (render/pathtracer/
+// PathTracer.ispc:75-249, PathSampler.ispc:109-415, NextEventEstimation.ispc:25-160, TransparentShadow.ispc:18-85,
+// VirtualLight.ispc:38-107); only the schedule differs:
 //
-//   TRACE<first>(d=0)   one thread per pixel sample: sampler init, pixel filter, camera ray, closest hit
-//   SHADE(d)            everything between two traces of samplePath(): background, virtual lights, postIntersect,
-//                       BSDF, NEE light sampling (shadow rays are EMITTED, not traced), BSDF sampling, roulette
-//   TRACE(d+1)          the shadow rays emitted at vertex d (transparent-shadow loop) and the continuation ray
-//   ...                 until maxPathLength; finished paths accumulate into the framebuffer where they end
+//   GEN                 one thread per pixel sample: sampler init, pixel filter, camera ray; the path joins the queues
+//   TRACE(d)            a persistent-thread RAY QUEUE kernel: every lane walks the two-level BVH for one ray -- a shadow ray
+//                       (any hit) emitted at vertex d-1 or the continuation ray (closest hit) -- and, when its ray is done,
+//                       fetches the next one from the queue once enough lanes of its warp are idle (warp-aggregated atomic
+//                       on a fetch cursor): warps stay full although rays take very different numbers of steps. The kernel
+//                       holds nothing but the walk: ray, compact hit (t, u, v, record, instance), stack.
+//   SHADE(d)            per path: fold the shadow-ray results of vertex d-1 into the contribution (transparent occluders take
+//                       the reference's closest-hit loop, out of line), then everything between two traces of samplePath():
+//                       hit -> geometric normal / ids from the leaf record, free-path sampling in volumes, background,
+//                       virtual lights, postIntersect, BSDF, NEE light sampling (shadow rays are EMITTED into the next ray
+//                       queue), BSDF sampling, roulette; finished paths accumulate into the framebuffer where they end
+//   ...                 until maxPathLength
 //
-// Why: the megakernel ran with 11.6 of 32 lanes active per instruction and stalled 7.3 issue slots per
-// instruction on instruction fetch (289 KB of SASS, profiles/r1_pt_megakernel_ncu.txt). Here every kernel is a
-// persistent grid-stride loop over a queue of live paths, appended with warp-aggregated atomics, so warps stay
-// full as paths die, and each kernel's code fits the instruction cache. Path state lives in HBM as float4
-// SoA arrays (128-bit coalesced accesses, ~180 B read + written per path and bounce).
+// Path state lives in HBM as float4 SoA arrays (128-bit coalesced accesses).
 #pragma once
 
 #include <cooperative_groups.h>
@@ -24,16 +27,16 @@ namespace cg = cooperative_groups;
 
 enum : uint32_t {
   PT_DEPTH_MASK = 0xffu, PT_SCAT_SHIFT = 8, PT_SCAT_MASK = 0xff00u,
-  PT_STRAIGHT = 1u << 16, PT_SPECTRANS = 1u << 17, PT_FIRSTBOUNCE = 1u << 18, PT_DONE = 1u << 19, PT_HAS_SHADOW = 1u << 20,
-  PT_VOLUME = 1u << 21 // the vertex TRACE found is a scattering event inside a volume (hit1.xyz = its albedo)
+  PT_STRAIGHT = 1u << 16, PT_SPECTRANS = 1u << 17, PT_FIRSTBOUNCE = 1u << 18, PT_DONE = 1u << 19, PT_HAS_SHADOW = 1u << 20
 };
+#define PT_SHADOW_RAY 0x80000000u // ray-queue ids: bit 31 set = shadow entry [slot * nls + i], clear = continuation ray of path `slot`
 
 struct PtScratch
 {
   float4 *rayO;   // org.xyz, t (far)
   float4 *rayD;   // dir.xyz, t0
   float4 *hit0;   // t, u, v, primID
-  float4 *hit1;   // Ng.xyz, geomID
+  float4 *hit1;   // Ng.xyz (instance space, unnormalised), geomID
   uint32_t *hitInst;
   float4 *thr;    // throughput.xyz, sample alpha
   float4 *con;    // contribution.xyz, lastVertex.pdf_w
@@ -44,10 +47,11 @@ struct PtScratch
   float4 *sZ;     // this sample: z, primID, geomID, instID
   float4 *sPos, *sFN, *sNrm, *sAlb; // this sample's AOVs (only when the framebuffer has the channel)
   float4 *shA, *shB, *shC;          // shadow entries [slot * nls + i]: org.xyz,tmax | dir.xyz,mis | contrib.xyz,valid
+  uint2 *shHit;                     // what TRACE found for shadow entry [slot * nls + i]: occluder (record, instance); instance ~0 = none
   float4 *accC, *accZ, *accPos, *accFN, *accNrm, *accAlb; // ScreenSample sums across the spp passes (spp > 1)
   uint4 *rnd;     // worlds with volumes: pathState.randomSampler (PCG32 state lo/hi, stream)
   float *shT0;    // worlds with volumes: t0 of shadow entry [slot * nls + i] after the transparent-shadow loop
-  uint32_t *queue[2];
+  uint32_t *pathQ[2], *contQ[2], *shadowQ[2];
   uint32_t *counters;
   uint32_t nls;
 };
@@ -61,11 +65,12 @@ struct PtArgs
   uint32_t nFirst, nIndirect;
   int pass;            // sample index within the pixel (0 .. spp-1)
   uint32_t depth;
-  const uint32_t *qIn;
-  uint32_t *qOut;
-  const uint32_t *cntIn;
-  uint32_t *cntOut;
-  uint32_t *fetchCursor;  // ptFusedKernel's work-fetch cursor into qIn (zeroed with the counters every pass)
+  // queues of this launch: SHADE reads pathIn and appends to pathOut / contOut / shadowOut; TRACE reads shadowIn then contIn
+  const uint32_t *pathIn, *contIn, *shadowIn;
+  const uint32_t *cntPathIn, *cntContIn, *cntShadowIn; // cntShadowIn == nullptr: no shadow rays (depth 0)
+  uint32_t *pathOut, *contOut, *shadowOut;
+  uint32_t *cntPathOut, *cntContOut, *cntShadowOut;
+  uint32_t *fetchCursor;  // TRACE's work-fetch cursor (zeroed with the counters every pass)
   uint32_t vol;           // the world holds volumes (host copy of OcWorld.hasVolumes): free-path sampling + transmittance
 };
 
@@ -326,43 +331,40 @@ static __device__ __noinline__ SampleRes HenyeyGreenstein_sample(float g, vec3f 
   return res;
 }
 
-// Does the surface hit by the any-hit query `ray` certainly take the shadow-ray contribution to exactly 0, as the
-// reference's closest-hit loop would (TransparentShadow.ispc:18-85: lightContrib *= transparency per hit, result 0 as
-// soon as reduce_max(lightContrib) <= minContribution)?  OBJ_getTransparency (OBJ.ispc:93-111) is T = Tf*d + (1-d) with
-// d = material.d * dg.color.w.
+// Does the occluder an any-hit query found (leaf record `rec` of instance `instID`) certainly take the shadow-ray
+// contribution to exactly 0, as the reference's closest-hit loop would (TransparentShadow.ispc:18-85: lightContrib *=
+// transparency per hit, result 0 as soon as reduce_max(lightContrib) <= minContribution)?  OBJ_getTransparency
+// (OBJ.ispc:93-111) is T = Tf*d + (1-d) with d = material.d * dg.color.w.
 //  * no colour alpha, d == 1, Tf == 0: T == 0 exactly.
 //  * vec4 vertex colours whose alphas are ALL 1.0f (cornell_box): the interpolated alpha is 1 up to a few ulp
 //    (barycentric / bilinear weights sum to 1 +- 4 ulp), so |T| <= 1e-6 and the product is <= maxContrib * 1e-6, which the
 //    reference zeroes whenever that is <= minContribution. Checked here with the actual contribution.
 // Anything else (per-primitive model colours, real alpha, thin glass, ...) answers "no" and takes the reference loop.
-__device__ __forceinline__ bool ptOccluderIsOpaque(const OcWorld *world, const OcRenderer &ren, const Ray &ray, float maxContrib)
+__device__ __forceinline__ bool ptOccluderIsOpaque(const OcWorld *world, const OcRenderer &ren, uint32_t rec, uint32_t instID, float maxContrib)
 {
-  const OcInstance *inst = world->instances + ray.instID;
-  const OcModel *m = inst->group->models + ray.geomID;
+  uint32_t primID, geomID;
+  resolveHitIds(world, rec, instID, primID, geomID);
+  const OcInstance *inst = world->instances + instID;
+  const OcModel *m = inst->group->models + geomID;
   if (m->color.addr) return false;
   const uint32_t gf = m->geom->flags;
   if (gf & OC_GEOMFLAG_HAS_ALPHA) {
     if (!(gf & OC_GEOMFLAG_ALPHA_ALL_ONE) || !(maxContrib * 1e-6f <= ren.minContribution)) return false;
   }
-  const OcMaterial *mat = getMaterial(world, ren, m, ray.primID);
+  const OcMaterial *mat = getMaterial(world, ren, m, primID);
   if (mat && mat->type == OC_MATERIAL_THINGLASS) return false;
   if (!mat || mat->type != OC_MATERIAL_OBJ) return true; // no / foreign material: transparency 0 (shading.cuh)
   return mat->d == 1.f && mat->Tf.x == 0.f && mat->Tf.y == 0.f && mat->Tf.z == 0.f;
 }
 
-struct PtCounts { uint32_t primary, secondary, shadow; };
-
-// The reference's closest-hit transparent-shadow loop (TransparentShadow.ispc:18-85), taken only when the any-hit
-// query of ptTraceStep found a non-opaque occluder (or the contribution is not finite). Kept out of line: inlined,
-// postIntersect + the material transparencies (OBJ, thin glass) doubled the spill traffic of the TRACE kernels for a
-// path that opaque scenes never take.
-// Returns the attenuated contribution in xyz and the number of additional shadow segments traced in w (by value: a
-// by-reference counter would pin the caller's ray counters into local memory).
-static __device__ __noinline__ float4 ptTransparentShadowSlow(const PtArgs &k, size_t e, float cx, float cy, float cz, uint32_t *stackBase)
+// The reference's closest-hit transparent-shadow loop (TransparentShadow.ispc:18-85), taken only when the any-hit query of
+// TRACE found a non-opaque occluder (or the contribution is not finite, in which case no query was made). Out of line:
+// opaque scenes never take it. Returns the attenuated contribution in xyz and the number of additional shadow segments
+// traced in w.
+static __device__ __noinline__ float4 ptTransparentShadowSlow(const PtArgs &k, size_t e, float cx, float cy, float cz, uint32_t *stackBase,
+    uint32_t stackStride)
 {
   uint32_t shadowCount = 0;
-  Stack stack;
-  stack.base = stackBase; stack.stride = PT_TRACE_BLOCK;
   vec3f lightContrib = make_vec3f(cx, cy, cz);
   const float4 a = k.s.shA[e], b = k.s.shB[e];
   Ray sr;
@@ -374,7 +376,8 @@ static __device__ __noinline__ float4 ptTransparentShadowSlow(const PtArgs &k, s
   while (1) {
     if (!counted) shadowCount++;
     counted = false;
-    traceWorld<false>(k.a.world, sr, stack);
+    const Hit h = traceHitNI<0>(k.a.world, sr.org, sr.dir, sr.t0, sr.t, stackBase, stackStride);
+    resolveHit(k.a.world, h, sr);
     if (!hadHit(sr)) break;
     DifferentialGeometry dg;
     postIntersect(k.a.world, ren, dg, sr, DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR);
@@ -385,131 +388,6 @@ static __device__ __noinline__ float4 ptTransparentShadowSlow(const PtArgs &k, s
   if (k.vol) k.s.shT0[e] = sr.t0; // where the ray stands after the transparent surfaces it crossed (volumeTransmittance starts there)
   return make_float4(lightContrib.x, lightContrib.y, lightContrib.z, __uint_as_float(shadowCount));
 }
-
-// TRACE step of one path: resolve the shadow rays emitted at the previous vertex, then (unless the path is
-// done) trace the continuation ray. Returns false when the path finished here.
-// VOL: the world holds volumes. A template parameter, not a run-time flag: with the volume calls compiled into the one
-// instantiation every world used, SHADE ran 12 % slower on cornell_box (register allocation around the call sites).
-template <bool FIRST, bool VOL>
-__device__ __forceinline__ bool ptTraceStep(const PtArgs &k, uint32_t p, Stack stack, PtCounts &cnt)
-{
-  const PtScratch &s = k.s;
-  const OcRenderer &ren = k.a.ren;
-  const OcFrameBuffer &fb = k.a.fb;
-  Ray ray;
-  if (FIRST) {
-    uint32_t ix, iy;
-    ptSlotToPixel(k, p, ix, iy);
-    if (ix >= (uint32_t)fb.sizeX || iy >= (uint32_t)fb.sizeY) return false;
-    // adaptive accumulation: pixels of a converged render task start no path (LocalFB.cpp:245-257)
-    if (fb.taskError && !(fb.taskError[(iy >> 3) * (((uint32_t)fb.sizeX + 7u) >> 3) + (ix >> 3)] > fb.errorThreshold)) return false;
-    // PathTracer_renderPixel, one sample (PathTracer.ispc:149-193)
-    uint32_t seed, sampleOffs, sampleOffsLight, bits, bitsLight;
-    ptSamplerParams(k, ix, iy, seed, sampleOffs, sampleOffsLight, bits, bitsLight);
-    const uint32_t sampleID = (uint32_t)fb.frameID * ren.spp + k.pass;
-    LDSampler ld;
-    LDSampler_init(ld, seed, sampleOffs + sampleID, sampleOffsLight + sampleID * k.nFirst, bits, bitsLight);
-    const vec2f rcpSize = make_vec2f(1.f / (float)fb.sizeX, 1.f / (float)fb.sizeY);
-    const vec2f pixel_center = make_vec2f(((float)ix + 0.5f) * rcpSize.x, ((float)iy + 0.5f) * rcpSize.y);
-    uint32_t ss234[3];
-    const vec2f pixelSample = LDSampler_getNext5Samples(ld, ss234);
-    const vec2f pfSample = pixelFilterSample(ren, pixelSample);
-    const vec2f screen = pixel_center + pfSample * rcpSize;
-    vec2f lens = make_vec2f(0.5f, 0.5f);
-    if (k.a.cam.needLensSample) lens = LDSampler_finalizeDim23(ld, ss234);
-    cameraInitRay(k.a.cam, ray, screen, lens);
-    // samplePath() prologue (PathSampler.ispc:116-133)
-    s.smp[p] = make_uint2(ld.revIndex, ld.scramble);
-    if (VOL) { // pathState.randomSampler (PathTracer.ispc:157)
-      RandomSampler rs;
-      RandomSampler_init(rs, seed, sampleOffs + sampleID);
-      ptStoreRs(s, p, rs);
-    }
-    s.flags[p] = PT_STRAIGHT | PT_SPECTRANS | PT_FIRSTBOUNCE;
-    s.thr[p] = make_float4(1.f, 1.f, 1.f, 1.f);
-    s.con[p] = make_float4(0.f, 0.f, 0.f, INFINITY);
-    s.lastP[p] = make_float4(ray.org.x, ray.org.y, ray.org.z, __uint_as_float(0u));
-    s.lastN[p] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, 0.f);
-    s.sZ[p] = make_float4(INFINITY, __uint_as_float(OC_INVALID_ID), __uint_as_float(OC_INVALID_ID), __uint_as_float(OC_INVALID_ID));
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (fb.position) s.sPos[p] = zero;
-    if (fb.firstNormal) s.sFN[p] = zero;
-    if (fb.normal) s.sNrm[p] = zero;
-    if (fb.albedo) s.sAlb[p] = zero;
-    s.rayO[p] = make_float4(ray.org.x, ray.org.y, ray.org.z, ray.t);
-    s.rayD[p] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, ray.t0);
-    cnt.primary++;
-  } else {
-    const uint32_t flags = s.flags[p];
-    if (flags & PT_HAS_SHADOW) {
-      // shadow rays of the previous vertex: transparentShadow (TransparentShadow.ispc:18-85) per light sample,
-      // summed in sample order like nextEventEstimation's L (NextEventEstimation.ispc:140-156)
-      vec3f L = make_vec3f(0.f);
-      for (uint32_t j = 0; j < s.nls; j++) {
-        const size_t e = (size_t)p * s.nls + j;
-        const float4 c = s.shC[e];
-        if (c.w == 0.f) continue;
-        const float4 a = s.shA[e], b = s.shB[e];
-        Ray sr;
-        setRay(sr, make_vec3f(a.x, a.y, a.z), make_vec3f(b.x, b.y, b.z), 0.f, a.w);
-        vec3f lightContrib = make_vec3f(c.x, c.y, c.z);
-        // fast path: ANY opaque occluder makes the product of transparencies exactly 0, whatever lies in front
-        // of it -> one any-hit query; only a non-opaque first find falls back to the reference's closest-hit loop
-        bool resolved = false;
-        float shadowT0 = 0.f;
-        if (isfinite(lightContrib.x) && isfinite(lightContrib.y) && isfinite(lightContrib.z)) {
-          Ray occ = sr;
-          cnt.shadow++;
-          if (!traceWorld<true>(k.a.world, occ, stack)) resolved = true; // unoccluded: lightContrib unchanged
-          else if (ptOccluderIsOpaque(k.a.world, ren, occ, reduce_max(lightContrib))) { lightContrib = make_vec3f(0.f); resolved = true; }
-        }
-        if (!resolved) {
-          const float4 r = ptTransparentShadowSlow(k, e, lightContrib.x, lightContrib.y, lightContrib.z, stack.base);
-          lightContrib = make_vec3f(r.x, r.y, r.z);
-          cnt.shadow += __float_as_uint(r.w);
-          if (VOL) shadowT0 = s.shT0[e];
-        }
-        if (reduce_max(lightContrib) > 0) {
-          // worlds with volumes: b.w = ls.pdf, c.w = fe.pdf (SHADE); the weight carries the transmittance estimates
-          const float w = VOL ? ptVolumeShadowWeight(k, p, make_vec3f(a.x, a.y, a.z), make_vec3f(b.x, b.y, b.z), shadowT0, a.w, b.w, c.w == FLT_MIN ? 0.f : c.w)
-                                : b.w;
-          if (VOL) L = L + w * lightContrib; else L = L + lightContrib * w;
-        }
-      }
-      float4 con = s.con[p];
-      con.x += L.x; con.y += L.y; con.z += L.z;
-      if (flags & PT_DONE) {
-        ptFinishPath(k, p, make_vec3f(con.x, con.y, con.z), s.thr[p].w);
-        return false;
-      }
-      s.con[p] = con;
-    }
-    const float4 o = s.rayO[p], d = s.rayD[p];
-    setRay(ray, make_vec3f(o.x, o.y, o.z), make_vec3f(d.x, d.y, d.z), d.w, o.w);
-    cnt.secondary++;
-  }
-  ray.u = ray.v = 0.f;
-  ray.Ng = make_vec3f(0.f);
-  const float rayLower = ray.t0, rayUpper = ray.t; // traceClippingRay without clipping geometry (World.ih:150-163)
-  traceWorld<false>(k.a.world, ray, stack);
-  if (VOL) { // volumeSampleFreePath (PathSampler.ispc:178-194): a scattering event before the surface replaces the hit
-    const PtFreePath fp = ptVolumeFreePath(k, p, ray.org, ray.dir, ray.t0, ray.t, ray.geomID, rayLower, rayUpper);
-    if (fp.albedoDist.w < INFINITY) {
-      s.hit0[p] = make_float4(fp.albedoDist.w, 0.f, 0.f, __uint_as_float(0u));
-      s.hit1[p] = make_float4(fp.albedoDist.x, fp.albedoDist.y, fp.albedoDist.z, __uint_as_float(fp.geomID));
-      s.hitInst[p] = fp.instID;
-      s.flags[p] |= PT_VOLUME;
-      return true;
-    }
-  }
-  s.hit0[p] = make_float4(ray.t, ray.u, ray.v, __uint_as_float(ray.primID));
-  s.hit1[p] = make_float4(ray.Ng.x, ray.Ng.y, ray.Ng.z, __uint_as_float(ray.geomID));
-  s.hitInst[p] = ray.instID;
-  return true;
-}
-
-template <bool VOL>
-__device__ bool ptShadeStep(const PtArgs &k, uint32_t p);
 
 // evaluateVirtualLights in a world with volumes (VirtualLight.ispc:76-101): the MIS weight of a light the path runs into
 // carries a transmittance estimate along the segment since the last vertex
@@ -544,273 +422,429 @@ static __device__ __noinline__ vec3f ptVirtualLightsVol(const PtArgs &k, uint32_
   return L;
 }
 
-// ---- TRACE --------------------------------------------------------------------------------------------------
-// Persistent grid-stride loop over the live-path queue. When few paths are left (RR has culled the frame down to
-// a long thin tail), every further TRACE/SHADE launch would cost a launch + drain latency for almost no work
-// (profiles/r1_pt_wavefront_launches.txt: 30 launches x ~35 us): instead each thread then carries its path to
-// the end right here (TAIL mode); the queue it leaves behind is empty and the remaining launches exit at once.
-template <bool FIRST, bool VOL>
-__global__ void __launch_bounds__(PT_TRACE_BLOCK, 5) ptTraceKernel(const __grid_constant__ PtArgs k)
-{
-  __shared__ uint32_t s_stack[OC_STACK_SIZE * PT_TRACE_BLOCK];
-  Stack stack;
-  stack.base = s_stack + threadIdx.x;
-  stack.stride = PT_TRACE_BLOCK;
-  PtCounts cnt = {0, 0, 0};
-  const uint32_t n = FIRST ? k.numPaths : *k.cntIn;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t p = FIRST ? i : k.qIn[i];
-    if (ptTraceStep<FIRST, VOL>(k, p, stack, cnt)) ptAppend(k.qOut, k.cntOut, p);
-  }
-  ptCountRays(k.a.fb, cnt.primary, cnt.secondary, cnt.shadow);
-}
-
-// FUSED, launched ONCE at the depth where Russian roulette starts to cull (PathTracer.cpp:33 rouletteDepth): every
-// remaining path is carried to its end here. Paths are independent, so instead of one launch + queue compaction per
-// bounce (15 launches for ~20 % of the frame's rays, each paying a launch + drain latency for an ever thinner queue:
-// profiles/r1_launches_bench_c1_wavefront.csv), each lane runs TRACE and SHADE back to back for its path and, when
-// the path dies, immediately fetches the next live path from the input queue (warp-aggregated atomic on a fetch
-// cursor). All lanes of a warp are at the same phase (trace, then shade) of *some* path until the queue runs dry.
+// ---- GEN --------------------------------------------------------------------------------------------------------------
+// PathTracer_renderPixel, one sample (PathTracer.ispc:149-193) up to the camera ray + samplePath()'s prologue
+// (PathSampler.ispc:116-133). Pixels outside the image and pixels of converged render tasks (adaptive accumulation,
+// LocalFB.cpp:245-257) start no path.
 template <bool VOL>
-__global__ void __launch_bounds__(PT_TRACE_BLOCK) ptFusedKernel(const __grid_constant__ PtArgs k)
-{
-  __shared__ uint32_t s_stack[OC_STACK_SIZE * PT_TRACE_BLOCK];
-  const uint32_t n = *k.cntIn;
-  if (n == 0) return;
-  Stack stack;
-  stack.base = s_stack + threadIdx.x;
-  stack.stride = PT_TRACE_BLOCK;
-  PtCounts cnt = {0, 0, 0};
-  const uint32_t lane = threadIdx.x & 31u;
-  bool alive = false;
-  uint32_t p = 0;
-  while (true) {
-    __syncwarp();
-    const uint32_t need = __ballot_sync(0xffffffffu, !alive);
-    if (need) {
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(k.fetchCursor, (uint32_t)__popc(need));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (!alive) {
-        const uint32_t i = base + __popc(need & ((1u << lane) - 1u));
-        if (i < n) { p = k.qIn[i]; alive = true; }
-      }
-      if (__ballot_sync(0xffffffffu, alive) == 0) break; // queue exhausted and every lane's path finished
-    }
-    if (alive) alive = ptTraceStep<false, VOL>(k, p, stack, cnt) && ptShadeStep<VOL>(k, p);
-  }
-  ptCountRays(k.a.fb, cnt.primary, cnt.secondary, cnt.shadow);
-  if (k.a.fb.rayCounters) { // [3]: rays traced by this kernel
-    uint32_t t = cnt.primary + cnt.secondary + cnt.shadow;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (lane == 0 && t) atomicAdd(k.a.fb.rayCounters + 3, (unsigned long long)t);
-  }
-}
-
-// SHADE step of one path; returns true when the path goes on to the next TRACE step (alive, or done with
-// shadow rays pending), false when it finished here.
-template <bool VOL>
-__device__ bool ptShadeStep(const PtArgs &k, uint32_t p)
+__global__ void __launch_bounds__(128) ptGenKernel(const __grid_constant__ PtArgs k)
 {
   const PtScratch &s = k.s;
   const OcRenderer &ren = k.a.ren;
   const OcFrameBuffer &fb = k.a.fb;
-  Stack dummy;
-  dummy.base = nullptr; dummy.stride = 0;
-  Ctx c(k.a.world, k.a.ren, k.a.cam, k.a.fb, dummy);
-  {
-    const bool volume = VOL && (s.flags[p] & PT_VOLUME) != 0; // scattering event inside a volume (ptVolumeFreePath)
-    uint32_t flags = s.flags[p] & ~(PT_HAS_SHADOW | PT_DONE | PT_VOLUME);
-    const uint32_t depth = flags & PT_DEPTH_MASK;
-    uint32_t scatteringEvents = (flags & PT_SCAT_MASK) >> PT_SCAT_SHIFT;
-    bool straightPath = flags & PT_STRAIGHT, specularTransmissionPath = flags & PT_SPECTRANS, firstBounceLight = flags & PT_FIRSTBOUNCE;
-    Ray ray;
-    {
-      const float4 o = s.rayO[p], d = s.rayD[p], h0 = s.hit0[p], h1 = s.hit1[p];
-      ray.org = make_vec3f(o.x, o.y, o.z); ray.dir = make_vec3f(d.x, d.y, d.z); ray.t0 = d.w;
-      ray.t = h0.x; ray.u = h0.y; ray.v = h0.z; ray.primID = __float_as_uint(h0.w);
-      ray.Ng = make_vec3f(h1.x, h1.y, h1.z); ray.geomID = __float_as_uint(h1.w);
-      ray.instID = s.hitInst[p];
-    }
-    float4 thr4 = s.thr[p], con4 = s.con[p];
-    vec3f throughput = make_vec3f(thr4.x, thr4.y, thr4.z), contribution = make_vec3f(con4.x, con4.y, con4.z);
-    float alpha = thr4.w;
-    PathVertexLite last;
-    {
-      const float4 lp = s.lastP[p], ln = s.lastN[p];
-      last.P = make_vec3f(lp.x, lp.y, lp.z); last.Ns = make_vec3f(ln.x, ln.y, ln.z);
-      last.pdf_w = con4.w; last.numLightSamples = __float_as_uint(lp.w);
-    }
+  uint32_t primary = 0;
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < k.numPaths; p += gridDim.x * blockDim.x) {
+    uint32_t ix, iy;
+    ptSlotToPixel(k, p, ix, iy);
+    if (ix >= (uint32_t)fb.sizeX || iy >= (uint32_t)fb.sizeY) continue;
+    if (fb.taskError && !(fb.taskError[(iy >> 3) * (((uint32_t)fb.sizeX + 7u) >> 3) + (ix >> 3)] > fb.errorThreshold)) continue;
+    uint32_t seed, sampleOffs, sampleOffsLight, bits, bitsLight;
+    ptSamplerParams(k, ix, iy, seed, sampleOffs, sampleOffsLight, bits, bitsLight);
+    const uint32_t sampleID = (uint32_t)fb.frameID * ren.spp + k.pass;
     LDSampler ld;
-    {
-      uint32_t ix, iy, seed, so, sol, bits, bitsLight;
-      ptSlotToPixel(k, p, ix, iy);
-      ptSamplerParams(k, ix, iy, seed, so, sol, bits, bitsLight);
-      const uint32_t sampleID = (uint32_t)fb.frameID * ren.spp + k.pass;
-      LDSampler_init(ld, seed, so + sampleID, sol + sampleID * k.nFirst, bits, bitsLight);
-      const uint2 sm = s.smp[p];
-      ld.revIndex = sm.x; ld.scramble = sm.y;
+    LDSampler_init(ld, seed, sampleOffs + sampleID, sampleOffsLight + sampleID * k.nFirst, bits, bitsLight);
+    const vec2f rcpSize = make_vec2f(1.f / (float)fb.sizeX, 1.f / (float)fb.sizeY);
+    const vec2f pixel_center = make_vec2f(((float)ix + 0.5f) * rcpSize.x, ((float)iy + 0.5f) * rcpSize.y);
+    uint32_t ss234[3];
+    const vec2f pixelSample = LDSampler_getNext5Samples(ld, ss234);
+    const vec2f pfSample = pixelFilterSample(ren, pixelSample);
+    const vec2f screen = pixel_center + pfSample * rcpSize;
+    vec2f lens = make_vec2f(0.5f, 0.5f);
+    if (k.a.cam.needLensSample) lens = LDSampler_finalizeDim23(ld, ss234);
+    Ray ray;
+    cameraInitRay(k.a.cam, ray, screen, lens);
+    s.smp[p] = make_uint2(ld.revIndex, ld.scramble);
+    if (VOL) { // pathState.randomSampler (PathTracer.ispc:157)
+      RandomSampler rs;
+      RandomSampler_init(rs, seed, sampleOffs + sampleID);
+      ptStoreRs(s, p, rs);
     }
-
-    // ---- one iteration of samplePath()'s loop, after the trace (PathSampler.ispc:196-412) ----
-    bool alive = false, hasShadow = false;
-    do {
-      const bool surface = !volume && hadHit(ray);
-      const bool environment = !surface && !volume;
-      const vec3f volumeAlbedo = ray.Ng; // hit1.xyz of a volume vertex
-      const OcVolume *vmodel = nullptr;
-      if (volume) {
-        throughput = throughput * volumeAlbedo; // PathSampler.ispc:189-192
-        vmodel = k.a.world->instances[ray.instID].group->volumes + ray.geomID;
-      }
-      const vec3f wo = neg(ray.dir);
-      if (depth == 0) {
-        float4 z = s.sZ[p];
-        z.x = fb.projectedDepth ? ray.t * dot(ray.dir, toV(k.a.cam.direction)) : ray.t;
-        s.sZ[p] = z;
-      }
-      if (environment && (ren.backgroundRefraction ? specularTransmissionPath : straightPath)) {
-        const vec4f bg = getBackground(ren);
-        alpha -= luminance(throughput) * (1.0f - bg.w);
-        contribution = contribution + throughput * make_vec3f(bg);
-      }
-      if (!volume) { // PathSampler.ispc:220-228
-        if (VOL)
-          contribution = contribution + ptVirtualLightsVol(k, p, straightPath, throughput, last.P, last.Ns, last.pdf_w, last.numLightSamples,
-                                            environment, ray.org, ray.dir, ray.t);
-        else
-          contribution = contribution + evaluateVirtualLights(c, straightPath, throughput, last, environment, ray);
-      }
-      if (environment) break;
-      if (depth >= ren.maxDepth) break; // numGeoLights == 0
-
-      DifferentialGeometry dg;
-      if (volume) { // postIntersect of a volume vertex (PathSampler.ispc:51-67) + VolumetricModel_postIntersect (VolumetricModel.ih:16-33)
-        dg.P = ray.org + ray.t * ray.dir;
-        dg.Ng = dg.Ns = dg.dPds = make_vec3f(0.f);
-        dg.color = make_vec4f(0.f, 0.f, 0.f, 0.f);
-        dg.epsilon = 0.f; dg.material = nullptr; dg.primID = 0;
-        dg.objID = vmodel->userID == OC_INVALID_ID ? ray.geomID : vmodel->userID;
-        dg.instID = ray.instID;
-        if (ray.instID != OC_INVALID_ID && k.a.world->instances[ray.instID].userID != OC_INVALID_ID)
-          dg.instID = k.a.world->instances[ray.instID].userID;
-      } else
-        postIntersect(k.a.world, ren, dg, ray,
-            DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR | DG_TANGENTS | DG_MOTIONBLUR);
-      if (depth == 0) {
-        float4 z = s.sZ[p];
-        z.y = __uint_as_float(dg.primID); z.z = __uint_as_float(dg.objID); z.w = __uint_as_float(dg.instID);
-        s.sZ[p] = z;
-        if (fb.position) s.sPos[p] = make_float4(dg.P.x, dg.P.y, dg.P.z, 0.f);
-        if (fb.firstNormal) s.sFN[p] = make_float4(dg.Ns.x, dg.Ns.y, dg.Ns.z, 0.f);
-      }
-      if (depth >= ren.maxDepth || scatteringEvents >= (uint32_t)ren.maxScatteringEvents) break;
-
-      ObjBSDF bsdf;
-      if (!volume) {
-        OBJ_getBSDF(bsdf, dg);
-        if (!bsdf.valid) break;
-      }
-
-      LDSampler_nextGroup(ld);
-      uint32_t vertexLightSamples = 0;
-      if (volume ? hgIsSmooth(vmodel->anisotropy) : (bsdf.scatteringType & SC_SMOOTH) != 0) { // isSmooth (PathTracerUtil.ih:15-28)
-        if (scatteringEvents == 0) { // updateAuxilliaryData (PathTracerUtil.ih:48-60)
-          if (fb.albedo) { const vec3f v = throughput * (volume ? volumeAlbedo : bsdf.albedo); s.sAlb[p] = make_float4(v.x, v.y, v.z, 0.f); }
-          if (fb.normal) { const vec3f v = throughput * (volume ? dg.Ns : bsdf.frame.vz); s.sNrm[p] = make_float4(v.x, v.y, v.z, 0.f); }
-        }
-        // nextEventEstimation up to the shadow ray (NextEventEstimation.ispc:36-118): emit, TRACE(d+1) resolves
-        const uint32_t numLightSamples = firstBounceLight ? k.nFirst : k.nIndirect;
-        vertexLightSamples = numLightSamples;
-        const uint32_t numLights = k.a.world->numLights;
-        for (uint32_t j = 0; j < s.nls; j++) {
-          const size_t e = (size_t)p * s.nls + j;
-          bool valid = false;
-          if (j < numLightSamples) {
-            float ss;
-            const vec2f sl = LDSampler_get3LightSamples(ld, j, numLightSamples > 1, ss);
-            const Sample1D sel = Distribution1D_sample((int)numLights, k.a.world->lightsCDF, 0, ss);
-            const float lightSelectionProb = sel.prob * numLightSamples;
-            LightSample ls = Light_sample(k.a.world->lights[sel.idx], dg, sl);
-            ls.weight = ls.weight / lightSelectionProb;
-            ls.pdf *= lightSelectionProb;
-            if (!(reduce_max(ls.weight) <= 0.0f || ls.pdf <= 0.0f)) {
-              const EvalRes fe = volume ? HenyeyGreenstein_eval(vmodel->anisotropy, wo, ls.dir) : OBJ_eval(bsdf, wo, ls.dir);
-              if (!(reduce_max(fe.value) <= 0.0f)) {
-                vec3f org = dg.P;
-                if (!volume && dot(dg.Ng, ls.dir) < 0.f) org = org - (2.0f * dg.epsilon) * dg.Ng;
-                const vec3f unshaded = throughput * fe.value * ls.weight;
-                s.shA[e] = make_float4(org.x, org.y, org.z, ls.dist);
-                // worlds with volumes: TRACE needs the two pdfs apart (the MIS weight carries a transmittance estimate)
-                s.shB[e] = make_float4(ls.dir.x, ls.dir.y, ls.dir.z, VOL ? ls.pdf : misHeuristic(ls.pdf, fe.pdf));
-                s.shC[e] = make_float4(unshaded.x, unshaded.y, unshaded.z, VOL ? (fe.pdf > 0.f ? fe.pdf : FLT_MIN) : 1.f);
-                valid = true;
-                hasShadow = true;
-              }
-            }
-          }
-          if (!valid) s.shC[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        firstBounceLight = false;
-      }
-
-      float ss;
-      uint32_t uu3;
-      const vec2f sb = LDSampler_getNext4Samples(ld, ss, uu3);
-      SampleRes fs = volume ? HenyeyGreenstein_sample(vmodel->anisotropy, wo, sb) : OBJ_sample(bsdf, wo, sb, ss);
-      if (!volume) {
-        const bool sameSide = dot(fs.wi, dg.Ng) >= 0.f;
-        const bool reflection = fs.type & SC_REFLECTION;
-        if (sameSide != reflection) fs.weight = make_vec3f(0.0f);
-      }
-      if (reduce_max(fs.weight) <= 0.0f || fs.pdf <= 0.0f) break;
-      throughput = throughput * fs.weight;
-      if (depth >= (uint32_t)ren.rouletteDepth) {
-        const float rr = LDSampler_finalizeDim3(ld, uu3);
-        const float contProb = fminf(reduce_max(throughput), 0.95f);
-        if (rr > contProb) break;
-        throughput = throughput * (1.f / contProb);
-      }
-      vec3f ray_org = dg.P;
-      if (!volume && (fs.type & SC_TRANSMISSION)) ray_org = ray_org - (2.0f * dg.epsilon) * dg.Ng;
-      if ((fs.type & ~SC_SPECULAR_TRANSMISSION) || volume) {
-        last.P = dg.P; last.Ns = dg.Ns; last.pdf_w = fs.pdf; last.numLightSamples = vertexLightSamples;
-      }
-      if (!eq3(ray.dir, fs.wi)) straightPath = false;
-      if (!(fs.type & SC_SPECULAR_TRANSMISSION)) specularTransmissionPath = false;
-      s.rayO[p] = make_float4(ray_org.x, ray_org.y, ray_org.z, INFINITY);
-      s.rayD[p] = make_float4(fs.wi.x, fs.wi.y, fs.wi.z, 0.f);
-      if (fs.type & SC_SMOOTH) scatteringEvents++;
-      alive = reduce_max(throughput) > ren.minContribution;
-    } while (false);
-
-    if (!alive && !hasShadow) {
-      ptFinishPath(k, p, contribution, alpha);
-      return false;
-    }
-    s.thr[p] = make_float4(throughput.x, throughput.y, throughput.z, alpha);
-    s.con[p] = make_float4(contribution.x, contribution.y, contribution.z, last.pdf_w);
-    if (alive) {
-      s.lastP[p] = make_float4(last.P.x, last.P.y, last.P.z, __uint_as_float(last.numLightSamples));
-      s.lastN[p] = make_float4(last.Ns.x, last.Ns.y, last.Ns.z, 0.f);
-      s.smp[p] = make_uint2(ld.revIndex, ld.scramble);
-    }
-    s.flags[p] = ((depth + 1) & PT_DEPTH_MASK) | (scatteringEvents << PT_SCAT_SHIFT) | (straightPath ? PT_STRAIGHT : 0u)
-        | (specularTransmissionPath ? PT_SPECTRANS : 0u) | (firstBounceLight ? PT_FIRSTBOUNCE : 0u) | (hasShadow ? PT_HAS_SHADOW : 0u)
-        | (alive ? 0u : PT_DONE);
-    return true;
+    s.flags[p] = PT_STRAIGHT | PT_SPECTRANS | PT_FIRSTBOUNCE;
+    s.thr[p] = make_float4(1.f, 1.f, 1.f, 1.f);
+    s.con[p] = make_float4(0.f, 0.f, 0.f, INFINITY);
+    s.lastP[p] = make_float4(ray.org.x, ray.org.y, ray.org.z, __uint_as_float(0u));
+    s.lastN[p] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, 0.f);
+    s.sZ[p] = make_float4(INFINITY, __uint_as_float(OC_INVALID_ID), __uint_as_float(OC_INVALID_ID), __uint_as_float(OC_INVALID_ID));
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (fb.position) s.sPos[p] = zero;
+    if (fb.firstNormal) s.sFN[p] = zero;
+    if (fb.normal) s.sNrm[p] = zero;
+    if (fb.albedo) s.sAlb[p] = zero;
+    s.rayO[p] = make_float4(ray.org.x, ray.org.y, ray.org.z, ray.t);
+    s.rayD[p] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, ray.t0);
+    primary++;
+    ptAppend(k.pathOut, k.cntPathOut, p); // depth 0: the path queue is the continuation-ray queue too
   }
+  ptCountRays(fb, primary, 0u, 0u);
 }
 
-template <bool VOL>
-__global__ void __launch_bounds__(128, 5) ptShadeKernel(const __grid_constant__ PtArgs k)
+// ---- TRACE ------------------------------------------------------------------------------------------------------------
+// Persistent-thread ray queue. The rays of one bounce -- the shadow queue, then the continuation queue -- form one index
+// space [0, n). A warp reserves PT_TRACE_CHUNK consecutive indices at a time (one atomic on the fetch cursor per chunk) and
+// hands them to its lanes. The walk runs in warp-synchronous rounds of three phases:
+//   A  every lane with an inner node descends until it holds a leaf        (Traversal::inner, node tests side by side)
+//   B  every lane with a leaf works it off and pops                        (Traversal::leaf, primitive tests side by side)
+//   C  lanes whose walk ended write their result
+// with __syncwarp() between them, so that the lanes of a warp do the same kind of work at the same time however different
+// their rays are. Before a round, once REFILL_IDLE lanes are idle they take the next rays of the chunk: the warp stays
+// filled while individual rays take anything from 2 to 200 steps. A lane holds nothing but the walk: instance-space ray,
+// compact hit, stack position; the world-space ray is re-read from the queue's arrays when the walk leaves a transformed
+// instance, the ids / geometric normal of the hit are read from its leaf record in phase C.
+#ifndef PT_TRACE_CHUNK
+#define PT_TRACE_CHUNK 128u
+#endif
+template <int REFILL_IDLE, int MIN_BLOCKS>
+__global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptTraceKernel(const __grid_constant__ PtArgs k)
 {
-  const uint32_t n = *k.cntIn;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t p = k.qIn[i];
-    if (ptShadeStep<VOL>(k, p)) ptAppend(k.qOut, k.cntOut, p);
+  __shared__ uint32_t s_stack[OC_STACK_SHARED * PT_TRACE_BLOCK];
+  const uint32_t nS = k.cntShadowIn ? *k.cntShadowIn : 0u;
+  const uint32_t n = nS + *k.cntContIn;
+  if (n == 0) return;
+  uint32_t ovf[OC_STACK_OVF];
+  Stack st;
+  st.base = s_stack + threadIdx.x; st.stride = PT_TRACE_BLOCK; st.ovf = ovf;
+  const PtScratch &s = k.s;
+  const OcWorld *__restrict__ world = k.a.world;
+  const uint32_t lane = threadIdx.x & 31u, ltMask = (1u << lane) - 1u;
+  uint32_t chunkNext = 0, chunkEnd = 0; // warp-uniform
+  bool exhausted = false;               // warp-uniform: the cursor has run past the queue
+  bool active = false;
+  uint32_t id = 0;
+  uint32_t nShadow = 0, nCont = 0;
+  Traversal<2> tr;
+  RayMem src;
+  src.po = src.pd = nullptr;
+  while (true) {
+    bool fin = false; // this lane's walk ended in this round
+    uint32_t idle = ~__ballot_sync(0xffffffffu, active);
+    if (!exhausted && __popc(idle) >= REFILL_IDLE) {
+      while (idle) {
+        if (chunkNext == chunkEnd) {
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(k.fetchCursor, PT_TRACE_CHUNK);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (base >= n) { exhausted = true; break; }
+          chunkNext = base;
+          chunkEnd = min(base + PT_TRACE_CHUNK, n);
+        }
+        const uint32_t avail = chunkEnd - chunkNext;
+        const uint32_t rank = __popc(idle & ltMask);
+        const bool take = ((idle >> lane) & 1u) && rank < avail;
+        if (take) {
+          const uint32_t i = chunkNext + rank;
+          const bool occ = i < nS;
+          if (occ) {
+            id = k.shadowIn[i];
+            const size_t e = id & ~PT_SHADOW_RAY;
+            src.po = s.shA + e; src.pd = s.shB + e;
+            nShadow++;
+          } else {
+            id = k.contIn[i - nS];
+            src.po = s.rayO + id; src.pd = s.rayD + id;
+            nCont++;
+          }
+          const float4 o4 = *src.po, d4 = *src.pd;
+          active = tr.init(world, make_vec3f(o4.x, o4.y, o4.z), make_vec3f(d4.x, d4.y, d4.z), occ ? 0.f : d4.w, o4.w, occ);
+          fin = !active; // empty world / empty group: the ray misses, phase C says so
+        }
+        const uint32_t took = __ballot_sync(0xffffffffu, take);
+        chunkNext += __popc(took);
+        idle &= ~took;
+      }
+    }
+    if (__ballot_sync(0xffffffffu, active || fin) == 0) break; // nothing in flight and nothing left to fetch
+    // ---- A: inner nodes ----
+    if (active) {
+      while (!tr.atLeaf())
+        if (!tr.inner(world, src, st)) { fin = true; active = false; break; }
+    }
+    __syncwarp();
+    // ---- B: leaves ----
+    if (active && !tr.leaf(world, src, st)) { fin = true; active = false; }
+    __syncwarp();
+    // ---- C: results ----
+    if (fin) {
+      if (id & PT_SHADOW_RAY) s.shHit[id & ~PT_SHADOW_RAY] = make_uint2(tr.h.rec, tr.h.inst);
+      else {
+        Ray r;
+        const float4 o4 = *src.po, d4 = *src.pd;
+        r.org = make_vec3f(o4.x, o4.y, o4.z); r.dir = make_vec3f(d4.x, d4.y, d4.z); r.t0 = d4.w;
+        resolveHit(world, tr.h, r);
+        s.hit0[id] = make_float4(r.t, r.u, r.v, __uint_as_float(r.primID));
+        s.hit1[id] = make_float4(r.Ng.x, r.Ng.y, r.Ng.z, __uint_as_float(r.geomID));
+        s.hitInst[id] = r.instID;
+      }
+    }
   }
+  ptCountRays(k.a.fb, 0u, k.depth == 0 ? 0u : nCont, nShadow);
+}
+
+// ---- SHADE ------------------------------------------------------------------------------------------------------------
+// One path, one vertex: returns true when the path goes on to the next bounce (alive, or done with shadow rays pending).
+template <bool VOL>
+__device__ __forceinline__ bool ptShadeStep(const PtArgs &k, uint32_t p, uint32_t *stackBase, uint32_t &extraShadow)
+{
+  const PtScratch &s = k.s;
+  const OcRenderer &ren = k.a.ren;
+  const OcFrameBuffer &fb = k.a.fb;
+  const OcWorld *world = k.a.world;
+  Stack dummy;
+  dummy.base = nullptr; dummy.stride = 0; dummy.ovf = nullptr;
+  Ctx c(k.a.world, k.a.ren, k.a.cam, k.a.fb, dummy);
+
+  uint32_t flags = s.flags[p];
+  float4 thr4 = s.thr[p], con4 = s.con[p];
+  if (flags & PT_HAS_SHADOW) {
+    // shadow rays of the previous vertex: transparentShadow (TransparentShadow.ispc:18-85) per light sample, summed in
+    // sample order like nextEventEstimation's L (NextEventEstimation.ispc:140-156). TRACE made ONE any-hit query per ray:
+    // any opaque occluder makes the product of transparencies exactly 0, whatever lies in front of it; only a non-opaque
+    // find takes the reference's closest-hit loop.
+    vec3f L = make_vec3f(0.f);
+    for (uint32_t j = 0; j < s.nls; j++) {
+      const size_t e = (size_t)p * s.nls + j;
+      const float4 cc = s.shC[e];
+      if (cc.w == 0.f) continue;
+      vec3f lightContrib = make_vec3f(cc.x, cc.y, cc.z);
+      bool resolved = false;
+      float shadowT0 = 0.f;
+      if (isfinite(lightContrib.x) && isfinite(lightContrib.y) && isfinite(lightContrib.z)) {
+        const uint2 occ = s.shHit[e];
+        if (occ.y == OC_INVALID_ID) resolved = true; // unoccluded: lightContrib unchanged
+        else if (ptOccluderIsOpaque(world, ren, occ.x, occ.y, reduce_max(lightContrib))) { lightContrib = make_vec3f(0.f); resolved = true; }
+      }
+      if (!resolved) {
+        const float4 r = ptTransparentShadowSlow(k, e, lightContrib.x, lightContrib.y, lightContrib.z, stackBase, PT_TRACE_BLOCK);
+        lightContrib = make_vec3f(r.x, r.y, r.z);
+        extraShadow += __float_as_uint(r.w);
+        if (VOL) shadowT0 = s.shT0[e];
+      }
+      if (reduce_max(lightContrib) > 0) {
+        const float4 b = s.shB[e];
+        if (VOL) { // b.w = ls.pdf, cc.w = fe.pdf: the weight carries the transmittance estimates
+          const float4 a = s.shA[e];
+          const float w = ptVolumeShadowWeight(k, p, make_vec3f(a.x, a.y, a.z), make_vec3f(b.x, b.y, b.z), shadowT0, a.w, b.w, cc.w == FLT_MIN ? 0.f : cc.w);
+          L = L + w * lightContrib;
+        } else
+          L = L + lightContrib * b.w;
+      }
+    }
+    con4.x += L.x; con4.y += L.y; con4.z += L.z;
+    if (flags & PT_DONE) {
+      ptFinishPath(k, p, make_vec3f(con4.x, con4.y, con4.z), thr4.w);
+      return false;
+    }
+  }
+  flags &= ~(PT_HAS_SHADOW | PT_DONE);
+  const uint32_t depth = flags & PT_DEPTH_MASK;
+  uint32_t scatteringEvents = (flags & PT_SCAT_MASK) >> PT_SCAT_SHIFT;
+  bool straightPath = flags & PT_STRAIGHT, specularTransmissionPath = flags & PT_SPECTRANS, firstBounceLight = flags & PT_FIRSTBOUNCE;
+  Ray ray;
+  {
+    const float4 o = s.rayO[p], d = s.rayD[p], h0 = s.hit0[p], h1 = s.hit1[p];
+    ray.org = make_vec3f(o.x, o.y, o.z); ray.dir = make_vec3f(d.x, d.y, d.z); ray.t0 = d.w;
+    ray.t = h0.x; ray.u = h0.y; ray.v = h0.z; ray.primID = __float_as_uint(h0.w);
+    ray.Ng = make_vec3f(h1.x, h1.y, h1.z); ray.geomID = __float_as_uint(h1.w);
+    ray.instID = s.hitInst[p];
+    const float rayUpper = o.w; // traceClippingRay without clipping geometry (World.ih:150-163)
+    // worlds with volumes: volumeSampleFreePath (PathSampler.ispc:178-194), a scattering event before the surface replaces the hit
+    if (VOL) {
+      const PtFreePath fp = ptVolumeFreePath(k, p, ray.org, ray.dir, ray.t0, ray.t, ray.geomID, ray.t0, rayUpper);
+      if (fp.albedoDist.w < INFINITY) {
+        ray.t = fp.albedoDist.w; ray.u = ray.v = 0.f; ray.primID = 0u;
+        ray.Ng = make_vec3f(fp.albedoDist.x, fp.albedoDist.y, fp.albedoDist.z); // the albedo travels in Ng
+        ray.geomID = fp.geomID; ray.instID = fp.instID;
+        flags |= 0x80000000u; // local marker: volume vertex
+      }
+    }
+  }
+  const bool volume = VOL && (flags & 0x80000000u) != 0;
+  flags &= 0x7fffffffu;
+  vec3f throughput = make_vec3f(thr4.x, thr4.y, thr4.z), contribution = make_vec3f(con4.x, con4.y, con4.z);
+  float alpha = thr4.w;
+  PathVertexLite last;
+  {
+    const float4 lp = s.lastP[p], ln = s.lastN[p];
+    last.P = make_vec3f(lp.x, lp.y, lp.z); last.Ns = make_vec3f(ln.x, ln.y, ln.z);
+    last.pdf_w = con4.w; last.numLightSamples = __float_as_uint(lp.w);
+  }
+  LDSampler ld;
+  {
+    uint32_t ix, iy, seed, so, sol, bits, bitsLight;
+    ptSlotToPixel(k, p, ix, iy);
+    ptSamplerParams(k, ix, iy, seed, so, sol, bits, bitsLight);
+    const uint32_t sampleID = (uint32_t)fb.frameID * ren.spp + k.pass;
+    LDSampler_init(ld, seed, so + sampleID, sol + sampleID * k.nFirst, bits, bitsLight);
+    const uint2 sm = s.smp[p];
+    ld.revIndex = sm.x; ld.scramble = sm.y;
+  }
+
+  // ---- one iteration of samplePath()'s loop, after the trace (PathSampler.ispc:196-412) ----
+  bool alive = false, hasShadow = false;
+  do {
+    const bool surface = !volume && hadHit(ray);
+    const bool environment = !surface && !volume;
+    const vec3f volumeAlbedo = ray.Ng;
+    const OcVolume *vmodel = nullptr;
+    if (volume) {
+      throughput = throughput * volumeAlbedo; // PathSampler.ispc:189-192
+      vmodel = world->instances[ray.instID].group->volumes + ray.geomID;
+    }
+    const vec3f wo = neg(ray.dir);
+    if (depth == 0) {
+      float4 z = s.sZ[p];
+      z.x = fb.projectedDepth ? ray.t * dot(ray.dir, toV(k.a.cam.direction)) : ray.t;
+      s.sZ[p] = z;
+    }
+    if (environment && (ren.backgroundRefraction ? specularTransmissionPath : straightPath)) {
+      const vec4f bg = getBackground(ren);
+      alpha -= luminance(throughput) * (1.0f - bg.w);
+      contribution = contribution + throughput * make_vec3f(bg);
+    }
+    if (!volume) { // PathSampler.ispc:220-228
+      if (VOL)
+        contribution = contribution + ptVirtualLightsVol(k, p, straightPath, throughput, last.P, last.Ns, last.pdf_w, last.numLightSamples,
+                                          environment, ray.org, ray.dir, ray.t);
+      else
+        contribution = contribution + evaluateVirtualLights(c, straightPath, throughput, last, environment, ray);
+    }
+    if (environment) break;
+    if (depth >= ren.maxDepth) break; // numGeoLights == 0
+
+    DifferentialGeometry dg;
+    if (volume) { // postIntersect of a volume vertex (PathSampler.ispc:51-67) + VolumetricModel_postIntersect (VolumetricModel.ih:16-33)
+      dg.P = ray.org + ray.t * ray.dir;
+      dg.Ng = dg.Ns = dg.dPds = make_vec3f(0.f);
+      dg.color = make_vec4f(0.f, 0.f, 0.f, 0.f);
+      dg.epsilon = 0.f; dg.material = nullptr; dg.primID = 0;
+      dg.objID = vmodel->userID == OC_INVALID_ID ? ray.geomID : vmodel->userID;
+      dg.instID = ray.instID;
+      if (ray.instID != OC_INVALID_ID && world->instances[ray.instID].userID != OC_INVALID_ID)
+        dg.instID = world->instances[ray.instID].userID;
+    } else
+      postIntersect(world, ren, dg, ray,
+          DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR | DG_TANGENTS | DG_MOTIONBLUR);
+    if (depth == 0) {
+      float4 z = s.sZ[p];
+      z.y = __uint_as_float(dg.primID); z.z = __uint_as_float(dg.objID); z.w = __uint_as_float(dg.instID);
+      s.sZ[p] = z;
+      if (fb.position) s.sPos[p] = make_float4(dg.P.x, dg.P.y, dg.P.z, 0.f);
+      if (fb.firstNormal) s.sFN[p] = make_float4(dg.Ns.x, dg.Ns.y, dg.Ns.z, 0.f);
+    }
+    if (depth >= ren.maxDepth || scatteringEvents >= (uint32_t)ren.maxScatteringEvents) break;
+
+    ObjBSDF bsdf;
+    if (!volume) {
+      OBJ_getBSDF(bsdf, dg);
+      if (!bsdf.valid) break;
+    }
+
+    LDSampler_nextGroup(ld);
+    uint32_t vertexLightSamples = 0;
+    if (volume ? hgIsSmooth(vmodel->anisotropy) : (bsdf.scatteringType & SC_SMOOTH) != 0) { // isSmooth (PathTracerUtil.ih:15-28)
+      if (scatteringEvents == 0) { // updateAuxilliaryData (PathTracerUtil.ih:48-60)
+        if (fb.albedo) { const vec3f v = throughput * (volume ? volumeAlbedo : bsdf.albedo); s.sAlb[p] = make_float4(v.x, v.y, v.z, 0.f); }
+        if (fb.normal) { const vec3f v = throughput * (volume ? dg.Ns : bsdf.frame.vz); s.sNrm[p] = make_float4(v.x, v.y, v.z, 0.f); }
+      }
+      // nextEventEstimation up to the shadow ray (NextEventEstimation.ispc:36-118): the ray joins the next TRACE's queue
+      const uint32_t numLightSamples = firstBounceLight ? k.nFirst : k.nIndirect;
+      vertexLightSamples = numLightSamples;
+      const uint32_t numLights = world->numLights;
+      for (uint32_t j = 0; j < s.nls; j++) {
+        const size_t e = (size_t)p * s.nls + j;
+        bool valid = false;
+        if (j < numLightSamples) {
+          float ss;
+          const vec2f sl = LDSampler_get3LightSamples(ld, j, numLightSamples > 1, ss);
+          const Sample1D sel = Distribution1D_sample((int)numLights, world->lightsCDF, 0, ss);
+          const float lightSelectionProb = sel.prob * numLightSamples;
+          LightSample ls = Light_sample(world->lights[sel.idx], dg, sl);
+          ls.weight = ls.weight / lightSelectionProb;
+          ls.pdf *= lightSelectionProb;
+          if (!(reduce_max(ls.weight) <= 0.0f || ls.pdf <= 0.0f)) {
+            const EvalRes fe = volume ? HenyeyGreenstein_eval(vmodel->anisotropy, wo, ls.dir) : OBJ_eval(bsdf, wo, ls.dir);
+            if (!(reduce_max(fe.value) <= 0.0f)) {
+              vec3f org = dg.P;
+              if (!volume && dot(dg.Ng, ls.dir) < 0.f) org = org - (2.0f * dg.epsilon) * dg.Ng;
+              const vec3f unshaded = throughput * fe.value * ls.weight;
+              s.shA[e] = make_float4(org.x, org.y, org.z, ls.dist);
+              // worlds with volumes: the fold needs the two pdfs apart (the MIS weight carries a transmittance estimate)
+              s.shB[e] = make_float4(ls.dir.x, ls.dir.y, ls.dir.z, VOL ? ls.pdf : misHeuristic(ls.pdf, fe.pdf));
+              s.shC[e] = make_float4(unshaded.x, unshaded.y, unshaded.z, VOL ? (fe.pdf > 0.f ? fe.pdf : FLT_MIN) : 1.f);
+              valid = true;
+              hasShadow = true;
+              // a contribution that is not finite takes the closest-hit loop in the fold (the reference's arithmetic on it)
+              if (isfinite(unshaded.x) && isfinite(unshaded.y) && isfinite(unshaded.z))
+                ptAppend(k.shadowOut, k.cntShadowOut, PT_SHADOW_RAY | (uint32_t)e);
+            }
+          }
+        }
+        if (!valid) s.shC[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      firstBounceLight = false;
+    }
+
+    float ss;
+    uint32_t uu3;
+    const vec2f sb = LDSampler_getNext4Samples(ld, ss, uu3);
+    SampleRes fs = volume ? HenyeyGreenstein_sample(vmodel->anisotropy, wo, sb) : OBJ_sample(bsdf, wo, sb, ss);
+    if (!volume) {
+      const bool sameSide = dot(fs.wi, dg.Ng) >= 0.f;
+      const bool reflection = fs.type & SC_REFLECTION;
+      if (sameSide != reflection) fs.weight = make_vec3f(0.0f);
+    }
+    if (reduce_max(fs.weight) <= 0.0f || fs.pdf <= 0.0f) break;
+    throughput = throughput * fs.weight;
+    if (depth >= (uint32_t)ren.rouletteDepth) {
+      const float rr = LDSampler_finalizeDim3(ld, uu3);
+      const float contProb = fminf(reduce_max(throughput), 0.95f);
+      if (rr > contProb) break;
+      throughput = throughput * (1.f / contProb);
+    }
+    vec3f ray_org = dg.P;
+    if (!volume && (fs.type & SC_TRANSMISSION)) ray_org = ray_org - (2.0f * dg.epsilon) * dg.Ng;
+    if ((fs.type & ~SC_SPECULAR_TRANSMISSION) || volume) {
+      last.P = dg.P; last.Ns = dg.Ns; last.pdf_w = fs.pdf; last.numLightSamples = vertexLightSamples;
+    }
+    if (!eq3(ray.dir, fs.wi)) straightPath = false;
+    if (!(fs.type & SC_SPECULAR_TRANSMISSION)) specularTransmissionPath = false;
+    s.rayO[p] = make_float4(ray_org.x, ray_org.y, ray_org.z, INFINITY);
+    s.rayD[p] = make_float4(fs.wi.x, fs.wi.y, fs.wi.z, 0.f);
+    if (fs.type & SC_SMOOTH) scatteringEvents++;
+    alive = reduce_max(throughput) > ren.minContribution;
+  } while (false);
+
+  if (!alive && !hasShadow) {
+    ptFinishPath(k, p, contribution, alpha);
+    return false;
+  }
+  s.thr[p] = make_float4(throughput.x, throughput.y, throughput.z, alpha);
+  s.con[p] = make_float4(contribution.x, contribution.y, contribution.z, last.pdf_w);
+  if (alive) {
+    s.lastP[p] = make_float4(last.P.x, last.P.y, last.P.z, __uint_as_float(last.numLightSamples));
+    s.lastN[p] = make_float4(last.Ns.x, last.Ns.y, last.Ns.z, 0.f);
+    s.smp[p] = make_uint2(ld.revIndex, ld.scramble);
+    ptAppend(k.contOut, k.cntContOut, p);
+  }
+  s.flags[p] = ((depth + 1) & PT_DEPTH_MASK) | (scatteringEvents << PT_SCAT_SHIFT) | (straightPath ? PT_STRAIGHT : 0u)
+      | (specularTransmissionPath ? PT_SPECTRANS : 0u) | (firstBounceLight ? PT_FIRSTBOUNCE : 0u) | (hasShadow ? PT_HAS_SHADOW : 0u)
+      | (alive ? 0u : PT_DONE);
+  return true;
+}
+
+#ifndef PT_SHADE_MIN_BLOCKS
+#define PT_SHADE_MIN_BLOCKS 4
+#endif
+template <bool VOL>
+__global__ void __launch_bounds__(PT_TRACE_BLOCK, PT_SHADE_MIN_BLOCKS) ptShadeKernel(const __grid_constant__ PtArgs k)
+{
+  __shared__ uint32_t s_stack[OC_STACK_SHARED * PT_TRACE_BLOCK]; // the out-of-line transparent-shadow loop walks the hierarchy
+  const uint32_t n = *k.cntPathIn;
+  uint32_t extraShadow = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t p = k.pathIn[i];
+    if (ptShadeStep<VOL>(k, p, s_stack + threadIdx.x, extraShadow)) ptAppend(k.pathOut, k.cntPathOut, p);
+  }
+  ptCountRays(k.a.fb, 0u, 0u, extraShadow);
 }
 
 } // namespace oc

@@ -686,14 +686,15 @@ __global__ void __launch_bounds__(64, OC_RENDER_MIN_BLOCKS) renderFrameKernel(co
   const uint32_t tx = tileID % a.tilesX, ty = tileID / a.tilesX;
   const uint32_t x = tx * 64 + (taskInTile & 7u) * 8 + (threadIdx.x & 7u);
   const uint32_t y = ty * 64 + (taskInTile >> 3) * 8 + (threadIdx.x >> 3);
-  __shared__ uint32_t s_stack[OC_STACK_SIZE * 64];
+  __shared__ uint32_t s_stack[OC_STACK_SHARED * 64];
   Stack stack;
   stack.base = s_stack + threadIdx.x;
   stack.stride = 64;
+  stack.ovf = nullptr; // traceHitNI keeps the overflow entries in its own frame
   Ctx c(a.world, a.ren, a.cam, a.fb, stack);
   // adaptive accumulation: a converged render task is skipped as a whole (one CTA = one task; LocalFB.cpp:245-257)
-  const bool active = !a.fb.taskError || a.fb.taskError[(y >> 3) * (((uint32_t)a.fb.sizeX + 7u) >> 3) + (x >> 3)] > a.fb.errorThreshold;
-  if (active && x < (uint32_t)a.fb.sizeX && y < (uint32_t)a.fb.sizeY) {
+  const bool inImage = x < (uint32_t)a.fb.sizeX && y < (uint32_t)a.fb.sizeY;
+  if (inImage && (!a.fb.taskError || a.fb.taskError[(y >> 3) * (((uint32_t)a.fb.sizeX + 7u) >> 3) + (x >> 3)] > a.fb.errorThreshold)) {
     ScreenSample ss;
     defaultRenderPixel<RENDERER>(c, x, y, ss);
     accumulateSample(a.fb, x, y, ss);
@@ -718,19 +719,24 @@ __global__ void __launch_bounds__(64, OC_RENDER_MIN_BLOCKS) renderFrameKernel(co
 __global__ void traceKernel(const OcWorld *world, OcRayHit *rays, uint32_t n, int occlusion)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  __shared__ uint32_t s_stack[OC_STACK_SIZE * OC_MAX_BLOCK];
+  __shared__ uint32_t s_stack[OC_STACK_SHARED * OC_MAX_BLOCK];
   if (i >= n) return;
+  uint32_t ovf[OC_STACK_OVF];
   Stack stack;
   stack.base = s_stack + threadIdx.x;
   stack.stride = blockDim.x;
+  stack.ovf = ovf;
   OcRayHit rh = rays[i];
   Ray r;
   setRay(r, make_vec3f(rh.org[0], rh.org[1], rh.org[2]), make_vec3f(rh.dir[0], rh.dir[1], rh.dir[2]), rh.t0, rh.t);
   r.u = r.v = 0.f; r.Ng = make_vec3f(0.f);
   if (occlusion) {
-    if (traceWorld<true>(world, r, stack)) r.t = -INFINITY;
-  } else
-    traceWorld<false>(world, r, stack);
+    const Hit h = traceHit<1>(world, r.org, r.dir, r.t0, r.t, stack);
+    if (h.inst != OC_INVALID_ID) { r.t = -INFINITY; r.instID = h.inst; resolveHitIds(world, h.rec, h.inst, r.primID, r.geomID); }
+  } else {
+    const Hit h = traceHit<0>(world, r.org, r.dir, r.t0, r.t, stack);
+    resolveHit(world, h, r);
+  }
   rh.t = r.t; rh.u = r.u; rh.v = r.v; rh.Ng[0] = r.Ng.x; rh.Ng[1] = r.Ng.y; rh.Ng[2] = r.Ng.z;
   rh.primID = r.primID; rh.geomID = r.geomID; rh.instID = r.instID;
   rays[i] = rh;
@@ -746,7 +752,7 @@ namespace {
 struct PtProfile
 {
   bool enabled = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3]; // 0 TRACE, 1 SHADE, 2 FUSED
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3]; // 0 TRACE, 1 SHADE, 2 GEN
   std::vector<cudaEvent_t> pool;
   size_t poolNext = 0;
   cudaEvent_t get()
@@ -768,7 +774,7 @@ struct PtHost
   void *block = nullptr;
   size_t blockBytes = 0;
   int device = -1;
-  int traceBlocks = 0, shadeBlocks = 0, fusedBlocks = 0; // persistent grids (resident CTAs per SM x SM count)
+  int traceBlocks = 0, shadeBlocks[2] = {0, 0}, genBlocks = 0, traceVariant = 1; // persistent grids (resident CTAs per SM x SM count)
 } g_pt;
 
 size_t alignUp(size_t v) { return (v + 255) & ~size_t(255); }
@@ -779,7 +785,7 @@ int ptCarve(oc::PtScratch &s, uint32_t paths, uint32_t nls, bool needAcc, uint32
   const size_t P = paths;
   size_t bytes = 0;
   auto take = [&](size_t n) { const size_t o = bytes; bytes += alignUp(n); return o; };
-  size_t off[32];
+  size_t off[40];
   int k = 0;
   for (int i = 0; i < 8; i++) off[k++] = take(P * 16);       // rayO rayD hit0 hit1 thr con lastP lastN
   off[k++] = take(P * 4);                                    // hitInst
@@ -787,10 +793,12 @@ int ptCarve(oc::PtScratch &s, uint32_t paths, uint32_t nls, bool needAcc, uint32
   off[k++] = take(P * 4);                                    // flags
   for (int i = 0; i < 5; i++) off[k++] = take(P * 16);       // sZ sPos sFN sNrm sAlb
   for (int i = 0; i < 3; i++) off[k++] = take(P * 16 * nls); // shA shB shC
+  off[k++] = take(P * 8 * nls);                              // shHit
   for (int i = 0; i < 6; i++) off[k++] = take(needAcc ? P * 16 : 0);
   off[k++] = take(hasVol ? P * 16 : 0);                      // rnd
   off[k++] = take(hasVol ? P * 4 * nls : 0);                 // shT0
-  off[k++] = take(P * 4); off[k++] = take(P * 4);            // queues
+  for (int i = 0; i < 4; i++) off[k++] = take(P * 4);        // pathQ, contQ
+  for (int i = 0; i < 2; i++) off[k++] = take(P * 4 * nls);  // shadowQ
   off[k++] = take(numCounters * 4);
   int dev = 0;
   cudaGetDevice(&dev);
@@ -799,7 +807,7 @@ int ptCarve(oc::PtScratch &s, uint32_t paths, uint32_t nls, bool needAcc, uint32
     g_pt.block = nullptr; g_pt.blockBytes = 0;
     OC_TRY(cudaMalloc(&g_pt.block, bytes));
     g_pt.blockBytes = bytes; g_pt.device = dev;
-    g_pt.traceBlocks = g_pt.shadeBlocks = g_pt.fusedBlocks = 0;
+    g_pt.traceBlocks = 0;
   }
   char *b = (char *)g_pt.block;
   k = 0;
@@ -809,10 +817,13 @@ int ptCarve(oc::PtScratch &s, uint32_t paths, uint32_t nls, bool needAcc, uint32
   s.sZ = (float4 *)(b + off[k++]); s.sPos = (float4 *)(b + off[k++]); s.sFN = (float4 *)(b + off[k++]); s.sNrm = (float4 *)(b + off[k++]);
   s.sAlb = (float4 *)(b + off[k++]);
   s.shA = (float4 *)(b + off[k++]); s.shB = (float4 *)(b + off[k++]); s.shC = (float4 *)(b + off[k++]);
+  s.shHit = (uint2 *)(b + off[k++]);
   s.accC = (float4 *)(b + off[k++]); s.accZ = (float4 *)(b + off[k++]); s.accPos = (float4 *)(b + off[k++]); s.accFN = (float4 *)(b + off[k++]);
   s.accNrm = (float4 *)(b + off[k++]); s.accAlb = (float4 *)(b + off[k++]);
   s.rnd = (uint4 *)(b + off[k++]); s.shT0 = (float *)(b + off[k++]);
-  s.queue[0] = (uint32_t *)(b + off[k++]); s.queue[1] = (uint32_t *)(b + off[k++]);
+  s.pathQ[0] = (uint32_t *)(b + off[k++]); s.pathQ[1] = (uint32_t *)(b + off[k++]);
+  s.contQ[0] = (uint32_t *)(b + off[k++]); s.contQ[1] = (uint32_t *)(b + off[k++]);
+  s.shadowQ[0] = (uint32_t *)(b + off[k++]); s.shadowQ[1] = (uint32_t *)(b + off[k++]);
   s.counters = (uint32_t *)(b + off[k++]);
   s.nls = nls;
   return 0;
@@ -820,9 +831,13 @@ int ptCarve(oc::PtScratch &s, uint32_t paths, uint32_t nls, bool needAcc, uint32
 
 size_t ptBytesPerPath(uint32_t nls, bool needAcc, bool hasVol)
 {
-  return 8 * 16 + 16 + 5 * 16 + 48 * (size_t)nls + (needAcc ? 96 : 0) + 8 + (hasVol ? 16 + 4 * (size_t)nls : 0);
+  return 8 * 16 + 16 + 5 * 16 + (48 + 8 + 8) * (size_t)nls + (needAcc ? 96 : 0) + 16 + (hasVol ? 16 + 4 * (size_t)nls : 0);
 }
 
+// Launch sequence of one sample pass: GEN, then TRACE(d) / SHADE(d) for d = 0 .. maxDepth. Every stage d owns four
+// counters (path / continuation / shadow queue sizes, TRACE's fetch cursor), zeroed once per pass; SHADE(d) appends to the
+// queues of stage d+1 (ping-pong on the parity of d), TRACE(d+1) and SHADE(d+1) consume them. Launches whose queues turn
+// out empty exit at once.
 int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
 {
   using namespace oc;
@@ -836,25 +851,36 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
   k.a.ren.maxDepth = maxDepth;
   const uint32_t nls = k.nFirst > 0 ? k.nFirst : 1;
   const bool needAcc = fa.ren.spp > 1;
-  const uint32_t numCounters = 2 * (maxDepth + 2) + 1; // queue counters of every launch + the fused kernel's fetch cursor
+  const uint32_t numCounters = 4 * (maxDepth + 2);
   // batch the owned tiles so that the path state stays under ~1.5 GB (many light samples / 4K frames)
   const size_t budget = size_t(1536) << 20;
   const bool hasVol = fa.ren.worldHasVolumes != 0;
   k.vol = hasVol ? 1u : 0u;
   uint32_t tilesPerBatch = (uint32_t)std::max<size_t>(1, budget / (ptBytesPerPath(nls, needAcc, hasVol) * 4096));
   if (tilesPerBatch > ownedTiles) tilesPerBatch = ownedTiles;
+  if ((uint64_t)tilesPerBatch * 4096u * nls >= (1ull << 31))
+    return oc_set_error(cudaErrorInvalidValue, "pathtracer: lightSamples x paths per batch exceeds the shadow-ray id space");
   if (int rc = ptCarve(k.s, tilesPerBatch * 4096u, nls, needAcc, numCounters, hasVol)) return rc;
   if (!g_pt.traceBlocks) {
-    int dev = 0, sms = 148, a = 1, b = 1, f = 1;
+    int dev = 0, sms = 148, a = 1, b = 1, bv = 1, g = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, ptTraceKernel<false, false>, PT_TRACE_BLOCK, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ptShadeKernel<false>, 128, 0);
+    // A/B knobs: OSPCUDA_PT_REFILL = idle lanes that trigger a refill (4 / 8 / 16), OSPCUDA_PT_TRACE_BLOCKS = resident CTAs per SM
+    // the register budget is set for (5: no spills, 6: 80 registers)
+    const int refill = getenv("OSPCUDA_PT_REFILL") ? atoi(getenv("OSPCUDA_PT_REFILL")) : 8;
+    const int minb = getenv("OSPCUDA_PT_TRACE_BLOCKS") ? atoi(getenv("OSPCUDA_PT_TRACE_BLOCKS")) : 5;
+    g_pt.traceVariant = (refill <= 4 ? 0 : refill <= 8 ? 1 : 2) + (minb >= 6 ? 3 : 0);
+    if (minb >= 6) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, ptTraceKernel<8, 6>, PT_TRACE_BLOCK, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, ptTraceKernel<8, 5>, PT_TRACE_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ptShadeKernel<false>, PT_TRACE_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bv, ptShadeKernel<true>, PT_TRACE_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g, ptGenKernel<false>, 128, 0);
     g_pt.traceBlocks = sms * (a > 0 ? a : 1);
-    g_pt.shadeBlocks = sms * (b > 0 ? b : 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f, ptFusedKernel<false>, PT_TRACE_BLOCK, 0);
-    g_pt.fusedBlocks = sms * (f > 0 ? f : 1);
+    g_pt.shadeBlocks[0] = sms * (b > 0 ? b : 1);
+    g_pt.shadeBlocks[1] = sms * (bv > 0 ? bv : 1);
+    g_pt.genBlocks = sms * (g > 0 ? g : 1);
   }
+  auto C = [&](uint32_t stage, int which) { return k.s.counters + 4 * stage + which; }; // 0 path, 1 cont, 2 shadow, 3 cursor
   for (uint32_t tile0 = 0; tile0 < ownedTiles; tile0 += tilesPerBatch) {
     const uint32_t nt = std::min(tilesPerBatch, ownedTiles - tile0);
     k.firstTile = tile0;
@@ -862,48 +888,43 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
     for (int pass = 0; pass < fa.ren.spp; pass++) {
       k.pass = pass;
       OC_TRY(cudaMemsetAsync(k.s.counters, 0, numCounters * sizeof(uint32_t), st));
-      // queue / counter ping-pong: every launch reads (queue[q], counters[c]) and appends to (queue[q^1], counters[c+1])
-      uint32_t q = 0, c = 0;
-      k.depth = 0; k.qIn = nullptr; k.cntIn = nullptr; k.qOut = k.s.queue[q]; k.cntOut = k.s.counters + c;
+      k.depth = 0;
+      k.pathIn = k.contIn = k.shadowIn = nullptr; k.cntPathIn = k.cntContIn = k.cntShadowIn = nullptr;
+      k.contOut = k.shadowOut = nullptr; k.cntContOut = k.cntShadowOut = nullptr; k.fetchCursor = nullptr;
+      k.pathOut = k.s.pathQ[0]; k.cntPathOut = C(0, 0);
       {
-        ProfScope ps(0, st);
-        if (hasVol) ptTraceKernel<true, true><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
-        else ptTraceKernel<true, false><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+        ProfScope ps(2, st);
+        const int gb = (int)std::min<uint32_t>((uint32_t)g_pt.genBlocks, (k.numPaths + 127u) / 128u);
+        if (hasVol) ptGenKernel<true><<<gb, 128, 0, st>>>(k);
+        else ptGenKernel<false><<<gb, 128, 0, st>>>(k);
       }
       oc_count_launch();
-      auto next = [&]() { k.qIn = k.s.queue[q]; k.cntIn = k.s.counters + c; q ^= 1u; c++; k.qOut = k.s.queue[q]; k.cntOut = k.s.counters + c; };
-      // separate TRACE / SHADE launches while the frame is densely populated, fused one-launch-per-bounce kernels
-      // (with the finish-in-place tail mode) once Russian roulette has started to cull
-      static const int fusedFromEnv = getenv("OSPCUDA_PT_FUSED_FROM") ? atoi(getenv("OSPCUDA_PT_FUSED_FROM")) : -1;
-      const uint32_t fusedFrom = fusedFromEnv > 0 ? std::min<uint32_t>(maxDepth, (uint32_t)fusedFromEnv)
-                                                  : std::min<uint32_t>(maxDepth, (uint32_t)std::max(1, fa.ren.rouletteDepth + 1));
       for (uint32_t d = 0; d <= maxDepth; d++) {
         k.depth = d;
-        if (d > 0 && d >= fusedFrom) { // one launch carries every remaining path to its end
-          next();
-          k.fetchCursor = k.s.counters + (numCounters - 1);
-          {
-            ProfScope ps(2, st);
-            if (hasVol) ptFusedKernel<true><<<g_pt.fusedBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
-            else ptFusedKernel<false><<<g_pt.fusedBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
-          }
-          oc_count_launch();
-          break;
+        const uint32_t q = d & 1u;
+        // TRACE(d): at depth 0 the path queue GEN wrote is the continuation-ray queue
+        k.contIn = d == 0 ? k.s.pathQ[0] : k.s.contQ[q]; k.cntContIn = d == 0 ? C(0, 0) : C(d, 1);
+        k.shadowIn = d == 0 ? nullptr : k.s.shadowQ[q]; k.cntShadowIn = d == 0 ? nullptr : C(d, 2);
+        k.fetchCursor = C(d, 3);
+        {
+          ProfScope ps(0, st);
+          if (g_pt.traceVariant == 0) ptTraceKernel<4, 5><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+          else if (g_pt.traceVariant == 1) ptTraceKernel<8, 5><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+          else if (g_pt.traceVariant == 2) ptTraceKernel<16, 5><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+          else if (g_pt.traceVariant == 3) ptTraceKernel<4, 6><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+          else if (g_pt.traceVariant == 4) ptTraceKernel<8, 6><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+          else ptTraceKernel<16, 6><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
         }
-        if (d > 0) {
-          next();
-          {
-            ProfScope ps(0, st);
-            if (hasVol) ptTraceKernel<false, true><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
-            else ptTraceKernel<false, false><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
-          }
-          oc_count_launch();
-        }
-        next();
+        oc_count_launch();
+        // SHADE(d)
+        k.pathIn = k.s.pathQ[q]; k.cntPathIn = C(d, 0);
+        k.pathOut = k.s.pathQ[q ^ 1u]; k.cntPathOut = C(d + 1, 0);
+        k.contOut = k.s.contQ[q ^ 1u]; k.cntContOut = C(d + 1, 1);
+        k.shadowOut = k.s.shadowQ[q ^ 1u]; k.cntShadowOut = C(d + 1, 2);
         {
           ProfScope ps(1, st);
-          if (hasVol) ptShadeKernel<true><<<g_pt.shadeBlocks, 128, 0, st>>>(k);
-          else ptShadeKernel<false><<<g_pt.shadeBlocks, 128, 0, st>>>(k);
+          if (hasVol) ptShadeKernel<true><<<g_pt.shadeBlocks[1], PT_TRACE_BLOCK, 0, st>>>(k);
+          else ptShadeKernel<false><<<g_pt.shadeBlocks[0], PT_TRACE_BLOCK, 0, st>>>(k);
         }
         oc_count_launch();
       }

@@ -824,16 +824,17 @@ void World::commit()
     instDev.upload(inst.data(), inst.size() * sizeof(OcInstance));
     sh.instances = instDev.as<OcInstance>();
     sh.numInstances = (uint32_t)inst.size();
-    if (inst.size() > 4) {
+    if (!inst.empty()) {
+      // the top level is always a hierarchy (one instance per leaf), also over a single instance: traversal is one state
+      // machine that switches between it and the group hierarchies on one stack (intersect.cuh Traversal)
       checkCuda(ospcuda_bvh_build_tlas(instBounds.data(), (uint32_t)inst.size(), &sh.tlas), "TLAS build");
-      // the top level may use half of the traversal stack, the group BVH continues above what it holds (intersect.cuh)
       const uint32_t tlasNeed = ospcuda_bvh_last_stack_need();
       uint32_t groupNeed = 0;
       for (size_t i = 0; i < inst.size(); i++) {
         Instance *in = dynamic_cast<Instance *>(instances->objectAt(i));
         groupNeed = std::max(groupNeed, in->group->stackNeed);
       }
-      if (tlasNeed > OSPCUDA_TRAVERSAL_STACK / 2 || tlasNeed + groupNeed > OSPCUDA_TRAVERSAL_STACK)
+      if (tlasNeed + groupNeed > OSPCUDA_TRAVERSAL_STACK)
         throw std::runtime_error("ospray::World: instance hierarchy + group hierarchy are too deep for the traversal stack (need "
             + std::to_string(tlasNeed) + " + " + std::to_string(groupNeed) + " entries, the device keeps "
             + std::to_string(OSPCUDA_TRAVERSAL_STACK) + ")");

@@ -176,7 +176,11 @@ def test_images_match_oracle(osp, name):
     assert res["ok"], res
     rc = fb.ray_counts()
     assert rc[0] == int(want.counters[0])
-    assert abs(sum(rc) - int(want.counters.sum())) <= (0.05 if ptvol else 0.01) * int(want.counters.sum()) + 4
+    assert abs(rc[0] + rc[1] - int(want.counters[:2].sum())) <= (0.05 if ptvol else 0.01) * int(want.counters[:2].sum()) + 4
+    # shadow segments: the device asks ONE any-hit question per shadow ray and walks the reference's closest-hit loop only
+    # when the occluder it found is not opaque; which occluder that is depends on the hierarchy, so behind transparent
+    # surfaces it may count fewer segments than the reference (never noticeably more)
+    assert rc[2] <= 1.01 * int(want.counters[2]) + 4 and rc[2] >= (0.80 if ptvol else 0.85) * int(want.counters[2]) - 4
     # the committed golden fixture (oracle output at generation time) tells the same story
     np.testing.assert_allclose(got.reshape(-1, 4).mean(axis=0), GOLD[name + "/color"].reshape(-1, 4).mean(axis=0), rtol=0.03 if ptvol else 0.01, atol=1e-4)
     if ptvol:  # the first vertex is sampled before any rounding can tell the two sides apart: depth of most pixels is identical
@@ -291,9 +295,10 @@ def test_debug_renderer_refuses_unsupported_methods(osp):
 def test_builder_reports_the_traversal_stack_need(osp, abi):
     """every hierarchy the builder hands out states the deepest traversal stack it can ask for; the device compares it with
     OSPCUDA_TRAVERSAL_STACK at commit (a scene beyond it is refused instead of traversed with dropped subtrees)"""
-    abi.ospcuda_bvh_last_stack_need.restype = C.c_uint32
-    world, keep = T.to_ospray(T.box_mesh(6))      # 2592 triangles: 4-wide depth 6..7
-    need = abi.ospcuda_bvh_last_stack_need()
+    abi.ospcuda_bvh_peak_stack_need.restype = C.c_uint32
+    abi.ospcuda_bvh_peak_stack_need(1)
+    world, keep = T.to_ospray(T.box_mesh(6))      # 2592 triangles: 4-wide depth 6..7 (+ a one-leaf top level)
+    need = abi.ospcuda_bvh_peak_stack_need(1)
     assert 6 <= need <= 30, need
     world, keep = T.to_ospray(T.cornell_box())    # 34 records
-    assert 1 <= abi.ospcuda_bvh_last_stack_need() <= 12
+    assert 1 <= abi.ospcuda_bvh_peak_stack_need(1) <= 12

@@ -78,8 +78,8 @@ def main():
             import ctypes as C
             from ospray_b200 import lib_path
             LC = C.CDLL(lib_path("libospcuda.so"))
-            LC.ospcuda_bvh_last_stack_need.restype = C.c_uint32
-            stack_need = int(LC.ospcuda_bvh_last_stack_need())  # of the hierarchy built last (device limit: 48)
+            LC.ospcuda_bvh_peak_stack_need.restype = C.c_uint32
+            stack_need = int(LC.ospcuda_bvh_peak_stack_need(1))  # deepest of the hierarchies built for this scene (device limit: 64)
             cam, pose = T.make_camera(world, w, h)
             ren = T.make_renderer(ren_kind, pixelSamples=spp, **rp)
             fb = osp.FrameBuffer(w, h, osp.OSP_FB_SRGBA, osp.OSP_FB_COLOR | osp.OSP_FB_ACCUM | osp.OSP_FB_DEPTH)

@@ -30,6 +30,7 @@ enum : uint32_t {
   PT_STRAIGHT = 1u << 16, PT_SPECTRANS = 1u << 17, PT_FIRSTBOUNCE = 1u << 18, PT_DONE = 1u << 19, PT_HAS_SHADOW = 1u << 20
 };
 #define PT_SHADOW_RAY 0x80000000u // ray-queue ids: bit 31 set = shadow entry [slot * nls + i], clear = continuation ray of path `slot`
+#define PT_Q_DONE 0x40000000u     // path-queue entries: the path has ended and only waits for its shadow rays (no continuation ray)
 
 struct PtScratch
 {
@@ -51,7 +52,7 @@ struct PtScratch
   float4 *accC, *accZ, *accPos, *accFN, *accNrm, *accAlb; // ScreenSample sums across the spp passes (spp > 1)
   uint4 *rnd;     // worlds with volumes: pathState.randomSampler (PCG32 state lo/hi, stream)
   float *shT0;    // worlds with volumes: t0 of shadow entry [slot * nls + i] after the transparent-shadow loop
-  uint32_t *pathQ[2], *contQ[2], *shadowQ[2];
+  uint32_t *pathQ[2], *shadowQ[2];
   uint32_t *counters;
   uint32_t nls;
 };
@@ -65,11 +66,12 @@ struct PtArgs
   uint32_t nFirst, nIndirect;
   int pass;            // sample index within the pixel (0 .. spp-1)
   uint32_t depth;
-  // queues of this launch: SHADE reads pathIn and appends to pathOut / contOut / shadowOut; TRACE reads shadowIn then contIn
-  const uint32_t *pathIn, *contIn, *shadowIn;
-  const uint32_t *cntPathIn, *cntContIn, *cntShadowIn; // cntShadowIn == nullptr: no shadow rays (depth 0)
-  uint32_t *pathOut, *contOut, *shadowOut;
-  uint32_t *cntPathOut, *cntContOut, *cntShadowOut;
+  // queues of this launch: SHADE reads pathIn and appends to pathOut / shadowOut; TRACE reads shadowIn, then the
+  // continuation rays of the paths in pathIn (entries without PT_Q_DONE)
+  const uint32_t *pathIn, *shadowIn;
+  const uint32_t *cntPathIn, *cntShadowIn; // cntShadowIn == nullptr: no shadow rays (depth 0)
+  uint32_t *pathOut, *shadowOut;
+  uint32_t *cntPathOut, *cntShadowOut;
   uint32_t *fetchCursor;  // TRACE's work-fetch cursor (zeroed with the counters every pass)
   uint32_t vol;           // the world holds volumes (host copy of OcWorld.hasVolumes): free-path sampling + transmittance
 };
@@ -498,7 +500,7 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptTraceKernel(cons
 {
   __shared__ uint32_t s_stack[OC_STACK_SHARED * PT_TRACE_BLOCK];
   const uint32_t nS = k.cntShadowIn ? *k.cntShadowIn : 0u;
-  const uint32_t n = nS + *k.cntContIn;
+  const uint32_t n = nS + *k.cntPathIn;
   if (n == 0) return;
   uint32_t ovf[OC_STACK_OVF];
   Stack st;
@@ -533,26 +535,30 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptTraceKernel(cons
         if (take) {
           const uint32_t i = chunkNext + rank;
           const bool occ = i < nS;
-          if (occ) {
-            id = k.shadowIn[i];
-            const size_t e = id & ~PT_SHADOW_RAY;
-            src.po = s.shA + e; src.pd = s.shB + e;
-            nShadow++;
-          } else {
-            id = k.contIn[i - nS];
-            src.po = s.rayO + id; src.pd = s.rayD + id;
-            nCont++;
+          id = occ ? k.shadowIn[i] : k.pathIn[i - nS];
+          if (occ || !(id & PT_Q_DONE)) { // a path that has ended has no continuation ray: the lane stays idle until the next refill
+            if (occ) {
+              const size_t e = id & ~PT_SHADOW_RAY;
+              src.po = s.shA + e; src.pd = s.shB + e;
+              nShadow++;
+            } else {
+              src.po = s.rayO + id; src.pd = s.rayD + id;
+              nCont++;
+            }
+            const float4 o4 = *src.po, d4 = *src.pd;
+            active = tr.init(world, make_vec3f(o4.x, o4.y, o4.z), make_vec3f(d4.x, d4.y, d4.z), occ ? 0.f : d4.w, o4.w, occ);
+            fin = !active; // empty world / empty group: the ray misses, phase C says so
           }
-          const float4 o4 = *src.po, d4 = *src.pd;
-          active = tr.init(world, make_vec3f(o4.x, o4.y, o4.z), make_vec3f(d4.x, d4.y, d4.z), occ ? 0.f : d4.w, o4.w, occ);
-          fin = !active; // empty world / empty group: the ray misses, phase C says so
         }
         const uint32_t took = __ballot_sync(0xffffffffu, take);
         chunkNext += __popc(took);
         idle &= ~took;
       }
     }
-    if (__ballot_sync(0xffffffffu, active || fin) == 0) break; // nothing in flight and nothing left to fetch
+    if (__ballot_sync(0xffffffffu, active || fin) == 0) {
+      if (exhausted) break; // nothing in flight and nothing left to fetch
+      continue;             // the entries just taken held no ray (ended paths): take the next ones
+    }
     // ---- A: inner nodes ----
     if (active) {
       while (!tr.atLeaf())
@@ -580,9 +586,10 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptTraceKernel(cons
 }
 
 // ---- SHADE ------------------------------------------------------------------------------------------------------------
-// One path, one vertex: returns true when the path goes on to the next bounce (alive, or done with shadow rays pending).
-template <bool VOL>
-__device__ __forceinline__ bool ptShadeStep(const PtArgs &k, uint32_t p, uint32_t *stackBase, uint32_t &extraShadow)
+// One path, one vertex: returns 0 when the path finished here, 1 when it goes on to the next bounce, 2 when it has ended
+// but shadow rays of this vertex are pending (the next SHADE folds them in and finishes it).
+template <bool VOL, bool QUEUE>
+__device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uint32_t *stackBase, uint32_t &extraShadow)
 {
   const PtScratch &s = k.s;
   const OcRenderer &ren = k.a.ren;
@@ -631,7 +638,7 @@ __device__ __forceinline__ bool ptShadeStep(const PtArgs &k, uint32_t p, uint32_
     con4.x += L.x; con4.y += L.y; con4.z += L.z;
     if (flags & PT_DONE) {
       ptFinishPath(k, p, make_vec3f(con4.x, con4.y, con4.z), thr4.w);
-      return false;
+      return 0u;
     }
   }
   flags &= ~(PT_HAS_SHADOW | PT_DONE);
@@ -773,7 +780,7 @@ __device__ __forceinline__ bool ptShadeStep(const PtArgs &k, uint32_t p, uint32_
               valid = true;
               hasShadow = true;
               // a contribution that is not finite takes the closest-hit loop in the fold (the reference's arithmetic on it)
-              if (isfinite(unshaded.x) && isfinite(unshaded.y) && isfinite(unshaded.z))
+              if (QUEUE && isfinite(unshaded.x) && isfinite(unshaded.y) && isfinite(unshaded.z))
                 ptAppend(k.shadowOut, k.cntShadowOut, PT_SHADOW_RAY | (uint32_t)e);
             }
           }
@@ -815,7 +822,7 @@ __device__ __forceinline__ bool ptShadeStep(const PtArgs &k, uint32_t p, uint32_
 
   if (!alive && !hasShadow) {
     ptFinishPath(k, p, contribution, alpha);
-    return false;
+    return 0u;
   }
   s.thr[p] = make_float4(throughput.x, throughput.y, throughput.z, alpha);
   s.con[p] = make_float4(contribution.x, contribution.y, contribution.z, last.pdf_w);
@@ -823,28 +830,91 @@ __device__ __forceinline__ bool ptShadeStep(const PtArgs &k, uint32_t p, uint32_
     s.lastP[p] = make_float4(last.P.x, last.P.y, last.P.z, __uint_as_float(last.numLightSamples));
     s.lastN[p] = make_float4(last.Ns.x, last.Ns.y, last.Ns.z, 0.f);
     s.smp[p] = make_uint2(ld.revIndex, ld.scramble);
-    ptAppend(k.contOut, k.cntContOut, p);
   }
   s.flags[p] = ((depth + 1) & PT_DEPTH_MASK) | (scatteringEvents << PT_SCAT_SHIFT) | (straightPath ? PT_STRAIGHT : 0u)
       | (specularTransmissionPath ? PT_SPECTRANS : 0u) | (firstBounceLight ? PT_FIRSTBOUNCE : 0u) | (hasShadow ? PT_HAS_SHADOW : 0u)
       | (alive ? 0u : PT_DONE);
-  return true;
+  return alive ? 1u : 2u;
 }
 
-#ifndef PT_SHADE_MIN_BLOCKS
-#define PT_SHADE_MIN_BLOCKS 4
-#endif
-template <bool VOL>
-__global__ void __launch_bounds__(PT_TRACE_BLOCK, PT_SHADE_MIN_BLOCKS) ptShadeKernel(const __grid_constant__ PtArgs k)
+// MIN_BLOCKS: resident CTAs per SM the register budget is set for (4: 128 registers, 5: 96, 6: 80)
+template <bool VOL, int MIN_BLOCKS>
+__global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptShadeKernel(const __grid_constant__ PtArgs k)
 {
   __shared__ uint32_t s_stack[OC_STACK_SHARED * PT_TRACE_BLOCK]; // the out-of-line transparent-shadow loop walks the hierarchy
   const uint32_t n = *k.cntPathIn;
   uint32_t extraShadow = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t p = k.pathIn[i];
-    if (ptShadeStep<VOL>(k, p, s_stack + threadIdx.x, extraShadow)) ptAppend(k.pathOut, k.cntPathOut, p);
+    const uint32_t p = k.pathIn[i] & ~PT_Q_DONE;
+    const uint32_t r = ptShadeStep<VOL, true>(k, p, s_stack + threadIdx.x, extraShadow);
+    if (r) ptAppend(k.pathOut, k.cntPathOut, r == 2u ? (p | PT_Q_DONE) : p);
   }
   ptCountRays(k.a.fb, 0u, 0u, extraShadow);
+}
+
+// ---- TAIL -------------------------------------------------------------------------------------------------------------
+// Launched ONCE, at the depth where Russian roulette has thinned the frame out (PathTracer.cpp:33 rouletteDepth): from there
+// on a TRACE + SHADE launch pair per bounce costs two launch + drain latencies (~45 us) for a queue that holds less and
+// less (C1: 14 more bounces for 3 % of the frame's rays, tools/gpu_launchlist.sh). Paths are independent, so here every lane
+// carries ITS path to the end -- the shadow rays of the previous vertex, the continuation ray, the shade step, again -- and
+// fetches the next path of the queue when its own is finished. Latency-bound by construction (the longest path's bounces
+// are a serial chain); what it saves is the per-bounce launch pair.
+template <bool VOL>
+__global__ void __launch_bounds__(PT_TRACE_BLOCK, 3) ptTailKernel(const __grid_constant__ PtArgs k)
+{
+  __shared__ uint32_t s_stack[OC_STACK_SHARED * PT_TRACE_BLOCK];
+  const uint32_t n = *k.cntPathIn;
+  if (n == 0) return;
+  const PtScratch &s = k.s;
+  const OcWorld *world = k.a.world;
+  uint32_t *stackBase = s_stack + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t nShadow = 0, nCont = 0, extraShadow = 0;
+  bool alive = false;
+  uint32_t p = 0, state = 0; // state of the path held: 1 goes on, 2 ended with shadow rays pending
+  while (true) {
+    __syncwarp();
+    const uint32_t need = __ballot_sync(0xffffffffu, !alive);
+    if (need) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(k.fetchCursor, (uint32_t)__popc(need));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (!alive) {
+        const uint32_t i = base + __popc(need & ((1u << lane) - 1u));
+        if (i < n) {
+          const uint32_t e = k.pathIn[i];
+          p = e & ~PT_Q_DONE; state = (e & PT_Q_DONE) ? 2u : 1u; alive = true;
+        }
+      }
+      if (__ballot_sync(0xffffffffu, alive) == 0) break; // queue exhausted and every lane's path finished
+    }
+    if (alive) {
+      if (s.flags[p] & PT_HAS_SHADOW)
+        for (uint32_t j = 0; j < s.nls; j++) {
+          const size_t e = (size_t)p * s.nls + j;
+          const float4 c = s.shC[e];
+          if (c.w == 0.f || !(isfinite(c.x) && isfinite(c.y) && isfinite(c.z))) continue;
+          const float4 a = s.shA[e], b = s.shB[e];
+          const Hit h = traceHitNI<1>(world, make_vec3f(a.x, a.y, a.z), make_vec3f(b.x, b.y, b.z), 0.f, a.w, stackBase, PT_TRACE_BLOCK);
+          s.shHit[e] = make_uint2(h.rec, h.inst);
+          nShadow++;
+        }
+      if (state == 1u) {
+        const float4 o = s.rayO[p], d = s.rayD[p];
+        Ray r;
+        r.org = make_vec3f(o.x, o.y, o.z); r.dir = make_vec3f(d.x, d.y, d.z); r.t0 = d.w;
+        const Hit h = traceHitNI<0>(world, r.org, r.dir, d.w, o.w, stackBase, PT_TRACE_BLOCK);
+        resolveHit(world, h, r);
+        s.hit0[p] = make_float4(r.t, r.u, r.v, __uint_as_float(r.primID));
+        s.hit1[p] = make_float4(r.Ng.x, r.Ng.y, r.Ng.z, __uint_as_float(r.geomID));
+        s.hitInst[p] = r.instID;
+        nCont++;
+      }
+      state = ptShadeStep<VOL, false>(k, p, stackBase, extraShadow);
+      alive = state != 0u;
+    }
+  }
+  ptCountRays(k.a.fb, 0u, nCont, nShadow + extraShadow);
 }
 
 } // namespace oc

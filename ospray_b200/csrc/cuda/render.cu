@@ -752,7 +752,7 @@ namespace {
 struct PtProfile
 {
   bool enabled = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3]; // 0 TRACE, 1 SHADE, 2 GEN
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3]; // 0 TRACE, 1 SHADE, 2 GEN + TAIL
   std::vector<cudaEvent_t> pool;
   size_t poolNext = 0;
   cudaEvent_t get()
@@ -774,7 +774,7 @@ struct PtHost
   void *block = nullptr;
   size_t blockBytes = 0;
   int device = -1;
-  int traceBlocks = 0, shadeBlocks[2] = {0, 0}, genBlocks = 0, traceVariant = 1; // persistent grids (resident CTAs per SM x SM count)
+  int traceBlocks = 0, shadeBlocks[2] = {0, 0}, genBlocks = 0, tailBlocks = 0, traceVariant = 1, shadeVariant = 4; // persistent grids (resident CTAs per SM x SM count)
 } g_pt;
 
 size_t alignUp(size_t v) { return (v + 255) & ~size_t(255); }
@@ -797,7 +797,7 @@ int ptCarve(oc::PtScratch &s, uint32_t paths, uint32_t nls, bool needAcc, uint32
   for (int i = 0; i < 6; i++) off[k++] = take(needAcc ? P * 16 : 0);
   off[k++] = take(hasVol ? P * 16 : 0);                      // rnd
   off[k++] = take(hasVol ? P * 4 * nls : 0);                 // shT0
-  for (int i = 0; i < 4; i++) off[k++] = take(P * 4);        // pathQ, contQ
+  for (int i = 0; i < 2; i++) off[k++] = take(P * 4);        // pathQ
   for (int i = 0; i < 2; i++) off[k++] = take(P * 4 * nls);  // shadowQ
   off[k++] = take(numCounters * 4);
   int dev = 0;
@@ -822,7 +822,6 @@ int ptCarve(oc::PtScratch &s, uint32_t paths, uint32_t nls, bool needAcc, uint32
   s.accNrm = (float4 *)(b + off[k++]); s.accAlb = (float4 *)(b + off[k++]);
   s.rnd = (uint4 *)(b + off[k++]); s.shT0 = (float *)(b + off[k++]);
   s.pathQ[0] = (uint32_t *)(b + off[k++]); s.pathQ[1] = (uint32_t *)(b + off[k++]);
-  s.contQ[0] = (uint32_t *)(b + off[k++]); s.contQ[1] = (uint32_t *)(b + off[k++]);
   s.shadowQ[0] = (uint32_t *)(b + off[k++]); s.shadowQ[1] = (uint32_t *)(b + off[k++]);
   s.counters = (uint32_t *)(b + off[k++]);
   s.nls = nls;
@@ -831,7 +830,7 @@ int ptCarve(oc::PtScratch &s, uint32_t paths, uint32_t nls, bool needAcc, uint32
 
 size_t ptBytesPerPath(uint32_t nls, bool needAcc, bool hasVol)
 {
-  return 8 * 16 + 16 + 5 * 16 + (48 + 8 + 8) * (size_t)nls + (needAcc ? 96 : 0) + 16 + (hasVol ? 16 + 4 * (size_t)nls : 0);
+  return 8 * 16 + 16 + 5 * 16 + (48 + 8 + 8) * (size_t)nls + (needAcc ? 96 : 0) + 8 + (hasVol ? 16 + 4 * (size_t)nls : 0);
 }
 
 // Launch sequence of one sample pass: GEN, then TRACE(d) / SHADE(d) for d = 0 .. maxDepth. Every stage d owns four
@@ -872,14 +871,25 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
     g_pt.traceVariant = (refill <= 4 ? 0 : refill <= 8 ? 1 : 2) + (minb >= 6 ? 3 : 0);
     if (minb >= 6) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, ptTraceKernel<8, 6>, PT_TRACE_BLOCK, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, ptTraceKernel<8, 5>, PT_TRACE_BLOCK, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ptShadeKernel<false>, PT_TRACE_BLOCK, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bv, ptShadeKernel<true>, PT_TRACE_BLOCK, 0);
+    const int smb = getenv("OSPCUDA_PT_SHADE_BLOCKS") ? atoi(getenv("OSPCUDA_PT_SHADE_BLOCKS")) : 4;
+    g_pt.shadeVariant = smb <= 4 ? 4 : smb == 5 ? 5 : 6;
+    if (g_pt.shadeVariant == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ptShadeKernel<false, 4>, PT_TRACE_BLOCK, 0);
+    else if (g_pt.shadeVariant == 5) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ptShadeKernel<false, 5>, PT_TRACE_BLOCK, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ptShadeKernel<false, 6>, PT_TRACE_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bv, ptShadeKernel<true, 4>, PT_TRACE_BLOCK, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g, ptGenKernel<false>, 128, 0);
     g_pt.traceBlocks = sms * (a > 0 ? a : 1);
     g_pt.shadeBlocks[0] = sms * (b > 0 ? b : 1);
     g_pt.shadeBlocks[1] = sms * (bv > 0 ? bv : 1);
     g_pt.genBlocks = sms * (g > 0 ? g : 1);
+    int t = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t, ptTailKernel<false>, PT_TRACE_BLOCK, 0);
+    g_pt.tailBlocks = sms * (t > 0 ? t : 1);
   }
+  // depth from which the tail kernel takes over: two bounces after Russian roulette starts (OSPCUDA_PT_TAIL_FROM overrides,
+  // 0 = never)
+  static const int tailEnv = getenv("OSPCUDA_PT_TAIL_FROM") ? atoi(getenv("OSPCUDA_PT_TAIL_FROM")) : -1;
+  const uint32_t tailFrom = tailEnv == 0 ? 0xffffffffu : tailEnv > 0 ? (uint32_t)tailEnv : (uint32_t)std::max(1, fa.ren.rouletteDepth + 2);
   auto C = [&](uint32_t stage, int which) { return k.s.counters + 4 * stage + which; }; // 0 path, 1 cont, 2 shadow, 3 cursor
   for (uint32_t tile0 = 0; tile0 < ownedTiles; tile0 += tilesPerBatch) {
     const uint32_t nt = std::min(tilesPerBatch, ownedTiles - tile0);
@@ -889,8 +899,8 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
       k.pass = pass;
       OC_TRY(cudaMemsetAsync(k.s.counters, 0, numCounters * sizeof(uint32_t), st));
       k.depth = 0;
-      k.pathIn = k.contIn = k.shadowIn = nullptr; k.cntPathIn = k.cntContIn = k.cntShadowIn = nullptr;
-      k.contOut = k.shadowOut = nullptr; k.cntContOut = k.cntShadowOut = nullptr; k.fetchCursor = nullptr;
+      k.pathIn = k.shadowIn = nullptr; k.cntPathIn = k.cntShadowIn = nullptr;
+      k.shadowOut = nullptr; k.cntShadowOut = nullptr; k.fetchCursor = nullptr;
       k.pathOut = k.s.pathQ[0]; k.cntPathOut = C(0, 0);
       {
         ProfScope ps(2, st);
@@ -902,8 +912,19 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
       for (uint32_t d = 0; d <= maxDepth; d++) {
         k.depth = d;
         const uint32_t q = d & 1u;
-        // TRACE(d): at depth 0 the path queue GEN wrote is the continuation-ray queue
-        k.contIn = d == 0 ? k.s.pathQ[0] : k.s.contQ[q]; k.cntContIn = d == 0 ? C(0, 0) : C(d, 1);
+        if (d > 0 && d >= tailFrom) { // one launch carries every remaining path to its end
+          k.pathIn = k.s.pathQ[q]; k.cntPathIn = C(d, 0);
+          k.fetchCursor = C(d, 3);
+          {
+            ProfScope ps(2, st);
+            if (hasVol) ptTailKernel<true><<<g_pt.tailBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+            else ptTailKernel<false><<<g_pt.tailBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+          }
+          oc_count_launch();
+          break;
+        }
+        // TRACE(d): the shadow rays emitted at vertex d-1, then the continuation rays of the paths in the path queue
+        k.pathIn = k.s.pathQ[q]; k.cntPathIn = C(d, 0);
         k.shadowIn = d == 0 ? nullptr : k.s.shadowQ[q]; k.cntShadowIn = d == 0 ? nullptr : C(d, 2);
         k.fetchCursor = C(d, 3);
         {
@@ -916,15 +937,15 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
           else ptTraceKernel<16, 6><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
         }
         oc_count_launch();
-        // SHADE(d)
-        k.pathIn = k.s.pathQ[q]; k.cntPathIn = C(d, 0);
+        // SHADE(d): same path queue in, queues of stage d+1 out
         k.pathOut = k.s.pathQ[q ^ 1u]; k.cntPathOut = C(d + 1, 0);
-        k.contOut = k.s.contQ[q ^ 1u]; k.cntContOut = C(d + 1, 1);
         k.shadowOut = k.s.shadowQ[q ^ 1u]; k.cntShadowOut = C(d + 1, 2);
         {
           ProfScope ps(1, st);
-          if (hasVol) ptShadeKernel<true><<<g_pt.shadeBlocks[1], PT_TRACE_BLOCK, 0, st>>>(k);
-          else ptShadeKernel<false><<<g_pt.shadeBlocks[0], PT_TRACE_BLOCK, 0, st>>>(k);
+          if (hasVol) ptShadeKernel<true, 4><<<g_pt.shadeBlocks[1], PT_TRACE_BLOCK, 0, st>>>(k);
+          else if (g_pt.shadeVariant == 4) ptShadeKernel<false, 4><<<g_pt.shadeBlocks[0], PT_TRACE_BLOCK, 0, st>>>(k);
+          else if (g_pt.shadeVariant == 5) ptShadeKernel<false, 5><<<g_pt.shadeBlocks[0], PT_TRACE_BLOCK, 0, st>>>(k);
+          else ptShadeKernel<false, 6><<<g_pt.shadeBlocks[0], PT_TRACE_BLOCK, 0, st>>>(k);
         }
         oc_count_launch();
       }

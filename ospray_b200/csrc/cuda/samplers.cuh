@@ -115,17 +115,18 @@ __device__ __forceinline__ uint32_t interleaveZOrder16(uint32_t x, uint32_t y)
 template <int DIMS>
 __device__ __forceinline__ void Sobol_revSample(uint32_t revIndex, uint32_t (&r)[4])
 {
-  // same XOR of matrix columns as the reference's bit-serial loop, visiting set bits only (clz)
-  r[0] = r[1] = r[2] = r[3] = 0;
-  while (revIndex) {
-    const uint32_t b = __clz(revIndex); // column index = position from the MSB
-    revIndex &= ~(0x80000000u >> b);
-    const uint4 col = __ldg(reinterpret_cast<const uint4 *>(kSobolRev) + b);
-    r[0] ^= col.x;
-    if (DIMS > 1) r[1] ^= col.y;
-    if (DIMS > 2) r[2] ^= col.z;
-    if (DIMS > 3) r[3] ^= col.w;
+  // The reference XORs one matrix column per set bit of the index (bit-serial loop). The map is linear over GF(2): the
+  // same value is the XOR of four table entries, one per byte of the index (kSobolRevByte, tools/gen_tables.py) -- no
+  // data-dependent trip count, so the lanes of a warp stay together. Zero bytes (indices masked to 16 bits) are skipped.
+  const uint4 *tab = reinterpret_cast<const uint4 *>(kSobolRevByte);
+  uint4 a = __ldg(tab + (revIndex >> 24));
+  const uint4 b = __ldg(tab + 256 + ((revIndex >> 16) & 0xffu));
+  a.x ^= b.x; a.y ^= b.y; a.z ^= b.z; a.w ^= b.w;
+  if (revIndex & 0xffffu) {
+    const uint4 c = __ldg(tab + 512 + ((revIndex >> 8) & 0xffu)), d = __ldg(tab + 768 + (revIndex & 0xffu));
+    a.x ^= c.x ^ d.x; a.y ^= c.y ^ d.y; a.z ^= c.z ^ d.z; a.w ^= c.w ^ d.w;
   }
+  r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
 }
 
 // ---- LDSampler (random.ih:283-394) -----------------------------------------------------

@@ -470,6 +470,19 @@ struct Traversal
     uint4 ch;
     const uint32_t mask = nodeTest(nodes + cur, org, rdir, t0, h.t, tn, ch);
     if (mask == 0) return popNext(world, src, st);
+    if (MODE == 1) { // any-hit walks of the megakernels: nearest child next, the others in node order (no sort: C3 101 -> 87 ms)
+      const uint32_t chs[4] = {ch.x, ch.y, ch.z, ch.w};
+      int best = 0;
+      float bestT = INFINITY;
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (((mask >> i) & 1u) && tn[i] < bestT) { bestT = tn[i]; best = i; }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (((mask >> i) & 1u) && i != best) st.push(sp, chs[i]);
+      cur = chs[best];
+      return true;
+    }
     float k0 = (mask & 1u) ? tn[0] : INFINITY, k1 = (mask & 2u) ? tn[1] : INFINITY, k2 = (mask & 4u) ? tn[2] : INFINITY,
           k3 = (mask & 8u) ? tn[3] : INFINITY;
     uint32_t c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
@@ -507,17 +520,25 @@ struct Traversal
   }
 };
 
-// a whole walk, for code that traces one ray at a time
+// a whole walk, for code that traces one ray at a time (megakernels, batch queries, the tail). The lanes that arrive here
+// together step together: every round the warp counts how many of them stand at an inner node and how many at a leaf and
+// takes the step the majority wants (one node test, or one leaf), the others wait. Left to itself the compiler lets every
+// lane run ahead on its own and the node / primitive tests execute a few lanes at a time.
 template <int MODE>
 __device__ __forceinline__ Hit traceHit(const OcWorld *__restrict__ world, vec3f org, vec3f dir, float t0, float t1, const Stack &st)
 {
   RayRegs src; src.o = org; src.d = dir;
   Traversal<MODE> tr;
-  if (tr.init(world, org, dir, t0, t1, MODE == 1)) {
-    bool go = true;
-    while (go) {
-      while (go && !tr.atLeaf()) go = tr.inner(world, src, st);
-      if (go) go = tr.leaf(world, src, st);
+  const unsigned together = __activemask();
+  bool go = tr.init(world, org, dir, t0, t1, MODE == 1);
+  while (true) {
+    const bool wantInner = go && !tr.atLeaf();
+    const uint32_t nGo = __popc(__ballot_sync(together, go)), nInner = __popc(__ballot_sync(together, wantInner));
+    if (nGo == 0) break;
+    if (2 * nInner >= nGo) {
+      if (wantInner) go = tr.inner(world, src, st);
+    } else {
+      if (go && !wantInner) go = tr.leaf(world, src, st);
     }
   }
   return tr.h;

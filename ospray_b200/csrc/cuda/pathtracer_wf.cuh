@@ -481,17 +481,15 @@ __global__ void __launch_bounds__(128) ptGenKernel(const __grid_constant__ PtArg
 }
 
 // ---- TRACE ------------------------------------------------------------------------------------------------------------
-// Persistent-thread ray queue. The rays of one bounce -- the shadow queue, then the continuation queue -- form one index
-// space [0, n). A warp reserves PT_TRACE_CHUNK consecutive indices at a time (one atomic on the fetch cursor per chunk) and
-// hands them to its lanes. The walk runs in warp-synchronous rounds of three phases:
-//   A  every lane with an inner node descends until it holds a leaf        (Traversal::inner, node tests side by side)
-//   B  every lane with a leaf works it off and pops                        (Traversal::leaf, primitive tests side by side)
-//   C  lanes whose walk ended write their result
-// with __syncwarp() between them, so that the lanes of a warp do the same kind of work at the same time however different
-// their rays are. Before a round, once REFILL_IDLE lanes are idle they take the next rays of the chunk: the warp stays
-// filled while individual rays take anything from 2 to 200 steps. A lane holds nothing but the walk: instance-space ray,
-// compact hit, stack position; the world-space ray is re-read from the queue's arrays when the walk leaves a transformed
-// instance, the ids / geometric normal of the hit are read from its leaf record in phase C.
+// Persistent-thread ray queue. The rays of one bounce -- the shadow queue, then the continuation rays of the path queue --
+// form one index space [0, n). A warp reserves PT_TRACE_CHUNK consecutive indices at a time (one atomic on the fetch cursor
+// per chunk) and hands them to its lanes. The walk runs in warp-synchronous steps: every round the warp counts how many of
+// its lanes stand at an inner node and how many at a leaf and takes the step the majority wants -- one node test
+// (Traversal::inner) or one leaf (Traversal::leaf) -- side by side; the others wait for their turn. Lanes whose walk has
+// ended stay idle until REFILL_IDLE of them have gathered: then they write their results together and take the next rays
+// of the chunk, so the warp stays filled while individual rays take anything from 2 to 200 steps. A lane holds nothing but
+// the walk: instance-space ray, compact hit, stack position; the world-space ray is re-read from the queue's arrays when
+// the walk leaves a transformed instance, the ids / geometric normal of the hit are read from its leaf record at the end.
 #ifndef PT_TRACE_CHUNK
 #define PT_TRACE_CHUNK 128u
 #endif
@@ -510,17 +508,31 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptTraceKernel(cons
   const uint32_t lane = threadIdx.x & 31u, ltMask = (1u << lane) - 1u;
   uint32_t chunkNext = 0, chunkEnd = 0; // warp-uniform
   bool exhausted = false;               // warp-uniform: the cursor has run past the queue
-  bool active = false;
+  bool active = false, fin = false;     // fin: the walk has ended, the result is not written yet
   uint32_t id = 0;
   uint32_t nShadow = 0, nCont = 0;
   Traversal<2> tr;
   RayMem src;
   src.po = src.pd = nullptr;
   while (true) {
-    bool fin = false; // this lane's walk ended in this round
     uint32_t idle = ~__ballot_sync(0xffffffffu, active);
-    if (!exhausted && __popc(idle) >= REFILL_IDLE) {
-      while (idle) {
+    if (__popc(idle) >= REFILL_IDLE) {
+      // ---- results of the walks that ended since the last time ----
+      if (fin) {
+        fin = false;
+        if (id & PT_SHADOW_RAY) s.shHit[id & ~PT_SHADOW_RAY] = make_uint2(tr.h.rec, tr.h.inst);
+        else {
+          Ray r;
+          const float4 o4 = *src.po, d4 = *src.pd;
+          r.org = make_vec3f(o4.x, o4.y, o4.z); r.dir = make_vec3f(d4.x, d4.y, d4.z); r.t0 = d4.w;
+          resolveHit(world, tr.h, r);
+          s.hit0[id] = make_float4(r.t, r.u, r.v, __uint_as_float(r.primID));
+          s.hit1[id] = make_float4(r.Ng.x, r.Ng.y, r.Ng.z, __uint_as_float(r.geomID));
+          s.hitInst[id] = r.instID;
+        }
+      }
+      // ---- the idle lanes take the next rays ----
+      while (idle && !exhausted) {
         if (chunkNext == chunkEnd) {
           uint32_t base = 0;
           if (lane == 0) base = atomicAdd(k.fetchCursor, PT_TRACE_CHUNK);
@@ -547,7 +559,7 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptTraceKernel(cons
             }
             const float4 o4 = *src.po, d4 = *src.pd;
             active = tr.init(world, make_vec3f(o4.x, o4.y, o4.z), make_vec3f(d4.x, d4.y, d4.z), occ ? 0.f : d4.w, o4.w, occ);
-            fin = !active; // empty world / empty group: the ray misses, phase C says so
+            fin = !active; // empty world / empty group: the ray misses, written with the next batch of results
           }
         }
         const uint32_t took = __ballot_sync(0xffffffffu, take);
@@ -555,31 +567,19 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptTraceKernel(cons
         idle &= ~took;
       }
     }
-    if (__ballot_sync(0xffffffffu, active || fin) == 0) {
-      if (exhausted) break; // nothing in flight and nothing left to fetch
-      continue;             // the entries just taken held no ray (ended paths): take the next ones
+    const uint32_t nActive = __popc(__ballot_sync(0xffffffffu, active));
+    if (nActive == 0) {
+      if (__ballot_sync(0xffffffffu, fin)) continue; // rays answered on the spot: write them, take the next
+      if (exhausted) break;                           // nothing in flight, nothing left to fetch
+      continue;                                       // the entries just taken held no ray (ended paths): take the next
     }
-    // ---- A: inner nodes ----
-    if (active) {
-      while (!tr.atLeaf())
-        if (!tr.inner(world, src, st)) { fin = true; active = false; break; }
-    }
-    __syncwarp();
-    // ---- B: leaves ----
-    if (active && !tr.leaf(world, src, st)) { fin = true; active = false; }
-    __syncwarp();
-    // ---- C: results ----
-    if (fin) {
-      if (id & PT_SHADOW_RAY) s.shHit[id & ~PT_SHADOW_RAY] = make_uint2(tr.h.rec, tr.h.inst);
-      else {
-        Ray r;
-        const float4 o4 = *src.po, d4 = *src.pd;
-        r.org = make_vec3f(o4.x, o4.y, o4.z); r.dir = make_vec3f(d4.x, d4.y, d4.z); r.t0 = d4.w;
-        resolveHit(world, tr.h, r);
-        s.hit0[id] = make_float4(r.t, r.u, r.v, __uint_as_float(r.primID));
-        s.hit1[id] = make_float4(r.Ng.x, r.Ng.y, r.Ng.z, __uint_as_float(r.geomID));
-        s.hitInst[id] = r.instID;
-      }
+    // ---- one step, the kind most lanes want ----
+    const bool wantInner = active && !tr.atLeaf();
+    const uint32_t nInner = __popc(__ballot_sync(0xffffffffu, wantInner));
+    if (2u * nInner >= nActive) {
+      if (wantInner && !tr.inner(world, src, st)) { active = false; fin = true; }
+    } else {
+      if (active && !wantInner && !tr.leaf(world, src, st)) { active = false; fin = true; }
     }
   }
   ptCountRays(k.a.fb, 0u, k.depth == 0 ? 0u : nCont, nShadow);

@@ -866,11 +866,12 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // A/B knobs: OSPCUDA_PT_REFILL = idle lanes that trigger a refill (4 / 8 / 16), OSPCUDA_PT_TRACE_BLOCKS = resident CTAs per SM
     // the register budget is set for (5: no spills, 6: 80 registers)
-    const int refill = getenv("OSPCUDA_PT_REFILL") ? atoi(getenv("OSPCUDA_PT_REFILL")) : 8;
+    const int refill = getenv("OSPCUDA_PT_REFILL") ? atoi(getenv("OSPCUDA_PT_REFILL")) : 16;
     const int minb = getenv("OSPCUDA_PT_TRACE_BLOCKS") ? atoi(getenv("OSPCUDA_PT_TRACE_BLOCKS")) : 5;
-    g_pt.traceVariant = (refill <= 4 ? 0 : refill <= 8 ? 1 : 2) + (minb >= 6 ? 3 : 0);
-    if (minb >= 6) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, ptTraceKernel<8, 6>, PT_TRACE_BLOCK, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, ptTraceKernel<8, 5>, PT_TRACE_BLOCK, 0);
+    if (minb >= 6) g_pt.traceVariant = refill <= 16 ? 4 : 5;
+    else g_pt.traceVariant = refill <= 8 ? 0 : refill <= 16 ? 1 : refill <= 24 ? 2 : 3;
+    if (minb >= 6) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, ptTraceKernel<16, 6>, PT_TRACE_BLOCK, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, ptTraceKernel<16, 5>, PT_TRACE_BLOCK, 0);
     const int smb = getenv("OSPCUDA_PT_SHADE_BLOCKS") ? atoi(getenv("OSPCUDA_PT_SHADE_BLOCKS")) : 4;
     g_pt.shadeVariant = smb <= 4 ? 4 : smb == 5 ? 5 : 6;
     if (g_pt.shadeVariant == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ptShadeKernel<false, 4>, PT_TRACE_BLOCK, 0);
@@ -929,12 +930,14 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
         k.fetchCursor = C(d, 3);
         {
           ProfScope ps(0, st);
-          if (g_pt.traceVariant == 0) ptTraceKernel<4, 5><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
-          else if (g_pt.traceVariant == 1) ptTraceKernel<8, 5><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
-          else if (g_pt.traceVariant == 2) ptTraceKernel<16, 5><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
-          else if (g_pt.traceVariant == 3) ptTraceKernel<4, 6><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
-          else if (g_pt.traceVariant == 4) ptTraceKernel<8, 6><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
-          else ptTraceKernel<16, 6><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+          switch (g_pt.traceVariant) {
+          case 0: ptTraceKernel<8, 5><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k); break;
+          case 1: ptTraceKernel<16, 5><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k); break;
+          case 2: ptTraceKernel<24, 5><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k); break;
+          case 3: ptTraceKernel<32, 5><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k); break;
+          case 4: ptTraceKernel<16, 6><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k); break;
+          default: ptTraceKernel<24, 6><<<g_pt.traceBlocks, PT_TRACE_BLOCK, 0, st>>>(k); break;
+          }
         }
         oc_count_launch();
         // SHADE(d): same path queue in, queues of stage d+1 out

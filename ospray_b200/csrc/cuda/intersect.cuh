@@ -315,30 +315,34 @@ __device__ __forceinline__ bool intersectRecordH(vec3f org, vec3f dir, float t0,
 }
 
 // ---- wide-BVH traversal -------------------------------------------------------------------
-// slab test of one 128-byte node against the ray: 7 x LDG.128, conservative (far side padded
-// by 2 ulp) so that the BVH never culls a primitive the exact test would accept.
+// slab test of one 128-byte node against the ray: 7 x LDG.128, conservative (far side padded by 2 ulp) so that the BVH
+// never culls a primitive the exact test would accept. The planes the ray enters / leaves through are picked by the sign of
+// the direction when the node is LOADED (lo and hi rows sit 16 bytes apart), not by min / max afterwards: (lo - o) * rd <=
+// (hi - o) * rd for rd >= 0 by monotonic rounding, so the values are the ones min / max would have kept -- 6 instructions
+// less per child.
 __device__ __forceinline__ uint32_t nodeTest(const OcNode4 *node, vec3f org, vec3f rdir, float t0, float t1,
     float (&tnear)[4], uint4 &child)
 {
   const float4 *n = reinterpret_cast<const float4 *>(node);
-  const float4 lox = __ldg(n + 0), hix = __ldg(n + 1), loy = __ldg(n + 2), hiy = __ldg(n + 3),
-               loz = __ldg(n + 4), hiz = __ldg(n + 5);
+  const int sx = rdir.x < 0.f, sy = rdir.y < 0.f, sz = rdir.z < 0.f;
+  const float4 nx = __ldg(n + sx), fx = __ldg(n + (sx ^ 1)), ny = __ldg(n + 2 + sy), fy = __ldg(n + 2 + (sy ^ 1)),
+               nz = __ldg(n + 4 + sz), fz = __ldg(n + 4 + (sz ^ 1));
   child = __ldg(reinterpret_cast<const uint4 *>(n + 6));
   uint32_t mask = 0;
-#define OC_SLAB(i, LX, HX, LY, HY, LZ, HZ, CH)                                                   \
+#define OC_SLAB(i, NX, FX, NY, FY, NZ, FZ, CH)                                                   \
   {                                                                                              \
-    const float ax = (LX - org.x) * rdir.x, bx = (HX - org.x) * rdir.x;                          \
-    const float ay = (LY - org.y) * rdir.y, by = (HY - org.y) * rdir.y;                          \
-    const float az = (LZ - org.z) * rdir.z, bz = (HZ - org.z) * rdir.z;                          \
-    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), t0));       \
-    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), t1)) * 1.0000005f; \
+    const float ax = (NX - org.x) * rdir.x, bx = (FX - org.x) * rdir.x;                          \
+    const float ay = (NY - org.y) * rdir.y, by = (FY - org.y) * rdir.y;                          \
+    const float az = (NZ - org.z) * rdir.z, bz = (FZ - org.z) * rdir.z;                          \
+    const float tn = fmaxf(fmaxf(ax, ay), fmaxf(az, t0));                                        \
+    const float tf = fminf(fminf(bx, by), fminf(bz, t1)) * 1.0000005f;                           \
     tnear[i] = tn;                                                                               \
     if (CH != OC_INVALID_ID && tn <= tf) mask |= 1u << i;                                        \
   }
-  OC_SLAB(0, lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, child.x)
-  OC_SLAB(1, lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, child.y)
-  OC_SLAB(2, lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, child.z)
-  OC_SLAB(3, lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, child.w)
+  OC_SLAB(0, nx.x, fx.x, ny.x, fy.x, nz.x, fz.x, child.x)
+  OC_SLAB(1, nx.y, fx.y, ny.y, fy.y, nz.y, fz.y, child.y)
+  OC_SLAB(2, nx.z, fx.z, ny.z, fy.z, nz.z, fz.z, child.z)
+  OC_SLAB(3, nx.w, fx.w, ny.w, fy.w, nz.w, fz.w, child.w)
 #undef OC_SLAB
   return mask;
 }
@@ -470,7 +474,8 @@ struct Traversal
     uint4 ch;
     const uint32_t mask = nodeTest(nodes + cur, org, rdir, t0, h.t, tn, ch);
     if (mask == 0) return popNext(world, src, st);
-    if (MODE == 1) { // any-hit walks of the megakernels: nearest child next, the others in node order (no sort: C3 101 -> 87 ms)
+    if (occlusion()) { // any-hit walks: nearest child next, the others in node order (no sort; queue kernels fetch shadow rays
+                       // before continuation rays, so warps are of one kind except at the boundary)
       const uint32_t chs[4] = {ch.x, ch.y, ch.z, ch.w};
       int best = 0;
       float bestT = INFINITY;

@@ -74,6 +74,7 @@ struct PtArgs
   uint32_t *cntPathOut, *cntShadowOut;
   uint32_t *fetchCursor;  // TRACE's work-fetch cursor (zeroed with the counters every pass)
   uint32_t vol;           // the world holds volumes (host copy of OcWorld.hasVolumes): free-path sampling + transmittance
+  uint32_t shadowT0InB;   // any-hit rays start at shB[e].w instead of 0 (ao renderer: the ambient-occlusion rays start at dg.epsilon)
 };
 
 __device__ __forceinline__ void ptAppend(uint32_t *q, uint32_t *cnt, uint32_t p)
@@ -112,7 +113,8 @@ __device__ __forceinline__ void ptSamplerParams(const PtArgs &k, uint32_t ix, ui
   }
 }
 
-// a path ended: clamp, fold into the pixel's ScreenSample (spp > 1) and accumulate into the framebuffer
+// a path ended: clamp (pathtracer), fold into the pixel's ScreenSample (spp > 1) and accumulate into the framebuffer
+template <bool PT = true>
 __device__ __forceinline__ void ptFinishPath(const PtArgs &k, uint32_t p, vec3f contribution, float alpha)
 {
   const PtScratch &s = k.s;
@@ -122,8 +124,10 @@ __device__ __forceinline__ void ptFinishPath(const PtArgs &k, uint32_t p, vec3f 
   ScreenSample sm;
   sm.rgb = contribution;
   sm.alpha = alpha;
-  if (isnan(contribution.x) || isnan(contribution.y) || isnan(contribution.z)) { sm.rgb = make_vec3f(0.f); sm.alpha = 1.0f; }
-  sm.rgb = vmin(sm.rgb, make_vec3f(k.a.ren.maxRadiance));
+  if (PT) {
+    if (isnan(contribution.x) || isnan(contribution.y) || isnan(contribution.z)) { sm.rgb = make_vec3f(0.f); sm.alpha = 1.0f; }
+    sm.rgb = vmin(sm.rgb, make_vec3f(k.a.ren.maxRadiance));
+  }
   const float4 z = s.sZ[p];
   sm.z = z.x; sm.primID = __float_as_uint(z.y); sm.geomID = __float_as_uint(z.z); sm.instID = __float_as_uint(z.w);
   sm.position = sm.firstNormal = sm.normal = sm.albedo = make_vec3f(0.f);
@@ -558,7 +562,7 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptTraceKernel(cons
               nCont++;
             }
             const float4 o4 = *src.po, d4 = *src.pd;
-            active = tr.init(world, make_vec3f(o4.x, o4.y, o4.z), make_vec3f(d4.x, d4.y, d4.z), occ ? 0.f : d4.w, o4.w, occ);
+            active = tr.init(world, make_vec3f(o4.x, o4.y, o4.z), make_vec3f(d4.x, d4.y, d4.z), (occ && !k.shadowT0InB) ? 0.f : d4.w, o4.w, occ);
             fin = !active; // empty world / empty group: the ray misses, written with the next batch of results
           }
         }
@@ -915,6 +919,182 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, 3) ptTailKernel(const __grid_c
     }
   }
   ptCountRays(k.a.fb, 0u, nCont, nShadow + extraShadow);
+}
+
+// ===================================== ao renderer as a wavefront =======================================================
+// AORenderer_renderSample (render/ao/AORenderer.ispc:23-149) + computeAO (render/util.ispc:12-54) over the same queues and
+// the same TRACE kernel as the pathtracer, for worlds without volumes (those keep the megakernel, which marches them):
+//   GEN        Renderer_default_renderTask's pixel sample (RendererRenderTaskFn.inl:30-60) -> camera ray
+//   TRACE(d)   the ambient-occlusion rays of vertex d-1 (any hit) and the primary / continuation ray (closest hit)
+//   SHADE(d)   fold the occlusion answers into vertex d-1's colour and blend it; then vertex d: postIntersect, surface
+//              colour, the AO directions (rays emitted into the next queue), continuation behind a transparent surface
+// Path state reuses the pathtracer's arrays: thr = outputColor, con = (surface colour, opacity) of the vertex waiting for
+// its occlusion answers, lastP.x = its intensity before AO, lastN = (primary direction, original ray far), shA / shB =
+// AO rays (org, radius | dir, epsilon), shHit = their answers (rays never traced because the direction grazes the surface
+// are entered as occluded on the spot, util.ispc:31-35).
+__device__ __forceinline__ vec4f aoBlendOver(vec4f out, vec4f c) // outputColor + (1 - outputColor.w) * blendedColor
+{
+  const float f = 1.f - out.w;
+  return make_vec4f(out.x + f * c.x, out.y + f * c.y, out.z + f * c.z, __fmaf_rn(f, c.w, out.w));
+}
+
+__global__ void __launch_bounds__(128) aoGenKernel(const __grid_constant__ PtArgs k)
+{
+  const PtScratch &s = k.s;
+  const OcRenderer &ren = k.a.ren;
+  const OcFrameBuffer &fb = k.a.fb;
+  uint32_t primary = 0;
+  const int sampleID = fb.frameID * ren.spp + 1 + k.pass; // startSampleID + s
+  const float pixel_du = Halton_sample2(sampleID);
+  const float pixel_dv = CranleyPattersonRotation(Halton_sample3(sampleID), 1.f / 6.f);
+  const vec2f pfSample = pixelFilterSample(ren, make_vec2f(pixel_du, pixel_dv));
+  const vec2f rcpSize = make_vec2f(1.f / (float)fb.sizeX, 1.f / (float)fb.sizeY);
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < k.numPaths; p += gridDim.x * blockDim.x) {
+    uint32_t ix, iy;
+    ptSlotToPixel(k, p, ix, iy);
+    if (ix >= (uint32_t)fb.sizeX || iy >= (uint32_t)fb.sizeY) continue;
+    if (fb.taskError && !(fb.taskError[(iy >> 3) * (((uint32_t)fb.sizeX + 7u) >> 3) + (ix >> 3)] > fb.errorThreshold)) continue;
+    const vec2f pixel_center = make_vec2f(((float)ix + 0.5f) * rcpSize.x, ((float)iy + 0.5f) * rcpSize.y);
+    Ray ray;
+    cameraInitRay(k.a.cam, ray, pixel_center + pfSample * rcpSize, make_vec2f(0.f, 0.f));
+    s.flags[p] = 0u;
+    s.thr[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    s.lastN[p] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, ray.t);
+    if (k.pass == 0) { // the reference's `sample` lives across the spp loop and is never re-zeroed (RendererRenderTaskFn.inl:32-33)
+      s.sZ[p] = make_float4(INFINITY, __uint_as_float(OC_INVALID_ID), __uint_as_float(OC_INVALID_ID), __uint_as_float(OC_INVALID_ID));
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (fb.position) s.sPos[p] = zero;
+      if (fb.firstNormal) s.sFN[p] = zero;
+      if (fb.normal) s.sNrm[p] = zero;
+      if (fb.albedo) s.sAlb[p] = zero;
+    }
+    s.rayO[p] = make_float4(ray.org.x, ray.org.y, ray.org.z, ray.t);
+    s.rayD[p] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, ray.t0);
+    primary++;
+    ptAppend(k.pathOut, k.cntPathOut, p);
+  }
+  ptCountRays(fb, primary, 0u, 0u);
+}
+
+// returns 0 finished, 1 goes on (continuation ray queued), 2 ended with occlusion rays pending
+__device__ __forceinline__ uint32_t aoShadeStep(const PtArgs &k, uint32_t p, uint32_t ix, uint32_t iy)
+{
+  const PtScratch &s = k.s;
+  const OcRenderer &ren = k.a.ren;
+  const OcFrameBuffer &fb = k.a.fb;
+  const OcWorld *world = k.a.world;
+  const uint32_t flags = s.flags[p];
+  const float4 out4 = s.thr[p];
+  vec4f outputColor = make_vec4f(out4.x, out4.y, out4.z, out4.w);
+  const uint32_t aoSamples = ren.aoSamples > 0 ? (uint32_t)ren.aoSamples : 0u;
+  if (flags & PT_HAS_SHADOW) { // the occlusion answers of the previous vertex: computeAO's count, then the blend
+    const float4 c = s.con[p];
+    float intensity = s.lastP[p].x;
+    int hits = 0;
+    for (uint32_t j = 0; j < aoSamples; j++)
+      if (s.shHit[(size_t)p * s.nls + j].y != OC_INVALID_ID) hits++;
+    const float ao = 1.0f - (hits / (float)aoSamples);
+    intensity *= (1.0f - ren.aoIntensity) + (ao * ren.aoIntensity);
+    outputColor = aoBlendOver(outputColor, make_vec4f(make_vec3f(c.x, c.y, c.z) * intensity, c.w));
+    if (flags & PT_DONE) {
+      ptFinishPath<false>(k, p, make_vec3f(outputColor), outputColor.w);
+      return 0u;
+    }
+  }
+  const uint32_t depth = flags & PT_DEPTH_MASK;
+  const bool firstHit = depth == 0;
+  const float4 pd = s.lastN[p];
+  const vec3f primaryDir = make_vec3f(pd.x, pd.y, pd.z);
+  Ray ray;
+  {
+    const float4 o = s.rayO[p], d = s.rayD[p], h0 = s.hit0[p], h1 = s.hit1[p];
+    ray.org = make_vec3f(o.x, o.y, o.z); ray.dir = make_vec3f(d.x, d.y, d.z); ray.t0 = d.w;
+    ray.t = h0.x; ray.u = h0.y; ray.v = h0.z; ray.primID = __float_as_uint(h0.w);
+    ray.Ng = make_vec3f(h1.x, h1.y, h1.z); ray.geomID = __float_as_uint(h1.w);
+    ray.instID = s.hitInst[p];
+  }
+  if (!hadHit(ray)) {
+    const vec4f bg = getBackground(ren);
+    if (firstHit) {
+      float4 z = s.sZ[p];
+      z.x = ray.t;
+      s.sZ[p] = z;
+      if (fb.albedo) s.sAlb[p] = make_float4(bg.x, bg.y, bg.z, 0.f);
+      if (fb.normal) s.sNrm[p] = make_float4(primaryDir.x, primaryDir.y, primaryDir.z, 0.f);
+    }
+    outputColor = aoBlendOver(outputColor, bg);
+    ptFinishPath<false>(k, p, make_vec3f(outputColor), outputColor.w);
+    return 0u;
+  }
+  DifferentialGeometry dg;
+  postIntersect(world, ren, dg, ray, DG_NG | DG_NS | DG_NORMALIZE | DG_FACEFORWARD | DG_COLOR | DG_TEXCOORD | DG_TANGENTS);
+  // getSurfaceColor (ao/surfaces.ispc:18-42)
+  vec3f surfaceColor = make_vec3f(1.f);
+  float opacity = 1.f;
+  if (dg.material && dg.material->type == OC_MATERIAL_OBJ) {
+    surfaceColor = toV(dg.material->Kd);
+    opacity *= dg.material->d;
+  }
+  const vec3f color = surfaceColor * make_vec3f(dg.color);
+  opacity = opacity * dg.color.w;
+  const float intensity = fabsf(dot(dg.Ns, primaryDir)) * opacity;
+  if (firstHit) {
+    float z = ray.t;
+    if (fb.projectedDepth) z *= dot(ray.dir, toV(k.a.cam.direction));
+    s.sZ[p] = make_float4(z, __uint_as_float(dg.primID), __uint_as_float(dg.objID), __uint_as_float(dg.instID));
+    if (fb.albedo) s.sAlb[p] = make_float4(color.x, color.y, color.z, 0.f);
+    if (fb.position) s.sPos[p] = make_float4(dg.P.x, dg.P.y, dg.P.z, 0.f);
+    if (fb.firstNormal) s.sFN[p] = make_float4(dg.Ns.x, dg.Ns.y, dg.Ns.z, 0.f);
+    if (fb.normal) s.sNrm[p] = make_float4(dg.Ns.x, dg.Ns.y, dg.Ns.z, 0.f);
+  }
+  const bool needAO = aoSamples > 0 && ren.aoIntensity > 0.01f;
+  // does the sample go on behind this surface? the alpha after the blend does not depend on the occlusion answers
+  const bool alive = aoBlendOver(outputColor, make_vec4f(0.f, 0.f, 0.f, opacity)).w < 0.99f;
+  if (needAO) {
+    // computeAO (render/util.ispc:12-54) up to the rays
+    const int sampleIDz = fb.frameID * ren.spp + 1 + k.pass;
+    const int accumID = sampleIDz * (int)aoSamples;
+    uint32_t v0 = ix, v1 = iy;
+    tea8(v0, v1);
+    const vec2f rot = make_vec2f(to_float_unorm(v0), to_float_unorm(v1));
+    const linear3f localToWorld = frame(dg.Ns);
+    for (uint32_t j = 0; j < aoSamples; j++) {
+      const size_t e = (size_t)p * s.nls + j;
+      const vec2f halton = make_vec2f(PermHalton_sample5(accumID + (int)j), PermHalton_sample7(accumID + (int)j));
+      const vec2f r = make_vec2f(CranleyPattersonRotation(halton.x, rot.x), CranleyPattersonRotation(halton.y, rot.y));
+      const vec3f ao_dir = localToWorld * cosineSampleHemisphere(r);
+      if (dot(ao_dir, dg.Ns) < 0.01f) { s.shHit[e] = make_uint2(0u, 0u); continue; } // counts as occluded, no ray
+      s.shA[e] = make_float4(dg.P.x, dg.P.y, dg.P.z, ren.aoRadius);
+      s.shB[e] = make_float4(ao_dir.x, ao_dir.y, ao_dir.z, dg.epsilon);
+      ptAppend(k.shadowOut, k.cntShadowOut, PT_SHADOW_RAY | (uint32_t)e);
+    }
+    s.con[p] = make_float4(color.x, color.y, color.z, opacity);
+    s.lastP[p] = make_float4(intensity, 0.f, 0.f, 0.f);
+  } else
+    outputColor = aoBlendOver(outputColor, make_vec4f(color * intensity, opacity));
+  if (!alive && !needAO) {
+    ptFinishPath<false>(k, p, make_vec3f(outputColor), outputColor.w);
+    return 0u;
+  }
+  s.thr[p] = make_float4(outputColor.x, outputColor.y, outputColor.z, outputColor.w);
+  if (alive) {
+    s.rayO[p] = make_float4(ray.org.x, ray.org.y, ray.org.z, pd.w);
+    s.rayD[p] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, ray.t + dg.epsilon);
+  }
+  s.flags[p] = ((depth + 1) & PT_DEPTH_MASK) | (needAO ? PT_HAS_SHADOW : 0u) | (alive ? 0u : PT_DONE);
+  return alive ? 1u : 2u;
+}
+
+__global__ void __launch_bounds__(128, 5) aoShadeKernel(const __grid_constant__ PtArgs k)
+{
+  const uint32_t n = *k.cntPathIn;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t p = k.pathIn[i] & ~PT_Q_DONE;
+    uint32_t ix, iy;
+    ptSlotToPixel(k, p, ix, iy);
+    const uint32_t r = aoShadeStep(k, p, ix, iy);
+    if (r) ptAppend(k.pathOut, k.cntPathOut, r == 2u ? (p | PT_Q_DONE) : p);
+  }
 }
 
 } // namespace oc

@@ -774,7 +774,7 @@ struct PtHost
   void *block = nullptr;
   size_t blockBytes = 0;
   int device = -1;
-  int traceBlocks = 0, shadeBlocks[2] = {0, 0}, genBlocks = 0, tailBlocks = 0, traceVariant = 1, shadeVariant = 4; // persistent grids (resident CTAs per SM x SM count)
+  int traceBlocks = 0, shadeBlocks[2] = {0, 0}, genBlocks = 0, tailBlocks = 0, aoShadeBlocks = 0, traceVariant = 1, shadeVariant = 4; // persistent grids (resident CTAs per SM x SM count)
 } g_pt;
 
 size_t alignUp(size_t v) { return (v + 255) & ~size_t(255); }
@@ -837,7 +837,7 @@ size_t ptBytesPerPath(uint32_t nls, bool needAcc, bool hasVol)
 // counters (path / continuation / shadow queue sizes, TRACE's fetch cursor), zeroed once per pass; SHADE(d) appends to the
 // queues of stage d+1 (ping-pong on the parity of d), TRACE(d+1) and SHADE(d+1) consume them. Launches whose queues turn
 // out empty exit at once.
-int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
+int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles, bool ao = false)
 {
   using namespace oc;
   cudaStream_t st = (cudaStream_t)ospcuda_stream();
@@ -846,14 +846,17 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
   // light sample counts (PathTracer.ispc:96-104); world->numLights lives in device memory: mirror it via the args
   k.nFirst = fa.ptFirstBounceLightSamples;
   k.nIndirect = fa.ptIndirectLightSamples;
-  const uint32_t maxDepth = fa.ren.maxDepth < 250u ? fa.ren.maxDepth : 250u;
-  k.a.ren.maxDepth = maxDepth;
-  const uint32_t nls = k.nFirst > 0 ? k.nFirst : 1;
+  // ao: one vertex per surface the sample passes through; the loop runs until every sample is opaque or has left the
+  // scene (the queue size is read back after each bounce from the second on), 250 bounds the counter space
+  const uint32_t maxDepth = ao ? 250u : (fa.ren.maxDepth < 250u ? fa.ren.maxDepth : 250u);
+  if (!ao) k.a.ren.maxDepth = maxDepth;
+  const uint32_t nls = ao ? (uint32_t)std::max(1, fa.ren.aoSamples) : (k.nFirst > 0 ? k.nFirst : 1);
+  k.shadowT0InB = ao ? 1u : 0u;
   const bool needAcc = fa.ren.spp > 1;
   const uint32_t numCounters = 4 * (maxDepth + 2);
   // batch the owned tiles so that the path state stays under ~1.5 GB (many light samples / 4K frames)
   const size_t budget = size_t(1536) << 20;
-  const bool hasVol = fa.ren.worldHasVolumes != 0;
+  const bool hasVol = !ao && fa.ren.worldHasVolumes != 0;
   k.vol = hasVol ? 1u : 0u;
   uint32_t tilesPerBatch = (uint32_t)std::max<size_t>(1, budget / (ptBytesPerPath(nls, needAcc, hasVol) * 4096));
   if (tilesPerBatch > ownedTiles) tilesPerBatch = ownedTiles;
@@ -883,7 +886,9 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
     g_pt.shadeBlocks[0] = sms * (b > 0 ? b : 1);
     g_pt.shadeBlocks[1] = sms * (bv > 0 ? bv : 1);
     g_pt.genBlocks = sms * (g > 0 ? g : 1);
-    int t = 1;
+    int t = 1, as = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&as, aoShadeKernel, 128, 0);
+    g_pt.aoShadeBlocks = sms * (as > 0 ? as : 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t, ptTailKernel<false>, PT_TRACE_BLOCK, 0);
     g_pt.tailBlocks = sms * (t > 0 ? t : 1);
   }
@@ -906,14 +911,15 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
       {
         ProfScope ps(2, st);
         const int gb = (int)std::min<uint32_t>((uint32_t)g_pt.genBlocks, (k.numPaths + 127u) / 128u);
-        if (hasVol) ptGenKernel<true><<<gb, 128, 0, st>>>(k);
+        if (ao) aoGenKernel<<<gb, 128, 0, st>>>(k);
+        else if (hasVol) ptGenKernel<true><<<gb, 128, 0, st>>>(k);
         else ptGenKernel<false><<<gb, 128, 0, st>>>(k);
       }
       oc_count_launch();
       for (uint32_t d = 0; d <= maxDepth; d++) {
         k.depth = d;
         const uint32_t q = d & 1u;
-        if (d > 0 && d >= tailFrom) { // one launch carries every remaining path to its end
+        if (!ao && d > 0 && d >= tailFrom) { // one launch carries every remaining path to its end
           k.pathIn = k.s.pathQ[q]; k.cntPathIn = C(d, 0);
           k.fetchCursor = C(d, 3);
           {
@@ -945,16 +951,23 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles)
         k.shadowOut = k.s.shadowQ[q ^ 1u]; k.cntShadowOut = C(d + 1, 2);
         {
           ProfScope ps(1, st);
-          if (hasVol) ptShadeKernel<true, 4><<<g_pt.shadeBlocks[1], PT_TRACE_BLOCK, 0, st>>>(k);
+          if (ao) aoShadeKernel<<<g_pt.aoShadeBlocks, 128, 0, st>>>(k);
+          else if (hasVol) ptShadeKernel<true, 4><<<g_pt.shadeBlocks[1], PT_TRACE_BLOCK, 0, st>>>(k);
           else if (g_pt.shadeVariant == 4) ptShadeKernel<false, 4><<<g_pt.shadeBlocks[0], PT_TRACE_BLOCK, 0, st>>>(k);
           else if (g_pt.shadeVariant == 5) ptShadeKernel<false, 5><<<g_pt.shadeBlocks[0], PT_TRACE_BLOCK, 0, st>>>(k);
           else ptShadeKernel<false, 6><<<g_pt.shadeBlocks[0], PT_TRACE_BLOCK, 0, st>>>(k);
         }
         oc_count_launch();
+        if (ao && d >= 1) { // anything left behind transparent surfaces?
+          uint32_t left = 0;
+          OC_TRY(cudaMemcpyAsync(&left, C(d + 1, 0), sizeof(left), cudaMemcpyDeviceToHost, st));
+          OC_TRY(cudaStreamSynchronize(st));
+          if (left == 0) break;
+        }
       }
     }
   }
-  return oc_check(cudaGetLastError(), "wavefront pathtracer");
+  return oc_check(cudaGetLastError(), ao ? "wavefront ao renderer" : "wavefront pathtracer");
 }
 } // namespace
 
@@ -1004,7 +1017,14 @@ extern "C" int ospcuda_render_frame(const OcWorld *d_world, const OcCamera *came
     return renderPathTracerWavefront(a, owned);
   }
   case OC_RENDERER_SCIVIS: renderFrameKernel<OC_RENDERER_SCIVIS><<<grid, block, 0, st>>>(a); break;
-  case OC_RENDERER_AO: renderFrameKernel<OC_RENDERER_AO><<<grid, block, 0, st>>>(a); break;
+  case OC_RENDERER_AO: {
+    // worlds without volumes: the ao renderer runs as a wavefront over the ray-queue TRACE kernel (pathtracer_wf.cuh);
+    // with volumes the megakernel marches them (OSPCUDA_AO_MEGAKERNEL=1 forces it, for A/B)
+    static const bool forceMega = getenv("OSPCUDA_AO_MEGAKERNEL") && atoi(getenv("OSPCUDA_AO_MEGAKERNEL")) > 0;
+    if (!renderer->worldHasVolumes && !forceMega) return renderPathTracerWavefront(a, owned, true);
+    renderFrameKernel<OC_RENDERER_AO><<<grid, block, 0, st>>>(a);
+    break;
+  }
   case OC_RENDERER_DEBUG: renderFrameKernel<OC_RENDERER_DEBUG><<<grid, block, 0, st>>>(a); break;
   default: return oc_set_error(cudaErrorInvalidValue, "ospcuda_render_frame: unknown renderer type");
   }

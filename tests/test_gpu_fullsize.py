@@ -1,5 +1,6 @@
-"""BASELINE.json-size checks through size-independent properties (the scalar oracle cannot render these sizes
-in test time): determinism, ray accounting, closed-scene alpha, tile-partition union == single device."""
+"""BASELINE.json-size checks through size-independent properties: determinism, ray accounting, closed-scene alpha,
+tile-partition union == single device. (The comparisons against the reference's kernels at the configurations' own sizes
+are in tests/test_gpu_config_size.py.)"""
 import ctypes as C
 
 import numpy as np

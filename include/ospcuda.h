@@ -288,9 +288,13 @@ typedef struct {
    * (y/8) * ceil(sizeX/8) + x/8; the errors are those of the Variance frame op (ospcuda_fb_variance) */
   const float *taskError;
   float errorThreshold;
-  /* per-frame ray statistics: [0] primary, [1] continuation, [2] shadow/occlusion segments; [3] = how many of those the
-   * pathtracer's fused tail kernel traced (bench.py: rays of the TRACE launches = total - [3]) */
+  /* per-frame ray statistics: [0] primary, [1] continuation, [2] shadow/occlusion segments; [3] unused */
   unsigned long long *rayCounters;
+  /* frame control words in device memory (may be NULL): [0] cancel flag -- every frame kernel looks at it when it starts
+   * and the persistent loops when they fetch work, a set flag makes them return (ospCancel; reference:
+   * fb/FrameBuffer.cpp:180-187, render/RendererRenderTaskFn.inl:21); [1] work units finished so far, [2] work units of
+   * the frame (ospGetProgress). Poked / peeked from the host through ospcuda_aux_* while the frame runs. */
+  uint32_t *control;
 } OcFrameBuffer;
 
 typedef struct {
@@ -318,6 +322,9 @@ OSPCUDA_API int ospcuda_memcpy_d2h(void *dst, const void *src, size_t bytes);
 OSPCUDA_API int ospcuda_memcpy_d2h_async(void *dst, const void *src, size_t bytes);
 OSPCUDA_API int ospcuda_memset(void *dst, int value, size_t bytes);
 OSPCUDA_API int ospcuda_synchronize(void);
+/* one 32-bit word of device memory written / read on a side stream, concurrently with whatever the render stream runs */
+OSPCUDA_API int ospcuda_aux_poke_u32(void *d_word, uint32_t value);
+OSPCUDA_API int ospcuda_aux_peek_u32(const void *d_word, uint32_t *value);
 /* render-stream events: create, record (on the render stream), wait, query, elapsed ms */
 OSPCUDA_API int ospcuda_event_create(void **ev);
 OSPCUDA_API int ospcuda_event_destroy(void *ev);

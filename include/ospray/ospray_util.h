@@ -8,7 +8,7 @@
 extern "C" {
 #endif
 OSPRAY_INTERFACE OSPData ospNewSharedData1D(const void *sharedData, OSPDataType, uint64_t numItems);
-OSPRAY_INTERFACE OSPData ospNewSharedData1DDeleter(const void *sharedData, OSPDataType, uint64_t numItems,
+OSPRAY_INTERFACE OSPData ospNewAssignedData1D(const void *sharedData, OSPDataType, uint64_t numItems,
     OSPDeleterCallback, const void *userPtr);
 OSPRAY_INTERFACE OSPData ospNewSharedData1DStride(const void *sharedData, OSPDataType, uint64_t numItems, int64_t byteStride);
 OSPRAY_INTERFACE OSPData ospNewSharedData2D(const void *sharedData, OSPDataType, uint64_t numItems1, uint64_t numItems2);

@@ -125,7 +125,7 @@ class FrameBuffer(C.Structure):
                 ("normal", C.c_void_p), ("firstNormal", C.c_void_p), ("albedo", C.c_void_p), ("position", C.c_void_p),
                 ("primID", C.c_void_p), ("objID", C.c_void_p), ("instID", C.c_void_p), ("numRanks", C.c_uint32),
                 ("rank", C.c_uint32), ("taskError", C.c_void_p), ("errorThreshold", C.c_float),
-                ("rayCounters", C.c_void_p)]
+                ("rayCounters", C.c_void_p), ("control", C.c_void_p)]
 
 
 class ToneMapper(C.Structure):

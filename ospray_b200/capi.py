@@ -422,6 +422,15 @@ class Future(Object):
     def duration(self):
         return float(lib().ospGetTaskDuration(self.h))
 
+    def cancel(self):
+        lib().ospCancel(self.h)
+        check_errors()
+
+    def progress(self):
+        L = lib()
+        L.ospGetProgress.restype = C.c_float
+        return float(L.ospGetProgress(self.h))
+
     def stage_ms(self):
         """(renderer kernel ms, post-process ms) of the finished frame"""
         ms = (C.c_float * 2)()

@@ -471,7 +471,7 @@ void ospPick(OSPPickResult *result, OSPFrameBuffer fb, OSPRenderer r, OSPCamera 
 
 // ---- ospray_util (ospray_util_impl.cpp:7-192) ---------------------------------------------
 OSPData ospNewSharedData1D(const void *d, OSPDataType t, uint64_t n) { return ospNewSharedData(d, t, n, 0, 1, 0, 1, 0, nullptr, nullptr); }
-OSPData ospNewSharedData1DDeleter(const void *d, OSPDataType t, uint64_t n, OSPDeleterCallback cb, const void *up)
+OSPData ospNewAssignedData1D(const void *d, OSPDataType t, uint64_t n, OSPDeleterCallback cb, const void *up)
 {
   return ospNewSharedData(d, t, n, 0, 1, 0, 1, 0, cb, up);
 }

@@ -74,6 +74,7 @@ struct PtArgs
   uint32_t *cntPathOut, *cntShadowOut;
   uint32_t *fetchCursor;  // TRACE's work-fetch cursor (zeroed with the counters every pass)
   uint32_t vol;           // the world holds volumes (host copy of OcWorld.hasVolumes): free-path sampling + transmittance
+  uint32_t progressUnit, progressTotal; // ospGetProgress: what the SHADE / TAIL launch of this stage reports when it starts
   uint32_t shadowT0InB;   // any-hit rays start at shB[e].w instead of 0 (ao renderer: the ambient-occlusion rays start at dg.epsilon)
 };
 
@@ -439,6 +440,8 @@ __global__ void __launch_bounds__(128) ptGenKernel(const __grid_constant__ PtArg
   const OcRenderer &ren = k.a.ren;
   const OcFrameBuffer &fb = k.a.fb;
   uint32_t primary = 0;
+  if (frameCancelled(fb)) return;
+  if (fb.control && blockIdx.x == 0 && threadIdx.x == 0) fb.control[2] = k.progressTotal;
   for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < k.numPaths; p += gridDim.x * blockDim.x) {
     uint32_t ix, iy;
     ptSlotToPixel(k, p, ix, iy);
@@ -503,7 +506,7 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptTraceKernel(cons
   __shared__ uint32_t s_stack[OC_STACK_SHARED * PT_TRACE_BLOCK];
   const uint32_t nS = k.cntShadowIn ? *k.cntShadowIn : 0u;
   const uint32_t n = nS + *k.cntPathIn;
-  if (n == 0) return;
+  if (n == 0 || frameCancelled(k.a.fb)) return;
   uint32_t ovf[OC_STACK_OVF];
   Stack st;
   st.base = s_stack + threadIdx.x; st.stride = PT_TRACE_BLOCK; st.ovf = ovf;
@@ -539,9 +542,9 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptTraceKernel(cons
       while (idle && !exhausted) {
         if (chunkNext == chunkEnd) {
           uint32_t base = 0;
-          if (lane == 0) base = atomicAdd(k.fetchCursor, PT_TRACE_CHUNK);
+          if (lane == 0) base = frameCancelled(k.a.fb) ? 0xffffffffu : atomicAdd(k.fetchCursor, PT_TRACE_CHUNK);
           base = __shfl_sync(0xffffffffu, base, 0);
-          if (base >= n) { exhausted = true; break; }
+          if (base >= n) { exhausted = true; break; } // queue drained (or the frame was cancelled: ospCancel)
           chunkNext = base;
           chunkEnd = min(base + PT_TRACE_CHUNK, n);
         }
@@ -846,6 +849,8 @@ template <bool VOL, int MIN_BLOCKS>
 __global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptShadeKernel(const __grid_constant__ PtArgs k)
 {
   __shared__ uint32_t s_stack[OC_STACK_SHARED * PT_TRACE_BLOCK]; // the out-of-line transparent-shadow loop walks the hierarchy
+  if (frameCancelled(k.a.fb)) return;
+  if (k.a.fb.control && blockIdx.x == 0 && threadIdx.x == 0) atomicMax(k.a.fb.control + 1, k.progressUnit);
   const uint32_t n = *k.cntPathIn;
   uint32_t extraShadow = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -868,7 +873,8 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, 3) ptTailKernel(const __grid_c
 {
   __shared__ uint32_t s_stack[OC_STACK_SHARED * PT_TRACE_BLOCK];
   const uint32_t n = *k.cntPathIn;
-  if (n == 0) return;
+  if (n == 0 || frameCancelled(k.a.fb)) return;
+  if (k.a.fb.control && blockIdx.x == 0 && threadIdx.x == 0) atomicMax(k.a.fb.control + 1, k.progressUnit);
   const PtScratch &s = k.s;
   const OcWorld *world = k.a.world;
   uint32_t *stackBase = s_stack + threadIdx.x;
@@ -881,11 +887,11 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, 3) ptTailKernel(const __grid_c
     const uint32_t need = __ballot_sync(0xffffffffu, !alive);
     if (need) {
       uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(k.fetchCursor, (uint32_t)__popc(need));
+      if (lane == 0) base = frameCancelled(k.a.fb) ? 0xffffffffu : atomicAdd(k.fetchCursor, (uint32_t)__popc(need));
       base = __shfl_sync(0xffffffffu, base, 0);
       if (!alive) {
         const uint32_t i = base + __popc(need & ((1u << lane) - 1u));
-        if (i < n) {
+        if (base < n && i < n) { // base = ~0: the frame was cancelled
           const uint32_t e = k.pathIn[i];
           p = e & ~PT_Q_DONE; state = (e & PT_Q_DONE) ? 2u : 1u; alive = true;
         }
@@ -944,6 +950,8 @@ __global__ void __launch_bounds__(128) aoGenKernel(const __grid_constant__ PtArg
   const OcRenderer &ren = k.a.ren;
   const OcFrameBuffer &fb = k.a.fb;
   uint32_t primary = 0;
+  if (frameCancelled(fb)) return;
+  if (fb.control && blockIdx.x == 0 && threadIdx.x == 0) fb.control[2] = k.progressTotal;
   const int sampleID = fb.frameID * ren.spp + 1 + k.pass; // startSampleID + s
   const float pixel_du = Halton_sample2(sampleID);
   const float pixel_dv = CranleyPattersonRotation(Halton_sample3(sampleID), 1.f / 6.f);
@@ -1087,6 +1095,8 @@ __device__ __forceinline__ uint32_t aoShadeStep(const PtArgs &k, uint32_t p, uin
 
 __global__ void __launch_bounds__(128, 5) aoShadeKernel(const __grid_constant__ PtArgs k)
 {
+  if (frameCancelled(k.a.fb)) return;
+  if (k.a.fb.control && blockIdx.x == 0 && threadIdx.x == 0) atomicMax(k.a.fb.control + 1, k.progressUnit);
   const uint32_t n = *k.cntPathIn;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t p = k.pathIn[i] & ~PT_Q_DONE;

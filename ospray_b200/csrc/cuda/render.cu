@@ -659,6 +659,12 @@ __device__ __forceinline__ void accumulateSample(const OcFrameBuffer &fb, uint32
   if (fb.position) accum3(fb.position, pixelID, s.position, accScale);
 }
 
+// frame control words (OcFrameBuffer.control): [0] cancel flag, [1] work units done, [2] work units of the frame
+__device__ __forceinline__ bool frameCancelled(const OcFrameBuffer &fb)
+{
+  return fb.control != nullptr && *reinterpret_cast<const volatile uint32_t *>(fb.control) != 0u;
+}
+
 // ======================================= kernels ===========================================
 struct FrameArgs
 {
@@ -692,6 +698,8 @@ __global__ void __launch_bounds__(64, OC_RENDER_MIN_BLOCKS) renderFrameKernel(co
   stack.stride = 64;
   stack.ovf = nullptr; // traceHitNI keeps the overflow entries in its own frame
   Ctx c(a.world, a.ren, a.cam, a.fb, stack);
+  if (frameCancelled(a.fb)) return; // ospCancel: render tasks that have not started yet do not start
+  if (a.fb.control && blockIdx.x == 0 && threadIdx.x == 0) a.fb.control[2] = gridDim.x;
   // adaptive accumulation: a converged render task is skipped as a whole (one CTA = one task; LocalFB.cpp:245-257)
   const bool inImage = x < (uint32_t)a.fb.sizeX && y < (uint32_t)a.fb.sizeY;
   if (inImage && (!a.fb.taskError || a.fb.taskError[(y >> 3) * (((uint32_t)a.fb.sizeX + 7u) >> 3) + (x >> 3)] > a.fb.errorThreshold)) {
@@ -713,6 +721,8 @@ __global__ void __launch_bounds__(64, OC_RENDER_MIN_BLOCKS) renderFrameKernel(co
       atomicAdd(a.fb.rayCounters + 2, (unsigned long long)h);
     }
   }
+  __syncthreads();
+  if (a.fb.control && threadIdx.x == 0) atomicAdd(a.fb.control + 1, 1u); // one render-task CTA finished (ospGetProgress)
 }
 
 // batch traversal for tests / ospPick-like queries
@@ -896,6 +906,9 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles, bool
   // 0 = never)
   static const int tailEnv = getenv("OSPCUDA_PT_TAIL_FROM") ? atoi(getenv("OSPCUDA_PT_TAIL_FROM")) : -1;
   const uint32_t tailFrom = tailEnv == 0 ? 0xffffffffu : tailEnv > 0 ? (uint32_t)tailEnv : (uint32_t)std::max(1, fa.ren.rouletteDepth + 2);
+  const uint32_t progressStages = ao ? 2u : std::min(maxDepth + 1u, tailFrom == 0xffffffffu ? maxDepth + 1u : tailFrom + 1u);
+  k.progressTotal = ((ownedTiles + tilesPerBatch - 1) / tilesPerBatch) * (uint32_t)fa.ren.spp * progressStages;
+  k.progressUnit = 0;
   auto C = [&](uint32_t stage, int which) { return k.s.counters + 4 * stage + which; }; // 0 path, 1 cont, 2 shadow, 3 cursor
   for (uint32_t tile0 = 0; tile0 < ownedTiles; tile0 += tilesPerBatch) {
     const uint32_t nt = std::min(tilesPerBatch, ownedTiles - tile0);
@@ -918,6 +931,8 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles, bool
       oc_count_launch();
       for (uint32_t d = 0; d <= maxDepth; d++) {
         k.depth = d;
+        // ospGetProgress: stages (bounces) finished out of those a frame can take; the tail / an early end skips the rest
+        k.progressUnit = ((tile0 / tilesPerBatch) * (uint32_t)fa.ren.spp + (uint32_t)pass) * progressStages + std::min(d, progressStages - 1u) + 1u;
         const uint32_t q = d & 1u;
         if (!ao && d > 0 && d >= tailFrom) { // one launch carries every remaining path to its end
           k.pathIn = k.s.pathQ[q]; k.cntPathIn = C(d, 0);

@@ -124,6 +124,27 @@ int ospcuda_memset(void *dst, int value, size_t bytes)
   OC_TRY(cudaMemsetAsync(dst, value, bytes, g_stream));
   return 0;
 }
+static cudaStream_t auxStream()
+{
+  static thread_local cudaStream_t s = nullptr;
+  static thread_local int dev = -1;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (!s || dev != cur) { cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking); dev = cur; }
+  return s;
+}
+int ospcuda_aux_poke_u32(void *d_word, uint32_t value)
+{
+  OC_TRY(cudaMemcpyAsync(d_word, &value, sizeof(value), cudaMemcpyHostToDevice, auxStream()));
+  OC_TRY(cudaStreamSynchronize(auxStream()));
+  return 0;
+}
+int ospcuda_aux_peek_u32(const void *d_word, uint32_t *value)
+{
+  OC_TRY(cudaMemcpyAsync(value, d_word, sizeof(*value), cudaMemcpyDeviceToHost, auxStream()));
+  OC_TRY(cudaStreamSynchronize(auxStream()));
+  return 0;
+}
 int ospcuda_synchronize(void)
 {
   OC_TRY(cudaStreamSynchronize(g_stream));

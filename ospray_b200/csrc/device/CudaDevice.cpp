@@ -209,8 +209,29 @@ OSPPickResult CudaDevice::pick(OSPFrameBuffer, OSPRenderer, OSPCamera _c, OSPWor
 
 int CudaDevice::isReady(OSPFuture f, OSPSyncEvent e) { return ((Future *)f)->isFinished(e); }
 void CudaDevice::wait(OSPFuture f, OSPSyncEvent e) { ((Future *)f)->wait(e); }
-void CudaDevice::cancel(OSPFuture) {} // a frame is a single kernel; nothing to cancel mid-flight
-float CudaDevice::getProgress(OSPFuture f) { return ((Future *)f)->isFinished(OSP_TASK_FINISHED) ? 1.f : 0.f; }
+// ospCancel (api/Device.h; fb/FrameBuffer.cpp:180-187 cancelFrame): the frame's kernels are already queued on the render
+// stream, so the request travels as a flag in device memory, set on a side stream: every kernel of the frame reads it when
+// it starts and the persistent loops when they fetch work; what has not started yet returns at once. The frame then ends
+// early with whatever was accumulated, like the reference's cancelled frame.
+void CudaDevice::cancel(OSPFuture _f)
+{
+  Future *f = (Future *)_f;
+  if (f->isFinished(OSP_TASK_FINISHED) || !f->fb || !f->fb->sh.control) return;
+  checkCuda(ospcuda_aux_poke_u32(f->fb->sh.control, 1u), "cancel flag");
+}
+// ospGetProgress (fb/FrameBuffer.ih:27-50 reportProgress): work units finished / work units of the frame, counted on the
+// device (render tasks of the megakernels, launch stages of the wavefront renderers) and read on the side stream
+float CudaDevice::getProgress(OSPFuture _f)
+{
+  Future *f = (Future *)_f;
+  if (f->isFinished(OSP_TASK_FINISHED)) return 1.f;
+  if (!f->fb || !f->fb->sh.control) return 0.f;
+  uint32_t done = 0, total = 0;
+  checkCuda(ospcuda_aux_peek_u32(f->fb->sh.control + 1, &done), "progress read");
+  checkCuda(ospcuda_aux_peek_u32(f->fb->sh.control + 2, &total), "progress read");
+  if (total == 0) return 0.f;
+  return std::min(0.99f, (float)done / (float)total);
+}
 float CudaDevice::getTaskDuration(OSPFuture f) { return ((Future *)f)->duration(); }
 
 uint32_t CudaDevice::allocMaterialSlot()

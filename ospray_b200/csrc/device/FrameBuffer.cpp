@@ -44,8 +44,9 @@ FrameBuffer::FrameBuffer(CudaDevice &d, const vec2i &sz, OSPFrameBufferFormat fo
   if (ch & OSP_FB_ID_OBJECT) { objBuf = mk(np * 4); sh.objID = objBuf->as<uint32_t>(); }
   if (ch & OSP_FB_ID_INSTANCE) { instBuf = mk(np * 4); sh.instID = instBuf->as<uint32_t>(); }
   if ((ch & OSP_FB_COLOR) && format != OSP_FB_NONE) convBuf = mk(np * (format == OSP_FB_RGBA32F ? 16 : 4));
-  counterBuf = mk(4 * sizeof(unsigned long long));
+  counterBuf = mk(6 * sizeof(unsigned long long)); // 4 ray counters + the frame control words (cancel, progress, total)
   sh.rayCounters = counterBuf->as<unsigned long long>();
+  sh.control = reinterpret_cast<uint32_t *>(counterBuf->as<unsigned long long>() + 4);
   sh.numRanks = device.numRanks;
   sh.rank = device.rank;
 }
@@ -98,7 +99,7 @@ void FrameBuffer::beginFrame()
     if (evenFrame) pickOdd = mtGen() & 1;
     sh.accumulateVariance = evenFrame != pickOdd;
   }
-  checkCuda(ospcuda_memset(counterBuf->p, 0, 4 * sizeof(unsigned long long)), "counter reset");
+  checkCuda(ospcuda_memset(counterBuf->p, 0, 6 * sizeof(unsigned long long)), "counter reset");
 }
 
 void FrameBuffer::postProcess()

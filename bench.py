@@ -35,8 +35,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = "C1: ospray_testing cornell_box, pathtracer, 1024x1024, 1 spp/frame, OSP_FB_SRGBA COLOR|ACCUM|DEPTH"
-BYTES_PER_RAY = 532  # 32 ray in + 20 hit out + D*128 nodes + L*48 records; cornell: 34 records, L = 2 per leaf, D = ceil(log4(17)) = 3
-BYTES_PER_PIXEL = 40 + 20               # accumulate colour+depth r/w (40) + colour conversion 16 r + 4 w (20)
+# Algorithmic HBM bytes per unit of each kernel class: the path / ray state the launch has to read and write
+# once. Hierarchy nodes and leaf records are NOT in these figures: on C1 (34 quads) they live in L1 / L2, and counting
+# them as HBM traffic would credit cache hits to the memory roofline.
+ALGO_BYTES = {
+    "GEN": 132,     # per path: flags 4 + thr/con/lastP/lastN/sZ 80 + smp 8 + ray 32 + queue entry 4, all written
+    "TRACE": 60,    # per ray: queue entry 4 + ray 32 read; result written (continuation 36 B, shadow 8 B: mean 24 on C1)
+    "SHADE": 360,   # per path vertex: state read 148 + shadow fold 40 + state written 112 + shadow ray emitted 52 + frame 8
+    "TAIL": 420,    # per path vertex carried by the tail kernel: SHADE's state + the ray / hit round trip it keeps in L1
+    "POST": 20,     # per pixel: float4 accumulation buffer read 16 + sRGBA8 written 4
+}
 
 
 def parse():
@@ -48,10 +56,108 @@ def parse():
     ap.add_argument("--width", type=int, default=1024)
     ap.add_argument("--height", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="C1", choices=sorted(WORKLOADS),
+                    help="C1 (default) is the configuration BASELINE.json's metric is quoted on; the others are BASELINE.json's "
+                         "larger configurations, timed the same way (their CPU arm is not run: the scalar checker needs minutes per frame)")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N>1: 'peer' = every rank stores its tiles into GPU 0's image over NVLink peer memory (CUDA IPC); "
                          "'nccl' = pack + one NCCL gather + unpack")
     return ap.parse_args()
+
+
+WORKLOADS = {
+    # name: (description, renderer, width, height, spp per step)
+    "C1": (WORKLOAD, "pathtracer", 1024, 1024, 1),
+    "C2": ("C2: ospray_testing gravity_spheres_volume 128^3, scivis, 1920x1080, 4 spp", "scivis", 1920, 1080, 4),
+    "C3": ("C3: 9.97 M-triangle procedural mesh (94^3 boxes), ao, 3840x2160, 16 spp", "ao", 3840, 2160, 16),
+    "C4": ("C4: ospray_testing random_spheres (thinGlass) + streamlines, pathtracer, 1920x1080, 1 spp/frame of the 64 accumulated", "pathtracer", 1920, 1080, 1),
+    "C5": ("C5: cornell_box + 9.97 M-triangle mesh, pathtracer, 3840x2160, 1 spp/frame of the 64 accumulated", "pathtracer", 3840, 2160, 1),
+}
+
+
+def workload_spec(name):
+    from ospray_b200 import testing as T
+    merged = lambda a, b: T.SceneSpec(instances=a.instances + b.instances, lights=a.lights)
+    if name == "C1":
+        return T.cornell_box()
+    if name == "C2":
+        return T.gravity_spheres_volume(128)
+    if name == "C3":
+        return T.box_mesh(94)
+    if name == "C4":
+        return merged(T.random_spheres(renderer_type="pathtracer"), T.streamlines())
+    return merged(T.cornell_box(), T.box_mesh(94))
+
+
+def kernel_class_profile():
+    """profiles/r2_c1_kernel_classes.json: measured DRAM bytes, lanes per instruction and issue-slot utilisation per kernel
+    class of one C1 frame (ncu, tools/ncu_classes.py), committed with the code it was taken from"""
+    p = os.path.join(ROOT, "profiles", "r2_c1_kernel_classes.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
+def fb_ops_4k(peak):
+    """the framebuffer pixel ops alone at 3840x2160 (the clean HBM-bound kernels): ospcuda_fb_accumulate over
+    colour + depth + variance and the fused tonemap + sRGBA8 conversion, CUDA events on the library's stream, L2 flushed"""
+    import ctypes as C
+    import torch
+    from ospray_b200 import lib_path
+
+    class OcFrameBuffer(C.Structure):  # include/ospcuda.h
+        _fields_ = [("sizeX", C.c_int32), ("sizeY", C.c_int32), ("frameID", C.c_int32), ("channels", C.c_uint32),
+                    ("accumulateVariance", C.c_uint32), ("projectedDepth", C.c_uint32), ("targetFrames", C.c_int32),
+                    ("colorFormat", C.c_uint32), ("color", C.c_void_p), ("variance", C.c_void_p), ("depth", C.c_void_p),
+                    ("normal", C.c_void_p), ("firstNormal", C.c_void_p), ("albedo", C.c_void_p), ("position", C.c_void_p),
+                    ("primID", C.c_void_p), ("objID", C.c_void_p), ("instID", C.c_void_p), ("numRanks", C.c_uint32),
+                    ("rank", C.c_uint32), ("taskError", C.c_void_p), ("errorThreshold", C.c_float),
+                    ("rayCounters", C.c_void_p), ("control", C.c_void_p)]
+
+    class OcToneMapper(C.Structure):
+        _fields_ = [("exposure", C.c_float), ("a", C.c_float), ("b", C.c_float), ("c", C.c_float), ("d", C.c_float), ("acesColor", C.c_uint32)]
+    L = C.CDLL(lib_path("libospcuda.so"))
+    w, h = 3840, 2160
+    n = w * h
+    dev = torch.device("cuda")
+    color = torch.rand(n, 4, device=dev)
+    var = torch.rand(n, 4, device=dev)
+    depth = torch.full((n,), 3.0, device=dev)
+    sample = torch.rand(n, 4, device=dev)
+    sdepth = torch.rand(n, device=dev)
+    out8 = torch.empty(n, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    fb = OcFrameBuffer()
+    fb.sizeX, fb.sizeY, fb.frameID, fb.accumulateVariance = w, h, 3, 1
+    fb.color, fb.variance, fb.depth = color.data_ptr(), var.data_ptr(), depth.data_ptr()
+    fb.numRanks, fb.rank = 1, 0
+    tm = OcToneMapper(1.0, 1.6773, 1.1174272, 0.2446756, 0.9714, 1)  # the tonemapper image operation's default curve
+    L.ospcuda_fb_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ospcuda_fb_postprocess.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    L.ospcuda_stream.restype = C.c_void_p
+    stream = torch.cuda.ExternalStream(L.ospcuda_stream())
+    res = {}
+    for name, call, nbytes in (
+            ("accumulate", lambda: L.ospcuda_fb_accumulate(C.byref(fb), sample.data_ptr(), sdepth.data_ptr()), n * (16 + 32 + 32 + 4 + 8)),
+            ("tonemap+convert", lambda: L.ospcuda_fb_postprocess(color.data_ptr(), None, out8.data_ptr(), n, 2, C.byref(tm)), n * (16 + 4))):
+        times = []
+        for i in range(8):
+            flush.zero_()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            if call() != 0:
+                raise RuntimeError(name)
+            b.record(stream)
+            torch.cuda.synchronize()
+            if i >= 3:
+                times.append(a.elapsed_time(b))
+        ms = sum(times) / len(times)
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        res[name] = {"ms": round(ms, 4), "algorithmic_bytes": nbytes, "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 3)}
+    res["size"] = "3840x2160"
+    return res
 
 
 def peaks():
@@ -213,17 +319,19 @@ def run_ours(args):
     os.dup2(2, 1)
     rank, world, local = multigpu.init_process_group_from_env()
     torch.cuda.set_device(local)
-    w, h, K, W = args.width, args.height, args.steps, max(args.warmup, 3)
+    wl_name, ren_kind, wl_w, wl_h, spp = WORKLOADS[args.workload]
+    w, h = (args.width, args.height) if args.workload == "C1" else (wl_w, wl_h)
+    K, W = args.steps, max(args.warmup, 3)
     osp.init(cudaDevice=local, numSubdevices=world, subdeviceRank=rank)
     stream = torch.cuda.Stream()
     osp.set_render_stream(stream.cuda_stream)
     with torch.cuda.stream(stream):
         launches0 = osp.kernel_launch_count()
         t_setup = time.perf_counter()
-        world_obj, keep = T.to_ospray(T.cornell_box())
+        world_obj, keep = T.to_ospray(workload_spec(args.workload))
         setup_ms = (time.perf_counter() - t_setup) * 1e3
         cam, pose = T.make_camera(world_obj, w, h)
-        ren = T.make_renderer("pathtracer", pixelSamples=1)
+        ren = T.make_renderer(ren_kind, pixelSamples=spp)
         fb = osp.FrameBuffer(w, h, osp.OSP_FB_SRGBA, osp.OSP_FB_COLOR | osp.OSP_FB_ACCUM | osp.OSP_FB_DEPTH)
         conv_ptr, bpp = fb.device_pointer(osp.OSP_FB_COLOR)
         assert bpp == 4
@@ -290,7 +398,7 @@ def run_ours(args):
             prof_rays += np.array(fb.ray_counts(), np.int64)
             prof_fused_rays += fb.fused_ray_count()
             flush.zero_()
-        cls_ms, cls_n = (C.c_float * 3)(), (C.c_uint32 * 3)()
+        cls_ms, cls_n = (C.c_float * 4)(), (C.c_uint32 * 4)()
         LC.ospcuda_profile_read(cls_ms, cls_n)
         LC.ospcuda_profile_enable(0)
         cls_ms, cls_n = [float(x) / PF for x in cls_ms], [int(x) // PF for x in cls_n]
@@ -301,6 +409,16 @@ def run_ours(args):
 
         # ---- end-to-end leg (public API, host buffers, wall clock) -------------------------------------
         e2e_rays = np.zeros(3, np.int64)
+        for i in range(W):                                       # warm the host path as well: first ospMapFrameBuffer pins its
+            cam.set("position", pose["position"]).commit()       # staging buffer, the allocator and the page cache settle
+            begin()
+            f = fb.render_frame(ren, cam, world_obj)
+            if gather is not None:
+                gather.gather(conv_ptr)
+            f.wait()
+            if rank == 0:
+                with fb.mapped(osp.OSP_FB_COLOR) as img:
+                    e2e_probe = int(img[h // 2, w // 2, 0])
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -333,42 +451,78 @@ def run_ours(args):
         peak, peak_src = peaks()
         value = tot[0] / (mx[0] * 1e-3) / 1e6
         e2e = tot[1] / mx[1] / 1e6
-        # roofline of the dominant kernel class: TRACE (ptTraceKernel: BVH traversal + intersection of the shadow and
-        # continuation rays). Its launches of one frame trace every ray except those of the fused tail launch (counted apart);
-        # algorithmic bytes = TRACE rays x BYTES_PER_RAY.
-        trace_ms, shade_ms, fused_ms = cls_ms
-        rays_frame = (prof_rays.sum() - prof_fused_rays) / PF  # rays traced by the TRACE launches (the fused tail kernel counts its own)
-        achieved = rays_frame * BYTES_PER_RAY / (trace_ms * 1e-3) / 1e9
+        # ---- roofline, per kernel class ------------------------------------------------------------------
+        # live: CUDA-event time per class (profile leg above) and the units each class processed; algorithmic bytes =
+        # units x ALGO_BYTES; measured DRAM bytes / lanes / issue utilisation per class come from the committed ncu capture
+        # of the same command (profiles/r2_c1_kernel_classes.json, tools/ncu_classes.py) -- bench.py never runs under ncu.
+        trace_ms, shade_ms, gen_ms, tail_ms = cls_ms
+        rays_frame = prof_rays / PF
+        tail_rays = prof_fused_rays / PF
+        vertices = rays_frame[0] + rays_frame[1]                   # every primary / continuation ray ends in one shaded vertex
+        tail_vertices = vertices * (tail_rays / max(rays_frame.sum(), 1.0))
+        units = {"GEN": float(rays_frame[0]), "TRACE": float(rays_frame.sum() - tail_rays), "SHADE": float(vertices - tail_vertices),
+                 "TAIL": float(tail_vertices), "POST": float(w * h)}
+        ms = {"GEN": gen_ms, "TRACE": trace_ms, "SHADE": shade_ms, "TAIL": tail_ms, "POST": post_ms / K}
+        nl = {"GEN": cls_n[2], "TRACE": cls_n[0], "SHADE": cls_n[1], "TAIL": cls_n[3], "POST": 1}
+        what = {"GEN": "ptGenKernel (sampler + camera ray per path)", "TRACE": "ptTraceKernel (ray queue: hierarchy traversal + intersection)",
+                "SHADE": "ptShadeKernel (shadow fold, postIntersect, BSDF, light sampling, roulette)",
+                "TAIL": "ptTailKernel (per-lane completion of the thinned-out frame)", "POST": "postprocessKernel (float4 -> sRGBA8)"}
+        measured = kernel_class_profile() if args.workload == "C1" and (w, h) == (1024, 1024) and world == 1 else None
+        classes = []
+        for c in ("GEN", "TRACE", "SHADE", "TAIL", "POST"):
+            if ms[c] <= 0:
+                continue
+            algo = units[c] * ALGO_BYTES[c]
+            gbs = algo / (ms[c] * 1e-3) / 1e9
+            e = {"class": c, "kernel": what[c], "ms_per_frame": round(ms[c], 4), "launches_per_frame": nl[c], "units_per_frame": int(units[c]),
+                 "algorithmic_bytes_per_unit": ALGO_BYTES[c], "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 4)}
+            mc = (measured or {}).get("classes", {}).get(c)
+            if mc:
+                e["measured_dram_bytes_per_frame"] = int(mc["dram_bytes"])
+                e["wasted_traffic"] = round(mc["dram_bytes"] / algo, 2) if algo else None   # measured / algorithmic
+                e["lanes_per_instruction"] = mc["lanes_per_instruction"]
+                e["issue_slot_utilisation_pct"] = mc["issue_slot_utilisation_pct"]
+            classes.append(e)
+        dom = max(classes, key=lambda e: e["ms_per_frame"])
+        dom_launch_ms = dom["ms_per_frame"] / max(dom["launches_per_frame"], 1)
         line = {"metric": "Mrays/s", "value": round(float(value), 2), "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": round(float(mx[0] / K), 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "partition": (f"image tiles 64x64, tile % {world} == rank, " + ("sRGBA8 tiles stored into GPU 0's image over NVLink peer memory (one push kernel per rank, flag handshake)"
+                "config": {"workload": wl_name if args.workload != "C1" else WORKLOAD, "partition": (f"image tiles 64x64, tile % {world} == rank, " + ("sRGBA8 tiles stored into GPU 0's image over NVLink peer memory (one push kernel per rank, flag handshake)"
                                                                                               if isinstance(gather, multigpu.PeerTileExchange) else (gather_note or "") + "NCCL gather of sRGBA8 to GPU 0")) if world > 1 else "single device",
                            "l2": "256 MiB memset between timed steps (L2 flush)", **({"composition_check": "GPU 0's image == every rank's own tiles (checksums)"} if composed_ok else {}), "frame_ms": round(float(mx[0] / K), 4),
-                           "rays_per_frame": int(tot[0] / K), "mpixel_samples_per_s": round(w * h * K / (mx[0] * 1e-3) / 1e6, 1),
+                           "rays_per_frame": int(tot[0] / K), "mpixel_samples_per_s": round(w * h * spp * K / (mx[0] * 1e-3) / 1e6, 1),
                            "scene_setup_ms_incl_bvh": round(setup_ms, 2)},
                 "e2e": {"value": round(float(e2e), 2), "unit": "Mrays/s", "h2d_bytes_per_step": 472, "d2h_bytes_per_step": w * h * 4 + 24,
-                        "ms_per_step": round(float(mx[1] / K * 1e3), 4)},
+                        "ms_per_step": round(float(mx[1] / K * 1e3), 4), "warmup_steps": W},
                 "gpu_launches": int(tot[2]),
                 "clocks": clk,
-                "roofline": {"bound": "hbm", "achieved": round(float(achieved), 1), "peak": peak, "unit": "GB/s",
-                             "frac": round(float(achieved / peak), 4), "traffic": 141.1e6, "peak_source": peak_src,
-                             "kernel": "ptTraceKernel (wavefront TRACE: traversal + intersection)",
-                             "kernel_ms_per_frame": round(trace_ms, 4), "launches_per_frame": cls_n[0],
-                             "avg_launch_ms": round(trace_ms / max(cls_n[0], 1), 4),
-                             "bytes_per_ray": BYTES_PER_RAY, "rays_per_frame": int(rays_frame),
-                             "other_classes_ms_per_frame": {"shade": round(shade_ms, 4), "fused_tail": round(fused_ms, 4),
-                                                            "postprocess": round(post_ms / K, 4)},
-                             "traffic_note": "dram read+write of the depth-1 TRACE launch, profiles/r1_pt_trace_ncu.txt",
-                             "note": "scene (34 triangles) is cache resident: issue/latency bound by construction "
-                                     "(DESIGN.md 4); ncu issue/divergence figures in profiles/"}}
-        if world == 1 and not args.no_cpu_baseline:
+                "roofline": {"bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac_of_hbm_peak"],
+                             "traffic": (dom.get("measured_dram_bytes_per_frame") / max(dom["launches_per_frame"], 1)) if dom.get("measured_dram_bytes_per_frame") else None,
+                             "peak_source": peak_src, "kernel": dom["kernel"], "kernel_class": dom["class"],
+                             "kernel_ms_per_frame": dom["ms_per_frame"], "launches_per_frame": dom["launches_per_frame"],
+                             "avg_launch_ms": round(dom_launch_ms, 4),
+                             "algorithmic_bytes_per_launch": int(dom["units_per_frame"] * dom["algorithmic_bytes_per_unit"] / max(dom["launches_per_frame"], 1)),
+                             "classes": classes,
+                             "traffic_source": (f"profiles/r2_c1_kernel_classes.json (ncu, commit {measured.get('commit')})" if measured else None),
+                             "note": "dominant class by time; `achieved` = algorithmic path-state bytes / time. No class of this frame is HBM-bound: "
+                                     "the scene (34 quads) lives in L1/L2 and the kernels are limited by issue slots, divergence (lanes_per_instruction) "
+                                     "and dependent-load latency -- the memory roofline is reported because the contract asks for it, the limiter is in "
+                                     "the per-class ncu figures (DESIGN.md 4, profiles/)"}}
+        if world == 1 and args.workload == "C1":
+            try:
+                line["roofline"]["fb_ops_4k"] = fb_ops_4k(peak)
+            except Exception as e:
+                line["roofline"]["fb_ops_4k"] = {"error": str(e)}
+        if world == 1 and not args.no_cpu_baseline and args.workload == "C1":
             try:
                 backend, kind = cpu_backend() if (w % 8 == 0 and h % 8 == 0) else ("oracle", "port")
                 stride = calibrate_stride(w, h, 6.0, backend)
                 r, s, threads = oracle_frames(w, h, 2, 1, stride, backend)
                 line["cpu_baseline"] = {"value": round(r / s / 1e6, 3), "unit": "Mrays/s", "cores": threads, "kind": kind,
                                         "sample": f"2 frames, tiles with tileID % {stride} == 0 of the {w}x{h} frame; " + CPU_NOTE[kind],
+                                        "caveat": "scalar build of the reference kernels, no ISPC SIMD, brute-force scene queries instead of Embree: "
+                                                  "the reference's real CPU device would be several times faster; a reported baseline, not a target",
                                         "frame_ms_full": round(s / 2 * stride * 1e3, 1)}
             except Exception as e:  # the baseline must never take the bench line down
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}

@@ -288,7 +288,8 @@ typedef struct {
    * (y/8) * ceil(sizeX/8) + x/8; the errors are those of the Variance frame op (ospcuda_fb_variance) */
   const float *taskError;
   float errorThreshold;
-  /* per-frame ray statistics: [0] primary, [1] continuation, [2] shadow/occlusion segments; [3] unused */
+  /* per-frame ray statistics: [0] primary, [1] continuation, [2] shadow/occlusion segments; [3] = how many of those the
+   * pathtracer's tail kernel traced (bench.py: rays of the TRACE launches = total - [3]) */
   unsigned long long *rayCounters;
   /* frame control words in device memory (may be NULL): [0] cancel flag -- every frame kernel looks at it when it starts
    * and the persistent loops when they fetch work, a set flag makes them return (ospCancel; reference:
@@ -311,6 +312,12 @@ typedef struct {
 
 /* ---- runtime ----------------------------------------------------------------------- */
 OSPCUDA_API int ospcuda_init(int deviceOrdinal);
+/* several CUDA devices in one process (the in-process multi-device, modules/multiDevice analogue): every device that was
+ * initialised keeps its own render stream; make_current switches which one the other entry points work on */
+OSPCUDA_API int ospcuda_make_current(int deviceOrdinal);
+OSPCUDA_API int ospcuda_current_device(void);
+/* let kernels of the current device read / write memory of `peerOrdinal` (NVLink peer access) */
+OSPCUDA_API int ospcuda_enable_peer(int peerOrdinal);
 OSPCUDA_API const char *ospcuda_last_error(void);
 OSPCUDA_API int ospcuda_device_count(void);
 OSPCUDA_API int ospcuda_malloc(void **ptr, size_t bytes);
@@ -330,6 +337,7 @@ OSPCUDA_API int ospcuda_event_create(void **ev);
 OSPCUDA_API int ospcuda_event_destroy(void *ev);
 OSPCUDA_API int ospcuda_event_record(void *ev);
 OSPCUDA_API int ospcuda_event_synchronize(void *ev);
+OSPCUDA_API int ospcuda_stream_wait_event(void *ev); /* the current render stream waits for an event of any device */
 OSPCUDA_API int ospcuda_event_query(void *ev); /* 1 done, 0 pending, <0 error */
 OSPCUDA_API int ospcuda_event_elapsed_ms(void *start, void *stop, float *ms);
 OSPCUDA_API void *ospcuda_stream(void); /* cudaStream_t of the render stream */
@@ -369,9 +377,9 @@ OSPCUDA_API int ospcuda_render_frame(const OcWorld *d_world, const OcCamera *cam
 
 /* per-launch-class device timing of the wavefront pathtracer (bench.py roofline leg): while enabled every
  * launch is bracketed by CUDA events on the render stream; read returns and clears the summed milliseconds and
- * launch counts of class 0 = TRACE (traversal), 1 = SHADE, 2 = FUSED trace+shade (tail). */
+ * launch counts of class 0 = TRACE (traversal), 1 = SHADE, 2 = GEN (camera rays), 3 = TAIL (per-lane path completion). */
 OSPCUDA_API int ospcuda_profile_enable(int on);
-OSPCUDA_API int ospcuda_profile_read(float ms[3], uint32_t launches[3]);
+OSPCUDA_API int ospcuda_profile_read(float ms[4], uint32_t launches[4]);
 
 /* ---- framebuffer ops --------------------------------------------------------------- */
 OSPCUDA_API int ospcuda_fb_accumulate(const OcFrameBuffer *fb, const OcVec4f *d_sampleColor,

@@ -925,6 +925,12 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, 3) ptTailKernel(const __grid_c
     }
   }
   ptCountRays(k.a.fb, 0u, nCont, nShadow + extraShadow);
+  if (k.a.fb.rayCounters) { // [3]: rays traced by this kernel (the others go through TRACE)
+    uint32_t t = nCont + nShadow + extraShadow;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0 && t) atomicAdd(k.a.fb.rayCounters + 3, (unsigned long long)t);
+  }
 }
 
 // ===================================== ao renderer as a wavefront =======================================================

@@ -762,7 +762,7 @@ namespace {
 struct PtProfile
 {
   bool enabled = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3]; // 0 TRACE, 1 SHADE, 2 GEN + TAIL
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[4]; // 0 TRACE, 1 SHADE, 2 GEN, 3 TAIL
   std::vector<cudaEvent_t> pool;
   size_t poolNext = 0;
   cudaEvent_t get()
@@ -938,7 +938,7 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles, bool
           k.pathIn = k.s.pathQ[q]; k.cntPathIn = C(d, 0);
           k.fetchCursor = C(d, 3);
           {
-            ProfScope ps(2, st);
+            ProfScope ps(3, st);
             if (hasVol) ptTailKernel<true><<<g_pt.tailBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
             else ptTailKernel<false><<<g_pt.tailBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
           }
@@ -994,10 +994,10 @@ extern "C" int ospcuda_profile_enable(int on)
   return 0;
 }
 
-extern "C" int ospcuda_profile_read(float ms[3], uint32_t launches[3])
+extern "C" int ospcuda_profile_read(float ms[4], uint32_t launches[4])
 {
   OC_TRY(cudaStreamSynchronize((cudaStream_t)ospcuda_stream()));
-  for (int c = 0; c < 3; c++) {
+  for (int c = 0; c < 4; c++) {
     ms[c] = 0.f;
     launches[c] = (uint32_t)g_prof.ev[c].size();
     for (auto &e : g_prof.ev[c]) {

@@ -11,6 +11,12 @@
 static thread_local std::string g_lastError;
 static std::string g_lastErrorGlobal;
 static std::mutex g_errMutex;
+// one render stream per CUDA device of the process; `g_stream` / `g_device` are the CURRENT ones: ospcuda_init() and
+// ospcuda_make_current() switch, every other entry point works on the current device (the in-process multi-device,
+// csrc/device/MultiDevice.cpp, switches before each forwarded call)
+#define OC_MAX_DEVICES 32
+struct DevCtx { cudaStream_t stream = nullptr, own = nullptr; bool ready = false; };
+static DevCtx g_ctx[OC_MAX_DEVICES];
 static cudaStream_t g_stream = nullptr;
 static int g_device = -1;
 static std::atomic<unsigned long long> g_launches{0};
@@ -50,26 +56,56 @@ int ospcuda_init(int deviceOrdinal)
   int n = 0;
   OC_TRY(cudaGetDeviceCount(&n));
   if (n == 0) return oc_set_error(cudaErrorNoDevice, "ospcuda_init: no CUDA device (the cuda OSPRay device has no CPU fallback)");
-  if (deviceOrdinal < 0 || deviceOrdinal >= n) return oc_set_error(cudaErrorInvalidDevice, "ospcuda_init: bad ordinal");
+  if (deviceOrdinal < 0 || deviceOrdinal >= n || deviceOrdinal >= OC_MAX_DEVICES)
+    return oc_set_error(cudaErrorInvalidDevice, "ospcuda_init: bad ordinal");
   OC_TRY(cudaSetDevice(deviceOrdinal));
-  if (g_stream && g_device != deviceOrdinal) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
-  if (!g_stream) OC_TRY(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  DevCtx &c = g_ctx[deviceOrdinal];
+  if (!c.ready) {
+    OC_TRY(cudaStreamCreateWithFlags(&c.own, cudaStreamNonBlocking));
+    c.stream = c.own;
+    // deep traversal + shading call chains: give local-memory stacks room
+    cudaDeviceSetLimit(cudaLimitStackSize, 4096);
+    c.ready = true;
+  }
   g_device = deviceOrdinal;
-  // deep traversal + shading call chains: give local-memory stacks room
-  cudaDeviceSetLimit(cudaLimitStackSize, 4096);
+  g_stream = c.stream;
+  return 0;
+}
+
+int ospcuda_make_current(int deviceOrdinal)
+{
+  if (deviceOrdinal == g_device) return 0;
+  if (deviceOrdinal < 0 || deviceOrdinal >= OC_MAX_DEVICES || !g_ctx[deviceOrdinal].ready) return ospcuda_init(deviceOrdinal);
+  OC_TRY(cudaSetDevice(deviceOrdinal));
+  g_device = deviceOrdinal;
+  g_stream = g_ctx[deviceOrdinal].stream;
+  return 0;
+}
+int ospcuda_current_device(void) { return g_device; }
+
+int ospcuda_enable_peer(int peerOrdinal)
+{
+  if (peerOrdinal == g_device) return 0;
+  int can = 0;
+  OC_TRY(cudaDeviceCanAccessPeer(&can, g_device, peerOrdinal));
+  if (!can) return oc_set_error(cudaErrorPeerAccessUnsupported, "ospcuda_enable_peer: no peer access between the two devices");
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peerOrdinal, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+  OC_TRY(e);
   return 0;
 }
 
 void *ospcuda_stream(void) { return (void *)g_stream; }
 
-static cudaStream_t g_ownStream = nullptr;
 int ospcuda_set_stream(void *stream)
 {
   // adopt an external stream (e.g. torch's current stream so that NCCL work and CUDA-event timing order
   // naturally with the frame); NULL restores the library's own stream
-  if (!g_ownStream) g_ownStream = g_stream;
+  if (g_device < 0) return oc_set_error(cudaErrorInitializationError, "ospcuda_set_stream before ospcuda_init");
   if (g_stream) OC_TRY(cudaStreamSynchronize(g_stream));
-  g_stream = stream ? (cudaStream_t)stream : g_ownStream;
+  DevCtx &c = g_ctx[g_device];
+  c.stream = stream ? (cudaStream_t)stream : c.own;
+  g_stream = c.stream;
   return 0;
 }
 unsigned long long ospcuda_kernel_launch_count(void) { return g_launches.load(); }
@@ -165,6 +201,11 @@ int ospcuda_event_destroy(void *ev)
 int ospcuda_event_record(void *ev)
 {
   OC_TRY(cudaEventRecord((cudaEvent_t)ev, g_stream));
+  return 0;
+}
+int ospcuda_stream_wait_event(void *ev)
+{
+  OC_TRY(cudaStreamWaitEvent(g_stream, (cudaEvent_t)ev, 0)); // the event may belong to another device's stream
   return 0;
 }
 int ospcuda_event_synchronize(void *ev)

@@ -26,6 +26,12 @@ void CudaDevice::commit()
   int rk = getParam<int>("subdeviceRank", getParam<int>("rank", 0));
   if (const char *e = getenv("OSPRAY_NUM_SUBDEVICES")) nr = atoi(e);
   if (const char *e = getenv("OSPRAY_SUBDEVICE_RANK")) rk = atoi(e);
+  // a sub-device of the in-process multidevice (MultiDevice.cpp): its share is fixed by the parent, whatever the environment says
+  if (hasParam("multiNumSubdevices")) {
+    nr = getParam<int>("multiNumSubdevices", 1);
+    rk = getParam<int>("multiSubdeviceRank", 0);
+    ord = getParam<int>("cudaDevice", 0);
+  }
   numRanks = (uint32_t)std::max(1, nr);
   rank = (uint32_t)std::max(0, rk) % numRanks;
   cudaOrdinal = ord;
@@ -269,34 +275,44 @@ extern "C" __attribute__((visibility("default"))) OSPError ospray_module_init_cu
     int16_t /*versionPatch*/)
 {
   const OSPError status = moduleVersionCheck(versionMajor, versionMinor);
-  if (status == OSP_NO_ERROR) api::Device::registerType<cuda::CudaDevice>("cuda");
+  if (status == OSP_NO_ERROR) {
+    api::Device::registerType<cuda::CudaDevice>("cuda");
+    cuda::registerMultiDevice(); // "multidevice": N cuda sub-devices in one process (modules/multiDevice analogue)
+  }
   return status;
 }
 
 extern "C" {
+// the handles may come from the cuda device or from the multidevice (sub-object 0 holds the composed image; counters add up)
 void *ospcudaFrameBufferDevicePointer(OSPFrameBuffer fb, OSPFrameBufferChannel ch, uint64_t *bpp)
 {
-  cuda::FrameBuffer *f = (cuda::FrameBuffer *)fb;
+  cuda::FrameBuffer *f = (cuda::FrameBuffer *)cuda::subObject(fb, 0);
   if (bpp) *bpp = f->bytesPerPixel(ch);
   return f->devicePointer(ch);
 }
-uint64_t ospcudaGetFusedRayCount(OSPFrameBuffer fb) { return ((ospray::cuda::FrameBuffer *)fb)->rayCounts[3]; }
+uint64_t ospcudaGetFusedRayCount(OSPFrameBuffer fb)
+{
+  uint64_t n = 0;
+  for (size_t i = 0; cuda::subObject(fb, i); i++) n += ((cuda::FrameBuffer *)cuda::subObject(fb, i))->rayCounts[3];
+  return n;
+}
 void ospcudaGetRayCounts(OSPFrameBuffer fb, uint64_t counts[3])
 {
-  cuda::FrameBuffer *f = (cuda::FrameBuffer *)fb;
-  for (int i = 0; i < 3; i++) counts[i] = f->rayCounts[i];
+  counts[0] = counts[1] = counts[2] = 0;
+  for (size_t i = 0; cuda::subObject(fb, i); i++)
+    for (int k = 0; k < 3; k++) counts[k] += ((cuda::FrameBuffer *)cuda::subObject(fb, i))->rayCounts[k];
 }
-float ospcudaGetGroupBuildTime(OSPGroup g) { return ((cuda::Group *)g)->lastBuildMs; }
+float ospcudaGetGroupBuildTime(OSPGroup g) { return ((cuda::Group *)cuda::subObject(g, 0))->lastBuildMs; }
 uint64_t ospcudaKernelLaunchCount(void) { return ospcuda_kernel_launch_count(); }
 void *ospcudaRenderStream(void) { return ospcuda_stream(); }
 void ospcudaGetFrameStageTimes(OSPFuture f, float ms[2])
 {
-  cuda::Future *fu = (cuda::Future *)f;
-  fu->wait(OSP_TASK_FINISHED);
+  api::currentDevice().wait(f, OSP_TASK_FINISHED);
+  cuda::Future *fu = (cuda::Future *)cuda::subObject(f, 0);
   ms[0] = ms[1] = 0.f;
   ospcuda_event_elapsed_ms(fu->evStart, fu->evRendered, &ms[0]);
   ospcuda_event_elapsed_ms(fu->evRendered, fu->evFinished, &ms[1]);
 }
 void ospcudaSetRenderStream(void *stream) { ospray::cuda::checkCuda(ospcuda_set_stream(stream), "set stream"); }
-const void *ospcudaWorldDevicePointer(OSPWorld w) { return ((cuda::World *)w)->prepareFrame(); }
+const void *ospcudaWorldDevicePointer(OSPWorld w) { return ((cuda::World *)cuda::subObject(w, 0))->prepareFrame(); }
 }

@@ -70,5 +70,8 @@ struct CudaDevice : public api::Device
   bool materialsDirty = true;
 };
 
+void registerMultiDevice();                          // MultiDevice.cpp
+ManagedObject *subObject(void *handle, size_t i);    // sub-object i of a multidevice handle; the handle itself for i == 0 otherwise
+
 } // namespace cuda
 } // namespace ospray

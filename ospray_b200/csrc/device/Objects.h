@@ -297,6 +297,7 @@ struct FrameBuffer : public ManagedObject
   bool pickOdd = false;
   friend struct Future;
   friend struct CudaDevice;
+  friend struct MultiCudaDevice;
 };
 
 struct Future : public ManagedObject

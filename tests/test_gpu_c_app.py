@@ -84,8 +84,9 @@ def test_cancel_and_progress_of_a_running_frame(osp):
     f.wait()
     full = time.perf_counter() - t0
     assert f.progress() == 1.0
-    assert all(0.0 <= p < 1.0 for p in seen) and seen == sorted(seen)
-    assert len(seen) > 3 and max(seen) > 0.3, (len(seen), max(seen) if seen else None)
+    assert all(0.0 <= p <= 1.0 for p in seen) and seen == sorted(seen)   # (the frame may end between is_ready() and progress())
+    running = [p for p in seen if p < 1.0]
+    assert len(running) > 3 and max(running) > 0.3, (len(running), max(running) if running else None)
     t0 = time.perf_counter()
     f = fb.render_frame(ren, cam, world)
     f.cancel()

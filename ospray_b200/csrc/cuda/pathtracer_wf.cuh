@@ -515,6 +515,10 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptTraceKernel(cons
   const uint32_t lane = threadIdx.x & 31u, ltMask = (1u << lane) - 1u;
   uint32_t chunkNext = 0, chunkEnd = 0; // warp-uniform
   bool exhausted = false;               // warp-uniform: the cursor has run past the queue
+  // rays a warp reserves at a time: PT_TRACE_CHUNK when the queue is long; when it holds only a few rays per resident warp
+  // (late bounces, small tiles of a multi-GPU frame) smaller chunks spread them over all warps instead of leaving most idle
+  const uint32_t warpsInGrid = gridDim.x * (PT_TRACE_BLOCK / 32);
+  const uint32_t chunk = n >= 2u * PT_TRACE_CHUNK * warpsInGrid ? PT_TRACE_CHUNK : (n >= 128u * warpsInGrid ? 64u : 32u);
   bool active = false, fin = false;     // fin: the walk has ended, the result is not written yet
   uint32_t id = 0;
   uint32_t nShadow = 0, nCont = 0;
@@ -542,11 +546,11 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptTraceKernel(cons
       while (idle && !exhausted) {
         if (chunkNext == chunkEnd) {
           uint32_t base = 0;
-          if (lane == 0) base = frameCancelled(k.a.fb) ? 0xffffffffu : atomicAdd(k.fetchCursor, PT_TRACE_CHUNK);
+          if (lane == 0) base = frameCancelled(k.a.fb) ? 0xffffffffu : atomicAdd(k.fetchCursor, chunk);
           base = __shfl_sync(0xffffffffu, base, 0);
           if (base >= n) { exhausted = true; break; } // queue drained (or the frame was cancelled: ospCancel)
           chunkNext = base;
-          chunkEnd = min(base + PT_TRACE_CHUNK, n);
+          chunkEnd = min(base + chunk, n);
         }
         const uint32_t avail = chunkEnd - chunkNext;
         const uint32_t rank = __popc(idle & ltMask);

@@ -812,14 +812,14 @@ int ptCarve(oc::PtScratch &s, uint32_t paths, uint32_t nls, bool needAcc, uint32
   off[k++] = take(numCounters * 4);
   int dev = 0;
   cudaGetDevice(&dev);
-  if (bytes > g_pt.blockBytes || dev != g_pt.device) {
-    if (g_pt.block) cudaFree(g_pt.block);
-    g_pt.block = nullptr; g_pt.blockBytes = 0;
-    OC_TRY(cudaMalloc(&g_pt.block, bytes));
-    g_pt.blockBytes = bytes; g_pt.device = dev;
-    g_pt.traceBlocks = 0;
+  PtHost &h = g_pt;
+  if (bytes > h.blockBytes) {
+    if (h.block) { OC_TRY(cudaDeviceSynchronize()); cudaFree(h.block); }
+    h.block = nullptr; h.blockBytes = 0;
+    OC_TRY(cudaMalloc(&h.block, bytes));
+    h.blockBytes = bytes; h.device = dev;
   }
-  char *b = (char *)g_pt.block;
+  char *b = (char *)h.block;
   k = 0;
   s.rayO = (float4 *)(b + off[k++]); s.rayD = (float4 *)(b + off[k++]); s.hit0 = (float4 *)(b + off[k++]); s.hit1 = (float4 *)(b + off[k++]);
   s.thr = (float4 *)(b + off[k++]); s.con = (float4 *)(b + off[k++]); s.lastP = (float4 *)(b + off[k++]); s.lastN = (float4 *)(b + off[k++]);
@@ -869,6 +869,11 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles, bool
   const bool hasVol = !ao && fa.ren.worldHasVolumes != 0;
   k.vol = hasVol ? 1u : 0u;
   uint32_t tilesPerBatch = (uint32_t)std::max<size_t>(1, budget / (ptBytesPerPath(nls, needAcc, hasVol) * 4096));
+  // (smaller batches were tried for L2 residency of the path state, alternating between two streams so that one batch's
+  // thinned-out end overlaps the next batch's dense bounces: SHADE -17 %, but every batch pays its own tail and the
+  // persistent grids leave no room for real overlap -- C1 2.54 -> 2.76 ms, C5s 35 -> 54 ms, C3 93 -> 120 ms; profiles/)
+  static const int batchEnv = getenv("OSPCUDA_PT_BATCH_TILES") ? atoi(getenv("OSPCUDA_PT_BATCH_TILES")) : 0;
+  if (batchEnv > 0 && tilesPerBatch > (uint32_t)batchEnv) tilesPerBatch = (uint32_t)batchEnv;
   if (tilesPerBatch > ownedTiles) tilesPerBatch = ownedTiles;
   if ((uint64_t)tilesPerBatch * 4096u * nls >= (1ull << 31))
     return oc_set_error(cudaErrorInvalidValue, "pathtracer: lightSamples x paths per batch exceeds the shadow-ray id space");
@@ -902,10 +907,16 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles, bool
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t, ptTailKernel<false>, PT_TRACE_BLOCK, 0);
     g_pt.tailBlocks = sms * (t > 0 ? t : 1);
   }
-  // depth from which the tail kernel takes over: two bounces after Russian roulette starts (OSPCUDA_PT_TAIL_FROM overrides,
-  // 0 = never)
+  // depth from which the tail kernel takes over. A TRACE + SHADE launch pair pays for itself while the queue holds many
+  // paths per resident lane; below that a launch costs its latency floor whatever it holds, and carrying the paths to their
+  // end lane by lane is cheaper. With the whole 1024^2 frame on one GPU that point is two bounces after Russian roulette
+  // starts to cull; a sub-device's share of a multi-GPU frame (or a small image) gets there at the roulette depth itself
+  // (tools/gpu_r2s.sh, one sub-device's tiles of C1: 1/2 1.48 -> 1.44 ms, 1/4 0.92 -> 0.86 ms, 1/8 0.63 -> 0.55 ms).
+  // OSPCUDA_PT_TAIL_FROM overrides, 0 = never.
   static const int tailEnv = getenv("OSPCUDA_PT_TAIL_FROM") ? atoi(getenv("OSPCUDA_PT_TAIL_FROM")) : -1;
-  const uint32_t tailFrom = tailEnv == 0 ? 0xffffffffu : tailEnv > 0 ? (uint32_t)tailEnv : (uint32_t)std::max(1, fa.ren.rouletteDepth + 2);
+  const uint32_t pathsPerBatch = tilesPerBatch * 4096u;
+  const uint32_t tailAuto = (uint32_t)std::max(1, fa.ren.rouletteDepth + (pathsPerBatch >= 768u * 1024u ? 2 : 0));
+  const uint32_t tailFrom = tailEnv == 0 ? 0xffffffffu : tailEnv > 0 ? (uint32_t)tailEnv : tailAuto;
   const uint32_t progressStages = ao ? 2u : std::min(maxDepth + 1u, tailFrom == 0xffffffffu ? maxDepth + 1u : tailFrom + 1u);
   k.progressTotal = ((ownedTiles + tilesPerBatch - 1) / tilesPerBatch) * (uint32_t)fa.ren.spp * progressStages;
   k.progressUnit = 0;

@@ -22,7 +22,7 @@ __device__ __forceinline__ float linear_to_srgb(float f)
 
 // cvt_uint32(linear_to_srgb(f)), bit for bit, without the full-precision powf for all but ~0.2 % of the values: the byte is
 // round(255 * s). s is first evaluated with the hardware exp2 / log2 (__powf: relative error < 1e-6, i.e. < 3e-4 in 255 * s);
-// unless that estimate lands within 1e-3 of a rounding boundary (x.5) it rounds to the same byte as the exact evaluation,
+// unless that estimate lands within 5e-4 of a rounding boundary (x.5) it rounds to the same byte as the exact evaluation,
 // and the few values that do land there take the exact path. The 4K tonemap + conversion pass goes from ALU-bound (0.12 of
 // the HBM roofline) towards the memory bound.
 __device__ __forceinline__ uint32_t srgb8(float f)
@@ -31,7 +31,7 @@ __device__ __forceinline__ uint32_t srgb8(float f)
   if (c <= 0.0031308f) return cvt_uint32(12.92f * c);
   const float v = 255.f * fminf(fmaxf(__powf(c, 1.f / 2.4f) * 1.055f - 0.055f, 0.f), 1.f);
   const float r = rintf(v);
-  if (fabsf(fabsf(v - r) - 0.5f) < 1e-3f) return cvt_uint32(linear_to_srgb(f));
+  if (fabsf(fabsf(v - r) - 0.5f) < 5e-4f) return cvt_uint32(linear_to_srgb(f));
   return (uint32_t)r;
 }
 // x^a / (x^(a d) b + c) with the hardware exp2 / log2: relative error < 3e-6 (the reference's own ISPC pow is no tighter)

@@ -785,7 +785,15 @@ struct PtHost
   size_t blockBytes = 0;
   int device = -1;
   int traceBlocks = 0, shadeBlocks[2] = {0, 0}, genBlocks = 0, tailBlocks = 0, aoShadeBlocks = 0, traceVariant = 1, shadeVariant = 4; // persistent grids (resident CTAs per SM x SM count)
-} g_pt;
+};
+PtHost g_ptPerDevice[32]; // one scratch block per CUDA device of the process (in-process multidevice)
+PtHost &ptHost()
+{
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return g_ptPerDevice[dev & 31];
+}
+#define g_pt (ptHost())
 
 size_t alignUp(size_t v) { return (v + 255) & ~size_t(255); }
 

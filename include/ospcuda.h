@@ -362,6 +362,10 @@ OSPCUDA_API int ospcuda_bvh_free(OcBVH *bvh);
 #define OSPCUDA_TRAVERSAL_STACK 64
 #endif
 OSPCUDA_API uint32_t ospcuda_bvh_last_stack_need(void);
+/* options of the builds that follow (0 = default): Morton bits per axis (<= 21) and records per leaf (<= 15). The device
+ * rebuilds a group with (10, 8) when the default hierarchy needs more stack than traversal keeps: equal keys are split by
+ * index, so the coarser grid bounds the depth, at the price of a less tight hierarchy for that group */
+OSPCUDA_API int ospcuda_bvh_set_build_options(uint32_t mortonBitsPerAxis, uint32_t leafMax);
 /* largest value over the builds since the last call with reset != 0 (a world commit builds group and top-level hierarchies) */
 OSPCUDA_API uint32_t ospcuda_bvh_peak_stack_need(int reset);
 /* macrocell (16^3 cells) value ranges of a structured volume; d_ranges: 2*mcx*mcy*mcz floats */

@@ -190,7 +190,9 @@ __device__ __forceinline__ uint64_t expandBits21(uint64_t v)
   v = (v | (v << 2)) & 0x1249249249249249ull;
   return v;
 }
-__global__ void mortonKernel(const Aabb *boxes, uint32_t n, const uint32_t *sceneBounds, uint64_t *keys, uint32_t *ids)
+// `bits` per axis (<= 21): fewer bits put more primitives into one cell; the hierarchy over equal keys is split by index,
+// i.e. balanced, which bounds its depth (the fall-back build of a group whose first hierarchy came out too deep)
+__global__ void mortonKernel(const Aabb *boxes, uint32_t n, const uint32_t *sceneBounds, uint64_t *keys, uint32_t *ids, uint32_t bits)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -201,8 +203,9 @@ __global__ void mortonKernel(const Aabb *boxes, uint32_t n, const uint32_t *scen
     const float c = 0.5f * (boxes[i].lo[a] + boxes[i].hi[a]);
     const float ext = hi - lo;
     float f = ext > 0.f ? (c - lo) / ext : 0.f;
-    f = fminf(fmaxf(f * 2097152.f, 0.f), 2097151.f);
-    key |= expandBits21((uint64_t)f) << (2 - a);
+    const float cells = (float)(1u << bits);
+    f = fminf(fmaxf(f * cells, 0.f), cells - 1.f);
+    key |= expandBits21((uint64_t)f << (21u - bits)) << (2 - a);
   }
   keys[i] = key;
   ids[i] = i;
@@ -383,6 +386,7 @@ struct DevBuf
   ~DevBuf() { if (p) cudaFree(p); }
 };
 
+static uint32_t g_optMortonBits = 0, g_optLeafMax = 0; // ospcuda_bvh_set_build_options (0 = default)
 static uint32_t g_lastStackNeed = 0; // of the most recent build (ospcuda_bvh_last_stack_need)
 static uint32_t g_peakStackNeed = 0; // largest since the last reset (ospcuda_bvh_peak_stack_need)
 
@@ -399,7 +403,7 @@ static int buildFromBoxes(Aabb *d_boxes, float4 *d_records, uint32_t n, const ui
   DevBuf<OcNode4> wideTmp;
   DevBuf<uint8_t> cubTmp;
   OC_TRY(keys.alloc(n)); OC_TRY(keysSorted.alloc(n)); OC_TRY(ids.alloc(n)); OC_TRY(idsSorted.alloc(n));
-  mortonKernel<<<G, B, 0, st>>>(d_boxes, n, d_sceneBounds, keys.p, ids.p);
+  mortonKernel<<<G, B, 0, st>>>(d_boxes, n, d_sceneBounds, keys.p, ids.p, g_optMortonBits ? std::min(21u, g_optMortonBits) : 21u);
   oc_count_launch();
   size_t tmpBytes = 0;
   OC_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys.p, keysSorted.p, ids.p, idsSorted.p, (int)n, 0, 63, st));
@@ -456,7 +460,8 @@ static int buildFromBoxes(Aabb *d_boxes, float4 *d_records, uint32_t n, const ui
   OC_TRY(cudaMemcpyAsync(q0.p, &root, sizeof(root), cudaMemcpyHostToDevice, st));
   uint32_t inCount = 1;
   WorkItem *inQ = q0.p, *outQ = q1.p;
-  static const uint32_t leafMax = getenv("OSPCUDA_LEAF_MAX") ? std::min(15u, std::max(1u, (uint32_t)atoi(getenv("OSPCUDA_LEAF_MAX")))) : OC_LEAF_MAX;
+  static const uint32_t leafMaxDefault = getenv("OSPCUDA_LEAF_MAX") ? std::min(15u, std::max(1u, (uint32_t)atoi(getenv("OSPCUDA_LEAF_MAX")))) : OC_LEAF_MAX;
+  const uint32_t leafMax = g_optLeafMax ? std::min(15u, g_optLeafMax) : leafMaxDefault;
   while (inCount) {
     collapseKernel<<<(inCount + 127) / 128, 128, 0, st>>>(bin.p, nodeBoxes.p, (int)n, inQ, inCount, outQ, counters.p, counters.p + 1,
         wideTmp.p, leafMax, idsSorted.p, leafOrder.p, counters.p + 3);
@@ -574,6 +579,12 @@ extern "C" int ospcuda_bvh_build_tlas(const float *h_bounds, uint32_t numInstanc
 }
 
 extern "C" uint32_t ospcuda_bvh_last_stack_need(void) { return g_lastStackNeed; }
+extern "C" int ospcuda_bvh_set_build_options(uint32_t mortonBitsPerAxis, uint32_t leafMax)
+{
+  g_optMortonBits = mortonBitsPerAxis;
+  g_optLeafMax = leafMax;
+  return 0;
+}
 extern "C" uint32_t ospcuda_bvh_peak_stack_need(int reset)
 {
   const uint32_t v = g_peakStackNeed;

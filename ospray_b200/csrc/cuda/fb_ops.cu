@@ -67,7 +67,8 @@ __device__ __forceinline__ float4 toneMap(float4 col, const OcToneMapper &tm)
 // numRanks > 1: only the pixels of the 64x64 tiles this rank owns (tile % numRanks == rank) are converted; the other
 // pixels of the display buffer belong to the tile exchange (peers store their tiles there, possibly while this runs)
 template <int FORMAT, bool TONEMAP>
-__global__ void __launch_bounds__(256) postprocessKernel(const float4 *__restrict__ in, float4 *__restrict__ ppOut,
+// (`in` and `ppOut` may be the same buffer: chained tonemappers run in place, every pixel is read before it is written)
+__global__ void __launch_bounds__(256) postprocessKernel(const float4 *in, float4 *ppOut,
     void *__restrict__ out, uint32_t n, OcToneMapper tm, uint32_t sizeX, uint32_t numRanks, uint32_t rank)
 {
   const uint32_t tilesX = (sizeX + 63u) >> 6;

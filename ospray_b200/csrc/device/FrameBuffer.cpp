@@ -71,9 +71,13 @@ void FrameBuffer::commit()
       if (op && op->type == "tonemapper") toneMappers.emplace_back(op);
     }
     if (!toneMappers.empty()) {
-      buffers.emplace_back(new DevMem);
-      buffers.back()->reserve((size_t)size.x * size.y * 16);
-      ppBuf = buffers.back().get();
+      // one post-processed colour buffer for the life of the framebuffer, however often it is committed
+      if (!ppStore) {
+        buffers.emplace_back(new DevMem);
+        buffers.back()->reserve((size_t)size.x * size.y * 16);
+        ppStore = buffers.back().get();
+      }
+      ppBuf = ppStore;
     }
   }
 }

@@ -413,6 +413,19 @@ void Material::commit()
   device.setMaterial(slot, m);
 }
 
+// stack entries a hierarchy may need: OSPCUDA_TRAVERSAL_STACK (what traversal keeps), or less when OSPCUDA_STACK_LIMIT says so
+// (lets a test drive the fall-back build with a hierarchy the device could still walk)
+static uint32_t stackLimit()
+{
+  const char *e = getenv("OSPCUDA_STACK_LIMIT");
+  const uint32_t v = e ? (uint32_t)atoi(e) : 0u;
+  return v > 0 && v < OSPCUDA_TRAVERSAL_STACK ? v : (uint32_t)OSPCUDA_TRAVERSAL_STACK;
+}
+
+static std::atomic<uint64_t> g_commitEpoch{0};
+uint64_t commitEpoch() { return g_commitEpoch.load(); }
+uint64_t nextCommitEpoch() { return g_commitEpoch.fetch_add(1) + 1; }
+
 // ---- GeometricModel (geometry/GeometricModel.cpp:21-87) -------------------------------------------
 GeometricModel::GeometricModel(Geometry *g) : geomAPI(g) { managedObjectType = OSP_GEOMETRIC_MODEL; }
 
@@ -452,6 +465,7 @@ void GeometricModel::commit()
   if (indexData) sh.index = indexData->deviceView1D();
   sh.invertedNormals = getParam<bool>("invertNormals", false);
   sh.userID = getParam<uint32_t>("id", 0xFFFFFFFFu);
+  epoch = nextCommitEpoch();
 }
 
 // ---- TransferFunction (LinearTransferFunction.cpp:22-155) -------------------------------------------
@@ -469,6 +483,7 @@ void TransferFunction::commit()
   sh.valueUpper = valueRange.upper;
   opacities.resize(opacityData->size());
   for (size_t i = 0; i < opacities.size(); i++) opacities[i] = opacityData->at<float>(i);
+  epoch = nextCommitEpoch();
 }
 
 std::vector<box1f> TransferFunction::positiveOpacityValueRanges() const
@@ -504,14 +519,22 @@ void Volume::commit()
     throw std::runtime_error("cuda device: volume type '" + type + "' is not supported (structuredRegular only)");
   gridOrigin = getParam<vec3f>("gridOrigin", make_vec3f(0.f));
   gridSpacing = getParam<vec3f>("gridSpacing", make_vec3f(1.f));
-  getParam<bool>("cellCentered", false);
-  getParam<uint32_t>("filter", OSP_VOLUME_FILTER_LINEAR);
-  getParam<uint32_t>("gradientFilter", OSP_VOLUME_FILTER_LINEAR);
-  getParam<float>("background", NAN);
+  // what the sampler implements: vertex-centred data, trilinear reconstruction, NaN outside (volume/Volume.cpp:120-180 ->
+  // Open VKL structuredRegular); anything else is said, not silently rendered differently
+  if (getParam<bool>("cellCentered", false))
+    postStatusMsg(OSP_LOG_WARNING, "cuda device: structuredRegular 'cellCentered' is not supported, the data is taken as vertex-centred");
+  if (getParam<uint32_t>("filter", OSP_VOLUME_FILTER_LINEAR) != OSP_VOLUME_FILTER_LINEAR)
+    postStatusMsg(OSP_LOG_WARNING, "cuda device: volume 'filter' other than OSP_VOLUME_FILTER_LINEAR is not supported, trilinear is used");
+  if (getParam<uint32_t>("gradientFilter", OSP_VOLUME_FILTER_LINEAR) != OSP_VOLUME_FILTER_LINEAR)
+    postStatusMsg(OSP_LOG_WARNING, "cuda device: volume 'gradientFilter' other than OSP_VOLUME_FILTER_LINEAR is not supported");
+  if (!std::isnan(getParam<float>("background", NAN)))
+    postStatusMsg(OSP_LOG_WARNING, "cuda device: volume 'background' is not supported, samples outside the grid are NaN");
   Data *d = getParamObject<Data>("data");
   if (!d) throw std::runtime_error("structuredRegular volume needs a 3-D 'data' array");
   data = d;
   dims[0] = (uint32_t)d->numItems.x; dims[1] = (uint32_t)d->numItems.y; dims[2] = (uint32_t)d->numItems.z;
+  if (dims[0] < 2 || dims[1] < 2 || dims[2] < 2) // the trilinear sampler reads the +1 neighbours of every cell
+    throw std::runtime_error("structuredRegular volume: every dimension of 'data' must be at least 2");
   const size_t n = d->size();
   if (d->type == OSP_FLOAT && d->compact()) {
     voxels.upload(d->addr, n * sizeof(float));
@@ -557,17 +580,27 @@ void VolumetricModel::commit()
   const box3f b = volume->getBounds();
   sh.bounds[0] = b.lower.x; sh.bounds[1] = b.lower.y; sh.bounds[2] = b.lower.z;
   sh.bounds[3] = b.upper.x; sh.bounds[4] = b.upper.y; sh.bounds[5] = b.upper.z;
-  sh.tf = tf->sh;
   sh.densityScale = getParam<float>("densityScale", 1.f);
   sh.anisotropy = getParam<float>("anisotropy", 0.f);
   sh.gradientShadingScale = getParam<float>("gradientShadingScale", 0.f);
   sh.userID = getParam<uint32_t>("id", 0xFFFFFFFFu);
+  epoch = 0;
+  refreshFromChildren();
+}
+
+// the part of the struct that mirrors the transfer function (the reference holds a pointer to it, VolumetricModel.cpp:72)
+bool VolumetricModel::refreshFromChildren()
+{
+  if (!tf || (epoch != 0 && tf->epoch <= epoch)) return false;
+  sh.tf = tf->sh;
   const std::vector<box1f> ranges = tf->positiveOpacityValueRanges();
   sh.numRanges = (uint32_t)std::min<size_t>(ranges.size(), 8);
   if (ranges.size() > 8) { // too many disjoint ranges: fall back to "everything"
     sh.numRanges = 1; sh.ranges[0] = -INFINITY; sh.ranges[1] = INFINITY;
   } else
     for (uint32_t i = 0; i < sh.numRanges; i++) { sh.ranges[2 * i] = ranges[i].lower; sh.ranges[2 * i + 1] = ranges[i].upper; }
+  epoch = nextCommitEpoch();
+  return true;
 }
 
 // ---- Light (lights/Light.cpp:20-25, AmbientLight.cpp, DirectionalLight.cpp, QuadLight.cpp:68-108) ---
@@ -727,7 +760,18 @@ void Group::commit()
     sh.numModels = (uint32_t)n;
     checkCuda(ospcuda_bvh_build_group(sh.models, sh.numModels, numPrims.data(), types.data(), &sh.bvh, &lastBuildMs), "BVH build");
     stackNeed = ospcuda_bvh_last_stack_need();
-    if (stackNeed > OSPCUDA_TRAVERSAL_STACK)
+    if (stackNeed > stackLimit()) {
+      // strongly clustered primitives make a long chain of the Morton hierarchy: build this group again over a coarser
+      // grid with larger leaves (equal keys are split by index, a balanced subtree) instead of refusing the scene
+      postStatusMsg(OSP_LOG_INFO, "cuda device: hierarchy of a group needs " + std::to_string(stackNeed) + " stack entries, rebuilding it over a coarser grid");
+      ospcuda_bvh_free(&sh.bvh);
+      ospcuda_bvh_set_build_options(10, 8);
+      const int rc = ospcuda_bvh_build_group(sh.models, sh.numModels, numPrims.data(), types.data(), &sh.bvh, &lastBuildMs);
+      ospcuda_bvh_set_build_options(0, 0);
+      checkCuda(rc, "BVH build");
+      stackNeed = ospcuda_bvh_last_stack_need();
+    }
+    if (stackNeed > stackLimit())
       throw std::runtime_error("ospray::Group: the hierarchy over this geometry is too deep for the traversal stack (needs "
           + std::to_string(stackNeed) + " entries, the device keeps " + std::to_string(OSPCUDA_TRAVERSAL_STACK) + ")");
     if (sh.bvh.numRecords) {
@@ -751,6 +795,37 @@ void Group::commit()
     sh.numVolumes = (uint32_t)n;
   }
   dev.upload(&sh, sizeof(sh));
+  snapshotEpoch = commitEpoch();
+}
+
+void Group::refreshSnapshots()
+{
+  if (snapshotEpoch == commitEpoch()) return;
+  bool models = false, vols = false;
+  if (geometricModels)
+    for (size_t i = 0; i < geometricModels->size() && !models; i++) {
+      GeometricModel *m = dynamic_cast<GeometricModel *>(geometricModels->objectAt(i));
+      models = m && m->epoch > snapshotEpoch;
+    }
+  if (volumetricModels)
+    for (size_t i = 0; i < volumetricModels->size(); i++) {
+      VolumetricModel *m = dynamic_cast<VolumetricModel *>(volumetricModels->objectAt(i));
+      if (m && (m->refreshFromChildren() || m->epoch > snapshotEpoch)) vols = true;
+    }
+  if (models) {
+    std::vector<OcModel> snap(geometricModels->size());
+    for (size_t i = 0; i < snap.size(); i++) snap[i] = dynamic_cast<GeometricModel *>(geometricModels->objectAt(i))->sh;
+    modelsDev.upload(snap.data(), snap.size() * sizeof(OcModel));
+    sh.models = modelsDev.as<OcModel>();
+  }
+  if (vols) {
+    std::vector<OcVolume> snap(volumetricModels->size());
+    for (size_t i = 0; i < snap.size(); i++) snap[i] = dynamic_cast<VolumetricModel *>(volumetricModels->objectAt(i))->sh;
+    volumesDev.upload(snap.data(), snap.size() * sizeof(OcVolume));
+    sh.volumes = volumesDev.as<OcVolume>();
+  }
+  if (models || vols) dev.upload(&sh, sizeof(sh)); // (the array may have moved)
+  snapshotEpoch = commitEpoch();
 }
 
 // ---- Instance (common/Instance.cpp:20-52) ----------------------------------------------------------------
@@ -889,6 +964,14 @@ void World::commit()
 
 const OcWorld *World::prepareFrame()
 {
+  // models / transfer functions committed since the last frame: the groups take their new state over (Group::refreshSnapshots)
+  if (seenEpoch != commitEpoch() && instances) {
+    for (size_t i = 0; i < instances->size(); i++) {
+      Instance *in = dynamic_cast<Instance *>(instances->objectAt(i));
+      if (in && in->group) in->group->refreshSnapshots();
+    }
+    seenEpoch = commitEpoch();
+  }
   const OcMaterial *mt = device.materialTable();
   if (dirty || mt != uploadedMaterials) {
     sh.materials = mt;

@@ -120,6 +120,9 @@ struct Material : public ManagedObject
   uint32_t slot;
 };
 
+uint64_t commitEpoch();     // counts the commits of objects whose state parents snapshot
+uint64_t nextCommitEpoch();
+
 struct GeometricModel : public ManagedObject
 {
   explicit GeometricModel(Geometry *g);
@@ -127,6 +130,7 @@ struct GeometricModel : public ManagedObject
   void commit() override;
   Ref<Geometry> geomAPI, geom;
   OcModel sh{};
+  uint64_t epoch = 0; // commitEpoch() at the last commit (parents compare it with the epoch of their snapshot)
 
  private:
   Ref<Data> materialData, colorData, indexData, promotedMat, promotedColor;
@@ -140,6 +144,7 @@ struct TransferFunction : public ManagedObject
   std::vector<box1f> positiveOpacityValueRanges() const;
   OcTransferFunction sh{};
   box1f valueRange{0.f, 1.f};
+  uint64_t epoch = 0;
 
  private:
   Ref<Data> colorData, opacityData, promC, promO;
@@ -171,6 +176,8 @@ struct VolumetricModel : public ManagedObject
   Ref<Volume> volumeAPI, volume;
   Ref<TransferFunction> tf;
   OcVolume sh{};
+  uint64_t epoch = 0;
+  bool refreshFromChildren(); // the transfer function was committed after this model: take its new state over
 };
 
 struct Light : public ManagedObject
@@ -196,6 +203,13 @@ struct Group : public ManagedObject
   box3f bounds = box_empty();
   float lastBuildMs = 0.f;
   uint32_t stackNeed = 0; // deepest traversal stack the group's BVH can ask for (ospcuda_bvh_last_stack_need)
+  // The device arrays of this group are SNAPSHOTS of its models' structs (the reference's Group keeps pointers to them,
+  // Group.cpp:139/157). A model or transfer function committed later -- new material list, colours, ids, opacities -- must
+  // show in the next frame without the group being committed again (OSPRay semantics), and a snapshot must never keep a
+  // pointer into a buffer the child has since replaced: World::prepareFrame calls this whenever anything was committed
+  // since the last frame. Geometry changes still need the group's commit (the hierarchy is built there).
+  void refreshSnapshots();
+  uint64_t snapshotEpoch = 0;
 
  private:
   DevMem dev, modelsDev, volumesDev;
@@ -230,6 +244,7 @@ struct World : public ManagedObject
   DevMem dev, instDev, lightsDev, cdfDev, scivisLightsDev;
   const void *uploadedMaterials = nullptr;
   bool dirty = true;
+  uint64_t seenEpoch = 0;
 };
 
 struct ImageOp : public ManagedObject
@@ -284,7 +299,7 @@ struct FrameBuffer : public ManagedObject
   std::vector<std::unique_ptr<DevMem>> buffers;
   DevMem *colorBuf = nullptr, *varianceBuf = nullptr, *depthBuf = nullptr, *normalBuf = nullptr, *firstNormalBuf = nullptr,
          *albedoBuf = nullptr, *positionBuf = nullptr, *primBuf = nullptr, *objBuf = nullptr, *instBuf = nullptr, *convBuf = nullptr,
-         *ppBuf = nullptr, *taskErrBuf = nullptr, *counterBuf = nullptr;
+         *ppBuf = nullptr, *ppStore = nullptr, *taskErrBuf = nullptr, *counterBuf = nullptr;
   Ref<Data> imageOpData;
   std::vector<Ref<ImageOp>> toneMappers;
   struct Staging { void *host; bool inUse; };

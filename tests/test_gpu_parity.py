@@ -302,3 +302,78 @@ def test_builder_reports_the_traversal_stack_need(osp, abi):
     assert 6 <= need <= 30, need
     world, keep = T.to_ospray(T.cornell_box())    # 34 records
     assert 1 <= abi.ospcuda_bvh_peak_stack_need(1) <= 12
+
+
+def _clustered_mesh(levels=20, per_level=6):
+    """triangles in clusters that shrink geometrically along the three axes: cluster (j, a) sits at 2^-j on axis a and is
+    2^-j wide, so that every bit of the 63-bit Morton key peels exactly one cluster off: the radix hierarchy is one long
+    chain (3 x levels deep)."""
+    rng = np.random.default_rng(5)
+    verts, index = [], []
+
+    def cluster(c, s):
+        for k in range(per_level):
+            tri = c + 0.2 * s * rng.uniform(0, 1, (3, 3))
+            index.append([len(verts), len(verts) + 1, len(verts) + 2])
+            verts.extend(tri)
+    cluster(np.array([0.9, 0.9, 0.9]), 0.5)              # anchors the scene bounds at the unit cube
+    for j in range(1, levels + 1):
+        for a in range(3):
+            c = np.zeros(3)
+            c[a] = 2.0 ** -j
+            cluster(c, 2.0 ** -j)
+    geom = T.GeometrySpec("mesh", vertex=np.array(verts, np.float32), index=np.array(index, np.uint32))
+    return T.SceneSpec(instances=[T.InstanceSpec(T.GroupSpec(models=[T.ModelSpec(geom, T.MaterialSpec())]))], lights=[])
+
+
+@pytest.mark.gpu
+def test_clustered_mesh_deep_hierarchy_is_rebuilt_not_refused(osp, abi):
+    """a hierarchy that would need more traversal stack than the device keeps (OSPCUDA_TRAVERSAL_STACK) is built again over a
+    coarser Morton grid with larger leaves instead of refusing the scene; the rebuilt one answers like brute force"""
+    from oracle import pyoracle as O
+    import os
+    abi.ospcuda_bvh_peak_stack_need.restype = C.c_uint32
+    abi.ospcuda_bvh_last_stack_need.restype = C.c_uint32
+    abi.ospcuda_bvh_peak_stack_need(1)
+    spec = _clustered_mesh()
+    # the chain needs ~38 entries with the default build (treelet restructuring already flattens it; the device keeps 64):
+    # a limit of 28 makes the device take the fall-back for it, while traversal can still walk whatever comes out
+    os.environ["OSPCUDA_STACK_LIMIT"] = "28"
+    try:
+        world, keep = T.to_ospray(spec)                   # would raise if the group were refused
+    finally:
+        del os.environ["OSPCUDA_STACK_LIMIT"]
+    peak = abi.ospcuda_bvh_peak_stack_need(1)
+    assert peak > 28, peak                                # the first build was too deep: the fall-back ran
+    sc = O.Scene(spec)
+    rays = _random_rays(*sc.bounds, 4000, seed=3)
+    rays["org"][:2000] = np.float32(1.5)                  # half the rays look at the corner the clusters shrink towards
+    d = -np.ones((2000, 3), np.float32) + np.random.default_rng(1).uniform(-0.3, 0.3, (2000, 3)).astype(np.float32)
+    rays["dir"][:2000] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    want = O.trace(sc, rays.copy())
+    got = _gpu_trace(abi, world, rays, False)
+    assert ((want["geomID"] != O.INVALID_ID) == (got["geomID"] != O.INVALID_ID)).all()
+    assert (got["t"].view(np.uint32) == want["t"].view(np.uint32)).all()
+    assert (want["geomID"] != O.INVALID_ID).mean() > 0.02   # thin clusters: few of the random rays hit, 150 is plenty
+
+
+@pytest.mark.gpu
+def test_model_and_transfer_function_commits_reach_the_next_frame(osp):
+    """OSPRay semantics: committing a geometric model (here: another material) or a transfer function takes effect in the
+    next frame without committing the group / world again (the reference's Group holds pointers to its models' structs,
+    Group.cpp:139-157); the device refreshes its snapshots before the frame"""
+    w, h = 64, 48
+    spec = T.cornell_box()
+    world, keep = T.to_ospray(spec)
+    cam, _ = T.make_camera(world, w, h)
+    ren = T.make_renderer("scivis", aoSamples=0)
+    fb = osp.FrameBuffer(w, h, osp.OSP_FB_RGBA32F, osp.OSP_FB_COLOR)
+    fb.render_frame(ren, cam, world).wait()
+    before = fb.map(osp.OSP_FB_COLOR)
+    model = [o for o in keep if isinstance(o, osp.Object) and o.kind == osp.OSP_GEOMETRIC_MODEL][0]
+    dark = osp.Material("obj")
+    dark.set("kd", (0.05, 0.05, 0.05)).commit()
+    model.set("material", dark).commit()                  # only the model is committed
+    fb.render_frame(ren, cam, world).wait()
+    after = fb.map(osp.OSP_FB_COLOR)
+    assert after[..., :3].mean() < 0.5 * before[..., :3].mean()

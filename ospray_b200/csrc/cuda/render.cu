@@ -272,13 +272,40 @@ __device__ __noinline__ SSI SciVis_computeShading(Ctx &c, const DifferentialGeom
   return ret;
 }
 
+// gradient shading of one volume sample (scivis/volumes.ispc:391-419), out of line: the marching loop of volumes without
+// gradient shading (the default) keeps its registers
+__device__ __noinline__ vec4f shadeVolumeSampleSciVis(Ctx &c, const VolumeHit &vh, vec3f p, vec4f sc, float dt, RandomSampler &rs, vec3f rayDir,
+    uint32_t px, uint32_t py, int sampleIDz)
+{
+  const OcVolume &v = *vh.vol;
+  vec3f ns = volumeGradient(v, p);
+  if (dot(ns, ns) > 1e-6f) {
+    ns = neg(ns);
+    DifferentialGeometry dg;
+    dg.color = sc;
+    dg.material = nullptr;
+    dg.epsilon = dt / 2.f;
+    const vec3f nw = vh.inst->isIdentity ? ns : xfmVector(transposed(toA(vh.inst->rcp_xfm).l), ns);
+    dg.Ns = dg.Ng = normalize(nw);
+    dg.P = p;
+    dg.dPds = make_vec3f(1.f, 0.f, 0.f);
+    dg.primID = 0; dg.objID = dg.instID = OC_INVALID_ID;
+    const SSI shading = SciVis_computeShading(c, dg, rs, rayDir, px, py, sampleIDz);
+    const vec4f shadedColor = make_vec4f(shading.shadedColor, 1.f - luminance(shading.transmission));
+    sc = lerp4(v.gradientShadingScale, sc, shadedColor);
+  }
+  return sc;
+}
+
 // single-volume marcher, SciVis flavour with gradient shading (scivis/volumes.ispc:302-439):
 // returns (rgb, transmission)
 // volT / volHit follow the reference CPU form (sampleAllVolumes, scivis/volumes.ispc:160-169): the
 // first sample in front of the surface hit that is not fully transparent defines depth and IDs.
-__device__ __noinline__ vec4f integrateVolumeSciVis(Ctx &c, const VolumeHit &vh, const Ray &ray, RandomSampler &rs, float samplingRate,
-    uint32_t px, uint32_t py, int sampleIDz, float &volT, bool &volHit)
+struct VolumeMarch { vec4f color; float volT; bool volHit; }; // handed back by value: references would pin volT / volHit to local memory
+__device__ __noinline__ VolumeMarch integrateVolumeSciVis(Ctx &c, const VolumeHit &vh, const Ray &ray, RandomSampler &rs, float samplingRate,
+    uint32_t px, uint32_t py, int sampleIDz, float volT)
 {
+  bool volHit = false;
   const OcVolume &v = *vh.vol;
   vec3f org = ray.org, dir = ray.dir;
   if (!vh.inst->isIdentity) {
@@ -303,7 +330,7 @@ __device__ __noinline__ vec4f integrateVolumeSciVis(Ctx &c, const VolumeHit &vh,
         iuLength = (ivUpper - ivLower) / samplingStep;
         distance = (distance == INFINITY) ? ivLower : distance;
       } else {
-        return make_vec4f(color, transmission);
+        return VolumeMarch{make_vec4f(color, transmission), volT, volHit};
       }
     }
     const float newDistance = ivLower + iuDistance * samplingStep;
@@ -312,24 +339,7 @@ __device__ __noinline__ vec4f integrateVolumeSciVis(Ctx &c, const VolumeHit &vh,
     if (!isnan(sampleVal)) {
       vec4f sc = transferFunctionGet(v.tf, sampleVal);
       const float dt = newDistance - distance - emptySpace;
-      if (v.gradientShadingScale > 0.f && sc.w > 0.0f) {
-        vec3f ns = volumeGradient(v, p);
-        if (dot(ns, ns) > 1e-6f) {
-          ns = neg(ns);
-          DifferentialGeometry dg;
-          dg.color = sc;
-          dg.material = nullptr;
-          dg.epsilon = dt / 2.f;
-          const vec3f nw = vh.inst->isIdentity ? ns : xfmVector(transposed(toA(vh.inst->rcp_xfm).l), ns);
-          dg.Ns = dg.Ng = normalize(nw);
-          dg.P = p;
-          dg.dPds = make_vec3f(1.f, 0.f, 0.f);
-          dg.primID = 0; dg.objID = dg.instID = OC_INVALID_ID;
-          const SSI shading = SciVis_computeShading(c, dg, rs, ray.dir, px, py, sampleIDz);
-          const vec4f shadedColor = make_vec4f(shading.shadedColor, 1.f - luminance(shading.transmission));
-          sc = lerp4(v.gradientShadingScale, sc, shadedColor);
-        }
-      }
+      if (v.gradientShadingScale > 0.f && sc.w > 0.0f) sc = shadeVolumeSampleSciVis(c, vh, p, sc, dt, rs, ray.dir, px, py, sampleIDz);
       sc.w = expf(-sc.w * dt * v.densityScale);
       if (newDistance < volT && sc.w < 1.0f - c.ren.minContribution) { volT = newDistance; volHit = true; }
       color = color + transmission * (1.f - sc.w) * make_vec3f(sc);
@@ -338,7 +348,7 @@ __device__ __noinline__ vec4f integrateVolumeSciVis(Ctx &c, const VolumeHit &vh,
     iuDistance += 1.f;
     distance = newDistance;
   }
-  return make_vec4f(color, transmission);
+  return VolumeMarch{make_vec4f(color, transmission), volT, volHit};
 }
 
 // visible lights (scivis/surfaces.ispc:130-150)
@@ -373,8 +383,10 @@ __device__ void SciVis_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint
     if (c.world->hasVolumes) {
       VolumeHit vh;
       if (traceVolumeRay(c.world, ray, vh)) {
-        bool volHit = false;
-        const vec4f volumeColor = integrateVolumeSciVis(c, vh, ray, rs, ren.volumeSamplingRate, px, py, sampleIDz, volumeT, volHit);
+        const VolumeMarch vm = integrateVolumeSciVis(c, vh, ray, rs, ren.volumeSamplingRate, px, py, sampleIDz, volumeT);
+        const vec4f volumeColor = vm.color;
+        const bool volHit = vm.volHit;
+        volumeT = vm.volT;
         outColor = outColor + outTransmission * make_vec3f(volumeColor);
         outTransmission = outTransmission * volumeColor.w;
         if (volHit && sample.geomID == OC_INVALID_ID) {

@@ -92,6 +92,28 @@ typedef struct {
   uint32_t userID;          /* 0xFFFFFFFF = unset */
 } OcModel;
 
+/* 2D texture (reference: ispc::Texture2D, texture/Texture2DShared.h:16-46; Texture2D.cpp:56-146: level 0 is the app's
+ * image, levels 1..maxLevel the MIP chain down to 1x1, all in `format`); format / filter / wrap are the OSPTextureFormat /
+ * OSPTextureFilter / OSPTextureWrapMode values of OSPEnums.h */
+#define OC_MAX_MIPMAP_LEVEL 32
+typedef struct {
+  const void *data[OC_MAX_MIPMAP_LEVEL];
+  int32_t sizeX, sizeY;
+  int32_t maxLevel;
+  uint32_t format, filter;
+  uint32_t wrapS, wrapT;
+  uint32_t hasAlpha;
+} OcTexture2D;
+/* texture + the optional 2D transform of its coordinates (reference: ispc::TextureParam, texture/TextureParamShared.h:21-38,
+ * Material::getTextureParam, render/Material.cpp:73-108): xform2f = (l.vx, l.vy, p), scale2f = sqrt(det l) */
+enum { OC_TEX_TRANSFORM_NONE = 0, OC_TEX_TRANSFORM_2D = 1 };
+typedef struct {
+  const OcTexture2D *tex;      /* NULL: no texture */
+  uint32_t transformFlags;
+  float scale2f;
+  float xform2f[6];
+} OcTextureParam;
+
 enum { OC_MATERIAL_OBJ = 0, OC_MATERIAL_OTHER = 1, OC_MATERIAL_THINGLASS = 2 };
 /* material (reference: ispc::OBJ, render/materials/OBJShared.h, OBJ.cpp:30-66; ispc::ThinGlass,
  * render/materials/ThinGlassShared.h, ThinGlass.cpp:33-48: eta = 1/ior, attenuationScale = thickness /
@@ -106,7 +128,10 @@ typedef struct {
   float eta;
   OcVec3f attenuation;
   float attenuationScale;
-  float pad[3];
+  uint32_t hasTextures;        /* any of the maps below is set (kernels without texture support skip them all) */
+  float bumpRot[4];            /* OBJ.cpp:43-44: orthogonal part of map_bump's 2D transform, transposed (vx, vy) */
+  /* OBJ: map_d, map_kd, map_ks, map_ns, map_bump (OBJShared.h:19-31); thinGlass: mapKd = map_attenuationColor */
+  OcTextureParam mapD, mapKd, mapKs, mapNs, mapBump;
 } OcMaterial;
 
 /* 4-wide BVH node, 128 B = one cache line, fetched as 8 x 128-bit loads */
@@ -265,6 +290,13 @@ typedef struct {
   /* host-side copy of OcWorld.hasVolumes of the world this frame renders (set per ospRenderFrame like worldNumLights):
    * the pathtracer then samples free paths / transmittance and carries a RandomSampler per path */
   uint32_t worldHasVolumes;
+  /* Renderer.cpp:41,91: 2^mipMapBias; map_backplate / map_maxDepth (Renderer.cpp:61-80, Renderer.ispc:18-39), NULL = none */
+  float mipBiasFactor;
+  const OcTexture2D *backplate;
+  const OcTexture2D *maxDepthTexture;
+  /* host-side: the world / renderer of this frame reference textures (set per ospRenderFrame like worldNumLights): the
+   * frame runs the kernels compiled with texture support (texture coordinates, tangents, ray cones) */
+  uint32_t hasTextures;
 } OcRenderer;
 
 /* framebuffer (reference: LocalFBShared.h, FrameBufferShared.h; LocalFB.cpp:49-180) */
@@ -374,6 +406,13 @@ OSPCUDA_API int ospcuda_volume_macrocells(const float *d_voxels, const uint32_t 
 
 /* ---- traversal (batch API) --------------------------------------------------------- */
 OSPCUDA_API int ospcuda_trace(const OcWorld *d_world, OcRayHit *d_rays, uint32_t numRays, int occlusionOnly);
+
+/* ---- texture lookups (batch API) -----------------------------------------------------
+ * get4f(TextureParam, dg) for n (st, pixelFootprint) pairs (reference: texture/TextureParam.ispc:10-22 ->
+ * Texture2D_get, texture/Texture2D.ispc:133-158). `d_param->tex` and the level pointers inside it are device memory
+ * (what a committed texture2d / material holds); d_st = 2n floats, d_footprint = n floats, d_out = 4n floats. */
+OSPCUDA_API int ospcuda_texture_sample(const OcTextureParam *param, const float *d_st, const float *d_footprint, uint32_t n,
+    float *d_out);
 
 /* ---- frame ------------------------------------------------------------------------- */
 OSPCUDA_API int ospcuda_render_frame(const OcWorld *d_world, const OcCamera *camera,

@@ -31,6 +31,9 @@ OSPRAY_INTERFACE void ospcudaSetRenderStream(void *stream);
 /* device pointer of the committed world's OcWorld (include/ospcuda.h), valid until the next commit;
  * lets a consumer call the batch traversal entry point ospcuda_trace directly */
 OSPRAY_INTERFACE const void *ospcudaWorldDevicePointer(OSPWorld);
+/* device pointer of a committed texture2d's OcTexture2D (include/ospcuda.h), valid until the next commit of the texture;
+ * lets a consumer call the batch lookup entry point ospcuda_texture_sample directly */
+OSPRAY_INTERFACE const void *ospcudaTextureDevicePointer(OSPTexture);
 #ifdef __cplusplus
 }
 #endif

@@ -2347,3 +2347,114 @@ ORACLE_API void oracle_fb_pack_tiles(void *packed, void *image, int sizeX, int s
     }
   }
 }
+
+// ---- 2D textures: texel formats and the MIP chain ------------------------------------------------------------------
+// texture/Texture2DFormats.ispc (getTexel_* :216-400, setTexel_* :46-214) and texture/MipMapGeneration.ispc:8-95 restated;
+// the chain layout is Texture2D::commit's (texture/Texture2D.cpp:103-141: level l+1 = max(size_l / 2, 1) down to 1x1).
+// The checker builds the chain with this code and hands it to the reference's own Texture2D_get (oracle/_ref); the device
+// builds its own at ospCommit. sRGB transfer = rkcommon's (un-vendored, see the header of this file).
+namespace {
+struct TexFmt { int chan; int kind; bool srgb; }; // kind: 0 u8, 1 u16, 2 f32, 3 f16; chan 1 R, 2 RA, 3 RGB, 4 RGBA
+bool texFmt(uint32_t f, TexFmt &t)
+{
+  // OSPTextureFormat order (OSPEnums.h): RGBA8 SRGBA RGBA32F RGB8 SRGB RGB32F R8 R32F L8 RA8 LA8 RGBA16 RGB16 RA16 R16 RA32F RGBA16F RGB16F RA16F R16F
+  static const TexFmt tab[20] = {{4, 0, false}, {4, 0, true}, {4, 2, false}, {3, 0, false}, {3, 0, true}, {3, 2, false}, {1, 0, false}, {1, 2, false},
+      {1, 0, true}, {2, 0, false}, {2, 0, true}, {4, 1, false}, {3, 1, false}, {2, 1, false}, {1, 1, false}, {2, 2, false}, {4, 3, false},
+      {3, 3, false}, {2, 3, false}, {1, 3, false}};
+  if (f >= 20) return false;
+  t = tab[f];
+  return true;
+}
+inline size_t texChanBytes(int kind) { return kind == 0 ? 1 : kind == 2 ? 4 : 2; }
+inline float texSrgbDecode(float x) { return x <= 0.04045f ? x * (1.f / 12.92f) : powf((x + 0.055f) * (1.f / 1.055f), 2.4f); }
+inline float texSrgbEncode(float f) { const float c = std::max(f, 0.f); return c <= 0.0031308f ? 12.92f * c : powf(c, 1.f / 2.4f) * 1.055f - 0.055f; }
+inline float texLoadChan(const TexFmt &t, const void *data, size_t i)
+{
+  switch (t.kind) {
+  case 0: return (float)((const uint8_t *)data)[i] * (1.f / 255.f);
+  case 1: return (float)((const uint16_t *)data)[i] * (1.f / 65535.f);
+  case 2: return ((const float *)data)[i];
+  default: { _Float16 h; memcpy(&h, (const uint16_t *)data + i, 2); return (float)h; }
+  }
+}
+inline void texStoreChan(const TexFmt &t, void *data, size_t i, float v)
+{
+  switch (t.kind) {
+  case 0: ((uint8_t *)data)[i] = (uint8_t)rintf(255.f * std::min(std::max(v, 0.f), 1.f)); break;
+  case 1: ((uint16_t *)data)[i] = (uint16_t)rintf(65535.f * std::min(std::max(v, 0.f), 1.f)); break;
+  case 2: ((float *)data)[i] = v; break;
+  default: { const _Float16 h = (_Float16)v; memcpy((uint16_t *)data + i, &h, 2); }
+  }
+}
+// vec4f of texel idx: missing channels read (r, 0, 0, 1) / (r, 0, 0, a) / (r, g, b, 1); luminance formats replicate
+V4 texGet(uint32_t f, const TexFmt &t, const void *data, uint32_t idx)
+{
+  const size_t b = (size_t)idx * t.chan;
+  V4 v{0.f, 0.f, 0.f, 1.f};
+  v.x = texLoadChan(t, data, b);
+  if (t.chan == 2) v.w = texLoadChan(t, data, b + 1);
+  if (t.chan >= 3) { v.y = texLoadChan(t, data, b + 1); v.z = texLoadChan(t, data, b + 2); }
+  if (t.chan == 4) v.w = texLoadChan(t, data, b + 3);
+  if (t.srgb) {
+    v.x = texSrgbDecode(v.x);
+    if (t.chan >= 3) { v.y = texSrgbDecode(v.y); v.z = texSrgbDecode(v.z); }
+    else v.y = v.z = v.x; // L8 / LA8
+  }
+  (void)f;
+  return v;
+}
+void texSet(const TexFmt &t, void *data, uint32_t idx, V4 v)
+{
+  const size_t b = (size_t)idx * t.chan;
+  if (t.srgb) { v.x = texSrgbEncode(v.x); v.y = texSrgbEncode(v.y); v.z = texSrgbEncode(v.z); if (t.chan == 4) v.w = std::max(v.w, 0.f); }
+  texStoreChan(t, data, b, v.x);
+  if (t.chan == 2) texStoreChan(t, data, b + 1, v.w);
+  if (t.chan >= 3) { texStoreChan(t, data, b + 1, v.y); texStoreChan(t, data, b + 2, v.z); }
+  if (t.chan == 4) texStoreChan(t, data, b + 3, v.w);
+}
+inline V4 tex3(float a, V4 x, float b, V4 y, float c, V4 z)
+{
+  return {a * x.x + b * y.x + c * z.x, a * x.y + b * y.y + c * z.y, a * x.z + b * y.z + c * z.z, a * x.w + b * y.w + c * z.w};
+}
+} // namespace
+
+// bytes of one texel, 0 for an unknown format
+ORACLE_API uint32_t oracle_texture_texel_bytes(uint32_t format)
+{
+  TexFmt t;
+  return texFmt(format, t) ? (uint32_t)(t.chan * texChanBytes(t.kind)) : 0u;
+}
+// one MIP level from the finer one (MipMap_generate)
+ORACLE_API void oracle_texture_mip_level(uint32_t format, const void *src, int sx, int sy, void *dst, int dx, int dy)
+{
+  TexFmt t;
+  if (!texFmt(format, t)) return;
+  if (sx > 1 && sy > 1) {
+    for (int y = 0; y < dy; y++) { // MipMap_generateRows, one task per destination row
+      const int dsty = y * dx, srcy = 2 * y * sx;
+      float rx = 1.f / (float)sx, ry = 1.f / (float)sy, hx = (float)dx * rx, hy = (float)dy * ry;
+      int ox = 2, oy = srcy + 2 * sx;
+      if (!(sx & 1)) { hx = 0.5f; rx = 0.f; ox = 0; }
+      if (!(sy & 1)) { hy = 0.5f; ry = 0.f; oy = srcy; }
+      const float wy0 = hy - y * ry, wy2 = ry + y * ry;
+      for (int x = 0; x < dx; x++) {
+        const float tx = x * rx;
+        const int s = 2 * x;
+        V4 v[3];
+        const int rows[3] = {srcy, srcy + sx, oy};
+        for (int k = 0; k < 3; k++)
+          v[k] = tex3(hx - tx, texGet(format, t, src, rows[k] + s), hx, texGet(format, t, src, rows[k] + s + 1), rx + tx, texGet(format, t, src, rows[k] + s + ox));
+        texSet(t, dst, dsty + x, tex3(wy0, v[0], hy, v[1], wy2, v[2]));
+      }
+    }
+  } else if (sx > 1 || sy > 1) { // MipMap_generateRow
+    const int sn = std::max(sx, sy), dn = std::max(dx, dy);
+    float r = 1.f / (float)sn, h = (float)dn * r;
+    int o = 2;
+    if (!(sn & 1)) { h = 0.5f; r = 0.f; o = 0; }
+    for (int x = 0; x < dn; x++) {
+      const float tx = x * r;
+      texSet(t, dst, x, tex3(h - tx, texGet(format, t, src, 2 * x), h, texGet(format, t, src, 2 * x + 1), r + tx, texGet(format, t, src, 2 * x + o)));
+    }
+  }
+}

@@ -53,9 +53,20 @@ class Model(C.Structure):
                 ("numMaterials", C.c_uint32), ("materialMode", C.c_uint32), ("invertedNormals", C.c_uint32), ("userID", C.c_uint32)]
 
 
+class Texture2D(C.Structure):
+    _fields_ = [("data", C.c_void_p * 32), ("sizeX", C.c_int32), ("sizeY", C.c_int32), ("maxLevel", C.c_int32), ("format", C.c_uint32),
+                ("filter", C.c_uint32), ("wrapS", C.c_uint32), ("wrapT", C.c_uint32), ("hasAlpha", C.c_uint32)]
+
+
+class TextureParam(C.Structure):
+    _fields_ = [("tex", C.POINTER(Texture2D)), ("transformFlags", C.c_uint32), ("scale2f", C.c_float), ("xform2f", C.c_float * 6)]
+
+
 class Material(C.Structure):
     _fields_ = [("type", C.c_uint32), ("d", C.c_float), ("Kd", Vec3), ("Ks", Vec3), ("Ns", C.c_float), ("Tf", Vec3),
-                ("eta", C.c_float), ("attenuation", Vec3), ("attenuationScale", C.c_float), ("pad", C.c_float * 3)]
+                ("eta", C.c_float), ("attenuation", Vec3), ("attenuationScale", C.c_float), ("hasTextures", C.c_uint32),
+                ("bumpRot", C.c_float * 4), ("mapD", TextureParam), ("mapKd", TextureParam), ("mapKs", TextureParam),
+                ("mapNs", TextureParam), ("mapBump", TextureParam)]
 
 
 class BVH(C.Structure):
@@ -115,7 +126,9 @@ class Renderer(C.Structure):
                 ("limitIndirectLightSamples", C.c_uint32), ("backgroundRefraction", C.c_uint32),
                 ("shadowsEnabled", C.c_uint32), ("visibleLights", C.c_uint32), ("aoSamples", C.c_int32),
                 ("aoRadius", C.c_float), ("aoIntensity", C.c_float), ("volumeSamplingRate", C.c_float),
-                ("worldNumLights", C.c_uint32), ("debugMethod", C.c_uint32), ("worldHasVolumes", C.c_uint32)]
+                ("worldNumLights", C.c_uint32), ("debugMethod", C.c_uint32), ("worldHasVolumes", C.c_uint32),
+                ("mipBiasFactor", C.c_float), ("backplate", C.POINTER(Texture2D)), ("maxDepthTexture", C.POINTER(Texture2D)),
+                ("hasTextures", C.c_uint32)]
 
 
 class FrameBuffer(C.Structure):
@@ -168,6 +181,9 @@ def lib():
         L.oracle_fb_color_convert.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
         L.oracle_fb_gather_tiles.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
         L.oracle_hardware_threads.restype = C.c_int
+        L.oracle_texture_texel_bytes.restype = C.c_uint32
+        L.oracle_texture_texel_bytes.argtypes = [C.c_uint32]
+        L.oracle_texture_mip_level.argtypes = [C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -197,6 +213,7 @@ def ref_lib():
         L.ospref_fb_tonemap.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(ToneMapper)]
         L.ospref_fb_color_convert.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
         L.ospref_ray_counters.argtypes = [C.c_void_p, C.c_int]
+        L.ospref_texture_sample.argtypes = [C.POINTER(TextureParam), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         _ref = L
     return _ref
 
@@ -273,10 +290,112 @@ def _xfm_bounds(m, lo, hi):
     return pts.min(axis=0), pts.max(axis=0)
 
 
+_TEX_FORMATS = ["RGBA8", "SRGBA", "RGBA32F", "RGB8", "SRGB", "RGB32F", "R8", "R32F", "L8", "RA8", "LA8", "RGBA16", "RGB16", "RA16", "R16",
+                "RA32F", "RGBA16F", "RGB16F", "RA16F", "R16F"]  # OSPTextureFormat order (OSPEnums.h)
+_TEX_ALPHA = {"RGBA8", "SRGBA", "RA8", "LA8", "RGBA32F", "RGBA16", "RA16", "RA16F", "RA32F", "RGBA16F"}  # Texture2D.cpp:28-32
+_TEX_FILTER = {"linear": 0, "nearest": 1}
+_TEX_WRAP = {"repeat": 0, "mirror": 1, "clamp": 2}
+
+
+def make_texture2d(ts, keep, mipmaps=True):
+    """ispc::Texture2D of a TextureSpec: level 0 = the image, then the MIP chain of Texture2D::commit (texture/Texture2D.cpp:
+    103-141), every level made from the finer one by oracle_texture_mip_level (texture/MipMapGeneration.ispc restated)"""
+    L = lib()
+    fmt = _TEX_FORMATS.index(ts.format)
+    a = np.ascontiguousarray(ts.data)
+    h, w = a.shape[:2]
+    assert a.nbytes == w * h * L.oracle_texture_texel_bytes(fmt), "texture data does not match its format"
+    t = Texture2D()
+    levels = [a]
+    if mipmaps and ts.mipmaps:
+        sx, sy = w, h
+        while (sx, sy) != (1, 1):
+            dx, dy = max(sx // 2, 1), max(sy // 2, 1)
+            dst = np.zeros(dx * dy * L.oracle_texture_texel_bytes(fmt), np.uint8)
+            L.oracle_texture_mip_level(fmt, levels[-1].ctypes.data, sx, sy, dst.ctypes.data, dx, dy)
+            levels.append(dst)
+            sx, sy = dx, dy
+    keep += levels
+    for l, lv in enumerate(levels):
+        t.data[l] = lv.ctypes.data
+    t.sizeX, t.sizeY, t.maxLevel, t.format = w, h, len(levels) - 1, fmt
+    t.filter, t.wrapS, t.wrapT = _TEX_FILTER[ts.filter], _TEX_WRAP[ts.wrap[0]], _TEX_WRAP[ts.wrap[1]]
+    t.hasAlpha = int(ts.format in _TEX_ALPHA)
+    keep.append(t)
+    return t
+
+
+def _a2_mul(a, b):
+    """affine2f product a * b; an affine map is (l00, l10, l01, l11, px, py) with l.vx = (l00, l10), l.vy = (l01, l11)"""
+    f = np.float32
+    return (f(a[0] * b[0] + a[2] * b[1]), f(a[1] * b[0] + a[3] * b[1]), f(a[0] * b[2] + a[2] * b[3]), f(a[1] * b[2] + a[3] * b[3]),
+            f(f(a[0] * b[4] + a[2] * b[5]) + a[4]), f(f(a[1] * b[4] + a[3] * b[5]) + a[5]))
+
+
+def texture_param(mp, keep, mipmaps=True):
+    """ispc::TextureParam of a MapSpec: Material::getTextureParam + getTextureTransform2f (render/Material.cpp:73-165)"""
+    f = np.float32
+    tp = TextureParam()
+    one = (f(1), f(0), f(0), f(1), f(0), f(0))
+    x, have = one, False
+    tr = lambda tx, ty: (f(1), f(0), f(0), f(1), f(tx), f(ty))
+    if mp is not None:
+        if mp.translation is not None:
+            x, have = tr(-f(mp.translation[0]), -f(mp.translation[1])), True
+        if mp.scale is not None:
+            x = _a2_mul(_a2_mul(_a2_mul(x, tr(0.5, 0.5)), (f(1) / f(mp.scale[0]), f(0), f(0), f(1) / f(mp.scale[1]), f(0), f(0))), tr(-0.5, -0.5))
+            have = True
+        if mp.rotation is not None:
+            r = -(f(mp.rotation) * f(np.pi / 180.0))
+            sn, cs = f(np.sin(r, dtype=np.float32)), f(np.cos(r, dtype=np.float32))
+            x = _a2_mul(_a2_mul(_a2_mul(x, tr(0.5, 0.5)), (cs, sn, -sn, cs, f(0), f(0))), tr(-0.5, -0.5))
+            have = True
+        if mp.transform is not None:
+            t = [f(v) for v in mp.transform]
+            x, have = _a2_mul(x, (t[0], t[1], t[2], t[3], f(0), f(0))), True
+        tex = make_texture2d(mp.texture, keep, mipmaps)
+        tp.tex = C.pointer(tex)
+    tp.transformFlags = 1 if have else 0
+    for k in range(6):
+        tp.xform2f[k] = float(x[k])
+    tp.scale2f = float(np.sqrt(f(f(x[0] * x[3]) - f(x[2] * x[1]))))
+    return tp
+
+
+def ref_texture_sample(map_spec, st, footprint, mipmaps=True):
+    """the reference's own get4f(TextureParam, dg) (oracle/_ref) for (n, 2) coordinates and n footprints -> (n, 4)"""
+    keep = []
+    tp = texture_param(map_spec, keep, mipmaps)
+    st, fp = np.ascontiguousarray(st, np.float32), np.ascontiguousarray(footprint, np.float32)
+    out = np.zeros((len(fp), 4), np.float32)
+    ref_lib().ospref_texture_sample(C.byref(tp), st.ctypes.data, fp.ctypes.data, len(fp), out.ctypes.data)
+    return out, tp
+
+
+def linear2f_orthogonal(m):
+    """rkcommon LinearSpace2::orthogonal() (un-vendored; restated): rotation part by m <- (m + m^-T) / 2; m = (vx.x, vx.y, vy.x, vy.y)"""
+    f = np.float32
+    m = [f(v) for v in m]
+    mirror = f(1)
+    if f(m[0] * m[3]) - f(m[2] * m[1]) < 0:
+        m[0], m[1], mirror = -m[0], -m[1], f(-1)
+    for _ in range(99):
+        ta, tb, tc, td = m[0], m[2], m[1], m[3]
+        r = f(1) / f(f(ta * td) - f(tc * tb))
+        inv = (f(td * r), f(-tb * r), f(-tc * r), f(ta * r))
+        n = [f(f(0.5) * f(m[k] + inv[k])) for k in range(4)]
+        d = [f(n[k] - m[k]) for k in range(4)]
+        m = n
+        if max(f(f(d[0] * d[0]) + f(d[1] * d[1])), f(f(d[2] * d[2]) + f(d[3] * d[3]))) < f(1e-8):
+            break
+    return [float(m[0] * mirror), float(m[1] * mirror), float(m[2]), float(m[3])]
+
+
 class Scene:
     """host-pointer OcWorld built from a SceneSpec; keeps every numpy / ctypes buffer alive"""
 
     def __init__(self, spec):
+        self.mipmaps = spec.uses_mipmaps() if hasattr(spec, "uses_mipmaps") else True
         self.keep = []
         self.materials = []
         L = lib()
@@ -399,6 +518,19 @@ class Scene:
 
     def _material(self, ms):
         m = Material()
+        for k in range(4):
+            m.bumpRot[k] = (1.0, 0.0, 0.0, 1.0)[k]
+        for f in ("mapD", "mapKd", "mapKs", "mapNs", "mapBump"):
+            setattr(m, f, texture_param(None, self.keep))
+        maps = {"mapD": ms.map_d, "mapKd": ms.map_kd if ms.type == "obj" else ms.map_attenuation_color, "mapKs": ms.map_ks,
+                "mapNs": ms.map_ns, "mapBump": ms.map_bump}
+        for f, mp in maps.items():
+            if mp is not None:
+                setattr(m, f, texture_param(mp, self.keep, self.mipmaps))
+                m.hasTextures = 1
+        if ms.map_bump is not None:  # OBJ.cpp:43-44: orthogonal().transposed() of the 2D transform's linear part
+            rot = linear2f_orthogonal([m.mapBump.xform2f[k] for k in range(4)])
+            m.bumpRot[0], m.bumpRot[1], m.bumpRot[2], m.bumpRot[3] = rot[0], rot[2], rot[1], rot[3]
         if ms.type == "obj":
             kd, ks, tf = (np.asarray(x, np.float32) for x in (ms.kd, ms.ks, ms.tf))
             total = np.float32(np.max(kd + ks + tf))
@@ -444,6 +576,9 @@ class Scene:
                     flags |= OC_GEOMFLAG_HAS_ALPHA | OC_GEOMFLAG_COLOR_VEC4
             else:
                 flags |= OC_GEOMFLAG_COLOR_FV
+            if getattr(gs, "vertex_texcoord", None) is not None:
+                g.texcoord = _data1d(np.ascontiguousarray(gs.vertex_texcoord, np.float32), self.keep)
+                flags &= ~OC_GEOMFLAG_TEX_FV
             g.flags = flags
             used = v[idx.ravel()]
             return g, used.min(axis=0), used.max(axis=0)
@@ -507,8 +642,14 @@ class RendererParams:
     def __init__(self, kind, pixelSamples=1, pixelFilter="gauss", maxPathLength=20, minContribution=0.001, backgroundColor=(0, 0, 0, 0),
                  roulettePathLength=5, maxScatteringEvents=20, maxContribution=np.inf, lightSamples=-1, limitIndirectLightSamples=True,
                  backgroundRefraction=False, shadows=False, visibleLights=False, aoSamples=None, aoDistance=1e20, aoIntensity=1.0,
-                 volumeSamplingRate=1.0, method="eyeLight"):
+                 volumeSamplingRate=1.0, method="eyeLight", mipMapBias=0.0, backplate=None, maxDepthTexture=None, mipmaps=True):
         r = Renderer()
+        self.keep = []
+        r.mipBiasFactor = float(np.power(np.float32(2.0), np.float32(mipMapBias)))  # Renderer.cpp:41,91
+        if backplate is not None:
+            r.backplate = C.pointer(make_texture2d(backplate, self.keep, mipmaps))
+        if maxDepthTexture is not None:
+            r.maxDepthTexture = C.pointer(make_texture2d(maxDepthTexture, self.keep, mipmaps))
         r.debugMethod = OC_DEBUG.get(method, 0)  # DebugRenderer.cpp:18-52: unknown names fall back to the test frame
         r.type, r.spp, r.maxDepth, r.minContribution = OC_RENDERER[kind], max(1, pixelSamples), maxPathLength, minContribution
         bg = list(backgroundColor) + [0.0] * (4 - len(backgroundColor))

@@ -30,6 +30,9 @@
 #include "render/MaterialShared.h"
 #include "render/materials/OBJShared.h"
 #include "render/materials/ThinGlassShared.h"
+#include "texture/Texture2DShared.h"
+#include "common/DifferentialGeometry.ih"
+#include "texture/TextureParamShared.h"
 #include "lights/QuadLightShared.h"
 #include "lights/PointLightShared.h"
 #include "lights/SpotLightShared.h"
@@ -154,6 +157,7 @@ struct Scene
   std::deque<std::vector<GeometricModel *>> modelPtrs;
   std::deque<std::vector<Material *>> materialPtrs;
   std::deque<OBJ> objs; std::deque<ThinGlass> glasses; std::vector<Material *> allMaterials;
+  std::deque<Texture2D> textures;
   std::vector<Instance *> instancePtrs;
   std::deque<QuadLight> quads; std::deque<PointLight> points; std::deque<SpotLight> spots; std::deque<DirectionalLight> dirs; std::deque<AmbientLight> ambients;
   std::vector<Light *> ptLights, svLights;
@@ -220,6 +224,32 @@ Geometry *makeGeometry(Scene &s, const OcGeometry *g)
   return &b.super;
 }
 
+// ispc::Texture2D::set (texture/Texture2D.cpp:12-39) from the committed levels; ispc::TextureParam as Material::getTextureParam
+// leaves it (render/Material.cpp:73-108)
+Texture2D *makeTexture(std::deque<Texture2D> &store, const OcTexture2D *t)
+{
+  if (!t) return nullptr;
+  store.emplace_back();
+  Texture2D &r = store.back();
+  r.size = make_vec2i(t->sizeX, t->sizeY);
+  r.maxLevel = t->maxLevel;
+  r.format = (OSPTextureFormat)t->format; r.filter = (OSPTextureFilter)t->filter;
+  r.wrapMode = make_vec2ui(t->wrapS, t->wrapT);
+  for (int l = 0; l <= t->maxLevel; l++) r.data[l] = (void *)t->data[l];
+  r.super.hasAlpha = t->hasAlpha != 0;
+  return &r;
+}
+TextureParam makeTextureParam(std::deque<Texture2D> &store, const OcTextureParam &p)
+{
+  TextureParam r;
+  Texture2D *t = makeTexture(store, p.tex);
+  r.ptr = t ? &t->super : nullptr;
+  r.transformFlags = (p.transformFlags & OC_TEX_TRANSFORM_2D) ? TRANSFORM_FLAG_2D : TRANSFORM_FLAG_NONE;
+  r.scale2f = p.scale2f;
+  r.xform2f = affine2f(linear2f(make_vec2f(p.xform2f[0], p.xform2f[1]), make_vec2f(p.xform2f[2], p.xform2f[3])), make_vec2f(p.xform2f[4], p.xform2f[5]));
+  return r;
+}
+
 void buildScene(Scene &s, const OcWorld *w, const OcRenderer *ren)
 {
   // materials: render/materials/OBJ.cpp:30-66 (values arrive already normalised by the commit)
@@ -229,12 +259,17 @@ void buildScene(Scene &s, const OcWorld *w, const OcRenderer *ren)
       s.glasses.emplace_back();
       ThinGlass &g = s.glasses.back();
       g.eta = m.eta; g.attenuation = v3(m.attenuation); g.attenuationScale = m.attenuationScale;
+      g.attenuationColorMap = makeTextureParam(s.textures, m.mapKd);
       s.allMaterials.push_back(&g.super);
       continue;
     }
     s.objs.emplace_back();
     OBJ &o = s.objs.back();
     o.d = m.d; o.Kd = v3(m.Kd); o.Ks = v3(m.Ks); o.Ns = m.Ns; o.Tf = v3(m.Tf);
+    o.dMap = makeTextureParam(s.textures, m.mapD); o.KdMap = makeTextureParam(s.textures, m.mapKd);
+    o.KsMap = makeTextureParam(s.textures, m.mapKs); o.NsMap = makeTextureParam(s.textures, m.mapNs);
+    o.bumpMap = makeTextureParam(s.textures, m.mapBump);
+    o.bumpRot = linear2f(make_vec2f(m.bumpRot[0], m.bumpRot[1]), make_vec2f(m.bumpRot[2], m.bumpRot[3]));
     s.allMaterials.push_back(&o.super);
   }
   bool anyGeometry = false, anyVolume = false;
@@ -361,6 +396,7 @@ struct RendererSet
   PathTracer pt; SciVis sv; AORenderer ao; DebugRenderer dbg;
   PixelFilter pf; LUTPixelFilter lut; Distribution2D dist;
   std::vector<Material *> materials;
+  std::deque<Texture2D> textures;
 };
 
 Renderer *buildRenderer(RendererSet &r, Scene &s, const OcRenderer *o)
@@ -385,7 +421,8 @@ Renderer *buildRenderer(RendererSet &r, Scene &s, const OcRenderer *o)
     r.pf.width = o->pfWidth;
     base->pixelFilter = &r.pf;
   }
-  base->mipBiasFactor = 1.f;
+  base->mipBiasFactor = o->mipBiasFactor; // Renderer.cpp:91
+  base->backplate = makeTexture(r.textures, o->backplate); base->maxDepthTexture = makeTexture(r.textures, o->maxDepthTexture); // :61-80
   if (o->type == OC_RENDERER_PATHTRACER) { // render/pathtracer/PathTracer.cpp:29-51
     r.pt.rouletteDepth = o->rouletteDepth; r.pt.maxScatteringEvents = o->maxScatteringEvents; r.pt.maxRadiance = o->maxRadiance;
     r.pt.numLightSamples = o->numLightSamples; r.pt.limitIndirectLightSamples = o->limitIndirectLightSamples != 0;
@@ -482,6 +519,23 @@ REF_API int ospref_render_frame(const OcWorld *w, const OcCamera *cam, const OcR
     (void)total;
   }
   return 0;
+}
+
+// get4f(TextureParam, dg) of the reference (texture/TextureParam.ispc:10-22 -> Texture_dispatch_get -> Texture2D_get) for n
+// (st, pixelFootprint) pairs; `param` and its texture hold HOST pointers
+namespace ispc { vec4f get4f(const TextureParam &tp, const DifferentialGeometry &dg); }
+REF_API void ospref_texture_sample(const OcTextureParam *param, const float *st, const float *footprint, uint32_t n, float *out)
+{
+  std::deque<Texture2D> store;
+  const TextureParam tp = makeTextureParam(store, *param);
+  for (uint32_t i = 0; i < n; i++) {
+    DifferentialGeometry dg;
+    dg.st = make_vec2f(st[2 * i], st[2 * i + 1]);
+    dg.pixelFootprint = footprint[i];
+    dg.lP = make_vec3f(0.f);
+    const vec4f v = get4f(tp, dg);
+    out[4 * i] = v.x; out[4 * i + 1] = v.y; out[4 * i + 2] = v.z; out[4 * i + 3] = v.w;
+  }
 }
 
 // ---- known-answer vectors straight from the reference's sampler sources (math/random.ih, sobol.ih, halton.ih,

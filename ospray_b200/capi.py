@@ -12,7 +12,15 @@ OSP_OBJECT = 0x8000000
  OSP_INSTANCE, OSP_LIGHT, OSP_MATERIAL, OSP_RENDERER, OSP_TEXTURE, OSP_TRANSFER_FUNCTION, OSP_VOLUME,
  OSP_VOLUMETRIC_MODEL, OSP_WORLD) = range(OSP_OBJECT + 100, OSP_OBJECT + 117)
 OSP_STRING = 1500
-OSP_UCHAR = 2500
+OSP_UCHAR, OSP_VEC2UC, OSP_VEC3UC, OSP_VEC4UC = 2500, 2501, 2502, 2503
+OSP_USHORT, OSP_VEC2US, OSP_VEC3US, OSP_VEC4US = 3500, 3501, 3502, 3503
+OSP_HALF, OSP_VEC2H, OSP_VEC3H, OSP_VEC4H = 5800, 5801, 5802, 5803
+OSP_LINEAR2F = 12000
+# OSPTextureFormat / OSPTextureFilter / OSPTextureWrapMode
+OSP_TEXTURE_FORMATS = ["RGBA8", "SRGBA", "RGBA32F", "RGB8", "SRGB", "RGB32F", "R8", "R32F", "L8", "RA8", "LA8", "RGBA16", "RGB16", "RA16", "R16",
+                       "RA32F", "RGBA16F", "RGB16F", "RA16F", "R16F"]
+OSP_TEXTURE_FILTER_LINEAR, OSP_TEXTURE_FILTER_NEAREST = 0, 1
+OSP_TEXTURE_WRAP_REPEAT, OSP_TEXTURE_WRAP_MIRRORED_REPEAT, OSP_TEXTURE_WRAP_CLAMP_TO_EDGE = 0, 1, 2
 OSP_INT, OSP_VEC2I, OSP_VEC3I, OSP_VEC4I = 4000, 4001, 4002, 4003
 OSP_UINT, OSP_VEC2UI, OSP_VEC3UI, OSP_VEC4UI = 4500, 4501, 4502, 4503
 OSP_FLOAT, OSP_VEC2F, OSP_VEC3F, OSP_VEC4F = 6000, 6001, 6002, 6003
@@ -102,6 +110,8 @@ def ext():
         E.ospcudaSetRenderStream.restype = None
         E.ospcudaSetRenderStream.argtypes = [C.c_void_p]
         E.ospcudaWorldDevicePointer.argtypes = [C.c_void_p]
+        E.ospcudaTextureDevicePointer.restype = C.c_void_p
+        E.ospcudaTextureDevicePointer.argtypes = [C.c_void_p]
         _ext = E
     return _ext
 
@@ -179,6 +189,14 @@ def new_device(device="cuda", warn_as_error=True, **device_params):
     return d
 
 
+def set_device_bool(name, value):
+    """ospDeviceSetParam + ospDeviceCommit of a bool parameter on the current device (e.g. disableMipMapGeneration)"""
+    b = C.c_bool(bool(value))
+    lib().ospDeviceSetParam(_device, name.encode(), OSP_BOOL, C.byref(b))
+    lib().ospDeviceCommit(_device)
+    check_errors()
+
+
 def set_current(device):
     global _device
     lib().ospSetCurrentDevice(device)
@@ -211,7 +229,8 @@ def _pack(value):
             return t, C.c_int(int(v))
         if t == OSP_BOOL:
             return t, C.c_bool(bool(v))
-        arr = np.ascontiguousarray(np.asarray(v, dtype=np.int32 if t in (OSP_VEC2I, OSP_VEC3I, OSP_VEC4I) else np.float32))
+        arr = np.ascontiguousarray(np.asarray(v, dtype=np.int32 if t in (OSP_VEC2I, OSP_VEC3I, OSP_VEC4I)
+                                              else np.uint32 if t in (OSP_VEC2UI, OSP_VEC3UI, OSP_VEC4UI) else np.float32))
         return t, (C.c_char * arr.nbytes).from_buffer_copy(arr.tobytes())
     if isinstance(value, bool):
         return OSP_BOOL, C.c_bool(value)
@@ -344,6 +363,24 @@ Material = _typed_object("Material", OSP_MATERIAL, "ospNewMaterial")
 TransferFunction = _typed_object("TransferFunction", OSP_TRANSFER_FUNCTION, "ospNewTransferFunction")
 Renderer = _typed_object("Renderer", OSP_RENDERER, "ospNewRenderer")
 ImageOperation = _typed_object("ImageOperation", OSP_IMAGE_OPERATION, "ospNewImageOperation")
+Texture = _typed_object("Texture", OSP_TEXTURE, "ospNewTexture")
+
+
+def texture2d(array, fmt, filter=OSP_TEXTURE_FILTER_LINEAR, wrap=(OSP_TEXTURE_WRAP_REPEAT, OSP_TEXTURE_WRAP_REPEAT)):
+    """texture2d from a (h, w[, channels]) array of uint8 / uint16 / float16 / float32; `fmt` names an OSPTextureFormat"""
+    a = np.ascontiguousarray(array)
+    h, w = a.shape[:2]
+    comps = 1 if a.ndim == 2 else a.shape[2]
+    base = {np.dtype(np.uint8): OSP_UCHAR, np.dtype(np.uint16): OSP_USHORT, np.dtype(np.float16): OSP_HALF, np.dtype(np.float32): OSP_FLOAT}[a.dtype]
+    t = Texture("texture2d")
+    t.set("format", Typed(OSP_UINT, OSP_TEXTURE_FORMATS.index(fmt)))
+    t.set("filter", Typed(OSP_UINT, filter))
+    t.set("wrapMode", Typed(OSP_VEC2UI, wrap))
+    d = Data(a, osp_type=base + comps - 1, dims=(w, h, 1))
+    hv = C.c_void_p(d.h)
+    lib().ospSetParam(t.h, b"data", OSP_DATA, C.byref(hv))
+    t._keep.append(d)
+    return t.commit()
 
 
 class GeometricModel(Object):

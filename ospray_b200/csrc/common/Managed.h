@@ -85,6 +85,8 @@ OSP_TYPEFOR(linear3f, OSP_LINEAR3F)
 OSP_TYPEFOR(affine3f, OSP_AFFINE3F)
 OSP_TYPEFOR(void *, OSP_VOID_PTR)
 OSP_TYPEFOR(uint8_t, OSP_UCHAR)
+OSP_TYPEFOR(vec2ui, OSP_VEC2UI)
+OSP_TYPEFOR(linear2f, OSP_LINEAR2F)
 OSP_TYPEFOR(vec3ui, OSP_VEC3UI)
 OSP_TYPEFOR(vec4ui, OSP_VEC4UI)
 #undef OSP_TYPEFOR

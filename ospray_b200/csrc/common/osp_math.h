@@ -19,7 +19,9 @@ struct vec3f { float x, y, z; };
 struct vec4f { float x, y, z, w; };
 struct vec2i { int x, y; };
 struct vec3i { int x, y, z; };
+struct vec2ui { uint32_t x, y; };
 struct vec3ui { uint32_t x, y, z; };
+struct linear2f { vec2f vx, vy; };
 struct vec4ui { uint32_t x, y, z, w; };
 struct vec3ul { uint64_t x, y, z; };
 struct vec3l { int64_t x, y, z; };

@@ -50,6 +50,7 @@ struct PtScratch
   float4 *shA, *shB, *shC;          // shadow entries [slot * nls + i]: org.xyz,tmax | dir.xyz,mis | contrib.xyz,valid
   uint2 *shHit;                     // what TRACE found for shadow entry [slot * nls + i]: occluder (record, instance); instance ~0 = none
   float4 *accC, *accZ, *accPos, *accFN, *accNrm, *accAlb; // ScreenSample sums across the spp passes (spp > 1)
+  float2 *cone;   // frames with textures: the path's ray cone (width at the last vertex, dwdt) (common/RayCone.ih)
   uint4 *rnd;     // worlds with volumes: pathState.randomSampler (PCG32 state lo/hi, stream)
   float *shT0;    // worlds with volumes: t0 of shadow entry [slot * nls + i] after the transparent-shadow loop
   uint32_t *pathQ[2], *shadowQ[2];
@@ -359,7 +360,7 @@ __device__ __forceinline__ bool ptOccluderIsOpaque(const OcWorld *world, const O
     if (!(gf & OC_GEOMFLAG_ALPHA_ALL_ONE) || !(maxContrib * 1e-6f <= ren.minContribution)) return false;
   }
   const OcMaterial *mat = getMaterial(world, ren, m, primID);
-  if (mat && mat->type == OC_MATERIAL_THINGLASS) return false;
+  if (mat && (mat->type == OC_MATERIAL_THINGLASS || mat->hasTextures)) return false; // texture maps may cut the surface out
   if (!mat || mat->type != OC_MATERIAL_OBJ) return true; // no / foreign material: transparency 0 (shading.cuh)
   return mat->d == 1.f && mat->Tf.x == 0.f && mat->Tf.y == 0.f && mat->Tf.z == 0.f;
 }
@@ -368,6 +369,7 @@ __device__ __forceinline__ bool ptOccluderIsOpaque(const OcWorld *world, const O
 // TRACE found a non-opaque occluder (or the contribution is not finite, in which case no query was made). Out of line:
 // opaque scenes never take it. Returns the attenuated contribution in xyz and the number of additional shadow segments
 // traced in w.
+template <bool TEX>
 static __device__ __noinline__ float4 ptTransparentShadowSlow(const PtArgs &k, size_t e, float cx, float cy, float cz, uint32_t *stackBase,
     uint32_t stackStride)
 {
@@ -380,6 +382,11 @@ static __device__ __noinline__ float4 ptTransparentShadowSlow(const PtArgs &k, s
   uint32_t maxDepth = ren.maxDepth;
   const float tOriginal = sr.t;
   bool counted = isfinite(lightContrib.x) && isfinite(lightContrib.y) && isfinite(lightContrib.z); // the any-hit query was this segment
+  // the shadow cone (NextEventEstimation.ispc:103-106) starts from `sample.rayCone.width` of a ScreenSample that
+  // PathTraceIntegrator_Li zero-initialises WITHOUT its rayCone (ScreenSample.ih:40-57, PathTracer.ispc:43): the reference
+  // reads an indeterminate value there; this device defines it as 0 (finest MIP level along shadow rays)
+  RayCone shadowCone;
+  shadowCone.width = 0.f; shadowCone.dwdt = 0.f;
   while (1) {
     if (!counted) shadowCount++;
     counted = false;
@@ -387,8 +394,9 @@ static __device__ __noinline__ float4 ptTransparentShadowSlow(const PtArgs &k, s
     resolveHit(k.a.world, h, sr);
     if (!hadHit(sr)) break;
     DifferentialGeometry dg;
-    postIntersect(k.a.world, ren, dg, sr, DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR);
-    lightContrib = lightContrib * materialTransparency(dg, sr.dir);
+    postIntersect<TEX>(k.a.world, ren, dg, sr, DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR, TEX ? &shadowCone : nullptr);
+    lightContrib = lightContrib * materialTransparency<TEX>(dg, sr.dir);
+    shadowCone.width = 0.f;
     if (reduce_max(lightContrib) <= ren.minContribution || --maxDepth <= 0) { lightContrib = make_vec3f(0.f); break; }
     setRay(sr, sr.org, sr.dir, sr.t + dg.epsilon, tOriginal);
   }
@@ -433,7 +441,7 @@ static __device__ __noinline__ vec3f ptVirtualLightsVol(const PtArgs &k, uint32_
 // PathTracer_renderPixel, one sample (PathTracer.ispc:149-193) up to the camera ray + samplePath()'s prologue
 // (PathSampler.ispc:116-133). Pixels outside the image and pixels of converged render tasks (adaptive accumulation,
 // LocalFB.cpp:245-257) start no path.
-template <bool VOL>
+template <bool VOL, bool TEX>
 __global__ void __launch_bounds__(128) ptGenKernel(const __grid_constant__ PtArgs k)
 {
   const PtScratch &s = k.s;
@@ -462,6 +470,12 @@ __global__ void __launch_bounds__(128) ptGenKernel(const __grid_constant__ PtArg
     if (k.a.cam.needLensSample) lens = LDSampler_finalizeDim23(ld, ss234);
     Ray ray;
     cameraInitRay(k.a.cam, ray, screen, lens);
+    if (TEX) { // ray cone in pixel units (PathTracer.ispc:182-187) and the optional depth limit (:189-192)
+      RayCone cone = cameraInitRayCone(k.a.cam, screen);
+      cone.dwdt *= rcpSize.y; cone.width *= rcpSize.y;
+      s.cone[p] = make_float2(cone.width, cone.dwdt);
+      ray.t = fminf(ray.t, rendererMaxDepth(ren, screen));
+    }
     s.smp[p] = make_uint2(ld.revIndex, ld.scramble);
     if (VOL) { // pathState.randomSampler (PathTracer.ispc:157)
       RandomSampler rs;
@@ -599,7 +613,7 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptTraceKernel(cons
 // ---- SHADE ------------------------------------------------------------------------------------------------------------
 // One path, one vertex: returns 0 when the path finished here, 1 when it goes on to the next bounce, 2 when it has ended
 // but shadow rays of this vertex are pending (the next SHADE folds them in and finishes it).
-template <bool VOL, bool QUEUE>
+template <bool VOL, bool QUEUE, bool TEX>
 __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uint32_t *stackBase, uint32_t &extraShadow)
 {
   const PtScratch &s = k.s;
@@ -631,7 +645,7 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
         else if (ptOccluderIsOpaque(world, ren, occ.x, occ.y, reduce_max(lightContrib))) { lightContrib = make_vec3f(0.f); resolved = true; }
       }
       if (!resolved) {
-        const float4 r = ptTransparentShadowSlow(k, e, lightContrib.x, lightContrib.y, lightContrib.z, stackBase, PT_TRACE_BLOCK);
+        const float4 r = ptTransparentShadowSlow<TEX>(k, e, lightContrib.x, lightContrib.y, lightContrib.z, stackBase, PT_TRACE_BLOCK);
         lightContrib = make_vec3f(r.x, r.y, r.z);
         extraShadow += __float_as_uint(r.w);
         if (VOL) shadowT0 = s.shT0[e];
@@ -686,9 +700,14 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
     last.pdf_w = con4.w; last.numLightSamples = __float_as_uint(lp.w);
   }
   LDSampler ld;
+  vec2f pixelCenter = make_vec2f(0.f, 0.f); // pathContext.screen (PathTracer.ispc:194): where the backplate is looked up
+  RayCone cone;
+  cone.width = cone.dwdt = 0.f;
+  if (TEX) { const float2 c2 = s.cone[p]; cone.width = c2.x; cone.dwdt = c2.y; }
   {
     uint32_t ix, iy, seed, so, sol, bits, bitsLight;
     ptSlotToPixel(k, p, ix, iy);
+    if (TEX) pixelCenter = make_vec2f(((float)ix + 0.5f) * (1.f / (float)fb.sizeX), ((float)iy + 0.5f) * (1.f / (float)fb.sizeY));
     ptSamplerParams(k, ix, iy, seed, so, sol, bits, bitsLight);
     const uint32_t sampleID = (uint32_t)fb.frameID * ren.spp + k.pass;
     LDSampler_init(ld, seed, so + sampleID, sol + sampleID * k.nFirst, bits, bitsLight);
@@ -714,7 +733,7 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
       s.sZ[p] = z;
     }
     if (environment && (ren.backgroundRefraction ? specularTransmissionPath : straightPath)) {
-      const vec4f bg = getBackground(ren);
+      const vec4f bg = TEX ? getBackgroundTex(ren, pixelCenter) : getBackground(ren);
       alpha -= luminance(throughput) * (1.0f - bg.w);
       contribution = contribution + throughput * make_vec3f(bg);
     }
@@ -739,8 +758,8 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
       if (ray.instID != OC_INVALID_ID && world->instances[ray.instID].userID != OC_INVALID_ID)
         dg.instID = world->instances[ray.instID].userID;
     } else
-      postIntersect(world, ren, dg, ray,
-          DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR | DG_TANGENTS | DG_MOTIONBLUR);
+      postIntersect<TEX>(world, ren, dg, ray,
+          DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR | DG_TANGENTS | DG_MOTIONBLUR, TEX ? &cone : nullptr);
     if (depth == 0) {
       float4 z = s.sZ[p];
       z.y = __uint_as_float(dg.primID); z.z = __uint_as_float(dg.objID); z.w = __uint_as_float(dg.instID);
@@ -752,7 +771,7 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
 
     ObjBSDF bsdf;
     if (!volume) {
-      OBJ_getBSDF(bsdf, dg);
+      OBJ_getBSDF<TEX>(bsdf, dg);
       if (!bsdf.valid) break;
     }
 
@@ -841,6 +860,7 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
     s.lastP[p] = make_float4(last.P.x, last.P.y, last.P.z, __uint_as_float(last.numLightSamples));
     s.lastN[p] = make_float4(last.Ns.x, last.Ns.y, last.Ns.z, 0.f);
     s.smp[p] = make_uint2(ld.revIndex, ld.scramble);
+    if (TEX) s.cone[p] = make_float2(cone.width, cone.dwdt);
   }
   s.flags[p] = ((depth + 1) & PT_DEPTH_MASK) | (scatteringEvents << PT_SCAT_SHIFT) | (straightPath ? PT_STRAIGHT : 0u)
       | (specularTransmissionPath ? PT_SPECTRANS : 0u) | (firstBounceLight ? PT_FIRSTBOUNCE : 0u) | (hasShadow ? PT_HAS_SHADOW : 0u)
@@ -849,7 +869,7 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
 }
 
 // MIN_BLOCKS: resident CTAs per SM the register budget is set for (4: 128 registers, 5: 96, 6: 80)
-template <bool VOL, int MIN_BLOCKS>
+template <bool VOL, int MIN_BLOCKS, bool TEX>
 __global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptShadeKernel(const __grid_constant__ PtArgs k)
 {
   __shared__ uint32_t s_stack[OC_STACK_SHARED * PT_TRACE_BLOCK]; // the out-of-line transparent-shadow loop walks the hierarchy
@@ -859,7 +879,7 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptShadeKernel(cons
   uint32_t extraShadow = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t p = k.pathIn[i] & ~PT_Q_DONE;
-    const uint32_t r = ptShadeStep<VOL, true>(k, p, s_stack + threadIdx.x, extraShadow);
+    const uint32_t r = ptShadeStep<VOL, true, TEX>(k, p, s_stack + threadIdx.x, extraShadow);
     if (r) ptAppend(k.pathOut, k.cntPathOut, r == 2u ? (p | PT_Q_DONE) : p);
   }
   ptCountRays(k.a.fb, 0u, 0u, extraShadow);
@@ -872,7 +892,7 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptShadeKernel(cons
 // carries ITS path to the end -- the shadow rays of the previous vertex, the continuation ray, the shade step, again -- and
 // fetches the next path of the queue when its own is finished. Latency-bound by construction (the longest path's bounces
 // are a serial chain); what it saves is the per-bounce launch pair.
-template <bool VOL>
+template <bool VOL, bool TEX>
 __global__ void __launch_bounds__(PT_TRACE_BLOCK, 3) ptTailKernel(const __grid_constant__ PtArgs k)
 {
   __shared__ uint32_t s_stack[OC_STACK_SHARED * PT_TRACE_BLOCK];
@@ -924,7 +944,7 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, 3) ptTailKernel(const __grid_c
         s.hitInst[p] = r.instID;
         nCont++;
       }
-      state = ptShadeStep<VOL, false>(k, p, stackBase, extraShadow);
+      state = ptShadeStep<VOL, false, TEX>(k, p, stackBase, extraShadow);
       alive = state != 0u;
     }
   }

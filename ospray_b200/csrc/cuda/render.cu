@@ -61,6 +61,22 @@ __device__ __forceinline__ vec4f getBackground(const OcRenderer &r)
   return make_vec4f(r.bgColor[0], r.bgColor[1], r.bgColor[2], r.bgColor[3]);
 }
 
+// Renderer_getBackground / Renderer_getMaxDepth with renderer textures (render/Renderer.ispc:18-39; Texture2D.ih:20-47:
+// a bare Texture2D is sampled at the finest footprint, the backplate coordinate is clamped to the texel centres)
+__device__ __forceinline__ vec4f getBackgroundTex(const OcRenderer &r, vec2f screenPos)
+{
+  if (!r.backplate) return getBackground(r);
+  const float hx = (1.f / (float)r.backplate->sizeX) * 0.5f, hy = (1.f / (float)r.backplate->sizeY) * 0.5f;
+  const vec2f p = make_vec2f(fmaxf(hx, fminf(screenPos.x, 1.0f - hx)), fmaxf(hy, fminf(screenPos.y, 1.0f - hy)));
+  return Texture2D_get(r.backplate, p, FLT_MIN);
+}
+__device__ __forceinline__ float rendererMaxDepth(const OcRenderer &r, vec2f screenPos)
+{
+  if (!r.maxDepthTexture) return INFINITY;
+  const float d = Texture2D_get(r.maxDepthTexture, screenPos, FLT_MIN).x;
+  return 0.f > d ? 0.f : d; // max(0.f, d)
+}
+
 // ===================================== path tracer =========================================
 struct PathVertexLite { vec3f P, Ns; float pdf_w; uint32_t numLightSamples; };
 
@@ -796,7 +812,7 @@ struct PtHost
   void *block = nullptr;
   size_t blockBytes = 0;
   int device = -1;
-  int traceBlocks = 0, shadeBlocks[2] = {0, 0}, genBlocks = 0, tailBlocks = 0, aoShadeBlocks = 0, traceVariant = 1, shadeVariant = 4; // persistent grids (resident CTAs per SM x SM count)
+  int traceBlocks = 0, shadeBlocks[3] = {0, 0, 0}, genBlocks = 0, tailBlocks = 0, aoShadeBlocks = 0, traceVariant = 1, shadeVariant = 4; // persistent grids (resident CTAs per SM x SM count)
 };
 PtHost g_ptPerDevice[32]; // one scratch block per CUDA device of the process (in-process multidevice)
 PtHost &ptHost()
@@ -827,6 +843,7 @@ int ptCarve(oc::PtScratch &s, uint32_t paths, uint32_t nls, bool needAcc, uint32
   for (int i = 0; i < 6; i++) off[k++] = take(needAcc ? P * 16 : 0);
   off[k++] = take(hasVol ? P * 16 : 0);                      // rnd
   off[k++] = take(hasVol ? P * 4 * nls : 0);                 // shT0
+  off[k++] = take(P * 8);                                    // cone
   for (int i = 0; i < 2; i++) off[k++] = take(P * 4);        // pathQ
   for (int i = 0; i < 2; i++) off[k++] = take(P * 4 * nls);  // shadowQ
   off[k++] = take(numCounters * 4);
@@ -851,6 +868,7 @@ int ptCarve(oc::PtScratch &s, uint32_t paths, uint32_t nls, bool needAcc, uint32
   s.accC = (float4 *)(b + off[k++]); s.accZ = (float4 *)(b + off[k++]); s.accPos = (float4 *)(b + off[k++]); s.accFN = (float4 *)(b + off[k++]);
   s.accNrm = (float4 *)(b + off[k++]); s.accAlb = (float4 *)(b + off[k++]);
   s.rnd = (uint4 *)(b + off[k++]); s.shT0 = (float *)(b + off[k++]);
+  s.cone = (float2 *)(b + off[k++]);
   s.pathQ[0] = (uint32_t *)(b + off[k++]); s.pathQ[1] = (uint32_t *)(b + off[k++]);
   s.shadowQ[0] = (uint32_t *)(b + off[k++]); s.shadowQ[1] = (uint32_t *)(b + off[k++]);
   s.counters = (uint32_t *)(b + off[k++]);
@@ -860,7 +878,7 @@ int ptCarve(oc::PtScratch &s, uint32_t paths, uint32_t nls, bool needAcc, uint32
 
 size_t ptBytesPerPath(uint32_t nls, bool needAcc, bool hasVol)
 {
-  return 8 * 16 + 16 + 5 * 16 + (48 + 8 + 8) * (size_t)nls + (needAcc ? 96 : 0) + 8 + (hasVol ? 16 + 4 * (size_t)nls : 0);
+  return 8 * 16 + 16 + 5 * 16 + (48 + 8 + 8) * (size_t)nls + (needAcc ? 96 : 0) + 8 + 8 + (hasVol ? 16 + 4 * (size_t)nls : 0);
 }
 
 // Launch sequence of one sample pass: GEN, then TRACE(d) / SHADE(d) for d = 0 .. maxDepth. Every stage d owns four
@@ -888,6 +906,7 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles, bool
   const size_t budget = size_t(1536) << 20;
   const bool hasVol = !ao && fa.ren.worldHasVolumes != 0;
   k.vol = hasVol ? 1u : 0u;
+  const bool hasTex = !ao && fa.ren.hasTextures != 0; // the kernels for worlds with volumes are compiled with texture support too
   uint32_t tilesPerBatch = (uint32_t)std::max<size_t>(1, budget / (ptBytesPerPath(nls, needAcc, hasVol) * 4096));
   // (smaller batches were tried for L2 residency of the path state, alternating between two streams so that one batch's
   // thinned-out end overlaps the next batch's dense bounces: SHADE -17 %, but every batch pays its own tail and the
@@ -912,11 +931,14 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles, bool
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, ptTraceKernel<16, 5>, PT_TRACE_BLOCK, 0);
     const int smb = getenv("OSPCUDA_PT_SHADE_BLOCKS") ? atoi(getenv("OSPCUDA_PT_SHADE_BLOCKS")) : 4;
     g_pt.shadeVariant = smb <= 4 ? 4 : smb == 5 ? 5 : 6;
-    if (g_pt.shadeVariant == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ptShadeKernel<false, 4>, PT_TRACE_BLOCK, 0);
-    else if (g_pt.shadeVariant == 5) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ptShadeKernel<false, 5>, PT_TRACE_BLOCK, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ptShadeKernel<false, 6>, PT_TRACE_BLOCK, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bv, ptShadeKernel<true, 4>, PT_TRACE_BLOCK, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g, ptGenKernel<false>, 128, 0);
+    int bt = 1;
+    if (g_pt.shadeVariant == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ptShadeKernel<false, 4, false>, PT_TRACE_BLOCK, 0);
+    else if (g_pt.shadeVariant == 5) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ptShadeKernel<false, 5, false>, PT_TRACE_BLOCK, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ptShadeKernel<false, 6, false>, PT_TRACE_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bv, ptShadeKernel<true, 4, true>, PT_TRACE_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bt, ptShadeKernel<false, 4, true>, PT_TRACE_BLOCK, 0);
+    g_pt.shadeBlocks[2] = sms * (bt > 0 ? bt : 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g, ptGenKernel<false, false>, 128, 0);
     g_pt.traceBlocks = sms * (a > 0 ? a : 1);
     g_pt.shadeBlocks[0] = sms * (b > 0 ? b : 1);
     g_pt.shadeBlocks[1] = sms * (bv > 0 ? bv : 1);
@@ -924,7 +946,7 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles, bool
     int t = 1, as = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&as, aoShadeKernel, 128, 0);
     g_pt.aoShadeBlocks = sms * (as > 0 ? as : 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t, ptTailKernel<false>, PT_TRACE_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t, ptTailKernel<false, false>, PT_TRACE_BLOCK, 0);
     g_pt.tailBlocks = sms * (t > 0 ? t : 1);
   }
   // depth from which the tail kernel takes over. A TRACE + SHADE launch pair pays for itself while the queue holds many
@@ -956,8 +978,9 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles, bool
         ProfScope ps(2, st);
         const int gb = (int)std::min<uint32_t>((uint32_t)g_pt.genBlocks, (k.numPaths + 127u) / 128u);
         if (ao) aoGenKernel<<<gb, 128, 0, st>>>(k);
-        else if (hasVol) ptGenKernel<true><<<gb, 128, 0, st>>>(k);
-        else ptGenKernel<false><<<gb, 128, 0, st>>>(k);
+        else if (hasVol) ptGenKernel<true, true><<<gb, 128, 0, st>>>(k);
+        else if (hasTex) ptGenKernel<false, true><<<gb, 128, 0, st>>>(k);
+        else ptGenKernel<false, false><<<gb, 128, 0, st>>>(k);
       }
       oc_count_launch();
       for (uint32_t d = 0; d <= maxDepth; d++) {
@@ -970,8 +993,9 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles, bool
           k.fetchCursor = C(d, 3);
           {
             ProfScope ps(3, st);
-            if (hasVol) ptTailKernel<true><<<g_pt.tailBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
-            else ptTailKernel<false><<<g_pt.tailBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+            if (hasVol) ptTailKernel<true, true><<<g_pt.tailBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+            else if (hasTex) ptTailKernel<false, true><<<g_pt.tailBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
+            else ptTailKernel<false, false><<<g_pt.tailBlocks, PT_TRACE_BLOCK, 0, st>>>(k);
           }
           oc_count_launch();
           break;
@@ -998,10 +1022,11 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles, bool
         {
           ProfScope ps(1, st);
           if (ao) aoShadeKernel<<<g_pt.aoShadeBlocks, 128, 0, st>>>(k);
-          else if (hasVol) ptShadeKernel<true, 4><<<g_pt.shadeBlocks[1], PT_TRACE_BLOCK, 0, st>>>(k);
-          else if (g_pt.shadeVariant == 4) ptShadeKernel<false, 4><<<g_pt.shadeBlocks[0], PT_TRACE_BLOCK, 0, st>>>(k);
-          else if (g_pt.shadeVariant == 5) ptShadeKernel<false, 5><<<g_pt.shadeBlocks[0], PT_TRACE_BLOCK, 0, st>>>(k);
-          else ptShadeKernel<false, 6><<<g_pt.shadeBlocks[0], PT_TRACE_BLOCK, 0, st>>>(k);
+          else if (hasVol) ptShadeKernel<true, 4, true><<<g_pt.shadeBlocks[1], PT_TRACE_BLOCK, 0, st>>>(k);
+          else if (hasTex) ptShadeKernel<false, 4, true><<<g_pt.shadeBlocks[2], PT_TRACE_BLOCK, 0, st>>>(k);
+          else if (g_pt.shadeVariant == 4) ptShadeKernel<false, 4, false><<<g_pt.shadeBlocks[0], PT_TRACE_BLOCK, 0, st>>>(k);
+          else if (g_pt.shadeVariant == 5) ptShadeKernel<false, 5, false><<<g_pt.shadeBlocks[0], PT_TRACE_BLOCK, 0, st>>>(k);
+          else ptShadeKernel<false, 6, false><<<g_pt.shadeBlocks[0], PT_TRACE_BLOCK, 0, st>>>(k);
         }
         oc_count_launch();
         if (ao && d >= 1) { // anything left behind transparent surfaces?
@@ -1076,6 +1101,25 @@ extern "C" int ospcuda_render_frame(const OcWorld *d_world, const OcCamera *came
   }
   oc_count_launch();
   return oc_check(cudaGetLastError(), "ospcuda_render_frame");
+}
+
+namespace oc {
+__global__ void textureSampleKernel(OcTextureParam tp, const float *st, const float *fp, uint32_t n, float4 *out)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const vec4f v = texParamGet4f(tp, make_vec2f(st[2 * i], st[2 * i + 1]), fp[i]);
+  out[i] = make_float4(v.x, v.y, v.z, v.w);
+}
+} // namespace oc
+
+extern "C" int ospcuda_texture_sample(const OcTextureParam *param, const float *d_st, const float *d_footprint, uint32_t n, float *d_out)
+{
+  if (n == 0) return 0;
+  if (!param || !param->tex) return oc_set_error(cudaErrorInvalidValue, "ospcuda_texture_sample: no texture");
+  oc::textureSampleKernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)ospcuda_stream()>>>(*param, d_st, d_footprint, n, (float4 *)d_out);
+  oc_count_launch();
+  return oc_check(cudaGetLastError(), "ospcuda_texture_sample");
 }
 
 extern "C" int ospcuda_trace(const OcWorld *d_world, OcRayHit *d_rays, uint32_t numRays, int occlusionOnly)

@@ -8,6 +8,7 @@
 #pragma once
 #include "intersect.cuh"
 #include "samplers.cuh"
+#include "texture.cuh"
 
 namespace oc {
 
@@ -32,7 +33,13 @@ struct DifferentialGeometry
   float epsilon;
   uint32_t primID, objID, instID;
   const OcMaterial *material;
+  // only filled by postIntersect<true> (frames whose world / renderer reference textures)
+  vec3f dPdt;
+  vec2f st;
+  float pixelFootprint;
 };
+// common/RayCone.ih: width at the current vertex, spread per unit distance
+struct RayCone { float width, dwdt; };
 
 __device__ __forceinline__ float calcEpsilon(vec3f P, float t)
 {
@@ -80,6 +87,25 @@ __device__ __forceinline__ const OcMaterial *getMaterial(const OcWorld *world, c
   return world->materials + matIdx;
 }
 
+__device__ __forceinline__ vec2f get2f(const OcData1D &d, uint32_t i)
+{
+  const float *p = reinterpret_cast<const float *>(d.addr + (int64_t)i * d.byteStride);
+  return make_vec2f(__ldg(p), __ldg(p + 1));
+}
+// texture-space tangents of a triangle / of a quad's (a, b, d) corner (Mesh.ispc:152-168, :253-268); false: degenerate
+__device__ __forceinline__ bool meshTexTangents(DifferentialGeometry &dg, vec2f a, vec2f b, vec2f c, vec3f va, vec3f vb, vec3f vc)
+{
+  const vec2f dst02 = a - c, dst12 = b - c;
+  const float det = dst02.x * dst12.y - dst02.y * dst12.x;
+  if (det == 0.f) return false;
+  const float invDet = 1.f / det;
+  const vec3f dp02 = va - vc, dp12 = vb - vc;
+  dg.dPds = (dst12.y * dp02 - dst02.y * dp12) * invDet;
+  dg.dPdt = (dst02.x * dp12 - dst12.x * dp02) * invDet;
+  return true;
+}
+
+template <bool TEX = false>
 __device__ __forceinline__ void geometryPostIntersect(const OcGeometry *g, DifferentialGeometry &dg,
     const Ray &ray, uint32_t flags)
 {
@@ -108,7 +134,19 @@ __device__ __forceinline__ void geometryPostIntersect(const OcGeometry *g, Diffe
     const vec3f va = get3f(g->vertex, i0), vb = get3f(g->vertex, i1), vc = get3f(g->vertex, i2),
                 vd = get3f(g->vertex, i3);
     dg.epsilon = reduce_max(vmax(vmax(vabs(va), vabs(vb)), vmax(vabs(vc), vabs(vd)))) * OC_ULP_EPSILON;
-    if (flags & DG_TANGENTS) dg.dPds = vb - va; // no texcoords: (Mesh.ispc:170-173)
+    if (TEX) {
+      bool tangents = flags & DG_TANGENTS;
+      if ((flags & (DG_TEXCOORD | DG_TANGENTS)) && g->texcoord.addr) {
+        const bool fv = g->flags & OC_GEOMFLAG_TEXCOORD_FACEVARYING;
+        const vec2f a = get2f(g->texcoord, fv ? fo : i0), b = get2f(g->texcoord, fv ? fo + 1 : i1), d = get2f(g->texcoord, fv ? fo + 3 : i3);
+        if (flags & DG_TEXCOORD) {
+          const vec2f c = get2f(g->texcoord, fv ? fo + 2 : i2);
+          dg.st = uv.x * a + uv.y * b + uv.z * c + uv.w * d;
+        }
+        if (tangents && meshTexTangents(dg, a, b, d, va, vb, vd)) tangents = false;
+      }
+      if (tangents) { dg.dPds = vb - va; dg.dPdt = vd - va; }
+    } else if (flags & DG_TANGENTS) dg.dPds = vb - va; // without texcoords (Mesh.ispc:170-173)
   } else if (g->type == OC_GEOM_TRIANGLES) {
     const uint32_t i0 = get1ui(g->index, ray.primID, 0), i1 = get1ui(g->index, ray.primID, 1),
                    i2 = get1ui(g->index, ray.primID, 2);
@@ -128,9 +166,19 @@ __device__ __forceinline__ void geometryPostIntersect(const OcGeometry *g, Diffe
     }
     const vec3f va = get3f(g->vertex, i0), vb = get3f(g->vertex, i1), vc = get3f(g->vertex, i2);
     dg.epsilon = reduce_max(vmax(vmax(vabs(va), vabs(vb)), vabs(vc))) * OC_ULP_EPSILON;
-    if (flags & DG_TANGENTS) dg.dPds = vb - va;
+    if (TEX) {
+      bool tangents = flags & DG_TANGENTS;
+      if ((flags & (DG_TEXCOORD | DG_TANGENTS)) && g->texcoord.addr) {
+        const bool fv = g->flags & OC_GEOMFLAG_TEXCOORD_FACEVARYING;
+        const vec2f a = get2f(g->texcoord, fv ? fo : i0), b = get2f(g->texcoord, fv ? fo + 1 : i1), c = get2f(g->texcoord, fv ? fo + 2 : i2);
+        if (flags & DG_TEXCOORD) dg.st = uv.x * a + uv.y * b + uv.z * c;
+        if (tangents && meshTexTangents(dg, a, b, c, va, vb, vc)) tangents = false;
+      }
+      if (tangents) { dg.dPds = vb - va; dg.dPdt = vc - va; }
+    } else if (flags & DG_TANGENTS) dg.dPds = vb - va;
   } else if (g->type == OC_GEOM_SPHERES) {
     dg.epsilon = get4f(g->sphere, ray.primID).w * OC_ULP_EPSILON;
+    if (TEX && (flags & DG_TEXCOORD) && g->texcoord.addr) dg.st = get2f(g->texcoord, ray.primID); // Spheres.ispc:39-41
   } else if (g->type == OC_GEOM_CURVES) {
     // Curves_postIntersect + interpolate<vec4f> (geometry/Curves.ispc:17-94): vertex colours through the curve basis at ray.u
     if ((flags & DG_COLOR) && g->color.addr) {
@@ -150,21 +198,27 @@ __device__ __forceinline__ void geometryPostIntersect(const OcGeometry *g, Diffe
   // boxes: nothing else (Boxes.ispc:65-71)
 }
 
-// World.ih:389-465
+// World.ih:389-465. TEX: also texture coordinates, both tangents and the texture-space footprint of the ray cone
+// (World.ih:459-464), which is propagated to the hit
+template <bool TEX = false>
 __device__ __forceinline__ void postIntersect(const OcWorld *world, const OcRenderer &ren,
-    DifferentialGeometry &dg, const Ray &ray, uint32_t flags)
+    DifferentialGeometry &dg, const Ray &ray, uint32_t flags, RayCone *rayCone = nullptr)
 {
   dg.primID = ray.primID;
   dg.material = nullptr;
   if (flags & DG_COLOR) dg.color = make_vec4f(1.f, 1.f, 1.f, 1.f);
   if (flags & DG_TANGENTS) dg.dPds = make_vec3f(1.f, 0.f, 0.f);
+  if (TEX) {
+    dg.st = make_vec2f(ray.u, ray.v);
+    if (flags & DG_TANGENTS) dg.dPdt = make_vec3f(0.f, 1.f, 0.f);
+  }
   dg.P = ray.org + ray.t * ray.dir;
   dg.epsilon = 0.f;
 
   if (ray.instID != OC_INVALID_ID) {
     const OcInstance *inst = world->instances + ray.instID;
     const OcModel *m = inst->group->models + ray.geomID;
-    geometryPostIntersect(m->geom, dg, ray, flags);
+    geometryPostIntersect<TEX>(m->geom, dg, ray, flags);
     dg.objID = (m->userID == OC_INVALID_ID) ? ray.geomID : m->userID;
     if ((flags & DG_COLOR) && m->color.addr) {
       uint32_t idx = ray.primID;
@@ -181,7 +235,10 @@ __device__ __forceinline__ void postIntersect(const OcWorld *world, const OcRend
       dg.Ns = xfmVector(rt, dg.Ns);
       dg.Ng = xfmVector(rt, dg.Ng);
       dg.epsilon *= fmaxf(fabsf(xfm.l.vx.x), fmaxf(fabsf(xfm.l.vy.y), fabsf(xfm.l.vz.z)));
-      if (flags & DG_TANGENTS) dg.dPds = xfmVector(xfm, dg.dPds);
+      if (flags & DG_TANGENTS) {
+        dg.dPds = xfmVector(xfm, dg.dPds);
+        if (TEX) dg.dPdt = xfmVector(xfm, dg.dPdt);
+      }
     }
   } else {
     dg.Ns = dg.Ng = ray.Ng;
@@ -200,6 +257,14 @@ __device__ __forceinline__ void postIntersect(const OcWorld *world, const OcRend
     if (dot(dg.Ng, dg.Ns) < 0.f) dg.Ns = neg(dg.Ns);
   }
   dg.P = dg.P + dg.epsilon * ffnng;
+  if (TEX) {
+    float width = 0.f;
+    if (rayCone) { rayCone->width += rayCone->dwdt * ray.t; width = rayCone->width; }
+    const float texArea = length(cross(dg.dPds, dg.dPdt));
+    const float world2tex = 1.0f / sqrtf(texArea);
+    const float projConeWidth = width / -dot(ray.dir, dg.Ng);
+    dg.pixelFootprint = projConeWidth * world2tex * ren.mipBiasFactor;
+  }
 }
 static __device__ __noinline__ void postIntersectNI(const OcWorld *world, const OcRenderer &ren, DifferentialGeometry &dg,
     const Ray &ray, uint32_t flags)
@@ -279,6 +344,24 @@ __device__ __forceinline__ linear3f makeShadingFrame(const DifferentialGeometry 
   return frame(N);
 }
 
+// render/Material.ih:39-81: shading frame from the bump (normal) map, rotated in tangent space by map_bump's 2D rotation
+__device__ __forceinline__ linear3f makeShadingFrameBump(const DifferentialGeometry &dg, const OcMaterial *m)
+{
+  linear3f f; f.vx = normalize(dg.dPds); f.vy = normalize(dg.dPdt); f.vz = dg.Ns;
+  const vec4f t = texParamGet4f(m->mapBump, dg.st, dg.pixelFootprint);
+  vec3f localN = make_vec3f(t.x, t.y, t.z) * 2.f - make_vec3f(1.f); // getNormal
+  const vec2f rotN = make_vec2f(m->bumpRot[0] * localN.x + m->bumpRot[2] * localN.y, m->bumpRot[1] * localN.x + m->bumpRot[3] * localN.y);
+  localN.x = rotN.x; localN.y = rotN.y;
+  const vec3f N = normalize(f * localN);
+  const vec3f U0 = f.vx;
+  vec3f V = cross(N, U0);
+  if (dot(V, V) > 0.f) {
+    V = normalize(V);
+    linear3f r; r.vx = cross(V, N); r.vy = V; r.vz = N; return r;
+  }
+  return frame(N);
+}
+
 // ---- thin glass: bsdfs/Fresnel.ih:19-47, Optics.ih:13-28, RobustThinDielectric.ih, materials/ThinGlass.ispc ----
 __device__ __forceinline__ float sqrCosT(float cosI, float eta) { return 1.0f - (eta * eta) * (1.0f - cosI * cosI); }
 __device__ __forceinline__ float fresnelDielectric3(float cosI, float cosT, float eta)
@@ -304,10 +387,16 @@ __device__ __forceinline__ vec3f expf3(vec3f v) { return make_vec3f(expf(v.x), e
 __device__ __forceinline__ vec3f logf3(vec3f v) { return make_vec3f(logf(v.x), logf(v.y), logf(v.z)); }
 __device__ __forceinline__ vec3f sqr3(vec3f v) { return v * v; }
 __device__ __forceinline__ vec3f rcp3(vec3f v) { return make_vec3f(1.f / v.x, 1.f / v.y, 1.f / v.z); }
-// ThinGlass.ispc:17-30 (no attenuationColor texture)
+// ThinGlass.ispc:17-30
+template <bool TEX = false>
 __device__ __forceinline__ vec3f ThinGlass_getAttenuation(const OcMaterial *m, const DifferentialGeometry &dg)
 {
-  return toV(m->attenuation) + logf3(make_vec3f(dg.color)) * m->attenuationScale;
+  vec3f attenuation = toV(m->attenuation) + logf3(make_vec3f(dg.color)) * m->attenuationScale;
+  if (TEX && m->mapKd.tex) { // map_attenuationColor
+    const vec4f t = texParamGet4f(m->mapKd, dg.st, dg.pixelFootprint);
+    attenuation = attenuation + logf3(make_vec3f(t.x, t.y, t.z)) * m->attenuationScale;
+  }
+  return attenuation;
 }
 // RobustThinDielectric.ih:99-117
 __device__ __forceinline__ vec3f RobustThinDielectric_getTransparency(float cosThetaO, float eta, vec3f attenuation)
@@ -322,6 +411,7 @@ __device__ __forceinline__ vec3f RobustThinDielectric_getTransparency(float cosT
 
 // materials/OBJ.ispc:29-91, materials/ThinGlass.ispc:32-50. A NULL / unsupported material yields no BSDF (path
 // terminates).
+template <bool TEX = false>
 __device__ __forceinline__ void OBJ_getBSDF(ObjBSDF &b, const DifferentialGeometry &dg)
 {
   const OcMaterial *m = dg.material;
@@ -331,7 +421,7 @@ __device__ __forceinline__ void OBJ_getBSDF(ObjBSDF &b, const DifferentialGeomet
     b.valid = true;
     b.thinGlass = true;
     b.frame = frame(dg.Ns);
-    b.Kd = ThinGlass_getAttenuation(m, dg);
+    b.Kd = ThinGlass_getAttenuation<TEX>(m, dg);
     b.ns = m->eta;
     b.albedo = expf3(b.Kd);
     b.scatteringType = SC_SPECULAR;
@@ -342,13 +432,22 @@ __device__ __forceinline__ void OBJ_getBSDF(ObjBSDF &b, const DifferentialGeomet
   if (!m || m->type != OC_MATERIAL_OBJ)
     return;
   b.valid = true;
-  b.frame = makeShadingFrame(dg);
+  const bool tex = TEX && m->hasTextures;
+  b.frame = (tex && m->mapBump.tex) ? makeShadingFrameBump(dg, m) : makeShadingFrame(dg);
   b.albedo = make_vec3f(0.f);
   b.scatteringType = 0;
   b.importanceSum = 0.f;
   b.impL = b.impT = b.impS = 0.f;
-  const float d = m->d * dg.color.w;
-  const vec3f Kd = toV(m->Kd) * d * make_vec3f(dg.color);
+  float d = m->d;
+  if (tex && m->mapD.tex) d = d * texParamGet4f(m->mapD, dg.st, dg.pixelFootprint).x;
+  d = d * dg.color.w;
+  vec3f Kd = toV(m->Kd);
+  if (tex && m->mapKd.tex) {
+    const vec4f t = texParamGet4f(m->mapKd, dg.st, dg.pixelFootprint);
+    Kd = Kd * make_vec3f(t.x, t.y, t.z);
+    d *= t.w;
+  }
+  Kd = Kd * d * make_vec3f(dg.color);
   b.Kd = Kd;
   if (reduce_max(Kd) > 0.0f) {
     b.albedo = b.albedo + Kd;
@@ -364,13 +463,19 @@ __device__ __forceinline__ void OBJ_getBSDF(ObjBSDF &b, const DifferentialGeomet
     b.impT = luminance(T);
     b.importanceSum += b.impT;
   }
-  const vec3f Ks = d * toV(m->Ks);
+  float Ns = m->Ns;
+  vec3f Ks = d * toV(m->Ks);
+  if (tex && m->mapNs.tex) Ns = Ns * texParamGet4f(m->mapNs, dg.st, dg.pixelFootprint).x;
+  if (tex && m->mapKs.tex) {
+    const vec4f t = texParamGet4f(m->mapKs, dg.st, dg.pixelFootprint);
+    Ks = Ks * make_vec3f(t.x, t.y, t.z);
+  }
   if (reduce_max(Ks) > 0.0f) {
     b.albedo = b.albedo + Ks;
     b.scatteringType |= SC_GLOSSY_REFLECTION;
     b.impS = luminance(Ks);
     b.importanceSum += b.impS;
-    b.ns = m->Ns * 4.f; // Phong -> Blinn (Specular.ih:71-79)
+    b.ns = Ns * 4.f; // Phong -> Blinn (Specular.ih:71-79)
     const float tmp = (b.ns + 2.f) * (1.f / (2.f - expf(b.ns * -OC_LNTWO_OVER_TWO)));
     b.ks = Ks * (OC_ONE_OVER_FOUR_PI * tmp);
     b.specWeight = Ks * (2.f * tmp * (1.f / (b.ns + 1.f)));
@@ -504,15 +609,19 @@ __device__ __forceinline__ SampleRes OBJ_sample(const ObjBSDF &b, vec3f wo, vec2
   return res;
 }
 // materials/OBJ.ispc:93-111, materials/ThinGlass.ispc:52-64
+template <bool TEX = false>
 __device__ __forceinline__ vec3f materialTransparency(const DifferentialGeometry &dg, vec3f rayDir)
 {
   const OcMaterial *m = dg.material;
   if (m && m->type == OC_MATERIAL_THINGLASS) {
     const float cosThetaO = fmaxf(-dot(rayDir, dg.Ns), 0.0f);
-    return RobustThinDielectric_getTransparency(cosThetaO, m->eta, ThinGlass_getAttenuation(m, dg));
+    return RobustThinDielectric_getTransparency(cosThetaO, m->eta, ThinGlass_getAttenuation<TEX>(m, dg));
   }
   if (!m || m->type != OC_MATERIAL_OBJ) return make_vec3f(0.f);
-  const float d = m->d * dg.color.w;
+  float d = m->d;
+  if (TEX && m->mapD.tex) d = d * texParamGet4f(m->mapD, dg.st, dg.pixelFootprint).x;
+  d = d * dg.color.w;
+  if (TEX && m->mapKd.tex && m->mapKd.tex->hasAlpha) d *= texParamGet4f(m->mapKd, dg.st, dg.pixelFootprint).w;
   return toV(m->Tf) * d + make_vec3f(1.f - d);
 }
 
@@ -880,6 +989,23 @@ __device__ __forceinline__ void cameraInitRay(const OcCamera &cam, Ray &ray, vec
     dir = dir - lp;
   }
   setRay(ray, org, normalize(dir), cam.nearClip, INFINITY);
+}
+// the ray cone a camera ray starts with (PerspectiveCamera.ispc:43-63, OrthographicCamera.ispc:50-53), before the
+// renderer scales it to pixel units; `screen` is the sample position before the sub-image mapping
+__device__ __forceinline__ RayCone cameraInitRayCone(const OcCamera &cam, vec2f screen)
+{
+  RayCone rc;
+  const float subH = fabsf(cam.subImage[3] - cam.subImage[1]);
+  if (cam.type == OC_CAMERA_ORTHOGRAPHIC) {
+    rc.width = cam.imgPlaneSizeY * subH; rc.dwdt = 0.f;
+    return rc;
+  }
+  screen = make_vec2f(lerpf(screen.x, cam.subImage[0], cam.subImage[2]), lerpf(screen.y, cam.subImage[1], cam.subImage[3]));
+  const vec3f dir = toV(cam.dir_00) + screen.x * toV(cam.du_size) + screen.y * toV(cam.dv_up);
+  const float coneShortening = 1.0f / sqrtf(dot(dir, dir));
+  rc.width = 0.f;
+  rc.dwdt = cam.imgPlaneSizeY * subH * coneShortening;
+  return rc;
 }
 
 } // namespace oc

@@ -32,6 +32,7 @@ void CudaDevice::commit()
     rk = getParam<int>("multiSubdeviceRank", 0);
     ord = getParam<int>("cudaDevice", 0);
   }
+  disableMipMapGeneration = getParam<bool>("disableMipMapGeneration", false);
   numRanks = (uint32_t)std::max(1, nr);
   rank = (uint32_t)std::max(0, rk) % numRanks;
   cudaOrdinal = ord;
@@ -87,7 +88,11 @@ OSPTransferFunction CudaDevice::newTransferFunction(const char *type)
   if (std::string(type) != "piecewiseLinear") return nullptr;
   return (OSPTransferFunction) new TransferFunction;
 }
-OSPTexture CudaDevice::newTexture(const char *) { return nullptr; } // textures: out of scope
+OSPTexture CudaDevice::newTexture(const char *type)
+{
+  if (std::string(type) != "texture2d") return nullptr; // volume textures are not built
+  return (OSPTexture) new Texture2D(*this);
+}
 OSPGroup CudaDevice::newGroup() { return (OSPGroup) new Group; }
 OSPInstance CudaDevice::newInstance(OSPGroup g) { return (OSPInstance) new Instance((Group *)g); }
 OSPWorld CudaDevice::newWorld() { return (OSPWorld) new World(*this); }
@@ -163,6 +168,7 @@ OSPFuture CudaDevice::renderFrame(OSPFrameBuffer _fb, OSPRenderer _r, OSPCamera 
     OcRenderer rsh = r->sh;
     rsh.worldNumLights = w->sh.numLights;
     rsh.worldHasVolumes = w->sh.hasVolumes;
+    rsh.hasTextures = (texturedMaterials > 0 || rsh.backplate || rsh.maxDepthTexture) ? 1u : 0u;
     if (!finished) checkCuda(ospcuda_render_frame(dw, &c->sh, &rsh, &fb->sh), "render kernel");
     checkCuda(ospcuda_event_record(f->evRendered), "event record");
     fb->postProcess();
@@ -314,5 +320,6 @@ void ospcudaGetFrameStageTimes(OSPFuture f, float ms[2])
   ospcuda_event_elapsed_ms(fu->evRendered, fu->evFinished, &ms[1]);
 }
 void ospcudaSetRenderStream(void *stream) { ospray::cuda::checkCuda(ospcuda_set_stream(stream), "set stream"); }
+const void *ospcudaTextureDevicePointer(OSPTexture t) { return ((cuda::Texture2D *)cuda::subObject(t, 0))->devPtr(); }
 const void *ospcudaWorldDevicePointer(OSPWorld w) { return ((cuda::World *)cuda::subObject(w, 0))->prepareFrame(); }
 }

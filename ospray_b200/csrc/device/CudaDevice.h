@@ -62,6 +62,8 @@ struct CudaDevice : public api::Device
   int cudaOrdinal = 0;
   uint32_t numRanks = 1, rank = 0; // image-tile partition (tile % numRanks == rank)
   bool initialized = false;
+  bool disableMipMapGeneration = false; // device parameter of the same name (ISPCDevice.cpp:232-233)
+  uint32_t texturedMaterials = 0;       // materials whose last commit referenced a texture
 
  private:
   std::vector<OcMaterial> materials;

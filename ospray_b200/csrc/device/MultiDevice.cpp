@@ -64,6 +64,7 @@ struct MultiCudaDevice : public api::Device
   void commit() override
   {
     api::Device::commit();
+    for (auto &d : subdevices) d->disableMipMapGeneration = getParam<bool>("disableMipMapGeneration", false);
     if (!subdevices.empty()) return; // the sub-devices are created once
     int n = getParam<int>("numSubdevices", 0);
     if (const char *e = getenv("OSPRAY_NUM_SUBDEVICES")) n = atoi(e);
@@ -80,6 +81,7 @@ struct MultiCudaDevice : public api::Device
       d->error_fcn = [this](void *, OSPError e, const char *m) { error_fcn(errorUserData, e, m); };
       d->warningsAreErrors = warningsAreErrors;
       d->commit();
+      d->disableMipMapGeneration = getParam<bool>("disableMipMapGeneration", false);
       subdevices.emplace_back(d);
       d->refDec();
     }

@@ -375,33 +375,63 @@ Material::Material(CudaDevice &d, const std::string &t) : device(d), type(t), sl
 {
   managedObjectType = OSP_MATERIAL;
 }
-Material::~Material() { device.freeMaterialSlot(slot); }
+Material::~Material()
+{
+  if (texD || texKd || texKs || texNs || texBump) device.texturedMaterials--;
+  device.freeMaterialSlot(slot);
+}
+
+// LinearSpace2::orthogonal() of rkcommon (un-vendored; restated): the rotation part of a 2x2 matrix by the iteration
+// m <- (m + m^-T) / 2, a mirrored x axis flipped first and restored at the end
+static void linear2fOrthogonal(float m[4]) // vx = (m[0], m[1]), vy = (m[2], m[3])
+{
+  float mirror = 1.f;
+  if (m[0] * m[3] - m[2] * m[1] < 0.f) { m[0] = -m[0]; m[1] = -m[1]; mirror = -1.f; }
+  for (int i = 0; i < 99; i++) {
+    // transposed(): rows become columns; inverse of [[a, c], [b, d]] (columns (a,b), (c,d))
+    const float ta = m[0], tb = m[2], tc = m[1], td = m[3]; // transposed columns (ta, tb), (tc, td)
+    const float det = ta * td - tc * tb, r = 1.f / det;
+    const float ia = td * r, ib = -tb * r, ic = -tc * r, id = ta * r; // inverse columns (ia, ib), (ic, id)
+    const float n[4] = {0.5f * (m[0] + ia), 0.5f * (m[1] + ib), 0.5f * (m[2] + ic), 0.5f * (m[3] + id)};
+    const float d0 = n[0] - m[0], d1 = n[1] - m[1], d2 = n[2] - m[2], d3 = n[3] - m[3];
+    for (int k = 0; k < 4; k++) m[k] = n[k];
+    if (std::max(d0 * d0 + d1 * d1, d2 * d2 + d3 * d3) < 1e-8f) break;
+  }
+  m[0] *= mirror; m[1] *= mirror;
+}
 
 void Material::commit()
 {
   OcMaterial m{};
+  const bool hadTextures = texD || texKd || texKs || texNs || texBump;
+  texD = texKd = texKs = texNs = texBump = nullptr;
   if (type == "obj") {
+    // render/materials/OBJ.cpp:30-66: a parameter with a map defaults to factor 1 (Material.cpp:110-133)
     m.type = OC_MATERIAL_OBJ;
+    m.mapD = getTextureParam("map_d", texD);
+    m.mapKd = getTextureParam("map_kd", texKd);
+    m.mapKs = getTextureParam("map_ks", texKs);
+    m.mapNs = getTextureParam("map_ns", texNs);
+    m.mapBump = getTextureParam("map_bump", texBump);
     float d = getParam<float>("d", 1.f);
-    vec3f Kd = getParam<vec3f>("kd", make_vec3f(0.8f));
-    vec3f Ks = getParam<vec3f>("ks", make_vec3f(0.f));
-    const float Ns = getParam<float>("ns", 10.f);
+    vec3f Kd = getParam<vec3f>("kd", make_vec3f(texKd ? 1.f : 0.8f));
+    vec3f Ks = getParam<vec3f>("ks", make_vec3f(texKs ? 1.f : 0.f));
+    const float Ns = getParam<float>("ns", texNs ? 1.f : 10.f);
     vec3f Tf = getParam<vec3f>("tf", make_vec3f(0.f));
     const float total = reduce_max(Kd + Ks + Tf);
     if (total > 1.f) { Kd = Kd / total; Ks = Ks / total; Tf = Tf / total; }
-    for (const char *tex : {"map_d", "map_kd", "map_ks", "map_ns", "map_bump"})
-      if (getParamObjectRaw(tex))
-        postStatusMsg(OSP_LOG_WARNING, std::string("cuda device: texture '") + tex + "' ignored (textures are out of scope)");
+    float rot[4] = {m.mapBump.xform2f[0], m.mapBump.xform2f[1], m.mapBump.xform2f[2], m.mapBump.xform2f[3]};
+    linear2fOrthogonal(rot);
+    m.bumpRot[0] = rot[0]; m.bumpRot[1] = rot[2]; m.bumpRot[2] = rot[1]; m.bumpRot[3] = rot[3]; // transposed()
     m.d = d; m.Kd = toOc(Kd); m.Ks = toOc(Ks); m.Ns = Ns; m.Tf = toOc(Tf);
   } else if (type == "thinGlass") {
     // render/materials/ThinGlass.cpp:33-48
     m.type = OC_MATERIAL_THINGLASS;
     const float eta = getParam<float>("eta", 1.5f);
+    m.mapKd = getTextureParam("map_attenuationColor", texKd);
     const vec3f acf = getParam<vec3f>("attenuationColor", make_vec3f(1.f));
     const float attenuationDistance = getParam<float>("attenuationDistance", 1.f);
     const float thickness = getParam<float>("thickness", 1.f);
-    if (getParamObjectRaw("map_attenuationColor"))
-      postStatusMsg(OSP_LOG_WARNING, "cuda device: texture 'map_attenuationColor' ignored (textures are out of scope)");
     m.eta = 1.f / eta;
     m.attenuationScale = thickness * (1.f / std::max(attenuationDistance, 1e-5f));
     m.attenuation = toOc(make_vec3f(std::log(acf.x), std::log(acf.y), std::log(acf.z)) * m.attenuationScale);
@@ -410,6 +440,10 @@ void Material::commit()
     for (auto &p : params) p.second.queried = true;
     postStatusMsg(OSP_LOG_INFO, "cuda device: material '" + type + "' is not implemented; surfaces using it terminate paths");
   }
+  const bool hasTextures = texD || texKd || texKs || texNs || texBump;
+  m.hasTextures = hasTextures ? 1u : 0u;
+  if (hasTextures && !hadTextures) device.texturedMaterials++;
+  if (!hasTextures && hadTextures) device.texturedMaterials--;
   device.setMaterial(slot, m);
 }
 
@@ -1047,12 +1081,17 @@ void Renderer::commit()
     sh.debugMethod = id;
   }
   sh.spp = std::max(1, getParam<int>("pixelSamples", 1));
-  getParam<float>("mipMapBias", 0.f);
+  sh.mipBiasFactor = std::pow(2.f, getParam<float>("mipMapBias", 0.f)); // Renderer.cpp:41,91
   sh.maxDepth = (uint32_t)std::max(0, getParam<int>("maxPathLength", 20));
   sh.minContribution = getParam<float>("minContribution", 0.001f);
   errorThreshold = getParam<float>("varianceThreshold", 0.f);
-  if (getParamObjectRaw("map_maxDepth") || getParamObjectRaw("map_backplate"))
-    postStatusMsg(OSP_LOG_WARNING, "cuda device: renderer textures (map_maxDepth, map_backplate) are not supported");
+  // Renderer.cpp:61-80
+  maxDepthTexture = getParamObject<Texture2D>("map_maxDepth");
+  backplate = getParamObject<Texture2D>("map_backplate");
+  if (maxDepthTexture && (maxDepthTexture->sh.format != OSP_TEXTURE_R32F || maxDepthTexture->sh.filter != OSP_TEXTURE_FILTER_NEAREST))
+    postStatusMsg(OSP_LOG_WARNING, "maxDepthTexture provided to the renderer needs to be of type OSP_TEXTURE_R32F and have the OSP_TEXTURE_FILTER_NEAREST flag");
+  sh.maxDepthTexture = maxDepthTexture ? maxDepthTexture->devPtr() : nullptr;
+  sh.backplate = backplate ? backplate->devPtr() : nullptr;
   const vec3f bg3 = getParam<vec3f>("backgroundColor", make_vec3f(getParam<float>("backgroundColor", 0.f)));
   const vec4f bg = getParam<vec4f>("backgroundColor", make_vec4f(bg3, 0.f));
   sh.bgColor[0] = bg.x; sh.bgColor[1] = bg.y; sh.bgColor[2] = bg.z; sh.bgColor[3] = bg.w;

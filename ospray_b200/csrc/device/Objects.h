@@ -109,6 +109,22 @@ struct Geometry : public ManagedObject
   DevMem dev, generated; // generated: soup index / interleaved spheres
 };
 
+// texture2d (texture/Texture2D.cpp:56-146): level 0 = the app's 2D data array, MIP levels generated at commit
+// (texture/MipMapGeneration.ispc:8-95) unless the device parameter disableMipMapGeneration is set
+struct Texture2D : public ManagedObject
+{
+  explicit Texture2D(CudaDevice &d) : device(d) { managedObjectType = OSP_TEXTURE; }
+  std::string toString() const override { return "ospray::Texture2D"; }
+  void commit() override;
+  const OcTexture2D *devPtr() const { return shDev.as<OcTexture2D>(); }
+  CudaDevice &device;
+  OcTexture2D sh{};
+
+ private:
+  Ref<Data> texData;
+  DevMem texels, shDev; // all levels back to back; the OcTexture2D itself
+};
+
 struct Material : public ManagedObject
 {
   Material(CudaDevice &device, const std::string &type);
@@ -118,6 +134,10 @@ struct Material : public ManagedObject
   CudaDevice &device;
   std::string type;
   uint32_t slot;
+
+ private:
+  OcTextureParam getTextureParam(const std::string &name, Ref<Texture2D> &keep); // render/Material.cpp:73-165
+  Ref<Texture2D> texD, texKd, texKs, texNs, texBump;
 };
 
 uint64_t commitEpoch();     // counts the commits of objects whose state parents snapshot
@@ -268,6 +288,7 @@ struct Renderer : public ManagedObject
 
  private:
   Ref<Data> materialData;
+  Ref<Texture2D> backplate, maxDepthTexture;
   DevMem pfCdfX, pfCdfY, matList;
 };
 

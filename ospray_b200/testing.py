@@ -17,6 +17,25 @@ from . import capi as osp
 
 # ---- spec ---------------------------------------------------------------------------------------
 @dataclass
+class TextureSpec:
+    data: np.ndarray                           # (h, w[, channels]) uint8 | uint16 | float16 | float32
+    format: str                                # OSPTextureFormat name without the prefix: "RGBA8", "SRGB", "R32F", ...
+    filter: str = "linear"                     # | "nearest"
+    wrap: tuple = ("repeat", "repeat")         # repeat | mirror | clamp, per axis
+    mipmaps: bool = True                       # False: rendered with the device parameter disableMipMapGeneration
+
+
+@dataclass
+class MapSpec:
+    """a material's texture parameter with its optional 2D coordinate transform (render/Material.cpp:73-165)"""
+    texture: TextureSpec
+    translation: Optional[tuple] = None
+    scale: Optional[tuple] = None
+    rotation: Optional[float] = None           # degrees
+    transform: Optional[tuple] = None          # linear2f (vx.x, vx.y, vy.x, vy.y)
+
+
+@dataclass
 class MaterialSpec:
     type: str = "obj"
     kd: tuple = (0.8, 0.8, 0.8)
@@ -28,6 +47,12 @@ class MaterialSpec:
     attenuation_color: tuple = (1.0, 1.0, 1.0)
     attenuation_distance: float = 1.0
     thickness: float = 1.0
+    map_kd: Optional["MapSpec"] = None
+    map_ks: Optional["MapSpec"] = None
+    map_ns: Optional["MapSpec"] = None
+    map_d: Optional["MapSpec"] = None
+    map_bump: Optional["MapSpec"] = None
+    map_attenuation_color: Optional["MapSpec"] = None
 
 
 @dataclass
@@ -38,6 +63,7 @@ class GeometrySpec:
     quad_soup: bool = False
     vertex_color: Optional[np.ndarray] = None  # (N,4) f32
     vertex_normal: Optional[np.ndarray] = None
+    vertex_texcoord: Optional[np.ndarray] = None  # (N,2) f32
     sphere_position: Optional[np.ndarray] = None
     sphere_radius: Optional[np.ndarray] = None
     radius: float = 0.01
@@ -91,6 +117,18 @@ class LightSpec:
 class SceneSpec:
     instances: List[InstanceSpec] = field(default_factory=list)
     lights: List[LightSpec] = field(default_factory=list)
+    backplate: Optional[TextureSpec] = None    # renderer parameter map_backplate
+    max_depth_texture: Optional[TextureSpec] = None  # renderer parameter map_maxDepth (R32F, nearest)
+
+    def uses_mipmaps(self):
+        """False when any texture of the scene asks for disableMipMapGeneration (a device parameter: all or none)"""
+        texs = [t for t in (self.backplate, self.max_depth_texture) if t is not None]
+        for inst in self.instances:
+            for m in inst.group.models:
+                if m.material is not None:
+                    texs += [getattr(m.material, a).texture for a in ("map_kd", "map_ks", "map_ns", "map_d", "map_bump", "map_attenuation_color")
+                             if getattr(m.material, a) is not None]
+        return all(t.mipmaps for t in texs)
 
 
 # ---- deterministic RNG ----------------------------------------------------------------------------
@@ -356,6 +394,8 @@ def _geometry(g: GeometrySpec):
             geo.set("vertex.color", g.vertex_color)
         if g.vertex_normal is not None:
             geo.set("vertex.normal", g.vertex_normal)
+        if g.vertex_texcoord is not None:
+            geo.set("vertex.texcoord", np.ascontiguousarray(g.vertex_texcoord, np.float32))
         if g.index is not None:
             geo.set("index", g.index)
         elif g.quad_soup:
@@ -378,18 +418,40 @@ def _geometry(g: GeometrySpec):
     return geo.commit()
 
 
+_FILTER = {"linear": 0, "nearest": 1}
+_WRAP = {"repeat": 0, "mirror": 1, "clamp": 2}
+
+
+def make_texture(t: TextureSpec):
+    return osp.texture2d(t.data, t.format, _FILTER[t.filter], tuple(_WRAP[w] for w in t.wrap))
+
+
+def _set_map(mat, name, ms: "MapSpec"):
+    if ms is None:
+        return
+    mat.set(name, make_texture(ms.texture))
+    if ms.translation is not None: mat.set(name + ".translation", tuple(float(x) for x in ms.translation))
+    if ms.scale is not None: mat.set(name + ".scale", tuple(float(x) for x in ms.scale))
+    if ms.rotation is not None: mat.set(name + ".rotation", float(ms.rotation))
+    if ms.transform is not None: mat.set(name + ".transform", osp.Typed(osp.OSP_LINEAR2F, ms.transform))
+
+
 def _material(m: MaterialSpec):
     mat = osp.Material(m.type)
     d = MaterialSpec()
+    for name in ("map_kd", "map_ks", "map_ns", "map_d", "map_bump"):
+        _set_map(mat, name, getattr(m, name))
+    _set_map(mat, "map_attenuationColor", m.map_attenuation_color)
     if m.type == "thinGlass":
         if m.eta != d.eta: mat.set("eta", float(m.eta))
         if m.attenuation_color != d.attenuation_color: mat.set("attenuationColor", tuple(float(x) for x in m.attenuation_color))
         if m.attenuation_distance != d.attenuation_distance: mat.set("attenuationDistance", float(m.attenuation_distance))
         if m.thickness != d.thickness: mat.set("thickness", float(m.thickness))
         return mat.commit()
-    if m.kd != d.kd: mat.set("kd", tuple(float(x) for x in m.kd))
-    if m.ks != d.ks: mat.set("ks", tuple(float(x) for x in m.ks))
-    if m.ns != d.ns or m.ks != d.ks: mat.set("ns", float(m.ns))
+    # a parameter with a map defaults to factor 1 (Material.cpp:110-133): the spec's values are always sent then
+    if m.kd != d.kd or m.map_kd: mat.set("kd", tuple(float(x) for x in m.kd))
+    if m.ks != d.ks or m.map_ks: mat.set("ks", tuple(float(x) for x in m.ks))
+    if m.ns != d.ns or m.ks != d.ks or m.map_ns: mat.set("ns", float(m.ns))
     if m.d != d.d: mat.set("d", float(m.d))
     if m.tf != d.tf: mat.set("tf", tuple(float(x) for x in m.tf))
     return mat.commit()

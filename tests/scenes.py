@@ -124,6 +124,91 @@ def linear_curves():
                        lights=[T.LightSpec("distant", {"direction": (-0.2, -0.6, 0.7), "intensity": 2.0}), T.LightSpec("ambient", {"intensity": 0.5})])
 
 
+def _tex_rng_image(h, w, c, seed, dtype=np.uint8, lo=0.15, hi=1.0):
+    """smooth-ish random image (random blocks of 2x2 texels): MIP levels differ from level 0 without being noise"""
+    rng = np.random.default_rng(seed)
+    a = rng.uniform(lo, hi, ((h + 1) // 2, (w + 1) // 2, c)).repeat(2, axis=0).repeat(2, axis=1)[:h, :w]
+    if dtype == np.uint8: return np.ascontiguousarray((a * 255).astype(np.uint8))
+    if dtype == np.uint16: return np.ascontiguousarray((a * 65535).astype(np.uint16))
+    return np.ascontiguousarray(a.astype(dtype))
+
+
+def _cornell_models(materials):
+    """the cornell box as one model per material: `materials` maps a tuple of quad indices to a MaterialSpec; every quad
+    carries texture coordinates (0,0) (2,0) (2,2) (0,2) so that wrap modes take part; the rest keeps the default material"""
+    base = T.cornell_box()
+    g = base.instances[0].group.models[0].geometry
+    v, c = g.vertex.reshape(-1, 4, 3), g.vertex_color.reshape(-1, 4, 4)
+    st = np.array([[0, 0], [2, 0], [2, 2], [0, 2]], np.float32)
+    used = set(q for qs in materials for q in qs)
+    groups = list(materials.items()) + [(tuple(q for q in range(len(v)) if q not in used), T.MaterialSpec())]
+    models = []
+    for qs, mat in groups:
+        if not qs: continue
+        qs = list(qs)
+        geom = T.GeometrySpec("mesh", vertex=np.ascontiguousarray(v[qs].reshape(-1, 3)), quad_soup=True,
+                              vertex_color=np.ascontiguousarray(c[qs].reshape(-1, 4)), vertex_texcoord=np.tile(st, (len(qs), 1)))
+        models.append(T.ModelSpec(geom, mat))
+    base.instances[0].group.models = models
+    return base
+
+
+def textured_cornell():
+    """OBJ texture maps on the cornell box: map_kd in several formats / filters / wrap modes (with MIP chains and a rotated,
+    scaled, shifted coordinate transform), map_ks + map_ns, and a bump map (texture/Texture2D.ispc, OBJ.ispc:29-91)"""
+    TS, MS = T.TextureSpec, T.MapSpec
+    white = (1.0, 1.0, 1.0)
+    nrm = _tex_rng_image(16, 16, 3, 7, np.float32, 0.3, 0.7)
+    nrm[..., 2] = 1.0
+    half_rgba = _tex_rng_image(8, 8, 4, 8, np.float16)
+    half_rgba[..., 3] = 1.0
+    mats = {
+        (0,): T.MaterialSpec(kd=white, map_kd=MS(TS(_tex_rng_image(32, 32, 3, 1), "RGB8"))),                                   # floor: bilinear + MIP
+        (2,): T.MaterialSpec(kd=white, map_kd=MS(TS(_tex_rng_image(24, 40, 3, 2), "SRGB", wrap=("mirror", "clamp")),
+                                                  rotation=30.0, scale=(0.5, 0.75), translation=(0.1, 0.2))),                   # back wall
+        (3,): T.MaterialSpec(kd=white, map_kd=MS(TS(_tex_rng_image(9, 7, 3, 3, np.float32), "RGB32F", filter="nearest"))),      # odd sizes: 3x3 MIP kernel
+        (4,): T.MaterialSpec(kd=(0.5, 0.5, 0.5), ks=(0.4, 0.4, 0.4), ns=30.0, map_ks=MS(TS(_tex_rng_image(16, 16, 4, 4, np.uint16), "RGBA16")),
+                             map_ns=MS(TS(_tex_rng_image(8, 8, 1, 5, np.float32)[..., 0], "R32F"), transform=(0.0, 1.0, -1.0, 0.0))),
+        (5, 11): T.MaterialSpec(map_bump=MS(TS(nrm, "RGB32F"), rotation=20.0)),                                                # box tops: bump map
+        (7, 13): T.MaterialSpec(kd=white, map_kd=MS(TS(_tex_rng_image(16, 16, 1, 6)[..., 0], "L8", wrap=("clamp", "mirror")))),
+        # (RGB16F / R16F are left to tests/test_gpu_textures.py: the reference's scalar form misreads those two formats)
+        # as map_ks: a map_kd with an alpha channel is looked up along shadow rays, where the reference's footprint is
+        # undefined (TransparentShadow.ispc:44-52 asks for no tangents, World.ih:459-464 uses them) -- see cutout_cornell
+        (12,): T.MaterialSpec(kd=(0.4, 0.4, 0.4), ks=(0.5, 0.5, 0.5), ns=15.0, map_ks=MS(TS(half_rgba, "RGBA16F"))),
+    }
+    return _cornell_models(mats)
+
+
+def cutout_cornell():
+    """cut-out opacity from map_d (R8, nearest) and from the alpha of map_kd (RGBA8) on the boxes, thin glass tinted by
+    map_attenuationColor on the back wall: textures along shadow rays (OBJ_getTransparency, ThinGlass.ispc:17-30). Rendered
+    with disableMipMapGeneration: the reference's shadow ray cone starts from an uninitialised width (see pathtracer_wf.cuh)"""
+    TS, MS = T.TextureSpec, T.MapSpec
+    rng = np.random.default_rng(9)
+    holes = np.ascontiguousarray((rng.uniform(0, 1, (8, 8)) > 0.4).astype(np.uint8) * 255)
+    rgba = _tex_rng_image(8, 8, 4, 10)
+    rgba[..., 3] = np.where(rng.uniform(0, 1, (8, 8)) > 0.5, 255, 60)
+    mats = {
+        (5, 6, 7, 8, 9): T.MaterialSpec(map_d=MS(TS(holes, "R8", filter="nearest", mipmaps=False))),
+        (11, 12, 13, 14, 15): T.MaterialSpec(kd=(1.0, 1.0, 1.0), map_kd=MS(TS(rgba, "RGBA8", mipmaps=False))),
+        (2,): T.MaterialSpec(type="thinGlass", eta=1.4, attenuation_distance=0.5,
+                             map_attenuation_color=MS(TS(_tex_rng_image(8, 8, 3, 11, np.float32, 0.4, 1.0), "RGB32F", mipmaps=False))),
+    }
+    s = _cornell_models(mats)
+    s.lights.append(T.LightSpec("ambient", {"intensity": 0.3}))
+    return s
+
+
+def backplate_scene():
+    """renderer textures: map_backplate behind random spheres and map_maxDepth cutting the primary rays (Renderer.ispc:18-39)"""
+    s = T.random_spheres(24, seed=3)
+    s.backplate = T.TextureSpec(_tex_rng_image(12, 20, 4, 12, np.float32), "RGBA32F")
+    depth = np.full((4, 4), 1e20, np.float32)
+    depth[1:3, 0:2] = 3.0
+    s.max_depth_texture = T.TextureSpec(depth, "R32F", filter="nearest")
+    return s
+
+
 # name -> (spec builder, renderer kind, renderer params, frames[, {camera: kind, height: h}])
 CASES = {
     "cornell_pt": (T.cornell_box, "pathtracer", {"pixelSamples": 2}, 2),
@@ -160,6 +245,11 @@ CASES = {
     "gravity_aniso_pt": (forward_scattering_volume, "pathtracer", {"pixelSamples": 2, "maxPathLength": 8}, 1),
     "volume_geometry_pt": (volume_with_opaque_geometry, "pathtracer", {"pixelSamples": 2}, 1),
     "volume_glass_geometry_pt": (volume_with_geometry, "pathtracer", {"pixelSamples": 2}, 1),  # transparent shadows through the medium
+    # 2D textures (texture/Texture2D.ispc, TextureParam.ispc, OBJ / ThinGlass maps, renderer backplate / maxDepth)
+    "textured_pt": (textured_cornell, "pathtracer", {"pixelSamples": 2}, 2),
+    "textured_bias_pt": (textured_cornell, "pathtracer", {"pixelSamples": 1, "mipMapBias": 1.5}, 1),
+    "cutout_pt": (cutout_cornell, "pathtracer", {"pixelSamples": 2}, 1),
+    "backplate_pt": (backplate_scene, "pathtracer", {"pixelSamples": 2, "backgroundColor": (0.1, 0.2, 0.3, 1.0)}, 1),
     # debug renderer (render/debug/DebugRenderer.ispc), every method the device accepts
     "debug_testFrame": (T.cornell_box, "debug", {"method": "testFrame", "pixelSamples": 2}, 2),
     "debug_rayDir": (T.cornell_box, "debug", {"method": "rayDir"}, 1),
@@ -179,6 +269,8 @@ CASES = {
 # numVolumeIntervals on every pass of their transparency loops (volume/Volume.ispc:68-71), so the pass after a
 # transmissive geometry hit indexes past it (common/World.ih:121-128).  Undefined in the reference's scalar mode.
 REF_UNSUPPORTED = {"volume_geometry"}
+# Cases only the reference's own kernels check (the restatement in oracle.cpp does not sample textures)
+ORACLE_UNSUPPORTED = {"textured_pt", "textured_bias_pt", "cutout_pt", "backplate_pt"}
 # Cases the cuda device does not render (none at present; the GPU parity tests skip what is listed here)
 DEVICE_UNSUPPORTED = set()
 # Volumes under the pathtracer: delta tracking takes hundreds of accept/reject decisions per path on logf / expf / lerp
@@ -202,6 +294,8 @@ def oracle_render(name, width=W, height=H, pixel_filter=None, threads=0, num_ran
     p = dict(params)
     if pixel_filter:
         p["pixelFilter"] = pixel_filter
+    if spec.backplate is not None or spec.max_depth_texture is not None:
+        p.update(backplate=spec.backplate, maxDepthTexture=spec.max_depth_texture, mipmaps=scene.mipmaps)
     ren = O.RendererParams(kind, **p)
     fb = O.HostFrameBuffer(width, height, channels or ("color", "depth", "primID", "objID", "instID", "normal", "albedo"),
                            num_ranks=num_ranks, rank=rank)
@@ -218,17 +312,26 @@ def device_render(osp, name, width=W, height=H, pixel_filter=None, channels=None
     build, kind, params, frames = CASES[name][:4]
     extra = CASES[name][4] if len(CASES[name]) > 4 else {}
     spec = build()
-    world, keep = T.to_ospray(spec)
+    if not spec.uses_mipmaps():  # a device parameter (ISPCDevice.cpp:232): textures committed meanwhile get no MIP chain
+        osp.set_device_bool("disableMipMapGeneration", True)
+    try:
+        world, keep = T.to_ospray(spec)
+        keep_tex = [T.make_texture(t) if t is not None else None for t in (spec.backplate, spec.max_depth_texture)]
+    finally:
+        if not spec.uses_mipmaps():
+            osp.set_device_bool("disableMipMapGeneration", False)
     cam, _ = T.make_camera(world, width, height, kind=extra.get("camera", "perspective"), ortho_height=extra.get("height", 1.0))
     p = {}
     for k, v in params.items():
         p[k] = tuple(float(x) for x in v) if isinstance(v, tuple) else v
     if pixel_filter:
         p["pixelFilter"] = osp.Typed(osp.OSP_UINT, _PF[pixel_filter])
+    if keep_tex[0] is not None: p["map_backplate"] = keep_tex[0]
+    if keep_tex[1] is not None: p["map_maxDepth"] = keep_tex[1]
     ren = T.make_renderer(kind, **p)
     ch = channels if channels is not None else (osp.OSP_FB_COLOR | osp.OSP_FB_ACCUM | osp.OSP_FB_DEPTH | osp.OSP_FB_ID_PRIMITIVE
                                                 | osp.OSP_FB_ID_OBJECT | osp.OSP_FB_ID_INSTANCE | osp.OSP_FB_NORMAL | osp.OSP_FB_ALBEDO)
     fb = osp.FrameBuffer(width, height, osp.OSP_FB_RGBA32F if fmt is None else fmt, ch)
     for _ in range(frames):
         fb.render_frame(ren, cam, world).wait()
-    return fb, (world, keep, cam, ren)
+    return fb, (world, keep + keep_tex, cam, ren)

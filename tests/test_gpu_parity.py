@@ -159,7 +159,11 @@ def test_images_match_oracle(osp, name):
     to rounding (fma contraction, libm) except where a last-bit difference flips a discrete decision. Bars:
     >= 98 % of the pixels within 2e-3 relative (+1e-4 absolute); mean colour within 1 %; the 8-bit sRGB images
     pass the reference's own ospTestSuite metric (test_tools.h:26-29); primary ray counts are identical."""
-    want = scenes.oracle_render(name)
+    from oracle import pyoracle as O
+    ref_only = name in scenes.ORACLE_UNSUPPORTED  # textures: the checker is the reference's own kernels (oracle/_ref)
+    if ref_only and not O.ref_available():
+        pytest.skip("oracle/_ref/libospref.so not built; the committed reference goldens cover this case")
+    want = scenes.oracle_render(name, backend="ref" if ref_only else "oracle")
     fb, keep = scenes.device_render(osp, name)
     got = fb.map(osp.OSP_FB_COLOR)
     wc = want.buf["color"]
@@ -176,13 +180,17 @@ def test_images_match_oracle(osp, name):
     assert res["ok"], res
     rc = fb.ray_counts()
     assert rc[0] == int(want.counters[0])
+    if ref_only:  # the reference traces every shadow segment as a closest-hit query: only the total is comparable
+        assert 0.85 * int(want.counters.sum()) - 4 <= sum(rc) <= 1.01 * int(want.counters.sum()) + 4
+        return
     assert abs(rc[0] + rc[1] - int(want.counters[:2].sum())) <= (0.05 if ptvol else 0.01) * int(want.counters[:2].sum()) + 4
     # shadow segments: the device asks ONE any-hit question per shadow ray and walks the reference's closest-hit loop only
     # when the occluder it found is not opaque; which occluder that is depends on the hierarchy, so behind transparent
     # surfaces it may count fewer segments than the reference (never noticeably more)
     assert rc[2] <= 1.01 * int(want.counters[2]) + 4 and rc[2] >= (0.80 if ptvol else 0.85) * int(want.counters[2]) - 4
     # the committed golden fixture (oracle output at generation time) tells the same story
-    np.testing.assert_allclose(got.reshape(-1, 4).mean(axis=0), GOLD[name + "/color"].reshape(-1, 4).mean(axis=0), rtol=0.03 if ptvol else 0.01, atol=1e-4)
+    gold = (REF_GOLD if ref_only else GOLD)[name + "/color"]
+    np.testing.assert_allclose(got.reshape(-1, 4).mean(axis=0), gold.reshape(-1, 4).mean(axis=0), rtol=0.03 if ptvol else 0.01, atol=1e-4)
     if ptvol:  # the first vertex is sampled before any rounding can tell the two sides apart: depth of most pixels is identical
         d, dw = fb.map(osp.OSP_FB_DEPTH), want.buf["depth"]
         assert (np.isinf(d) == np.isinf(dw)).mean() >= 0.97

@@ -22,7 +22,7 @@ from oracle import pyoracle as O
 sys_path_golden = os.path.join(os.path.dirname(__file__), "golden")
 REF_RENDERS = np.load(os.path.join(sys_path_golden, "ref_renders.npz"))
 REF_KATS = np.load(os.path.join(sys_path_golden, "ref_kats.npz"))
-REF_CASES = [n for n in scenes.CASES if n not in scenes.REF_UNSUPPORTED]
+REF_CASES = [n for n in scenes.CASES if n not in scenes.REF_UNSUPPORTED | scenes.ORACLE_UNSUPPORTED]
 VOLUME_CASES = {"gravity_scivis", "gravity_ao", "gravity_shaded", "volume_opaque_geometry"}
 # volumes under the pathtracer: ids / depth of volume vertices are part of the path state on both sides and compared in
 # full; delta tracking chains hundreds of logf / expf / lerp steps per path, so the 1-ulp libm differences between the two

@@ -114,7 +114,7 @@ typedef struct {
   float xform2f[6];
 } OcTextureParam;
 
-enum { OC_MATERIAL_OBJ = 0, OC_MATERIAL_OTHER = 1, OC_MATERIAL_THINGLASS = 2 };
+enum { OC_MATERIAL_OBJ = 0, OC_MATERIAL_OTHER = 1, OC_MATERIAL_THINGLASS = 2, OC_MATERIAL_LUMINOUS = 3 };
 /* material (reference: ispc::OBJ, render/materials/OBJShared.h, OBJ.cpp:30-66; ispc::ThinGlass,
  * render/materials/ThinGlassShared.h, ThinGlass.cpp:33-48: eta = 1/ior, attenuationScale = thickness /
  * max(attenuationDistance, EPS), attenuation = log(attenuationColor) * attenuationScale) */
@@ -128,6 +128,11 @@ typedef struct {
   float eta;
   OcVec3f attenuation;
   float attenuationScale;
+  /* luminous (ispc::Luminous, render/materials/LuminousShared.h, Luminous.cpp:33-45): emission = color * intensity
+   * (times map_color = mapKd), transparency; isEmissive = any emission (Material::isEmissive) */
+  OcVec3f emission;
+  float transparency;
+  uint32_t isEmissive;
   uint32_t hasTextures;        /* any of the maps below is set (kernels without texture support skip them all) */
   float bumpRot[4];            /* OBJ.cpp:43-44: orthogonal part of map_bump's 2D transform, transposed (vx, vy) */
   /* OBJ: map_d, map_kd, map_ks, map_ns, map_bump (OBJShared.h:19-31); thinGlass: mapKd = map_attenuationColor */
@@ -186,15 +191,21 @@ typedef struct {
 } OcGroup;
 
 /* instance (reference: ispc::Instance, common/InstanceShared.h; Instance.cpp:20-34) */
-typedef struct {
+typedef struct OcInstanceS {
   OcAffine3f xfm, rcp_xfm;
   const OcGroup *group;
   uint32_t userID;
   uint32_t isIdentity;
   float bounds[6]; /* world-space */
+  /* 1 / (world-space area of the emissive primitives) per geometric model of the group, NULL when the instance holds no
+   * geometry light (what GeometricModel_gatherEmissivePrimIDs leaves in ispc::GeometricModel::areaPDF,
+   * geometry/GeometricModel.ispc:48-53; kept per instance here because the area depends on the instance transform) */
+  const float *modelAreaPDF;
 } OcInstance;
 
-enum { OC_LIGHT_AMBIENT = 0, OC_LIGHT_DISTANT = 2, OC_LIGHT_SPHERE = 4, OC_LIGHT_QUAD = 5, OC_LIGHT_SPOT = 6 }; /* values of ispc::LightType */
+enum { OC_LIGHT_AMBIENT = 0, OC_LIGHT_DISTANT = 2, OC_LIGHT_SPHERE = 4, OC_LIGHT_QUAD = 5, OC_LIGHT_SPOT = 6,
+       OC_LIGHT_GEOMETRY = 8 }; /* values of ispc::LightType */
+struct OcInstanceS;
 /* lights (reference: lights/LightShared.h:79-110, QuadLightShared.h, DirectionalLightShared.h,
  * AmbientLightShared.h) */
 typedef struct {
@@ -210,6 +221,15 @@ typedef struct {
   /* spot (ispc::SpotLight, lights/SpotLightShared.h): position, fx/fy/fz = c0/c90/direction, radiance, intensity,
    * cosAngle = cosAngleMax, ppdf = areaPdf (ring), radius, plus: */
   float cosAngleScale, innerRadius;
+  /* geometry light: the proxy the pathtracer makes for every geometric model with emissive primitives
+   * (ispc::GeometryLight, render/pathtracer/GeometryLightShared.h; PathTracerData.cpp:87-160): the model and the instance
+   * it sits in, the emissive primitives, the CDF of their world-space areas, pdf = 1 / total area */
+  const OcModel *geoModel;
+  const struct OcInstanceS *geoInstance;
+  const int32_t *geoPrimIDs;
+  const float *geoDistribution;
+  uint32_t geoNumPrimitives;
+  float geoPdf;
 } OcLight;
 
 typedef struct {
@@ -219,8 +239,9 @@ typedef struct {
   OcBVH tlas;                  /* top level over the instance bounds, one instance per leaf record (always built) */
   const OcMaterial *materials;
   uint32_t numMaterials;
-  /* pathtracer light list (PathTracerData.cpp:32-82): geo lights first (none), world, instance */
+  /* pathtracer light list (PathTracerData.cpp:32-82): geometry lights first, world, instance */
   uint32_t numLights;
+  uint32_t numGeoLights;
   const OcLight *lights;
   const float *lightsCDF;
   /* scivis light list (SciVisData.cpp:74-105): visible-only lights first, ambient folded */
@@ -294,9 +315,12 @@ typedef struct {
   float mipBiasFactor;
   const OcTexture2D *backplate;
   const OcTexture2D *maxDepthTexture;
-  /* host-side: the world / renderer of this frame reference textures (set per ospRenderFrame like worldNumLights): the
-   * frame runs the kernels compiled with texture support (texture coordinates, tangents, ray cones) */
+  /* host-side: the world / renderer of this frame reference textures or emissive materials (set per ospRenderFrame like
+   * worldNumLights): the frame runs the kernels compiled with the extended material support (texture coordinates,
+   * tangents, ray cones, emission / geometry lights) */
   uint32_t hasTextures;
+  /* pathtracer parameter geometryLights (PathTracer.cpp:44): emissive geometry is sampled as light sources */
+  uint32_t geometryLights;
 } OcRenderer;
 
 /* framebuffer (reference: LocalFBShared.h, FrameBufferShared.h; LocalFB.cpp:49-180) */

@@ -64,7 +64,8 @@ class TextureParam(C.Structure):
 
 class Material(C.Structure):
     _fields_ = [("type", C.c_uint32), ("d", C.c_float), ("Kd", Vec3), ("Ks", Vec3), ("Ns", C.c_float), ("Tf", Vec3),
-                ("eta", C.c_float), ("attenuation", Vec3), ("attenuationScale", C.c_float), ("hasTextures", C.c_uint32),
+                ("eta", C.c_float), ("attenuation", Vec3), ("attenuationScale", C.c_float), ("emission", Vec3),
+                ("transparency", C.c_float), ("isEmissive", C.c_uint32), ("hasTextures", C.c_uint32),
                 ("bumpRot", C.c_float * 4), ("mapD", TextureParam), ("mapKd", TextureParam), ("mapKs", TextureParam),
                 ("mapNs", TextureParam), ("mapBump", TextureParam)]
 
@@ -93,20 +94,21 @@ class Group(C.Structure):
 
 class Instance(C.Structure):
     _fields_ = [("xfm", Affine), ("rcp_xfm", Affine), ("group", C.POINTER(Group)), ("userID", C.c_uint32),
-                ("isIdentity", C.c_uint32), ("bounds", C.c_float * 6)]
+                ("isIdentity", C.c_uint32), ("bounds", C.c_float * 6), ("modelAreaPDF", C.POINTER(C.c_float))]
 
 
 class Light(C.Structure):
     _fields_ = [("type", C.c_uint32), ("isVisible", C.c_uint32), ("radiance", Vec3), ("position", Vec3), ("edge1", Vec3),
                 ("edge2", Vec3), ("nnormal", Vec3), ("ppdf", C.c_float), ("fx", Vec3), ("fy", Vec3), ("fz", Vec3),
                 ("cosAngle", C.c_float), ("pdf", C.c_float), ("intensity", Vec3), ("radius", C.c_float),
-                ("cosAngleScale", C.c_float), ("innerRadius", C.c_float)]
+                ("cosAngleScale", C.c_float), ("innerRadius", C.c_float), ("geoModel", C.c_void_p), ("geoInstance", C.c_void_p),
+                ("geoPrimIDs", C.c_void_p), ("geoDistribution", C.c_void_p), ("geoNumPrimitives", C.c_uint32), ("geoPdf", C.c_float)]
 
 
 class World(C.Structure):
     _fields_ = [("instances", C.POINTER(Instance)), ("numInstances", C.c_uint32), ("hasVolumes", C.c_uint32), ("tlas", BVH),
                 ("materials", C.POINTER(Material)), ("numMaterials", C.c_uint32), ("numLights", C.c_uint32),
-                ("lights", C.POINTER(Light)), ("lightsCDF", C.POINTER(C.c_float)), ("scivisLights", C.POINTER(Light)),
+                ("numGeoLights", C.c_uint32), ("lights", C.POINTER(Light)), ("lightsCDF", C.POINTER(C.c_float)), ("scivisLights", C.POINTER(Light)),
                 ("numScivisLights", C.c_uint32), ("numScivisLightsVisibleOnly", C.c_uint32), ("aoColorPi", Vec3),
                 ("bounds", C.c_float * 6)]
 
@@ -128,7 +130,7 @@ class Renderer(C.Structure):
                 ("aoRadius", C.c_float), ("aoIntensity", C.c_float), ("volumeSamplingRate", C.c_float),
                 ("worldNumLights", C.c_uint32), ("debugMethod", C.c_uint32), ("worldHasVolumes", C.c_uint32),
                 ("mipBiasFactor", C.c_float), ("backplate", C.POINTER(Texture2D)), ("maxDepthTexture", C.POINTER(Texture2D)),
-                ("hasTextures", C.c_uint32)]
+                ("hasTextures", C.c_uint32), ("geometryLights", C.c_uint32)]
 
 
 class FrameBuffer(C.Structure):
@@ -538,6 +540,13 @@ class Scene:
                 kd, ks, tf = kd / total, ks / total, tf / total
             m.type, m.d, m.Ns = 0, float(ms.d), float(ms.ns)
             m.Kd, m.Ks, m.Tf = Vec3(*map(float, kd)), Vec3(*map(float, ks)), Vec3(*map(float, tf))
+        elif ms.type == "luminous":  # render/materials/Luminous.cpp:33-45
+            m.type = 3
+            em = (np.asarray(ms.color, np.float32) * np.float32(ms.intensity)).astype(np.float32)
+            m.emission, m.transparency, m.isEmissive = Vec3(*map(float, em)), float(ms.transparency), int(em.max() > 0)
+            if ms.map_color is not None:
+                m.mapKd = texture_param(ms.map_color, self.keep, self.mipmaps)
+                m.hasTextures = 1
         elif ms.type == "thinGlass":
             # render/materials/ThinGlass.cpp:33-48 in float32 (std::log of a float is the float overload)
             f = np.float32
@@ -642,8 +651,10 @@ class RendererParams:
     def __init__(self, kind, pixelSamples=1, pixelFilter="gauss", maxPathLength=20, minContribution=0.001, backgroundColor=(0, 0, 0, 0),
                  roulettePathLength=5, maxScatteringEvents=20, maxContribution=np.inf, lightSamples=-1, limitIndirectLightSamples=True,
                  backgroundRefraction=False, shadows=False, visibleLights=False, aoSamples=None, aoDistance=1e20, aoIntensity=1.0,
-                 volumeSamplingRate=1.0, method="eyeLight", mipMapBias=0.0, backplate=None, maxDepthTexture=None, mipmaps=True):
+                 volumeSamplingRate=1.0, method="eyeLight", mipMapBias=0.0, backplate=None, maxDepthTexture=None, mipmaps=True,
+                 geometryLights=True):
         r = Renderer()
+        r.geometryLights = int(geometryLights)
         self.keep = []
         r.mipBiasFactor = float(np.power(np.float32(2.0), np.float32(mipMapBias)))  # Renderer.cpp:41,91
         if backplate is not None:

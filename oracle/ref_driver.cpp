@@ -30,6 +30,8 @@
 #include "render/MaterialShared.h"
 #include "render/materials/OBJShared.h"
 #include "render/materials/ThinGlassShared.h"
+#include "render/materials/LuminousShared.h"
+#include "render/pathtracer/GeometryLightShared.h"
 #include "texture/Texture2DShared.h"
 #include "common/DifferentialGeometry.ih"
 #include "texture/TextureParamShared.h"
@@ -81,6 +83,9 @@ namespace ispc {
 void LocalFB_accumulateSample(FrameBuffer *fb, const ScreenSample &screenSample, RenderTaskDesc &);
 void LUTPixelFilter_buildLUT(void *self);
 float Distribution1D_create(const int size, float *cdf);
+int GeometricModel_gatherEmissivePrimIDs(void *model, void *renderer, void *instance, int *primIDs, float *distribution, float &pdf);
+void Mesh_getAreas(const Geometry *const, const int32 *const, const int32, const affine3f &, float *const);
+void Spheres_getAreas(const Geometry *const, const int32 *const, const int32, const affine3f &, float *const);
 }
 
 namespace {
@@ -158,6 +163,9 @@ struct Scene
   std::deque<std::vector<Material *>> materialPtrs;
   std::deque<OBJ> objs; std::deque<ThinGlass> glasses; std::vector<Material *> allMaterials;
   std::deque<Texture2D> textures;
+  std::deque<Luminous> luminous; std::deque<GeometryLight> geoLights;
+  std::deque<std::vector<int>> geoPrimIDs; std::deque<std::vector<float>> geoDistributions;
+  std::vector<float> geoCDF;
   std::vector<Instance *> instancePtrs;
   std::deque<QuadLight> quads; std::deque<PointLight> points; std::deque<SpotLight> spots; std::deque<DirectionalLight> dirs; std::deque<AmbientLight> ambients;
   std::vector<Light *> ptLights, svLights;
@@ -188,6 +196,7 @@ Geometry *makeGeometry(Scene &s, const OcGeometry *g)
     m.isColorFaceVarying = (g->flags & OC_GEOMFLAG_COLOR_FACEVARYING) != 0;
     m.isTexcoordFaceVarying = (g->flags & OC_GEOMFLAG_TEXCOORD_FACEVARYING) != 0;
     m.isNormalFaceVarying = (g->flags & OC_GEOMFLAG_NORMAL_FACEVARYING) != 0;
+    m.super.getAreas = Mesh_getAreas; // geometry/Mesh.cpp:26-29
     m.flagMask = -1;
     if (!g->normal.addr) m.flagMask &= int64(~DG_NS);
     if (!g->color.addr) m.flagMask &= int64(~DG_COLOR);
@@ -202,6 +211,7 @@ Geometry *makeGeometry(Scene &s, const OcGeometry *g)
     sp.sphere = d1(g->sphere); sp.texcoord = d1(g->texcoord);
     Data1D_Constructor(&sp.normalData);
     sp.sphereType = OSP_SPHERE;
+    sp.super.getAreas = Spheres_getAreas; // geometry/Spheres.cpp:32-38
     return &sp.super;
   }
   if (g->type == OC_GEOM_CURVES) {
@@ -261,6 +271,15 @@ void buildScene(Scene &s, const OcWorld *w, const OcRenderer *ren)
       g.eta = m.eta; g.attenuation = v3(m.attenuation); g.attenuationScale = m.attenuationScale;
       g.attenuationColorMap = makeTextureParam(s.textures, m.mapKd);
       s.allMaterials.push_back(&g.super);
+      continue;
+    }
+    if (m.type == OC_MATERIAL_LUMINOUS) { // render/materials/Luminous.cpp:33-45 (committed values)
+      s.luminous.emplace_back();
+      Luminous &lm = s.luminous.back();
+      lm.radiance = v3(m.emission); lm.transparency = m.transparency;
+      lm.emissionMap = makeTextureParam(s.textures, m.mapKd);
+      lm.super.isEmissive = m.isEmissive != 0;
+      s.allMaterials.push_back(&lm.super);
       continue;
     }
     s.objs.emplace_back();
@@ -391,6 +410,44 @@ void buildScene(Scene &s, const OcWorld *w, const OcRenderer *ren)
   (void)ren; (void)anyVolume;
 }
 
+// PathTracerData::generateGeometryLights (render/pathtracer/PathTracerData.cpp:87-160) with the reference's own
+// GeometricModel_gatherEmissivePrimIDs: proxy lights in front of the light list, then the uniform CDF over all of them
+void addGeometryLights(Scene &s, Renderer *renderer)
+{
+  std::vector<Light *> geo;
+  for (Instance &inst : s.instances) {
+    Group *grp = inst.group;
+    for (int32 g = 0; g < grp->numGeometricModels; g++) {
+      GeometricModel *model = grp->geometricModels[g];
+      if (model->numMaterials == 0) continue;
+      bool emissive = false; // GeometricModel::hasEmissiveMaterials
+      for (int32 k = 0; k < model->numMaterials; k++) {
+        Material *m = model->material ? model->material[k]
+                                      : (renderer->material ? renderer->material[std::min<uint32_t>(model->materialID[k], renderer->numMaterials - 1)] : nullptr);
+        if (m && m->isEmissive) emissive = true;
+      }
+      if (!emissive || !model->geom->getAreas) continue;
+      s.geoPrimIDs.emplace_back(model->geom->numPrimitives); s.geoDistributions.emplace_back(model->geom->numPrimitives);
+      float pdf = 0.f;
+      const int n = GeometricModel_gatherEmissivePrimIDs(model, renderer, &inst, s.geoPrimIDs.back().data(), s.geoDistributions.back().data(), pdf);
+      if (!n) continue;
+      s.geoLights.emplace_back();
+      GeometryLight &gl = s.geoLights.back();
+      gl.super.instance = &inst; gl.super.isVisible = true;
+      gl.model = model; gl.numPrimitives = n; gl.pdf = pdf;
+      gl.primIDs = s.geoPrimIDs.back().data(); gl.distribution = s.geoDistributions.back().data();
+      geo.push_back(&gl.super);
+    }
+  }
+  if (geo.empty()) return;
+  geo.insert(geo.end(), s.ptLights.begin(), s.ptLights.end());
+  s.ptLights = geo;
+  s.geoCDF.assign(s.ptLights.size(), 1.f);
+  Distribution1D_create((int)s.geoCDF.size(), s.geoCDF.data());
+  s.ptData.lights = s.ptLights.data(); s.ptData.numLights = (uint32_t)s.ptLights.size();
+  s.ptData.numGeoLights = (uint32_t)s.geoLights.size(); s.ptData.lightsCDF = s.geoCDF.data();
+}
+
 struct RendererSet
 {
   PathTracer pt; SciVis sv; AORenderer ao; DebugRenderer dbg;
@@ -451,6 +508,7 @@ REF_API int ospref_render_frame(const OcWorld *w, const OcCamera *cam, const OcR
   buildScene(*s, w, ren);
   auto rs = std::make_unique<RendererSet>();
   Renderer *renderer = buildRenderer(*rs, *s, ren);
+  if (ren->type == OC_RENDERER_PATHTRACER && ren->geometryLights) addGeometryLights(*s, renderer);
 
   // camera/OrthographicCamera.cpp:25-49 (committed values)
   OrthographicCamera oc;

@@ -361,6 +361,7 @@ __device__ __forceinline__ bool ptOccluderIsOpaque(const OcWorld *world, const O
   }
   const OcMaterial *mat = getMaterial(world, ren, m, primID);
   if (mat && (mat->type == OC_MATERIAL_THINGLASS || mat->hasTextures)) return false; // texture maps may cut the surface out
+  if (mat && mat->type == OC_MATERIAL_LUMINOUS) return mat->transparency == 0.f; // Luminous_getTransparency
   if (!mat || mat->type != OC_MATERIAL_OBJ) return true; // no / foreign material: transparency 0 (shading.cuh)
   return mat->d == 1.f && mat->Tf.x == 0.f && mat->Tf.y == 0.f && mat->Tf.z == 0.f;
 }
@@ -411,13 +412,13 @@ static __device__ __noinline__ vec3f ptVirtualLightsVol(const PtArgs &k, uint32_
 {
   const OcWorld *world = k.a.world;
   vec3f L = make_vec3f(0.f);
-  const uint32_t numLights = world->numLights;
-  if (numLights == 0) return L;
+  const uint32_t numLights = world->numLights, numGeoLights = world->numGeoLights;
+  if (numLights <= numGeoLights) return L;
   const float lower = length(lastP - rorg);
   const float upper = environment ? INFINITY : length(lastP - (rorg + rt * rdir));
   const float selectionPDF = lastNumLightSamples / (float)numLights;
   RandomSampler rs = ptLoadRs(k.s, p);
-  for (uint32_t i = 0; i < numLights; i++) {
+  for (uint32_t i = numGeoLights; i < numLights; i++) {
     const OcLight &l = world->lights[i];
     if (!straightPath || l.isVisible) {
       const LightEval le = Light_eval(l, lastP, lastNs, rdir, lower, upper);
@@ -745,7 +746,8 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
         contribution = contribution + evaluateVirtualLights(c, straightPath, throughput, last, environment, ray);
     }
     if (environment) break;
-    if (depth >= ren.maxDepth) break; // numGeoLights == 0
+    // (with geometry lights the vertex is still needed: what the path ran into may emit, PathSampler.ispc:247-254)
+    if (depth >= ren.maxDepth && !(TEX && world->numGeoLights)) break;
 
     DifferentialGeometry dg;
     if (volume) { // postIntersect of a volume vertex (PathSampler.ispc:51-67) + VolumetricModel_postIntersect (VolumetricModel.ih:16-33)
@@ -760,6 +762,20 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
     } else
       postIntersect<TEX>(world, ren, dg, ray,
           DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR | DG_TANGENTS | DG_MOTIONBLUR, TEX ? &cone : nullptr);
+    if (TEX && !volume) { // evaluateGeometryLights (GeometryLight.ispc:22-58): emission of the surface the path ran into
+      const vec3f emission = materialEmission(dg);
+      if (reduce_max(emission) > 0.f) {
+        float misWeight = 1.0f;
+        if (world->numGeoLights > 0 && last.numLightSamples > 0) {
+          const float lightSelectionPDF = last.numLightSamples / (float)world->numLights;
+          const float cosd = dot(dg.Ng, ray.dir);
+          const vec3f vdis = last.P - dg.P;
+          const float lePdf = dg.areaPDF * dot(vdis, vdis) / fabsf(cosd);
+          misWeight = misHeuristic(last.pdf_w, lightSelectionPDF * lePdf);
+        }
+        contribution = contribution + throughput * emission * misWeight;
+      }
+    }
     if (depth == 0) {
       float4 z = s.sZ[p];
       z.y = __uint_as_float(dg.primID); z.z = __uint_as_float(dg.objID); z.w = __uint_as_float(dg.instID);
@@ -794,7 +810,8 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
           const vec2f sl = LDSampler_get3LightSamples(ld, j, numLightSamples > 1, ss);
           const Sample1D sel = Distribution1D_sample((int)numLights, world->lightsCDF, 0, ss);
           const float lightSelectionProb = sel.prob * numLightSamples;
-          LightSample ls = Light_sample(world->lights[sel.idx], dg, sl);
+          const OcLight &light = world->lights[sel.idx];
+          LightSample ls = (TEX && light.type == OC_LIGHT_GEOMETRY) ? GeometryLight_sample(world, ren, light, dg, sl) : Light_sample(light, dg, sl);
           ls.weight = ls.weight / lightSelectionProb;
           ls.pdf *= lightSelectionProb;
           if (!(reduce_max(ls.weight) <= 0.0f || ls.pdf <= 0.0f)) {

@@ -90,12 +90,12 @@ __device__ __forceinline__ vec3f evaluateVirtualLights(Ctx &c, bool straightPath
     bool environment, const Ray &ray)
 {
   vec3f L = make_vec3f(0.f);
-  const uint32_t numLights = c.world->numLights;
-  if (numLights == 0) return L;
+  const uint32_t numLights = c.world->numLights, numGeoLights = c.world->numGeoLights;
+  if (numLights <= numGeoLights) return L; // no virtual lights (geometry lights come first and are hit, not evaluated)
   const float lower = length(last.P - ray.org);
   const float upper = environment ? INFINITY : length(last.P - (ray.org + ray.t * ray.dir));
   const float selectionPDF = last.numLightSamples / (float)numLights;
-  for (uint32_t i = 0; i < numLights; i++) {
+  for (uint32_t i = numGeoLights; i < numLights; i++) {
     const OcLight &l = c.world->lights[i];
     if (!straightPath || l.isVisible) {
       const LightEval le = Light_eval(l, last.P, last.Ns, ray.dir, lower, upper);

@@ -9,6 +9,7 @@
 #include "intersect.cuh"
 #include "samplers.cuh"
 #include "texture.cuh"
+#include <cfloat>
 
 namespace oc {
 
@@ -37,6 +38,7 @@ struct DifferentialGeometry
   vec3f dPdt;
   vec2f st;
   float pixelFootprint;
+  float areaPDF; // geometry lights: 1 / emissive area of the model (GeometricModel.ih:58)
 };
 // common/RayCone.ih: width at the current vertex, spread per unit distance
 struct RayCone { float width, dwdt; };
@@ -227,6 +229,7 @@ __device__ __forceinline__ void postIntersect(const OcWorld *world, const OcRend
       dg.color = get4f(m->color, min(idx, m->color.numItems - 1));
     }
     dg.material = getMaterial(world, ren, m, ray.primID);
+    if (TEX) dg.areaPDF = inst->modelAreaPDF ? __ldg(inst->modelAreaPDF + ray.geomID) : 0.f;
     if ((flags & DG_NS) && m->invertedNormals) dg.Ns = neg(dg.Ns);
     dg.instID = (inst->userID == OC_INVALID_ID) ? ray.instID : inst->userID;
     if (!inst->isIdentity) {
@@ -328,6 +331,7 @@ struct ObjBSDF
   uint32_t scatteringType;
   bool valid;
   bool thinGlass;          // RobustThinDielectric (materials/ThinGlass.ispc): eta in `ns`, attenuation in `Kd`
+  bool pureTransmission;   // a lone Transmission BSDF (materials/Luminous.ispc:18-35): T in `T`
 };
 
 // render/Material.ih:25-37
@@ -417,6 +421,22 @@ __device__ __forceinline__ void OBJ_getBSDF(ObjBSDF &b, const DifferentialGeomet
   const OcMaterial *m = dg.material;
   b.valid = false;
   b.thinGlass = false;
+  b.pureTransmission = false;
+  if (TEX && m && m->type == OC_MATERIAL_LUMINOUS) { // Luminous_getBSDF: no BSDF unless the emitter is transparent
+    if (m->transparency > 0.0f) {
+      b.valid = true;
+      b.pureTransmission = true;
+      b.frame = frame(dg.Ns);
+      b.T = make_vec3f(m->transparency);
+      b.Kd = make_vec3f(0.f);
+      b.albedo = b.T;
+      b.scatteringType = SC_SPECULAR_TRANSMISSION;
+      b.importanceSum = 1.f;
+      b.impL = b.impT = b.impS = 0.f;
+      b.ns = 0.f;
+    }
+    return;
+  }
   if (m && m->type == OC_MATERIAL_THINGLASS) {
     b.valid = true;
     b.thinGlass = true;
@@ -519,7 +539,7 @@ __device__ __forceinline__ void OBJ_evalChildren(const ObjBSDF &b, vec3f wo, vec
 __device__ __forceinline__ EvalRes OBJ_eval(const ObjBSDF &b, vec3f wo, vec3f wi)
 {
   EvalRes e; e.value = make_vec3f(0.f); e.pdf = 0.f;
-  if (b.thinGlass) return e; // purely specular
+  if (b.thinGlass || b.pureTransmission) return e; // purely specular
   OBJ_evalChildren(b, wo, wi, -1, e);
   e.pdf *= 1.f / b.importanceSum;
   return e;
@@ -557,6 +577,10 @@ __device__ __forceinline__ SampleRes RobustThinDielectric_sample(const ObjBSDF &
 __device__ __forceinline__ SampleRes OBJ_sample(const ObjBSDF &b, vec3f wo, vec2f s, float ss)
 {
   if (b.thinGlass) return RobustThinDielectric_sample(b, wo, ss);
+  if (b.pureTransmission) { // Transmission_sample (bsdfs/Transmission.ih:17-27)
+    SampleRes r; r.wi = neg(wo); r.pdf = INFINITY; r.type = SC_SPECULAR_TRANSMISSION; r.weight = b.T;
+    return r;
+  }
   SampleRes res; res.weight = make_vec3f(0.f); res.wi = make_vec3f(0.f); res.pdf = 0.f; res.type = 0;
   if (b.importanceSum == 0.f) return res;
   const float x = ss * b.importanceSum;
@@ -617,12 +641,26 @@ __device__ __forceinline__ vec3f materialTransparency(const DifferentialGeometry
     const float cosThetaO = fmaxf(-dot(rayDir, dg.Ns), 0.0f);
     return RobustThinDielectric_getTransparency(cosThetaO, m->eta, ThinGlass_getAttenuation<TEX>(m, dg));
   }
+  if (TEX && m && m->type == OC_MATERIAL_LUMINOUS) return make_vec3f(m->transparency); // Luminous_getTransparency
   if (!m || m->type != OC_MATERIAL_OBJ) return make_vec3f(0.f);
   float d = m->d;
   if (TEX && m->mapD.tex) d = d * texParamGet4f(m->mapD, dg.st, dg.pixelFootprint).x;
   d = d * dg.color.w;
   if (TEX && m->mapKd.tex && m->mapKd.tex->hasAlpha) d *= texParamGet4f(m->mapKd, dg.st, dg.pixelFootprint).w;
   return toV(m->Tf) * d + make_vec3f(1.f - d);
+}
+
+// Material_dispatch_getEmission (render/MaterialDispatch.ispc; materials/Luminous.ispc:62-70): radiance * map_color
+__device__ __forceinline__ vec3f materialEmission(const DifferentialGeometry &dg)
+{
+  const OcMaterial *m = dg.material;
+  if (!m || !m->isEmissive) return make_vec3f(0.f);
+  vec3f e = toV(m->emission);
+  if (m->mapKd.tex) {
+    const vec4f t = texParamGet4f(m->mapKd, dg.st, dg.pixelFootprint);
+    e = e * make_vec3f(t.x, t.y, t.z);
+  }
+  return e;
 }
 
 // ---- lights -------------------------------------------------------------------------------
@@ -882,6 +920,82 @@ __device__ __forceinline__ LightEval SpotLight_eval(const OcLight &l, vec3f P, v
   return res;
 }
 
+struct Sample1D { int idx; float frac, pdf, prob; };
+__device__ __forceinline__ Sample1D Distribution1D_sample(int size, const float *cdf, int start, float s);
+struct SampleAreaRes { vec3f pos, normal; vec2f st; float epsilon; };
+// Mesh_sampleArea (geometry/Mesh.ispc:270-383): uniform point on a triangle / quad (Embree's split of the quad)
+__device__ __forceinline__ SampleAreaRes Mesh_sampleArea(const OcGeometry *g, uint32_t primID, const affine3f &xfm, vec2f s)
+{
+  SampleAreaRes res;
+  uint32_t ix, iy, iz, iw;
+  bool quad = false;
+  if (g->type == OC_GEOM_TRIANGLES) {
+    ix = get1ui(g->index, primID, 0); iy = get1ui(g->index, primID, 1); iz = get1ui(g->index, primID, 2); iw = iz;
+  } else {
+    ix = get1ui(g->index, primID, 0); iy = get1ui(g->index, primID, 1); iz = get1ui(g->index, primID, 2); iw = get1ui(g->index, primID, 3);
+    quad = iz != iw;
+  }
+  const vec3f a = get3f(g->vertex, ix), b = get3f(g->vertex, iy), d = get3f(g->vertex, iw);
+  const vec3f c = quad ? get3f(g->vertex, iz) : d;
+  res.epsilon = reduce_max(vmax(vmax(vabs(a), vabs(b)), vmax(vabs(c), vabs(d)))) * OC_ULP_EPSILON;
+  res.epsilon *= fmaxf(fabsf(xfm.l.vx.x), fmaxf(fabsf(xfm.l.vy.y), fabsf(xfm.l.vz.z)));
+  const vec3f e1 = xfmVector(xfm, a - d), e2 = xfmVector(xfm, b - d);
+  const vec3f m1 = cross(e1, e2);
+  res.normal = m1;
+  vec3f v0 = a, v1 = b, v2 = d;
+  vec2f sp = s;
+  bool invertUV = false;
+  if (quad) {
+    const vec3f e3 = xfmVector(xfm, c - d);
+    const vec3f m2 = cross(e2, e3);
+    const float a1 = length(m1), a2 = length(m2);
+    const float p1 = a1 * (1.f / (a1 + a2));
+    if (s.x < p1) sp.x *= 1.f / p1;
+    else {
+      sp.x = (s.x - p1) * (1.f / (1.f - p1));
+      invertUV = true;
+      v0 = c; v1 = d; v2 = b;
+      res.normal = m2;
+    }
+  }
+  const float su = sqrtf(sp.x);
+  const vec2f uv = make_vec2f(sp.y * su, (1.0f - sp.y) * su); // uniformSampleTriangleUV
+  const vec3f localPos = v0 + uv.x * (v1 - v0) + uv.y * (v2 - v0);
+  res.normal = normalize(res.normal);
+  res.pos = xfmPoint(xfm, localPos);
+  res.st = invertUV ? make_vec2f(1.0f - uv.x, 1.0f - uv.y) : uv;
+  if (g->texcoord.addr) {
+    const float u = res.st.x, v = res.st.y;
+    const vec4f uv4 = quad ? make_vec4f((1 - v) * (1 - u), (1 - v) * u, v * u, v * (1 - u)) : make_vec4f(1.f - u - v, u, v, 0.f);
+    const uint32_t fo = primID * (g->type == OC_GEOM_TRIANGLES ? 3u : 4u);
+    const bool fv = g->flags & OC_GEOMFLAG_TEXCOORD_FACEVARYING;
+    const vec2f ta = get2f(g->texcoord, fv ? fo : ix), tb = get2f(g->texcoord, fv ? fo + 1 : iy), tc = get2f(g->texcoord, fv ? fo + 2 : iz);
+    if (g->type == OC_GEOM_TRIANGLES) res.st = uv4.x * ta + uv4.y * tb + uv4.z * tc;
+    else {
+      const vec2f td = get2f(g->texcoord, fv ? fo + 3 : iw);
+      res.st = uv4.x * ta + uv4.y * tb + uv4.z * tc + uv4.w * td;
+    }
+  }
+  return res;
+}
+// Spheres_sampleArea (geometry/Spheres.ispc:44-74), sphere type OSP_SPHERE
+__device__ __forceinline__ SampleAreaRes Spheres_sampleArea(const OcGeometry *g, uint32_t primID, const affine3f &xfm, const affine3f &rcp_xfm, vec2f s)
+{
+  const vec4f vertex = get4f(g->sphere, primID);
+  const vec3f localNormal = uniformSampleSphere(vertex.w, s);
+  SampleAreaRes res;
+  res.pos = xfmPoint(xfm, make_vec3f(vertex) + localNormal);
+  res.normal = normalize(xfmVector(transposed(rcp_xfm.l), localNormal));
+  res.st = g->texcoord.addr ? get2f(g->texcoord, primID) : make_vec2f(0.f, 0.f);
+  res.epsilon = vertex.w * OC_ULP_EPSILON;
+  res.epsilon *= fmaxf(fabsf(xfm.l.vx.x), fmaxf(fabsf(xfm.l.vy.y), fabsf(xfm.l.vz.z)));
+  return res;
+}
+struct LightSample;
+// GeometryLight_sample (render/pathtracer/GeometryLight.ispc:62-128): a primitive by area, a point on it, its emission
+static __device__ __noinline__ LightSample GeometryLight_sample(const OcWorld *world, const OcRenderer &ren, const OcLight &l,
+    const DifferentialGeometry &dg, vec2f s);
+
 __device__ __forceinline__ LightSample Light_sample(const OcLight &l, const DifferentialGeometry &dg, vec2f s)
 {
   LightSample r;
@@ -938,7 +1052,6 @@ __device__ __forceinline__ LightEval Light_eval(const OcLight &l, vec3f P, vec3f
 }
 
 // Distribution1D_sample (math/Distribution1D.ih:26-57)
-struct Sample1D { int idx; float frac, pdf, prob; };
 __device__ __forceinline__ Sample1D Distribution1D_sample(int size, const float *cdf, int start, float s)
 {
   int first = start, len = size;
@@ -958,6 +1071,35 @@ __device__ __forceinline__ Sample1D Distribution1D_sample(int size, const float 
 }
 
 // pixel filter (pf/PixelFilter.ih:20-28, pf/LUTPixelFilter.ispc:9-15, Distribution2D.ispc:9-25)
+static __device__ __noinline__ LightSample GeometryLight_sample(const OcWorld *world, const OcRenderer &ren, const OcLight &l,
+    const DifferentialGeometry &dg, vec2f s)
+{
+  LightSample res;
+  res.weight = make_vec3f(0.0f); res.dir = make_vec3f(0.f); res.dist = INFINITY; res.pdf = 0.f;
+  const OcModel *model = l.geoModel;
+  const OcGeometry *geo = model->geom;
+  const Sample1D sample = Distribution1D_sample((int)l.geoNumPrimitives, l.geoDistribution, 0, s.x);
+  const uint32_t primID = (uint32_t)__ldg(l.geoPrimIDs + sample.idx);
+  const OcMaterial *mat = getMaterial(world, ren, model, primID);
+  if (!mat) return res;
+  const vec2f ns = make_vec2f(sample.frac, s.y); // reproject s.x
+  const OcInstance *inst = l.geoInstance;
+  const affine3f xfm = toA(inst->xfm), rxfm = toA(inst->rcp_xfm);
+  const SampleAreaRes as = geo->type == OC_GEOM_SPHERES ? Spheres_sampleArea(geo, primID, xfm, rxfm, ns) : Mesh_sampleArea(geo, primID, xfm, ns);
+  const vec3f dir = as.pos - dg.P;
+  const float dist = length(dir);
+  res.dir = dir / dist;
+  const float rcosd = 1.f / fabsf(dot(as.normal, res.dir));
+  res.pdf = l.geoPdf * sqr(dist) * rcosd;
+  res.dist = dist - fmaxf(as.epsilon, calcEpsilon(as.pos, dist)) * rcosd;
+  DifferentialGeometry texDg;
+  texDg.primID = 0xffffffffu; texDg.st = as.st; texDg.pixelFootprint = FLT_MIN; texDg.P = as.pos; texDg.Ns = as.normal; texDg.Ng = as.normal;
+  texDg.material = mat;
+  const vec3f radiance = materialEmission(texDg);
+  res.weight = radiance * (1.f / res.pdf);
+  return res;
+}
+
 __device__ __forceinline__ vec2f pixelFilterSample(const OcRenderer &r, vec2f s)
 {
   if (r.pfType == OC_PF_POINT) return make_vec2f(0.f, 0.f);

@@ -162,13 +162,14 @@ OSPFuture CudaDevice::renderFrame(OSPFrameBuffer _fb, OSPRenderer _r, OSPCamera 
     if (r->errorThreshold > 0.f && fb->hasVariance && fb->taskErrBuf
         && fb->sh.frameID >= (int32_t)std::max(2u, 16u / (uint32_t)std::max(1, r->sh.spp)))
       fb->sh.taskError = fb->taskErrBuf->as<float>();
-    const OcWorld *dw = w->prepareFrame();
+    const OcWorld *dw = w->prepareFrame(r);
     checkCuda(ospcuda_event_record(f->evStart), "event record");
     const bool finished = fb->sh.targetFrames && fb->doAccum && fb->sh.frameID >= fb->sh.targetFrames; // accumulationFinished()
     OcRenderer rsh = r->sh;
     rsh.worldNumLights = w->sh.numLights;
     rsh.worldHasVolumes = w->sh.hasVolumes;
-    rsh.hasTextures = (texturedMaterials > 0 || rsh.backplate || rsh.maxDepthTexture) ? 1u : 0u;
+    rsh.worldNumLights = w->sh.numLights; // (with the geometry lights prepareFrame added)
+    rsh.hasTextures = (texturedMaterials > 0 || emissiveMaterials > 0 || rsh.backplate || rsh.maxDepthTexture) ? 1u : 0u;
     if (!finished) checkCuda(ospcuda_render_frame(dw, &c->sh, &rsh, &fb->sh), "render kernel");
     checkCuda(ospcuda_event_record(f->evRendered), "event record");
     fb->postProcess();
@@ -261,6 +262,7 @@ void CudaDevice::setMaterial(uint32_t slot, const OcMaterial &m)
 {
   materials[slot] = m;
   materialsDirty = true;
+  materialVersion++;
 }
 const OcMaterial *CudaDevice::materialTable()
 {

@@ -64,9 +64,14 @@ struct CudaDevice : public api::Device
   bool initialized = false;
   bool disableMipMapGeneration = false; // device parameter of the same name (ISPCDevice.cpp:232-233)
   uint32_t texturedMaterials = 0;       // materials whose last commit referenced a texture
+  uint32_t emissiveMaterials = 0;       // materials whose last commit made them emit
+  uint64_t materialVersion = 0;         // bumped by every material commit
 
  private:
   std::vector<OcMaterial> materials;
+ public:
+  const std::vector<OcMaterial> &materialTableHost() const { return materials; }
+ private:
   std::vector<uint32_t> freeSlots;
   DevMem materialsDev;
   bool materialsDirty = true;

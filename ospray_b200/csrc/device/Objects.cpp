@@ -321,6 +321,7 @@ void Geometry::commit()
     const uint32_t sphereType = getParam<uint32_t>("type", OSP_SPHERE);
     if (sphereType != OSP_SPHERE) throw std::runtime_error("cuda device: only OSP_SPHERE sphere geometry is supported");
     const float radius = getParam<float>("radius", 0.01f);
+    sphereRadius = radius;
     vertexData = getParamData(*this, "sphere.position", OSP_VEC3F, true);
     radiusData = getParamData(*this, "sphere.radius", OSP_FLOAT);
     texcoordData = getParamData(*this, "sphere.texcoord", OSP_VEC2F);
@@ -377,6 +378,7 @@ Material::Material(CudaDevice &d, const std::string &t) : device(d), type(t), sl
 }
 Material::~Material()
 {
+  if (wasEmissive) device.emissiveMaterials--;
   if (texD || texKd || texKs || texNs || texBump) device.texturedMaterials--;
   device.freeMaterialSlot(slot);
 }
@@ -435,11 +437,22 @@ void Material::commit()
     m.eta = 1.f / eta;
     m.attenuationScale = thickness * (1.f / std::max(attenuationDistance, 1e-5f));
     m.attenuation = toOc(make_vec3f(std::log(acf.x), std::log(acf.y), std::log(acf.z)) * m.attenuationScale);
+  } else if (type == "luminous") {
+    // render/materials/Luminous.cpp:33-45: radiance = color * intensity (times map_color), isEmissive = any of it
+    m.type = OC_MATERIAL_LUMINOUS;
+    m.mapKd = getTextureParam("map_color", texKd);
+    const vec3f color = getParam<vec3f>("color", make_vec3f(1.f));
+    m.emission = toOc(color * getParam<float>("intensity", 1.f));
+    m.transparency = getParam<float>("transparency", 0.f);
+    m.isEmissive = std::max(m.emission.x, std::max(m.emission.y, m.emission.z)) > 0.f ? 1u : 0u;
   } else {
     m.type = OC_MATERIAL_OTHER;
     for (auto &p : params) p.second.queried = true;
     postStatusMsg(OSP_LOG_INFO, "cuda device: material '" + type + "' is not implemented; surfaces using it terminate paths");
   }
+  if (m.isEmissive && !wasEmissive) device.emissiveMaterials++;
+  if (!m.isEmissive && wasEmissive) device.emissiveMaterials--;
+  wasEmissive = m.isEmissive != 0;
   const bool hasTextures = texD || texKd || texKs || texNs || texBump;
   m.hasTextures = hasTextures ? 1u : 0u;
   if (hasTextures && !hadTextures) device.texturedMaterials++;
@@ -479,6 +492,7 @@ void GeometricModel::commit()
       slots[i] = m->slot;
     }
     matList.upload(slots.data(), slots.size() * sizeof(uint32_t));
+    hostMaterials = slots;
     sh.material = matList.as<uint32_t>();
     sh.numMaterials = (uint32_t)slots.size();
     sh.materialMode = OC_MAT_FROM_MODEL;
@@ -488,6 +502,7 @@ void GeometricModel::commit()
       std::vector<uint32_t> ids(materialData->size());
       for (size_t i = 0; i < ids.size(); i++) ids[i] = materialData->at<uint32_t>(i);
       matList.upload(ids.data(), ids.size() * sizeof(uint32_t));
+      hostMaterials = ids;
       sh.material = matList.as<uint32_t>();
       sh.numMaterials = (uint32_t)ids.size();
       sh.materialMode = OC_MAT_FROM_RENDERER;
@@ -500,6 +515,51 @@ void GeometricModel::commit()
   sh.invertedNormals = getParam<bool>("invertNormals", false);
   sh.userID = getParam<uint32_t>("id", 0xFFFFFFFFu);
   epoch = nextCommitEpoch();
+}
+
+int GeometricModel::materialSlotOf(uint32_t primID, const std::vector<uint32_t> &rendererSlots) const
+{
+  if (sh.materialMode == OC_MAT_NONE || hostMaterials.empty()) return -1;
+  uint32_t idx = primID;
+  if (indexData) idx = indexData->at<uint8_t>(std::min<size_t>(idx, indexData->size() - 1));
+  uint32_t mat = hostMaterials[std::min<size_t>(idx, hostMaterials.size() - 1)];
+  if (sh.materialMode == OC_MAT_FROM_RENDERER) {
+    if (rendererSlots.empty()) return -1;
+    mat = rendererSlots[std::min<size_t>(mat, rendererSlots.size() - 1)];
+  }
+  return (int)mat;
+}
+
+void Geometry::getAreas(const std::vector<int32_t> &primIDs, const affine3f &xfm, std::vector<float> &areas) const
+{
+  areas.resize(primIDs.size());
+  if (type == "sphere") {
+    const vec3f sc = make_vec3f(length(xfm.l.vx), length(xfm.l.vy), length(xfm.l.vz));
+    const float s3 = (sc.x + sc.y + sc.z) / 3.f;
+    const float scale = 4.0f * (float)M_PI * (s3 * s3);
+    const float radius = radiusData ? 0.f : sphereRadius;
+    // (the reference indexes the spheres by position in the list, not by primID: Spheres.ispc:99-102)
+    for (size_t i = 0; i < primIDs.size(); i++) {
+      const float r = radiusData ? radiusData->at<float>(i) : radius;
+      areas[i] = scale * (r * r);
+    }
+    return;
+  }
+  const bool isTri = indexData->type == OSP_VEC3UI;
+  for (size_t i = 0; i < primIDs.size(); i++) {
+    const uint32_t *ix = (const uint32_t *)indexData->data((size_t)primIDs[i]);
+    const uint32_t i0 = ix[0], i1 = ix[1], i2 = ix[2], i3 = isTri ? ix[2] : ix[3];
+    const bool quad = !isTri && i2 != i3;
+    const vec3f a = vertexData->at<vec3f>(i0), b = vertexData->at<vec3f>(i1), d = vertexData->at<vec3f>(i3);
+    const vec3f e1 = xfmVector(xfm, a - d), e2 = xfmVector(xfm, b - d);
+    float area = length(cross(e1, e2));
+    if (quad) {
+      const vec3f c = vertexData->at<vec3f>(i2);
+      const vec3f e3 = xfmVector(xfm, c - d);
+      area += length(cross(e2, e3));
+    }
+    areas[i] = area * 0.5f;
+  }
 }
 
 // ---- TransferFunction (LinearTransferFunction.cpp:22-155) -------------------------------------------
@@ -931,6 +991,7 @@ void World::commit()
       if (in->group->hasVolumes()) sh.hasVolumes = 1;
     }
     instDev.upload(inst.data(), inst.size() * sizeof(OcInstance));
+    hostInstances = inst;
     sh.instances = instDev.as<OcInstance>();
     sh.numInstances = (uint32_t)inst.size();
     if (!inst.empty()) {
@@ -987,6 +1048,10 @@ void World::commit()
     sh.lightsCDF = cdfDev.as<float>();
     sh.scivisLights = scivisLightsDev.as<OcLight>();
   }
+  hostLights = pt;
+  geoKey[0] = geoKey[1] = geoKey[2] = ~0ull;
+  geoActive = false;
+  if (!instances) hostInstances.clear();
   sh.numLights = (uint32_t)pt.size();
   sh.numScivisLights = (uint32_t)sv.size();
   sh.numScivisLightsVisibleOnly = visibleOnly;
@@ -996,7 +1061,87 @@ void World::commit()
   dirty = true;
 }
 
-const OcWorld *World::prepareFrame()
+// PathTracerData::generateGeometryLights + GeometricModel_gatherEmissivePrimIDs (render/pathtracer/PathTracerData.cpp:87-160,
+// geometry/GeometricModel.ispc:14-56): one proxy light per (instance, model) that has emissive primitives
+void World::buildGeometryLights(const Renderer &renderer)
+{
+  std::vector<OcLight> geo;
+  std::vector<OcInstance> inst = hostInstances;
+  geoBuffers.clear();
+  const std::vector<OcMaterial> &table = device.materialTableHost();
+  for (size_t i = 0; instances && i < instances->size(); i++) {
+    Instance *in = dynamic_cast<Instance *>(instances->objectAt(i));
+    if (!in || !in->group || !in->group->geometricModels) continue;
+    Data *models = in->group->geometricModels.get();
+    std::vector<float> areaPDF(models->size(), 0.f);
+    bool any = false;
+    for (size_t g = 0; g < models->size(); g++) {
+      GeometricModel *model = dynamic_cast<GeometricModel *>(models->objectAt(g));
+      if (!model || !model->geom) continue;
+      // hasEmissiveMaterials: any material the model can reach emits
+      bool emissive = false;
+      for (uint32_t hm : model->hostMaterials) {
+        uint32_t slot = hm;
+        if (model->sh.materialMode == OC_MAT_FROM_RENDERER) {
+          if (renderer.materialSlots.empty()) continue;
+          slot = renderer.materialSlots[std::min<size_t>(hm, renderer.materialSlots.size() - 1)];
+        }
+        if (slot < table.size() && table[slot].isEmissive) emissive = true;
+      }
+      if (!emissive) continue;
+      if (!model->geom->supportAreaLighting()) {
+        postStatusMsg(OSP_LOG_WARNING, "#osp:pt Geometry " + model->toString() + " does not implement area sampling! Cannot use importance sampling for that geometry with emissive material!");
+        continue;
+      }
+      std::vector<int32_t> primIDs;
+      for (uint32_t p = 0; p < model->geom->numPrimitives(); p++) {
+        const int slot = model->materialSlotOf(p, renderer.materialSlots);
+        if (slot >= 0 && (size_t)slot < table.size() && table[slot].isEmissive) primIDs.push_back((int32_t)p);
+      }
+      if (primIDs.empty()) continue;
+      std::vector<float> distribution;
+      model->geom->getAreas(primIDs, in->xfm, distribution);
+      const float pdf = 1.f / distribution1D_create(distribution);
+      areaPDF[g] = pdf;
+      any = true;
+      OcLight l{};
+      l.type = OC_LIGHT_GEOMETRY;
+      l.isVisible = 1;
+      l.geoModel = in->group->sh.models + g;
+      l.geoInstance = instDevGeo() + i;
+      geoBuffers.emplace_back(new DevMem); geoBuffers.back()->upload(primIDs.data(), primIDs.size() * sizeof(int32_t));
+      l.geoPrimIDs = geoBuffers.back()->as<int32_t>();
+      geoBuffers.emplace_back(new DevMem); geoBuffers.back()->upload(distribution.data(), distribution.size() * sizeof(float));
+      l.geoDistribution = geoBuffers.back()->as<float>();
+      l.geoNumPrimitives = (uint32_t)primIDs.size();
+      l.geoPdf = pdf;
+      geo.push_back(l);
+    }
+    if (any) {
+      geoBuffers.emplace_back(new DevMem); geoBuffers.back()->upload(areaPDF.data(), areaPDF.size() * sizeof(float));
+      inst[i].modelAreaPDF = geoBuffers.back()->as<float>();
+    }
+  }
+  geoActive = !geo.empty();
+  if (!geoActive) return;
+  std::vector<OcLight> all = geo;
+  all.insert(all.end(), hostLights.begin(), hostLights.end());
+  std::vector<float> cdf(all.size(), 1.f);
+  distribution1D_create(cdf);
+  geoLightsDev.upload(all.data(), all.size() * sizeof(OcLight));
+  geoCdfDev.upload(cdf.data(), cdf.size() * sizeof(float));
+  geoInstDev.upload(inst.data(), inst.size() * sizeof(OcInstance));
+  geoNumLights = (uint32_t)all.size();
+  geoNumGeo = (uint32_t)geo.size();
+}
+
+const OcInstance *World::instDevGeo()
+{
+  geoInstDev.reserve(std::max<size_t>(1, hostInstances.size()) * sizeof(OcInstance));
+  return geoInstDev.as<OcInstance>();
+}
+
+const OcWorld *World::prepareFrame(const Renderer *renderer)
 {
   // models / transfer functions committed since the last frame: the groups take their new state over (Group::refreshSnapshots)
   if (seenEpoch != commitEpoch() && instances) {
@@ -1005,6 +1150,30 @@ const OcWorld *World::prepareFrame()
       if (in && in->group) in->group->refreshSnapshots();
     }
     seenEpoch = commitEpoch();
+  }
+  // geometry lights: only a pathtracer that asks for them, only when some material emits; rebuilt when the scene, a
+  // material or the renderer was committed since
+  const bool wantGeo = renderer && renderer->sh.type == OC_RENDERER_PATHTRACER && renderer->sh.geometryLights && device.emissiveMaterials > 0;
+  if (wantGeo) {
+    const uint64_t key[3] = {commitEpoch(), device.materialVersion, (uint64_t)(uintptr_t)renderer ^ (renderer->commitCount << 48)};
+    if (key[0] != geoKey[0] || key[1] != geoKey[1] || key[2] != geoKey[2]) {
+      buildGeometryLights(*renderer);
+      geoKey[0] = key[0]; geoKey[1] = key[1]; geoKey[2] = key[2];
+      dirty = true;
+    }
+  }
+  const bool useGeo = wantGeo && geoActive;
+  if (useGeo != geoInUse) { geoInUse = useGeo; dirty = true; }
+  if (dirty) {
+    if (useGeo) {
+      sh.lights = geoLightsDev.as<OcLight>(); sh.lightsCDF = geoCdfDev.as<float>();
+      sh.numLights = geoNumLights; sh.numGeoLights = geoNumGeo;
+      sh.instances = geoInstDev.as<OcInstance>();
+    } else {
+      sh.lights = hostLights.empty() ? nullptr : lightsDev.as<OcLight>(); sh.lightsCDF = hostLights.empty() ? nullptr : cdfDev.as<float>();
+      sh.numLights = (uint32_t)hostLights.size(); sh.numGeoLights = 0;
+      sh.instances = hostInstances.empty() ? nullptr : instDev.as<OcInstance>();
+    }
   }
   const OcMaterial *mt = device.materialTable();
   if (dirty || mt != uploadedMaterials) {
@@ -1097,6 +1266,8 @@ void Renderer::commit()
   sh.bgColor[0] = bg.x; sh.bgColor[1] = bg.y; sh.bgColor[2] = bg.z; sh.bgColor[3] = bg.w;
 
   materialData = getParamData(*this, "material", OSP_MATERIAL);
+  materialSlots.clear();
+  commitCount++;
   if (materialData) {
     std::vector<uint32_t> slots(materialData->size());
     for (size_t i = 0; i < slots.size(); i++) {
@@ -1104,6 +1275,7 @@ void Renderer::commit()
       if (!m) throw std::runtime_error("renderer 'material' array holds a non-material object");
       slots[i] = m->slot;
     }
+    materialSlots = slots;
     matList.upload(slots.data(), slots.size() * sizeof(uint32_t));
     sh.materials = matList.as<uint32_t>();
     sh.numMaterials = (uint32_t)slots.size();
@@ -1147,7 +1319,7 @@ void Renderer::commit()
     const vec4f scp = getParam<vec4f>("shadowCatcherPlane", make_vec4f(0.f, 0.f, 0.f, 0.f));
     if (scp.x != 0.f || scp.y != 0.f || scp.z != 0.f)
       postStatusMsg(OSP_LOG_WARNING, "cuda device: the shadow catcher plane is not supported");
-    getParam<bool>("geometryLights", true);
+    sh.geometryLights = getParam<bool>("geometryLights", true);
     sh.backgroundRefraction = getParam<bool>("backgroundRefraction", false);
   } else if (sh.type == OC_RENDERER_SCIVIS) {
     sh.shadowsEnabled = getParam<bool>("shadows", false);

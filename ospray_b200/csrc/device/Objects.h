@@ -19,6 +19,7 @@ namespace ospray {
 namespace cuda {
 
 struct CudaDevice;
+struct Renderer;
 
 void checkCuda(int rc, const char *what); // throws std::runtime_error with ospcuda_last_error()
 
@@ -101,11 +102,16 @@ struct Geometry : public ManagedObject
   void commit() override;
   uint32_t numPrimitives() const { return sh.numPrims; }
   const OcGeometry *devicePtr() const { return dev.as<OcGeometry>(); }
+  // geometry lights: meshes and spheres can be sampled by area (Geometry::supportAreaLighting); world-space areas of the
+  // given primitives under `xfm` (Mesh_getAreas geometry/Mesh.ispc:385-420, Spheres_getAreas geometry/Spheres.ispc:76-104)
+  bool supportAreaLighting() const { return type == "mesh" || type == "sphere"; }
+  void getAreas(const std::vector<int32_t> &primIDs, const affine3f &xfm, std::vector<float> &areas) const;
   std::string type;
   OcGeometry sh{};
 
  private:
   Ref<Data> vertexData, indexData, normalData, colorData, texcoordData, sphereData, radiusData, boxData;
+  float sphereRadius = 0.01f;
   DevMem dev, generated; // generated: soup index / interleaved spheres
 };
 
@@ -136,6 +142,7 @@ struct Material : public ManagedObject
   uint32_t slot;
 
  private:
+  bool wasEmissive = false;
   OcTextureParam getTextureParam(const std::string &name, Ref<Texture2D> &keep); // render/Material.cpp:73-165
   Ref<Texture2D> texD, texKd, texKs, texNs, texBump;
 };
@@ -151,6 +158,10 @@ struct GeometricModel : public ManagedObject
   Ref<Geometry> geomAPI, geom;
   OcModel sh{};
   uint64_t epoch = 0; // commitEpoch() at the last commit (parents compare it with the epoch of their snapshot)
+  // material table slot of primitive `primID` (GeometricModel_getMaterial, geometry/GeometricModel.ih:21-46), -1 = none;
+  // rendererSlots = the renderer's material list for models that index it
+  int materialSlotOf(uint32_t primID, const std::vector<uint32_t> &rendererSlots) const;
+  std::vector<uint32_t> hostMaterials; // what sh.material holds (slots or renderer indices)
 
  private:
   Ref<Data> materialData, colorData, indexData, promotedMat, promotedColor;
@@ -254,7 +265,9 @@ struct World : public ManagedObject
   std::string toString() const override { return "ospray::World"; }
   void commit() override;
   box3f getBounds() const override { return bounds; }
-  const OcWorld *prepareFrame(); // refresh material table pointer, upload the struct when dirty
+  // refresh material table pointer, upload the struct when dirty; for a pathtracer with geometryLights the emissive
+  // geometry is scanned and its proxy lights put in front of the light list (PathTracerData.cpp:32-160)
+  const OcWorld *prepareFrame(const Renderer *renderer = nullptr);
   CudaDevice &device;
   Ref<Data> instances, lights;
   OcWorld sh{};
@@ -262,6 +275,16 @@ struct World : public ManagedObject
 
  private:
   DevMem dev, instDev, lightsDev, cdfDev, scivisLightsDev;
+  // geometry lights of the last frame that asked for them
+  std::vector<OcInstance> hostInstances;
+  std::vector<OcLight> hostLights;
+  std::vector<std::unique_ptr<DevMem>> geoBuffers;
+  DevMem geoLightsDev, geoCdfDev, geoInstDev;
+  uint64_t geoKey[3] = {~0ull, ~0ull, ~0ull};
+  bool geoActive = false, geoInUse = false;
+  uint32_t geoNumLights = 0, geoNumGeo = 0;
+  void buildGeometryLights(const Renderer &renderer);
+  const OcInstance *instDevGeo();
   const void *uploadedMaterials = nullptr;
   bool dirty = true;
   uint64_t seenEpoch = 0;
@@ -285,6 +308,8 @@ struct Renderer : public ManagedObject
   std::string type;
   OcRenderer sh{};
   float errorThreshold = 0.f;
+  std::vector<uint32_t> materialSlots; // the renderer's material list (material table slots)
+  uint64_t commitCount = 0;
 
  private:
   Ref<Data> materialData;

@@ -53,6 +53,10 @@ class MaterialSpec:
     map_d: Optional["MapSpec"] = None
     map_bump: Optional["MapSpec"] = None
     map_attenuation_color: Optional["MapSpec"] = None
+    color: tuple = (1.0, 1.0, 1.0)              # luminous (render/materials/Luminous.cpp:33-45)
+    intensity: float = 1.0
+    transparency: float = 0.0
+    map_color: Optional["MapSpec"] = None
 
 
 @dataclass
@@ -128,6 +132,7 @@ class SceneSpec:
                 if m.material is not None:
                     texs += [getattr(m.material, a).texture for a in ("map_kd", "map_ks", "map_ns", "map_d", "map_bump", "map_attenuation_color")
                              if getattr(m.material, a) is not None]
+                    if m.material.map_color is not None: texs.append(m.material.map_color.texture)
         return all(t.mipmaps for t in texs)
 
 
@@ -442,6 +447,12 @@ def _material(m: MaterialSpec):
     for name in ("map_kd", "map_ks", "map_ns", "map_d", "map_bump"):
         _set_map(mat, name, getattr(m, name))
     _set_map(mat, "map_attenuationColor", m.map_attenuation_color)
+    if m.type == "luminous":
+        _set_map(mat, "map_color", m.map_color)
+        mat.set("color", tuple(float(x) for x in m.color))
+        if m.intensity != d.intensity: mat.set("intensity", float(m.intensity))
+        if m.transparency != d.transparency: mat.set("transparency", float(m.transparency))
+        return mat.commit()
     if m.type == "thinGlass":
         if m.eta != d.eta: mat.set("eta", float(m.eta))
         if m.attenuation_color != d.attenuation_color: mat.set("attenuationColor", tuple(float(x) for x in m.attenuation_color))

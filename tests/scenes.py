@@ -199,6 +199,30 @@ def cutout_cornell():
     return s
 
 
+def emissive_cornell(transparency=0.0, textured=False):
+    """cornell box lit by emissive GEOMETRY instead of a light object: a luminous quad under the ceiling (two triangles +
+    one quad in an indexed mesh, so both primitive kinds are sampled), a luminous sphere in an instance with a non-uniform
+    scale, and a weak quad light (MIS between geometry lights and virtual lights): materials/Luminous.ispc,
+    pathtracer/GeometryLight.ispc:22-128, PathTracerData.cpp:87-160, Mesh_sampleArea / Spheres_sampleArea"""
+    s = T.cornell_box()
+    s.lights = [T.LightSpec("quad", {"color": (0.78, 0.551, 0.183), "intensity": 6.0, "position": (0.3, 0.98, -0.4),
+                                     "edge1": (0.3, 0.0, 0.0), "edge2": (0.0, 0.0, 0.3)})]
+    y = 0.97
+    verts = np.array([[-0.6, y, -0.3], [-0.1, y, -0.3], [-0.1, y, 0.2], [-0.6, y, 0.2], [-0.05, y, -0.3], [0.2, y, -0.3], [0.2, y, 0.1]], np.float32)
+    idx = np.array([[0, 1, 2, 3], [4, 5, 6, 6]], np.uint32)  # a quad and a triangle (z == w)
+    st = np.array([[0, 0], [1, 0], [1, 1], [0, 1], [0, 0], [1, 0], [1, 1]], np.float32)
+    lum = T.MaterialSpec(type="luminous", color=(1.0, 0.9, 0.7), intensity=12.0, transparency=transparency)
+    if textured:
+        lum.map_color = T.MapSpec(T.TextureSpec(_tex_rng_image(8, 8, 3, 21, np.float32, 0.2, 1.0), "RGB32F"))
+    panel = T.ModelSpec(T.GeometrySpec("mesh", vertex=verts, index=idx, vertex_texcoord=st), lum)
+    s.instances[0].group.models.append(panel)
+    ball = T.GeometrySpec("sphere", sphere_position=np.array([[0.0, 0.0, 0.0]], np.float32), sphere_radius=np.array([0.12], np.float32))
+    glow = T.MaterialSpec(type="luminous", color=(0.3, 0.5, 1.0), intensity=8.0)
+    xf = np.array([1.2, 0, 0, 0, 0.8, 0, 0, 0, 1.0, 0.45, -0.25, -0.55], np.float32)
+    s.instances.append(T.InstanceSpec(T.GroupSpec(models=[T.ModelSpec(ball, glow)]), xfm=xf))
+    return s
+
+
 def backplate_scene():
     """renderer textures: map_backplate behind random spheres and map_maxDepth cutting the primary rays (Renderer.ispc:18-39)"""
     s = T.random_spheres(24, seed=3)
@@ -250,6 +274,10 @@ CASES = {
     "textured_bias_pt": (textured_cornell, "pathtracer", {"pixelSamples": 1, "mipMapBias": 1.5}, 1),
     "cutout_pt": (cutout_cornell, "pathtracer", {"pixelSamples": 2}, 1),
     "backplate_pt": (backplate_scene, "pathtracer", {"pixelSamples": 2, "backgroundColor": (0.1, 0.2, 0.3, 1.0)}, 1),
+    # emissive geometry: luminous material, geometry lights (pathtracer/GeometryLight.ispc) and the paths that run into them
+    "emissive_pt": (emissive_cornell, "pathtracer", {"pixelSamples": 2}, 2),
+    "emissive_nogeolights_pt": (emissive_cornell, "pathtracer", {"pixelSamples": 2, "geometryLights": False}, 1),
+    "emissive_transparent_pt": (lambda: emissive_cornell(0.5, True), "pathtracer", {"pixelSamples": 2, "lightSamples": 2, "maxPathLength": 4}, 1),
     # debug renderer (render/debug/DebugRenderer.ispc), every method the device accepts
     "debug_testFrame": (T.cornell_box, "debug", {"method": "testFrame", "pixelSamples": 2}, 2),
     "debug_rayDir": (T.cornell_box, "debug", {"method": "rayDir"}, 1),
@@ -270,7 +298,8 @@ CASES = {
 # transmissive geometry hit indexes past it (common/World.ih:121-128).  Undefined in the reference's scalar mode.
 REF_UNSUPPORTED = {"volume_geometry"}
 # Cases only the reference's own kernels check (the restatement in oracle.cpp does not sample textures)
-ORACLE_UNSUPPORTED = {"textured_pt", "textured_bias_pt", "cutout_pt", "backplate_pt"}
+ORACLE_UNSUPPORTED = {"textured_pt", "textured_bias_pt", "cutout_pt", "backplate_pt", "emissive_pt", "emissive_nogeolights_pt",
+                      "emissive_transparent_pt"}
 # Cases the cuda device does not render (none at present; the GPU parity tests skip what is listed here)
 DEVICE_UNSUPPORTED = set()
 # Volumes under the pathtracer: delta tracking takes hundreds of accept/reject decisions per path on logf / expf / lerp

@@ -242,6 +242,11 @@ typedef struct {
   /* pathtracer light list (PathTracerData.cpp:32-82): geometry lights first, world, instance */
   uint32_t numLights;
   uint32_t numGeoLights;
+  /* what a shadow ray can run into, decided on the host before a frame (World::prepareFrame): 2 = every surface of the
+   * world takes a shadow-ray contribution to exactly 0 (no model colours, no vertex alpha, every material an OBJ with d = 1
+   * and tf = 0 or none); 1 = the same provided the contribution is <= 1e6 * minContribution (vec4 vertex colours whose
+   * alphas are all 1, see ptOccluderIsOpaque in pathtracer_wf.cuh); 0 = look at the occluder */
+  uint32_t shadowOpaque;
   const OcLight *lights;
   const float *lightsCDF;
   /* scivis light list (SciVisData.cpp:74-105): visible-only lights first, ambient folded */

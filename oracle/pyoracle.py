@@ -108,7 +108,7 @@ class Light(C.Structure):
 class World(C.Structure):
     _fields_ = [("instances", C.POINTER(Instance)), ("numInstances", C.c_uint32), ("hasVolumes", C.c_uint32), ("tlas", BVH),
                 ("materials", C.POINTER(Material)), ("numMaterials", C.c_uint32), ("numLights", C.c_uint32),
-                ("numGeoLights", C.c_uint32), ("lights", C.POINTER(Light)), ("lightsCDF", C.POINTER(C.c_float)), ("scivisLights", C.POINTER(Light)),
+                ("numGeoLights", C.c_uint32), ("shadowOpaque", C.c_uint32), ("lights", C.POINTER(Light)), ("lightsCDF", C.POINTER(C.c_float)), ("scivisLights", C.POINTER(Light)),
                 ("numScivisLights", C.c_uint32), ("numScivisLightsVisibleOnly", C.c_uint32), ("aoColorPi", Vec3),
                 ("bounds", C.c_float * 6)]
 

@@ -350,6 +350,9 @@ static __device__ __noinline__ SampleRes HenyeyGreenstein_sample(float g, vec3f 
 // Anything else (per-primitive model colours, real alpha, thin glass, ...) answers "no" and takes the reference loop.
 __device__ __forceinline__ bool ptOccluderIsOpaque(const OcWorld *world, const OcRenderer &ren, uint32_t rec, uint32_t instID, float maxContrib)
 {
+  const uint32_t so = world->shadowOpaque; // the host looked at every model and material of the world already
+  if (so == 2u) return true;
+  if (so == 1u) return maxContrib * 1e-6f <= ren.minContribution;
   uint32_t primID, geomID;
   resolveHitIds(world, rec, instID, primID, geomID);
   const OcInstance *inst = world->instances + instID;

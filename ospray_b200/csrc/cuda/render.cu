@@ -52,6 +52,8 @@ struct Ctx
   const OcFrameBuffer &fb;
   Stack stack;
   Counters cnt;
+  RayCone cone;      // frames with textures: ray cone of the sample being rendered (ScreenSample::rayCone)
+  vec2f pixelCenter; // ScreenSample::pos: where the backplate is looked up
   __device__ Ctx(const OcWorld *w, const OcRenderer &r, const OcCamera &c, const OcFrameBuffer &f, Stack s)
       : world(w), ren(r), cam(c), fb(f), stack(s) { cnt.primary = cnt.secondary = cnt.shadow = 0; }
 };
@@ -110,10 +112,16 @@ __device__ __forceinline__ vec3f evaluateVirtualLights(Ctx &c, bool straightPath
 }
 
 // ============================== scivis / ao shared pieces ==================================
+// Everything the scivis / ao / debug frame kernel calls, as static members of one class template: TEX = the frame references
+// textures (material maps, backplate, depth limit), so hits carry texture coordinates, both tangents and the ray cone
+// (camera -> c.cone -> postIntersect footprint; shadow cones per scivis/surfaces.ispc:64-67, SciVis.ispc:262-264). Frames
+// without textures run the TEX = false instantiation, whose code is what it was before textures existed.
+template <bool TEX>
+struct Mega {
 struct SciVisBSDF { vec3f diffuse, specular, transmission, albedo; float shininess, opacity; };
 
 // scivis/surfaces.ih:49-92
-__device__ __forceinline__ SciVisBSDF evalMaterial(const DifferentialGeometry &dg)
+static __device__ __forceinline__ SciVisBSDF evalMaterial(const DifferentialGeometry &dg)
 {
   SciVisBSDF r;
   r.diffuse = make_vec3f(dg.color);
@@ -123,11 +131,21 @@ __device__ __forceinline__ SciVisBSDF evalMaterial(const DifferentialGeometry &d
   r.opacity = dg.color.w;
   const OcMaterial *m = dg.material;
   if (m && m->type == OC_MATERIAL_OBJ) {
-    const float d = m->d * dg.color.w;
+    const bool tex = TEX && m->hasTextures;
+    float d = m->d;
+    if (tex && m->mapD.tex) d = d * texParamGet4f(m->mapD, dg.st, dg.pixelFootprint).x;
+    d = d * dg.color.w;
     r.diffuse = r.diffuse * toV(m->Kd);
+    if (tex && m->mapKd.tex) {
+      const vec4f t = texParamGet4f(m->mapKd, dg.st, dg.pixelFootprint);
+      r.diffuse = r.diffuse * make_vec3f(t.x, t.y, t.z);
+      d *= t.w;
+    }
     r.diffuse = r.diffuse * d;
     r.specular = d * toV(m->Ks);
+    if (tex && m->mapKs.tex) { const vec4f t = texParamGet4f(m->mapKs, dg.st, dg.pixelFootprint); r.specular = r.specular * make_vec3f(t.x, t.y, t.z); }
     r.shininess = m->Ns;
+    if (tex && m->mapNs.tex) r.shininess = r.shininess * texParamGet4f(m->mapNs, dg.st, dg.pixelFootprint).x;
     r.transmission = toV(m->Tf) * d + make_vec3f(1.f - d);
     r.opacity = d;
   }
@@ -139,7 +157,7 @@ __device__ __forceinline__ SciVisBSDF evalMaterial(const DifferentialGeometry &d
 }
 
 // single-volume marcher, AO flavour (ao/volumes.ispc:244-330): returns (rgb, alpha)
-__device__ __noinline__ vec4f integrateVolumeAO(Ctx &c, const VolumeHit &vh, const Ray &ray, RandomSampler &rs, float samplingRate)
+static __device__ __noinline__ vec4f integrateVolumeAO(Ctx &c, const VolumeHit &vh, const Ray &ray, RandomSampler &rs, float samplingRate)
 {
   const OcVolume &v = *vh.vol;
   vec3f org = ray.org, dir = ray.dir;
@@ -185,14 +203,13 @@ __device__ __noinline__ vec4f integrateVolumeAO(Ctx &c, const VolumeHit &vh, con
 }
 
 struct SSI { vec3f shadedColor, transmission, albedo; float opacity; };
-__device__ SSI SciVis_computeShading(Ctx &c, const DifferentialGeometry &dg, RandomSampler &rs, vec3f inDir, uint32_t px,
-    uint32_t py, int sampleIDz);
 
 // lightAlpha (scivis/lightAlpha.ispc:19-122)
-__device__ __noinline__ vec3f lightAlpha(Ctx &c, Ray &ray, RandomSampler &rs, vec3f weight, float quality)
+static __device__ __noinline__ vec3f lightAlpha(Ctx &c, Ray &ray, RayCone shadowCone, RandomSampler &rs, vec3f weight, float quality)
 {
   vec3f alpha = make_vec3f(1.f);
   const float org_t_max = ray.t;
+  const float org_width = shadowCone.width;
   while (true) {
     c.cnt.shadow++;
     traceWorldNI<false>(c.world, ray, c.stack);
@@ -205,10 +222,11 @@ __device__ __noinline__ vec3f lightAlpha(Ctx &c, Ray &ray, RandomSampler &rs, ve
     }
     if (hadHit(ray)) {
       DifferentialGeometry dg;
-      postIntersectNI(c.world, c.ren, dg, ray, DG_COLOR | DG_TEXCOORD);
+      postIntersectNI<TEX>(c.world, c.ren, dg, ray, DG_COLOR | DG_TEXCOORD, TEX ? &shadowCone : nullptr);
       const SciVisBSDF bsdf = evalMaterial(dg);
       alpha = alpha * bsdf.transmission;
       setRay(ray, ray.org, ray.dir, ray.t + dg.epsilon, org_t_max);
+      shadowCone.width = org_width;
     } else
       break;
     if (luminance(alpha * weight) < c.ren.minContribution) {
@@ -220,9 +238,11 @@ __device__ __noinline__ vec3f lightAlpha(Ctx &c, Ray &ray, RandomSampler &rs, ve
 }
 
 // SciVis_computeAO (scivis/SciVis.ispc:224-281)
-__device__ __noinline__ vec3f SciVis_computeAO(Ctx &c, RandomSampler &rs, const DifferentialGeometry &dg, int sampleCnt, float aoRadius,
-    uint32_t px, uint32_t py, int sampleIDz)
+static __device__ __noinline__ vec3f SciVis_computeAO(Ctx &c, RandomSampler &rs, const DifferentialGeometry &dg, int sampleCnt, float aoRadius,
+    uint32_t px, uint32_t py, int sampleIDz, float coneWidth)
 {
+  RayCone shadowCone;
+  shadowCone.width = coneWidth; shadowCone.dwdt = 0.0f; // constant for AO (SciVis.ispc:262-264)
   const int accumID = sampleIDz * sampleCnt;
   uint32_t v0 = px, v1 = py;
   tea8(v0, v1);
@@ -239,14 +259,14 @@ __device__ __noinline__ vec3f SciVis_computeAO(Ctx &c, RandomSampler &rs, const 
     }
     Ray ao_ray;
     setRay(ao_ray, dg.P, ao_dir, dg.epsilon, aoRadius);
-    hits = hits + (make_vec3f(1.f) - lightAlpha(c, ao_ray, rs, make_vec3f(1.f), 0.1f));
+    hits = hits + (make_vec3f(1.f) - lightAlpha(c, ao_ray, shadowCone, rs, make_vec3f(1.f), 0.1f));
   }
   return make_vec3f(1.0f) - (hits / (float)sampleCnt);
 }
 
 // scivis/surfaces.ispc:17-128
-__device__ __noinline__ SSI SciVis_computeShading(Ctx &c, const DifferentialGeometry &dg, RandomSampler &rs, vec3f inDir, uint32_t px,
-    uint32_t py, int sampleIDz)
+static __device__ __noinline__ SSI SciVis_computeShading(Ctx &c, const DifferentialGeometry &dg, RandomSampler &rs, vec3f inDir, uint32_t px,
+    uint32_t py, int sampleIDz, float coneWidth)
 {
   SSI ret;
   const SciVisBSDF bsdf = evalMaterial(dg);
@@ -269,7 +289,9 @@ __device__ __noinline__ SSI SciVis_computeShading(Ctx &c, const DifferentialGeom
           if (dot(dg.Ng, light.dir) < 0.0f) P = P - (2.f * dg.epsilon) * dg.Ng;
           Ray shadowRay;
           setRay(shadowRay, P, light.dir, 0.0f, light.dist);
-          const vec3f la = lightAlpha(c, shadowRay, rs, light_contrib, 0.25f);
+          RayCone shadowCone; // connects the vertex's cone to the point on the light (surfaces.ispc:64-67)
+          shadowCone.width = coneWidth; shadowCone.dwdt = -coneWidth * (1.f / light.dist);
+          const vec3f la = lightAlpha(c, shadowRay, shadowCone, rs, light_contrib, 0.25f);
           color = color + la * light_contrib;
         }
       } else {
@@ -280,7 +302,7 @@ __device__ __noinline__ SSI SciVis_computeShading(Ctx &c, const DifferentialGeom
   vec3f ao = make_vec3f(1.f);
   const vec3f aoColorPi = toV(w->aoColorPi);
   if (c.ren.aoSamples > 0 && luminance(aoColorPi) > c.ren.minContribution)
-    ao = SciVis_computeAO(c, rs, dg, c.ren.aoSamples, c.ren.aoRadius, px, py, sampleIDz);
+    ao = SciVis_computeAO(c, rs, dg, c.ren.aoSamples, c.ren.aoRadius, px, py, sampleIDz, coneWidth);
   color = color + bsdf.diffuse * ao * aoColorPi;
   ret.shadedColor = color;
   ret.transmission = bsdf.transmission;
@@ -290,7 +312,7 @@ __device__ __noinline__ SSI SciVis_computeShading(Ctx &c, const DifferentialGeom
 
 // gradient shading of one volume sample (scivis/volumes.ispc:391-419), out of line: the marching loop of volumes without
 // gradient shading (the default) keeps its registers
-__device__ __noinline__ vec4f shadeVolumeSampleSciVis(Ctx &c, const VolumeHit &vh, vec3f p, vec4f sc, float dt, RandomSampler &rs, vec3f rayDir,
+static __device__ __noinline__ vec4f shadeVolumeSampleSciVis(Ctx &c, const VolumeHit &vh, vec3f p, vec4f sc, float dt, RandomSampler &rs, vec3f rayDir,
     uint32_t px, uint32_t py, int sampleIDz)
 {
   const OcVolume &v = *vh.vol;
@@ -306,7 +328,7 @@ __device__ __noinline__ vec4f shadeVolumeSampleSciVis(Ctx &c, const VolumeHit &v
     dg.P = p;
     dg.dPds = make_vec3f(1.f, 0.f, 0.f);
     dg.primID = 0; dg.objID = dg.instID = OC_INVALID_ID;
-    const SSI shading = SciVis_computeShading(c, dg, rs, rayDir, px, py, sampleIDz);
+    const SSI shading = SciVis_computeShading(c, dg, rs, rayDir, px, py, sampleIDz, 0.f); // no coneWidth used (volumes.ispc:414)
     const vec4f shadedColor = make_vec4f(shading.shadedColor, 1.f - luminance(shading.transmission));
     sc = lerp4(v.gradientShadingScale, sc, shadedColor);
   }
@@ -318,7 +340,7 @@ __device__ __noinline__ vec4f shadeVolumeSampleSciVis(Ctx &c, const VolumeHit &v
 // volT / volHit follow the reference CPU form (sampleAllVolumes, scivis/volumes.ispc:160-169): the
 // first sample in front of the surface hit that is not fully transparent defines depth and IDs.
 struct VolumeMarch { vec4f color; float volT; bool volHit; }; // handed back by value: references would pin volT / volHit to local memory
-__device__ __noinline__ VolumeMarch integrateVolumeSciVis(Ctx &c, const VolumeHit &vh, const Ray &ray, RandomSampler &rs, float samplingRate,
+static __device__ __noinline__ VolumeMarch integrateVolumeSciVis(Ctx &c, const VolumeHit &vh, const Ray &ray, RandomSampler &rs, float samplingRate,
     uint32_t px, uint32_t py, int sampleIDz, float volT)
 {
   bool volHit = false;
@@ -368,7 +390,7 @@ __device__ __noinline__ VolumeMarch integrateVolumeSciVis(Ctx &c, const VolumeHi
 }
 
 // visible lights (scivis/surfaces.ispc:130-150)
-__device__ vec3f evaluateLightsSciVis(Ctx &c, const Ray &ray)
+static __device__ vec3f evaluateLightsSciVis(Ctx &c, const Ray &ray)
 {
   vec3f color = make_vec3f(0.f);
   const OcWorld *w = c.world;
@@ -382,7 +404,7 @@ __device__ vec3f evaluateLightsSciVis(Ctx &c, const Ray &ray)
 }
 
 // SciVis_renderSample (scivis/SciVis.ispc:24-222)
-__device__ void SciVis_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint32_t px, uint32_t py, int sampleIDz)
+static __device__ void SciVis_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint32_t px, uint32_t py, int sampleIDz)
 {
   const OcRenderer &ren = c.ren;
   RandomSampler rs;
@@ -420,8 +442,8 @@ __device__ void SciVis_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint
     }
     if (hadHit(ray)) {
       DifferentialGeometry dg;
-      postIntersectNI(c.world, ren, dg, ray, DG_NG | DG_NS | DG_NORMALIZE | DG_FACEFORWARD | DG_COLOR | DG_TANGENTS | DG_TEXCOORD);
-      const SSI sh = SciVis_computeShading(c, dg, rs, ray.dir, px, py, sampleIDz);
+      postIntersectNI<TEX>(c.world, ren, dg, ray, DG_NG | DG_NS | DG_NORMALIZE | DG_FACEFORWARD | DG_COLOR | DG_TANGENTS | DG_TEXCOORD, TEX ? &c.cone : nullptr);
+      const SSI sh = SciVis_computeShading(c, dg, rs, ray.dir, px, py, sampleIDz, c.cone.width);
       if (firstHit || allHitsFullyTransmissive) {
         sample.position = dg.P; sample.firstNormal = dg.Ns; sample.normal = dg.Ns; sample.albedo = sh.albedo;
         if (sample.geomID == OC_INVALID_ID) { sample.instID = dg.instID; sample.geomID = dg.objID; sample.primID = dg.primID; }
@@ -436,7 +458,7 @@ __device__ void SciVis_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint
       }
       setRay(ray, ray.org, ray.dir, ray.t + dg.epsilon, originalRayTFar);
     } else {
-      const vec4f bg = getBackground(ren);
+      const vec4f bg = TEX ? getBackgroundTex(ren, c.pixelCenter) : getBackground(ren);
       outColor = outColor + outTransmission * make_vec3f(bg);
       outTransmission = outTransmission * (1.f - bg.w);
       break;
@@ -447,7 +469,7 @@ __device__ void SciVis_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint
 }
 
 // computeAO (render/util.ispc:12-54)
-__device__ __noinline__ float computeAO(Ctx &c, const DifferentialGeometry &dg, int sampleCnt, float aoRadius, uint32_t px, uint32_t py,
+static __device__ __noinline__ float computeAO(Ctx &c, const DifferentialGeometry &dg, int sampleCnt, float aoRadius, uint32_t px, uint32_t py,
     int sampleIDz)
 {
   const int accumID = sampleIDz * sampleCnt;
@@ -470,7 +492,7 @@ __device__ __noinline__ float computeAO(Ctx &c, const DifferentialGeometry &dg, 
 }
 
 // AORenderer_renderSample (render/ao/AORenderer.ispc:23-149)
-__device__ void AO_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint32_t px, uint32_t py, int sampleIDz)
+static __device__ void AO_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint32_t px, uint32_t py, int sampleIDz)
 {
   const OcRenderer &ren = c.ren;
   RandomSampler rs;
@@ -493,13 +515,19 @@ __device__ void AO_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint32_t
     const bool rayHadHit = hadHit(ray);
     if (rayHadHit) {
       DifferentialGeometry dg;
-      postIntersectNI(c.world, ren, dg, ray, DG_NG | DG_NS | DG_NORMALIZE | DG_FACEFORWARD | DG_COLOR | DG_TEXCOORD | DG_TANGENTS);
+      postIntersectNI<TEX>(c.world, ren, dg, ray, DG_NG | DG_NS | DG_NORMALIZE | DG_FACEFORWARD | DG_COLOR | DG_TEXCOORD | DG_TANGENTS, TEX ? &c.cone : nullptr);
       // getSurfaceColor (ao/surfaces.ispc:18-42)
       vec3f surfaceColor = make_vec3f(1.f);
       float opacity = 1.f;
       if (dg.material && dg.material->type == OC_MATERIAL_OBJ) {
-        surfaceColor = toV(dg.material->Kd);
-        opacity *= dg.material->d;
+        const OcMaterial *m = dg.material;
+        surfaceColor = toV(m->Kd);
+        if (TEX && m->mapKd.tex) {
+          const vec4f t = texParamGet4f(m->mapKd, dg.st, dg.pixelFootprint);
+          surfaceColor = surfaceColor * make_vec3f(t.x, t.y, t.z);
+          opacity *= t.w;
+        }
+        opacity *= m->d * ((TEX && m->mapD.tex) ? texParamGet4f(m->mapD, dg.st, dg.pixelFootprint).x : 1.f);
       }
       const vec3f color = surfaceColor * make_vec3f(dg.color);
       opacity = opacity * dg.color.w;
@@ -517,7 +545,7 @@ __device__ void AO_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint32_t
       }
       setRay(ray, ray.org, ray.dir, ray.t + dg.epsilon, originalRayTFar);
     } else {
-      blendedColor = getBackground(ren);
+      blendedColor = TEX ? getBackgroundTex(ren, c.pixelCenter) : getBackground(ren);
       if (firstHit) {
         sample.z = ray.t;
         sample.albedo = make_vec3f(blendedColor);
@@ -535,15 +563,15 @@ __device__ void AO_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint32_t
 // ======================================= debug renderer ======================================
 // render/debug/DebugRenderer.ispc:27-420 (methods of DebugRendererShared.h:12-30; texCoord, dPdt and volume are refused at
 // commit: no texture coordinates / second tangent / debug volume marcher on this device)
-__device__ __forceinline__ vec3f makeRandomColor(uint32_t i) // rkcommon/utility/random.ih (un-vendored; restated)
+static __device__ __forceinline__ vec3f makeRandomColor(uint32_t i) // rkcommon/utility/random.ih (un-vendored; restated)
 {
   const uint32_t mx = 13 * 17 * 43, my = 11 * 29, mz = 7 * 23 * 63;
   const uint32_t g = i * (3 * 5 * 127) + 12312314;
   if (i == 0xFFFFFFFFu) return make_vec3f(0.f);
   return make_vec3f((g % mx) * (1.f / (mx - 1)), (g % my) * (1.f / (my - 1)), (g % mz) * (1.f / (mz - 1)));
 }
-__device__ __forceinline__ float debugEyeLight(const Ray &ray) { return 0.2f + 0.8f * fabsf(dot(normalize(ray.Ng), ray.dir)); }
-__device__ __forceinline__ vec3f debugTangentColor(vec3f t)
+static __device__ __forceinline__ float debugEyeLight(const Ray &ray) { return 0.2f + 0.8f * fabsf(dot(normalize(ray.Ng), ray.dir)); }
+static __device__ __forceinline__ vec3f debugTangentColor(vec3f t)
 {
   vec3f c = normalize(t);
   if (c.x < 0.f) c.x = c.x * -0.3f;
@@ -552,7 +580,7 @@ __device__ __forceinline__ vec3f debugTangentColor(vec3f t)
   return c;
 }
 
-__device__ void Debug_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint32_t px, uint32_t py, int sampleIDz)
+static __device__ void Debug_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint32_t px, uint32_t py, int sampleIDz)
 {
   const OcRenderer &ren = c.ren;
   const uint32_t method = ren.debugMethod;
@@ -570,10 +598,18 @@ __device__ void Debug_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint3
     traceWorldNI<false>(c.world, ray, c.stack);
     sample.z = ray.t;
     sample.alpha = 1.f;
-    sample.rgb = make_vec3f(getBackground(ren));
+    sample.rgb = make_vec3f(TEX ? getBackgroundTex(ren, c.pixelCenter) : getBackground(ren));
     if (hadHit(ray)) {
       DifferentialGeometry dg;
       switch (method) {
+      case OC_DEBUG_TEX_COORD: // DebugRenderer.ispc:112-122
+        postIntersect<true>(c.world, ren, dg, ray, DG_TEXCOORD, &c.cone);
+        sample.rgb = vabs(make_vec3f(dg.st.x, dg.st.y, 0.0f));
+        break;
+      case OC_DEBUG_DPDT: // :142-160
+        postIntersect<true>(c.world, ren, dg, ray, DG_TANGENTS, &c.cone);
+        sample.rgb = debugTangentColor(dg.dPdt);
+        break;
       case OC_DEBUG_EYE_LIGHT: sample.rgb = make_vec3f(debugEyeLight(ray)); break;
       case OC_DEBUG_NG:
         postIntersect(c.world, ren, dg, ray, DG_NORMALIZE | DG_NG);
@@ -614,7 +650,7 @@ __device__ void Debug_renderSample(Ctx &c, Ray &ray, ScreenSample &sample, uint3
 
 // Renderer_default_renderTask pixel body (render/RendererRenderTaskFn.inl:30-86)
 template <int RENDERER>
-__device__ void defaultRenderPixel(Ctx &c, uint32_t x, uint32_t y, ScreenSample &screenSample)
+static __device__ void defaultRenderPixel(Ctx &c, uint32_t x, uint32_t y, ScreenSample &screenSample)
 {
   const OcRenderer &ren = c.ren;
   const OcFrameBuffer &fb = c.fb;
@@ -626,6 +662,9 @@ __device__ void defaultRenderPixel(Ctx &c, uint32_t x, uint32_t y, ScreenSample 
   ScreenSample sample;
   ScreenSample_zero(sample);
   const vec2f rcpSize = make_vec2f(1.f / (float)fb.sizeX, 1.f / (float)fb.sizeY);
+  c.pixelCenter = make_vec2f(((float)x + 0.5f) * rcpSize.x, ((float)y + 0.5f) * rcpSize.y);
+  c.cone.width = c.cone.dwdt = 0.f;
+  const float tMax = TEX ? rendererMaxDepth(ren, c.pixelCenter) : INFINITY; // depth limit from map_maxDepth (:41-43)
   for (int s = 0; s < spp; s++) {
     const float pixel_du = Halton_sample2(startSampleID + s);
     const float pixel_dv = CranleyPattersonRotation(Halton_sample3(startSampleID + s), 1.f / 6.f);
@@ -634,6 +673,11 @@ __device__ void defaultRenderPixel(Ctx &c, uint32_t x, uint32_t y, ScreenSample 
     const vec2f screen = pixel_center + pfSample * rcpSize;
     Ray ray;
     cameraInitRay(c.cam, ray, screen, make_vec2f(0.f, 0.f));
+    if (TEX || RENDERER == OC_RENDERER_DEBUG) { // the sample's ray cone in pixel units (:64-71)
+      c.cone = cameraInitRayCone(c.cam, screen);
+      c.cone.dwdt *= rcpSize.y; c.cone.width *= rcpSize.y;
+    }
+    if (TEX) ray.t = fminf(ray.t, tMax);
     if (RENDERER == OC_RENDERER_SCIVIS) SciVis_renderSample(c, ray, sample, x, y, startSampleID + s);
     else if (RENDERER == OC_RENDERER_DEBUG) Debug_renderSample(c, ray, sample, x, y, startSampleID + s);
     else AO_renderSample(c, ray, sample, x, y, startSampleID + s);
@@ -641,6 +685,7 @@ __device__ void defaultRenderPixel(Ctx &c, uint32_t x, uint32_t y, ScreenSample 
   }
   ScreenSample_normalize(screenSample, 1.f / (float)spp);
 }
+}; // struct Mega
 
 // ================================ framebuffer accumulation ==================================
 // LocalFB_accumulateSample (fb/LocalFB.ispc:14-78), FRAMEBUFFER_ACCUMULATE_VALUE (FrameBuffer.ih:17-22)
@@ -711,7 +756,7 @@ namespace oc {
 #ifndef OC_RENDER_MIN_BLOCKS
 #define OC_RENDER_MIN_BLOCKS 10 // 96 registers: C2 7.9 -> 7.5 ms, C3 143 -> 137 ms vs the unconstrained 128 (tools/ab_workloads.sh)
 #endif
-template <int RENDERER>
+template <int RENDERER, bool TEX>
 __global__ void __launch_bounds__(64, OC_RENDER_MIN_BLOCKS) renderFrameKernel(const __grid_constant__ FrameArgs a)
 {
   // block -> (owned tile, 8x8 task inside the 64x64 tile); thread -> pixel inside the task
@@ -732,7 +777,7 @@ __global__ void __launch_bounds__(64, OC_RENDER_MIN_BLOCKS) renderFrameKernel(co
   const bool inImage = x < (uint32_t)a.fb.sizeX && y < (uint32_t)a.fb.sizeY;
   if (inImage && (!a.fb.taskError || a.fb.taskError[(y >> 3) * (((uint32_t)a.fb.sizeX + 7u) >> 3) + (x >> 3)] > a.fb.errorThreshold)) {
     ScreenSample ss;
-    defaultRenderPixel<RENDERER>(c, x, y, ss);
+    Mega<TEX>::template defaultRenderPixel<RENDERER>(c, x, y, ss);
     accumulateSample(a.fb, x, y, ss);
   }
   if (a.fb.rayCounters) {
@@ -1087,16 +1132,24 @@ extern "C" int ospcuda_render_frame(const OcWorld *d_world, const OcCamera *came
     a.ptIndirectLightSamples = (renderer->limitIndirectLightSamples && a.ptFirstBounceLightSamples >= 1) ? 1u : a.ptFirstBounceLightSamples;
     return renderPathTracerWavefront(a, owned);
   }
-  case OC_RENDERER_SCIVIS: renderFrameKernel<OC_RENDERER_SCIVIS><<<grid, block, 0, st>>>(a); break;
+  case OC_RENDERER_SCIVIS:
+    if (renderer->hasTextures) renderFrameKernel<OC_RENDERER_SCIVIS, true><<<grid, block, 0, st>>>(a);
+    else renderFrameKernel<OC_RENDERER_SCIVIS, false><<<grid, block, 0, st>>>(a);
+    break;
   case OC_RENDERER_AO: {
     // worlds without volumes: the ao renderer runs as a wavefront over the ray-queue TRACE kernel (pathtracer_wf.cuh);
     // with volumes the megakernel marches them (OSPCUDA_AO_MEGAKERNEL=1 forces it, for A/B)
     static const bool forceMega = getenv("OSPCUDA_AO_MEGAKERNEL") && atoi(getenv("OSPCUDA_AO_MEGAKERNEL")) > 0;
-    if (!renderer->worldHasVolumes && !forceMega) return renderPathTracerWavefront(a, owned, true);
-    renderFrameKernel<OC_RENDERER_AO><<<grid, block, 0, st>>>(a);
+    // (frames that reference textures take the frame kernel as well: it carries the ray cones)
+    if (!renderer->worldHasVolumes && !forceMega && !renderer->hasTextures) return renderPathTracerWavefront(a, owned, true);
+    if (renderer->hasTextures) renderFrameKernel<OC_RENDERER_AO, true><<<grid, block, 0, st>>>(a);
+    else renderFrameKernel<OC_RENDERER_AO, false><<<grid, block, 0, st>>>(a);
     break;
   }
-  case OC_RENDERER_DEBUG: renderFrameKernel<OC_RENDERER_DEBUG><<<grid, block, 0, st>>>(a); break;
+  case OC_RENDERER_DEBUG:
+    if (renderer->hasTextures) renderFrameKernel<OC_RENDERER_DEBUG, true><<<grid, block, 0, st>>>(a);
+    else renderFrameKernel<OC_RENDERER_DEBUG, false><<<grid, block, 0, st>>>(a);
+    break;
   default: return oc_set_error(cudaErrorInvalidValue, "ospcuda_render_frame: unknown renderer type");
   }
   oc_count_launch();

@@ -136,19 +136,19 @@ __device__ __forceinline__ void geometryPostIntersect(const OcGeometry *g, Diffe
     const vec3f va = get3f(g->vertex, i0), vb = get3f(g->vertex, i1), vc = get3f(g->vertex, i2),
                 vd = get3f(g->vertex, i3);
     dg.epsilon = reduce_max(vmax(vmax(vabs(va), vabs(vb)), vmax(vabs(vc), vabs(vd)))) * OC_ULP_EPSILON;
-    if (TEX) {
+    { // texture coordinates (TEX only) and tangents: along texture space when the mesh has texcoords, else along its edges
       bool tangents = flags & DG_TANGENTS;
-      if ((flags & (DG_TEXCOORD | DG_TANGENTS)) && g->texcoord.addr) {
+      if ((tangents || (TEX && (flags & DG_TEXCOORD))) && g->texcoord.addr) {
         const bool fv = g->flags & OC_GEOMFLAG_TEXCOORD_FACEVARYING;
         const vec2f a = get2f(g->texcoord, fv ? fo : i0), b = get2f(g->texcoord, fv ? fo + 1 : i1), d = get2f(g->texcoord, fv ? fo + 3 : i3);
-        if (flags & DG_TEXCOORD) {
+        if (TEX && (flags & DG_TEXCOORD)) {
           const vec2f c = get2f(g->texcoord, fv ? fo + 2 : i2);
           dg.st = uv.x * a + uv.y * b + uv.z * c + uv.w * d;
         }
         if (tangents && meshTexTangents(dg, a, b, d, va, vb, vd)) tangents = false;
       }
-      if (tangents) { dg.dPds = vb - va; dg.dPdt = vd - va; }
-    } else if (flags & DG_TANGENTS) dg.dPds = vb - va; // without texcoords (Mesh.ispc:170-173)
+      if (tangents) { dg.dPds = vb - va; dg.dPdt = vd - va; } // (Mesh.ispc:170-173)
+    }
   } else if (g->type == OC_GEOM_TRIANGLES) {
     const uint32_t i0 = get1ui(g->index, ray.primID, 0), i1 = get1ui(g->index, ray.primID, 1),
                    i2 = get1ui(g->index, ray.primID, 2);
@@ -168,16 +168,16 @@ __device__ __forceinline__ void geometryPostIntersect(const OcGeometry *g, Diffe
     }
     const vec3f va = get3f(g->vertex, i0), vb = get3f(g->vertex, i1), vc = get3f(g->vertex, i2);
     dg.epsilon = reduce_max(vmax(vmax(vabs(va), vabs(vb)), vabs(vc))) * OC_ULP_EPSILON;
-    if (TEX) {
+    {
       bool tangents = flags & DG_TANGENTS;
-      if ((flags & (DG_TEXCOORD | DG_TANGENTS)) && g->texcoord.addr) {
+      if ((tangents || (TEX && (flags & DG_TEXCOORD))) && g->texcoord.addr) {
         const bool fv = g->flags & OC_GEOMFLAG_TEXCOORD_FACEVARYING;
         const vec2f a = get2f(g->texcoord, fv ? fo : i0), b = get2f(g->texcoord, fv ? fo + 1 : i1), c = get2f(g->texcoord, fv ? fo + 2 : i2);
-        if (flags & DG_TEXCOORD) dg.st = uv.x * a + uv.y * b + uv.z * c;
+        if (TEX && (flags & DG_TEXCOORD)) dg.st = uv.x * a + uv.y * b + uv.z * c;
         if (tangents && meshTexTangents(dg, a, b, c, va, vb, vc)) tangents = false;
       }
       if (tangents) { dg.dPds = vb - va; dg.dPdt = vc - va; }
-    } else if (flags & DG_TANGENTS) dg.dPds = vb - va;
+    }
   } else if (g->type == OC_GEOM_SPHERES) {
     dg.epsilon = get4f(g->sphere, ray.primID).w * OC_ULP_EPSILON;
     if (TEX && (flags & DG_TEXCOORD) && g->texcoord.addr) dg.st = get2f(g->texcoord, ray.primID); // Spheres.ispc:39-41
@@ -269,10 +269,11 @@ __device__ __forceinline__ void postIntersect(const OcWorld *world, const OcRend
     dg.pixelFootprint = projConeWidth * world2tex * ren.mipBiasFactor;
   }
 }
+template <bool TEX = false>
 static __device__ __noinline__ void postIntersectNI(const OcWorld *world, const OcRenderer &ren, DifferentialGeometry &dg,
-    const Ray &ray, uint32_t flags)
+    const Ray &ray, uint32_t flags, RayCone *rayCone = nullptr)
 {
-  postIntersect(world, ren, dg, ray, flags);
+  postIntersect<TEX>(world, ren, dg, ray, flags, rayCone);
 }
 
 // ---- sampling helpers (math/sampling.ih) ---------------------------------------------------

@@ -1141,6 +1141,43 @@ const OcInstance *World::instDevGeo()
   return geoInstDev.as<OcInstance>();
 }
 
+// OcWorld.shadowOpaque: the host-side mirror of ptOccluderIsOpaque (pathtracer_wf.cuh) over every model of the world
+uint32_t World::computeShadowOpaque(const Renderer *renderer) const
+{
+  if (!instances) return 2u;
+  const std::vector<OcMaterial> &table = device.materialTableHost();
+  uint32_t level = 2u;
+  for (size_t i = 0; i < instances->size(); i++) {
+    Instance *in = dynamic_cast<Instance *>(instances->objectAt(i));
+    if (!in || !in->group || !in->group->geometricModels) continue;
+    Data *models = in->group->geometricModels.get();
+    for (size_t g = 0; g < models->size(); g++) {
+      GeometricModel *m = dynamic_cast<GeometricModel *>(models->objectAt(g));
+      if (!m || !m->geom) return 0u;
+      if (m->sh.color.addr) return 0u;
+      const uint32_t gf = m->geom->sh.flags;
+      if (gf & OC_GEOMFLAG_HAS_ALPHA) {
+        if (!(gf & OC_GEOMFLAG_ALPHA_ALL_ONE)) return 0u;
+        level = 1u;
+      }
+      for (uint32_t hm : m->hostMaterials) {
+        uint32_t slot = hm;
+        if (m->sh.materialMode == OC_MAT_FROM_RENDERER) {
+          if (!renderer) return 0u;
+          if (renderer->materialSlots.empty()) continue; // no material: opaque
+          slot = renderer->materialSlots[std::min<size_t>(hm, renderer->materialSlots.size() - 1)];
+        }
+        if (slot >= table.size()) return 0u;
+        const OcMaterial &mt = table[slot];
+        if (mt.hasTextures || mt.type == OC_MATERIAL_THINGLASS) return 0u;
+        if (mt.type == OC_MATERIAL_LUMINOUS && mt.transparency != 0.f) return 0u;
+        if (mt.type == OC_MATERIAL_OBJ && !(mt.d == 1.f && mt.Tf.x == 0.f && mt.Tf.y == 0.f && mt.Tf.z == 0.f)) return 0u;
+      }
+    }
+  }
+  return level;
+}
+
 const OcWorld *World::prepareFrame(const Renderer *renderer)
 {
   // models / transfer functions committed since the last frame: the groups take their new state over (Group::refreshSnapshots)
@@ -1161,6 +1198,10 @@ const OcWorld *World::prepareFrame(const Renderer *renderer)
       geoKey[0] = key[0]; geoKey[1] = key[1]; geoKey[2] = key[2];
       dirty = true;
     }
+  }
+  { // (every frame: a walk over the models and their material lists, no primitive data)
+    const uint32_t so = computeShadowOpaque(renderer);
+    if (so != sh.shadowOpaque) { sh.shadowOpaque = so; dirty = true; }
   }
   const bool useGeo = wantGeo && geoActive;
   if (useGeo != geoInUse) { geoInUse = useGeo; dirty = true; }
@@ -1245,8 +1286,8 @@ void Renderer::commit()
     uint32_t id = OC_DEBUG_TEST_FRAME;
     for (const auto &m : methods)
       if (method == m.name) id = m.id;
-    if (id == OC_DEBUG_TEX_COORD || id == OC_DEBUG_DPDT || id == OC_DEBUG_VOLUME)
-      throw std::runtime_error("cuda device: debug renderer method '" + method + "' is not supported (texCoord, dPdt, volume)");
+    if (id == OC_DEBUG_VOLUME)
+      throw std::runtime_error("cuda device: debug renderer method '" + method + "' is not supported");
     sh.debugMethod = id;
   }
   sh.spp = std::max(1, getParam<int>("pixelSamples", 1));

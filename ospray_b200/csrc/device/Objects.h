@@ -285,6 +285,7 @@ struct World : public ManagedObject
   uint32_t geoNumLights = 0, geoNumGeo = 0;
   void buildGeometryLights(const Renderer &renderer);
   const OcInstance *instDevGeo();
+  uint32_t computeShadowOpaque(const Renderer *renderer) const;
   const void *uploadedMaterials = nullptr;
   bool dirty = true;
   uint64_t seenEpoch = 0;

@@ -223,6 +223,22 @@ def emissive_cornell(transparency=0.0, textured=False):
     return s
 
 
+def texcoord_cornell():
+    """the cornell box (one model, as the builder makes it) with sheared texture coordinates on every quad: texture-space
+    tangents (Mesh.ispc:152-168) differ from the quad's edges"""
+    s = T.cornell_box()
+    g = s.instances[0].group.models[0].geometry
+    st = np.array([[0.0, 0.0], [1.5, 0.2], [1.8, 1.1], [0.3, 0.9]], np.float32)
+    g.vertex_texcoord = np.tile(st, (len(g.vertex) // 4, 1))
+    return s
+
+
+def lit(s):
+    """the scene under a distant + an ambient light (the scivis renderer ignores the cornell box's quad light)"""
+    s.lights = [T.LightSpec("distant", {"direction": (0.2, -0.7, 0.6), "intensity": 2.5}), T.LightSpec("ambient", {"intensity": 0.4})]
+    return s
+
+
 def backplate_scene():
     """renderer textures: map_backplate behind random spheres and map_maxDepth cutting the primary rays (Renderer.ispc:18-39)"""
     s = T.random_spheres(24, seed=3)
@@ -274,6 +290,16 @@ CASES = {
     "textured_bias_pt": (textured_cornell, "pathtracer", {"pixelSamples": 1, "mipMapBias": 1.5}, 1),
     "cutout_pt": (cutout_cornell, "pathtracer", {"pixelSamples": 2}, 1),
     "backplate_pt": (backplate_scene, "pathtracer", {"pixelSamples": 2, "backgroundColor": (0.1, 0.2, 0.3, 1.0)}, 1),
+    "textured_scivis": (lambda: lit(textured_cornell()), "scivis", {"pixelSamples": 2, "shadows": True, "aoSamples": 1}, 1),
+    "textured_ao": (textured_cornell, "ao", {"pixelSamples": 2, "aoSamples": 2}, 1),
+    "cutout_scivis": (lambda: lit(cutout_cornell()), "scivis", {"shadows": True, "aoSamples": 1}, 1),
+    "cutout_ao": (cutout_cornell, "ao", {"aoSamples": 1}, 1),
+    "backplate_scivis": (backplate_scene, "scivis", {"pixelSamples": 2}, 1),
+    "backplate_ao": (backplate_scene, "ao", {}, 1),
+    "debug_texCoord": (texcoord_cornell, "debug", {"method": "texCoord"}, 1),
+    "debug_dPdt": (texcoord_cornell, "debug", {"method": "dPdt"}, 1),
+    "debug_dPds_tex": (texcoord_cornell, "debug", {"method": "dPds"}, 1),
+    "debug_backplate": (backplate_scene, "debug", {"method": "eyeLight"}, 1),
     # emissive geometry: luminous material, geometry lights (pathtracer/GeometryLight.ispc) and the paths that run into them
     "emissive_pt": (emissive_cornell, "pathtracer", {"pixelSamples": 2}, 2),
     "emissive_nogeolights_pt": (emissive_cornell, "pathtracer", {"pixelSamples": 2, "geometryLights": False}, 1),
@@ -299,7 +325,8 @@ CASES = {
 REF_UNSUPPORTED = {"volume_geometry"}
 # Cases only the reference's own kernels check (the restatement in oracle.cpp does not sample textures)
 ORACLE_UNSUPPORTED = {"textured_pt", "textured_bias_pt", "cutout_pt", "backplate_pt", "emissive_pt", "emissive_nogeolights_pt",
-                      "emissive_transparent_pt"}
+                      "emissive_transparent_pt", "textured_scivis", "textured_ao", "cutout_scivis", "cutout_ao", "backplate_scivis",
+                      "backplate_ao", "debug_texCoord", "debug_dPdt", "debug_dPds_tex", "debug_backplate"}
 # Cases the cuda device does not render (none at present; the GPU parity tests skip what is listed here)
 DEVICE_UNSUPPORTED = set()
 # Volumes under the pathtracer: delta tracking takes hundreds of accept/reject decisions per path on logf / expf / lerp

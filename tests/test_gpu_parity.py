@@ -288,10 +288,10 @@ def test_pick_matches_oracle_primary_hit(osp):
 
 @pytest.mark.gpu
 def test_debug_renderer_refuses_unsupported_methods(osp):
-    """texCoord / dPdt / volume need data this device does not carry: the commit fails through the API's error convention
+    """the volume method needs data this device does not carry: the commit fails through the API's error convention
     (API.cpp:45-66) instead of rendering something else; unknown names fall back to the test frame like the reference
     (DebugRenderer.cpp:18-52)"""
-    for method in ("texCoord", "dPdt", "volume"):
+    for method in ("volume",):
         r = osp.Renderer("debug")
         r.set("method", method)
         with pytest.raises(osp.OSPRayError, match="not supported"):

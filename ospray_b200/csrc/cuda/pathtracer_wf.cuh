@@ -77,6 +77,11 @@ struct PtArgs
   uint32_t vol;           // the world holds volumes (host copy of OcWorld.hasVolumes): free-path sampling + transmittance
   uint32_t progressUnit, progressTotal; // ospGetProgress: what the SHADE / TAIL launch of this stage reports when it starts
   uint32_t shadowT0InB;   // any-hit rays start at shB[e].w instead of 0 (ao renderer: the ambient-occlusion rays start at dg.epsilon)
+  // pathtracer with ONE light sample per vertex, world without volumes: the TRACE lane that answers a shadow ray folds the
+  // answer into its path (and finishes a path that only waited for it) instead of leaving that to the next SHADE.
+  // foldInTrace: this TRACE launch does so; skipDoneAppend: this SHADE launch does not queue ended paths whose shadow ray it
+  // queued (the TRACE launch that follows takes care of them)
+  uint32_t foldInTrace, skipDoneAppend;
 };
 
 __device__ __forceinline__ void ptAppend(uint32_t *q, uint32_t *cnt, uint32_t p)
@@ -184,6 +189,7 @@ __device__ __forceinline__ void ptCountRays(const OcFrameBuffer &fb, uint32_t a,
 }
 
 #define PT_TRACE_BLOCK 128
+__device__ __forceinline__ void ptPrefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- volumes under the pathtracer ------------------------------------------------------------------------------------
 // pathtracer/volumes/VolumeSampler.ispc:13-282 in its single-volume-interval form (what the reference compiles for its GPU
@@ -505,6 +511,37 @@ __global__ void __launch_bounds__(128) ptGenKernel(const __grid_constant__ PtArg
   ptCountRays(fb, primary, 0u, 0u);
 }
 
+// The answer to the one shadow ray of path p (= shadow entry p: one light sample per vertex), folded where it is found:
+// unoccluded -> the sample's contribution joins the path's (same sum, same order as the fold in SHADE: there is one term);
+// opaque occluder -> nothing to add; anything else (transparent occluder) is left to SHADE's closest-hit loop. A path that
+// had ended and only waited for this answer is finished here (or handed back to the path queue when SHADE has to look).
+static __device__ __noinline__ void ptFoldShadowInTrace(const PtArgs &k, uint32_t p, uint32_t rec, uint32_t inst)
+{
+  const PtScratch &s = k.s;
+  const float4 cc = s.shC[p];
+  const vec3f lightContrib = make_vec3f(cc.x, cc.y, cc.z);
+  const bool miss = inst == OC_INVALID_ID;
+  const uint32_t flags = s.flags[p];
+  if (!miss && !ptOccluderIsOpaque(k.a.world, k.a.ren, rec, inst, reduce_max(lightContrib))) {
+    s.shHit[p] = make_uint2(rec, inst);
+    if (flags & PT_DONE) ptAppend(const_cast<uint32_t *>(k.pathIn), const_cast<uint32_t *>(k.cntPathIn), p | PT_Q_DONE);
+    return;
+  }
+  float4 con4 = s.con[p];
+  if (miss && reduce_max(lightContrib) > 0) {
+    const float w = s.shB[p].w;
+    // L = lightContrib * misWeight, then contribution + L: two roundings, as in SHADE's fold and in the reference
+    con4.x = __fadd_rn(con4.x, __fmul_rn(lightContrib.x, w)); con4.y = __fadd_rn(con4.y, __fmul_rn(lightContrib.y, w));
+    con4.z = __fadd_rn(con4.z, __fmul_rn(lightContrib.z, w));
+  }
+  if (flags & PT_DONE) {
+    ptFinishPath(k, p, make_vec3f(con4.x, con4.y, con4.z), s.thr[p].w);
+    return;
+  }
+  s.con[p] = con4;
+  s.flags[p] = flags & ~PT_HAS_SHADOW;
+}
+
 // ---- TRACE ------------------------------------------------------------------------------------------------------------
 // Persistent-thread ray queue. The rays of one bounce -- the shadow queue, then the continuation rays of the path queue --
 // form one index space [0, n). A warp reserves PT_TRACE_CHUNK consecutive indices at a time (one atomic on the fetch cursor
@@ -549,8 +586,10 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptTraceKernel(cons
       // ---- results of the walks that ended since the last time ----
       if (fin) {
         fin = false;
-        if (id & PT_SHADOW_RAY) s.shHit[id & ~PT_SHADOW_RAY] = make_uint2(tr.h.rec, tr.h.inst);
-        else {
+        if (id & PT_SHADOW_RAY) {
+          if (k.foldInTrace) ptFoldShadowInTrace(k, id & ~PT_SHADOW_RAY, tr.h.rec, tr.h.inst);
+          else s.shHit[id & ~PT_SHADOW_RAY] = make_uint2(tr.h.rec, tr.h.inst);
+        } else {
           Ray r;
           const float4 o4 = *src.po, d4 = *src.pd;
           r.org = make_vec3f(o4.x, o4.y, o4.z); r.dir = make_vec3f(d4.x, d4.y, d4.z); r.t0 = d4.w;
@@ -582,6 +621,9 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptTraceKernel(cons
               const size_t e = id & ~PT_SHADOW_RAY;
               src.po = s.shA + e; src.pd = s.shB + e;
               nShadow++;
+              if (k.foldInTrace) { // what the fold reads when this walk ends: asked for now, there when needed
+                ptPrefetchL2(s.shC + e); ptPrefetchL2(s.flags + e); ptPrefetchL2(s.con + e);
+              }
             } else {
               src.po = s.rayO + id; src.pd = s.rayD + id;
               nCont++;
@@ -614,6 +656,47 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptTraceKernel(cons
   ptCountRays(k.a.fb, 0u, k.depth == 0 ? 0u : nCont, nShadow);
 }
 
+// The shadow rays of the previous vertex folded into one radiance term, in sample order. TRACE folds the common case itself
+// (ptFoldShadowInTrace); this runs for several light samples per vertex, transparent occluders and worlds with volumes.
+// (Inlined: out of line it costs the shade step 1 % on C1, tools/ab_c1.sh.)
+template <bool VOL, bool TEX>
+__device__ __forceinline__ vec3f ptFoldShadows(const PtArgs &k, uint32_t p, uint32_t *stackBase, uint32_t &extraShadow)
+{
+  const PtScratch &s = k.s;
+  const OcRenderer &ren = k.a.ren;
+  const OcWorld *world = k.a.world;
+  vec3f L = make_vec3f(0.f);
+  for (uint32_t j = 0; j < s.nls; j++) {
+    const size_t e = (size_t)p * s.nls + j;
+    const float4 cc = s.shC[e];
+    if (cc.w == 0.f) continue;
+    vec3f lightContrib = make_vec3f(cc.x, cc.y, cc.z);
+    bool resolved = false;
+    float shadowT0 = 0.f;
+    if (isfinite(lightContrib.x) && isfinite(lightContrib.y) && isfinite(lightContrib.z)) {
+      const uint2 occ = s.shHit[e];
+      if (occ.y == OC_INVALID_ID) resolved = true; // unoccluded: lightContrib unchanged
+      else if (ptOccluderIsOpaque(world, ren, occ.x, occ.y, reduce_max(lightContrib))) { lightContrib = make_vec3f(0.f); resolved = true; }
+    }
+    if (!resolved) {
+      const float4 r = ptTransparentShadowSlow<TEX>(k, e, lightContrib.x, lightContrib.y, lightContrib.z, stackBase, PT_TRACE_BLOCK);
+      lightContrib = make_vec3f(r.x, r.y, r.z);
+      extraShadow += __float_as_uint(r.w);
+      if (VOL) shadowT0 = s.shT0[e];
+    }
+    if (reduce_max(lightContrib) > 0) {
+      const float4 b = s.shB[e];
+      if (VOL) { // b.w = ls.pdf, cc.w = fe.pdf: the weight carries the transmittance estimates
+        const float4 a = s.shA[e];
+        const float w = ptVolumeShadowWeight(k, p, make_vec3f(a.x, a.y, a.z), make_vec3f(b.x, b.y, b.z), shadowT0, a.w, b.w, cc.w == FLT_MIN ? 0.f : cc.w);
+        L = L + w * lightContrib;
+      } else
+        L = L + lightContrib * b.w;
+    }
+  }
+  return L;
+}
+
 // ---- SHADE ------------------------------------------------------------------------------------------------------------
 // One path, one vertex: returns 0 when the path finished here, 1 when it goes on to the next bounce, 2 when it has ended
 // but shadow rays of this vertex are pending (the next SHADE folds them in and finishes it).
@@ -635,35 +718,7 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
     // sample order like nextEventEstimation's L (NextEventEstimation.ispc:140-156). TRACE made ONE any-hit query per ray:
     // any opaque occluder makes the product of transparencies exactly 0, whatever lies in front of it; only a non-opaque
     // find takes the reference's closest-hit loop.
-    vec3f L = make_vec3f(0.f);
-    for (uint32_t j = 0; j < s.nls; j++) {
-      const size_t e = (size_t)p * s.nls + j;
-      const float4 cc = s.shC[e];
-      if (cc.w == 0.f) continue;
-      vec3f lightContrib = make_vec3f(cc.x, cc.y, cc.z);
-      bool resolved = false;
-      float shadowT0 = 0.f;
-      if (isfinite(lightContrib.x) && isfinite(lightContrib.y) && isfinite(lightContrib.z)) {
-        const uint2 occ = s.shHit[e];
-        if (occ.y == OC_INVALID_ID) resolved = true; // unoccluded: lightContrib unchanged
-        else if (ptOccluderIsOpaque(world, ren, occ.x, occ.y, reduce_max(lightContrib))) { lightContrib = make_vec3f(0.f); resolved = true; }
-      }
-      if (!resolved) {
-        const float4 r = ptTransparentShadowSlow<TEX>(k, e, lightContrib.x, lightContrib.y, lightContrib.z, stackBase, PT_TRACE_BLOCK);
-        lightContrib = make_vec3f(r.x, r.y, r.z);
-        extraShadow += __float_as_uint(r.w);
-        if (VOL) shadowT0 = s.shT0[e];
-      }
-      if (reduce_max(lightContrib) > 0) {
-        const float4 b = s.shB[e];
-        if (VOL) { // b.w = ls.pdf, cc.w = fe.pdf: the weight carries the transmittance estimates
-          const float4 a = s.shA[e];
-          const float w = ptVolumeShadowWeight(k, p, make_vec3f(a.x, a.y, a.z), make_vec3f(b.x, b.y, b.z), shadowT0, a.w, b.w, cc.w == FLT_MIN ? 0.f : cc.w);
-          L = L + w * lightContrib;
-        } else
-          L = L + lightContrib * b.w;
-      }
-    }
+    const vec3f L = ptFoldShadows<VOL, TEX>(k, p, stackBase, extraShadow);
     con4.x += L.x; con4.y += L.y; con4.z += L.z;
     if (flags & PT_DONE) {
       ptFinishPath(k, p, make_vec3f(con4.x, con4.y, con4.z), thr4.w);
@@ -720,7 +775,7 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
   }
 
   // ---- one iteration of samplePath()'s loop, after the trace (PathSampler.ispc:196-412) ----
-  bool alive = false, hasShadow = false;
+  bool alive = false, hasShadow = false, shadowQueued = false;
   do {
     const bool surface = !volume && hadHit(ray);
     const bool environment = !surface && !volume;
@@ -830,8 +885,10 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
               valid = true;
               hasShadow = true;
               // a contribution that is not finite takes the closest-hit loop in the fold (the reference's arithmetic on it)
-              if (QUEUE && isfinite(unshaded.x) && isfinite(unshaded.y) && isfinite(unshaded.z))
+              if (QUEUE && isfinite(unshaded.x) && isfinite(unshaded.y) && isfinite(unshaded.z)) {
                 ptAppend(k.shadowOut, k.cntShadowOut, PT_SHADOW_RAY | (uint32_t)e);
+                shadowQueued = true;
+              }
             }
           }
         }
@@ -885,7 +942,7 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
   s.flags[p] = ((depth + 1) & PT_DEPTH_MASK) | (scatteringEvents << PT_SCAT_SHIFT) | (straightPath ? PT_STRAIGHT : 0u)
       | (specularTransmissionPath ? PT_SPECTRANS : 0u) | (firstBounceLight ? PT_FIRSTBOUNCE : 0u) | (hasShadow ? PT_HAS_SHADOW : 0u)
       | (alive ? 0u : PT_DONE);
-  return alive ? 1u : 2u;
+  return alive ? 1u : ((QUEUE && shadowQueued) ? 3u : 2u); // 3: ended, and its shadow ray sits in the queue
 }
 
 // MIN_BLOCKS: resident CTAs per SM the register budget is set for (4: 128 registers, 5: 96, 6: 80)
@@ -900,7 +957,7 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptShadeKernel(cons
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t p = k.pathIn[i] & ~PT_Q_DONE;
     const uint32_t r = ptShadeStep<VOL, true, TEX>(k, p, s_stack + threadIdx.x, extraShadow);
-    if (r) ptAppend(k.pathOut, k.cntPathOut, r == 2u ? (p | PT_Q_DONE) : p);
+    if (r == 1u || r == 2u || (r == 3u && !k.skipDoneAppend)) ptAppend(k.pathOut, k.cntPathOut, r >= 2u ? (p | PT_Q_DONE) : p);
   }
   ptCountRays(k.a.fb, 0u, 0u, extraShadow);
 }

@@ -1004,6 +1004,8 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles, bool
   const uint32_t pathsPerBatch = tilesPerBatch * 4096u;
   const uint32_t tailAuto = (uint32_t)std::max(1, fa.ren.rouletteDepth + (pathsPerBatch >= 768u * 1024u ? 2 : 0));
   const uint32_t tailFrom = tailEnv == 0 ? 0xffffffffu : tailEnv > 0 ? (uint32_t)tailEnv : tailAuto;
+  static const bool foldEnv = !(getenv("OSPCUDA_PT_FOLD_IN_TRACE") && atoi(getenv("OSPCUDA_PT_FOLD_IN_TRACE")) == 0);
+  const bool foldInTrace = !ao && !hasVol && nls == 1 && foldEnv;
   const uint32_t progressStages = ao ? 2u : std::min(maxDepth + 1u, tailFrom == 0xffffffffu ? maxDepth + 1u : tailFrom + 1u);
   k.progressTotal = ((ownedTiles + tilesPerBatch - 1) / tilesPerBatch) * (uint32_t)fa.ren.spp * progressStages;
   k.progressUnit = 0;
@@ -1049,6 +1051,7 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles, bool
         k.pathIn = k.s.pathQ[q]; k.cntPathIn = C(d, 0);
         k.shadowIn = d == 0 ? nullptr : k.s.shadowQ[q]; k.cntShadowIn = d == 0 ? nullptr : C(d, 2);
         k.fetchCursor = C(d, 3);
+        k.foldInTrace = foldInTrace ? 1u : 0u;
         {
           ProfScope ps(0, st);
           switch (g_pt.traceVariant) {
@@ -1064,6 +1067,8 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles, bool
         // SHADE(d): same path queue in, queues of stage d+1 out
         k.pathOut = k.s.pathQ[q ^ 1u]; k.cntPathOut = C(d + 1, 0);
         k.shadowOut = k.s.shadowQ[q ^ 1u]; k.cntShadowOut = C(d + 1, 2);
+        // (only when a TRACE launch follows: the tail kernel traces and folds the shadow rays of the paths it is handed)
+        k.skipDoneAppend = (foldInTrace && d + 1 <= maxDepth && d + 1 < tailFrom) ? 1u : 0u;
         {
           ProfScope ps(1, st);
           if (ao) aoShadeKernel<<<g_pt.aoShadeBlocks, 128, 0, st>>>(k);

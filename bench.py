@@ -40,8 +40,9 @@ WORKLOAD = "C1: ospray_testing cornell_box, pathtracer, 1024x1024, 1 spp/frame, 
 # them as HBM traffic would credit cache hits to the memory roofline.
 ALGO_BYTES = {
     "GEN": 132,     # per path: flags 4 + thr/con/lastP/lastN/sZ 80 + smp 8 + ray 32 + queue entry 4, all written
-    "TRACE": 60,    # per ray: queue entry 4 + ray 32 read; result written (continuation 36 B, shadow 8 B: mean 24 on C1)
-    "SHADE": 360,   # per path vertex: state read 148 + shadow fold 40 + state written 112 + shadow ray emitted 52 + frame 8
+    "TRACE": 84,    # per ray: queue entry 4 + ray 32 read; continuation: hit 36 B written; shadow: folded into its path (shC 16 +
+                    # flags 4 + con 16 read, con 16 + flags 4 written = 56 B); C1 mix ~ 60 % continuation: mean 48
+    "SHADE": 320,   # per path vertex: state read 148 + state written 112 + shadow ray emitted 52 + frame 8 (the fold moved to TRACE)
     "TAIL": 420,    # per path vertex carried by the tail kernel: SHADE's state + the ray / hit round trip it keeps in L1
     "POST": 20,     # per pixel: float4 accumulation buffer read 16 + sRGBA8 written 4
 }

@@ -326,6 +326,8 @@ typedef struct {
   uint32_t hasTextures;
   /* pathtracer parameter geometryLights (PathTracer.cpp:44): emissive geometry is sampled as light sources */
   uint32_t geometryLights;
+  /* host-side copy of OcWorld.shadowOpaque of the world this frame renders (set per ospRenderFrame) */
+  uint32_t worldShadowOpaque;
 } OcRenderer;
 
 /* framebuffer (reference: LocalFBShared.h, FrameBufferShared.h; LocalFB.cpp:49-180) */

@@ -17,14 +17,27 @@ inline float dot3(F3 a, F3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 inline F3 sub3(F3 a, F3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
 inline F3 madd3(F3 a, float s, F3 b) { return {a.x + s * b.x, a.y + s * b.y, a.z + s * b.z}; }
 
-// basis == 0: linear over (v0, v1); else Catmull-Rom over (v0..v3), the segment spanning v1 -> v2
+// the cubic basis polynomials of geometry/Curves.ispc:40-75 at t (basis = OSPCurveBasis: 1 Bezier, 2 B-spline, 4 Catmull-Rom):
+// weights b[0..3] of the four control points and the common factor c
+inline void curveBasisWeights(int basis, float t, float b[4], float &c)
+{
+  const float s = 1.0f - t;
+  const float s2 = s * s, t2 = t * t, s2t = s2 * t, t2s = t2 * s, s3 = s2 * s, t3 = t2 * t;
+  if (basis == 1) { b[0] = s3; b[1] = 3.0f * s2t; b[2] = 3.0f * t2s; b[3] = t3; c = 1.0f; }
+  else if (basis == 2) {
+    b[0] = s3; b[1] = (4.0f * s3 + t3) + (12.0f * s2t + 6.0f * t2s); b[2] = (4.0f * t3 + s3) + (12.0f * t2s + 6.0f * s2t); b[3] = t3;
+    c = 1.0f / 6.0f;
+  } else { b[0] = -s2t; b[1] = 2.0f + t2 * (3.0f * t - 5.0f); b[2] = 2.0f + s2 * (3.0f * s - 5.0f); b[3] = -t2s; c = 0.5f; }
+}
+// basis == 0: linear over (v0, v1); else the cubic basis over (v0..v3)
 inline F4 curveEval(int basis, F4 v0, F4 v1, F4 v2, F4 v3, float t)
 {
   const float s = 1.0f - t;
   if (basis == 0) return {s * v0.x + t * v1.x, s * v0.y + t * v1.y, s * v0.z + t * v1.z, s * v0.w + t * v1.w};
-  const float s2 = s * s, t2 = t * t, s2t = s2 * t, t2s = t2 * s;
-  const float b0 = -s2t, b1 = 2.0f + t2 * (3.0f * t - 5.0f), b2 = 2.0f + s2 * (3.0f * s - 5.0f), b3 = -t2s;
-  auto comb = [&](float a, float b, float c, float d) { return 0.5f * (((b0 * a + b1 * b) + b2 * c) + b3 * d); };
+  float bw[4], cf;
+  curveBasisWeights(basis, t, bw, cf);
+  const float b0 = bw[0], b1 = bw[1], b2 = bw[2], b3 = bw[3];
+  auto comb = [&](float a, float b, float c, float d) { return cf * (((b0 * a + b1 * b) + b2 * c) + b3 * d); };
   return {comb(v0.x, v1.x, v2.x, v3.x), comb(v0.y, v1.y, v2.y, v3.y), comb(v0.z, v1.z, v2.z, v3.z), comb(v0.w, v1.w, v2.w, v3.w)};
 }
 

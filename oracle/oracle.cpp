@@ -413,7 +413,7 @@ bool traceGroup(const OcGroup *g, Ray &ray, uint32_t instID, bool occl)
           const V4 c = need ? get4f(geo->sphere, first + k) : V4{0, 0, 0, 0};
           cv[k] = {c.x, c.y, c.z, c.w};
         }
-        const int basis = geo->curveBasis == OC_CURVE_BASIS_LINEAR ? 0 : 1;
+        const int basis = (int)geo->curveBasis;
         for (uint32_t k = 0; k < curvecap::CURVE_SUBDIV; k++) {
           const float u0 = (float)k * (1.f / curvecap::CURVE_SUBDIV), u1 = (float)(k + 1) * (1.f / curvecap::CURVE_SUBDIV);
           const curvecap::F4 a4 = curvecap::curveEval(basis, cv[0], cv[1], cv[2], cv[3], u0), b4 = curvecap::curveEval(basis, cv[0], cv[1], cv[2], cv[3], u1);
@@ -528,9 +528,9 @@ void geometryPostIntersect(const OcGeometry *g, DG &dg, const Ray &ray, uint32_t
       if (g->curveBasis == OC_CURVE_BASIS_LINEAR) dg.color = lerp(t, v0, v1);
       else {
         const V4 v2 = get4f(g->color, index + 2), v3 = get4f(g->color, index + 3);
-        const float s = 1.0f - t, s2 = s * s, t2 = t * t, s2t = s2 * t, t2s = t2 * s;
-        const float b0 = -s2t, b1 = 2.0f + t2 * (3.0f * t - 5.0f), b2 = 2.0f + s2 * (3.0f * s - 5.0f), b3 = -t2s;
-        dg.color = 0.5f * (((b0 * v0 + b1 * v1) + b2 * v2) + b3 * v3);
+        float bw[4], cf;
+        curvecap::curveBasisWeights((int)g->curveBasis, t, bw, cf);
+        dg.color = cf * (((bw[0] * v0 + bw[1] * v1) + bw[2] * v2) + bw[3] * v3);
       }
     }
   }

@@ -130,7 +130,7 @@ class Renderer(C.Structure):
                 ("aoRadius", C.c_float), ("aoIntensity", C.c_float), ("volumeSamplingRate", C.c_float),
                 ("worldNumLights", C.c_uint32), ("debugMethod", C.c_uint32), ("worldHasVolumes", C.c_uint32),
                 ("mipBiasFactor", C.c_float), ("backplate", C.POINTER(Texture2D)), ("maxDepthTexture", C.POINTER(Texture2D)),
-                ("hasTextures", C.c_uint32), ("geometryLights", C.c_uint32)]
+                ("hasTextures", C.c_uint32), ("geometryLights", C.c_uint32), ("worldShadowOpaque", C.c_uint32)]
 
 
 class FrameBuffer(C.Structure):
@@ -228,9 +228,15 @@ def curve_eval(basis, v, t):
     if basis == 0:
         return s * v[0] + t * v[1]
     s2, t2 = s * s, t * t
-    s2t, t2s = s2 * t, t2 * s
-    b0, b1, b2, b3 = -s2t, f(2.0) + t2 * (f(3.0) * t - f(5.0)), f(2.0) + s2 * (f(3.0) * s - f(5.0)), -t2s
-    return f(0.5) * (((b0 * v[0] + b1 * v[1]) + b2 * v[2]) + b3 * v[3])
+    s2t, t2s, s3, t3 = s2 * t, t2 * s, s2 * s, t2 * t
+    if basis == 1:    # Bezier
+        b0, b1, b2, b3, c = s3, f(3.0) * s2t, f(3.0) * t2s, t3, f(1.0)
+    elif basis == 2:  # B-spline
+        b0, b1 = s3, (f(4.0) * s3 + t3) + (f(12.0) * s2t + f(6.0) * t2s)
+        b2, b3, c = (f(4.0) * t3 + s3) + (f(12.0) * t2s + f(6.0) * s2t), t3, f(1.0) / f(6.0)
+    else:             # Catmull-Rom
+        b0, b1, b2, b3, c = -s2t, f(2.0) + t2 * (f(3.0) * t - f(5.0)), f(2.0) + s2 * (f(3.0) * s - f(5.0)), -t2s, f(0.5)
+    return c * (((b0 * v[0] + b1 * v[1]) + b2 * v[2]) + b3 * v[3])
 
 
 def curve_bounds(pos_radius, index, basis, subdiv=8):
@@ -601,7 +607,7 @@ class Scene:
         if gs.type == "curve":
             pr = np.ascontiguousarray(gs.curve_vertex, np.float32)
             idx = np.ascontiguousarray(gs.curve_index, np.uint32).reshape(-1, 1)
-            g.type, g.numPrims, g.curveBasis = 4, len(idx), {"linear": 0, "catmull-rom": 4}[gs.curve_basis]
+            g.type, g.numPrims, g.curveBasis = 4, len(idx), {"linear": 0, "bezier": 1, "bspline": 2, "catmull-rom": 4}[gs.curve_basis]
             g.sphere, g.index = _data1d(pr, self.keep), _data1d(idx, self.keep)
             if gs.vertex_color is not None:
                 g.color = _data1d(np.asarray(gs.vertex_color, np.float32), self.keep)

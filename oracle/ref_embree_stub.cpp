@@ -146,7 +146,7 @@ bool traceGroup(const RTCSceneTy *s, uint32_t instIdx, RTCRayHit &rh, const Call
           const float *c = (const float *)(geo->sphere.addr + (int64_t)(first + k) * geo->sphere.byteStride);
           cv[k] = {c[0], c[1], c[2], c[3]};
         }
-        const int basis = geo->curveBasis == OC_CURVE_BASIS_LINEAR ? 0 : 1;
+        const int basis = (int)geo->curveBasis;
         for (uint32_t k = 0; k < curvecap::CURVE_SUBDIV; k++) {
           const float u0 = (float)k * (1.f / curvecap::CURVE_SUBDIV), u1 = (float)(k + 1) * (1.f / curvecap::CURVE_SUBDIV);
           const curvecap::F4 a4 = curvecap::curveEval(basis, cv[0], cv[1], cv[2], cv[3], u0), b4 = curvecap::curveEval(basis, cv[0], cv[1], cv[2], cv[3], u1);

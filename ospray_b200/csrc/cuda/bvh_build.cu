@@ -56,10 +56,20 @@ __device__ __forceinline__ vec4f curveEval(const OcGeometry *g, uint32_t first, 
         __fadd_rn(__fmul_rn(s, v0.z), __fmul_rn(t, v1.z)), __fadd_rn(__fmul_rn(s, v0.w), __fmul_rn(t, v1.w)));
   const vec4f v2 = get4f(g->sphere, first + 2), v3 = get4f(g->sphere, first + 3);
   const float s2 = __fmul_rn(s, s), t2 = __fmul_rn(t, t), s2t = __fmul_rn(s2, t), t2s = __fmul_rn(t2, s);
-  const float b0 = -s2t, b1 = __fadd_rn(2.0f, __fmul_rn(t2, __fsub_rn(__fmul_rn(3.0f, t), 5.0f))),
-              b2 = __fadd_rn(2.0f, __fmul_rn(s2, __fsub_rn(__fmul_rn(3.0f, s), 5.0f))), b3 = -t2s;
+  const float s3 = __fmul_rn(s2, s), t3 = __fmul_rn(t2, t);
+  float b0, b1, b2, b3, cf;
+  if (g->curveBasis == OC_CURVE_BASIS_BEZIER) {
+    b0 = s3; b1 = __fmul_rn(3.0f, s2t); b2 = __fmul_rn(3.0f, t2s); b3 = t3; cf = 1.0f;
+  } else if (g->curveBasis == OC_CURVE_BASIS_BSPLINE) {
+    b0 = s3; b3 = t3; cf = 1.0f / 6.0f;
+    b1 = __fadd_rn(__fadd_rn(__fmul_rn(4.0f, s3), t3), __fadd_rn(__fmul_rn(12.0f, s2t), __fmul_rn(6.0f, t2s)));
+    b2 = __fadd_rn(__fadd_rn(__fmul_rn(4.0f, t3), s3), __fadd_rn(__fmul_rn(12.0f, t2s), __fmul_rn(6.0f, s2t)));
+  } else {
+    b0 = -s2t; b1 = __fadd_rn(2.0f, __fmul_rn(t2, __fsub_rn(__fmul_rn(3.0f, t), 5.0f)));
+    b2 = __fadd_rn(2.0f, __fmul_rn(s2, __fsub_rn(__fmul_rn(3.0f, s), 5.0f))); b3 = -t2s; cf = 0.5f;
+  }
   auto comb = [&](float a, float b, float c, float d) {
-    return __fmul_rn(0.5f, __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(b0, a), __fmul_rn(b1, b)), __fmul_rn(b2, c)), __fmul_rn(b3, d)));
+    return __fmul_rn(cf, __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(b0, a), __fmul_rn(b1, b)), __fmul_rn(b2, c)), __fmul_rn(b3, d)));
   };
   return make_vec4f(comb(v0.x, v1.x, v2.x, v3.x), comb(v0.y, v1.y, v2.y, v3.y), comb(v0.z, v1.z, v2.z, v3.z), comb(v0.w, v1.w, v2.w, v3.w));
 }

@@ -29,6 +29,7 @@ enum : uint32_t {
   PT_DEPTH_MASK = 0xffu, PT_SCAT_SHIFT = 8, PT_SCAT_MASK = 0xff00u,
   PT_STRAIGHT = 1u << 16, PT_SPECTRANS = 1u << 17, PT_FIRSTBOUNCE = 1u << 18, PT_DONE = 1u << 19, PT_HAS_SHADOW = 1u << 20
 };
+#define PT_DEAD 0xffffffffu       // flags of a path that TRACE finished (its queue entry remains and is skipped)
 #define PT_SHADOW_RAY 0x80000000u // ray-queue ids: bit 31 set = shadow entry [slot * nls + i], clear = continuation ray of path `slot`
 #define PT_Q_DONE 0x40000000u     // path-queue entries: the path has ended and only waits for its shadow rays (no continuation ray)
 
@@ -77,11 +78,10 @@ struct PtArgs
   uint32_t vol;           // the world holds volumes (host copy of OcWorld.hasVolumes): free-path sampling + transmittance
   uint32_t progressUnit, progressTotal; // ospGetProgress: what the SHADE / TAIL launch of this stage reports when it starts
   uint32_t shadowT0InB;   // any-hit rays start at shB[e].w instead of 0 (ao renderer: the ambient-occlusion rays start at dg.epsilon)
-  // pathtracer with ONE light sample per vertex, world without volumes: the TRACE lane that answers a shadow ray folds the
-  // answer into its path (and finishes a path that only waited for it) instead of leaving that to the next SHADE.
-  // foldInTrace: this TRACE launch does so; skipDoneAppend: this SHADE launch does not queue ended paths whose shadow ray it
-  // queued (the TRACE launch that follows takes care of them)
-  uint32_t foldInTrace, skipDoneAppend;
+  // pathtracer with ONE light sample per vertex, a world without volumes whose surfaces are all opaque occluders: the TRACE
+  // lane that answers a shadow ray folds the answer into its path and finishes a path that only waited for it (its entry in
+  // the path queue stays and is skipped by the next SHADE through the PT_DEAD flags word)
+  uint32_t foldInTrace;
 };
 
 __device__ __forceinline__ void ptAppend(uint32_t *q, uint32_t *cnt, uint32_t p)
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(128) ptGenKernel(const __grid_constant__ PtArg
 // The answer to the one shadow ray of path p (= shadow entry p: one light sample per vertex), folded where it is found:
 // unoccluded -> the sample's contribution joins the path's (same sum, same order as the fold in SHADE: there is one term);
 // opaque occluder -> nothing to add; anything else (transparent occluder) is left to SHADE's closest-hit loop. A path that
-// had ended and only waited for this answer is finished here (or handed back to the path queue when SHADE has to look).
+// had ended and only waited for this answer is finished here and marked PT_DEAD.
 static __device__ __noinline__ void ptFoldShadowInTrace(const PtArgs &k, uint32_t p, uint32_t rec, uint32_t inst)
 {
   const PtScratch &s = k.s;
@@ -524,8 +524,7 @@ static __device__ __noinline__ void ptFoldShadowInTrace(const PtArgs &k, uint32_
   const uint32_t flags = s.flags[p];
   if (!miss && !ptOccluderIsOpaque(k.a.world, k.a.ren, rec, inst, reduce_max(lightContrib))) {
     s.shHit[p] = make_uint2(rec, inst);
-    if (flags & PT_DONE) ptAppend(const_cast<uint32_t *>(k.pathIn), const_cast<uint32_t *>(k.cntPathIn), p | PT_Q_DONE);
-    return;
+    return; // (the path's entry is in the path queue: the next SHADE walks the reference's closest-hit loop and finishes it)
   }
   float4 con4 = s.con[p];
   if (miss && reduce_max(lightContrib) > 0) {
@@ -536,6 +535,7 @@ static __device__ __noinline__ void ptFoldShadowInTrace(const PtArgs &k, uint32_
   }
   if (flags & PT_DONE) {
     ptFinishPath(k, p, make_vec3f(con4.x, con4.y, con4.z), s.thr[p].w);
+    s.flags[p] = PT_DEAD; // its entry in the path queue is skipped by the next SHADE
     return;
   }
   s.con[p] = con4;
@@ -712,6 +712,7 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
   Ctx c(k.a.world, k.a.ren, k.a.cam, k.a.fb, dummy);
 
   uint32_t flags = s.flags[p];
+  if (QUEUE && flags == PT_DEAD) return 0u;
   float4 thr4 = s.thr[p], con4 = s.con[p];
   if (flags & PT_HAS_SHADOW) {
     // shadow rays of the previous vertex: transparentShadow (TransparentShadow.ispc:18-85) per light sample, summed in
@@ -775,7 +776,7 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
   }
 
   // ---- one iteration of samplePath()'s loop, after the trace (PathSampler.ispc:196-412) ----
-  bool alive = false, hasShadow = false, shadowQueued = false;
+  bool alive = false, hasShadow = false;
   do {
     const bool surface = !volume && hadHit(ray);
     const bool environment = !surface && !volume;
@@ -885,10 +886,8 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
               valid = true;
               hasShadow = true;
               // a contribution that is not finite takes the closest-hit loop in the fold (the reference's arithmetic on it)
-              if (QUEUE && isfinite(unshaded.x) && isfinite(unshaded.y) && isfinite(unshaded.z)) {
+              if (QUEUE && isfinite(unshaded.x) && isfinite(unshaded.y) && isfinite(unshaded.z))
                 ptAppend(k.shadowOut, k.cntShadowOut, PT_SHADOW_RAY | (uint32_t)e);
-                shadowQueued = true;
-              }
             }
           }
         }
@@ -942,7 +941,7 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
   s.flags[p] = ((depth + 1) & PT_DEPTH_MASK) | (scatteringEvents << PT_SCAT_SHIFT) | (straightPath ? PT_STRAIGHT : 0u)
       | (specularTransmissionPath ? PT_SPECTRANS : 0u) | (firstBounceLight ? PT_FIRSTBOUNCE : 0u) | (hasShadow ? PT_HAS_SHADOW : 0u)
       | (alive ? 0u : PT_DONE);
-  return alive ? 1u : ((QUEUE && shadowQueued) ? 3u : 2u); // 3: ended, and its shadow ray sits in the queue
+  return alive ? 1u : 2u;
 }
 
 // MIN_BLOCKS: resident CTAs per SM the register budget is set for (4: 128 registers, 5: 96, 6: 80)
@@ -957,7 +956,7 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptShadeKernel(cons
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t p = k.pathIn[i] & ~PT_Q_DONE;
     const uint32_t r = ptShadeStep<VOL, true, TEX>(k, p, s_stack + threadIdx.x, extraShadow);
-    if (r == 1u || r == 2u || (r == 3u && !k.skipDoneAppend)) ptAppend(k.pathOut, k.cntPathOut, r >= 2u ? (p | PT_Q_DONE) : p);
+    if (r) ptAppend(k.pathOut, k.cntPathOut, r == 2u ? (p | PT_Q_DONE) : p);
   }
   ptCountRays(k.a.fb, 0u, 0u, extraShadow);
 }

@@ -191,9 +191,13 @@ __device__ __forceinline__ void geometryPostIntersect(const OcGeometry *g, Diffe
         dg.color = (1.f - t) * v0 + t * v1;
       else {
         const vec4f v2 = get4f(g->color, index + 2), v3 = get4f(g->color, index + 3);
-        const float s = 1.0f - t, s2 = s * s, t2 = t * t, s2t = s2 * t, t2s = t2 * s;
-        const float b0 = -s2t, b1 = 2.0f + t2 * (3.0f * t - 5.0f), b2 = 2.0f + s2 * (3.0f * s - 5.0f), b3 = -t2s;
-        dg.color = 0.5f * (b0 * v0 + b1 * v1 + b2 * v2 + b3 * v3);
+        const float s = 1.0f - t, s2 = s * s, t2 = t * t, s2t = s2 * t, t2s = t2 * s, s3 = s2 * s, t3 = t2 * t;
+        float b0, b1, b2, b3, cf;
+        if (g->curveBasis == OC_CURVE_BASIS_BEZIER) { b0 = s3; b1 = 3.0f * s2t; b2 = 3.0f * t2s; b3 = t3; cf = 1.0f; }
+        else if (g->curveBasis == OC_CURVE_BASIS_BSPLINE) {
+          b0 = s3; b1 = (4.0f * s3 + t3) + (12.0f * s2t + 6.0f * t2s); b2 = (4.0f * t3 + s3) + (12.0f * t2s + 6.0f * s2t); b3 = t3; cf = 1.0f / 6.0f;
+        } else { b0 = -s2t; b1 = 2.0f + t2 * (3.0f * t - 5.0f); b2 = 2.0f + s2 * (3.0f * s - 5.0f); b3 = -t2s; cf = 0.5f; }
+        dg.color = cf * (b0 * v0 + b1 * v1 + b2 * v2 + b3 * v3);
       }
     }
   }

@@ -169,6 +169,7 @@ OSPFuture CudaDevice::renderFrame(OSPFrameBuffer _fb, OSPRenderer _r, OSPCamera 
     rsh.worldNumLights = w->sh.numLights;
     rsh.worldHasVolumes = w->sh.hasVolumes;
     rsh.worldNumLights = w->sh.numLights; // (with the geometry lights prepareFrame added)
+    rsh.worldShadowOpaque = w->sh.shadowOpaque;
     rsh.hasTextures = (texturedMaterials > 0 || emissiveMaterials > 0 || rsh.backplate || rsh.maxDepthTexture) ? 1u : 0u;
     if (!finished) checkCuda(ospcuda_render_frame(dw, &c->sh, &rsh, &fb->sh), "render kernel");
     checkCuda(ospcuda_event_record(f->evRendered), "event record");

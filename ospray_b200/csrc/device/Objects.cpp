@@ -353,8 +353,8 @@ void Geometry::commit()
     const uint32_t curveType = getParam<uint32_t>("type", OSP_UNKNOWN_CURVE_TYPE);
     const uint32_t basis = getParam<uint32_t>("basis", OSP_UNKNOWN_CURVE_BASIS);
     if (curveType != OSP_ROUND) throw std::runtime_error("cuda device: only OSP_ROUND curves are supported");
-    if (basis != OSP_LINEAR && basis != OSP_CATMULL_ROM)
-      throw std::runtime_error("cuda device: curve basis must be OSP_LINEAR or OSP_CATMULL_ROM");
+    if (basis != OSP_LINEAR && basis != OSP_CATMULL_ROM && basis != OSP_BEZIER && basis != OSP_BSPLINE)
+      throw std::runtime_error("cuda device: curve basis must be OSP_LINEAR, OSP_BEZIER, OSP_BSPLINE or OSP_CATMULL_ROM (Hermite curves carry tangents and are not built)");
     const uint32_t need = basis == OSP_LINEAR ? 2u : 4u;
     for (size_t i = 0; i < indexData->size(); i++)
       if ((size_t)indexData->at<uint32_t>(i) + need > vertexData->size())

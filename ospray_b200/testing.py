@@ -419,7 +419,7 @@ def _geometry(g: GeometrySpec):
         if g.vertex_color is not None:
             geo.set("vertex.color", g.vertex_color)
         geo.set("type", osp.Typed(osp.OSP_UINT, 0))                                               # OSP_ROUND
-        geo.set("basis", osp.Typed(osp.OSP_UINT, {"linear": 0, "catmull-rom": 4}[g.curve_basis]))  # OSPCurveBasis
+        geo.set("basis", osp.Typed(osp.OSP_UINT, {"linear": 0, "bezier": 1, "bspline": 2, "catmull-rom": 4}[g.curve_basis]))  # OSPCurveBasis
     return geo.commit()
 
 

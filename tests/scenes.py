@@ -249,6 +249,25 @@ def backplate_scene():
     return s
 
 
+def cubic_curves(basis):
+    """round Bezier / B-spline curves (geometry/Curves.ispc:40-75): a few 4-point segments with per-vertex colour and radius"""
+    rng = np.random.default_rng(17)
+    pts, idx = [], []
+    for k in range(8):
+        base = rng.uniform(-0.8, 0.8, 3)
+        first = len(pts)
+        for j in range(6):
+            p = base + 0.35 * j * np.array([np.cos(0.9 * k), 0.3 * np.sin(k + j), np.sin(0.9 * k)]) + 0.08 * rng.normal(size=3)
+            pts.append(np.append(p, 0.07 + 0.015 * ((j + k) % 3)))
+        idx += [first, first + 1, first + 2] if basis == "bspline" else [first, first + 3 - 1]
+    pts = np.array(pts, np.float32)
+    col = np.concatenate([rng.uniform(0.3, 1.0, (len(pts), 3)), np.ones((len(pts), 1))], axis=1).astype(np.float32)
+    geom = T.GeometrySpec("curve", curve_vertex=pts, curve_index=np.array(idx, np.uint32), vertex_color=col, curve_basis=basis)
+    grp = T.GroupSpec(models=[T.ModelSpec(geom, T.MaterialSpec())])
+    return T.SceneSpec(instances=[T.InstanceSpec(grp)],
+                       lights=[T.LightSpec("distant", {"direction": (-0.2, -0.6, 0.7), "intensity": 2.0}), T.LightSpec("ambient", {"intensity": 0.5})])
+
+
 # name -> (spec builder, renderer kind, renderer params, frames[, {camera: kind, height: h}])
 CASES = {
     "cornell_pt": (T.cornell_box, "pathtracer", {"pixelSamples": 2}, 2),
@@ -272,6 +291,8 @@ CASES = {
     "streamlines_pt": (few_streamlines, "pathtracer", {"pixelSamples": 2}, 1),
     "streamlines_scivis": (few_streamlines, "scivis", {"shadows": True, "aoSamples": 1}, 1),
     "linear_curves_ao": (linear_curves, "ao", {"aoSamples": 2}, 1),
+    "bezier_curves_scivis": (lambda: cubic_curves("bezier"), "scivis", {"shadows": True, "aoSamples": 1}, 1),
+    "bspline_curves_pt": (lambda: cubic_curves("bspline"), "pathtracer", {"pixelSamples": 2}, 1),
     "instanced_scivis": (instanced_boxes_and_spheres, "scivis", {"shadows": True}, 1),
     "instanced_pt": (instanced_boxes_and_spheres, "pathtracer", {"pixelSamples": 1}, 1),
     "mesh_ao": (lambda: T.box_mesh(5), "ao", {"aoSamples": 2}, 1),

@@ -114,7 +114,8 @@ typedef struct {
   float xform2f[6];
 } OcTextureParam;
 
-enum { OC_MATERIAL_OBJ = 0, OC_MATERIAL_OTHER = 1, OC_MATERIAL_THINGLASS = 2, OC_MATERIAL_LUMINOUS = 3 };
+enum { OC_MATERIAL_OBJ = 0, OC_MATERIAL_OTHER = 1, OC_MATERIAL_THINGLASS = 2, OC_MATERIAL_LUMINOUS = 3, OC_MATERIAL_METAL = 4,
+       OC_MATERIAL_PLASTIC = 5 };
 /* material (reference: ispc::OBJ, render/materials/OBJShared.h, OBJ.cpp:30-66; ispc::ThinGlass,
  * render/materials/ThinGlassShared.h, ThinGlass.cpp:33-48: eta = 1/ior, attenuationScale = thickness /
  * max(attenuationDistance, EPS), attenuation = log(attenuationColor) * attenuationScale) */
@@ -133,6 +134,10 @@ typedef struct {
   OcVec3f emission;
   float transparency;
   uint32_t isEmissive;
+  /* metal (ispc::Metal, render/materials/MetalShared.h, Metal.cpp:30-76; RGB form): Kd = eta, Ks = k, Ns = roughness, mapNs =
+   * map_roughness. plastic (ispc::Plastic, PlasticShared.h, Plastic.cpp): Kd = pigmentColor, eta, Ns = roughness.
+   * microfacetTables: the device's albedo tables (ospcuda_microfacet_albedo_tables; MicrofacetAlbedoTables.ispc) */
+  const float *microfacetTables;
   uint32_t hasTextures;        /* any of the maps below is set (kernels without texture support skip them all) */
   float bumpRot[4];            /* OBJ.cpp:43-44: orthogonal part of map_bump's 2D transform, transposed (vx, vy) */
   /* OBJ: map_d, map_kd, map_ks, map_ns, map_bump (OBJShared.h:19-31); thinGlass: mapKd = map_attenuationColor */
@@ -442,6 +447,10 @@ OSPCUDA_API int ospcuda_trace(const OcWorld *d_world, OcRayHit *d_rays, uint32_t
  * get4f(TextureParam, dg) for n (st, pixelFootprint) pairs (reference: texture/TextureParam.ispc:10-22 ->
  * Texture2D_get, texture/Texture2D.ispc:133-158). `d_param->tex` and the level pointers inside it are device memory
  * (what a committed texture2d / material holds); d_st = 2n floats, d_footprint = n floats, d_out = 4n floats. */
+/* the microfacet albedo tables of the energy compensation (reference: precomputeMicrofacetAlbedoTables,
+ * render/bsdfs/MicrofacetAlbedoTables.ispc:148-158), computed once per device on first use; *d_tables = the float block
+ * (layout: csrc/cuda/microfacet.cuh OC_MFT_*), numFloats its length */
+OSPCUDA_API int ospcuda_microfacet_albedo_tables(const float **d_tables, uint32_t *numFloats);
 OSPCUDA_API int ospcuda_texture_sample(const OcTextureParam *param, const float *d_st, const float *d_footprint, uint32_t n,
     float *d_out);
 

@@ -65,7 +65,7 @@ class TextureParam(C.Structure):
 class Material(C.Structure):
     _fields_ = [("type", C.c_uint32), ("d", C.c_float), ("Kd", Vec3), ("Ks", Vec3), ("Ns", C.c_float), ("Tf", Vec3),
                 ("eta", C.c_float), ("attenuation", Vec3), ("attenuationScale", C.c_float), ("emission", Vec3),
-                ("transparency", C.c_float), ("isEmissive", C.c_uint32), ("hasTextures", C.c_uint32),
+                ("transparency", C.c_float), ("isEmissive", C.c_uint32), ("microfacetTables", C.c_void_p), ("hasTextures", C.c_uint32),
                 ("bumpRot", C.c_float * 4), ("mapD", TextureParam), ("mapKd", TextureParam), ("mapKs", TextureParam),
                 ("mapNs", TextureParam), ("mapBump", TextureParam)]
 
@@ -546,6 +546,15 @@ class Scene:
                 kd, ks, tf = kd / total, ks / total, tf / total
             m.type, m.d, m.Ns = 0, float(ms.d), float(ms.ns)
             m.Kd, m.Ks, m.Tf = Vec3(*map(float, kd)), Vec3(*map(float, ks)), Vec3(*map(float, tf))
+        elif ms.type == "metal":  # render/materials/Metal.cpp:30-76, RGB form (Kd = eta, Ks = k, Ns = roughness)
+            m.type = 4
+            m.Kd, m.Ks, m.Ns = Vec3(*map(float, np.asarray(ms.metal_eta, np.float32))), Vec3(*map(float, np.asarray(ms.metal_k, np.float32))), float(np.float32(ms.roughness))
+            if ms.map_roughness is not None:
+                m.mapNs = texture_param(ms.map_roughness, self.keep, self.mipmaps)
+                m.hasTextures = 1
+        elif ms.type == "plastic":  # render/materials/Plastic.cpp:28-38
+            m.type = 5
+            m.Kd, m.eta, m.Ns = Vec3(*map(float, np.asarray(ms.pigment_color, np.float32))), float(np.float32(1.0) / np.float32(ms.eta)), float(np.float32(ms.roughness))
         elif ms.type == "luminous":  # render/materials/Luminous.cpp:33-45
             m.type = 3
             em = (np.asarray(ms.color, np.float32) * np.float32(ms.intensity)).astype(np.float32)

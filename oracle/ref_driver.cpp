@@ -31,6 +31,9 @@
 #include "render/materials/OBJShared.h"
 #include "render/materials/ThinGlassShared.h"
 #include "render/materials/LuminousShared.h"
+#include "render/materials/MetalShared.h"
+#include "render/materials/PlasticShared.h"
+#include "render/bsdfs/MicrofacetAlbedoTablesShared.h"
 #include "render/pathtracer/GeometryLightShared.h"
 #include "texture/Texture2DShared.h"
 #include "common/DifferentialGeometry.ih"
@@ -84,6 +87,7 @@ void LocalFB_accumulateSample(FrameBuffer *fb, const ScreenSample &screenSample,
 void LUTPixelFilter_buildLUT(void *self);
 float Distribution1D_create(const int size, float *cdf);
 int GeometricModel_gatherEmissivePrimIDs(void *model, void *renderer, void *instance, int *primIDs, float *distribution, float &pdf);
+void precomputeMicrofacetAlbedoTables(void *tables);
 void Mesh_getAreas(const Geometry *const, const int32 *const, const int32, const affine3f &, float *const);
 void Spheres_getAreas(const Geometry *const, const int32 *const, const int32, const affine3f &, float *const);
 }
@@ -164,6 +168,7 @@ struct Scene
   std::deque<OBJ> objs; std::deque<ThinGlass> glasses; std::vector<Material *> allMaterials;
   std::deque<Texture2D> textures;
   std::deque<Luminous> luminous; std::deque<GeometryLight> geoLights;
+  std::deque<Metal> metals; std::deque<Plastic> plastics;
   std::deque<std::vector<int>> geoPrimIDs; std::deque<std::vector<float>> geoDistributions;
   std::vector<float> geoCDF;
   std::vector<Instance *> instancePtrs;
@@ -260,6 +265,28 @@ TextureParam makeTextureParam(std::deque<Texture2D> &store, const OcTextureParam
   return r;
 }
 
+// the reference's microfacet albedo tables, computed once per process by the reference's own precompute routine
+// (render/bsdfs/MicrofacetAlbedoTables.ispc:148-158; storage as MicrofacetAlbedoTables.cpp allocates it)
+MicrofacetAlbedoTables *refAlbedoTables()
+{
+  static MicrofacetAlbedoTables t;
+  static std::vector<float> store;
+  static bool done = false;
+  if (!done) {
+    const size_t a = MICROFACET_ALBEDO_TABLE_SIZE, d = MICROFACET_DIELECTRIC_ALBEDO_TABLE_SIZE, sh = MICROFACET_SHEEN_ALBEDO_TABLE_SIZE;
+    store.assign(a * a + a + 3 * (d * d * d + d * d) + sh * sh, 0.f);
+    float *p = store.data();
+    t.albedo_dir = p; p += a * a; t.albedo_avg = p; p += a;
+    t.dielectricAlbedo_dir = p; p += d * d * d; t.dielectricAlbedo_avg = p; p += d * d;
+    t.dielectricRcpEtaAlbedo_dir = p; p += d * d * d; t.dielectricRcpEtaAlbedo_avg = p; p += d * d;
+    t.dielectricReflectionAlbedo_dir = p; p += d * d * d; t.dielectricReflectionAlbedo_avg = p; p += d * d;
+    t.sheenAlbedo_dir = p;
+    precomputeMicrofacetAlbedoTables(&t);
+    done = true;
+  }
+  return &t;
+}
+
 void buildScene(Scene &s, const OcWorld *w, const OcRenderer *ren)
 {
   // materials: render/materials/OBJ.cpp:30-66 (values arrive already normalised by the commit)
@@ -271,6 +298,23 @@ void buildScene(Scene &s, const OcWorld *w, const OcRenderer *ren)
       g.eta = m.eta; g.attenuation = v3(m.attenuation); g.attenuationScale = m.attenuationScale;
       g.attenuationColorMap = makeTextureParam(s.textures, m.mapKd);
       s.allMaterials.push_back(&g.super);
+      continue;
+    }
+    if (m.type == OC_MATERIAL_METAL) { // render/materials/Metal.cpp:30-76, RGB form
+      s.metals.emplace_back();
+      Metal &mt = s.metals.back();
+      mt.spectral = false; mt.etaRGB = v3(m.Kd); mt.kRGB = v3(m.Ks); mt.roughness = m.Ns;
+      mt.roughnessMap = makeTextureParam(s.textures, m.mapNs);
+      mt.super.microfacetAlbedoTables = refAlbedoTables();
+      s.allMaterials.push_back(&mt.super);
+      continue;
+    }
+    if (m.type == OC_MATERIAL_PLASTIC) { // render/materials/Plastic.cpp:28-38 (eta arrives as 1 / ior)
+      s.plastics.emplace_back();
+      Plastic &pl = s.plastics.back();
+      pl.pigmentColor = v3(m.Kd); pl.eta = m.eta; pl.roughness = m.Ns;
+      pl.super.microfacetAlbedoTables = refAlbedoTables();
+      s.allMaterials.push_back(&pl.super);
       continue;
     }
     if (m.type == OC_MATERIAL_LUMINOUS) { // render/materials/Luminous.cpp:33-45 (committed values)

@@ -845,8 +845,9 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
     if (depth >= ren.maxDepth || scatteringEvents >= (uint32_t)ren.maxScatteringEvents) break;
 
     ObjBSDF bsdf;
+    ExtBSDF xbsdf; // metal / plastic state (extended-material kernels only)
     if (!volume) {
-      OBJ_getBSDF<TEX>(bsdf, dg);
+      if (!(TEX && Ext_getBSDF(bsdf, xbsdf, dg))) OBJ_getBSDF<TEX>(bsdf, dg);
       if (!bsdf.valid) break;
     }
 
@@ -874,7 +875,8 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
           ls.weight = ls.weight / lightSelectionProb;
           ls.pdf *= lightSelectionProb;
           if (!(reduce_max(ls.weight) <= 0.0f || ls.pdf <= 0.0f)) {
-            const EvalRes fe = volume ? HenyeyGreenstein_eval(vmodel->anisotropy, wo, ls.dir) : OBJ_eval(bsdf, wo, ls.dir);
+            const EvalRes fe = volume ? HenyeyGreenstein_eval(vmodel->anisotropy, wo, ls.dir)
+                : (TEX && bsdf.kind != BSDF_KIND_OBJ) ? Ext_eval(bsdf, xbsdf, wo, ls.dir) : OBJ_eval(bsdf, wo, ls.dir);
             if (!(reduce_max(fe.value) <= 0.0f)) {
               vec3f org = dg.P;
               if (!volume && dot(dg.Ng, ls.dir) < 0.f) org = org - (2.0f * dg.epsilon) * dg.Ng;
@@ -899,7 +901,8 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
     float ss;
     uint32_t uu3;
     const vec2f sb = LDSampler_getNext4Samples(ld, ss, uu3);
-    SampleRes fs = volume ? HenyeyGreenstein_sample(vmodel->anisotropy, wo, sb) : OBJ_sample(bsdf, wo, sb, ss);
+    SampleRes fs = volume ? HenyeyGreenstein_sample(vmodel->anisotropy, wo, sb)
+        : (TEX && bsdf.kind != BSDF_KIND_OBJ) ? Ext_sample(bsdf, xbsdf, wo, sb, ss) : OBJ_sample(bsdf, wo, sb, ss);
     if (!volume) {
       const bool sameSide = dot(fs.wi, dg.Ng) >= 0.f;
       const bool reflection = fs.type & SC_REFLECTION;

@@ -1162,6 +1162,59 @@ extern "C" int ospcuda_render_frame(const OcWorld *d_world, const OcCamera *came
 }
 
 namespace oc {
+// precomputeMicrofacetAlbedoTables (MicrofacetAlbedoTables.ispc:34-160): one thread per directional table entry integrates
+// its 32 x 32 stratified samples (MicrofacetAlbedo.ih:131-190); the averages follow by the trapezoidal rule over cosThetaO
+__global__ void albedoTablesDirKernel(float *t)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = 32; // sqrt(1024) samples per dimension
+  int which, idx;
+  if (i < OC_MFA_SIZE * OC_MFA_SIZE) { which = 0; idx = (int)i; }
+  else if (i < OC_MFA_SIZE * OC_MFA_SIZE + 3u * OC_MFD_SIZE * OC_MFD_SIZE * OC_MFD_SIZE) {
+    const uint32_t j = i - OC_MFA_SIZE * OC_MFA_SIZE;
+    which = 1 + (int)(j / (OC_MFD_SIZE * OC_MFD_SIZE * OC_MFD_SIZE)); idx = (int)(j % (OC_MFD_SIZE * OC_MFD_SIZE * OC_MFD_SIZE));
+  } else return;
+  float cosThetaO, roughness, eta = 1.f;
+  float *dst;
+  if (which == 0) {
+    cosThetaO = (float)(idx % OC_MFA_SIZE) / (OC_MFA_SIZE - 1); roughness = (float)(idx / OC_MFA_SIZE) / (OC_MFA_SIZE - 1);
+    dst = t + OC_MFT_ALBEDO_DIR + idx;
+  } else {
+    const int ic = idx % OC_MFD_SIZE, ie = (idx / OC_MFD_SIZE) % OC_MFD_SIZE, ir = idx / (OC_MFD_SIZE * OC_MFD_SIZE);
+    cosThetaO = (float)ic / (OC_MFD_SIZE - 1); roughness = (float)ir / (OC_MFD_SIZE - 1);
+    const float f = (float)ie / (OC_MFD_SIZE - 1);
+    // dielectric / reflection tables: eta in [1/3, 1]; rcp-eta table: eta in [1, 3]
+    const float minEta = which == 2 ? 1.f : 1.f / 3.f, maxEta = which == 2 ? 3.f : 1.f;
+    eta = (1.f - f) * minEta + f * maxEta;
+    dst = t + (which == 1 ? OC_MFT_DIEL_DIR : which == 2 ? OC_MFT_DIELRCP_DIR : OC_MFT_DIELREFL_DIR) + idx;
+  }
+  const GGX g = makeGGX(roughness, 0.f);
+  float sum = 0.f;
+  for (int a = 0; a < n; a++)
+    for (int b = 0; b < n; b++) {
+      const vec2f s = make_vec2f(fminf(((float)a + 0.5f) / n, 1.f - 1e-6f), fminf(((float)b + 0.5f) / n, 1.f - 1e-6f));
+      sum += which == 0 ? mfAlbedoSample(cosThetaO, g, s) : mfDielAlbedoSample(cosThetaO, eta, g, s, which == 3);
+    }
+  *dst = fminf(sum / (n * n), 1.f);
+}
+__global__ void albedoTablesAvgKernel(float *t)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float *dir; float *avg; int size;
+  if (i < OC_MFA_SIZE) { dir = t + OC_MFT_ALBEDO_DIR + i * OC_MFA_SIZE; avg = t + OC_MFT_ALBEDO_AVG + i; size = OC_MFA_SIZE; }
+  else if (i < OC_MFA_SIZE + 3u * OC_MFD_SIZE * OC_MFD_SIZE) {
+    const uint32_t j = i - OC_MFA_SIZE, w = j / (OC_MFD_SIZE * OC_MFD_SIZE), r = j % (OC_MFD_SIZE * OC_MFD_SIZE);
+    dir = t + (w == 0 ? OC_MFT_DIEL_DIR : w == 1 ? OC_MFT_DIELRCP_DIR : OC_MFT_DIELREFL_DIR) + r * OC_MFD_SIZE;
+    avg = t + (w == 0 ? OC_MFT_DIEL_AVG : w == 1 ? OC_MFT_DIELRCP_AVG : OC_MFT_DIELREFL_AVG) + r; size = OC_MFD_SIZE;
+  } else return;
+  const int n = 1024 + 1; // MicrofacetAlbedoTable_integrateAvg (:10-32)
+  float sum = 0.f;
+  for (int k = 0; k < n; k++) {
+    const float cosThetaO = (float)k / (n - 1);
+    sum += interp1D(cosThetaO * (size - 1), dir, size) * cosThetaO * ((k == 0 || k == n - 1) ? 0.5f : 1.f);
+  }
+  *avg = fminf(2.f * (sum / (n - 1)), 1.f);
+}
 __global__ void textureSampleKernel(OcTextureParam tp, const float *st, const float *fp, uint32_t n, float4 *out)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1170,6 +1223,27 @@ __global__ void textureSampleKernel(OcTextureParam tp, const float *st, const fl
   out[i] = make_float4(v.x, v.y, v.z, v.w);
 }
 } // namespace oc
+
+extern "C" int ospcuda_microfacet_albedo_tables(const float **d_tables, uint32_t *numFloats)
+{
+  static float *tables[32] = {nullptr}; // per CUDA device of the process
+  int dev = 0;
+  cudaGetDevice(&dev);
+  float *&t = tables[dev & 31];
+  if (!t) {
+    OC_TRY(cudaMalloc(&t, OC_MFT_TOTAL * sizeof(float)));
+    cudaStream_t st = (cudaStream_t)ospcuda_stream();
+    const uint32_t nDir = OC_MFA_SIZE * OC_MFA_SIZE + 3u * OC_MFD_SIZE * OC_MFD_SIZE * OC_MFD_SIZE;
+    oc::albedoTablesDirKernel<<<(nDir + 127) / 128, 128, 0, st>>>(t);
+    const uint32_t nAvg = OC_MFA_SIZE + 3u * OC_MFD_SIZE * OC_MFD_SIZE;
+    oc::albedoTablesAvgKernel<<<(nAvg + 127) / 128, 128, 0, st>>>(t);
+    oc_count_launch(); oc_count_launch();
+    OC_TRY(cudaStreamSynchronize(st));
+  }
+  if (d_tables) *d_tables = t;
+  if (numFloats) *numFloats = OC_MFT_TOTAL;
+  return oc_check(cudaGetLastError(), "ospcuda_microfacet_albedo_tables");
+}
 
 extern "C" int ospcuda_texture_sample(const OcTextureParam *param, const float *d_st, const float *d_footprint, uint32_t n, float *d_out)
 {

@@ -337,7 +337,9 @@ struct ObjBSDF
   bool valid;
   bool thinGlass;          // RobustThinDielectric (materials/ThinGlass.ispc): eta in `ns`, attenuation in `Kd`
   bool pureTransmission;   // a lone Transmission BSDF (materials/Luminous.ispc:18-35): T in `T`
+  uint32_t kind;           // BSDF_KIND_*: 0 = the cases above; the others only exist in the extended-material kernels
 };
+enum { BSDF_KIND_OBJ = 0, BSDF_KIND_CONDUCTOR, BSDF_KIND_MICROFACET_CONDUCTOR, BSDF_KIND_PLASTIC_SMOOTH, BSDF_KIND_PLASTIC_ROUGH };
 
 // render/Material.ih:25-37
 __device__ __forceinline__ linear3f makeShadingFrame(const DifferentialGeometry &dg)
@@ -396,6 +398,12 @@ __device__ __forceinline__ vec3f expf3(vec3f v) { return make_vec3f(expf(v.x), e
 __device__ __forceinline__ vec3f logf3(vec3f v) { return make_vec3f(logf(v.x), logf(v.y), logf(v.z)); }
 __device__ __forceinline__ vec3f sqr3(vec3f v) { return v * v; }
 __device__ __forceinline__ vec3f rcp3(vec3f v) { return make_vec3f(1.f / v.x, 1.f / v.y, 1.f / v.z); }
+} // namespace oc
+#include "microfacet.cuh"
+namespace oc {
+// state of the microfacet-family BSDFs (metal, plastic): kept apart from ObjBSDF so that the OBJ path's registers stay as they are
+struct ExtBSDF { ConductorBSDF cond; LayerParams layer; LambertSub lambert; };
+
 // ThinGlass.ispc:17-30
 template <bool TEX = false>
 __device__ __forceinline__ vec3f ThinGlass_getAttenuation(const OcMaterial *m, const DifferentialGeometry &dg)
@@ -427,6 +435,7 @@ __device__ __forceinline__ void OBJ_getBSDF(ObjBSDF &b, const DifferentialGeomet
   b.valid = false;
   b.thinGlass = false;
   b.pureTransmission = false;
+  b.kind = BSDF_KIND_OBJ;
   if (TEX && m && m->type == OC_MATERIAL_LUMINOUS) { // Luminous_getBSDF: no BSDF unless the emitter is transparent
     if (m->transparency > 0.0f) {
       b.valid = true;
@@ -637,6 +646,71 @@ __device__ __forceinline__ SampleRes OBJ_sample(const ObjBSDF &b, vec3f wo, vec2
   res.weight = e.value * (1.f / res.pdf);
   return res;
 }
+// ---- metal and plastic (extended-material kernels only) -------------------------------------------------------------
+// Metal_getBSDF (materials/Metal.ispc:18-46, RGB form) and Plastic_getBSDF (materials/Plastic.ispc:25-67): fills `b` (frame,
+// albedo, scattering type, kind) and the family state `x`; false: not one of these materials
+__device__ __forceinline__ bool Ext_getBSDF(ObjBSDF &b, ExtBSDF &x, const DifferentialGeometry &dg)
+{
+  const OcMaterial *m = dg.material;
+  if (!m || (m->type != OC_MATERIAL_METAL && m->type != OC_MATERIAL_PLASTIC)) return false;
+  b.valid = true;
+  b.frame = frame(dg.Ns);
+  b.importanceSum = 1.f; b.impL = b.impT = b.impS = 0.f;
+  b.Kd = b.T = b.ks = b.specWeight = make_vec3f(0.f); b.ns = 0.f;
+  if (m->type == OC_MATERIAL_METAL) {
+    x.cond.frame = b.frame;
+    x.cond.eta = toV(m->Kd); x.cond.k = toV(m->Ks);
+    x.cond.tables = m->microfacetTables;
+    if (m->Ns == 0.0f) {
+      b.kind = BSDF_KIND_CONDUCTOR;
+      b.albedo = make_vec3f(0.f); // Fresnel_dispatch_evalAvg of the RGB conductor is 0 (Fresnel.ih:307-320)
+      b.scatteringType = SC_SPECULAR_REFLECTION;
+    } else {
+      float roughness = m->Ns;
+      if (m->mapNs.tex) roughness = roughness * texParamGet4f(m->mapNs, dg.st, dg.pixelFootprint).x;
+      b.kind = BSDF_KIND_MICROFACET_CONDUCTOR;
+      x.cond.Eavg = mfAlbedoAvg(x.cond.tables, roughness);
+      x.cond.fmsScale = make_vec3f(0.f); // sqr(Favg) * Eavg / (1 - Favg * (1 - Eavg)) with Favg = 0
+      x.cond.mf = makeGGX(roughness, 0.f);
+      x.cond.roughness = roughness;
+      b.albedo = make_vec3f(0.f);
+      b.scatteringType = SC_GLOSSY_REFLECTION;
+    }
+    return true;
+  }
+  x.lambert.init(b.frame, toV(m->Kd));
+  if (m->Ns == 0.0f) {
+    b.kind = BSDF_KIND_PLASTIC_SMOOTH;
+    DielectricLayer_init(x.layer, x.lambert.albedo, x.lambert.scatteringType, m->eta, make_vec3f(1.0f), 1.0f, 1.0f);
+  } else {
+    b.kind = BSDF_KIND_PLASTIC_ROUGH;
+    MicrofacetDielectricLayer_init(x.layer, m->microfacetTables, x.lambert.albedo, x.lambert.scatteringType, m->eta, make_vec3f(1.0f), 1.0f,
+        m->Ns, 0.f, 1.0f);
+  }
+  b.albedo = x.layer.albedo;
+  b.scatteringType = x.layer.scatteringType;
+  return true;
+}
+static __device__ __noinline__ EvalRes Ext_eval(const ObjBSDF &b, const ExtBSDF &x, vec3f wo, vec3f wi)
+{
+  EvalRes e; e.value = make_vec3f(0.f); e.pdf = 0.f;
+  switch (b.kind) {
+  case BSDF_KIND_MICROFACET_CONDUCTOR: return MicrofacetConductor_eval(x.cond, wo, wi);
+  case BSDF_KIND_PLASTIC_SMOOTH: return DielectricLayer_eval(x.layer, b.frame.vz, x.lambert, wo, wi);
+  case BSDF_KIND_PLASTIC_ROUGH: return MicrofacetDielectricLayer_eval(x.layer, b.frame, x.lambert, wo, wi);
+  default: return e; // smooth conductor: purely specular
+  }
+}
+static __device__ __noinline__ SampleRes Ext_sample(const ObjBSDF &b, const ExtBSDF &x, vec3f wo, vec2f s, float ss)
+{
+  switch (b.kind) {
+  case BSDF_KIND_CONDUCTOR: return Conductor_sample(x.cond, wo);
+  case BSDF_KIND_MICROFACET_CONDUCTOR: return MicrofacetConductor_sample(x.cond, wo, s);
+  case BSDF_KIND_PLASTIC_SMOOTH: return DielectricLayer_sample(x.layer, b.frame.vz, x.lambert, wo, s, ss);
+  default: return MicrofacetDielectricLayer_sample(x.layer, b.frame, x.lambert, wo, s, ss);
+  }
+}
+
 // materials/OBJ.ispc:93-111, materials/ThinGlass.ispc:52-64
 template <bool TEX = false>
 __device__ __forceinline__ vec3f materialTransparency(const DifferentialGeometry &dg, vec3f rayDir)

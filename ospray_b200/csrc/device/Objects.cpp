@@ -379,6 +379,7 @@ Material::Material(CudaDevice &d, const std::string &t) : device(d), type(t), sl
 Material::~Material()
 {
   if (wasEmissive) device.emissiveMaterials--;
+  if (wasExtended) device.emissiveMaterials--;
   if (texD || texKd || texKs || texNs || texBump) device.texturedMaterials--;
   device.freeMaterialSlot(slot);
 }
@@ -405,6 +406,7 @@ static void linear2fOrthogonal(float m[4]) // vx = (m[0], m[1]), vy = (m[2], m[3
 void Material::commit()
 {
   OcMaterial m{};
+  bool extended = false; // needs the extended-material kernels and the microfacet albedo tables
   const bool hadTextures = texD || texKd || texKs || texNs || texBump;
   texD = texKd = texKs = texNs = texBump = nullptr;
   if (type == "obj") {
@@ -437,6 +439,22 @@ void Material::commit()
     m.eta = 1.f / eta;
     m.attenuationScale = thickness * (1.f / std::max(attenuationDistance, 1e-5f));
     m.attenuation = toOc(make_vec3f(std::log(acf.x), std::log(acf.y), std::log(acf.z)) * m.attenuationScale);
+  } else if (type == "metal") {
+    // render/materials/Metal.cpp:30-76, RGB form (eta / k per channel; default aluminium, math/spectrum.h:41-48)
+    if (getParamObjectRaw("ior")) throw std::runtime_error("cuda device: metal with spectral 'ior' data is not supported (use eta / k)");
+    m.type = OC_MATERIAL_METAL;
+    m.mapNs = getTextureParam("map_roughness", texNs);
+    m.Kd = toOc(getParam<vec3f>("eta", make_vec3f(1.47f, 0.984f, 0.602f)));
+    m.Ks = toOc(getParam<vec3f>("k", make_vec3f(7.64f, 6.55f, 5.36f)));
+    m.Ns = getParam<float>("roughness", texNs ? 1.f : 0.1f);
+    extended = true;
+  } else if (type == "plastic") {
+    // render/materials/Plastic.cpp:28-38
+    m.type = OC_MATERIAL_PLASTIC;
+    m.Kd = toOc(getParam<vec3f>("pigmentColor", make_vec3f(1.f)));
+    m.eta = 1.f / getParam<float>("eta", 1.4f);
+    m.Ns = getParam<float>("roughness", 0.01f);
+    extended = true;
   } else if (type == "luminous") {
     // render/materials/Luminous.cpp:33-45: radiance = color * intensity (times map_color), isEmissive = any of it
     m.type = OC_MATERIAL_LUMINOUS;
@@ -450,6 +468,13 @@ void Material::commit()
     for (auto &p : params) p.second.queried = true;
     postStatusMsg(OSP_LOG_INFO, "cuda device: material '" + type + "' is not implemented; surfaces using it terminate paths");
   }
+  if (extended) {
+    uint32_t n = 0;
+    checkCuda(ospcuda_microfacet_albedo_tables(&m.microfacetTables, &n), "microfacet albedo tables");
+  }
+  if (extended && !wasExtended) device.emissiveMaterials++; // (the counter of materials that need the extended kernels)
+  if (!extended && wasExtended) device.emissiveMaterials--;
+  wasExtended = extended;
   if (m.isEmissive && !wasEmissive) device.emissiveMaterials++;
   if (!m.isEmissive && wasEmissive) device.emissiveMaterials--;
   wasEmissive = m.isEmissive != 0;

@@ -142,7 +142,7 @@ struct Material : public ManagedObject
   uint32_t slot;
 
  private:
-  bool wasEmissive = false;
+  bool wasEmissive = false, wasExtended = false;
   OcTextureParam getTextureParam(const std::string &name, Ref<Texture2D> &keep); // render/Material.cpp:73-165
   Ref<Texture2D> texD, texKd, texKs, texNs, texBump;
 };

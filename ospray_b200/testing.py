@@ -57,6 +57,11 @@ class MaterialSpec:
     intensity: float = 1.0
     transparency: float = 0.0
     map_color: Optional["MapSpec"] = None
+    metal_eta: tuple = (1.47, 0.984, 0.602)     # metal (render/materials/Metal.cpp:30-76): complex index per channel (aluminium)
+    metal_k: tuple = (7.64, 6.55, 5.36)
+    roughness: float = 0.1                      # metal / plastic
+    map_roughness: Optional["MapSpec"] = None
+    pigment_color: tuple = (1.0, 1.0, 1.0)      # plastic (Plastic.cpp:28-38); `eta` above is its index of refraction
 
 
 @dataclass
@@ -133,6 +138,7 @@ class SceneSpec:
                     texs += [getattr(m.material, a).texture for a in ("map_kd", "map_ks", "map_ns", "map_d", "map_bump", "map_attenuation_color")
                              if getattr(m.material, a) is not None]
                     if m.material.map_color is not None: texs.append(m.material.map_color.texture)
+                    if m.material.map_roughness is not None: texs.append(m.material.map_roughness.texture)
         return all(t.mipmaps for t in texs)
 
 
@@ -447,6 +453,13 @@ def _material(m: MaterialSpec):
     for name in ("map_kd", "map_ks", "map_ns", "map_d", "map_bump"):
         _set_map(mat, name, getattr(m, name))
     _set_map(mat, "map_attenuationColor", m.map_attenuation_color)
+    if m.type == "metal":
+        _set_map(mat, "map_roughness", m.map_roughness)
+        mat.set("eta", tuple(float(x) for x in m.metal_eta)).set("k", tuple(float(x) for x in m.metal_k)).set("roughness", float(m.roughness))
+        return mat.commit()
+    if m.type == "plastic":
+        mat.set("pigmentColor", tuple(float(x) for x in m.pigment_color)).set("eta", float(m.eta)).set("roughness", float(m.roughness))
+        return mat.commit()
     if m.type == "luminous":
         _set_map(mat, "map_color", m.map_color)
         mat.set("color", tuple(float(x) for x in m.color))

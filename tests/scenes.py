@@ -239,6 +239,26 @@ def lit(s):
     return s
 
 
+def metal_cornell(rough):
+    """cornell box whose boxes are metal: aluminium (the default eta / k) on the short box, gold-ish on the tall one; smooth
+    (Conductor) or rough (MicrofacetConductor with the albedo tables, roughness modulated by a texture on one box)"""
+    TS, MS = T.TextureSpec, T.MapSpec
+    r = 0.3 if rough else 0.0
+    mats = {(5, 6, 7, 8, 9, 10): T.MaterialSpec(type="metal", roughness=r),
+            (11, 12, 13, 14, 15, 16): T.MaterialSpec(type="metal", metal_eta=(0.18, 0.42, 1.37), metal_k=(3.4, 2.35, 1.77), roughness=1.0 if rough else 0.0,
+                                                     map_roughness=MS(TS(_tex_rng_image(8, 8, 1, 31, np.float32, 0.2, 0.6)[..., 0], "R32F")) if rough else None)}
+    return _cornell_models(mats)
+
+
+def plastic_cornell(rough):
+    """cornell box with plastic boxes: a smooth (DielectricLayer) or rough (MicrofacetDielectricLayer) clear coat over a
+    Lambertian pigment"""
+    r = 0.25 if rough else 0.0
+    mats = {(5, 6, 7, 8, 9, 10): T.MaterialSpec(type="plastic", pigment_color=(0.8, 0.3, 0.2), eta=1.5, roughness=r),
+            (11, 12, 13, 14, 15, 16): T.MaterialSpec(type="plastic", pigment_color=(0.2, 0.4, 0.8), eta=1.3, roughness=r)}
+    return _cornell_models(mats)
+
+
 def backplate_scene():
     """renderer textures: map_backplate behind random spheres and map_maxDepth cutting the primary rays (Renderer.ispc:18-39)"""
     s = T.random_spheres(24, seed=3)
@@ -325,6 +345,11 @@ CASES = {
     "emissive_pt": (emissive_cornell, "pathtracer", {"pixelSamples": 2}, 2),
     "emissive_nogeolights_pt": (emissive_cornell, "pathtracer", {"pixelSamples": 2, "geometryLights": False}, 1),
     "emissive_transparent_pt": (lambda: emissive_cornell(0.5, True), "pathtracer", {"pixelSamples": 2, "lightSamples": 2, "maxPathLength": 4}, 1),
+    # microfacet family: metal (Conductor / MicrofacetConductor) and plastic (DielectricLayer / MicrofacetDielectricLayer over Lambert)
+    "metal_smooth_pt": (lambda: metal_cornell(False), "pathtracer", {"pixelSamples": 2}, 2),
+    "metal_rough_pt": (lambda: metal_cornell(True), "pathtracer", {"pixelSamples": 2}, 2),
+    "plastic_smooth_pt": (lambda: plastic_cornell(False), "pathtracer", {"pixelSamples": 2}, 2),
+    "plastic_rough_pt": (lambda: plastic_cornell(True), "pathtracer", {"pixelSamples": 2}, 2),
     # debug renderer (render/debug/DebugRenderer.ispc), every method the device accepts
     "debug_testFrame": (T.cornell_box, "debug", {"method": "testFrame", "pixelSamples": 2}, 2),
     "debug_rayDir": (T.cornell_box, "debug", {"method": "rayDir"}, 1),
@@ -347,7 +372,13 @@ REF_UNSUPPORTED = {"volume_geometry"}
 # Cases only the reference's own kernels check (the restatement in oracle.cpp does not sample textures)
 ORACLE_UNSUPPORTED = {"textured_pt", "textured_bias_pt", "cutout_pt", "backplate_pt", "emissive_pt", "emissive_nogeolights_pt",
                       "emissive_transparent_pt", "textured_scivis", "textured_ao", "cutout_scivis", "cutout_ao", "backplate_scivis",
-                      "backplate_ao", "debug_texCoord", "debug_dPdt", "debug_dPds_tex", "debug_backplate"}
+                      "backplate_ao", "debug_texCoord", "debug_dPdt", "debug_dPds_tex", "debug_backplate", "metal_smooth_pt", "metal_rough_pt",
+                      "plastic_smooth_pt", "plastic_rough_pt"}
+# Rough dielectric coatings: MicrofacetDielectricLayer_Constructor reads self->eta for Ravg BEFORE assigning it
+# (bsdfs/MicrofacetDielectricLayer.ih:55 vs :68), i.e. whatever the shading context's memory held from the previous BSDF. The
+# device uses the intended value; against the reference's kernels the coated surfaces then differ by ~0.5 % in brightness
+# (measured: 4.6 % of the pixels beyond 2e-3 relative, median 0.3 %). Looser per-pixel bar, same bar on the image mean.
+REF_UNDEFINED_STATE_CASES = {"plastic_rough_pt"}
 # Cases the cuda device does not render (none at present; the GPU parity tests skip what is listed here)
 DEVICE_UNSUPPORTED = set()
 # Volumes under the pathtracer: delta tracking takes hundreds of accept/reject decisions per path on logf / expf / lerp

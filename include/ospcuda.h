@@ -115,7 +115,25 @@ typedef struct {
 } OcTextureParam;
 
 enum { OC_MATERIAL_OBJ = 0, OC_MATERIAL_OTHER = 1, OC_MATERIAL_THINGLASS = 2, OC_MATERIAL_LUMINOUS = 3, OC_MATERIAL_METAL = 4,
-       OC_MATERIAL_PLASTIC = 5 };
+       OC_MATERIAL_PLASTIC = 5, OC_MATERIAL_PRINCIPLED = 6 };
+/* principled (reference: ispc::Principled, render/materials/PrincipledShared.h:17-170, Principled.cpp:33-150), the solid form
+ * without sheen and without texture maps: factors as committed; outsideIor = outsideIor >= 1 ? outsideIor : 1 / outsideIor,
+ * outsideAttenuation = log(outsideTransmissionColor) / outsideTransmissionDepth (the medium around the object) */
+typedef struct {
+  OcVec3f baseColor, edgeColor;
+  float metallic, diffuse, specular;
+  uint32_t specularMetallic;
+  float ior, transmission;
+  OcVec3f transmissionColor;
+  float transmissionDepth;
+  float roughness, anisotropy, rotation;
+  float coat, coatIor;
+  OcVec3f coatColor;
+  float coatThickness, coatRoughness;
+  float opacity;
+  float outsideIor;
+  OcVec3f outsideAttenuation;
+} OcPrincipled;
 /* material (reference: ispc::OBJ, render/materials/OBJShared.h, OBJ.cpp:30-66; ispc::ThinGlass,
  * render/materials/ThinGlassShared.h, ThinGlass.cpp:33-48: eta = 1/ior, attenuationScale = thickness /
  * max(attenuationDistance, EPS), attenuation = log(attenuationColor) * attenuationScale) */
@@ -142,6 +160,7 @@ typedef struct {
   float bumpRot[4];            /* OBJ.cpp:43-44: orthogonal part of map_bump's 2D transform, transposed (vx, vy) */
   /* OBJ: map_d, map_kd, map_ks, map_ns, map_bump (OBJShared.h:19-31); thinGlass: mapKd = map_attenuationColor */
   OcTextureParam mapD, mapKd, mapKs, mapNs, mapBump;
+  OcPrincipled principled;     /* type OC_MATERIAL_PRINCIPLED (emission / isEmissive above: emissiveColor * intensity) */
 } OcMaterial;
 
 /* 4-wide BVH node, 128 B = one cache line, fetched as 8 x 128-bit loads */

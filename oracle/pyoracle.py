@@ -62,12 +62,30 @@ class TextureParam(C.Structure):
     _fields_ = [("tex", C.POINTER(Texture2D)), ("transformFlags", C.c_uint32), ("scale2f", C.c_float), ("xform2f", C.c_float * 6)]
 
 
+class Principled(C.Structure):  # OcPrincipled
+    _fields_ = [("baseColor", Vec3), ("edgeColor", Vec3), ("metallic", C.c_float), ("diffuse", C.c_float), ("specular", C.c_float),
+                ("specularMetallic", C.c_uint32), ("ior", C.c_float), ("transmission", C.c_float), ("transmissionColor", Vec3),
+                ("transmissionDepth", C.c_float), ("roughness", C.c_float), ("anisotropy", C.c_float), ("rotation", C.c_float),
+                ("coat", C.c_float), ("coatIor", C.c_float), ("coatColor", Vec3), ("coatThickness", C.c_float),
+                ("coatRoughness", C.c_float), ("opacity", C.c_float), ("outsideIor", C.c_float), ("outsideAttenuation", Vec3)]
+
+
+# parameters of the principled material this build takes (ospray name -> default), Principled.cpp:33-77
+PRINCIPLED_DEFAULTS = {
+    "baseColor": (0.8, 0.8, 0.8), "edgeColor": (1.0, 1.0, 1.0), "metallic": 0.0, "diffuse": 1.0, "specular": 1.0,
+    "specularMetallic": True, "ior": 1.0, "transmission": 0.0, "transmissionColor": (1.0, 1.0, 1.0), "transmissionDepth": 1.0,
+    "roughness": 0.0, "anisotropy": 0.0, "rotation": 0.0, "coat": 0.0, "coatIor": 1.5, "coatColor": (1.0, 1.0, 1.0),
+    "coatThickness": 1.0, "coatRoughness": 0.0, "opacity": 1.0, "outsideIor": 1.0, "outsideTransmissionColor": (1.0, 1.0, 1.0),
+    "outsideTransmissionDepth": 1.0, "emissiveColor": (0.0, 0.0, 0.0), "intensity": 1.0,
+}
+
+
 class Material(C.Structure):
     _fields_ = [("type", C.c_uint32), ("d", C.c_float), ("Kd", Vec3), ("Ks", Vec3), ("Ns", C.c_float), ("Tf", Vec3),
                 ("eta", C.c_float), ("attenuation", Vec3), ("attenuationScale", C.c_float), ("emission", Vec3),
                 ("transparency", C.c_float), ("isEmissive", C.c_uint32), ("microfacetTables", C.c_void_p), ("hasTextures", C.c_uint32),
                 ("bumpRot", C.c_float * 4), ("mapD", TextureParam), ("mapKd", TextureParam), ("mapKs", TextureParam),
-                ("mapNs", TextureParam), ("mapBump", TextureParam)]
+                ("mapNs", TextureParam), ("mapBump", TextureParam), ("principled", Principled)]
 
 
 class BVH(C.Structure):
@@ -555,6 +573,27 @@ class Scene:
         elif ms.type == "plastic":  # render/materials/Plastic.cpp:28-38
             m.type = 5
             m.Kd, m.eta, m.Ns = Vec3(*map(float, np.asarray(ms.pigment_color, np.float32))), float(np.float32(1.0) / np.float32(ms.eta)), float(np.float32(ms.roughness))
+        elif ms.type == "principled":  # render/materials/Principled.cpp:33-150 (solid, no sheen, no maps)
+            f = np.float32
+            prm = dict(PRINCIPLED_DEFAULTS)
+            unknown = set(ms.principled) - set(prm)
+            if unknown:
+                raise ValueError(f"principled parameters not supported: {sorted(unknown)}")
+            prm.update(ms.principled)
+            m.type = 6
+            q = m.principled
+            for name in ("baseColor", "edgeColor", "transmissionColor", "coatColor"):
+                setattr(q, name, Vec3(*map(float, np.asarray(prm[name], np.float32))))
+            for name in ("metallic", "diffuse", "specular", "ior", "transmission", "transmissionDepth", "roughness", "anisotropy",
+                         "rotation", "coat", "coatIor", "coatThickness", "coatRoughness", "opacity"):
+                setattr(q, name, float(f(prm[name])))
+            q.specularMetallic = int(bool(prm["specularMetallic"]))
+            oi = f(prm["outsideIor"])
+            q.outsideIor = float(oi if oi >= 1.0 else f(1.0) / oi)
+            otc = np.log(np.asarray(prm["outsideTransmissionColor"], np.float32)).astype(np.float32) / f(prm["outsideTransmissionDepth"])
+            q.outsideAttenuation = Vec3(*map(float, otc))
+            em = (np.asarray(prm["emissiveColor"], np.float32) * f(prm["intensity"])).astype(np.float32)
+            m.emission, m.isEmissive = Vec3(*map(float, em)), int(em.max() > 0)
         elif ms.type == "luminous":  # render/materials/Luminous.cpp:33-45
             m.type = 3
             em = (np.asarray(ms.color, np.float32) * np.float32(ms.intensity)).astype(np.float32)

@@ -33,6 +33,7 @@
 #include "render/materials/LuminousShared.h"
 #include "render/materials/MetalShared.h"
 #include "render/materials/PlasticShared.h"
+#include "render/materials/PrincipledShared.h"
 #include "render/bsdfs/MicrofacetAlbedoTablesShared.h"
 #include "render/pathtracer/GeometryLightShared.h"
 #include "texture/Texture2DShared.h"
@@ -168,7 +169,7 @@ struct Scene
   std::deque<OBJ> objs; std::deque<ThinGlass> glasses; std::vector<Material *> allMaterials;
   std::deque<Texture2D> textures;
   std::deque<Luminous> luminous; std::deque<GeometryLight> geoLights;
-  std::deque<Metal> metals; std::deque<Plastic> plastics;
+  std::deque<Metal> metals; std::deque<Plastic> plastics; std::deque<Principled> principleds;
   std::deque<std::vector<int>> geoPrimIDs; std::deque<std::vector<float>> geoDistributions;
   std::vector<float> geoCDF;
   std::vector<Instance *> instancePtrs;
@@ -315,6 +316,23 @@ void buildScene(Scene &s, const OcWorld *w, const OcRenderer *ren)
       pl.pigmentColor = v3(m.Kd); pl.eta = m.eta; pl.roughness = m.Ns;
       pl.super.microfacetAlbedoTables = refAlbedoTables();
       s.allMaterials.push_back(&pl.super);
+      continue;
+    }
+    if (m.type == OC_MATERIAL_PRINCIPLED) { // render/materials/Principled.cpp:33-150 (committed values, no maps)
+      s.principleds.emplace_back();
+      Principled &pr = s.principleds.back();
+      const OcPrincipled &q = m.principled;
+      pr.baseColor = v3(q.baseColor); pr.edgeColor = v3(q.edgeColor);
+      pr.metallic = q.metallic; pr.diffuse = q.diffuse; pr.specular = q.specular; pr.specularMetallic = q.specularMetallic != 0;
+      pr.ior = q.ior; pr.transmission = q.transmission; pr.transmissionColor = v3(q.transmissionColor);
+      pr.transmissionDepth = q.transmissionDepth; pr.roughness = q.roughness; pr.anisotropy = q.anisotropy; pr.rotation = q.rotation;
+      pr.coat = q.coat; pr.coatIor = q.coatIor; pr.coatColor = v3(q.coatColor); pr.coatThickness = q.coatThickness;
+      pr.coatRoughness = q.coatRoughness; pr.opacity = q.opacity;
+      pr.outsideMedium.ior = q.outsideIor; pr.outsideMedium.attenuation = v3(q.outsideAttenuation);
+      pr.emission = v3(m.emission);
+      pr.super.isEmissive = m.isEmissive != 0;
+      pr.super.microfacetAlbedoTables = refAlbedoTables();
+      s.allMaterials.push_back(&pr.super);
       continue;
     }
     if (m.type == OC_MATERIAL_LUMINOUS) { // render/materials/Luminous.cpp:33-45 (committed values)

@@ -52,6 +52,8 @@ struct PtScratch
   uint2 *shHit;                     // what TRACE found for shadow entry [slot * nls + i]: occluder (record, instance); instance ~0 = none
   float4 *accC, *accZ, *accPos, *accFN, *accNrm, *accAlb; // ScreenSample sums across the spp passes (spp > 1)
   float2 *cone;   // frames with textures: the path's ray cone (width at the last vertex, dwdt) (common/RayCone.ih)
+  float4 *med;    // extended materials: the medium the path is in (attenuation, ior) (PathStructs.ih:78 currentMedium)
+  float4 *shMed;  //   and the one its pending shadow rays started in (NextEventEstimation.ispc:123)
   uint4 *rnd;     // worlds with volumes: pathState.randomSampler (PCG32 state lo/hi, stream)
   float *shT0;    // worlds with volumes: t0 of shadow entry [slot * nls + i] after the transparent-shadow loop
   uint32_t *pathQ[2], *shadowQ[2];
@@ -371,6 +373,8 @@ __device__ __forceinline__ bool ptOccluderIsOpaque(const OcWorld *world, const O
   const OcMaterial *mat = getMaterial(world, ren, m, primID);
   if (mat && (mat->type == OC_MATERIAL_THINGLASS || mat->hasTextures)) return false; // texture maps may cut the surface out
   if (mat && mat->type == OC_MATERIAL_LUMINOUS) return mat->transparency == 0.f; // Luminous_getTransparency
+  if (mat && mat->type == OC_MATERIAL_PRINCIPLED) // Principled_getTransparency's early exit (Principled.ispc:452-454)
+    return 1.f - clampf(mat->principled.opacity, 0.f, 1.f) <= PR_EPS && clampf(mat->principled.transmission, 0.f, 1.f) <= PR_EPS;
   if (!mat || mat->type != OC_MATERIAL_OBJ) return true; // no / foreign material: transparency 0 (shading.cuh)
   return mat->d == 1.f && mat->Tf.x == 0.f && mat->Tf.y == 0.f && mat->Tf.z == 0.f;
 }
@@ -397,6 +401,8 @@ static __device__ __noinline__ float4 ptTransparentShadowSlow(const PtArgs &k, s
   // reads an indeterminate value there; this device defines it as 0 (finest MIP level along shadow rays)
   RayCone shadowCone;
   shadowCone.width = 0.f; shadowCone.dwdt = 0.f;
+  Medium medium = mediumVacuum();
+  if (TEX) { const float4 m4 = k.s.shMed[e / k.s.nls]; medium.attenuation = make_vec3f(m4.x, m4.y, m4.z); medium.ior = m4.w; }
   while (1) {
     if (!counted) shadowCount++;
     counted = false;
@@ -405,9 +411,12 @@ static __device__ __noinline__ float4 ptTransparentShadowSlow(const PtArgs &k, s
     if (!hadHit(sr)) break;
     DifferentialGeometry dg;
     postIntersect<TEX>(k.a.world, ren, dg, sr, DG_NS | DG_NG | DG_FACEFORWARD | DG_NORMALIZE | DG_TEXCOORD | DG_COLOR, TEX ? &shadowCone : nullptr);
-    lightContrib = lightContrib * materialTransparency<TEX>(dg, sr.dir);
+    lightContrib = lightContrib * materialTransparency<TEX>(dg, sr.dir, medium);
     shadowCone.width = 0.f;
+    if (TEX && (medium.attenuation.x != 0.f || medium.attenuation.y != 0.f || medium.attenuation.z != 0.f)) // Beer's law (:66-69)
+      lightContrib = lightContrib * expf3(medium.attenuation * (sr.t - sr.t0));
     if (reduce_max(lightContrib) <= ren.minContribution || --maxDepth <= 0) { lightContrib = make_vec3f(0.f); break; }
+    if (TEX) materialSelectNextMedium(dg, medium);
     setRay(sr, sr.org, sr.dir, sr.t + dg.epsilon, tOriginal);
   }
   if (k.vol) k.s.shT0[e] = sr.t0; // where the ray stands after the transparent surfaces it crossed (volumeTransmittance starts there)
@@ -484,6 +493,7 @@ __global__ void __launch_bounds__(128) ptGenKernel(const __grid_constant__ PtArg
       RayCone cone = cameraInitRayCone(k.a.cam, screen);
       cone.dwdt *= rcpSize.y; cone.width *= rcpSize.y;
       s.cone[p] = make_float2(cone.width, cone.dwdt);
+      s.med[p] = make_float4(0.f, 0.f, 0.f, 1.f); // make_Medium_vacuum (PathTracer.ispc:56)
       ray.t = fminf(ray.t, rendererMaxDepth(ren, screen));
     }
     s.smp[p] = make_uint2(ld.revIndex, ld.scramble);
@@ -763,7 +773,11 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
   vec2f pixelCenter = make_vec2f(0.f, 0.f); // pathContext.screen (PathTracer.ispc:194): where the backplate is looked up
   RayCone cone;
   cone.width = cone.dwdt = 0.f;
-  if (TEX) { const float2 c2 = s.cone[p]; cone.width = c2.x; cone.dwdt = c2.y; }
+  Medium medium = mediumVacuum();
+  if (TEX) {
+    const float2 c2 = s.cone[p]; cone.width = c2.x; cone.dwdt = c2.y;
+    const float4 m4 = s.med[p]; medium.attenuation = make_vec3f(m4.x, m4.y, m4.z); medium.ior = m4.w;
+  }
   {
     uint32_t ix, iy, seed, so, sol, bits, bitsLight;
     ptSlotToPixel(k, p, ix, iy);
@@ -847,7 +861,7 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
     ObjBSDF bsdf;
     ExtBSDF xbsdf; // metal / plastic state (extended-material kernels only)
     if (!volume) {
-      if (!(TEX && Ext_getBSDF(bsdf, xbsdf, dg))) OBJ_getBSDF<TEX>(bsdf, dg);
+      if (!(TEX && Ext_getBSDF(bsdf, xbsdf, dg, medium))) OBJ_getBSDF<TEX>(bsdf, dg);
       if (!bsdf.valid) break;
     }
 
@@ -896,6 +910,7 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
         if (!valid) s.shC[e] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       firstBounceLight = false;
+      if (TEX && hasShadow) s.shMed[p] = make_float4(medium.attenuation.x, medium.attenuation.y, medium.attenuation.z, medium.ior);
     }
 
     float ss;
@@ -916,8 +931,12 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
       if (rr > contProb) break;
       throughput = throughput * (1.f / contProb);
     }
+    if (TEX && reduce_min(medium.attenuation) < 0.f) throughput = throughput * expf3(medium.attenuation * ray.t); // Beer's law (:365-368)
     vec3f ray_org = dg.P;
-    if (!volume && (fs.type & SC_TRANSMISSION)) ray_org = ray_org - (2.0f * dg.epsilon) * dg.Ng;
+    if (!volume && (fs.type & SC_TRANSMISSION)) {
+      ray_org = ray_org - (2.0f * dg.epsilon) * dg.Ng;
+      if (TEX) materialSelectNextMedium(dg, medium); // the path crosses an interface (:371-383)
+    }
     if ((fs.type & ~SC_SPECULAR_TRANSMISSION) || volume) {
       last.P = dg.P; last.Ns = dg.Ns; last.pdf_w = fs.pdf; last.numLightSamples = vertexLightSamples;
     }
@@ -939,7 +958,10 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
     s.lastP[p] = make_float4(last.P.x, last.P.y, last.P.z, __uint_as_float(last.numLightSamples));
     s.lastN[p] = make_float4(last.Ns.x, last.Ns.y, last.Ns.z, 0.f);
     s.smp[p] = make_uint2(ld.revIndex, ld.scramble);
-    if (TEX) s.cone[p] = make_float2(cone.width, cone.dwdt);
+    if (TEX) {
+      s.cone[p] = make_float2(cone.width, cone.dwdt);
+      s.med[p] = make_float4(medium.attenuation.x, medium.attenuation.y, medium.attenuation.z, medium.ior);
+    }
   }
   s.flags[p] = ((depth + 1) & PT_DEPTH_MASK) | (scatteringEvents << PT_SCAT_SHIFT) | (straightPath ? PT_STRAIGHT : 0u)
       | (specularTransmissionPath ? PT_SPECTRANS : 0u) | (firstBounceLight ? PT_FIRSTBOUNCE : 0u) | (hasShadow ? PT_HAS_SHADOW : 0u)

@@ -1,0 +1,595 @@
+// The principled material: the reference's layered uber-BSDF as one statically composed structure.
+// reference: render/materials/Principled.ispc:34-428 (Principled_getBSDF), :430-573 (getTransparency), :575-601
+// (selectNextMedium), :603-1040 (the eval / sample dispatch through the nesting), bsdfs/MultiBSDF.ih:58-128,
+// OrenNayar.ih:18-45, Dielectric.ih:18-50, MicrofacetDielectric.ih:27-268, Fresnel.ih:227-284 (artistic conductor).
+//
+//   root   MultiBSDF(2)   [0] Transmission(1 - opacity)            [1] coat( base )            (sheen layer: not built)
+//   coat   passthrough | DielectricLayer | MicrofacetDielectricLayer over base
+//   base   MultiBSDF(3)   [0] metal: Conductor | MicrofacetConductor (artistic Fresnel)
+//                         [1] glass: Transmission | Dielectric | MicrofacetDielectric          (thin variants: not built)
+//                         [2] plastic: passthrough | DielectricLayer | MicrofacetDielectricLayer over diffuse
+//   diffuse MultiBSDF(2)  [0] Lambert | OrenNayar                                              ([1] LambertTransmission: thin only)
+#pragma once
+
+namespace oc {
+
+#define PR_EPS 1e-5f
+
+struct PrDiffuse
+{
+  linear3f frame;
+  vec3f R, albedo;
+  float roughness; // OrenNayar when > 0 (the material's roughness >= EPS), else Lambert
+  bool orenNayar;
+  uint32_t scatteringType;
+  float weight, importance, importanceSum; // the enclosing 2-child MultiBSDF (child 0)
+  __device__ __forceinline__ EvalRes lobeEval(vec3f wo, vec3f wi) const
+  {
+    EvalRes r;
+    if (!orenNayar) {
+      const float c = fmaxf(dot(wi, frame.vz), 0.f);
+      r.pdf = c * OC_ONE_OVER_PI; r.value = R * OC_ONE_OVER_PI * c;
+      return r;
+    }
+    const float cosThetaO = fmaxf(dot(wo, frame.vz), 0.f), cosThetaI = fmaxf(dot(wi, frame.vz), 0.f);
+    const float s = dot(wo, wi) - cosThetaO * cosThetaI;
+    const float sInvt = (s > 0.f) ? (s * rcpSafe(fmaxf(cosThetaO, cosThetaI))) : s;
+    r.value = R * (cosThetaI * (1.f + roughness * sInvt) * (1.f / (OC_PI + (OC_PI / 2.f - 2.f / 3.f) * roughness)));
+    r.pdf = cosThetaI * OC_ONE_OVER_PI;
+    return r;
+  }
+  __device__ __forceinline__ SampleRes lobeSample(vec3f wo, vec2f s) const
+  {
+    const vec3f l = cosineSampleHemisphere(s);
+    SampleRes r;
+    r.wi = frame * l; r.type = SC_DIFFUSE_REFLECTION;
+    if (!orenNayar) { r.pdf = l.z * OC_ONE_OVER_PI; r.weight = R; return r; }
+    const EvalRes e = lobeEval(wo, r.wi);
+    r.pdf = e.pdf; r.weight = e.value * (1.f / e.pdf);
+    return r;
+  }
+  // DiffuseBSDF_eval / _sample: the MultiBSDF macros with one live child
+  __device__ __forceinline__ EvalRes eval(vec3f wo, vec3f wi) const
+  {
+    EvalRes e; e.value = make_vec3f(0.f); e.pdf = 0.f;
+    if (importance > 0.f) {
+      const EvalRes c = lobeEval(wo, wi);
+      e.value = e.value + c.value * weight;
+      e.pdf += c.pdf * importance;
+    }
+    e.pdf *= 1.f / importanceSum;
+    return e;
+  }
+  __device__ __forceinline__ SampleRes sample(vec3f wo, vec2f s, float ss) const
+  {
+    SampleRes res; res.weight = make_vec3f(0.f); res.wi = make_vec3f(0.f); res.pdf = 0.f; res.type = 0;
+    if (importanceSum == 0.f) return res;
+    const float x = ss * importanceSum;
+    if (!(x < importance)) return res; // (no second child)
+    res = lobeSample(wo, s);
+    res.weight = res.weight * weight;
+    if ((res.weight.x == 0.f && res.weight.y == 0.f && res.weight.z == 0.f) || res.pdf == 0.0f) { res.weight = make_vec3f(0.f); res.wi = make_vec3f(0.f); res.pdf = 0.f; res.type = 0; return res; }
+    EvalRes e;
+    e.value = res.weight * res.pdf;
+    res.pdf *= importance;
+    e.pdf = res.pdf;
+    res.pdf = e.pdf * (1.f / importanceSum);
+    res.weight = e.value * (1.f / res.pdf);
+    return res;
+  }
+};
+
+struct PrGlass
+{
+  linear3f frame;
+  int kind; // 0 Transmission(1), 1 Dielectric, 2 MicrofacetDielectric
+  float eta;
+  GGX mf;
+  float roughness, EavgEta, EavgRcpEta, fmsRatio;
+  const float *tables;
+  vec3f albedo;
+  uint32_t scatteringType;
+};
+// MicrofacetDielectricAlbedoTable_eval / _evalAvg (MicrofacetAlbedoTables.ih:29-78)
+__device__ __forceinline__ float mfDielAlbedo(const float *t, float cosThetaO, float eta, float roughness)
+{
+  const bool le = eta <= 1.f;
+  const float minEta = le ? 1.f / 3.f : 1.f, maxEta = le ? 1.f : 3.f;
+  const float etaParam = (eta - minEta) / (maxEta - minEta);
+  return interp3D(cosThetaO * (OC_MFD_SIZE - 1), etaParam * (OC_MFD_SIZE - 1), roughness * (OC_MFD_SIZE - 1),
+      t + (le ? OC_MFT_DIEL_DIR : OC_MFT_DIELRCP_DIR), OC_MFD_SIZE);
+}
+__device__ __forceinline__ float mfDielAlbedoAvg(const float *t, float eta, float roughness)
+{
+  const bool le = eta <= 1.f;
+  const float minEta = le ? 1.f / 3.f : 1.f, maxEta = le ? 1.f : 3.f;
+  const float etaParam = (eta - minEta) / (maxEta - minEta);
+  return interp2D(etaParam * (OC_MFD_SIZE - 1), roughness * (OC_MFD_SIZE - 1), t + (le ? OC_MFT_DIEL_AVG : OC_MFT_DIELRCP_AVG), OC_MFD_SIZE, OC_MFD_SIZE);
+}
+__device__ __forceinline__ void PrGlass_initMicrofacet(PrGlass &g, const float *tables, float eta, float roughness, float anisotropy)
+{
+  g.kind = 2; g.eta = eta; g.tables = tables; g.roughness = roughness;
+  g.albedo = make_vec3f(0.9f); g.scatteringType = SC_GLOSSY | SC_DIFFUSE;
+  g.mf = makeGGX(roughness, anisotropy);
+  g.EavgEta = mfDielAlbedoAvg(tables, eta, roughness);
+  g.EavgRcpEta = mfDielAlbedoAvg(tables, 1.f / eta, roughness);
+  const float FavgEta = fresnelDielectricAvg(eta), FavgRcpEta = fresnelDielectricAvg(1.f / eta);
+  const float a = (1.f - FavgEta) * (1.f / (1.f - g.EavgRcpEta));
+  const float b = (1.f - FavgRcpEta) * (1.f / (1.f - g.EavgEta));
+  const float x = b * (1.f / (a + b));
+  g.fmsRatio = 1.f - x * (1.f - FavgEta);
+}
+__device__ __forceinline__ EvalRes MicrofacetDielectric_evalSingle(const PrGlass &g, vec3f wo, vec3f wi)
+{
+  EvalRes res; res.value = make_vec3f(0.f); res.pdf = 0.f;
+  const vec3f N = g.frame.vz;
+  const float cosThetaO = dot(wo, N);
+  if (cosThetaO <= 0.f) return res;
+  const float cosThetaI = dot(wi, N);
+  const bool isReflection = cosThetaI > 0.f;
+  vec3f wh = isReflection ? wo + wi : g.eta * wo + wi;
+  wh = normalize(wh);
+  if (dot(wh, N) < 0.f) wh = neg(wh);
+  const float cosThetaOH = dot(wo, wh), cosThetaIH = dot(wi, wh);
+  const float F = fresnelDielectric(cosThetaOH, g.eta);
+  float value;
+  if (isReflection) {
+    res.pdf = F * (1.f / (4.f * fabsf(cosThetaOH)));
+    value = F * (1.f / (4.f * cosThetaO));
+  } else {
+    res.pdf = (1.f - F) * (1.f / sqr(g.eta)) * fabsf(cosThetaIH) * (1.f / sqr(cosThetaOH + (1.f / g.eta) * cosThetaIH));
+    value = res.pdf * fabsf(cosThetaOH) * (1.f / cosThetaO);
+  }
+  const vec3f wo0 = toLocal(g.frame, wo), wi0 = toLocal(g.frame, wi), wh0 = toLocal(g.frame, wh);
+  float whPdf;
+  const float D = ggxEvalVisible(g.mf, wh0, wo0, cosThetaOH, whPdf);
+  const float G = ggxG2(g.mf, wo0, wi0, cosThetaOH, cosThetaIH);
+  res.pdf *= whPdf;
+  res.value = make_vec3f(value * D * G);
+  return res;
+}
+__device__ __forceinline__ EvalRes MicrofacetDielectric_fms(const PrGlass &g, float Eo, float cosThetaI, bool reflection)
+{
+  EvalRes fms;
+  if (reflection) {
+    const float Ei = mfDielAlbedo(g.tables, cosThetaI, g.eta, g.roughness);
+    fms.pdf = g.fmsRatio * (cosThetaI * OC_ONE_OVER_PI);
+    fms.value = make_vec3f(g.fmsRatio * (1.f - Eo) * (1.f - Ei) * (1.f / (OC_PI * (1.f - g.EavgEta))) * cosThetaI);
+  } else {
+    const float Ei = mfDielAlbedo(g.tables, fabsf(cosThetaI), 1.f / g.eta, g.roughness);
+    fms.pdf = (1.f - g.fmsRatio) * (fabsf(cosThetaI) * OC_ONE_OVER_PI);
+    fms.value = make_vec3f((1.f - g.fmsRatio) * (1.f - Eo) * (1.f - Ei) * (1.f / (OC_PI * (1.f - g.EavgRcpEta))) * fabsf(cosThetaI));
+  }
+  return fms;
+}
+__device__ __forceinline__ EvalRes PrGlass_eval(const PrGlass &g, vec3f wo, vec3f wi)
+{
+  EvalRes res; res.value = make_vec3f(0.f); res.pdf = 0.f;
+  if (g.kind != 2) return res; // Transmission, Dielectric: delta lobes
+  const float cosThetaO = dot(wo, g.frame.vz);
+  if (cosThetaO <= 0.f) return res;
+  const float cosThetaI = dot(wi, g.frame.vz);
+  const float Eo = mfDielAlbedo(g.tables, cosThetaO, g.eta, g.roughness);
+  const EvalRes fms = MicrofacetDielectric_fms(g, Eo, cosThetaI, cosThetaI > 0.f);
+  const EvalRes single = MicrofacetDielectric_evalSingle(g, wo, wi);
+  res.pdf = Eo * single.pdf + (1.f - Eo) * fms.pdf;
+  res.value = single.value + fms.value;
+  return res;
+}
+__device__ __forceinline__ SampleRes PrGlass_sample(const PrGlass &g, vec3f wo, vec2f s, float ss)
+{
+  SampleRes res; res.weight = make_vec3f(0.f); res.wi = make_vec3f(0.f); res.pdf = 0.f; res.type = 0;
+  const vec3f N = g.frame.vz;
+  if (g.kind == 0) { res.wi = neg(wo); res.pdf = INFINITY; res.type = SC_SPECULAR_TRANSMISSION; res.weight = make_vec3f(1.f); return res; }
+  if (g.kind == 1) { // Dielectric_sample (Dielectric.ih:24-50)
+    const float cosThetaO = fmaxf(dot(wo, N), 0.f);
+    float cosThetaT;
+    const float F = fresnelDielectricEx(cosThetaO, cosThetaT, g.eta);
+    res.pdf = INFINITY;
+    res.weight = make_vec3f(1.f);
+    if (ss <= F) { res.wi = reflectDir(wo, N, cosThetaO); res.type = SC_SPECULAR_REFLECTION; }
+    else { res.wi = refractDir(wo, N, cosThetaO, cosThetaT, g.eta); res.type = SC_SPECULAR_TRANSMISSION; }
+    return res;
+  }
+  const float cosThetaO = dot(wo, N);
+  if (cosThetaO <= 0.f) return res;
+  const float Eo = mfDielAlbedo(g.tables, cosThetaO, g.eta, g.roughness);
+  const float singlePickProb = Eo;
+  bool doReflection;
+  if (ss <= singlePickProb) {
+    const vec3f wo0 = toLocal(g.frame, wo);
+    float whPdf;
+    const vec3f wh = g.frame * ggxSampleVisible(g.mf, wo0, whPdf, s);
+    const float cosThetaOH = dot(wo, wh);
+    float cosThetaTH;
+    const float F = fresnelDielectricEx(cosThetaOH, cosThetaTH, g.eta);
+    const float ss1 = ss * (1.f / singlePickProb);
+    doReflection = ss1 <= F;
+    if (doReflection) { res.type = SC_GLOSSY_REFLECTION; res.wi = reflectDir(wo, wh, cosThetaOH); }
+    else { res.type = SC_GLOSSY_TRANSMISSION; res.wi = refractDir(wo, wh, cosThetaOH, cosThetaTH, g.eta); }
+  } else {
+    const float ss1 = (ss - singlePickProb) * (1.f / (1.f - singlePickProb));
+    doReflection = ss1 <= g.fmsRatio;
+    res.wi = g.frame * cosineSampleHemisphere(s);
+    if (doReflection) res.type = SC_DIFFUSE_REFLECTION;
+    else { res.type = SC_DIFFUSE_TRANSMISSION; res.wi = neg(res.wi); }
+  }
+  const float cosThetaI = dot(res.wi, N);
+  if ((doReflection && cosThetaI <= 0.f) || (!doReflection && cosThetaI >= 0.f)) {
+    res.weight = make_vec3f(0.f); res.wi = make_vec3f(0.f); res.pdf = 0.f; res.type = 0;
+    return res;
+  }
+  const EvalRes fms = MicrofacetDielectric_fms(g, Eo, cosThetaI, doReflection);
+  const EvalRes single = MicrofacetDielectric_evalSingle(g, wo, res.wi);
+  res.pdf = singlePickProb * single.pdf + (1.f - singlePickProb) * fms.pdf;
+  res.weight = (single.value + fms.value) * (1.f / res.pdf);
+  return res;
+}
+
+struct PrPlastic
+{
+  linear3f frame;
+  int layerKind; // 0 passthrough (specular == 0), 1 DielectricLayer, 2 MicrofacetDielectricLayer
+  LayerParams layer;
+  PrDiffuse diffuse;
+  vec3f albedo;
+  uint32_t scatteringType;
+  __device__ __forceinline__ EvalRes eval(vec3f wo, vec3f wi) const
+  {
+    if (layerKind == 0 || layer.weight < PR_EPS) return diffuse.eval(wo, wi);
+    if (layerKind == 2) return MicrofacetDielectricLayer_eval(layer, frame, diffuse, wo, wi);
+    return DielectricLayer_eval(layer, frame.vz, diffuse, wo, wi);
+  }
+  __device__ __forceinline__ SampleRes sample(vec3f wo, vec2f s, float ss) const
+  {
+    if (layerKind == 0 || layer.weight < PR_EPS) return diffuse.sample(wo, s, ss);
+    if (layerKind == 2) return MicrofacetDielectricLayer_sample(layer, frame, diffuse, wo, s, ss);
+    return DielectricLayer_sample(layer, frame.vz, diffuse, wo, s, ss);
+  }
+};
+
+// the 3-child base MultiBSDF; albedo / scatteringType are read by the coat layered over it
+struct PrBase
+{
+  linear3f frame;
+  float w[3], imp[3], importanceSum;
+  int metalKind; // 0 none, 1 Conductor, 2 MicrofacetConductor
+  ConductorBSDF metal;
+  bool hasGlass, hasPlastic;
+  PrGlass glass;
+  PrPlastic plastic;
+  vec3f albedo;
+  uint32_t scatteringType;
+
+  __device__ __forceinline__ EvalRes childEval(int id, vec3f wo, vec3f wi) const
+  {
+    if (id == 0) { if (metalKind == 2) return MicrofacetConductor_eval(metal, wo, wi); EvalRes z; z.value = make_vec3f(0.f); z.pdf = 0.f; return z; }
+    if (id == 1) return PrGlass_eval(glass, wo, wi);
+    return plastic.eval(wo, wi);
+  }
+  __device__ __forceinline__ void evalChildren(vec3f wo, vec3f wi, int skip, EvalRes &e) const
+  {
+#pragma unroll
+    for (int id = 0; id < 3; id++)
+      if (imp[id] > 0.f && skip != id) {
+        EvalRes c = childEval(id, wo, wi);
+        c.value = c.value * w[id];
+        e.value = e.value + c.value;
+        e.pdf += c.pdf * imp[id];
+      }
+  }
+  __device__ EvalRes eval(vec3f wo, vec3f wi) const
+  {
+    EvalRes e; e.value = make_vec3f(0.f); e.pdf = 0.f;
+    evalChildren(wo, wi, -1, e);
+    e.pdf *= 1.f / importanceSum;
+    return e;
+  }
+  __device__ SampleRes sample(vec3f wo, vec2f s, float ss) const
+  {
+    SampleRes res; res.weight = make_vec3f(0.f); res.wi = make_vec3f(0.f); res.pdf = 0.f; res.type = 0;
+    if (importanceSum == 0.f) return res;
+    const float x = ss * importanceSum;
+    int choice = -1;
+    float prefix = 0.f;
+#pragma unroll
+    for (int id = 0; id < 3; id++)
+      if (choice < 0 && x < (prefix += imp[id])) {
+        choice = id;
+        const float ssc = (x + imp[id] - prefix) * (1.f / imp[id]);
+        if (id == 0) res = metalKind == 2 ? MicrofacetConductor_sample(metal, wo, s) : Conductor_sample(metal, wo);
+        else if (id == 1) res = PrGlass_sample(glass, wo, s, ssc);
+        else res = plastic.sample(wo, s, ssc);
+        res.weight = res.weight * w[id];
+      }
+    if (choice < 0 || (res.weight.x == 0.f && res.weight.y == 0.f && res.weight.z == 0.f) || res.pdf == 0.0f) {
+      res.weight = make_vec3f(0.f); res.wi = make_vec3f(0.f); res.pdf = 0.f; res.type = 0;
+      return res;
+    }
+    if (res.type & SC_SPECULAR) { res.weight = res.weight * (importanceSum * (1.f / imp[choice])); return res; }
+    EvalRes e;
+    e.value = res.weight * res.pdf;
+    res.pdf *= imp[choice];
+    e.pdf = res.pdf;
+    evalChildren(wo, res.wi, choice, e);
+    res.pdf = e.pdf * (1.f / importanceSum);
+    res.weight = e.value * (1.f / res.pdf);
+    return res;
+  }
+};
+
+struct PrBSDF
+{
+  linear3f frame;
+  float opacity;     // weight and importance of the coated base in the root MultiBSDF
+  float transparency; // importance of the cut-out Transmission child (its weight is 1), 0 = absent
+  bool hasBase;
+  int coatKind; // 0 passthrough, 1 DielectricLayer, 2 MicrofacetDielectricLayer
+  LayerParams coat;
+  PrBase base;
+  vec3f albedo;
+  uint32_t scatteringType;
+  float importanceSum;
+};
+
+__device__ __forceinline__ vec3f clamp01(vec3f v) { return make_vec3f(clampf(v.x, 0.f, 1.f), clampf(v.y, 0.f, 1.f), clampf(v.z, 0.f, 1.f)); }
+__device__ __forceinline__ vec3f rotateAxis(vec3f v, vec3f axis, float theta) // rkcommon rotate (Rodrigues), restated
+{
+  float s, c;
+  sincosf(theta, &s, &c);
+  return v * c + cross(axis, v) * s + axis * dot(axis, v) * (1.f - c);
+}
+
+// Principled_getBSDF (Principled.ispc:84-428) for solid materials without sheen and without texture maps; mediumIsOutside =
+// eq(currentMedium, outsideMedium)
+__device__ __forceinline__ void Principled_getBSDF(PrBSDF &b, const OcPrincipled &m, const float *tables, const DifferentialGeometry &dg, bool mediumIsOutside)
+{
+  b.frame = makeShadingFrame(dg);
+  const float rotation = clampf(m.rotation, 0.f, 1.f);
+  const float theta = 2.f * OC_PI * rotation;
+  if (theta > 0.f) {
+    b.frame.vx = rotateAxis(b.frame.vx, b.frame.vz, theta);
+    b.frame.vy = cross(b.frame.vz, b.frame.vx);
+  }
+  const float opacity = clampf(m.opacity, 0.f, 1.f);
+  b.albedo = make_vec3f(0.f); b.scatteringType = 0; b.importanceSum = 0.f;
+  b.hasBase = false; b.coatKind = 0; b.opacity = 0.f; b.transparency = 0.f;
+  if (m.opacity > PR_EPS) {
+    PrBase &B = b.base;
+    B.frame = b.frame;
+    B.albedo = make_vec3f(0.f); B.scatteringType = 0; B.importanceSum = 0.f;
+    B.w[0] = B.w[1] = B.w[2] = 0.f; B.imp[0] = B.imp[1] = B.imp[2] = 0.f;
+    B.metalKind = 0; B.hasGlass = B.hasPlastic = false;
+    const vec3f baseColor = clamp01(toV(m.baseColor) * make_vec3f(dg.color));
+    const float specular = clampf(m.specular, 0.f, 1.f), metallic = clampf(m.metallic, 0.f, 1.f);
+    const float roughness = clampf(m.roughness, 0.f, 1.f), anisotropy = clampf(m.anisotropy, 0.f, 1.f);
+    const bool fromOutside = mediumIsOutside;
+    const float dielectric = 1.f - metallic;
+    if (dielectric > PR_EPS) {
+      const float transmission = clampf(m.transmission, 0.f, 1.f);
+      float ior = m.ior;
+      if (ior < 1.f) ior = 1.f / ior;
+      float eta = fromOutside ? m.outsideIor * (1.f / ior) : ior * (1.f / m.outsideIor);
+      eta = clampf(eta, 1.f / 3.f, 3.f);
+      const float plastic = dielectric * (1.f - transmission);
+      if (plastic > PR_EPS) {
+        PrPlastic &P = B.plastic;
+        P.frame = b.frame;
+        const float diffuse = clampf(m.diffuse, 0.f, 1.f);
+        const vec3f diffuseColor = baseColor * diffuse;
+        PrDiffuse &D = P.diffuse;
+        D.frame = b.frame; D.R = diffuseColor; D.roughness = roughness; D.orenNayar = !(m.roughness < PR_EPS);
+        // (solid: backlight = 0, diffuseTransmission = 0, diffuseReflection = 1)
+        D.weight = 1.f; D.importance = 1.f; D.importanceSum = 1.f;
+        D.albedo = diffuseColor * 1.f; D.scatteringType = SC_DIFFUSE_REFLECTION;
+        if (m.specular > PR_EPS) {
+          if (m.roughness < PR_EPS) { P.layerKind = 1; DielectricLayer_init(P.layer, D.albedo, D.scatteringType, eta, make_vec3f(1.f), 1.f, specular); }
+          else { P.layerKind = 2; MicrofacetDielectricLayer_init(P.layer, tables, D.albedo, D.scatteringType, eta, make_vec3f(1.f), 1.f, roughness, anisotropy, specular); }
+          P.albedo = P.layer.albedo; P.scatteringType = P.layer.scatteringType;
+        } else {
+          P.layerKind = 0; P.layer.weight = 0.f;
+          P.albedo = D.albedo; P.scatteringType = D.scatteringType;
+        }
+        B.hasPlastic = true;
+        B.w[2] = plastic; B.imp[2] = plastic * fmaxf(diffuse, specular);
+        B.albedo = B.albedo + P.albedo * plastic; B.scatteringType |= P.scatteringType; B.importanceSum += B.imp[2];
+      }
+      const float glass = dielectric * transmission * specular;
+      if (glass > PR_EPS) {
+        PrGlass &G = B.glass;
+        G.frame = b.frame;
+        if (fabsf(eta - 1.f) > PR_EPS) {
+          if (m.roughness < PR_EPS) { G.kind = 1; G.eta = eta; G.albedo = make_vec3f(1.0f); G.scatteringType = SC_SPECULAR; }
+          else PrGlass_initMicrofacet(G, tables, eta, roughness, anisotropy);
+        } else { G.kind = 0; G.eta = 1.f; G.albedo = make_vec3f(1.f); G.scatteringType = SC_SPECULAR_TRANSMISSION; }
+        B.hasGlass = true;
+        B.w[1] = glass; B.imp[1] = glass;
+        B.albedo = B.albedo + G.albedo * glass; B.scatteringType |= G.scatteringType; B.importanceSum += glass;
+      }
+    }
+    const float conductor = metallic * (m.specularMetallic ? specular : 1.0f);
+    if (conductor > PR_EPS) {
+      const vec3f edgeColor = clamp01(toV(m.edgeColor));
+      // FresnelConductorArtistic_create (Fresnel.ih:264-284)
+      const vec3f r = vmin(baseColor, make_vec3f(0.99f)), g = edgeColor;
+      const vec3f one = make_vec3f(1.f);
+      const vec3f sq = make_vec3f(sqrtf(r.x), sqrtf(r.y), sqrtf(r.z));
+      const vec3f n_min = (one - r) * rcp3(one + r);
+      const vec3f n_max = (one + sq) * rcp3(one - sq);
+      const vec3f n = g * n_min + (one - g) * n_max;
+      const vec3f k2 = (sqr3(n + one) * r - sqr3(n - one)) * rcp3(one - r);
+      ConductorBSDF &M = B.metal;
+      M.frame = b.frame; M.tables = tables;
+      M.eta = n;
+      M.k = make_vec3f(sqrtf(fmaxf(k2.x, 0.f)), sqrtf(fmaxf(k2.y, 0.f)), sqrtf(fmaxf(k2.z, 0.f))); // sqrt_safe
+      // FresnelConductorArtistic_evalAvg (:248-262)
+      const vec3f r2 = r * r, r3 = r2 * r, g2 = g * g, g3 = g2 * g;
+      const vec3f Favg = make_vec3f(0.087237f) + 0.0230685f * g - 0.0864902f * g2 + 0.0774594f * g3 + 0.782654f * r - 0.136432f * r2 + 0.278708f * r3
+          + 0.19744f * g * r + 0.0360605f * g2 * r - 0.2586f * g * r2;
+      vec3f metalAlbedo;
+      if (m.roughness < PR_EPS) { B.metalKind = 1; metalAlbedo = Favg; }
+      else {
+        B.metalKind = 2;
+        M.Eavg = mfAlbedoAvg(tables, roughness);
+        M.fmsScale = sqr3(Favg) * M.Eavg * rcp3(one - Favg * (1.f - M.Eavg));
+        M.mf = makeGGX(roughness, anisotropy);
+        M.roughness = roughness;
+        metalAlbedo = Favg * M.Eavg;
+      }
+      B.w[0] = conductor; B.imp[0] = conductor;
+      B.albedo = B.albedo + metalAlbedo * conductor;
+      B.scatteringType |= (B.metalKind == 1 ? SC_SPECULAR_REFLECTION : SC_GLOSSY_REFLECTION);
+      B.importanceSum += conductor;
+    }
+    // clear coat
+    vec3f topAlbedo = B.albedo;
+    uint32_t topType = B.scatteringType;
+    if (m.coat > PR_EPS) {
+      const float coat = clampf(m.coat, 0.f, 1.f);
+      float coatIor = m.coatIor;
+      if (coatIor < 1.f) coatIor = 1.f / coatIor;
+      float coatEta = fromOutside ? m.outsideIor * (1.f / coatIor) : coatIor * (1.f / m.outsideIor);
+      coatEta = clampf(coatEta, 1.f / 3.f, 3.f);
+      const vec3f coatColor = clamp01(toV(m.coatColor));
+      const float coatThickness = fmaxf(m.coatThickness, 0.f);
+      if (m.coatRoughness < PR_EPS || fabsf(coatEta - 1.f) < PR_EPS) {
+        b.coatKind = 1;
+        DielectricLayer_init(b.coat, B.albedo, B.scatteringType, coatEta, coatColor, coatThickness, coat);
+      } else {
+        b.coatKind = 2;
+        MicrofacetDielectricLayer_init(b.coat, tables, B.albedo, B.scatteringType, coatEta, coatColor, coatThickness, clampf(m.coatRoughness, 0.f, 1.f), 0.f, coat);
+      }
+      topAlbedo = b.coat.albedo; topType = b.coat.scatteringType;
+    } else
+      b.coat.weight = 0.f;
+    b.hasBase = true;
+    b.opacity = opacity;
+    b.albedo = b.albedo + topAlbedo * opacity; b.scatteringType |= topType; b.importanceSum += opacity;
+  }
+  if (1.f - m.opacity > PR_EPS) {
+    const float transparency = 1.f - opacity;
+    b.transparency = transparency;
+    b.albedo = b.albedo + make_vec3f(transparency) * 1.f; b.scatteringType |= SC_SPECULAR_TRANSMISSION; b.importanceSum += transparency;
+  }
+}
+
+// ClearCoatBSDF_eval / _sample (Principled.ispc:900-960): the coat over the base MultiBSDF
+__device__ __forceinline__ EvalRes PrCoat_eval(const PrBSDF &b, vec3f wo, vec3f wi)
+{
+  if (b.coatKind == 0 || b.coat.weight < PR_EPS) return b.base.eval(wo, wi);
+  if (b.coatKind == 2) return MicrofacetDielectricLayer_eval(b.coat, b.frame, b.base, wo, wi);
+  return DielectricLayer_eval(b.coat, b.frame.vz, b.base, wo, wi);
+}
+__device__ __forceinline__ SampleRes PrCoat_sample(const PrBSDF &b, vec3f wo, vec2f s, float ss)
+{
+  if (b.coatKind == 0 || b.coat.weight < PR_EPS) return b.base.sample(wo, s, ss);
+  if (b.coatKind == 2) return MicrofacetDielectricLayer_sample(b.coat, b.frame, b.base, wo, s, ss);
+  return DielectricLayer_sample(b.coat, b.frame.vz, b.base, wo, s, ss);
+}
+// Principled_BSDF_eval / _sample (Principled.ispc:1000-1040): the root MultiBSDF (child 0 = cut-out transmission)
+static __device__ __noinline__ EvalRes Principled_eval(const PrBSDF &b, vec3f wo, vec3f wi)
+{
+  EvalRes e; e.value = make_vec3f(0.f); e.pdf = 0.f;
+  if (b.hasBase && b.opacity > 0.f) {
+    EvalRes c = PrCoat_eval(b, wo, wi);
+    c.value = c.value * b.opacity;
+    e.value = e.value + c.value;
+    e.pdf += c.pdf * b.opacity;
+  }
+  e.pdf *= 1.f / b.importanceSum;
+  return e;
+}
+static __device__ __noinline__ SampleRes Principled_sample(const PrBSDF &b, vec3f wo, vec2f s, float ss)
+{
+  SampleRes res; res.weight = make_vec3f(0.f); res.wi = make_vec3f(0.f); res.pdf = 0.f; res.type = 0;
+  if (b.importanceSum == 0.f) return res;
+  const float x = ss * b.importanceSum;
+  int choice;
+  float prefix = 0.f;
+  if (x < (prefix += b.transparency)) {
+    choice = 0;
+    res.wi = neg(wo); res.pdf = INFINITY; res.type = SC_SPECULAR_TRANSMISSION; res.weight = make_vec3f(b.transparency);
+    res.weight = res.weight * 1.f;
+  } else if (x < (prefix += (b.hasBase ? b.opacity : 0.f))) {
+    choice = 1;
+    const float ssc = (x + b.opacity - prefix) * (1.f / b.opacity);
+    res = PrCoat_sample(b, wo, s, ssc);
+    res.weight = res.weight * b.opacity;
+  } else return res;
+  if ((res.weight.x == 0.f && res.weight.y == 0.f && res.weight.z == 0.f) || res.pdf == 0.0f) {
+    res.weight = make_vec3f(0.f); res.wi = make_vec3f(0.f); res.pdf = 0.f; res.type = 0;
+    return res;
+  }
+  const float choiceImp = choice == 0 ? b.transparency : b.opacity;
+  if (res.type & SC_SPECULAR) { res.weight = res.weight * (b.importanceSum * (1.f / choiceImp)); return res; }
+  EvalRes e;
+  e.value = res.weight * res.pdf;
+  res.pdf *= choiceImp;
+  e.pdf = res.pdf;
+  // (child 0 has no evaluation; child 1 is the one sampled)
+  res.pdf = e.pdf * (1.f / b.importanceSum);
+  res.weight = e.value * (1.f / res.pdf);
+  return res;
+}
+
+// Principled_getTransparency (Principled.ispc:430-573), same scope
+__device__ __forceinline__ vec3f Principled_getTransparency(const OcPrincipled &m, const float *tables, const DifferentialGeometry &dg, vec3f rayDir, bool mediumIsOutside)
+{
+  vec3f T = make_vec3f(0.f);
+  const float opacity = clampf(m.opacity, 0.f, 1.f);
+  const float transparency = 1.f - opacity;
+  const float transmission = clampf(m.transmission, 0.f, 1.f);
+  if (transparency <= PR_EPS && transmission <= PR_EPS) return T;
+  if (m.opacity > PR_EPS) {
+    const float specular = clampf(m.specular, 0.f, 1.f), metallic = clampf(m.metallic, 0.f, 1.f);
+    const float glass = (1.f - metallic) * transmission * specular;
+    if (glass > PR_EPS) {
+      const bool fromOutside = mediumIsOutside;
+      float ior = m.ior;
+      if (ior < 1.f) ior = 1.f / ior;
+      float eta = fromOutside ? m.outsideIor * (1.f / ior) : ior * (1.f / m.outsideIor);
+      eta = clampf(eta, 1.f / 3.f, 3.f);
+      const float cosThetaO = fmaxf(-dot(rayDir, dg.Ns), 0.f);
+      if (fabsf(eta - 1.f) > PR_EPS) {
+        if (m.roughness < PR_EPS) T = make_vec3f(1.f - fresnelDielectric(cosThetaO, eta)); // Dielectric_getTransparency
+      } else
+        T = make_vec3f(1.f);
+      if (reduce_max(T) > 0.f) {
+        if (m.coat > PR_EPS) {
+          const float coat = clampf(m.coat, 0.f, 1.f);
+          float coatIor = m.coatIor;
+          if (coatIor < 1.f) coatIor = 1.f / coatIor;
+          float coatEta = fromOutside ? m.outsideIor * (1.f / coatIor) : coatIor * (1.f / m.outsideIor);
+          const float coatEtaClamped = clampf(coatEta, 1.f / 3.f, 3.f);
+          if (fabsf(coatEtaClamped - 1.f) > PR_EPS) {
+            const vec3f coatColor = clamp01(toV(m.coatColor));
+            const float coatThickness = fmaxf(m.coatThickness, 0.f);
+            if (m.coatRoughness < PR_EPS) { // DielectricLayer_getTransparency (DielectricLayer.ih:52-76), unclamped eta
+              float e = coatEta;
+              if (e < 1.f) e = 1.f / e;
+              float cosThetaO1;
+              const float Fo = fresnelDielectricEx(cosThetaO, cosThetaO1, e) * coat;
+              vec3f value = lerpv(coat, make_vec3f(1.f), powv(coatColor, coatThickness * (1.f / cosThetaO1)));
+              T = T * (value * (1.f - Fo));
+            } else { // MicrofacetDielectricLayer_getTransparency (MicrofacetDielectricLayer.ih:113-146)
+              float e = coatEta;
+              if (e > 1.f) e = 1.f / e;
+              const float cr = clampf(m.coatRoughness, 0.f, 1.f);
+              vec3f value = lerpv(coat, make_vec3f(1.f), powv(coatColor, coatThickness * (1.f / refractCos(cosThetaO, e))));
+              const float Eavg = mfAlbedoAvg(tables, cr);
+              const float Favg = fresnelDielectricAvg(e);
+              const float fmsScale = Favg * (1.f - Eavg) * (1.f / (1.f - Favg * Eavg));
+              const float Eo = mfAlbedo(tables, cosThetaO, cr);
+              const float Ro = (mfDielReflAlbedo(tables, cosThetaO, e, cr) + fmsScale * (1.f - Eo)) * coat;
+              T = T * (value * (1.f - Ro));
+            }
+          }
+        }
+        T = T * glass;
+      }
+    }
+  }
+  return T * opacity + make_vec3f(transparency);
+}
+
+} // namespace oc

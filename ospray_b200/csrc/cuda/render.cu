@@ -889,6 +889,7 @@ int ptCarve(oc::PtScratch &s, uint32_t paths, uint32_t nls, bool needAcc, uint32
   off[k++] = take(hasVol ? P * 16 : 0);                      // rnd
   off[k++] = take(hasVol ? P * 4 * nls : 0);                 // shT0
   off[k++] = take(P * 8);                                    // cone
+  for (int i = 0; i < 2; i++) off[k++] = take(P * 16);       // med shMed
   for (int i = 0; i < 2; i++) off[k++] = take(P * 4);        // pathQ
   for (int i = 0; i < 2; i++) off[k++] = take(P * 4 * nls);  // shadowQ
   off[k++] = take(numCounters * 4);
@@ -914,6 +915,7 @@ int ptCarve(oc::PtScratch &s, uint32_t paths, uint32_t nls, bool needAcc, uint32
   s.accNrm = (float4 *)(b + off[k++]); s.accAlb = (float4 *)(b + off[k++]);
   s.rnd = (uint4 *)(b + off[k++]); s.shT0 = (float *)(b + off[k++]);
   s.cone = (float2 *)(b + off[k++]);
+  s.med = (float4 *)(b + off[k++]); s.shMed = (float4 *)(b + off[k++]);
   s.pathQ[0] = (uint32_t *)(b + off[k++]); s.pathQ[1] = (uint32_t *)(b + off[k++]);
   s.shadowQ[0] = (uint32_t *)(b + off[k++]); s.shadowQ[1] = (uint32_t *)(b + off[k++]);
   s.counters = (uint32_t *)(b + off[k++]);
@@ -923,7 +925,7 @@ int ptCarve(oc::PtScratch &s, uint32_t paths, uint32_t nls, bool needAcc, uint32
 
 size_t ptBytesPerPath(uint32_t nls, bool needAcc, bool hasVol)
 {
-  return 8 * 16 + 16 + 5 * 16 + (48 + 8 + 8) * (size_t)nls + (needAcc ? 96 : 0) + 8 + 8 + (hasVol ? 16 + 4 * (size_t)nls : 0);
+  return 8 * 16 + 16 + 5 * 16 + (48 + 8 + 8) * (size_t)nls + (needAcc ? 96 : 0) + 8 + 8 + 32 + (hasVol ? 16 + 4 * (size_t)nls : 0);
 }
 
 // Launch sequence of one sample pass: GEN, then TRACE(d) / SHADE(d) for d = 0 .. maxDepth. Every stage d owns four

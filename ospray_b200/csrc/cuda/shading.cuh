@@ -339,7 +339,8 @@ struct ObjBSDF
   bool pureTransmission;   // a lone Transmission BSDF (materials/Luminous.ispc:18-35): T in `T`
   uint32_t kind;           // BSDF_KIND_*: 0 = the cases above; the others only exist in the extended-material kernels
 };
-enum { BSDF_KIND_OBJ = 0, BSDF_KIND_CONDUCTOR, BSDF_KIND_MICROFACET_CONDUCTOR, BSDF_KIND_PLASTIC_SMOOTH, BSDF_KIND_PLASTIC_ROUGH };
+enum { BSDF_KIND_OBJ = 0, BSDF_KIND_CONDUCTOR, BSDF_KIND_MICROFACET_CONDUCTOR, BSDF_KIND_PLASTIC_SMOOTH, BSDF_KIND_PLASTIC_ROUGH,
+       BSDF_KIND_PRINCIPLED };
 
 // render/Material.ih:25-37
 __device__ __forceinline__ linear3f makeShadingFrame(const DifferentialGeometry &dg)
@@ -400,9 +401,19 @@ __device__ __forceinline__ vec3f sqr3(vec3f v) { return v * v; }
 __device__ __forceinline__ vec3f rcp3(vec3f v) { return make_vec3f(1.f / v.x, 1.f / v.y, 1.f / v.z); }
 } // namespace oc
 #include "microfacet.cuh"
+#include "principled.cuh"
 namespace oc {
-// state of the microfacet-family BSDFs (metal, plastic): kept apart from ObjBSDF so that the OBJ path's registers stay as they are
-struct ExtBSDF { ConductorBSDF cond; LayerParams layer; LambertSub lambert; };
+// state of the microfacet-family BSDFs (metal, plastic, principled): kept apart from ObjBSDF so that the OBJ path's registers
+// stay as they are
+struct ExtBSDF { ConductorBSDF cond; LayerParams layer; LambertSub lambert; PrBSDF pr; };
+// the medium a path travels in (render/materials/MediumShared.h:10-18; vacuum = no attenuation, ior 1)
+struct Medium { vec3f attenuation; float ior; };
+__device__ __forceinline__ Medium mediumVacuum() { Medium m; m.attenuation = make_vec3f(0.f); m.ior = 1.f; return m; }
+__device__ __forceinline__ bool mediumIsOutside(const Medium &a, const OcPrincipled &q) // eq(currentMedium, self->outsideMedium)
+{
+  return a.ior == q.outsideIor && a.attenuation.x == q.outsideAttenuation.x && a.attenuation.y == q.outsideAttenuation.y
+      && a.attenuation.z == q.outsideAttenuation.z;
+}
 
 // ThinGlass.ispc:17-30
 template <bool TEX = false>
@@ -649,14 +660,22 @@ __device__ __forceinline__ SampleRes OBJ_sample(const ObjBSDF &b, vec3f wo, vec2
 // ---- metal and plastic (extended-material kernels only) -------------------------------------------------------------
 // Metal_getBSDF (materials/Metal.ispc:18-46, RGB form) and Plastic_getBSDF (materials/Plastic.ispc:25-67): fills `b` (frame,
 // albedo, scattering type, kind) and the family state `x`; false: not one of these materials
-__device__ __forceinline__ bool Ext_getBSDF(ObjBSDF &b, ExtBSDF &x, const DifferentialGeometry &dg)
+__device__ __forceinline__ bool Ext_getBSDF(ObjBSDF &b, ExtBSDF &x, const DifferentialGeometry &dg, const Medium &medium)
 {
   const OcMaterial *m = dg.material;
-  if (!m || (m->type != OC_MATERIAL_METAL && m->type != OC_MATERIAL_PLASTIC)) return false;
+  if (!m || (m->type != OC_MATERIAL_METAL && m->type != OC_MATERIAL_PLASTIC && m->type != OC_MATERIAL_PRINCIPLED)) return false;
   b.valid = true;
-  b.frame = frame(dg.Ns);
   b.importanceSum = 1.f; b.impL = b.impT = b.impS = 0.f;
   b.Kd = b.T = b.ks = b.specWeight = make_vec3f(0.f); b.ns = 0.f;
+  if (m->type == OC_MATERIAL_PRINCIPLED) {
+    Principled_getBSDF(x.pr, m->principled, m->microfacetTables, dg, mediumIsOutside(medium, m->principled));
+    b.kind = BSDF_KIND_PRINCIPLED;
+    b.frame = x.pr.frame;
+    b.albedo = x.pr.albedo;
+    b.scatteringType = x.pr.scatteringType;
+    return true;
+  }
+  b.frame = frame(dg.Ns);
   if (m->type == OC_MATERIAL_METAL) {
     x.cond.frame = b.frame;
     x.cond.eta = toV(m->Kd); x.cond.k = toV(m->Ks);
@@ -698,6 +717,7 @@ static __device__ __noinline__ EvalRes Ext_eval(const ObjBSDF &b, const ExtBSDF 
   case BSDF_KIND_MICROFACET_CONDUCTOR: return MicrofacetConductor_eval(x.cond, wo, wi);
   case BSDF_KIND_PLASTIC_SMOOTH: return DielectricLayer_eval(x.layer, b.frame.vz, x.lambert, wo, wi);
   case BSDF_KIND_PLASTIC_ROUGH: return MicrofacetDielectricLayer_eval(x.layer, b.frame, x.lambert, wo, wi);
+  case BSDF_KIND_PRINCIPLED: return Principled_eval(x.pr, wo, wi);
   default: return e; // smooth conductor: purely specular
   }
 }
@@ -707,15 +727,38 @@ static __device__ __noinline__ SampleRes Ext_sample(const ObjBSDF &b, const ExtB
   case BSDF_KIND_CONDUCTOR: return Conductor_sample(x.cond, wo);
   case BSDF_KIND_MICROFACET_CONDUCTOR: return MicrofacetConductor_sample(x.cond, wo, s);
   case BSDF_KIND_PLASTIC_SMOOTH: return DielectricLayer_sample(x.layer, b.frame.vz, x.lambert, wo, s, ss);
+  case BSDF_KIND_PRINCIPLED: return Principled_sample(x.pr, wo, s, ss);
   default: return MicrofacetDielectricLayer_sample(x.layer, b.frame, x.lambert, wo, s, ss);
   }
 }
 
 // materials/OBJ.ispc:93-111, materials/ThinGlass.ispc:52-64
-template <bool TEX = false>
-__device__ __forceinline__ vec3f materialTransparency(const DifferentialGeometry &dg, vec3f rayDir)
+// Principled_selectNextMedium (Principled.ispc:582-608); the other materials built here have no interface (Material.ispc)
+__device__ __forceinline__ void materialSelectNextMedium(const DifferentialGeometry &dg, Medium &medium)
 {
   const OcMaterial *m = dg.material;
+  if (!m || m->type != OC_MATERIAL_PRINCIPLED) return;
+  const OcPrincipled &q = m->principled;
+  if (q.transmission <= PR_EPS) return;
+  if (mediumIsOutside(medium, q)) {
+    float ior = q.ior;
+    if (ior < 1.f) ior = 1.f / ior;
+    const vec3f tc = clamp01(toV(q.transmissionColor));
+    const float depth = fmaxf(q.transmissionDepth, PR_EPS);
+    medium.ior = ior;
+    medium.attenuation = logf3(tc) / depth;
+  } else {
+    medium.ior = q.outsideIor;
+    medium.attenuation = toV(q.outsideAttenuation);
+  }
+}
+
+template <bool TEX = false>
+__device__ __forceinline__ vec3f materialTransparency(const DifferentialGeometry &dg, vec3f rayDir, const Medium &medium = mediumVacuum())
+{
+  const OcMaterial *m = dg.material;
+  if (TEX && m && m->type == OC_MATERIAL_PRINCIPLED)
+    return Principled_getTransparency(m->principled, m->microfacetTables, dg, rayDir, mediumIsOutside(medium, m->principled));
   if (m && m->type == OC_MATERIAL_THINGLASS) {
     const float cosThetaO = fmaxf(-dot(rayDir, dg.Ns), 0.0f);
     return RobustThinDielectric_getTransparency(cosThetaO, m->eta, ThinGlass_getAttenuation<TEX>(m, dg));

@@ -455,6 +455,44 @@ void Material::commit()
     m.eta = 1.f / getParam<float>("eta", 1.4f);
     m.Ns = getParam<float>("roughness", 0.01f);
     extended = true;
+  } else if (type == "principled") {
+    // render/materials/Principled.cpp:33-150. Built: the solid form (thin = false) without sheen; texture maps and normal
+    // maps of this material are refused rather than ignored.
+    for (auto &p : params)
+      if (p.first.rfind("map_", 0) == 0) throw std::runtime_error("cuda device: principled texture maps are not supported ('" + p.first + "')");
+    if (getParam<bool>("thin", false)) throw std::runtime_error("cuda device: principled 'thin' mode is not supported");
+    if (getParam<float>("sheen", 0.f) > 1e-5f) throw std::runtime_error("cuda device: principled 'sheen' is not supported");
+    for (const char *ign : {"sheenColor", "sheenTint", "sheenRoughness", "backlight", "thickness", "normal", "baseNormal", "coatNormal"})
+      if (auto it = params.find(ign); it != params.end()) it->second.queried = true; // no effect on a solid, unmapped, sheen-less material
+    m.type = OC_MATERIAL_PRINCIPLED;
+    OcPrincipled &q = m.principled;
+    q.baseColor = toOc(getParam<vec3f>("baseColor", make_vec3f(0.8f)));
+    q.edgeColor = toOc(getParam<vec3f>("edgeColor", make_vec3f(1.f)));
+    q.metallic = getParam<float>("metallic", 0.f);
+    q.diffuse = getParam<float>("diffuse", 1.f);
+    q.specular = getParam<float>("specular", 1.f);
+    q.specularMetallic = getParam<bool>("specularMetallic", true) ? 1u : 0u;
+    q.ior = getParam<float>("ior", 1.f);
+    q.transmission = getParam<float>("transmission", 0.f);
+    q.transmissionColor = toOc(getParam<vec3f>("transmissionColor", make_vec3f(1.f)));
+    q.transmissionDepth = getParam<float>("transmissionDepth", 1.f);
+    q.roughness = getParam<float>("roughness", 0.f);
+    q.anisotropy = getParam<float>("anisotropy", 0.f);
+    q.rotation = getParam<float>("rotation", 0.f);
+    q.coat = getParam<float>("coat", 0.f);
+    q.coatIor = getParam<float>("coatIor", 1.5f);
+    q.coatColor = toOc(getParam<vec3f>("coatColor", make_vec3f(1.f)));
+    q.coatThickness = getParam<float>("coatThickness", 1.f);
+    q.coatRoughness = getParam<float>("coatRoughness", 0.f);
+    q.opacity = getParam<float>("opacity", 1.f);
+    const float outsideIor = getParam<float>("outsideIor", 1.f);
+    const vec3f otc = getParam<vec3f>("outsideTransmissionColor", make_vec3f(1.f));
+    const float otd = getParam<float>("outsideTransmissionDepth", 1.f);
+    q.outsideIor = outsideIor >= 1.f ? outsideIor : 1.f / outsideIor;
+    q.outsideAttenuation = toOc(make_vec3f(std::log(otc.x), std::log(otc.y), std::log(otc.z)) / otd);
+    m.emission = toOc(getParam<vec3f>("emissiveColor", make_vec3f(0.f)) * getParam<float>("intensity", 1.f));
+    m.isEmissive = std::max(m.emission.x, std::max(m.emission.y, m.emission.z)) > 0.f ? 1u : 0u;
+    extended = true;
   } else if (type == "luminous") {
     // render/materials/Luminous.cpp:33-45: radiance = color * intensity (times map_color), isEmissive = any of it
     m.type = OC_MATERIAL_LUMINOUS;
@@ -1196,6 +1234,7 @@ uint32_t World::computeShadowOpaque(const Renderer *renderer) const
         const OcMaterial &mt = table[slot];
         if (mt.hasTextures || mt.type == OC_MATERIAL_THINGLASS) return 0u;
         if (mt.type == OC_MATERIAL_LUMINOUS && mt.transparency != 0.f) return 0u;
+        if (mt.type == OC_MATERIAL_PRINCIPLED) return 0u; // (cut-out opacity, transmission: decided per occluder)
         if (mt.type == OC_MATERIAL_OBJ && !(mt.d == 1.f && mt.Tf.x == 0.f && mt.Tf.y == 0.f && mt.Tf.z == 0.f)) return 0u;
       }
     }

@@ -62,6 +62,7 @@ class MaterialSpec:
     roughness: float = 0.1                      # metal / plastic
     map_roughness: Optional["MapSpec"] = None
     pigment_color: tuple = (1.0, 1.0, 1.0)      # plastic (Plastic.cpp:28-38); `eta` above is its index of refraction
+    principled: dict = field(default_factory=dict)  # principled (Principled.cpp:33-150): ospray parameter name -> value
 
 
 @dataclass
@@ -459,6 +460,12 @@ def _material(m: MaterialSpec):
         return mat.commit()
     if m.type == "plastic":
         mat.set("pigmentColor", tuple(float(x) for x in m.pigment_color)).set("eta", float(m.eta)).set("roughness", float(m.roughness))
+        return mat.commit()
+    if m.type == "principled":
+        for name, v in m.principled.items():
+            if isinstance(v, bool): mat.set(name, bool(v))
+            elif isinstance(v, (tuple, list)): mat.set(name, tuple(float(x) for x in v))
+            else: mat.set(name, float(v))
         return mat.commit()
     if m.type == "luminous":
         _set_map(mat, "map_color", m.map_color)

@@ -133,14 +133,16 @@ def _tex_rng_image(h, w, c, seed, dtype=np.uint8, lo=0.15, hi=1.0):
     return np.ascontiguousarray(a.astype(dtype))
 
 
-def _cornell_models(materials):
+def _cornell_models(materials, drop=()):
     """the cornell box as one model per material: `materials` maps a tuple of quad indices to a MaterialSpec; every quad
-    carries texture coordinates (0,0) (2,0) (2,2) (0,2) so that wrap modes take part; the rest keeps the default material"""
+    carries texture coordinates (0,0) (2,0) (2,2) (0,2) so that wrap modes take part; the rest keeps the default material.
+    `drop`: quads left out (the boxes' bottom faces are coplanar with the floor: once a box lets rays in, which of the two a
+    ray meets first is a tie that every traversal order breaks its own way)"""
     base = T.cornell_box()
     g = base.instances[0].group.models[0].geometry
     v, c = g.vertex.reshape(-1, 4, 3), g.vertex_color.reshape(-1, 4, 4)
     st = np.array([[0, 0], [2, 0], [2, 2], [0, 2]], np.float32)
-    used = set(q for qs in materials for q in qs)
+    used = set(q for qs in materials for q in qs) | set(drop)
     groups = list(materials.items()) + [(tuple(q for q in range(len(v)) if q not in used), T.MaterialSpec())]
     models = []
     for qs, mat in groups:
@@ -259,6 +261,33 @@ def plastic_cornell(rough):
     return _cornell_models(mats)
 
 
+def principled_cornell(variant):
+    """cornell box whose boxes carry the principled material (render/materials/Principled.ispc), one lobe family per variant:
+    short box | tall box"""
+    P = lambda **kw: T.MaterialSpec(type="principled", principled=kw)
+    a, b = {
+        # smooth plastic (DielectricLayer over Lambert) | smooth metal with an edge tint (Conductor, artistic Fresnel)
+        "plastic": (P(baseColor=(0.8, 0.3, 0.2), ior=1.5, diffuse=0.9, specular=0.8),
+                    P(baseColor=(0.9, 0.6, 0.2), edgeColor=(0.9, 0.9, 0.6), metallic=1.0)),
+        # rough anisotropic metal (MicrofacetConductor) | half metal, half smooth plastic (the base MultiBSDF mixes them)
+        "metal": (P(baseColor=(0.7, 0.7, 0.8), edgeColor=(1.0, 0.8, 0.7), metallic=1.0, roughness=0.3, anisotropy=0.6, rotation=0.15),
+                  P(baseColor=(0.3, 0.6, 0.3), metallic=0.6, specularMetallic=False, specular=0.7, ior=1.4)),
+        # smooth coloured glass (Dielectric + medium) | rough glass (MicrofacetDielectric)
+        "glass": (P(transmission=1.0, ior=1.5, transmissionColor=(0.6, 0.9, 0.7), transmissionDepth=0.5),
+                  P(transmission=1.0, ior=1.4, roughness=0.25, transmissionColor=(0.9, 0.7, 0.6), transmissionDepth=1.5)),
+        # tinted smooth clear coat over smooth plastic | coated metal cut out by opacity
+        "coat": (P(baseColor=(0.2, 0.3, 0.8), ior=1.45, coat=1.0, coatIor=1.6, coatColor=(0.9, 0.6, 0.6), coatThickness=2.0),
+                 P(baseColor=(0.8, 0.8, 0.3), metallic=1.0, coat=0.7, coatIor=1.3, opacity=0.6)),
+        # rough dielectric layers (MicrofacetDielectricLayer as plastic and as coat): see REF_UNDEFINED_STATE_CASES
+        "rough_layers": (P(baseColor=(0.8, 0.4, 0.2), ior=1.5, roughness=0.3),
+                         P(baseColor=(0.3, 0.5, 0.8), ior=1.4, coat=0.8, coatRoughness=0.2, coatIor=1.5)),
+        # emissive surface (a geometry light) | partly transmissive plastic-glass mixture in a non-vacuum outside medium
+        "emissive": (P(baseColor=(0.5, 0.5, 0.5), emissiveColor=(1.0, 0.6, 0.3), intensity=1.5, ior=1.3),
+                     P(baseColor=(0.6, 0.8, 0.9), transmission=0.5, ior=1.6, outsideIor=1.1, transmissionColor=(0.8, 0.9, 1.0))),
+    }[variant]
+    return _cornell_models({(5, 6, 7, 8, 9): a, (11, 12, 13, 14, 15): b}, drop=(10, 16))
+
+
 def backplate_scene():
     """renderer textures: map_backplate behind random spheres and map_maxDepth cutting the primary rays (Renderer.ispc:18-39)"""
     s = T.random_spheres(24, seed=3)
@@ -350,6 +379,12 @@ CASES = {
     "metal_rough_pt": (lambda: metal_cornell(True), "pathtracer", {"pixelSamples": 2}, 2),
     "plastic_smooth_pt": (lambda: plastic_cornell(False), "pathtracer", {"pixelSamples": 2}, 2),
     "plastic_rough_pt": (lambda: plastic_cornell(True), "pathtracer", {"pixelSamples": 2}, 2),
+    "principled_plastic_pt": (lambda: principled_cornell("plastic"), "pathtracer", {"pixelSamples": 2}, 2),
+    "principled_metal_pt": (lambda: principled_cornell("metal"), "pathtracer", {"pixelSamples": 2}, 2),
+    "principled_glass_pt": (lambda: principled_cornell("glass"), "pathtracer", {"pixelSamples": 2}, 2),
+    "principled_coat_pt": (lambda: principled_cornell("coat"), "pathtracer", {"pixelSamples": 2}, 2),
+    "principled_rough_layers_pt": (lambda: principled_cornell("rough_layers"), "pathtracer", {"pixelSamples": 2}, 2),
+    "principled_emissive_pt": (lambda: principled_cornell("emissive"), "pathtracer", {"pixelSamples": 2}, 2),
     # debug renderer (render/debug/DebugRenderer.ispc), every method the device accepts
     "debug_testFrame": (T.cornell_box, "debug", {"method": "testFrame", "pixelSamples": 2}, 2),
     "debug_rayDir": (T.cornell_box, "debug", {"method": "rayDir"}, 1),
@@ -373,12 +408,13 @@ REF_UNSUPPORTED = {"volume_geometry"}
 ORACLE_UNSUPPORTED = {"textured_pt", "textured_bias_pt", "cutout_pt", "backplate_pt", "emissive_pt", "emissive_nogeolights_pt",
                       "emissive_transparent_pt", "textured_scivis", "textured_ao", "cutout_scivis", "cutout_ao", "backplate_scivis",
                       "backplate_ao", "debug_texCoord", "debug_dPdt", "debug_dPds_tex", "debug_backplate", "metal_smooth_pt", "metal_rough_pt",
-                      "plastic_smooth_pt", "plastic_rough_pt"}
+                      "plastic_smooth_pt", "plastic_rough_pt", "principled_plastic_pt", "principled_metal_pt", "principled_glass_pt",
+                      "principled_coat_pt", "principled_rough_layers_pt", "principled_emissive_pt"}
 # Rough dielectric coatings: MicrofacetDielectricLayer_Constructor reads self->eta for Ravg BEFORE assigning it
 # (bsdfs/MicrofacetDielectricLayer.ih:55 vs :68), i.e. whatever the shading context's memory held from the previous BSDF. The
 # device uses the intended value; against the reference's kernels the coated surfaces then differ by ~0.5 % in brightness
 # (measured: 4.6 % of the pixels beyond 2e-3 relative, median 0.3 %). Looser per-pixel bar, same bar on the image mean.
-REF_UNDEFINED_STATE_CASES = {"plastic_rough_pt"}
+REF_UNDEFINED_STATE_CASES = {"plastic_rough_pt", "principled_rough_layers_pt"}
 # Cases the cuda device does not render (none at present; the GPU parity tests skip what is listed here)
 DEVICE_UNSUPPORTED = set()
 # Volumes under the pathtracer: delta tracking takes hundreds of accept/reject decisions per path on logf / expf / lerp

@@ -16,7 +16,12 @@ tag, names = sys.argv[1], sys.argv[2:]
 out = os.path.join(ROOT, "gpurun_out", tag)
 os.makedirs(out, exist_ok=True)
 osp.init()
+import json  # noqa: E402
+extra = json.loads(os.environ.get("DBG_EXTRA", "{}"))  # renderer parameters laid over the case's own
 for name in names:
+    if extra:
+        c = scenes.CASES[name]
+        scenes.CASES[name] = (c[0], c[1], {**c[2], **extra}) + tuple(c[3:])
     backend = "ref" if name in scenes.ORACLE_UNSUPPORTED else "oracle"
     pf = "point" if os.environ.get("DBG_POINT") else None
     w, h = (int(os.environ.get("DBG_W", scenes.W)), int(os.environ.get("DBG_H", scenes.H)))

@@ -115,7 +115,7 @@ typedef struct {
 } OcTextureParam;
 
 enum { OC_MATERIAL_OBJ = 0, OC_MATERIAL_OTHER = 1, OC_MATERIAL_THINGLASS = 2, OC_MATERIAL_LUMINOUS = 3, OC_MATERIAL_METAL = 4,
-       OC_MATERIAL_PLASTIC = 5, OC_MATERIAL_PRINCIPLED = 6 };
+       OC_MATERIAL_PLASTIC = 5, OC_MATERIAL_PRINCIPLED = 6, OC_MATERIAL_GLASS = 7, OC_MATERIAL_ALLOY = 8 };
 /* principled (reference: ispc::Principled, render/materials/PrincipledShared.h:17-170, Principled.cpp:33-150), the solid form
  * without sheen and without texture maps: factors as committed; outsideIor = outsideIor >= 1 ? outsideIor : 1 / outsideIor,
  * outsideAttenuation = log(outsideTransmissionColor) / outsideTransmissionDepth (the medium around the object) */
@@ -160,7 +160,11 @@ typedef struct {
   float bumpRot[4];            /* OBJ.cpp:43-44: orthogonal part of map_bump's 2D transform, transposed (vx, vy) */
   /* OBJ: map_d, map_kd, map_ks, map_ns, map_bump (OBJShared.h:19-31); thinGlass: mapKd = map_attenuationColor */
   OcTextureParam mapD, mapKd, mapKs, mapNs, mapBump;
-  OcPrincipled principled;     /* type OC_MATERIAL_PRINCIPLED (emission / isEmissive above: emissiveColor * intensity) */
+  /* type OC_MATERIAL_PRINCIPLED (emission / isEmissive above: emissiveColor * intensity).
+   * glass (ispc::Glass, render/materials/GlassShared.h, Glass.cpp:35-63): eta / attenuation above = the inside medium (ior,
+   * log(attenuationColorInside) / max(attenuationDistance, EPS)), principled.outsideIor / outsideAttenuation = the outside one.
+   * alloy (ispc::Alloy, AlloyShared.h, Alloy.cpp:28-40): Kd = color, Ks = edgeColor, Ns = roughness, mapKd / mapKs / mapNs their maps */
+  OcPrincipled principled;
 } OcMaterial;
 
 /* 4-wide BVH node, 128 B = one cache line, fetched as 8 x 128-bit loads */

@@ -573,6 +573,21 @@ class Scene:
         elif ms.type == "plastic":  # render/materials/Plastic.cpp:28-38
             m.type = 5
             m.Kd, m.eta, m.Ns = Vec3(*map(float, np.asarray(ms.pigment_color, np.float32))), float(np.float32(1.0) / np.float32(ms.eta)), float(np.float32(ms.roughness))
+        elif ms.type == "glass":  # render/materials/Glass.cpp:35-63 (inside medium in eta / attenuation, outside one in principled.outside*)
+            f = np.float32
+            m.type = 7
+            dist = max(f(ms.attenuation_distance), f(1e-5))
+            m.eta = float(f(ms.eta))
+            m.attenuation = Vec3(*map(float, (np.log(np.asarray(ms.attenuation_color, np.float32)).astype(np.float32) / dist)))
+            m.principled.outsideIor = float(f(ms.eta_outside))
+            m.principled.outsideAttenuation = Vec3(*map(float, (np.log(np.asarray(ms.attenuation_color_outside, np.float32)).astype(np.float32) / dist)))
+        elif ms.type == "alloy":  # render/materials/Alloy.cpp:28-40 (Kd = color, Ks = edgeColor, Ns = roughness)
+            m.type = 8
+            m.Kd, m.Ks, m.Ns = Vec3(*map(float, np.asarray(ms.alloy_color, np.float32))), Vec3(*map(float, np.asarray(ms.edge_color, np.float32))), float(np.float32(ms.roughness))
+            for f_, mp in (("mapKd", ms.map_color), ("mapKs", ms.map_edge_color), ("mapNs", ms.map_roughness)):
+                if mp is not None:
+                    setattr(m, f_, texture_param(mp, self.keep, self.mipmaps))
+                    m.hasTextures = 1
         elif ms.type == "principled":  # render/materials/Principled.cpp:33-150 (solid, no sheen, no maps)
             f = np.float32
             prm = dict(PRINCIPLED_DEFAULTS)

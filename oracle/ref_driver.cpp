@@ -34,6 +34,8 @@
 #include "render/materials/MetalShared.h"
 #include "render/materials/PlasticShared.h"
 #include "render/materials/PrincipledShared.h"
+#include "render/materials/GlassShared.h"
+#include "render/materials/AlloyShared.h"
 #include "render/bsdfs/MicrofacetAlbedoTablesShared.h"
 #include "render/pathtracer/GeometryLightShared.h"
 #include "texture/Texture2DShared.h"
@@ -169,7 +171,7 @@ struct Scene
   std::deque<OBJ> objs; std::deque<ThinGlass> glasses; std::vector<Material *> allMaterials;
   std::deque<Texture2D> textures;
   std::deque<Luminous> luminous; std::deque<GeometryLight> geoLights;
-  std::deque<Metal> metals; std::deque<Plastic> plastics; std::deque<Principled> principleds;
+  std::deque<Metal> metals; std::deque<Plastic> plastics; std::deque<Principled> principleds; std::deque<Glass> solidGlasses; std::deque<Alloy> alloys;
   std::deque<std::vector<int>> geoPrimIDs; std::deque<std::vector<float>> geoDistributions;
   std::vector<float> geoCDF;
   std::vector<Instance *> instancePtrs;
@@ -316,6 +318,24 @@ void buildScene(Scene &s, const OcWorld *w, const OcRenderer *ren)
       pl.pigmentColor = v3(m.Kd); pl.eta = m.eta; pl.roughness = m.Ns;
       pl.super.microfacetAlbedoTables = refAlbedoTables();
       s.allMaterials.push_back(&pl.super);
+      continue;
+    }
+    if (m.type == OC_MATERIAL_GLASS) { // render/materials/Glass.cpp:35-63 (committed values)
+      s.solidGlasses.emplace_back();
+      Glass &gl = s.solidGlasses.back();
+      gl.mediumInside.ior = m.eta; gl.mediumInside.attenuation = v3(m.attenuation);
+      gl.mediumOutside.ior = m.principled.outsideIor; gl.mediumOutside.attenuation = v3(m.principled.outsideAttenuation);
+      s.allMaterials.push_back(&gl.super);
+      continue;
+    }
+    if (m.type == OC_MATERIAL_ALLOY) { // render/materials/Alloy.cpp:28-40
+      s.alloys.emplace_back();
+      Alloy &al = s.alloys.back();
+      al.color = v3(m.Kd); al.edgeColor = v3(m.Ks); al.roughness = m.Ns;
+      al.colorMap = makeTextureParam(s.textures, m.mapKd); al.edgeColorMap = makeTextureParam(s.textures, m.mapKs);
+      al.roughnessMap = makeTextureParam(s.textures, m.mapNs);
+      al.super.microfacetAlbedoTables = refAlbedoTables();
+      s.allMaterials.push_back(&al.super);
       continue;
     }
     if (m.type == OC_MATERIAL_PRINCIPLED) { // render/materials/Principled.cpp:33-150 (committed values, no maps)

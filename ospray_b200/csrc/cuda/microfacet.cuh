@@ -193,12 +193,31 @@ __device__ __forceinline__ float mfDielAlbedoSample(float cosThetaO, float eta, 
 struct ConductorBSDF
 {
   linear3f frame;
-  vec3f eta, k;       // complex refraction index per channel (FresnelConductorRGBUniform)
+  vec3f eta, k;       // complex refraction index per channel (FresnelConductorRGBUniform, FresnelConductorArtistic);
+                      // schlick: reflectivity at normal incidence (r) and at grazing angles (g) (FresnelSchlick)
+  bool schlick;
   GGX mf;
   float roughness, Eavg;
   vec3f fmsScale;
   const float *tables;
 };
+// Fresnel_dispatch_eval of the conductor's Fresnel term (Fresnel.ih:165-171 Schlick, :73-81 conductor)
+__device__ __forceinline__ vec3f conductorFresnel(const ConductorBSDF &b, float cosI)
+{
+  if (b.schlick) {
+    const float c = 1.f - cosI;
+    const float f = sqr(sqr(c)) * c;
+    return (1.f - f) * b.eta + f * b.k;
+  }
+  return fresnelConductorRGB(cosI, b.eta, b.k);
+}
+// FresnelSchlick_evalAvg (Fresnel.ih:175-185)
+__device__ __forceinline__ vec3f fresnelSchlickAvg(vec3f r, vec3f g)
+{
+  const float p = 1.f / 5.f;
+  const float p2 = p * p;
+  return (2.f * g * p2 + r + 3.f * p * r) * (1.f / (1.f + 3.f * p + 2.f * p2));
+}
 // Conductor_sample (Conductor.ih:17-29)
 __device__ __forceinline__ SampleRes Conductor_sample(const ConductorBSDF &b, vec3f wo)
 {
@@ -208,7 +227,7 @@ __device__ __forceinline__ SampleRes Conductor_sample(const ConductorBSDF &b, ve
   r.wi = reflectDir(wo, N, c);
   r.pdf = INFINITY;
   r.type = SC_SPECULAR_REFLECTION;
-  r.weight = fresnelConductorRGB(c, b.eta, b.k);
+  r.weight = conductorFresnel(b, c);
   return r;
 }
 __device__ __forceinline__ vec3f toLocal(const linear3f &f, vec3f v) { return make_vec3f(dot(f.vx, v), dot(f.vy, v), dot(f.vz, v)); }
@@ -222,7 +241,7 @@ __device__ __forceinline__ EvalRes MicrofacetConductor_eval(const ConductorBSDF 
   const vec3f wh = normalize(wi + wo);
   const float cosThetaOH = dot(wo, wh), cosThetaIH = dot(wi, wh);
   const vec3f wo0 = toLocal(b.frame, wo), wi0 = toLocal(b.frame, wi), wh0 = toLocal(b.frame, wh);
-  const vec3f F = fresnelConductorRGB(cosThetaOH, b.eta, b.k);
+  const vec3f F = conductorFresnel(b, cosThetaOH);
   float whPdf;
   const float D = ggxEvalVisible(b.mf, wh0, wo0, cosThetaOH, whPdf);
   const float G = ggxG2(b.mf, wo0, wi0, cosThetaOH, cosThetaIH);
@@ -247,7 +266,7 @@ __device__ __forceinline__ SampleRes MicrofacetConductor_sample(const ConductorB
   if (cosThetaI <= 0.f) { res.wi = make_vec3f(0.f); return res; }
   const float cosThetaOH = dot(wo, wh), cosThetaIH = dot(res.wi, wh);
   const vec3f wi0 = toLocal(b.frame, res.wi);
-  const vec3f F = fresnelConductorRGB(cosThetaOH, b.eta, b.k);
+  const vec3f F = conductorFresnel(b, cosThetaOH);
   const float G = ggxG2(b.mf, wo0, wi0, cosThetaOH, cosThetaIH);
   const float Eo = mfAlbedo(b.tables, cosThetaO, b.roughness), Ei = mfAlbedo(b.tables, cosThetaI, b.roughness);
   const vec3f fms = b.fmsScale * ((1.f - Eo) * (1.f - Ei) * (1.f / (OC_PI * (1.f - b.Eavg))) * cosThetaI);

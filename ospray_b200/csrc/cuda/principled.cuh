@@ -419,7 +419,7 @@ __device__ __forceinline__ void Principled_getBSDF(PrBSDF &b, const OcPrincipled
       const vec3f n = g * n_min + (one - g) * n_max;
       const vec3f k2 = (sqr3(n + one) * r - sqr3(n - one)) * rcp3(one - r);
       ConductorBSDF &M = B.metal;
-      M.frame = b.frame; M.tables = tables;
+      M.frame = b.frame; M.tables = tables; M.schlick = false;
       M.eta = n;
       M.k = make_vec3f(sqrtf(fmaxf(k2.x, 0.f)), sqrtf(fmaxf(k2.y, 0.f)), sqrtf(fmaxf(k2.z, 0.f))); // sqrt_safe
       // FresnelConductorArtistic_evalAvg (:248-262)
@@ -431,7 +431,7 @@ __device__ __forceinline__ void Principled_getBSDF(PrBSDF &b, const OcPrincipled
       else {
         B.metalKind = 2;
         M.Eavg = mfAlbedoAvg(tables, roughness);
-        M.fmsScale = sqr3(Favg) * M.Eavg * rcp3(one - Favg * (1.f - M.Eavg));
+        M.fmsScale = sqr3(Favg) * M.Eavg / (one - Favg * (1.f - M.Eavg));
         M.mf = makeGGX(roughness, anisotropy);
         M.roughness = roughness;
         metalAlbedo = Favg * M.Eavg;

@@ -340,7 +340,7 @@ struct ObjBSDF
   uint32_t kind;           // BSDF_KIND_*: 0 = the cases above; the others only exist in the extended-material kernels
 };
 enum { BSDF_KIND_OBJ = 0, BSDF_KIND_CONDUCTOR, BSDF_KIND_MICROFACET_CONDUCTOR, BSDF_KIND_PLASTIC_SMOOTH, BSDF_KIND_PLASTIC_ROUGH,
-       BSDF_KIND_PRINCIPLED };
+       BSDF_KIND_PRINCIPLED, BSDF_KIND_GLASS };
 
 // render/Material.ih:25-37
 __device__ __forceinline__ linear3f makeShadingFrame(const DifferentialGeometry &dg)
@@ -405,7 +405,11 @@ __device__ __forceinline__ vec3f rcp3(vec3f v) { return make_vec3f(1.f / v.x, 1.
 namespace oc {
 // state of the microfacet-family BSDFs (metal, plastic, principled): kept apart from ObjBSDF so that the OBJ path's registers
 // stay as they are
-struct ExtBSDF { ConductorBSDF cond; LayerParams layer; LambertSub lambert; PrBSDF pr; };
+struct ExtBSDF
+{
+  ConductorBSDF cond; LayerParams layer; LambertSub lambert; PrBSDF pr;
+  vec3f glassNg, glassNs; float glassEta; // RobustDielectric (bsdfs/RobustDielectric.ih:14-25)
+};
 // the medium a path travels in (render/materials/MediumShared.h:10-18; vacuum = no attenuation, ior 1)
 struct Medium { vec3f attenuation; float ior; };
 __device__ __forceinline__ Medium mediumVacuum() { Medium m; m.attenuation = make_vec3f(0.f); m.ior = 1.f; return m; }
@@ -663,7 +667,7 @@ __device__ __forceinline__ SampleRes OBJ_sample(const ObjBSDF &b, vec3f wo, vec2
 __device__ __forceinline__ bool Ext_getBSDF(ObjBSDF &b, ExtBSDF &x, const DifferentialGeometry &dg, const Medium &medium)
 {
   const OcMaterial *m = dg.material;
-  if (!m || (m->type != OC_MATERIAL_METAL && m->type != OC_MATERIAL_PLASTIC && m->type != OC_MATERIAL_PRINCIPLED)) return false;
+  if (!m || m->type < OC_MATERIAL_METAL) return false;
   b.valid = true;
   b.importanceSum = 1.f; b.impL = b.impT = b.impS = 0.f;
   b.Kd = b.T = b.ks = b.specWeight = make_vec3f(0.f); b.ns = 0.f;
@@ -676,23 +680,41 @@ __device__ __forceinline__ bool Ext_getBSDF(ObjBSDF &b, ExtBSDF &x, const Differ
     return true;
   }
   b.frame = frame(dg.Ns);
-  if (m->type == OC_MATERIAL_METAL) {
+  if (m->type == OC_MATERIAL_GLASS) { // Glass_getBSDF (materials/Glass.ispc:14-33): eta = the side the path is on over the other
+    x.glassEta = mediumIsOutside(medium, m->principled) ? m->principled.outsideIor * (1.f / m->eta) : m->eta * (1.f / m->principled.outsideIor);
+    x.glassNg = dg.Ng; x.glassNs = dg.Ns;
+    b.kind = BSDF_KIND_GLASS;
+    b.albedo = make_vec3f(1.0f);
+    b.scatteringType = SC_SPECULAR;
+    return true;
+  }
+  if (m->type == OC_MATERIAL_METAL || m->type == OC_MATERIAL_ALLOY) {
+    // Metal_getBSDF (Metal.ispc:18-46, RGB form), Alloy_getBSDF (Alloy.ispc:16-51: Schlick Fresnel between color and edgeColor)
+    const bool alloy = m->type == OC_MATERIAL_ALLOY;
     x.cond.frame = b.frame;
     x.cond.eta = toV(m->Kd); x.cond.k = toV(m->Ks);
+    x.cond.schlick = alloy;
+    vec3f Favg = make_vec3f(0.f); // Fresnel_dispatch_evalAvg of the RGB conductor is 0 (Fresnel.ih:307-320)
+    if (alloy) {
+      x.cond.eta = x.cond.eta * make_vec3f(dg.color);
+      if (m->mapKd.tex) { const vec4f t = texParamGet4f(m->mapKd, dg.st, dg.pixelFootprint); x.cond.eta = x.cond.eta * make_vec3f(t.x, t.y, t.z); }
+      if (m->mapKs.tex) { const vec4f t = texParamGet4f(m->mapKs, dg.st, dg.pixelFootprint); x.cond.k = x.cond.k * make_vec3f(t.x, t.y, t.z); }
+      Favg = fresnelSchlickAvg(x.cond.eta, x.cond.k);
+    }
     x.cond.tables = m->microfacetTables;
     if (m->Ns == 0.0f) {
       b.kind = BSDF_KIND_CONDUCTOR;
-      b.albedo = make_vec3f(0.f); // Fresnel_dispatch_evalAvg of the RGB conductor is 0 (Fresnel.ih:307-320)
+      b.albedo = Favg;
       b.scatteringType = SC_SPECULAR_REFLECTION;
     } else {
       float roughness = m->Ns;
       if (m->mapNs.tex) roughness = roughness * texParamGet4f(m->mapNs, dg.st, dg.pixelFootprint).x;
       b.kind = BSDF_KIND_MICROFACET_CONDUCTOR;
       x.cond.Eavg = mfAlbedoAvg(x.cond.tables, roughness);
-      x.cond.fmsScale = make_vec3f(0.f); // sqr(Favg) * Eavg / (1 - Favg * (1 - Eavg)) with Favg = 0
+      x.cond.fmsScale = sqr3(Favg) * x.cond.Eavg / (make_vec3f(1.f) - Favg * (1.f - x.cond.Eavg));
       x.cond.mf = makeGGX(roughness, 0.f);
       x.cond.roughness = roughness;
-      b.albedo = make_vec3f(0.f);
+      b.albedo = Favg * x.cond.Eavg;
       b.scatteringType = SC_GLOSSY_REFLECTION;
     }
     return true;
@@ -721,9 +743,70 @@ static __device__ __noinline__ EvalRes Ext_eval(const ObjBSDF &b, const ExtBSDF 
   default: return e; // smooth conductor: purely specular
   }
 }
+// RobustDielectric_sample (bsdfs/RobustDielectric.ih:27-176): reflection / refraction with the normals flipped to the incoming
+// ray's side, grazing directions nudged off the surface, directions that end on the wrong side of the geometry mirrored back
+__device__ __forceinline__ SampleRes RobustDielectric_sample(const ExtBSDF &x, vec3f wo, float randomF)
+{
+  SampleRes res;
+  res.pdf = INFINITY;
+  const vec3f incomingDir = neg(wo);
+  vec3f shadingNormal = x.glassNs, geometricNormal = x.glassNg;
+  const float eta = 1.f / x.glassEta;
+  const float glass_epsilon = 1e-6f;
+  const bool canReflect = (eta < 1.f - glass_epsilon || eta > 1.f + glass_epsilon);
+  if (dot(incomingDir, shadingNormal) > 0.f) shadingNormal = neg(shadingNormal);
+  if (dot(incomingDir, geometricNormal) > 0.f) geometricNormal = neg(geometricNormal);
+  // ReflectionDirection (:79-88)
+  const vec3f par = dot(incomingDir, shadingNormal) * shadingNormal;
+  const vec3f dirR = (incomingDir - par) - par;
+  // RefractionDirection (:34-77); the head-on test of the reference (1 - 1e-6 < |cos| && |cos| < 1 - 1e-6) is never true
+  vec3f dirT;
+  float FresnelR;
+  bool mustReflect = false;
+  {
+    const float cos1 = dot(incomingDir, shadingNormal);
+    const float cos1_abs = cos1 < 0.f ? -cos1 : cos1;
+    const vec3f dirPar = cos1 * shadingNormal;
+    const vec3f dirPerp = incomingDir - dirPar;
+    const vec3f bb = normalize(dirPerp);
+    const float sin1 = dot(dirPerp, bb);
+    const float sin2 = sin1 / eta;
+    if (sin2 > 1.0f) { dirT = make_vec3f(0.f); FresnelR = 1.f; mustReflect = true; }
+    else {
+      const float cos2 = sqrtf(clampf(1.f - sin2 * sin2, 0.f, 1.f));
+      const vec3f N2 = normalize(dirPar);
+      dirT = N2 * cos2 + bb * sin2;
+      const float c1 = cos1_abs, c2 = cos2;
+      const float r1 = (eta * c1 - c2) / (eta * c1 + c2);
+      const float r2 = (c1 - eta * c2) / (c1 + eta * c2);
+      FresnelR = 0.5f * (r1 * r1 + r2 * r2);
+    }
+    FresnelR = clampf(FresnelR, 0.f, 1.f);
+  }
+  res.weight = make_vec3f(1.f);
+  if ((randomF < FresnelR && canReflect) || mustReflect) {
+    res.wi = dirR;
+    res.type = SC_SPECULAR_REFLECTION;
+    const float geometricCosine = dot(res.wi, geometricNormal);
+    if (geometricCosine >= 0.f) {
+      if (geometricCosine < glass_epsilon) res.wi = normalize(res.wi + glass_epsilon * geometricNormal);
+    } else
+      res.wi = res.wi - 2.f * geometricNormal * geometricCosine;
+  } else {
+    res.wi = dirT;
+    res.type = SC_SPECULAR_TRANSMISSION;
+    const float geometricCosine = dot(res.wi, geometricNormal);
+    if (geometricCosine <= 0.f) {
+      if (geometricCosine > -glass_epsilon) res.wi = normalize(res.wi - glass_epsilon * geometricNormal);
+    } else
+      res.type = SC_SPECULAR_REFLECTION;
+  }
+  return res;
+}
 static __device__ __noinline__ SampleRes Ext_sample(const ObjBSDF &b, const ExtBSDF &x, vec3f wo, vec2f s, float ss)
 {
   switch (b.kind) {
+  case BSDF_KIND_GLASS: return RobustDielectric_sample(x, wo, ss);
   case BSDF_KIND_CONDUCTOR: return Conductor_sample(x.cond, wo);
   case BSDF_KIND_MICROFACET_CONDUCTOR: return MicrofacetConductor_sample(x.cond, wo, s);
   case BSDF_KIND_PLASTIC_SMOOTH: return DielectricLayer_sample(x.layer, b.frame.vz, x.lambert, wo, s, ss);
@@ -737,6 +820,11 @@ static __device__ __noinline__ SampleRes Ext_sample(const ObjBSDF &b, const ExtB
 __device__ __forceinline__ void materialSelectNextMedium(const DifferentialGeometry &dg, Medium &medium)
 {
   const OcMaterial *m = dg.material;
+  if (m && m->type == OC_MATERIAL_GLASS) { // Glass_selectNextMedium (Glass.ispc:53-63)
+    if (mediumIsOutside(medium, m->principled)) { medium.ior = m->eta; medium.attenuation = toV(m->attenuation); }
+    else { medium.ior = m->principled.outsideIor; medium.attenuation = toV(m->principled.outsideAttenuation); }
+    return;
+  }
   if (!m || m->type != OC_MATERIAL_PRINCIPLED) return;
   const OcPrincipled &q = m->principled;
   if (q.transmission <= PR_EPS) return;
@@ -759,6 +847,11 @@ __device__ __forceinline__ vec3f materialTransparency(const DifferentialGeometry
   const OcMaterial *m = dg.material;
   if (TEX && m && m->type == OC_MATERIAL_PRINCIPLED)
     return Principled_getTransparency(m->principled, m->microfacetTables, dg, rayDir, mediumIsOutside(medium, m->principled));
+  if (TEX && m && m->type == OC_MATERIAL_GLASS) { // Glass_getTransparency (Glass.ispc:35-51)
+    const float eta = mediumIsOutside(medium, m->principled) ? m->principled.outsideIor * (1.f / m->eta) : m->eta * (1.f / m->principled.outsideIor);
+    const float cosThetaO = fmaxf(-dot(rayDir, dg.Ns), 0.0f);
+    return make_vec3f(1.0f - fresnelDielectric(cosThetaO, eta));
+  }
   if (m && m->type == OC_MATERIAL_THINGLASS) {
     const float cosThetaO = fmaxf(-dot(rayDir, dg.Ns), 0.0f);
     return RobustThinDielectric_getTransparency(cosThetaO, m->eta, ThinGlass_getAttenuation<TEX>(m, dg));

@@ -455,6 +455,29 @@ void Material::commit()
     m.eta = 1.f / getParam<float>("eta", 1.4f);
     m.Ns = getParam<float>("roughness", 0.01f);
     extended = true;
+  } else if (type == "glass") {
+    // render/materials/Glass.cpp:35-63
+    m.type = OC_MATERIAL_GLASS;
+    const float etaInside = getParam<float>("etaInside", getParam<float>("eta", 1.5f));
+    const float etaOutside = getParam<float>("etaOutside", 1.f);
+    const vec3f aci = getParam<vec3f>("attenuationColorInside", getParam<vec3f>("attenuationColor", make_vec3f(1.f)));
+    const vec3f aco = getParam<vec3f>("attenuationColorOutside", make_vec3f(1.f));
+    const float dist = std::max(getParam<float>("attenuationDistance", 1.0f), 1e-5f);
+    m.eta = etaInside;
+    m.attenuation = toOc(make_vec3f(std::log(aci.x), std::log(aci.y), std::log(aci.z)) / dist);
+    m.principled.outsideIor = etaOutside;
+    m.principled.outsideAttenuation = toOc(make_vec3f(std::log(aco.x), std::log(aco.y), std::log(aco.z)) / dist);
+    extended = true;
+  } else if (type == "alloy") {
+    // render/materials/Alloy.cpp:28-40
+    m.type = OC_MATERIAL_ALLOY;
+    m.mapKd = getTextureParam("map_color", texKd);
+    m.mapKs = getTextureParam("map_edgeColor", texKs);
+    m.mapNs = getTextureParam("map_roughness", texNs);
+    m.Kd = toOc(getParam<vec3f>("color", make_vec3f(texKd ? 1.f : 0.9f)));
+    m.Ks = toOc(getParam<vec3f>("edgeColor", make_vec3f(1.f)));
+    m.Ns = getParam<float>("roughness", texNs ? 1.f : 0.1f);
+    extended = true;
   } else if (type == "principled") {
     // render/materials/Principled.cpp:33-150. Built: the solid form (thin = false) without sheen; texture maps and normal
     // maps of this material are refused rather than ignored.
@@ -1234,7 +1257,7 @@ uint32_t World::computeShadowOpaque(const Renderer *renderer) const
         const OcMaterial &mt = table[slot];
         if (mt.hasTextures || mt.type == OC_MATERIAL_THINGLASS) return 0u;
         if (mt.type == OC_MATERIAL_LUMINOUS && mt.transparency != 0.f) return 0u;
-        if (mt.type == OC_MATERIAL_PRINCIPLED) return 0u; // (cut-out opacity, transmission: decided per occluder)
+        if (mt.type == OC_MATERIAL_PRINCIPLED || mt.type == OC_MATERIAL_GLASS) return 0u; // (cut-out opacity, transmission: decided per occluder)
         if (mt.type == OC_MATERIAL_OBJ && !(mt.d == 1.f && mt.Tf.x == 0.f && mt.Tf.y == 0.f && mt.Tf.z == 0.f)) return 0u;
       }
     }

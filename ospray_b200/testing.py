@@ -62,6 +62,11 @@ class MaterialSpec:
     roughness: float = 0.1                      # metal / plastic
     map_roughness: Optional["MapSpec"] = None
     pigment_color: tuple = (1.0, 1.0, 1.0)      # plastic (Plastic.cpp:28-38); `eta` above is its index of refraction
+    eta_outside: float = 1.0                    # glass (Glass.cpp:35-63): `eta`, attenuation_color / _distance above = the inside medium
+    attenuation_color_outside: tuple = (1.0, 1.0, 1.0)
+    alloy_color: tuple = (0.9, 0.9, 0.9)        # alloy (Alloy.cpp:28-40): reflectivity at normal incidence / at grazing angles, `roughness`,
+    edge_color: tuple = (1.0, 1.0, 1.0)         #   maps map_color / map_edge_color / map_roughness
+    map_edge_color: Optional["MapSpec"] = None
     principled: dict = field(default_factory=dict)  # principled (Principled.cpp:33-150): ospray parameter name -> value
 
 
@@ -460,6 +465,18 @@ def _material(m: MaterialSpec):
         return mat.commit()
     if m.type == "plastic":
         mat.set("pigmentColor", tuple(float(x) for x in m.pigment_color)).set("eta", float(m.eta)).set("roughness", float(m.roughness))
+        return mat.commit()
+    if m.type == "glass":
+        mat.set("eta", float(m.eta)).set("attenuationColor", tuple(float(x) for x in m.attenuation_color))
+        mat.set("attenuationDistance", float(m.attenuation_distance))
+        if m.eta_outside != d.eta_outside: mat.set("etaOutside", float(m.eta_outside))
+        if m.attenuation_color_outside != d.attenuation_color_outside: mat.set("attenuationColorOutside", tuple(float(x) for x in m.attenuation_color_outside))
+        return mat.commit()
+    if m.type == "alloy":
+        _set_map(mat, "map_color", m.map_color)
+        _set_map(mat, "map_edgeColor", m.map_edge_color)
+        _set_map(mat, "map_roughness", m.map_roughness)
+        mat.set("color", tuple(float(x) for x in m.alloy_color)).set("edgeColor", tuple(float(x) for x in m.edge_color)).set("roughness", float(m.roughness))
         return mat.commit()
     if m.type == "principled":
         for name, v in m.principled.items():

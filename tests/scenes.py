@@ -288,6 +288,21 @@ def principled_cornell(variant):
     return _cornell_models({(5, 6, 7, 8, 9): a, (11, 12, 13, 14, 15): b}, drop=(10, 16))
 
 
+def glass_alloy_cornell(rough):
+    """cornell box with a solid glass box (materials/Glass.ispc: RobustDielectric, attenuating inside medium, transparent
+    shadows) and an alloy box (materials/Alloy.ispc: conductor with Schlick Fresnel; rough: MicrofacetConductor with a roughness
+    map and a colour map)"""
+    TS, MS = T.TextureSpec, T.MapSpec
+    glass = T.MaterialSpec(type="glass", eta=1.45, attenuation_color=(0.7, 0.9, 0.8), attenuation_distance=0.6)
+    if rough:
+        alloy = T.MaterialSpec(type="alloy", alloy_color=(1.0, 1.0, 1.0), edge_color=(1.0, 0.9, 0.8), roughness=1.0,
+                               map_color=MS(TS(_tex_rng_image(8, 8, 3, 41, np.float32, 0.4, 0.9), "RGB32F")),
+                               map_roughness=MS(TS(_tex_rng_image(8, 8, 1, 42, np.float32, 0.15, 0.5)[..., 0], "R32F")))
+    else:
+        alloy = T.MaterialSpec(type="alloy", alloy_color=(0.83, 0.68, 0.21), edge_color=(1.0, 0.95, 0.9), roughness=0.0)
+    return _cornell_models({(5, 6, 7, 8, 9): glass, (11, 12, 13, 14, 15): alloy}, drop=(10, 16))
+
+
 def backplate_scene():
     """renderer textures: map_backplate behind random spheres and map_maxDepth cutting the primary rays (Renderer.ispc:18-39)"""
     s = T.random_spheres(24, seed=3)
@@ -379,6 +394,8 @@ CASES = {
     "metal_rough_pt": (lambda: metal_cornell(True), "pathtracer", {"pixelSamples": 2}, 2),
     "plastic_smooth_pt": (lambda: plastic_cornell(False), "pathtracer", {"pixelSamples": 2}, 2),
     "plastic_rough_pt": (lambda: plastic_cornell(True), "pathtracer", {"pixelSamples": 2}, 2),
+    "glass_alloy_pt": (lambda: glass_alloy_cornell(False), "pathtracer", {"pixelSamples": 2}, 2),
+    "glass_alloy_rough_pt": (lambda: glass_alloy_cornell(True), "pathtracer", {"pixelSamples": 2}, 2),
     "principled_plastic_pt": (lambda: principled_cornell("plastic"), "pathtracer", {"pixelSamples": 2}, 2),
     "principled_metal_pt": (lambda: principled_cornell("metal"), "pathtracer", {"pixelSamples": 2}, 2),
     "principled_glass_pt": (lambda: principled_cornell("glass"), "pathtracer", {"pixelSamples": 2}, 2),
@@ -409,7 +426,7 @@ ORACLE_UNSUPPORTED = {"textured_pt", "textured_bias_pt", "cutout_pt", "backplate
                       "emissive_transparent_pt", "textured_scivis", "textured_ao", "cutout_scivis", "cutout_ao", "backplate_scivis",
                       "backplate_ao", "debug_texCoord", "debug_dPdt", "debug_dPds_tex", "debug_backplate", "metal_smooth_pt", "metal_rough_pt",
                       "plastic_smooth_pt", "plastic_rough_pt", "principled_plastic_pt", "principled_metal_pt", "principled_glass_pt",
-                      "principled_coat_pt", "principled_rough_layers_pt", "principled_emissive_pt"}
+                      "principled_coat_pt", "principled_rough_layers_pt", "principled_emissive_pt", "glass_alloy_pt", "glass_alloy_rough_pt"}
 # Rough dielectric coatings: MicrofacetDielectricLayer_Constructor reads self->eta for Ravg BEFORE assigning it
 # (bsdfs/MicrofacetDielectricLayer.ih:55 vs :68), i.e. whatever the shading context's memory held from the previous BSDF. The
 # device uses the intended value; against the reference's kernels the coated surfaces then differ by ~0.5 % in brightness

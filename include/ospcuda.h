@@ -116,8 +116,7 @@ typedef struct {
 
 enum { OC_MATERIAL_OBJ = 0, OC_MATERIAL_OTHER = 1, OC_MATERIAL_THINGLASS = 2, OC_MATERIAL_LUMINOUS = 3, OC_MATERIAL_METAL = 4,
        OC_MATERIAL_PLASTIC = 5, OC_MATERIAL_PRINCIPLED = 6, OC_MATERIAL_GLASS = 7, OC_MATERIAL_ALLOY = 8 };
-/* principled (reference: ispc::Principled, render/materials/PrincipledShared.h:17-170, Principled.cpp:33-150), the solid form
- * without sheen and without texture maps: factors as committed; outsideIor = outsideIor >= 1 ? outsideIor : 1 / outsideIor,
+/* principled (reference: ispc::Principled, render/materials/PrincipledShared.h:17-170, Principled.cpp:33-150), without texture maps: factors as committed; outsideIor = outsideIor >= 1 ? outsideIor : 1 / outsideIor,
  * outsideAttenuation = log(outsideTransmissionColor) / outsideTransmissionDepth (the medium around the object) */
 typedef struct {
   OcVec3f baseColor, edgeColor;
@@ -133,6 +132,11 @@ typedef struct {
   float opacity;
   float outsideIor;
   OcVec3f outsideAttenuation;
+  float sheen;
+  OcVec3f sheenColor;
+  float sheenTint, sheenRoughness;
+  uint32_t thin;               /* thin-walled mode: no medium change, ThinDielectric glass, backlight = diffuse transmission */
+  float backlight, thickness;
 } OcPrincipled;
 /* material (reference: ispc::OBJ, render/materials/OBJShared.h, OBJ.cpp:30-66; ispc::ThinGlass,
  * render/materials/ThinGlassShared.h, ThinGlass.cpp:33-48: eta = 1/ior, attenuationScale = thickness /

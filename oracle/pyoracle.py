@@ -67,7 +67,9 @@ class Principled(C.Structure):  # OcPrincipled
                 ("specularMetallic", C.c_uint32), ("ior", C.c_float), ("transmission", C.c_float), ("transmissionColor", Vec3),
                 ("transmissionDepth", C.c_float), ("roughness", C.c_float), ("anisotropy", C.c_float), ("rotation", C.c_float),
                 ("coat", C.c_float), ("coatIor", C.c_float), ("coatColor", Vec3), ("coatThickness", C.c_float),
-                ("coatRoughness", C.c_float), ("opacity", C.c_float), ("outsideIor", C.c_float), ("outsideAttenuation", Vec3)]
+                ("coatRoughness", C.c_float), ("opacity", C.c_float), ("outsideIor", C.c_float), ("outsideAttenuation", Vec3),
+                ("sheen", C.c_float), ("sheenColor", Vec3), ("sheenTint", C.c_float), ("sheenRoughness", C.c_float), ("thin", C.c_uint32),
+                ("backlight", C.c_float), ("thickness", C.c_float)]
 
 
 # parameters of the principled material this build takes (ospray name -> default), Principled.cpp:33-77
@@ -77,6 +79,7 @@ PRINCIPLED_DEFAULTS = {
     "roughness": 0.0, "anisotropy": 0.0, "rotation": 0.0, "coat": 0.0, "coatIor": 1.5, "coatColor": (1.0, 1.0, 1.0),
     "coatThickness": 1.0, "coatRoughness": 0.0, "opacity": 1.0, "outsideIor": 1.0, "outsideTransmissionColor": (1.0, 1.0, 1.0),
     "outsideTransmissionDepth": 1.0, "emissiveColor": (0.0, 0.0, 0.0), "intensity": 1.0,
+    "sheen": 0.0, "sheenColor": (1.0, 1.0, 1.0), "sheenTint": 0.0, "sheenRoughness": 0.2, "thin": False, "backlight": 0.0, "thickness": 1.0,
 }
 
 
@@ -597,12 +600,14 @@ class Scene:
             prm.update(ms.principled)
             m.type = 6
             q = m.principled
-            for name in ("baseColor", "edgeColor", "transmissionColor", "coatColor"):
+            for name in ("baseColor", "edgeColor", "transmissionColor", "coatColor", "sheenColor"):
                 setattr(q, name, Vec3(*map(float, np.asarray(prm[name], np.float32))))
             for name in ("metallic", "diffuse", "specular", "ior", "transmission", "transmissionDepth", "roughness", "anisotropy",
-                         "rotation", "coat", "coatIor", "coatThickness", "coatRoughness", "opacity"):
+                         "rotation", "coat", "coatIor", "coatThickness", "coatRoughness", "opacity", "sheen", "sheenTint", "sheenRoughness",
+                         "backlight", "thickness"):
                 setattr(q, name, float(f(prm[name])))
             q.specularMetallic = int(bool(prm["specularMetallic"]))
+            q.thin = int(bool(prm["thin"]))
             oi = f(prm["outsideIor"])
             q.outsideIor = float(oi if oi >= 1.0 else f(1.0) / oi)
             otc = np.log(np.asarray(prm["outsideTransmissionColor"], np.float32)).astype(np.float32) / f(prm["outsideTransmissionDepth"])

@@ -348,6 +348,8 @@ void buildScene(Scene &s, const OcWorld *w, const OcRenderer *ren)
       pr.transmissionDepth = q.transmissionDepth; pr.roughness = q.roughness; pr.anisotropy = q.anisotropy; pr.rotation = q.rotation;
       pr.coat = q.coat; pr.coatIor = q.coatIor; pr.coatColor = v3(q.coatColor); pr.coatThickness = q.coatThickness;
       pr.coatRoughness = q.coatRoughness; pr.opacity = q.opacity;
+      pr.sheen = q.sheen; pr.sheenColor = v3(q.sheenColor); pr.sheenTint = q.sheenTint; pr.sheenRoughness = q.sheenRoughness;
+      pr.thin = q.thin != 0; pr.backlight = q.backlight; pr.thickness = q.thickness;
       pr.outsideMedium.ior = q.outsideIor; pr.outsideMedium.attenuation = v3(q.outsideAttenuation);
       pr.emission = v3(m.emission);
       pr.super.isEmissive = m.isEmissive != 0;

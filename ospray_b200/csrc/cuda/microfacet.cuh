@@ -18,7 +18,9 @@ namespace oc {
 #define OC_MFT_DIELRCP_AVG (OC_MFT_DIELRCP_DIR + OC_MFD_SIZE * OC_MFD_SIZE * OC_MFD_SIZE)
 #define OC_MFT_DIELREFL_DIR (OC_MFT_DIELRCP_AVG + OC_MFD_SIZE * OC_MFD_SIZE)
 #define OC_MFT_DIELREFL_AVG (OC_MFT_DIELREFL_DIR + OC_MFD_SIZE * OC_MFD_SIZE * OC_MFD_SIZE)
-#define OC_MFT_TOTAL (OC_MFT_DIELREFL_AVG + OC_MFD_SIZE * OC_MFD_SIZE)
+#define OC_MFS_SIZE 16  // sheen albedo table [16 x 16] (cosThetaO fastest, roughness)
+#define OC_MFT_SHEEN_DIR (OC_MFT_DIELREFL_AVG + OC_MFD_SIZE * OC_MFD_SIZE)
+#define OC_MFT_TOTAL (OC_MFT_SHEEN_DIR + OC_MFS_SIZE * OC_MFS_SIZE)
 
 __device__ __forceinline__ float rcpSafe(float f) { return 1.f / (fabsf(f) < 1e-8f ? (f < 0.f ? -1e-8f : 1e-8f) : f); }
 
@@ -187,6 +189,64 @@ __device__ __forceinline__ float mfDielAlbedoSample(float cosThetaO, float eta, 
     weight += (1.f - F) * (G * rcpSafe(ggxG1(g, wo, cosThetaOH)));
   }
   return weight;
+}
+
+// ---- sheen distribution (SheenDistribution.ih:10-88; [Conty and Kulla 2017]) ---------------------------------------------
+__device__ __forceinline__ float sheenD(float r, float cosTheta)
+{
+  const float sinTheta = cos2sin(cosTheta);
+  const float invr = 1.f / r;
+  return (2.f + invr) * powf(sinTheta, invr) * (float)(0.5 / 3.14159265358979323846);
+}
+__device__ __forceinline__ float sheenL(float r, float x)
+{
+  const float w0 = sqr(1.f - r), w1 = 1.f - w0;
+  const float a = w0 * 25.3245f + w1 * 21.5473f;
+  const float b = w0 * 3.32435f + w1 * 3.82987f;
+  const float c = w0 * 0.16801f + w1 * 0.19823f;
+  const float d = w0 * -1.27393f + w1 * -1.97760f;
+  const float e = w0 * -4.85967f + w1 * -4.32054f;
+  return a / (1.f + b * powf(x, c)) + d * x + e;
+}
+__device__ __forceinline__ float sheenLambda(float r, float cosTheta)
+{
+  if (cosTheta < 0.5f) return expf(sheenL(r, cosTheta));
+  return expf(2.f * sheenL(r, 0.5f) - sheenL(r, 1.f - cosTheta));
+}
+__device__ __forceinline__ float sheenLambdaI(float r, float cosTheta)
+{
+  const float x = 1.f + 2.f * sqr(sqr(sqr(1.f - cosTheta)));
+  return powf(sheenLambda(r, cosTheta), x);
+}
+__device__ __forceinline__ float sheenG2(float r, float cosThetaO, float cosThetaI, float cosThetaOH, float cosThetaIH)
+{
+  if (cosThetaO * cosThetaOH <= 0.f || cosThetaI * cosThetaIH <= 0.f) return 0.f;
+  return 1.f / (1.f + sheenLambda(r, cosThetaO) + sheenLambdaI(r, cosThetaI));
+}
+__device__ __forceinline__ vec3f uniformSampleHemisphere(vec2f s) // math/sampling.ih:33-39
+{
+  const float phi = (float)(2.0 * 3.14159265358979323846) * s.x;
+  const float cosTheta = s.y, sinTheta = cos2sin(s.y);
+  float sp, cp;
+  sincosf(phi, &sp, &cp);
+  return make_vec3f(cp * sinTheta, sp * sinTheta, cosTheta);
+}
+#define OC_ONE_OVER_TWO_PI ((float)(0.5 / 3.14159265358979323846))
+// MicrofacetSheenAlbedo_sample (MicrofacetAlbedo.ih:116-141)
+__device__ __forceinline__ float mfSheenAlbedoSample(float cosThetaO, float r, vec2f s)
+{
+  cosThetaO = fmaxf(cosThetaO, 1e-6f);
+  const vec3f wo = make_vec3f(cos2sin(cosThetaO), 0.f, cosThetaO);
+  const vec3f wi = uniformSampleHemisphere(s);
+  const vec3f wh = normalize(wo + wi);
+  const float D = sheenD(r, wh.z);
+  const float G = sheenG2(r, cosThetaO, wi.z, dot(wo, wh), dot(wi, wh));
+  return D * G * (1.f / (4.f * cosThetaO * OC_ONE_OVER_TWO_PI));
+}
+// MicrofacetSheenAlbedoTable_eval (MicrofacetAlbedoTables.ih:145-153)
+__device__ __forceinline__ float mfSheenAlbedo(const float *t, float cosThetaO, float roughness)
+{
+  return interp2D(cosThetaO * (OC_MFS_SIZE - 1), roughness * (OC_MFS_SIZE - 1), t + OC_MFT_SHEEN_DIR, OC_MFS_SIZE, OC_MFS_SIZE);
 }
 
 // ---- conductors -------------------------------------------------------------------------------------------------------

@@ -3,12 +3,13 @@
 // (selectNextMedium), :603-1040 (the eval / sample dispatch through the nesting), bsdfs/MultiBSDF.ih:58-128,
 // OrenNayar.ih:18-45, Dielectric.ih:18-50, MicrofacetDielectric.ih:27-268, Fresnel.ih:227-284 (artistic conductor).
 //
-//   root   MultiBSDF(2)   [0] Transmission(1 - opacity)            [1] coat( base )            (sheen layer: not built)
+//   root   MultiBSDF(2)   [0] Transmission(1 - opacity)            [1] sheen( coat( base ) )
+//   sheen  passthrough | MicrofacetSheenLayer over the coated base
 //   coat   passthrough | DielectricLayer | MicrofacetDielectricLayer over base
 //   base   MultiBSDF(3)   [0] metal: Conductor | MicrofacetConductor (artistic Fresnel)
-//                         [1] glass: Transmission | Dielectric | MicrofacetDielectric          (thin variants: not built)
+//                         [1] glass: Transmission | Dielectric | MicrofacetDielectric | ThinDielectric | ThinMicrofacetDielectric
 //                         [2] plastic: passthrough | DielectricLayer | MicrofacetDielectricLayer over diffuse
-//   diffuse MultiBSDF(2)  [0] Lambert | OrenNayar                                              ([1] LambertTransmission: thin only)
+//   diffuse MultiBSDF(2)  [0] Lambert | OrenNayar                  [1] LambertTransmission (thin: backlight)
 #pragma once
 
 namespace oc {
@@ -48,15 +49,26 @@ struct PrDiffuse
     r.pdf = e.pdf; r.weight = e.value * (1.f / e.pdf);
     return r;
   }
-  // DiffuseBSDF_eval / _sample: the MultiBSDF macros with one live child
-  __device__ __forceinline__ EvalRes eval(vec3f wo, vec3f wi) const
+  // second child: LambertTransmission (LambertTransmission.ih:10-32), thin materials with backlight
+  float weightT, importanceT; // 0: absent
+  // DiffuseBSDF_eval / _sample (Principled.ispc:634-661): the MultiBSDF macros over the two children
+  __device__ __forceinline__ void evalChildren(vec3f wo, vec3f wi, int skip, EvalRes &e) const
   {
-    EvalRes e; e.value = make_vec3f(0.f); e.pdf = 0.f;
-    if (importance > 0.f) {
+    if (importance > 0.f && skip != 0) {
       const EvalRes c = lobeEval(wo, wi);
       e.value = e.value + c.value * weight;
       e.pdf += c.pdf * importance;
     }
+    if (importanceT > 0.f && skip != 1) {
+      const float cosThetaI = fmaxf(-dot(wi, frame.vz), 0.f);
+      e.value = e.value + (R * OC_ONE_OVER_PI * cosThetaI) * weightT;
+      e.pdf += (cosThetaI * OC_ONE_OVER_PI) * importanceT;
+    }
+  }
+  __device__ __forceinline__ EvalRes eval(vec3f wo, vec3f wi) const
+  {
+    EvalRes e; e.value = make_vec3f(0.f); e.pdf = 0.f;
+    evalChildren(wo, wi, -1, e);
     e.pdf *= 1.f / importanceSum;
     return e;
   }
@@ -65,14 +77,24 @@ struct PrDiffuse
     SampleRes res; res.weight = make_vec3f(0.f); res.wi = make_vec3f(0.f); res.pdf = 0.f; res.type = 0;
     if (importanceSum == 0.f) return res;
     const float x = ss * importanceSum;
-    if (!(x < importance)) return res; // (no second child)
-    res = lobeSample(wo, s);
-    res.weight = res.weight * weight;
+    int choice;
+    float prefix = 0.f, choiceImp;
+    if (x < (prefix += importance)) {
+      choice = 0; choiceImp = importance;
+      res = lobeSample(wo, s);
+      res.weight = res.weight * weight;
+    } else if (x < (prefix += importanceT)) {
+      choice = 1; choiceImp = importanceT;
+      const vec3f l = cosineSampleHemisphere(s);
+      res.wi = neg(frame * l); res.pdf = l.z * OC_ONE_OVER_PI; res.type = SC_DIFFUSE_TRANSMISSION; res.weight = R;
+      res.weight = res.weight * weightT;
+    } else return res;
     if ((res.weight.x == 0.f && res.weight.y == 0.f && res.weight.z == 0.f) || res.pdf == 0.0f) { res.weight = make_vec3f(0.f); res.wi = make_vec3f(0.f); res.pdf = 0.f; res.type = 0; return res; }
     EvalRes e;
     e.value = res.weight * res.pdf;
-    res.pdf *= importance;
+    res.pdf *= choiceImp;
     e.pdf = res.pdf;
+    evalChildren(wo, res.wi, choice, e);
     res.pdf = e.pdf * (1.f / importanceSum);
     res.weight = e.value * (1.f / res.pdf);
     return res;
@@ -82,8 +104,10 @@ struct PrDiffuse
 struct PrGlass
 {
   linear3f frame;
-  int kind; // 0 Transmission(1), 1 Dielectric, 2 MicrofacetDielectric
+  int kind; // 0 Transmission(1), 1 Dielectric, 2 MicrofacetDielectric, 3 ThinDielectric, 4 ThinMicrofacetDielectric
   float eta;
+  vec3f attenuation;   // thin: log(transmissionColor) / transmissionDepth * thickness
+  float thinEavg, thinFmsScale;
   GGX mf;
   float roughness, EavgEta, EavgRcpEta, fmsRatio;
   const float *tables;
@@ -162,10 +186,76 @@ __device__ __forceinline__ EvalRes MicrofacetDielectric_fms(const PrGlass &g, fl
   }
   return fms;
 }
+// ThinMicrofacetDielectric_Constructor / _eval / _sample (ThinMicrofacetDielectric.ih:25-178)
+__device__ __forceinline__ void PrGlass_initThinMicrofacet(PrGlass &g, const float *tables, float eta, float roughness, float anisotropy, vec3f attenuation)
+{
+  g.kind = 4; g.eta = eta; g.tables = tables; g.roughness = roughness; g.attenuation = attenuation;
+  g.albedo = expf3(attenuation); g.scatteringType = SC_GLOSSY_REFLECTION | SC_SPECULAR_TRANSMISSION;
+  g.mf = makeGGX(roughness, anisotropy);
+  g.thinEavg = mfAlbedoAvg(tables, roughness);
+  const float Favg = fresnelDielectricAvg(eta);
+  g.thinFmsScale = Favg * (1.f - g.thinEavg) * (1.f / (1.f - Favg * g.thinEavg));
+}
+__device__ __forceinline__ EvalRes ThinMicrofacetDielectric_eval(const PrGlass &g, vec3f wo, vec3f wi)
+{
+  EvalRes res; res.value = make_vec3f(0.f); res.pdf = 0.f;
+  const vec3f N = g.frame.vz;
+  const float cosThetaO = dot(wo, N);
+  if (cosThetaO <= 0.f) return res;
+  const float cosThetaI = dot(wi, N);
+  if (!(cosThetaI > 0.f)) return res;
+  const vec3f wh = normalize(wo + wi);
+  const float cosThetaOH = dot(wo, wh), cosThetaIH = dot(wi, wh);
+  const vec3f wo0 = toLocal(g.frame, wo), wi0 = toLocal(g.frame, wi), wh0 = toLocal(g.frame, wh);
+  const float F = fresnelDielectric(cosThetaOH, g.eta);
+  float whPdf;
+  const float D = ggxEvalVisible(g.mf, wh0, wo0, cosThetaOH, whPdf);
+  const float G = ggxG2(g.mf, wo0, wi0, cosThetaOH, cosThetaIH);
+  const float Eo = mfAlbedo(g.tables, cosThetaO, g.roughness), Ei = mfAlbedo(g.tables, cosThetaI, g.roughness);
+  const float fms = g.thinFmsScale * ((1.f - Eo) * (1.f - Ei) * (1.f / (OC_PI * (1.f - g.thinEavg))) * cosThetaI);
+  const float R = mfDielReflAlbedo(g.tables, cosThetaO, g.eta, g.roughness) + g.thinFmsScale * (1.f - Eo);
+  res.pdf = whPdf * (1.f / (4.f * cosThetaOH)) * R;
+  res.value = make_vec3f(F * D * G * (1.f / (4.f * cosThetaO)) + fms);
+  return res;
+}
+__device__ __forceinline__ SampleRes ThinMicrofacetDielectric_sample(const PrGlass &g, vec3f wo, vec2f s, float ss)
+{
+  SampleRes res; res.weight = make_vec3f(0.f); res.wi = make_vec3f(0.f); res.pdf = 0.f; res.type = 0;
+  const vec3f N = g.frame.vz;
+  const float cosThetaO = dot(wo, N);
+  if (cosThetaO <= 0.f) return res;
+  const float Eo = mfAlbedo(g.tables, cosThetaO, g.roughness);
+  const float R = mfDielReflAlbedo(g.tables, cosThetaO, g.eta, g.roughness) + g.thinFmsScale * (1.f - Eo);
+  if (ss < R) {
+    const vec3f wo0 = toLocal(g.frame, wo);
+    float whPdf;
+    const vec3f wh = g.frame * ggxSampleVisible(g.mf, wo0, whPdf, s);
+    res.wi = reflectDir(wo, wh, dot(wo, wh));
+    const float cosThetaI = dot(res.wi, N);
+    if (cosThetaI <= 0.f) { res.wi = make_vec3f(0.f); return res; }
+    const float cosThetaOH = dot(wo, wh), cosThetaIH = dot(res.wi, wh);
+    const vec3f wi0 = toLocal(g.frame, res.wi);
+    const float F = fresnelDielectric(cosThetaOH, g.eta);
+    const float G = ggxG2(g.mf, wo0, wi0, cosThetaOH, cosThetaIH);
+    const float Ei = mfAlbedo(g.tables, cosThetaI, g.roughness);
+    const float fms = g.thinFmsScale * ((1.f - Eo) * (1.f - Ei) * (1.f / (OC_PI * (1.f - g.thinEavg))) * cosThetaI);
+    res.type = SC_GLOSSY_REFLECTION;
+    res.pdf = whPdf * (1.f / (4.f * fabsf(cosThetaOH))) * R;
+    res.weight = make_vec3f(F * G * rcpSafe(ggxG1(g.mf, wo0, cosThetaOH)) * (1.f / R)) + make_vec3f(fms * (1.f / res.pdf));
+  } else {
+    const float length = 1.f / refractCos(cosThetaO, g.eta);
+    res.type = SC_SPECULAR_TRANSMISSION;
+    res.wi = neg(wo);
+    res.pdf = INFINITY;
+    res.weight = expf3(g.attenuation * length);
+  }
+  return res;
+}
 __device__ __forceinline__ EvalRes PrGlass_eval(const PrGlass &g, vec3f wo, vec3f wi)
 {
   EvalRes res; res.value = make_vec3f(0.f); res.pdf = 0.f;
-  if (g.kind != 2) return res; // Transmission, Dielectric: delta lobes
+  if (g.kind == 4) return ThinMicrofacetDielectric_eval(g, wo, wi);
+  if (g.kind != 2) return res; // Transmission, Dielectric, ThinDielectric: delta lobes
   const float cosThetaO = dot(wo, g.frame.vz);
   if (cosThetaO <= 0.f) return res;
   const float cosThetaI = dot(wi, g.frame.vz);
@@ -181,6 +271,16 @@ __device__ __forceinline__ SampleRes PrGlass_sample(const PrGlass &g, vec3f wo, 
   SampleRes res; res.weight = make_vec3f(0.f); res.wi = make_vec3f(0.f); res.pdf = 0.f; res.type = 0;
   const vec3f N = g.frame.vz;
   if (g.kind == 0) { res.wi = neg(wo); res.pdf = INFINITY; res.type = SC_SPECULAR_TRANSMISSION; res.weight = make_vec3f(1.f); return res; }
+  if (g.kind == 4) return ThinMicrofacetDielectric_sample(g, wo, s, ss);
+  if (g.kind == 3) { // ThinDielectric_sample (ThinDielectric.ih:25-53)
+    const float cosThetaO = fmaxf(dot(wo, N), 0.f);
+    float cosThetaT;
+    const float F = fresnelDielectricEx(cosThetaO, cosThetaT, g.eta);
+    res.pdf = INFINITY;
+    if (ss <= F) { res.wi = reflectDir(wo, N, cosThetaO); res.type = SC_SPECULAR_REFLECTION; res.weight = make_vec3f(1.f); }
+    else { res.wi = neg(wo); res.type = SC_SPECULAR_TRANSMISSION; res.weight = expf3(g.attenuation * (1.f / cosThetaT)); }
+    return res;
+  }
   if (g.kind == 1) { // Dielectric_sample (Dielectric.ih:24-50)
     const float cosThetaO = fmaxf(dot(wo, N), 0.f);
     float cosThetaT;
@@ -326,6 +426,10 @@ struct PrBSDF
   bool hasBase;
   int coatKind; // 0 passthrough, 1 DielectricLayer, 2 MicrofacetDielectricLayer
   LayerParams coat;
+  float sheenWeight;   // 0: passthrough (MicrofacetSheenLayer.ih:14-47)
+  vec3f sheenR;
+  float sheenAlpha, sheenRoughness;
+  const float *tables;
   PrBase base;
   vec3f albedo;
   uint32_t scatteringType;
@@ -363,7 +467,7 @@ __device__ __forceinline__ void Principled_getBSDF(PrBSDF &b, const OcPrincipled
     const vec3f baseColor = clamp01(toV(m.baseColor) * make_vec3f(dg.color));
     const float specular = clampf(m.specular, 0.f, 1.f), metallic = clampf(m.metallic, 0.f, 1.f);
     const float roughness = clampf(m.roughness, 0.f, 1.f), anisotropy = clampf(m.anisotropy, 0.f, 1.f);
-    const bool fromOutside = mediumIsOutside;
+    const bool fromOutside = m.thin ? true : mediumIsOutside;
     const float dielectric = 1.f - metallic;
     if (dielectric > PR_EPS) {
       const float transmission = clampf(m.transmission, 0.f, 1.f);
@@ -379,9 +483,19 @@ __device__ __forceinline__ void Principled_getBSDF(PrBSDF &b, const OcPrincipled
         const vec3f diffuseColor = baseColor * diffuse;
         PrDiffuse &D = P.diffuse;
         D.frame = b.frame; D.R = diffuseColor; D.roughness = roughness; D.orenNayar = !(m.roughness < PR_EPS);
-        // (solid: backlight = 0, diffuseTransmission = 0, diffuseReflection = 1)
-        D.weight = 1.f; D.importance = 1.f; D.importanceSum = 1.f;
-        D.albedo = diffuseColor * 1.f; D.scatteringType = SC_DIFFUSE_REFLECTION;
+        const float backlight = m.thin ? clampf(m.backlight, 0.f, 2.f) : 0.f;
+        const float diffuseTransmission = backlight * 0.5f;
+        const float diffuseReflection = 1.f - diffuseTransmission;
+        D.weight = D.importance = D.weightT = D.importanceT = 0.f; D.importanceSum = 0.f;
+        D.albedo = make_vec3f(0.f); D.scatteringType = 0;
+        if (diffuseReflection > PR_EPS) {
+          D.weight = D.importance = diffuseReflection; D.importanceSum += diffuseReflection;
+          D.albedo = D.albedo + diffuseColor * diffuseReflection; D.scatteringType |= SC_DIFFUSE_REFLECTION;
+        }
+        if (diffuseTransmission > PR_EPS) {
+          D.weightT = D.importanceT = diffuseTransmission; D.importanceSum += diffuseTransmission;
+          D.albedo = D.albedo + diffuseColor * diffuseTransmission; D.scatteringType |= SC_DIFFUSE_TRANSMISSION;
+        }
         if (m.specular > PR_EPS) {
           if (m.roughness < PR_EPS) { P.layerKind = 1; DielectricLayer_init(P.layer, D.albedo, D.scatteringType, eta, make_vec3f(1.f), 1.f, specular); }
           else { P.layerKind = 2; MicrofacetDielectricLayer_init(P.layer, tables, D.albedo, D.scatteringType, eta, make_vec3f(1.f), 1.f, roughness, anisotropy, specular); }
@@ -399,8 +513,17 @@ __device__ __forceinline__ void Principled_getBSDF(PrBSDF &b, const OcPrincipled
         PrGlass &G = B.glass;
         G.frame = b.frame;
         if (fabsf(eta - 1.f) > PR_EPS) {
-          if (m.roughness < PR_EPS) { G.kind = 1; G.eta = eta; G.albedo = make_vec3f(1.0f); G.scatteringType = SC_SPECULAR; }
-          else PrGlass_initMicrofacet(G, tables, eta, roughness, anisotropy);
+          if (!m.thin) {
+            if (m.roughness < PR_EPS) { G.kind = 1; G.eta = eta; G.albedo = make_vec3f(1.0f); G.scatteringType = SC_SPECULAR; }
+            else PrGlass_initMicrofacet(G, tables, eta, roughness, anisotropy);
+          } else {
+            const vec3f transmissionColor = clamp01(toV(m.transmissionColor));
+            const float transmissionDepth = fmaxf(m.transmissionDepth, PR_EPS);
+            const float thickness = fmaxf(m.thickness, 0.f);
+            const vec3f attenuation = logf3(transmissionColor) / transmissionDepth * thickness;
+            if (m.roughness < PR_EPS) { G.kind = 3; G.eta = eta; G.attenuation = attenuation; G.albedo = expf3(attenuation); G.scatteringType = SC_SPECULAR; }
+            else PrGlass_initThinMicrofacet(G, tables, eta, roughness, anisotropy, attenuation);
+          }
         } else { G.kind = 0; G.eta = 1.f; G.albedo = make_vec3f(1.f); G.scatteringType = SC_SPECULAR_TRANSMISSION; }
         B.hasGlass = true;
         B.w[1] = glass; B.imp[1] = glass;
@@ -462,6 +585,19 @@ __device__ __forceinline__ void Principled_getBSDF(PrBSDF &b, const OcPrincipled
       topAlbedo = b.coat.albedo; topType = b.coat.scatteringType;
     } else
       b.coat.weight = 0.f;
+    // sheen (Principled.ispc:392-413)
+    b.sheenWeight = 0.f; b.tables = tables;
+    if (m.sheen > PR_EPS) {
+      const float sheen = clampf(m.sheen, 0.f, 1.f);
+      vec3f sheenColor = clamp01(toV(m.sheenColor));
+      const float sheenTint = clampf(m.sheenTint, 0.f, 1.f);
+      sheenColor = lerpv(sheenTint, sheenColor, baseColor);
+      const float sheenRoughness = clampf(m.sheenRoughness, 0.f, 1.f);
+      b.sheenWeight = sheen; b.sheenR = sheenColor; b.sheenRoughness = sheenRoughness;
+      b.sheenAlpha = fmaxf(sqr(sheenRoughness), 0.001f);
+      topAlbedo = lerpv(sheen * 0.1f, topAlbedo, sheenColor);
+      topType = SC_DIFFUSE_REFLECTION | topType;
+    }
     b.hasBase = true;
     b.opacity = opacity;
     b.albedo = b.albedo + topAlbedo * opacity; b.scatteringType |= topType; b.importanceSum += opacity;
@@ -486,12 +622,79 @@ __device__ __forceinline__ SampleRes PrCoat_sample(const PrBSDF &b, vec3f wo, ve
   if (b.coatKind == 2) return MicrofacetDielectricLayer_sample(b.coat, b.frame, b.base, wo, s, ss);
   return DielectricLayer_sample(b.coat, b.frame.vz, b.base, wo, s, ss);
 }
+// SheenLayerBSDF_eval / _sample (Principled.ispc:990-1019) = MICROFACETSHEENLAYER_EVAL / _SAMPLE (MicrofacetSheenLayer.ih:82-222)
+__device__ __forceinline__ EvalRes PrSheen_eval(const PrBSDF &b, vec3f wo, vec3f wi)
+{
+  if (b.sheenWeight < PR_EPS) return PrCoat_eval(b, wo, wi);
+  EvalRes zero; zero.value = make_vec3f(0.f); zero.pdf = 0.f;
+  const vec3f N = b.frame.vz;
+  const float cosThetaO = dot(wo, N);
+  if (cosThetaO <= 0.f) return zero;
+  const float cosThetaI = dot(wi, N);
+  EvalRes substrate = PrCoat_eval(b, wo, wi);
+  const float Ro = mfSheenAlbedo(b.tables, cosThetaO, b.sheenRoughness) * b.sheenWeight;
+  const float Ri = mfSheenAlbedo(b.tables, fabsf(cosThetaI), b.sheenRoughness) * b.sheenWeight;
+  const float T = fminf(1.f - Ro, 1.f - Ri);
+  substrate.value = substrate.value * T;
+  const float coatPickProb = Ro, substratePickProb = 1.f - coatPickProb;
+  if (cosThetaI > 0.f) {
+    const vec3f wh = normalize(wo + wi);
+    const float cosThetaH = dot(wh, N), cosThetaOH = dot(wo, wh), cosThetaIH = dot(wi, wh);
+    const float D = sheenD(b.sheenAlpha, cosThetaH);
+    const float G = sheenG2(b.sheenAlpha, cosThetaO, cosThetaI, cosThetaOH, cosThetaIH);
+    const vec3f coatValue = b.sheenR * (D * G * (1.f / (4.f * cosThetaO)) * b.sheenWeight);
+    substrate.pdf = coatPickProb * OC_ONE_OVER_TWO_PI + substratePickProb * substrate.pdf;
+    substrate.value = coatValue + substrate.value;
+  } else
+    substrate.pdf *= substratePickProb;
+  return substrate;
+}
+__device__ __forceinline__ SampleRes PrSheen_sample(const PrBSDF &b, vec3f wo, vec2f s, float ss)
+{
+  if (b.sheenWeight < PR_EPS) return PrCoat_sample(b, wo, s, ss);
+  SampleRes res; res.weight = make_vec3f(0.f); res.wi = make_vec3f(0.f); res.pdf = 0.f; res.type = 0;
+  const vec3f N = b.frame.vz;
+  const float cosThetaO = dot(wo, N);
+  if (cosThetaO <= 0.f) return res;
+  const float Ro = mfSheenAlbedo(b.tables, cosThetaO, b.sheenRoughness) * b.sheenWeight;
+  EvalRes substrate;
+  const float coatPickProb = Ro, substratePickProb = 1.f - coatPickProb;
+  if (ss < coatPickProb) {
+    res.type = SC_DIFFUSE_REFLECTION;
+    res.wi = b.frame * uniformSampleHemisphere(s);
+    substrate = PrCoat_eval(b, wo, res.wi);
+  } else {
+    const float ss1 = (ss - coatPickProb) * (1.f / substratePickProb);
+    res = PrCoat_sample(b, wo, s, ss1);
+    if (reduce_max(res.weight) <= 0.f) return res;
+    substrate.pdf = res.pdf;
+    substrate.value = res.weight * ((res.type & SC_SPECULAR) ? 1.f : res.pdf);
+  }
+  const float cosThetaI = dot(res.wi, N);
+  const float Ri = mfSheenAlbedo(b.tables, fabsf(cosThetaI), b.sheenRoughness) * b.sheenWeight;
+  const float T = fminf(1.f - Ro, 1.f - Ri);
+  substrate.value = substrate.value * T;
+  if (res.type & SC_SPECULAR) res.weight = substrate.value * (1.f / substratePickProb);
+  else if (cosThetaI <= 0.f) {
+    res.pdf = substratePickProb * substrate.pdf;
+    res.weight = substrate.value * (1.f / res.pdf);
+  } else {
+    const vec3f wh = normalize(wo + res.wi);
+    const float cosThetaH = dot(wh, N), cosThetaOH = dot(wo, wh), cosThetaIH = dot(res.wi, wh);
+    const float D = sheenD(b.sheenAlpha, cosThetaH);
+    const float G = sheenG2(b.sheenAlpha, cosThetaO, cosThetaI, cosThetaOH, cosThetaIH);
+    const vec3f coatValue = b.sheenR * (D * G * (1.f / (4.f * cosThetaO)) * b.sheenWeight);
+    res.pdf = coatPickProb * OC_ONE_OVER_TWO_PI + substratePickProb * substrate.pdf;
+    res.weight = (coatValue + substrate.value) * (1.f / res.pdf);
+  }
+  return res;
+}
 // Principled_BSDF_eval / _sample (Principled.ispc:1000-1040): the root MultiBSDF (child 0 = cut-out transmission)
 static __device__ __noinline__ EvalRes Principled_eval(const PrBSDF &b, vec3f wo, vec3f wi)
 {
   EvalRes e; e.value = make_vec3f(0.f); e.pdf = 0.f;
   if (b.hasBase && b.opacity > 0.f) {
-    EvalRes c = PrCoat_eval(b, wo, wi);
+    EvalRes c = PrSheen_eval(b, wo, wi);
     c.value = c.value * b.opacity;
     e.value = e.value + c.value;
     e.pdf += c.pdf * b.opacity;
@@ -513,7 +716,7 @@ static __device__ __noinline__ SampleRes Principled_sample(const PrBSDF &b, vec3
   } else if (x < (prefix += (b.hasBase ? b.opacity : 0.f))) {
     choice = 1;
     const float ssc = (x + b.opacity - prefix) * (1.f / b.opacity);
-    res = PrCoat_sample(b, wo, s, ssc);
+    res = PrSheen_sample(b, wo, s, ssc);
     res.weight = res.weight * b.opacity;
   } else return res;
   if ((res.weight.x == 0.f && res.weight.y == 0.f && res.weight.z == 0.f) || res.pdf == 0.0f) {
@@ -544,14 +747,34 @@ __device__ __forceinline__ vec3f Principled_getTransparency(const OcPrincipled &
     const float specular = clampf(m.specular, 0.f, 1.f), metallic = clampf(m.metallic, 0.f, 1.f);
     const float glass = (1.f - metallic) * transmission * specular;
     if (glass > PR_EPS) {
-      const bool fromOutside = mediumIsOutside;
+      const bool fromOutside = m.thin ? true : mediumIsOutside;
       float ior = m.ior;
       if (ior < 1.f) ior = 1.f / ior;
       float eta = fromOutside ? m.outsideIor * (1.f / ior) : ior * (1.f / m.outsideIor);
       eta = clampf(eta, 1.f / 3.f, 3.f);
       const float cosThetaO = fmaxf(-dot(rayDir, dg.Ns), 0.f);
       if (fabsf(eta - 1.f) > PR_EPS) {
-        if (m.roughness < PR_EPS) T = make_vec3f(1.f - fresnelDielectric(cosThetaO, eta)); // Dielectric_getTransparency
+        if (!m.thin) {
+          if (m.roughness < PR_EPS) T = make_vec3f(1.f - fresnelDielectric(cosThetaO, eta)); // Dielectric_getTransparency
+        } else {
+          const vec3f transmissionColor = clamp01(toV(m.transmissionColor));
+          const float transmissionDepth = fmaxf(m.transmissionDepth, PR_EPS);
+          const float thickness = fmaxf(m.thickness, 0.f);
+          const vec3f attenuation = logf3(transmissionColor) / transmissionDepth * thickness;
+          if (m.roughness < PR_EPS) { // ThinDielectric_getTransparency (ThinDielectric.ih:88-98)
+            float cosThetaT;
+            const float F = fresnelDielectricEx(cosThetaO, cosThetaT, eta);
+            T = (1.f - F) * expf3(attenuation * (1.f / cosThetaT));
+          } else { // ThinMicrofacetDielectric_getTransparency (ThinMicrofacetDielectric.ih:209-231)
+            const float roughness = clampf(m.roughness, 0.f, 1.f);
+            const float Eavg = mfAlbedoAvg(tables, roughness);
+            const float Favg = fresnelDielectricAvg(eta);
+            const float fmsScale = Favg * (1.f - Eavg) * (1.f / (1.f - Favg * Eavg));
+            const float Eo = mfAlbedo(tables, cosThetaO, roughness);
+            const float R = mfDielReflAlbedo(tables, cosThetaO, eta, roughness) + fmsScale * (1.f - Eo);
+            T = (1.f - R) * expf3(attenuation * (1.f / refractCos(cosThetaO, eta)));
+          }
+        }
       } else
         T = make_vec3f(1.f);
       if (reduce_max(T) > 0.f) {
@@ -584,6 +807,10 @@ __device__ __forceinline__ vec3f Principled_getTransparency(const OcPrincipled &
               T = T * (value * (1.f - Ro));
             }
           }
+        }
+        if (m.sheen > PR_EPS) { // MicrofacetSheenLayer_getTransparency (MicrofacetSheenLayer.ih:66-78)
+          const float sheen = clampf(m.sheen, 0.f, 1.f), sheenRoughness = clampf(m.sheenRoughness, 0.f, 1.f);
+          T = T * make_vec3f(1.f - mfSheenAlbedo(tables, cosThetaO, sheenRoughness) * sheen);
         }
         T = T * glass;
       }

@@ -1175,12 +1175,17 @@ __global__ void albedoTablesDirKernel(float *t)
   else if (i < OC_MFA_SIZE * OC_MFA_SIZE + 3u * OC_MFD_SIZE * OC_MFD_SIZE * OC_MFD_SIZE) {
     const uint32_t j = i - OC_MFA_SIZE * OC_MFA_SIZE;
     which = 1 + (int)(j / (OC_MFD_SIZE * OC_MFD_SIZE * OC_MFD_SIZE)); idx = (int)(j % (OC_MFD_SIZE * OC_MFD_SIZE * OC_MFD_SIZE));
+  } else if (i < OC_MFA_SIZE * OC_MFA_SIZE + 3u * OC_MFD_SIZE * OC_MFD_SIZE * OC_MFD_SIZE + OC_MFS_SIZE * OC_MFS_SIZE) {
+    which = 4; idx = (int)(i - (OC_MFA_SIZE * OC_MFA_SIZE + 3u * OC_MFD_SIZE * OC_MFD_SIZE * OC_MFD_SIZE)); // sheen (:140-160)
   } else return;
   float cosThetaO, roughness, eta = 1.f;
   float *dst;
   if (which == 0) {
     cosThetaO = (float)(idx % OC_MFA_SIZE) / (OC_MFA_SIZE - 1); roughness = (float)(idx / OC_MFA_SIZE) / (OC_MFA_SIZE - 1);
     dst = t + OC_MFT_ALBEDO_DIR + idx;
+  } else if (which == 4) {
+    cosThetaO = (float)(idx % OC_MFS_SIZE) / (OC_MFS_SIZE - 1); roughness = (float)(idx / OC_MFS_SIZE) / (OC_MFS_SIZE - 1);
+    dst = t + OC_MFT_SHEEN_DIR + idx;
   } else {
     const int ic = idx % OC_MFD_SIZE, ie = (idx / OC_MFD_SIZE) % OC_MFD_SIZE, ir = idx / (OC_MFD_SIZE * OC_MFD_SIZE);
     cosThetaO = (float)ic / (OC_MFD_SIZE - 1); roughness = (float)ir / (OC_MFD_SIZE - 1);
@@ -1191,11 +1196,13 @@ __global__ void albedoTablesDirKernel(float *t)
     dst = t + (which == 1 ? OC_MFT_DIEL_DIR : which == 2 ? OC_MFT_DIELRCP_DIR : OC_MFT_DIELREFL_DIR) + idx;
   }
   const GGX g = makeGGX(roughness, 0.f);
+  const float sheenAlpha = fmaxf(sqr(roughness), 0.001f); // roughnessToAlpha
   float sum = 0.f;
   for (int a = 0; a < n; a++)
     for (int b = 0; b < n; b++) {
       const vec2f s = make_vec2f(fminf(((float)a + 0.5f) / n, 1.f - 1e-6f), fminf(((float)b + 0.5f) / n, 1.f - 1e-6f));
-      sum += which == 0 ? mfAlbedoSample(cosThetaO, g, s) : mfDielAlbedoSample(cosThetaO, eta, g, s, which == 3);
+      sum += which == 0 ? mfAlbedoSample(cosThetaO, g, s) : which == 4 ? mfSheenAlbedoSample(cosThetaO, sheenAlpha, s)
+                                                          : mfDielAlbedoSample(cosThetaO, eta, g, s, which == 3);
     }
   *dst = fminf(sum / (n * n), 1.f);
 }
@@ -1235,7 +1242,7 @@ extern "C" int ospcuda_microfacet_albedo_tables(const float **d_tables, uint32_t
   if (!t) {
     OC_TRY(cudaMalloc(&t, OC_MFT_TOTAL * sizeof(float)));
     cudaStream_t st = (cudaStream_t)ospcuda_stream();
-    const uint32_t nDir = OC_MFA_SIZE * OC_MFA_SIZE + 3u * OC_MFD_SIZE * OC_MFD_SIZE * OC_MFD_SIZE;
+    const uint32_t nDir = OC_MFA_SIZE * OC_MFA_SIZE + 3u * OC_MFD_SIZE * OC_MFD_SIZE * OC_MFD_SIZE + OC_MFS_SIZE * OC_MFS_SIZE;
     oc::albedoTablesDirKernel<<<(nDir + 127) / 128, 128, 0, st>>>(t);
     const uint32_t nAvg = OC_MFA_SIZE + 3u * OC_MFD_SIZE * OC_MFD_SIZE;
     oc::albedoTablesAvgKernel<<<(nAvg + 127) / 128, 128, 0, st>>>(t);

@@ -827,7 +827,7 @@ __device__ __forceinline__ void materialSelectNextMedium(const DifferentialGeome
   }
   if (!m || m->type != OC_MATERIAL_PRINCIPLED) return;
   const OcPrincipled &q = m->principled;
-  if (q.transmission <= PR_EPS) return;
+  if (q.thin || q.transmission <= PR_EPS) return;
   if (mediumIsOutside(medium, q)) {
     float ior = q.ior;
     if (ior < 1.f) ior = 1.f / ior;

@@ -479,14 +479,11 @@ void Material::commit()
     m.Ns = getParam<float>("roughness", texNs ? 1.f : 0.1f);
     extended = true;
   } else if (type == "principled") {
-    // render/materials/Principled.cpp:33-150. Built: the solid form (thin = false) without sheen; texture maps and normal
-    // maps of this material are refused rather than ignored.
+    // render/materials/Principled.cpp:33-150. Texture maps and normal maps of this material are refused rather than ignored.
     for (auto &p : params)
       if (p.first.rfind("map_", 0) == 0) throw std::runtime_error("cuda device: principled texture maps are not supported ('" + p.first + "')");
-    if (getParam<bool>("thin", false)) throw std::runtime_error("cuda device: principled 'thin' mode is not supported");
-    if (getParam<float>("sheen", 0.f) > 1e-5f) throw std::runtime_error("cuda device: principled 'sheen' is not supported");
-    for (const char *ign : {"sheenColor", "sheenTint", "sheenRoughness", "backlight", "thickness", "normal", "baseNormal", "coatNormal"})
-      if (auto it = params.find(ign); it != params.end()) it->second.queried = true; // no effect on a solid, unmapped, sheen-less material
+    for (const char *ign : {"normal", "baseNormal", "coatNormal"})
+      if (auto it = params.find(ign); it != params.end()) it->second.queried = true; // scales of the normal maps: no effect without one
     m.type = OC_MATERIAL_PRINCIPLED;
     OcPrincipled &q = m.principled;
     q.baseColor = toOc(getParam<vec3f>("baseColor", make_vec3f(0.8f)));
@@ -508,6 +505,13 @@ void Material::commit()
     q.coatThickness = getParam<float>("coatThickness", 1.f);
     q.coatRoughness = getParam<float>("coatRoughness", 0.f);
     q.opacity = getParam<float>("opacity", 1.f);
+    q.sheen = getParam<float>("sheen", 0.f);
+    q.sheenColor = toOc(getParam<vec3f>("sheenColor", make_vec3f(1.f)));
+    q.sheenTint = getParam<float>("sheenTint", 0.f);
+    q.sheenRoughness = getParam<float>("sheenRoughness", 0.2f);
+    q.thin = getParam<bool>("thin", false) ? 1u : 0u;
+    q.backlight = getParam<float>("backlight", 0.f);
+    q.thickness = getParam<float>("thickness", 1.f);
     const float outsideIor = getParam<float>("outsideIor", 1.f);
     const vec3f otc = getParam<vec3f>("outsideTransmissionColor", make_vec3f(1.f));
     const float otd = getParam<float>("outsideTransmissionDepth", 1.f);

@@ -284,6 +284,13 @@ def principled_cornell(variant):
         # emissive surface (a geometry light) | partly transmissive plastic-glass mixture in a non-vacuum outside medium
         "emissive": (P(baseColor=(0.5, 0.5, 0.5), emissiveColor=(1.0, 0.6, 0.3), intensity=1.5, ior=1.3),
                      P(baseColor=(0.6, 0.8, 0.9), transmission=0.5, ior=1.6, outsideIor=1.1, transmissionColor=(0.8, 0.9, 1.0))),
+        # sheen over plastic (MicrofacetSheenLayer, tinted towards the base colour) | sheen over a coated metal
+        "sheen": (P(baseColor=(0.7, 0.1, 0.1), ior=1.45, specular=0.5, sheen=1.0, sheenTint=0.6, sheenRoughness=0.3),
+                  P(baseColor=(0.3, 0.6, 0.8), metallic=0.8, coat=0.5, sheen=0.6, sheenColor=(1.0, 0.8, 0.6), sheenRoughness=0.5)),
+        # thin-walled: smooth glass sheet with absorbing thickness + backlit diffuse | rough thin glass (ThinMicrofacetDielectric)
+        "thin": (P(baseColor=(0.9, 0.8, 0.3), thin=True, transmission=0.6, ior=1.5, transmissionColor=(0.5, 0.9, 0.6), transmissionDepth=0.4,
+                   thickness=0.2, backlight=0.8),
+                 P(thin=True, transmission=1.0, ior=1.4, roughness=0.3, transmissionColor=(0.9, 0.6, 0.5), thickness=0.5)),
     }[variant]
     return _cornell_models({(5, 6, 7, 8, 9): a, (11, 12, 13, 14, 15): b}, drop=(10, 16))
 
@@ -402,6 +409,8 @@ CASES = {
     "principled_coat_pt": (lambda: principled_cornell("coat"), "pathtracer", {"pixelSamples": 2}, 2),
     "principled_rough_layers_pt": (lambda: principled_cornell("rough_layers"), "pathtracer", {"pixelSamples": 2}, 2),
     "principled_emissive_pt": (lambda: principled_cornell("emissive"), "pathtracer", {"pixelSamples": 2}, 2),
+    "principled_sheen_pt": (lambda: principled_cornell("sheen"), "pathtracer", {"pixelSamples": 2}, 2),
+    "principled_thin_pt": (lambda: principled_cornell("thin"), "pathtracer", {"pixelSamples": 2}, 2),
     # debug renderer (render/debug/DebugRenderer.ispc), every method the device accepts
     "debug_testFrame": (T.cornell_box, "debug", {"method": "testFrame", "pixelSamples": 2}, 2),
     "debug_rayDir": (T.cornell_box, "debug", {"method": "rayDir"}, 1),
@@ -426,7 +435,7 @@ ORACLE_UNSUPPORTED = {"textured_pt", "textured_bias_pt", "cutout_pt", "backplate
                       "emissive_transparent_pt", "textured_scivis", "textured_ao", "cutout_scivis", "cutout_ao", "backplate_scivis",
                       "backplate_ao", "debug_texCoord", "debug_dPdt", "debug_dPds_tex", "debug_backplate", "metal_smooth_pt", "metal_rough_pt",
                       "plastic_smooth_pt", "plastic_rough_pt", "principled_plastic_pt", "principled_metal_pt", "principled_glass_pt",
-                      "principled_coat_pt", "principled_rough_layers_pt", "principled_emissive_pt", "glass_alloy_pt", "glass_alloy_rough_pt"}
+                      "principled_coat_pt", "principled_rough_layers_pt", "principled_emissive_pt", "glass_alloy_pt", "glass_alloy_rough_pt", "principled_sheen_pt", "principled_thin_pt"}
 # Rough dielectric coatings: MicrofacetDielectricLayer_Constructor reads self->eta for Ravg BEFORE assigning it
 # (bsdfs/MicrofacetDielectricLayer.ih:55 vs :68), i.e. whatever the shading context's memory held from the previous BSDF. The
 # device uses the intended value; against the reference's kernels the coated surfaces then differ by ~0.5 % in brightness

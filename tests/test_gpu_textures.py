@@ -101,9 +101,9 @@ def test_uncommitted_texture_is_refused(osp):
         t.commit()
 
 
-@pytest.mark.parametrize("name,value", [("thin", True), ("sheen", 0.5), ("map_baseColor", "texture"), ("map_normal", "texture")])
+@pytest.mark.parametrize("name,value", [("map_baseColor", "texture"), ("map_normal", "texture")])
 def test_principled_refuses_what_it_does_not_build(osp, name, value):
-    """principled: the solid, sheen-less, unmapped form is built (Principled.ispc); the rest is refused at commit, not ignored"""
+    """principled: every factor is built (Principled.ispc); its texture and normal maps are refused at commit, not ignored"""
     m = osp.Material("principled")
     if value == "texture":
         value = osp.texture2d(np.full((2, 2, 3), 0.5, np.float32), "RGB32F", 0, (0, 0))
@@ -111,5 +111,5 @@ def test_principled_refuses_what_it_does_not_build(osp, name, value):
     with pytest.raises(osp.OSPRayError):
         m.commit()
     ok = osp.Material("principled")
-    ok.set("baseColor", (0.2, 0.4, 0.6)).set("sheenColor", (1.0, 0.5, 0.5)).set("backlight", 0.3)  # inert on a solid, sheen-less material
+    ok.set("baseColor", (0.2, 0.4, 0.6)).set("sheenColor", (1.0, 0.5, 0.5)).set("backlight", 0.3).set("thin", True)
     ok.commit()

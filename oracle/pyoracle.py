@@ -401,6 +401,16 @@ def ref_texture_sample(map_spec, st, footprint, mipmaps=True):
     return out, tp
 
 
+def ref_albedo_tables():
+    """the reference's microfacet albedo tables (oracle/_ref) as one block in ospcuda_microfacet_albedo_tables' order"""
+    L = ref_lib()
+    L.ospref_albedo_tables.restype = C.c_uint32
+    n = L.ospref_albedo_tables(None, 0)
+    out = np.zeros(n, np.float32)
+    L.ospref_albedo_tables(C.c_void_p(out.ctypes.data), n)
+    return out
+
+
 def linear2f_orthogonal(m):
     """rkcommon LinearSpace2::orthogonal() (un-vendored; restated): rotation part by m <- (m + m^-T) / 2; m = (vx.x, vx.y, vy.x, vy.y)"""
     f = np.float32

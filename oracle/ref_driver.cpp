@@ -777,3 +777,14 @@ REF_API void ospref_fb_accumulate(const OcFrameBuffer *fb, const OcVec4f *sc, co
     }
 }
 REF_API int ospref_hardware_threads(void) { return (int)std::max(1u, std::thread::hardware_concurrency()); }
+
+extern "C" uint32_t ospref_albedo_tables(float *out, uint32_t capacity)
+{
+  // precomputeMicrofacetAlbedoTables (render/bsdfs/MicrofacetAlbedoTables.ispc:162-172) in the order of ospcuda.h's block:
+  // albedo dir / avg, dielectric dir / avg, 1/eta dir / avg, reflection dir / avg, sheen
+  const size_t a = MICROFACET_ALBEDO_TABLE_SIZE, d = MICROFACET_DIELECTRIC_ALBEDO_TABLE_SIZE, sh = MICROFACET_SHEEN_ALBEDO_TABLE_SIZE;
+  const uint32_t n = (uint32_t)(a * a + a + 3 * (d * d * d + d * d) + sh * sh);
+  if (out && capacity >= n) std::memcpy(out, refAlbedoTables()->albedo_dir, n * sizeof(float));
+  return n;
+}
+

@@ -6,7 +6,7 @@
 
 Writes tests/golden/ref_renders.npz (every case of tests/scenes.py the scalar reference kernels define, 48x40: colour,
 depth, ids) and tests/golden/ref_kats.npz (sampler streams, Gaussian pixel-filter LUT, frame ops and accumulation on
-seeded inputs).  The committed files let the oracle (and through it the CUDA path) be checked against the reference on
+seeded inputs) and tests/golden/ref_albedo_tables.npy (the microfacet albedo tables).  The committed files let the oracle (and through it the CUDA path) be checked against the reference on
 machines where neither /root/reference nor oracle/_ref exists."""
 import os
 import sys
@@ -60,6 +60,7 @@ def main():
             renders[f"{name}/{ch}"] = fb.buf[ch]
     np.savez_compressed(os.path.join(HERE, "ref_renders.npz"), **renders)
     np.savez_compressed(os.path.join(HERE, "ref_kats.npz"), **kats("ref"))
+    np.save(os.path.join(HERE, "ref_albedo_tables.npy"), O.ref_albedo_tables())  # precomputeMicrofacetAlbedoTables
     print("wrote ref_renders.npz (%d arrays), ref_kats.npz" % len(renders))
 
 

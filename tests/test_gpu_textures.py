@@ -113,3 +113,21 @@ def test_principled_refuses_what_it_does_not_build(osp, name, value):
     ok = osp.Material("principled")
     ok.set("baseColor", (0.2, 0.4, 0.6)).set("sheenColor", (1.0, 0.5, 0.5)).set("backlight", 0.3).set("thin", True)
     ok.commit()
+
+
+def test_microfacet_albedo_tables_match_reference():
+    """the energy-compensation tables the device integrates (albedoTablesDirKernel / AvgKernel) against
+    precomputeMicrofacetAlbedoTables of the reference (golden copy written by tests/golden/gen_ref_golden.py): same 1024
+    stratified samples per entry, libm differences only"""
+    import torch
+    L = _abi()
+    L.ospcuda_microfacet_albedo_tables.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]
+    ptr, n = C.c_void_p(), C.c_uint32()
+    assert L.ospcuda_microfacet_albedo_tables(C.byref(ptr), C.byref(n)) == 0
+    want = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_albedo_tables.npy"))
+    assert n.value == want.size
+    got = torch.zeros(n.value, dtype=torch.float32, device="cuda")
+    L.ospcuda_synchronize()
+    cudart = C.CDLL("libcudart.so.12")
+    assert cudart.cudaMemcpy(C.c_void_p(got.data_ptr()), ptr, C.c_size_t(4 * n.value), C.c_int(3)) == 0  # device to device
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=2e-4, atol=2e-6)

@@ -116,7 +116,19 @@ typedef struct {
 
 enum { OC_MATERIAL_OBJ = 0, OC_MATERIAL_OTHER = 1, OC_MATERIAL_THINGLASS = 2, OC_MATERIAL_LUMINOUS = 3, OC_MATERIAL_METAL = 4,
        OC_MATERIAL_PLASTIC = 5, OC_MATERIAL_PRINCIPLED = 6, OC_MATERIAL_GLASS = 7, OC_MATERIAL_ALLOY = 8 };
-/* principled (reference: ispc::Principled, render/materials/PrincipledShared.h:17-170, Principled.cpp:33-150), without texture maps: factors as committed; outsideIor = outsideIor >= 1 ? outsideIor : 1 / outsideIor,
+/* texture maps of the principled material (PrincipledShared.h: one TextureParam per factor; the three normal maps come with the
+ * orthogonal part of their 2D transform, transposed, and a scale: Material::getMaterialParam1f, render/Material.cpp:103-113) */
+enum { OC_PRMAP_BASECOLOR = 0, OC_PRMAP_EDGECOLOR, OC_PRMAP_METALLIC, OC_PRMAP_DIFFUSE, OC_PRMAP_SPECULAR, OC_PRMAP_IOR,
+       OC_PRMAP_TRANSMISSION, OC_PRMAP_TRANSMISSIONCOLOR, OC_PRMAP_TRANSMISSIONDEPTH, OC_PRMAP_ROUGHNESS, OC_PRMAP_ANISOTROPY,
+       OC_PRMAP_ROTATION, OC_PRMAP_NORMAL, OC_PRMAP_BASENORMAL, OC_PRMAP_COAT, OC_PRMAP_COATIOR, OC_PRMAP_COATCOLOR,
+       OC_PRMAP_COATTHICKNESS, OC_PRMAP_COATROUGHNESS, OC_PRMAP_COATNORMAL, OC_PRMAP_SHEEN, OC_PRMAP_SHEENCOLOR, OC_PRMAP_SHEENTINT,
+       OC_PRMAP_SHEENROUGHNESS, OC_PRMAP_OPACITY, OC_PRMAP_BACKLIGHT, OC_PRMAP_THICKNESS, OC_PRMAP_EMISSION, OC_PRMAP_COUNT };
+typedef struct {
+  OcTextureParam map[OC_PRMAP_COUNT];
+  float normalRot[4], baseNormalRot[4], coatNormalRot[4]; /* (vx, vy) */
+  float normalScale, baseNormalScale, coatNormalScale;
+} OcPrincipledMaps;
+/* principled (reference: ispc::Principled, render/materials/PrincipledShared.h:17-170, Principled.cpp:33-150): factors as committed; outsideIor = outsideIor >= 1 ? outsideIor : 1 / outsideIor,
  * outsideAttenuation = log(outsideTransmissionColor) / outsideTransmissionDepth (the medium around the object) */
 typedef struct {
   OcVec3f baseColor, edgeColor;
@@ -137,6 +149,7 @@ typedef struct {
   float sheenTint, sheenRoughness;
   uint32_t thin;               /* thin-walled mode: no medium change, ThinDielectric glass, backlight = diffuse transmission */
   float backlight, thickness;
+  const OcPrincipledMaps *maps; /* NULL: no texture maps (a factor with a map defaults to 1, Material.cpp:103-126) */
 } OcPrincipled;
 /* material (reference: ispc::OBJ, render/materials/OBJShared.h, OBJ.cpp:30-66; ispc::ThinGlass,
  * render/materials/ThinGlassShared.h, ThinGlass.cpp:33-48: eta = 1/ior, attenuationScale = thickness /

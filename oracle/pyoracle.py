@@ -62,6 +62,16 @@ class TextureParam(C.Structure):
     _fields_ = [("tex", C.POINTER(Texture2D)), ("transformFlags", C.c_uint32), ("scale2f", C.c_float), ("xform2f", C.c_float * 6)]
 
 
+PRMAP_NAMES = ["baseColor", "edgeColor", "metallic", "diffuse", "specular", "ior", "transmission", "transmissionColor", "transmissionDepth",
+               "roughness", "anisotropy", "rotation", "normal", "baseNormal", "coat", "coatIor", "coatColor", "coatThickness", "coatRoughness",
+               "coatNormal", "sheen", "sheenColor", "sheenTint", "sheenRoughness", "opacity", "backlight", "thickness", "emissiveColor"]  # OC_PRMAP_*
+
+
+class PrincipledMaps(C.Structure):  # OcPrincipledMaps
+    _fields_ = [("map", TextureParam * len(PRMAP_NAMES)), ("normalRot", C.c_float * 4), ("baseNormalRot", C.c_float * 4),
+                ("coatNormalRot", C.c_float * 4), ("normalScale", C.c_float), ("baseNormalScale", C.c_float), ("coatNormalScale", C.c_float)]
+
+
 class Principled(C.Structure):  # OcPrincipled
     _fields_ = [("baseColor", Vec3), ("edgeColor", Vec3), ("metallic", C.c_float), ("diffuse", C.c_float), ("specular", C.c_float),
                 ("specularMetallic", C.c_uint32), ("ior", C.c_float), ("transmission", C.c_float), ("transmissionColor", Vec3),
@@ -69,7 +79,7 @@ class Principled(C.Structure):  # OcPrincipled
                 ("coat", C.c_float), ("coatIor", C.c_float), ("coatColor", Vec3), ("coatThickness", C.c_float),
                 ("coatRoughness", C.c_float), ("opacity", C.c_float), ("outsideIor", C.c_float), ("outsideAttenuation", Vec3),
                 ("sheen", C.c_float), ("sheenColor", Vec3), ("sheenTint", C.c_float), ("sheenRoughness", C.c_float), ("thin", C.c_uint32),
-                ("backlight", C.c_float), ("thickness", C.c_float)]
+                ("backlight", C.c_float), ("thickness", C.c_float), ("maps", C.POINTER(PrincipledMaps))]
 
 
 # parameters of the principled material this build takes (ospray name -> default), Principled.cpp:33-77
@@ -604,10 +614,27 @@ class Scene:
         elif ms.type == "principled":  # render/materials/Principled.cpp:33-150 (solid, no sheen, no maps)
             f = np.float32
             prm = dict(PRINCIPLED_DEFAULTS)
-            unknown = set(ms.principled) - set(prm)
+            given = dict(ms.principled)
+            map_specs = {k[4:]: given.pop(k) for k in list(given) if k.startswith("map_")}
+            scales = {k: float(given.pop(k)) for k in ("normal", "baseNormal", "coatNormal") if k in given}
+            unknown = (set(given) - set(prm)) | (set(map_specs) - set(PRMAP_NAMES))
             if unknown:
                 raise ValueError(f"principled parameters not supported: {sorted(unknown)}")
-            prm.update(ms.principled)
+            for name in map_specs:  # a factor with a map defaults to 1 (Material.cpp:103-126)
+                if name in prm:
+                    prm[name] = 1.0 if not isinstance(prm[name], tuple) else (1.0, 1.0, 1.0)
+            prm.update(given)
+            if map_specs:
+                pm = PrincipledMaps()
+                for i, name in enumerate(PRMAP_NAMES):
+                    pm.map[i] = texture_param(map_specs.get(name), self.keep, self.mipmaps)
+                for fld, name in (("normalRot", "normal"), ("baseNormalRot", "baseNormal"), ("coatNormalRot", "coatNormal")):
+                    t = pm.map[PRMAP_NAMES.index(name)]
+                    rot = linear2f_orthogonal([t.xform2f[k] for k in range(4)])
+                    getattr(pm, fld)[0], getattr(pm, fld)[1], getattr(pm, fld)[2], getattr(pm, fld)[3] = rot[0], rot[2], rot[1], rot[3]
+                pm.normalScale, pm.baseNormalScale, pm.coatNormalScale = (scales.get(k, 1.0) for k in ("normal", "baseNormal", "coatNormal"))
+                self.keep.append(pm)
+                m.principled.maps = C.pointer(pm)
             m.type = 6
             q = m.principled
             for name in ("baseColor", "edgeColor", "transmissionColor", "coatColor", "sheenColor"):

@@ -352,6 +352,23 @@ void buildScene(Scene &s, const OcWorld *w, const OcRenderer *ren)
       pr.thin = q.thin != 0; pr.backlight = q.backlight; pr.thickness = q.thickness;
       pr.outsideMedium.ior = q.outsideIor; pr.outsideMedium.attenuation = v3(q.outsideAttenuation);
       pr.emission = v3(m.emission);
+      if (const OcPrincipledMaps *mp = q.maps) { // PrincipledShared.h: one TextureParam per factor, rotations of the normal maps
+        auto tp = [&](int i) { return makeTextureParam(s.textures, mp->map[i]); };
+        auto rot = [](const float *r) { return linear2f(make_vec2f(r[0], r[1]), make_vec2f(r[2], r[3])); };
+        pr.baseColorMap = tp(OC_PRMAP_BASECOLOR); pr.edgeColorMap = tp(OC_PRMAP_EDGECOLOR); pr.metallicMap = tp(OC_PRMAP_METALLIC);
+        pr.diffuseMap = tp(OC_PRMAP_DIFFUSE); pr.specularMap = tp(OC_PRMAP_SPECULAR); pr.iorMap = tp(OC_PRMAP_IOR);
+        pr.transmissionMap = tp(OC_PRMAP_TRANSMISSION); pr.transmissionColorMap = tp(OC_PRMAP_TRANSMISSIONCOLOR);
+        pr.transmissionDepthMap = tp(OC_PRMAP_TRANSMISSIONDEPTH); pr.roughnessMap = tp(OC_PRMAP_ROUGHNESS);
+        pr.anisotropyMap = tp(OC_PRMAP_ANISOTROPY); pr.rotationMap = tp(OC_PRMAP_ROTATION);
+        pr.normalMap = tp(OC_PRMAP_NORMAL); pr.normalRot = rot(mp->normalRot); pr.normal = mp->normalScale;
+        pr.baseNormalMap = tp(OC_PRMAP_BASENORMAL); pr.baseNormalRot = rot(mp->baseNormalRot); pr.baseNormal = mp->baseNormalScale;
+        pr.coatMap = tp(OC_PRMAP_COAT); pr.coatIorMap = tp(OC_PRMAP_COATIOR); pr.coatColorMap = tp(OC_PRMAP_COATCOLOR);
+        pr.coatThicknessMap = tp(OC_PRMAP_COATTHICKNESS); pr.coatRoughnessMap = tp(OC_PRMAP_COATROUGHNESS);
+        pr.coatNormalMap = tp(OC_PRMAP_COATNORMAL); pr.coatNormalRot = rot(mp->coatNormalRot); pr.coatNormal = mp->coatNormalScale;
+        pr.sheenMap = tp(OC_PRMAP_SHEEN); pr.sheenColorMap = tp(OC_PRMAP_SHEENCOLOR); pr.sheenTintMap = tp(OC_PRMAP_SHEENTINT);
+        pr.sheenRoughnessMap = tp(OC_PRMAP_SHEENROUGHNESS); pr.opacityMap = tp(OC_PRMAP_OPACITY); pr.backlightMap = tp(OC_PRMAP_BACKLIGHT);
+        pr.thicknessMap = tp(OC_PRMAP_THICKNESS); pr.emissionMap = tp(OC_PRMAP_EMISSION);
+      }
       pr.super.isEmissive = m.isEmissive != 0;
       pr.super.microfacetAlbedoTables = refAlbedoTables();
       s.allMaterials.push_back(&pr.super);

@@ -375,7 +375,7 @@ __device__ __forceinline__ bool ptOccluderIsOpaque(const OcWorld *world, const O
   if (mat && mat->type == OC_MATERIAL_LUMINOUS) return mat->transparency == 0.f; // Luminous_getTransparency
   if (mat && mat->type == OC_MATERIAL_GLASS) return false;
   if (mat && mat->type == OC_MATERIAL_PRINCIPLED) // Principled_getTransparency's early exit (Principled.ispc:452-454)
-    return 1.f - clampf(mat->principled.opacity, 0.f, 1.f) <= PR_EPS && clampf(mat->principled.transmission, 0.f, 1.f) <= PR_EPS;
+    return !mat->principled.maps && 1.f - clampf(mat->principled.opacity, 0.f, 1.f) <= PR_EPS && clampf(mat->principled.transmission, 0.f, 1.f) <= PR_EPS;
   if (!mat || mat->type != OC_MATERIAL_OBJ) return true; // no / foreign material: transparency 0 (shading.cuh)
   return mat->d == 1.f && mat->Tf.x == 0.f && mat->Tf.y == 0.f && mat->Tf.z == 0.f;
 }

@@ -426,6 +426,8 @@ struct PrBSDF
   bool hasBase;
   int coatKind; // 0 passthrough, 1 DielectricLayer, 2 MicrofacetDielectricLayer
   LayerParams coat;
+  linear3f coatFrame;  // of the coat and the sheen layer (the coat's normal map)
+  vec3f rootN;         // normal of the root MultiBSDF's frame = the first child added (MultiBSDF.ih:35-36): coat frame, else base frame
   float sheenWeight;   // 0: passthrough (MicrofacetSheenLayer.ih:14-47)
   vec3f sheenR;
   float sheenAlpha, sheenRoughness;
@@ -444,46 +446,102 @@ __device__ __forceinline__ vec3f rotateAxis(vec3f v, vec3f axis, float theta) //
   return v * c + cross(axis, v) * s + axis * dot(axis, v) * (1.f - c);
 }
 
+// factor * get1f / get3f(map, dg, 1) for every factor that has a map (Principled.ispc, throughout); baseAlpha = the alpha of the
+// base colour map's sample when that texture has an alpha channel (it multiplies the opacity), cutout = valid(opacityMap) ||
+// hasAlpha(baseColorMap)
+static __device__ __noinline__ void prApplyMaps(OcPrincipled &v, const OcPrincipledMaps &mp, const DifferentialGeometry &dg, float &baseAlpha, bool &cutout)
+{
+  auto has = [&](int i) { return mp.map[i].tex != nullptr; };
+  auto get = [&](int i) { return texParamGet4f(mp.map[i], dg.st, dg.pixelFootprint); };
+  auto mul3 = [&](OcVec3f &f, int i) { if (has(i)) { const vec4f t = get(i); f.x *= t.x; f.y *= t.y; f.z *= t.z; } };
+  auto mul1 = [&](float &f, int i) { if (has(i)) f *= get(i).x; };
+  if (has(OC_PRMAP_BASECOLOR)) {
+    const vec4f t = get(OC_PRMAP_BASECOLOR);
+    v.baseColor.x *= t.x; v.baseColor.y *= t.y; v.baseColor.z *= t.z;
+    if (mp.map[OC_PRMAP_BASECOLOR].tex->hasAlpha) { baseAlpha = t.w; cutout = true; }
+  }
+  if (has(OC_PRMAP_OPACITY)) cutout = true;
+  mul3(v.edgeColor, OC_PRMAP_EDGECOLOR); mul1(v.metallic, OC_PRMAP_METALLIC); mul1(v.diffuse, OC_PRMAP_DIFFUSE);
+  mul1(v.specular, OC_PRMAP_SPECULAR); mul1(v.ior, OC_PRMAP_IOR); mul1(v.transmission, OC_PRMAP_TRANSMISSION);
+  mul3(v.transmissionColor, OC_PRMAP_TRANSMISSIONCOLOR); mul1(v.transmissionDepth, OC_PRMAP_TRANSMISSIONDEPTH);
+  mul1(v.roughness, OC_PRMAP_ROUGHNESS); mul1(v.anisotropy, OC_PRMAP_ANISOTROPY); mul1(v.rotation, OC_PRMAP_ROTATION);
+  mul1(v.coat, OC_PRMAP_COAT); mul1(v.coatIor, OC_PRMAP_COATIOR); mul3(v.coatColor, OC_PRMAP_COATCOLOR);
+  mul1(v.coatThickness, OC_PRMAP_COATTHICKNESS); mul1(v.coatRoughness, OC_PRMAP_COATROUGHNESS); mul1(v.sheen, OC_PRMAP_SHEEN);
+  mul3(v.sheenColor, OC_PRMAP_SHEENCOLOR); mul1(v.sheenTint, OC_PRMAP_SHEENTINT); mul1(v.sheenRoughness, OC_PRMAP_SHEENROUGHNESS);
+  mul1(v.opacity, OC_PRMAP_OPACITY); mul1(v.backlight, OC_PRMAP_BACKLIGHT); mul1(v.thickness, OC_PRMAP_THICKNESS);
+}
+// makeShadingFrame(dg, normalMap, normalRot, normalScale) (render/Material.ih:59-81)
+__device__ __forceinline__ linear3f prNormalMapFrame(const DifferentialGeometry &dg, const OcTextureParam &map, const float *rot, float scale)
+{
+  linear3f f; f.vx = normalize(dg.dPds); f.vy = normalize(dg.dPdt); f.vz = dg.Ns;
+  const vec4f t = texParamGet4f(map, dg.st, dg.pixelFootprint);
+  vec3f localN = (make_vec3f(t.x, t.y, t.z) * 2.f - make_vec3f(1.f)) * make_vec3f(scale, scale, 1.f);
+  const vec2f rotN = make_vec2f(rot[0] * localN.x + rot[2] * localN.y, rot[1] * localN.x + rot[3] * localN.y);
+  localN.x = rotN.x; localN.y = rotN.y;
+  const vec3f N = normalize(f * localN);
+  vec3f V = cross(N, f.vx);
+  if (dot(V, V) > 0.f) {
+    V = normalize(V);
+    linear3f r; r.vx = cross(V, N); r.vy = V; r.vz = N; return r;
+  }
+  return frame(N);
+}
+
 // Principled_getBSDF (Principled.ispc:84-428) for solid materials without sheen and without texture maps; mediumIsOutside =
 // eq(currentMedium, outsideMedium)
 __device__ __forceinline__ void Principled_getBSDF(PrBSDF &b, const OcPrincipled &m, const float *tables, const DifferentialGeometry &dg, bool mediumIsOutside)
 {
-  b.frame = makeShadingFrame(dg);
-  const float rotation = clampf(m.rotation, 0.f, 1.f);
+  OcPrincipled v = m; // factor * map
+  float baseAlpha = 1.f;
+  bool cutout = false;
+  const OcPrincipledMaps *mp = m.maps;
+  if (mp) prApplyMaps(v, *mp, dg, baseAlpha, cutout);
+  b.frame = (mp && mp->map[OC_PRMAP_NORMAL].tex) ? prNormalMapFrame(dg, mp->map[OC_PRMAP_NORMAL], mp->normalRot, mp->normalScale) : makeShadingFrame(dg);
+  const float rotation = clampf(v.rotation, 0.f, 1.f);
   const float theta = 2.f * OC_PI * rotation;
   if (theta > 0.f) {
     b.frame.vx = rotateAxis(b.frame.vx, b.frame.vz, theta);
     b.frame.vy = cross(b.frame.vz, b.frame.vx);
   }
-  const float opacity = clampf(m.opacity, 0.f, 1.f);
+  const float opacity = clampf(v.opacity, 0.f, 1.f) * baseAlpha;
+  b.coatFrame = b.frame;
+  b.rootN = b.frame.vz;
   b.albedo = make_vec3f(0.f); b.scatteringType = 0; b.importanceSum = 0.f;
   b.hasBase = false; b.coatKind = 0; b.opacity = 0.f; b.transparency = 0.f;
   if (m.opacity > PR_EPS) {
+    linear3f baseFrame = b.frame;
+    if (mp && mp->map[OC_PRMAP_BASENORMAL].tex) {
+      baseFrame = prNormalMapFrame(dg, mp->map[OC_PRMAP_BASENORMAL], mp->baseNormalRot, mp->baseNormalScale);
+      if (theta > 0.f) {
+        baseFrame.vx = rotateAxis(baseFrame.vx, baseFrame.vz, theta);
+        baseFrame.vy = cross(baseFrame.vz, baseFrame.vx);
+      }
+    }
     PrBase &B = b.base;
-    B.frame = b.frame;
+    B.frame = baseFrame;
     B.albedo = make_vec3f(0.f); B.scatteringType = 0; B.importanceSum = 0.f;
     B.w[0] = B.w[1] = B.w[2] = 0.f; B.imp[0] = B.imp[1] = B.imp[2] = 0.f;
     B.metalKind = 0; B.hasGlass = B.hasPlastic = false;
-    const vec3f baseColor = clamp01(toV(m.baseColor) * make_vec3f(dg.color));
-    const float specular = clampf(m.specular, 0.f, 1.f), metallic = clampf(m.metallic, 0.f, 1.f);
-    const float roughness = clampf(m.roughness, 0.f, 1.f), anisotropy = clampf(m.anisotropy, 0.f, 1.f);
+    const vec3f baseColor = clamp01(toV(v.baseColor) * make_vec3f(dg.color));
+    const float specular = clampf(v.specular, 0.f, 1.f), metallic = clampf(v.metallic, 0.f, 1.f);
+    const float roughness = clampf(v.roughness, 0.f, 1.f), anisotropy = clampf(v.anisotropy, 0.f, 1.f);
     const bool fromOutside = m.thin ? true : mediumIsOutside;
     const float dielectric = 1.f - metallic;
     if (dielectric > PR_EPS) {
-      const float transmission = clampf(m.transmission, 0.f, 1.f);
-      float ior = m.ior;
+      const float transmission = clampf(v.transmission, 0.f, 1.f);
+      float ior = v.ior;
       if (ior < 1.f) ior = 1.f / ior;
       float eta = fromOutside ? m.outsideIor * (1.f / ior) : ior * (1.f / m.outsideIor);
       eta = clampf(eta, 1.f / 3.f, 3.f);
       const float plastic = dielectric * (1.f - transmission);
       if (plastic > PR_EPS) {
         PrPlastic &P = B.plastic;
-        P.frame = b.frame;
-        const float diffuse = clampf(m.diffuse, 0.f, 1.f);
+        P.frame = baseFrame;
+        const float diffuse = clampf(v.diffuse, 0.f, 1.f);
         const vec3f diffuseColor = baseColor * diffuse;
         PrDiffuse &D = P.diffuse;
-        D.frame = b.frame; D.R = diffuseColor; D.roughness = roughness; D.orenNayar = !(m.roughness < PR_EPS);
-        const float backlight = m.thin ? clampf(m.backlight, 0.f, 2.f) : 0.f;
+        D.frame = baseFrame; D.R = diffuseColor; D.roughness = roughness; D.orenNayar = !(m.roughness < PR_EPS);
+        const float backlight = m.thin ? clampf(v.backlight, 0.f, 2.f) : 0.f;
         const float diffuseTransmission = backlight * 0.5f;
         const float diffuseReflection = 1.f - diffuseTransmission;
         D.weight = D.importance = D.weightT = D.importanceT = 0.f; D.importanceSum = 0.f;
@@ -511,15 +569,15 @@ __device__ __forceinline__ void Principled_getBSDF(PrBSDF &b, const OcPrincipled
       const float glass = dielectric * transmission * specular;
       if (glass > PR_EPS) {
         PrGlass &G = B.glass;
-        G.frame = b.frame;
+        G.frame = baseFrame;
         if (fabsf(eta - 1.f) > PR_EPS) {
           if (!m.thin) {
             if (m.roughness < PR_EPS) { G.kind = 1; G.eta = eta; G.albedo = make_vec3f(1.0f); G.scatteringType = SC_SPECULAR; }
             else PrGlass_initMicrofacet(G, tables, eta, roughness, anisotropy);
           } else {
-            const vec3f transmissionColor = clamp01(toV(m.transmissionColor));
-            const float transmissionDepth = fmaxf(m.transmissionDepth, PR_EPS);
-            const float thickness = fmaxf(m.thickness, 0.f);
+            const vec3f transmissionColor = clamp01(toV(v.transmissionColor));
+            const float transmissionDepth = fmaxf(v.transmissionDepth, PR_EPS);
+            const float thickness = fmaxf(v.thickness, 0.f);
             const vec3f attenuation = logf3(transmissionColor) / transmissionDepth * thickness;
             if (m.roughness < PR_EPS) { G.kind = 3; G.eta = eta; G.attenuation = attenuation; G.albedo = expf3(attenuation); G.scatteringType = SC_SPECULAR; }
             else PrGlass_initThinMicrofacet(G, tables, eta, roughness, anisotropy, attenuation);
@@ -532,7 +590,7 @@ __device__ __forceinline__ void Principled_getBSDF(PrBSDF &b, const OcPrincipled
     }
     const float conductor = metallic * (m.specularMetallic ? specular : 1.0f);
     if (conductor > PR_EPS) {
-      const vec3f edgeColor = clamp01(toV(m.edgeColor));
+      const vec3f edgeColor = clamp01(toV(v.edgeColor));
       // FresnelConductorArtistic_create (Fresnel.ih:264-284)
       const vec3f r = vmin(baseColor, make_vec3f(0.99f)), g = edgeColor;
       const vec3f one = make_vec3f(1.f);
@@ -542,7 +600,7 @@ __device__ __forceinline__ void Principled_getBSDF(PrBSDF &b, const OcPrincipled
       const vec3f n = g * n_min + (one - g) * n_max;
       const vec3f k2 = (sqr3(n + one) * r - sqr3(n - one)) * rcp3(one - r);
       ConductorBSDF &M = B.metal;
-      M.frame = b.frame; M.tables = tables; M.schlick = false;
+      M.frame = baseFrame; M.tables = tables; M.schlick = false;
       M.eta = n;
       M.k = make_vec3f(sqrtf(fmaxf(k2.x, 0.f)), sqrtf(fmaxf(k2.y, 0.f)), sqrtf(fmaxf(k2.z, 0.f))); // sqrt_safe
       // FresnelConductorArtistic_evalAvg (:248-262)
@@ -568,19 +626,20 @@ __device__ __forceinline__ void Principled_getBSDF(PrBSDF &b, const OcPrincipled
     vec3f topAlbedo = B.albedo;
     uint32_t topType = B.scatteringType;
     if (m.coat > PR_EPS) {
-      const float coat = clampf(m.coat, 0.f, 1.f);
-      float coatIor = m.coatIor;
+      const float coat = clampf(v.coat, 0.f, 1.f);
+      float coatIor = v.coatIor;
       if (coatIor < 1.f) coatIor = 1.f / coatIor;
       float coatEta = fromOutside ? m.outsideIor * (1.f / coatIor) : coatIor * (1.f / m.outsideIor);
       coatEta = clampf(coatEta, 1.f / 3.f, 3.f);
-      const vec3f coatColor = clamp01(toV(m.coatColor));
-      const float coatThickness = fmaxf(m.coatThickness, 0.f);
+      const vec3f coatColor = clamp01(toV(v.coatColor));
+      const float coatThickness = fmaxf(v.coatThickness, 0.f);
+      if (mp && mp->map[OC_PRMAP_COATNORMAL].tex) b.coatFrame = prNormalMapFrame(dg, mp->map[OC_PRMAP_COATNORMAL], mp->coatNormalRot, mp->coatNormalScale);
       if (m.coatRoughness < PR_EPS || fabsf(coatEta - 1.f) < PR_EPS) {
         b.coatKind = 1;
         DielectricLayer_init(b.coat, B.albedo, B.scatteringType, coatEta, coatColor, coatThickness, coat);
       } else {
         b.coatKind = 2;
-        MicrofacetDielectricLayer_init(b.coat, tables, B.albedo, B.scatteringType, coatEta, coatColor, coatThickness, clampf(m.coatRoughness, 0.f, 1.f), 0.f, coat);
+        MicrofacetDielectricLayer_init(b.coat, tables, B.albedo, B.scatteringType, coatEta, coatColor, coatThickness, clampf(v.coatRoughness, 0.f, 1.f), 0.f, coat);
       }
       topAlbedo = b.coat.albedo; topType = b.coat.scatteringType;
     } else
@@ -588,21 +647,22 @@ __device__ __forceinline__ void Principled_getBSDF(PrBSDF &b, const OcPrincipled
     // sheen (Principled.ispc:392-413)
     b.sheenWeight = 0.f; b.tables = tables;
     if (m.sheen > PR_EPS) {
-      const float sheen = clampf(m.sheen, 0.f, 1.f);
-      vec3f sheenColor = clamp01(toV(m.sheenColor));
-      const float sheenTint = clampf(m.sheenTint, 0.f, 1.f);
+      const float sheen = clampf(v.sheen, 0.f, 1.f);
+      vec3f sheenColor = clamp01(toV(v.sheenColor));
+      const float sheenTint = clampf(v.sheenTint, 0.f, 1.f);
       sheenColor = lerpv(sheenTint, sheenColor, baseColor);
-      const float sheenRoughness = clampf(m.sheenRoughness, 0.f, 1.f);
+      const float sheenRoughness = clampf(v.sheenRoughness, 0.f, 1.f);
       b.sheenWeight = sheen; b.sheenR = sheenColor; b.sheenRoughness = sheenRoughness;
       b.sheenAlpha = fmaxf(sqr(sheenRoughness), 0.001f);
       topAlbedo = lerpv(sheen * 0.1f, topAlbedo, sheenColor);
       topType = SC_DIFFUSE_REFLECTION | topType;
     }
     b.hasBase = true;
+    b.rootN = (m.coat > PR_EPS) ? b.coatFrame.vz : baseFrame.vz;
     b.opacity = opacity;
     b.albedo = b.albedo + topAlbedo * opacity; b.scatteringType |= topType; b.importanceSum += opacity;
   }
-  if (1.f - m.opacity > PR_EPS) {
+  if (1.f - m.opacity > PR_EPS || cutout) {
     const float transparency = 1.f - opacity;
     b.transparency = transparency;
     b.albedo = b.albedo + make_vec3f(transparency) * 1.f; b.scatteringType |= SC_SPECULAR_TRANSMISSION; b.importanceSum += transparency;
@@ -613,21 +673,21 @@ __device__ __forceinline__ void Principled_getBSDF(PrBSDF &b, const OcPrincipled
 __device__ __forceinline__ EvalRes PrCoat_eval(const PrBSDF &b, vec3f wo, vec3f wi)
 {
   if (b.coatKind == 0 || b.coat.weight < PR_EPS) return b.base.eval(wo, wi);
-  if (b.coatKind == 2) return MicrofacetDielectricLayer_eval(b.coat, b.frame, b.base, wo, wi);
-  return DielectricLayer_eval(b.coat, b.frame.vz, b.base, wo, wi);
+  if (b.coatKind == 2) return MicrofacetDielectricLayer_eval(b.coat, b.coatFrame, b.base, wo, wi);
+  return DielectricLayer_eval(b.coat, b.coatFrame.vz, b.base, wo, wi);
 }
 __device__ __forceinline__ SampleRes PrCoat_sample(const PrBSDF &b, vec3f wo, vec2f s, float ss)
 {
   if (b.coatKind == 0 || b.coat.weight < PR_EPS) return b.base.sample(wo, s, ss);
-  if (b.coatKind == 2) return MicrofacetDielectricLayer_sample(b.coat, b.frame, b.base, wo, s, ss);
-  return DielectricLayer_sample(b.coat, b.frame.vz, b.base, wo, s, ss);
+  if (b.coatKind == 2) return MicrofacetDielectricLayer_sample(b.coat, b.coatFrame, b.base, wo, s, ss);
+  return DielectricLayer_sample(b.coat, b.coatFrame.vz, b.base, wo, s, ss);
 }
 // SheenLayerBSDF_eval / _sample (Principled.ispc:990-1019) = MICROFACETSHEENLAYER_EVAL / _SAMPLE (MicrofacetSheenLayer.ih:82-222)
 __device__ __forceinline__ EvalRes PrSheen_eval(const PrBSDF &b, vec3f wo, vec3f wi)
 {
   if (b.sheenWeight < PR_EPS) return PrCoat_eval(b, wo, wi);
   EvalRes zero; zero.value = make_vec3f(0.f); zero.pdf = 0.f;
-  const vec3f N = b.frame.vz;
+  const vec3f N = b.coatFrame.vz;
   const float cosThetaO = dot(wo, N);
   if (cosThetaO <= 0.f) return zero;
   const float cosThetaI = dot(wi, N);
@@ -653,7 +713,7 @@ __device__ __forceinline__ SampleRes PrSheen_sample(const PrBSDF &b, vec3f wo, v
 {
   if (b.sheenWeight < PR_EPS) return PrCoat_sample(b, wo, s, ss);
   SampleRes res; res.weight = make_vec3f(0.f); res.wi = make_vec3f(0.f); res.pdf = 0.f; res.type = 0;
-  const vec3f N = b.frame.vz;
+  const vec3f N = b.coatFrame.vz;
   const float cosThetaO = dot(wo, N);
   if (cosThetaO <= 0.f) return res;
   const float Ro = mfSheenAlbedo(b.tables, cosThetaO, b.sheenRoughness) * b.sheenWeight;
@@ -661,7 +721,7 @@ __device__ __forceinline__ SampleRes PrSheen_sample(const PrBSDF &b, vec3f wo, v
   const float coatPickProb = Ro, substratePickProb = 1.f - coatPickProb;
   if (ss < coatPickProb) {
     res.type = SC_DIFFUSE_REFLECTION;
-    res.wi = b.frame * uniformSampleHemisphere(s);
+    res.wi = b.coatFrame * uniformSampleHemisphere(s);
     substrate = PrCoat_eval(b, wo, res.wi);
   } else {
     const float ss1 = (ss - coatPickProb) * (1.f / substratePickProb);
@@ -739,16 +799,20 @@ static __device__ __noinline__ SampleRes Principled_sample(const PrBSDF &b, vec3
 __device__ __forceinline__ vec3f Principled_getTransparency(const OcPrincipled &m, const float *tables, const DifferentialGeometry &dg, vec3f rayDir, bool mediumIsOutside)
 {
   vec3f T = make_vec3f(0.f);
-  const float opacity = clampf(m.opacity, 0.f, 1.f);
+  OcPrincipled v = m; // factor * map
+  float baseAlpha = 1.f;
+  bool cutout = false;
+  if (m.maps) prApplyMaps(v, *m.maps, dg, baseAlpha, cutout);
+  const float opacity = clampf(v.opacity, 0.f, 1.f) * baseAlpha;
   const float transparency = 1.f - opacity;
-  const float transmission = clampf(m.transmission, 0.f, 1.f);
+  const float transmission = clampf(v.transmission, 0.f, 1.f);
   if (transparency <= PR_EPS && transmission <= PR_EPS) return T;
   if (m.opacity > PR_EPS) {
-    const float specular = clampf(m.specular, 0.f, 1.f), metallic = clampf(m.metallic, 0.f, 1.f);
+    const float specular = clampf(v.specular, 0.f, 1.f), metallic = clampf(v.metallic, 0.f, 1.f);
     const float glass = (1.f - metallic) * transmission * specular;
     if (glass > PR_EPS) {
       const bool fromOutside = m.thin ? true : mediumIsOutside;
-      float ior = m.ior;
+      float ior = v.ior;
       if (ior < 1.f) ior = 1.f / ior;
       float eta = fromOutside ? m.outsideIor * (1.f / ior) : ior * (1.f / m.outsideIor);
       eta = clampf(eta, 1.f / 3.f, 3.f);
@@ -757,16 +821,16 @@ __device__ __forceinline__ vec3f Principled_getTransparency(const OcPrincipled &
         if (!m.thin) {
           if (m.roughness < PR_EPS) T = make_vec3f(1.f - fresnelDielectric(cosThetaO, eta)); // Dielectric_getTransparency
         } else {
-          const vec3f transmissionColor = clamp01(toV(m.transmissionColor));
-          const float transmissionDepth = fmaxf(m.transmissionDepth, PR_EPS);
-          const float thickness = fmaxf(m.thickness, 0.f);
+          const vec3f transmissionColor = clamp01(toV(v.transmissionColor));
+          const float transmissionDepth = fmaxf(v.transmissionDepth, PR_EPS);
+          const float thickness = fmaxf(v.thickness, 0.f);
           const vec3f attenuation = logf3(transmissionColor) / transmissionDepth * thickness;
           if (m.roughness < PR_EPS) { // ThinDielectric_getTransparency (ThinDielectric.ih:88-98)
             float cosThetaT;
             const float F = fresnelDielectricEx(cosThetaO, cosThetaT, eta);
             T = (1.f - F) * expf3(attenuation * (1.f / cosThetaT));
           } else { // ThinMicrofacetDielectric_getTransparency (ThinMicrofacetDielectric.ih:209-231)
-            const float roughness = clampf(m.roughness, 0.f, 1.f);
+            const float roughness = clampf(v.roughness, 0.f, 1.f);
             const float Eavg = mfAlbedoAvg(tables, roughness);
             const float Favg = fresnelDielectricAvg(eta);
             const float fmsScale = Favg * (1.f - Eavg) * (1.f / (1.f - Favg * Eavg));
@@ -779,14 +843,14 @@ __device__ __forceinline__ vec3f Principled_getTransparency(const OcPrincipled &
         T = make_vec3f(1.f);
       if (reduce_max(T) > 0.f) {
         if (m.coat > PR_EPS) {
-          const float coat = clampf(m.coat, 0.f, 1.f);
-          float coatIor = m.coatIor;
+          const float coat = clampf(v.coat, 0.f, 1.f);
+          float coatIor = v.coatIor;
           if (coatIor < 1.f) coatIor = 1.f / coatIor;
           float coatEta = fromOutside ? m.outsideIor * (1.f / coatIor) : coatIor * (1.f / m.outsideIor);
           const float coatEtaClamped = clampf(coatEta, 1.f / 3.f, 3.f);
           if (fabsf(coatEtaClamped - 1.f) > PR_EPS) {
-            const vec3f coatColor = clamp01(toV(m.coatColor));
-            const float coatThickness = fmaxf(m.coatThickness, 0.f);
+            const vec3f coatColor = clamp01(toV(v.coatColor));
+            const float coatThickness = fmaxf(v.coatThickness, 0.f);
             if (m.coatRoughness < PR_EPS) { // DielectricLayer_getTransparency (DielectricLayer.ih:52-76), unclamped eta
               float e = coatEta;
               if (e < 1.f) e = 1.f / e;
@@ -797,7 +861,7 @@ __device__ __forceinline__ vec3f Principled_getTransparency(const OcPrincipled &
             } else { // MicrofacetDielectricLayer_getTransparency (MicrofacetDielectricLayer.ih:113-146)
               float e = coatEta;
               if (e > 1.f) e = 1.f / e;
-              const float cr = clampf(m.coatRoughness, 0.f, 1.f);
+              const float cr = clampf(v.coatRoughness, 0.f, 1.f);
               vec3f value = lerpv(coat, make_vec3f(1.f), powv(coatColor, coatThickness * (1.f / refractCos(cosThetaO, e))));
               const float Eavg = mfAlbedoAvg(tables, cr);
               const float Favg = fresnelDielectricAvg(e);
@@ -809,7 +873,7 @@ __device__ __forceinline__ vec3f Principled_getTransparency(const OcPrincipled &
           }
         }
         if (m.sheen > PR_EPS) { // MicrofacetSheenLayer_getTransparency (MicrofacetSheenLayer.ih:66-78)
-          const float sheen = clampf(m.sheen, 0.f, 1.f), sheenRoughness = clampf(m.sheenRoughness, 0.f, 1.f);
+          const float sheen = clampf(v.sheen, 0.f, 1.f), sheenRoughness = clampf(v.sheenRoughness, 0.f, 1.f);
           T = T * make_vec3f(1.f - mfSheenAlbedo(tables, cosThetaO, sheenRoughness) * sheen);
         }
         T = T * glass;

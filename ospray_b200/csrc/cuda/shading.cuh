@@ -675,6 +675,7 @@ __device__ __forceinline__ bool Ext_getBSDF(ObjBSDF &b, ExtBSDF &x, const Differ
     Principled_getBSDF(x.pr, m->principled, m->microfacetTables, dg, mediumIsOutside(medium, m->principled));
     b.kind = BSDF_KIND_PRINCIPLED;
     b.frame = x.pr.frame;
+    b.frame.vz = x.pr.rootN; // (only the normal AOV reads it)
     b.albedo = x.pr.albedo;
     b.scatteringType = x.pr.scatteringType;
     return true;
@@ -830,9 +831,19 @@ __device__ __forceinline__ void materialSelectNextMedium(const DifferentialGeome
   if (q.thin || q.transmission <= PR_EPS) return;
   if (mediumIsOutside(medium, q)) {
     float ior = q.ior;
+    vec3f tc = toV(q.transmissionColor);
+    float depth = q.transmissionDepth;
+    if (const OcPrincipledMaps *mp = q.maps) { // ior, transmissionColor and transmissionDepth maps (:594-601)
+      if (mp->map[OC_PRMAP_IOR].tex) ior *= texParamGet4f(mp->map[OC_PRMAP_IOR], dg.st, dg.pixelFootprint).x;
+      if (mp->map[OC_PRMAP_TRANSMISSIONCOLOR].tex) {
+        const vec4f t = texParamGet4f(mp->map[OC_PRMAP_TRANSMISSIONCOLOR], dg.st, dg.pixelFootprint);
+        tc = tc * make_vec3f(t.x, t.y, t.z);
+      }
+      if (mp->map[OC_PRMAP_TRANSMISSIONDEPTH].tex) depth *= texParamGet4f(mp->map[OC_PRMAP_TRANSMISSIONDEPTH], dg.st, dg.pixelFootprint).x;
+    }
     if (ior < 1.f) ior = 1.f / ior;
-    const vec3f tc = clamp01(toV(q.transmissionColor));
-    const float depth = fmaxf(q.transmissionDepth, PR_EPS);
+    tc = clamp01(tc);
+    depth = fmaxf(depth, PR_EPS);
     medium.ior = ior;
     medium.attenuation = logf3(tc) / depth;
   } else {
@@ -871,6 +882,13 @@ __device__ __forceinline__ vec3f materialEmission(const DifferentialGeometry &dg
   const OcMaterial *m = dg.material;
   if (!m || !m->isEmissive) return make_vec3f(0.f);
   vec3f e = toV(m->emission);
+  if (m->type == OC_MATERIAL_PRINCIPLED) { // Principled_getEmission (Principled.ispc:1055-1062)
+    if (m->principled.maps && m->principled.maps->map[OC_PRMAP_EMISSION].tex) {
+      const vec4f t = texParamGet4f(m->principled.maps->map[OC_PRMAP_EMISSION], dg.st, dg.pixelFootprint);
+      e = e * make_vec3f(t.x, t.y, t.z);
+    }
+    return e;
+  }
   if (m->mapKd.tex) {
     const vec4f t = texParamGet4f(m->mapKd, dg.st, dg.pixelFootprint);
     e = e * make_vec3f(t.x, t.y, t.z);

@@ -409,6 +409,7 @@ void Material::commit()
   bool extended = false; // needs the extended-material kernels and the microfacet albedo tables
   const bool hadTextures = texD || texKd || texKs || texNs || texBump;
   texD = texKd = texKs = texNs = texBump = nullptr;
+  texPrincipled.clear();
   if (type == "obj") {
     // render/materials/OBJ.cpp:30-66: a parameter with a map defaults to factor 1 (Material.cpp:110-133)
     m.type = OC_MATERIAL_OBJ;
@@ -479,46 +480,69 @@ void Material::commit()
     m.Ns = getParam<float>("roughness", texNs ? 1.f : 0.1f);
     extended = true;
   } else if (type == "principled") {
-    // render/materials/Principled.cpp:33-150. Texture maps and normal maps of this material are refused rather than ignored.
-    for (auto &p : params)
-      if (p.first.rfind("map_", 0) == 0) throw std::runtime_error("cuda device: principled texture maps are not supported ('" + p.first + "')");
-    for (const char *ign : {"normal", "baseNormal", "coatNormal"})
-      if (auto it = params.find(ign); it != params.end()) it->second.queried = true; // scales of the normal maps: no effect without one
+    // render/materials/Principled.cpp:33-150; a factor with a map defaults to 1 (getMaterialParam1f / 3f, Material.cpp:103-126)
+    static const char *const mapNames[OC_PRMAP_COUNT] = {"baseColor", "edgeColor", "metallic", "diffuse", "specular", "ior", "transmission",
+        "transmissionColor", "transmissionDepth", "roughness", "anisotropy", "rotation", "normal", "baseNormal", "coat", "coatIor", "coatColor",
+        "coatThickness", "coatRoughness", "coatNormal", "sheen", "sheenColor", "sheenTint", "sheenRoughness", "opacity", "backlight",
+        "thickness", "emissiveColor"};
+    OcPrincipledMaps maps{};
+    texPrincipled.assign(OC_PRMAP_COUNT, nullptr);
+    bool anyMap = false;
+    for (int i = 0; i < OC_PRMAP_COUNT; i++) {
+      maps.map[i] = getTextureParam(std::string("map_") + mapNames[i], texPrincipled[i]);
+      anyMap |= maps.map[i].tex != nullptr;
+    }
+    auto mapped = [&](int i) { return maps.map[i].tex != nullptr; };
+    auto rotOf = [&](int i, float *dst) { // orthogonal().transposed() of the map's 2D linear part
+      float rot[4] = {maps.map[i].xform2f[0], maps.map[i].xform2f[1], maps.map[i].xform2f[2], maps.map[i].xform2f[3]};
+      linear2fOrthogonal(rot);
+      dst[0] = rot[0]; dst[1] = rot[2]; dst[2] = rot[1]; dst[3] = rot[3];
+    };
+    rotOf(OC_PRMAP_NORMAL, maps.normalRot); rotOf(OC_PRMAP_BASENORMAL, maps.baseNormalRot); rotOf(OC_PRMAP_COATNORMAL, maps.coatNormalRot);
+    maps.normalScale = getParam<float>("normal", 1.f);
+    maps.baseNormalScale = getParam<float>("baseNormal", 1.f);
+    maps.coatNormalScale = getParam<float>("coatNormal", 1.f);
+    auto f1 = [&](const char *name, int i, float def) { return getParam<float>(name, mapped(i) ? 1.f : def); };
+    auto f3 = [&](const char *name, int i, float def) { return getParam<vec3f>(name, make_vec3f(mapped(i) ? 1.f : def)); };
     m.type = OC_MATERIAL_PRINCIPLED;
     OcPrincipled &q = m.principled;
-    q.baseColor = toOc(getParam<vec3f>("baseColor", make_vec3f(0.8f)));
-    q.edgeColor = toOc(getParam<vec3f>("edgeColor", make_vec3f(1.f)));
-    q.metallic = getParam<float>("metallic", 0.f);
-    q.diffuse = getParam<float>("diffuse", 1.f);
-    q.specular = getParam<float>("specular", 1.f);
+    q.baseColor = toOc(f3("baseColor", OC_PRMAP_BASECOLOR, 0.8f));
+    q.edgeColor = toOc(f3("edgeColor", OC_PRMAP_EDGECOLOR, 1.f));
+    q.metallic = f1("metallic", OC_PRMAP_METALLIC, 0.f);
+    q.diffuse = f1("diffuse", OC_PRMAP_DIFFUSE, 1.f);
+    q.specular = f1("specular", OC_PRMAP_SPECULAR, 1.f);
     q.specularMetallic = getParam<bool>("specularMetallic", true) ? 1u : 0u;
-    q.ior = getParam<float>("ior", 1.f);
-    q.transmission = getParam<float>("transmission", 0.f);
-    q.transmissionColor = toOc(getParam<vec3f>("transmissionColor", make_vec3f(1.f)));
-    q.transmissionDepth = getParam<float>("transmissionDepth", 1.f);
-    q.roughness = getParam<float>("roughness", 0.f);
-    q.anisotropy = getParam<float>("anisotropy", 0.f);
-    q.rotation = getParam<float>("rotation", 0.f);
-    q.coat = getParam<float>("coat", 0.f);
-    q.coatIor = getParam<float>("coatIor", 1.5f);
-    q.coatColor = toOc(getParam<vec3f>("coatColor", make_vec3f(1.f)));
-    q.coatThickness = getParam<float>("coatThickness", 1.f);
-    q.coatRoughness = getParam<float>("coatRoughness", 0.f);
-    q.opacity = getParam<float>("opacity", 1.f);
-    q.sheen = getParam<float>("sheen", 0.f);
-    q.sheenColor = toOc(getParam<vec3f>("sheenColor", make_vec3f(1.f)));
-    q.sheenTint = getParam<float>("sheenTint", 0.f);
-    q.sheenRoughness = getParam<float>("sheenRoughness", 0.2f);
+    q.ior = f1("ior", OC_PRMAP_IOR, 1.f);
+    q.transmission = f1("transmission", OC_PRMAP_TRANSMISSION, 0.f);
+    q.transmissionColor = toOc(f3("transmissionColor", OC_PRMAP_TRANSMISSIONCOLOR, 1.f));
+    q.transmissionDepth = f1("transmissionDepth", OC_PRMAP_TRANSMISSIONDEPTH, 1.f);
+    q.roughness = f1("roughness", OC_PRMAP_ROUGHNESS, 0.f);
+    q.anisotropy = f1("anisotropy", OC_PRMAP_ANISOTROPY, 0.f);
+    q.rotation = f1("rotation", OC_PRMAP_ROTATION, 0.f);
+    q.coat = f1("coat", OC_PRMAP_COAT, 0.f);
+    q.coatIor = f1("coatIor", OC_PRMAP_COATIOR, 1.5f);
+    q.coatColor = toOc(f3("coatColor", OC_PRMAP_COATCOLOR, 1.f));
+    q.coatThickness = f1("coatThickness", OC_PRMAP_COATTHICKNESS, 1.f);
+    q.coatRoughness = f1("coatRoughness", OC_PRMAP_COATROUGHNESS, 0.f);
+    q.opacity = f1("opacity", OC_PRMAP_OPACITY, 1.f);
+    q.sheen = f1("sheen", OC_PRMAP_SHEEN, 0.f);
+    q.sheenColor = toOc(f3("sheenColor", OC_PRMAP_SHEENCOLOR, 1.f));
+    q.sheenTint = f1("sheenTint", OC_PRMAP_SHEENTINT, 0.f);
+    q.sheenRoughness = f1("sheenRoughness", OC_PRMAP_SHEENROUGHNESS, 0.2f);
     q.thin = getParam<bool>("thin", false) ? 1u : 0u;
-    q.backlight = getParam<float>("backlight", 0.f);
-    q.thickness = getParam<float>("thickness", 1.f);
+    q.backlight = f1("backlight", OC_PRMAP_BACKLIGHT, 0.f);
+    q.thickness = f1("thickness", OC_PRMAP_THICKNESS, 1.f);
     const float outsideIor = getParam<float>("outsideIor", 1.f);
     const vec3f otc = getParam<vec3f>("outsideTransmissionColor", make_vec3f(1.f));
     const float otd = getParam<float>("outsideTransmissionDepth", 1.f);
     q.outsideIor = outsideIor >= 1.f ? outsideIor : 1.f / outsideIor;
     q.outsideAttenuation = toOc(make_vec3f(std::log(otc.x), std::log(otc.y), std::log(otc.z)) / otd);
-    m.emission = toOc(getParam<vec3f>("emissiveColor", make_vec3f(0.f)) * getParam<float>("intensity", 1.f));
+    m.emission = toOc(f3("emissiveColor", OC_PRMAP_EMISSION, 0.f) * getParam<float>("intensity", 1.f));
     m.isEmissive = std::max(m.emission.x, std::max(m.emission.y, m.emission.z)) > 0.f ? 1u : 0u;
+    if (anyMap) {
+      principledMaps.upload(&maps, sizeof(maps));
+      q.maps = principledMaps.as<OcPrincipledMaps>();
+    }
     extended = true;
   } else if (type == "luminous") {
     // render/materials/Luminous.cpp:33-45: radiance = color * intensity (times map_color), isEmissive = any of it

@@ -145,6 +145,8 @@ class SceneSpec:
                              if getattr(m.material, a) is not None]
                     if m.material.map_color is not None: texs.append(m.material.map_color.texture)
                     if m.material.map_roughness is not None: texs.append(m.material.map_roughness.texture)
+                    if m.material.map_edge_color is not None: texs.append(m.material.map_edge_color.texture)
+                    texs += [v.texture for k, v in m.material.principled.items() if k.startswith("map_")]
         return all(t.mipmaps for t in texs)
 
 
@@ -480,7 +482,8 @@ def _material(m: MaterialSpec):
         return mat.commit()
     if m.type == "principled":
         for name, v in m.principled.items():
-            if isinstance(v, bool): mat.set(name, bool(v))
+            if name.startswith("map_"): _set_map(mat, name, v)
+            elif isinstance(v, bool): mat.set(name, bool(v))
             elif isinstance(v, (tuple, list)): mat.set(name, tuple(float(x) for x in v))
             else: mat.set(name, float(v))
         return mat.commit()

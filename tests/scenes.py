@@ -295,6 +295,38 @@ def principled_cornell(variant):
     return _cornell_models({(5, 6, 7, 8, 9): a, (11, 12, 13, 14, 15): b}, drop=(10, 16))
 
 
+def principled_tex_cornell(cutout):
+    """texture maps of the principled material (factor * map per Principled.ispc). cutout = False: base colour / metallic /
+    roughness / specular maps, a rotated normal map on the base, a coat normal map, sheen colour map (MIP chains on). cutout =
+    True: the maps that shadow rays see -- opacity, base-colour alpha, transmission, transmission colour on a thin sheet, an
+    emission map -- rendered with disableMipMapGeneration like the other cut-out scenes"""
+    TS, MS = T.TextureSpec, T.MapSpec
+    P = lambda **kw: T.MaterialSpec(type="principled", principled=kw)
+    img = lambda c, seed, lo=0.0, hi=1.0, n=8: _tex_rng_image(n, n, c, seed, np.float32, lo, hi)
+    if not cutout:
+        nrm = img(3, 51, 0.3, 0.7, 16); nrm[..., 2] = 1.0
+        nrm2 = img(3, 52, 0.35, 0.65); nrm2[..., 2] = 1.0
+        a = P(map_baseColor=MS(TS(img(3, 53, 0.1, 0.9, 16), "RGB32F")), ior=1.45, roughness=0.0,
+              map_metallic=MS(TS(img(1, 56)[..., 0], "R32F", filter="nearest")), metallic=1.0,
+              map_specular=MS(TS(img(1, 54, 0.2, 1.0)[..., 0], "R32F")), map_normal=MS(TS(nrm, "RGB32F"), rotation=30.0, scale=(2.0, 1.5)),
+              normal=0.8, coat=0.8, coatIor=1.6, map_coatNormal=MS(TS(nrm2, "RGB32F")), coatNormal=1.2,
+              map_coatColor=MS(TS(img(3, 55, 0.5, 1.0), "RGB32F")))
+        b = P(baseColor=(0.9, 0.8, 0.7), metallic=1.0,  # (rough plastic would meet the reference's Ravg defect, see REF_UNDEFINED_STATE_CASES)
+              roughness=1.0, map_roughness=MS(TS(img(1, 57, 0.2, 0.5)[..., 0], "R32F")), map_edgeColor=MS(TS(img(3, 58, 0.6, 1.0), "RGB32F")),
+              map_baseNormal=MS(TS(nrm2, "RGB32F"), translation=(0.2, 0.1)), specularMetallic=False,
+              map_anisotropy=MS(TS(img(1, 59, 0.0, 0.8)[..., 0], "R32F")), map_rotation=MS(TS(img(1, 60)[..., 0], "R32F")))
+    else:
+        nm = dict(mipmaps=False)
+        rgba = _tex_rng_image(8, 8, 4, 61)
+        rgba[..., 3] = np.where(np.random.default_rng(62).uniform(0, 1, (8, 8)) > 0.4, 255, 80)
+        a = P(map_baseColor=MS(TS(rgba, "RGBA8", **nm)), ior=1.4, map_opacity=MS(TS(img(1, 63, 0.3, 1.0)[..., 0], "R32F", filter="nearest", **nm)),
+              map_emissiveColor=MS(TS(img(3, 64, 0.0, 0.6), "RGB32F", **nm)), intensity=0.8)
+        b = P(thin=True, ior=1.5, map_transmission=MS(TS(img(1, 65, 0.2, 1.0)[..., 0], "R32F", **nm)), thickness=0.3,
+              map_transmissionColor=MS(TS(img(3, 66, 0.4, 1.0), "RGB32F", **nm)), map_backlight=MS(TS(img(1, 67)[..., 0], "R32F", **nm)), backlight=1.5,
+              map_sheen=MS(TS(img(1, 68)[..., 0], "R32F", **nm)), sheenRoughness=0.4)
+    return _cornell_models({(5, 6, 7, 8, 9): a, (11, 12, 13, 14, 15): b}, drop=(10, 16))
+
+
 def glass_alloy_cornell(rough):
     """cornell box with a solid glass box (materials/Glass.ispc: RobustDielectric, attenuating inside medium, transparent
     shadows) and an alloy box (materials/Alloy.ispc: conductor with Schlick Fresnel; rough: MicrofacetConductor with a roughness
@@ -409,6 +441,8 @@ CASES = {
     "principled_coat_pt": (lambda: principled_cornell("coat"), "pathtracer", {"pixelSamples": 2}, 2),
     "principled_rough_layers_pt": (lambda: principled_cornell("rough_layers"), "pathtracer", {"pixelSamples": 2}, 2),
     "principled_emissive_pt": (lambda: principled_cornell("emissive"), "pathtracer", {"pixelSamples": 2}, 2),
+    "principled_tex_pt": (lambda: principled_tex_cornell(False), "pathtracer", {"pixelSamples": 2}, 2),
+    "principled_tex_cutout_pt": (lambda: principled_tex_cornell(True), "pathtracer", {"pixelSamples": 2}, 2),
     "principled_sheen_pt": (lambda: principled_cornell("sheen"), "pathtracer", {"pixelSamples": 2}, 2),
     "principled_thin_pt": (lambda: principled_cornell("thin"), "pathtracer", {"pixelSamples": 2}, 2),
     # debug renderer (render/debug/DebugRenderer.ispc), every method the device accepts
@@ -435,7 +469,7 @@ ORACLE_UNSUPPORTED = {"textured_pt", "textured_bias_pt", "cutout_pt", "backplate
                       "emissive_transparent_pt", "textured_scivis", "textured_ao", "cutout_scivis", "cutout_ao", "backplate_scivis",
                       "backplate_ao", "debug_texCoord", "debug_dPdt", "debug_dPds_tex", "debug_backplate", "metal_smooth_pt", "metal_rough_pt",
                       "plastic_smooth_pt", "plastic_rough_pt", "principled_plastic_pt", "principled_metal_pt", "principled_glass_pt",
-                      "principled_coat_pt", "principled_rough_layers_pt", "principled_emissive_pt", "glass_alloy_pt", "glass_alloy_rough_pt", "principled_sheen_pt", "principled_thin_pt"}
+                      "principled_coat_pt", "principled_rough_layers_pt", "principled_emissive_pt", "glass_alloy_pt", "glass_alloy_rough_pt", "principled_sheen_pt", "principled_thin_pt", "principled_tex_pt", "principled_tex_cutout_pt"}
 # Rough dielectric coatings: MicrofacetDielectricLayer_Constructor reads self->eta for Ravg BEFORE assigning it
 # (bsdfs/MicrofacetDielectricLayer.ih:55 vs :68), i.e. whatever the shading context's memory held from the previous BSDF. The
 # device uses the intended value; against the reference's kernels the coated surfaces then differ by ~0.5 % in brightness

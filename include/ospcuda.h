@@ -115,7 +115,8 @@ typedef struct {
 } OcTextureParam;
 
 enum { OC_MATERIAL_OBJ = 0, OC_MATERIAL_OTHER = 1, OC_MATERIAL_THINGLASS = 2, OC_MATERIAL_LUMINOUS = 3, OC_MATERIAL_METAL = 4,
-       OC_MATERIAL_PLASTIC = 5, OC_MATERIAL_PRINCIPLED = 6, OC_MATERIAL_GLASS = 7, OC_MATERIAL_ALLOY = 8 };
+       OC_MATERIAL_PLASTIC = 5, OC_MATERIAL_PRINCIPLED = 6, OC_MATERIAL_GLASS = 7, OC_MATERIAL_ALLOY = 8,
+       OC_MATERIAL_VELVET = 9, OC_MATERIAL_METALLICPAINT = 10 };
 /* texture maps of the principled material (PrincipledShared.h: one TextureParam per factor; the three normal maps come with the
  * orthogonal part of their 2D transform, transposed, and a scale: Material::getMaterialParam1f, render/Material.cpp:103-113) */
 enum { OC_PRMAP_BASECOLOR = 0, OC_PRMAP_EDGECOLOR, OC_PRMAP_METALLIC, OC_PRMAP_DIFFUSE, OC_PRMAP_SPECULAR, OC_PRMAP_IOR,
@@ -180,7 +181,10 @@ typedef struct {
   /* type OC_MATERIAL_PRINCIPLED (emission / isEmissive above: emissiveColor * intensity).
    * glass (ispc::Glass, render/materials/GlassShared.h, Glass.cpp:35-63): eta / attenuation above = the inside medium (ior,
    * log(attenuationColorInside) / max(attenuationDistance, EPS)), principled.outsideIor / outsideAttenuation = the outside one.
-   * alloy (ispc::Alloy, AlloyShared.h, Alloy.cpp:28-40): Kd = color, Ks = edgeColor, Ns = roughness, mapKd / mapKs / mapNs their maps */
+   * alloy (ispc::Alloy, AlloyShared.h, Alloy.cpp:28-40): Kd = color, Ks = edgeColor, Ns = roughness, mapKd / mapKs / mapNs their maps.
+   * velvet (ispc::Velvet, VelvetShared.h, Velvet.cpp:27-39): Kd = reflectance, Ns = backScattering, Ks = horizonScatteringColor,
+   * eta = horizonScatteringFallOff. metallicPaint (ispc::MetallicPaint, MetallicPaint.cpp:27-40): Kd = baseColor * (1 - flakeAmount),
+   * mapKd = map_baseColor, Ks = flakeColor * flakeAmount, attenuationScale = flakeAmount, Ns = flakeSpread, eta = 1 / eta */
   OcPrincipled principled;
 } OcMaterial;
 

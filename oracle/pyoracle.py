@@ -611,6 +611,30 @@ class Scene:
                 if mp is not None:
                     setattr(m, f_, texture_param(mp, self.keep, self.mipmaps))
                     m.hasTextures = 1
+        elif ms.type == "velvet":  # render/materials/Velvet.cpp:27-39
+            f = np.float32
+            q = {"reflectance": (0.4, 0.0, 0.0), "backScattering": 0.5, "horizonScatteringColor": (0.75, 0.1, 0.1), "horizonScatteringFallOff": 10.0}
+            assert set(ms.params) <= set(q), ms.params
+            q.update(ms.params)
+            m.type = 9
+            m.Kd, m.Ks = Vec3(*map(float, np.asarray(q["reflectance"], f))), Vec3(*map(float, np.asarray(q["horizonScatteringColor"], f)))
+            m.Ns, m.eta = float(f(q["backScattering"])), float(f(q["horizonScatteringFallOff"]))
+        elif ms.type == "metallicPaint":  # render/materials/MetallicPaint.cpp:27-40
+            f = np.float32
+            q = {"baseColor": (0.8, 0.8, 0.8), "flakeAmount": 0.3, "flakeColor": (0.909, 0.916, 0.923), "flakeSpread": 0.5, "eta": 1.5}
+            given = dict(ms.params)
+            mp = given.pop("map_baseColor", None)
+            assert set(given) <= set(q), ms.params
+            if mp is not None:
+                q["baseColor"] = (1.0, 1.0, 1.0)
+                m.mapKd = texture_param(mp, self.keep, self.mipmaps)
+                m.hasTextures = 1
+            q.update(given)
+            m.type = 10
+            fa = f(q["flakeAmount"])
+            m.Kd = Vec3(*map(float, np.asarray(q["baseColor"], f) * (f(1.0) - fa)))
+            m.Ks = Vec3(*map(float, np.asarray(q["flakeColor"], f) * fa))
+            m.attenuationScale, m.Ns, m.eta = float(fa), float(f(q["flakeSpread"])), float(f(1.0) / f(q["eta"]))
         elif ms.type == "principled":  # render/materials/Principled.cpp:33-150 (solid, no sheen, no maps)
             f = np.float32
             prm = dict(PRINCIPLED_DEFAULTS)

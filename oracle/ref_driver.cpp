@@ -36,6 +36,8 @@
 #include "render/materials/PrincipledShared.h"
 #include "render/materials/GlassShared.h"
 #include "render/materials/AlloyShared.h"
+#include "render/materials/VelvetShared.h"
+#include "render/materials/MetallicPaintShared.h"
 #include "render/bsdfs/MicrofacetAlbedoTablesShared.h"
 #include "render/pathtracer/GeometryLightShared.h"
 #include "texture/Texture2DShared.h"
@@ -171,7 +173,7 @@ struct Scene
   std::deque<OBJ> objs; std::deque<ThinGlass> glasses; std::vector<Material *> allMaterials;
   std::deque<Texture2D> textures;
   std::deque<Luminous> luminous; std::deque<GeometryLight> geoLights;
-  std::deque<Metal> metals; std::deque<Plastic> plastics; std::deque<Principled> principleds; std::deque<Glass> solidGlasses; std::deque<Alloy> alloys;
+  std::deque<Metal> metals; std::deque<Plastic> plastics; std::deque<Principled> principleds; std::deque<Glass> solidGlasses; std::deque<Alloy> alloys; std::deque<Velvet> velvets; std::deque<MetallicPaint> paints;
   std::deque<std::vector<int>> geoPrimIDs; std::deque<std::vector<float>> geoDistributions;
   std::vector<float> geoCDF;
   std::vector<Instance *> instancePtrs;
@@ -336,6 +338,22 @@ void buildScene(Scene &s, const OcWorld *w, const OcRenderer *ren)
       al.roughnessMap = makeTextureParam(s.textures, m.mapNs);
       al.super.microfacetAlbedoTables = refAlbedoTables();
       s.allMaterials.push_back(&al.super);
+      continue;
+    }
+    if (m.type == OC_MATERIAL_VELVET) { // render/materials/Velvet.cpp:27-39
+      s.velvets.emplace_back();
+      Velvet &ve = s.velvets.back();
+      ve.reflectance = v3(m.Kd); ve.backScattering = m.Ns; ve.horizonScatteringColor = v3(m.Ks); ve.horizonScatteringFallOff = m.eta;
+      s.allMaterials.push_back(&ve.super);
+      continue;
+    }
+    if (m.type == OC_MATERIAL_METALLICPAINT) { // render/materials/MetallicPaint.cpp:27-40 (committed values)
+      s.paints.emplace_back();
+      MetallicPaint &mp = s.paints.back();
+      mp.baseColor = v3(m.Kd); mp.baseColorMap = makeTextureParam(s.textures, m.mapKd);
+      mp.flakeAmount = m.attenuationScale; mp.flakeColor = v3(m.Ks); mp.flakeSpread = m.Ns; mp.eta = m.eta;
+      mp.super.microfacetAlbedoTables = refAlbedoTables();
+      s.allMaterials.push_back(&mp.super);
       continue;
     }
     if (m.type == OC_MATERIAL_PRINCIPLED) { // render/materials/Principled.cpp:33-150 (committed values, no maps)

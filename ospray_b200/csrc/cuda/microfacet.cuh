@@ -567,4 +567,107 @@ __device__ __forceinline__ SampleRes MicrofacetDielectricLayer_sample(const Laye
   return res;
 }
 
+// ---- velvet (materials/Velvet.ispc:14-99): MultiBSDF of a Minneart lobe (bsdfs/Minneart.ih) and a Velvety lobe (Velvety.ih) ------
+struct VelvetBSDF
+{
+  linear3f frame;
+  vec3f R0, R1;   // reflectance, horizon scattering colour
+  float b, f;     // back scattering exponent, horizon falloff
+  float imp0, imp1, importanceSum;
+  __device__ __forceinline__ EvalRes lobe(int id, vec3f wo, vec3f wi) const
+  {
+    EvalRes r;
+    const float cosThetaI = clampf(dot(wi, frame.vz), 0.f, 1.f);
+    r.pdf = cosThetaI * OC_ONE_OVER_PI;
+    if (id == 0) {
+      const float backScatter = powf(clampf(dot(wo, wi), 0.f, 1.f), b);
+      r.value = (backScatter * cosThetaI * OC_ONE_OVER_PI) * R0;
+    } else {
+      const float cosThetaO = clampf(dot(wo, frame.vz), 0.f, 1.f);
+      const float sinThetaO = sqrtf(1.0f - cosThetaO * cosThetaO);
+      const float horizonScatter = powf(sinThetaO, f);
+      r.value = (horizonScatter * cosThetaI * OC_ONE_OVER_PI) * R1;
+    }
+    return r;
+  }
+  __device__ __forceinline__ EvalRes eval(vec3f wo, vec3f wi) const
+  {
+    EvalRes e; e.value = make_vec3f(0.f); e.pdf = 0.f;
+    if (imp0 > 0.f) { const EvalRes c = lobe(0, wo, wi); e.value = e.value + c.value * 1.f; e.pdf += c.pdf * imp0; }
+    if (imp1 > 0.f) { const EvalRes c = lobe(1, wo, wi); e.value = e.value + c.value * 1.f; e.pdf += c.pdf * imp1; }
+    e.pdf *= 1.f / importanceSum;
+    return e;
+  }
+  __device__ __forceinline__ SampleRes sample(vec3f wo, vec2f s, float ss) const
+  {
+    SampleRes res; res.weight = make_vec3f(0.f); res.wi = make_vec3f(0.f); res.pdf = 0.f; res.type = 0;
+    if (importanceSum == 0.f) return res;
+    const float x = ss * importanceSum;
+    int choice;
+    float prefix = 0.f;
+    if (x < (prefix += imp0)) choice = 0;
+    else if (x < (prefix += imp1)) choice = 1;
+    else return res;
+    res.wi = frame * cosineSampleHemisphere(s);
+    res.type = SC_DIFFUSE_REFLECTION;
+    const EvalRes ev = lobe(choice, wo, res.wi);
+    res.pdf = ev.pdf;
+    res.weight = ev.value * (1.f / ev.pdf) * 1.f;
+    if ((res.weight.x == 0.f && res.weight.y == 0.f && res.weight.z == 0.f) || res.pdf == 0.0f) { res.weight = make_vec3f(0.f); res.wi = make_vec3f(0.f); res.pdf = 0.f; res.type = 0; return res; }
+    const float choiceImp = choice == 0 ? imp0 : imp1, otherImp = choice == 0 ? imp1 : imp0;
+    EvalRes e;
+    e.value = res.weight * res.pdf;
+    res.pdf *= choiceImp;
+    e.pdf = res.pdf;
+    if (otherImp > 0.f) { const EvalRes c = lobe(1 - choice, wo, res.wi); e.value = e.value + c.value * 1.f; e.pdf += c.pdf * otherImp; }
+    res.pdf = e.pdf * (1.f / importanceSum);
+    res.weight = e.value * (1.f / res.pdf);
+    return res;
+  }
+};
+
+// ---- metallic paint (materials/MetallicPaint.ispc:22-161): a smooth dielectric coat over MultiBSDF(Lambert, flakes =
+// MicrofacetConductor with Schlick Fresnel); this is the substrate the DielectricLayer templates take
+struct MetallicPaintSub
+{
+  LambertSub lambert;
+  ConductorBSDF flakes;
+  float imp0, imp1, importanceSum; // luminance(color), luminance(flakeColor) (0: no flakes)
+  vec3f albedo;
+  uint32_t scatteringType;
+  __device__ __forceinline__ void others(vec3f wo, vec3f wi, int skip, EvalRes &e) const
+  {
+    if (imp0 > 0.f && skip != 0) { const EvalRes c = lambert.eval(wo, wi); e.value = e.value + c.value * 1.f; e.pdf += c.pdf * imp0; }
+    if (imp1 > 0.f && skip != 1) { const EvalRes c = MicrofacetConductor_eval(flakes, wo, wi); e.value = e.value + c.value * 1.f; e.pdf += c.pdf * imp1; }
+  }
+  __device__ __forceinline__ EvalRes eval(vec3f wo, vec3f wi) const
+  {
+    EvalRes e; e.value = make_vec3f(0.f); e.pdf = 0.f;
+    others(wo, wi, -1, e);
+    e.pdf *= 1.f / importanceSum;
+    return e;
+  }
+  __device__ __forceinline__ SampleRes sample(vec3f wo, vec2f s, float ss) const
+  {
+    SampleRes res; res.weight = make_vec3f(0.f); res.wi = make_vec3f(0.f); res.pdf = 0.f; res.type = 0;
+    if (importanceSum == 0.f) return res;
+    const float x = ss * importanceSum;
+    int choice;
+    float prefix = 0.f;
+    if (x < (prefix += imp0)) { choice = 0; res = lambert.sample(wo, s, 0.f); }
+    else if (x < (prefix += imp1)) { choice = 1; res = MicrofacetConductor_sample(flakes, wo, s); }
+    else return res;
+    res.weight = res.weight * 1.f;
+    if ((res.weight.x == 0.f && res.weight.y == 0.f && res.weight.z == 0.f) || res.pdf == 0.0f) { res.weight = make_vec3f(0.f); res.wi = make_vec3f(0.f); res.pdf = 0.f; res.type = 0; return res; }
+    EvalRes e;
+    e.value = res.weight * res.pdf;
+    res.pdf *= choice == 0 ? imp0 : imp1;
+    e.pdf = res.pdf;
+    others(wo, res.wi, choice, e);
+    res.pdf = e.pdf * (1.f / importanceSum);
+    res.weight = e.value * (1.f / res.pdf);
+    return res;
+  }
+};
+
 } // namespace oc

@@ -340,7 +340,7 @@ struct ObjBSDF
   uint32_t kind;           // BSDF_KIND_*: 0 = the cases above; the others only exist in the extended-material kernels
 };
 enum { BSDF_KIND_OBJ = 0, BSDF_KIND_CONDUCTOR, BSDF_KIND_MICROFACET_CONDUCTOR, BSDF_KIND_PLASTIC_SMOOTH, BSDF_KIND_PLASTIC_ROUGH,
-       BSDF_KIND_PRINCIPLED, BSDF_KIND_GLASS };
+       BSDF_KIND_PRINCIPLED, BSDF_KIND_GLASS, BSDF_KIND_VELVET, BSDF_KIND_METALLICPAINT };
 
 // render/Material.ih:25-37
 __device__ __forceinline__ linear3f makeShadingFrame(const DifferentialGeometry &dg)
@@ -409,6 +409,8 @@ struct ExtBSDF
 {
   ConductorBSDF cond; LayerParams layer; LambertSub lambert; PrBSDF pr;
   vec3f glassNg, glassNs; float glassEta; // RobustDielectric (bsdfs/RobustDielectric.ih:14-25)
+  VelvetBSDF velvet;
+  MetallicPaintSub paint;                 // under `layer`
 };
 // the medium a path travels in (render/materials/MediumShared.h:10-18; vacuum = no attenuation, ior 1)
 struct Medium { vec3f attenuation; float ior; };
@@ -689,6 +691,46 @@ __device__ __forceinline__ bool Ext_getBSDF(ObjBSDF &b, ExtBSDF &x, const Differ
     b.scatteringType = SC_SPECULAR;
     return true;
   }
+  if (m->type == OC_MATERIAL_VELVET) { // Velvet_getBSDF (materials/Velvet.ispc:22-60)
+    VelvetBSDF &v = x.velvet;
+    v.frame = b.frame;
+    v.R0 = toV(m->Kd); v.b = m->Ns; v.R1 = toV(m->Ks); v.f = m->eta;
+    v.imp0 = luminance(v.R0); v.imp1 = luminance(v.R1);
+    v.importanceSum = 0.f; v.importanceSum += v.imp0; v.importanceSum += v.imp1;
+    b.kind = BSDF_KIND_VELVET;
+    b.albedo = make_vec3f(0.f) + v.R0 * 1.f + v.R1 * 1.f;
+    b.scatteringType = SC_DIFFUSE_REFLECTION;
+    return true;
+  }
+  if (m->type == OC_MATERIAL_METALLICPAINT) { // MetallicPaint_getBSDF (materials/MetallicPaint.ispc:36-89)
+    MetallicPaintSub &p = x.paint;
+    vec3f color = toV(m->Kd) * make_vec3f(dg.color);
+    if (m->mapKd.tex) { const vec4f t = texParamGet4f(m->mapKd, dg.st, dg.pixelFootprint); color = color * make_vec3f(t.x, t.y, t.z); }
+    p.lambert.init(b.frame, color);
+    p.imp0 = luminance(color); p.imp1 = 0.f;
+    p.importanceSum = 0.f; p.importanceSum += p.imp0;
+    p.albedo = make_vec3f(0.f) + color * 1.f;
+    p.scatteringType = SC_DIFFUSE_REFLECTION;
+    const float flakeAmount = m->attenuationScale;
+    if (flakeAmount > 0.f) {
+      ConductorBSDF &c = p.flakes;
+      c.frame = b.frame; c.tables = m->microfacetTables; c.schlick = true;
+      c.eta = toV(m->Ks); c.k = make_vec3f(flakeAmount);
+      const vec3f Favg = fresnelSchlickAvg(c.eta, c.k);
+      c.Eavg = mfAlbedoAvg(c.tables, m->Ns);
+      c.fmsScale = sqr3(Favg) * c.Eavg / (make_vec3f(1.f) - Favg * (1.f - c.Eavg));
+      c.mf = makeGGX(m->Ns, 0.f);
+      c.roughness = m->Ns;
+      p.imp1 = luminance(c.eta);
+      p.importanceSum += p.imp1;
+      p.albedo = p.albedo + (Favg * c.Eavg) * 1.f;
+      p.scatteringType |= SC_GLOSSY_REFLECTION;
+    }
+    DielectricLayer_init(x.layer, p.albedo, p.scatteringType, m->eta, make_vec3f(1.0f), 1.0f, 1.0f);
+    b.kind = BSDF_KIND_METALLICPAINT;
+    b.albedo = x.layer.albedo; b.scatteringType = x.layer.scatteringType;
+    return true;
+  }
   if (m->type == OC_MATERIAL_METAL || m->type == OC_MATERIAL_ALLOY) {
     // Metal_getBSDF (Metal.ispc:18-46, RGB form), Alloy_getBSDF (Alloy.ispc:16-51: Schlick Fresnel between color and edgeColor)
     const bool alloy = m->type == OC_MATERIAL_ALLOY;
@@ -741,6 +783,8 @@ static __device__ __noinline__ EvalRes Ext_eval(const ObjBSDF &b, const ExtBSDF 
   case BSDF_KIND_PLASTIC_SMOOTH: return DielectricLayer_eval(x.layer, b.frame.vz, x.lambert, wo, wi);
   case BSDF_KIND_PLASTIC_ROUGH: return MicrofacetDielectricLayer_eval(x.layer, b.frame, x.lambert, wo, wi);
   case BSDF_KIND_PRINCIPLED: return Principled_eval(x.pr, wo, wi);
+  case BSDF_KIND_VELVET: return x.velvet.eval(wo, wi);
+  case BSDF_KIND_METALLICPAINT: return DielectricLayer_eval(x.layer, b.frame.vz, x.paint, wo, wi);
   default: return e; // smooth conductor: purely specular
   }
 }
@@ -812,6 +856,8 @@ static __device__ __noinline__ SampleRes Ext_sample(const ObjBSDF &b, const ExtB
   case BSDF_KIND_MICROFACET_CONDUCTOR: return MicrofacetConductor_sample(x.cond, wo, s);
   case BSDF_KIND_PLASTIC_SMOOTH: return DielectricLayer_sample(x.layer, b.frame.vz, x.lambert, wo, s, ss);
   case BSDF_KIND_PRINCIPLED: return Principled_sample(x.pr, wo, s, ss);
+  case BSDF_KIND_VELVET: return x.velvet.sample(wo, s, ss);
+  case BSDF_KIND_METALLICPAINT: return DielectricLayer_sample(x.layer, b.frame.vz, x.paint, wo, s, ss);
   default: return MicrofacetDielectricLayer_sample(x.layer, b.frame, x.lambert, wo, s, ss);
   }
 }

@@ -479,6 +479,27 @@ void Material::commit()
     m.Ks = toOc(getParam<vec3f>("edgeColor", make_vec3f(1.f)));
     m.Ns = getParam<float>("roughness", texNs ? 1.f : 0.1f);
     extended = true;
+  } else if (type == "velvet") {
+    // render/materials/Velvet.cpp:27-39
+    m.type = OC_MATERIAL_VELVET;
+    m.Kd = toOc(getParam<vec3f>("reflectance", make_vec3f(.4f, 0.f, 0.f)));
+    m.Ns = getParam<float>("backScattering", .5f);
+    m.Ks = toOc(getParam<vec3f>("horizonScatteringColor", make_vec3f(.75f, .1f, .1f)));
+    m.eta = getParam<float>("horizonScatteringFallOff", 10.f);
+    extended = true;
+  } else if (type == "metallicPaint") {
+    // render/materials/MetallicPaint.cpp:27-40 (default flake colour = aluminium's reflectivity, math/spectrum.h:50-53)
+    m.type = OC_MATERIAL_METALLICPAINT;
+    m.mapKd = getTextureParam("map_baseColor", texKd);
+    const vec3f color = getParam<vec3f>("baseColor", make_vec3f(texKd ? 1.f : 0.8f));
+    const float flakeAmount = getParam<float>("flakeAmount", 0.3f);
+    const vec3f flakeColor = getParam<vec3f>("flakeColor", make_vec3f(0.909f, 0.916f, 0.923f));
+    m.Kd = toOc(color * (1.f - flakeAmount));
+    m.attenuationScale = flakeAmount;
+    m.Ks = toOc(flakeColor * flakeAmount);
+    m.Ns = getParam<float>("flakeSpread", 0.5f);
+    m.eta = 1.f / getParam<float>("eta", 1.5f);
+    extended = true;
   } else if (type == "principled") {
     // render/materials/Principled.cpp:33-150; a factor with a map defaults to 1 (getMaterialParam1f / 3f, Material.cpp:103-126)
     static const char *const mapNames[OC_PRMAP_COUNT] = {"baseColor", "edgeColor", "metallic", "diffuse", "specular", "ior", "transmission",

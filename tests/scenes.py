@@ -327,6 +327,17 @@ def principled_tex_cornell(cutout):
     return _cornell_models({(5, 6, 7, 8, 9): a, (11, 12, 13, 14, 15): b}, drop=(10, 16))
 
 
+def velvet_paint_cornell():
+    """cornell box with a velvet box (materials/Velvet.ispc: Minneart + Velvety lobes) and a metallic-paint box
+    (materials/MetallicPaint.ispc: dielectric coat over Lambert + Schlick-Fresnel flakes, base colour from a map)"""
+    TS, MS = T.TextureSpec, T.MapSpec
+    velvet = T.MaterialSpec(type="velvet", params=dict(reflectance=(0.4, 0.1, 0.3), backScattering=0.8, horizonScatteringColor=(0.7, 0.3, 0.5),
+                                                       horizonScatteringFallOff=6.0))
+    paint = T.MaterialSpec(type="metallicPaint", params=dict(map_baseColor=MS(TS(_tex_rng_image(8, 8, 3, 71, np.float32, 0.2, 0.9), "RGB32F")),
+                                                             flakeAmount=0.4, flakeSpread=0.3, eta=1.6))
+    return _cornell_models({(5, 6, 7, 8, 9, 10): velvet, (11, 12, 13, 14, 15, 16): paint})
+
+
 def glass_alloy_cornell(rough):
     """cornell box with a solid glass box (materials/Glass.ispc: RobustDielectric, attenuating inside medium, transparent
     shadows) and an alloy box (materials/Alloy.ispc: conductor with Schlick Fresnel; rough: MicrofacetConductor with a roughness
@@ -435,6 +446,7 @@ CASES = {
     "plastic_rough_pt": (lambda: plastic_cornell(True), "pathtracer", {"pixelSamples": 2}, 2),
     "glass_alloy_pt": (lambda: glass_alloy_cornell(False), "pathtracer", {"pixelSamples": 2}, 2),
     "glass_alloy_rough_pt": (lambda: glass_alloy_cornell(True), "pathtracer", {"pixelSamples": 2}, 2),
+    "velvet_paint_pt": (lambda: velvet_paint_cornell(), "pathtracer", {"pixelSamples": 2}, 2),
     "principled_plastic_pt": (lambda: principled_cornell("plastic"), "pathtracer", {"pixelSamples": 2}, 2),
     "principled_metal_pt": (lambda: principled_cornell("metal"), "pathtracer", {"pixelSamples": 2}, 2),
     "principled_glass_pt": (lambda: principled_cornell("glass"), "pathtracer", {"pixelSamples": 2}, 2),
@@ -469,7 +481,7 @@ ORACLE_UNSUPPORTED = {"textured_pt", "textured_bias_pt", "cutout_pt", "backplate
                       "emissive_transparent_pt", "textured_scivis", "textured_ao", "cutout_scivis", "cutout_ao", "backplate_scivis",
                       "backplate_ao", "debug_texCoord", "debug_dPdt", "debug_dPds_tex", "debug_backplate", "metal_smooth_pt", "metal_rough_pt",
                       "plastic_smooth_pt", "plastic_rough_pt", "principled_plastic_pt", "principled_metal_pt", "principled_glass_pt",
-                      "principled_coat_pt", "principled_rough_layers_pt", "principled_emissive_pt", "glass_alloy_pt", "glass_alloy_rough_pt", "principled_sheen_pt", "principled_thin_pt", "principled_tex_pt", "principled_tex_cutout_pt"}
+                      "principled_coat_pt", "principled_rough_layers_pt", "principled_emissive_pt", "glass_alloy_pt", "glass_alloy_rough_pt", "principled_sheen_pt", "principled_thin_pt", "principled_tex_pt", "principled_tex_cutout_pt", "velvet_paint_pt"}
 # Rough dielectric coatings: MicrofacetDielectricLayer_Constructor reads self->eta for Ravg BEFORE assigning it
 # (bsdfs/MicrofacetDielectricLayer.ih:55 vs :68), i.e. whatever the shading context's memory held from the previous BSDF. The
 # device uses the intended value; against the reference's kernels the coated surfaces then differ by ~0.5 % in brightness

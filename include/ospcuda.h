@@ -116,7 +116,7 @@ typedef struct {
 
 enum { OC_MATERIAL_OBJ = 0, OC_MATERIAL_OTHER = 1, OC_MATERIAL_THINGLASS = 2, OC_MATERIAL_LUMINOUS = 3, OC_MATERIAL_METAL = 4,
        OC_MATERIAL_PLASTIC = 5, OC_MATERIAL_PRINCIPLED = 6, OC_MATERIAL_GLASS = 7, OC_MATERIAL_ALLOY = 8,
-       OC_MATERIAL_VELVET = 9, OC_MATERIAL_METALLICPAINT = 10 };
+       OC_MATERIAL_VELVET = 9, OC_MATERIAL_METALLICPAINT = 10, OC_MATERIAL_CARPAINT = 11 };
 /* texture maps of the principled material (PrincipledShared.h: one TextureParam per factor; the three normal maps come with the
  * orthogonal part of their 2D transform, transposed, and a scale: Material::getMaterialParam1f, render/Material.cpp:103-113) */
 enum { OC_PRMAP_BASECOLOR = 0, OC_PRMAP_EDGECOLOR, OC_PRMAP_METALLIC, OC_PRMAP_DIFFUSE, OC_PRMAP_SPECULAR, OC_PRMAP_IOR,
@@ -129,6 +129,27 @@ typedef struct {
   float normalRot[4], baseNormalRot[4], coatNormalRot[4]; /* (vx, vy) */
   float normalScale, baseNormalScale, coatNormalScale;
 } OcPrincipledMaps;
+/* carPaint (reference: ispc::CarPaint, render/materials/CarPaintShared.h:14-100, CarPaint.cpp:27-87): factors as committed (a
+ * factor with a map defaults to 1), one TextureParam per factor, the two normal maps with rotation and scale */
+enum { OC_CPMAP_BASECOLOR = 0, OC_CPMAP_ROUGHNESS, OC_CPMAP_NORMAL, OC_CPMAP_FLAKECOLOR, OC_CPMAP_FLAKESCALE, OC_CPMAP_FLAKEDENSITY,
+       OC_CPMAP_FLAKESPREAD, OC_CPMAP_FLAKEJITTER, OC_CPMAP_FLAKEROUGHNESS, OC_CPMAP_COAT, OC_CPMAP_COATIOR, OC_CPMAP_COATCOLOR,
+       OC_CPMAP_COATTHICKNESS, OC_CPMAP_COATROUGHNESS, OC_CPMAP_COATNORMAL, OC_CPMAP_FLIPFLOPCOLOR, OC_CPMAP_FLIPFLOPFALLOFF,
+       OC_CPMAP_COUNT };
+typedef struct {
+  OcVec3f baseColor;
+  float roughness;
+  uint32_t useFlakeColor;      /* 0: the flakes are aluminium (CarPaint.ispc:86-92) */
+  OcVec3f flakeColor;
+  float flakeScale, flakeDensity, flakeSpread, flakeJitter, flakeRoughness;
+  float coat, coatIor;
+  OcVec3f coatColor;
+  float coatThickness, coatRoughness;
+  OcVec3f flipflopColor;
+  float flipflopFalloff;
+  float normalScale, coatNormalScale;
+  float normalRot[4], coatNormalRot[4];
+  OcTextureParam map[OC_CPMAP_COUNT];
+} OcCarPaint;
 /* principled (reference: ispc::Principled, render/materials/PrincipledShared.h:17-170, Principled.cpp:33-150): factors as committed; outsideIor = outsideIor >= 1 ? outsideIor : 1 / outsideIor,
  * outsideAttenuation = log(outsideTransmissionColor) / outsideTransmissionDepth (the medium around the object) */
 typedef struct {
@@ -186,6 +207,7 @@ typedef struct {
    * eta = horizonScatteringFallOff. metallicPaint (ispc::MetallicPaint, MetallicPaint.cpp:27-40): Kd = baseColor * (1 - flakeAmount),
    * mapKd = map_baseColor, Ks = flakeColor * flakeAmount, attenuationScale = flakeAmount, Ns = flakeSpread, eta = 1 / eta */
   OcPrincipled principled;
+  const OcCarPaint *carPaint;  /* type OC_MATERIAL_CARPAINT (device memory) */
 } OcMaterial;
 
 /* 4-wide BVH node, 128 B = one cache line, fetched as 8 x 128-bit loads */

@@ -72,6 +72,22 @@ class PrincipledMaps(C.Structure):  # OcPrincipledMaps
                 ("coatNormalRot", C.c_float * 4), ("normalScale", C.c_float), ("baseNormalScale", C.c_float), ("coatNormalScale", C.c_float)]
 
 
+CPMAP_NAMES = ["baseColor", "roughness", "normal", "flakeColor", "flakeScale", "flakeDensity", "flakeSpread", "flakeJitter", "flakeRoughness",
+               "coat", "coatIor", "coatColor", "coatThickness", "coatRoughness", "coatNormal", "flipflopColor", "flipflopFalloff"]  # OC_CPMAP_*
+CARPAINT_DEFAULTS = {"baseColor": (0.8, 0.8, 0.8), "roughness": 0.0, "normal": 1.0, "flakeColor": (0.0, 0.0, 0.0), "flakeScale": 100.0,
+                     "flakeDensity": 0.0, "flakeSpread": 0.3, "flakeJitter": 0.75, "flakeRoughness": 0.3, "coat": 1.0, "coatIor": 1.5,
+                     "coatColor": (1.0, 1.0, 1.0), "coatThickness": 1.0, "coatRoughness": 0.0, "coatNormal": 1.0,
+                     "flipflopColor": (1.0, 1.0, 1.0), "flipflopFalloff": 1.0}  # CarPaint.cpp:27-50
+
+
+class CarPaint(C.Structure):  # OcCarPaint
+    _fields_ = [("baseColor", Vec3), ("roughness", C.c_float), ("useFlakeColor", C.c_uint32), ("flakeColor", Vec3), ("flakeScale", C.c_float),
+                ("flakeDensity", C.c_float), ("flakeSpread", C.c_float), ("flakeJitter", C.c_float), ("flakeRoughness", C.c_float),
+                ("coat", C.c_float), ("coatIor", C.c_float), ("coatColor", Vec3), ("coatThickness", C.c_float), ("coatRoughness", C.c_float),
+                ("flipflopColor", Vec3), ("flipflopFalloff", C.c_float), ("normalScale", C.c_float), ("coatNormalScale", C.c_float),
+                ("normalRot", C.c_float * 4), ("coatNormalRot", C.c_float * 4), ("map", TextureParam * len(CPMAP_NAMES))]
+
+
 class Principled(C.Structure):  # OcPrincipled
     _fields_ = [("baseColor", Vec3), ("edgeColor", Vec3), ("metallic", C.c_float), ("diffuse", C.c_float), ("specular", C.c_float),
                 ("specularMetallic", C.c_uint32), ("ior", C.c_float), ("transmission", C.c_float), ("transmissionColor", Vec3),
@@ -98,7 +114,7 @@ class Material(C.Structure):
                 ("eta", C.c_float), ("attenuation", Vec3), ("attenuationScale", C.c_float), ("emission", Vec3),
                 ("transparency", C.c_float), ("isEmissive", C.c_uint32), ("microfacetTables", C.c_void_p), ("hasTextures", C.c_uint32),
                 ("bumpRot", C.c_float * 4), ("mapD", TextureParam), ("mapKd", TextureParam), ("mapKs", TextureParam),
-                ("mapNs", TextureParam), ("mapBump", TextureParam), ("principled", Principled)]
+                ("mapNs", TextureParam), ("mapBump", TextureParam), ("principled", Principled), ("carPaint", C.POINTER(CarPaint))]
 
 
 class BVH(C.Structure):
@@ -611,6 +627,32 @@ class Scene:
                 if mp is not None:
                     setattr(m, f_, texture_param(mp, self.keep, self.mipmaps))
                     m.hasTextures = 1
+        elif ms.type == "carPaint":  # render/materials/CarPaint.cpp:27-87
+            f = np.float32
+            q = dict(CARPAINT_DEFAULTS)
+            given = dict(ms.params)
+            map_specs = {k[4:]: given.pop(k) for k in list(given) if k.startswith("map_")}
+            assert set(given) <= set(q) and set(map_specs) <= set(CPMAP_NAMES), ms.params
+            for name in map_specs:
+                q[name] = 1.0 if not isinstance(q[name], tuple) else (1.0, 1.0, 1.0)
+            q.update(given)
+            cp = CarPaint()
+            for i, name in enumerate(CPMAP_NAMES):
+                cp.map[i] = texture_param(map_specs.get(name), self.keep, self.mipmaps)
+            for fld, name in (("normalRot", "normal"), ("coatNormalRot", "coatNormal")):
+                t = cp.map[CPMAP_NAMES.index(name)]
+                rot = linear2f_orthogonal([t.xform2f[k] for k in range(4)])
+                getattr(cp, fld)[0], getattr(cp, fld)[1], getattr(cp, fld)[2], getattr(cp, fld)[3] = rot[0], rot[2], rot[1], rot[3]
+            for name in ("baseColor", "flakeColor", "coatColor", "flipflopColor"):
+                setattr(cp, name, Vec3(*map(float, np.asarray(q[name], f))))
+            for name in ("roughness", "flakeScale", "flakeDensity", "flakeSpread", "flakeJitter", "flakeRoughness", "coat", "coatIor", "coatThickness",
+                         "coatRoughness", "flipflopFalloff"):
+                setattr(cp, name, float(f(q[name])))
+            cp.normalScale, cp.coatNormalScale = float(f(q["normal"])), float(f(q["coatNormal"]))
+            cp.useFlakeColor = int("flakeColor" in given)
+            self.keep.append(cp)
+            m.type = 11
+            m.carPaint = C.pointer(cp)
         elif ms.type == "velvet":  # render/materials/Velvet.cpp:27-39
             f = np.float32
             q = {"reflectance": (0.4, 0.0, 0.0), "backScattering": 0.5, "horizonScatteringColor": (0.75, 0.1, 0.1), "horizonScatteringFallOff": 10.0}

@@ -37,6 +37,7 @@
 #include "render/materials/GlassShared.h"
 #include "render/materials/AlloyShared.h"
 #include "render/materials/VelvetShared.h"
+#include "render/materials/CarPaintShared.h"
 #include "render/materials/MetallicPaintShared.h"
 #include "render/bsdfs/MicrofacetAlbedoTablesShared.h"
 #include "render/pathtracer/GeometryLightShared.h"
@@ -173,7 +174,7 @@ struct Scene
   std::deque<OBJ> objs; std::deque<ThinGlass> glasses; std::vector<Material *> allMaterials;
   std::deque<Texture2D> textures;
   std::deque<Luminous> luminous; std::deque<GeometryLight> geoLights;
-  std::deque<Metal> metals; std::deque<Plastic> plastics; std::deque<Principled> principleds; std::deque<Glass> solidGlasses; std::deque<Alloy> alloys; std::deque<Velvet> velvets; std::deque<MetallicPaint> paints;
+  std::deque<Metal> metals; std::deque<Plastic> plastics; std::deque<Principled> principleds; std::deque<Glass> solidGlasses; std::deque<Alloy> alloys; std::deque<Velvet> velvets; std::deque<MetallicPaint> paints; std::deque<CarPaint> carPaints;
   std::deque<std::vector<int>> geoPrimIDs; std::deque<std::vector<float>> geoDistributions;
   std::vector<float> geoCDF;
   std::vector<Instance *> instancePtrs;
@@ -338,6 +339,32 @@ void buildScene(Scene &s, const OcWorld *w, const OcRenderer *ren)
       al.roughnessMap = makeTextureParam(s.textures, m.mapNs);
       al.super.microfacetAlbedoTables = refAlbedoTables();
       s.allMaterials.push_back(&al.super);
+      continue;
+    }
+    if (m.type == OC_MATERIAL_CARPAINT) { // render/materials/CarPaint.cpp:27-87 (committed values)
+      s.carPaints.emplace_back();
+      CarPaint &c = s.carPaints.back();
+      const OcCarPaint &q = *m.carPaint;
+      auto tp = [&](int i) { return makeTextureParam(s.textures, q.map[i]); };
+      auto rot = [](const float *r) { return linear2f(make_vec2f(r[0], r[1]), make_vec2f(r[2], r[3])); };
+      c.baseColor = v3(q.baseColor); c.baseColorMap = tp(OC_CPMAP_BASECOLOR);
+      c.roughness = q.roughness; c.roughnessMap = tp(OC_CPMAP_ROUGHNESS);
+      c.normal = q.normalScale; c.normalMap = tp(OC_CPMAP_NORMAL); c.normalRot = rot(q.normalRot);
+      c.useFlakeColor = q.useFlakeColor != 0; c.flakeColor = v3(q.flakeColor); c.flakeColorMap = tp(OC_CPMAP_FLAKECOLOR);
+      c.flakeScale = q.flakeScale; c.flakeScaleMap = tp(OC_CPMAP_FLAKESCALE);
+      c.flakeDensity = q.flakeDensity; c.flakeDensityMap = tp(OC_CPMAP_FLAKEDENSITY);
+      c.flakeSpread = q.flakeSpread; c.flakeSpreadMap = tp(OC_CPMAP_FLAKESPREAD);
+      c.flakeJitter = q.flakeJitter; c.flakeJitterMap = tp(OC_CPMAP_FLAKEJITTER);
+      c.flakeRoughness = q.flakeRoughness; c.flakeRoughnessMap = tp(OC_CPMAP_FLAKEROUGHNESS);
+      c.coat = q.coat; c.coatMap = tp(OC_CPMAP_COAT); c.coatIor = q.coatIor; c.coatIorMap = tp(OC_CPMAP_COATIOR);
+      c.coatColor = v3(q.coatColor); c.coatColorMap = tp(OC_CPMAP_COATCOLOR);
+      c.coatThickness = q.coatThickness; c.coatThicknessMap = tp(OC_CPMAP_COATTHICKNESS);
+      c.coatRoughness = q.coatRoughness; c.coatRoughnessMap = tp(OC_CPMAP_COATROUGHNESS);
+      c.coatNormal = q.coatNormalScale; c.coatNormalMap = tp(OC_CPMAP_COATNORMAL); c.coatNormalRot = rot(q.coatNormalRot);
+      c.flipflopColor = v3(q.flipflopColor); c.flipflopColorMap = tp(OC_CPMAP_FLIPFLOPCOLOR);
+      c.flipflopFalloff = q.flipflopFalloff; c.flipflopFalloffMap = tp(OC_CPMAP_FLIPFLOPFALLOFF);
+      c.super.microfacetAlbedoTables = refAlbedoTables();
+      s.allMaterials.push_back(&c.super);
       continue;
     }
     if (m.type == OC_MATERIAL_VELVET) { // render/materials/Velvet.cpp:27-39

@@ -862,7 +862,7 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
     ObjBSDF bsdf;
     ExtBSDF xbsdf; // metal / plastic state (extended-material kernels only)
     if (!volume) {
-      if (!(TEX && Ext_getBSDF(bsdf, xbsdf, dg, medium))) OBJ_getBSDF<TEX>(bsdf, dg);
+      if (!(TEX && Ext_getBSDF(bsdf, xbsdf, dg, medium, ray.dir))) OBJ_getBSDF<TEX>(bsdf, dg);
       if (!bsdf.valid) break;
     }
 

@@ -883,4 +883,183 @@ __device__ __forceinline__ vec3f Principled_getTransparency(const OcPrincipled &
   return T * opacity + make_vec3f(transparency);
 }
 
+// ---- carPaint (materials/CarPaint.ispc:29-365): flakes (a conductor on a perturbed frame where the cellular noise of
+// shaders/Flakes.ih says there is one) or a diffuse base, under a smooth / rough dielectric coat whose colour flip-flops with the
+// viewing angle over flakes
+__device__ __forceinline__ uint32_t cpNoiseHash(vec3f cell, uint32_t seed) // noiseHash(intbits(floor(v)), seed) (shaders/Noise.ih:10-24)
+{
+  uint32_t h = seed;
+  h = murmur3_mix(h, __float_as_uint(floorf(cell.x)));
+  h = murmur3_mix(h, __float_as_uint(floorf(cell.y)));
+  h = murmur3_mix(h, __float_as_uint(floorf(cell.z)));
+  h ^= 3 * 4;
+  return murmur3_finalize(h);
+}
+__device__ __forceinline__ float cpLcgFloat(uint32_t &state) { state = state * 1664525u + 1013904223u; return to_float_unorm(state); }
+// Flakes_eval (shaders/Flakes.ih:17-65): nearest jittered cell centre; a flake there with probability `density`, its normal a
+// Beckmann sample (bsdfs/BeckmannDistribution.ih:18-41)
+static __device__ __noinline__ vec3f Flakes_eval(float scale, float density, float spread, float jitter, vec3f P, int &mask)
+{
+  vec3f N = make_vec3f(0.f, 0.f, 1.f);
+  mask = 0;
+  if (density <= 0.f || spread <= 0.f) return N;
+  const float alpha = fmaxf(sqr(spread), 0.001f);
+  P = P * scale;
+  const vec3f thisCell = make_vec3f(floorf(P.x) + 0.5f, floorf(P.y) + 0.5f, floorf(P.z) + 0.5f);
+  float f1 = 1000.f;
+  uint32_t cellRnd = 0;
+  for (int i = -1; i <= 1; i++)
+    for (int j = -1; j <= 1; j++)
+      for (int k = -1; k <= 1; k++) {
+        const vec3f testCell = thisCell + make_vec3f((float)i, (float)j, (float)k);
+        uint32_t rnd = cpNoiseHash(testCell, 0x537e6612u);
+        const float rx = cpLcgFloat(rnd), ry = cpLcgFloat(rnd), rz = cpLcgFloat(rnd);
+        const vec3f pos = testCell + jitter * (make_vec3f(rx, ry, rz) - make_vec3f(0.5f));
+        const vec3f offset = pos - P;
+        const float dist = dot(offset, offset);
+        if (dist < f1) { f1 = dist; cellRnd = rnd; }
+      }
+  if (cpLcgFloat(cellRnd) <= density) {
+    const float sx = cpLcgFloat(cellRnd), sy = cpLcgFloat(cellRnd);
+    const float alpha2 = sqr(alpha);
+    const float tanTheta2 = -alpha2 * logf(1.f - sx);
+    const float cosTheta = 1.f / sqrtf(1.f + tanTheta2);
+    const float sinTheta = cos2sin(cosTheta);
+    const float phi = 2.f * OC_PI * sy;
+    float sinPhi, cosPhi;
+    sincosf(phi, &sinPhi, &cosPhi);
+    N = make_vec3f(cosPhi * sinTheta, sinPhi * sinTheta, cosTheta);
+    mask = 1;
+  }
+  return normalize(N);
+}
+// makeShadingFrame(dg, localN) (render/Material.ih:36-57)
+__device__ __forceinline__ linear3f cpFrameFromLocalNormal(const DifferentialGeometry &dg, vec3f localN)
+{
+  const linear3f f = makeShadingFrame(dg);
+  const vec3f N = normalize(f * localN);
+  vec3f V = cross(N, f.vx);
+  if (dot(V, V) > 0.f) {
+    V = normalize(V);
+    linear3f r; r.vx = cross(V, N); r.vy = V; r.vz = N; return r;
+  }
+  return frame(N);
+}
+struct CarPaintBSDF
+{
+  int flakeMask, condKind;   // condKind: 1 Conductor, 2 MicrofacetConductor
+  ConductorBSDF cond;
+  PrDiffuse diff;            // Lambert | OrenNayar (lobeEval / lobeSample)
+  int coatKind;              // 0 passthrough, 1 DielectricLayer, 2 MicrofacetDielectricLayer
+  LayerParams coat;
+  linear3f coatFrame;
+  vec3f albedo;              // of the substrate (what the coat macros read), then of the whole
+  uint32_t scatteringType;
+  __device__ __forceinline__ EvalRes eval(vec3f wo, vec3f wi) const // BaseBSDF_eval
+  {
+    if (flakeMask) { if (condKind == 2) return MicrofacetConductor_eval(cond, wo, wi); EvalRes z; z.value = make_vec3f(0.f); z.pdf = 0.f; return z; }
+    return diff.lobeEval(wo, wi);
+  }
+  __device__ __forceinline__ SampleRes sample(vec3f wo, vec2f s, float) const // BaseBSDF_sample
+  {
+    if (flakeMask) return condKind == 2 ? MicrofacetConductor_sample(cond, wo, s) : Conductor_sample(cond, wo);
+    return diff.lobeSample(wo, s);
+  }
+};
+static __device__ __noinline__ void CarPaint_getBSDF(CarPaintBSDF &b, vec3f &rootN, vec3f &rootAlbedo, uint32_t &rootType, const OcCarPaint &m,
+    const float *tables, const DifferentialGeometry &dg, vec3f rayDir)
+{
+  auto has = [&](int i) { return m.map[i].tex != nullptr; };
+  auto get1 = [&](int i) { return has(i) ? texParamGet4f(m.map[i], dg.st, dg.pixelFootprint).x : 1.f; };
+  auto get3 = [&](int i) { if (!has(i)) return make_vec3f(1.f); const vec4f t = texParamGet4f(m.map[i], dg.st, dg.pixelFootprint); return make_vec3f(t.x, t.y, t.z); };
+  const linear3f frm = has(OC_CPMAP_NORMAL) ? prNormalMapFrame(dg, m.map[OC_CPMAP_NORMAL], m.normalRot, m.normalScale) : makeShadingFrame(dg);
+  const float flakeDensity = clampf(m.flakeDensity * get1(OC_CPMAP_FLAKEDENSITY), 0.f, 1.f);
+  int flakeMask = 0;
+  linear3f flakeFrame = frm;
+  if (flakeDensity > PR_EPS) {
+    const float flakeScale = fmaxf(m.flakeScale * get1(OC_CPMAP_FLAKESCALE), 0.f);
+    const float flakeSpread = fmaxf(m.flakeSpread * get1(OC_CPMAP_FLAKESPREAD), 0.f);
+    const float flakeJitter = clampf(m.flakeJitter * get1(OC_CPMAP_FLAKEJITTER), 0.f, 1.f);
+    const vec3f flakeN = Flakes_eval(flakeScale, flakeDensity, flakeSpread, flakeJitter, dg.P, flakeMask);
+    if (flakeMask) {
+      flakeFrame = cpFrameFromLocalNormal(dg, flakeN);
+      ConductorBSDF &c = b.cond;
+      c.frame = flakeFrame; c.tables = tables;
+      vec3f Favg;
+      if (m.useFlakeColor) {
+        c.schlick = true;
+        c.eta = clamp01(toV(m.flakeColor) * get3(OC_CPMAP_FLAKECOLOR)); c.k = make_vec3f(1.f);
+        Favg = fresnelSchlickAvg(c.eta, c.k);
+      } else { // aluminium; the RGB conductor has no average (Fresnel.ih:307-320)
+        c.schlick = false;
+        c.eta = make_vec3f(1.69700277f, 0.879832864f, 0.5301736f); c.k = make_vec3f(9.30200672f, 6.27604008f, 4.89433956f);
+        Favg = make_vec3f(0.f);
+      }
+      if (m.flakeRoughness < PR_EPS) { b.condKind = 1; b.albedo = Favg; b.scatteringType = SC_SPECULAR_REFLECTION; }
+      else {
+        const float r = fmaxf(m.flakeRoughness * get1(OC_CPMAP_FLAKEROUGHNESS), 0.f);
+        b.condKind = 2;
+        c.Eavg = mfAlbedoAvg(tables, r);
+        c.fmsScale = sqr3(Favg) * c.Eavg / (make_vec3f(1.f) - Favg * (1.f - c.Eavg));
+        c.mf = makeGGX(r, 0.f);
+        c.roughness = r;
+        b.albedo = Favg * c.Eavg; b.scatteringType = SC_GLOSSY_REFLECTION;
+      }
+    }
+  }
+  rootN = flakeMask ? flakeFrame.vz : frm.vz;
+  if (!flakeMask) {
+    const vec3f baseColor = clamp01(toV(m.baseColor) * get3(OC_CPMAP_BASECOLOR) * make_vec3f(dg.color));
+    PrDiffuse &D = b.diff;
+    D.frame = frm; D.R = baseColor;
+    D.orenNayar = !(m.roughness < PR_EPS);
+    D.roughness = D.orenNayar ? fmaxf(m.roughness * get1(OC_CPMAP_ROUGHNESS), 0.f) : 0.f;
+    b.albedo = baseColor; b.scatteringType = SC_DIFFUSE_REFLECTION;
+  }
+  b.flakeMask = flakeMask;
+  b.coatKind = 0; b.coat.weight = 0.f; b.coatFrame = frm;
+  rootAlbedo = b.albedo; rootType = b.scatteringType;
+  if ((m.coat > PR_EPS) && (fabsf(m.coatIor - 1.f) > PR_EPS || has(OC_CPMAP_COATIOR))) {
+    const float coat = fmaxf(m.coat * get1(OC_CPMAP_COAT), 0.f);
+    float coatIor = m.coatIor * get1(OC_CPMAP_COATIOR);
+    if (coatIor < 1.f) coatIor = 1.f / coatIor;
+    coatIor = clampf(coatIor, 1.f, 3.f);
+    const vec3f coatColor = clamp01(toV(m.coatColor) * get3(OC_CPMAP_COATCOLOR));
+    vec3f coatFinalColor = coatColor;
+    if (flakeMask) {
+      const float flipflopFalloff = clampf(m.flipflopFalloff * get1(OC_CPMAP_FLIPFLOPFALLOFF), 0.f, 1.f);
+      if (flipflopFalloff < 1.f - PR_EPS) {
+        const vec3f flipflopColor = clamp01(toV(m.flipflopColor) * get3(OC_CPMAP_FLIPFLOPCOLOR));
+        const float cosThetaO = fmaxf(-dot(rayDir, flakeFrame.vz), 0.f);
+        const float weight = powf(1.f - cosThetaO, 1.f / (1.f - flipflopFalloff));
+        coatFinalColor = lerpv(weight, coatColor, flipflopColor);
+      }
+    }
+    const float coatThickness = fmaxf(m.coatThickness * get1(OC_CPMAP_COATTHICKNESS), 0.f);
+    b.coatFrame = has(OC_CPMAP_COATNORMAL) ? prNormalMapFrame(dg, m.map[OC_CPMAP_COATNORMAL], m.coatNormalRot, m.coatNormalScale) : makeShadingFrame(dg);
+    if (m.coatRoughness < PR_EPS) {
+      b.coatKind = 1;
+      DielectricLayer_init(b.coat, b.albedo, b.scatteringType, 1.f / coatIor, coatFinalColor, coatThickness, coat);
+    } else {
+      b.coatKind = 2;
+      MicrofacetDielectricLayer_init(b.coat, tables, b.albedo, b.scatteringType, 1.f / coatIor, coatFinalColor, coatThickness,
+          fmaxf(m.coatRoughness * get1(OC_CPMAP_COATROUGHNESS), 0.f), 0.f, coat);
+    }
+    rootAlbedo = b.coat.albedo; rootType = b.coat.scatteringType;
+    rootN = b.coatFrame.vz;
+  }
+}
+__device__ __forceinline__ EvalRes CarPaint_eval(const CarPaintBSDF &b, vec3f wo, vec3f wi)
+{
+  if (b.coatKind == 0 || b.coat.weight < PR_EPS) return b.eval(wo, wi);
+  if (b.coatKind == 2) return MicrofacetDielectricLayer_eval(b.coat, b.coatFrame, b, wo, wi);
+  return DielectricLayer_eval(b.coat, b.coatFrame.vz, b, wo, wi);
+}
+__device__ __forceinline__ SampleRes CarPaint_sample(const CarPaintBSDF &b, vec3f wo, vec2f s, float ss)
+{
+  if (b.coatKind == 0 || b.coat.weight < PR_EPS) return b.sample(wo, s, ss);
+  if (b.coatKind == 2) return MicrofacetDielectricLayer_sample(b.coat, b.coatFrame, b, wo, s, ss);
+  return DielectricLayer_sample(b.coat, b.coatFrame.vz, b, wo, s, ss);
+}
+
 } // namespace oc

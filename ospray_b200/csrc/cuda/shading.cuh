@@ -340,7 +340,7 @@ struct ObjBSDF
   uint32_t kind;           // BSDF_KIND_*: 0 = the cases above; the others only exist in the extended-material kernels
 };
 enum { BSDF_KIND_OBJ = 0, BSDF_KIND_CONDUCTOR, BSDF_KIND_MICROFACET_CONDUCTOR, BSDF_KIND_PLASTIC_SMOOTH, BSDF_KIND_PLASTIC_ROUGH,
-       BSDF_KIND_PRINCIPLED, BSDF_KIND_GLASS, BSDF_KIND_VELVET, BSDF_KIND_METALLICPAINT };
+       BSDF_KIND_PRINCIPLED, BSDF_KIND_GLASS, BSDF_KIND_VELVET, BSDF_KIND_METALLICPAINT, BSDF_KIND_CARPAINT };
 
 // render/Material.ih:25-37
 __device__ __forceinline__ linear3f makeShadingFrame(const DifferentialGeometry &dg)
@@ -411,6 +411,7 @@ struct ExtBSDF
   vec3f glassNg, glassNs; float glassEta; // RobustDielectric (bsdfs/RobustDielectric.ih:14-25)
   VelvetBSDF velvet;
   MetallicPaintSub paint;                 // under `layer`
+  CarPaintBSDF car;
 };
 // the medium a path travels in (render/materials/MediumShared.h:10-18; vacuum = no attenuation, ior 1)
 struct Medium { vec3f attenuation; float ior; };
@@ -666,7 +667,7 @@ __device__ __forceinline__ SampleRes OBJ_sample(const ObjBSDF &b, vec3f wo, vec2
 // ---- metal and plastic (extended-material kernels only) -------------------------------------------------------------
 // Metal_getBSDF (materials/Metal.ispc:18-46, RGB form) and Plastic_getBSDF (materials/Plastic.ispc:25-67): fills `b` (frame,
 // albedo, scattering type, kind) and the family state `x`; false: not one of these materials
-__device__ __forceinline__ bool Ext_getBSDF(ObjBSDF &b, ExtBSDF &x, const DifferentialGeometry &dg, const Medium &medium)
+__device__ __forceinline__ bool Ext_getBSDF(ObjBSDF &b, ExtBSDF &x, const DifferentialGeometry &dg, const Medium &medium, vec3f rayDir)
 {
   const OcMaterial *m = dg.material;
   if (!m || m->type < OC_MATERIAL_METAL) return false;
@@ -683,6 +684,11 @@ __device__ __forceinline__ bool Ext_getBSDF(ObjBSDF &b, ExtBSDF &x, const Differ
     return true;
   }
   b.frame = frame(dg.Ns);
+  if (m->type == OC_MATERIAL_CARPAINT) {
+    CarPaint_getBSDF(x.car, b.frame.vz, b.albedo, b.scatteringType, *m->carPaint, m->microfacetTables, dg, rayDir);
+    b.kind = BSDF_KIND_CARPAINT;
+    return true;
+  }
   if (m->type == OC_MATERIAL_GLASS) { // Glass_getBSDF (materials/Glass.ispc:14-33): eta = the side the path is on over the other
     x.glassEta = mediumIsOutside(medium, m->principled) ? m->principled.outsideIor * (1.f / m->eta) : m->eta * (1.f / m->principled.outsideIor);
     x.glassNg = dg.Ng; x.glassNs = dg.Ns;
@@ -783,6 +789,7 @@ static __device__ __noinline__ EvalRes Ext_eval(const ObjBSDF &b, const ExtBSDF 
   case BSDF_KIND_PLASTIC_SMOOTH: return DielectricLayer_eval(x.layer, b.frame.vz, x.lambert, wo, wi);
   case BSDF_KIND_PLASTIC_ROUGH: return MicrofacetDielectricLayer_eval(x.layer, b.frame, x.lambert, wo, wi);
   case BSDF_KIND_PRINCIPLED: return Principled_eval(x.pr, wo, wi);
+  case BSDF_KIND_CARPAINT: return CarPaint_eval(x.car, wo, wi);
   case BSDF_KIND_VELVET: return x.velvet.eval(wo, wi);
   case BSDF_KIND_METALLICPAINT: return DielectricLayer_eval(x.layer, b.frame.vz, x.paint, wo, wi);
   default: return e; // smooth conductor: purely specular
@@ -856,6 +863,7 @@ static __device__ __noinline__ SampleRes Ext_sample(const ObjBSDF &b, const ExtB
   case BSDF_KIND_MICROFACET_CONDUCTOR: return MicrofacetConductor_sample(x.cond, wo, s);
   case BSDF_KIND_PLASTIC_SMOOTH: return DielectricLayer_sample(x.layer, b.frame.vz, x.lambert, wo, s, ss);
   case BSDF_KIND_PRINCIPLED: return Principled_sample(x.pr, wo, s, ss);
+  case BSDF_KIND_CARPAINT: return CarPaint_sample(x.car, wo, s, ss);
   case BSDF_KIND_VELVET: return x.velvet.sample(wo, s, ss);
   case BSDF_KIND_METALLICPAINT: return DielectricLayer_sample(x.layer, b.frame.vz, x.paint, wo, s, ss);
   default: return MicrofacetDielectricLayer_sample(x.layer, b.frame, x.lambert, wo, s, ss);

@@ -479,6 +479,45 @@ void Material::commit()
     m.Ks = toOc(getParam<vec3f>("edgeColor", make_vec3f(1.f)));
     m.Ns = getParam<float>("roughness", texNs ? 1.f : 0.1f);
     extended = true;
+  } else if (type == "carPaint") {
+    // render/materials/CarPaint.cpp:27-87; a factor with a map defaults to 1
+    static const char *const mapNames[OC_CPMAP_COUNT] = {"baseColor", "roughness", "normal", "flakeColor", "flakeScale", "flakeDensity",
+        "flakeSpread", "flakeJitter", "flakeRoughness", "coat", "coatIor", "coatColor", "coatThickness", "coatRoughness", "coatNormal",
+        "flipflopColor", "flipflopFalloff"};
+    OcCarPaint cp{};
+    texPrincipled.assign(OC_CPMAP_COUNT, nullptr);
+    for (int i = 0; i < OC_CPMAP_COUNT; i++) cp.map[i] = getTextureParam(std::string("map_") + mapNames[i], texPrincipled[i]);
+    auto mapped = [&](int i) { return cp.map[i].tex != nullptr; };
+    auto rotOf = [&](int i, float *dst) {
+      float rot[4] = {cp.map[i].xform2f[0], cp.map[i].xform2f[1], cp.map[i].xform2f[2], cp.map[i].xform2f[3]};
+      linear2fOrthogonal(rot);
+      dst[0] = rot[0]; dst[1] = rot[2]; dst[2] = rot[1]; dst[3] = rot[3];
+    };
+    rotOf(OC_CPMAP_NORMAL, cp.normalRot); rotOf(OC_CPMAP_COATNORMAL, cp.coatNormalRot);
+    auto f1 = [&](const char *name, int i, float def) { return getParam<float>(name, mapped(i) ? 1.f : def); };
+    auto f3 = [&](const char *name, int i, float def) { return toOc(getParam<vec3f>(name, make_vec3f(mapped(i) ? 1.f : def))); };
+    cp.baseColor = f3("baseColor", OC_CPMAP_BASECOLOR, 0.8f);
+    cp.roughness = f1("roughness", OC_CPMAP_ROUGHNESS, 0.f);
+    cp.normalScale = f1("normal", OC_CPMAP_NORMAL, 1.f);
+    cp.useFlakeColor = hasParam("flakeColor") ? 1u : 0u;
+    cp.flakeColor = f3("flakeColor", OC_CPMAP_FLAKECOLOR, 0.f);
+    cp.flakeScale = f1("flakeScale", OC_CPMAP_FLAKESCALE, 100.f);
+    cp.flakeDensity = f1("flakeDensity", OC_CPMAP_FLAKEDENSITY, 0.f);
+    cp.flakeSpread = f1("flakeSpread", OC_CPMAP_FLAKESPREAD, 0.3f);
+    cp.flakeJitter = f1("flakeJitter", OC_CPMAP_FLAKEJITTER, 0.75f);
+    cp.flakeRoughness = f1("flakeRoughness", OC_CPMAP_FLAKEROUGHNESS, 0.3f);
+    cp.coat = f1("coat", OC_CPMAP_COAT, 1.f);
+    cp.coatIor = f1("coatIor", OC_CPMAP_COATIOR, 1.5f);
+    cp.coatColor = f3("coatColor", OC_CPMAP_COATCOLOR, 1.f);
+    cp.coatThickness = f1("coatThickness", OC_CPMAP_COATTHICKNESS, 1.f);
+    cp.coatRoughness = f1("coatRoughness", OC_CPMAP_COATROUGHNESS, 0.f);
+    cp.coatNormalScale = f1("coatNormal", OC_CPMAP_COATNORMAL, 1.f);
+    cp.flipflopColor = f3("flipflopColor", OC_CPMAP_FLIPFLOPCOLOR, 1.f);
+    cp.flipflopFalloff = f1("flipflopFalloff", OC_CPMAP_FLIPFLOPFALLOFF, 1.f);
+    principledMaps.upload(&cp, sizeof(cp));
+    m.type = OC_MATERIAL_CARPAINT;
+    m.carPaint = principledMaps.as<OcCarPaint>();
+    extended = true;
   } else if (type == "velvet") {
     // render/materials/Velvet.cpp:27-39
     m.type = OC_MATERIAL_VELVET;

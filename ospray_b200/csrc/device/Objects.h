@@ -146,7 +146,7 @@ struct Material : public ManagedObject
   OcTextureParam getTextureParam(const std::string &name, Ref<Texture2D> &keep); // render/Material.cpp:73-165
   Ref<Texture2D> texD, texKd, texKs, texNs, texBump;
   std::vector<Ref<Texture2D>> texPrincipled; // the principled material's maps (OC_PRMAP_*)
-  DevMem principledMaps;                     // OcPrincipledMaps on the device
+  DevMem principledMaps;                     // OcPrincipledMaps / OcCarPaint on the device
 };
 
 uint64_t commitEpoch();     // counts the commits of objects whose state parents snapshot

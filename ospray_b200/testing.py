@@ -67,7 +67,7 @@ class MaterialSpec:
     alloy_color: tuple = (0.9, 0.9, 0.9)        # alloy (Alloy.cpp:28-40): reflectivity at normal incidence / at grazing angles, `roughness`,
     edge_color: tuple = (1.0, 1.0, 1.0)         #   maps map_color / map_edge_color / map_roughness
     map_edge_color: Optional["MapSpec"] = None
-    params: dict = field(default_factory=dict)   # velvet / metallicPaint: ospray parameter name -> value (maps as MapSpec)
+    params: dict = field(default_factory=dict)   # velvet / metallicPaint / carPaint: ospray parameter name -> value (maps as MapSpec)
     principled: dict = field(default_factory=dict)  # principled (Principled.cpp:33-150): ospray parameter name -> value
 
 
@@ -482,7 +482,7 @@ def _material(m: MaterialSpec):
         _set_map(mat, "map_roughness", m.map_roughness)
         mat.set("color", tuple(float(x) for x in m.alloy_color)).set("edgeColor", tuple(float(x) for x in m.edge_color)).set("roughness", float(m.roughness))
         return mat.commit()
-    if m.type in ("velvet", "metallicPaint"):
+    if m.type in ("velvet", "metallicPaint", "carPaint"):
         for name, v in m.params.items():
             if name.startswith("map_"): _set_map(mat, name, v)
             elif isinstance(v, (tuple, list)): mat.set(name, tuple(float(x) for x in v))

@@ -338,6 +338,21 @@ def velvet_paint_cornell():
     return _cornell_models({(5, 6, 7, 8, 9, 10): velvet, (11, 12, 13, 14, 15, 16): paint})
 
 
+def carpaint_cornell():
+    """cornell box with two carPaint boxes (materials/CarPaint.ispc): coloured rough flakes under a smooth tinted coat whose
+    colour flip-flops, base colour from a map where there is no flake | aluminium mirror flakes with a density map, OrenNayar
+    base, no coat (coatIor = 1). (A rough coat would meet the reference's Ravg defect, see REF_UNDEFINED_STATE_CASES.)"""
+    TS, MS = T.TextureSpec, T.MapSpec
+    a = T.MaterialSpec(type="carPaint", params=dict(map_baseColor=MS(TS(_tex_rng_image(8, 8, 3, 81, np.float32, 0.2, 0.9), "RGB32F")),
+                                                    flakeColor=(0.9, 0.5, 0.2), flakeDensity=0.6, flakeScale=9.0, flakeSpread=0.4, flakeJitter=0.6,
+                                                    flakeRoughness=0.35, coatColor=(0.8, 0.9, 1.0), coatThickness=1.5, coatIor=1.6,
+                                                    flipflopColor=(1.0, 0.4, 0.8), flipflopFalloff=0.4))
+    b = T.MaterialSpec(type="carPaint", params=dict(baseColor=(0.2, 0.5, 0.3), roughness=0.4, flakeDensity=1.0, flakeScale=7.0, flakeRoughness=0.0,
+                                                    map_flakeDensity=MS(TS(_tex_rng_image(8, 8, 1, 82, np.float32, 0.1, 0.9)[..., 0], "R32F", filter="nearest")),
+                                                    coatIor=1.0))
+    return _cornell_models({(5, 6, 7, 8, 9, 10): a, (11, 12, 13, 14, 15, 16): b})
+
+
 def glass_alloy_cornell(rough):
     """cornell box with a solid glass box (materials/Glass.ispc: RobustDielectric, attenuating inside medium, transparent
     shadows) and an alloy box (materials/Alloy.ispc: conductor with Schlick Fresnel; rough: MicrofacetConductor with a roughness
@@ -446,6 +461,7 @@ CASES = {
     "plastic_rough_pt": (lambda: plastic_cornell(True), "pathtracer", {"pixelSamples": 2}, 2),
     "glass_alloy_pt": (lambda: glass_alloy_cornell(False), "pathtracer", {"pixelSamples": 2}, 2),
     "glass_alloy_rough_pt": (lambda: glass_alloy_cornell(True), "pathtracer", {"pixelSamples": 2}, 2),
+    "carpaint_pt": (lambda: carpaint_cornell(), "pathtracer", {"pixelSamples": 2}, 2),
     "velvet_paint_pt": (lambda: velvet_paint_cornell(), "pathtracer", {"pixelSamples": 2}, 2),
     "principled_plastic_pt": (lambda: principled_cornell("plastic"), "pathtracer", {"pixelSamples": 2}, 2),
     "principled_metal_pt": (lambda: principled_cornell("metal"), "pathtracer", {"pixelSamples": 2}, 2),
@@ -481,7 +497,7 @@ ORACLE_UNSUPPORTED = {"textured_pt", "textured_bias_pt", "cutout_pt", "backplate
                       "emissive_transparent_pt", "textured_scivis", "textured_ao", "cutout_scivis", "cutout_ao", "backplate_scivis",
                       "backplate_ao", "debug_texCoord", "debug_dPdt", "debug_dPds_tex", "debug_backplate", "metal_smooth_pt", "metal_rough_pt",
                       "plastic_smooth_pt", "plastic_rough_pt", "principled_plastic_pt", "principled_metal_pt", "principled_glass_pt",
-                      "principled_coat_pt", "principled_rough_layers_pt", "principled_emissive_pt", "glass_alloy_pt", "glass_alloy_rough_pt", "principled_sheen_pt", "principled_thin_pt", "principled_tex_pt", "principled_tex_cutout_pt", "velvet_paint_pt"}
+                      "principled_coat_pt", "principled_rough_layers_pt", "principled_emissive_pt", "glass_alloy_pt", "glass_alloy_rough_pt", "principled_sheen_pt", "principled_thin_pt", "principled_tex_pt", "principled_tex_cutout_pt", "velvet_paint_pt", "carpaint_pt"}
 # Rough dielectric coatings: MicrofacetDielectricLayer_Constructor reads self->eta for Ravg BEFORE assigning it
 # (bsdfs/MicrofacetDielectricLayer.ih:55 vs :68), i.e. whatever the shading context's memory held from the previous BSDF. The
 # device uses the intended value; against the reference's kernels the coated surfaces then differ by ~0.5 % in brightness

@@ -2174,6 +2174,35 @@ ORACLE_API void oracle_commit_camera(const float pos[3], const float dir[3], con
   out->nearClip = 1e-6f; out->subImage[0] = 0.f; out->subImage[1] = 0.f; out->subImage[2] = 1.f; out->subImage[3] = 1.f;
   out->scaledAperture = scaledAperture; out->aspect = aspect; out->imgPlaneSizeY = imgY; out->needLensSample = scaledAperture > 0.f;
 }
+// a light of a (static) transformed instance: QuadLight.ispc:14-33, PointLight.ispc:17-29, SpotLight.ispc:14-24 (Transform),
+// DirectionalLight.cpp:36-44 (frame = xfm.l * frame); xfm = 12 floats (l.vx, l.vy, l.vz, p)
+ORACLE_API void oracle_transform_light(OcLight *l, const float *x)
+{
+  A3 xfm;
+  xfm.l.vx = v3(x[0], x[1], x[2]); xfm.l.vy = v3(x[3], x[4], x[5]); xfm.l.vz = v3(x[6], x[7], x[8]); xfm.p = v3(x[9], x[10], x[11]);
+  auto oc = [](V3 v) { return OcVec3f{v.x, v.y, v.z}; };
+  switch (l->type) {
+  case OC_LIGHT_QUAD: {
+    const V3 position = xfmPoint(xfm, v3(l->position)), e1 = xfmVector(xfm.l, v3(l->edge1)), e2 = xfmVector(xfm.l, v3(l->edge2));
+    const V3 ndirection = cross(e2, e1);
+    const float ppdf = 1.f / length(ndirection);
+    l->position = oc(position); l->edge1 = oc(e1); l->edge2 = oc(e2); l->ppdf = ppdf; l->nnormal = oc(ndirection * ppdf);
+    break;
+  }
+  case OC_LIGHT_SPHERE: l->position = oc(xfmPoint(xfm, v3(l->position))); break;
+  case OC_LIGHT_SPOT: { // fx / fy / fz = c0 / c90 / direction
+    const V3 direction = normalize(xfmVector(xfm.l, v3(l->fz)));
+    const V3 c90 = normalize(cross(xfmVector(xfm.l, v3(l->fx)), direction));
+    l->position = oc(xfmPoint(xfm, v3(l->position)));
+    l->fz = oc(direction); l->fy = oc(c90); l->fx = oc(cross(direction, c90));
+    break;
+  }
+  case OC_LIGHT_DISTANT:
+    l->fx = oc(xfmVector(xfm.l, v3(l->fx))); l->fy = oc(xfmVector(xfm.l, v3(l->fy))); l->fz = oc(xfmVector(xfm.l, v3(l->fz)));
+    break;
+  default: break; // ambient
+  }
+}
 // lights: Light.cpp:20-25, QuadLight.cpp:68-108 + QuadLight.ispc:15-30, AmbientLight.cpp, DirectionalLight.cpp
 ORACLE_API void oracle_commit_light(int type, const float color[3], float intensity, int visible, const float position[3],
     const float edge1[3], const float edge2[3], const float direction[3], float angularDiameter, OcLight *out)

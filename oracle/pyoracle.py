@@ -534,7 +534,12 @@ class Scene:
         # lights: PathTracerData (world lights in order, uniform CDF) and SciVisData (ambient first)
         pt, sv, visible_only = [], [], 0
         ao = np.zeros(3, np.float32)
-        for ls in spec.lights:
+        # world lights, then the lights of the instances' groups moved into world space (World.cpp:120-150, *Light::createSh)
+        all_lights = [(ls, None) for ls in spec.lights]
+        for inst in spec.instances:
+            for ls in getattr(inst.group, "lights", []):
+                all_lights.append((ls, None if inst.xfm is None else np.ascontiguousarray(inst.xfm, np.float32)))
+        for ls, lxfm in all_lights:
             l = Light()
             p = ls.params
             t = {"ambient": OC_LIGHT_AMBIENT, "distant": OC_LIGHT_DISTANT, "quad": OC_LIGHT_QUAD, "sphere": 4, "spot": 6}[ls.type]
@@ -550,6 +555,8 @@ class Scene:
                 L.oracle_commit_light(t, _f3(p.get("color", (1, 1, 1))), float(p.get("intensity", 1.0)), int(p.get("visible", True)),
                                   _f3(p.get("position", (0, 0, 0))), _f3(p.get("edge1", (1, 0, 0))), _f3(p.get("edge2", (0, 1, 0))),
                                   _f3(p.get("direction", (0, 0, 1))), float(p.get("angularDiameter", 0.0)), C.byref(l))
+            if lxfm is not None:
+                L.oracle_transform_light(C.byref(l), lxfm.ctypes.data_as(C.POINTER(C.c_float)))
             pt.append(l)
             if t == OC_LIGHT_AMBIENT:
                 if visible_only == len(sv):

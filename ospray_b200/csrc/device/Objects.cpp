@@ -1184,33 +1184,60 @@ void World::commit()
             + std::to_string(OSPCUDA_TRAVERSAL_STACK) + ")");
     }
   }
-  // light lists: world lights, then instance (group) lights -- the latter are not transformed yet
-  std::vector<Light *> all;
+  // light lists: world lights, then the lights of the instances' groups, moved into world space with the instance
+  // (World.cpp:120-150 + *Light::createSh(instance): QuadLight.ispc:14-33, PointLight.ispc:17-29, SpotLight.ispc:14-24,
+  // DirectionalLight.cpp:36-44)
+  auto inWorldSpace = [](OcLight l, const affine3f &xfm) {
+    auto V = [](const OcVec3f &v) { return make_vec3f(v.x, v.y, v.z); };
+    switch (l.type) {
+    case OC_LIGHT_QUAD: {
+      const vec3f position = xfmPoint(xfm, V(l.position)), e1 = xfmVector(xfm.l, V(l.edge1)), e2 = xfmVector(xfm.l, V(l.edge2));
+      const vec3f ndirection = cross(e2, e1);
+      const float ppdf = 1.f / length(ndirection);
+      l.position = toOc(position); l.edge1 = toOc(e1); l.edge2 = toOc(e2); l.ppdf = ppdf; l.nnormal = toOc(ndirection * ppdf);
+      break;
+    }
+    case OC_LIGHT_SPHERE: l.position = toOc(xfmPoint(xfm, V(l.position))); break;
+    case OC_LIGHT_SPOT: { // fx / fy / fz = c0 / c90 / direction
+      const vec3f direction = normalize(xfmVector(xfm.l, V(l.fz)));
+      const vec3f c90 = normalize(cross(xfmVector(xfm.l, V(l.fx)), direction));
+      l.position = toOc(xfmPoint(xfm, V(l.position)));
+      l.fz = toOc(direction); l.fy = toOc(c90); l.fx = toOc(cross(direction, c90));
+      break;
+    }
+    case OC_LIGHT_DISTANT:
+      l.fx = toOc(xfmVector(xfm.l, V(l.fx))); l.fy = toOc(xfmVector(xfm.l, V(l.fy))); l.fz = toOc(xfmVector(xfm.l, V(l.fz)));
+      break;
+    default: break; // ambient
+    }
+    return l;
+  };
+  std::vector<std::pair<OcLight, vec3f>> all; // (light in world space, ambient radiance)
   if (lights)
-    for (size_t i = 0; i < lights->size(); i++) all.push_back(dynamic_cast<Light *>(lights->objectAt(i)));
+    for (size_t i = 0; i < lights->size(); i++)
+      if (Light *l = dynamic_cast<Light *>(lights->objectAt(i))) all.push_back({l->sh, l->ambientRadiance});
   if (instances)
     for (size_t i = 0; i < instances->size(); i++) {
       Instance *in = dynamic_cast<Instance *>(instances->objectAt(i));
       if (in && in->group && in->group->lights)
-        for (size_t k = 0; k < in->group->lights->size(); k++) {
-          if (!in->identity) postStatusMsg(OSP_LOG_WARNING, "cuda device: lights in transformed instances are used untransformed");
-          all.push_back(dynamic_cast<Light *>(in->group->lights->objectAt(k)));
-        }
+        for (size_t k = 0; k < in->group->lights->size(); k++)
+          if (Light *l = dynamic_cast<Light *>(in->group->lights->objectAt(k)))
+            all.push_back({in->identity ? l->sh : inWorldSpace(l->sh, in->xfm), l->ambientRadiance});
     }
   std::vector<OcLight> pt, sv;
   uint32_t visibleOnly = 0;
   vec3f aoColor = make_vec3f(0.f);
-  for (Light *l : all) {
-    if (!l) continue;
-    pt.push_back(l->sh);
-    if (l->sh.type == OC_LIGHT_AMBIENT) {
+  for (const auto &la : all) {
+    const OcLight &lsh = la.first;
+    pt.push_back(lsh);
+    if (lsh.type == OC_LIGHT_AMBIENT) {
       // SciVisData.cpp:17-30: ambient lights go to the visible-only front partition
-      if (visibleOnly == sv.size()) sv.push_back(l->sh);
-      else { sv.push_back(sv[visibleOnly]); sv[visibleOnly] = l->sh; }
+      if (visibleOnly == sv.size()) sv.push_back(lsh);
+      else { sv.push_back(sv[visibleOnly]); sv[visibleOnly] = lsh; }
       visibleOnly++;
-      aoColor = aoColor + l->ambientRadiance;
+      aoColor = aoColor + la.second;
     } else
-      sv.push_back(l->sh);
+      sv.push_back(lsh);
   }
   if (!pt.empty()) {
     std::vector<float> cdf(pt.size(), 1.f);

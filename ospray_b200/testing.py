@@ -114,6 +114,7 @@ class VolumeSpec:
 class GroupSpec:
     models: List[ModelSpec] = field(default_factory=list)
     volumes: List[VolumeSpec] = field(default_factory=list)
+    lights: List["LightSpec"] = field(default_factory=list)   # group lights: they move with the instance
 
 
 @dataclass
@@ -551,6 +552,14 @@ def to_ospray(scene: SceneSpec):
         group = osp.Group()
         if models: group.set("geometry", models)
         if vmodels: group.set("volume", vmodels)
+        glights = []
+        for ls in inst.group.lights:
+            l = osp.Light(ls.type)
+            for k, v in ls.params.items():
+                l.set(k, v)
+            glights.append(l.commit())
+        if glights: group.set("light", glights)
+        keep += glights
         group.commit()
         oi = osp.Instance(group)
         if inst.xfm is not None:

@@ -20,6 +20,27 @@ def instanced_boxes_and_spheres():
     return T.SceneSpec(instances=inst, lights=lights)
 
 
+def instance_lights():
+    """lights that live in the instances' groups and move with them (World.cpp:120-150, QuadLight.ispc:14-33, PointLight.ispc:17-29,
+    SpotLight.ispc:14-24, DirectionalLight.cpp:36-44): a rotated + scaled + shifted instance carries a quad, a spot and a
+    sphere light, a second (sheared) instance a distant light; one more group light sits in an identity instance"""
+    s = instanced_boxes_and_spheres()
+    s.lights = [T.LightSpec("ambient", {"intensity": 0.15})]
+    boxes = s.instances[1].group
+    boxes.lights = [T.LightSpec("quad", {"position": (-2.0, 6.0, -1.0), "edge1": (4.0, 0.0, 0.0), "edge2": (0.0, 1.0, 3.0), "intensity": 4.0,
+                                          "color": (1.0, 0.8, 0.6)}),
+                    T.LightSpec("spot", {"position": (6.0, 5.0, 8.0), "direction": (-0.5, -0.6, -0.7), "openingAngle": 70.0, "penumbraAngle": 10.0,
+                                          "radius": 1.5, "intensity": 300.0, "color": (0.6, 0.8, 1.0)}),
+                    T.LightSpec("sphere", {"position": (-5.0, 3.0, 6.0), "radius": 1.0, "intensity": 150.0})]
+    shear = np.array([1.0, 0.2, 0.0, -0.3, 0.9, 0.1, 0.0, 0.4, 1.1, 0.2, -0.1, 0.3], np.float32)
+    sph = T.GroupSpec(models=s.instances[0].group.models, lights=[T.LightSpec("distant", {"direction": (0.5, -0.6, 0.3), "intensity": 1.5,
+                                                                                            "angularDiameter": 3.0})])
+    s.instances[0] = T.InstanceSpec(sph, xfm=shear, id=11)
+    s.instances[2].group = T.GroupSpec(models=s.instances[2].group.models,
+                                       lights=[T.LightSpec("sphere", {"position": (0.0, 1.5, -1.0), "intensity": 2.0, "color": (1.0, 0.5, 0.5)})])
+    return s
+
+
 def translucent_cornell():
     """cornell box with a semi-transparent specular material: transparent shadows, Specular + Transmission lobes"""
     s = T.cornell_box()
@@ -475,6 +496,8 @@ CASES = {
     "principled_thin_pt": (lambda: principled_cornell("thin"), "pathtracer", {"pixelSamples": 2}, 2),
     # debug renderer (render/debug/DebugRenderer.ispc), every method the device accepts
     "debug_testFrame": (T.cornell_box, "debug", {"method": "testFrame", "pixelSamples": 2}, 2),
+    "instance_lights_pt": (instance_lights, "pathtracer", {"pixelSamples": 2, "lightSamples": 2}, 1),
+    "instance_lights_scivis": (instance_lights, "scivis", {"pixelSamples": 1, "aoSamples": 1, "shadows": True, "visibleLights": True}, 1),
     "debug_rayDir": (T.cornell_box, "debug", {"method": "rayDir"}, 1),
     "debug_eyeLight": (T.cornell_box, "debug", {"method": "eyeLight", "pixelSamples": 2, "backgroundColor": (0.1, 0.2, 0.3, 1.0)}, 1),
     "debug_Ng": (instanced_boxes_and_spheres, "debug", {"method": "Ng"}, 1),

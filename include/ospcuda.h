@@ -196,6 +196,7 @@ typedef struct {
    * microfacetTables: the device's albedo tables (ospcuda_microfacet_albedo_tables; MicrofacetAlbedoTables.ispc) */
   const float *microfacetTables;
   uint32_t hasTextures;        /* any of the maps below is set (kernels without texture support skip them all) */
+  uint32_t cutout;             /* a map can make the surface transmit along shadow rays: map_d, or map_kd with an alpha channel */
   float bumpRot[4];            /* OBJ.cpp:43-44: orthogonal part of map_bump's 2D transform, transposed (vx, vy) */
   /* OBJ: map_d, map_kd, map_ks, map_ns, map_bump (OBJShared.h:19-31); thinGlass: mapKd = map_attenuationColor */
   OcTextureParam mapD, mapKd, mapKs, mapNs, mapBump;

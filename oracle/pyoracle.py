@@ -112,7 +112,7 @@ PRINCIPLED_DEFAULTS = {
 class Material(C.Structure):
     _fields_ = [("type", C.c_uint32), ("d", C.c_float), ("Kd", Vec3), ("Ks", Vec3), ("Ns", C.c_float), ("Tf", Vec3),
                 ("eta", C.c_float), ("attenuation", Vec3), ("attenuationScale", C.c_float), ("emission", Vec3),
-                ("transparency", C.c_float), ("isEmissive", C.c_uint32), ("microfacetTables", C.c_void_p), ("hasTextures", C.c_uint32),
+                ("transparency", C.c_float), ("isEmissive", C.c_uint32), ("microfacetTables", C.c_void_p), ("hasTextures", C.c_uint32), ("cutout", C.c_uint32),
                 ("bumpRot", C.c_float * 4), ("mapD", TextureParam), ("mapKd", TextureParam), ("mapKs", TextureParam),
                 ("mapNs", TextureParam), ("mapBump", TextureParam), ("principled", Principled), ("carPaint", C.POINTER(CarPaint))]
 

@@ -84,6 +84,7 @@ struct PtArgs
   // lane that answers a shadow ray folds the answer into its path and finishes a path that only waited for it (its entry in
   // the path queue stays and is skipped by the next SHADE through the PT_DEAD flags word)
   uint32_t foldInTrace;
+  uint32_t sortShade;   // extended-material frames: SHADE sorts each CTA's queue entries by material class (OSPCUDA_PT_SORT_SHADE)
 };
 
 __device__ __forceinline__ void ptAppend(uint32_t *q, uint32_t *cnt, uint32_t p)
@@ -371,7 +372,7 @@ __device__ __forceinline__ bool ptOccluderIsOpaque(const OcWorld *world, const O
     if (!(gf & OC_GEOMFLAG_ALPHA_ALL_ONE) || !(maxContrib * 1e-6f <= ren.minContribution)) return false;
   }
   const OcMaterial *mat = getMaterial(world, ren, m, primID);
-  if (mat && (mat->type == OC_MATERIAL_THINGLASS || mat->hasTextures)) return false; // texture maps may cut the surface out
+  if (mat && (mat->type == OC_MATERIAL_THINGLASS || mat->cutout)) return false; // map_d / the alpha of map_kd may cut the surface out
   if (mat && mat->type == OC_MATERIAL_LUMINOUS) return mat->transparency == 0.f; // Luminous_getTransparency
   if (mat && mat->type == OC_MATERIAL_GLASS) return false;
   if (mat && mat->type == OC_MATERIAL_PRINCIPLED) // Principled_getTransparency's early exit (Principled.ispc:452-454)
@@ -970,20 +971,67 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
   return alive ? 1u : 2u;
 }
 
+// Does the vertex this path is about to shade carry one of the extended materials (metal ... carPaint)?  Read from the hit the
+// way postIntersect will (instance -> model -> material); ended paths and misses answer no.
+__device__ __forceinline__ bool ptPathShadesExtendedMaterial(const PtArgs &k, uint32_t entry)
+{
+  if (entry & PT_Q_DONE) return false;
+  const uint32_t p = entry & ~PT_Q_DONE;
+  const uint32_t geomID = __float_as_uint(k.s.hit1[p].w);
+  if (geomID == OC_INVALID_ID) return false;
+  const uint32_t instID = k.s.hitInst[p], primID = __float_as_uint(k.s.hit0[p].w);
+  const OcInstance *inst = k.a.world->instances + instID;
+  if (geomID >= inst->group->numModels) return false;
+  const OcMaterial *mat = getMaterial(k.a.world, k.a.ren, inst->group->models + geomID, primID);
+  return mat && mat->type >= OC_MATERIAL_METAL;
+}
+
 // MIN_BLOCKS: resident CTAs per SM the register budget is set for (4: 128 registers, 5: 96, 6: 80)
 template <bool VOL, int MIN_BLOCKS, bool TEX>
 __global__ void __launch_bounds__(PT_TRACE_BLOCK, MIN_BLOCKS) ptShadeKernel(const __grid_constant__ PtArgs k)
 {
   __shared__ uint32_t s_stack[OC_STACK_SHARED * PT_TRACE_BLOCK]; // the out-of-line transparent-shadow loop walks the hierarchy
-  if (frameCancelled(k.a.fb)) return;
+  if (TEX) { // (one answer per CTA: its threads meet at barriers below)
+    __shared__ int s_cancelled;
+    if (threadIdx.x == 0) s_cancelled = frameCancelled(k.a.fb) ? 1 : 0;
+    __syncthreads();
+    if (s_cancelled) return;
+  } else if (frameCancelled(k.a.fb)) return;
   if (k.a.fb.control && blockIdx.x == 0 && threadIdx.x == 0) atomicMax(k.a.fb.control + 1, k.progressUnit);
   const uint32_t n = *k.cntPathIn;
   uint32_t extraShadow = 0;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t p = k.pathIn[i] & ~PT_Q_DONE;
-    const uint32_t r = ptShadeStep<VOL, true, TEX>(k, p, s_stack + threadIdx.x, extraShadow);
-    if (r) ptAppend(k.pathOut, k.cntPathOut, r == 2u ? (p | PT_Q_DONE) : p);
-  }
+  if (TEX) {
+    // Extended-material frames: after the first bounce the paths of a warp sit on unrelated surfaces, and a warp that holds
+    // ONE principled vertex among 31 OBJ ones runs both material codes one after the other. Every CTA therefore sorts its 128
+    // queue entries by material class first -- extended materials to the front lanes, the rest to the back -- so that all but
+    // one of its warps shade one class. (Which lane shades which path has no effect on the results: a path owns its pixel.)
+    __shared__ uint32_t s_perm[PT_TRACE_BLOCK];
+    __shared__ uint32_t s_cnt[2];
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+      if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0u;
+      __syncthreads();
+      const uint32_t i = base + threadIdx.x;
+      if (i < n) {
+        const uint32_t entry = k.pathIn[i];
+        if (k.sortShade && ptPathShadesExtendedMaterial(k, entry)) s_perm[atomicAdd(&s_cnt[0], 1u)] = entry;
+        else s_perm[blockDim.x - 1u - atomicAdd(&s_cnt[1], 1u)] = entry;
+      }
+      __syncthreads();
+      const bool mine = threadIdx.x < s_cnt[0] || threadIdx.x >= blockDim.x - s_cnt[1];
+      const uint32_t entry = mine ? s_perm[threadIdx.x] : 0u;
+      __syncthreads(); // s_perm / s_cnt are rewritten by the next chunk
+      if (mine) {
+        const uint32_t p = entry & ~PT_Q_DONE;
+        const uint32_t r = ptShadeStep<VOL, true, TEX>(k, p, s_stack + threadIdx.x, extraShadow);
+        if (r) ptAppend(k.pathOut, k.cntPathOut, r == 2u ? (p | PT_Q_DONE) : p);
+      }
+    }
+  } else
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const uint32_t p = k.pathIn[i] & ~PT_Q_DONE;
+      const uint32_t r = ptShadeStep<VOL, true, TEX>(k, p, s_stack + threadIdx.x, extraShadow);
+      if (r) ptAppend(k.pathOut, k.cntPathOut, r == 2u ? (p | PT_Q_DONE) : p);
+    }
   ptCountRays(k.a.fb, 0u, 0u, extraShadow);
 }
 

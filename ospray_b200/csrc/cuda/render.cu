@@ -1009,6 +1009,7 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles, bool
   static const bool foldEnv = !(getenv("OSPCUDA_PT_FOLD_IN_TRACE") && atoi(getenv("OSPCUDA_PT_FOLD_IN_TRACE")) == 0);
   // (worlds whose occluders may be transparent keep the fold in SHADE: the occluder's material chain and the closest-hit
   // loop are better off there -- C4 5.0 vs 5.6 ms)
+  static const bool sortShade = !(getenv("OSPCUDA_PT_SORT_SHADE") && atoi(getenv("OSPCUDA_PT_SORT_SHADE")) == 0);
   const bool foldInTrace = !ao && !hasVol && nls == 1 && foldEnv && fa.ren.worldShadowOpaque != 0;
   const uint32_t progressStages = ao ? 2u : std::min(maxDepth + 1u, tailFrom == 0xffffffffu ? maxDepth + 1u : tailFrom + 1u);
   k.progressTotal = ((ownedTiles + tilesPerBatch - 1) / tilesPerBatch) * (uint32_t)fa.ren.spp * progressStages;
@@ -1056,6 +1057,7 @@ int renderPathTracerWavefront(const oc::FrameArgs &fa, uint32_t ownedTiles, bool
         k.shadowIn = d == 0 ? nullptr : k.s.shadowQ[q]; k.cntShadowIn = d == 0 ? nullptr : C(d, 2);
         k.fetchCursor = C(d, 3);
         k.foldInTrace = foldInTrace ? 1u : 0u;
+        k.sortShade = sortShade ? 1u : 0u;
         {
           ProfScope ps(0, st);
           switch (g_pt.traceVariant) {

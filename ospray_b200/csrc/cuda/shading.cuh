@@ -667,10 +667,18 @@ __device__ __forceinline__ SampleRes OBJ_sample(const ObjBSDF &b, vec3f wo, vec2
 // ---- metal and plastic (extended-material kernels only) -------------------------------------------------------------
 // Metal_getBSDF (materials/Metal.ispc:18-46, RGB form) and Plastic_getBSDF (materials/Plastic.ispc:25-67): fills `b` (frame,
 // albedo, scattering type, kind) and the family state `x`; false: not one of these materials
+// (out of line: the OBJ path of the extended-material kernels keeps its registers)
+static __device__ __noinline__ void Ext_getBSDFImpl(ObjBSDF &b, ExtBSDF &x, const DifferentialGeometry &dg, const Medium &medium, vec3f rayDir);
 __device__ __forceinline__ bool Ext_getBSDF(ObjBSDF &b, ExtBSDF &x, const DifferentialGeometry &dg, const Medium &medium, vec3f rayDir)
 {
   const OcMaterial *m = dg.material;
   if (!m || m->type < OC_MATERIAL_METAL) return false;
+  Ext_getBSDFImpl(b, x, dg, medium, rayDir);
+  return true;
+}
+static __device__ __noinline__ void Ext_getBSDFImpl(ObjBSDF &b, ExtBSDF &x, const DifferentialGeometry &dg, const Medium &medium, vec3f rayDir)
+{
+  const OcMaterial *m = dg.material;
   b.valid = true;
   b.importanceSum = 1.f; b.impL = b.impT = b.impS = 0.f;
   b.Kd = b.T = b.ks = b.specWeight = make_vec3f(0.f); b.ns = 0.f;
@@ -681,13 +689,13 @@ __device__ __forceinline__ bool Ext_getBSDF(ObjBSDF &b, ExtBSDF &x, const Differ
     b.frame.vz = x.pr.rootN; // (only the normal AOV reads it)
     b.albedo = x.pr.albedo;
     b.scatteringType = x.pr.scatteringType;
-    return true;
+    return;
   }
   b.frame = frame(dg.Ns);
   if (m->type == OC_MATERIAL_CARPAINT) {
     CarPaint_getBSDF(x.car, b.frame.vz, b.albedo, b.scatteringType, *m->carPaint, m->microfacetTables, dg, rayDir);
     b.kind = BSDF_KIND_CARPAINT;
-    return true;
+    return;
   }
   if (m->type == OC_MATERIAL_GLASS) { // Glass_getBSDF (materials/Glass.ispc:14-33): eta = the side the path is on over the other
     x.glassEta = mediumIsOutside(medium, m->principled) ? m->principled.outsideIor * (1.f / m->eta) : m->eta * (1.f / m->principled.outsideIor);
@@ -695,7 +703,7 @@ __device__ __forceinline__ bool Ext_getBSDF(ObjBSDF &b, ExtBSDF &x, const Differ
     b.kind = BSDF_KIND_GLASS;
     b.albedo = make_vec3f(1.0f);
     b.scatteringType = SC_SPECULAR;
-    return true;
+    return;
   }
   if (m->type == OC_MATERIAL_VELVET) { // Velvet_getBSDF (materials/Velvet.ispc:22-60)
     VelvetBSDF &v = x.velvet;
@@ -706,7 +714,7 @@ __device__ __forceinline__ bool Ext_getBSDF(ObjBSDF &b, ExtBSDF &x, const Differ
     b.kind = BSDF_KIND_VELVET;
     b.albedo = make_vec3f(0.f) + v.R0 * 1.f + v.R1 * 1.f;
     b.scatteringType = SC_DIFFUSE_REFLECTION;
-    return true;
+    return;
   }
   if (m->type == OC_MATERIAL_METALLICPAINT) { // MetallicPaint_getBSDF (materials/MetallicPaint.ispc:36-89)
     MetallicPaintSub &p = x.paint;
@@ -735,7 +743,7 @@ __device__ __forceinline__ bool Ext_getBSDF(ObjBSDF &b, ExtBSDF &x, const Differ
     DielectricLayer_init(x.layer, p.albedo, p.scatteringType, m->eta, make_vec3f(1.0f), 1.0f, 1.0f);
     b.kind = BSDF_KIND_METALLICPAINT;
     b.albedo = x.layer.albedo; b.scatteringType = x.layer.scatteringType;
-    return true;
+    return;
   }
   if (m->type == OC_MATERIAL_METAL || m->type == OC_MATERIAL_ALLOY) {
     // Metal_getBSDF (Metal.ispc:18-46, RGB form), Alloy_getBSDF (Alloy.ispc:16-51: Schlick Fresnel between color and edgeColor)
@@ -766,7 +774,7 @@ __device__ __forceinline__ bool Ext_getBSDF(ObjBSDF &b, ExtBSDF &x, const Differ
       b.albedo = Favg * x.cond.Eavg;
       b.scatteringType = SC_GLOSSY_REFLECTION;
     }
-    return true;
+    return;
   }
   x.lambert.init(b.frame, toV(m->Kd));
   if (m->Ns == 0.0f) {
@@ -779,7 +787,6 @@ __device__ __forceinline__ bool Ext_getBSDF(ObjBSDF &b, ExtBSDF &x, const Differ
   }
   b.albedo = x.layer.albedo;
   b.scatteringType = x.layer.scatteringType;
-  return true;
 }
 static __device__ __noinline__ EvalRes Ext_eval(const ObjBSDF &b, const ExtBSDF &x, vec3f wo, vec3f wi)
 {

@@ -629,6 +629,7 @@ void Material::commit()
   wasEmissive = m.isEmissive != 0;
   const bool hasTextures = texD || texKd || texKs || texNs || texBump;
   m.hasTextures = hasTextures ? 1u : 0u;
+  m.cutout = (m.type == OC_MATERIAL_OBJ && (texD || (texKd && texKd->sh.hasAlpha))) ? 1u : 0u;
   if (hasTextures && !hadTextures) device.texturedMaterials++;
   if (!hasTextures && hadTextures) device.texturedMaterials--;
   device.setMaterial(slot, m);
@@ -1370,7 +1371,7 @@ uint32_t World::computeShadowOpaque(const Renderer *renderer) const
         }
         if (slot >= table.size()) return 0u;
         const OcMaterial &mt = table[slot];
-        if (mt.hasTextures || mt.type == OC_MATERIAL_THINGLASS) return 0u;
+        if (mt.cutout || mt.type == OC_MATERIAL_THINGLASS) return 0u;
         if (mt.type == OC_MATERIAL_LUMINOUS && mt.transparency != 0.f) return 0u;
         if (mt.type == OC_MATERIAL_PRINCIPLED || mt.type == OC_MATERIAL_GLASS) return 0u; // (cut-out opacity, transmission: decided per occluder)
         if (mt.type == OC_MATERIAL_OBJ && !(mt.d == 1.f && mt.Tf.x == 0.f && mt.Tf.y == 0.f && mt.Tf.z == 0.f)) return 0u;

@@ -15,10 +15,12 @@ enum { // OSPTextureFormat (OSPEnums.h)
 enum { TEX_FILTER_LINEAR = 0, TEX_FILTER_NEAREST = 1 };
 enum { TEX_WRAP_REPEAT = 0, TEX_WRAP_MIRRORED_REPEAT = 1, TEX_WRAP_CLAMP_TO_EDGE = 2 };
 
-__device__ __forceinline__ float texSrgbToLinear(float x)
-{
-  return x <= 0.04045f ? x * (1.f / 12.92f) : powf((x + 0.055f) * (1.f / 1.055f), 2.4f);
-}
+// srgb_to_linear of an 8-bit texel value: the 256 possible results as a table (tools/gen_srgb_table.py: the C library's powf, i.e.
+// the values the reference's scalar form computes), instead of a ~150-instruction powf body per channel per texel
+static __device__ const float texSrgbTable[256] = {
+#include "srgb_table.inc"
+};
+__device__ __forceinline__ float texSrgb8ToLinear(uint32_t c) { return __ldg(texSrgbTable + c); }
 __device__ __forceinline__ float texHalf(uint32_t bits) { return __half2float(__ushort_as_half((unsigned short)bits)); }
 
 // Texture2DFormats.ispc getTexel_*
@@ -33,25 +35,24 @@ static __device__ __noinline__ vec4f texGetTexel(uint32_t format, const void *da
   case TEXF_RGBA8:
   case TEXF_SRGBA: {
     const uint32_t c = __ldg(u32 + idx);
-    const vec4f v = make_vec4f((float)(c & 0xff), (float)((c >> 8) & 0xff), (float)((c >> 16) & 0xff), (float)(c >> 24)) * B2F;
-    if (format == TEXF_RGBA8) return v;
-    return make_vec4f(texSrgbToLinear(v.x), texSrgbToLinear(v.y), texSrgbToLinear(v.z), v.w);
+    if (format == TEXF_RGBA8) return make_vec4f((float)(c & 0xff), (float)((c >> 8) & 0xff), (float)((c >> 16) & 0xff), (float)(c >> 24)) * B2F;
+    return make_vec4f(texSrgb8ToLinear(c & 0xff), texSrgb8ToLinear((c >> 8) & 0xff), texSrgb8ToLinear((c >> 16) & 0xff), (float)(c >> 24) * B2F);
   }
   case TEXF_RGBA32F: { const float4 v = __ldg((const float4 *)data + idx); return make_vec4f(v.x, v.y, v.z, v.w); }
   case TEXF_RGB8:
   case TEXF_SRGB: {
-    const vec3f v = make_vec3f((float)__ldg(u8 + 3 * idx), (float)__ldg(u8 + 3 * idx + 1), (float)__ldg(u8 + 3 * idx + 2)) * B2F;
-    if (format == TEXF_RGB8) return make_vec4f(v, 1.f);
-    return make_vec4f(texSrgbToLinear(v.x), texSrgbToLinear(v.y), texSrgbToLinear(v.z), 1.f);
+    const uint32_t r = __ldg(u8 + 3 * idx), g = __ldg(u8 + 3 * idx + 1), b = __ldg(u8 + 3 * idx + 2);
+    if (format == TEXF_RGB8) return make_vec4f(make_vec3f((float)r, (float)g, (float)b) * B2F, 1.f);
+    return make_vec4f(texSrgb8ToLinear(r), texSrgb8ToLinear(g), texSrgb8ToLinear(b), 1.f);
   }
   case TEXF_RGB32F: return make_vec4f(__ldg(f32 + 3 * idx), __ldg(f32 + 3 * idx + 1), __ldg(f32 + 3 * idx + 2), 1.f);
   case TEXF_R8: return make_vec4f(__ldg(u8 + idx) * B2F, 0.f, 0.f, 1.f);
   case TEXF_R32F: return make_vec4f(__ldg(f32 + idx), 0.f, 0.f, 1.f);
-  case TEXF_L8: { const float l = texSrgbToLinear(__ldg(u8 + idx) * B2F); return make_vec4f(l, l, l, 1.f); }
+  case TEXF_L8: { const float l = texSrgb8ToLinear(__ldg(u8 + idx)); return make_vec4f(l, l, l, 1.f); }
   case TEXF_RA8: { const uint32_t t = __ldg(u16 + idx); return make_vec4f((t & 0xff) * B2F, 0.f, 0.f, (t >> 8) * B2F); }
   case TEXF_LA8: {
     const uint32_t t = __ldg(u16 + idx);
-    const float l = texSrgbToLinear((t & 0xff) * B2F);
+    const float l = texSrgb8ToLinear(t & 0xff);
     return make_vec4f(l, l, l, (t >> 8) * B2F);
   }
   case TEXF_RGBA16: {

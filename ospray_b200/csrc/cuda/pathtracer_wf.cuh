@@ -375,8 +375,21 @@ __device__ __forceinline__ bool ptOccluderIsOpaque(const OcWorld *world, const O
   if (mat && (mat->type == OC_MATERIAL_THINGLASS || mat->cutout)) return false; // map_d / the alpha of map_kd may cut the surface out
   if (mat && mat->type == OC_MATERIAL_LUMINOUS) return mat->transparency == 0.f; // Luminous_getTransparency
   if (mat && mat->type == OC_MATERIAL_GLASS) return false;
-  if (mat && mat->type == OC_MATERIAL_PRINCIPLED) // Principled_getTransparency's early exit (Principled.ispc:452-454)
-    return !mat->principled.maps && 1.f - clampf(mat->principled.opacity, 0.f, 1.f) <= PR_EPS && clampf(mat->principled.transmission, 0.f, 1.f) <= PR_EPS;
+  if (mat && mat->type == OC_MATERIAL_PRINCIPLED) {
+    const OcPrincipled &q = mat->principled;
+    if (q.maps) return false;
+    // Principled_getTransparency's early exit (Principled.ispc:452-454)
+    if (1.f - clampf(q.opacity, 0.f, 1.f) <= PR_EPS && clampf(q.transmission, 0.f, 1.f) <= PR_EPS) return true;
+    // solid ROUGH glass lets no shadow ray through either (:477-483: T stays 0 unless roughness < EPS or eta == 1), whichever
+    // side the ray comes from; with opacity 1 the cut-out term is exactly 0 too
+    if (!q.thin && q.opacity >= 1.f && !(q.roughness < PR_EPS)) {
+      float ior = q.ior;
+      if (ior < 1.f) ior = 1.f / ior;
+      const float etaIn = clampf(q.outsideIor * (1.f / ior), 1.f / 3.f, 3.f), etaOut = clampf(ior * (1.f / q.outsideIor), 1.f / 3.f, 3.f);
+      if (fabsf(etaIn - 1.f) > PR_EPS && fabsf(etaOut - 1.f) > PR_EPS) return true;
+    }
+    return false;
+  }
   if (!mat || mat->type != OC_MATERIAL_OBJ) return true; // no / foreign material: transparency 0 (shading.cuh)
   return mat->d == 1.f && mat->Tf.x == 0.f && mat->Tf.y == 0.f && mat->Tf.z == 0.f;
 }

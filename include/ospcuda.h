@@ -275,7 +275,7 @@ typedef struct OcInstanceS {
   const float *modelAreaPDF;
 } OcInstance;
 
-enum { OC_LIGHT_AMBIENT = 0, OC_LIGHT_DISTANT = 2, OC_LIGHT_SPHERE = 4, OC_LIGHT_QUAD = 5, OC_LIGHT_SPOT = 6,
+enum { OC_LIGHT_AMBIENT = 0, OC_LIGHT_DISTANT = 2, OC_LIGHT_HDRI = 3, OC_LIGHT_SPHERE = 4, OC_LIGHT_QUAD = 5, OC_LIGHT_SPOT = 6,
        OC_LIGHT_GEOMETRY = 8 }; /* values of ispc::LightType */
 struct OcInstanceS;
 /* lights (reference: lights/LightShared.h:79-110, QuadLightShared.h, DirectionalLightShared.h,
@@ -296,6 +296,12 @@ typedef struct {
   /* geometry light: the proxy the pathtracer makes for every geometric model with emissive primitives
    * (ispc::GeometryLight, render/pathtracer/GeometryLightShared.h; PathTracerData.cpp:87-160): the model and the instance
    * it sits in, the emissive primitives, the CDF of their world-space areas, pdf = 1 / total area */
+  /* hdri (ispc::HDRILight, lights/HDRILightShared.h, HDRILight.cpp:20-97): fx / fy / fz = light2world, wx / wy / wz =
+   * world2light, radiance = radianceScale, the latitude / longitude map and the CDFs of its importance distribution
+   * (ospcuda_hdri_distribution: cdfX = sizeX * sizeY floats, row-wise; cdfY = sizeY floats) */
+  const OcTexture2D *hdriMap;
+  const float *hdriCdfX, *hdriCdfY;
+  OcVec3f wx, wy, wz;
   const OcModel *geoModel;
   const struct OcInstanceS *geoInstance;
   const int32_t *geoPrimIDs;
@@ -518,6 +524,10 @@ OSPCUDA_API int ospcuda_trace(const OcWorld *d_world, OcRayHit *d_rays, uint32_t
  * render/bsdfs/MicrofacetAlbedoTables.ispc:148-158), computed once per device on first use; *d_tables = the float block
  * (layout: csrc/cuda/microfacet.cuh OC_MFT_*), numFloats its length */
 OSPCUDA_API int ospcuda_microfacet_albedo_tables(const float **d_tables, uint32_t *numFloats);
+/* the importance distribution of an hdri light (reference: HDRILight_initDistribution, lights/HDRILight.ispc:152-231 +
+ * Distribution1D_create, math/Distribution1D.ispc:14-42): importance = sin(theta) * luminance(texel) per texel, row CDFs in
+ * d_cdfX (sizeX * sizeY floats), the CDF of the row sums in d_cdfY (sizeY floats); d_map = a committed texture (device) */
+OSPCUDA_API int ospcuda_hdri_distribution(const OcTexture2D *d_map, int32_t sizeX, int32_t sizeY, float *d_cdfX, float *d_cdfY);
 OSPCUDA_API int ospcuda_texture_sample(const OcTextureParam *param, const float *d_st, const float *d_footprint, uint32_t n,
     float *d_out);
 

@@ -2198,6 +2198,7 @@ ORACLE_API void oracle_transform_light(OcLight *l, const float *x)
     break;
   }
   case OC_LIGHT_DISTANT:
+  case OC_LIGHT_HDRI: // HDRILight.cpp:52-55: light2world = xfm.l * light2world (world2light = its inverse, taken by the user of the struct)
     l->fx = oc(xfmVector(xfm.l, v3(l->fx))); l->fy = oc(xfmVector(xfm.l, v3(l->fy))); l->fz = oc(xfmVector(xfm.l, v3(l->fz)));
     break;
   default: break; // ambient

@@ -148,7 +148,8 @@ class Light(C.Structure):
     _fields_ = [("type", C.c_uint32), ("isVisible", C.c_uint32), ("radiance", Vec3), ("position", Vec3), ("edge1", Vec3),
                 ("edge2", Vec3), ("nnormal", Vec3), ("ppdf", C.c_float), ("fx", Vec3), ("fy", Vec3), ("fz", Vec3),
                 ("cosAngle", C.c_float), ("pdf", C.c_float), ("intensity", Vec3), ("radius", C.c_float),
-                ("cosAngleScale", C.c_float), ("innerRadius", C.c_float), ("geoModel", C.c_void_p), ("geoInstance", C.c_void_p),
+                ("cosAngleScale", C.c_float), ("innerRadius", C.c_float), ("hdriMap", C.c_void_p), ("hdriCdfX", C.c_void_p), ("hdriCdfY", C.c_void_p),
+                ("wx", Vec3), ("wy", Vec3), ("wz", Vec3), ("geoModel", C.c_void_p), ("geoInstance", C.c_void_p),
                 ("geoPrimIDs", C.c_void_p), ("geoDistribution", C.c_void_p), ("geoNumPrimitives", C.c_uint32), ("geoPdf", C.c_float)]
 
 
@@ -542,8 +543,19 @@ class Scene:
         for ls, lxfm in all_lights:
             l = Light()
             p = ls.params
-            t = {"ambient": OC_LIGHT_AMBIENT, "distant": OC_LIGHT_DISTANT, "quad": OC_LIGHT_QUAD, "sphere": 4, "spot": 6}[ls.type]
-            if ls.type == "spot":
+            t = {"ambient": OC_LIGHT_AMBIENT, "distant": OC_LIGHT_DISTANT, "quad": OC_LIGHT_QUAD, "sphere": 4, "spot": 6, "hdri": 3}[ls.type]
+            if ls.type == "hdri":  # lights/HDRILight.cpp:73-97 (frame from direction / up; the distribution is built by the checker's own code)
+                f = np.float32
+                nrm = lambda v: (v / np.sqrt(np.dot(v, v), dtype=np.float32)).astype(np.float32)
+                d, up = np.asarray(p.get("direction", (0, 0, 1)), f), np.asarray(p.get("up", (0, 1, 0)), f)
+                vx = nrm(-d); vy = nrm(np.cross(vx, up).astype(f)); vz = np.cross(vx, vy).astype(f)
+                scale = (np.asarray(p.get("color", (1, 1, 1)), f) * f(p.get("intensity", 1.0))).astype(f)
+                l.type, l.isVisible, l.radiance = 3, int(p.get("visible", True)), Vec3(*map(float, scale))
+                l.fx, l.fy, l.fz = Vec3(*map(float, vx)), Vec3(*map(float, vy)), Vec3(*map(float, vz))
+                tex = make_texture2d(p["map"], self.keep, self.mipmaps)
+                self.keep.append(tex)
+                l.hdriMap = C.cast(C.pointer(tex), C.c_void_p)
+            elif ls.type == "spot":
                 L.oracle_commit_spot_light(_f3(p.get("color", (1, 1, 1))), float(p.get("intensity", 1.0)), int(p.get("visible", True)),
                                            _f3(p.get("position", (0, 0, 0))), _f3(p.get("direction", (0, 0, 1))),
                                            float(p.get("openingAngle", 180.0)), float(p.get("penumbraAngle", 5.0)),
@@ -558,14 +570,15 @@ class Scene:
             if lxfm is not None:
                 L.oracle_transform_light(C.byref(l), lxfm.ctypes.data_as(C.POINTER(C.c_float)))
             pt.append(l)
-            if t == OC_LIGHT_AMBIENT:
+            if t == OC_LIGHT_AMBIENT or t == 3:  # ambient and hdri: visible only under scivis (SciVisData.cpp:17-52)
                 if visible_only == len(sv):
                     sv.append(l)
                 else:
                     sv.append(sv[visible_only])
                     sv[visible_only] = l
                 visible_only += 1
-                ao += np.array([l.radiance.x, l.radiance.y, l.radiance.z], np.float32)
+                if t == OC_LIGHT_AMBIENT:
+                    ao += np.array([l.radiance.x, l.radiance.y, l.radiance.z], np.float32)
             else:
                 sv.append(l)
         if pt:

@@ -49,6 +49,8 @@
 #include "lights/SpotLightShared.h"
 #include "lights/DirectionalLightShared.h"
 #include "lights/AmbientLightShared.h"
+#include "lights/HDRILightShared.h"
+#include "math/Distribution2DShared.h"
 #include "render/pathtracer/PathTracerShared.h"
 #include "render/scivis/SciVisShared.h"
 #include "render/ao/AORendererShared.h"
@@ -94,6 +96,7 @@ void LUTPixelFilter_buildLUT(void *self);
 float Distribution1D_create(const int size, float *cdf);
 int GeometricModel_gatherEmissivePrimIDs(void *model, void *renderer, void *instance, int *primIDs, float *distribution, float &pdf);
 void precomputeMicrofacetAlbedoTables(void *tables);
+void HDRILight_initDistribution(const void *map, void *distribution);
 void Mesh_getAreas(const Geometry *const, const int32 *const, const int32, const affine3f &, float *const);
 void Spheres_getAreas(const Geometry *const, const int32 *const, const int32, const affine3f &, float *const);
 }
@@ -178,7 +181,7 @@ struct Scene
   std::deque<std::vector<int>> geoPrimIDs; std::deque<std::vector<float>> geoDistributions;
   std::vector<float> geoCDF;
   std::vector<Instance *> instancePtrs;
-  std::deque<QuadLight> quads; std::deque<PointLight> points; std::deque<SpotLight> spots; std::deque<DirectionalLight> dirs; std::deque<AmbientLight> ambients;
+  std::deque<QuadLight> quads; std::deque<PointLight> points; std::deque<SpotLight> spots; std::deque<DirectionalLight> dirs; std::deque<AmbientLight> ambients; std::deque<HDRILight> hdris; std::deque<Distribution2D> hdriDists; std::deque<std::vector<float>> hdriCdfs;
   std::vector<Light *> ptLights, svLights;
   Instance identityInstance; // stands in for the NULL instance of world lights: the scalar light dispatch reads
                              // self->instance->motionBlur unconditionally (lights/LightDispatch.ispc:36-60)
@@ -529,6 +532,24 @@ void buildScene(Scene &s, const OcWorld *w, const OcRenderer *ren)
       d.frame = linear3f(v3(l.fx), v3(l.fy), v3(l.fz));
       d.irradiance = v3(l.radiance); d.cosAngle = l.cosAngle; d.pdf = l.pdf;
       return &d.super;
+    }
+    if (l.type == OC_LIGHT_HDRI) { // lights/HDRILight.cpp:20-97: the reference builds the importance distribution of the map itself
+      s.hdris.emplace_back();
+      HDRILight &h = s.hdris.back();
+      h.super.isVisible = l.isVisible != 0; h.super.instance = &s.identityInstance;
+      h.radianceScale = v3(l.radiance);
+      h.light2world = linear3f(v3(l.fx), v3(l.fy), v3(l.fz));
+      h.world2light = rcp(h.light2world);
+      h.map = makeTexture(s.textures, l.hdriMap);
+      h.rcpSize = make_vec2f(1.f / h.map->size.x, 1.f / h.map->size.y);
+      s.hdriDists.emplace_back();
+      Distribution2D &d = s.hdriDists.back();
+      d.size = h.map->size; d.rcpSize = make_vec2f(1.f / d.size.x, 1.f / d.size.y);
+      s.hdriCdfs.emplace_back((size_t)d.size.x * d.size.y); d.cdf_x = s.hdriCdfs.back().data();
+      s.hdriCdfs.emplace_back((size_t)d.size.y); d.cdf_y = s.hdriCdfs.back().data();
+      HDRILight_initDistribution(h.map, &d);
+      h.distribution = &d;
+      return &h.super;
     }
     s.ambients.emplace_back();
     AmbientLight &a = s.ambients.back();

@@ -454,7 +454,7 @@ static __device__ __noinline__ vec3f ptVirtualLightsVol(const PtArgs &k, uint32_
   for (uint32_t i = numGeoLights; i < numLights; i++) {
     const OcLight &l = world->lights[i];
     if (!straightPath || l.isVisible) {
-      const LightEval le = Light_eval(l, lastP, lastNs, rdir, lower, upper);
+      const LightEval le = l.type == OC_LIGHT_HDRI ? HDRILight_eval(l, rdir, upper) : Light_eval(l, lastP, lastNs, rdir, lower, upper);
       if (reduce_max(le.radiance) > 0.0f) {
         float misWeight = 1.0f;
         if (selectionPDF) {
@@ -831,7 +831,7 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
         contribution = contribution + ptVirtualLightsVol(k, p, straightPath, throughput, last.P, last.Ns, last.pdf_w, last.numLightSamples,
                                           environment, ray.org, ray.dir, ray.t);
       else
-        contribution = contribution + evaluateVirtualLights(c, straightPath, throughput, last, environment, ray);
+        contribution = contribution + evaluateVirtualLights<TEX>(c, straightPath, throughput, last, environment, ray);
     }
     if (environment) break;
     // (with geometry lights the vertex is still needed: what the path ran into may emit, PathSampler.ispc:247-254)
@@ -900,7 +900,8 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
           const Sample1D sel = Distribution1D_sample((int)numLights, world->lightsCDF, 0, ss);
           const float lightSelectionProb = sel.prob * numLightSamples;
           const OcLight &light = world->lights[sel.idx];
-          LightSample ls = (TEX && light.type == OC_LIGHT_GEOMETRY) ? GeometryLight_sample(world, ren, light, dg, sl) : Light_sample(light, dg, sl);
+          LightSample ls = (TEX && light.type == OC_LIGHT_GEOMETRY) ? GeometryLight_sample(world, ren, light, dg, sl)
+              : (TEX && light.type == OC_LIGHT_HDRI) ? HDRILight_sample(light, sl) : Light_sample(light, dg, sl);
           ls.weight = ls.weight / lightSelectionProb;
           ls.pdf *= lightSelectionProb;
           if (!(reduce_max(ls.weight) <= 0.0f || ls.pdf <= 0.0f)) {

@@ -88,6 +88,7 @@ __device__ __forceinline__ float misHeuristic(float pdf1, float pdf2)
   return pdf1 > 1e17f ? 1.0f : p;
 }
 
+template <bool TEX = false>
 __device__ __forceinline__ vec3f evaluateVirtualLights(Ctx &c, bool straightPath, vec3f throughput, const PathVertexLite &last,
     bool environment, const Ray &ray)
 {
@@ -100,7 +101,7 @@ __device__ __forceinline__ vec3f evaluateVirtualLights(Ctx &c, bool straightPath
   for (uint32_t i = numGeoLights; i < numLights; i++) {
     const OcLight &l = c.world->lights[i];
     if (!straightPath || l.isVisible) {
-      const LightEval le = Light_eval(l, last.P, last.Ns, ray.dir, lower, upper);
+      const LightEval le = (TEX && l.type == OC_LIGHT_HDRI) ? HDRILight_eval(l, ray.dir, upper) : Light_eval(l, last.P, last.Ns, ray.dir, lower, upper);
       if (reduce_max(le.radiance) > 0.0f) {
         float misWeight = 1.0f;
         if (selectionPDF) misWeight = misHeuristic(last.pdf_w, selectionPDF * le.pdf);
@@ -397,7 +398,7 @@ static __device__ vec3f evaluateLightsSciVis(Ctx &c, const Ray &ray)
   for (uint32_t i = 0; i < w->numScivisLights; i++) {
     const OcLight &l = w->scivisLights[i];
     if (!l.isVisible) continue;
-    const LightEval le = Light_eval(l, ray.org, make_vec3f(0.f), ray.dir, ray.t0, ray.t);
+    const LightEval le = (TEX && l.type == OC_LIGHT_HDRI) ? HDRILight_eval(l, ray.dir, ray.t) : Light_eval(l, ray.org, make_vec3f(0.f), ray.dir, ray.t0, ray.t);
     color = color + le.radiance;
   }
   return color;
@@ -1226,6 +1227,34 @@ __global__ void albedoTablesAvgKernel(float *t)
   }
   *avg = fminf(2.f * (sum / (n - 1)), 1.f);
 }
+// HDRILight_calcRowImportance + Distribution1D_create per row (lights/HDRILight.ispc:152-186, math/Distribution1D.ispc:14-42):
+// one thread per row of the map
+__device__ __forceinline__ float hdriCreateCdf(int size, float *cdf)
+{
+  float sum = cdf[0];
+  for (int i = 1; i < size; i++) cdf[i] = sum += cdf[i];
+  const float rcpSum = 1.0f / sum;
+  for (int i = 0; i < size; i++) {
+    const float c = cdf[i];
+    cdf[i] = c >= sum ? 0x1.000002p+0f : c * rcpSum;
+  }
+  return sum;
+}
+__global__ void hdriRowImportanceKernel(const OcTexture2D *map, int sizeX, int sizeY, float *cdfX, float *cdfY)
+{
+  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+  if (y >= sizeY) return;
+  const float rcpX = 1.f / (float)sizeX, rcpY = 1.f / (float)sizeY;
+  const float fy = y * rcpY;
+  const float sinTheta = (float)sin((double)fy * 3.14159265358979323846);
+  float *row = cdfX + (size_t)y * sizeX;
+  for (int x = 0; x < sizeX; x++) {
+    const vec4f col = Texture2D_get(map, make_vec2f(x * rcpX, fy), FLT_MIN);
+    row[x] = sinTheta * luminance(make_vec3f(col.x, col.y, col.z));
+  }
+  cdfY[y] = hdriCreateCdf(sizeX, row);
+}
+__global__ void hdriColumnCdfKernel(int sizeY, float *cdfY) { hdriCreateCdf(sizeY, cdfY); }
 __global__ void textureSampleKernel(OcTextureParam tp, const float *st, const float *fp, uint32_t n, float4 *out)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1254,6 +1283,16 @@ extern "C" int ospcuda_microfacet_albedo_tables(const float **d_tables, uint32_t
   if (d_tables) *d_tables = t;
   if (numFloats) *numFloats = OC_MFT_TOTAL;
   return oc_check(cudaGetLastError(), "ospcuda_microfacet_albedo_tables");
+}
+
+extern "C" int ospcuda_hdri_distribution(const OcTexture2D *d_map, int32_t sizeX, int32_t sizeY, float *d_cdfX, float *d_cdfY)
+{
+  if (!d_map || sizeX <= 0 || sizeY <= 0) return oc_set_error(cudaErrorInvalidValue, "ospcuda_hdri_distribution: no map");
+  cudaStream_t st = (cudaStream_t)ospcuda_stream();
+  oc::hdriRowImportanceKernel<<<(sizeY + 63) / 64, 64, 0, st>>>(d_map, sizeX, sizeY, d_cdfX, d_cdfY);
+  oc::hdriColumnCdfKernel<<<1, 1, 0, st>>>(sizeY, d_cdfY);
+  oc_count_launch(); oc_count_launch();
+  return oc_check(cudaGetLastError(), "ospcuda_hdri_distribution");
 }
 
 extern "C" int ospcuda_texture_sample(const OcTextureParam *param, const float *d_st, const float *d_footprint, uint32_t n, float *d_out)

@@ -1290,6 +1290,60 @@ struct LightSample;
 static __device__ __noinline__ LightSample GeometryLight_sample(const OcWorld *world, const OcRenderer &ren, const OcLight &l,
     const DifferentialGeometry &dg, vec2f s);
 
+// HDRILight_sample / _eval (lights/HDRILight.ispc:14-46, 82-110) with Distribution2D_sample / _pdf (math/Distribution2D.ispc:9-43);
+// only the kernels with texture support know this light (a frame with one runs them)
+static __device__ __noinline__ LightSample HDRILight_sample(const OcLight &l, vec2f s)
+{
+  LightSample res;
+  const OcTexture2D &map = *l.hdriMap;
+  const vec2f rcpSize = make_vec2f(1.f / map.sizeX, 1.f / map.sizeY);
+  const Sample1D sy = Distribution1D_sample(map.sizeY, l.hdriCdfY, 0, s.y);
+  const Sample1D sx = Distribution1D_sample(map.sizeX, l.hdriCdfX, sy.idx * map.sizeX, s.x);
+  vec2f uv = make_vec2f((sx.idx + sx.frac) * rcpSize.x, (sy.idx + sy.frac) * rcpSize.y);
+  const float pdf2d = sx.pdf * sy.pdf;
+  const vec2f halfTexel = make_vec2f((1.f / (float)map.sizeX) * 0.5f, (1.f / (float)map.sizeY) * 0.5f);
+  uv = make_vec2f(uv.x - halfTexel.x, uv.y - halfTexel.y);
+  const float phi = OC_TWO_PI * uv.x, theta = OC_PI * uv.y;
+  float sinTheta, cosTheta;
+  sincosf(theta, &sinTheta, &cosTheta);
+  const vec3f localDir = cartesian(phi, sinTheta, cosTheta);
+  linear3f l2w; l2w.vx = toV(l.fx); l2w.vy = toV(l.fy); l2w.vz = toV(l.fz);
+  res.dir = l2w * localDir;
+  res.pdf = pdf2d * 0.050660591821168885722f * (1.f / sinTheta);
+  res.dist = INFINITY;
+  uv.y = clampf(uv.y, halfTexel.y, 1.0f - halfTexel.y);
+  const vec4f t = Texture2D_get(l.hdriMap, uv, FLT_MIN);
+  res.weight = make_vec3f(t.x, t.y, t.z) * toV(l.radiance) / res.pdf;
+  return res;
+}
+static __device__ __noinline__ LightEval HDRILight_eval(const OcLight &l, vec3f dir, float maxDist)
+{
+  LightEval res; res.radiance = make_vec3f(0.f); res.pdf = 0.f;
+  if (INFINITY > maxDist) return res;
+  const OcTexture2D &map = *l.hdriMap;
+  linear3f w2l; w2l.vx = toV(l.wx); w2l.vy = toV(l.wy); w2l.vz = toV(l.wz);
+  const vec3f localDir = w2l * dir;
+  const float u = atan2f(localDir.y, localDir.x) * OC_ONE_OVER_TWO_PI;
+  const float v = acosf(clampf(localDir.z, -1.f, 1.f)) * OC_ONE_OVER_PI;
+  const vec2f halfTexel = make_vec2f((1.f / (float)map.sizeX) * 0.5f, (1.f / (float)map.sizeY) * 0.5f);
+  const vec2f uvc = make_vec2f(u, clampf(v, halfTexel.y, 1.0f - halfTexel.y));
+  const vec4f t = Texture2D_get(l.hdriMap, uvc, FLT_MIN);
+  res.radiance = make_vec3f(t.x, t.y, t.z) * toV(l.radiance);
+  vec2f uv = make_vec2f(uvc.x + halfTexel.x, uvc.y + halfTexel.y);
+  uv.x = uv.x - floorf(uv.x);
+  // Distribution2D_pdf
+  const int idy = min(max((int)(uv.y * map.sizeY), 0), map.sizeY - 1);
+  const float befy = idy == 0 ? 0.0f : __ldg(l.hdriCdfY + idy - 1);
+  const float pdf_y = (__ldg(l.hdriCdfY + idy) - befy) * map.sizeY;
+  const int idx = min(max((int)(uv.x * map.sizeX), 0), map.sizeX - 1);
+  const int x0 = idy * map.sizeX;
+  const float befx = idx == 0 ? 0.0f : __ldg(l.hdriCdfX + x0 + idx - 1);
+  const float pdf_x = (__ldg(l.hdriCdfX + x0 + idx) - befx) * map.sizeX;
+  res.pdf = pdf_x * pdf_y;
+  res.pdf *= 0.050660591821168885722f * (1.f / sqrtf(1.f - sqr(localDir.z)));
+  return res;
+}
+
 __device__ __forceinline__ LightSample Light_sample(const OcLight &l, const DifferentialGeometry &dg, vec2f s)
 {
   LightSample r;

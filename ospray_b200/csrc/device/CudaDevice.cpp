@@ -60,7 +60,7 @@ void CudaDevice::copyData(const OSPData source, OSPData destination, const vec3u
 OSPLight CudaDevice::newLight(const char *type)
 {
   const std::string t(type);
-  if (t != "ambient" && t != "distant" && t != "quad" && t != "sphere" && t != "spot") return nullptr;
+  if (t != "ambient" && t != "distant" && t != "quad" && t != "sphere" && t != "spot" && t != "hdri") return nullptr;
   return (OSPLight) new Light(t);
 }
 OSPCamera CudaDevice::newCamera(const char *type)
@@ -170,7 +170,7 @@ OSPFuture CudaDevice::renderFrame(OSPFrameBuffer _fb, OSPRenderer _r, OSPCamera 
     rsh.worldHasVolumes = w->sh.hasVolumes;
     rsh.worldNumLights = w->sh.numLights; // (with the geometry lights prepareFrame added)
     rsh.worldShadowOpaque = w->sh.shadowOpaque;
-    rsh.hasTextures = (texturedMaterials > 0 || emissiveMaterials > 0 || rsh.backplate || rsh.maxDepthTexture) ? 1u : 0u;
+    rsh.hasTextures = (texturedMaterials > 0 || emissiveMaterials > 0 || rsh.backplate || rsh.maxDepthTexture || w->hasHdriLight) ? 1u : 0u;
     if (!finished) checkCuda(ospcuda_render_frame(dw, &c->sh, &rsh, &fb->sh), "render kernel");
     checkCuda(ospcuda_event_record(f->evRendered), "event record");
     fb->postProcess();

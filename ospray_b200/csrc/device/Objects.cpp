@@ -989,8 +989,36 @@ void Light::commit()
     sh.ppdf = 1.f / ((float)M_PI * (radius * radius - innerRadius * innerRadius));
     sh.intensity = toOc(radIntensity);
     sh.radiance = toOc(radiance);
+  } else if (type == "hdri") {
+    // lights/HDRILight.cpp:73-110: frame from direction / up, intensityQuantity must be SCALE, the importance distribution
+    // of the map (HDRILight_initDistribution) rebuilt at every commit
+    const vec3f up = getParam<vec3f>("up", make_vec3f(0.f, 1.f, 0.f));
+    const vec3f dir = getParam<vec3f>("direction", make_vec3f(0.f, 0.f, 1.f));
+    hdriMap = dynamic_cast<Texture2D *>(getParamObjectRaw("map"));
+    if (!hdriMap) throw std::runtime_error(toString() + " must have 'map'");
+    const uint32_t iq = getParam<uint32_t>("intensityQuantity", OSP_INTENSITY_QUANTITY_SCALE);
+    vec3f scale = coloredIntensity;
+    if (iq != OSP_INTENSITY_QUANTITY_SCALE) {
+      postStatusMsg(OSP_LOG_WARNING, toString() + " unsupported 'intensityQuantity' value");
+      scale = make_vec3f(0.f);
+    }
+    linear3f f;
+    f.vx = normalize(-dir);
+    f.vy = normalize(cross(f.vx, up));
+    f.vz = cross(f.vx, f.vy);
+    const linear3f inv = rcp(f);
+    const int sx = hdriMap->sh.sizeX, sy = hdriMap->sh.sizeY;
+    hdriCdfX.reserve((size_t)sx * sy * sizeof(float));
+    hdriCdfY.reserve((size_t)sy * sizeof(float));
+    checkCuda(ospcuda_hdri_distribution(hdriMap->devPtr(), sx, sy, hdriCdfX.as<float>(), hdriCdfY.as<float>()), "hdri distribution");
+    sh.type = OC_LIGHT_HDRI;
+    sh.radiance = toOc(scale);
+    sh.fx = toOc(f.vx); sh.fy = toOc(f.vy); sh.fz = toOc(f.vz);
+    sh.wx = toOc(inv.vx); sh.wy = toOc(inv.vy); sh.wz = toOc(inv.vz);
+    sh.hdriMap = hdriMap->devPtr();
+    sh.hdriCdfX = hdriCdfX.as<float>(); sh.hdriCdfY = hdriCdfY.as<float>();
   } else
-    throw std::runtime_error("cuda device: light type '" + type + "' is not supported (ambient, distant, quad, sphere, spot)");
+    throw std::runtime_error("cuda device: light type '" + type + "' is not supported (ambient, distant, quad, sphere, spot, hdri)");
 }
 
 // ---- Group (common/Group.cpp:69-209) ------------------------------------------------------------------
@@ -1209,6 +1237,14 @@ void World::commit()
     case OC_LIGHT_DISTANT:
       l.fx = toOc(xfmVector(xfm.l, V(l.fx))); l.fy = toOc(xfmVector(xfm.l, V(l.fy))); l.fz = toOc(xfmVector(xfm.l, V(l.fz)));
       break;
+    case OC_LIGHT_HDRI: { // HDRILight.cpp:52-55: light2world = xfm.l * light2world, world2light its inverse
+      linear3f f;
+      f.vx = xfmVector(xfm.l, V(l.fx)); f.vy = xfmVector(xfm.l, V(l.fy)); f.vz = xfmVector(xfm.l, V(l.fz));
+      const linear3f inv = rcp(f);
+      l.fx = toOc(f.vx); l.fy = toOc(f.vy); l.fz = toOc(f.vz);
+      l.wx = toOc(inv.vx); l.wy = toOc(inv.vy); l.wz = toOc(inv.vz);
+      break;
+    }
     default: break; // ambient
     }
     return l;
@@ -1228,11 +1264,13 @@ void World::commit()
   std::vector<OcLight> pt, sv;
   uint32_t visibleOnly = 0;
   vec3f aoColor = make_vec3f(0.f);
+  hasHdriLight = false;
   for (const auto &la : all) {
     const OcLight &lsh = la.first;
     pt.push_back(lsh);
-    if (lsh.type == OC_LIGHT_AMBIENT) {
-      // SciVisData.cpp:17-30: ambient lights go to the visible-only front partition
+    if (lsh.type == OC_LIGHT_HDRI) hasHdriLight = true;
+    if (lsh.type == OC_LIGHT_AMBIENT || lsh.type == OC_LIGHT_HDRI) {
+      // SciVisData.cpp:17-52: ambient and hdri lights go to the visible-only front partition (no illumination from them)
       if (visibleOnly == sv.size()) sv.push_back(lsh);
       else { sv.push_back(sv[visibleOnly]); sv[visibleOnly] = lsh; }
       visibleOnly++;

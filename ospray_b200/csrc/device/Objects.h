@@ -221,6 +221,10 @@ struct Light : public ManagedObject
   std::string type;
   OcLight sh{};
   vec3f ambientRadiance{0, 0, 0};
+
+ private:
+  Ref<Texture2D> hdriMap;      // hdri: the environment map and the CDFs of its importance distribution
+  DevMem hdriCdfX, hdriCdfY;
 };
 
 struct Group : public ManagedObject
@@ -273,6 +277,7 @@ struct World : public ManagedObject
   CudaDevice &device;
   Ref<Data> instances, lights;
   OcWorld sh{};
+  bool hasHdriLight = false;   // frames of this world run the kernels with texture support
   box3f bounds = box_empty();
 
  private:
@@ -284,6 +289,7 @@ struct World : public ManagedObject
   DevMem geoLightsDev, geoCdfDev, geoInstDev;
   uint64_t geoKey[3] = {~0ull, ~0ull, ~0ull};
   bool geoActive = false, geoInUse = false;
+
   uint32_t geoNumLights = 0, geoNumGeo = 0;
   void buildGeometryLights(const Renderer &renderer);
   const OcInstance *instDevGeo();

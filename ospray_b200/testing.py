@@ -140,6 +140,7 @@ class SceneSpec:
     def uses_mipmaps(self):
         """False when any texture of the scene asks for disableMipMapGeneration (a device parameter: all or none)"""
         texs = [t for t in (self.backplate, self.max_depth_texture) if t is not None]
+        texs += [v for ls in self.lights for v in ls.params.values() if isinstance(v, TextureSpec)]
         for inst in self.instances:
             for m in inst.group.models:
                 if m.material is not None:
@@ -556,7 +557,7 @@ def to_ospray(scene: SceneSpec):
         for ls in inst.group.lights:
             l = osp.Light(ls.type)
             for k, v in ls.params.items():
-                l.set(k, v)
+                l.set(k, make_texture(v) if isinstance(v, TextureSpec) else v)
             glights.append(l.commit())
         if glights: group.set("light", glights)
         keep += glights
@@ -575,7 +576,7 @@ def to_ospray(scene: SceneSpec):
     for ls in scene.lights:
         l = osp.Light(ls.type)
         for k, v in ls.params.items():
-            l.set(k, v)
+            l.set(k, make_texture(v) if isinstance(v, TextureSpec) else v)
         lights.append(l.commit())
     if lights:
         world.set("light", lights)

@@ -41,6 +41,27 @@ def instance_lights():
     return s
 
 
+def hdri_lit(instanced=False):
+    """an environment map as the light (lights/HDRILight.ispc: importance-sampled latitude / longitude texture, MIS against the
+    BSDF sample that leaves the scene), turned by direction / up; instanced: the light sits in a rotated instance's group"""
+    s = T.random_spheres(24, seed=5)
+    rng = np.random.default_rng(21)
+    env = (rng.uniform(0.05, 0.4, (16, 32, 3)) ** 2).astype(np.float32)
+    env[3:6, 8:11] = (12.0, 10.0, 7.0)    # a "sun"
+    env[10:, :] *= 0.3                     # darker ground half
+    light = T.LightSpec("hdri", {"map": T.TextureSpec(env, "RGB32F"), "direction": (0.3, 0.1, 1.0), "up": (0.1, 1.0, 0.2), "intensity": 0.8,
+                                 "color": (1.0, 0.95, 0.9)})
+    if instanced:
+        c, sn = np.float32(np.cos(0.7)), np.float32(np.sin(0.7))
+        rot = np.array([c, 0, -sn, 0, 1, 0, sn, 0, c, 0.5, 0.0, -0.2], np.float32)  # columns vx, vy, vz, p
+        extra = T.random_spheres(3, seed=9, add_plane=False).instances[0].group.models  # (a group needs bounds of its own)
+        s.instances.append(T.InstanceSpec(T.GroupSpec(models=extra, lights=[light]), xfm=rot))
+        s.lights = []
+    else:
+        s.lights = [light]
+    return s
+
+
 def translucent_cornell():
     """cornell box with a semi-transparent specular material: transparent shadows, Specular + Transmission lobes"""
     s = T.cornell_box()
@@ -496,6 +517,9 @@ CASES = {
     "principled_thin_pt": (lambda: principled_cornell("thin"), "pathtracer", {"pixelSamples": 2}, 2),
     # debug renderer (render/debug/DebugRenderer.ispc), every method the device accepts
     "debug_testFrame": (T.cornell_box, "debug", {"method": "testFrame", "pixelSamples": 2}, 2),
+    "hdri_pt": (hdri_lit, "pathtracer", {"pixelSamples": 2}, 2),
+    "hdri_instanced_pt": (lambda: hdri_lit(True), "pathtracer", {"pixelSamples": 2, "lightSamples": 2}, 1),
+    "hdri_scivis": (hdri_lit, "scivis", {"pixelSamples": 1, "aoSamples": 1, "shadows": True, "visibleLights": True}, 1),
     "instance_lights_pt": (instance_lights, "pathtracer", {"pixelSamples": 2, "lightSamples": 2}, 1),
     "instance_lights_scivis": (instance_lights, "scivis", {"pixelSamples": 1, "aoSamples": 1, "shadows": True, "visibleLights": True}, 1),
     "debug_rayDir": (T.cornell_box, "debug", {"method": "rayDir"}, 1),
@@ -520,7 +544,7 @@ ORACLE_UNSUPPORTED = {"textured_pt", "textured_bias_pt", "cutout_pt", "backplate
                       "emissive_transparent_pt", "textured_scivis", "textured_ao", "cutout_scivis", "cutout_ao", "backplate_scivis",
                       "backplate_ao", "debug_texCoord", "debug_dPdt", "debug_dPds_tex", "debug_backplate", "metal_smooth_pt", "metal_rough_pt",
                       "plastic_smooth_pt", "plastic_rough_pt", "principled_plastic_pt", "principled_metal_pt", "principled_glass_pt",
-                      "principled_coat_pt", "principled_rough_layers_pt", "principled_emissive_pt", "glass_alloy_pt", "glass_alloy_rough_pt", "principled_sheen_pt", "principled_thin_pt", "principled_tex_pt", "principled_tex_cutout_pt", "velvet_paint_pt", "carpaint_pt"}
+                      "principled_coat_pt", "principled_rough_layers_pt", "principled_emissive_pt", "glass_alloy_pt", "glass_alloy_rough_pt", "principled_sheen_pt", "principled_thin_pt", "principled_tex_pt", "principled_tex_cutout_pt", "velvet_paint_pt", "carpaint_pt", "hdri_pt", "hdri_instanced_pt", "hdri_scivis"}
 # Rough dielectric coatings: MicrofacetDielectricLayer_Constructor reads self->eta for Ravg BEFORE assigning it
 # (bsdfs/MicrofacetDielectricLayer.ih:55 vs :68), i.e. whatever the shading context's memory held from the previous BSDF. The
 # device uses the intended value; against the reference's kernels the coated surfaces then differ by ~0.5 % in brightness

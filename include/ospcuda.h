@@ -346,6 +346,10 @@ typedef struct {
   float scaledAperture, aspect, imgPlaneSizeY;
   uint32_t needLensSample, needTimeSample;
   uint32_t type;
+  /* perspective: OSPStereoMode (PerspectiveCamera.cpp:35-100: LEFT / RIGHT are folded into org at commit, SIDE_BY_SIDE /
+   * TOP_BOTTOM pick the eye per pixel, PerspectiveCamera.ispc:28-40) and half the interpupillary distance along du */
+  uint32_t stereoMode;
+  OcVec3f ipdOffset;
 } OcCamera;
 
 enum { OC_RENDERER_PATHTRACER = 0, OC_RENDERER_SCIVIS = 1, OC_RENDERER_AO = 2, OC_RENDERER_DEBUG = 3 };

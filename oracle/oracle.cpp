@@ -1098,14 +1098,23 @@ V2 pixelFilterSample(const OcRenderer &r, V2 s)
   return (uv + V2{-0.5f, -0.5f}) * r.pfWidth;
 }
 // camera/PerspectiveCamera.ispc:16-64 (no stereo / motion blur)
-void cameraInitRay(const OcCamera &cam, Ray &ray, V2 screen, V2 lens)
+void cameraInitRay(const OcCamera &cam, Ray &ray, V2 screen, V2 lens, V2 pixelCenter)
 {
+  V3 eyeOffset = v3(0.f);
+  if (cam.type != OC_CAMERA_ORTHOGRAPHIC && cam.stereoMode >= 3u) { // side by side / top-bottom stereo (:28-40)
+    const bool sbs = cam.stereoMode == 3u;
+    float &split = sbs ? screen.x : screen.y;
+    const float pc = sbs ? pixelCenter.x : pixelCenter.y;
+    split *= 2.f;
+    if (pc < 0.5f) eyeOffset = -1.f * v3(cam.ipdOffset);
+    else { eyeOffset = v3(cam.ipdOffset); split -= 1.f; }
+  }
   screen = {lerp(screen.x, cam.subImage[0], cam.subImage[2]), lerp(screen.y, cam.subImage[1], cam.subImage[3])};
   if (cam.type == OC_CAMERA_ORTHOGRAPHIC) { // OrthographicCamera_initRay (camera/OrthographicCamera.ispc:12-50)
     setRay(ray, v3(cam.org) + screen.x * v3(cam.du_size) + screen.y * v3(cam.dv_up), v3(cam.dir_00), cam.nearClip, INF);
     return;
   }
-  V3 org = v3(cam.org);
+  V3 org = v3(cam.org) + eyeOffset;
   V3 dir = v3(cam.dir_00) + screen.x * v3(cam.du_size) + screen.y * v3(cam.dv_up);
   if (cam.scaledAperture > 0.f) { // uniformSampleDisk(radius, s)
     const float r = sqrtf(lens.x) * cam.scaledAperture, phi = TWO_PI * lens.y;
@@ -1464,7 +1473,7 @@ ScreenSample PathTracer_renderPixel(Ctx &c, uint32_t ix, uint32_t iy) // pathtra
     V2 lens = {0.5f, 0.5f};
     if (c.cam.needLensSample) lens = LDSampler_finalizeDim23(ld, ss234);
     Ray ray;
-    cameraInitRay(c.cam, ray, screen, lens);
+    cameraInitRay(c.cam, ray, screen, lens, pixel_center);
     ScreenSample sample = make_ScreenSample_zero(); // PathTraceIntegrator_Li (PathTracer.ispc:37-63)
     RandomSampler rs;
     RandomSampler_init(rs, seed, sampleOffs + sampleID); // pathState.randomSampler (PathTracer.ispc:157): volumes only
@@ -1951,7 +1960,7 @@ ScreenSample defaultRenderPixel(Ctx &c, uint32_t x, uint32_t y)
     const V2 pixel_center = {((float)x + 0.5f) * rcpSize.x, ((float)y + 0.5f) * rcpSize.y};
     const V2 screen = pixel_center + pfSample * rcpSize;
     Ray ray;
-    cameraInitRay(c.cam, ray, screen, {0.f, 0.f});
+    cameraInitRay(c.cam, ray, screen, {0.f, 0.f}, pixel_center);
     if (ren.type == OC_RENDERER_SCIVIS) SciVis_renderSample(c, ray, sample, x, y, startSampleID + s);
     else if (ren.type == OC_RENDERER_DEBUG) Debug_renderSample(c, ray, sample, x, y, startSampleID + s);
     else AO_renderSample(c, ray, sample, x, y, startSampleID + s);
@@ -2069,9 +2078,10 @@ ORACLE_API void oracle_camera_rays(const OcCamera *cam, const OcRenderer *ren, c
       pixelSample = {Halton_sample2(sampleIndex + 1), CranleyPattersonRotation(Halton_sample3(sampleIndex + 1), 1.f / 6.f)};
     }
     const V2 pf = pixelFilterSample(*ren, pixelSample);
-    const V2 screen = V2{((float)px[i] + 0.5f) * rcpSize.x, ((float)py[i] + 0.5f) * rcpSize.y} + pf * rcpSize;
+    const V2 pixelCenter = V2{((float)px[i] + 0.5f) * rcpSize.x, ((float)py[i] + 0.5f) * rcpSize.y};
+    const V2 screen = pixelCenter + pf * rcpSize;
     Ray r;
-    cameraInitRay(*cam, r, screen, {0.5f, 0.5f});
+    cameraInitRay(*cam, r, screen, {0.5f, 0.5f}, pixelCenter);
     OcRayHit &o = out[i];
     o.org[0] = r.org.x; o.org[1] = r.org.y; o.org[2] = r.org.z; o.t0 = r.t0;
     o.dir[0] = r.dir.x; o.dir[1] = r.dir.y; o.dir[2] = r.dir.z; o.t = r.t;
@@ -2156,20 +2166,36 @@ ORACLE_API void oracle_gauss_pixelfilter_lut(float width, int lut, float *cdfX, 
   Distribution1D_create(lut, cdfY);
 }
 // camera/Camera.cpp:33-126 + PerspectiveCamera.cpp:26-117 (no transform / stereo / motion blur)
+ORACLE_API void oracle_commit_camera_stereo(const float pos[3], const float dir[3], const float up[3], float fovy, float aspect,
+    float apertureRadius, float focusDistance, int stereoMode, float interpupillaryDistance, OcCamera *out);
 ORACLE_API void oracle_commit_camera(const float pos[3], const float dir[3], const float up[3], float fovy, float aspect,
     float apertureRadius, float focusDistance, OcCamera *out)
 {
+  oracle_commit_camera_stereo(pos, dir, up, fovy, aspect, apertureRadius, focusDistance, 0, 0.0635f, out);
+}
+// + PerspectiveCamera.cpp:35-100: stereo modes (aspect of the halves, eye offset along du, LEFT / RIGHT folded into org)
+ORACLE_API void oracle_commit_camera_stereo(const float pos[3], const float dir[3], const float up[3], float fovy, float aspect,
+    float apertureRadius, float focusDistance, int stereoMode, float interpupillaryDistance, OcCamera *out)
+{
+  if (stereoMode == 3) aspect *= 0.5f;
+  else if (stereoMode == 4) aspect *= 2.f;
   const V3 d = normalize(v3(dir[0], dir[1], dir[2])), u = normalize(v3(up[0], up[1], up[2]));
   const float imgY = 2.f * tanf((0.5f * fovy) * (float)(M_PI / 180.0)), imgX = imgY * aspect;
   const float scaledAperture = apertureRadius ? apertureRadius / (imgX * focusDistance) : 0.0f;
   V3 dir_00 = normalize(d);
   V3 du = normalize(cross(dir_00, u));
   V3 dv = cross(du, dir_00);
+  V3 ipd = (0.5f * interpupillaryDistance) * du;
+  V3 org = v3(pos[0], pos[1], pos[2]);
+  if (stereoMode == 1) org = org - ipd;
+  else if (stereoMode == 2) org = org + ipd;
+  else if (stereoMode == 4) ipd = -1.f * ipd;
   du = du * imgX; dv = dv * imgY;
   dir_00 = dir_00 - 0.5f * du - 0.5f * dv;
   if (scaledAperture > 0.f) { du = du * focusDistance; dv = dv * focusDistance; dir_00 = dir_00 * focusDistance; }
   memset(out, 0, sizeof(*out));
-  out->org = {pos[0], pos[1], pos[2]}; out->dir_00 = {dir_00.x, dir_00.y, dir_00.z}; out->du_size = {du.x, du.y, du.z};
+  out->stereoMode = (uint32_t)stereoMode; out->ipdOffset = {ipd.x, ipd.y, ipd.z};
+  out->org = {org.x, org.y, org.z}; out->dir_00 = {dir_00.x, dir_00.y, dir_00.z}; out->du_size = {du.x, du.y, du.z};
   out->dv_up = {dv.x, dv.y, dv.z}; out->direction = {d.x, d.y, d.z};
   out->nearClip = 1e-6f; out->subImage[0] = 0.f; out->subImage[1] = 0.f; out->subImage[2] = 1.f; out->subImage[3] = 1.f;
   out->scaledAperture = scaledAperture; out->aspect = aspect; out->imgPlaneSizeY = imgY; out->needLensSample = scaledAperture > 0.f;

@@ -164,7 +164,8 @@ class World(C.Structure):
 class Camera(C.Structure):
     _fields_ = [("org", Vec3), ("dir_00", Vec3), ("du_size", Vec3), ("dv_up", Vec3), ("direction", Vec3),
                 ("nearClip", C.c_float), ("subImage", C.c_float * 4), ("scaledAperture", C.c_float), ("aspect", C.c_float),
-                ("imgPlaneSizeY", C.c_float), ("needLensSample", C.c_uint32), ("needTimeSample", C.c_uint32), ("type", C.c_uint32)]
+                ("imgPlaneSizeY", C.c_float), ("needLensSample", C.c_uint32), ("needTimeSample", C.c_uint32), ("type", C.c_uint32),
+                ("stereoMode", C.c_uint32), ("ipdOffset", Vec3)]
 
 
 class Renderer(C.Structure):
@@ -833,12 +834,17 @@ class Scene:
 
 
 def make_camera(position, direction=(0, 0, 1), up=(0, 1, 0), fovy=60.0, aspect=1.0, aperture_radius=0.0, focus_distance=1.0,
-                kind="perspective", height=1.0):
+                kind="perspective", height=1.0, stereo_mode=0, interpupillary_distance=0.0635):
     cam = Camera()
     if kind == "orthographic":
         lib().oracle_commit_ortho_camera(_f3(position), _f3(direction), _f3(up), float(height), float(np.float32(aspect)), C.byref(cam))
         return cam
-    lib().oracle_commit_camera(_f3(position), _f3(direction), _f3(up), fovy, float(np.float32(aspect)), aperture_radius, focus_distance, C.byref(cam))
+    L = lib()
+    L.oracle_commit_camera_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p]
+    p3 = lambda v: np.ascontiguousarray(v, np.float32)
+    a, b, c = p3(position), p3(direction), p3(up)
+    L.oracle_commit_camera_stereo(a.ctypes.data, b.ctypes.data, c.ctypes.data, fovy, float(np.float32(aspect)), aperture_radius, focus_distance,
+                                  int(stereo_mode), float(interpupillary_distance), C.cast(C.pointer(cam), C.c_void_p))
     return cam
 
 

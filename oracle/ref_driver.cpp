@@ -692,6 +692,7 @@ REF_API int ospref_render_frame(const OcWorld *w, const OcCamera *cam, const OcR
   pc.org = v3(cam->org); pc.dir_00 = v3(cam->dir_00); pc.du_size = v3(cam->du_size); pc.dv_up = v3(cam->dv_up);
   pc.imgPlaneSize = make_vec2f(cam->imgPlaneSizeY * cam->aspect, cam->imgPlaneSizeY);
   pc.scaledAperture = cam->scaledAperture; pc.aspect = cam->aspect;
+  pc.stereoMode = (OSPStereoMode)cam->stereoMode; pc.ipd_offset = v3(cam->ipdOffset); // PerspectiveCamera.cpp:61,85-100
 
   // fb/LocalFB.cpp:49-180, fb/FrameBuffer.cpp:31-137
   LocalFB lfb;

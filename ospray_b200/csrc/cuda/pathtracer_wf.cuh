@@ -503,9 +503,9 @@ __global__ void __launch_bounds__(128) ptGenKernel(const __grid_constant__ PtArg
     vec2f lens = make_vec2f(0.5f, 0.5f);
     if (k.a.cam.needLensSample) lens = LDSampler_finalizeDim23(ld, ss234);
     Ray ray;
-    cameraInitRay(k.a.cam, ray, screen, lens);
+    cameraInitRay(k.a.cam, ray, screen, lens, pixel_center);
     if (TEX) { // ray cone in pixel units (PathTracer.ispc:182-187) and the optional depth limit (:189-192)
-      RayCone cone = cameraInitRayCone(k.a.cam, screen);
+      RayCone cone = cameraInitRayCone(k.a.cam, screen, pixel_center);
       cone.dwdt *= rcpSize.y; cone.width *= rcpSize.y;
       s.cone[p] = make_float2(cone.width, cone.dwdt);
       s.med[p] = make_float4(0.f, 0.f, 0.f, 1.f); // make_Medium_vacuum (PathTracer.ispc:56)
@@ -1158,7 +1158,7 @@ __global__ void __launch_bounds__(128) aoGenKernel(const __grid_constant__ PtArg
     if (fb.taskError && !(fb.taskError[(iy >> 3) * (((uint32_t)fb.sizeX + 7u) >> 3) + (ix >> 3)] > fb.errorThreshold)) continue;
     const vec2f pixel_center = make_vec2f(((float)ix + 0.5f) * rcpSize.x, ((float)iy + 0.5f) * rcpSize.y);
     Ray ray;
-    cameraInitRay(k.a.cam, ray, pixel_center + pfSample * rcpSize, make_vec2f(0.f, 0.f));
+    cameraInitRay(k.a.cam, ray, pixel_center + pfSample * rcpSize, make_vec2f(0.f, 0.f), pixel_center);
     s.flags[p] = 0u;
     s.thr[p] = make_float4(0.f, 0.f, 0.f, 0.f);
     s.lastN[p] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, ray.t);

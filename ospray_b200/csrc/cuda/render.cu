@@ -673,9 +673,9 @@ static __device__ void defaultRenderPixel(Ctx &c, uint32_t x, uint32_t y, Screen
     const vec2f pixel_center = make_vec2f(((float)x + 0.5f) * rcpSize.x, ((float)y + 0.5f) * rcpSize.y);
     const vec2f screen = pixel_center + pfSample * rcpSize;
     Ray ray;
-    cameraInitRay(c.cam, ray, screen, make_vec2f(0.f, 0.f));
+    cameraInitRay(c.cam, ray, screen, make_vec2f(0.f, 0.f), pixel_center);
     if (TEX || RENDERER == OC_RENDERER_DEBUG) { // the sample's ray cone in pixel units (:64-71)
-      c.cone = cameraInitRayCone(c.cam, screen);
+      c.cone = cameraInitRayCone(c.cam, screen, pixel_center);
       c.cone.dwdt *= rcpSize.y; c.cone.width *= rcpSize.y;
     }
     if (TEX) ray.t = fminf(ray.t, tMax);

@@ -1461,14 +1461,32 @@ __device__ __forceinline__ vec2f pixelFilterSample(const OcRenderer &r, vec2f s)
 
 // PerspectiveCamera_initRay (camera/PerspectiveCamera.ispc:16-64), OrthographicCamera_initRay
 // (camera/OrthographicCamera.ispc:12-50); no stereo / motion blur
-__device__ __forceinline__ void cameraInitRay(const OcCamera &cam, Ray &ray, vec2f screen, vec2f lens)
+// side-by-side / top-bottom stereo (PerspectiveCamera.ispc:28-40): the half of the image the PIXEL lies in picks the eye, the
+// sample position is stretched back over the whole image plane; returns the eye's offset sign (0: no per-pixel stereo)
+__device__ __forceinline__ float cameraStereoSplit(const OcCamera &cam, vec2f &screen, vec2f pixelCenter)
 {
+  if (cam.stereoMode < 3u) return 0.f;
+  const bool sbs = cam.stereoMode == 3u;
+  float &split = sbs ? screen.x : screen.y;
+  const float pc = sbs ? pixelCenter.x : pixelCenter.y;
+  split *= 2.f;
+  if (pc < 0.5f) return -1.f;
+  split -= 1.f;
+  return 1.f;
+}
+__device__ __forceinline__ void cameraInitRay(const OcCamera &cam, Ray &ray, vec2f screen, vec2f lens, vec2f pixelCenter)
+{
+  vec3f org = toV(cam.org);
+  if (cam.type != OC_CAMERA_ORTHOGRAPHIC) {
+    const float eye = cameraStereoSplit(cam, screen, pixelCenter);
+    if (eye < 0.f) org = org - toV(cam.ipdOffset);
+    else if (eye > 0.f) org = org + toV(cam.ipdOffset);
+  }
   screen = make_vec2f(lerpf(screen.x, cam.subImage[0], cam.subImage[2]), lerpf(screen.y, cam.subImage[1], cam.subImage[3]));
   if (cam.type == OC_CAMERA_ORTHOGRAPHIC) {
     setRay(ray, toV(cam.org) + screen.x * toV(cam.du_size) + screen.y * toV(cam.dv_up), toV(cam.dir_00), cam.nearClip, INFINITY);
     return;
   }
-  vec3f org = toV(cam.org);
   vec3f dir = toV(cam.dir_00) + screen.x * toV(cam.du_size) + screen.y * toV(cam.dv_up);
   if (cam.scaledAperture > 0.f) {
     const float r = sqrtf(lens.x) * cam.scaledAperture;
@@ -1482,7 +1500,7 @@ __device__ __forceinline__ void cameraInitRay(const OcCamera &cam, Ray &ray, vec
 }
 // the ray cone a camera ray starts with (PerspectiveCamera.ispc:43-63, OrthographicCamera.ispc:50-53), before the
 // renderer scales it to pixel units; `screen` is the sample position before the sub-image mapping
-__device__ __forceinline__ RayCone cameraInitRayCone(const OcCamera &cam, vec2f screen)
+__device__ __forceinline__ RayCone cameraInitRayCone(const OcCamera &cam, vec2f screen, vec2f pixelCenter)
 {
   RayCone rc;
   const float subH = fabsf(cam.subImage[3] - cam.subImage[1]);
@@ -1490,11 +1508,13 @@ __device__ __forceinline__ RayCone cameraInitRayCone(const OcCamera &cam, vec2f 
     rc.width = cam.imgPlaneSizeY * subH; rc.dwdt = 0.f;
     return rc;
   }
+  cameraStereoSplit(cam, screen, pixelCenter);
   screen = make_vec2f(lerpf(screen.x, cam.subImage[0], cam.subImage[2]), lerpf(screen.y, cam.subImage[1], cam.subImage[3]));
   const vec3f dir = toV(cam.dir_00) + screen.x * toV(cam.du_size) + screen.y * toV(cam.dv_up);
   const float coneShortening = 1.0f / sqrtf(dot(dir, dir));
   rc.width = 0.f;
   rc.dwdt = cam.imgPlaneSizeY * subH * coneShortening;
+  if (cam.stereoMode == 4u) rc.dwdt *= 2.f;
   return rc;
 }
 

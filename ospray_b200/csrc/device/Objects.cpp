@@ -239,9 +239,9 @@ void Camera::commit()
   const float focusDistance = getParam<float>("focusDistance", 1.f);
   const bool architectural = getParam<bool>("architectural", false);
   const uint32_t stereoMode = getParam<uint32_t>("stereoMode", OSP_STEREO_NONE);
-  getParam<float>("interpupillaryDistance", 0.0635f);
-  if (stereoMode != OSP_STEREO_NONE)
-    postStatusMsg(OSP_LOG_WARNING, "cuda device: stereo cameras are not supported, rendering mono");
+  const float interpupillaryDistance = getParam<float>("interpupillaryDistance", 0.0635f);
+  if (stereoMode == OSP_STEREO_SIDE_BY_SIDE) aspect *= 0.5f; // PerspectiveCamera.cpp:39-48
+  else if (stereoMode == OSP_STEREO_TOP_BOTTOM) aspect *= 2.f;
 
   const float imgPlaneY = 2.f * tanf((0.5f * fovy) * (float)(M_PI / 180.0));
   const float imgPlaneX = imgPlaneY * aspect;
@@ -249,6 +249,10 @@ void Camera::commit()
   vec3f dir_00 = normalize(dir);
   vec3f du = normalize(cross(dir_00, up));
   vec3f dv = architectural ? normalize(up) : cross(du, dir_00);
+  vec3f ipdOffset = 0.5f * interpupillaryDistance * du; // :85-100
+  if (stereoMode == OSP_STEREO_LEFT) pos = pos - ipdOffset;
+  else if (stereoMode == OSP_STEREO_RIGHT) pos = pos + ipdOffset;
+  else if (stereoMode == OSP_STEREO_TOP_BOTTOM) ipdOffset = -ipdOffset; // left eye at the top (image origin at the lower left)
   du = du * imgPlaneX;
   dv = dv * imgPlaneY;
   dir_00 = dir_00 - 0.5f * du - 0.5f * dv;
@@ -270,6 +274,8 @@ void Camera::commit()
   sh.needLensSample = scaledAperture > 0.f;
   sh.needTimeSample = 0;
   sh.type = OC_CAMERA_PERSPECTIVE;
+  sh.stereoMode = stereoMode;
+  sh.ipdOffset = toOc(ipdOffset);
 }
 
 // ---- Geometry (geometry/Mesh.cpp:37-204, Spheres.cpp:46-106, Boxes.cpp:33-42) ----------------------

@@ -585,13 +585,17 @@ def to_ospray(scene: SceneSpec):
     return world, keep
 
 
-def make_camera(world, width, height, kind="perspective", ortho_height=1.0):
+def make_camera(world, width, height, kind="perspective", ortho_height=1.0, stereo_mode=0, interpupillary_distance=None):
     """BaseFixture::Init camera (BaseFixture.cpp:36-47)"""
     lo, hi = world.bounds()
     p = arcball_camera(lo, hi)
     cam = osp.Camera(kind)
     if kind == "orthographic":
         cam.set("height", float(ortho_height))
+    if stereo_mode:
+        cam.set("stereoMode", osp.Typed(osp.OSP_UINT, int(stereo_mode)))
+    if interpupillary_distance is not None:
+        cam.set("interpupillaryDistance", float(interpupillary_distance))
     cam.set("aspect", float(np.float32(width) / np.float32(height)))
     cam.set("position", p["position"]).set("direction", p["direction"]).set("up", p["up"])
     return cam.commit(), p

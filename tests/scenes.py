@@ -453,6 +453,10 @@ CASES = {
     "spheres_pt": (T.random_spheres, "pathtracer", {"pixelSamples": 1, "backgroundColor": (1.0, 1.0, 1.0, 1.0)}, 2),
     "glass_spheres_pt": (glass_spheres, "pathtracer", {"pixelSamples": 2, "backgroundColor": (0.2, 0.3, 0.4, 1.0)}, 2),
     "glass_cornell_pt": (tinted_glass_cornell, "pathtracer", {"pixelSamples": 2, "maxPathLength": 12}, 1),
+    # stereo modes of the perspective camera (PerspectiveCamera.cpp:35-100, PerspectiveCamera.ispc:28-40): the eye per pixel half
+    "cornell_stereo_sbs_pt": (T.cornell_box, "pathtracer", {"pixelSamples": 2}, 1, {"stereoMode": 3, "interpupillaryDistance": 0.4}),
+    "spheres_stereo_tb_scivis": (T.random_spheres, "scivis", {"shadows": True, "aoSamples": 1}, 1, {"stereoMode": 4, "interpupillaryDistance": 0.3}),
+    "boxes_stereo_left_ao": (lambda: T.boxes(lit=True), "ao", {"aoSamples": 2}, 1, {"stereoMode": 1, "interpupillaryDistance": 0.5}),
     "cornell_ortho_pt": (T.cornell_box, "pathtracer", {"pixelSamples": 2}, 1, {"camera": "orthographic", "height": 2.2}),
     "spheres_ortho_scivis": (T.random_spheres, "scivis", {"shadows": True, "aoSamples": 1}, 1, {"camera": "orthographic", "height": 2.6}),
     "sphere_lights_pt": (sphere_lit_boxes, "pathtracer", {"pixelSamples": 2}, 2),
@@ -569,7 +573,8 @@ def oracle_render(name, width=W, height=H, pixel_filter=None, threads=0, num_ran
     scene = O.Scene(spec)
     pose = T.arcball_camera(*scene.bounds)
     cam = O.make_camera(pose["position"], pose["direction"], pose["up"], aspect=np.float32(width) / np.float32(height),
-                        kind=extra.get("camera", "perspective"), height=extra.get("height", 1.0))
+                        kind=extra.get("camera", "perspective"), height=extra.get("height", 1.0), stereo_mode=extra.get("stereoMode", 0),
+                        interpupillary_distance=extra.get("interpupillaryDistance", 0.0635))
     p = dict(params)
     if pixel_filter:
         p["pixelFilter"] = pixel_filter
@@ -599,7 +604,8 @@ def device_render(osp, name, width=W, height=H, pixel_filter=None, channels=None
     finally:
         if not spec.uses_mipmaps():
             osp.set_device_bool("disableMipMapGeneration", False)
-    cam, _ = T.make_camera(world, width, height, kind=extra.get("camera", "perspective"), ortho_height=extra.get("height", 1.0))
+    cam, _ = T.make_camera(world, width, height, kind=extra.get("camera", "perspective"), ortho_height=extra.get("height", 1.0),
+                           stereo_mode=extra.get("stereoMode", 0), interpupillary_distance=extra.get("interpupillaryDistance"))
     p = {}
     for k, v in params.items():
         p[k] = tuple(float(x) for x in v) if isinstance(v, tuple) else v

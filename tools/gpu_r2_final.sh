@@ -12,3 +12,4 @@ python bench.py --impl reference --steps 3 --warmup 1 > $OUT/r2_bench_c1_referen
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/r2_launches_bench_c1.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1; echo "ncu launch list rc=$?"
 python tools/bench_workloads.py C2 C3 C4 C5s > $OUT/r2_workloads.json 2> $OUT/workloads.err; echo "workloads rc=$?"; cat $OUT/r2_workloads.json | head -c 1500
+python tools/bench_materials.py 2>/dev/null > $OUT/r2_material_frames.json; echo "materials rc=$?"; cut -c1-70 $OUT/r2_material_frames.json

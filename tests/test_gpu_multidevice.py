@@ -26,10 +26,23 @@ def _render(osp, spec, kind, w, h, frames, channels, fmt, **params):
     return fb, (world, keep, cam, ren)
 
 
-@pytest.mark.parametrize("case", ["cornell_pt", "spheres_ao", "gravity_scivis"])
+def _materials_and_hdri():
+    """principled boxes with texture maps (device-side map tables per material) under an hdri light (device-side distribution per
+    light) plus a group light in a rotated instance: everything a sub-device has to build for itself"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import scenes
+    spec = scenes.principled_tex_cornell(False)
+    spec.lights += scenes.hdri_lit().lights
+    spec.instances.append(scenes.hdri_lit(True).instances[-1])
+    return spec
+
+
+@pytest.mark.parametrize("case", ["cornell_pt", "spheres_ao", "gravity_scivis", "materials_hdri_pt"])
 @pytest.mark.parametrize("n", [2, 3])
 def test_multidevice_frame_equals_the_single_device_frame(osp, case, n):
     spec, kind, params = {"cornell_pt": (T.cornell_box(), "pathtracer", {"pixelSamples": 2}),
+                          "materials_hdri_pt": (_materials_and_hdri(), "pathtracer", {"pixelSamples": 1}),
                           "spheres_ao": (T.random_spheres(), "ao", {"pixelSamples": 2}),
                           "gravity_scivis": (T.gravity_spheres_volume(32), "scivis", {"pixelSamples": 1})}[case]
     w, h = 320, 200   # 5 x 4 tiles, the last row and column clipped

@@ -335,7 +335,7 @@ typedef struct {
   float bounds[6];
 } OcWorld;
 
-enum { OC_CAMERA_PERSPECTIVE = 0, OC_CAMERA_ORTHOGRAPHIC = 1 };
+enum { OC_CAMERA_PERSPECTIVE = 0, OC_CAMERA_ORTHOGRAPHIC = 1, OC_CAMERA_PANORAMIC = 2 };
 /* camera (reference: PerspectiveCameraShared.h, PerspectiveCamera.cpp:26-117; OrthographicCameraShared.h,
  * OrthographicCamera.cpp:25-49: for the orthographic type dir_00 is the (normalised) view direction, org the lower
  * left corner of the image plane, du_size / dv_up its extents, imgPlaneSizeY the `height` parameter) */

@@ -1100,6 +1100,28 @@ V2 pixelFilterSample(const OcRenderer &r, V2 s)
 // camera/PerspectiveCamera.ispc:16-64 (no stereo / motion blur)
 void cameraInitRay(const OcCamera &cam, Ray &ray, V2 screen, V2 lens, V2 pixelCenter)
 {
+  if (cam.type == OC_CAMERA_PANORAMIC) { // PanoramicCamera_initRay (camera/PanoramicCamera.ispc:14-92)
+    float offset = 0.f;
+    const float ipd = cam.ipdOffset.x;
+    if (cam.stereoMode == 1u) offset = -ipd;
+    else if (cam.stereoMode == 2u) offset = ipd;
+    else if (cam.stereoMode >= 3u) {
+      const bool sbs = cam.stereoMode == 3u;
+      float &split = sbs ? screen.x : screen.y;
+      const float pc = sbs ? pixelCenter.x : pixelCenter.y;
+      split *= 2.f;
+      if (pc < 0.5f) offset = -ipd;
+      else { offset = ipd; split -= 1.f; }
+    }
+    screen = {lerp(screen.x, cam.subImage[0], cam.subImage[2]), lerp(screen.y, cam.subImage[1], cam.subImage[3])};
+    const float phi = TWO_PI * screen.x, theta = (float)M_PI * screen.y;
+    const float sinTheta = sinf(theta), cosTheta = cosf(theta);
+    const V3 localDir = cartesian(phi, sinTheta, cosTheta);
+    const V3 vx = v3(cam.du_size), vy = v3(cam.dv_up), vz = v3(cam.dir_00);
+    const V3 dir = (-localDir.y) * vx + (-localDir.z) * vy + localDir.x * vz;
+    setRay(ray, v3(cam.org) + offset * cross(dir, vy), dir, cam.nearClip, INF);
+    return;
+  }
   V3 eyeOffset = v3(0.f);
   if (cam.type != OC_CAMERA_ORTHOGRAPHIC && cam.stereoMode >= 3u) { // side by side / top-bottom stereo (:28-40)
     const bool sbs = cam.stereoMode == 3u;
@@ -2172,6 +2194,24 @@ ORACLE_API void oracle_commit_camera(const float pos[3], const float dir[3], con
     float apertureRadius, float focusDistance, OcCamera *out)
 {
   oracle_commit_camera_stereo(pos, dir, up, fovy, aspect, apertureRadius, focusDistance, 0, 0.0635f, out);
+}
+// camera/PanoramicCamera.cpp:29-53
+ORACLE_API void oracle_commit_pano_camera(const float pos[3], const float dir[3], const float up[3], int stereoMode, float interpupillaryDistance,
+    OcCamera *out)
+{
+  const V3 d = normalize(v3(dir[0], dir[1], dir[2])), u = normalize(v3(up[0], up[1], up[2]));
+  const V3 vz = -1.f * normalize(d);
+  const V3 vx = normalize(cross(u, vz));
+  const V3 vy = cross(vz, vx);
+  memset(out, 0, sizeof(*out));
+  out->type = OC_CAMERA_PANORAMIC;
+  out->org = {pos[0], pos[1], pos[2]};
+  out->du_size = {vx.x, vx.y, vx.z}; out->dv_up = {vy.x, vy.y, vy.z}; out->dir_00 = {vz.x, vz.y, vz.z}; out->direction = {d.x, d.y, d.z};
+  out->nearClip = 1e-6f; out->subImage[2] = 1.f; out->subImage[3] = 1.f;
+  out->stereoMode = (uint32_t)stereoMode;
+  float ipd = 0.5f * interpupillaryDistance;
+  if (stereoMode == 4) ipd = -ipd;
+  out->ipdOffset = {ipd, 0.f, 0.f};
 }
 // + PerspectiveCamera.cpp:35-100: stereo modes (aspect of the halves, eye offset along du, LEFT / RIGHT folded into org)
 ORACLE_API void oracle_commit_camera_stereo(const float pos[3], const float dir[3], const float up[3], float fovy, float aspect,

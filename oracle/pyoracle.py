@@ -836,6 +836,13 @@ class Scene:
 def make_camera(position, direction=(0, 0, 1), up=(0, 1, 0), fovy=60.0, aspect=1.0, aperture_radius=0.0, focus_distance=1.0,
                 kind="perspective", height=1.0, stereo_mode=0, interpupillary_distance=0.0635):
     cam = Camera()
+    if kind == "panoramic":
+        L = lib()
+        L.oracle_commit_pano_camera.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p]
+        a, b, c = (np.ascontiguousarray(v, np.float32) for v in (position, direction, up))
+        L.oracle_commit_pano_camera(a.ctypes.data, b.ctypes.data, c.ctypes.data, int(stereo_mode), float(interpupillary_distance),
+                                    C.cast(C.pointer(cam), C.c_void_p))
+        return cam
     if kind == "orthographic":
         lib().oracle_commit_ortho_camera(_f3(position), _f3(direction), _f3(up), float(height), float(np.float32(aspect)), C.byref(cam))
         return cam

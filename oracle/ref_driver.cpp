@@ -58,6 +58,7 @@
 #include "pf/LUTPixelFilterShared.h"
 #include "camera/PerspectiveCameraShared.h"
 #include "camera/OrthographicCameraShared.h"
+#include "camera/PanoramicCameraShared.h"
 #include "fb/LocalFBShared.h"
 #include "fb/FrameBufferView.ih"
 #include "fb/RenderTaskDesc.ih"
@@ -724,7 +725,16 @@ REF_API int ospref_render_frame(const OcWorld *w, const OcCamera *cam, const OcR
   sycl::event ev;
   const ospray::FeatureFlags ff = allFeatures();
   const vec3ui dims = make_vec3ui(8, 8, (uint32_t)taskIDs.size());
-  Camera *camera = cam->type == OC_CAMERA_ORTHOGRAPHIC ? &oc.super : &pc.super;
+  PanoramicCamera pano; // camera/PanoramicCamera.cpp:29-53 (committed values)
+  if (cam->type == OC_CAMERA_PANORAMIC) {
+    pano.super.direction = v3(cam->direction); pano.super.nearClip = cam->nearClip;
+    pano.super.subImage = box2f(make_vec2f(cam->subImage[0], cam->subImage[1]), make_vec2f(cam->subImage[2], cam->subImage[3]));
+    pano.super.shutter = box1f(0.5f, 0.5f);
+    pano.org = v3(cam->org);
+    pano.frame = linear3f(v3(cam->du_size), v3(cam->dv_up), v3(cam->dir_00));
+    pano.stereoMode = (int)cam->stereoMode; pano.ipd_offset = cam->ipdOffset.x;
+  }
+  Camera *camera = cam->type == OC_CAMERA_PANORAMIC ? &pano.super : cam->type == OC_CAMERA_ORTHOGRAPHIC ? &oc.super : &pc.super;
   uint64_t before[2]; ospref_ray_counters(before, 0);
   if (ren->type == OC_RENDERER_PATHTRACER)
     PathTracer_renderTaskLauncher(&q, &ev, dims, renderer, &lfb.super, camera, &s->world, taskIDs.data(), ff);

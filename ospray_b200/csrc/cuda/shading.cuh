@@ -1474,8 +1474,28 @@ __device__ __forceinline__ float cameraStereoSplit(const OcCamera &cam, vec2f &s
   split -= 1.f;
   return 1.f;
 }
+// PanoramicCamera_initRay (camera/PanoramicCamera.ispc:14-92): latitude / longitude directions around the camera frame, the eye
+// offset perpendicular to each ray's direction; returns sin(theta) for the ray cone
+static __device__ __noinline__ float panoramicInitRay(const OcCamera &cam, Ray &ray, vec2f screen, vec2f pixelCenter)
+{
+  float offset = 0.f;
+  if (cam.stereoMode == 1u) offset = -cam.ipdOffset.x;
+  else if (cam.stereoMode == 2u) offset = cam.ipdOffset.x;
+  else offset = cameraStereoSplit(cam, screen, pixelCenter) * cam.ipdOffset.x;
+  screen = make_vec2f(lerpf(screen.x, cam.subImage[0], cam.subImage[2]), lerpf(screen.y, cam.subImage[1], cam.subImage[3]));
+  const float phi = OC_TWO_PI * screen.x, theta = OC_PI * screen.y;
+  float sinTheta, cosTheta;
+  sincosf(theta, &sinTheta, &cosTheta);
+  const vec3f localDir = cartesian(phi, sinTheta, cosTheta);
+  linear3f f; f.vx = toV(cam.du_size); f.vy = toV(cam.dv_up); f.vz = toV(cam.dir_00);
+  const vec3f dir = f * make_vec3f(-localDir.y, -localDir.z, localDir.x);
+  const vec3f org = toV(cam.org) + offset * cross(dir, f.vy);
+  setRay(ray, org, dir, cam.nearClip, INFINITY);
+  return sinTheta;
+}
 __device__ __forceinline__ void cameraInitRay(const OcCamera &cam, Ray &ray, vec2f screen, vec2f lens, vec2f pixelCenter)
 {
+  if (cam.type == OC_CAMERA_PANORAMIC) { panoramicInitRay(cam, ray, screen, pixelCenter); return; }
   vec3f org = toV(cam.org);
   if (cam.type != OC_CAMERA_ORTHOGRAPHIC) {
     const float eye = cameraStereoSplit(cam, screen, pixelCenter);
@@ -1504,6 +1524,13 @@ __device__ __forceinline__ RayCone cameraInitRayCone(const OcCamera &cam, vec2f 
 {
   RayCone rc;
   const float subH = fabsf(cam.subImage[3] - cam.subImage[1]);
+  if (cam.type == OC_CAMERA_PANORAMIC) { // PanoramicCamera.ispc:84-91
+    Ray unused;
+    rc.width = 0.f;
+    rc.dwdt = OC_PI * panoramicInitRay(cam, unused, screen, pixelCenter) * subH;
+    if (cam.stereoMode == 4u) rc.dwdt *= 2.f;
+    return rc;
+  }
   if (cam.type == OC_CAMERA_ORTHOGRAPHIC) {
     rc.width = cam.imgPlaneSizeY * subH; rc.dwdt = 0.f;
     return rc;

@@ -65,7 +65,7 @@ OSPLight CudaDevice::newLight(const char *type)
 }
 OSPCamera CudaDevice::newCamera(const char *type)
 {
-  if (std::string(type) != "perspective" && std::string(type) != "orthographic") return nullptr;
+  if (std::string(type) != "perspective" && std::string(type) != "orthographic" && std::string(type) != "panoramic") return nullptr;
   return (OSPCamera) new Camera(type);
 }
 OSPGeometry CudaDevice::newGeometry(const char *type)

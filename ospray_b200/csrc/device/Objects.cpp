@@ -217,6 +217,22 @@ void Camera::commit()
   dir = normalize(xfmVector(xfm, dir));
   up = normalize(xfmVector(xfm, up));
 
+  if (type == "panoramic") { // camera/PanoramicCamera.cpp:29-53
+    sh = OcCamera{};
+    sh.type = OC_CAMERA_PANORAMIC;
+    const vec3f vz = -normalize(dir);
+    const vec3f vx = normalize(cross(up, vz));
+    const vec3f vy = cross(vz, vx);
+    sh.org = toOc(pos);
+    sh.du_size = toOc(vx); sh.dv_up = toOc(vy); sh.dir_00 = toOc(vz); sh.direction = toOc(dir);
+    sh.nearClip = nearClip;
+    sh.subImage[0] = imageStart.x; sh.subImage[1] = imageStart.y; sh.subImage[2] = imageEnd.x; sh.subImage[3] = imageEnd.y;
+    sh.stereoMode = getParam<uint32_t>("stereoMode", OSP_STEREO_NONE);
+    float ipd = 0.5f * getParam<float>("interpupillaryDistance", 0.0635f);
+    if (sh.stereoMode == OSP_STEREO_TOP_BOTTOM) ipd = -ipd; // left eye at the top (image origin at the lower left)
+    sh.ipdOffset = toOc(make_vec3f(ipd, 0.f, 0.f));
+    return;
+  }
   if (type == "orthographic") { // camera/OrthographicCamera.cpp:25-49
     const float height = getParam<float>("height", 1.f);
     const float oaspect = getParam<float>("aspect", 1.f);

@@ -89,7 +89,7 @@ Data *getParamData(ManagedObject &o, const std::string &name, OSPDataType elemTy
 struct Camera : public ManagedObject
 {
   explicit Camera(const std::string &type);
-  std::string toString() const override { return type == "orthographic" ? "ospray::OrthographicCamera" : "ospray::PerspectiveCamera"; }
+  std::string toString() const override { return type == "orthographic" ? "ospray::OrthographicCamera" : type == "panoramic" ? "ospray::PanoramicCamera" : "ospray::PerspectiveCamera"; }
   void commit() override;
   std::string type;
   OcCamera sh{};

@@ -596,7 +596,8 @@ def make_camera(world, width, height, kind="perspective", ortho_height=1.0, ster
         cam.set("stereoMode", osp.Typed(osp.OSP_UINT, int(stereo_mode)))
     if interpupillary_distance is not None:
         cam.set("interpupillaryDistance", float(interpupillary_distance))
-    cam.set("aspect", float(np.float32(width) / np.float32(height)))
+    if kind != "panoramic":  # (the panoramic camera has no aspect: a full sphere whatever the image shape)
+        cam.set("aspect", float(np.float32(width) / np.float32(height)))
     cam.set("position", p["position"]).set("direction", p["direction"]).set("up", p["up"])
     return cam.commit(), p
 

@@ -457,6 +457,11 @@ CASES = {
     "cornell_stereo_sbs_pt": (T.cornell_box, "pathtracer", {"pixelSamples": 2}, 1, {"stereoMode": 3, "interpupillaryDistance": 0.4}),
     "spheres_stereo_tb_scivis": (T.random_spheres, "scivis", {"shadows": True, "aoSamples": 1}, 1, {"stereoMode": 4, "interpupillaryDistance": 0.3}),
     "boxes_stereo_left_ao": (lambda: T.boxes(lit=True), "ao", {"aoSamples": 2}, 1, {"stereoMode": 1, "interpupillaryDistance": 0.5}),
+    # panoramic camera (camera/PanoramicCamera.ispc): latitude / longitude rays, mono and with the eyes side by side / one above the other
+    "spheres_pano_pt": (T.random_spheres, "pathtracer", {"pixelSamples": 2}, 1, {"camera": "panoramic"}),
+    "boxes_pano_sbs_scivis": (lambda: T.boxes(lit=True), "scivis", {"shadows": True, "aoSamples": 1}, 1,
+                              {"camera": "panoramic", "stereoMode": 3, "interpupillaryDistance": 0.6}),
+    "spheres_pano_tb_ao": (T.random_spheres, "ao", {"aoSamples": 2}, 1, {"camera": "panoramic", "stereoMode": 4, "interpupillaryDistance": 0.4}),
     "cornell_ortho_pt": (T.cornell_box, "pathtracer", {"pixelSamples": 2}, 1, {"camera": "orthographic", "height": 2.2}),
     "spheres_ortho_scivis": (T.random_spheres, "scivis", {"shadows": True, "aoSamples": 1}, 1, {"camera": "orthographic", "height": 2.6}),
     "sphere_lights_pt": (sphere_lit_boxes, "pathtracer", {"pixelSamples": 2}, 2),

@@ -275,7 +275,7 @@ typedef struct OcInstanceS {
   const float *modelAreaPDF;
 } OcInstance;
 
-enum { OC_LIGHT_AMBIENT = 0, OC_LIGHT_DISTANT = 2, OC_LIGHT_HDRI = 3, OC_LIGHT_SPHERE = 4, OC_LIGHT_QUAD = 5, OC_LIGHT_SPOT = 6,
+enum { OC_LIGHT_AMBIENT = 0, OC_LIGHT_CYLINDER = 1, OC_LIGHT_DISTANT = 2, OC_LIGHT_HDRI = 3, OC_LIGHT_SPHERE = 4, OC_LIGHT_QUAD = 5, OC_LIGHT_SPOT = 6,
        OC_LIGHT_GEOMETRY = 8 }; /* values of ispc::LightType */
 struct OcInstanceS;
 /* lights (reference: lights/LightShared.h:79-110, QuadLightShared.h, DirectionalLightShared.h,
@@ -296,6 +296,8 @@ typedef struct {
   /* geometry light: the proxy the pathtracer makes for every geometric model with emissive primitives
    * (ispc::GeometryLight, render/pathtracer/GeometryLightShared.h; PathTracerData.cpp:87-160): the model and the instance
    * it sits in, the emissive primitives, the CDF of their world-space areas, pdf = 1 / total area */
+  /* cylinder (ispc::CylinderLight, lights/CylinderLightShared.h, CylinderLight.cpp:22-97): position = position0, edge1 =
+   * position1, radius, radiance (0 when the cylinder is degenerate) */
   /* hdri (ispc::HDRILight, lights/HDRILightShared.h, HDRILight.cpp:20-97): fx / fy / fz = light2world, wx / wy / wz =
    * world2light, radiance = radianceScale, the latitude / longitude map and the CDFs of its importance distribution
    * (ospcuda_hdri_distribution: cdfX = sizeX * sizeY floats, row-wise; cdfY = sizeY floats) */

@@ -2256,6 +2256,7 @@ ORACLE_API void oracle_transform_light(OcLight *l, const float *x)
     break;
   }
   case OC_LIGHT_SPHERE: l->position = oc(xfmPoint(xfm, v3(l->position))); break;
+  case OC_LIGHT_CYLINDER: l->position = oc(xfmPoint(xfm, v3(l->position))); l->edge1 = oc(xfmPoint(xfm, v3(l->edge1))); break; // CylinderLight.ispc:12-19
   case OC_LIGHT_SPOT: { // fx / fy / fz = c0 / c90 / direction
     const V3 direction = normalize(xfmVector(xfm.l, v3(l->fz)));
     const V3 c90 = normalize(cross(xfmVector(xfm.l, v3(l->fx)), direction));

@@ -544,8 +544,23 @@ class Scene:
         for ls, lxfm in all_lights:
             l = Light()
             p = ls.params
-            t = {"ambient": OC_LIGHT_AMBIENT, "distant": OC_LIGHT_DISTANT, "quad": OC_LIGHT_QUAD, "sphere": 4, "spot": 6, "hdri": 3}[ls.type]
-            if ls.type == "hdri":  # lights/HDRILight.cpp:73-97 (frame from direction / up; the distribution is built by the checker's own code)
+            t = {"ambient": OC_LIGHT_AMBIENT, "distant": OC_LIGHT_DISTANT, "quad": OC_LIGHT_QUAD, "sphere": 4, "spot": 6, "hdri": 3, "cylinder": 1}[ls.type]
+            if ls.type == "cylinder":  # lights/CylinderLight.cpp:22-97
+                f = np.float32
+                p0, p1 = np.asarray(p.get("position0", (0, 0, 0)), f), np.asarray(p.get("position1", (0, 0, 1)), f)
+                radius = f(p.get("radius", 1.0))
+                ci = (np.asarray(p.get("color", (1, 1, 1)), f) * f(p.get("intensity", 1.0))).astype(f)
+                zmax = np.sqrt(np.dot(p1 - p0, p1 - p0), dtype=f)
+                area = f(f(f(2.0) * f(np.pi)) * zmax * radius)
+                iq = p.get("intensityQuantity", 0)  # OSP_INTENSITY_QUANTITY_RADIANCE = 0, IRRADIANCE = 1, INTENSITY = 2, POWER = 3
+                iq = getattr(iq, "value", iq)
+                rad = ci if iq == 0 else (f(np.pi) * ci / area).astype(f) if iq == 2 else (ci / f(f(np.pi) * area)).astype(f) if iq == 3 else np.zeros(3, f)
+                if zmax <= 0 or radius <= 0 or (iq in (2, 3) and area <= 0):
+                    rad = np.zeros(3, f)
+                l.type, l.isVisible, l.radiance, l.radius = 1, int(p.get("visible", True)), Vec3(*map(float, rad)), float(radius)
+                l.position, l.edge1 = Vec3(*map(float, p0)), Vec3(*map(float, p1))
+                t = 1
+            elif ls.type == "hdri":  # lights/HDRILight.cpp:73-97 (frame from direction / up; the distribution is built by the checker's own code)
                 f = np.float32
                 nrm = lambda v: (v / np.sqrt(np.dot(v, v), dtype=np.float32)).astype(np.float32)
                 d, up = np.asarray(p.get("direction", (0, 0, 1)), f), np.asarray(p.get("up", (0, 1, 0)), f)

@@ -50,6 +50,7 @@
 #include "lights/DirectionalLightShared.h"
 #include "lights/AmbientLightShared.h"
 #include "lights/HDRILightShared.h"
+#include "lights/CylinderLightShared.h"
 #include "math/Distribution2DShared.h"
 #include "render/pathtracer/PathTracerShared.h"
 #include "render/scivis/SciVisShared.h"
@@ -182,7 +183,7 @@ struct Scene
   std::deque<std::vector<int>> geoPrimIDs; std::deque<std::vector<float>> geoDistributions;
   std::vector<float> geoCDF;
   std::vector<Instance *> instancePtrs;
-  std::deque<QuadLight> quads; std::deque<PointLight> points; std::deque<SpotLight> spots; std::deque<DirectionalLight> dirs; std::deque<AmbientLight> ambients; std::deque<HDRILight> hdris; std::deque<Distribution2D> hdriDists; std::deque<std::vector<float>> hdriCdfs;
+  std::deque<QuadLight> quads; std::deque<PointLight> points; std::deque<SpotLight> spots; std::deque<DirectionalLight> dirs; std::deque<AmbientLight> ambients; std::deque<HDRILight> hdris; std::deque<CylinderLight> cylinders; std::deque<Distribution2D> hdriDists; std::deque<std::vector<float>> hdriCdfs;
   std::vector<Light *> ptLights, svLights;
   Instance identityInstance; // stands in for the NULL instance of world lights: the scalar light dispatch reads
                              // self->instance->motionBlur unconditionally (lights/LightDispatch.ispc:36-60)
@@ -533,6 +534,14 @@ void buildScene(Scene &s, const OcWorld *w, const OcRenderer *ren)
       d.frame = linear3f(v3(l.fx), v3(l.fy), v3(l.fz));
       d.irradiance = v3(l.radiance); d.cosAngle = l.cosAngle; d.pdf = l.pdf;
       return &d.super;
+    }
+    if (l.type == OC_LIGHT_CYLINDER) { // lights/CylinderLight.cpp:22-55 (committed values)
+      s.cylinders.emplace_back();
+      CylinderLight &c = s.cylinders.back();
+      c.super.isVisible = l.isVisible != 0; c.super.instance = &s.identityInstance;
+      c.radiance = v3(l.radiance); c.radius = l.radius;
+      c.pre.position0 = v3(l.position); c.pre.position1 = v3(l.edge1);
+      return &c.super;
     }
     if (l.type == OC_LIGHT_HDRI) { // lights/HDRILight.cpp:20-97: the reference builds the importance distribution of the map itself
       s.hdris.emplace_back();

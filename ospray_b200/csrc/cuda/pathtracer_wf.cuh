@@ -454,7 +454,8 @@ static __device__ __noinline__ vec3f ptVirtualLightsVol(const PtArgs &k, uint32_
   for (uint32_t i = numGeoLights; i < numLights; i++) {
     const OcLight &l = world->lights[i];
     if (!straightPath || l.isVisible) {
-      const LightEval le = l.type == OC_LIGHT_HDRI ? HDRILight_eval(l, rdir, upper) : Light_eval(l, lastP, lastNs, rdir, lower, upper);
+      const LightEval le = l.type == OC_LIGHT_HDRI ? HDRILight_eval(l, rdir, upper)
+          : l.type == OC_LIGHT_CYLINDER ? CylinderLight_eval(l, lastP, rdir, lower, upper) : Light_eval(l, lastP, lastNs, rdir, lower, upper);
       if (reduce_max(le.radiance) > 0.0f) {
         float misWeight = 1.0f;
         if (selectionPDF) {
@@ -901,7 +902,8 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
           const float lightSelectionProb = sel.prob * numLightSamples;
           const OcLight &light = world->lights[sel.idx];
           LightSample ls = (TEX && light.type == OC_LIGHT_GEOMETRY) ? GeometryLight_sample(world, ren, light, dg, sl)
-              : (TEX && light.type == OC_LIGHT_HDRI) ? HDRILight_sample(light, sl) : Light_sample(light, dg, sl);
+              : (TEX && light.type == OC_LIGHT_HDRI) ? HDRILight_sample(light, sl)
+              : (TEX && light.type == OC_LIGHT_CYLINDER) ? CylinderLight_sample(light, dg, sl) : Light_sample(light, dg, sl);
           ls.weight = ls.weight / lightSelectionProb;
           ls.pdf *= lightSelectionProb;
           if (!(reduce_max(ls.weight) <= 0.0f || ls.pdf <= 0.0f)) {

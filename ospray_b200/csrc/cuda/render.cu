@@ -101,7 +101,8 @@ __device__ __forceinline__ vec3f evaluateVirtualLights(Ctx &c, bool straightPath
   for (uint32_t i = numGeoLights; i < numLights; i++) {
     const OcLight &l = c.world->lights[i];
     if (!straightPath || l.isVisible) {
-      const LightEval le = (TEX && l.type == OC_LIGHT_HDRI) ? HDRILight_eval(l, ray.dir, upper) : Light_eval(l, last.P, last.Ns, ray.dir, lower, upper);
+      const LightEval le = (TEX && l.type == OC_LIGHT_HDRI) ? HDRILight_eval(l, ray.dir, upper)
+          : (TEX && l.type == OC_LIGHT_CYLINDER) ? CylinderLight_eval(l, last.P, ray.dir, lower, upper) : Light_eval(l, last.P, last.Ns, ray.dir, lower, upper);
       if (reduce_max(le.radiance) > 0.0f) {
         float misWeight = 1.0f;
         if (selectionPDF) misWeight = misHeuristic(last.pdf_w, selectionPDF * le.pdf);
@@ -275,7 +276,8 @@ static __device__ __noinline__ SSI SciVis_computeShading(Ctx &c, const Different
   vec3f color = make_vec3f(0.f);
   const OcWorld *w = c.world;
   for (uint32_t i = w->numScivisLightsVisibleOnly; i < w->numScivisLights; i++) {
-    const LightSample light = Light_sample(w->scivisLights[i], dg, make_vec2f(0.f, 0.f));
+    const LightSample light = (TEX && w->scivisLights[i].type == OC_LIGHT_CYLINDER) ? CylinderLight_sample(w->scivisLights[i], dg, make_vec2f(0.f, 0.f))
+                                                                                   : Light_sample(w->scivisLights[i], dg, make_vec2f(0.f, 0.f));
     if (reduce_max(light.weight) > 0.f) {
       const float cosNL = dot(light.dir, dg.Ns);
       if (cosNL < 0.0f) continue;
@@ -398,7 +400,8 @@ static __device__ vec3f evaluateLightsSciVis(Ctx &c, const Ray &ray)
   for (uint32_t i = 0; i < w->numScivisLights; i++) {
     const OcLight &l = w->scivisLights[i];
     if (!l.isVisible) continue;
-    const LightEval le = (TEX && l.type == OC_LIGHT_HDRI) ? HDRILight_eval(l, ray.dir, ray.t) : Light_eval(l, ray.org, make_vec3f(0.f), ray.dir, ray.t0, ray.t);
+    const LightEval le = (TEX && l.type == OC_LIGHT_HDRI) ? HDRILight_eval(l, ray.dir, ray.t)
+        : (TEX && l.type == OC_LIGHT_CYLINDER) ? CylinderLight_eval(l, ray.org, ray.dir, ray.t0, ray.t) : Light_eval(l, ray.org, make_vec3f(0.f), ray.dir, ray.t0, ray.t);
     color = color + le.radiance;
   }
   return color;

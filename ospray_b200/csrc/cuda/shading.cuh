@@ -1290,6 +1290,96 @@ struct LightSample;
 static __device__ __noinline__ LightSample GeometryLight_sample(const OcWorld *world, const OcRenderer &ren, const OcLight &l,
     const DifferentialGeometry &dg, vec2f s);
 
+// CylinderLight (lights/CylinderLight.ispc:30-231): the rectangle that bounds the cylinder as seen from P is sampled by solid
+// angle (cosine-weighted, like the quad light), the sample counts if its direction meets the cylinder's body
+// (intersectCylinder, common/Intersect.ih:80-131: entry.hit only for body hits). Like the hdri light it is known to the
+// kernels of the extended instantiation only.
+__device__ __forceinline__ bool cylinderBodyEntry(vec3f rayOrg, vec3f rayDir, vec3f v0, vec3f v1, float radius, float &t)
+{
+  const vec3f cZ = v1 - v0, q = rayOrg - v0;
+  const float z2 = dot(cZ, cZ), d = dot(cZ, rayDir), c = dot(cZ, q);
+  const float A = z2 - sqr(d);
+  const float B = z2 * dot(q, rayDir) - c * d;
+  const float C = z2 * dot(q, q) - sqr(c) - sqr(radius) * z2;
+  float radical = B * B - A * C;
+  if (radical < 0.f) return false;
+  radical = sqrtf(radical);
+  const float tin = (-B - radical) / A;
+  const float yin = c + tin * d;
+  t = tin;
+  return yin > 0.f && yin < z2;
+}
+__device__ __forceinline__ void cylinderComputeRectBounds(vec3f position0, vec3f position1, float radius, vec3f P, vec3f &q0, vec3f &e0,
+    vec3f &e1, float &S)
+{
+  vec3f O = position0;
+  vec3f Z = position1 - position0;
+  const float H = length(Z);
+  Z = Z / H;
+  vec3f Dp = P - O;
+  float h0 = -dot(Dp, Z);
+  if (h0 < -H) {
+    O = position1;
+    Z = -1.f * Z;
+    Dp = P - O;
+    h0 = -dot(Dp, Z);
+  }
+  const vec3f D = -h0 * Z - Dp;
+  const float d = length(D);
+  const float srad = fminf(radius / d, 1.f);
+  const float q = fmaxf(1.f - sqr(srad), 4.e-6f);
+  const float b = d * q;
+  const float c = radius * sqrtf(q);
+  const float b2c2 = sqr(b) + sqr(c);
+  const vec3f X = normalize(cross(D, Z));
+  const float h1 = (1.f + srad) * (h0 + H);
+  const float hO = h0 < 0.f ? (1.f + srad) * h0 : h0;
+  q0 = P + D * q - c * X + hO * Z;
+  e0 = 2.f * c * X;
+  e1 = (h1 - hO) * Z;
+  S = 2.f * atanf(c * h1 / (b * sqrtf(b2c2 + sqr(h1)))) - 2.f * atanf(c * hO / (b * sqrtf(b2c2 + sqr(hO)))); // cylinderAxialSolidAngle
+}
+static __device__ __noinline__ LightSample CylinderLight_sample(const OcLight &l, const DifferentialGeometry &dg, vec2f sp)
+{
+  LightSample res; res.weight = make_vec3f(0.f); res.pdf = 0.f; res.dir = make_vec3f(0.f); res.dist = 0.f;
+  const vec3f p0 = toV(l.position), p1 = toV(l.edge1);
+  float S = 0.f, pdf = 0.f;
+  vec3f dir, q0, e0, e1;
+  cylinderComputeRectBounds(p0, p1, l.radius, dg.P, q0, e0, e1, S);
+  if (sp.x == 0.0f && sp.y == 0.0f) { // scivis: towards the centre
+    dir = 0.5f * (p0 + p1) - dg.P;
+    if (S > 0.f) pdf = 1.f;
+  } else {
+    const vec3f n = normalize(cross(e0, e1));
+    const SphericalQuad quad = SphericalQuad_create(q0, e0, e1, n, dg.P);
+    const vec3f cosW = computeCosineWeightedRNG(q0, e0, e1, dg.P, dg.Ng, sp);
+    dir = sampleSphericalQuad(quad, make_vec2f(cosW.x, cosW.y));
+    pdf = cosW.z;
+  }
+  if (S <= 0.f || pdf == 0.f) return res;
+  res.dir = normalize(dir);
+  float t;
+  if (cylinderBodyEntry(dg.P, res.dir, p0, p1, l.radius, t)) {
+    res.pdf = pdf / S;
+    res.weight = toV(l.radiance) * (1.f / res.pdf);
+    res.dist = t;
+  }
+  return res;
+}
+static __device__ __noinline__ LightEval CylinderLight_eval(const OcLight &l, vec3f P, vec3f dir, float minDist, float maxDist)
+{
+  LightEval res; res.radiance = make_vec3f(0.f); res.pdf = 0.f;
+  const vec3f p0 = toV(l.position), p1 = toV(l.edge1);
+  float t;
+  if (cylinderBodyEntry(P, dir, p0, p1, l.radius, t) && minDist < t && t <= maxDist) {
+    vec3f q0, e0, e1;
+    float S;
+    cylinderComputeRectBounds(p0, p1, l.radius, P, q0, e0, e1, S);
+    if (S > 0.f) { res.radiance = toV(l.radiance); res.pdf = 1.f / S; }
+  }
+  return res;
+}
+
 // HDRILight_sample / _eval (lights/HDRILight.ispc:14-46, 82-110) with Distribution2D_sample / _pdf (math/Distribution2D.ispc:9-43);
 // only the kernels with texture support know this light (a frame with one runs them)
 static __device__ __noinline__ LightSample HDRILight_sample(const OcLight &l, vec2f s)

@@ -60,7 +60,7 @@ void CudaDevice::copyData(const OSPData source, OSPData destination, const vec3u
 OSPLight CudaDevice::newLight(const char *type)
 {
   const std::string t(type);
-  if (t != "ambient" && t != "distant" && t != "quad" && t != "sphere" && t != "spot" && t != "hdri") return nullptr;
+  if (t != "ambient" && t != "distant" && t != "quad" && t != "sphere" && t != "spot" && t != "hdri" && t != "cylinder") return nullptr;
   return (OSPLight) new Light(t);
 }
 OSPCamera CudaDevice::newCamera(const char *type)

@@ -1011,6 +1011,22 @@ void Light::commit()
     sh.ppdf = 1.f / ((float)M_PI * (radius * radius - innerRadius * innerRadius));
     sh.intensity = toOc(radIntensity);
     sh.radiance = toOc(radiance);
+  } else if (type == "cylinder") {
+    // lights/CylinderLight.cpp:22-97
+    const vec3f position0 = getParam<vec3f>("position0", make_vec3f(0.f));
+    const vec3f position1 = getParam<vec3f>("position1", make_vec3f(0.f, 0.f, 1.f));
+    const float radius = getParam<float>("radius", 1.f);
+    const uint32_t iq = getParam<uint32_t>("intensityQuantity", OSP_INTENSITY_QUANTITY_RADIANCE);
+    const float cylinderArea = 2.f * (float)M_PI * length(position1 - position0) * radius;
+    vec3f radiance = make_vec3f(0.f);
+    if (iq == OSP_INTENSITY_QUANTITY_POWER) { if (cylinderArea > 0.f) radiance = coloredIntensity / ((float)M_PI * cylinderArea); }
+    else if (iq == OSP_INTENSITY_QUANTITY_INTENSITY) { if (cylinderArea > 0.f) radiance = (float)M_PI * coloredIntensity / cylinderArea; }
+    else if (iq == OSP_INTENSITY_QUANTITY_RADIANCE) radiance = coloredIntensity;
+    else postStatusMsg(OSP_LOG_WARNING, toString() + " unsupported 'intensityQuantity' value");
+    if (length(position1 - position0) <= 0.f || radius <= 0.f) radiance = make_vec3f(0.f);
+    sh.type = OC_LIGHT_CYLINDER;
+    sh.position = toOc(position0); sh.edge1 = toOc(position1); sh.radius = radius;
+    sh.radiance = toOc(radiance);
   } else if (type == "hdri") {
     // lights/HDRILight.cpp:73-110: frame from direction / up, intensityQuantity must be SCALE, the importance distribution
     // of the map (HDRILight_initDistribution) rebuilt at every commit
@@ -1040,7 +1056,7 @@ void Light::commit()
     sh.hdriMap = hdriMap->devPtr();
     sh.hdriCdfX = hdriCdfX.as<float>(); sh.hdriCdfY = hdriCdfY.as<float>();
   } else
-    throw std::runtime_error("cuda device: light type '" + type + "' is not supported (ambient, distant, quad, sphere, spot, hdri)");
+    throw std::runtime_error("cuda device: light type '" + type + "' is not supported (ambient, cylinder, distant, quad, sphere, spot, hdri)");
 }
 
 // ---- Group (common/Group.cpp:69-209) ------------------------------------------------------------------
@@ -1249,6 +1265,9 @@ void World::commit()
       break;
     }
     case OC_LIGHT_SPHERE: l.position = toOc(xfmPoint(xfm, V(l.position))); break;
+    case OC_LIGHT_CYLINDER: // CylinderLight.ispc:12-19: both end points
+      l.position = toOc(xfmPoint(xfm, V(l.position))); l.edge1 = toOc(xfmPoint(xfm, V(l.edge1)));
+      break;
     case OC_LIGHT_SPOT: { // fx / fy / fz = c0 / c90 / direction
       const vec3f direction = normalize(xfmVector(xfm.l, V(l.fz)));
       const vec3f c90 = normalize(cross(xfmVector(xfm.l, V(l.fx)), direction));
@@ -1290,7 +1309,7 @@ void World::commit()
   for (const auto &la : all) {
     const OcLight &lsh = la.first;
     pt.push_back(lsh);
-    if (lsh.type == OC_LIGHT_HDRI) hasHdriLight = true;
+    if (lsh.type == OC_LIGHT_HDRI || lsh.type == OC_LIGHT_CYLINDER) hasHdriLight = true; // (lights only the extended kernels know)
     if (lsh.type == OC_LIGHT_AMBIENT || lsh.type == OC_LIGHT_HDRI) {
       // SciVisData.cpp:17-52: ambient and hdri lights go to the visible-only front partition (no illumination from them)
       if (visibleOnly == sv.size()) sv.push_back(lsh);

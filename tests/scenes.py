@@ -62,6 +62,17 @@ def hdri_lit(instanced=False):
     return s
 
 
+def cylinder_lit():
+    """tube lights (lights/CylinderLight.ispc): one over the boxes, a thin one in a rotated + scaled instance's group"""
+    s = instanced_boxes_and_spheres()
+    s.lights = [T.LightSpec("cylinder", {"position0": (-1.5, 1.6, -0.5), "position1": (1.0, 1.8, 0.8), "radius": 0.15, "intensity": 6.0,
+                                         "color": (1.0, 0.9, 0.7)}),
+                T.LightSpec("ambient", {"intensity": 0.1})]
+    s.instances[1].group.lights = [T.LightSpec("cylinder", {"position0": (-8.0, 9.0, 2.0), "position1": (6.0, 7.0, -3.0), "radius": 0.8,
+                                                           "intensity": 30.0, "color": (0.6, 0.8, 1.0)})]
+    return s
+
+
 def translucent_cornell():
     """cornell box with a semi-transparent specular material: transparent shadows, Specular + Transmission lobes"""
     s = T.cornell_box()
@@ -529,6 +540,8 @@ CASES = {
     "hdri_pt": (hdri_lit, "pathtracer", {"pixelSamples": 2}, 2),
     "hdri_instanced_pt": (lambda: hdri_lit(True), "pathtracer", {"pixelSamples": 2, "lightSamples": 2}, 1),
     "hdri_scivis": (hdri_lit, "scivis", {"pixelSamples": 1, "aoSamples": 1, "shadows": True, "visibleLights": True}, 1),
+    "cylinder_lights_pt": (cylinder_lit, "pathtracer", {"pixelSamples": 2, "lightSamples": 2}, 2),
+    "cylinder_lights_scivis": (cylinder_lit, "scivis", {"pixelSamples": 1, "aoSamples": 1, "shadows": True, "visibleLights": True}, 1),
     "instance_lights_pt": (instance_lights, "pathtracer", {"pixelSamples": 2, "lightSamples": 2}, 1),
     "instance_lights_scivis": (instance_lights, "scivis", {"pixelSamples": 1, "aoSamples": 1, "shadows": True, "visibleLights": True}, 1),
     "debug_rayDir": (T.cornell_box, "debug", {"method": "rayDir"}, 1),
@@ -553,7 +566,7 @@ ORACLE_UNSUPPORTED = {"textured_pt", "textured_bias_pt", "cutout_pt", "backplate
                       "emissive_transparent_pt", "textured_scivis", "textured_ao", "cutout_scivis", "cutout_ao", "backplate_scivis",
                       "backplate_ao", "debug_texCoord", "debug_dPdt", "debug_dPds_tex", "debug_backplate", "metal_smooth_pt", "metal_rough_pt",
                       "plastic_smooth_pt", "plastic_rough_pt", "principled_plastic_pt", "principled_metal_pt", "principled_glass_pt",
-                      "principled_coat_pt", "principled_rough_layers_pt", "principled_emissive_pt", "glass_alloy_pt", "glass_alloy_rough_pt", "principled_sheen_pt", "principled_thin_pt", "principled_tex_pt", "principled_tex_cutout_pt", "velvet_paint_pt", "carpaint_pt", "hdri_pt", "hdri_instanced_pt", "hdri_scivis"}
+                      "principled_coat_pt", "principled_rough_layers_pt", "principled_emissive_pt", "glass_alloy_pt", "glass_alloy_rough_pt", "principled_sheen_pt", "principled_thin_pt", "principled_tex_pt", "principled_tex_cutout_pt", "velvet_paint_pt", "carpaint_pt", "hdri_pt", "hdri_instanced_pt", "hdri_scivis", "cylinder_lights_pt", "cylinder_lights_scivis"}
 # Rough dielectric coatings: MicrofacetDielectricLayer_Constructor reads self->eta for Ravg BEFORE assigning it
 # (bsdfs/MicrofacetDielectricLayer.ih:55 vs :68), i.e. whatever the shading context's memory held from the previous BSDF. The
 # device uses the intended value; against the reference's kernels the coated surfaces then differ by ~0.5 % in brightness

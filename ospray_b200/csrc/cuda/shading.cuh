@@ -1566,7 +1566,9 @@ __device__ __forceinline__ float cameraStereoSplit(const OcCamera &cam, vec2f &s
 }
 // PanoramicCamera_initRay (camera/PanoramicCamera.ispc:14-92): latitude / longitude directions around the camera frame, the eye
 // offset perpendicular to each ray's direction; returns sin(theta) for the ray cone
-static __device__ __noinline__ float panoramicInitRay(const OcCamera &cam, Ray &ray, vec2f screen, vec2f pixelCenter)
+// (by value: a Ray handed over by reference would move the callers' ray into local memory)
+struct PanoRay { vec3f org, dir; float sinTheta; };
+__device__ __forceinline__ PanoRay panoramicInitRay(const OcCamera &cam, vec2f screen, vec2f pixelCenter)
 {
   float offset = 0.f;
   if (cam.stereoMode == 1u) offset = -cam.ipdOffset.x;
@@ -1579,13 +1581,17 @@ static __device__ __noinline__ float panoramicInitRay(const OcCamera &cam, Ray &
   const vec3f localDir = cartesian(phi, sinTheta, cosTheta);
   linear3f f; f.vx = toV(cam.du_size); f.vy = toV(cam.dv_up); f.vz = toV(cam.dir_00);
   const vec3f dir = f * make_vec3f(-localDir.y, -localDir.z, localDir.x);
-  const vec3f org = toV(cam.org) + offset * cross(dir, f.vy);
-  setRay(ray, org, dir, cam.nearClip, INFINITY);
-  return sinTheta;
+  PanoRay r;
+  r.org = toV(cam.org) + offset * cross(dir, f.vy); r.dir = dir; r.sinTheta = sinTheta;
+  return r;
 }
 __device__ __forceinline__ void cameraInitRay(const OcCamera &cam, Ray &ray, vec2f screen, vec2f lens, vec2f pixelCenter)
 {
-  if (cam.type == OC_CAMERA_PANORAMIC) { panoramicInitRay(cam, ray, screen, pixelCenter); return; }
+  if (cam.type == OC_CAMERA_PANORAMIC) {
+    const PanoRay r = panoramicInitRay(cam, screen, pixelCenter);
+    setRay(ray, r.org, r.dir, cam.nearClip, INFINITY);
+    return;
+  }
   vec3f org = toV(cam.org);
   if (cam.type != OC_CAMERA_ORTHOGRAPHIC) {
     const float eye = cameraStereoSplit(cam, screen, pixelCenter);
@@ -1615,9 +1621,8 @@ __device__ __forceinline__ RayCone cameraInitRayCone(const OcCamera &cam, vec2f 
   RayCone rc;
   const float subH = fabsf(cam.subImage[3] - cam.subImage[1]);
   if (cam.type == OC_CAMERA_PANORAMIC) { // PanoramicCamera.ispc:84-91
-    Ray unused;
     rc.width = 0.f;
-    rc.dwdt = OC_PI * panoramicInitRay(cam, unused, screen, pixelCenter) * subH;
+    rc.dwdt = OC_PI * panoramicInitRay(cam, screen, pixelCenter).sinTheta * subH;
     if (cam.stereoMode == 4u) rc.dwdt *= 2.f;
     return rc;
   }

@@ -195,7 +195,16 @@ OSPPickResult CudaDevice::pick(OSPFrameBuffer, OSPRenderer, OSPCamera _c, OSPWor
   const float sx = lerpf(screenPos.x, cam.subImage[0], cam.subImage[2]), sy = lerpf(screenPos.y, cam.subImage[1], cam.subImage[3]);
   const vec3f du = make_vec3f(cam.du_size.x, cam.du_size.y, cam.du_size.z), dv = make_vec3f(cam.dv_up.x, cam.dv_up.y, cam.dv_up.z);
   vec3f org = make_vec3f(cam.org.x, cam.org.y, cam.org.z), dir = make_vec3f(cam.dir_00.x, cam.dir_00.y, cam.dir_00.z);
-  if (cam.type == OC_CAMERA_ORTHOGRAPHIC) org = org + sx * du + sy * dv;
+  if (cam.type == OC_CAMERA_PANORAMIC) { // PanoramicCamera_initRay (camera/PanoramicCamera.ispc:14-92); du / dv / dir_00 = the frame
+    // (the eye of the per-pixel stereo modes depends on CameraSample::pixel_center, which Renderer_pick leaves unset: mono there)
+    const float offset = cam.stereoMode == OSP_STEREO_LEFT ? -cam.ipdOffset.x : cam.stereoMode == OSP_STEREO_RIGHT ? cam.ipdOffset.x : 0.f;
+    const float phi = 6.28318530717958647692f * sx, theta = 3.14159265358979323846f * sy;
+    const float sinTheta = std::sin(theta), cosTheta = std::cos(theta);
+    const vec3f local = make_vec3f(std::cos(phi) * sinTheta, std::sin(phi) * sinTheta, cosTheta);
+    const vec3f vz = dir;
+    dir = (-local.y) * du + (-local.z) * dv + local.x * vz;
+    org = org + offset * cross(dir, dv);
+  } else if (cam.type == OC_CAMERA_ORTHOGRAPHIC) org = org + sx * du + sy * dv;
   else dir = normalize(dir + sx * du + sy * dv);
   OcRayHit rh{};
   rh.org[0] = org.x; rh.org[1] = org.y; rh.org[2] = org.z; rh.t0 = cam.nearClip;

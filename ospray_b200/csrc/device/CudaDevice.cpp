@@ -170,7 +170,12 @@ OSPFuture CudaDevice::renderFrame(OSPFrameBuffer _fb, OSPRenderer _r, OSPCamera 
     rsh.worldHasVolumes = w->sh.hasVolumes;
     rsh.worldNumLights = w->sh.numLights; // (with the geometry lights prepareFrame added)
     rsh.worldShadowOpaque = w->sh.shadowOpaque;
-    rsh.hasTextures = (texturedMaterials > 0 || emissiveMaterials > 0 || rsh.backplate || rsh.maxDepthTexture || w->hasHdriLight) ? 1u : 0u;
+    // which kernel instantiation the frame needs: texture maps concern every renderer; emitters and the microfacet materials only
+    // the pathtracer (scivis / ao shade non-OBJ materials with the default surface, like the reference); hdri / cylinder lights
+    // the pathtracer and scivis (ao ignores lights)
+    const bool maps = texturedMaterials > 0 || rsh.backplate || rsh.maxDepthTexture;
+    const bool pt = rsh.type == OC_RENDERER_PATHTRACER, lit = pt || rsh.type == OC_RENDERER_SCIVIS;
+    rsh.hasTextures = (maps || (pt && emissiveMaterials > 0) || (lit && w->hasHdriLight)) ? 1u : 0u;
     if (!finished) checkCuda(ospcuda_render_frame(dw, &c->sh, &rsh, &fb->sh), "render kernel");
     checkCuda(ospcuda_event_record(f->evRendered), "event record");
     fb->postProcess();

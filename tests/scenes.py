@@ -524,6 +524,9 @@ CASES = {
     "glass_alloy_pt": (lambda: glass_alloy_cornell(False), "pathtracer", {"pixelSamples": 2}, 2),
     "glass_alloy_rough_pt": (lambda: glass_alloy_cornell(True), "pathtracer", {"pixelSamples": 2}, 2),
     "carpaint_pt": (lambda: carpaint_cornell(), "pathtracer", {"pixelSamples": 2}, 2),
+    # the same materials under the renderers that do not know them (default surface, plain kernels: scivis / ao evalMaterial)
+    "principled_coat_scivis": (lambda: principled_cornell("coat"), "scivis", {"shadows": True, "aoSamples": 1}, 1),
+    "carpaint_ao": (lambda: carpaint_cornell(), "ao", {"aoSamples": 2}, 1),
     "velvet_paint_pt": (lambda: velvet_paint_cornell(), "pathtracer", {"pixelSamples": 2}, 2),
     "principled_plastic_pt": (lambda: principled_cornell("plastic"), "pathtracer", {"pixelSamples": 2}, 2),
     "principled_metal_pt": (lambda: principled_cornell("metal"), "pathtracer", {"pixelSamples": 2}, 2),
@@ -566,7 +569,7 @@ ORACLE_UNSUPPORTED = {"textured_pt", "textured_bias_pt", "cutout_pt", "backplate
                       "emissive_transparent_pt", "textured_scivis", "textured_ao", "cutout_scivis", "cutout_ao", "backplate_scivis",
                       "backplate_ao", "debug_texCoord", "debug_dPdt", "debug_dPds_tex", "debug_backplate", "metal_smooth_pt", "metal_rough_pt",
                       "plastic_smooth_pt", "plastic_rough_pt", "principled_plastic_pt", "principled_metal_pt", "principled_glass_pt",
-                      "principled_coat_pt", "principled_rough_layers_pt", "principled_emissive_pt", "glass_alloy_pt", "glass_alloy_rough_pt", "principled_sheen_pt", "principled_thin_pt", "principled_tex_pt", "principled_tex_cutout_pt", "velvet_paint_pt", "carpaint_pt", "hdri_pt", "hdri_instanced_pt", "hdri_scivis", "cylinder_lights_pt", "cylinder_lights_scivis"}
+                      "principled_coat_pt", "principled_rough_layers_pt", "principled_emissive_pt", "glass_alloy_pt", "glass_alloy_rough_pt", "principled_sheen_pt", "principled_thin_pt", "principled_tex_pt", "principled_tex_cutout_pt", "velvet_paint_pt", "carpaint_pt", "hdri_pt", "hdri_instanced_pt", "hdri_scivis", "cylinder_lights_pt", "cylinder_lights_scivis", "principled_coat_scivis", "carpaint_ao"}
 # Rough dielectric coatings: MicrofacetDielectricLayer_Constructor reads self->eta for Ravg BEFORE assigning it
 # (bsdfs/MicrofacetDielectricLayer.ih:55 vs :68), i.e. whatever the shading context's memory held from the previous BSDF. The
 # device uses the intended value; against the reference's kernels the coated surfaces then differ by ~0.5 % in brightness

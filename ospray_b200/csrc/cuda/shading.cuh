@@ -966,11 +966,21 @@ struct SphericalQuad
   vec3f e0, e1, z;
   float S, k, n0z, n0z2, n2z, x0, x1, y0, y1, z0;
 };
+// a / s, bit for bit, for vectors with many ZERO components (the edges of an axis-aligned light): an IEEE division whose numerator
+// is 0 leaves the division's fast path (exponent 0) for a ~50-instruction subroutine -- on C1 that was 11 % of the shade step's
+// instructions, all from the two edge normalisations below (ncu source page, profiles/r2_c1_trace_shade_ncu.txt). For a normal
+// (finite, non-zero, non-denormal) divisor 0 / s == 0 * s exactly, sign included.
+__device__ __forceinline__ float divZeroAware(float a, float s, bool sNormal) { return (a == 0.f && sNormal) ? a * s : a / s; }
+__device__ __forceinline__ vec3f divZeroAware(vec3f a, float s)
+{
+  const bool sNormal = ((__float_as_uint(s) >> 23) & 0xffu) - 1u < 254u;
+  return make_vec3f(divZeroAware(a.x, s, sNormal), divZeroAware(a.y, s, sNormal), divZeroAware(a.z, s, sNormal));
+}
 __device__ __forceinline__ SphericalQuad SphericalQuad_create(vec3f q0, vec3f e0, vec3f e1, vec3f n, vec3f P)
 {
   SphericalQuad q;
   const float e0l = length(e0), e1l = length(e1);
-  q.e0 = e0 / e0l; q.e1 = e1 / e1l; q.z = n;
+  q.e0 = divZeroAware(e0, e0l); q.e1 = divZeroAware(e1, e1l); q.z = n;
   const vec3f d = q0 - P;
   q.z0 = dot(d, q.z);
   q.z = q.z0 > 0.f ? neg(q.z) : q.z;

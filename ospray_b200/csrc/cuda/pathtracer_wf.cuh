@@ -904,7 +904,7 @@ __device__ __forceinline__ uint32_t ptShadeStep(const PtArgs &k, uint32_t p, uin
           LightSample ls = (TEX && light.type == OC_LIGHT_GEOMETRY) ? GeometryLight_sample(world, ren, light, dg, sl)
               : (TEX && light.type == OC_LIGHT_HDRI) ? HDRILight_sample(light, sl)
               : (TEX && light.type == OC_LIGHT_CYLINDER) ? CylinderLight_sample(light, dg, sl) : Light_sample(light, dg, sl);
-          ls.weight = ls.weight / lightSelectionProb;
+          ls.weight = divZeroAware(ls.weight, lightSelectionProb); // (rejected samples carry a zero weight: see divZeroAware)
           ls.pdf *= lightSelectionProb;
           if (!(reduce_max(ls.weight) <= 0.0f || ls.pdf <= 0.0f)) {
             const EvalRes fe = volume ? HenyeyGreenstein_eval(vmodel->anisotropy, wo, ls.dir)

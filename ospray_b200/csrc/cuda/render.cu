@@ -95,7 +95,10 @@ __device__ __forceinline__ vec3f evaluateVirtualLights(Ctx &c, bool straightPath
   vec3f L = make_vec3f(0.f);
   const uint32_t numLights = c.world->numLights, numGeoLights = c.world->numGeoLights;
   if (numLights <= numGeoLights) return L; // no virtual lights (geometry lights come first and are hit, not evaluated)
-  const float lower = length(last.P - ray.org);
+  // (the last vertex usually IS the ray's origin: sqrtf(0) would take the square root's slow path; +0 either way)
+  const vec3f toOrg = last.P - ray.org;
+  const float toOrg2 = dot(toOrg, toOrg);
+  const float lower = toOrg2 == 0.f ? 0.f : sqrtf(toOrg2);
   const float upper = environment ? INFINITY : length(last.P - (ray.org + ray.t * ray.dir));
   const float selectionPDF = last.numLightSamples / (float)numLights;
   for (uint32_t i = numGeoLights; i < numLights; i++) {

@@ -14,6 +14,9 @@ namespace oc {
 
 #define OC_MACROCELL_WIDTH 16
 
+// nextafterf(u, 0.f) for the positive, finite u this file hands it (a grid dimension minus one, >= 1): the float below is the
+// bit pattern minus one -- one instruction instead of the library routine, per sample (it was 6 % of the marcher's instructions)
+__device__ __forceinline__ float floatBelow(float u) { return u > 0.f ? __uint_as_float(__float_as_uint(u) - 1u) : nextafterf(u, 0.f); }
 __device__ __forceinline__ float volumeSample(const OcVolume &v, vec3f p)
 {
   const vec3f lc = make_vec3f((p.x - v.gridOrigin.x) / v.gridSpacing.x, (p.y - v.gridOrigin.y) / v.gridSpacing.y,
@@ -21,7 +24,7 @@ __device__ __forceinline__ float volumeSample(const OcVolume &v, vec3f p)
   const float ux = (float)(v.dims[0] - 1), uy = (float)(v.dims[1] - 1), uz = (float)(v.dims[2] - 1);
   if (!(lc.x >= 0.f && lc.y >= 0.f && lc.z >= 0.f && lc.x <= ux && lc.y <= uy && lc.z <= uz))
     return NAN;
-  const float cx = fminf(lc.x, nextafterf(ux, 0.f)), cy = fminf(lc.y, nextafterf(uy, 0.f)), cz = fminf(lc.z, nextafterf(uz, 0.f));
+  const float cx = fminf(lc.x, floatBelow(ux)), cy = fminf(lc.y, floatBelow(uy)), cz = fminf(lc.z, floatBelow(uz));
   const float fx0 = floorf(cx), fy0 = floorf(cy), fz0 = floorf(cz);
   const uint32_t ix = (uint32_t)fx0, iy = (uint32_t)fy0, iz = (uint32_t)fz0;
   const float fx = cx - fx0, fy = cy - fy0, fz = cz - fz0;
